@@ -1,0 +1,412 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into or loaded by the product path.
+//
+// C-callable driver around the UNMODIFIED reference classes, compiled from the
+// sources under /root/reference by oracle/ref_build.mk into
+// oracle/_ref/libxara_ref.a.  This file is ours; it only *calls* the
+// reference's public C++ API (Domain, Node, Brick, FourNodeQuad, NDMaterial,
+// PlainHandler, PlainNumberer / DOF_Numberer+RCM, SparseGenRowLinSOE,
+// LoadControl, NewtonRaphson ...).  It plays the part that
+// runtime/runtime/BasicAnalysisBuilder.cpp plays in the reference (that file
+// needs Tcl and is not built): domainChanged() (BasicAnalysisBuilder.cpp:225)
+// and analyzeStatic() (BasicAnalysisBuilder.cpp:337) are restated below in
+// their Increment / Iterate / Commit order.
+//
+// Used by tests/ to pin the oracle (oracle/xara_oracle.c) and by
+// `bench.py --impl reference` / cpu_baseline as the "reference" CPU arm.
+
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <map>
+#include <vector>
+#include <array>
+
+#include <Domain.h>
+#include <Node.h>
+#include <NodeIter.h>
+#include <Element.h>
+#include <ElementIter.h>
+#include <Vector.h>
+#include <Matrix.h>
+#include <ID.h>
+#include <SP_Constraint.h>
+#include <MP_Constraint.h>
+#include <LoadPattern.h>
+#include <NodalLoad.h>
+#include <LinearSeries.h>
+
+#include <NDMaterial.h>
+#include <ElasticIsotropicMaterial.h>
+#include <J2Plasticity.h>
+#include <UniaxialMaterial.h>
+
+#include <Brick.h>
+#include <FourNodeQuad.h>
+
+#include <AnalysisModel.h>
+#include <PlainHandler.h>
+#include <PlainNumberer.h>
+#include <DOF_Numberer.h>
+#include <RCM.h>
+#include <DOF_Group.h>
+#include <DOF_GrpIter.h>
+#include <FE_Element.h>
+#include <FE_EleIter.h>
+#include <Graph.h>
+// The two general sparse SOEs keep their arrays private and offer no accessor;
+// the harness has to read A/colA/rowStartA, so it opens them up for this
+// translation unit only (the reference sources are not touched).
+#define private public
+#define protected public
+#include <SparseGenRowLinSOE.h>
+#include <SparseGenColLinSOE.h>
+#undef private
+#undef protected
+#include <SparseGenRowLinSolver.h>
+#include <SparseGenColLinSolver.h>
+#include <LoadControl.h>
+#include <DisplacementControl.h>
+#include <NewtonRaphson.h>
+#include <CTestNormDispIncr.h>
+#include <CTestNormUnbalance.h>
+#include <CTestEnergyIncr.h>
+
+// ---------------------------------------------------------------------------
+// A dense LU solver for SparseGenRowLinSOE.  The linear solve is outside the
+// hot path (BASELINE.json: "left to the reference's SOE solver and timed
+// separately"); the reference's own SparseGenRow solvers need SuperLU/PETSc,
+// so the harness supplies the simplest exact one.
+// ---------------------------------------------------------------------------
+static int dense_solve(int n, const int* ptr, const int* idx, const double* A, bool csc,
+                       const double* Bv, double* X) {
+  std::vector<double> M((size_t)n * n, 0.0), b(n);
+  for (int r = 0; r < n; r++) {
+    for (int k = ptr[r]; k < ptr[r + 1]; k++) {
+      if (csc) M[(size_t)idx[k] * n + r] += A[k];
+      else     M[(size_t)r * n + idx[k]] += A[k];
+    }
+    b[r] = Bv[r];
+  }
+  for (int c = 0; c < n; c++) {
+    int p = c; double best = std::fabs(M[(size_t)c * n + c]);
+    for (int r = c + 1; r < n; r++)
+      if (std::fabs(M[(size_t)r * n + c]) > best) { best = std::fabs(M[(size_t)r * n + c]); p = r; }
+    if (best == 0.0) return -1;
+    if (p != c) {
+      for (int k = 0; k < n; k++) std::swap(M[(size_t)p * n + k], M[(size_t)c * n + k]);
+      std::swap(b[p], b[c]);
+    }
+    for (int r = c + 1; r < n; r++) {
+      double f = M[(size_t)r * n + c] / M[(size_t)c * n + c];
+      if (f == 0.0) continue;
+      for (int k = c; k < n; k++) M[(size_t)r * n + k] -= f * M[(size_t)c * n + k];
+      b[r] -= f * b[c];
+    }
+  }
+  for (int r = n - 1; r >= 0; r--) {
+    double s = b[r];
+    for (int k = r + 1; k < n; k++) s -= M[(size_t)r * n + k] * X[k];
+    X[r] = s / M[(size_t)r * n + r];
+  }
+  return 0;
+}
+
+class HarnessRowSolver : public SparseGenRowLinSolver {
+public:
+  HarnessRowSolver() : SparseGenRowLinSolver(0) {}
+  int setSize() override { return 0; }
+  int solve() override {
+    return dense_solve(theSOE->size, theSOE->rowStartA, theSOE->colA, theSOE->A, false,
+                       &theSOE->B[0], &theSOE->X[0]);
+  }
+  int sendSelf(int, Channel&) override { return 0; }
+  int recvSelf(int, Channel&, FEM_ObjectBroker&) override { return 0; }
+};
+
+class HarnessColSolver : public SparseGenColLinSolver {
+public:
+  HarnessColSolver() : SparseGenColLinSolver(0) {}
+  int setSize() override { return 0; }
+  int solve() override {
+    return dense_solve(theSOE->size, theSOE->colStartA, theSOE->rowA, theSOE->A, true,
+                       &theSOE->B[0], &theSOE->X[0]);
+  }
+  int sendSelf(int, Channel&) override { return 0; }
+  int recvSelf(int, Channel&, FEM_ObjectBroker&) override { return 0; }
+};
+
+// SparseGenRowLinSOE leaves LinearSOE::setX pure (its definitions sit under
+// "#if 0" in SparseGenRowLinSOE.h:66); give it the obvious one so it can be built.
+class RowSOE : public SparseGenRowLinSOE {
+public:
+  RowSOE(SparseGenRowLinSolver& s) : SparseGenRowLinSOE(s) {}
+  void setX(int loc, double value) override { if (loc >= 0 && loc < size) X[loc] = value; }
+  void setX(const Vector& x) override { X = x; }
+};
+
+struct RefModel {
+  int ndm, ndf;
+  Domain* domain = nullptr;
+  std::map<int, NDMaterial*> ndmats;
+  AnalysisModel* amodel = nullptr;
+  PlainHandler* handler = nullptr;
+  DOF_Numberer* numberer = nullptr;
+  LinearSOE* soe = nullptr;
+  SparseGenRowLinSOE* rsoe = nullptr;   // soeKind 1
+  SparseGenColLinSOE* csoe = nullptr;   // soeKind 0
+  int n() const { return rsoe ? rsoe->size : csoe->size; }
+  const int* ptr() const { return rsoe ? rsoe->rowStartA : csoe->colStartA; }
+  const int* idx() const { return rsoe ? rsoe->colA : csoe->rowA; }
+  const double* A() const { return rsoe ? rsoe->A : csoe->A; }
+  StaticIntegrator* integ = nullptr;
+  ConvergenceTest* test = nullptr;
+  NewtonRaphson* algo = nullptr;
+  int nloads = 0;
+};
+
+extern "C" {
+
+void* ref_model_new(int ndm, int ndf) {
+  RefModel* m = new RefModel;
+  m->ndm = ndm; m->ndf = ndf;
+  m->domain = new Domain();
+  return m;
+}
+
+int ref_add_node(void* h, int tag, const double* x) {
+  RefModel* m = (RefModel*)h;
+  Node* n = (m->ndm == 2) ? new Node(tag, m->ndf, x[0], x[1])
+                          : new Node(tag, m->ndf, x[0], x[1], x[2]);
+  return m->domain->addNode(n) ? 0 : -1;
+}
+
+int ref_fix(void* h, int nodeTag, int dof) {
+  RefModel* m = (RefModel*)h;
+  SP_Constraint* sp = new SP_Constraint(nodeTag, dof, 0.0, true);
+  return m->domain->addSP_Constraint(sp) ? 0 : -1;
+}
+
+// kind 0: ElasticIsotropic (E, nu, rho)        -- runtime/commands/modeling/nDMaterial.cpp
+// kind 1: J2Plasticity (K,G,sig0,sigInf,delta,H,eta) -- commands/modeling/material/plastic.cpp:927
+int ref_add_nd_material(void* h, int tag, int kind, const double* p) {
+  RefModel* m = (RefModel*)h;
+  NDMaterial* mat = nullptr;
+  if (kind == 0) mat = new ElasticIsotropicMaterial(tag, p[0], p[1], p[2]);
+  else if (kind == 1) mat = new J2Plasticity(tag, 0, p[0], p[1], p[2], p[3], p[4], p[5], p[6], 0.0);
+  if (!mat) return -1;
+  m->ndmats[tag] = mat;
+  return 0;
+}
+
+int ref_add_brick(void* h, int tag, const int* nd, int matTag, const double* b) {
+  RefModel* m = (RefModel*)h;
+  Element* e = new Brick(tag, nd[0], nd[1], nd[2], nd[3], nd[4], nd[5], nd[6], nd[7],
+                         *m->ndmats.at(matTag), b[0], b[1], b[2]);
+  return m->domain->addElement(e) ? 0 : -1;
+}
+
+// type: 0 PlaneStrain, 1 PlaneStress
+int ref_add_quad(void* h, int tag, const int* nd, int matTag, double thick, int type,
+                 double pressure, double rho, const double* b) {
+  RefModel* m = (RefModel*)h;
+  NDMaterial* copy = m->ndmats.at(matTag)->getCopy(type == 0 ? "PlaneStrain" : "PlaneStress");
+  if (!copy) return -2;
+  std::array<int, 4> nodes{nd[0], nd[1], nd[2], nd[3]};
+  Element* e = new FourNodeQuad(tag, nodes, *copy, thick, pressure, rho, b[0], b[1]);
+  delete copy;
+  return m->domain->addElement(e) ? 0 : -1;
+}
+
+int ref_add_load(void* h, int nodeTag, const double* vals) {
+  RefModel* m = (RefModel*)h;
+  if (m->domain->getLoadPattern(1) == nullptr) {
+    LoadPattern* lp = new LoadPattern(1);
+    lp->setTimeSeries(new LinearSeries());
+    m->domain->addLoadPattern(lp);
+  }
+  Vector v(m->ndf);
+  for (int i = 0; i < m->ndf; i++) v(i) = vals[i];
+  NodalLoad* nl = new NodalLoad(m->nloads++, nodeTag, v);
+  return m->domain->addNodalLoad(nl, 1) ? 0 : -1;
+}
+
+// restates BasicAnalysisBuilder::domainChanged (BasicAnalysisBuilder.cpp:225-300)
+// numberer: 0 Plain, 1 RCM.  integrator: LoadControl(dlambda).
+// soeKind: 0 SparseGenColLinSOE (CSC, the live "SparseGeneral" system), 1 SparseGenRowLinSOE (CSR)
+int ref_setup(void* h, int numberer, int soeKind, double dlambda, int testKind, double tol, int maxIter) {
+  RefModel* m = (RefModel*)h;
+  m->amodel = new AnalysisModel();
+  m->handler = new PlainHandler();
+  if (numberer == 0) m->numberer = new PlainNumberer();
+  else { RCM* rcm = new RCM(false); m->numberer = new DOF_Numberer(*rcm); }
+  if (soeKind == 1) { m->rsoe = new RowSOE(*new HarnessRowSolver()); m->soe = m->rsoe; }
+  else { m->csoe = new SparseGenColLinSOE(*new HarnessColSolver()); m->soe = m->csoe; }
+  m->integ = new LoadControl(dlambda, 1, dlambda, dlambda);
+  if (testKind == 0) m->test = new CTestNormDispIncr(tol, maxIter, 0);
+  else if (testKind == 1) m->test = new CTestNormUnbalance(tol, maxIter, 0);
+  else m->test = new CTestEnergyIncr(tol, maxIter, 0);
+  m->algo = new NewtonRaphson(*m->test);
+
+  m->amodel->setLinks(*m->domain, *m->handler);
+  m->handler->setLinks(*m->domain, *m->amodel, *m->integ);
+  m->numberer->setLinks(*m->amodel);
+  m->integ->setLinks(*m->amodel, *m->soe, m->test);
+  m->algo->setLinks(*m->amodel, *m->integ, *m->soe, m->test);
+  m->soe->setLinks(*m->amodel);
+
+  m->amodel->clearAll();
+  m->handler->clearAll();
+  if (m->handler->handle() < 0) return -1;
+  if (m->numberer->numberDOF() < 0) return -2;
+  if (m->handler->doneNumberingDOF() < 0) return -2;
+  Graph& g = m->amodel->getDOFGraph();
+  if (m->soe->setSize(g) < 0) return -3;
+  m->amodel->clearDOFGraph();
+  if (m->integ->domainChanged() < 0) return -4;
+  return m->amodel->getNumEqn();
+}
+
+int ref_num_eqn(void* h) { return ((RefModel*)h)->soe->getNumEqn(); }
+int ref_nnz(void* h) { RefModel* m = (RefModel*)h; return m->ptr()[m->n()]; }
+
+// equation ids of a node's DOF_Group (DOF_Group::getID)
+int ref_node_ids(void* h, int nodeTag, int* ids) {
+  RefModel* m = (RefModel*)h;
+  Node* n = m->domain->getNode(nodeTag);
+  if (!n || !n->getDOF_GroupPtr()) return -1;
+  const ID& id = n->getDOF_GroupPtr()->getID();
+  for (int i = 0; i < id.Size(); i++) ids[i] = id(i);
+  return id.Size();
+}
+
+// FE_Element::getID in AnalysisModel iteration order; returns count of FE elements
+int ref_fe_ids(void* h, int* eleTags, int* ids, int stride) {
+  RefModel* m = (RefModel*)h;
+  FE_EleIter& it = m->amodel->getFEs();
+  FE_Element* fe; int c = 0;
+  while ((fe = it()) != nullptr) {
+    const ID& id = fe->getID();
+    if (eleTags) eleTags[c] = fe->getTag();
+    for (int i = 0; i < id.Size() && i < stride; i++) ids[(size_t)c * stride + i] = id(i);
+    c++;
+  }
+  return c;
+}
+
+void ref_get_csr(void* h, int* rowStart, int* colA) {
+  RefModel* m = (RefModel*)h;
+  int n = m->n();
+  memcpy(rowStart, m->ptr(), sizeof(int) * (n + 1));
+  memcpy(colA, m->idx(), sizeof(int) * m->ptr()[n]);
+}
+
+// Node::setTrialDisp for every node (u is [nNodes][ndf] in the given tag order),
+// then Domain::update -> Element::update (state determination)
+int ref_set_trial_disp(void* h, int n, const int* tags, const double* u) {
+  RefModel* m = (RefModel*)h;
+  Vector v(m->ndf);
+  for (int i = 0; i < n; i++) {
+    Node* nd = m->domain->getNode(tags[i]);
+    for (int j = 0; j < m->ndf; j++) v(j) = u[(size_t)i * m->ndf + j];
+    nd->setTrialDisp(v);
+  }
+  return m->domain->update();
+}
+
+int ref_get_trial_disp(void* h, int n, const int* tags, double* u) {
+  RefModel* m = (RefModel*)h;
+  for (int i = 0; i < n; i++) {
+    const Vector& d = m->domain->getNode(tags[i])->getTrialDisp();
+    for (int j = 0; j < m->ndf; j++) u[(size_t)i * m->ndf + j] = d(j);
+  }
+  return 0;
+}
+
+void ref_apply_load(void* h, double lambda) { ((RefModel*)h)->amodel->applyLoadDomain(lambda); }
+
+// IncrementalIntegrator::formTangent (IncrementalIntegrator.cpp:74) -> A values (CSR order)
+int ref_form_tangent(void* h, double* A) {
+  RefModel* m = (RefModel*)h;
+  int r = m->integ->formTangent(CURRENT_TANGENT);
+  if (A) memcpy(A, m->A(), sizeof(double) * ref_nnz(h));
+  return r;
+}
+
+// IncrementalIntegrator::formUnbalance -> B
+int ref_form_unbalance(void* h, double* B) {
+  RefModel* m = (RefModel*)h;
+  int r = m->integ->formUnbalance();
+  if (B) { const Vector& b = m->soe->getB(); for (int i = 0; i < b.Size(); i++) B[i] = b(i); }
+  return r;
+}
+
+int ref_commit(void* h) { return ((RefModel*)h)->domain->commit(); }
+int ref_revert(void* h) { return ((RefModel*)h)->domain->revertToLastCommit(); }
+
+// element level: Element::getTangentStiff / getResistingForce
+int ref_ele_tangent(void* h, int tag, double* K) {
+  Element* e = ((RefModel*)h)->domain->getElement(tag);
+  if (!e) return -1;
+  const Matrix& k = e->getTangentStiff();
+  for (int i = 0; i < k.noRows(); i++)
+    for (int j = 0; j < k.noCols(); j++) K[(size_t)i * k.noCols() + j] = k(i, j);
+  return k.noRows();
+}
+int ref_ele_resid(void* h, int tag, double* R) {
+  Element* e = ((RefModel*)h)->domain->getElement(tag);
+  if (!e) return -1;
+  const Vector& r = e->getResistingForce();
+  for (int i = 0; i < r.Size(); i++) R[i] = r(i);
+  return r.Size();
+}
+
+// restates BasicAnalysisBuilder::analyzeStatic (BasicAnalysisBuilder.cpp:337-420):
+// newStep / solveCurrentStep / commit; iters[i] = Newton iterations of step i
+// (ConvergenceTest::getNumTests), norms[i*maxIter + k] = test norms.
+int ref_analyze_static(void* h, int nsteps, int* iters, double* norms, int maxIter) {
+  RefModel* m = (RefModel*)h;
+  for (int s = 0; s < nsteps; s++) {
+    if (m->amodel->analysisStep(0.0) < 0) return -2;
+    if (m->integ->newStep() < 0) return -2;
+    int r = m->algo->solveCurrentStep();
+    iters[s] = m->test->getNumTests();
+    if (norms) {
+      const Vector& nv = m->test->getNorms();
+      for (int k = 0; k < maxIter && k < nv.Size(); k++) norms[(size_t)s * maxIter + k] = nv(k);
+    }
+    if (r < 0) { m->domain->revertToLastCommit(); m->integ->revertToLastStep(); return -3; }
+    if (m->integ->commit() < 0) return -4;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// material level: strain path through NDMaterial (setTrialStrain / getStress /
+// getTangent / commitState).  type: "ThreeDimensional" | "PlaneStrain" ...
+// strains [n][order]; commit[n] flags; out stress [n][order], tangent [n][order*order]
+// ---------------------------------------------------------------------------
+int ref_nd_path(int kind, const double* p, const char* type, int n, const double* strains,
+                const int* commit, double* stress, double* tangent) {
+  NDMaterial* base = nullptr;
+  if (kind == 0) base = new ElasticIsotropicMaterial(1, p[0], p[1], p[2]);
+  else base = new J2Plasticity(1, 0, p[0], p[1], p[2], p[3], p[4], p[5], p[6], 0.0);
+  NDMaterial* mat = base->getCopy(type);
+  if (!mat) return -1;
+  int order = mat->getOrder();
+  Vector e(order);
+  for (int s = 0; s < n; s++) {
+    for (int i = 0; i < order; i++) e(i) = strains[(size_t)s * order + i];
+    if (mat->setTrialStrain(e) < 0) return -2;
+    const Vector& sig = mat->getStress();
+    const Matrix& D = mat->getTangent();
+    for (int i = 0; i < order; i++) {
+      stress[(size_t)s * order + i] = sig(i);
+      for (int j = 0; j < order; j++) tangent[((size_t)s * order + i) * order + j] = D(i, j);
+    }
+    if (commit[s]) mat->commitState();
+  }
+  delete mat; delete base;
+  return order;
+}
+
+} // extern "C"
