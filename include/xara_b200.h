@@ -1,0 +1,159 @@
+/* xara_b200 -- B200-native element state determination + global assembly.
+ *
+ * C-ABI drop-in boundary for the reference's (peer-open-source/xara, OpenSeesRT)
+ * hot path:  Domain::update -> Element::update -> NDMaterial::setTrialStrain,
+ * IncrementalIntegrator::formTangent / formUnbalance -> FE_Element::getTangent /
+ * getResidual -> LinearSOE::addA / addB.
+ *
+ * Plain pointers and sizes only.  Every entry point names the reference
+ * interface it stands in for (path under /root/reference/SRC : line).
+ * INTEGRATION.md shows the C++ glue a maintainer adds on the reference side.
+ *
+ * There is NO CPU fallback: every xb_* call that needs the device fails with
+ * XB_ERR_CUDA when no sm_100a device is available.
+ */
+#ifndef XARA_B200_H
+#define XARA_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct xb_model xb_model;
+
+/* return codes */
+enum {
+  XB_OK = 0,
+  XB_ERR_ARG = -1,        /* bad argument (unknown tag, wrong size, order ...)   */
+  XB_ERR_STATE = -2,      /* call made in the wrong phase (e.g. before xb_setup) */
+  XB_ERR_CUDA = -3,       /* CUDA runtime error or no device                      */
+  XB_ERR_MATERIAL = -4,   /* constitutive update failed (J2 return map > 25 its,  */
+                          /*   J2Plasticity.cpp:296-301 returns -1)               */
+  XB_ERR_UNSUPPORTED = -5 /* model feature outside the device path               */
+};
+
+/* nDMaterial kinds (runtime/commands/modeling/nDMaterial.cpp, material/plastic.cpp:927) */
+enum {
+  XB_MAT_ELASTIC_ISOTROPIC = 0, /* par = E, nu, rho          (ElasticIsotropicMaterial.h)   */
+  XB_MAT_J2PLASTICITY = 1       /* par = K, G, sig0, sigInf, delta, H, eta (J2Plasticity.h:47) */
+};
+
+/* element kinds */
+enum {
+  XB_ELE_STDBRICK = 0,    /* element/Brick/Brick.cpp, 8 nodes x 3 dof, 2x2x2 Gauss; par = b1,b2,b3 */
+  XB_ELE_FOURNODEQUAD = 1 /* element/Plane/FourNodeQuad.cpp, 4 nodes x 2 dof, 2x2 Gauss;
+                             par = thickness, type(0 PlaneStrain), pressure(=0), rho, b1, b2        */
+};
+
+/* DOF numberers (analysis/numberer) */
+enum {
+  XB_NUMBERER_PLAIN = 0, /* PlainNumberer::numberDOF, PlainNumberer.cpp:73            */
+  XB_NUMBERER_RCM = 1    /* DOF_Numberer::numberDOF + RCM(false), DOF_Numberer.cpp:92, RCM.cpp:66 */
+};
+
+/* LinearSOE storage whose addA semantics the scatter map reproduces */
+enum {
+  XB_SOE_SPARSE_GEN_COL = 0, /* SparseGenColLinSOE (colStartA,rowA), SparseGenColLinSOE.cpp:161,264 */
+  XB_SOE_SPARSE_GEN_ROW = 1  /* SparseGenRowLinSOE (rowStartA,colA), SparseGenRowLinSOE.cpp:127,224 */
+};
+
+const char* xb_version(void);
+/* message for the last failing call on this thread */
+const char* xb_last_error(void);
+/* number of usable CUDA devices (0 on a CPU-only box; never an error) */
+int xb_device_count(void);
+
+/* ---- model definition: what the reference's model commands put in the Domain ---- */
+
+/* Domain::Domain (domain/domain/Domain.cpp:84); ndm, ndf as in `model basic -ndm -ndf` */
+xb_model* xb_model_create(int ndm, int ndf);
+void xb_model_destroy(xb_model*);
+
+/* Domain::addNode (Domain.cpp:576) for n nodes; crd is [n][ndm]; tags unique, any order */
+int xb_add_nodes(xb_model*, int n, const int* tags, const double* crd);
+/* Domain::addSP_Constraint (Domain.cpp:636) -- homogeneous `fix`; dof is 0-based */
+int xb_add_sp(xb_model*, int n, const int* node_tags, const int* dofs);
+/* OPS nDMaterial command; par has npar doubles in the order listed at the kind */
+int xb_add_nd_material(xb_model*, int tag, int kind, const double* par, int npar);
+/* Domain::addElement (Domain.cpp:442) for n elements of one kind; conn is [n][nen] node
+ * tags, mat_tags [n], par [n][par_stride] (par_stride >= the kind's parameter count).
+ * All materials referenced by one call must be of one nDMaterial kind. */
+int xb_add_elements(xb_model*, int kind, int n, const int* tags, const int* conn,
+                    const int* mat_tags, const double* par, int par_stride);
+/* LoadPattern 1 with a Linear series + NodalLoad (domain/node/NodalLoad.cpp:97):
+ * values is [n][ndf]; loads on one node accumulate */
+int xb_add_nodal_loads(xb_model*, int n, const int* node_tags, const double* values);
+
+/* ---- analysis set-up: BasicAnalysisBuilder::domainChanged (runtime/runtime/
+ * BasicAnalysisBuilder.cpp:225): PlainHandler::handle (analysis/handler/PlainHandler.cpp:60),
+ * numberDOF, AnalysisModel::getDOFGraph (analysis/model/AnalysisModel.cpp:286),
+ * LinearSOE::setSize.  Host-side integer work; needs no device.  Returns numEqn >= 0. */
+int xb_setup(xb_model*, int numberer, int soe_kind);
+
+int xb_num_nodes(const xb_model*);
+long long xb_num_elements(const xb_model*);
+long long xb_num_gauss_points(const xb_model*);
+int xb_num_eqn(const xb_model*);
+long long xb_nnz(const xb_model*);
+/* node tags in Domain iteration order (ascending, MapOfTaggedObjects); every [nn][..]
+ * array below uses this order */
+int xb_get_node_tags(const xb_model*, int* tags);
+/* DOF_Group::getID for every node: ids [nn][ndf]; -1 = constrained (PlainHandler.cpp:117) */
+int xb_get_ids(const xb_model*, int* ids);
+/* element tags in FE_Element order (ascending element tag, PlainHandler.cpp:233) */
+int xb_get_element_tags(const xb_model*, int* tags);
+/* colStartA/rowA (CSC) or rowStartA/colA (CSR): ptr [neq+1] (64-bit), idx [nnz] */
+int xb_get_pattern(const xb_model*, long long* ptr, int* idx);
+/* the addA location of every entry of FE elements [e0,e1): map[(e-e0)*nd*nd + i*nd + j]
+ * = index into A that receives element-matrix entry (i,j), -1 when dropped */
+int xb_get_scatter_map(const xb_model*, long long e0, long long e1, long long* map);
+
+/* ---- device phase ---- */
+
+/* allocate HBM, upload the model, bind to a CUDA stream (cudaStream_t as void*; NULL =
+ * a stream the library creates).  Must follow xb_setup. */
+int xb_device_init(xb_model*, int device, void* cuda_stream);
+
+/* Node::setTrialDisp for all nodes, u [nn][ndf] in host memory (H2D inside) */
+int xb_set_trial_disp(xb_model*, const double* u);
+/* AnalysisModel::incrDisp (analysis/model/AnalysisModel.cpp): trial += dU[id], dU [neq] host */
+int xb_incr_trial_disp(xb_model*, const double* dU);
+int xb_get_trial_disp(xb_model*, double* u);
+/* Domain::update -> Element::update -> NDMaterial::setTrialStrain for every Gauss point */
+int xb_update(xb_model*);
+/* AnalysisModel::applyLoadDomain(lambda) for the Linear-series pattern */
+int xb_apply_load(xb_model*, double lambda);
+/* IncrementalIntegrator::formTangent(CURRENT_TANGENT), analysis/integrator/
+ * IncrementalIntegrator.cpp:74.  A (nnz doubles, host) may be NULL to keep A resident. */
+int xb_form_tangent(xb_model*, double* A);
+/* IncrementalIntegrator::formUnbalance (formElementResidual :221 + formNodalUnbalance :202).
+ * B (neq doubles, host) may be NULL. */
+int xb_form_unbalance(xb_model*, double* B);
+/* Domain::commit / Domain::revertToLastCommit */
+int xb_commit(xb_model*);
+int xb_revert_to_last_commit(xb_model*);
+/* blocks until the model's stream is idle; surfaces asynchronous errors */
+int xb_synchronize(xb_model*);
+
+/* resident buffers (device pointers) for callers that keep the SOE on the GPU */
+double* xb_device_A(xb_model*);
+double* xb_device_B(xb_model*);
+double* xb_device_trial_disp(xb_model*);
+
+/* parity / debugging taps: Element::getTangentStiff / getResistingForce of FE element e
+ * as last formed on the device (row-major nd*nd / nd doubles), and the material response
+ * (stress [order], tangent [order*order]) of Gauss point g of element e */
+int xb_get_element_tangent(xb_model*, long long e, double* K);
+int xb_get_element_resid(xb_model*, long long e, double* R);
+int xb_get_gp_response(xb_model*, long long e, int g, double* stress, double* tangent);
+
+/* kernel launches issued by this model since creation (bench.py's gpu_launches) */
+long long xb_launch_count(const xb_model*);
+/* bytes the last xb_form_tangent / xb_form_unbalance / xb_update moved algorithmically
+ * (DESIGN.md "algorithmic bytes"): which = 0 update, 1 formUnbalance, 2 formTangent */
+long long xb_algorithmic_bytes(const xb_model*, int which);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XARA_B200_H */

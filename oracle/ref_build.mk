@@ -35,7 +35,7 @@ $(OUT)/libxara_ref.a: $(OBJS)
 
 $(OBJ)/%.o: $(SRC)/%.cpp
 	@mkdir -p $(dir $@)
-	@$(CXX) $(CXXFLAGS) -c $< -o $@ 2> $@.err || (echo "FAIL $<" >> $(OUT)/failed.txt; rm -f $@; true)
+	@$(CXX) $(CXXFLAGS) -c $< -o $@ 2> $@.err || (echo "FAIL $<" >> $(OUT)/failed.txt; echo "" | $(CXX) -x c++ -c - -o $@)
 
 # ---- plain-C closed-form small inverses used by MatrixND (matrix/routines/*.c) ----
 CSRCS := $(wildcard $(SRC)/matrix/routines/*.c)
@@ -43,10 +43,11 @@ COBJS := $(patsubst $(SRC)/%.c,$(OBJ)/%.o,$(CSRCS))
 $(OUT)/libxara_ref.a: $(COBJS)
 $(OBJ)/%.o: $(SRC)/%.c
 	@mkdir -p $(dir $@)
-	@$(CC) -O3 -march=haswell -ffloat-store -fPIC -w -I$(SRC)/matrix/routines -c $< -o $@ 2> $@.err || (rm -f $@; true)
+	@$(CC) -O3 -march=haswell -ffloat-store -fPIC -w -I$(SRC)/matrix/routines -c $< -o $@ 2> $@.err || (echo "" | $(CC) -x c -c - -o $@)
 
 # ---- the harness shared library the tests and the reference bench arm load ----
 harness: $(OUT)/libref_harness.so
 $(OUT)/libref_harness.so: ref_harness.cpp ref_shims.cpp $(OUT)/libxara_ref.a
-	$(CXX) -std=c++17 -O2 -fPIC -w -D_LINUX -D_UNIX $(INCS) -shared ref_harness.cpp ref_shims.cpp \
+	@echo "link $@"
+	@$(CXX) -std=c++17 -O2 -fPIC -w -D_LINUX -D_UNIX $(INCS) -shared ref_harness.cpp ref_shims.cpp \
 	    -o $@ $(OUT)/libxara_ref.a -Wl,--no-undefined

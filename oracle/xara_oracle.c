@@ -1,0 +1,898 @@
+/* TEST INFRASTRUCTURE ONLY -- CPU restatement ("oracle") of the reference's
+ * element-state-determination + assembly hot path.  Nothing under xara_b200/
+ * may include, link or load this file; only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs use it, as the checker.
+ *
+ * Parity is PINNED: tests/test_oracle_vs_reference.py checks every function
+ * below against the reference's own classes compiled from /root/reference
+ * (oracle/ref_build.mk + oracle/ref_harness.cpp) and against the fixtures
+ * under tests/golden/ that the same harness generated.
+ *
+ * Each function cites the reference file:line it restates.  The arithmetic
+ * keeps the reference's operation order so that, built with
+ * -ffp-contract=off, results agree with the reference to the last bits.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+
+/* ------------------------------------------------------------------------ */
+/* material kinds / element kinds shared with tests (mirrors include/xara_b200.h) */
+enum { ORC_MAT_ELASTIC_ISOTROPIC = 0, ORC_MAT_J2 = 1 };
+enum { ORC_ELE_BRICK = 0, ORC_ELE_QUAD = 1 };
+enum { ORC_ND_3D = 0, ORC_ND_PLANE_STRAIN = 1 };
+
+/* ======================================================================== */
+/* J2Plasticity  (SRC/material/plastic/J2Plasticity.cpp)                     */
+/* ======================================================================== */
+typedef struct {
+  /* parameters, J2Plasticity.h:123-130 */
+  double bulk, shear, sigma_0, sigma_infty, delta, Hard, eta;
+  /* internal variables, J2Plasticity.h:133-136 */
+  double epsilon_p_n[3][3], epsilon_p_nplus1[3][3], xi_n, xi_nplus1;
+  /* response, J2Plasticity.h:139-144 */
+  double stress[3][3], tangent[3][3][3][3], strain[3][3];
+} OrcJ2;
+
+/* SRC/matrix/identity.h: rank-4 I (x) I and the deviatoric projector */
+static double IbunI(int i, int j, int k, int l) { return (i == j && k == l) ? 1.0 : 0.0; }
+static double IIdev(int i, int j, int k, int l) {
+  /* identity.h:42-77, entries are the literals 2./3., -1./3., 0.5 */
+  if (i == j) {
+    if (k == l) return (i == k) ? 2. / 3. : -1. / 3.;
+    return 0.0;
+  }
+  if ((i == k && j == l) || (i == l && j == k)) return 0.5;
+  return 0.0;
+}
+
+/* J2Plasticity.cpp:437-448 */
+static double j2_q(const OrcJ2* m, double xi) {
+  return m->Hard * xi + m->sigma_infty + (m->sigma_0 - m->sigma_infty) * exp(-m->delta * xi);
+}
+static double j2_qprime(const OrcJ2* m, double xi) {
+  return (m->sigma_0 - m->sigma_infty) * (-m->delta) * exp(-m->delta * xi) + m->Hard;
+}
+
+/* J2Plasticity.cpp:452-504 (matrix index -> tensor indices) */
+static void j2_index_map(int mi, int* i, int* j) {
+  static const int I[6] = {0, 1, 2, 0, 1, 2}, J[6] = {0, 1, 2, 1, 2, 0};
+  *i = I[mi]; *j = J[mi];
+}
+
+/* J2Plasticity.cpp:215-228 */
+static void j2_zero(OrcJ2* m) {
+  m->xi_n = m->xi_nplus1 = 0.0;
+  memset(m->epsilon_p_n, 0, sizeof m->epsilon_p_n);
+  memset(m->epsilon_p_nplus1, 0, sizeof m->epsilon_p_nplus1);
+  memset(m->stress, 0, sizeof m->stress);
+  memset(m->strain, 0, sizeof m->strain);
+}
+
+/* J2Plasticity::plastic_integrator, J2Plasticity.cpp:231-405.  dt = ops_Dt. */
+static int j2_plastic_integrator(OrcJ2* m, double dt) {
+  const double root23 = sqrt(2.0 / 3.0);
+  const double tolerance = 1.0e-10 * m->sigma_0;
+  const double shear = m->shear, bulk = m->bulk, eta = m->eta;
+  double dev_stress[3][3], normal[3][3], dev_strain[3][3];
+  double inv_norm_tau = 0.0, tang = 0.0;
+  const int max_iterations = 25;
+  int i, j;
+
+  double trace = m->strain[0][0] + m->strain[1][1] + m->strain[2][2];
+  memcpy(dev_strain, m->strain, sizeof dev_strain);
+  for (i = 0; i < 3; i++) dev_strain[i][i] -= 1. / 3. * trace;
+
+  for (i = 0; i < 3; i++)
+    for (j = 0; j < 3; j++) {
+      dev_stress[i][j] = dev_strain[i][j];
+      dev_stress[i][j] -= m->epsilon_p_n[i][j];
+      dev_stress[i][j] *= 2.0 * shear;
+    }
+
+  double norm_tau = 0.0;
+  for (i = 0; i < 3; i++)
+    for (j = 0; j < 3; j++) norm_tau += dev_stress[i][j] * dev_stress[i][j];
+  norm_tau = sqrt(norm_tau);
+
+  if (norm_tau > tolerance) {
+    inv_norm_tau = 1.0 / norm_tau;
+    for (i = 0; i < 3; i++)
+      for (j = 0; j < 3; j++) normal[i][j] = inv_norm_tau * dev_stress[i][j];
+  } else {
+    memset(normal, 0, sizeof normal);
+    inv_norm_tau = 0.0;
+  }
+
+  double phi = norm_tau - root23 * j2_q(m, m->xi_n);
+  double c1, c2, c3, theta_inv = 0.0, gamma = 0.0;
+
+  if (phi > 0.0) {
+    double resid = 1.0;
+    int iteration_counter = 0;
+    while (fabs(resid) > tolerance) {
+      resid = norm_tau - (2.0 * shear) * gamma - root23 * j2_q(m, m->xi_n + root23 * gamma);
+      if (eta > 0.0 && dt > 0.0) resid -= (eta / dt) * gamma;
+      tang = -(2.0 * shear) - 2. / 3. * j2_qprime(m, m->xi_n + root23 * gamma);
+      if (eta > 0.0 && dt > 0.0) tang -= (eta / dt);
+      gamma -= (resid / tang);
+      iteration_counter++;
+      if (iteration_counter > max_iterations) return -1;
+    }
+    gamma *= 1.0 - 1e-08;
+
+    for (i = 0; i < 3; i++)
+      for (j = 0; j < 3; j++) m->epsilon_p_nplus1[i][j] = m->epsilon_p_n[i][j] + gamma * normal[i][j];
+    m->xi_nplus1 = m->xi_n + root23 * gamma;
+
+    for (i = 0; i < 3; i++)
+      for (j = 0; j < 3; j++) dev_stress[i][j] = (2.0 * shear) * (dev_strain[i][j] - m->epsilon_p_nplus1[i][j]);
+
+    double theta = (2.0 * shear) + 2. / 3. * j2_qprime(m, m->xi_nplus1);
+    if (eta > 0.0 && dt > 0.0) theta += (eta / dt);
+    theta_inv = 1.0 / theta;
+  } else {
+    memcpy(m->epsilon_p_nplus1, m->epsilon_p_n, sizeof m->epsilon_p_n);
+    m->xi_nplus1 = m->xi_n;
+    gamma = 0.0;
+    theta_inv = 0.0;
+  }
+
+  memcpy(m->stress, dev_stress, sizeof dev_stress);
+  for (i = 0; i < 3; i++) m->stress[i][i] += bulk * trace;
+
+  c1 = -4.0 * shear * shear;
+  c2 = c1 * theta_inv;
+  c3 = c1 * gamma * inv_norm_tau;
+
+  for (int ii = 0; ii < 6; ii++)
+    for (int jj = 0; jj < 6; jj++) {
+      int k, l;
+      j2_index_map(ii, &i, &j);
+      j2_index_map(jj, &k, &l);
+      double NbunN = normal[i][j] * normal[k][l];
+      double t = bulk * IbunI(i, j, k, l);
+      t += (2.0 * shear) * IIdev(i, j, k, l);
+      t += c2 * NbunN;
+      t += c3 * (IIdev(i, j, k, l) - NbunN);
+      m->tangent[i][j][k][l] = t;
+      m->tangent[j][i][k][l] = t;
+      m->tangent[i][j][l][k] = t;
+      m->tangent[j][i][l][k] = t;
+    }
+  return 0;
+}
+
+static void j2_init(OrcJ2* m, const double* p) {
+  /* J2Plasticity.cpp:78-107 (full constructor) */
+  m->bulk = p[0]; m->shear = p[1]; m->sigma_0 = p[2]; m->sigma_infty = p[3];
+  m->delta = p[4]; m->Hard = p[5]; m->eta = p[6];
+  j2_zero(m);
+  j2_plastic_integrator(m, 0.0);
+}
+
+/* J2ThreeDimensional::setTrialStrain (J2ThreeDimensional.cpp:118-136) and
+ * J2PlaneStrain::setTrialStrain (material/Plane/J2PlaneStrain.cpp:80-92) */
+static int j2_set_trial_strain(OrcJ2* m, int type, const double* e, double dt) {
+  memset(m->strain, 0, sizeof m->strain);
+  if (type == ORC_ND_3D) {
+    m->strain[0][0] = e[0]; m->strain[1][1] = e[1]; m->strain[2][2] = e[2];
+    m->strain[0][1] = 0.50 * e[3]; m->strain[1][0] = m->strain[0][1];
+    m->strain[1][2] = 0.50 * e[4]; m->strain[2][1] = m->strain[1][2];
+    m->strain[2][0] = 0.50 * e[5]; m->strain[0][2] = m->strain[2][0];
+  } else {
+    m->strain[0][0] = e[0]; m->strain[1][1] = e[1];
+    m->strain[0][1] = 0.50 * e[2]; m->strain[1][0] = m->strain[0][1];
+  }
+  return j2_plastic_integrator(m, dt);
+}
+
+/* getStress / getTangent: J2ThreeDimensional.cpp:183-226, J2PlaneStrain.cpp:118-146 */
+static void j2_get_stress(const OrcJ2* m, int type, double* s) {
+  if (type == ORC_ND_3D) {
+    s[0] = m->stress[0][0]; s[1] = m->stress[1][1]; s[2] = m->stress[2][2];
+    s[3] = m->stress[0][1]; s[4] = m->stress[1][2]; s[5] = m->stress[2][0];
+  } else {
+    s[0] = m->stress[0][0]; s[1] = m->stress[1][1]; s[2] = m->stress[0][1];
+  }
+}
+static void j2_get_tangent(const OrcJ2* m, int type, double* D) {
+  if (type == ORC_ND_3D) {
+    for (int ii = 0; ii < 6; ii++)
+      for (int jj = 0; jj < 6; jj++) {
+        int i, j, k, l;
+        j2_index_map(ii, &i, &j); j2_index_map(jj, &k, &l);
+        D[ii * 6 + jj] = m->tangent[i][j][k][l];
+      }
+  } else {
+    D[0] = m->tangent[0][0][0][0]; D[4] = m->tangent[1][1][1][1]; D[8] = m->tangent[0][1][0][1];
+    D[1] = m->tangent[0][0][1][1]; D[3] = m->tangent[1][1][0][0];
+    D[2] = m->tangent[0][0][0][1]; D[6] = m->tangent[0][1][0][0];
+    D[5] = m->tangent[1][1][0][1]; D[7] = m->tangent[0][1][1][1];
+  }
+}
+/* J2Plasticity::commitState, J2Plasticity.cpp:538-544 */
+static void j2_commit(OrcJ2* m) {
+  memcpy(m->epsilon_p_n, m->epsilon_p_nplus1, sizeof m->epsilon_p_n);
+  m->xi_n = m->xi_nplus1;
+}
+
+/* ======================================================================== */
+/* ElasticIsotropic (SRC/material/elastic/ElasticIsotropicThreeDimensional.cpp:88-128,
+ *                   ElasticIsotropicPlaneStrain2D.cpp:100-131)                */
+/* ======================================================================== */
+typedef struct { double E, v; double epsilon[6], Cepsilon[6]; } OrcElastic;
+
+static void el_get_tangent(const OrcElastic* m, int type, double* D) {
+  double mu2 = m->E / (1.0 + m->v);
+  double lam = m->v * mu2 / (1.0 - 2.0 * m->v);
+  double mu = 0.50 * mu2;
+  if (type == ORC_ND_3D) {
+    memset(D, 0, 36 * sizeof(double));
+    mu2 += lam;
+    D[0] = D[7] = D[14] = mu2;
+    D[1] = D[6] = D[2] = D[12] = D[8] = D[13] = lam;
+    D[21] = mu; D[28] = mu; D[35] = mu;
+  } else {
+    memset(D, 0, 9 * sizeof(double));
+    D[0] = D[4] = mu2 + lam;
+    D[1] = D[3] = lam;
+    D[8] = mu;
+  }
+}
+static void el_get_stress(const OrcElastic* m, int type, double* s) {
+  double mu2 = m->E / (1.0 + m->v);
+  double lam = m->v * mu2 / (1.0 - 2.0 * m->v);
+  double mu = 0.50 * mu2;
+  mu2 += lam;
+  const double* e = m->epsilon;
+  if (type == ORC_ND_3D) {
+    s[0] = mu2 * e[0] + lam * (e[1] + e[2]);
+    s[1] = mu2 * e[1] + lam * (e[0] + e[2]);
+    s[2] = mu2 * e[2] + lam * (e[0] + e[1]);
+    s[3] = mu * e[3]; s[4] = mu * e[4]; s[5] = mu * e[5];
+  } else {
+    s[0] = mu2 * e[0] + lam * e[1];
+    s[1] = lam * e[0] + mu2 * e[1];
+    s[2] = mu * e[2];
+  }
+}
+
+/* ------------------------------------------------------------------------ */
+/* one integration point of either kind */
+typedef struct {
+  int kind, type;
+  union { OrcJ2 j2; OrcElastic el; } u;
+} OrcGP;
+
+static void gp_init(OrcGP* g, int kind, int type, const double* p) {
+  memset(g, 0, sizeof *g);
+  g->kind = kind; g->type = type;
+  if (kind == ORC_MAT_J2) j2_init(&g->u.j2, p);
+  else { g->u.el.E = p[0]; g->u.el.v = p[1]; }
+}
+static int gp_set_trial_strain(OrcGP* g, const double* e) {
+  int n = (g->type == ORC_ND_3D) ? 6 : 3;
+  if (g->kind == ORC_MAT_J2) return j2_set_trial_strain(&g->u.j2, g->type, e, 0.0);
+  memcpy(g->u.el.epsilon, e, n * sizeof(double));
+  return 0;
+}
+static void gp_get_stress(const OrcGP* g, double* s) {
+  if (g->kind == ORC_MAT_J2) j2_get_stress(&g->u.j2, g->type, s); else el_get_stress(&g->u.el, g->type, s);
+}
+static void gp_get_tangent(const OrcGP* g, double* D) {
+  if (g->kind == ORC_MAT_J2) j2_get_tangent(&g->u.j2, g->type, D); else el_get_tangent(&g->u.el, g->type, D);
+}
+static void gp_commit(OrcGP* g) {
+  if (g->kind == ORC_MAT_J2) j2_commit(&g->u.j2);
+  else memcpy(g->u.el.Cepsilon, g->u.el.epsilon, sizeof g->u.el.epsilon);
+}
+static void gp_revert(OrcGP* g) {
+  /* J2Plasticity::revertToLastCommit is a no-op (J2Plasticity.cpp:546-550);
+   * ElasticIsotropicThreeDimensional.cpp:139-144 restores epsilon */
+  if (g->kind != ORC_MAT_J2) memcpy(g->u.el.epsilon, g->u.el.Cepsilon, sizeof g->u.el.epsilon);
+}
+
+/* material-level strain path; mirrors ref_nd_path in ref_harness.cpp */
+int orc_nd_path(int kind, const double* p, int type, int n, const double* strains,
+                const int* commit, double* stress, double* tangent) {
+  OrcGP g; gp_init(&g, kind, type, p);
+  int order = (type == ORC_ND_3D) ? 6 : 3;
+  for (int s = 0; s < n; s++) {
+    if (gp_set_trial_strain(&g, strains + (size_t)s * order) < 0) return -2;
+    gp_get_stress(&g, stress + (size_t)s * order);
+    gp_get_tangent(&g, tangent + (size_t)s * order * order);
+    if (commit[s]) gp_commit(&g);
+  }
+  return order;
+}
+
+/* ======================================================================== */
+/* shp3d  (SRC/interpolate/shp3d.cpp:33-168)                                  */
+/* ======================================================================== */
+static void shp3d(const double xn[3], double* xsj, double shp[4][8], const double xl[3][8]) {
+  double ap1 = 1.0 + xn[0], am1 = 1.0 - xn[0];
+  double ap2 = 1.0 + xn[1], am2 = 1.0 - xn[1];
+  double ap3 = 1.0 + xn[2], am3 = 1.0 - xn[2];
+  { double c1 = 0.125 * am1 * am2, c2 = 0.125 * am2 * am3, c3 = 0.125 * am1 * am3;
+    shp[0][0] = -c2; shp[0][1] = c2; shp[1][0] = -c3; shp[1][3] = c3;
+    shp[2][0] = -c1; shp[2][4] = c1; shp[3][0] = c1 * am3; shp[3][4] = c1 * ap3; }
+  { double c1 = 0.125 * ap1 * ap2, c2 = 0.125 * ap2 * ap3, c3 = 0.125 * ap1 * ap3;
+    shp[0][7] = -c2; shp[0][6] = c2; shp[1][5] = -c3; shp[1][6] = c3;
+    shp[2][2] = -c1; shp[2][6] = c1; shp[3][2] = c1 * am3; shp[3][6] = c1 * ap3; }
+  { double c1 = 0.125 * am1 * ap2, c2 = 0.125 * am2 * ap3, c3 = 0.125 * am1 * ap3;
+    shp[0][4] = -c2; shp[0][5] = c2; shp[1][4] = -c3; shp[1][7] = c3;
+    shp[2][3] = -c1; shp[2][7] = c1; shp[3][3] = c1 * am3; shp[3][7] = c1 * ap3; }
+  { double c1 = 0.125 * ap1 * am2, c2 = 0.125 * ap2 * am3, c3 = 0.125 * ap1 * am3;
+    shp[0][3] = -c2; shp[0][2] = c2; shp[1][1] = -c3; shp[1][2] = c3;
+    shp[2][1] = -c1; shp[2][5] = c1; shp[3][1] = c1 * am3; shp[3][5] = c1 * ap3; }
+
+  double xs[3][3];
+  for (int j = 0; j < 3; j++) {
+    xs[j][0] = (xl[j][1] - xl[j][0]) * shp[0][1] + (xl[j][2] - xl[j][3]) * shp[0][2]
+             + (xl[j][5] - xl[j][4]) * shp[0][5] + (xl[j][6] - xl[j][7]) * shp[0][6];
+    xs[j][1] = (xl[j][2] - xl[j][1]) * shp[1][2] + (xl[j][3] - xl[j][0]) * shp[1][3]
+             + (xl[j][6] - xl[j][5]) * shp[1][6] + (xl[j][7] - xl[j][4]) * shp[1][7];
+    xs[j][2] = (xl[j][4] - xl[j][0]) * shp[2][4] + (xl[j][5] - xl[j][1]) * shp[2][5]
+             + (xl[j][6] - xl[j][2]) * shp[2][6] + (xl[j][7] - xl[j][3]) * shp[2][7];
+  }
+  double ad[3][3];
+  ad[0][0] = xs[1][1] * xs[2][2] - xs[1][2] * xs[2][1];
+  ad[0][1] = xs[2][1] * xs[0][2] - xs[2][2] * xs[0][1];
+  ad[0][2] = xs[0][1] * xs[1][2] - xs[0][2] * xs[1][1];
+  ad[1][0] = xs[1][2] * xs[2][0] - xs[1][0] * xs[2][2];
+  ad[1][1] = xs[2][2] * xs[0][0] - xs[2][0] * xs[0][2];
+  ad[1][2] = xs[0][2] * xs[1][0] - xs[0][0] * xs[1][2];
+  ad[2][0] = xs[1][0] * xs[2][1] - xs[1][1] * xs[2][0];
+  ad[2][1] = xs[2][0] * xs[0][1] - xs[2][1] * xs[0][0];
+  ad[2][2] = xs[0][0] * xs[1][1] - xs[0][1] * xs[1][0];
+
+  *xsj = xs[0][0] * ad[0][0] + xs[0][1] * ad[1][0] + xs[0][2] * ad[2][0];
+  double rxsj = 1.0 / *xsj;
+  for (int j = 0; j < 3; j++)
+    for (int i = 0; i < 3; i++) xs[i][j] = ad[i][j] * rxsj;
+
+  for (int k = 0; k < 8; k++) {
+    double c1 = shp[0][k] * xs[0][0] + shp[1][k] * xs[1][0] + shp[2][k] * xs[2][0];
+    double c2 = shp[0][k] * xs[0][1] + shp[1][k] * xs[1][1] + shp[2][k] * xs[2][1];
+    double c3 = shp[0][k] * xs[0][2] + shp[1][k] * xs[1][2] + shp[2][k] * xs[2][2];
+    shp[0][k] = c1; shp[1][k] = c2; shp[2][k] = c3;
+  }
+}
+
+/* ======================================================================== */
+/* the model: Domain + AnalysisModel + LinearSOE flattened                    */
+/* ======================================================================== */
+typedef struct {
+  int kind;          /* ORC_ELE_* */
+  int tag;
+  int nen, ndf_e;    /* nodes, dofs per node used by the element */
+  int node[8];       /* node indices (into model arrays, tag-sorted) */
+  int mat;           /* material index */
+  double par[8];     /* brick: b1,b2,b3 ; quad: thickness,type,pressure,rho,b1,b2 */
+  OrcGP gp[8];
+  int nip;
+} OrcEle;
+
+typedef struct {
+  int ndm, ndf;
+  int nn; int* node_tag; double* crd; /* [nn][ndm], ascending tag (MapOfTaggedObjects order, Domain.cpp:98) */
+  double* trial; double* commit_disp; /* [nn][ndf] */
+  double* load;                       /* [nn][ndf] reference nodal loads (pattern 1, Linear series) */
+  int* fixed;                         /* [nn][ndf] 1 when an SP_Constraint holds the dof */
+  int nmat; int* mat_tag; int* mat_kind; double* mat_par; /* [nmat][8] */
+  int ne, ecap; OrcEle* ele;          /* ascending element tag after setup */
+  /* analysis side */
+  int neq; int* id;                   /* [nn][ndf] equation numbers (DOF_Group::myID) */
+  int soe_kind;                       /* 0 SparseGenCol (CSC), 1 SparseGenRow (CSR) */
+  int* ptr; int* idx; int nnz;        /* colStartA/rowA or rowStartA/colA */
+  double* A; double* B;
+  double lambda;
+} OrcModel;
+
+static int find_node(const OrcModel* m, int tag) {
+  int lo = 0, hi = m->nn - 1;
+  while (lo <= hi) { int mid = (lo + hi) / 2; if (m->node_tag[mid] == tag) return mid; if (m->node_tag[mid] < tag) lo = mid + 1; else hi = mid - 1; }
+  return -1;
+}
+
+/* nodes must be given with ascending tags (the Domain iterates its std::map that way) */
+void* orc_model_new(int ndm, int ndf, int nn, const int* tags, const double* crd) {
+  OrcModel* m = (OrcModel*)calloc(1, sizeof *m);
+  m->ndm = ndm; m->ndf = ndf; m->nn = nn;
+  m->node_tag = (int*)malloc(sizeof(int) * nn); memcpy(m->node_tag, tags, sizeof(int) * nn);
+  for (int i = 1; i < nn; i++) if (tags[i] <= tags[i - 1]) { free(m->node_tag); free(m); return NULL; }
+  m->crd = (double*)malloc(sizeof(double) * nn * ndm); memcpy(m->crd, crd, sizeof(double) * nn * ndm);
+  m->trial = (double*)calloc((size_t)nn * ndf, sizeof(double));
+  m->commit_disp = (double*)calloc((size_t)nn * ndf, sizeof(double));
+  m->load = (double*)calloc((size_t)nn * ndf, sizeof(double));
+  m->fixed = (int*)calloc((size_t)nn * ndf, sizeof(int));
+  m->mat_tag = NULL; m->nmat = 0;
+  return m;
+}
+int orc_fix(void* h, int nodeTag, int dof) {
+  OrcModel* m = (OrcModel*)h; int n = find_node(m, nodeTag);
+  if (n < 0 || dof < 0 || dof >= m->ndf) return -1;
+  m->fixed[n * m->ndf + dof] = 1; return 0;
+}
+int orc_add_nd_material(void* h, int tag, int kind, const double* p) {
+  OrcModel* m = (OrcModel*)h;
+  m->mat_tag = (int*)realloc(m->mat_tag, sizeof(int) * (m->nmat + 1));
+  m->mat_kind = (int*)realloc(m->mat_kind, sizeof(int) * (m->nmat + 1));
+  m->mat_par = (double*)realloc(m->mat_par, sizeof(double) * 8 * (m->nmat + 1));
+  m->mat_tag[m->nmat] = tag; m->mat_kind[m->nmat] = kind;
+  memset(m->mat_par + 8 * m->nmat, 0, 8 * sizeof(double));
+  memcpy(m->mat_par + 8 * m->nmat, p, sizeof(double) * (kind == ORC_MAT_J2 ? 7 : 3));
+  m->nmat++; return 0;
+}
+static int find_mat(const OrcModel* m, int tag) { for (int i = 0; i < m->nmat; i++) if (m->mat_tag[i] == tag) return i; return -1; }
+
+int orc_add_element(void* h, int kind, int tag, const int* nodeTags, int matTag, const double* par) {
+  OrcModel* m = (OrcModel*)h;
+  if (m->ne == m->ecap) { m->ecap = m->ecap ? 2 * m->ecap : 64; m->ele = (OrcEle*)realloc(m->ele, sizeof(OrcEle) * m->ecap); }
+  OrcEle* e = &m->ele[m->ne];
+  memset(e, 0, sizeof *e);
+  e->kind = kind; e->tag = tag;
+  e->nen = (kind == ORC_ELE_BRICK) ? 8 : 4;
+  e->ndf_e = (kind == ORC_ELE_BRICK) ? 3 : 2;
+  e->nip = (kind == ORC_ELE_BRICK) ? 8 : 4;
+  for (int i = 0; i < e->nen; i++) { e->node[i] = find_node(m, nodeTags[i]); if (e->node[i] < 0) return -1; }
+  e->mat = find_mat(m, matTag); if (e->mat < 0) return -2;
+  memcpy(e->par, par, 8 * sizeof(double));
+  int type = (kind == ORC_ELE_BRICK) ? ORC_ND_3D : ORC_ND_PLANE_STRAIN;
+  for (int i = 0; i < e->nip; i++) gp_init(&e->gp[i], m->mat_kind[e->mat], type, m->mat_par + 8 * e->mat);
+  m->ne++; return 0;
+}
+int orc_add_load(void* h, int nodeTag, const double* v) {
+  OrcModel* m = (OrcModel*)h; int n = find_node(m, nodeTag); if (n < 0) return -1;
+  for (int i = 0; i < m->ndf; i++) m->load[n * m->ndf + i] += v[i];
+  return 0;
+}
+
+static int cmp_ele(const void* a, const void* b) { return ((const OrcEle*)a)->tag - ((const OrcEle*)b)->tag; }
+
+/* sorted-unique insert, restating ID::insert (SRC/matrix/ID.cpp:512-575) */
+typedef struct { int* d; int n, cap; } IntSet;
+static int iset_insert(IntSet* s, int x) {
+  int left = 0, right = s->n - 1, middle;
+  while (left <= right) { middle = (left + right) / 2; if (x == s->d[middle]) return 1; if (x > s->d[middle]) left = middle + 1; else right = middle - 1; }
+  if (s->n == s->cap) { s->cap = (s->n + 1) * 2; s->d = (int*)realloc(s->d, sizeof(int) * s->cap); }
+  for (int i = s->n; i > left; i--) s->d[i] = s->d[i - 1];
+  s->d[left] = x; s->n++; return 0;
+}
+
+/* PlainHandler::handle (PlainHandler.cpp:60-250) -> initial ids (-2 free, -1 fixed);
+ * numberer 0: PlainNumberer::numberDOF (PlainNumberer.cpp:73-157)
+ * numberer 1: DOF_Numberer::numberDOF (DOF_Numberer.cpp:92-205) over
+ *             AnalysisModel::getDOFGroupGraph (AnalysisModel.cpp:355-400) with
+ *             RCM::number, GPS off (RCM.cpp:66-276; numberer.cpp:46 builds RCM(false))
+ * then AnalysisModel::getDOFGraph (AnalysisModel.cpp:286-351) and
+ * SparseGenColLinSOE::setSize (SparseGenColLinSOE.cpp:161-261) /
+ * SparseGenRowLinSOE::setSize (SparseGenRowLinSOE.cpp:127-220). */
+int orc_setup(void* h, int numberer, int soe_kind) {
+  OrcModel* m = (OrcModel*)h;
+  int nn = m->nn, ndf = m->ndf;
+  qsort(m->ele, m->ne, sizeof(OrcEle), cmp_ele); /* Domain element map iterates by tag */
+  m->id = (int*)malloc(sizeof(int) * nn * ndf);
+  for (int i = 0; i < nn * ndf; i++) m->id[i] = m->fixed[i] ? -1 : -2;
+
+  int* order = (int*)malloc(sizeof(int) * nn);
+  if (numberer == 0) {
+    for (int i = 0; i < nn; i++) order[i] = i;
+  } else {
+    /* DOF_Group graph: vertex per node (DOF_Group tag = position in tag order) */
+    IntSet* adj = (IntSet*)calloc(nn, sizeof(IntSet));
+    for (int e = 0; e < m->ne; e++) {
+      OrcEle* el = &m->ele[e];
+      for (int i = 0; i < el->nen; i++)
+        for (int j = 0; j < el->nen; j++)
+          if (i != j && el->node[i] != el->node[j]) {
+            /* Graph::addEdge (Graph.cpp:178-213): insert in both, skip when present */
+            if (iset_insert(&adj[el->node[i]], el->node[j]) == 0) iset_insert(&adj[el->node[j]], el->node[i]);
+          }
+    }
+    int* tmp = (int*)malloc(sizeof(int) * nn);
+    for (int i = 0; i < nn; i++) tmp[i] = -1;
+    int iter = 0;                       /* vertexIter4 */
+    int currentMark = nn - 1, nextMark = currentMark - 1;
+    order[currentMark] = 0; tmp[0] = currentMark;   /* first vertex from the iterator */
+    iter = 0;
+    while (nextMark >= 0) {
+      int v = order[currentMark];
+      for (int a = 0; a < adj[v].n; a++) {
+        int w = adj[v].d[a];
+        if (tmp[w] == -1) { tmp[w] = nextMark; order[nextMark--] = w; }
+      }
+      currentMark--;
+      if (currentMark == nextMark && currentMark >= 0) {
+        while (iter < nn && tmp[iter] != -1) iter++;
+        nextMark--;
+        tmp[iter] = currentMark; order[currentMark] = iter; iter++;
+      }
+    }
+    for (int i = 0; i < nn; i++) free(adj[i].d);
+    free(adj); free(tmp);
+  }
+  int eqn = 0;
+  for (int i = 0; i < nn; i++) {
+    int n = order[i];
+    for (int j = 0; j < ndf; j++) if (m->id[n * ndf + j] == -2) m->id[n * ndf + j] = eqn++;
+  }
+  free(order);
+  m->neq = eqn;
+
+  /* DOF graph: per equation a sorted adjacency (Vertex::addEdge skips self) */
+  IntSet* adj = (IntSet*)calloc(eqn > 0 ? eqn : 1, sizeof(IntSet));
+  for (int e = 0; e < m->ne; e++) {
+    OrcEle* el = &m->ele[e];
+    int ids[24], n = 0;
+    for (int i = 0; i < el->nen; i++) for (int j = 0; j < el->ndf_e; j++) ids[n++] = m->id[el->node[i] * ndf + j];
+    for (int i = 0; i < n; i++) if (ids[i] >= 0)
+      for (int j = i + 1; j < n; j++) if (ids[j] >= 0 && ids[j] != ids[i])
+        if (iset_insert(&adj[ids[i]], ids[j]) == 0) iset_insert(&adj[ids[j]], ids[i]);
+  }
+  m->soe_kind = soe_kind;
+  m->ptr = (int*)malloc(sizeof(int) * (eqn + 1));
+  int nnz = 0; for (int a = 0; a < eqn; a++) nnz += adj[a].n + 1;
+  m->nnz = nnz;
+  m->idx = (int*)malloc(sizeof(int) * (nnz > 0 ? nnz : 1));
+  m->ptr[0] = 0;
+  int startLoc = 0, lastLoc = 0;
+  for (int a = 0; a < eqn; a++) {
+    m->idx[lastLoc++] = a;                       /* "place diag in first" */
+    for (int i = 0; i < adj[a].n; i++) {
+      int row = adj[a].d[i], found = 0;
+      for (int j = startLoc; j < lastLoc; j++)
+        if (m->idx[j] > row) {
+          for (int k = lastLoc; k > j; k--) m->idx[k] = m->idx[k - 1];
+          m->idx[j] = row; found = 1; j = lastLoc;
+        }
+      if (!found) m->idx[lastLoc] = row;
+      lastLoc++;
+    }
+    m->ptr[a + 1] = lastLoc; startLoc = lastLoc;
+  }
+  for (int a = 0; a < eqn; a++) free(adj[a].d);
+  free(adj);
+  m->A = (double*)calloc(nnz > 0 ? nnz : 1, sizeof(double));
+  m->B = (double*)calloc(eqn > 0 ? eqn : 1, sizeof(double));
+  return eqn;
+}
+
+int orc_num_eqn(void* h) { return ((OrcModel*)h)->neq; }
+int orc_nnz(void* h) { return ((OrcModel*)h)->nnz; }
+void orc_get_ids(void* h, int* ids) { OrcModel* m = (OrcModel*)h; memcpy(ids, m->id, sizeof(int) * m->nn * m->ndf); }
+void orc_get_csr(void* h, int* ptr, int* idx) { OrcModel* m = (OrcModel*)h; memcpy(ptr, m->ptr, sizeof(int) * (m->neq + 1)); memcpy(idx, m->idx, sizeof(int) * m->nnz); }
+int orc_num_ele(void* h) { return ((OrcModel*)h)->ne; }
+
+/* FE_Element::setID (FE_Element.cpp:209-231): element dof -> equation */
+static int ele_ids(const OrcModel* m, const OrcEle* el, int* ids) {
+  int n = 0;
+  for (int i = 0; i < el->nen; i++) for (int j = 0; j < m->ndf; j++) ids[n++] = m->id[el->node[i] * m->ndf + j];
+  return n;
+}
+/* FE ids in FE_Element order, [ne][stride] */
+void orc_fe_ids(void* h, int* tags, int* ids, int stride) {
+  OrcModel* m = (OrcModel*)h;
+  for (int e = 0; e < m->ne; e++) { int t[32]; int n = ele_ids(m, &m->ele[e], t); tags[e] = m->ele[e].tag; for (int i = 0; i < n && i < stride; i++) ids[(size_t)e * stride + i] = t[i]; }
+}
+
+/* scatter map: position in A where addA puts m(i,j); -1 if dropped.
+ * SparseGenColLinSOE::addA (SparseGenColLinSOE.cpp:264-330): column id(i), row id(j) gets m(j,i)
+ * SparseGenRowLinSOE::addA (SparseGenRowLinSOE.cpp:224-282): row id(i), column id(j) gets m(i,j)
+ * map[e][i*nd+j] is for element-matrix entry (i,j) in both cases. */
+static int soe_find(const OrcModel* m, int major, int minor) {
+  for (int k = m->ptr[major]; k < m->ptr[major + 1]; k++) if (m->idx[k] == minor) return k;
+  return -1;
+}
+void orc_scatter_map(void* h, int e, int* map) {
+  OrcModel* m = (OrcModel*)h; int ids[32]; int n = ele_ids(m, &m->ele[e], ids);
+  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) {
+    int r = ids[i], c = ids[j], k = -1;
+    if (r >= 0 && c >= 0) k = (m->soe_kind == 1) ? soe_find(m, r, c) : soe_find(m, c, r);
+    map[i * n + j] = k;
+  }
+}
+
+/* ---- element state determination ---------------------------------------- */
+
+
+/* Brick::update, Brick.cpp:718-840 */
+static int brick_update(OrcModel* m, OrcEle* el) {
+  double xl[3][8];
+  for (int i = 0; i < 8; i++) for (int d = 0; d < 3; d++) xl[d][i] = m->crd[el->node[i] * 3 + d];
+  const double one_over_root3 = 1.0 / sqrt(3.0);
+  const double sg[2] = { -one_over_root3, one_over_root3 };
+  int count = 0, rc = 0;
+
+  for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) for (int k = 0; k < 2; k++) {
+    double gp[3] = { sg[i], sg[j], sg[k] }, xsj, shp[4][8], strain[6] = {0, 0, 0, 0, 0, 0};
+    shp3d(gp, &xsj, shp, xl);
+    for (int n = 0; n < 8; n++) {
+      const double* ul = m->trial + (size_t)el->node[n] * m->ndf;
+      double b00 = shp[0][n], b11 = shp[1][n], b22 = shp[2][n], b30 = shp[1][n], b31 = shp[0][n],
+             b41 = shp[2][n], b42 = shp[1][n], b50 = shp[2][n], b52 = shp[0][n];
+      strain[0] += b00 * ul[0];
+      strain[1] += b11 * ul[1];
+      strain[2] += b22 * ul[2];
+      strain[3] += b30 * ul[0] + b31 * ul[1];
+      strain[4] += b41 * ul[1] + b42 * ul[2];
+      strain[5] += b50 * ul[0] + b52 * ul[2];
+    }
+    if (gp_set_trial_strain(&el->gp[count], strain) < 0) rc = -1;
+    count++;
+  }
+  return rc;
+}
+
+/* Brick::formResidAndTangent, Brick.cpp:843-1022; K row-major [24][24], R[24].
+ * The tangent products keep Matrix::addMatrixProduct's j,k,i loop order
+ * (Matrix.cpp:693-720) so the floating point sums match the reference. */
+static void brick_form(OrcModel* m, OrcEle* el, int tang_flag, double* K, double* R) {
+  double xl[3][8];
+  for (int i = 0; i < 8; i++) for (int d = 0; d < 3; d++) xl[d][i] = m->crd[el->node[i] * 3 + d];
+  const double one_over_root3 = 1.0 / sqrt(3.0);
+  const double sg[2] = { -one_over_root3, one_over_root3 };
+  double Shape[8][4][8], dvol[8];
+  int count = 0;
+  for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) for (int k = 0; k < 2; k++) {
+    double gp[3] = { sg[i], sg[j], sg[k] }, xsj;
+    shp3d(gp, &xsj, Shape[count], xl);
+    dvol[count] = 1.0 * xsj;
+    count++;
+  }
+  if (K) memset(K, 0, 576 * sizeof(double));
+  memset(R, 0, 24 * sizeof(double));
+  for (int g = 0; g < 8; g++) {
+    double (*shp)[8] = Shape[g];
+    double stress[6], dd[36];
+    gp_get_stress(&el->gp[g], stress);
+    for (int i = 0; i < 6; i++) stress[i] *= dvol[g];
+    if (tang_flag) { gp_get_tangent(&el->gp[g], dd); for (int i = 0; i < 36; i++) dd[i] *= dvol[g]; }
+    int jj = 0;
+    for (int j = 0; j < 8; j++) {
+      double b00 = shp[0][j], b11 = shp[1][j], b22 = shp[2][j], b30 = shp[1][j], b31 = shp[0][j],
+             b41 = shp[2][j], b42 = shp[1][j], b50 = shp[2][j], b52 = shp[0][j];
+      double residJ[3];
+      residJ[0] = b00 * stress[0] + b30 * stress[3] + b50 * stress[5];
+      residJ[1] = b11 * stress[1] + b31 * stress[3] + b41 * stress[4];
+      residJ[2] = b22 * stress[2] + b42 * stress[4] + b52 * stress[5];
+      for (int p = 0; p < 3; p++) {
+        R[jj + p] += residJ[p];
+        R[jj + p] -= dvol[g] * el->par[p] * shp[3][j];
+      }
+      if (tang_flag) {
+        /* BJ (6x3), BJtran (3x6) */
+        double BJ[6][3] = {{shp[0][j], 0, 0}, {0, shp[1][j], 0}, {0, 0, shp[2][j]},
+                           {shp[1][j], shp[0][j], 0}, {0, shp[2][j], shp[1][j]}, {shp[2][j], 0, shp[0][j]}};
+        double BJtranD[3][6];
+        /* BJtranD = BJtran * dd : for col j2, for k2, tmp = dd(k2,j2); for i2: out(i2,j2) += BJtran(i2,k2)*tmp */
+        for (int j2 = 0; j2 < 6; j2++) {
+          for (int i2 = 0; i2 < 3; i2++) BJtranD[i2][j2] = 0.0;
+          for (int k2 = 0; k2 < 6; k2++) {
+            double tmp = dd[k2 * 6 + j2] * 1.0;
+            for (int i2 = 0; i2 < 3; i2++) BJtranD[i2][j2] += BJ[k2][i2] * tmp;
+          }
+        }
+        int kk = 0;
+        for (int k = 0; k < 8; k++) {
+          double BK[6][3] = {{shp[0][k], 0, 0}, {0, shp[1][k], 0}, {0, 0, shp[2][k]},
+                             {shp[1][k], shp[0][k], 0}, {0, shp[2][k], shp[1][k]}, {shp[2][k], 0, shp[0][k]}};
+          double stiffJK[3][3];
+          for (int j2 = 0; j2 < 3; j2++) {
+            for (int i2 = 0; i2 < 3; i2++) stiffJK[i2][j2] = 0.0;
+            for (int k2 = 0; k2 < 6; k2++) {
+              double tmp = BK[k2][j2] * 1.0;
+              for (int i2 = 0; i2 < 3; i2++) stiffJK[i2][j2] += BJtranD[i2][k2] * tmp;
+            }
+          }
+          for (int p = 0; p < 3; p++) for (int q = 0; q < 3; q++) K[(jj + p) * 24 + kk + q] += stiffJK[p][q];
+          kk += 3;
+        }
+      }
+      jj += 3;
+    }
+  }
+}
+
+/* FourNodeQuad::shapeFunction, FourNodeQuad.cpp:1128-1196 */
+static double quad_shape(const OrcModel* m, const OrcEle* el, double xi, double eta, double shp[3][4]) {
+  const double* c1 = m->crd + el->node[0] * 2; const double* c2 = m->crd + el->node[1] * 2;
+  const double* c3 = m->crd + el->node[2] * 2; const double* c4 = m->crd + el->node[3] * 2;
+  double oneMinuseta = 1.0 - eta, onePluseta = 1.0 + eta, oneMinusxi = 1.0 - xi, onePlusxi = 1.0 + xi;
+  shp[2][0] = 0.25 * oneMinusxi * oneMinuseta;
+  shp[2][1] = 0.25 * onePlusxi * oneMinuseta;
+  shp[2][2] = 0.25 * onePlusxi * onePluseta;
+  shp[2][3] = 0.25 * oneMinusxi * onePluseta;
+  double J[2][2], L[2][2];
+  J[0][0] = 0.25 * (-c1[0] * oneMinuseta + c2[0] * oneMinuseta + c3[0] * (onePluseta) - c4[0] * (onePluseta));
+  J[0][1] = 0.25 * (-c1[0] * oneMinusxi - c2[0] * onePlusxi + c3[0] * onePlusxi + c4[0] * oneMinusxi);
+  J[1][0] = 0.25 * (-c1[1] * oneMinuseta + c2[1] * oneMinuseta + c3[1] * onePluseta - c4[1] * onePluseta);
+  J[1][1] = 0.25 * (-c1[1] * oneMinusxi - c2[1] * onePlusxi + c3[1] * onePlusxi + c4[1] * oneMinusxi);
+  double detJ = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+  double oneOverdetJ = 1.0 / detJ;
+  L[0][0] = J[1][1] * oneOverdetJ; L[1][0] = -J[0][1] * oneOverdetJ;
+  L[0][1] = -J[1][0] * oneOverdetJ; L[1][1] = J[0][0] * oneOverdetJ;
+  double L00 = 0.25 * L[0][0], L10 = 0.25 * L[1][0], L01 = 0.25 * L[0][1], L11 = 0.25 * L[1][1];
+  double L00oneMinuseta = L00 * oneMinuseta, L00onePluseta = L00 * onePluseta;
+  double L01oneMinusxi = L01 * oneMinusxi, L01onePlusxi = L01 * onePlusxi;
+  double L10oneMinuseta = L10 * oneMinuseta, L10onePluseta = L10 * onePluseta;
+  double L11oneMinusxi = L11 * oneMinusxi, L11onePlusxi = L11 * onePlusxi;
+  shp[0][0] = -L00oneMinuseta - L01oneMinusxi;
+  shp[0][1] = L00oneMinuseta - L01onePlusxi;
+  shp[0][2] = L00onePluseta + L01onePlusxi;
+  shp[0][3] = -L00onePluseta + L01oneMinusxi;
+  shp[1][0] = -L10oneMinuseta - L11oneMinusxi;
+  shp[1][1] = L10oneMinuseta - L11onePlusxi;
+  shp[1][2] = L10onePluseta + L11onePlusxi;
+  shp[1][3] = -L10onePluseta + L11oneMinusxi;
+  return detJ;
+}
+/* integration points: FourNodeQuad.h pts/wts (Gauss 2x2, counter-clockwise) */
+static const double quad_pts[4][2] = {
+  {-0.577350269189626, -0.577350269189626}, { 0.577350269189626, -0.577350269189626},
+  { 0.577350269189626,  0.577350269189626}, {-0.577350269189626,  0.577350269189626}};
+static const double quad_wts[4] = {1.0, 1.0, 1.0, 1.0};
+
+/* FourNodeQuad::update, FourNodeQuad.cpp:190-222 */
+static int quad_update(OrcModel* m, OrcEle* el) {
+  double u[2][4]; int ret = 0;
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 2; j++) u[j][i] = m->trial[(size_t)el->node[i] * m->ndf + j];
+  for (int i = 0; i < 4; i++) {
+    double shp[3][4]; quad_shape(m, el, quad_pts[i][0], quad_pts[i][1], shp);
+    double eps[3] = {0, 0, 0};
+    for (int beta = 0; beta < 4; beta++) {
+      eps[0] += shp[0][beta] * u[0][beta];
+      eps[1] += shp[1][beta] * u[1][beta];
+      eps[2] += shp[0][beta] * u[1][beta] + shp[1][beta] * u[0][beta];
+    }
+    ret += gp_set_trial_strain(&el->gp[i], eps);
+  }
+  return ret;
+}
+/* FourNodeQuad::getTangentStiff (FourNodeQuad.cpp:226-281), getResistingForce (507-553);
+ * pressure load and Q (element loads) are zero in the hot path models. */
+static void quad_form(OrcModel* m, OrcEle* el, int tang_flag, double* K, double* P) {
+  double thickness = el->par[0];
+  if (tang_flag) {
+    memset(K, 0, 64 * sizeof(double));
+    for (int i = 0; i < 4; i++) {
+      double shp[3][4]; double dvol = quad_shape(m, el, quad_pts[i][0], quad_pts[i][1], shp);
+      dvol *= (thickness * quad_wts[i]);
+      double D[9]; gp_get_tangent(&el->gp[i], D);
+      const double D00 = D[0], D01 = D[1], D02 = D[2], D10 = D[3], D11 = D[4], D12 = D[5], D20 = D[6], D21 = D[7], D22 = D[8];
+      double DB[3][2];
+      for (int alpha = 0, ia = 0; alpha < 4; alpha++, ia += 2)
+        for (int beta = 0, ib = 0; beta < 4; beta++, ib += 2) {
+          DB[0][0] = dvol * (D00 * shp[0][beta] + D02 * shp[1][beta]);
+          DB[1][0] = dvol * (D10 * shp[0][beta] + D12 * shp[1][beta]);
+          DB[2][0] = dvol * (D20 * shp[0][beta] + D22 * shp[1][beta]);
+          DB[0][1] = dvol * (D01 * shp[1][beta] + D02 * shp[0][beta]);
+          DB[1][1] = dvol * (D11 * shp[1][beta] + D12 * shp[0][beta]);
+          DB[2][1] = dvol * (D21 * shp[1][beta] + D22 * shp[0][beta]);
+          K[ia * 8 + ib]           += shp[0][alpha] * DB[0][0] + shp[1][alpha] * DB[2][0];
+          K[ia * 8 + ib + 1]       += shp[0][alpha] * DB[0][1] + shp[1][alpha] * DB[2][1];
+          K[(ia + 1) * 8 + ib]     += shp[1][alpha] * DB[1][0] + shp[0][alpha] * DB[2][0];
+          K[(ia + 1) * 8 + ib + 1] += shp[1][alpha] * DB[1][1] + shp[0][alpha] * DB[2][1];
+        }
+    }
+  }
+  memset(P, 0, 8 * sizeof(double));
+  for (int i = 0; i < 4; i++) {
+    double shp[3][4]; double dvol = quad_shape(m, el, quad_pts[i][0], quad_pts[i][1], shp);
+    dvol *= (thickness * quad_wts[i]);
+    double sigma[3]; gp_get_stress(&el->gp[i], sigma);
+    for (int alpha = 0, ia = 0; alpha < 4; alpha++, ia += 2) {
+      P[ia]     += dvol * (shp[0][alpha] * sigma[0] + shp[1][alpha] * sigma[2]);
+      P[ia + 1] += dvol * (shp[1][alpha] * sigma[1] + shp[0][alpha] * sigma[2]);
+      P[ia]     -= dvol * (shp[2][alpha] * el->par[4]);
+      P[ia + 1] -= dvol * (shp[2][alpha] * el->par[5]);
+    }
+  }
+}
+
+/* Node::setTrialDisp for all nodes + Domain::update -> Element::update */
+int orc_set_trial_disp(void* h, const double* u) {
+  OrcModel* m = (OrcModel*)h; int rc = 0;
+  memcpy(m->trial, u, sizeof(double) * m->nn * m->ndf);
+  for (int e = 0; e < m->ne; e++) rc |= (m->ele[e].kind == ORC_ELE_BRICK) ? brick_update(m, &m->ele[e]) : quad_update(m, &m->ele[e]);
+  return rc;
+}
+void orc_apply_load(void* h, double lambda) { ((OrcModel*)h)->lambda = lambda; }
+
+/* Element::getTangentStiff / getResistingForce of FE element e (row-major) */
+int orc_ele_tangent(void* h, int e, double* K) {
+  OrcModel* m = (OrcModel*)h; double R[24];
+  if (m->ele[e].kind == ORC_ELE_BRICK) { brick_form(m, &m->ele[e], 1, K, R); return 24; }
+  quad_form(m, &m->ele[e], 1, K, R); return 8;
+}
+int orc_ele_resid(void* h, int e, double* R) {
+  OrcModel* m = (OrcModel*)h;
+  if (m->ele[e].kind == ORC_ELE_BRICK) { brick_form(m, &m->ele[e], 0, NULL, R); return 24; }
+  double K[64]; quad_form(m, &m->ele[e], 0, K, R); return 8;
+}
+
+/* IncrementalIntegrator::formTangent (IncrementalIntegrator.cpp:74-102):
+ * zeroA; for each FE_Element: addA(getTangent, getID).  getTangent =
+ * StaticIntegrator::formEleTangent (StaticIntegrator.cpp:80-97): zeroTangent; addKtToTang(1.0)
+ * -> Matrix::addMatrix(K, 1.0): tang = 0*1.0 + K (adds K to a zeroed matrix). */
+int orc_form_tangent(void* h, double* A) {
+  OrcModel* m = (OrcModel*)h;
+  memset(m->A, 0, sizeof(double) * m->nnz);
+  for (int e = 0; e < m->ne; e++) {
+    OrcEle* el = &m->ele[e]; double K[576], R[24]; int ids[32];
+    int nd_e = el->nen * el->ndf_e;
+    if (el->kind == ORC_ELE_BRICK) brick_form(m, el, 1, K, R); else quad_form(m, el, 1, K, R);
+    int n = ele_ids(m, el, ids); (void)n;
+    for (int i = 0; i < nd_e; i++) for (int j = 0; j < nd_e; j++) K[i * nd_e + j] = 0.0 + K[i * nd_e + j];
+    if (m->soe_kind == 1) {
+      for (int i = 0; i < nd_e; i++) { int row = ids[i]; if (row < 0) continue;
+        for (int j = 0; j < nd_e; j++) { int col = ids[j]; if (col < 0) continue;
+          int k = soe_find(m, row, col); if (k >= 0) m->A[k] += K[i * nd_e + j]; } }
+    } else {
+      for (int i = 0; i < nd_e; i++) { int col = ids[i]; if (col < 0) continue;
+        for (int j = 0; j < nd_e; j++) { int row = ids[j]; if (row < 0) continue;
+          int k = soe_find(m, col, row); if (k >= 0) m->A[k] += K[j * nd_e + i]; } }
+    }
+  }
+  if (A) memcpy(A, m->A, sizeof(double) * m->nnz);
+  return 0;
+}
+
+/* IncrementalIntegrator::formUnbalance: zeroB; formElementResidual
+ * (IncrementalIntegrator.cpp:221-238) then formNodalUnbalance (202-218).
+ * FE_Element::getResidual -> StaticIntegrator::formEleResidual
+ * (StaticIntegrator.cpp:100-108): zeroResidual; addRtoResidual(1.0) ->
+ * theResidual->addVector(1.0, R, -1.0) (FE_Element.cpp:401-414).
+ * DOF_Group::getUnbalance -> Node::getUnbalancedLoad = lambda * load
+ * (NodalLoad::applyLoad -> Node::addUnbalancedLoad: unbal += load*fact). */
+int orc_form_unbalance(void* h, double* B) {
+  OrcModel* m = (OrcModel*)h;
+  memset(m->B, 0, sizeof(double) * (m->neq > 0 ? m->neq : 1));
+  for (int e = 0; e < m->ne; e++) {
+    OrcEle* el = &m->ele[e]; double K[64], R[24]; int ids[32];
+    int nd_e = el->nen * el->ndf_e;
+    if (el->kind == ORC_ELE_BRICK) brick_form(m, el, 0, NULL, R); else quad_form(m, el, 0, K, R);
+    ele_ids(m, el, ids);
+    for (int i = 0; i < nd_e; i++) {
+      double res = 0.0 * 1.0 + R[i] * -1.0;   /* Vector::addVector(1.0, R, -1.0) on a zeroed residual */
+      if (ids[i] >= 0) m->B[ids[i]] += res;
+    }
+  }
+  for (int n = 0; n < m->nn; n++)
+    for (int j = 0; j < m->ndf; j++) {
+      int pos = m->id[n * m->ndf + j];
+      if (pos >= 0) m->B[pos] += 0.0 + m->load[n * m->ndf + j] * m->lambda;
+    }
+  if (B) memcpy(B, m->B, sizeof(double) * m->neq);
+  return 0;
+}
+
+/* Domain::commit -> Element::commitState -> material commitState; nodes commit trial */
+int orc_commit(void* h) {
+  OrcModel* m = (OrcModel*)h;
+  memcpy(m->commit_disp, m->trial, sizeof(double) * m->nn * m->ndf);
+  for (int e = 0; e < m->ne; e++) for (int g = 0; g < m->ele[e].nip; g++) gp_commit(&m->ele[e].gp[g]);
+  return 0;
+}
+int orc_revert(void* h) {
+  OrcModel* m = (OrcModel*)h;
+  memcpy(m->trial, m->commit_disp, sizeof(double) * m->nn * m->ndf);
+  for (int e = 0; e < m->ne; e++) for (int g = 0; g < m->ele[e].nip; g++) gp_revert(&m->ele[e].gp[g]);
+  return 0;
+}
+
+/* per-GP peek for kernel-level parity: stress (order) and tangent (order^2) of FE element e, point g */
+int orc_gp_response(void* h, int e, int g, double* stress, double* tangent) {
+  OrcModel* m = (OrcModel*)h; OrcGP* gp = &m->ele[e].gp[g];
+  gp_get_stress(gp, stress); gp_get_tangent(gp, tangent);
+  return gp->type == ORC_ND_3D ? 6 : 3;
+}
+
+void orc_model_free(void* h) {
+  OrcModel* m = (OrcModel*)h; if (!m) return;
+  free(m->node_tag); free(m->crd); free(m->trial); free(m->commit_disp); free(m->load); free(m->fixed);
+  free(m->mat_tag); free(m->mat_kind); free(m->mat_par); free(m->ele); free(m->id); free(m->ptr); free(m->idx);
+  free(m->A); free(m->B); free(m);
+}

@@ -1,0 +1,12 @@
+"""The models behind tests/golden/*.npz (generated from the reference by tests/golden/make_golden.py)."""
+from modelspec import ELASTIC, J2_STEEL, brick_block, quad_plane
+
+# name -> (spec factory, numberer, soe, displacement scale)
+CASES = {
+    "brick_j2_plain_csc": (lambda: brick_block(3, 3, 2, mat=J2_STEEL, distort=0.25, seed=1, body=(0.0, 0.0, -0.01)), 0, 0, 2e-3),
+    "brick_j2_rcm_csr": (lambda: brick_block(4, 2, 3, mat=J2_STEEL, distort=0.2, seed=2), 1, 1, 2e-3),
+    "brick_elastic_rcm_csc": (lambda: brick_block(2, 3, 3, mat=ELASTIC, distort=0.3, seed=3), 1, 0, 2e-3),
+    "quad_elastic_rcm_csc": (lambda: quad_plane(10, 4, mat=ELASTIC, distort=0.0, seed=4), 1, 0, 2e-2),
+    "quad_j2_plain_csr": (lambda: quad_plane(6, 5, mat=J2_STEEL, lx=6.0, ly=5.0, distort=0.3, seed=5, body=(0.0, -0.02)), 0, 1, 2e-3),
+}
+NSTEPS = 3

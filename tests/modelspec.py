@@ -1,0 +1,333 @@
+"""Model descriptions shared by every backend the tests compare.
+
+A ``ModelSpec`` is the flat, array-of-arrays form of what the reference's model
+commands (``node``, ``fix``, ``nDMaterial``, ``element stdBrick|quad``, ``load``)
+build in a ``Domain``.  Three backends consume it:
+
+* ``RefBackend``    -- the reference's own classes (oracle/_ref/libref_harness.so)
+* ``OracleBackend`` -- the C restatement (oracle/liboracle.so)
+* ``xara_b200.DeviceModel`` -- the product (CUDA, through the C-ABI)
+
+Only tests/, bench.py's CPU legs and __graft_entry__.smoke() import this.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libref_harness.so")
+
+MAT_ELASTIC, MAT_J2 = 0, 1
+ELE_BRICK, ELE_QUAD = 0, 1
+ND_3D, ND_PLANE_STRAIN = 0, 1
+NUMBERER_PLAIN, NUMBERER_RCM = 0, 1
+SOE_CSC, SOE_CSR = 0, 1
+
+
+@dataclass
+class ElementGroup:
+    kind: int                 # ELE_BRICK | ELE_QUAD
+    tags: np.ndarray          # [ne] int32
+    conn: np.ndarray          # [ne, nen] int32 node TAGS
+    mat: np.ndarray           # [ne] int32 material tags
+    par: np.ndarray           # [ne, 8] float64 (brick: b1,b2,b3; quad: thick,type,pressure,rho,b1,b2)
+
+
+@dataclass
+class ModelSpec:
+    ndm: int
+    ndf: int
+    node_tags: np.ndarray     # [nn] int32 ascending
+    crd: np.ndarray           # [nn, ndm]
+    fix: np.ndarray           # [nfix, 2] (node tag, dof)
+    materials: list           # (tag, kind, params[<=8])
+    groups: list = field(default_factory=list)
+    loads: np.ndarray = None  # [nload, 1+ndf] (node tag, values...)
+
+    @property
+    def nn(self):
+        return len(self.node_tags)
+
+    @property
+    def ne(self):
+        return sum(len(g.tags) for g in self.groups)
+
+
+J2_STEEL = (MAT_J2, [166.67e3, 76.92e3, 250.0, 400.0, 16.93, 500.0, 0.0])   # K G sig0 sigInf delta H eta
+ELASTIC = (MAT_ELASTIC, [1000.0, 0.25, 6.75])                                # E nu rho (Verification/Plane/PlaneStrain.tcl)
+
+
+def brick_block(nx, ny, nz, mat=J2_STEEL, lx=1.0, ly=1.0, lz=1.0, distort=0.0, seed=0,
+                body=(0.0, 0.0, 0.0), fix_face="z0", load=None):
+    """nx*ny*nz stdBrick block, node tags 1.. in x-fastest order, base fixed."""
+    rng = np.random.default_rng(seed)
+    X, Y, Z = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij")
+    idx = (X + (nx + 1) * (Y + (ny + 1) * Z))
+    nn = (nx + 1) * (ny + 1) * (nz + 1)
+    crd = np.zeros((nn, 3))
+    crd[idx.ravel(), 0] = X.ravel() * lx / nx
+    crd[idx.ravel(), 1] = Y.ravel() * ly / ny
+    crd[idx.ravel(), 2] = Z.ravel() * lz / nz
+    if distort:
+        h = min(lx / nx, ly / ny, lz / nz)
+        crd += distort * h * (rng.random(crd.shape) - 0.5)
+    ex, ey, ez = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    ex, ey, ez = [a.transpose(2, 1, 0).ravel() for a in (ex, ey, ez)]
+
+    def nid(i, j, k):
+        return i + (nx + 1) * (j + (ny + 1) * k) + 1
+
+    conn = np.stack([nid(ex, ey, ez), nid(ex + 1, ey, ez), nid(ex + 1, ey + 1, ez), nid(ex, ey + 1, ez),
+                     nid(ex, ey, ez + 1), nid(ex + 1, ey, ez + 1), nid(ex + 1, ey + 1, ez + 1),
+                     nid(ex, ey + 1, ez + 1)], axis=1).astype(np.int32)
+    ne = len(conn)
+    par = np.zeros((ne, 8)); par[:, :3] = body
+    base = np.where(idx[:, :, 0].ravel() >= 0)[0]
+    base_tags = (idx[:, :, 0].ravel() + 1)
+    fix = np.array([(t, d) for t in base_tags for d in range(3)], dtype=np.int32).reshape(-1, 2)
+    top_tags = idx[:, :, nz].ravel() + 1
+    if load is None:
+        load = (0.3, 0.0, -1.0)
+    loads = np.array([[t, *load] for t in top_tags], dtype=np.float64)
+    return ModelSpec(3, 3, np.arange(1, nn + 1, dtype=np.int32), crd, fix, [(1, *mat)],
+                     [ElementGroup(ELE_BRICK, np.arange(1, ne + 1, dtype=np.int32), conn,
+                                   np.ones(ne, np.int32), par)], loads)
+
+
+def quad_plane(nx, ny, mat=ELASTIC, lx=40.0, ly=10.0, thick=1.0, distort=0.0, seed=0, body=(0.0, 0.0)):
+    """nx*ny FourNodeQuad plane-strain mesh (Verification/Plane/PlaneStrain.tcl shape), left edge fixed."""
+    rng = np.random.default_rng(seed)
+    X, Y = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), indexing="ij")
+    idx = X + (nx + 1) * Y
+    nn = (nx + 1) * (ny + 1)
+    crd = np.zeros((nn, 2))
+    crd[idx.ravel(), 0] = X.ravel() * lx / nx
+    crd[idx.ravel(), 1] = Y.ravel() * ly / ny
+    if distort:
+        crd += distort * min(lx / nx, ly / ny) * (rng.random(crd.shape) - 0.5)
+    ex, ey = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    ex, ey = ex.T.ravel(), ey.T.ravel()
+
+    def nid(i, j):
+        return i + (nx + 1) * j + 1
+
+    conn = np.stack([nid(ex, ey), nid(ex + 1, ey), nid(ex + 1, ey + 1), nid(ex, ey + 1)], axis=1).astype(np.int32)
+    ne = len(conn)
+    par = np.zeros((ne, 8)); par[:, 0] = thick; par[:, 1] = 0; par[:, 4:6] = body
+    left = idx[0, :].ravel() + 1
+    fix = np.array([(t, d) for t in left for d in range(2)], dtype=np.int32).reshape(-1, 2)
+    right = idx[nx, :].ravel() + 1
+    loads = np.array([[t, 0.5, -1.0] for t in right], dtype=np.float64)
+    return ModelSpec(2, 2, np.arange(1, nn + 1, dtype=np.int32), crd, fix, [(1, *mat)],
+                     [ElementGroup(ELE_QUAD, np.arange(1, ne + 1, dtype=np.int32), conn,
+                                   np.ones(ne, np.int32), par)], loads)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class _Backend:
+    """common numpy-facing surface: setup / ids / csr / update / form_* / commit"""
+
+    def num_eqn(self): ...
+
+
+class OracleBackend(_Backend):
+    def __init__(self, spec: ModelSpec, numberer=NUMBERER_PLAIN, soe=SOE_CSC):
+        L = ctypes.CDLL(ORACLE_SO)
+        self.L, self.spec = L, spec
+        L.orc_model_new.restype = ctypes.c_void_p
+        tags = np.ascontiguousarray(spec.node_tags, np.int32)
+        crd = np.ascontiguousarray(spec.crd, np.float64)
+        self.h = ctypes.c_void_p(L.orc_model_new(spec.ndm, spec.ndf, spec.nn, _p(tags), _p(crd)))
+        assert self.h, "node tags must ascend"
+        for t, d in spec.fix:
+            assert L.orc_fix(self.h, int(t), int(d)) == 0
+        for tag, kind, p in spec.materials:
+            pp = np.zeros(8); pp[:len(p)] = p
+            assert L.orc_add_nd_material(self.h, tag, kind, _p(pp)) == 0
+        for g in spec.groups:
+            for i in range(len(g.tags)):
+                c = np.ascontiguousarray(g.conn[i], np.int32); pr = np.ascontiguousarray(g.par[i], np.float64)
+                assert L.orc_add_element(self.h, g.kind, int(g.tags[i]), _p(c), int(g.mat[i]), _p(pr)) == 0
+        if spec.loads is not None:
+            for row in spec.loads:
+                v = np.ascontiguousarray(row[1:], np.float64)
+                assert L.orc_add_load(self.h, int(row[0]), _p(v)) == 0
+        self.neq = L.orc_setup(self.h, numberer, soe)
+        self.nnz = L.orc_nnz(self.h)
+        self.ne = L.orc_num_ele(self.h)
+
+    def ids(self):
+        a = np.zeros((self.spec.nn, self.spec.ndf), np.int32); self.L.orc_get_ids(self.h, _p(a)); return a
+
+    def csr(self):
+        ptr = np.zeros(self.neq + 1, np.int32); idx = np.zeros(self.nnz, np.int32)
+        self.L.orc_get_csr(self.h, _p(ptr), _p(idx)); return ptr, idx
+
+    def fe_ids(self, stride=24):
+        tags = np.zeros(self.ne, np.int32); ids = np.full((self.ne, stride), -9, np.int32)
+        self.L.orc_fe_ids(self.h, _p(tags), _p(ids), stride); return tags, ids
+
+    def scatter_map(self, e, nd):
+        m = np.zeros(nd * nd, np.int32); self.L.orc_scatter_map(self.h, e, _p(m)); return m.reshape(nd, nd)
+
+    def set_trial_disp(self, u):
+        u = np.ascontiguousarray(u, np.float64); return self.L.orc_set_trial_disp(self.h, _p(u))
+
+    def apply_load(self, lam):
+        self.L.orc_apply_load.argtypes = [ctypes.c_void_p, ctypes.c_double]; self.L.orc_apply_load(self.h, lam)
+
+    def form_tangent(self):
+        A = np.zeros(self.nnz); self.L.orc_form_tangent(self.h, _p(A)); return A
+
+    def form_unbalance(self):
+        B = np.zeros(self.neq); self.L.orc_form_unbalance(self.h, _p(B)); return B
+
+    def ele_tangent(self, e, nd):
+        K = np.zeros(nd * nd); self.L.orc_ele_tangent(self.h, e, _p(K)); return K.reshape(nd, nd)
+
+    def ele_resid(self, e, nd):
+        R = np.zeros(nd); self.L.orc_ele_resid(self.h, e, _p(R)); return R
+
+    def commit(self):
+        return self.L.orc_commit(self.h)
+
+    def revert(self):
+        return self.L.orc_revert(self.h)
+
+    def __del__(self):
+        try:
+            self.L.orc_model_free(self.h)
+        except Exception:
+            pass
+
+
+def oracle_nd_path(kind, p, type_, strains, commit):
+    L = ctypes.CDLL(ORACLE_SO)
+    order = 6 if type_ == ND_3D else 3
+    strains = np.ascontiguousarray(strains, np.float64); n = len(strains)
+    commit = np.ascontiguousarray(commit, np.int32)
+    pp = np.zeros(8); pp[:len(p)] = p
+    s = np.zeros((n, order)); t = np.zeros((n, order, order))
+    r = L.orc_nd_path(kind, _p(pp), type_, n, _p(strains), _p(commit), _p(s), _p(t))
+    assert r == order, r
+    return s, t
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def ref_nd_path(kind, p, type_, strains, commit):
+    L = ctypes.CDLL(REF_SO)
+    order = 6 if type_ == ND_3D else 3
+    strains = np.ascontiguousarray(strains, np.float64); n = len(strains)
+    commit = np.ascontiguousarray(commit, np.int32)
+    pp = np.zeros(8); pp[:len(p)] = p
+    s = np.zeros((n, order)); t = np.zeros((n, order, order))
+    name = b"ThreeDimensional" if type_ == ND_3D else b"PlaneStrain"
+    r = L.ref_nd_path(kind, _p(pp), name, n, _p(strains), _p(commit), _p(s), _p(t))
+    assert r == order, r
+    return s, t
+
+
+class RefBackend(_Backend):
+    """The reference's own Domain / AnalysisModel / LinearSOE, through oracle/ref_harness.cpp."""
+
+    def __init__(self, spec: ModelSpec, numberer=NUMBERER_PLAIN, soe=SOE_CSC, dlambda=1.0,
+                 test=0, tol=1e-8, max_iter=20):
+        L = ctypes.CDLL(REF_SO)
+        self.L, self.spec = L, spec
+        L.ref_model_new.restype = ctypes.c_void_p
+        self.h = ctypes.c_void_p(L.ref_model_new(spec.ndm, spec.ndf))
+        self.tags = np.ascontiguousarray(spec.node_tags, np.int32)
+        for t, x in zip(spec.node_tags, spec.crd):
+            xx = np.zeros(3); xx[:spec.ndm] = x
+            assert L.ref_add_node(self.h, int(t), _p(xx)) == 0
+        for t, d in spec.fix:
+            assert L.ref_fix(self.h, int(t), int(d)) == 0
+        for tag, kind, p in spec.materials:
+            pp = np.zeros(8); pp[:len(p)] = p
+            assert L.ref_add_nd_material(self.h, tag, kind, _p(pp)) == 0
+        L.ref_add_quad.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_double,
+                                   ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_void_p]
+        self.ele_tags = []
+        for g in spec.groups:
+            for i in range(len(g.tags)):
+                c = np.ascontiguousarray(g.conn[i], np.int32)
+                if g.kind == ELE_BRICK:
+                    b = np.ascontiguousarray(g.par[i, :3], np.float64)
+                    assert L.ref_add_brick(self.h, int(g.tags[i]), _p(c), int(g.mat[i]), _p(b)) == 0
+                else:
+                    b = np.ascontiguousarray(g.par[i, 4:6], np.float64)
+                    assert L.ref_add_quad(self.h, int(g.tags[i]), _p(c), int(g.mat[i]), float(g.par[i, 0]),
+                                          int(g.par[i, 1]), float(g.par[i, 2]), float(g.par[i, 3]), _p(b)) == 0
+                self.ele_tags.append(int(g.tags[i]))
+        self.ele_tags.sort()
+        if spec.loads is not None:
+            for row in spec.loads:
+                v = np.ascontiguousarray(row[1:], np.float64)
+                assert L.ref_add_load(self.h, int(row[0]), _p(v)) == 0
+        L.ref_setup.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,
+                                ctypes.c_double, ctypes.c_int]
+        self.neq = L.ref_setup(self.h, numberer, soe, dlambda, test, tol, max_iter)
+        assert self.neq >= 0, self.neq
+        self.nnz = L.ref_nnz(self.h)
+        self.ne = len(self.ele_tags)
+        self.max_iter = max_iter
+
+    def ids(self):
+        a = np.zeros((self.spec.nn, self.spec.ndf), np.int32)
+        row = np.zeros(self.spec.ndf, np.int32)
+        for i, t in enumerate(self.spec.node_tags):
+            self.L.ref_node_ids(self.h, int(t), _p(row)); a[i] = row
+        return a
+
+    def csr(self):
+        ptr = np.zeros(self.neq + 1, np.int32); idx = np.zeros(self.nnz, np.int32)
+        self.L.ref_get_csr(self.h, _p(ptr), _p(idx)); return ptr, idx
+
+    def fe_ids(self, stride=24):
+        tags = np.zeros(self.ne, np.int32); ids = np.full((self.ne, stride), -9, np.int32)
+        self.L.ref_fe_ids(self.h, _p(tags), _p(ids), stride); return tags, ids
+
+    def set_trial_disp(self, u):
+        u = np.ascontiguousarray(u, np.float64)
+        return self.L.ref_set_trial_disp(self.h, self.spec.nn, _p(self.tags), _p(u))
+
+    def get_trial_disp(self):
+        u = np.zeros((self.spec.nn, self.spec.ndf))
+        self.L.ref_get_trial_disp(self.h, self.spec.nn, _p(self.tags), _p(u)); return u
+
+    def apply_load(self, lam):
+        self.L.ref_apply_load.argtypes = [ctypes.c_void_p, ctypes.c_double]; self.L.ref_apply_load(self.h, lam)
+
+    def form_tangent(self):
+        A = np.zeros(self.nnz); self.L.ref_form_tangent(self.h, _p(A)); return A
+
+    def form_unbalance(self):
+        B = np.zeros(self.neq); self.L.ref_form_unbalance(self.h, _p(B)); return B
+
+    def ele_tangent(self, e, nd):
+        K = np.zeros(nd * nd); self.L.ref_ele_tangent(self.h, self.ele_tags[e], _p(K)); return K.reshape(nd, nd)
+
+    def ele_resid(self, e, nd):
+        R = np.zeros(nd); self.L.ref_ele_resid(self.h, self.ele_tags[e], _p(R)); return R
+
+    def commit(self):
+        return self.L.ref_commit(self.h)
+
+    def revert(self):
+        return self.L.ref_revert(self.h)
+
+    def analyze_static(self, nsteps):
+        iters = np.zeros(nsteps, np.int32); norms = np.zeros((nsteps, self.max_iter))
+        rc = self.L.ref_analyze_static(self.h, nsteps, _p(iters), _p(norms), self.max_iter)
+        return rc, iters, norms

@@ -1,0 +1,194 @@
+"""GPU: the CUDA path (through the C-ABI, xara_b200.DeviceModel) against the oracle and the
+golden vectors generated from the reference.
+
+Bar (BASELINE.json north_star): DOF numbering and scatter maps bit-exact (tests/test_host_setup.py),
+element forces / tangents and the assembled A, B within 1e-12 relative, identical Newton
+iteration counts.  "Relative" is to the largest entry of the object compared (an element
+matrix, A, B): entries that cancel to ~0 cannot agree to 1e-12 of themselves between two
+compilers of the reference either (FMA contraction).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import xara_b200 as xb
+from golden_cases import CASES, NSTEPS
+from modelspec import ELASTIC, J2_STEEL, OracleBackend, brick_block, quad_plane
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+RTOL = 1e-12
+
+
+def relerr(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_device_vs_golden_reference_vectors(name):
+    mk, numberer, soe, _ = CASES[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    spec = mk()
+    D = xb.DeviceModel.from_spec(spec, numberer, soe).to_device(0)
+    nd = 24 if spec.ndm == 3 else 8
+    for s in range(NSTEPS):
+        D.set_trial_disp(g[f"u{s}"]); D.update(); D.apply_load(0.25 * (s + 1))
+        A, B = D.form_tangent(), D.form_unbalance()
+        assert relerr(A, g[f"A{s}"]) < RTOL
+        assert relerr(B, g[f"B{s}"]) < RTOL
+        for e in range(len(g[f"K{s}"])):
+            assert relerr(D.element_tangent(e, nd), g[f"K{s}"][e]) < RTOL
+            assert relerr(D.element_resid(e, nd), g[f"R{s}"][e]) < RTOL
+        D.commit()
+
+
+@pytest.mark.parametrize("mat", [J2_STEEL, ELASTIC], ids=["j2", "elastic"])
+@pytest.mark.parametrize("shape", ["brick", "quad"])
+@pytest.mark.parametrize("numberer,soe", [(0, 0), (1, 1)])
+def test_device_vs_oracle_load_history(mat, shape, numberer, soe):
+    """several update/commit cycles with growing random displacements (well past yield)"""
+    rng = np.random.default_rng(42)
+    spec = (brick_block(5, 4, 3, mat=mat, distort=0.25, seed=3, body=(0.01, 0.0, -0.02)) if shape == "brick"
+            else quad_plane(9, 6, mat=mat, lx=9.0, ly=6.0, distort=0.25, seed=4, body=(0.0, -0.03)))
+    nd, order = (24, 6) if shape == "brick" else (8, 3)
+    O = OracleBackend(spec, numberer, soe)
+    D = xb.DeviceModel.from_spec(spec, numberer, soe).to_device(0)
+    ids = O.ids()
+    # untouched model: elastic tangent, zero residual
+    assert relerr(D.form_tangent(), O.form_tangent()) < RTOL
+    for s in range(5):
+        u = rng.normal(0, 1.5e-3 * (s + 1), (spec.nn, spec.ndf)); u[ids < 0] = 0
+        O.set_trial_disp(u); D.set_trial_disp(u); D.update()
+        O.apply_load(0.2 * s); D.apply_load(0.2 * s)
+        assert relerr(D.form_tangent(), O.form_tangent()) < RTOL
+        assert relerr(D.form_unbalance(), O.form_unbalance()) < RTOL
+        for e in (0, O.ne // 2, O.ne - 1):
+            assert relerr(D.element_tangent(e, nd), O.ele_tangent(e, nd)) < RTOL
+            assert relerr(D.element_resid(e, nd), O.ele_resid(e, nd)) < RTOL
+        if s % 2 == 0:
+            O.commit(); D.commit()
+
+
+def _newton(model, solve, nsteps, dlam, tol, max_iter, is_dev):
+    """BasicAnalysisBuilder::analyzeStatic with LoadControl + NewtonRaphson + CTestNormDispIncr
+    (newStep / solveCurrentStep / commit), the linear solve delegated to `solve`."""
+    hist = []
+    lam = 0.0
+    for _ in range(nsteps):
+        lam += dlam
+        model.apply_load(lam)                      # LoadControl::newStep
+        if is_dev:
+            model.update()
+        B = model.form_unbalance()
+        norms = []
+        for it in range(max_iter):
+            A = model.form_tangent()
+            dU = solve(A, B)
+            if is_dev:
+                model.incr_trial_disp(dU); model.update()
+            else:
+                u = model._u; ids = model.ids()
+                u[ids >= 0] += dU[ids[ids >= 0]]
+                model.set_trial_disp(u)
+            B = model.form_unbalance()
+            norms.append(float(np.linalg.norm(dU)))
+            if norms[-1] <= tol:
+                break
+        hist.append(norms)
+        model.commit()
+    return hist
+
+
+@pytest.mark.parametrize("shape", ["brick", "quad"])
+def test_newton_iteration_counts_match_oracle(shape):
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    if shape == "brick":
+        spec = brick_block(4, 4, 6, mat=J2_STEEL, lx=1.0, ly=1.0, lz=3.0, load=(2.2, 0.0, -1.0))
+    else:
+        spec = quad_plane(16, 4, mat=J2_STEEL, lx=8.0, ly=2.0)
+        spec.loads[:, 1:] = [0.0, -14.0]
+    O = OracleBackend(spec, 1, 1); O._u = np.zeros((spec.nn, spec.ndf))
+    D = xb.DeviceModel.from_spec(spec, 1, 1).to_device(0)
+    ptr, idx = O.csr()
+
+    def solve(A, B):
+        return spla.spsolve(sp.csr_matrix((A, idx, ptr), shape=(O.neq, O.neq)).tocsc(), B)
+
+    ho = _newton(O, solve, 8, 1.0, 1e-10, 25, False)
+    hd = _newton(D, solve, 8, 1.0, 1e-10, 25, True)
+    assert [len(h) for h in ho] == [len(h) for h in hd]          # identical iteration counts
+    assert max(len(h) for h in ho) >= 4                            # the steps really go plastic
+    for a, b in zip(ho, hd):
+        assert np.allclose(a[:-1], b[:-1], rtol=1e-6, atol=1e-13)  # same convergence history
+    assert relerr(D.trial_disp(), O._u) < 1e-9
+
+
+def test_revert_to_last_commit_and_incr():
+    rng = np.random.default_rng(0)
+    spec = brick_block(3, 3, 3, distort=0.1)
+    O = OracleBackend(spec, 0, 1); D = xb.DeviceModel.from_spec(spec, 0, 1).to_device(0)
+    ids = O.ids()
+    u1 = rng.normal(0, 4e-3, (spec.nn, 3)); u1[ids < 0] = 0
+    O.set_trial_disp(u1); D.set_trial_disp(u1); D.update(); O.commit(); D.commit()
+    u2 = u1 + rng.normal(0, 4e-3, (spec.nn, 3)); u2[ids < 0] = 0
+    O.set_trial_disp(u2); D.set_trial_disp(u2); D.update()
+    O.revert(); O.set_trial_disp(u1); D.revert_to_last_commit()
+    assert relerr(D.trial_disp(), u1) == 0.0
+    assert relerr(D.form_unbalance(), O.form_unbalance()) < RTOL
+    dU = rng.normal(0, 1e-3, O.neq)
+    D.incr_trial_disp(dU)
+    u3 = u1.copy(); u3[ids >= 0] += dU[ids[ids >= 0]]
+    assert relerr(D.trial_disp(), u3) < 1e-15
+
+
+def test_full_size_properties_brick():
+    """A 200k-element J2 block (too large for the oracle in seconds): properties that do not
+    depend on size -- symmetry of A, rigid-body null space of the elastic operator, row sums of
+    B equal to the applied load, determinism (bitwise identical A on a second pass)."""
+    import scipy.sparse as sp
+    n = 58
+    spec = brick_block(n, n, n, mat=J2_STEEL, fix_face="z0")
+    D = xb.DeviceModel.from_spec(spec, 0, 1).to_device(0)
+    ids = D.ids()
+    ptr, idx = D.pattern()
+    A0 = D.form_tangent()
+    M = sp.csr_matrix((A0, idx, ptr), shape=(D.neq, D.neq))
+    asym = abs(M - M.T).max() / abs(M).max()
+    assert asym < 1e-13
+    # elastic state: K * (uniform translation) must vanish on rows not coupled to the fixed base
+    t = np.zeros((spec.nn, 3)); t[:, 0] = 1.0
+    x = np.zeros(D.neq); x[ids[ids >= 0]] = t[ids >= 0]
+    r = M @ x
+    far = ids[spec.crd[:, 2] > 1.5 / n]
+    far = far[far >= 0]
+    assert np.abs(r[far]).max() < 1e-9 * abs(M).max()
+    # plastic state + determinism
+    rng = np.random.default_rng(1)
+    u = rng.normal(0, 3e-3, (spec.nn, 3)); u[ids < 0] = 0
+    D.set_trial_disp(u); D.update(); D.apply_load(1.0)
+    A1 = D.form_tangent(); A2 = D.form_tangent()
+    assert np.array_equal(A1, A2)
+    assert np.abs(A1 - A0).max() > 1e-3 * np.abs(A0).max()
+    M1 = sp.csr_matrix((A1, idx, ptr), shape=(D.neq, D.neq))
+    assert abs(M1 - M1.T).max() / abs(M1).max() < 1e-13
+    # B = lambda*P - sum R: with zero displacement the residual is the load itself
+    D.set_trial_disp(np.zeros_like(u)); D.update()
+    B = D.form_unbalance()
+    P = np.zeros(D.neq); ld = spec.loads
+    for row in ld:
+        nidx = int(row[0]) - 1
+        for d in range(3):
+            if ids[nidx, d] >= 0:
+                P[ids[nidx, d]] += row[1 + d]
+    # committed plastic strains are still zero (nothing was committed), so R(0) = 0
+    assert np.abs(B - P).max() < 1e-12 * max(np.abs(P).max(), 1.0)
+
+
+def test_launch_and_byte_accounting():
+    D = xb.DeviceModel.from_spec(brick_block(3, 3, 3), 0, 0).to_device(0)
+    n0 = D.launch_count()
+    D.update(); D.form_unbalance(host=False); D.form_tangent(host=False); D.synchronize()
+    assert D.launch_count() - n0 == 5      # update, resid, assemble_B, tangent, assemble_A
+    assert D.algorithmic_bytes(2) > D.nnz * 8

@@ -1,0 +1,139 @@
+"""CPU: the product's host side (xara_b200/csrc/host_model.cpp, through the C-ABI) against the
+oracle -- DOF numbering, FE order, sparse pattern and scatter maps are BIT-EXACT -- plus the
+library/ABI surface.  No device call is made here."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import xara_b200 as xb
+from golden_cases import CASES
+from modelspec import ELASTIC, J2_STEEL, OracleBackend, brick_block, quad_plane
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "xara_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(xb_[a-z_A-Z0-9]+)\s*\(", hdr))
+    assert len(declared) >= 35
+    import ctypes
+    L = ctypes.CDLL(xb.LIB_PATH)
+    missing = [n for n in sorted(declared) if not hasattr(L, n)]
+    assert not missing, missing
+    assert declared == set(xb.EXPORTS), declared ^ set(xb.EXPORTS)
+
+
+def relabel(spec, seed):
+    """random gappy node tags and shuffled element tags: tag->index maps and FE ordering"""
+    rng = np.random.default_rng(seed)
+    nn = spec.nn
+    new = rng.choice(np.arange(1, 7 * nn), nn, replace=False).astype(np.int32)   # new tag of old node i
+    order = np.argsort(new)
+    spec.node_tags, spec.crd = new[order], spec.crd[order]
+    for g in spec.groups:
+        g.conn = new[g.conn - 1].astype(np.int32)
+        g.tags = rng.permutation(g.tags * 3 + 1).astype(np.int32)
+    spec.fix[:, 0] = new[spec.fix[:, 0] - 1]
+    spec.loads[:, 0] = new[spec.loads[:, 0].astype(int) - 1]
+    return spec
+
+
+SPECS = {
+    "brick": lambda: brick_block(4, 3, 2, distort=0.2),
+    "brick_relabel": lambda: relabel(brick_block(3, 3, 3), 5),
+    "quad_relabel": lambda: relabel(quad_plane(7, 4, distort=0.2), 6),
+    "brick_sliver": lambda: brick_block(9, 1, 1),
+}
+
+
+@pytest.mark.parametrize("name", list(SPECS))
+@pytest.mark.parametrize("numberer", [0, 1])
+@pytest.mark.parametrize("soe", [0, 1])
+def test_numbering_pattern_scatter_bit_exact(name, numberer, soe):
+    spec = SPECS[name]()
+    O = OracleBackend(spec, numberer, soe)
+    D = xb.DeviceModel.from_spec(spec, numberer, soe)
+    nd = 24 if spec.ndm == 3 else 8
+    assert D.neq == O.neq and D.nnz == O.nnz
+    assert np.array_equal(D.node_tags(), spec.node_tags)
+    assert np.array_equal(D.ids(), O.ids())
+    ptr, idx = D.pattern(); po, io = O.csr()
+    assert np.array_equal(ptr, po) and np.array_equal(idx, io)
+    assert np.array_equal(D.element_tags(), O.fe_ids(nd)[0])
+    sm = D.scatter_map(0, D.ne, nd)
+    for e in range(D.ne):
+        assert np.array_equal(sm[e], O.scatter_map(e, nd))
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_host_setup_vs_golden(name):
+    mk, numberer, soe, _ = CASES[name]
+    g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    D = xb.DeviceModel.from_spec(mk(), numberer, soe)
+    assert np.array_equal(D.ids(), g["ids"])
+    ptr, idx = D.pattern()
+    assert np.array_equal(ptr, g["ptr"]) and np.array_equal(idx, g["idx"])
+
+
+def test_nodes_may_arrive_unsorted_and_in_batches():
+    spec = brick_block(2, 2, 2, distort=0.1)
+    D0 = xb.DeviceModel.from_spec(spec, 1, 0)
+    perm = np.random.default_rng(0).permutation(spec.nn)
+    m = xb.DeviceModel(3, 3)
+    h = spec.nn // 2
+    m.add_nodes(spec.node_tags[perm[:h]], spec.crd[perm[:h]])
+    m.add_nodes(spec.node_tags[perm[h:]], spec.crd[perm[h:]])
+    m.fix(spec.fix[:, 0], spec.fix[:, 1])
+    m.nd_material(1, *spec.materials[0][1:])
+    g = spec.groups[0]
+    m.add_elements(g.kind, g.tags[::-1], g.conn[::-1], g.mat[::-1], g.par[::-1])
+    m.setup(1, 0)
+    assert np.array_equal(m.ids(), D0.ids())
+    assert all(np.array_equal(a, b) for a, b in zip(m.pattern(), D0.pattern()))
+    assert np.array_equal(m.scatter_map(0, m.ne, 24), D0.scatter_map(0, D0.ne, 24))
+
+
+def test_error_behaviour():
+    m = xb.DeviceModel(3, 3)
+    m.add_nodes([1, 2], np.zeros((2, 3)))
+    with pytest.raises(xb.XaraB200Error):
+        m.nd_material(1, 99, [1.0, 2.0])                      # unknown kind
+    m.nd_material(1, xb.MAT_ELASTIC_ISOTROPIC, [100.0, 0.3, 0.0])
+    with pytest.raises(xb.XaraB200Error):
+        m.nd_material(1, xb.MAT_ELASTIC_ISOTROPIC, [100.0, 0.3, 0.0])   # duplicate tag
+    with pytest.raises(xb.XaraB200Error):
+        m.add_elements(xb.ELE_STDBRICK, [1], [[1, 2, 3, 4, 5, 6, 7, 8]], [7], np.zeros((1, 3)))  # unknown material
+    m.add_elements(xb.ELE_STDBRICK, [1], [[1, 2, 3, 4, 5, 6, 7, 8]], [1], np.zeros((1, 3)))
+    with pytest.raises(xb.XaraB200Error):
+        m.setup(0, 0)                                          # unknown node tags 3..8
+    m2 = xb.DeviceModel(3, 3)
+    with pytest.raises(xb.XaraB200Error):
+        m2.update()                                            # no device phase yet: never a CPU fallback
+    with pytest.raises(xb.XaraB200Error):
+        xb.DeviceModel(2, 2).add_elements(xb.ELE_STDBRICK, [1], [[1] * 8], [1], np.zeros((1, 3)))
+
+
+@pytest.mark.skipif(xb.device_count() > 0, reason="only meaningful on a box without a GPU")
+def test_no_cpu_fallback_without_device():
+    D = xb.DeviceModel.from_spec(brick_block(1, 1, 1), 0, 0)
+    with pytest.raises(xb.XaraB200Error):
+        D.to_device(0)
+    with pytest.raises(xb.XaraB200Error):
+        D.form_tangent()
+
+
+def test_all_fixed_and_isolated_nodes():
+    spec = brick_block(1, 1, 1)
+    spec.fix = np.array([(t, d) for t in spec.node_tags for d in range(3)], np.int32)
+    D = xb.DeviceModel.from_spec(spec, 0, 0)
+    assert D.neq == 0 and D.nnz == 0
+    spec = brick_block(1, 1, 1)
+    spec.node_tags = np.append(spec.node_tags, 100).astype(np.int32)
+    spec.crd = np.vstack([spec.crd, [5.0, 5.0, 5.0]])
+    for numberer in (0, 1):
+        O = OracleBackend(spec, numberer, 1); D = xb.DeviceModel.from_spec(spec, numberer, 1)
+        assert np.array_equal(D.ids(), O.ids())
+        assert all(np.array_equal(a, b) for a, b in zip(D.pattern(), O.csr()))

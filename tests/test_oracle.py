@@ -1,0 +1,126 @@
+"""CPU: the oracle (oracle/xara_oracle.c) against the golden vectors generated from the
+reference, and -- when oracle/_ref is present -- against the reference itself.
+
+Tolerances: integer work (DOF ids, FE ids, sparse pattern) bit-exact; FP64 results within
+1e-12 of the result's own scale (BASELINE.json north_star: "1e-12 relative FP64").
+"""
+import os
+
+import numpy as np
+import pytest
+
+from golden_cases import CASES, NSTEPS
+from modelspec import (ELASTIC, J2_STEEL, MAT_ELASTIC, MAT_J2, ND_3D, ND_PLANE_STRAIN, OracleBackend, RefBackend,
+                       brick_block, have_ref, oracle_nd_path, quad_plane, ref_nd_path)
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+RTOL = 1e-12
+
+
+def close(a, b, rtol=RTOL):
+    scale = max(np.abs(b).max(), 1e-300)
+    return np.abs(np.asarray(a) - np.asarray(b)).max() <= rtol * scale
+
+
+@pytest.mark.parametrize("key,kind,type_", [("j2_3d", MAT_J2, ND_3D), ("j2_pstrain", MAT_J2, ND_PLANE_STRAIN),
+                                            ("elastic_3d", MAT_ELASTIC, ND_3D),
+                                            ("elastic_pstrain", MAT_ELASTIC, ND_PLANE_STRAIN)])
+def test_material_paths_vs_golden(key, kind, type_):
+    g = np.load(os.path.join(GOLD, "material_paths.npz"))
+    s, t = oracle_nd_path(kind, g[key + "_par"], type_, g[key + "_strain"], g[key + "_commit"])
+    assert close(s, g[key + "_stress"])
+    assert close(t, g[key + "_tangent"])
+    if kind == MAT_J2:  # the path must actually yield, or the test says nothing about the return map
+        el = g[key + "_tangent"][0]
+        assert np.abs(g[key + "_tangent"] - el).max() > 1e-3 * np.abs(el).max()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_model_vs_golden(name):
+    mk, numberer, soe, _ = CASES[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    spec = mk()
+    O = OracleBackend(spec, numberer, soe)
+    nd = 24 if spec.ndm == 3 else 8
+    assert np.array_equal(O.ids(), g["ids"])                       # bit-exact DOF numbering
+    ptr, idx = O.csr()
+    assert np.array_equal(ptr, g["ptr"]) and np.array_equal(idx, g["idx"])   # bit-exact pattern
+    assert np.array_equal(O.fe_ids(nd)[1], g["fe_ids"])
+    for s in range(NSTEPS):
+        O.set_trial_disp(g[f"u{s}"]); O.apply_load(0.25 * (s + 1))
+        assert close(O.form_tangent(), g[f"A{s}"])
+        assert close(O.form_unbalance(), g[f"B{s}"])
+        for e in range(len(g[f"K{s}"])):
+            assert close(O.ele_tangent(e, nd), g[f"K{s}"][e])
+            assert close(O.ele_resid(e, nd), g[f"R{s}"][e])
+        O.commit()
+
+
+def test_scatter_map_is_where_addA_lands():
+    """oracle scatter map == the positions its own addA loop writes (unit impulse per entry)."""
+    spec = brick_block(2, 2, 1, distort=0.1)
+    for soe in (0, 1):
+        O = OracleBackend(spec, 1, soe)
+        ptr, idx = O.csr()
+        _, fe = O.fe_ids(24)
+        for e in range(O.ne):
+            m = O.scatter_map(e, 24)
+            for i in range(24):
+                for j in range(24):
+                    r, c = fe[e, i], fe[e, j]
+                    if r < 0 or c < 0:
+                        assert m[i, j] == -1
+                        continue
+                    major, minor = (r, c) if soe == 1 else (c, r)
+                    k = m[i, j]
+                    assert ptr[major] <= k < ptr[major + 1] and idx[k] == minor
+
+
+def test_empty_and_constrained_edge_cases():
+    # every dof fixed: zero equations, empty pattern
+    spec = brick_block(1, 1, 1)
+    spec.fix = np.array([(t, d) for t in spec.node_tags for d in range(3)], np.int32)
+    O = OracleBackend(spec, 0, 0)
+    assert O.neq == 0 and O.nnz == 0
+    # an isolated node (no element) keeps a diagonal-only row
+    spec = brick_block(1, 1, 1)
+    spec.node_tags = np.append(spec.node_tags, 100).astype(np.int32)
+    spec.crd = np.vstack([spec.crd, [5.0, 5.0, 5.0]])
+    O = OracleBackend(spec, 0, 1)
+    ptr, idx = O.csr()
+    ids = O.ids()
+    for r in ids[-1]:
+        assert ptr[r + 1] - ptr[r] == 1 and idx[ptr[r]] == r
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("mat", [J2_STEEL, ELASTIC])
+@pytest.mark.parametrize("numberer", [0, 1])
+@pytest.mark.parametrize("soe", [0, 1])
+def test_oracle_vs_live_reference(mat, numberer, soe):
+    rng = np.random.default_rng(7)
+    for spec in (brick_block(3, 2, 2, mat=mat, distort=0.2, seed=11), quad_plane(5, 4, mat=mat, distort=0.2, seed=12)):
+        O, R = OracleBackend(spec, numberer, soe), RefBackend(spec, numberer, soe)
+        assert O.neq == R.neq and O.nnz == R.nnz
+        assert np.array_equal(O.ids(), R.ids())
+        assert all(np.array_equal(a, b) for a, b in zip(O.csr(), R.csr()))
+        for s in range(3):
+            u = rng.normal(0, 2e-3 * (s + 1), (spec.nn, spec.ndf)); u[O.ids() < 0] = 0
+            O.set_trial_disp(u); R.set_trial_disp(u)
+            O.apply_load(0.3 * s); R.apply_load(0.3 * s)
+            assert close(O.form_tangent(), R.form_tangent())
+            assert close(O.form_unbalance(), R.form_unbalance())
+            O.commit(); R.commit()
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+def test_material_paths_vs_live_reference():
+    rng = np.random.default_rng(3)
+    for kind, p in (J2_STEEL, ELASTIC):
+        for type_ in (ND_3D, ND_PLANE_STRAIN):
+            order = 6 if type_ == ND_3D else 3
+            strains = np.cumsum(rng.normal(0, 1e-3, (120, order)), axis=0)
+            commit = (rng.random(120) < 0.5).astype(np.int32)
+            so, to = oracle_nd_path(kind, p, type_, strains, commit)
+            sr, tr = ref_nd_path(kind, p, type_, strains, commit)
+            assert close(so, sr) and close(to, tr)

@@ -1,0 +1,272 @@
+"""xara_b200 -- B200-native element state determination and global assembly.
+
+Python face of the C-ABI in ``include/xara_b200.h`` (ctypes, no torch types cross the
+boundary).  It mirrors the reference's analysis-side vocabulary for the hot path:
+
+==============================  =====================================================
+reference (OpenSeesRT / xara)   here
+==============================  =====================================================
+``model basic -ndm -ndf``       ``DeviceModel(ndm, ndf)``
+``node`` / ``fix``              ``add_nodes`` / ``fix``
+``nDMaterial``                  ``nd_material``
+``element stdBrick | quad``     ``add_elements``
+``load`` in ``pattern Plain``   ``add_nodal_loads``
+``numberer`` + ``system``       ``setup(numberer, soe)``   (domainChanged)
+``Domain::update``              ``update``
+``formTangent/formUnbalance``   ``form_tangent`` / ``form_unbalance``
+``Domain::commit``              ``commit``
+==============================  =====================================================
+
+There is no CPU fallback: if ``libxara_b200.so`` is missing the import fails, and every
+device call raises ``XaraB200Error`` when no sm_100a GPU is present.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+__all__ = ["DeviceModel", "XaraB200Error", "lib", "LIB_PATH", "device_count",
+           "MAT_ELASTIC_ISOTROPIC", "MAT_J2PLASTICITY", "ELE_STDBRICK", "ELE_FOURNODEQUAD",
+           "NUMBERER_PLAIN", "NUMBERER_RCM", "SOE_SPARSE_GEN_COL", "SOE_SPARSE_GEN_ROW"]
+
+MAT_ELASTIC_ISOTROPIC, MAT_J2PLASTICITY = 0, 1
+ELE_STDBRICK, ELE_FOURNODEQUAD = 0, 1
+NUMBERER_PLAIN, NUMBERER_RCM = 0, 1
+SOE_SPARSE_GEN_COL, SOE_SPARSE_GEN_ROW = 0, 1
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libxara_b200.so")
+
+
+class XaraB200Error(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(xara_b200 has no CPU fallback)")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, f64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_double
+    sig = {
+        "xb_version": (ctypes.c_char_p, []),
+        "xb_last_error": (ctypes.c_char_p, []),
+        "xb_device_count": (i32, []),
+        "xb_model_create": (vp, [i32, i32]),
+        "xb_model_destroy": (None, [vp]),
+        "xb_add_nodes": (i32, [vp, i32, vp, vp]),
+        "xb_add_sp": (i32, [vp, i32, vp, vp]),
+        "xb_add_nd_material": (i32, [vp, i32, i32, vp, i32]),
+        "xb_add_elements": (i32, [vp, i32, i32, vp, vp, vp, vp, i32]),
+        "xb_add_nodal_loads": (i32, [vp, i32, vp, vp]),
+        "xb_setup": (i32, [vp, i32, i32]),
+        "xb_num_nodes": (i32, [vp]),
+        "xb_num_elements": (i64, [vp]),
+        "xb_num_gauss_points": (i64, [vp]),
+        "xb_num_eqn": (i32, [vp]),
+        "xb_nnz": (i64, [vp]),
+        "xb_get_node_tags": (i32, [vp, vp]),
+        "xb_get_ids": (i32, [vp, vp]),
+        "xb_get_element_tags": (i32, [vp, vp]),
+        "xb_get_pattern": (i32, [vp, vp, vp]),
+        "xb_get_scatter_map": (i32, [vp, i64, i64, vp]),
+        "xb_device_init": (i32, [vp, i32, vp]),
+        "xb_set_trial_disp": (i32, [vp, vp]),
+        "xb_incr_trial_disp": (i32, [vp, vp]),
+        "xb_get_trial_disp": (i32, [vp, vp]),
+        "xb_update": (i32, [vp]),
+        "xb_apply_load": (i32, [vp, f64]),
+        "xb_form_tangent": (i32, [vp, vp]),
+        "xb_form_unbalance": (i32, [vp, vp]),
+        "xb_commit": (i32, [vp]),
+        "xb_revert_to_last_commit": (i32, [vp]),
+        "xb_synchronize": (i32, [vp]),
+        "xb_device_A": (vp, [vp]),
+        "xb_device_B": (vp, [vp]),
+        "xb_device_trial_disp": (vp, [vp]),
+        "xb_get_element_tangent": (i32, [vp, i64, vp]),
+        "xb_get_element_resid": (i32, [vp, i64, vp]),
+        "xb_get_gp_response": (i32, [vp, i64, i32, vp, vp]),
+        "xb_launch_count": (i64, [vp]),
+        "xb_algorithmic_bytes": (i64, [vp, i32]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    return L, tuple(sig)
+
+
+lib, EXPORTS = _load()
+
+
+def device_count() -> int:
+    return lib.xb_device_count()
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class DeviceModel:
+    """A Domain + AnalysisModel + LinearSOE whose hot path runs on one B200."""
+
+    def __init__(self, ndm: int, ndf: int):
+        self._h = lib.xb_model_create(ndm, ndf)
+        if not self._h:
+            raise XaraB200Error(lib.xb_last_error().decode())
+        self.ndm, self.ndf = ndm, ndf
+        self.neq = None
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise XaraB200Error(f"[{rc}] {lib.xb_last_error().decode()}")
+        return rc
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.xb_model_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- model commands ----
+    def add_nodes(self, tags, crd):
+        tags, crd = _i32(tags), _f64(crd)
+        assert crd.shape == (len(tags), self.ndm)
+        self._ck(lib.xb_add_nodes(self._h, len(tags), _ptr(tags), _ptr(crd)))
+
+    def fix(self, node_tags, dofs):
+        node_tags, dofs = _i32(node_tags), _i32(dofs)
+        self._ck(lib.xb_add_sp(self._h, len(node_tags), _ptr(node_tags), _ptr(dofs)))
+
+    def nd_material(self, tag, kind, par):
+        par = _f64(par)
+        self._ck(lib.xb_add_nd_material(self._h, tag, kind, _ptr(par), len(par)))
+
+    def add_elements(self, kind, tags, conn, mat_tags, par):
+        tags, conn, mat_tags, par = _i32(tags), _i32(conn), _i32(mat_tags), _f64(par)
+        assert par.ndim == 2 and len(par) == len(tags)
+        self._ck(lib.xb_add_elements(self._h, kind, len(tags), _ptr(tags), _ptr(conn), _ptr(mat_tags),
+                                     _ptr(par), par.shape[1]))
+
+    def add_nodal_loads(self, node_tags, values):
+        node_tags, values = _i32(node_tags), _f64(values)
+        self._ck(lib.xb_add_nodal_loads(self._h, len(node_tags), _ptr(node_tags), _ptr(values)))
+
+    @classmethod
+    def from_spec(cls, spec, numberer=NUMBERER_PLAIN, soe=SOE_SPARSE_GEN_COL):
+        """Build from a tests/modelspec.py ModelSpec (duck-typed)."""
+        m = cls(spec.ndm, spec.ndf)
+        m.add_nodes(spec.node_tags, spec.crd)
+        if len(spec.fix):
+            m.fix(spec.fix[:, 0], spec.fix[:, 1])
+        for tag, kind, p in spec.materials:
+            m.nd_material(tag, kind, p)
+        for g in spec.groups:
+            m.add_elements(g.kind, g.tags, g.conn, g.mat, g.par)
+        if spec.loads is not None and len(spec.loads):
+            m.add_nodal_loads(spec.loads[:, 0].astype(np.int32), spec.loads[:, 1:])
+        m.setup(numberer, soe)
+        return m
+
+    # ---- analysis set-up (host) ----
+    def setup(self, numberer=NUMBERER_PLAIN, soe=SOE_SPARSE_GEN_COL):
+        self.neq = self._ck(lib.xb_setup(self._h, numberer, soe))
+        self.nn = lib.xb_num_nodes(self._h)
+        self.ne = lib.xb_num_elements(self._h)
+        self.ngp = lib.xb_num_gauss_points(self._h)
+        self.nnz = lib.xb_nnz(self._h)
+        return self.neq
+
+    def node_tags(self):
+        a = np.zeros(self.nn, np.int32); self._ck(lib.xb_get_node_tags(self._h, _ptr(a))); return a
+
+    def ids(self):
+        a = np.zeros((self.nn, self.ndf), np.int32); self._ck(lib.xb_get_ids(self._h, _ptr(a))); return a
+
+    def element_tags(self):
+        a = np.zeros(self.ne, np.int32); self._ck(lib.xb_get_element_tags(self._h, _ptr(a))); return a
+
+    def pattern(self):
+        ptr = np.zeros(self.neq + 1, np.int64); idx = np.zeros(self.nnz, np.int32)
+        self._ck(lib.xb_get_pattern(self._h, _ptr(ptr), _ptr(idx))); return ptr, idx
+
+    def scatter_map(self, e0, e1, nd):
+        m = np.zeros((e1 - e0, nd, nd), np.int64)
+        self._ck(lib.xb_get_scatter_map(self._h, e0, e1, _ptr(m))); return m
+
+    # ---- device ----
+    def to_device(self, device=0, stream=None):
+        """stream: a raw cudaStream_t (int), e.g. torch.cuda.current_stream().cuda_stream"""
+        self._ck(lib.xb_device_init(self._h, device, ctypes.c_void_p(stream) if stream else None))
+        return self
+
+    def set_trial_disp(self, u):
+        u = _f64(u); assert u.size == self.nn * self.ndf
+        self._ck(lib.xb_set_trial_disp(self._h, _ptr(u)))
+        self._keep = u
+
+    def incr_trial_disp(self, dU):
+        dU = _f64(dU); assert dU.size == self.neq
+        self._ck(lib.xb_incr_trial_disp(self._h, _ptr(dU)))
+        self._keep = dU
+
+    def trial_disp(self):
+        u = np.zeros((self.nn, self.ndf)); self._ck(lib.xb_get_trial_disp(self._h, _ptr(u))); return u
+
+    def update(self):
+        self._ck(lib.xb_update(self._h))
+
+    def apply_load(self, lam):
+        self._ck(lib.xb_apply_load(self._h, float(lam)))
+
+    def form_tangent(self, out=None, host=True):
+        if host and out is None:
+            out = np.empty(self.nnz)
+        self._ck(lib.xb_form_tangent(self._h, _ptr(out) if host else None))
+        return out
+
+    def form_unbalance(self, out=None, host=True):
+        if host and out is None:
+            out = np.empty(self.neq)
+        self._ck(lib.xb_form_unbalance(self._h, _ptr(out) if host else None))
+        return out
+
+    def commit(self):
+        self._ck(lib.xb_commit(self._h))
+
+    def revert_to_last_commit(self):
+        self._ck(lib.xb_revert_to_last_commit(self._h))
+
+    def synchronize(self):
+        self._ck(lib.xb_synchronize(self._h))
+
+    def element_tangent(self, e, nd):
+        K = np.zeros((nd, nd)); self._ck(lib.xb_get_element_tangent(self._h, e, _ptr(K))); return K
+
+    def element_resid(self, e, nd):
+        R = np.zeros(nd); self._ck(lib.xb_get_element_resid(self._h, e, _ptr(R))); return R
+
+    def gp_response(self, e, g, order):
+        s = np.zeros(order); t = np.zeros((order, order))
+        self._ck(lib.xb_get_gp_response(self._h, e, g, _ptr(s), _ptr(t))); return s, t
+
+    def launch_count(self):
+        return lib.xb_launch_count(self._h)
+
+    def algorithmic_bytes(self, which):
+        return lib.xb_algorithmic_bytes(self._h, which)

@@ -1,0 +1,1003 @@
+// xara_b200 device path: element state determination, element tangent / residual
+// formation and deterministic CSR/CSC assembly, plus the C-ABI of include/xara_b200.h.
+// Compiled for sm_100a only; there is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/xara_b200.h"
+#include "host_model.hpp"
+#include "kernels.cuh"
+
+using namespace xbk;
+
+// =====================================================================================
+// device views
+// =====================================================================================
+struct GroupView {
+  long long n;          // elements
+  const int* conn;      // [n][nen] node indices
+  const int* mat;       // [n] material index
+  const double* par;    // [npar][n]
+  const double* mpar;   // [nmat][8]
+  // Gauss-point state, SoA over gp = e*nip + g  (ngp = n*nip)
+  double* hc;           // J2: committed epsilon_p (6) + xi   [7][ngp]
+  double* ht;           // J2: trial     epsilon_p (6) + xi   [7][ngp]
+  double* sig;          // stress                              [nst][ngp]
+  double* tan;          // J2: normal (6), c2, c3              [8][ngp]
+  double* Ke;           // [n][nd*nd]
+  double* Re;           // [n][nd]
+};
+
+// =====================================================================================
+// state determination: Element::update -> NDMaterial::setTrialStrain
+// =====================================================================================
+
+// Brick::update (Brick.cpp:718-840); one thread per Gauss point
+template <int MATK>
+__global__ void __launch_bounds__(128) brick_update_kernel(GroupView G, const double* __restrict__ X,
+                                                           const double* __restrict__ U, int* fail) {
+  const long long gp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long ngp = G.n * 8;
+  if (gp >= ngp) return;
+  const long long e = gp >> 3;
+  const int g = (int)(gp & 7);
+  const int* c = G.conn + e * 8;
+  double xl[3][8], ul[3][8];
+#pragma unroll
+  for (int a = 0; a < 8; a++) {
+    const int nd = __ldg(c + a);
+#pragma unroll
+    for (int d = 0; d < 3; d++) { xl[d][a] = __ldg(X + (size_t)nd * 3 + d); ul[d][a] = __ldg(U + (size_t)nd * 3 + d); }
+  }
+  double shp[4][8], xsj;
+  brick_shp(g, xl, shp, xsj);
+  double s[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    s[0] += shp[0][j] * ul[0][j];
+    s[1] += shp[1][j] * ul[1][j];
+    s[2] += shp[2][j] * ul[2][j];
+    s[3] += shp[1][j] * ul[0][j] + shp[0][j] * ul[1][j];
+    s[4] += shp[2][j] * ul[1][j] + shp[1][j] * ul[2][j];
+    s[5] += shp[2][j] * ul[0][j] + shp[0][j] * ul[2][j];
+  }
+  const double* p = G.mpar + (size_t)__ldg(G.mat + e) * 8;
+  if (MATK == XB_MAT_J2PLASTICITY) {
+    double par[7], epn[6], et[6];
+#pragma unroll
+    for (int i = 0; i < 7; i++) par[i] = __ldg(p + i);
+#pragma unroll
+    for (int i = 0; i < 6; i++) epn[i] = G.hc[(size_t)i * ngp + gp];
+    const double xin = G.hc[(size_t)6 * ngp + gp];
+    et[0] = s[0]; et[1] = s[1]; et[2] = s[2]; et[3] = 0.50 * s[3]; et[4] = 0.50 * s[4]; et[5] = 0.50 * s[5];
+    J2Result r;
+    j2_integrate(par, et, epn, xin, 0.0, r);
+    if (r.fail) atomicExch(fail, 1);
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      G.ht[(size_t)i * ngp + gp] = r.ep[i];
+      G.sig[(size_t)i * ngp + gp] = r.sig[i];
+      G.tan[(size_t)i * ngp + gp] = r.nrm[i];
+    }
+    G.ht[(size_t)6 * ngp + gp] = r.xi;
+    G.tan[(size_t)6 * ngp + gp] = r.c2;
+    G.tan[(size_t)7 * ngp + gp] = r.c3;
+  } else {
+    const double E = __ldg(p), v = __ldg(p + 1);
+    double mu2 = E / (1.0 + v);
+    const double lam = v * mu2 / (1.0 - 2.0 * v);
+    const double mu = 0.50 * mu2;
+    mu2 += lam;
+    G.sig[(size_t)0 * ngp + gp] = mu2 * s[0] + lam * (s[1] + s[2]);
+    G.sig[(size_t)1 * ngp + gp] = mu2 * s[1] + lam * (s[0] + s[2]);
+    G.sig[(size_t)2 * ngp + gp] = mu2 * s[2] + lam * (s[0] + s[1]);
+    G.sig[(size_t)3 * ngp + gp] = mu * s[3];
+    G.sig[(size_t)4 * ngp + gp] = mu * s[4];
+    G.sig[(size_t)5 * ngp + gp] = mu * s[5];
+  }
+}
+
+// FourNodeQuad::update (FourNodeQuad.cpp:190-222); one thread per Gauss point
+template <int MATK>
+__global__ void __launch_bounds__(128) quad_update_kernel(GroupView G, const double* __restrict__ X,
+                                                          const double* __restrict__ U, int* fail) {
+  const long long gp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long ngp = G.n * 4;
+  if (gp >= ngp) return;
+  const long long e = gp >> 2;
+  const int g = (int)(gp & 3);
+  const int* c = G.conn + e * 4;
+  double xc[4][2], u[2][4];
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    const int nd = __ldg(c + a);
+    xc[a][0] = __ldg(X + (size_t)nd * 2); xc[a][1] = __ldg(X + (size_t)nd * 2 + 1);
+    u[0][a] = __ldg(U + (size_t)nd * 2); u[1][a] = __ldg(U + (size_t)nd * 2 + 1);
+  }
+  double xi, eta, shp[3][4];
+  quad_point(g, xi, eta);
+  quad_shp(xi, eta, xc, shp);
+  double eps[3] = {0, 0, 0};
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    eps[0] += shp[0][b] * u[0][b];
+    eps[1] += shp[1][b] * u[1][b];
+    eps[2] += shp[0][b] * u[1][b] + shp[1][b] * u[0][b];
+  }
+  const double* p = G.mpar + (size_t)__ldg(G.mat + e) * 8;
+  if (MATK == XB_MAT_J2PLASTICITY) {
+    double par[7], epn[6], et[6];
+#pragma unroll
+    for (int i = 0; i < 7; i++) par[i] = __ldg(p + i);
+#pragma unroll
+    for (int i = 0; i < 6; i++) epn[i] = G.hc[(size_t)i * ngp + gp];
+    const double xin = G.hc[(size_t)6 * ngp + gp];
+    // J2PlaneStrain::setTrialStrain (material/Plane/J2PlaneStrain.cpp:80-92)
+    et[0] = eps[0]; et[1] = eps[1]; et[2] = 0.0; et[3] = 0.50 * eps[2]; et[4] = 0.0; et[5] = 0.0;
+    J2Result r;
+    j2_integrate(par, et, epn, xin, 0.0, r);
+    if (r.fail) atomicExch(fail, 1);
+#pragma unroll
+    for (int i = 0; i < 6; i++) { G.ht[(size_t)i * ngp + gp] = r.ep[i]; G.tan[(size_t)i * ngp + gp] = r.nrm[i]; }
+    G.ht[(size_t)6 * ngp + gp] = r.xi;
+    G.tan[(size_t)6 * ngp + gp] = r.c2;
+    G.tan[(size_t)7 * ngp + gp] = r.c3;
+    G.sig[(size_t)0 * ngp + gp] = r.sig[0];
+    G.sig[(size_t)1 * ngp + gp] = r.sig[1];
+    G.sig[(size_t)2 * ngp + gp] = r.sig[3];
+  } else {
+    const double E = __ldg(p), v = __ldg(p + 1);
+    double mu2 = E / (1.0 + v);
+    const double lam = v * mu2 / (1.0 - 2.0 * v);
+    const double mu = 0.50 * mu2;
+    mu2 += lam;
+    G.sig[(size_t)0 * ngp + gp] = mu2 * eps[0] + lam * eps[1];
+    G.sig[(size_t)1 * ngp + gp] = lam * eps[0] + mu2 * eps[1];
+    G.sig[(size_t)2 * ngp + gp] = mu * eps[2];
+  }
+}
+
+// =====================================================================================
+// element residual: Element::getResistingForce
+// =====================================================================================
+
+// Brick::formResidAndTangent(tang_flag=0) (Brick.cpp:843-1022); thread per Gauss point,
+// the 8 points of an element sit in 8 adjacent lanes and are summed by a fixed butterfly.
+__global__ void __launch_bounds__(128) brick_resid_kernel(GroupView G, const double* __restrict__ X) {
+  const long long gp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long ngp = G.n * 8;
+  const bool live = gp < ngp;
+  const long long e = live ? (gp >> 3) : (ngp - 1) >> 3;
+  const int g = (int)(gp & 7);
+  const int* c = G.conn + e * 8;
+  double xl[3][8];
+#pragma unroll
+  for (int a = 0; a < 8; a++) {
+    const int nd = __ldg(c + a);
+#pragma unroll
+    for (int d = 0; d < 3; d++) xl[d][a] = __ldg(X + (size_t)nd * 3 + d);
+  }
+  double shp[4][8], dvol;
+  brick_shp(g, xl, shp, dvol);  // wg = 1 (Brick.cpp:61)
+  const long long gpc = live ? gp : ngp - 1;
+  double st[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) st[i] = G.sig[(size_t)i * ngp + gpc] * dvol;
+  const double b0 = __ldg(G.par + e), b1 = __ldg(G.par + G.n + e), b2 = __ldg(G.par + 2 * G.n + e);
+  double r[24];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    r[3 * j + 0] = shp[0][j] * st[0] + shp[1][j] * st[3] + shp[2][j] * st[5] - dvol * b0 * shp[3][j];
+    r[3 * j + 1] = shp[1][j] * st[1] + shp[0][j] * st[3] + shp[2][j] * st[4] - dvol * b1 * shp[3][j];
+    r[3 * j + 2] = shp[2][j] * st[2] + shp[1][j] * st[4] + shp[0][j] * st[5] - dvol * b2 * shp[3][j];
+  }
+#pragma unroll
+  for (int i = 0; i < 24; i++) {
+    r[i] += __shfl_xor_sync(0xffffffffu, r[i], 1);
+    r[i] += __shfl_xor_sync(0xffffffffu, r[i], 2);
+    r[i] += __shfl_xor_sync(0xffffffffu, r[i], 4);
+  }
+  if (!live) return;
+  double* out = G.Re + e * 24;
+#pragma unroll
+  for (int a = 0; a < 8; a++)
+    if (g == a) { out[3 * a] = r[3 * a]; out[3 * a + 1] = r[3 * a + 1]; out[3 * a + 2] = r[3 * a + 2]; }
+}
+
+// FourNodeQuad::getResistingForce (FourNodeQuad.cpp:507-553); thread per element
+__global__ void __launch_bounds__(128) quad_resid_kernel(GroupView G, const double* __restrict__ X) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= G.n) return;
+  const long long ngp = G.n * 4;
+  const int* c = G.conn + e * 4;
+  double xc[4][2];
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    const int nd = __ldg(c + a);
+    xc[a][0] = __ldg(X + (size_t)nd * 2); xc[a][1] = __ldg(X + (size_t)nd * 2 + 1);
+  }
+  const double th = __ldg(G.par + e), b0 = __ldg(G.par + G.n + e), b1 = __ldg(G.par + 2 * G.n + e);
+  double P[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    double xi, eta, shp[3][4];
+    quad_point(i, xi, eta);
+    double dvol = quad_shp(xi, eta, xc, shp);
+    dvol *= th;
+    const double s0 = G.sig[(size_t)0 * ngp + e * 4 + i], s1 = G.sig[(size_t)1 * ngp + e * 4 + i],
+                 s2 = G.sig[(size_t)2 * ngp + e * 4 + i];
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      P[2 * a] += dvol * (shp[0][a] * s0 + shp[1][a] * s2);
+      P[2 * a + 1] += dvol * (shp[1][a] * s1 + shp[0][a] * s2);
+      P[2 * a] -= dvol * (shp[2][a] * b0);
+      P[2 * a + 1] -= dvol * (shp[2][a] * b1);
+    }
+  }
+  double* out = G.Re + e * 8;
+#pragma unroll
+  for (int i = 0; i < 8; i++) out[i] = P[i];
+}
+
+// =====================================================================================
+// element tangent: Element::getTangentStiff
+// =====================================================================================
+
+// material tangent (6x6, packed symmetric) of Gauss point gp, scaled by dvol
+template <int MATK>
+__device__ __forceinline__ void brick_D(const GroupView& G, long long e, long long gp, long long ngp,
+                                        double dvol, double* d21) {
+  const double* p = G.mpar + (size_t)__ldg(G.mat + e) * 8;
+  if (MATK == XB_MAT_J2PLASTICITY) {
+    const double bulk = __ldg(p), shear = __ldg(p + 1);
+    double n[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) n[i] = G.tan[(size_t)i * ngp + gp];
+    const double c2 = G.tan[(size_t)6 * ngp + gp], c3 = G.tan[(size_t)7 * ngp + gp];
+#pragma unroll
+    for (int a = 0; a < 6; a++)
+#pragma unroll
+      for (int b = a; b < 6; b++) d21[sym6(a, b)] = j2_tangent_entry(a, b, bulk, shear, n, c2, c3) * dvol;
+  } else {
+    const double E = __ldg(p), v = __ldg(p + 1);
+    double mu2 = E / (1.0 + v);
+    const double lam = v * mu2 / (1.0 - 2.0 * v);
+    const double mu = 0.50 * mu2;
+    mu2 += lam;
+#pragma unroll
+    for (int a = 0; a < 6; a++)
+#pragma unroll
+      for (int b = a; b < 6; b++)
+        d21[sym6(a, b)] = ((a < 3 && b < 3) ? (a == b ? mu2 : lam) : (a == b ? mu : 0.0)) * dvol;
+  }
+}
+
+// Brick::formResidAndTangent(tang_flag=1), stiffness part (Brick.cpp:955-1016).
+// 8 lanes per element: lane k first evaluates Gauss point k (shape functions, D*dvol)
+// into shared memory, then owns column block k of the 24x24 matrix and accumulates
+// B_J^T (D B_k) over the 8 points for all 8 row blocks J in registers.
+constexpr int BT_ELEMS = 16;  // elements per CTA (128 threads)
+template <int MATK>
+__global__ void __launch_bounds__(BT_ELEMS * 8) brick_tangent_kernel(GroupView G, const double* __restrict__ X,
+                                                                     int transpose) {
+  extern __shared__ double smem[];
+  double* sN = smem;                         // [BT_ELEMS][8 g][3][8]
+  double* sD = smem + BT_ELEMS * 8 * 24;     // [BT_ELEMS][8 g][21]
+  const int tid = threadIdx.x;
+  const int le = tid >> 3, k = tid & 7;
+  const long long e_raw = (long long)blockIdx.x * BT_ELEMS + le;
+  const bool live = e_raw < G.n;
+  const long long e = live ? e_raw : G.n - 1;
+  const long long ngp = G.n * 8;
+  {
+    const int* c = G.conn + e * 8;
+    double xl[3][8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      const int nd = __ldg(c + a);
+#pragma unroll
+      for (int d = 0; d < 3; d++) xl[d][a] = __ldg(X + (size_t)nd * 3 + d);
+    }
+    double shp[4][8], dvol;
+    brick_shp(k, xl, shp, dvol);
+    double* n = sN + (le * 8 + k) * 24;
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+#pragma unroll
+      for (int a = 0; a < 8; a++) n[d * 8 + a] = shp[d][a];
+    double d21[21];
+    brick_D<MATK>(G, e, e * 8 + k, ngp, dvol, d21);
+    double* dd = sD + (le * 8 + k) * 21;
+#pragma unroll
+    for (int i = 0; i < 21; i++) dd[i] = d21[i];
+  }
+  __syncwarp();  // the 8 lanes of an element live in one warp
+  double acc[8][3][3];
+#pragma unroll
+  for (int J = 0; J < 8; J++)
+#pragma unroll
+    for (int p = 0; p < 3; p++)
+#pragma unroll
+      for (int q = 0; q < 3; q++) acc[J][p][q] = 0.0;
+
+#pragma unroll 1
+  for (int g = 0; g < 8; g++) {
+    const double* n = sN + (le * 8 + g) * 24;
+    const double* d = sD + (le * 8 + g) * 21;
+    const double N1 = n[k], N2 = n[8 + k], N3 = n[16 + k];
+    double DB[6][3];
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+      const double dr0 = d[sym6(r, 0)], dr1 = d[sym6(r, 1)], dr2 = d[sym6(r, 2)], dr3 = d[sym6(r, 3)],
+                   dr4 = d[sym6(r, 4)], dr5 = d[sym6(r, 5)];
+      DB[r][0] = dr0 * N1 + dr3 * N2 + dr5 * N3;
+      DB[r][1] = dr1 * N2 + dr3 * N1 + dr4 * N3;
+      DB[r][2] = dr2 * N3 + dr4 * N2 + dr5 * N1;
+    }
+#pragma unroll
+    for (int J = 0; J < 8; J++) {
+      const double M1 = n[J], M2 = n[8 + J], M3 = n[16 + J];
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        acc[J][0][q] += M1 * DB[0][q] + M2 * DB[3][q] + M3 * DB[5][q];
+        acc[J][1][q] += M2 * DB[1][q] + M1 * DB[3][q] + M3 * DB[4][q];
+        acc[J][2][q] += M3 * DB[2][q] + M2 * DB[4][q] + M1 * DB[5][q];
+      }
+    }
+  }
+  if (!live) return;
+  double* out = G.Ke + e * 576;
+  if (!transpose) {
+#pragma unroll
+    for (int J = 0; J < 8; J++)
+#pragma unroll
+      for (int p = 0; p < 3; p++)
+#pragma unroll
+        for (int q = 0; q < 3; q++) out[(3 * J + p) * 24 + 3 * k + q] = acc[J][p][q];
+  } else {
+#pragma unroll
+    for (int J = 0; J < 8; J++)
+#pragma unroll
+      for (int p = 0; p < 3; p++)
+#pragma unroll
+        for (int q = 0; q < 3; q++) out[(3 * k + q) * 24 + 3 * J + p] = acc[J][p][q];
+  }
+}
+
+// FourNodeQuad::getTangentStiff (FourNodeQuad.cpp:226-281).  4 lanes per element, lane b
+// owns column block beta=b (8 rows x 2 columns); shape functions are recomputed per lane.
+template <int MATK>
+__global__ void __launch_bounds__(128) quad_tangent_kernel(GroupView G, const double* __restrict__ X,
+                                                           int transpose) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long e = t >> 2;
+  const int beta = (int)(t & 3);
+  if (e >= G.n) return;
+  const long long ngp = G.n * 4;
+  const int* c = G.conn + e * 4;
+  double xc[4][2];
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    const int nd = __ldg(c + a);
+    xc[a][0] = __ldg(X + (size_t)nd * 2); xc[a][1] = __ldg(X + (size_t)nd * 2 + 1);
+  }
+  const double th = __ldg(G.par + e);
+  const double* p = G.mpar + (size_t)__ldg(G.mat + e) * 8;
+  double K[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; i++) K[i][0] = K[i][1] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    double xi, eta, shp[3][4];
+    quad_point(i, xi, eta);
+    double dvol = quad_shp(xi, eta, xc, shp);
+    dvol *= th;
+    double D00, D01, D02, D10, D11, D12, D20, D21, D22;
+    if (MATK == XB_MAT_J2PLASTICITY) {
+      const double bulk = __ldg(p), shear = __ldg(p + 1);
+      const long long gp = e * 4 + i;
+      double n[6];
+#pragma unroll
+      for (int q = 0; q < 6; q++) n[q] = G.tan[(size_t)q * ngp + gp];
+      const double c2 = G.tan[(size_t)6 * ngp + gp], c3 = G.tan[(size_t)7 * ngp + gp];
+      // J2PlaneStrain::getTangent (material/Plane/J2PlaneStrain.cpp:127-146): rows/cols (00,11,01)
+      D00 = j2_tangent_entry(0, 0, bulk, shear, n, c2, c3); D01 = j2_tangent_entry(0, 1, bulk, shear, n, c2, c3);
+      D02 = j2_tangent_entry(0, 3, bulk, shear, n, c2, c3); D11 = j2_tangent_entry(1, 1, bulk, shear, n, c2, c3);
+      D12 = j2_tangent_entry(1, 3, bulk, shear, n, c2, c3); D22 = j2_tangent_entry(3, 3, bulk, shear, n, c2, c3);
+      D10 = D01; D20 = D02; D21 = D12;
+    } else {
+      const double E = __ldg(p), v = __ldg(p + 1);
+      const double mu2 = E / (1.0 + v);
+      const double lam = v * mu2 / (1.0 - 2.0 * v);
+      const double mu = 0.50 * mu2;
+      D00 = D11 = mu2 + lam; D01 = D10 = lam; D22 = mu; D02 = D20 = D12 = D21 = 0.0;
+    }
+    double sb0 = shp[0][0], sb1 = shp[1][0];
+#pragma unroll
+    for (int b = 1; b < 4; b++) if (beta == b) { sb0 = shp[0][b]; sb1 = shp[1][b]; }
+    const double DB00 = dvol * (D00 * sb0 + D02 * sb1), DB10 = dvol * (D10 * sb0 + D12 * sb1),
+                 DB20 = dvol * (D20 * sb0 + D22 * sb1), DB01 = dvol * (D01 * sb1 + D02 * sb0),
+                 DB11 = dvol * (D11 * sb1 + D12 * sb0), DB21 = dvol * (D21 * sb1 + D22 * sb0);
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      K[2 * a][0] += shp[0][a] * DB00 + shp[1][a] * DB20;
+      K[2 * a][1] += shp[0][a] * DB01 + shp[1][a] * DB21;
+      K[2 * a + 1][0] += shp[1][a] * DB10 + shp[0][a] * DB20;
+      K[2 * a + 1][1] += shp[1][a] * DB11 + shp[0][a] * DB21;
+    }
+  }
+  double* out = G.Ke + e * 64;
+  if (!transpose) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) { out[i * 8 + 2 * beta] = K[i][0]; out[i * 8 + 2 * beta + 1] = K[i][1]; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; i++) { out[(2 * beta) * 8 + i] = K[i][0]; out[(2 * beta + 1) * 8 + i] = K[i][1]; }
+  }
+}
+
+// =====================================================================================
+// assembly: LinearSOE::addA / addB as a node-owned, fixed-order gather (no atomics)
+// =====================================================================================
+struct AsmView {
+  int nn, ndf, cp_stride, max_row;
+  const int* id;              // [nn][ndf]
+  const long long* ptr;       // [neq+1]
+  const long long* n2e_ptr;   // [nn+1]
+  const long long* n2e_koff;  // [*]
+  const long long* n2e_roff;  // [*]
+  const unsigned char* n2e_nd;
+  const unsigned short* colpos;  // [*][cp_stride]
+  const long long* ncol_ptr;  // [nn+1]
+  const double* load;         // [nn][ndf]
+};
+
+// One warp per node.  The node's equations own rows (CSR) / columns (CSC) that share one
+// column list; contributions of the adjacent elements are added in FE_Element order, i.e.
+// the order IncrementalIntegrator::formTangent (IncrementalIntegrator.cpp:91-99) calls addA.
+// Every entry of A is written exactly once, so no zeroA pass is needed.
+template <int NDF>
+__global__ void __launch_bounds__(256) assemble_A_kernel(AsmView V, const double* __restrict__ Ke,
+                                                         double* __restrict__ A) {
+  extern __shared__ double sacc[];  // [warps][NDF][max_row]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long n = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (n >= V.nn) return;
+  double* acc = sacc + (size_t)warp * NDF * V.max_row;
+  const long long t0 = V.n2e_ptr[n], t1 = V.n2e_ptr[n + 1];
+  int L = (int)(V.ncol_ptr[n + 1] - V.ncol_ptr[n]);
+  if (t0 == t1) L = 1;  // a node with no element: its rows hold the (zero) diagonal only
+  for (int c = lane; c < NDF * V.max_row; c += 32) acc[c] = 0.0;
+  __syncwarp();
+  for (long long t = t0; t < t1; t++) {
+    const int nd = V.n2e_nd[t];
+    const double* row = Ke + V.n2e_koff[t];
+    const unsigned short* cp = V.colpos + (size_t)t * V.cp_stride;
+    for (int j = lane; j < nd; j += 32) {
+      const unsigned short pos = cp[j];
+      if (pos != 0xFFFF) {
+#pragma unroll
+        for (int p = 0; p < NDF; p++) acc[p * V.max_row + pos] += row[p * nd + j];
+      }
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int p = 0; p < NDF; p++) {
+    const int r = V.id[n * NDF + p];
+    if (r < 0) continue;
+    double* out = A + V.ptr[r];
+    for (int c = lane; c < L; c += 32) out[c] = acc[p * V.max_row + c];
+  }
+}
+
+// formUnbalance: B = sum_e -(R_e)  (FE order)  +  lambda * P   (formElementResidual then
+// formNodalUnbalance, IncrementalIntegrator.cpp:202-238).  One thread per node dof.
+__global__ void __launch_bounds__(256) assemble_B_kernel(AsmView V, const double* __restrict__ Re,
+                                                         double lambda, double* __restrict__ B) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)V.nn * V.ndf) return;
+  const long long n = i / V.ndf;
+  const int p = (int)(i - n * V.ndf);
+  const int r = V.id[i];
+  if (r < 0) return;
+  double acc = 0.0;
+  for (long long t = V.n2e_ptr[n]; t < V.n2e_ptr[n + 1]; t++) acc += -Re[V.n2e_roff[t] + p];
+  acc += V.load[i] * lambda;
+  B[r] = acc;
+}
+
+// AnalysisModel::incrDisp: trial += dU[id]
+__global__ void incr_disp_kernel(long long ndof, const int* __restrict__ id, const double* __restrict__ dU,
+                                 double* __restrict__ U) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ndof) return;
+  const int r = id[i];
+  if (r >= 0) U[i] += dU[r];
+}
+
+// =====================================================================================
+// host-side model object and the C-ABI
+// =====================================================================================
+static thread_local std::string g_err;
+
+struct DevGroup {
+  GroupView v{};
+  int kind = 0, mat_kind = 0, nip = 0, nst = 0, nd = 0;
+  long long ngp = 0;
+};
+
+struct xb_model {
+  xb::HostModel h;
+  bool on_device = false;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::vector<DevGroup> dg;
+  std::vector<void*> allocs;
+  double *dX = nullptr, *dU = nullptr, *dUc = nullptr, *dKe = nullptr, *dRe = nullptr, *dA = nullptr,
+         *dB = nullptr, *dLoad = nullptr, *dMpar = nullptr, *dTmp = nullptr;
+  int* dId = nullptr;
+  int* dFail = nullptr;
+  AsmView av{};
+  double lambda = 0.0;
+  long long launches = 0;
+  long long alg_bytes[3] = {0, 0, 0};
+};
+
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(x)                                                                         \
+  do {                                                                                \
+    cudaError_t _e = (x);                                                             \
+    if (_e != cudaSuccess)                                                            \
+      return fail(XB_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(_e));      \
+  } while (0)
+
+template <class T>
+static cudaError_t dev_alloc(xb_model* m, T** p, size_t count) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+  if (e == cudaSuccess) { m->allocs.push_back(q); *p = (T*)q; }
+  return e;
+}
+template <class T>
+static cudaError_t dev_upload(xb_model* m, T** p, const std::vector<T>& v) {
+  cudaError_t e = dev_alloc(m, p, v.size());
+  if (e != cudaSuccess) return e;
+  if (v.empty()) return cudaSuccess;
+  return cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+extern "C" {
+
+const char* xb_version(void) { return "xara_b200 0.1 (sm_100a)"; }
+const char* xb_last_error(void) { return g_err.c_str(); }
+int xb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+xb_model* xb_model_create(int ndm, int ndf) {
+  if (ndm < 2 || ndm > 3 || ndf < 1 || ndf > 3) { g_err = "xb_model_create: ndm in {2,3}, ndf in {1..3}"; return nullptr; }
+  xb_model* m = new xb_model;
+  m->h.ndm = ndm; m->h.ndf = ndf;
+  return m;
+}
+
+void xb_model_destroy(xb_model* m) {
+  if (!m) return;
+  if (m->on_device) {
+    cudaSetDevice(m->device);
+    for (void* p : m->allocs) cudaFree(p);
+    if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
+  }
+  delete m;
+}
+
+#define HOSTCALL(expr)                         \
+  do {                                         \
+    if (!m) return fail(XB_ERR_ARG, "null model"); \
+    int _rc = (expr);                          \
+    if (_rc < 0) g_err = m->h.err;             \
+    return _rc;                                \
+  } while (0)
+
+int xb_add_nodes(xb_model* m, int n, const int* tags, const double* crd) { HOSTCALL(m->h.add_nodes(n, tags, crd)); }
+int xb_add_sp(xb_model* m, int n, const int* t, const int* d) { HOSTCALL(m->h.add_sp(n, t, d)); }
+int xb_add_nd_material(xb_model* m, int tag, int kind, const double* par, int npar) { HOSTCALL(m->h.add_material(tag, kind, par, npar)); }
+int xb_add_elements(xb_model* m, int kind, int n, const int* tags, const int* conn, const int* mt, const double* par, int ps) {
+  HOSTCALL(m->h.add_elements(kind, n, tags, conn, mt, par, ps));
+}
+int xb_add_nodal_loads(xb_model* m, int n, const int* t, const double* v) { HOSTCALL(m->h.add_loads(n, t, v)); }
+int xb_setup(xb_model* m, int numberer, int soe_kind) { HOSTCALL(m->h.setup(numberer, soe_kind)); }
+
+int xb_num_nodes(const xb_model* m) { return m ? m->h.nn() : 0; }
+long long xb_num_elements(const xb_model* m) { return m ? m->h.ne : 0; }
+long long xb_num_gauss_points(const xb_model* m) { return m ? m->h.ngp : 0; }
+int xb_num_eqn(const xb_model* m) { return m ? m->h.neq : 0; }
+long long xb_nnz(const xb_model* m) { return m ? m->h.nnz() : 0; }
+
+#define NEED_SETUP() if (!m || !m->h.is_setup) return fail(XB_ERR_STATE, "call xb_setup first")
+#define NEED_DEVICE() if (!m || !m->on_device) return fail(XB_ERR_STATE, "call xb_device_init first (no CPU fallback)")
+
+int xb_get_node_tags(const xb_model* m, int* tags) {
+  NEED_SETUP();
+  std::memcpy(tags, m->h.node_tag.data(), sizeof(int) * m->h.nn());
+  return XB_OK;
+}
+int xb_get_ids(const xb_model* m, int* ids) {
+  NEED_SETUP();
+  std::memcpy(ids, m->h.id.data(), sizeof(int) * m->h.id.size());
+  return XB_OK;
+}
+int xb_get_element_tags(const xb_model* m, int* tags) {
+  NEED_SETUP();
+  for (long long e = 0; e < m->h.ne; e++) tags[e] = m->h.groups[m->h.fe_group[e]].tag[m->h.fe_local[e]];
+  return XB_OK;
+}
+int xb_get_pattern(const xb_model* m, long long* ptr, int* idx) {
+  NEED_SETUP();
+  std::memcpy(ptr, m->h.ptr.data(), sizeof(long long) * m->h.ptr.size());
+  std::memcpy(idx, m->h.idx.data(), sizeof(int) * m->h.idx.size());
+  return XB_OK;
+}
+int xb_get_scatter_map(const xb_model* m, long long e0, long long e1, long long* map) {
+  NEED_SETUP();
+  int rc = m->h.scatter_map(e0, e1, map);
+  if (rc < 0) g_err = "xb_get_scatter_map: bad element range";
+  return rc;
+}
+
+int xb_device_init(xb_model* m, int device, void* cuda_stream) {
+  NEED_SETUP();
+  if (m->on_device) return fail(XB_ERR_STATE, "xb_device_init called twice");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(XB_ERR_CUDA, "no such CUDA device");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(XB_ERR_CUDA, "xara_b200 kernels are built for sm_100a only");
+  m->device = device;
+  if (cuda_stream) m->stream = (cudaStream_t)cuda_stream;
+  else { CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking)); m->own_stream = true; }
+  m->on_device = true;  // from here xb_model_destroy frees what was allocated
+
+  xb::HostModel& h = m->h;
+  const size_t nn = h.nn();
+  CU(dev_upload(m, &m->dX, h.crd));
+  CU(dev_alloc(m, &m->dU, nn * h.ndf));
+  CU(dev_alloc(m, &m->dUc, nn * h.ndf));
+  CU(cudaMemset(m->dU, 0, sizeof(double) * std::max<size_t>(nn * h.ndf, 1)));
+  CU(cudaMemset(m->dUc, 0, sizeof(double) * std::max<size_t>(nn * h.ndf, 1)));
+  CU(dev_upload(m, &m->dId, h.id));
+  CU(dev_upload(m, &m->dLoad, h.load));
+  std::vector<double> mp(h.mats.size() * 8);
+  for (size_t i = 0; i < h.mats.size(); i++) std::memcpy(&mp[i * 8], h.mats[i].par, sizeof(double) * 8);
+  CU(dev_upload(m, &m->dMpar, mp));
+  CU(dev_alloc(m, &m->dKe, (size_t)h.ke_total));
+  CU(dev_alloc(m, &m->dRe, (size_t)h.re_total));
+  CU(dev_alloc(m, &m->dA, (size_t)h.nnz()));
+  CU(dev_alloc(m, &m->dB, (size_t)h.neq));
+  CU(dev_alloc(m, &m->dTmp, (size_t)h.neq));
+  CU(dev_alloc(m, &m->dFail, 1));
+  CU(cudaMemset(m->dFail, 0, sizeof(int)));
+  CU(cudaMemset(m->dKe, 0, sizeof(double) * std::max<size_t>(h.ke_total, 1)));
+  CU(cudaMemset(m->dRe, 0, sizeof(double) * std::max<size_t>(h.re_total, 1)));
+
+  for (auto& g : h.groups) {
+    const xb::EleKind& k = xb::ele_kind(g.kind);
+    DevGroup d;
+    d.kind = g.kind; d.mat_kind = g.mat_kind; d.nip = k.nip; d.nst = k.nst; d.nd = k.nen * k.ndf;
+    d.ngp = g.n() * k.nip;
+    d.v.n = g.n();
+    int* conn = nullptr; int* mat = nullptr; double* par = nullptr;
+    CU(dev_upload(m, &conn, g.conn));
+    CU(dev_upload(m, &mat, g.mat));
+    std::vector<double> soa((size_t)k.npar * g.n());
+    for (long long i = 0; i < g.n(); i++)
+      for (int q = 0; q < k.npar; q++) soa[(size_t)q * g.n() + i] = g.par[(size_t)i * k.npar + q];
+    CU(dev_upload(m, &par, soa));
+    d.v.conn = conn; d.v.mat = mat; d.v.par = par; d.v.mpar = m->dMpar;
+    CU(dev_alloc(m, &d.v.sig, (size_t)k.nst * d.ngp));
+    CU(cudaMemset(d.v.sig, 0, sizeof(double) * k.nst * d.ngp));
+    if (g.mat_kind == XB_MAT_J2PLASTICITY) {
+      CU(dev_alloc(m, &d.v.hc, (size_t)7 * d.ngp));
+      CU(dev_alloc(m, &d.v.ht, (size_t)7 * d.ngp));
+      CU(dev_alloc(m, &d.v.tan, (size_t)8 * d.ngp));
+      CU(cudaMemset(d.v.hc, 0, sizeof(double) * 7 * d.ngp));
+      CU(cudaMemset(d.v.ht, 0, sizeof(double) * 7 * d.ngp));
+      CU(cudaMemset(d.v.tan, 0, sizeof(double) * 8 * d.ngp));
+    }
+    d.v.Ke = m->dKe + g.ke_off;
+    d.v.Re = m->dRe + g.re_off;
+    m->dg.push_back(d);
+  }
+
+  AsmView& a = m->av;
+  a.nn = (int)nn; a.ndf = h.ndf; a.cp_stride = h.cp_stride; a.max_row = std::max(h.max_row, 1);
+  a.id = m->dId; a.load = m->dLoad;
+  long long *ptr = nullptr, *n2e_ptr = nullptr, *koff = nullptr, *roff = nullptr, *ncol_ptr = nullptr;
+  unsigned char* nd = nullptr; unsigned short* cp = nullptr;
+  CU(dev_upload(m, &ptr, h.ptr));
+  CU(dev_upload(m, &n2e_ptr, h.n2e_ptr));
+  CU(dev_upload(m, &koff, h.n2e_koff));
+  CU(dev_upload(m, &roff, h.n2e_roff));
+  CU(dev_upload(m, &nd, h.n2e_nd));
+  CU(dev_upload(m, &cp, h.colpos));
+  CU(dev_upload(m, &ncol_ptr, h.ncol_ptr));
+  a.ptr = ptr; a.n2e_ptr = n2e_ptr; a.n2e_koff = koff; a.n2e_roff = roff; a.n2e_nd = nd; a.colpos = cp;
+  a.ncol_ptr = ncol_ptr;
+
+  // the state determination of an untouched model: J2Plasticity's constructor runs
+  // plastic_integrator() on zero strain (J2Plasticity.cpp:105) so that getTangent()
+  // is the elastic tangent before the first update; an update at U=0 reproduces that.
+  int rc = xb_update(m);
+  if (rc < 0) return rc;
+  CU(cudaStreamSynchronize(m->stream));
+  m->launches = 0;
+  return XB_OK;
+}
+
+static int check_fail_flag(xb_model* m) {
+  int f = 0;
+  CU(cudaMemcpyAsync(&f, m->dFail, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  if (f) {
+    cudaMemsetAsync(m->dFail, 0, sizeof(int), m->stream);
+    return fail(XB_ERR_MATERIAL, "More than 25 iterations in J2-plasticity (J2Plasticity.cpp:296)");
+  }
+  return XB_OK;
+}
+
+int xb_set_trial_disp(xb_model* m, const double* u) {
+  NEED_DEVICE();
+  CU(cudaSetDevice(m->device));
+  CU(cudaMemcpyAsync(m->dU, u, sizeof(double) * m->h.nn() * m->h.ndf, cudaMemcpyHostToDevice, m->stream));
+  return XB_OK;
+}
+
+int xb_incr_trial_disp(xb_model* m, const double* dU) {
+  NEED_DEVICE();
+  CU(cudaSetDevice(m->device));
+  CU(cudaMemcpyAsync(m->dTmp, dU, sizeof(double) * m->h.neq, cudaMemcpyHostToDevice, m->stream));
+  const long long ndof = (long long)m->h.nn() * m->h.ndf;
+  incr_disp_kernel<<<(unsigned)((ndof + 255) / 256), 256, 0, m->stream>>>(ndof, m->dId, m->dTmp, m->dU);
+  m->launches++;
+  CU(cudaGetLastError());
+  return XB_OK;
+}
+
+int xb_get_trial_disp(xb_model* m, double* u) {
+  NEED_DEVICE();
+  CU(cudaSetDevice(m->device));
+  CU(cudaMemcpyAsync(u, m->dU, sizeof(double) * m->h.nn() * m->h.ndf, cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
+  return XB_OK;
+}
+
+int xb_update(xb_model* m) {
+  NEED_DEVICE();
+  CU(cudaSetDevice(m->device));
+  long long bytes = 0;
+  for (auto& d : m->dg) {
+    if (d.v.n == 0) continue;
+    const unsigned blocks = (unsigned)((d.ngp + 127) / 128);
+    const bool j2 = d.mat_kind == XB_MAT_J2PLASTICITY;
+    if (d.kind == XB_ELE_STDBRICK) {
+      if (j2) brick_update_kernel<XB_MAT_J2PLASTICITY><<<blocks, 128, 0, m->stream>>>(d.v, m->dX, m->dU, m->dFail);
+      else brick_update_kernel<XB_MAT_ELASTIC_ISOTROPIC><<<blocks, 128, 0, m->stream>>>(d.v, m->dX, m->dU, m->dFail);
+    } else {
+      if (j2) quad_update_kernel<XB_MAT_J2PLASTICITY><<<blocks, 128, 0, m->stream>>>(d.v, m->dX, m->dU, m->dFail);
+      else quad_update_kernel<XB_MAT_ELASTIC_ISOTROPIC><<<blocks, 128, 0, m->stream>>>(d.v, m->dX, m->dU, m->dFail);
+    }
+    m->launches++;
+    // per Gauss point: committed history read (7) + trial history, stress, compact tangent written
+    bytes += d.ngp * 8 * (j2 ? (7 + 7 + d.nst + 8) : d.nst);
+  }
+  bytes += (long long)m->h.nn() * (m->h.ndm + m->h.ndf) * 8;  // coordinates + trial displacement, once
+  for (auto& g : m->h.groups) bytes += (long long)g.conn.size() * 4;
+  m->alg_bytes[0] = bytes;
+  CU(cudaGetLastError());
+  return XB_OK;
+}
+
+int xb_apply_load(xb_model* m, double lambda) {
+  if (!m) return fail(XB_ERR_ARG, "null model");
+  m->lambda = lambda;
+  return XB_OK;
+}
+
+int xb_form_tangent(xb_model* m, double* A) {
+  NEED_DEVICE();
+  CU(cudaSetDevice(m->device));
+  const int transpose = m->h.soe_kind == XB_SOE_SPARSE_GEN_COL ? 1 : 0;
+  long long bytes = 0;
+  for (auto& d : m->dg) {
+    if (d.v.n == 0) continue;
+    const bool j2 = d.mat_kind == XB_MAT_J2PLASTICITY;
+    if (d.kind == XB_ELE_STDBRICK) {
+      const unsigned blocks = (unsigned)((d.v.n + BT_ELEMS - 1) / BT_ELEMS);
+      const size_t sm = sizeof(double) * BT_ELEMS * 8 * (24 + 21);
+      if (j2) {
+        CU(cudaFuncSetAttribute(brick_tangent_kernel<XB_MAT_J2PLASTICITY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        brick_tangent_kernel<XB_MAT_J2PLASTICITY><<<blocks, BT_ELEMS * 8, sm, m->stream>>>(d.v, m->dX, transpose);
+      } else {
+        CU(cudaFuncSetAttribute(brick_tangent_kernel<XB_MAT_ELASTIC_ISOTROPIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        brick_tangent_kernel<XB_MAT_ELASTIC_ISOTROPIC><<<blocks, BT_ELEMS * 8, sm, m->stream>>>(d.v, m->dX, transpose);
+      }
+    } else {
+      const unsigned blocks = (unsigned)((d.v.n * 4 + 127) / 128);
+      if (j2) quad_tangent_kernel<XB_MAT_J2PLASTICITY><<<blocks, 128, 0, m->stream>>>(d.v, m->dX, transpose);
+      else quad_tangent_kernel<XB_MAT_ELASTIC_ISOTROPIC><<<blocks, 128, 0, m->stream>>>(d.v, m->dX, transpose);
+    }
+    m->launches++;
+    bytes += d.ngp * 8 * (j2 ? 8 : 0);  // compact tangent read
+  }
+  {
+    const int warps = 8;
+    const size_t sm = sizeof(double) * warps * m->h.ndf * m->av.max_row;
+    if (sm > 200 * 1024) return fail(XB_ERR_UNSUPPORTED, "row too long for the node-owned assembly kernel");
+    const unsigned blocks = (unsigned)((m->h.nn() + warps - 1) / warps);
+    if (blocks) {
+      if (m->h.ndf == 3) {
+        CU(cudaFuncSetAttribute(assemble_A_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        assemble_A_kernel<3><<<blocks, warps * 32, sm, m->stream>>>(m->av, m->dKe, m->dA);
+      } else if (m->h.ndf == 2) {
+        CU(cudaFuncSetAttribute(assemble_A_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        assemble_A_kernel<2><<<blocks, warps * 32, sm, m->stream>>>(m->av, m->dKe, m->dA);
+      } else {
+        CU(cudaFuncSetAttribute(assemble_A_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        assemble_A_kernel<1><<<blocks, warps * 32, sm, m->stream>>>(m->av, m->dKe, m->dA);
+      }
+      m->launches++;
+    }
+  }
+  // compulsory traffic of formTangent: tangent data in, connectivity + coordinates in, A out
+  bytes += m->h.nnz() * 8 + (long long)m->h.nn() * m->h.ndm * 8;
+  for (auto& g : m->h.groups) bytes += (long long)g.conn.size() * 4;
+  m->alg_bytes[2] = bytes;
+  CU(cudaGetLastError());
+  if (A) {
+    CU(cudaMemcpyAsync(A, m->dA, sizeof(double) * m->h.nnz(), cudaMemcpyDeviceToHost, m->stream));
+    return check_fail_flag(m);
+  }
+  return XB_OK;
+}
+
+int xb_form_unbalance(xb_model* m, double* B) {
+  NEED_DEVICE();
+  CU(cudaSetDevice(m->device));
+  long long bytes = 0;
+  for (auto& d : m->dg) {
+    if (d.v.n == 0) continue;
+    if (d.kind == XB_ELE_STDBRICK) {
+      brick_resid_kernel<<<(unsigned)((d.ngp + 127) / 128), 128, 0, m->stream>>>(d.v, m->dX);
+    } else {
+      quad_resid_kernel<<<(unsigned)((d.v.n + 127) / 128), 128, 0, m->stream>>>(d.v, m->dX);
+    }
+    m->launches++;
+    bytes += d.ngp * 8 * d.nst;
+  }
+  const long long ndof = (long long)m->h.nn() * m->h.ndf;
+  if (ndof) {
+    assemble_B_kernel<<<(unsigned)((ndof + 255) / 256), 256, 0, m->stream>>>(m->av, m->dRe, m->lambda, m->dB);
+    m->launches++;
+  }
+  bytes += (long long)m->h.neq * 8 + (long long)m->h.nn() * (m->h.ndm + m->h.ndf) * 8;
+  for (auto& g : m->h.groups) bytes += (long long)g.conn.size() * 4;
+  m->alg_bytes[1] = bytes;
+  CU(cudaGetLastError());
+  if (B) {
+    CU(cudaMemcpyAsync(B, m->dB, sizeof(double) * m->h.neq, cudaMemcpyDeviceToHost, m->stream));
+    return check_fail_flag(m);
+  }
+  return XB_OK;
+}
+
+int xb_commit(xb_model* m) {
+  NEED_DEVICE();
+  CU(cudaSetDevice(m->device));
+  // J2Plasticity::commitState (J2Plasticity.cpp:538): epsilon_p_n = epsilon_p_nplus1, xi_n = xi_nplus1.
+  // Every update rewrites the whole trial set, so committing is a buffer swap.
+  for (auto& d : m->dg)
+    if (d.mat_kind == XB_MAT_J2PLASTICITY) std::swap(d.v.hc, d.v.ht);
+  CU(cudaMemcpyAsync(m->dUc, m->dU, sizeof(double) * m->h.nn() * m->h.ndf, cudaMemcpyDeviceToDevice, m->stream));
+  return XB_OK;
+}
+
+int xb_revert_to_last_commit(xb_model* m) {
+  NEED_DEVICE();
+  CU(cudaSetDevice(m->device));
+  // Node::revertToLastCommit restores the trial displacement; the material history is
+  // untouched (J2Plasticity::revertToLastCommit is empty) and the next update rebuilds
+  // the trial state from the committed one.
+  CU(cudaMemcpyAsync(m->dU, m->dUc, sizeof(double) * m->h.nn() * m->h.ndf, cudaMemcpyDeviceToDevice, m->stream));
+  return xb_update(m);
+}
+
+int xb_synchronize(xb_model* m) {
+  NEED_DEVICE();
+  CU(cudaSetDevice(m->device));
+  return check_fail_flag(m);
+}
+
+double* xb_device_A(xb_model* m) { return m ? m->dA : nullptr; }
+double* xb_device_B(xb_model* m) { return m ? m->dB : nullptr; }
+double* xb_device_trial_disp(xb_model* m) { return m ? m->dU : nullptr; }
+
+int xb_get_element_tangent(xb_model* m, long long e, double* K) {
+  NEED_DEVICE();
+  if (e < 0 || e >= m->h.ne) return fail(XB_ERR_ARG, "element index out of range");
+  CU(cudaSetDevice(m->device));
+  const xb::Group& g = m->h.groups[m->h.fe_group[e]];
+  const xb::EleKind& k = xb::ele_kind(g.kind);
+  const int nd = k.nen * k.ndf;
+  std::vector<double> tmp((size_t)nd * nd);
+  CU(cudaStreamSynchronize(m->stream));
+  CU(cudaMemcpy(tmp.data(), m->dKe + g.ke_off + (long long)m->h.fe_local[e] * nd * nd, sizeof(double) * nd * nd, cudaMemcpyDeviceToHost));
+  const bool tr = m->h.soe_kind == XB_SOE_SPARSE_GEN_COL;
+  for (int i = 0; i < nd; i++)
+    for (int j = 0; j < nd; j++) K[i * nd + j] = tr ? tmp[j * nd + i] : tmp[i * nd + j];
+  return nd;
+}
+
+int xb_get_element_resid(xb_model* m, long long e, double* R) {
+  NEED_DEVICE();
+  if (e < 0 || e >= m->h.ne) return fail(XB_ERR_ARG, "element index out of range");
+  CU(cudaSetDevice(m->device));
+  const xb::Group& g = m->h.groups[m->h.fe_group[e]];
+  const xb::EleKind& k = xb::ele_kind(g.kind);
+  const int nd = k.nen * k.ndf;
+  CU(cudaStreamSynchronize(m->stream));
+  CU(cudaMemcpy(R, m->dRe + g.re_off + (long long)m->h.fe_local[e] * nd, sizeof(double) * nd, cudaMemcpyDeviceToHost));
+  return nd;
+}
+
+int xb_get_gp_response(xb_model* m, long long e, int gpt, double* stress, double* tangent) {
+  NEED_DEVICE();
+  if (e < 0 || e >= m->h.ne) return fail(XB_ERR_ARG, "element index out of range");
+  CU(cudaSetDevice(m->device));
+  const int gi = m->h.fe_group[e];
+  const xb::Group& g = m->h.groups[gi];
+  const DevGroup& d = m->dg[gi];
+  if (gpt < 0 || gpt >= d.nip) return fail(XB_ERR_ARG, "gauss point out of range");
+  const long long gp = (long long)m->h.fe_local[e] * d.nip + gpt;
+  CU(cudaStreamSynchronize(m->stream));
+  for (int i = 0; i < d.nst; i++)
+    CU(cudaMemcpy(stress + i, d.v.sig + (size_t)i * d.ngp + gp, sizeof(double), cudaMemcpyDeviceToHost));
+  const double* p = m->h.mats[g.mat[m->h.fe_local[e]]].par;
+  static const int map3[3] = {0, 1, 3};
+  if (g.mat_kind == XB_MAT_J2PLASTICITY) {
+    double t[8];
+    for (int i = 0; i < 8; i++) CU(cudaMemcpy(t + i, d.v.tan + (size_t)i * d.ngp + gp, sizeof(double), cudaMemcpyDeviceToHost));
+    for (int a = 0; a < d.nst; a++)
+      for (int b = 0; b < d.nst; b++) {
+        int A6 = d.nst == 6 ? a : map3[a], B6 = d.nst == 6 ? b : map3[b];
+        tangent[a * d.nst + b] = j2_tangent_entry(A6, B6, p[0], p[1], t, t[6], t[7]);
+      }
+  } else {
+    double mu2 = p[0] / (1.0 + p[1]);
+    const double lam = p[1] * mu2 / (1.0 - 2.0 * p[1]);
+    const double mu = 0.50 * mu2;
+    mu2 += lam;
+    for (int a = 0; a < d.nst; a++)
+      for (int b = 0; b < d.nst; b++) {
+        int A6 = d.nst == 6 ? a : map3[a], B6 = d.nst == 6 ? b : map3[b];
+        tangent[a * d.nst + b] = (A6 < 3 && B6 < 3) ? (A6 == B6 ? mu2 : lam) : (A6 == B6 ? mu : 0.0);
+      }
+  }
+  return d.nst;
+}
+
+long long xb_launch_count(const xb_model* m) { return m ? m->launches : 0; }
+long long xb_algorithmic_bytes(const xb_model* m, int which) {
+  return (m && which >= 0 && which < 3) ? m->alg_bytes[which] : 0;
+}
+
+}  // extern "C"
