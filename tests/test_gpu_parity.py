@@ -102,27 +102,44 @@ def _newton(model, solve, nsteps, dlam, tol, max_iter, is_dev):
 
 @pytest.mark.parametrize("shape", ["brick", "quad"])
 def test_newton_iteration_counts_match_oracle(shape):
+    """Static Newton (LoadControl, NormDispIncr) driven once by the oracle and once by the device:
+    identical iteration counts per step and the same convergence history.  The tolerance is picked
+    from a fixed list so that, in the oracle's own history, no deciding norm sits within 3x of it:
+    an iteration count must not hinge on the last bits of a norm."""
     import scipy.sparse as sp
     import scipy.sparse.linalg as spla
-    if shape == "brick":
-        spec = brick_block(4, 4, 6, mat=J2_STEEL, lx=1.0, ly=1.0, lz=3.0, load=(2.2, 0.0, -1.0))
-    else:
+
+    def make():
+        if shape == "brick":
+            return brick_block(4, 4, 6, mat=J2_STEEL, lx=1.0, ly=1.0, lz=3.0, load=(1.2, 0.0, -0.5))
         spec = quad_plane(16, 4, mat=J2_STEEL, lx=8.0, ly=2.0)
-        spec.loads[:, 1:] = [0.0, -14.0]
-    O = OracleBackend(spec, 1, 1); O._u = np.zeros((spec.nn, spec.ndf))
-    D = xb.DeviceModel.from_spec(spec, 1, 1).to_device(0)
+        spec.loads[:, 1:] = [0.0, -10.0]
+        return spec
+
+    spec = make()
+    O = OracleBackend(spec, 1, 1)
     ptr, idx = O.csr()
+    neq = O.neq
 
     def solve(A, B):
-        return spla.spsolve(sp.csr_matrix((A, idx, ptr), shape=(O.neq, O.neq)).tocsc(), B)
+        return spla.spsolve(sp.csr_matrix((A, idx, ptr), shape=(neq, neq)).tocsc(), B)
 
-    ho = _newton(O, solve, 8, 1.0, 1e-10, 25, False)
-    hd = _newton(D, solve, 8, 1.0, 1e-10, 25, True)
+    best = None
+    for tol in (1e-6, 3e-7, 1e-7, 3e-8, 1e-8, 3e-9, 1e-9):
+        O = OracleBackend(spec, 1, 1); O._u = np.zeros((spec.nn, spec.ndf))
+        h = _newton(O, solve, 8, 1.0, tol, 25, False)
+        margin = min(min(x[-2] / tol, tol / max(x[-1], 1e-300)) for x in h)
+        if best is None or margin > best[0]:
+            best = (margin, tol, h, O._u.copy())
+    margin, tol, ho, uo = best
+    assert margin >= 3.0, (margin, tol)
+    D = xb.DeviceModel.from_spec(spec, 1, 1).to_device(0)
+    hd = _newton(D, solve, 8, 1.0, tol, 25, True)
     assert [len(h) for h in ho] == [len(h) for h in hd]          # identical iteration counts
-    assert max(len(h) for h in ho) >= 4                            # the steps really go plastic
+    assert max(len(h) for h in ho) >= 6                            # the steps really go plastic
     for a, b in zip(ho, hd):
         assert np.allclose(a[:-1], b[:-1], rtol=1e-6, atol=1e-13)  # same convergence history
-    assert relerr(D.trial_disp(), O._u) < 1e-9
+    assert relerr(D.trial_disp(), uo) < 1e-9
 
 
 def test_revert_to_last_commit_and_incr():
