@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline hot path on B200.
+
+Metric (BASELINE.json): Gauss-point state updates/s through one pass of the hot path
+  step = Domain::update (state determination) + formUnbalance + formTangent
+on the 3D stdBrick / J2Plasticity block (configs[2], 160^3 = 4.096M elements, 32.8M Gauss
+points, 12.4M equations, 0.98G non-zeros), synthetic mesh and displacement field.
+
+  python bench.py --gpus N --steps K --warmup W            (ours; torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  (the reference's CPU path)
+
+One JSON line on stdout (rank 0).  Timing: CUDA events on the stream the kernels are
+launched on, barrier + synchronize on both sides, max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "gauss_point_state_updates_per_s (update + formUnbalance + formTangent pass)"
+UNIT = "GP updates/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.p = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": reasons}
+
+
+def workload_spec(n, z0=0, z1=None):
+    """n^3 J2 stdBrick block (z slab [z0,z1) of it), base fixed, top loaded."""
+    from modelspec import J2_STEEL, brick_block
+    return brick_block(n, n, n, mat=J2_STEEL)
+
+
+def displacement_field(crd, amp=4e-3):
+    """smooth synthetic trial displacement: shear + bending + a ripple; strains ~0.1-0.6 %, i.e. a
+    mix of elastic and yielded Gauss points for sig0/(2G) ~ 0.16 %"""
+    x, y, z = crd[:, 0], crd[:, 1], crd[:, 2]
+    u = np.empty_like(crd)
+    u[:, 0] = amp * (z * z + 0.3 * np.sin(7.0 * y) * z)
+    u[:, 1] = amp * (0.5 * z * x + 0.2 * np.sin(5.0 * x) * z)
+    u[:, 2] = amp * (-0.4 * z + 0.3 * x * z * y)
+    return u
+
+
+# ---------------------------------------------------------------------------------------
+# CPU arms
+# ---------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """one process = one core: the reference's own classes (oracle/_ref) when built, else the
+    oracle port; times `steps` passes of update + formUnbalance + formTangent on an m^3 sample"""
+    m, steps, warmup, use_ref, seed = args
+    from modelspec import J2_STEEL, OracleBackend, RefBackend, brick_block
+    spec = brick_block(m, m, m, mat=J2_STEEL)
+    B = (RefBackend if use_ref else OracleBackend)(spec, 0, 0)
+    u = displacement_field(spec.crd)
+    u[B.ids() < 0] = 0.0
+    B.apply_load(1.0)
+    for _ in range(warmup):
+        B.set_trial_disp(u); B.form_unbalance(); B.form_tangent()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        B.set_trial_disp(u)      # Node::setTrialDisp + Domain::update (state determination)
+        B.form_unbalance()
+        B.form_tangent()
+    dt = time.perf_counter() - t0
+    return spec.ne * 8 * steps, dt
+
+
+def cpu_arm(steps, warmup, procs, m):
+    from modelspec import have_ref
+    use_ref = have_ref()
+    if procs == 1:
+        res = [_cpu_worker((m, steps, warmup, use_ref, 0))]
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_cpu_worker, [(m, steps, warmup, use_ref, i) for i in range(procs)])
+    gp = sum(r[0] for r in res)
+    dt = max(r[1] for r in res)
+    return {"value": gp / dt, "unit": UNIT, "cores": procs, "kind": "reference" if use_ref else "port",
+            "sample": f"{procs} x ({m}^3 = {m ** 3} stdBrick/J2 elements, {steps} passes of update+formUnbalance+formTangent"
+                      f", SparseGenCol addA) ; {dt:.1f} s wall"}, dt / steps
+
+
+def reference_main(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    procs = max(1, min(os.cpu_count() or 1, 64))
+    cb, step_s = cpu_arm(max(1, a.steps), max(1, min(a.warmup, 1)), procs, a.cpu_sample)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a.n), "sample_per_core": f"{a.cpu_sample}^3 elements",
+                       "note": "reference CPU path (sequential OpenSees classes), one independent sample per host core"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(n):
+    return f"3D stdBrick J2Plasticity block {n}x{n}x{n} = {n ** 3} elements (BASELINE configs[2])"
+
+
+# ---------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------
+def ours_main(a):
+    import torch
+    import torch.distributed as dist
+
+    import xara_b200 as xb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("launch N > 1 with torch.distributed.run (see module docstring)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        raise SystemExit("multi-GPU partitioned path: see bench_multi in a later commit")
+
+    n = a.n
+    t0 = time.time()
+    spec = workload_spec(n)
+    t_mesh = time.time() - t0
+    t0 = time.time()
+    D = xb.DeviceModel.from_spec(spec, xb.NUMBERER_PLAIN, xb.SOE_SPARSE_GEN_COL)
+    t_setup = time.time() - t0
+    stream = torch.cuda.current_stream()
+    t0 = time.time()
+    D.to_device(local, stream=stream.cuda_stream)
+    t_upload = time.time() - t0
+    ids = D.ids()
+    u = displacement_field(spec.crd); u[ids < 0] = 0.0
+    D.set_trial_disp(u); D.apply_load(1.0); D.synchronize()
+
+    def step():
+        D.update(); D.form_unbalance(host=False); D.form_tangent(host=False)
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    D.synchronize()
+
+    names = ["update", "element_resid", "assemble_B", "element_tangent", "assemble_A"]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(a.steps)]
+    clocks = ClockSampler(local); clocks.start()
+    l0 = D.launch_count()
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record(stream)
+    for k in range(a.steps):
+        e = ev[k]
+        e[0].record(stream); D.update()
+        e[1].record(stream); D.form_element_resids()
+        e[2].record(stream); D.assemble_unbalance()
+        e[3].record(stream); D.form_element_tangents()
+        e[4].record(stream); D.assemble_tangent()
+        e[5].record(stream)
+    end.record(stream)
+    torch.cuda.synchronize()
+    D.synchronize()
+    total_ms = start.elapsed_time(end)
+    launches = D.launch_count() - l0
+    clk = clocks.stop()
+    ms = {nm: float(np.mean([ev[k][i].elapsed_time(ev[k][i + 1]) for k in range(a.steps)])) for i, nm in enumerate(names)}
+    ms_per_step = total_ms / a.steps
+    value = D.ngp / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel, live numbers ----
+    peak, peak_src = peaks()
+    which = {"update": 0, "element_resid": 5, "assemble_B": 1, "element_tangent": 3, "assemble_A": 4}
+    dom = max(ms, key=ms.get)
+    alg = D.algorithmic_bytes(which[dom])
+    achieved = alg / (ms[dom] * 1e-3) / 1e9
+    path_alg = D.algorithmic_bytes(0) + D.algorithmic_bytes(1) + D.algorithmic_bytes(2)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms[dom],
+                "path": {"algorithmic_bytes_per_step": path_alg, "achieved": path_alg / (ms_per_step * 1e-3) / 1e9,
+                         "frac": path_alg / (ms_per_step * 1e-3) / 1e9 / peak,
+                         "note": "compulsory bytes of update+formUnbalance+formTangent (state in/out, A and B out) "
+                                 "over the whole step; the element-matrix round trip through HBM is overhead here"}}
+
+    # ---- end to end through the C-ABI with HOST buffers (pinned), copies inside the timed region ----
+    e2e_steps = max(1, min(a.steps, a.e2e_steps))
+    u_pin = torch.empty(u.size, dtype=torch.float64, pin_memory=True); u_pin.numpy()[:] = u.ravel()
+    A_pin = torch.empty(D.nnz, dtype=torch.float64, pin_memory=True)
+    B_pin = torch.empty(max(D.neq, 1), dtype=torch.float64, pin_memory=True)
+    un, An, Bn = u_pin.numpy(), A_pin.numpy(), B_pin.numpy()[:D.neq]
+
+    def e2e_step():
+        D.set_trial_disp(un); D.update(); D.form_unbalance(out=Bn); D.form_tangent(out=An)
+
+    e2e_step()
+    torch.cuda.synchronize()
+    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s2.record(stream)
+    for _ in range(e2e_steps):
+        e2e_step()
+    e2.record(stream)
+    torch.cuda.synchronize()
+    e2e_ms = s2.elapsed_time(e2) / e2e_steps
+    checksum = float(An[:1000].sum() + Bn[:1000].sum())
+    e2e = {"value": D.ngp / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": int(u.size * 8), "d2h_bytes_per_step": int((D.nnz + D.neq) * 8),
+           "steps": e2e_steps, "result_checksum": checksum,
+           "note": "xb_set_trial_disp(host u) + xb_update + xb_form_unbalance(host B) + xb_form_tangent(host A), pinned host buffers"}
+
+    cb = None
+    if not a.no_cpu_baseline:
+        cb, _ = cpu_arm(a.cpu_steps, 1, 1, a.cpu_sample)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(n), "elements": int(D.ne), "gauss_points": int(D.ngp),
+                       "equations": int(D.neq), "nnz": int(D.nnz), "numberer": "Plain", "soe": "SparseGenCol (CSC)",
+                       "l2": "inputs larger than L2 (state 7 GB, element matrices 19 GB, A 8 GB vs 126 MB)",
+                       "setup_s": {"mesh": t_mesh, "host_setup": t_setup, "upload": t_upload}},
+            "kernel_ms": ms, "formTangent_ms": ms["element_tangent"] + ms["assemble_A"],
+            "formUnbalance_ms": ms["element_resid"] + ms["assemble_B"], "update_ms": ms["update"],
+            "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roofline, "cpu_baseline": cb}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=160, help="elements per side of the block (160 -> 4.096M)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-sample", type=int, default=22, help="CPU arm sample: elements per side")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        reference_main(a)
+    else:
+        ours_main(a)
+
+
+if __name__ == "__main__":
+    main()

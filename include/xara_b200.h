@@ -129,6 +129,14 @@ int xb_form_tangent(xb_model*, double* A);
 /* IncrementalIntegrator::formUnbalance (formElementResidual :221 + formNodalUnbalance :202).
  * B (neq doubles, host) may be NULL. */
 int xb_form_unbalance(xb_model*, double* B);
+/* the two halves of formTangent / formUnbalance, separately callable (profiling, overlap):
+ * FE_Element::getTangent / getResidual for every element into device-resident element
+ * matrices / vectors (analysis/fe_ele/FE_Element.cpp:235,370), then LinearSOE::addA / addB
+ * as a fixed-order gather.  xb_form_tangent == elements + assemble. */
+int xb_form_element_tangents(xb_model*);
+int xb_assemble_tangent(xb_model*, double* A);
+int xb_form_element_resids(xb_model*);
+int xb_assemble_unbalance(xb_model*, double* B);
 /* Domain::commit / Domain::revertToLastCommit */
 int xb_commit(xb_model*);
 int xb_revert_to_last_commit(xb_model*);
@@ -150,7 +158,9 @@ int xb_get_gp_response(xb_model*, long long e, int g, double* stress, double* ta
 /* kernel launches issued by this model since creation (bench.py's gpu_launches) */
 long long xb_launch_count(const xb_model*);
 /* bytes the last xb_form_tangent / xb_form_unbalance / xb_update moved algorithmically
- * (DESIGN.md "algorithmic bytes"): which = 0 update, 1 formUnbalance, 2 formTangent */
+ * (DESIGN.md "algorithmic bytes"): which = 0 update, 1 formUnbalance, 2 formTangent (compulsory
+ * traffic of the whole operation), 3 element-tangent kernel, 4 tangent-assembly kernel,
+ * 5 element-residual kernel (what each kernel must move given its inputs and outputs) */
 long long xb_algorithmic_bytes(const xb_model*, int which);
 
 #ifdef __cplusplus

@@ -80,6 +80,10 @@ def _load():
         "xb_apply_load": (i32, [vp, f64]),
         "xb_form_tangent": (i32, [vp, vp]),
         "xb_form_unbalance": (i32, [vp, vp]),
+        "xb_form_element_tangents": (i32, [vp]),
+        "xb_assemble_tangent": (i32, [vp, vp]),
+        "xb_form_element_resids": (i32, [vp]),
+        "xb_assemble_unbalance": (i32, [vp, vp]),
         "xb_commit": (i32, [vp]),
         "xb_revert_to_last_commit": (i32, [vp]),
         "xb_synchronize": (i32, [vp]),
@@ -244,6 +248,20 @@ class DeviceModel:
         if host and out is None:
             out = np.empty(self.neq)
         self._ck(lib.xb_form_unbalance(self._h, _ptr(out) if host else None))
+        return out
+
+    def form_element_tangents(self):
+        self._ck(lib.xb_form_element_tangents(self._h))
+
+    def assemble_tangent(self, out=None):
+        self._ck(lib.xb_assemble_tangent(self._h, _ptr(out)))
+        return out
+
+    def form_element_resids(self):
+        self._ck(lib.xb_form_element_resids(self._h))
+
+    def assemble_unbalance(self, out=None):
+        self._ck(lib.xb_assemble_unbalance(self._h, _ptr(out)))
         return out
 
     def commit(self):

@@ -546,7 +546,7 @@ struct xb_model {
   AsmView av{};
   double lambda = 0.0;
   long long launches = 0;
-  long long alg_bytes[3] = {0, 0, 0};
+  long long alg_bytes[6] = {0, 0, 0, 0, 0, 0};
 };
 
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -813,7 +813,7 @@ int xb_apply_load(xb_model* m, double lambda) {
   return XB_OK;
 }
 
-int xb_form_tangent(xb_model* m, double* A) {
+int xb_form_element_tangents(xb_model* m) {
   NEED_DEVICE();
   CU(cudaSetDevice(m->device));
   const int transpose = m->h.soe_kind == XB_SOE_SPARSE_GEN_COL ? 1 : 0;
@@ -837,8 +837,18 @@ int xb_form_tangent(xb_model* m, double* A) {
       else quad_tangent_kernel<XB_MAT_ELASTIC_ISOTROPIC><<<blocks, 128, 0, m->stream>>>(d.v, m->dX, transpose);
     }
     m->launches++;
-    bytes += d.ngp * 8 * (j2 ? 8 : 0);  // compact tangent read
+    // compact tangent + connectivity in, element matrix out
+    bytes += d.ngp * 8 * (j2 ? 8 : 0) + d.v.n * ((long long)d.nd * d.nd * 8 + (d.nd / m->h.ndf) * 4);
   }
+  bytes += (long long)m->h.nn() * m->h.ndm * 8;
+  m->alg_bytes[3] = bytes;
+  CU(cudaGetLastError());
+  return XB_OK;
+}
+
+int xb_assemble_tangent(xb_model* m, double* A) {
+  NEED_DEVICE();
+  CU(cudaSetDevice(m->device));
   {
     const int warps = 8;
     const size_t sm = sizeof(double) * warps * m->h.ndf * m->av.max_row;
@@ -858,8 +868,11 @@ int xb_form_tangent(xb_model* m, double* A) {
       m->launches++;
     }
   }
-  // compulsory traffic of formTangent: tangent data in, connectivity + coordinates in, A out
-  bytes += m->h.nnz() * 8 + (long long)m->h.nn() * m->h.ndm * 8;
+  // element matrices + per-(node,element) position map in, A out
+  m->alg_bytes[4] = m->h.ke_total * 8 + (long long)m->h.colpos.size() * 2 + m->h.nnz() * 8;
+  // compulsory traffic of formTangent as a whole: tangent data, connectivity, coordinates in, A out
+  long long bytes = m->h.nnz() * 8 + (long long)m->h.nn() * m->h.ndm * 8;
+  for (auto& d : m->dg) bytes += d.ngp * 8 * (d.mat_kind == XB_MAT_J2PLASTICITY ? 8 : 0);
   for (auto& g : m->h.groups) bytes += (long long)g.conn.size() * 4;
   m->alg_bytes[2] = bytes;
   CU(cudaGetLastError());
@@ -870,7 +883,13 @@ int xb_form_tangent(xb_model* m, double* A) {
   return XB_OK;
 }
 
-int xb_form_unbalance(xb_model* m, double* B) {
+int xb_form_tangent(xb_model* m, double* A) {
+  int rc = xb_form_element_tangents(m);
+  if (rc < 0) return rc;
+  return xb_assemble_tangent(m, A);
+}
+
+int xb_form_element_resids(xb_model* m) {
   NEED_DEVICE();
   CU(cudaSetDevice(m->device));
   long long bytes = 0;
@@ -882,14 +901,24 @@ int xb_form_unbalance(xb_model* m, double* B) {
       quad_resid_kernel<<<(unsigned)((d.v.n + 127) / 128), 128, 0, m->stream>>>(d.v, m->dX);
     }
     m->launches++;
-    bytes += d.ngp * 8 * d.nst;
+    bytes += d.ngp * 8 * d.nst + d.v.n * ((long long)d.nd * 8 + (d.nd / m->h.ndf) * 4);
   }
+  bytes += (long long)m->h.nn() * m->h.ndm * 8;
+  m->alg_bytes[5] = bytes;
+  CU(cudaGetLastError());
+  return XB_OK;
+}
+
+int xb_assemble_unbalance(xb_model* m, double* B) {
+  NEED_DEVICE();
+  CU(cudaSetDevice(m->device));
   const long long ndof = (long long)m->h.nn() * m->h.ndf;
   if (ndof) {
     assemble_B_kernel<<<(unsigned)((ndof + 255) / 256), 256, 0, m->stream>>>(m->av, m->dRe, m->lambda, m->dB);
     m->launches++;
   }
-  bytes += (long long)m->h.neq * 8 + (long long)m->h.nn() * (m->h.ndm + m->h.ndf) * 8;
+  long long bytes = (long long)m->h.neq * 8 + (long long)m->h.nn() * (m->h.ndm + m->h.ndf) * 8;
+  for (auto& d : m->dg) bytes += d.ngp * 8 * d.nst;
   for (auto& g : m->h.groups) bytes += (long long)g.conn.size() * 4;
   m->alg_bytes[1] = bytes;
   CU(cudaGetLastError());
@@ -898,6 +927,12 @@ int xb_form_unbalance(xb_model* m, double* B) {
     return check_fail_flag(m);
   }
   return XB_OK;
+}
+
+int xb_form_unbalance(xb_model* m, double* B) {
+  int rc = xb_form_element_resids(m);
+  if (rc < 0) return rc;
+  return xb_assemble_unbalance(m, B);
 }
 
 int xb_commit(xb_model* m) {
@@ -997,7 +1032,7 @@ int xb_get_gp_response(xb_model* m, long long e, int gpt, double* stress, double
 
 long long xb_launch_count(const xb_model* m) { return m ? m->launches : 0; }
 long long xb_algorithmic_bytes(const xb_model* m, int which) {
-  return (m && which >= 0 && which < 3) ? m->alg_bytes[which] : 0;
+  return (m && which >= 0 && which < 6) ? m->alg_bytes[which] : 0;
 }
 
 }  // extern "C"
