@@ -180,7 +180,8 @@ def ours_main(a):
     t0 = time.time()
     D = xb.DeviceModel.from_spec(spec, xb.NUMBERER_PLAIN, xb.SOE_SPARSE_GEN_COL)
     t_setup = time.time() - t0
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real (non-default) stream: the kernels and the events share it
+    torch.cuda.set_stream(stream)
     t0 = time.time()
     D.to_device(local, stream=stream.cuda_stream)
     t_upload = time.time() - t0

@@ -77,9 +77,7 @@ def _newton(model, solve, nsteps, dlam, tol, max_iter, is_dev):
     lam = 0.0
     for _ in range(nsteps):
         lam += dlam
-        model.apply_load(lam)                      # LoadControl::newStep
-        if is_dev:
-            model.update()
+        model.apply_load(lam)                      # LoadControl::newStep: no state determination here
         B = model.form_unbalance()
         norms = []
         for it in range(max_iter):

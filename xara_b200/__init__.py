@@ -215,7 +215,9 @@ class DeviceModel:
 
     # ---- device ----
     def to_device(self, device=0, stream=None):
-        """stream: a raw cudaStream_t (int), e.g. torch.cuda.current_stream().cuda_stream"""
+        """stream: a raw cudaStream_t (int), e.g. torch.cuda.Stream().cuda_stream.  None (or 0, the
+        legacy default stream's handle) lets the library create its own non-blocking stream; to run
+        on the legacy default stream itself pass cudaStreamLegacy (1)."""
         self._ck(lib.xb_device_init(self._h, device, ctypes.c_void_p(stream) if stream else None))
         return self
 
