@@ -277,19 +277,30 @@ __device__ __forceinline__ void brick_D(const GroupView& G, long long e, long lo
 }
 
 // Brick::formResidAndTangent(tang_flag=1), stiffness part (Brick.cpp:955-1016).
-// 8 lanes per element: lane k first evaluates Gauss point k (shape functions, D*dvol)
-// into shared memory, then owns column block k of the 24x24 matrix and accumulates
-// B_J^T (D B_k) over the 8 points for all 8 row blocks J in registers.
-constexpr int BT_ELEMS = 16;  // elements per CTA (128 threads)
+// 8 lanes per element, 4 elements per warp, warps independent (only __syncwarp):
+//   A  lane k evaluates Gauss point k (shape functions, D*dvol) into shared memory;
+//   B  lane k owns column block k of the 24x24 matrix and accumulates B_J^T (D B_k) over the
+//      8 points for all 8 row blocks J in registers (72 FP64 accumulators);
+//   C  the warp's 4 matrices go through a padded shared tile and leave as full 256-byte
+//      coalesced stores (the 4 elements of a warp are contiguous in Ke).
+constexpr int BT_ELEMS = 16;          // elements per CTA (128 threads)
+constexpr int BT_NSTR = 32;           // per (element, point): 8 nodes x (N,1 N,2 N,3 pad)
+constexpr int BT_DSTR = 22;           // per (element, point): 21 packed D entries + pad
+constexpr int BT_TROW = 25;           // padded row stride of the output tile (bank spread)
+constexpr int BT_TILE = 24 * BT_TROW; // 600 doubles: = 8 mod 16, so two elements interleave banks
+constexpr int BT_WARP_DOUBLES = 4 * BT_TILE;   // >= 4*8*(BT_NSTR+BT_DSTR) = 1728
 template <int MATK>
-__global__ void __launch_bounds__(BT_ELEMS * 8) brick_tangent_kernel(GroupView G, const double* __restrict__ X,
-                                                                     int transpose) {
-  extern __shared__ double smem[];
-  double* sN = smem;                         // [BT_ELEMS][8 g][3][8]
-  double* sD = smem + BT_ELEMS * 8 * 24;     // [BT_ELEMS][8 g][21]
+__global__ void __launch_bounds__(BT_ELEMS * 8, 2) brick_tangent_kernel(GroupView G, const double* __restrict__ X,
+                                                                        int transpose) {
+  extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x;
-  const int le = tid >> 3, k = tid & 7;
-  const long long e_raw = (long long)blockIdx.x * BT_ELEMS + le;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int s = lane >> 3, k = lane & 7;           // element within the warp, lane within the element
+  double* wbase = smem + warp * BT_WARP_DOUBLES;
+  double* sN = wbase;                              // [4][8 g][8 n][4]
+  double* sD = wbase + 4 * 8 * BT_NSTR;            // [4][8 g][22]
+  const long long e0 = (long long)blockIdx.x * BT_ELEMS + warp * 4;   // first element of the warp
+  const long long e_raw = e0 + s;
   const bool live = e_raw < G.n;
   const long long e = live ? e_raw : G.n - 1;
   const long long ngp = G.n * 8;
@@ -304,18 +315,20 @@ __global__ void __launch_bounds__(BT_ELEMS * 8) brick_tangent_kernel(GroupView G
     }
     double shp[4][8], dvol;
     brick_shp(k, xl, shp, dvol);
-    double* n = sN + (le * 8 + k) * 24;
+    double* n = sN + (s * 8 + k) * BT_NSTR;
 #pragma unroll
-    for (int d = 0; d < 3; d++)
-#pragma unroll
-      for (int a = 0; a < 8; a++) n[d * 8 + a] = shp[d][a];
-    double d21[21];
+    for (int a = 0; a < 8; a++) {
+      *reinterpret_cast<double2*>(n + a * 4) = make_double2(shp[0][a], shp[1][a]);
+      *reinterpret_cast<double2*>(n + a * 4 + 2) = make_double2(shp[2][a], 0.0);
+    }
+    double d21[22];
     brick_D<MATK>(G, e, e * 8 + k, ngp, dvol, d21);
-    double* dd = sD + (le * 8 + k) * 21;
+    d21[21] = 0.0;
+    double* dd = sD + (s * 8 + k) * BT_DSTR;
 #pragma unroll
-    for (int i = 0; i < 21; i++) dd[i] = d21[i];
+    for (int i = 0; i < 11; i++) *reinterpret_cast<double2*>(dd + 2 * i) = make_double2(d21[2 * i], d21[2 * i + 1]);
   }
-  __syncwarp();  // the 8 lanes of an element live in one warp
+  __syncwarp();
   double acc[8][3][3];
 #pragma unroll
   for (int J = 0; J < 8; J++)
@@ -326,9 +339,16 @@ __global__ void __launch_bounds__(BT_ELEMS * 8) brick_tangent_kernel(GroupView G
 
 #pragma unroll 1
   for (int g = 0; g < 8; g++) {
-    const double* n = sN + (le * 8 + g) * 24;
-    const double* d = sD + (le * 8 + g) * 21;
-    const double N1 = n[k], N2 = n[8 + k], N3 = n[16 + k];
+    const double* n = sN + (s * 8 + g) * BT_NSTR;
+    const double* dp = sD + (s * 8 + g) * BT_DSTR;
+    double d[22];
+#pragma unroll
+    for (int i = 0; i < 11; i++) {
+      const double2 t = *reinterpret_cast<const double2*>(dp + 2 * i);
+      d[2 * i] = t.x; d[2 * i + 1] = t.y;
+    }
+    const double2 nk = *reinterpret_cast<const double2*>(n + k * 4);
+    const double N1 = nk.x, N2 = nk.y, N3 = n[k * 4 + 2];
     double DB[6][3];
 #pragma unroll
     for (int r = 0; r < 6; r++) {
@@ -340,7 +360,8 @@ __global__ void __launch_bounds__(BT_ELEMS * 8) brick_tangent_kernel(GroupView G
     }
 #pragma unroll
     for (int J = 0; J < 8; J++) {
-      const double M1 = n[J], M2 = n[8 + J], M3 = n[16 + J];
+      const double2 mj = *reinterpret_cast<const double2*>(n + J * 4);
+      const double M1 = mj.x, M2 = mj.y, M3 = n[J * 4 + 2];
 #pragma unroll
       for (int q = 0; q < 3; q++) {
         acc[J][0][q] += M1 * DB[0][q] + M2 * DB[3][q] + M3 * DB[5][q];
@@ -349,22 +370,34 @@ __global__ void __launch_bounds__(BT_ELEMS * 8) brick_tangent_kernel(GroupView G
       }
     }
   }
-  if (!live) return;
-  double* out = G.Ke + e * 576;
+  __syncwarp();   // every lane is done reading sN / sD: the region becomes the output tile
+  double* tile = wbase + s * BT_TILE;
   if (!transpose) {
 #pragma unroll
     for (int J = 0; J < 8; J++)
 #pragma unroll
       for (int p = 0; p < 3; p++)
 #pragma unroll
-        for (int q = 0; q < 3; q++) out[(3 * J + p) * 24 + 3 * k + q] = acc[J][p][q];
+        for (int q = 0; q < 3; q++) tile[(3 * J + p) * BT_TROW + 3 * k + q] = acc[J][p][q];
   } else {
 #pragma unroll
     for (int J = 0; J < 8; J++)
 #pragma unroll
       for (int p = 0; p < 3; p++)
 #pragma unroll
-        for (int q = 0; q < 3; q++) out[(3 * k + q) * 24 + 3 * J + p] = acc[J][p][q];
+        for (int q = 0; q < 3; q++) tile[(3 * k + q) * BT_TROW + 3 * J + p] = acc[J][p][q];
+  }
+  __syncwarp();
+  long long nlive = G.n - e0;
+  if (nlive > 4) nlive = 4;
+  if (nlive <= 0) return;
+  double* out = G.Ke + e0 * 576;
+  const int total = (int)nlive * 576;
+#pragma unroll 4
+  for (int i = lane; i < total; i += 32) {
+    const int el = i / 576, off = i - el * 576;
+    const int row = off / 24, col = off - row * 24;
+    out[i] = wbase[el * BT_TILE + row * BT_TROW + col];
   }
 }
 
@@ -471,20 +504,34 @@ __global__ void __launch_bounds__(256) assemble_A_kernel(AsmView V, const double
   const long long t0 = V.n2e_ptr[n], t1 = V.n2e_ptr[n + 1];
   int L = (int)(V.ncol_ptr[n + 1] - V.ncol_ptr[n]);
   if (t0 == t1) L = 1;  // a node with no element: its rows hold the (zero) diagonal only
-  for (int c = lane; c < NDF * V.max_row; c += 32) acc[c] = 0.0;
+  for (int c = lane; c < NDF * L; c += 32) acc[(c / L) * V.max_row + (c % L)] = 0.0;
   __syncwarp();
-  for (long long t = t0; t < t1; t++) {
-    const int nd = V.n2e_nd[t];
-    const double* row = Ke + V.n2e_koff[t];
-    const unsigned short* cp = V.colpos + (size_t)t * V.cp_stride;
-    for (int j = lane; j < nd; j += 32) {
-      const unsigned short pos = cp[j];
-      if (pos != 0xFFFF) {
+  constexpr int CH = 8;  // adjacent elements whose rows are in flight together (memory-level parallelism)
+  for (long long tb = t0; tb < t1; tb += CH) {
+    double v[CH][NDF];
+    unsigned short pos[CH];
 #pragma unroll
-        for (int p = 0; p < NDF; p++) acc[p * V.max_row + pos] += row[p * nd + j];
+    for (int c = 0; c < CH; c++) {
+      pos[c] = 0xFFFF;
+      const long long t = tb + c;
+      if (t < t1) {
+        const int nd = V.n2e_nd[t];
+        if (lane < nd) {
+          const double* row = Ke + V.n2e_koff[t];
+          pos[c] = V.colpos[(size_t)t * V.cp_stride + lane];
+#pragma unroll
+          for (int p = 0; p < NDF; p++) v[c][p] = row[p * nd + lane];
+        }
       }
     }
-    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < CH; c++) {   // FE_Element order: the order addA is called in
+      if (pos[c] != 0xFFFF) {
+#pragma unroll
+        for (int p = 0; p < NDF; p++) acc[p * V.max_row + pos[c]] += v[c][p];
+      }
+      __syncwarp();
+    }
   }
 #pragma unroll
   for (int p = 0; p < NDF; p++) {
@@ -823,7 +870,7 @@ int xb_form_element_tangents(xb_model* m) {
     const bool j2 = d.mat_kind == XB_MAT_J2PLASTICITY;
     if (d.kind == XB_ELE_STDBRICK) {
       const unsigned blocks = (unsigned)((d.v.n + BT_ELEMS - 1) / BT_ELEMS);
-      const size_t sm = sizeof(double) * BT_ELEMS * 8 * (24 + 21);
+      const size_t sm = sizeof(double) * (BT_ELEMS / 4) * BT_WARP_DOUBLES;
       if (j2) {
         CU(cudaFuncSetAttribute(brick_tangent_kernel<XB_MAT_J2PLASTICITY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         brick_tangent_kernel<XB_MAT_J2PLASTICITY><<<blocks, BT_ELEMS * 8, sm, m->stream>>>(d.v, m->dX, transpose);

@@ -139,7 +139,7 @@ int HostModel::setup(int numberer_, int soe_kind_) {
   long long bad = 0;
   for (auto& g : groups) {
     const EleKind& k = ele_kind(g.kind);
-    cp_stride = std::max(cp_stride, k.nen * k.ndf);
+    cp_stride = std::max(cp_stride, k.nen * k.ndf);   // <= 32: one lane per element dof in assemble_A
     const long long m = (long long)g.conn.size();
 #pragma omp parallel for reduction(+ : bad) schedule(static)
     for (long long i = 0; i < m; i++) {
