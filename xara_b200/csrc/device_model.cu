@@ -494,35 +494,40 @@ struct AsmView {
 // the order IncrementalIntegrator::formTangent (IncrementalIntegrator.cpp:91-99) calls addA.
 // Every entry of A is written exactly once, so no zeroA pass is needed.
 template <int NDF>
-__global__ void __launch_bounds__(256) assemble_A_kernel(AsmView V, const double* __restrict__ Ke,
-                                                         double* __restrict__ A) {
+__global__ void __launch_bounds__(256, 2) assemble_A_kernel(AsmView V, const double* __restrict__ Ke,
+                                                            double* __restrict__ A) {
   extern __shared__ double sacc[];  // [warps][NDF][max_row]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long n = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (n >= V.nn) return;
   double* acc = sacc + (size_t)warp * NDF * V.max_row;
-  const long long t0 = V.n2e_ptr[n], t1 = V.n2e_ptr[n + 1];
-  int L = (int)(V.ncol_ptr[n + 1] - V.ncol_ptr[n]);
+  // everything that does not depend on the element loop is requested up front
+  const long long t0 = __ldg(V.n2e_ptr + n), t1 = __ldg(V.n2e_ptr + n + 1);
+  int L = (int)(__ldg(V.ncol_ptr + n + 1) - __ldg(V.ncol_ptr + n));
+  long long rowptr = -1;
+  if (lane < NDF) {
+    const int r = __ldg(V.id + n * NDF + lane);
+    if (r >= 0) rowptr = __ldg(V.ptr + r);
+  }
   if (t0 == t1) L = 1;  // a node with no element: its rows hold the (zero) diagonal only
   for (int c = lane; c < NDF * L; c += 32) acc[(c / L) * V.max_row + (c % L)] = 0.0;
   __syncwarp();
-  constexpr int CH = 8;  // adjacent elements whose rows are in flight together (memory-level parallelism)
+  constexpr int CH = 8;  // adjacent elements whose rows are in flight together
   for (long long tb = t0; tb < t1; tb += CH) {
+    // lane c fetches the descriptor of slot tb+c; one round trip for all CH slots
+    long long koff_l = 0;
+    int nd_l = 0;
+    if (lane < CH && tb + lane < t1) { koff_l = __ldg(V.n2e_koff + tb + lane); nd_l = __ldg(V.n2e_nd + tb + lane); }
     double v[CH][NDF];
     unsigned short pos[CH];
 #pragma unroll
     for (int c = 0; c < CH; c++) {
-      pos[c] = 0xFFFF;
-      const long long t = tb + c;
-      if (t < t1) {
-        const int nd = V.n2e_nd[t];
-        if (lane < nd) {
-          const double* row = Ke + V.n2e_koff[t];
-          pos[c] = V.colpos[(size_t)t * V.cp_stride + lane];
+      const long long koff = __shfl_sync(0xffffffffu, koff_l, c);
+      const int nd = __shfl_sync(0xffffffffu, nd_l, c);
+      const bool on = lane < nd;                     // nd = 0 for slots past the end
+      pos[c] = on ? __ldg(V.colpos + (size_t)(tb + c) * V.cp_stride + lane) : (unsigned short)0xFFFF;
 #pragma unroll
-          for (int p = 0; p < NDF; p++) v[c][p] = row[p * nd + lane];
-        }
-      }
+      for (int p = 0; p < NDF; p++) v[c][p] = on ? __ldg(Ke + koff + p * nd + lane) : 0.0;
     }
 #pragma unroll
     for (int c = 0; c < CH; c++) {   // FE_Element order: the order addA is called in
@@ -535,9 +540,9 @@ __global__ void __launch_bounds__(256) assemble_A_kernel(AsmView V, const double
   }
 #pragma unroll
   for (int p = 0; p < NDF; p++) {
-    const int r = V.id[n * NDF + p];
-    if (r < 0) continue;
-    double* out = A + V.ptr[r];
+    const long long rp = __shfl_sync(0xffffffffu, rowptr, p);
+    if (rp < 0) continue;
+    double* out = A + rp;
     for (int c = lane; c < L; c += 32) out[c] = acc[p * V.max_row + c];
   }
 }
