@@ -157,37 +157,49 @@ def workload_name(n):
 # our arm
 # ---------------------------------------------------------------------------------------
 def ours_main(a):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and a.gpus > 1:
+        raise SystemExit("launch N > 1 with torch.distributed.run (see module docstring)")
+    if world > 1:   # the host-side set-up is OpenMP-parallel: share the cores between the ranks
+        os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or world) // world)))
+
     import torch
     import torch.distributed as dist
 
     import xara_b200 as xb
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != a.gpus:
-        if world == 1 and a.gpus > 1:
-            raise SystemExit("launch N > 1 with torch.distributed.run (see module docstring)")
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        raise SystemExit("multi-GPU partitioned path: see bench_multi in a later commit")
 
     n = a.n
     t0 = time.time()
     spec = workload_spec(n)
     t_mesh = time.time() - t0
     t0 = time.time()
-    D = xb.DeviceModel.from_spec(spec, xb.NUMBERER_PLAIN, xb.SOE_SPARSE_GEN_COL)
+    D = xb.DeviceModel.from_spec(spec, xb.NUMBERER_PLAIN, xb.SOE_SPARSE_GEN_COL, world, rank)
     t_setup = time.time() - t0
     stream = torch.cuda.Stream()          # a real (non-default) stream: the kernels and the events share it
     torch.cuda.set_stream(stream)
     t0 = time.time()
     D.to_device(local, stream=stream.cuda_stream)
+    if world > 1:
+        box = [xb.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, 0)
+        D.comm_init(box[0])
     t_upload = time.time() - t0
     ids = D.ids()
-    u = displacement_field(spec.crd); u[ids < 0] = 0.0
+    u = displacement_field(spec.crd[D.node_tags() - 1]); u[ids < 0] = 0.0
+    ngp_global, ne_global = spec.ne * 8, spec.ne
+    del spec
     D.set_trial_disp(u); D.apply_load(1.0); D.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     def step():
         D.update(); D.form_unbalance(host=False); D.form_tangent(host=False)
@@ -196,35 +208,45 @@ def ours_main(a):
         step()
     D.synchronize()
 
-    names = ["update", "element_resid", "assemble_B", "element_tangent", "assemble_A"]
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(a.steps)]
+    names = ["update", "element_resid", "exchange_B", "assemble_B", "element_tangent", "exchange_A", "assemble_A"]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(8)] for _ in range(a.steps)]
     clocks = ClockSampler(local); clocks.start()
     l0 = D.launch_count()
-    torch.cuda.synchronize()
+    barrier()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record(stream)
     for k in range(a.steps):
         e = ev[k]
         e[0].record(stream); D.update()
         e[1].record(stream); D.form_element_resids()
-        e[2].record(stream); D.assemble_unbalance()
-        e[3].record(stream); D.form_element_tangents()
-        e[4].record(stream); D.assemble_tangent()
-        e[5].record(stream)
+        e[2].record(stream); D.exchange(1)
+        e[3].record(stream); D.assemble_unbalance()
+        e[4].record(stream); D.form_element_tangents()
+        e[5].record(stream); D.exchange(0)
+        e[6].record(stream); D.assemble_tangent()
+        e[7].record(stream)
     end.record(stream)
-    torch.cuda.synchronize()
+    barrier()
     D.synchronize()
     total_ms = start.elapsed_time(end)
     launches = D.launch_count() - l0
     clk = clocks.stop()
     ms = {nm: float(np.mean([ev[k][i].elapsed_time(ev[k][i + 1]) for k in range(a.steps)])) for i, nm in enumerate(names)}
+    if world > 1:   # time on the device, MAX over ranks
+        t = torch.tensor([total_ms] + [ms[nm] for nm in names] + [float(launches)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t[0]); ms_max = {nm: float(t[1 + i]) for i, nm in enumerate(names)}
+        tl = torch.tensor([float(launches)], device="cuda", dtype=torch.float64); dist.all_reduce(tl)
+        launches_all = int(tl[0])
+    else:
+        ms_max, launches_all = ms, launches
     ms_per_step = total_ms / a.steps
-    value = D.ngp / (ms_per_step * 1e-3)
+    value = ngp_global / (ms_per_step * 1e-3)
 
-    # ---- roofline of the dominant kernel, live numbers ----
+    # ---- roofline of the dominant kernel (this rank's launches), live numbers ----
     peak, peak_src = peaks()
     which = {"update": 0, "element_resid": 5, "assemble_B": 1, "element_tangent": 3, "assemble_A": 4}
-    dom = max(ms, key=ms.get)
+    dom = max(which, key=lambda k: ms[k])
     alg = D.algorithmic_bytes(which[dom])
     achieved = alg / (ms[dom] * 1e-3) / 1e9
     path_alg = D.algorithmic_bytes(0) + D.algorithmic_bytes(1) + D.algorithmic_bytes(2)
@@ -233,49 +255,64 @@ def ours_main(a):
                 "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms[dom],
                 "path": {"algorithmic_bytes_per_step": path_alg, "achieved": path_alg / (ms_per_step * 1e-3) / 1e9,
                          "frac": path_alg / (ms_per_step * 1e-3) / 1e9 / peak,
-                         "note": "compulsory bytes of update+formUnbalance+formTangent (state in/out, A and B out) "
-                                 "over the whole step; the element-matrix round trip through HBM is overhead here"}}
+                         "note": "compulsory bytes of update+formUnbalance+formTangent on this rank (state in/out, A and B "
+                                 "out) over the whole step; the element-matrix round trip through HBM is overhead here"}}
 
     # ---- end to end through the C-ABI with HOST buffers (pinned), copies inside the timed region ----
     e2e_steps = max(1, min(a.steps, a.e2e_steps))
     u_pin = torch.empty(u.size, dtype=torch.float64, pin_memory=True); u_pin.numpy()[:] = u.ravel()
     A_pin = torch.empty(D.nnz, dtype=torch.float64, pin_memory=True)
-    B_pin = torch.empty(max(D.neq, 1), dtype=torch.float64, pin_memory=True)
-    un, An, Bn = u_pin.numpy(), A_pin.numpy(), B_pin.numpy()[:D.neq]
+    B_pin = torch.empty(max(D.nrows, 1), dtype=torch.float64, pin_memory=True)
+    un, An, Bn = u_pin.numpy(), A_pin.numpy(), B_pin.numpy()[:D.nrows]
 
     def e2e_step():
         D.set_trial_disp(un); D.update(); D.form_unbalance(out=Bn); D.form_tangent(out=An)
 
     e2e_step()
-    torch.cuda.synchronize()
+    barrier()
     s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s2.record(stream)
     for _ in range(e2e_steps):
         e2e_step()
     e2.record(stream)
-    torch.cuda.synchronize()
+    barrier()
     e2e_ms = s2.elapsed_time(e2) / e2e_steps
+    h2d, d2h = float(u.size * 8), float((D.nnz + D.nrows) * 8)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_ms = float(t[0])
+        t = torch.tensor([h2d, d2h], device="cuda", dtype=torch.float64); dist.all_reduce(t); h2d, d2h = float(t[0]), float(t[1])
     checksum = float(An[:1000].sum() + Bn[:1000].sum())
-    e2e = {"value": D.ngp / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": int(u.size * 8), "d2h_bytes_per_step": int((D.nnz + D.neq) * 8),
-           "steps": e2e_steps, "result_checksum": checksum,
-           "note": "xb_set_trial_disp(host u) + xb_update + xb_form_unbalance(host B) + xb_form_tangent(host A), pinned host buffers"}
+    e2e = {"value": ngp_global / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "steps": e2e_steps, "result_checksum_rank0": checksum,
+           "note": "xb_set_trial_disp(host u) + xb_update + xb_form_unbalance(host B) + xb_form_tangent(host A), pinned "
+                   "host buffers; every rank moves its own nodes' u in and its owned rows of A, B out (bytes summed over ranks)"}
 
     cb = None
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and world == 1:
         cb, _ = cpu_arm(a.cpu_steps, 1, 1, a.cpu_sample)
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": max(a.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(n), "elements": int(D.ne), "gauss_points": int(D.ngp),
-                       "equations": int(D.neq), "nnz": int(D.nnz), "numberer": "Plain", "soe": "SparseGenCol (CSC)",
-                       "l2": "inputs larger than L2 (state 7 GB, element matrices 19 GB, A 8 GB vs 126 MB)",
-                       "setup_s": {"mesh": t_mesh, "host_setup": t_setup, "upload": t_upload}},
-            "kernel_ms": ms, "formTangent_ms": ms["element_tangent"] + ms["assemble_A"],
-            "formUnbalance_ms": ms["element_resid"] + ms["assemble_B"], "update_ms": ms["update"],
-            "gpu_launches": int(launches), "clocks": clk, "e2e": e2e, "roofline": roofline, "cpu_baseline": cb}
-    print(json.dumps(line), flush=True)
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+                "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(n), "elements": int(ne_global), "gauss_points": int(ngp_global),
+                           "equations": int(D.neq), "rank0": {"elements": int(D.ne), "rows": int(D.nrows), "nnz": int(D.nnz),
+                                                              "peers": [[int(r), int(c[0]), int(c[1])] for r, c in D.peers()]},
+                           "partition": "none" if world == 1 else f"recursive coordinate bisection, {world} parts, "
+                                        "interface rows exchanged with NCCL send/recv",
+                           "numberer": "Plain", "soe": "SparseGenCol (CSC)",
+                           "l2": "inputs larger than L2 (per GPU at N=1: state 7 GB, element matrices 19 GB, A 8 GB vs 126 MB)",
+                           "setup_s": {"mesh": t_mesh, "host_setup": t_setup, "upload": t_upload}},
+                "kernel_ms": ms_max, "kernel_ms_rank0": ms,
+                "formTangent_ms": ms_max["element_tangent"] + ms_max["exchange_A"] + ms_max["assemble_A"],
+                "formUnbalance_ms": ms_max["element_resid"] + ms_max["exchange_B"] + ms_max["assemble_B"],
+                "update_ms": ms_max["update"],
+                "gpu_launches": int(launches_all), "clocks": clk, "e2e": e2e, "roofline": roofline, "cpu_baseline": cb}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():

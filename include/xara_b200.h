@@ -90,6 +90,25 @@ int xb_add_nodal_loads(xb_model*, int n, const int* node_tags, const double* val
  * LinearSOE::setSize.  Host-side integer work; needs no device.  Returns numEqn >= 0. */
 int xb_setup(xb_model*, int numberer, int soe_kind);
 
+/* Multi-GPU: the same set-up for rank `rank` of `nparts` (one process per GPU).  Every rank
+ * is given the WHOLE model and computes the one global numbering; elements are then split
+ * (part = NULL: built-in recursive coordinate bisection; else part[e] = rank of the e-th
+ * element in FE_Element order, e.g. from METIS as domain/partitioner/DomainPartitioner.cpp
+ * does), a node's equations are owned by the lowest rank holding one of its elements, and the
+ * model is cut down to this rank's elements, their nodes, and the COMPLETE rows of its owned
+ * equations (global column numbers).  Rows of element matrices / residuals computed here for
+ * nodes owned elsewhere travel in xb_exchange; the owner adds all contributions in global
+ * FE_Element order, so the assembled rows equal the single-GPU ones bit for bit. */
+int xb_setup_partitioned(xb_model*, int numberer, int soe_kind, int nparts, int rank, const int* part);
+/* owned equations of this rank (== xb_num_eqn when unpartitioned) and their global numbers */
+int xb_num_rows(const xb_model*);
+int xb_get_row_eqns(const xb_model*, int* eqns);
+/* partition of every element, global FE_Element order [xb_num_elements of the whole model] */
+int xb_get_partition(const xb_model*, int* part);
+int xb_num_peers(const xb_model*);
+/* counts = {send_k, recv_k, send_r, recv_r (doubles), chunks_out, chunks_in} */
+int xb_get_peer(const xb_model*, int i, int* rank, long long* counts);
+
 int xb_num_nodes(const xb_model*);
 long long xb_num_elements(const xb_model*);
 long long xb_num_gauss_points(const xb_model*);
@@ -98,7 +117,7 @@ long long xb_nnz(const xb_model*);
 /* node tags in Domain iteration order (ascending, MapOfTaggedObjects); every [nn][..]
  * array below uses this order */
 int xb_get_node_tags(const xb_model*, int* tags);
-/* DOF_Group::getID for every node: ids [nn][ndf]; -1 = constrained (PlainHandler.cpp:117) */
+/* DOF_Group::getID for every (local) node: GLOBAL ids [nn][ndf]; -1 = constrained (PlainHandler.cpp:117) */
 int xb_get_ids(const xb_model*, int* ids);
 /* element tags in FE_Element order (ascending element tag, PlainHandler.cpp:233) */
 int xb_get_element_tags(const xb_model*, int* tags);
@@ -116,7 +135,8 @@ int xb_device_init(xb_model*, int device, void* cuda_stream);
 
 /* Node::setTrialDisp for all nodes, u [nn][ndf] in host memory (H2D inside) */
 int xb_set_trial_disp(xb_model*, const double* u);
-/* AnalysisModel::incrDisp (analysis/model/AnalysisModel.cpp): trial += dU[id], dU [neq] host */
+/* AnalysisModel::incrDisp (analysis/model/AnalysisModel.cpp): trial += dU[id], dU [neq] host
+ * (the GLOBAL increment, also on a partitioned model) */
 int xb_incr_trial_disp(xb_model*, const double* dU);
 int xb_get_trial_disp(xb_model*, double* u);
 /* Domain::update -> Element::update -> NDMaterial::setTrialStrain for every Gauss point */
@@ -137,6 +157,16 @@ int xb_form_element_tangents(xb_model*);
 int xb_assemble_tangent(xb_model*, double* A);
 int xb_form_element_resids(xb_model*);
 int xb_assemble_unbalance(xb_model*, double* B);
+/* Interface exchange between the ranks of a partitioned model (NCCL send/recv over NVLink on
+ * the model's stream); which = 0 element-tangent rows, 1 element-residual entries.
+ * xb_form_tangent / xb_form_unbalance call it between their two halves.
+ * xb_comm_unique_id: 128 bytes from ncclGetUniqueId on one rank, to be broadcast by the caller
+ * (MPI / torch.distributed / a file); xb_comm_init: ncclCommInitRank(nparts, id, rank). */
+int xb_comm_unique_id(char* out128);
+int xb_comm_init(xb_model*, const char* id128);
+int xb_exchange(xb_model*, int which);
+/* the same exchange between n models (ranks 0..n-1) living in one process: plain device copies */
+int xb_exchange_local(xb_model** models, int n, int which);
 /* Domain::commit / Domain::revertToLastCommit */
 int xb_commit(xb_model*);
 int xb_revert_to_last_commit(xb_model*);

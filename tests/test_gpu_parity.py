@@ -207,3 +207,113 @@ def test_launch_and_byte_accounting():
     D.update(); D.form_unbalance(host=False); D.form_tangent(host=False); D.synchronize()
     assert D.launch_count() - n0 == 5      # update, resid, assemble_B, tangent, assemble_A
     assert D.algorithmic_bytes(2) > D.nnz * 8
+
+
+def _partitioned_pass(ranks, u_global, lam):
+    """update + formUnbalance + formTangent on every rank of a partition held in this process,
+    with the interface exchange done by device copies (xb_exchange_local)."""
+    for m in ranks:
+        m.set_trial_disp(u_global[m.node_tags() - 1]); m.update(); m.apply_load(lam)
+        m.form_element_resids(); m.form_element_tangents()
+    xb.exchange_local(ranks, 1); xb.exchange_local(ranks, 0)
+    out = []
+    for m in ranks:
+        B = np.empty(m.nrows); A = np.empty(m.nnz)
+        m.assemble_unbalance(B); m.assemble_tangent(A)
+        out.append((A, B))
+    return out
+
+
+@pytest.mark.parametrize("nparts,numberer,soe", [(2, 0, 0), (3, 1, 1), (8, 1, 0)])
+def test_partitioned_ranks_reproduce_single_gpu_bitwise(nparts, numberer, soe):
+    """Every rank's owned rows of A and B equal the single-GPU rows BIT FOR BIT: remote element
+    rows are added in the same global FE_Element order, whatever the partition."""
+    rng = np.random.default_rng(5)
+    mk = lambda: brick_block(6, 5, 7, mat=J2_STEEL, distort=0.2, seed=9, body=(0.0, 0.01, -0.02))
+    spec = mk()
+    G = xb.DeviceModel.from_spec(spec, numberer, soe).to_device(0)
+    O = OracleBackend(spec, numberer, soe)
+    gptr, _ = G.pattern()
+    ranks = [xb.DeviceModel.from_spec(mk(), numberer, soe, nparts, r).to_device(0) for r in range(nparts)]
+    ids = G.ids()
+    for s in range(3):
+        u = rng.normal(0, 2e-3 * (s + 1), (spec.nn, 3)); u[ids < 0] = 0
+        lam = 0.4 * s
+        G.set_trial_disp(u); G.update(); G.apply_load(lam)
+        Ag, Bg = G.form_tangent(), G.form_unbalance()
+        O.set_trial_disp(u); O.apply_load(lam)
+        assert relerr(Ag, O.form_tangent()) < RTOL and relerr(Bg, O.form_unbalance()) < RTOL
+        for m, (A, B) in zip(ranks, _partitioned_pass(ranks, u, lam)):
+            rows = m.row_eqns()
+            assert np.array_equal(B, Bg[rows])
+            ptr, _ = m.pattern()
+            for lr, q in enumerate(rows):
+                assert np.array_equal(A[ptr[lr]:ptr[lr + 1]], Ag[gptr[q]:gptr[q + 1]])
+        G.commit()
+        for m in ranks:
+            m.commit()
+
+
+def test_partitioned_quad_and_scattered_partition():
+    rng = np.random.default_rng(6)
+    mk = lambda: quad_plane(12, 9, mat=J2_STEEL, lx=12.0, ly=9.0, distort=0.2, seed=2)
+    spec = mk()
+    part = rng.integers(0, 3, spec.ne).astype(np.int32)          # worst case: no locality at all
+    G = xb.DeviceModel.from_spec(spec, 1, 1).to_device(0)
+    gptr, _ = G.pattern()
+    ranks = [xb.DeviceModel.from_spec(mk(), 1, 1, 3, r, part).to_device(0) for r in range(3)]
+    u = rng.normal(0, 4e-3, (spec.nn, 2)); u[G.ids() < 0] = 0
+    G.set_trial_disp(u); G.update(); G.apply_load(1.0)
+    Ag, Bg = G.form_tangent(), G.form_unbalance()
+    for m, (A, B) in zip(ranks, _partitioned_pass(ranks, u, 1.0)):
+        rows = m.row_eqns(); ptr, _ = m.pattern()
+        assert np.array_equal(B, Bg[rows])
+        assert np.array_equal(A, np.concatenate([Ag[gptr[q]:gptr[q + 1]] for q in rows]))
+
+
+NCCL_WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, torch, torch.distributed as dist
+import xara_b200 as xb
+from modelspec import J2_STEEL, brick_block
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+spec = brick_block(8, 6, 10, mat=J2_STEEL, distort=0.2, seed=3)
+m = xb.DeviceModel.from_spec(spec, 1, 0, world, rank).to_device(rank)
+box = [xb.comm_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(box, 0)
+m.comm_init(box[0])
+rng = np.random.default_rng(1)
+u = rng.normal(0, 3e-3, (spec.nn, 3))
+m.set_trial_disp(u[m.node_tags() - 1]); m.update(); m.apply_load(0.7)
+A, B = m.form_tangent(), m.form_unbalance()          # NCCL exchange inside
+np.savez(sys.argv[1] + f".{{rank}}.npz", A=A, B=B, rows=m.row_eqns(), ptr=m.pattern()[0])
+dist.barrier()
+print("rank", rank, "done")
+'''
+
+
+@pytest.mark.skipif(xb.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_two_gpus_nccl_exchange_matches_single_gpu(tmp_path):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "w.py"
+    script.write_text(NCCL_WORKER.format(root=root))
+    out = str(tmp_path / "out")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29731", str(script), out],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    spec = brick_block(8, 6, 10, mat=J2_STEEL, distort=0.2, seed=3)
+    G = xb.DeviceModel.from_spec(spec, 1, 0).to_device(0)
+    u = np.random.default_rng(1).normal(0, 3e-3, (spec.nn, 3))
+    G.set_trial_disp(u); G.update(); G.apply_load(0.7)
+    Ag, Bg = G.form_tangent(), G.form_unbalance()
+    gptr, _ = G.pattern()
+    for rank in range(2):
+        d = np.load(out + f".{rank}.npz")
+        assert np.array_equal(d["B"], Bg[d["rows"]])
+        assert np.array_equal(d["A"], np.concatenate([Ag[gptr[q]:gptr[q + 1]] for q in d["rows"]]))

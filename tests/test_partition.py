@@ -1,0 +1,115 @@
+"""Multi-GPU path, host side (CPU): element partition, row ownership, interface exchange lists.
+
+The partitioned set-up must leave the ONE global system untouched: the ranks' owned rows are
+a disjoint cover of the global equations, each rank's rows carry the global pattern, and what
+rank r packs for rank s is exactly what s expects from r.  The 2-process test runs the same
+checks across real ranks over gloo."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import xara_b200 as xb
+from modelspec import ELASTIC, J2_STEEL, brick_block, quad_plane
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def check_partition(spec_fn, nparts, numberer, soe, part=None):
+    G = xb.DeviceModel.from_spec(spec_fn(), numberer, soe)
+    gptr, gidx = G.pattern()
+    gids = dict(zip(G.node_tags().tolist(), G.ids().tolist()))
+    ranks = [xb.DeviceModel.from_spec(spec_fn(), numberer, soe, nparts, r, part) for r in range(nparts)]
+    rows = np.concatenate([m.row_eqns() for m in ranks])
+    assert len(rows) == G.neq and np.array_equal(np.sort(rows), np.arange(G.neq))      # disjoint cover
+    ne = sum(m.ne for m in ranks)
+    assert ne == G.ne
+    p0 = ranks[0].partition(G.ne)
+    for r, m in enumerate(ranks):
+        assert m.neq == G.neq
+        assert np.array_equal(m.partition(G.ne), p0)
+        assert (p0 == r).sum() == m.ne
+        # global ids of the local nodes
+        for t, i in zip(m.node_tags().tolist(), m.ids().tolist()):
+            assert gids[t] == i
+        # owned rows carry the global pattern
+        ptr, idx = m.pattern()
+        for lr, q in enumerate(m.row_eqns()):
+            assert np.array_equal(idx[ptr[lr]:ptr[lr + 1]], gidx[gptr[q]:gptr[q + 1]])
+    # exchange lists are symmetric
+    table = {(r, pr): c for r, m in enumerate(ranks) for pr, c in m.peers()}
+    for (r, s), c in table.items():
+        d = table[(s, r)]
+        assert c[0] == d[1] and c[1] == d[0] and c[2] == d[3] and c[3] == d[2] and c[4] == d[5] and c[5] == d[4]
+    if part is not None:
+        assert np.array_equal(p0, part)
+    return ranks
+
+
+@pytest.mark.parametrize("nparts", [2, 3, 4, 8])
+@pytest.mark.parametrize("numberer,soe", [(0, 0), (1, 1)])
+def test_brick_partition_covers_global_system(nparts, numberer, soe):
+    check_partition(lambda: brick_block(5, 4, 6, distort=0.1), nparts, numberer, soe)
+
+
+def test_quad_partition_and_user_partition():
+    check_partition(lambda: quad_plane(9, 7, mat=ELASTIC), 3, 1, 0)
+    spec = brick_block(4, 4, 4)
+    part = (np.arange(spec.ne) * 7 % 3).astype(np.int32)          # a deliberately scattered partition
+    check_partition(lambda: brick_block(4, 4, 4), 3, 0, 1, part)
+
+
+def test_rcb_is_balanced_and_compact():
+    m = xb.DeviceModel.from_spec(brick_block(8, 8, 8), 0, 0, 8, 0)
+    p = m.partition(512)
+    assert np.bincount(p, minlength=8).tolist() == [64] * 8
+    # 8 compact octants: far fewer interface nodes than a scattered split
+    assert sum(c[4] for _, c in m.peers()) < 9 * 9 * 3 * 4
+
+
+def test_single_rank_partition_is_the_serial_model():
+    a = xb.DeviceModel.from_spec(brick_block(3, 3, 3), 1, 0)
+    b = xb.DeviceModel.from_spec(brick_block(3, 3, 3), 1, 0, 1, 0)
+    assert np.array_equal(a.ids(), b.ids()) and a.nrows == a.neq == b.nrows
+    assert all(np.array_equal(x, y) for x, y in zip(a.pattern(), b.pattern()))
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import numpy as np, torch, torch.distributed as dist
+import xara_b200 as xb
+from modelspec import brick_block
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+m = xb.DeviceModel.from_spec(brick_block(6, 5, 4, distort=0.1), 1, 0, 2, rank)
+# every rank computed the same global numbering and partition
+part = torch.from_numpy(m.partition(120).astype(np.int64)); ref = part.clone(); dist.broadcast(ref, 0)
+assert torch.equal(part, ref)
+# owned rows: gather both ranks' lists, they must tile 0..neq-1
+rows = torch.full((m.neq,), -1, dtype=torch.int64); rows[: m.nrows] = torch.from_numpy(m.row_eqns().astype(np.int64))
+both = [torch.empty_like(rows) for _ in range(2)]; dist.all_gather(both, rows)
+allrows = torch.cat([b[b >= 0] for b in both]).sort().values
+assert torch.equal(allrows, torch.arange(m.neq))
+# what I send is what the peer expects
+(peer, c), = m.peers()
+mine = torch.tensor([int(x) for x in c]); theirs = [torch.empty_like(mine) for _ in range(2)]; dist.all_gather(theirs, mine)
+o = theirs[1 - rank]
+assert peer == 1 - rank and mine[0] == o[1] and mine[1] == o[0] and mine[2] == o[3] and mine[3] == o[2]
+dist.barrier(); print("rank", rank, "ok", m.nrows, m.ne, c.tolist())
+'''
+
+
+def test_two_ranks_over_gloo(tmp_path):
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                              text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o

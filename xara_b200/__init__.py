@@ -27,7 +27,7 @@ import os
 
 import numpy as np
 
-__all__ = ["DeviceModel", "XaraB200Error", "lib", "LIB_PATH", "device_count",
+__all__ = ["DeviceModel", "XaraB200Error", "lib", "LIB_PATH", "device_count", "comm_unique_id", "exchange_local",
            "MAT_ELASTIC_ISOTROPIC", "MAT_J2PLASTICITY", "ELE_STDBRICK", "ELE_FOURNODEQUAD",
            "NUMBERER_PLAIN", "NUMBERER_RCM", "SOE_SPARSE_GEN_COL", "SOE_SPARSE_GEN_ROW"]
 
@@ -62,6 +62,16 @@ def _load():
         "xb_add_elements": (i32, [vp, i32, i32, vp, vp, vp, vp, i32]),
         "xb_add_nodal_loads": (i32, [vp, i32, vp, vp]),
         "xb_setup": (i32, [vp, i32, i32]),
+        "xb_setup_partitioned": (i32, [vp, i32, i32, i32, i32, vp]),
+        "xb_num_rows": (i32, [vp]),
+        "xb_get_row_eqns": (i32, [vp, vp]),
+        "xb_get_partition": (i32, [vp, vp]),
+        "xb_num_peers": (i32, [vp]),
+        "xb_get_peer": (i32, [vp, i32, vp, vp]),
+        "xb_comm_unique_id": (i32, [vp]),
+        "xb_comm_init": (i32, [vp, vp]),
+        "xb_exchange": (i32, [vp, i32]),
+        "xb_exchange_local": (i32, [vp, i32, i32]),
         "xb_num_nodes": (i32, [vp]),
         "xb_num_elements": (i64, [vp]),
         "xb_num_gauss_points": (i64, [vp]),
@@ -107,6 +117,23 @@ lib, EXPORTS = _load()
 
 def device_count() -> int:
     return lib.xb_device_count()
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId (128 bytes); broadcast it to every rank and hand it to DeviceModel.comm_init"""
+    buf = ctypes.create_string_buffer(128)
+    rc = lib.xb_comm_unique_id(ctypes.addressof(buf))
+    if rc < 0:
+        raise XaraB200Error(f"[{rc}] {lib.xb_last_error().decode()}")
+    return buf.raw
+
+
+def exchange_local(models, which):
+    """interface exchange between the ranks of one partition held in THIS process (device copies)"""
+    arr = (ctypes.c_void_p * len(models))(*[m._h for m in models])
+    rc = lib.xb_exchange_local(ctypes.addressof(arr), len(models), which)
+    if rc < 0:
+        raise XaraB200Error(f"[{rc}] {lib.xb_last_error().decode()}")
 
 
 def _ptr(a):
@@ -172,7 +199,7 @@ class DeviceModel:
         self._ck(lib.xb_add_nodal_loads(self._h, len(node_tags), _ptr(node_tags), _ptr(values)))
 
     @classmethod
-    def from_spec(cls, spec, numberer=NUMBERER_PLAIN, soe=SOE_SPARSE_GEN_COL):
+    def from_spec(cls, spec, numberer=NUMBERER_PLAIN, soe=SOE_SPARSE_GEN_COL, nparts=1, rank=0, part=None):
         """Build from a tests/modelspec.py ModelSpec (duck-typed)."""
         m = cls(spec.ndm, spec.ndf)
         m.add_nodes(spec.node_tags, spec.crd)
@@ -184,12 +211,21 @@ class DeviceModel:
             m.add_elements(g.kind, g.tags, g.conn, g.mat, g.par)
         if spec.loads is not None and len(spec.loads):
             m.add_nodal_loads(spec.loads[:, 0].astype(np.int32), spec.loads[:, 1:])
-        m.setup(numberer, soe)
+        m.setup(numberer, soe, nparts, rank, part)
         return m
 
     # ---- analysis set-up (host) ----
-    def setup(self, numberer=NUMBERER_PLAIN, soe=SOE_SPARSE_GEN_COL):
-        self.neq = self._ck(lib.xb_setup(self._h, numberer, soe))
+    def setup(self, numberer=NUMBERER_PLAIN, soe=SOE_SPARSE_GEN_COL, nparts=1, rank=0, part=None):
+        """domainChanged().  nparts > 1: this process is `rank` of a partitioned run (every rank is
+        given the whole model); part = None -> built-in coordinate bisection, else ranks per element
+        in FE_Element (ascending tag) order."""
+        if nparts == 1:
+            self.neq = self._ck(lib.xb_setup(self._h, numberer, soe))
+        else:
+            part = _i32(part) if part is not None else None
+            self.neq = self._ck(lib.xb_setup_partitioned(self._h, numberer, soe, nparts, rank, _ptr(part)))
+        self.nparts, self.rank = nparts, rank
+        self.nrows = lib.xb_num_rows(self._h)
         self.nn = lib.xb_num_nodes(self._h)
         self.ne = lib.xb_num_elements(self._h)
         self.ngp = lib.xb_num_gauss_points(self._h)
@@ -205,8 +241,29 @@ class DeviceModel:
     def element_tags(self):
         a = np.zeros(self.ne, np.int32); self._ck(lib.xb_get_element_tags(self._h, _ptr(a))); return a
 
+    def row_eqns(self):
+        a = np.zeros(self.nrows, np.int32); self._ck(lib.xb_get_row_eqns(self._h, _ptr(a))); return a
+
+    def partition(self, ne_global):
+        a = np.zeros(ne_global, np.int32); self._ck(lib.xb_get_partition(self._h, _ptr(a))); return a
+
+    def peers(self):
+        out = []
+        for i in range(lib.xb_num_peers(self._h)):
+            r = ctypes.c_int(0); c = np.zeros(6, np.int64)
+            self._ck(lib.xb_get_peer(self._h, i, ctypes.addressof(r), _ptr(c)))
+            out.append((r.value, c))
+        return out
+
+    def comm_init(self, id128: bytes):
+        buf = ctypes.create_string_buffer(id128, 128)
+        self._ck(lib.xb_comm_init(self._h, ctypes.addressof(buf)))
+
+    def exchange(self, which):
+        self._ck(lib.xb_exchange(self._h, which))
+
     def pattern(self):
-        ptr = np.zeros(self.neq + 1, np.int64); idx = np.zeros(self.nnz, np.int32)
+        ptr = np.zeros(self.nrows + 1, np.int64); idx = np.zeros(self.nnz, np.int32)
         self._ck(lib.xb_get_pattern(self._h, _ptr(ptr), _ptr(idx))); return ptr, idx
 
     def scatter_map(self, e0, e1, nd):
@@ -248,7 +305,7 @@ class DeviceModel:
 
     def form_unbalance(self, out=None, host=True):
         if host and out is None:
-            out = np.empty(self.neq)
+            out = np.empty(self.nrows)
         self._ck(lib.xb_form_unbalance(self._h, _ptr(out) if host else None))
         return out
 

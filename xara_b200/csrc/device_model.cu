@@ -3,6 +3,10 @@
 // Compiled for sm_100a only; there is no CPU fallback anywhere in this file.
 #include <cuda_runtime.h>
 
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -478,8 +482,8 @@ __global__ void __launch_bounds__(128) quad_tangent_kernel(GroupView G, const do
 // =====================================================================================
 struct AsmView {
   int nn, ndf, cp_stride, max_row;
-  const int* id;              // [nn][ndf]
-  const long long* ptr;       // [neq+1]
+  const int* row_of;          // [nn][ndf] local row of an owned free dof, else -1
+  const long long* ptr;       // [nrows+1]
   const long long* n2e_ptr;   // [nn+1]
   const long long* n2e_koff;  // [*]
   const long long* n2e_roff;  // [*]
@@ -487,6 +491,8 @@ struct AsmView {
   const unsigned short* colpos;  // [*][cp_stride]
   const long long* ncol_ptr;  // [nn+1]
   const double* load;         // [nn][ndf]
+  const double* recvK;        // element-matrix rows received from other ranks (slots with koff < 0)
+  const double* recvR;        // element-residual entries received from other ranks (roff < 0)
 };
 
 // One warp per node.  The node's equations own rows (CSR) / columns (CSC) that share one
@@ -506,7 +512,7 @@ __global__ void __launch_bounds__(256, 2) assemble_A_kernel(AsmView V, const dou
   int L = (int)(__ldg(V.ncol_ptr + n + 1) - __ldg(V.ncol_ptr + n));
   long long rowptr = -1;
   if (lane < NDF) {
-    const int r = __ldg(V.id + n * NDF + lane);
+    const int r = __ldg(V.row_of + n * NDF + lane);
     if (r >= 0) rowptr = __ldg(V.ptr + r);
   }
   if (t0 == t1) L = 1;  // a node with no element: its rows hold the (zero) diagonal only
@@ -525,9 +531,11 @@ __global__ void __launch_bounds__(256, 2) assemble_A_kernel(AsmView V, const dou
       const long long koff = __shfl_sync(0xffffffffu, koff_l, c);
       const int nd = __shfl_sync(0xffffffffu, nd_l, c);
       const bool on = lane < nd;                     // nd = 0 for slots past the end
+      // koff < 0: the element lives on another rank, its rows arrived in the receive buffer
+      const double* row = koff >= 0 ? Ke + koff : V.recvK + (-koff - 1);
       pos[c] = on ? __ldg(V.colpos + (size_t)(tb + c) * V.cp_stride + lane) : (unsigned short)0xFFFF;
 #pragma unroll
-      for (int p = 0; p < NDF; p++) v[c][p] = on ? __ldg(Ke + koff + p * nd + lane) : 0.0;
+      for (int p = 0; p < NDF; p++) v[c][p] = on ? __ldg(row + p * nd + lane) : 0.0;
     }
 #pragma unroll
     for (int c = 0; c < CH; c++) {   // FE_Element order: the order addA is called in
@@ -555,10 +563,13 @@ __global__ void __launch_bounds__(256) assemble_B_kernel(AsmView V, const double
   if (i >= (long long)V.nn * V.ndf) return;
   const long long n = i / V.ndf;
   const int p = (int)(i - n * V.ndf);
-  const int r = V.id[i];
+  const int r = V.row_of[i];
   if (r < 0) return;
   double acc = 0.0;
-  for (long long t = V.n2e_ptr[n]; t < V.n2e_ptr[n + 1]; t++) acc += -Re[V.n2e_roff[t] + p];
+  for (long long t = V.n2e_ptr[n]; t < V.n2e_ptr[n + 1]; t++) {
+    const long long ro = V.n2e_roff[t];
+    acc += -(ro >= 0 ? Re[ro + p] : V.recvR[(-ro - 1) + p]);
+  }
   acc += V.load[i] * lambda;
   B[r] = acc;
 }
@@ -570,6 +581,30 @@ __global__ void incr_disp_kernel(long long ndof, const int* __restrict__ id, con
   if (i >= ndof) return;
   const int r = id[i];
   if (r >= 0) U[i] += dU[r];
+}
+
+// interface exchange, send side: copy the rows of local element matrices (residual entries)
+// that belong to nodes another rank owns into the per-peer send buffer.  One warp per chunk.
+__global__ void __launch_bounds__(256) pack_rows_kernel(long long nchunks, const long long* __restrict__ src,
+                                                        const long long* __restrict__ dst,
+                                                        const unsigned char* __restrict__ nd, int ndf,
+                                                        const double* __restrict__ Ke, double* __restrict__ send) {
+  const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c >= nchunks) return;
+  const int len = ndf * nd[c];
+  const double* s = Ke + src[c];
+  double* d = send + dst[c];
+  for (int i = lane; i < len; i += 32) d[i] = s[i];
+}
+__global__ void __launch_bounds__(256) pack_resid_kernel(long long nchunks, const long long* __restrict__ src,
+                                                         const long long* __restrict__ dst, int ndf,
+                                                         const double* __restrict__ Re, double* __restrict__ send) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nchunks * ndf) return;
+  const long long c = i / ndf;
+  const int p = (int)(i - c * ndf);
+  send[dst[c] + p] = Re[src[c] + p];
 }
 
 // =====================================================================================
@@ -594,7 +629,13 @@ struct xb_model {
   double *dX = nullptr, *dU = nullptr, *dUc = nullptr, *dKe = nullptr, *dRe = nullptr, *dA = nullptr,
          *dB = nullptr, *dLoad = nullptr, *dMpar = nullptr, *dTmp = nullptr;
   int* dId = nullptr;
+  int* dRowOf = nullptr;
   int* dFail = nullptr;
+  // interface exchange (nparts > 1)
+  double *dSendK = nullptr, *dRecvK = nullptr, *dSendR = nullptr, *dRecvR = nullptr;
+  long long *dPkSrc = nullptr, *dPkDst = nullptr, *dPrSrc = nullptr, *dPrDst = nullptr;
+  unsigned char* dPkNd = nullptr;
+  ncclComm_t comm = nullptr;
   AsmView av{};
   double lambda = 0.0;
   long long launches = 0;
@@ -607,6 +648,47 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
     cudaError_t _e = (x);                                                             \
     if (_e != cudaSuccess)                                                            \
       return fail(XB_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(_e));      \
+  } while (0)
+
+// NCCL is bound at run time (dlopen "libnccl.so.2"): inside a torch process that is the copy
+// torch already loaded, in a C++ host program the system one.  Nothing here needs it for N = 1.
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+  if (g_nccl.h) return XB_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(XB_ERR_CUDA, std::string("cannot load libnccl.so.2: ") + dlerror());
+#define XB_SYM(field, name)                                                       \
+  *(void**)(&g_nccl.field) = dlsym(h, name);                                      \
+  if (!g_nccl.field) return fail(XB_ERR_CUDA, std::string("libnccl lacks ") + name)
+  XB_SYM(GetUniqueId, "ncclGetUniqueId");
+  XB_SYM(CommInitRank, "ncclCommInitRank");
+  XB_SYM(CommDestroy, "ncclCommDestroy");
+  XB_SYM(Send, "ncclSend");
+  XB_SYM(Recv, "ncclRecv");
+  XB_SYM(GroupStart, "ncclGroupStart");
+  XB_SYM(GroupEnd, "ncclGroupEnd");
+  XB_SYM(GetErrorString, "ncclGetErrorString");
+#undef XB_SYM
+  g_nccl.h = h;
+  return XB_OK;
+}
+#define NC(x)                                                                          \
+  do {                                                                                 \
+    ncclResult_t _r = (x);                                                             \
+    if (_r != ncclSuccess)                                                             \
+      return fail(XB_ERR_CUDA, std::string(#x) + ": " + g_nccl.GetErrorString(_r));    \
   } while (0)
 
 template <class T>
@@ -645,6 +727,7 @@ void xb_model_destroy(xb_model* m) {
   if (!m) return;
   if (m->on_device) {
     cudaSetDevice(m->device);
+    if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
     for (void* p : m->allocs) cudaFree(p);
     if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
   }
@@ -667,6 +750,11 @@ int xb_add_elements(xb_model* m, int kind, int n, const int* tags, const int* co
 }
 int xb_add_nodal_loads(xb_model* m, int n, const int* t, const double* v) { HOSTCALL(m->h.add_loads(n, t, v)); }
 int xb_setup(xb_model* m, int numberer, int soe_kind) { HOSTCALL(m->h.setup(numberer, soe_kind)); }
+int xb_setup_partitioned(xb_model* m, int numberer, int soe_kind, int nparts, int rank, const int* part) {
+  HOSTCALL(m->h.setup(numberer, soe_kind, nparts, rank, part));
+}
+int xb_num_rows(const xb_model* m) { return m ? m->h.nrows : 0; }
+int xb_num_peers(const xb_model* m) { return m ? (int)m->h.peers.size() : 0; }
 
 int xb_num_nodes(const xb_model* m) { return m ? m->h.nn() : 0; }
 long long xb_num_elements(const xb_model* m) { return m ? m->h.ne : 0; }
@@ -685,6 +773,25 @@ int xb_get_node_tags(const xb_model* m, int* tags) {
 int xb_get_ids(const xb_model* m, int* ids) {
   NEED_SETUP();
   std::memcpy(ids, m->h.id.data(), sizeof(int) * m->h.id.size());
+  return XB_OK;
+}
+int xb_get_row_eqns(const xb_model* m, int* eqns) {
+  NEED_SETUP();
+  std::memcpy(eqns, m->h.row_geq.data(), sizeof(int) * m->h.row_geq.size());
+  return XB_OK;
+}
+int xb_get_partition(const xb_model* m, int* part) {
+  NEED_SETUP();
+  std::memcpy(part, m->h.part_fe.data(), sizeof(int) * m->h.part_fe.size());
+  return XB_OK;
+}
+int xb_get_peer(const xb_model* m, int i, int* rank, long long* counts) {
+  NEED_SETUP();
+  if (i < 0 || i >= (int)m->h.peers.size()) return fail(XB_ERR_ARG, "peer index out of range");
+  const xb::Peer& p = m->h.peers[i];
+  *rank = p.rank;
+  counts[0] = p.send_k; counts[1] = p.recv_k; counts[2] = p.send_r; counts[3] = p.recv_r;
+  counts[4] = p.chunks_out; counts[5] = p.chunks_in;
   return XB_OK;
 }
 int xb_get_element_tags(const xb_model* m, int* tags) {
@@ -728,6 +835,7 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
   CU(cudaMemset(m->dU, 0, sizeof(double) * std::max<size_t>(nn * h.ndf, 1)));
   CU(cudaMemset(m->dUc, 0, sizeof(double) * std::max<size_t>(nn * h.ndf, 1)));
   CU(dev_upload(m, &m->dId, h.id));
+  CU(dev_upload(m, &m->dRowOf, h.row_of));
   CU(dev_upload(m, &m->dLoad, h.load));
   std::vector<double> mp(h.mats.size() * 8);
   for (size_t i = 0; i < h.mats.size(); i++) std::memcpy(&mp[i * 8], h.mats[i].par, sizeof(double) * 8);
@@ -735,7 +843,7 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
   CU(dev_alloc(m, &m->dKe, (size_t)h.ke_total));
   CU(dev_alloc(m, &m->dRe, (size_t)h.re_total));
   CU(dev_alloc(m, &m->dA, (size_t)h.nnz()));
-  CU(dev_alloc(m, &m->dB, (size_t)h.neq));
+  CU(dev_alloc(m, &m->dB, (size_t)h.nrows));
   CU(dev_alloc(m, &m->dTmp, (size_t)h.neq));
   CU(dev_alloc(m, &m->dFail, 1));
   CU(cudaMemset(m->dFail, 0, sizeof(int)));
@@ -773,7 +881,21 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
 
   AsmView& a = m->av;
   a.nn = (int)nn; a.ndf = h.ndf; a.cp_stride = h.cp_stride; a.max_row = std::max(h.max_row, 1);
-  a.id = m->dId; a.load = m->dLoad;
+  a.row_of = m->dRowOf; a.load = m->dLoad;
+  if (h.nparts > 1) {
+    CU(dev_alloc(m, &m->dSendK, (size_t)h.send_k_total));
+    CU(dev_alloc(m, &m->dRecvK, (size_t)h.recv_k_total));
+    CU(dev_alloc(m, &m->dSendR, (size_t)h.send_r_total));
+    CU(dev_alloc(m, &m->dRecvR, (size_t)h.recv_r_total));
+    CU(cudaMemset(m->dRecvK, 0, sizeof(double) * std::max<size_t>(h.recv_k_total, 1)));
+    CU(cudaMemset(m->dRecvR, 0, sizeof(double) * std::max<size_t>(h.recv_r_total, 1)));
+    CU(dev_upload(m, &m->dPkSrc, h.pk_src));
+    CU(dev_upload(m, &m->dPkDst, h.pk_dst));
+    CU(dev_upload(m, &m->dPrSrc, h.pr_src));
+    CU(dev_upload(m, &m->dPrDst, h.pr_dst));
+    CU(dev_upload(m, &m->dPkNd, h.pk_nd));
+  }
+  a.recvK = m->dRecvK; a.recvR = m->dRecvR;
   long long *ptr = nullptr, *n2e_ptr = nullptr, *koff = nullptr, *roff = nullptr, *ncol_ptr = nullptr;
   unsigned char* nd = nullptr; unsigned short* cp = nullptr;
   CU(dev_upload(m, &ptr, h.ptr));
@@ -865,6 +987,8 @@ int xb_apply_load(xb_model* m, double lambda) {
   return XB_OK;
 }
 
+static int pack_for_peers(xb_model* m, int which);
+
 int xb_form_element_tangents(xb_model* m) {
   NEED_DEVICE();
   CU(cudaSetDevice(m->device));
@@ -895,6 +1019,86 @@ int xb_form_element_tangents(xb_model* m) {
   bytes += (long long)m->h.nn() * m->h.ndm * 8;
   m->alg_bytes[3] = bytes;
   CU(cudaGetLastError());
+  return pack_for_peers(m, 0);
+}
+
+// ---- interface exchange -------------------------------------------------------------
+// which = 0: rows of element tangents, 1: element residual entries
+static int pack_for_peers(xb_model* m, int which) {
+  const long long nch = (long long)m->h.pk_src.size();
+  if (nch == 0) return XB_OK;
+  if (which == 0) {
+    pack_rows_kernel<<<(unsigned)((nch * 32 + 255) / 256), 256, 0, m->stream>>>(nch, m->dPkSrc, m->dPkDst, m->dPkNd, m->h.ndf, m->dKe, m->dSendK);
+  } else {
+    pack_resid_kernel<<<(unsigned)((nch * m->h.ndf + 255) / 256), 256, 0, m->stream>>>(nch, m->dPrSrc, m->dPrDst, m->h.ndf, m->dRe, m->dSendR);
+  }
+  m->launches++;
+  CU(cudaGetLastError());
+  return XB_OK;
+}
+
+int xb_comm_unique_id(char* out128) {
+  int rc = nccl_load();
+  if (rc < 0) return rc;
+  ncclUniqueId id;
+  NC(g_nccl.GetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  std::memcpy(out128, &id, 128);
+  return XB_OK;
+}
+
+int xb_comm_init(xb_model* m, const char* id128) {
+  NEED_DEVICE();
+  if (m->h.nparts < 2) return fail(XB_ERR_STATE, "xb_comm_init on an unpartitioned model");
+  int rc = nccl_load();
+  if (rc < 0) return rc;
+  CU(cudaSetDevice(m->device));
+  ncclUniqueId id;
+  std::memcpy(&id, id128, 128);
+  NC(g_nccl.CommInitRank(&m->comm, m->h.nparts, id, m->h.rank));
+  return XB_OK;
+}
+
+// NCCL point-to-point exchange with every neighbouring rank, on the model's stream
+int xb_exchange(xb_model* m, int which) {
+  NEED_DEVICE();
+  if (m->h.nparts < 2 || m->h.peers.empty()) return XB_OK;
+  if (!m->comm) return fail(XB_ERR_STATE, "no communicator: call xb_comm_init (or drive xb_exchange_local)");
+  CU(cudaSetDevice(m->device));
+  NC(g_nccl.GroupStart());
+  for (const xb::Peer& p : m->h.peers) {
+    const long long ns = which == 0 ? p.send_k : p.send_r, nr = which == 0 ? p.recv_k : p.recv_r;
+    const double* sb = which == 0 ? m->dSendK + p.send_k_base : m->dSendR + p.send_r_base;
+    double* rb = which == 0 ? m->dRecvK + p.recv_k_base : m->dRecvR + p.recv_r_base;
+    if (ns) NC(g_nccl.Send(sb, (size_t)ns, ncclDouble, p.rank, m->comm, m->stream));
+    if (nr) NC(g_nccl.Recv(rb, (size_t)nr, ncclDouble, p.rank, m->comm, m->stream));
+  }
+  NC(g_nccl.GroupEnd());
+  return XB_OK;
+}
+
+// the same exchange between models that live in ONE process (all ranks of a partition on one
+// or several GPUs of the box): device-to-device copies instead of NCCL.  Test / single-process use.
+int xb_exchange_local(xb_model** ms, int n, int which) {
+  for (int r = 0; r < n; r++) {
+    if (!ms[r] || !ms[r]->on_device) return fail(XB_ERR_STATE, "xb_exchange_local: model not on a device");
+    if (ms[r]->h.nparts != n || ms[r]->h.rank != r) return fail(XB_ERR_ARG, "xb_exchange_local: models must be ranks 0..n-1 of one partition");
+    CU(cudaSetDevice(ms[r]->device));
+    CU(cudaStreamSynchronize(ms[r]->stream));
+  }
+  for (int r = 0; r < n; r++)
+    for (const xb::Peer& p : ms[r]->h.peers) {
+      xb_model* d = ms[p.rank];
+      const xb::Peer* back = nullptr;
+      for (const xb::Peer& q : d->h.peers) if (q.rank == r) back = &q;
+      if (!back) return fail(XB_ERR_STATE, "xb_exchange_local: peer lists are not symmetric");
+      const long long ns = which == 0 ? p.send_k : p.send_r, nr = which == 0 ? back->recv_k : back->recv_r;
+      if (ns != nr) return fail(XB_ERR_STATE, "xb_exchange_local: send / receive sizes differ");
+      if (!ns) continue;
+      const double* sb = which == 0 ? ms[r]->dSendK + p.send_k_base : ms[r]->dSendR + p.send_r_base;
+      double* rb = which == 0 ? d->dRecvK + back->recv_k_base : d->dRecvR + back->recv_r_base;
+      CU(cudaMemcpy(rb, sb, sizeof(double) * ns, cudaMemcpyDefault));
+    }
   return XB_OK;
 }
 
@@ -938,6 +1142,7 @@ int xb_assemble_tangent(xb_model* m, double* A) {
 int xb_form_tangent(xb_model* m, double* A) {
   int rc = xb_form_element_tangents(m);
   if (rc < 0) return rc;
+  if (m->h.nparts > 1 && (rc = xb_exchange(m, 0)) < 0) return rc;
   return xb_assemble_tangent(m, A);
 }
 
@@ -958,7 +1163,7 @@ int xb_form_element_resids(xb_model* m) {
   bytes += (long long)m->h.nn() * m->h.ndm * 8;
   m->alg_bytes[5] = bytes;
   CU(cudaGetLastError());
-  return XB_OK;
+  return pack_for_peers(m, 1);
 }
 
 int xb_assemble_unbalance(xb_model* m, double* B) {
@@ -969,13 +1174,13 @@ int xb_assemble_unbalance(xb_model* m, double* B) {
     assemble_B_kernel<<<(unsigned)((ndof + 255) / 256), 256, 0, m->stream>>>(m->av, m->dRe, m->lambda, m->dB);
     m->launches++;
   }
-  long long bytes = (long long)m->h.neq * 8 + (long long)m->h.nn() * (m->h.ndm + m->h.ndf) * 8;
+  long long bytes = (long long)m->h.nrows * 8 + (long long)m->h.nn() * (m->h.ndm + m->h.ndf) * 8;
   for (auto& d : m->dg) bytes += d.ngp * 8 * d.nst;
   for (auto& g : m->h.groups) bytes += (long long)g.conn.size() * 4;
   m->alg_bytes[1] = bytes;
   CU(cudaGetLastError());
   if (B) {
-    CU(cudaMemcpyAsync(B, m->dB, sizeof(double) * m->h.neq, cudaMemcpyDeviceToHost, m->stream));
+    CU(cudaMemcpyAsync(B, m->dB, sizeof(double) * m->h.nrows, cudaMemcpyDeviceToHost, m->stream));
     return check_fail_flag(m);
   }
   return XB_OK;
@@ -984,6 +1189,7 @@ int xb_assemble_unbalance(xb_model* m, double* B) {
 int xb_form_unbalance(xb_model* m, double* B) {
   int rc = xb_form_element_resids(m);
   if (rc < 0) return rc;
+  if (m->h.nparts > 1 && (rc = xb_exchange(m, 1)) < 0) return rc;
   return xb_assemble_unbalance(m, B);
 }
 

@@ -112,12 +112,60 @@ struct TagIndex {
 };
 }  // namespace
 
-int HostModel::setup(int numberer_, int soe_kind_) {
+namespace {
+// global connectivity view used while setting up
+struct GlobalMesh {
+  const std::vector<Group>* groups;
+  std::vector<int> fe_group, fe_local;       // [ne] FE order
+  std::vector<long long> n2e_ptr;            // [nn+1]
+  std::vector<int> n2e_fe;                   // [*] FE index
+  std::vector<uint8_t> n2e_loc;              // [*]
+  const int* conn_of(long long e, const EleKind** k) const {
+    const Group& g = (*groups)[fe_group[e]];
+    *k = &ele_kind(g.kind);
+    return &g.conn[(size_t)fe_local[e] * (*k)->nen];
+  }
+  // neighbours of node n (sorted, unique, including n when it has an element)
+  void nbrs(int n, std::vector<int>& out) const {
+    out.clear();
+    for (long long t = n2e_ptr[n]; t < n2e_ptr[n + 1]; t++) {
+      const EleKind* k;
+      const int* c = conn_of(n2e_fe[t], &k);
+      out.insert(out.end(), c, c + k->nen);
+    }
+    std::sort(out.begin(), out.end());
+    out.erase(std::unique(out.begin(), out.end()), out.end());
+  }
+};
+
+// recursive coordinate bisection of element centroids into `np` parts, deterministic
+void rcb(std::vector<long long>& items, long long lo, long long hi, int np, int first, const double* cen,
+         int ndm, std::vector<int>& part) {
+  if (np == 1) { for (long long i = lo; i < hi; i++) part[items[i]] = first; return; }
+  double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+  for (long long i = lo; i < hi; i++)
+    for (int d = 0; d < ndm; d++) { double v = cen[items[i] * 3 + d]; mn[d] = std::min(mn[d], v); mx[d] = std::max(mx[d], v); }
+  int ax = 0;
+  for (int d = 1; d < ndm; d++) if (mx[d] - mn[d] > mx[ax] - mn[ax]) ax = d;
+  const int nl = np / 2;
+  const long long k = lo + (hi - lo) * nl / np;
+  std::nth_element(items.begin() + lo, items.begin() + k, items.begin() + hi, [&](long long a, long long b) {
+    double va = cen[a * 3 + ax], vb = cen[b * 3 + ax];
+    return va < vb || (va == vb && a < b);
+  });
+  rcb(items, lo, k, nl, first, cen, ndm, part);
+  rcb(items, k, hi, np - nl, first + nl, cen, ndm, part);
+}
+}  // namespace
+
+int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const int* part_in) {
   if (is_setup) { err = "xb_setup called twice"; return XB_ERR_STATE; }
   if (numberer_ != XB_NUMBERER_PLAIN && numberer_ != XB_NUMBERER_RCM) { err = "unknown numberer"; return XB_ERR_ARG; }
   if (soe_kind_ != XB_SOE_SPARSE_GEN_COL && soe_kind_ != XB_SOE_SPARSE_GEN_ROW) { err = "unknown SOE kind"; return XB_ERR_ARG; }
-  numberer = numberer_; soe_kind = soe_kind_;
+  if (nparts_ < 1 || rank_ < 0 || rank_ >= nparts_) { err = "bad nparts / rank"; return XB_ERR_ARG; }
+  numberer = numberer_; soe_kind = soe_kind_; nparts = nparts_; rank = rank_;
   const int n_nodes = (int)node_tag.size();
+  nn_global = n_nodes;
 
   // ---- Domain node map iterates by ascending tag (MapOfTaggedObjects, Domain.cpp:98) ----
   if (!std::is_sorted(node_tag.begin(), node_tag.end())) {
@@ -134,7 +182,7 @@ int HostModel::setup(int numberer_, int soe_kind_) {
   for (int i = 1; i < n_nodes; i++) if (node_tag[i] == node_tag[i - 1]) { err = "duplicate node tag"; return XB_ERR_ARG; }
   TagIndex nidx(node_tag);
 
-  // ---- element connectivity: tags -> node indices ----
+  // ---- element connectivity: tags -> (global) node indices ----
   cp_stride = 0;
   long long bad = 0;
   for (auto& g : groups) {
@@ -151,91 +199,62 @@ int HostModel::setup(int numberer_, int soe_kind_) {
   if (bad) { err = "element references an unknown node tag"; return XB_ERR_ARG; }
 
   // ---- PlainHandler::handle: every dof -2 (free) unless an SP_Constraint sets -1 ----
-  id.assign((size_t)n_nodes * ndf, -2);
+  std::vector<int> gid((size_t)n_nodes * ndf, -2);
   for (size_t i = 0; i < sp_node.size(); i++) {
     int ix = nidx(sp_node[i]);
     if (ix < 0) { err = "fix references an unknown node tag"; return XB_ERR_ARG; }
-    id[(size_t)ix * ndf + sp_dof[i]] = -1;
+    gid[(size_t)ix * ndf + sp_dof[i]] = -1;
   }
-  load.assign((size_t)n_nodes * ndf, 0.0);
+  std::vector<double> gload((size_t)n_nodes * ndf, 0.0);
   for (size_t i = 0; i < load_node.size(); i++) {
     int ix = nidx(load_node[i]);
     if (ix < 0) { err = "load references an unknown node tag"; return XB_ERR_ARG; }
-    for (int j = 0; j < ndf; j++) load[(size_t)ix * ndf + j] += load_val[i * ndf + j];
+    for (int j = 0; j < ndf; j++) gload[(size_t)ix * ndf + j] += load_val[i * ndf + j];
   }
 
   // ---- FE_Element order: Domain element map by ascending tag (PlainHandler.cpp:228-250) ----
-  ne = 0;
-  for (auto& g : groups) ne += g.n();
-  fe_group.resize(ne); fe_local.resize(ne);
+  GlobalMesh G;
+  G.groups = &groups;
+  long long neg = 0;
+  for (auto& g : groups) neg += g.n();
+  ne_global = neg;
+  G.fe_group.resize(neg); G.fe_local.resize(neg);
   {
     bool simple = groups.size() == 1 && std::is_sorted(groups[0].tag.begin(), groups[0].tag.end());
     if (simple) {
-      for (long long e = 0; e < ne; e++) { fe_group[e] = 0; fe_local[e] = (int)e; }
+      for (long long e = 0; e < neg; e++) { G.fe_group[e] = 0; G.fe_local[e] = (int)e; }
+      for (size_t i = 1; i < groups[0].tag.size(); i++)
+        if (groups[0].tag[i] == groups[0].tag[i - 1]) { err = "duplicate element tag"; return XB_ERR_ARG; }
     } else {
-      std::vector<long long> order(ne);
-      std::vector<int> tg(ne), gg(ne), ll(ne);
+      std::vector<long long> order(neg);
+      std::vector<int> tg(neg), gg(neg), ll(neg);
       long long c = 0;
       for (size_t gi = 0; gi < groups.size(); gi++)
         for (long long l = 0; l < groups[gi].n(); l++) { tg[c] = groups[gi].tag[l]; gg[c] = (int)gi; ll[c] = (int)l; c++; }
       std::iota(order.begin(), order.end(), 0LL);
       std::sort(order.begin(), order.end(), [&](long long a, long long b) { return tg[a] < tg[b]; });
-      for (long long e = 0; e < ne; e++) { fe_group[e] = gg[order[e]]; fe_local[e] = ll[order[e]]; }
-      for (long long e = 1; e < ne; e++) if (tg[order[e]] == tg[order[e - 1]]) { err = "duplicate element tag"; return XB_ERR_ARG; }
+      for (long long e = 0; e < neg; e++) { G.fe_group[e] = gg[order[e]]; G.fe_local[e] = ll[order[e]]; }
+      for (long long e = 1; e < neg; e++) if (tg[order[e]] == tg[order[e - 1]]) { err = "duplicate element tag"; return XB_ERR_ARG; }
     }
-    for (auto& g : groups) for (size_t i = 1; i < g.tag.size() && groups.size() == 1; i++)
-      if (g.tag[i] == g.tag[i - 1]) { err = "duplicate element tag"; return XB_ERR_ARG; }
-  }
-  ke_total = re_total = ngp = 0;
-  for (auto& g : groups) {
-    const EleKind& k = ele_kind(g.kind);
-    const long long nd = k.nen * k.ndf;
-    g.ke_off = ke_total; g.re_off = re_total; g.gp_off = ngp;
-    ke_total += g.n() * nd * nd; re_total += g.n() * nd; ngp += g.n() * k.nip;
   }
 
-  // ---- node -> FE elements (FE order) ----
-  n2e_ptr.assign((size_t)n_nodes + 1, 0);
-  for (long long e = 0; e < ne; e++) {
-    const Group& g = groups[fe_group[e]];
-    const EleKind& k = ele_kind(g.kind);
-    const int* c = &g.conn[(size_t)fe_local[e] * k.nen];
-    for (int a = 0; a < k.nen; a++) n2e_ptr[c[a] + 1]++;
+  // ---- node -> FE elements (global, FE order) ----
+  G.n2e_ptr.assign((size_t)n_nodes + 1, 0);
+  for (long long e = 0; e < neg; e++) {
+    const EleKind* k; const int* c = G.conn_of(e, &k);
+    for (int a = 0; a < k->nen; a++) G.n2e_ptr[c[a] + 1]++;
   }
-  for (int n = 0; n < n_nodes; n++) n2e_ptr[n + 1] += n2e_ptr[n];
-  const long long n2e_total = n2e_ptr[n_nodes];
-  n2e_koff.resize(n2e_total); n2e_roff.resize(n2e_total); n2e_nd.resize(n2e_total);
-  n2e_fe.resize(n2e_total); n2e_loc.resize(n2e_total);
+  for (int n = 0; n < n_nodes; n++) G.n2e_ptr[n + 1] += G.n2e_ptr[n];
+  G.n2e_fe.resize(G.n2e_ptr[n_nodes]); G.n2e_loc.resize(G.n2e_ptr[n_nodes]);
   {
-    std::vector<long long> fill(n2e_ptr.begin(), n2e_ptr.end() - 1);
-    for (long long e = 0; e < ne; e++) {
-      const Group& g = groups[fe_group[e]];
-      const EleKind& k = ele_kind(g.kind);
-      const long long nd = k.nen * k.ndf, l = fe_local[e];
-      const int* c = &g.conn[(size_t)l * k.nen];
-      for (int a = 0; a < k.nen; a++) {
-        long long t = fill[c[a]]++;
-        n2e_fe[t] = (int)e; n2e_loc[t] = (uint8_t)a; n2e_nd[t] = (uint8_t)nd;
-        n2e_koff[t] = g.ke_off + l * nd * nd + (long long)a * k.ndf * nd;
-        n2e_roff[t] = g.re_off + l * nd + (long long)a * k.ndf;
-      }
+    std::vector<long long> fill(G.n2e_ptr.begin(), G.n2e_ptr.end() - 1);
+    for (long long e = 0; e < neg; e++) {
+      const EleKind* k; const int* c = G.conn_of(e, &k);
+      for (int a = 0; a < k->nen; a++) { long long t = fill[c[a]]++; G.n2e_fe[t] = (int)e; G.n2e_loc[t] = (uint8_t)a; }
     }
   }
 
-  // neighbours of node n (sorted, unique, including n when it has an element)
-  auto collect_nbrs = [&](int n, std::vector<int>& out) {
-    out.clear();
-    for (long long t = n2e_ptr[n]; t < n2e_ptr[n + 1]; t++) {
-      const Group& g = groups[fe_group[n2e_fe[t]]];
-      const EleKind& k = ele_kind(g.kind);
-      const int* c = &g.conn[(size_t)fe_local[n2e_fe[t]] * k.nen];
-      out.insert(out.end(), c, c + k.nen);
-    }
-    std::sort(out.begin(), out.end());
-    out.erase(std::unique(out.begin(), out.end()), out.end());
-  };
-
-  // ---- numbering ----
+  // ---- numbering (global, identical on every rank) ----
   std::vector<int> order(n_nodes);
   if (numberer == XB_NUMBERER_PLAIN) {
     std::iota(order.begin(), order.end(), 0);
@@ -249,7 +268,7 @@ int HostModel::setup(int numberer_, int soe_kind_) {
     {
       std::vector<int> tmp;
 #pragma omp for schedule(dynamic, 4096)
-      for (int n = 0; n < n_nodes; n++) { collect_nbrs(n, tmp); nb_ptr[n + 1] = (long long)tmp.size(); }
+      for (int n = 0; n < n_nodes; n++) { G.nbrs(n, tmp); nb_ptr[n + 1] = (long long)tmp.size(); }
     }
     for (int n = 0; n < n_nodes; n++) nb_ptr[n + 1] += nb_ptr[n];
     std::vector<int> nb(nb_ptr[n_nodes]);
@@ -257,7 +276,7 @@ int HostModel::setup(int numberer_, int soe_kind_) {
     {
       std::vector<int> tmp;
 #pragma omp for schedule(dynamic, 4096)
-      for (int n = 0; n < n_nodes; n++) { collect_nbrs(n, tmp); std::copy(tmp.begin(), tmp.end(), nb.begin() + nb_ptr[n]); }
+      for (int n = 0; n < n_nodes; n++) { G.nbrs(n, tmp); std::copy(tmp.begin(), tmp.end(), nb.begin() + nb_ptr[n]); }
     }
     std::vector<int> mark(n_nodes, -1);
     if (n_nodes > 0) {
@@ -281,90 +300,301 @@ int HostModel::setup(int numberer_, int soe_kind_) {
   int eqn = 0;
   for (int i = 0; i < n_nodes; i++) {
     int n = order[i];
-    for (int j = 0; j < ndf; j++) if (id[(size_t)n * ndf + j] == -2) id[(size_t)n * ndf + j] = eqn++;
+    for (int j = 0; j < ndf; j++) if (gid[(size_t)n * ndf + j] == -2) gid[(size_t)n * ndf + j] = eqn++;
   }
   neq = eqn;
+  { std::vector<int>().swap(order); }
 
-  // ---- DOF graph -> sparse pattern.  Every free dof of node n is coupled with every free
-  // dof of every node sharing an element with n (FE_Element::getID spans all dofs of its
-  // nodes), so the rows/columns of one node share a single sorted list.  setSize() then
-  // insertion-sorts diag + adjacency, i.e. the list including the dof itself. ----
-  ncol_ptr.assign((size_t)n_nodes + 1, 0);
+  // ---- element partition and node ownership (DomainPartitioner's role; the numbering above
+  // is untouched, so every rank's rows are rows of the one global system) ----
+  part_fe.assign(neg, 0);
+  if (nparts > 1) {
+    if (part_in) {
+      for (long long e = 0; e < neg; e++) {
+        if (part_in[e] < 0 || part_in[e] >= nparts) { err = "partition entry out of range"; return XB_ERR_ARG; }
+        part_fe[e] = part_in[e];
+      }
+    } else {
+      std::vector<double> cen((size_t)neg * 3, 0.0);
+#pragma omp parallel for schedule(static)
+      for (long long e = 0; e < neg; e++) {
+        const EleKind* k; const int* c = G.conn_of(e, &k);
+        for (int a = 0; a < k->nen; a++)
+          for (int d = 0; d < ndm; d++) cen[e * 3 + d] += crd[(size_t)c[a] * ndm + d];
+        for (int d = 0; d < ndm; d++) cen[e * 3 + d] /= k->nen;
+      }
+      std::vector<long long> items(neg);
+      std::iota(items.begin(), items.end(), 0LL);
+      rcb(items, 0, neg, nparts, 0, cen.data(), ndm, part_fe);
+    }
+  }
+  // a node's equations belong to the lowest rank holding one of its elements
+  std::vector<int> owner(n_nodes, 0);
+  if (nparts > 1) {
+#pragma omp parallel for schedule(static)
+    for (int n = 0; n < n_nodes; n++) {
+      int o = nparts;
+      for (long long t = G.n2e_ptr[n]; t < G.n2e_ptr[n + 1]; t++) o = std::min(o, part_fe[G.n2e_fe[t]]);
+      owner[n] = (o == nparts) ? 0 : o;
+    }
+  }
+
+  // ---- local nodes: nodes of local elements and owned nodes, ascending global index ----
+  std::vector<int> g2l(n_nodes, -1);
+  std::vector<int> lnode;
+  if (nparts == 1) {
+    lnode.resize(n_nodes);
+    std::iota(lnode.begin(), lnode.end(), 0);
+    std::iota(g2l.begin(), g2l.end(), 0);
+  } else {
+    std::vector<uint8_t> mark(n_nodes, 0);
+    for (int n = 0; n < n_nodes; n++) if (owner[n] == rank) mark[n] = 1;
+    for (long long e = 0; e < neg; e++) if (part_fe[e] == rank) {
+      const EleKind* k; const int* c = G.conn_of(e, &k);
+      for (int a = 0; a < k->nen; a++) mark[c[a]] = 1;
+    }
+    for (int n = 0; n < n_nodes; n++) if (mark[n]) { g2l[n] = (int)lnode.size(); lnode.push_back(n); }
+  }
+  const int nl = (int)lnode.size();
+
+  // ---- local element groups (subset of every batch, FE order preserved) ----
+  std::vector<Group> lgroups;
+  std::vector<long long> g_fe_to_local(nparts == 1 ? 0 : neg, -1);   // global FE -> local FE
+  fe_group.clear(); fe_local.clear(); fe_global.clear();
+  if (nparts == 1) {
+    fe_group = G.fe_group; fe_local = G.fe_local;
+    fe_global.resize(neg); std::iota(fe_global.begin(), fe_global.end(), 0LL);
+    ne = neg;
+  } else {
+    lgroups.resize(groups.size());
+    std::vector<std::vector<int>> keep(groups.size());   // batch index -> kept element indices
+    for (size_t gi = 0; gi < groups.size(); gi++) { lgroups[gi].kind = groups[gi].kind; lgroups[gi].mat_kind = groups[gi].mat_kind; }
+    std::vector<std::vector<int>> newidx(groups.size());
+    for (size_t gi = 0; gi < groups.size(); gi++) newidx[gi].assign(groups[gi].n(), -1);
+    // kept elements of a batch keep their batch order
+    std::vector<std::vector<uint8_t>> mine(groups.size());
+    for (size_t gi = 0; gi < groups.size(); gi++) mine[gi].assign(groups[gi].n(), 0);
+    for (long long e = 0; e < neg; e++) if (part_fe[e] == rank) mine[G.fe_group[e]][G.fe_local[e]] = 1;
+    for (size_t gi = 0; gi < groups.size(); gi++) {
+      const Group& g = groups[gi]; Group& lg = lgroups[gi];
+      const EleKind& k = ele_kind(g.kind);
+      for (long long l = 0; l < g.n(); l++) if (mine[gi][l]) {
+        newidx[gi][l] = (int)lg.tag.size();
+        lg.tag.push_back(g.tag[l]); lg.mat.push_back(g.mat[l]);
+        for (int a = 0; a < k.nen; a++) lg.conn.push_back(g2l[g.conn[(size_t)l * k.nen + a]]);
+        for (int q = 0; q < k.npar; q++) lg.par.push_back(g.par[(size_t)l * k.npar + q]);
+      }
+    }
+    ne = 0;
+    for (long long e = 0; e < neg; e++) if (part_fe[e] == rank) {
+      g_fe_to_local[e] = ne++;
+      fe_group.push_back(G.fe_group[e]); fe_local.push_back(newidx[G.fe_group[e]][G.fe_local[e]]); fe_global.push_back(e);
+    }
+  }
+  const std::vector<Group>& LG = nparts == 1 ? groups : lgroups;
+  // offsets of the local element matrices / residuals
+  std::vector<long long> ke_off(LG.size()), re_off(LG.size()), gp_off(LG.size());
+  ke_total = re_total = ngp = 0;
+  for (size_t gi = 0; gi < LG.size(); gi++) {
+    const EleKind& k = ele_kind(LG[gi].kind);
+    const long long nd = k.nen * k.ndf;
+    ke_off[gi] = ke_total; re_off[gi] = re_total; gp_off[gi] = ngp;
+    ke_total += LG[gi].n() * nd * nd; re_total += LG[gi].n() * nd; ngp += LG[gi].n() * k.nip;
+  }
+
+  // ---- local node tables ----
+  id.resize((size_t)nl * ndf); load.resize((size_t)nl * ndf); owned.assign(nl, 0);
+  {
+    std::vector<int> t(nl); std::vector<double> c((size_t)nl * ndm);
+    for (int i = 0; i < nl; i++) {
+      const int n = lnode[i];
+      t[i] = node_tag[n];
+      std::memcpy(&c[(size_t)i * ndm], &crd[(size_t)n * ndm], sizeof(double) * ndm);
+      for (int j = 0; j < ndf; j++) { id[(size_t)i * ndf + j] = gid[(size_t)n * ndf + j]; load[(size_t)i * ndf + j] = gload[(size_t)n * ndf + j]; }
+      owned[i] = owner[n] == rank;
+    }
+    node_tag.swap(t); crd.swap(c);
+  }
+  // owned rows, ascending global equation number
+  row_geq.clear();
+  for (int i = 0; i < nl; i++) if (owned[i])
+    for (int j = 0; j < ndf; j++) if (id[(size_t)i * ndf + j] >= 0) row_geq.push_back(id[(size_t)i * ndf + j]);
+  std::sort(row_geq.begin(), row_geq.end());
+  nrows = (int)row_geq.size();
+  row_of.assign((size_t)nl * ndf, -1);
+  for (int i = 0; i < nl; i++) if (owned[i])
+    for (int j = 0; j < ndf; j++) {
+      const int q = id[(size_t)i * ndf + j];
+      if (q >= 0) row_of[(size_t)i * ndf + j] = (int)(std::lower_bound(row_geq.begin(), row_geq.end(), q) - row_geq.begin());
+    }
+
+  // ---- slots of the owned nodes: every adjacent element (local or remote) in global FE order ----
+  n2e_ptr.assign((size_t)nl + 1, 0);
+  for (int i = 0; i < nl; i++) if (owned[i]) n2e_ptr[i + 1] = G.n2e_ptr[lnode[i] + 1] - G.n2e_ptr[lnode[i]];
+  for (int i = 0; i < nl; i++) n2e_ptr[i + 1] += n2e_ptr[i];
+  const long long n2e_total = n2e_ptr[nl];
+  n2e_koff.resize(n2e_total); n2e_roff.resize(n2e_total); n2e_nd.resize(n2e_total);
+  n2e_fe.resize(n2e_total); n2e_loc.resize(n2e_total);
+  // receive-buffer layout: per source rank, chunks in (owned node ascending, FE order)
+  std::vector<long long> rk(nparts, 0), rr(nparts, 0), rc(nparts, 0);
+  for (int i = 0; i < nl; i++) if (owned[i]) {
+    const int n = lnode[i];
+    for (long long t = G.n2e_ptr[n], u = n2e_ptr[i]; t < G.n2e_ptr[n + 1]; t++, u++) {
+      const long long e = G.n2e_fe[t];
+      const EleKind* k; G.conn_of(e, &k);
+      const int a = G.n2e_loc[t];
+      const long long nd = k->nen * k->ndf;
+      n2e_fe[u] = e; n2e_loc[u] = (uint8_t)a; n2e_nd[u] = (uint8_t)nd;
+      const int src = part_fe[e];
+      if (src == rank) {
+        const int gi = G.fe_group[e];
+        const long long l = nparts == 1 ? G.fe_local[e] : fe_local[g_fe_to_local[e]];
+        n2e_koff[u] = ke_off[gi] + l * nd * nd + (long long)a * k->ndf * nd;
+        n2e_roff[u] = re_off[gi] + l * nd + (long long)a * k->ndf;
+      } else {
+        n2e_koff[u] = rk[src]; n2e_roff[u] = rr[src];      // relative to that peer's block, fixed below
+        rk[src] += (long long)k->ndf * nd; rr[src] += k->ndf; rc[src]++;
+      }
+    }
+  }
+  // send side: for every other rank s, the chunks of MY elements at nodes s owns, enumerated the
+  // way s enumerates them (its owned nodes ascending, global FE order)
+  std::vector<long long> sk(nparts, 0), sr(nparts, 0), sc(nparts, 0);
+  std::vector<std::vector<long long>> out_ksrc(nparts), out_rsrc(nparts);
+  std::vector<std::vector<uint8_t>> out_nd(nparts);
+  if (nparts > 1) {
+    for (int i = 0; i < nl; i++) {
+      const int n = lnode[i];
+      const int s = owner[n];
+      if (s == rank) continue;
+      for (long long t = G.n2e_ptr[n]; t < G.n2e_ptr[n + 1]; t++) {
+        const long long e = G.n2e_fe[t];
+        if (part_fe[e] != rank) continue;
+        const EleKind* k; G.conn_of(e, &k);
+        const int a = G.n2e_loc[t], gi = G.fe_group[e];
+        const long long nd = k->nen * k->ndf, l = fe_local[g_fe_to_local[e]];
+        out_ksrc[s].push_back(ke_off[gi] + l * nd * nd + (long long)a * k->ndf * nd);
+        out_rsrc[s].push_back(re_off[gi] + l * nd + (long long)a * k->ndf);
+        out_nd[s].push_back((uint8_t)nd);
+        sk[s] += (long long)k->ndf * nd; sr[s] += k->ndf; sc[s]++;
+      }
+    }
+  }
+  peers.clear(); pk_src.clear(); pk_dst.clear(); pr_src.clear(); pr_dst.clear(); pk_nd.clear();
+  send_k_total = recv_k_total = send_r_total = recv_r_total = 0;
+  std::vector<long long> recv_k_base(nparts, 0), recv_r_base(nparts, 0);
+  for (int s = 0; s < nparts; s++) {
+    if (s == rank || (sc[s] == 0 && rc[s] == 0)) continue;
+    Peer p; p.rank = s;
+    p.send_k = sk[s]; p.send_r = sr[s]; p.recv_k = rk[s]; p.recv_r = rr[s];
+    p.chunks_out = sc[s]; p.chunks_in = rc[s];
+    p.send_k_base = send_k_total; p.send_r_base = send_r_total; p.recv_k_base = recv_k_total; p.recv_r_base = recv_r_total;
+    recv_k_base[s] = recv_k_total; recv_r_base[s] = recv_r_total;
+    long long dk = send_k_total, dr = send_r_total;
+    for (size_t c = 0; c < out_ksrc[s].size(); c++) {
+      pk_src.push_back(out_ksrc[s][c]); pk_dst.push_back(dk); pk_nd.push_back(out_nd[s][c]);
+      pr_src.push_back(out_rsrc[s][c]); pr_dst.push_back(dr);
+      dk += (long long)ndf * out_nd[s][c]; dr += ndf;
+    }
+    send_k_total += sk[s]; send_r_total += sr[s]; recv_k_total += rk[s]; recv_r_total += rr[s];
+    peers.push_back(p);
+  }
+  // remote slots: absolute offset into the receive buffers, encoded as -(x+1)
+  if (nparts > 1)
+    for (long long u = 0; u < n2e_total; u++) {
+      const int src = part_fe[n2e_fe[u]];
+      if (src != rank) {
+        n2e_koff[u] = -(recv_k_base[src] + n2e_koff[u] + 1);
+        n2e_roff[u] = -(recv_r_base[src] + n2e_roff[u] + 1);
+      }
+    }
+
+  // ---- DOF graph -> sparse pattern of the owned rows.  Every free dof of node n is coupled
+  // with every free dof of every node sharing an element with n (FE_Element::getID spans all
+  // dofs of its nodes), so the rows/columns of one node share a single sorted list.  setSize()
+  // then insertion-sorts diag + adjacency, i.e. the list including the dof itself. ----
+  ncol_ptr.assign((size_t)nl + 1, 0);
 #pragma omp parallel
   {
     std::vector<int> tmp;
 #pragma omp for schedule(dynamic, 4096)
-    for (int n = 0; n < n_nodes; n++) {
-      collect_nbrs(n, tmp);
+    for (int i = 0; i < nl; i++) {
+      if (!owned[i]) continue;
+      G.nbrs(lnode[i], tmp);
       long long c = 0;
-      for (int w : tmp) for (int j = 0; j < ndf; j++) if (id[(size_t)w * ndf + j] >= 0) c++;
-      ncol_ptr[n + 1] = c;
+      for (int w : tmp) for (int j = 0; j < ndf; j++) if (gid[(size_t)w * ndf + j] >= 0) c++;
+      ncol_ptr[i + 1] = c;
     }
   }
-  for (int n = 0; n < n_nodes; n++) ncol_ptr[n + 1] += ncol_ptr[n];
-  ncol.resize(ncol_ptr[n_nodes]);
+  for (int i = 0; i < nl; i++) ncol_ptr[i + 1] += ncol_ptr[i];
+  ncol.resize(ncol_ptr[nl]);
   long long too_long = 0;
 #pragma omp parallel
   {
     std::vector<int> tmp;
 #pragma omp for schedule(dynamic, 4096) reduction(+ : too_long)
-    for (int n = 0; n < n_nodes; n++) {
-      collect_nbrs(n, tmp);
-      int* out = &ncol[ncol_ptr[n]];
+    for (int i = 0; i < nl; i++) {
+      if (!owned[i]) continue;
+      G.nbrs(lnode[i], tmp);
+      int* out = &ncol[ncol_ptr[i]];
       long long c = 0;
-      for (int w : tmp) for (int j = 0; j < ndf; j++) { int q = id[(size_t)w * ndf + j]; if (q >= 0) out[c++] = q; }
+      for (int w : tmp) for (int j = 0; j < ndf; j++) { int q = gid[(size_t)w * ndf + j]; if (q >= 0) out[c++] = q; }
       std::sort(out, out + c);
       if (c >= 0xFFFF) too_long++;
     }
   }
   if (too_long) { err = "a node couples with more than 65534 equations"; return XB_ERR_UNSUPPORTED; }
 
-  ptr.assign((size_t)neq + 1, 0);
+  ptr.assign((size_t)nrows + 1, 0);
   max_row = 0;
-  for (int n = 0; n < n_nodes; n++) {
-    long long L = ncol_ptr[n + 1] - ncol_ptr[n];
-    bool isolated = n2e_ptr[n + 1] == n2e_ptr[n];
+  for (int i = 0; i < nl; i++) {
+    if (!owned[i]) continue;
+    long long L = ncol_ptr[i + 1] - ncol_ptr[i];
+    bool isolated = n2e_ptr[i + 1] == n2e_ptr[i];
     for (int j = 0; j < ndf; j++) {
-      int r = id[(size_t)n * ndf + j];
+      int r = row_of[(size_t)i * ndf + j];
       if (r >= 0) { ptr[r + 1] = isolated ? 1 : L; max_row = std::max<long long>(max_row, ptr[r + 1]); }
     }
   }
-  for (int r = 0; r < neq; r++) ptr[r + 1] += ptr[r];
-  const long long nz = ptr[neq];
-  if (nz > 0x7fffffffLL * 4) { err = "pattern too large"; return XB_ERR_UNSUPPORTED; }
+  for (int r = 0; r < nrows; r++) ptr[r + 1] += ptr[r];
+  const long long nz = ptr[nrows];
   idx.resize(nz);
 #pragma omp parallel for schedule(dynamic, 4096)
-  for (int n = 0; n < n_nodes; n++) {
-    long long L = ncol_ptr[n + 1] - ncol_ptr[n];
-    bool isolated = n2e_ptr[n + 1] == n2e_ptr[n];
+  for (int i = 0; i < nl; i++) {
+    if (!owned[i]) continue;
+    long long L = ncol_ptr[i + 1] - ncol_ptr[i];
+    bool isolated = n2e_ptr[i + 1] == n2e_ptr[i];
     for (int j = 0; j < ndf; j++) {
-      int r = id[(size_t)n * ndf + j];
+      int r = row_of[(size_t)i * ndf + j];
       if (r < 0) continue;
-      if (isolated) idx[ptr[r]] = r;
-      else std::copy(&ncol[ncol_ptr[n]], &ncol[ncol_ptr[n]] + L, &idx[ptr[r]]);
+      if (isolated) idx[ptr[r]] = id[(size_t)i * ndf + j];
+      else std::copy(&ncol[ncol_ptr[i]], &ncol[ncol_ptr[i]] + L, &idx[ptr[r]]);
     }
   }
 
-  // ---- per (node, adjacent element) positions of the element's dofs in the node's list ----
+  // ---- per (owned node, adjacent element) positions of the element's dofs in the node's list ----
   colpos.assign((size_t)n2e_total * cp_stride, 0xFFFF);
 #pragma omp parallel for schedule(dynamic, 4096)
-  for (int n = 0; n < n_nodes; n++) {
-    const int* cols = &ncol[ncol_ptr[n]];
-    const long long L = ncol_ptr[n + 1] - ncol_ptr[n];
-    for (long long t = n2e_ptr[n]; t < n2e_ptr[n + 1]; t++) {
-      const Group& g = groups[fe_group[n2e_fe[t]]];
-      const EleKind& k = ele_kind(g.kind);
-      const int* c = &g.conn[(size_t)fe_local[n2e_fe[t]] * k.nen];
+  for (int i = 0; i < nl; i++) {
+    if (!owned[i]) continue;
+    const int* cols = &ncol[ncol_ptr[i]];
+    const long long L = ncol_ptr[i + 1] - ncol_ptr[i];
+    for (long long t = n2e_ptr[i]; t < n2e_ptr[i + 1]; t++) {
+      const EleKind* k; const int* c = G.conn_of(n2e_fe[t], &k);
       uint16_t* cp = &colpos[(size_t)t * cp_stride];
-      for (int a = 0; a < k.nen; a++)
-        for (int j = 0; j < k.ndf; j++) {
-          int q = id[(size_t)c[a] * ndf + j];
+      for (int a = 0; a < k->nen; a++)
+        for (int j = 0; j < k->ndf; j++) {
+          int q = gid[(size_t)c[a] * ndf + j];
           if (q < 0) continue;
           const int* it = std::lower_bound(cols, cols + L, q);
-          cp[a * k.ndf + j] = (uint16_t)(it - cols);
+          cp[a * k->ndf + j] = (uint16_t)(it - cols);
         }
     }
   }
+
+  // ---- commit the local element groups ----
+  if (nparts > 1) groups.swap(lgroups);
+  for (size_t gi = 0; gi < groups.size(); gi++) { groups[gi].ke_off = ke_off[gi]; groups[gi].re_off = re_off[gi]; groups[gi].gp_off = gp_off[gi]; }
   is_setup = true;
   return neq;
 }
@@ -375,22 +605,24 @@ int HostModel::scatter_map(long long e0, long long e1, long long* map) const {
     const Group& g = groups[fe_group[e]];
     const EleKind& k = ele_kind(g.kind);
     const int nd = k.nen * k.ndf;
-    const int* c = &g.conn[(size_t)fe_local[e] * k.nen];
+    const int* c = &g.conn[(size_t)fe_local[e] * k.nen];   // local node indices
     long long* out = map + (e - e0) * nd * nd;
-    // the n2e slot of (node c[a], element e)
+    const long long ge = fe_global[e];
+    // the slot of (node c[a], element e) on the rank owning that node
     std::vector<long long> slot(k.nen);
     for (int a = 0; a < k.nen; a++) {
       slot[a] = -1;
       for (long long t = n2e_ptr[c[a]]; t < n2e_ptr[c[a] + 1]; t++)
-        if (n2e_fe[t] == e && n2e_loc[t] == a) { slot[a] = t; break; }
+        if (n2e_fe[t] == ge && n2e_loc[t] == a) { slot[a] = t; break; }
     }
     for (int i = 0; i < nd; i++)
       for (int j = 0; j < nd; j++) {
         // CSR: entry (i,j) -> row id(i), column id(j).  CSC: entry (i,j) -> column id(j), row id(i).
-        int owner = soe_kind == XB_SOE_SPARSE_GEN_ROW ? i : j;
+        int ownerdof = soe_kind == XB_SOE_SPARSE_GEN_ROW ? i : j;
         int other = soe_kind == XB_SOE_SPARSE_GEN_ROW ? j : i;
-        int ro = id[(size_t)c[owner / k.ndf] * ndf + owner % k.ndf];
-        uint16_t cp = colpos[(size_t)slot[owner / k.ndf] * cp_stride + other];
+        int ro = row_of[(size_t)c[ownerdof / k.ndf] * ndf + ownerdof % k.ndf];
+        long long sl = slot[ownerdof / k.ndf];
+        uint16_t cp = sl < 0 ? (uint16_t)0xFFFF : colpos[(size_t)sl * cp_stride + other];
         out[i * nd + j] = (ro < 0 || cp == 0xFFFF) ? -1 : ptr[ro] + cp;
       }
   }

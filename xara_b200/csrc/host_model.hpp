@@ -1,6 +1,7 @@
 // Host-side mirror of the reference's Domain / AnalysisModel / LinearSOE set-up for
 // the device path.  Integer work only: DOF_Group ids, FE_Element order, the sparse
-// pattern and the per-node gather maps the assembly kernels consume.
+// pattern and the per-node gather maps the assembly kernels consume; for multi-GPU
+// runs also the element partition, node ownership and the interface exchange lists.
 //
 // Reference counterparts (paths under /root/reference/SRC):
 //   Domain (domain/domain/Domain.cpp)            -> HostModel node/element/SP/load tables
@@ -10,6 +11,8 @@
 //                                          graph/numberer/RCM.cpp:66)
 //   AnalysisModel::getDOFGraph (analysis/model/AnalysisModel.cpp:286)
 //   SparseGenColLinSOE::setSize / SparseGenRowLinSOE::setSize
+//   DomainPartitioner / PartitionedDomain (domain/partitioner, domain/domain/partitioned)
+//       -> element partition + row ownership; the numbering stays the GLOBAL one
 #pragma once
 #include <cstdint>
 #include <string>
@@ -31,48 +34,68 @@ struct Material {
   double par[8];
 };
 
-// one xb_add_elements call: a homogeneous batch (one element kind, one material kind)
+// one xb_add_elements call: a homogeneous batch (one element kind, one material kind).
+// After setup() it holds only the elements of this rank's partition.
 struct Group {
   int kind = 0, mat_kind = 0;
   std::vector<int> tag;      // [n]
-  std::vector<int> conn;     // [n][nen] node TAGS until setup(), node indices after
+  std::vector<int> conn;     // [n][nen] node TAGS until setup(), LOCAL node indices after
   std::vector<int> mat;      // [n] material index into HostModel::mats
   std::vector<double> par;   // [n][npar]
   long long ke_off = 0;      // offset (doubles) of this group's element matrices in the Ke buffer
   long long re_off = 0;      // offset (doubles) of this group's element residuals
-  long long gp_off = 0;      // first Gauss point (global numbering, for reporting)
+  long long gp_off = 0;      // first Gauss point (for reporting)
   long long n() const { return (long long)tag.size(); }
+};
+
+// one neighbour rank in the interface exchange
+struct Peer {
+  int rank = 0;
+  long long send_k = 0, recv_k = 0;   // doubles of element-matrix rows sent to / received from it
+  long long send_r = 0, recv_r = 0;   // doubles of element-residual entries
+  long long send_k_base = 0, recv_k_base = 0, send_r_base = 0, recv_r_base = 0;  // offsets in the buffers
+  long long chunks_out = 0, chunks_in = 0;
 };
 
 struct HostModel {
   int ndm = 0, ndf = 0;
-  // --- Domain ---
-  std::vector<int> node_tag;        // ascending after setup()
+  // --- Domain (global until setup(), then restricted to this rank's local nodes) ---
+  std::vector<int> node_tag;        // ascending
   std::vector<double> crd;          // [nn][ndm]
   std::vector<int> sp_node, sp_dof; // fix
   std::vector<Material> mats;
   std::vector<Group> groups;
   std::vector<int> load_node;       // pending nodal loads (tags)
   std::vector<double> load_val;     // [nload][ndf]
-  std::vector<double> load;         // [nn][ndf] after setup()
+  std::vector<double> load;         // [nn][ndf]
 
   // --- analysis (valid after setup) ---
   bool is_setup = false;
   int numberer = 0, soe_kind = 0;
-  int neq = 0;
-  std::vector<int> id;              // [nn][ndf] DOF_Group ids
-  long long ne = 0;                 // FE_Elements
-  std::vector<int> fe_group;        // [ne] group of FE element e (FE order = ascending element tag)
+  int nparts = 1, rank = 0;
+  int neq = 0;                      // GLOBAL number of equations
+  int nn_global = 0;
+  long long ne_global = 0;
+  std::vector<int> id;              // [nn][ndf] GLOBAL DOF_Group ids of the local nodes
+  std::vector<int> row_of;          // [nn][ndf] local row of an owned free dof, else -1
+  std::vector<uint8_t> owned;       // [nn] this rank owns the node's equations
+  int nrows = 0;                    // owned equations (== neq when nparts == 1)
+  std::vector<int> row_geq;         // [nrows] their global numbers, ascending
+  long long ne = 0;                 // local FE_Elements
+  std::vector<int> fe_group;        // [ne] group of local FE element e (FE order = ascending element tag)
   std::vector<int> fe_local;        // [ne] index within the group
-  std::vector<long long> ptr;       // [neq+1] colStartA / rowStartA
-  std::vector<int> idx;             // [nnz]   rowA / colA
-  // node -> FE elements, FE order within a node (this IS the reference's addA/addB
-  // accumulation order for every entry owned by the node's equations)
+  std::vector<long long> fe_global; // [ne] position in the global FE_Element order
+  std::vector<long long> ptr;       // [nrows+1] colStartA / rowStartA of the owned rows
+  std::vector<int> idx;             // [nnz]     rowA / colA (GLOBAL equation numbers)
+  // node -> FE elements, GLOBAL FE order within a node (this IS the reference's addA/addB
+  // accumulation order for every entry owned by the node's equations).  Only owned nodes
+  // carry slots.  A slot whose element lives on another rank reads the received rows:
+  // koff / roff < 0 encode offset -(x+1) into the receive buffers.
   std::vector<long long> n2e_ptr;   // [nn+1]
   std::vector<long long> n2e_koff;  // [*] offset in Ke of row (a*ndf) of that element's matrix
   std::vector<long long> n2e_roff;  // [*] offset in Re of entry (a*ndf)
   std::vector<uint8_t> n2e_nd;      // [*] nd = nen*ndf of that element
-  std::vector<int> n2e_fe;          // [*] FE index
+  std::vector<long long> n2e_fe;    // [*] GLOBAL FE index
   std::vector<uint8_t> n2e_loc;     // [*] local node a
   // node-level column lists: equations coupled to node n (sorted) = the pattern of each of
   // its free dofs' rows/columns
@@ -84,6 +107,14 @@ struct HostModel {
   int max_row = 0;                  // longest row
   long long ke_total = 0, re_total = 0, ngp = 0;
 
+  // --- interface exchange (nparts > 1) ---
+  std::vector<Peer> peers;          // ascending rank
+  std::vector<long long> pk_src, pk_dst;   // per outgoing matrix chunk: offset in Ke, offset in the send buffer
+  std::vector<long long> pr_src, pr_dst;   // per outgoing residual chunk
+  std::vector<uint8_t> pk_nd;              // nd of the chunk's element
+  long long send_k_total = 0, recv_k_total = 0, send_r_total = 0, recv_r_total = 0;
+  std::vector<int> part_fe;         // [ne_global] partition of every element (global FE order)
+
   std::string err;
 
   int add_nodes(int n, const int* tags, const double* c);
@@ -92,10 +123,11 @@ struct HostModel {
   int add_elements(int kind, int n, const int* tags, const int* conn, const int* mat_tags,
                    const double* par, int par_stride);
   int add_loads(int n, const int* tags, const double* vals);
-  int setup(int numberer, int soe_kind);
+  // part: nullptr (built-in recursive coordinate bisection) or [ne] ranks in FE order
+  int setup(int numberer, int soe_kind, int nparts = 1, int rank = 0, const int* part = nullptr);
   long long nnz() const { return ptr.empty() ? 0 : ptr.back(); }
   int nn() const { return (int)node_tag.size(); }
-  // addA location of element-matrix entries, FE elements [e0,e1)
+  // addA location of element-matrix entries, local FE elements [e0,e1); -1 = not owned here / dropped
   int scatter_map(long long e0, long long e1, long long* map) const;
 };
 
