@@ -249,7 +249,7 @@ def test_partitioned_ranks_reproduce_single_gpu_bitwise(nparts, numberer, soe):
             ptr, _ = m.pattern()
             for lr, q in enumerate(rows):
                 assert np.array_equal(A[ptr[lr]:ptr[lr + 1]], Ag[gptr[q]:gptr[q + 1]])
-        G.commit()
+        G.commit(); O.commit()
         for m in ranks:
             m.commit()
 
