@@ -32,7 +32,10 @@ struct GroupView {
   double* ht;           // J2: trial     epsilon_p (6) + xi   [7][ngp]
   double* sig;          // stress                              [nst][ngp]
   double* tan;          // J2: normal (6), c2, c3              [8][ngp]
-  double* Ke;           // [n][nd*nd]
+  const long long* kdst;  // [n][nen] destination of the rows of node a: >= 0 in KeN, < 0 -(x+1) in sendK
+  double* KeN;          // node-major element-tangent rows of the owned nodes
+  double* sendK;        // rows for nodes other ranks own (interface exchange send buffer)
+  int cps;              // columns per row in a slot (cp_stride)
   double* Re;           // [n][nd]
 };
 
@@ -392,16 +395,20 @@ __global__ void __launch_bounds__(BT_ELEMS * 8, 2) brick_tangent_kernel(GroupVie
         for (int q = 0; q < 3; q++) tile[(3 * k + q) * BT_TROW + 3 * J + p] = acc[J][p][q];
   }
   __syncwarp();
-  long long nlive = G.n - e0;
-  if (nlive > 4) nlive = 4;
-  if (nlive <= 0) return;
-  double* out = G.Ke + e0 * 576;
-  const int total = (int)nlive * 576;
+  // lane (s,k) fetches the destination of the rows of node k of element s; then the warp streams
+  // its 4 x 8 node chunks (3 rows x 24 columns each) out, 24 consecutive doubles per row
+  long long dst_l = 0;
+  if (live) dst_l = __ldg(G.kdst + e * 8 + k);
+  const int nlive = (int)((G.n - e0) < 4 ? (G.n - e0) : 4);
+  const int cps = G.cps;
 #pragma unroll 4
-  for (int i = lane; i < total; i += 32) {
+  for (int i = lane; i < nlive * 576; i += 32) {
     const int el = i / 576, off = i - el * 576;
-    const int row = off / 24, col = off - row * 24;
-    out[i] = wbase[el * BT_TILE + row * BT_TROW + col];
+    const int row = off / 24, col = off - row * 24;     // row = 3a + p
+    const int a = row / 3, p = row - 3 * a;
+    const long long d = __shfl_sync(0xffffffffu, dst_l, el * 8 + a);
+    double* base = d >= 0 ? G.KeN + d : G.sendK + (-d - 1);
+    base[p * cps + col] = wbase[el * BT_TILE + row * BT_TROW + col];
   }
 }
 
@@ -467,13 +474,24 @@ __global__ void __launch_bounds__(128) quad_tangent_kernel(GroupView G, const do
       K[2 * a + 1][1] += shp[1][a] * DB11 + shp[0][a] * DB21;
     }
   }
-  double* out = G.Ke + e * 64;
-  if (!transpose) {
+  // rows of node a go to that node's slot (node-major storage) or to the send buffer
+  const int cps = G.cps;
 #pragma unroll
-    for (int i = 0; i < 8; i++) { out[i * 8 + 2 * beta] = K[i][0]; out[i * 8 + 2 * beta + 1] = K[i][1]; }
-  } else {
+  for (int a = 0; a < 4; a++) {
+    if (!transpose) {
+      const long long d = __ldg(G.kdst + e * 4 + a);
+      double* base = d >= 0 ? G.KeN + d : G.sendK + (-d - 1);
+      base[2 * beta] = K[2 * a][0]; base[2 * beta + 1] = K[2 * a][1];
+      base[cps + 2 * beta] = K[2 * a + 1][0]; base[cps + 2 * beta + 1] = K[2 * a + 1][1];
+    }
+  }
+  if (transpose) {
+    // K^T: this lane's two columns become rows 2*beta, 2*beta+1 of the stored matrix, i.e. the
+    // two rows of node beta's slot
+    const long long d = __ldg(G.kdst + e * 4 + beta);
+    double* base = d >= 0 ? G.KeN + d : G.sendK + (-d - 1);
 #pragma unroll
-    for (int i = 0; i < 8; i++) { out[(2 * beta) * 8 + i] = K[i][0]; out[(2 * beta + 1) * 8 + i] = K[i][1]; }
+    for (int i = 0; i < 8; i++) { base[i] = K[i][0]; base[cps + i] = K[i][1]; }
   }
 }
 
@@ -485,9 +503,7 @@ struct AsmView {
   const int* row_of;          // [nn][ndf] local row of an owned free dof, else -1
   const long long* ptr;       // [nrows+1]
   const long long* n2e_ptr;   // [nn+1]
-  const long long* n2e_koff;  // [*]
   const long long* n2e_roff;  // [*]
-  const unsigned char* n2e_nd;
   const unsigned short* colpos;  // [*][cp_stride]
   const long long* ncol_ptr;  // [nn+1]
   const double* load;         // [nn][ndf]
@@ -500,8 +516,8 @@ struct AsmView {
 // the order IncrementalIntegrator::formTangent (IncrementalIntegrator.cpp:91-99) calls addA.
 // Every entry of A is written exactly once, so no zeroA pass is needed.
 template <int NDF>
-__global__ void __launch_bounds__(256, 2) assemble_A_kernel(AsmView V, const double* __restrict__ Ke,
-                                                            double* __restrict__ A) {
+__global__ void __launch_bounds__(256, 4) assemble_A_kernel(AsmView V, const double* __restrict__ KeN,
+                                                         double* __restrict__ A) {
   extern __shared__ double sacc[];  // [warps][NDF][max_row]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long n = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -518,24 +534,19 @@ __global__ void __launch_bounds__(256, 2) assemble_A_kernel(AsmView V, const dou
   if (t0 == t1) L = 1;  // a node with no element: its rows hold the (zero) diagonal only
   for (int c = lane; c < NDF * L; c += 32) acc[(c / L) * V.max_row + (c % L)] = 0.0;
   __syncwarp();
-  constexpr int CH = 8;  // adjacent elements whose rows are in flight together
+  const int cps = V.cp_stride;
+  const bool on = lane < cps;
+  constexpr int CH = 4;  // slots in flight together; the node's slots are one contiguous stream
   for (long long tb = t0; tb < t1; tb += CH) {
-    // lane c fetches the descriptor of slot tb+c; one round trip for all CH slots
-    long long koff_l = 0;
-    int nd_l = 0;
-    if (lane < CH && tb + lane < t1) { koff_l = __ldg(V.n2e_koff + tb + lane); nd_l = __ldg(V.n2e_nd + tb + lane); }
     double v[CH][NDF];
     unsigned short pos[CH];
 #pragma unroll
     for (int c = 0; c < CH; c++) {
-      const long long koff = __shfl_sync(0xffffffffu, koff_l, c);
-      const int nd = __shfl_sync(0xffffffffu, nd_l, c);
-      const bool on = lane < nd;                     // nd = 0 for slots past the end
-      // koff < 0: the element lives on another rank, its rows arrived in the receive buffer
-      const double* row = koff >= 0 ? Ke + koff : V.recvK + (-koff - 1);
-      pos[c] = on ? __ldg(V.colpos + (size_t)(tb + c) * V.cp_stride + lane) : (unsigned short)0xFFFF;
+      const long long t = tb + c;
+      const bool ok = on && t < t1;
+      pos[c] = ok ? __ldg(V.colpos + (size_t)t * cps + lane) : (unsigned short)0xFFFF;
 #pragma unroll
-      for (int p = 0; p < NDF; p++) v[c][p] = on ? __ldg(row + p * nd + lane) : 0.0;
+      for (int p = 0; p < NDF; p++) v[c][p] = ok ? __ldg(KeN + (size_t)t * (NDF * cps) + p * cps + lane) : 0.0;
     }
 #pragma unroll
     for (int c = 0; c < CH; c++) {   // FE_Element order: the order addA is called in
@@ -553,6 +564,18 @@ __global__ void __launch_bounds__(256, 2) assemble_A_kernel(AsmView V, const dou
     double* out = A + rp;
     for (int c = lane; c < L; c += 32) out[c] = acc[p * V.max_row + c];
   }
+}
+
+// interface exchange, receive side: rows that arrived from other ranks go to their slots
+__global__ void __launch_bounds__(256) unpack_rows_kernel(long long nchunks, const long long* __restrict__ src,
+                                                          const long long* __restrict__ dst, int chunk,
+                                                          const double* __restrict__ recv, double* __restrict__ KeN) {
+  const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c >= nchunks) return;
+  const double* s = recv + src[c];
+  double* d = KeN + dst[c];
+  for (int i = lane; i < chunk; i += 32) d[i] = s[i];
 }
 
 // formUnbalance: B = sum_e -(R_e)  (FE order)  +  lambda * P   (formElementResidual then
@@ -583,20 +606,8 @@ __global__ void incr_disp_kernel(long long ndof, const int* __restrict__ id, con
   if (r >= 0) U[i] += dU[r];
 }
 
-// interface exchange, send side: copy the rows of local element matrices (residual entries)
-// that belong to nodes another rank owns into the per-peer send buffer.  One warp per chunk.
-__global__ void __launch_bounds__(256) pack_rows_kernel(long long nchunks, const long long* __restrict__ src,
-                                                        const long long* __restrict__ dst,
-                                                        const unsigned char* __restrict__ nd, int ndf,
-                                                        const double* __restrict__ Ke, double* __restrict__ send) {
-  const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (c >= nchunks) return;
-  const int len = ndf * nd[c];
-  const double* s = Ke + src[c];
-  double* d = send + dst[c];
-  for (int i = lane; i < len; i += 32) d[i] = s[i];
-}
+// interface exchange, send side.  Element-tangent rows need no packing: the element kernel
+// writes them straight into the send buffer (GroupView::kdst < 0).  Residual entries are packed.
 __global__ void __launch_bounds__(256) pack_resid_kernel(long long nchunks, const long long* __restrict__ src,
                                                          const long long* __restrict__ dst, int ndf,
                                                          const double* __restrict__ Re, double* __restrict__ send) {
@@ -633,8 +644,7 @@ struct xb_model {
   int* dFail = nullptr;
   // interface exchange (nparts > 1)
   double *dSendK = nullptr, *dRecvK = nullptr, *dSendR = nullptr, *dRecvR = nullptr;
-  long long *dPkSrc = nullptr, *dPkDst = nullptr, *dPrSrc = nullptr, *dPrDst = nullptr;
-  unsigned char* dPkNd = nullptr;
+  long long *dPrSrc = nullptr, *dPrDst = nullptr, *dUkSrc = nullptr, *dUkDst = nullptr;
   ncclComm_t comm = nullptr;
   AsmView av{};
   double lambda = 0.0;
@@ -840,14 +850,14 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
   std::vector<double> mp(h.mats.size() * 8);
   for (size_t i = 0; i < h.mats.size(); i++) std::memcpy(&mp[i * 8], h.mats[i].par, sizeof(double) * 8);
   CU(dev_upload(m, &m->dMpar, mp));
-  CU(dev_alloc(m, &m->dKe, (size_t)h.ke_total));
+  CU(dev_alloc(m, &m->dKe, (size_t)h.kn_total));   // KeN: node-major element-tangent rows
   CU(dev_alloc(m, &m->dRe, (size_t)h.re_total));
   CU(dev_alloc(m, &m->dA, (size_t)h.nnz()));
   CU(dev_alloc(m, &m->dB, (size_t)h.nrows));
   CU(dev_alloc(m, &m->dTmp, (size_t)h.neq));
   CU(dev_alloc(m, &m->dFail, 1));
   CU(cudaMemset(m->dFail, 0, sizeof(int)));
-  CU(cudaMemset(m->dKe, 0, sizeof(double) * std::max<size_t>(h.ke_total, 1)));
+  CU(cudaMemset(m->dKe, 0, sizeof(double) * std::max<size_t>(h.kn_total, 1)));
   CU(cudaMemset(m->dRe, 0, sizeof(double) * std::max<size_t>(h.re_total, 1)));
 
   for (auto& g : h.groups) {
@@ -874,7 +884,9 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
       CU(cudaMemset(d.v.ht, 0, sizeof(double) * 7 * d.ngp));
       CU(cudaMemset(d.v.tan, 0, sizeof(double) * 8 * d.ngp));
     }
-    d.v.Ke = m->dKe + g.ke_off;
+    long long* kdst = nullptr;
+    CU(dev_upload(m, &kdst, g.kdst));
+    d.v.kdst = kdst; d.v.KeN = m->dKe; d.v.cps = h.cp_stride;
     d.v.Re = m->dRe + g.re_off;
     m->dg.push_back(d);
   }
@@ -889,23 +901,21 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
     CU(dev_alloc(m, &m->dRecvR, (size_t)h.recv_r_total));
     CU(cudaMemset(m->dRecvK, 0, sizeof(double) * std::max<size_t>(h.recv_k_total, 1)));
     CU(cudaMemset(m->dRecvR, 0, sizeof(double) * std::max<size_t>(h.recv_r_total, 1)));
-    CU(dev_upload(m, &m->dPkSrc, h.pk_src));
-    CU(dev_upload(m, &m->dPkDst, h.pk_dst));
+    CU(dev_upload(m, &m->dUkSrc, h.uk_src));
+    CU(dev_upload(m, &m->dUkDst, h.uk_dst));
     CU(dev_upload(m, &m->dPrSrc, h.pr_src));
     CU(dev_upload(m, &m->dPrDst, h.pr_dst));
-    CU(dev_upload(m, &m->dPkNd, h.pk_nd));
   }
   a.recvK = m->dRecvK; a.recvR = m->dRecvR;
-  long long *ptr = nullptr, *n2e_ptr = nullptr, *koff = nullptr, *roff = nullptr, *ncol_ptr = nullptr;
-  unsigned char* nd = nullptr; unsigned short* cp = nullptr;
+  for (auto& d : m->dg) d.v.sendK = m->dSendK;
+  long long *ptr = nullptr, *n2e_ptr = nullptr, *roff = nullptr, *ncol_ptr = nullptr;
+  unsigned short* cp = nullptr;
   CU(dev_upload(m, &ptr, h.ptr));
   CU(dev_upload(m, &n2e_ptr, h.n2e_ptr));
-  CU(dev_upload(m, &koff, h.n2e_koff));
   CU(dev_upload(m, &roff, h.n2e_roff));
-  CU(dev_upload(m, &nd, h.n2e_nd));
   CU(dev_upload(m, &cp, h.colpos));
   CU(dev_upload(m, &ncol_ptr, h.ncol_ptr));
-  a.ptr = ptr; a.n2e_ptr = n2e_ptr; a.n2e_koff = koff; a.n2e_roff = roff; a.n2e_nd = nd; a.colpos = cp;
+  a.ptr = ptr; a.n2e_ptr = n2e_ptr; a.n2e_roff = roff; a.colpos = cp;
   a.ncol_ptr = ncol_ptr;
 
   // the state determination of an untouched model: J2Plasticity's constructor runs
@@ -1025,13 +1035,10 @@ int xb_form_element_tangents(xb_model* m) {
 // ---- interface exchange -------------------------------------------------------------
 // which = 0: rows of element tangents, 1: element residual entries
 static int pack_for_peers(xb_model* m, int which) {
-  const long long nch = (long long)m->h.pk_src.size();
+  if (which == 0) return XB_OK;   // tangent rows were written into the send buffer by the element kernel
+  const long long nch = (long long)m->h.pr_src.size();
   if (nch == 0) return XB_OK;
-  if (which == 0) {
-    pack_rows_kernel<<<(unsigned)((nch * 32 + 255) / 256), 256, 0, m->stream>>>(nch, m->dPkSrc, m->dPkDst, m->dPkNd, m->h.ndf, m->dKe, m->dSendK);
-  } else {
-    pack_resid_kernel<<<(unsigned)((nch * m->h.ndf + 255) / 256), 256, 0, m->stream>>>(nch, m->dPrSrc, m->dPrDst, m->h.ndf, m->dRe, m->dSendR);
-  }
+  pack_resid_kernel<<<(unsigned)((nch * m->h.ndf + 255) / 256), 256, 0, m->stream>>>(nch, m->dPrSrc, m->dPrDst, m->h.ndf, m->dRe, m->dSendR);
   m->launches++;
   CU(cudaGetLastError());
   return XB_OK;
@@ -1105,6 +1112,11 @@ int xb_exchange_local(xb_model** ms, int n, int which) {
 int xb_assemble_tangent(xb_model* m, double* A) {
   NEED_DEVICE();
   CU(cudaSetDevice(m->device));
+  if (!m->h.uk_src.empty()) {   // rows received from other ranks -> their slots
+    const long long nch = (long long)m->h.uk_src.size();
+    unpack_rows_kernel<<<(unsigned)((nch * 32 + 255) / 256), 256, 0, m->stream>>>(nch, m->dUkSrc, m->dUkDst, m->h.chunk, m->dRecvK, m->dKe);
+    m->launches++;
+  }
   {
     const int warps = 8;
     const size_t sm = sizeof(double) * warps * m->h.ndf * m->av.max_row;
@@ -1125,7 +1137,7 @@ int xb_assemble_tangent(xb_model* m, double* A) {
     }
   }
   // element matrices + per-(node,element) position map in, A out
-  m->alg_bytes[4] = m->h.ke_total * 8 + (long long)m->h.colpos.size() * 2 + m->h.nnz() * 8;
+  m->alg_bytes[4] = m->h.kn_total * 8 + (long long)m->h.colpos.size() * 2 + m->h.nnz() * 8;
   // compulsory traffic of formTangent as a whole: tangent data, connectivity, coordinates in, A out
   long long bytes = m->h.nnz() * 8 + (long long)m->h.nn() * m->h.ndm * 8;
   for (auto& d : m->dg) bytes += d.ngp * 8 * (d.mat_kind == XB_MAT_J2PLASTICITY ? 8 : 0);
@@ -1230,10 +1242,18 @@ int xb_get_element_tangent(xb_model* m, long long e, double* K) {
   CU(cudaSetDevice(m->device));
   const xb::Group& g = m->h.groups[m->h.fe_group[e]];
   const xb::EleKind& k = xb::ele_kind(g.kind);
-  const int nd = k.nen * k.ndf;
-  std::vector<double> tmp((size_t)nd * nd);
+  const int nd = k.nen * k.ndf, cps = m->h.cp_stride;
+  std::vector<double> tmp((size_t)nd * nd), chunk((size_t)m->h.chunk);
   CU(cudaStreamSynchronize(m->stream));
-  CU(cudaMemcpy(tmp.data(), m->dKe + g.ke_off + (long long)m->h.fe_local[e] * nd * nd, sizeof(double) * nd * nd, cudaMemcpyDeviceToHost));
+  // the matrix is stored as one slot per node (node-major); rows of nodes another rank owns sit
+  // in the send buffer
+  for (int a = 0; a < k.nen; a++) {
+    const long long d = g.kdst[(size_t)m->h.fe_local[e] * k.nen + a];
+    const double* src = d >= 0 ? m->dKe + d : m->dSendK + (-d - 1);
+    CU(cudaMemcpy(chunk.data(), src, sizeof(double) * m->h.chunk, cudaMemcpyDeviceToHost));
+    for (int p = 0; p < k.ndf; p++)
+      for (int j = 0; j < nd; j++) tmp[(size_t)(a * k.ndf + p) * nd + j] = chunk[(size_t)p * cps + j];
+  }
   const bool tr = m->h.soe_kind == XB_SOE_SPARSE_GEN_COL;
   for (int i = 0; i < nd; i++)
     for (int j = 0; j < nd; j++) K[i * nd + j] = tr ? tmp[j * nd + i] : tmp[i * nd + j];

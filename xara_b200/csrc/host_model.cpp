@@ -435,8 +435,14 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
   const long long n2e_total = n2e_ptr[nl];
   n2e_koff.resize(n2e_total); n2e_roff.resize(n2e_total); n2e_nd.resize(n2e_total);
   n2e_fe.resize(n2e_total); n2e_loc.resize(n2e_total);
+  // node-major storage of the element-tangent rows: slot u lives at KeN[u*chunk]
+  chunk = ndf * cp_stride;
+  kn_total = n2e_total * chunk;
+  std::vector<Group>& WG = nparts == 1 ? groups : lgroups;   // the local groups being built
+  for (auto& g : WG) g.kdst.assign((size_t)g.n() * ele_kind(g.kind).nen, 0);
   // receive-buffer layout: per source rank, chunks in (owned node ascending, FE order)
   std::vector<long long> rk(nparts, 0), rr(nparts, 0), rc(nparts, 0);
+  std::vector<std::vector<long long>> in_kdst(nparts);
   for (int i = 0; i < nl; i++) if (owned[i]) {
     const int n = lnode[i];
     for (long long t = G.n2e_ptr[n], u = n2e_ptr[i]; t < G.n2e_ptr[n + 1]; t++, u++) {
@@ -445,23 +451,25 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
       const int a = G.n2e_loc[t];
       const long long nd = k->nen * k->ndf;
       n2e_fe[u] = e; n2e_loc[u] = (uint8_t)a; n2e_nd[u] = (uint8_t)nd;
+      n2e_koff[u] = u * chunk;
       const int src = part_fe[e];
       if (src == rank) {
         const int gi = G.fe_group[e];
         const long long l = nparts == 1 ? G.fe_local[e] : fe_local[g_fe_to_local[e]];
-        n2e_koff[u] = ke_off[gi] + l * nd * nd + (long long)a * k->ndf * nd;
+        WG[gi].kdst[(size_t)l * k->nen + a] = u * chunk;
         n2e_roff[u] = re_off[gi] + l * nd + (long long)a * k->ndf;
       } else {
-        n2e_koff[u] = rk[src]; n2e_roff[u] = rr[src];      // relative to that peer's block, fixed below
-        rk[src] += (long long)k->ndf * nd; rr[src] += k->ndf; rc[src]++;
+        in_kdst[src].push_back(u * chunk);
+        n2e_roff[u] = rr[src];      // relative to that peer's block, fixed below
+        rk[src] += chunk; rr[src] += k->ndf; rc[src]++;
       }
     }
   }
   // send side: for every other rank s, the chunks of MY elements at nodes s owns, enumerated the
   // way s enumerates them (its owned nodes ascending, global FE order)
   std::vector<long long> sk(nparts, 0), sr(nparts, 0), sc(nparts, 0);
-  std::vector<std::vector<long long>> out_ksrc(nparts), out_rsrc(nparts);
-  std::vector<std::vector<uint8_t>> out_nd(nparts);
+  struct Out { int gi; long long l; int a, nen; long long rsrc; };
+  std::vector<std::vector<Out>> outs(nparts);
   if (nparts > 1) {
     for (int i = 0; i < nl; i++) {
       const int n = lnode[i];
@@ -473,40 +481,37 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
         const EleKind* k; G.conn_of(e, &k);
         const int a = G.n2e_loc[t], gi = G.fe_group[e];
         const long long nd = k->nen * k->ndf, l = fe_local[g_fe_to_local[e]];
-        out_ksrc[s].push_back(ke_off[gi] + l * nd * nd + (long long)a * k->ndf * nd);
-        out_rsrc[s].push_back(re_off[gi] + l * nd + (long long)a * k->ndf);
-        out_nd[s].push_back((uint8_t)nd);
-        sk[s] += (long long)k->ndf * nd; sr[s] += k->ndf; sc[s]++;
+        outs[s].push_back({gi, l, a, k->nen, re_off[gi] + l * nd + (long long)a * k->ndf});
+        sk[s] += chunk; sr[s] += k->ndf; sc[s]++;
       }
     }
   }
-  peers.clear(); pk_src.clear(); pk_dst.clear(); pr_src.clear(); pr_dst.clear(); pk_nd.clear();
+  peers.clear(); pr_src.clear(); pr_dst.clear(); uk_src.clear(); uk_dst.clear();
   send_k_total = recv_k_total = send_r_total = recv_r_total = 0;
-  std::vector<long long> recv_k_base(nparts, 0), recv_r_base(nparts, 0);
+  std::vector<long long> recv_r_base(nparts, 0);
   for (int s = 0; s < nparts; s++) {
     if (s == rank || (sc[s] == 0 && rc[s] == 0)) continue;
     Peer p; p.rank = s;
     p.send_k = sk[s]; p.send_r = sr[s]; p.recv_k = rk[s]; p.recv_r = rr[s];
     p.chunks_out = sc[s]; p.chunks_in = rc[s];
     p.send_k_base = send_k_total; p.send_r_base = send_r_total; p.recv_k_base = recv_k_total; p.recv_r_base = recv_r_total;
-    recv_k_base[s] = recv_k_total; recv_r_base[s] = recv_r_total;
+    recv_r_base[s] = recv_r_total;
     long long dk = send_k_total, dr = send_r_total;
-    for (size_t c = 0; c < out_ksrc[s].size(); c++) {
-      pk_src.push_back(out_ksrc[s][c]); pk_dst.push_back(dk); pk_nd.push_back(out_nd[s][c]);
-      pr_src.push_back(out_rsrc[s][c]); pr_dst.push_back(dr);
-      dk += (long long)ndf * out_nd[s][c]; dr += ndf;
+    for (const Out& o : outs[s]) {
+      WG[o.gi].kdst[(size_t)o.l * o.nen + o.a] = -(dk + 1);     // the element kernel writes straight into the send buffer
+      pr_src.push_back(o.rsrc); pr_dst.push_back(dr);
+      dk += chunk; dr += ndf;
     }
+    long long rkpos = recv_k_total;
+    for (long long d : in_kdst[s]) { uk_src.push_back(rkpos); uk_dst.push_back(d); rkpos += chunk; }
     send_k_total += sk[s]; send_r_total += sr[s]; recv_k_total += rk[s]; recv_r_total += rr[s];
     peers.push_back(p);
   }
-  // remote slots: absolute offset into the receive buffers, encoded as -(x+1)
+  // remote residual slots: absolute offset into the receive buffer, encoded as -(x+1)
   if (nparts > 1)
     for (long long u = 0; u < n2e_total; u++) {
       const int src = part_fe[n2e_fe[u]];
-      if (src != rank) {
-        n2e_koff[u] = -(recv_k_base[src] + n2e_koff[u] + 1);
-        n2e_roff[u] = -(recv_r_base[src] + n2e_roff[u] + 1);
-      }
+      if (src != rank) n2e_roff[u] = -(recv_r_base[src] + n2e_roff[u] + 1);
     }
 
   // ---- DOF graph -> sparse pattern of the owned rows.  Every free dof of node n is coupled

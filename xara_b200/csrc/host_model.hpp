@@ -42,7 +42,10 @@ struct Group {
   std::vector<int> conn;     // [n][nen] node TAGS until setup(), LOCAL node indices after
   std::vector<int> mat;      // [n] material index into HostModel::mats
   std::vector<double> par;   // [n][npar]
-  long long ke_off = 0;      // offset (doubles) of this group's element matrices in the Ke buffer
+  std::vector<long long> kdst;  // [n][nen] where the rows of node a of element l go: >= 0 offset of the
+                                //   slot in the node-major buffer KeN (node owned here), < 0 offset
+                                //   -(x+1) in the send buffer (node owned by another rank)
+  long long ke_off = 0;      // (legacy element-major offset; sizes the residual bookkeeping)
   long long re_off = 0;      // offset (doubles) of this group's element residuals
   long long gp_off = 0;      // first Gauss point (for reporting)
   long long n() const { return (long long)tag.size(); }
@@ -89,10 +92,13 @@ struct HostModel {
   std::vector<int> idx;             // [nnz]     rowA / colA (GLOBAL equation numbers)
   // node -> FE elements, GLOBAL FE order within a node (this IS the reference's addA/addB
   // accumulation order for every entry owned by the node's equations).  Only owned nodes
-  // carry slots.  A slot whose element lives on another rank reads the received rows:
-  // koff / roff < 0 encode offset -(x+1) into the receive buffers.
+  // carry slots.  Element-tangent rows are stored NODE-MAJOR: slot t of the list occupies
+  // KeN[t*chunk ...] (ndf rows x cp_stride columns), written directly by the element kernel
+  // (or copied from the receive buffer when the element lives on another rank), so a node's
+  // rows are one contiguous stream.  Residual entries of remote elements are read from the
+  // receive buffer: roff < 0 encodes offset -(x+1).
   std::vector<long long> n2e_ptr;   // [nn+1]
-  std::vector<long long> n2e_koff;  // [*] offset in Ke of row (a*ndf) of that element's matrix
+  std::vector<long long> n2e_koff;  // [*] offset of the slot in KeN (= slot index * chunk)
   std::vector<long long> n2e_roff;  // [*] offset in Re of entry (a*ndf)
   std::vector<uint8_t> n2e_nd;      // [*] nd = nen*ndf of that element
   std::vector<long long> n2e_fe;    // [*] GLOBAL FE index
@@ -106,12 +112,13 @@ struct HostModel {
                                     //   inside node n's column list, 0xFFFF if constrained
   int max_row = 0;                  // longest row
   long long ke_total = 0, re_total = 0, ngp = 0;
+  int chunk = 0;                    // doubles per slot: ndf rows x cp_stride columns
+  long long kn_total = 0;           // doubles in KeN (node-major element rows of the owned nodes)
+  std::vector<long long> uk_src, uk_dst;   // received matrix chunk -> its slot in KeN
 
   // --- interface exchange (nparts > 1) ---
   std::vector<Peer> peers;          // ascending rank
-  std::vector<long long> pk_src, pk_dst;   // per outgoing matrix chunk: offset in Ke, offset in the send buffer
-  std::vector<long long> pr_src, pr_dst;   // per outgoing residual chunk
-  std::vector<uint8_t> pk_nd;              // nd of the chunk's element
+  std::vector<long long> pr_src, pr_dst;   // per outgoing residual chunk: offset in Re, offset in the send buffer
   long long send_k_total = 0, recv_k_total = 0, send_r_total = 0, recv_r_total = 0;
   std::vector<int> part_fe;         // [ne_global] partition of every element (global FE order)
 
