@@ -401,14 +401,20 @@ __global__ void __launch_bounds__(BT_ELEMS * 8, 2) brick_tangent_kernel(GroupVie
   if (live) dst_l = __ldg(G.kdst + e * 8 + k);
   const int nlive = (int)((G.n - e0) < 4 ? (G.n - e0) : 4);
   const int cps = G.cps;
-#pragma unroll 4
-  for (int i = lane; i < nlive * 576; i += 32) {
-    const int el = i / 576, off = i - el * 576;
-    const int row = off / 24, col = off - row * 24;     // row = 3a + p
-    const int a = row / 3, p = row - 3 * a;
-    const long long d = __shfl_sync(0xffffffffu, dst_l, el * 8 + a);
-    double* base = d >= 0 ? G.KeN + d : G.sendK + (-d - 1);
-    base[p * cps + col] = wbase[el * BT_TILE + row * BT_TROW + col];
+#pragma unroll
+  for (int el = 0; el < 4; el++) {
+    if (el >= nlive) break;
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      const long long d = __shfl_sync(0xffffffffu, dst_l, el * 8 + a);
+      if (lane < 24) {
+        double* base = (d >= 0 ? G.KeN + d : G.sendK + (-d - 1)) + lane;
+        const double* t = wbase + el * BT_TILE + (3 * a) * BT_TROW + lane;
+        base[0] = t[0];
+        base[cps] = t[BT_TROW];
+        base[2 * cps] = t[2 * BT_TROW];
+      }
+    }
   }
 }
 
@@ -516,7 +522,7 @@ struct AsmView {
 // the order IncrementalIntegrator::formTangent (IncrementalIntegrator.cpp:91-99) calls addA.
 // Every entry of A is written exactly once, so no zeroA pass is needed.
 template <int NDF>
-__global__ void __launch_bounds__(256, 4) assemble_A_kernel(AsmView V, const double* __restrict__ KeN,
+__global__ void __launch_bounds__(256, 3) assemble_A_kernel(AsmView V, const double* __restrict__ KeN,
                                                          double* __restrict__ A) {
   extern __shared__ double sacc[];  // [warps][NDF][max_row]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
