@@ -311,6 +311,8 @@ __global__ void __launch_bounds__(BT_ELEMS * 8, 2) brick_tangent_kernel(GroupVie
   const bool live = e_raw < G.n;
   const long long e = live ? e_raw : G.n - 1;
   const long long ngp = G.n * 8;
+  // destination of the rows of node k of element s (needed only in phase C: requested now)
+  const long long dst_l = live ? __ldg(G.kdst + e * 8 + k) : 0;
   {
     const int* c = G.conn + e * 8;
     double xl[3][8];
@@ -397,22 +399,26 @@ __global__ void __launch_bounds__(BT_ELEMS * 8, 2) brick_tangent_kernel(GroupVie
   __syncwarp();
   // lane (s,k) fetches the destination of the rows of node k of element s; then the warp streams
   // its 4 x 8 node chunks (3 rows x 24 columns each) out, 24 consecutive doubles per row
-  long long dst_l = 0;
-  if (live) dst_l = __ldg(G.kdst + e * 8 + k);
   const int nlive = (int)((G.n - e0) < 4 ? (G.n - e0) : 4);
   const int cps = G.cps;
 #pragma unroll
   for (int el = 0; el < 4; el++) {
     if (el >= nlive) break;
+    // 4 node chunks at a time: 12 shared loads in flight, then 12 row stores (192 B each)
 #pragma unroll
-    for (int a = 0; a < 8; a++) {
-      const long long d = __shfl_sync(0xffffffffu, dst_l, el * 8 + a);
+    for (int a0 = 0; a0 < 8; a0 += 4) {
+      double v[4][3];
+      double* base[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const long long d = __shfl_sync(0xffffffffu, dst_l, el * 8 + a0 + u);
+        base[u] = (d >= 0 ? G.KeN + d : G.sendK + (-d - 1)) + lane;
+        const double* t = wbase + el * BT_TILE + (3 * (a0 + u)) * BT_TROW + lane;
+        if (lane < 24) { v[u][0] = t[0]; v[u][1] = t[BT_TROW]; v[u][2] = t[2 * BT_TROW]; }
+      }
       if (lane < 24) {
-        double* base = (d >= 0 ? G.KeN + d : G.sendK + (-d - 1)) + lane;
-        const double* t = wbase + el * BT_TILE + (3 * a) * BT_TROW + lane;
-        base[0] = t[0];
-        base[cps] = t[BT_TROW];
-        base[2 * cps] = t[2 * BT_TROW];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { base[u][0] = v[u][0]; base[u][cps] = v[u][1]; base[u][2 * cps] = v[u][2]; }
       }
     }
   }
