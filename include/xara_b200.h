@@ -38,11 +38,20 @@ enum {
   XB_MAT_J2PLASTICITY = 1       /* par = K, G, sig0, sigInf, delta, H, eta (J2Plasticity.h:47) */
 };
 
+/* uniaxialMaterial kinds (fibres of a fibre section) */
+enum {
+  XB_UNI_STEEL02 = 0,   /* material/uniaxial/steel/Steel02.h:47: Fy,E0,b,R0,cR1,cR2,a1,a2,a3,a4[,sigInit] */
+  XB_UNI_CONCRETE02 = 1 /* material/uniaxial/concrete/Concrete02.cpp:93: fc,epsc0,fcu,epscu,rat,ft,Ets     */
+};
+
 /* element kinds */
 enum {
   XB_ELE_STDBRICK = 0,    /* element/Brick/Brick.cpp, 8 nodes x 3 dof, 2x2x2 Gauss; par = b1,b2,b3 */
-  XB_ELE_FOURNODEQUAD = 1 /* element/Plane/FourNodeQuad.cpp, 4 nodes x 2 dof, 2x2 Gauss;
+  XB_ELE_FOURNODEQUAD = 1,/* element/Plane/FourNodeQuad.cpp, 4 nodes x 2 dof, 2x2 Gauss;
                              par = thickness, type(0 PlaneStrain), pressure(=0), rho, b1, b2        */
+  XB_ELE_FORCEBEAMCOLUMN2D = 2 /* element/Frame/Other/Force/ForceBeamColumn2d.cpp, 2 nodes x 3 dof, Lobatto
+                             integration, Linear transformation; mat_tags name the fibre section;
+                             par = nIP, maxIters, tol (one section/nIP/maxIters/tol per call)          */
 };
 
 /* DOF numberers (analysis/numberer) */
@@ -75,6 +84,11 @@ int xb_add_nodes(xb_model*, int n, const int* tags, const double* crd);
 int xb_add_sp(xb_model*, int n, const int* node_tags, const int* dofs);
 /* OPS nDMaterial command; par has npar doubles in the order listed at the kind */
 int xb_add_nd_material(xb_model*, int tag, int kind, const double* par, int npar);
+/* uniaxialMaterial Steel02 | Concrete02 (runtime/commands/modeling/uniaxial.cpp) */
+int xb_add_uniaxial_material(xb_model*, int tag, int kind, const double* par, int npar);
+/* section Fiber -> FiberSection2d (material/section/FiberSection2d.cpp:99 addFiber): nf fibres
+ * (y, A, uniaxial material tag) in the order given; the centroid is computed as the command does */
+int xb_add_fiber_section(xb_model*, int tag, int nf, const double* y, const double* A, const int* mat_tags);
 /* Domain::addElement (Domain.cpp:442) for n elements of one kind; conn is [n][nen] node
  * tags, mat_tags [n], par [n][par_stride] (par_stride >= the kind's parameter count).
  * All materials referenced by one call must be of one nDMaterial kind. */

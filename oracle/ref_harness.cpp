@@ -42,6 +42,12 @@
 
 #include <Brick.h>
 #include <FourNodeQuad.h>
+#include <Steel02.h>
+#include <Concrete02.h>
+#include <FiberSection2d.h>
+#include <ForceBeamColumn2d.h>
+#include <LinearCrdTransf2d.h>
+#include <LobattoBeamIntegration.h>
 
 #include <AnalysisModel.h>
 #include <PlainHandler.h>
@@ -148,6 +154,8 @@ struct RefModel {
   int ndm, ndf;
   Domain* domain = nullptr;
   std::map<int, NDMaterial*> ndmats;
+  std::map<int, UniaxialMaterial*> unimats;
+  std::map<int, FiberSection2d*> sections2d;
   AnalysisModel* amodel = nullptr;
   PlainHandler* handler = nullptr;
   DOF_Numberer* numberer = nullptr;
@@ -215,6 +223,51 @@ int ref_add_quad(void* h, int tag, const int* nd, int matTag, double thick, int 
   Element* e = new FourNodeQuad(tag, nodes, *copy, thick, pressure, rho, b[0], b[1]);
   delete copy;
   return m->domain->addElement(e) ? 0 : -1;
+}
+
+// kind 0: Steel02 (Fy,E0,b,R0,cR1,cR2,a1,a2,a3,a4,sigInit); kind 1: Concrete02 (fc,epsc0,fcu,epscu,rat,ft,Ets)
+static UniaxialMaterial* make_uniaxial(int tag, int kind, const double* p) {
+  if (kind == 0) return new Steel02(tag, p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8], p[9], p[10]);
+  if (kind == 1) return new Concrete02(tag, p[0], p[1], p[2], p[3], p[4], p[5], p[6]);
+  return nullptr;
+}
+int ref_add_uniaxial(void* h, int tag, int kind, const double* p) {
+  RefModel* m = (RefModel*)h;
+  UniaxialMaterial* u = make_uniaxial(tag, kind, p);
+  if (!u) return -1;
+  m->unimats[tag] = u;
+  return 0;
+}
+// section Fiber (FiberSection2d, centroid computed as the section command does by default)
+int ref_add_fiber_section(void* h, int tag, int nf, const double* y, const double* A, const int* matTags) {
+  RefModel* m = (RefModel*)h;
+  FiberSection2d* s = new FiberSection2d(tag, nf, true);
+  for (int i = 0; i < nf; i++)
+    if (s->addFiber(*m->unimats.at(matTags[i]), A[i], y[i]) < 0) return -1;
+  m->sections2d[tag] = s;
+  return 0;
+}
+// element forceBeamColumn (2D): Lobatto integration, Linear transformation, nIP copies of one section
+int ref_add_force_beam2d(void* h, int tag, const int* nd, int secTag, int nip, int maxIters, double tol) {
+  RefModel* m = (RefModel*)h;
+  std::vector<SectionForceDeformation*> secs(nip, m->sections2d.at(secTag));
+  LobattoBeamIntegration bi;
+  LinearCrdTransf2d transf(tag);
+  Element* e = new ForceBeamColumn2d(tag, nd[0], nd[1], nip, secs.data(), bi, transf, 0.0, maxIters, tol);
+  return m->domain->addElement(e) ? 0 : -1;
+}
+
+int ref_uni_path(int kind, const double* p, int n, const double* strains, const int* commit,
+                 double* stress, double* tangent) {
+  UniaxialMaterial* mat = make_uniaxial(1, kind, p);
+  if (!mat) return -1;
+  for (int s = 0; s < n; s++) {
+    if (mat->setTrialStrain(strains[s]) < 0) return -2;
+    stress[s] = mat->getStress(); tangent[s] = mat->getTangent();
+    if (commit[s]) mat->commitState();
+  }
+  delete mat;
+  return 0;
 }
 
 int ref_add_load(void* h, int nodeTag, const double* vals) {

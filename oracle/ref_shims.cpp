@@ -89,6 +89,7 @@ void dgemm_(const char* ta, const char* tb, int* M, int* N, int* K, double* alph
 static void never(const char* what) { fprintf(stderr, "oracle/ref_shims: %s reached\n", what); abort(); }
 int OPS_GetNumRemainingInputArgs() { never("OPS_GetNumRemainingInputArgs"); return 0; }
 int ops_getdoubleinput_(int*, double*) { never("OPS_GetDoubleInput"); return -1; }
+int ops_getintinput_(int*, int*) { never("OPS_GetIntInput"); return -1; }
 const char* ops_getstring() { never("OPS_GetString"); return ""; }
 
 // DataOutputFileHandler.cpp does not compile stand-alone (missing class tag);

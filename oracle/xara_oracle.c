@@ -20,7 +20,8 @@
 /* ------------------------------------------------------------------------ */
 /* material kinds / element kinds shared with tests (mirrors include/xara_b200.h) */
 enum { ORC_MAT_ELASTIC_ISOTROPIC = 0, ORC_MAT_J2 = 1 };
-enum { ORC_ELE_BRICK = 0, ORC_ELE_QUAD = 1 };
+enum { ORC_ELE_BRICK = 0, ORC_ELE_QUAD = 1, ORC_ELE_FBC2D = 2 };
+enum { ORC_UNI_STEEL02 = 0, ORC_UNI_CONCRETE02 = 1 };
 enum { ORC_ND_3D = 0, ORC_ND_PLANE_STRAIN = 1 };
 
 /* ======================================================================== */
@@ -362,6 +363,451 @@ static void shp3d(const double xn[3], double* xsj, double shp[4][8], const doubl
 }
 
 /* ======================================================================== */
+/* Steel02  (SRC/material/uniaxial/steel/Steel02.cpp)                         */
+/* ======================================================================== */
+#include <float.h>
+typedef struct {
+  int kind;
+  /* Steel02 parameters (Steel02.h:47) / Concrete02 parameters (Concrete02.cpp:93) */
+  double Fy, E0, b, R0, cR1, cR2, a1, a2, a3, a4, sigini;
+  double fc, epsc0, fcu, epscu, rat, ft, Ets;
+  /* Steel02 history */
+  double epsminP, epsmaxP, epsplP, epss0P, sigs0P, epssrP, sigsrP; int konP;
+  double epsmin, epsmax, epspl, epss0, sigs0, epsr, sigr; int kon;
+  /* Concrete02 history */
+  double ecminP, deptP, ecmin, dept;
+  /* common */
+  double eP, sigP, epsP, e, sig, eps;
+} OrcUni;
+
+/* Steel02::revertToStart, Steel02.cpp:70-104 ; Concrete02 constructor, Concrete02.cpp:93-112 */
+static void uni_init(OrcUni* m, int kind, const double* p) {
+  memset(m, 0, sizeof *m);
+  m->kind = kind;
+  if (kind == ORC_UNI_STEEL02) {
+    m->Fy = p[0]; m->E0 = p[1]; m->b = p[2]; m->R0 = p[3]; m->cR1 = p[4]; m->cR2 = p[5];
+    m->a1 = p[6]; m->a2 = p[7]; m->a3 = p[8]; m->a4 = p[9]; m->sigini = p[10];
+    m->eP = m->E0; m->epsP = 0.0; m->sigP = 0.0; m->sig = 0.0; m->eps = 0.0; m->e = m->E0;
+    m->konP = 0; m->epsmaxP = m->Fy / m->E0; m->epsminP = -m->epsmaxP;
+    m->epsplP = 0.0; m->epss0P = 0.0; m->sigs0P = 0.0; m->epssrP = 0.0; m->sigsrP = 0.0;
+    if (m->sigini != 0.0) { m->epsP = m->sigini / m->E0; m->sigP = m->sigini; }
+  } else {
+    m->fc = p[0]; m->epsc0 = p[1]; m->fcu = p[2]; m->epscu = p[3]; m->rat = p[4]; m->ft = p[5]; m->Ets = p[6];
+    m->ecminP = 0.0; m->deptP = 0.0;
+    if (m->fc > 0) m->fc = -m->fc;
+    if (m->epsc0 > 0) m->epsc0 = -m->epsc0;
+    if (m->fcu > 0) m->fcu = -m->fcu;
+    if (m->epscu > 0) m->epscu = -m->epscu;
+    m->eP = 2.0 * m->fc / m->epsc0; m->epsP = 0.0; m->sigP = 0.0; m->eps = 0.0; m->sig = 0.0;
+    m->e = 2.0 * m->fc / m->epsc0;
+  }
+}
+static double uni_initial_tangent(const OrcUni* m) {
+  return m->kind == ORC_UNI_STEEL02 ? m->E0 : 2.0 * m->fc / m->epsc0;   /* Steel02.cpp:107, Concrete02.cpp:161 */
+}
+
+/* Steel02::setTrialStrain, Steel02.cpp:113-245 */
+static int steel02_set_trial(OrcUni* m, double trialStrain) {
+  const double Fy = m->Fy, E0 = m->E0, b = m->b;
+  double Esh = b * E0;
+  double epsy = Fy / E0;
+  if (m->sigini != 0.0) { double epsini = m->sigini / E0; m->eps = trialStrain + epsini; }
+  else m->eps = trialStrain;
+  double deps = m->eps - m->epsP;
+  m->epsmax = m->epsmaxP; m->epsmin = m->epsminP; m->epspl = m->epsplP; m->epss0 = m->epss0P;
+  m->sigs0 = m->sigs0P; m->epsr = m->epssrP; m->sigr = m->sigsrP; m->kon = m->konP;
+  if (m->kon == 0 || m->kon == 3) {
+    if (fabs(deps) < 10.0 * DBL_EPSILON) {
+      m->e = E0; m->sig = m->sigini; m->kon = 3;
+      return 0;
+    } else {
+      m->epsmax = epsy; m->epsmin = -epsy;
+      if (deps < 0.0) { m->kon = 2; m->epss0 = m->epsmin; m->sigs0 = -Fy; m->epspl = m->epsmin; }
+      else { m->kon = 1; m->epss0 = m->epsmax; m->sigs0 = Fy; m->epspl = m->epsmax; }
+    }
+  }
+  if (m->kon == 2 && deps > 0.0) {
+    m->kon = 1; m->epsr = m->epsP; m->sigr = m->sigP;
+    if (m->epsP < m->epsmin) m->epsmin = m->epsP;
+    double d1 = (m->epsmax - m->epsmin) / (2.0 * (m->a4 * epsy));
+    double shft = 1.0 + m->a3 * pow(d1, 0.8);
+    m->epss0 = (Fy * shft - Esh * epsy * shft - m->sigr + E0 * m->epsr) / (E0 - Esh);
+    m->sigs0 = Fy * shft + Esh * (m->epss0 - epsy * shft);
+    m->epspl = m->epsmax;
+  } else if (m->kon == 1 && deps < 0.0) {
+    m->kon = 2; m->epsr = m->epsP; m->sigr = m->sigP;
+    if (m->epsP > m->epsmax) m->epsmax = m->epsP;
+    double d1 = (m->epsmax - m->epsmin) / (2.0 * (m->a2 * epsy));
+    double shft = 1.0 + m->a1 * pow(d1, 0.8);
+    m->epss0 = (-Fy * shft + Esh * epsy * shft - m->sigr + E0 * m->epsr) / (E0 - Esh);
+    m->sigs0 = -Fy * shft + Esh * (m->epss0 + epsy * shft);
+    m->epspl = m->epsmin;
+  }
+  double xi = fabs((m->epspl - m->epss0) / epsy);
+  double R = m->R0 * (1.0 - (m->cR1 * xi) / (m->cR2 + xi));
+  double epsrat = (m->eps - m->epsr) / (m->epss0 - m->epsr);
+  double dum1 = 1.0 + pow(fabs(epsrat), R);
+  double dum2 = pow(dum1, (1 / R));
+  m->sig = b * epsrat + (1.0 - b) * epsrat / dum2;
+  m->sig = m->sig * (m->sigs0 - m->sigr) + m->sigr;
+  m->e = b + (1.0 - b) / (dum1 * dum2);
+  m->e = m->e * (m->sigs0 - m->sigr) / (m->epss0 - m->epsr);
+  return 0;
+}
+
+/* Concrete02::Tens_Envlp / Compr_Envlp, Concrete02.cpp:421-498 */
+static void c02_tens(const OrcUni* m, double epsc, double* sigc, double* Ect) {
+  double Ec0 = 2.0 * m->fc / m->epsc0;
+  double eps0 = m->ft / Ec0;
+  double epsu = m->ft * (1.0 / m->Ets + 1.0 / Ec0);
+  if (epsc <= eps0) { *sigc = epsc * Ec0; *Ect = Ec0; }
+  else if (epsc <= epsu) { *Ect = -m->Ets; *sigc = m->ft - m->Ets * (epsc - eps0); }
+  else { *Ect = 1.0e-10; *sigc = 0.0; }
+}
+static void c02_compr(const OrcUni* m, double epsc, double* sigc, double* Ect) {
+  double Ec0 = 2.0 * m->fc / m->epsc0;
+  double ratLocal = epsc / m->epsc0;
+  if (epsc >= m->epsc0) { *sigc = m->fc * ratLocal * (2.0 - ratLocal); *Ect = Ec0 * (1.0 - ratLocal); }
+  else if (epsc > m->epscu) {
+    *sigc = (m->fcu - m->fc) * (epsc - m->epsc0) / (m->epscu - m->epsc0) + m->fc;
+    *Ect = (m->fcu - m->fc) / (m->epscu - m->epsc0);
+  } else { *sigc = m->fcu; *Ect = 1.0e-10; }
+}
+/* Concrete02::setTrialStrain, Concrete02.cpp:167-270 */
+static int concrete02_set_trial(OrcUni* m, double trialStrain) {
+  double ec0 = m->fc * 2. / m->epsc0;
+  m->ecmin = m->ecminP; m->dept = m->deptP;
+  m->eps = trialStrain;
+  double deps = m->eps - m->epsP;
+  if (fabs(deps) < DBL_EPSILON) return 0;
+  if (m->eps < m->ecmin) {
+    c02_compr(m, m->eps, &m->sig, &m->e);
+    m->ecmin = m->eps;
+  } else {
+    double epsr = (m->fcu - m->rat * ec0 * m->epscu) / (ec0 * (1.0 - m->rat));
+    double sigmr = ec0 * epsr;
+    double sigmm, dumy;
+    c02_compr(m, m->ecmin, &sigmm, &dumy);
+    double er = (sigmm - sigmr) / (m->ecmin - epsr);
+    double ept = m->ecmin - sigmm / er;
+    if (m->eps <= ept) {
+      double sigmin = sigmm + er * (m->eps - m->ecmin);
+      double sigmax = er * .5f * (m->eps - ept);
+      m->sig = m->sigP + ec0 * deps;
+      m->e = ec0;
+      if (m->sig <= sigmin) { m->sig = sigmin; m->e = er; }
+      if (m->sig >= sigmax) { m->sig = sigmax; m->e = 0.5 * er; }
+    } else {
+      double epn = ept + m->dept;
+      double sicn;
+      if (m->eps <= epn) {
+        c02_tens(m, m->dept, &sicn, &m->e);
+        if (m->dept != 0.0) m->e = sicn / m->dept; else m->e = ec0;
+        m->sig = m->e * (m->eps - ept);
+      } else {
+        double epstmp = m->eps - ept;
+        c02_tens(m, epstmp, &m->sig, &m->e);
+        m->dept = m->eps - ept;
+      }
+    }
+  }
+  return 0;
+}
+static int uni_set_trial(OrcUni* m, double strain) {
+  return m->kind == ORC_UNI_STEEL02 ? steel02_set_trial(m, strain) : concrete02_set_trial(m, strain);
+}
+/* commitState / revertToLastCommit: Steel02.cpp:248-285, Concrete02.cpp:292-320 */
+static void uni_commit(OrcUni* m) {
+  if (m->kind == ORC_UNI_STEEL02) {
+    m->epsminP = m->epsmin; m->epsmaxP = m->epsmax; m->epsplP = m->epspl; m->epss0P = m->epss0;
+    m->sigs0P = m->sigs0; m->epssrP = m->epsr; m->sigsrP = m->sigr; m->konP = m->kon;
+  } else { m->ecminP = m->ecmin; m->deptP = m->dept; }
+  m->eP = m->e; m->sigP = m->sig; m->epsP = m->eps;
+}
+static void uni_revert(OrcUni* m) {
+  if (m->kind == ORC_UNI_STEEL02) {
+    m->epsmin = m->epsminP; m->epsmax = m->epsmaxP; m->epspl = m->epsplP; m->epss0 = m->epss0P;
+    m->sigs0 = m->sigs0P; m->epsr = m->epssrP; m->sigr = m->sigsrP; m->kon = m->konP;
+  } else { m->ecmin = m->ecminP; m->dept = m->deptP; }
+  m->e = m->eP; m->sig = m->sigP; m->eps = m->epsP;
+}
+
+/* uniaxial strain path; mirrors ref_uni_path in ref_harness.cpp */
+int orc_uni_path(int kind, const double* p, int n, const double* strains, const int* commit,
+                 double* stress, double* tangent) {
+  OrcUni m; uni_init(&m, kind, p);
+  for (int s = 0; s < n; s++) {
+    if (uni_set_trial(&m, strains[s]) < 0) return -1;
+    stress[s] = m.sig; tangent[s] = m.e;
+    if (commit[s]) uni_commit(&m);
+  }
+  return 0;
+}
+
+/* ======================================================================== */
+/* FiberSection2d (SRC/material/section/FiberSection2d.cpp)                   */
+/* ======================================================================== */
+typedef struct {
+  int nf; double* y; double* A; OrcUni* mat; double yBar;
+  double e[2], s[2], k[4];     /* kData column-major 2x2: k[0]=k00 k[1]=k10 k[2]=k01 k[3]=k11 */
+} OrcSec;
+
+/* FiberSection2d::setTrialSectionDeformation, FiberSection2d.cpp:225-262 */
+static int sec_set_trial(OrcSec* S, const double* d) {
+  S->e[0] = d[0]; S->e[1] = d[1];
+  S->k[0] = S->k[1] = S->k[2] = S->k[3] = 0.0; S->s[0] = S->s[1] = 0.0;
+  const double d0 = d[0], d1 = d[1];
+  int res = 0;
+  for (int i = 0; i < S->nf; i++) {
+    const double y = S->y[i] - S->yBar, A = S->A[i];
+    double strain = d0 - y * d1;
+    res += uni_set_trial(&S->mat[i], strain);
+    double tangent = S->mat[i].e, stress = S->mat[i].sig;
+    double ks0 = tangent * A;
+    double ks1 = ks0 * -y;
+    S->k[0] += ks0; S->k[1] += ks1; S->k[3] += ks1 * -y;
+    double fs0 = stress * A;
+    S->s[0] += fs0; S->s[1] += fs0 * -y;
+  }
+  S->k[2] = S->k[1];
+  return res;
+}
+/* FiberSection2d::revertToLastCommit, FiberSection2d.cpp:376-408 (note sData is ASSIGNED, not summed) */
+static void sec_revert(OrcSec* S) {
+  S->k[0] = S->k[1] = S->k[2] = S->k[3] = 0.0; S->s[0] = S->s[1] = 0.0;
+  for (int i = 0; i < S->nf; i++) {
+    const double y = S->y[i] - S->yBar, A = S->A[i];
+    uni_revert(&S->mat[i]);
+    double ks0 = S->mat[i].e * A, ks1 = ks0 * -y;
+    S->k[0] += ks0; S->k[1] += ks1; S->k[3] += ks1 * -y;
+    double fs0 = S->mat[i].sig * A;
+    S->s[0] = fs0; S->s[1] = fs0 * -y;
+  }
+  S->k[2] = S->k[1];
+}
+/* SectionForceDeformation::getSectionFlexibility -> Matrix::Invert -> cmx_inv2
+ * (SectionForceDeformation.cpp, matrix/routines/invGL2.c); k, f column-major */
+static void inv2(const double* a, double* ainv) {
+  const double det = a[0] * a[3] - a[2] * a[1];
+  ainv[0] = a[3] / det; ainv[1] = -a[1] / det; ainv[2] = -a[2] / det; ainv[3] = a[0] / det;
+}
+/* matrix/routines/invGL3.c (column-major 3x3) */
+static void inv3(const double* a, double* ainv) {
+  const double* A = a - 4; double* I = ainv - 4;
+  const double det = A[4]*A[8]*A[12] - A[4]*A[11]*A[9] - A[7]*A[5]*A[12] + A[7]*A[11]*A[6] + A[10]*A[5]*A[9] - A[10]*A[8]*A[6];
+  double c[9];
+  c[0] =  A[8]*A[12] - A[11]*A[9];  c[3] = -(A[5]*A[12] - A[11]*A[6]); c[6] =  A[5]*A[9] - A[8]*A[6];
+  c[1] = -(A[7]*A[12] - A[10]*A[9]); c[4] =  A[4]*A[12] - A[10]*A[6];  c[7] = -(A[4]*A[9] - A[7]*A[6]);
+  c[2] =  A[7]*A[11] - A[10]*A[8];  c[5] = -(A[4]*A[11] - A[10]*A[5]); c[8] =  A[4]*A[8] - A[7]*A[5];
+  for (int i = 1; i <= 3; ++i) for (int j = 1; j <= 3; ++j) I[j + i * 3] = c[i + j * 3 - 4] / det;
+}
+static void sec_initial_flex(const OrcSec* S, double* f) {   /* FiberSection2d::getInitialTangent + Invert */
+  double k[4] = {0, 0, 0, 0};
+  for (int i = 0; i < S->nf; i++) {
+    const double y = S->y[i] - S->yBar, A = S->A[i];
+    double ks0 = uni_initial_tangent(&S->mat[i]) * A, ks1 = ks0 * -y;
+    k[0] += ks0; k[1] += ks1; k[3] += ks1 * -y;
+  }
+  k[2] = k[1];
+  inv2(k, f);
+}
+
+/* ======================================================================== */
+/* ForceBeamColumn2d (SRC/element/Frame/Other/Force/ForceBeamColumn2d.cpp)    */
+/* with LinearCrdTransf2d and LobattoBeamIntegration                          */
+/* ======================================================================== */
+#define ORC_MAXSEC 10
+typedef struct {
+  int nip, maxIters; double tol;
+  OrcSec sec[ORC_MAXSEC];
+  double L, cosTheta, sinTheta;
+  int initialFlag;
+  double kv[9], Se[3], kvcommit[9], Secommit[3];       /* kv column-major 3x3 */
+  double fs[ORC_MAXSEC][4], vs[ORC_MAXSEC][2], Ssr[ORC_MAXSEC][2], vscommit[ORC_MAXSEC][2];
+} OrcBeam;
+
+/* quadrature/Frame/LobattoBeamIntegration.cpp: getSectionLocations / getSectionWeights */
+static int lobatto(int n, double* xi, double* wt) {
+  static const double X[11][10] = {{0},{0},{-1.0,1.0},{-1.0,0.0,1.0},{-1.0,-0.44721360,0.44721360,1.0},
+    {-1.0,-0.65465367,0.0,0.65465367,1.0},{-1.0,-0.7650553239,-0.2852315164,0.2852315164,0.7650553239,1.0},
+    {-1.0,-0.8302238962,-0.4688487934,0.0,0.4688487934,0.8302238962,1.0},
+    {-1.0,-0.8717401485,-0.5917001814,-0.2092992179,0.2092992179,0.5917001814,0.8717401485,1.0},
+    {-1.0,-0.8997579954,-0.6771862795,-0.3631174638,0.0,0.3631174638,0.6771862795,0.8997579954,1.0},
+    {-1.0,-0.9195339082,-0.7387738651,-0.4779249498,-0.1652789577,0.1652789577,0.4779249498,0.7387738651,0.9195339082,1.0}};
+  static const double W[11][10] = {{0},{0},{1.0,1.0},{0.333333333333333,1.333333333333333,0.333333333333333},
+    {0.166666666666667,0.833333333333333,0.833333333333333,0.166666666666667},
+    {0.1,0.5444444444,0.7111111111,0.5444444444,0.1},
+    {0.06666666667,0.3784749562,0.5548583770,0.5548583770,0.3784749562,0.06666666667},
+    {0.04761904762,0.2768260473,0.4317453812,0.4876190476,0.4317453812,0.2768260473,0.04761904762},
+    {0.03571428571,0.2107042271,0.3411226924,0.4124587946,0.4124587946,0.3411226924,0.2107042271,0.03571428571},
+    {0.02777777778,0.1654953615,0.2745387125,0.3464285109,0.3715192743,0.3464285109,0.2745387125,0.1654953615,0.02777777778},
+    {0.02222222222,0.1333059908,0.2248893421,0.2920426836,0.3275397611,0.3275397611,0.2920426836,0.2248893421,0.1333059908,0.02222222222}};
+  if (n < 2 || n > 10) return -1;
+  for (int i = 0; i < n; i++) { xi[i] = 0.5 * (X[n][i] + 1.0); wt[i] = W[n][i] * 0.5; }
+  return 0;
+}
+
+/* LinearCrdTransf2d::getBasicTrialDisp / getBasicIncrDeltaDisp (no offsets), LinearCrdTransf2d.cpp */
+static void crd2d_basic(const OrcBeam* b, const double* ug, double* ub) {
+  double oneOverL = 1.0 / b->L;
+  double sl = b->sinTheta * oneOverL, cl = b->cosTheta * oneOverL;
+  ub[0] = -b->cosTheta * ug[0] - b->sinTheta * ug[1] + b->cosTheta * ug[3] + b->sinTheta * ug[4];
+  ub[1] = -sl * ug[0] + cl * ug[1] + ug[2] + sl * ug[3] - cl * ug[4];
+  ub[2] = ub[1] + ug[5] - ug[2];
+}
+
+/* ForceBeamColumn2d::update, ForceBeamColumn2d.cpp:559-933 (no element loads) */
+static int beam_update(OrcBeam* b, const double* ug, const double* dug) {
+  double v[3], dv[3], vin[3];
+  crd2d_basic(b, ug, v);
+  crd2d_basic(b, dug, dv);
+  double nrm = sqrt(dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]);
+  if (b->initialFlag != 0 && nrm <= DBL_EPSILON) return 0;
+  for (int i = 0; i < 3; i++) vin[i] = v[i] - dv[i];
+  const double L = b->L, oneOverL = 1.0 / L;
+  double xi[ORC_MAXSEC], wt[ORC_MAXSEC];
+  lobatto(b->nip, xi, wt);
+  double vr[3], f[9], dSe[3], SeTrial[3], kvTrial[9], dvTrial[3], dvToDo[3];
+  double vsSub[ORC_MAXSEC][2], fsSub[ORC_MAXSEC][4], SsrSub[ORC_MAXSEC][2];
+  int numSubdivide = 1, converged = 0;
+  for (int i = 0; i < 3; i++) { dvToDo[i] = dv[i]; dvTrial[i] = dvToDo[i]; }
+  const double factor = 10;
+  const int maxSubdivisions = 4;
+  (void)oneOverL;
+  while (!converged && numSubdivide <= maxSubdivisions) {
+    for (int l = 0; l < 3; l++) {
+      memcpy(SeTrial, b->Se, sizeof SeTrial); memcpy(kvTrial, b->kv, sizeof kvTrial);
+      for (int i = 0; i < b->nip; i++) {
+        memcpy(vsSub[i], b->vs[i], sizeof vsSub[i]); memcpy(fsSub[i], b->fs[i], sizeof fsSub[i]);
+        memcpy(SsrSub[i], b->Ssr[i], sizeof SsrSub[i]);
+      }
+      /* dSe = kv * dv (Matrix::addMatrixVector: column by column) */
+      for (int i = 0; i < 3; i++) dSe[i] = 0.0;
+      for (int j = 0; j < 3; j++) for (int i = 0; i < 3; i++) dSe[i] += kvTrial[i + 3 * j] * dvTrial[j];
+      for (int i = 0; i < 3; i++) SeTrial[i] += dSe[i];
+      int numIters = b->maxIters;
+      if (l == 1) numIters = 10 * b->maxIters;
+      for (int j = 0; j < numIters; j++) {
+        for (int i = 0; i < 9; i++) f[i] = 0.0;
+        vr[0] = vr[1] = vr[2] = 0.0;
+        for (int i = 0; i < b->nip; i++) {
+          OrcSec* S = &b->sec[i];
+          double Ss[2], dSs[2], dvs[2], fb[6];   /* fb (order x 3) column-major */
+          double xL = xi[i], xL1 = xL - 1.0, wtL = wt[i] * L;
+          Ss[0] = SeTrial[0];
+          Ss[1] = xL1 * SeTrial[1] + xL * SeTrial[2];
+          dSs[0] = Ss[0] - SsrSub[i][0]; dSs[1] = Ss[1] - SsrSub[i][1];
+          const double* fuse;
+          double fs0[4];
+          if (l == 0) fuse = fsSub[i];
+          else if (l == 2) { if (j == 0) { sec_initial_flex(S, fs0); fuse = fs0; } else fuse = fsSub[i]; }
+          else { sec_initial_flex(S, fs0); fuse = fs0; }
+          /* dvs = fs * dSs */
+          dvs[0] = 0.0; dvs[1] = 0.0;
+          for (int c = 0; c < 2; c++) for (int r = 0; r < 2; r++) dvs[r] += fuse[r + 2 * c] * dSs[c];
+          if (b->initialFlag != 0) { vsSub[i][0] += dvs[0]; vsSub[i][1] += dvs[1]; }
+          if (sec_set_trial(S, vsSub[i]) < 0) return -1;
+          SsrSub[i][0] = S->s[0]; SsrSub[i][1] = S->s[1];
+          inv2(S->k, fsSub[i]);
+          dSs[0] = Ss[0] - SsrSub[i][0]; dSs[1] = Ss[1] - SsrSub[i][1];
+          dvs[0] = 0.0; dvs[1] = 0.0;
+          for (int c = 0; c < 2; c++) for (int r = 0; r < 2; r++) dvs[r] += fsSub[i][r + 2 * c] * dSs[c];
+          /* fb = fs * b * wtL ; code = {P, MZ} */
+          for (int q = 0; q < 6; q++) fb[q] = 0.0;
+          const double* fSec = fsSub[i];
+          for (int jj = 0; jj < 2; jj++) fb[jj + 2 * 0] += fSec[jj + 2 * 0] * wtL;
+          for (int jj = 0; jj < 2; jj++) { double tmp = fSec[jj + 2 * 1] * wtL; fb[jj + 2 * 1] += xL1 * tmp; fb[jj + 2 * 2] += xL * tmp; }
+          /* f += b^T fb */
+          for (int jj = 0; jj < 3; jj++) f[0 + 3 * jj] += fb[0 + 2 * jj];
+          for (int jj = 0; jj < 3; jj++) { double tmp = fb[1 + 2 * jj]; f[1 + 3 * jj] += xL1 * tmp; f[2 + 3 * jj] += xL * tmp; }
+          /* vr += b^T (vs + dvs) wtL */
+          dvs[0] += vsSub[i][0]; dvs[1] += vsSub[i][1];
+          { double dei = dvs[0] * wtL; vr[0] += dei; }
+          { double dei = dvs[1] * wtL; vr[1] += xL1 * dei; vr[2] += xL * dei; }
+        }
+        inv3(f, kvTrial);
+        for (int i = 0; i < 3; i++) { dv[i] = vin[i]; dv[i] += dvTrial[i]; dv[i] -= vr[i]; }
+        for (int i = 0; i < 3; i++) dSe[i] = 0.0;
+        for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) dSe[r] += kvTrial[r + 3 * c] * dv[c];
+        double dW = 0.0;
+        for (int i = 0; i < 3; i++) dW += dv[i] * dSe[i];
+        for (int i = 0; i < 3; i++) SeTrial[i] += dSe[i];
+        if (fabs(dW) < b->tol) {
+          for (int i = 0; i < 3; i++) { dvToDo[i] -= dvTrial[i]; vin[i] += dvTrial[i]; }
+          double nn = sqrt(dvToDo[0] * dvToDo[0] + dvToDo[1] * dvToDo[1] + dvToDo[2] * dvToDo[2]);
+          if (nn <= DBL_EPSILON) converged = 1;
+          else { for (int i = 0; i < 3; i++) dvTrial[i] = dvToDo[i]; numSubdivide = 1; }
+          memcpy(b->kv, kvTrial, sizeof kvTrial); memcpy(b->Se, SeTrial, sizeof SeTrial);
+          for (int k = 0; k < b->nip; k++) {
+            memcpy(b->vs[k], vsSub[k], sizeof vsSub[k]); memcpy(b->fs[k], fsSub[k], sizeof fsSub[k]);
+            memcpy(b->Ssr[k], SsrSub[k], sizeof SsrSub[k]);
+          }
+          j = numIters + 1; l = 3;
+        } else {
+          if (j == (numIters - 1) && (l == 2)) { for (int i = 0; i < 3; i++) dvTrial[i] /= factor; numSubdivide++; }
+        }
+      }
+    }
+  }
+  if (!converged) return -1;
+  b->initialFlag = 1;
+  return 0;
+}
+
+/* LinearCrdTransf2d::getGlobalStiffMatrix (no offsets) and getGlobalResistingForce; K row-major 6x6 */
+static void beam_form(const OrcBeam* b, double* K, double* R) {
+  const double cosTheta = b->cosTheta, sinTheta = b->sinTheta, oneOverL = 1.0 / b->L;
+  if (K) {
+    const double* kb = b->kv;
+    double kb00 = kb[0], kb10 = kb[1], kb20 = kb[2], kb01 = kb[3], kb11 = kb[4], kb21 = kb[5], kb02 = kb[6], kb12 = kb[7], kb22 = kb[8];
+    double tmp[3][6], kg[6][6];
+    double sl = sinTheta * oneOverL, cl = cosTheta * oneOverL;
+    tmp[0][0] = -cosTheta * kb00 - sl * (kb01 + kb02); tmp[0][1] = -sinTheta * kb00 + cl * (kb01 + kb02);
+    tmp[0][2] = kb01; tmp[0][3] = -tmp[0][0]; tmp[0][4] = -tmp[0][1]; tmp[0][5] = kb02;
+    tmp[1][0] = -cosTheta * kb10 - sl * (kb11 + kb12); tmp[1][1] = -sinTheta * kb10 + cl * (kb11 + kb12);
+    tmp[1][2] = kb11; tmp[1][3] = -tmp[1][0]; tmp[1][4] = -tmp[1][1]; tmp[1][5] = kb12;
+    tmp[2][0] = -cosTheta * kb20 - sl * (kb21 + kb22); tmp[2][1] = -sinTheta * kb20 + cl * (kb21 + kb22);
+    tmp[2][2] = kb21; tmp[2][3] = -tmp[2][0]; tmp[2][4] = -tmp[2][1]; tmp[2][5] = kb22;
+    for (int c = 0; c < 6; c++) {
+      kg[0][c] = -cosTheta * tmp[0][c] - sl * (tmp[1][c] + tmp[2][c]);
+      kg[1][c] = -sinTheta * tmp[0][c] + cl * (tmp[1][c] + tmp[2][c]);
+      kg[2][c] = tmp[1][c];
+      kg[3][c] = -kg[0][c]; kg[4][c] = -kg[1][c];
+      kg[5][c] = tmp[2][c];
+    }
+    for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) K[r * 6 + c] = kg[r][c];
+  }
+  double q0 = b->Se[0], q1 = b->Se[1], q2 = b->Se[2];
+  double V = oneOverL * (q1 + q2);
+  double pl[6] = { -q0, V, q1, q0, -V, q2 };
+  pl[0] += 0.0; pl[1] += 0.0; pl[4] += 0.0;
+  R[0] = cosTheta * pl[0] - sinTheta * pl[1];
+  R[1] = sinTheta * pl[0] + cosTheta * pl[1];
+  R[3] = cosTheta * pl[3] - sinTheta * pl[4];
+  R[4] = sinTheta * pl[3] + cosTheta * pl[4];
+  R[2] = pl[2]; R[5] = pl[5];
+}
+/* ForceBeamColumn2d::commitState / revertToLastCommit, ForceBeamColumn2d.cpp:276-342 */
+static void beam_commit(OrcBeam* b) {
+  for (int i = 0; i < b->nip; i++) {
+    memcpy(b->vscommit[i], b->vs[i], sizeof b->vs[i]);
+    for (int f = 0; f < b->sec[i].nf; f++) uni_commit(&b->sec[i].mat[f]);
+  }
+  memcpy(b->kvcommit, b->kv, sizeof b->kv); memcpy(b->Secommit, b->Se, sizeof b->Se);
+}
+static void beam_revert(OrcBeam* b) {
+  for (int i = 0; i < b->nip; i++) {
+    memcpy(b->vs[i], b->vscommit[i], sizeof b->vs[i]);
+    sec_revert(&b->sec[i]);
+    sec_set_trial(&b->sec[i], b->vs[i]);
+    b->Ssr[i][0] = b->sec[i].s[0]; b->Ssr[i][1] = b->sec[i].s[1];
+    inv2(b->sec[i].k, b->fs[i]);
+  }
+  memcpy(b->Se, b->Secommit, sizeof b->Se); memcpy(b->kv, b->kvcommit, sizeof b->kv);
+  b->initialFlag = 0;
+}
+
+/* ======================================================================== */
 /* the model: Domain + AnalysisModel + LinearSOE flattened                    */
 /* ======================================================================== */
 typedef struct {
@@ -373,12 +819,18 @@ typedef struct {
   double par[8];     /* brick: b1,b2,b3 ; quad: thickness,type,pressure,rho,b1,b2 */
   OrcGP gp[8];
   int nip;
+  OrcBeam* beam;     /* ORC_ELE_FBC2D */
 } OrcEle;
+
+typedef struct { int tag, nf; double* y; double* A; int* mat; } OrcSecDef;
 
 typedef struct {
   int ndm, ndf;
   int nn; int* node_tag; double* crd; /* [nn][ndm], ascending tag (MapOfTaggedObjects order, Domain.cpp:98) */
   double* trial; double* commit_disp; /* [nn][ndf] */
+  double* incr;                       /* [nn][ndf] Node::getIncrDeltaDisp (Node.cpp:435) */
+  int nuni; int* uni_tag; int* uni_kind; double* uni_par;   /* uniaxial materials [nuni][12] */
+  int nsec; OrcSecDef* sec;           /* fibre section definitions */
   double* load;                       /* [nn][ndf] reference nodal loads (pattern 1, Linear series) */
   int* fixed;                         /* [nn][ndf] 1 when an SP_Constraint holds the dof */
   int nmat; int* mat_tag; int* mat_kind; double* mat_par; /* [nmat][8] */
@@ -406,6 +858,7 @@ void* orc_model_new(int ndm, int ndf, int nn, const int* tags, const double* crd
   m->crd = (double*)malloc(sizeof(double) * nn * ndm); memcpy(m->crd, crd, sizeof(double) * nn * ndm);
   m->trial = (double*)calloc((size_t)nn * ndf, sizeof(double));
   m->commit_disp = (double*)calloc((size_t)nn * ndf, sizeof(double));
+  m->incr = (double*)calloc((size_t)nn * ndf, sizeof(double));
   m->load = (double*)calloc((size_t)nn * ndf, sizeof(double));
   m->fixed = (int*)calloc((size_t)nn * ndf, sizeof(int));
   m->mat_tag = NULL; m->nmat = 0;
@@ -426,6 +879,32 @@ int orc_add_nd_material(void* h, int tag, int kind, const double* p) {
   memcpy(m->mat_par + 8 * m->nmat, p, sizeof(double) * (kind == ORC_MAT_J2 ? 7 : 3));
   m->nmat++; return 0;
 }
+/* uniaxialMaterial Steel02 / Concrete02 ; section Fiber (fibers in the order given) */
+int orc_add_uniaxial(void* h, int tag, int kind, const double* p) {
+  OrcModel* m = (OrcModel*)h;
+  m->uni_tag = (int*)realloc(m->uni_tag, sizeof(int) * (m->nuni + 1));
+  m->uni_kind = (int*)realloc(m->uni_kind, sizeof(int) * (m->nuni + 1));
+  m->uni_par = (double*)realloc(m->uni_par, sizeof(double) * 12 * (m->nuni + 1));
+  m->uni_tag[m->nuni] = tag; m->uni_kind[m->nuni] = kind;
+  memset(m->uni_par + 12 * m->nuni, 0, 12 * sizeof(double));
+  memcpy(m->uni_par + 12 * m->nuni, p, sizeof(double) * (kind == ORC_UNI_STEEL02 ? 11 : 7));
+  m->nuni++; return 0;
+}
+int orc_add_fiber_section(void* h, int tag, int nf, const double* y, const double* A, const int* matTags) {
+  OrcModel* m = (OrcModel*)h;
+  m->sec = (OrcSecDef*)realloc(m->sec, sizeof(OrcSecDef) * (m->nsec + 1));
+  OrcSecDef* d = &m->sec[m->nsec];
+  d->tag = tag; d->nf = nf;
+  d->y = (double*)malloc(sizeof(double) * nf); d->A = (double*)malloc(sizeof(double) * nf); d->mat = (int*)malloc(sizeof(int) * nf);
+  memcpy(d->y, y, sizeof(double) * nf); memcpy(d->A, A, sizeof(double) * nf);
+  for (int i = 0; i < nf; i++) {
+    d->mat[i] = -1;
+    for (int j = 0; j < m->nuni; j++) if (m->uni_tag[j] == matTags[i]) d->mat[i] = j;
+    if (d->mat[i] < 0) return -1;
+  }
+  m->nsec++; return 0;
+}
+static int beam_update(OrcBeam* b, const double* ug, const double* dug);
 static int find_mat(const OrcModel* m, int tag) { for (int i = 0; i < m->nmat; i++) if (m->mat_tag[i] == tag) return i; return -1; }
 
 int orc_add_element(void* h, int kind, int tag, const int* nodeTags, int matTag, const double* par) {
@@ -434,10 +913,42 @@ int orc_add_element(void* h, int kind, int tag, const int* nodeTags, int matTag,
   OrcEle* e = &m->ele[m->ne];
   memset(e, 0, sizeof *e);
   e->kind = kind; e->tag = tag;
-  e->nen = (kind == ORC_ELE_BRICK) ? 8 : 4;
-  e->ndf_e = (kind == ORC_ELE_BRICK) ? 3 : 2;
+  e->nen = (kind == ORC_ELE_BRICK) ? 8 : (kind == ORC_ELE_QUAD ? 4 : 2);
+  e->ndf_e = (kind == ORC_ELE_BRICK) ? 3 : (kind == ORC_ELE_QUAD ? 2 : 3);
   e->nip = (kind == ORC_ELE_BRICK) ? 8 : 4;
   for (int i = 0; i < e->nen; i++) { e->node[i] = find_node(m, nodeTags[i]); if (e->node[i] < 0) return -1; }
+  if (kind == ORC_ELE_FBC2D) {
+    /* forceBeamColumn: matTag names the fibre section; par = nIP, maxIters, tol.
+     * Lobatto integration, Linear transformation (no offsets). */
+    int sd = -1;
+    for (int i = 0; i < m->nsec; i++) if (m->sec[i].tag == matTag) sd = i;
+    if (sd < 0) return -2;
+    OrcBeam* b = (OrcBeam*)calloc(1, sizeof(OrcBeam));
+    b->nip = (int)par[0]; b->maxIters = (int)par[1]; b->tol = par[2];
+    if (b->nip < 2 || b->nip > ORC_MAXSEC) return -3;
+    const OrcSecDef* d = &m->sec[sd];
+    for (int i = 0; i < b->nip; i++) {
+      OrcSec* S = &b->sec[i];
+      S->nf = d->nf; S->y = d->y; S->A = d->A;
+      S->mat = (OrcUni*)malloc(sizeof(OrcUni) * d->nf);
+      double ABar = 0.0, QzBar = 0.0;
+      for (int f = 0; f < d->nf; f++) {
+        uni_init(&S->mat[f], m->uni_kind[d->mat[f]], m->uni_par + 12 * d->mat[f]);
+        ABar += d->A[f]; QzBar += d->y[f] * d->A[f]; S->yBar = QzBar / ABar;   /* FiberSection2d::addFiber */
+      }
+    }
+    /* LinearCrdTransf2d::computeElemtLengthAndOrient */
+    double dx0 = m->crd[e->node[1] * 2] - m->crd[e->node[0] * 2], dx1 = m->crd[e->node[1] * 2 + 1] - m->crd[e->node[0] * 2 + 1];
+    b->L = sqrt(dx0 * dx0 + dx1 * dx1);
+    b->cosTheta = dx0 / b->L; b->sinTheta = dx1 / b->L;
+    e->beam = b; e->nip = b->nip; e->mat = sd;
+    memcpy(e->par, par, 8 * sizeof(double));
+    /* Domain::addElement calls element->update() (Domain.cpp:391) */
+    double ug[6], dug[6];
+    for (int a = 0; a < 2; a++) for (int j = 0; j < 3; j++) { ug[a * 3 + j] = m->trial[e->node[a] * 3 + j]; dug[a * 3 + j] = m->incr[e->node[a] * 3 + j]; }
+    if (beam_update(b, ug, dug) < 0) return -4;
+    m->ne++; return 0;
+  }
   e->mat = find_mat(m, matTag); if (e->mat < 0) return -2;
   memcpy(e->par, par, 8 * sizeof(double));
   int type = (kind == ORC_ELE_BRICK) ? ORC_ND_3D : ORC_ND_PLANE_STRAIN;
@@ -793,10 +1304,18 @@ static void quad_form(OrcModel* m, OrcEle* el, int tang_flag, double* K, double*
 }
 
 /* Node::setTrialDisp for all nodes + Domain::update -> Element::update */
+static int ele_update(OrcModel* m, OrcEle* el) {
+  if (el->kind == ORC_ELE_BRICK) return brick_update(m, el);
+  if (el->kind == ORC_ELE_QUAD) return quad_update(m, el);
+  double ug[6], dug[6];
+  for (int a = 0; a < 2; a++) for (int j = 0; j < 3; j++) { ug[a * 3 + j] = m->trial[el->node[a] * 3 + j]; dug[a * 3 + j] = m->incr[el->node[a] * 3 + j]; }
+  return beam_update(el->beam, ug, dug);
+}
+/* Node::setTrialDisp (Node.cpp: incrDeltaDisp = new - trial) + Domain::update */
 int orc_set_trial_disp(void* h, const double* u) {
   OrcModel* m = (OrcModel*)h; int rc = 0;
-  memcpy(m->trial, u, sizeof(double) * m->nn * m->ndf);
-  for (int e = 0; e < m->ne; e++) rc |= (m->ele[e].kind == ORC_ELE_BRICK) ? brick_update(m, &m->ele[e]) : quad_update(m, &m->ele[e]);
+  for (int i = 0; i < m->nn * m->ndf; i++) { m->incr[i] = u[i] - m->trial[i]; m->trial[i] = u[i]; }
+  for (int e = 0; e < m->ne; e++) rc |= ele_update(m, &m->ele[e]);
   return rc;
 }
 void orc_apply_load(void* h, double lambda) { ((OrcModel*)h)->lambda = lambda; }
@@ -804,11 +1323,13 @@ void orc_apply_load(void* h, double lambda) { ((OrcModel*)h)->lambda = lambda; }
 /* Element::getTangentStiff / getResistingForce of FE element e (row-major) */
 int orc_ele_tangent(void* h, int e, double* K) {
   OrcModel* m = (OrcModel*)h; double R[24];
+  if (m->ele[e].kind == ORC_ELE_FBC2D) { beam_form(m->ele[e].beam, K, R); return 6; }
   if (m->ele[e].kind == ORC_ELE_BRICK) { brick_form(m, &m->ele[e], 1, K, R); return 24; }
   quad_form(m, &m->ele[e], 1, K, R); return 8;
 }
 int orc_ele_resid(void* h, int e, double* R) {
   OrcModel* m = (OrcModel*)h;
+  if (m->ele[e].kind == ORC_ELE_FBC2D) { beam_form(m->ele[e].beam, NULL, R); return 6; }
   if (m->ele[e].kind == ORC_ELE_BRICK) { brick_form(m, &m->ele[e], 0, NULL, R); return 24; }
   double K[64]; quad_form(m, &m->ele[e], 0, K, R); return 8;
 }
@@ -823,7 +1344,9 @@ int orc_form_tangent(void* h, double* A) {
   for (int e = 0; e < m->ne; e++) {
     OrcEle* el = &m->ele[e]; double K[576], R[24]; int ids[32];
     int nd_e = el->nen * el->ndf_e;
-    if (el->kind == ORC_ELE_BRICK) brick_form(m, el, 1, K, R); else quad_form(m, el, 1, K, R);
+    if (el->kind == ORC_ELE_BRICK) brick_form(m, el, 1, K, R);
+    else if (el->kind == ORC_ELE_QUAD) quad_form(m, el, 1, K, R);
+    else beam_form(el->beam, K, R);
     int n = ele_ids(m, el, ids); (void)n;
     for (int i = 0; i < nd_e; i++) for (int j = 0; j < nd_e; j++) K[i * nd_e + j] = 0.0 + K[i * nd_e + j];
     if (m->soe_kind == 1) {
@@ -853,7 +1376,9 @@ int orc_form_unbalance(void* h, double* B) {
   for (int e = 0; e < m->ne; e++) {
     OrcEle* el = &m->ele[e]; double K[64], R[24]; int ids[32];
     int nd_e = el->nen * el->ndf_e;
-    if (el->kind == ORC_ELE_BRICK) brick_form(m, el, 0, NULL, R); else quad_form(m, el, 0, K, R);
+    if (el->kind == ORC_ELE_BRICK) brick_form(m, el, 0, NULL, R);
+    else if (el->kind == ORC_ELE_QUAD) quad_form(m, el, 0, K, R);
+    else beam_form(el->beam, NULL, R);
     ele_ids(m, el, ids);
     for (int i = 0; i < nd_e; i++) {
       double res = 0.0 * 1.0 + R[i] * -1.0;   /* Vector::addVector(1.0, R, -1.0) on a zeroed residual */
@@ -873,14 +1398,25 @@ int orc_form_unbalance(void* h, double* B) {
 int orc_commit(void* h) {
   OrcModel* m = (OrcModel*)h;
   memcpy(m->commit_disp, m->trial, sizeof(double) * m->nn * m->ndf);
-  for (int e = 0; e < m->ne; e++) for (int g = 0; g < m->ele[e].nip; g++) gp_commit(&m->ele[e].gp[g]);
+  memset(m->incr, 0, sizeof(double) * m->nn * m->ndf);        /* Node::commitState */
+  for (int e = 0; e < m->ne; e++) {
+    if (m->ele[e].kind == ORC_ELE_FBC2D) beam_commit(m->ele[e].beam);
+    else for (int g = 0; g < m->ele[e].nip; g++) gp_commit(&m->ele[e].gp[g]);
+  }
   return 0;
 }
 int orc_revert(void* h) {
   OrcModel* m = (OrcModel*)h;
+  /* Domain::revertToLastCommit (Domain.cpp:1925): nodes, elements, then update() */
   memcpy(m->trial, m->commit_disp, sizeof(double) * m->nn * m->ndf);
-  for (int e = 0; e < m->ne; e++) for (int g = 0; g < m->ele[e].nip; g++) gp_revert(&m->ele[e].gp[g]);
-  return 0;
+  memset(m->incr, 0, sizeof(double) * m->nn * m->ndf);
+  for (int e = 0; e < m->ne; e++) {
+    if (m->ele[e].kind == ORC_ELE_FBC2D) beam_revert(m->ele[e].beam);
+    else for (int g = 0; g < m->ele[e].nip; g++) gp_revert(&m->ele[e].gp[g]);
+  }
+  int rc = 0;
+  for (int e = 0; e < m->ne; e++) rc |= ele_update(m, &m->ele[e]);
+  return rc;
 }
 
 /* per-GP peek for kernel-level parity: stress (order) and tangent (order^2) of FE element e, point g */

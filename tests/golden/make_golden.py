@@ -13,8 +13,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 import zlib  # noqa: E402
 
-from golden_cases import CASES, NSTEPS  # noqa: E402
-from modelspec import ELASTIC, J2_STEEL, ND_3D, ND_PLANE_STRAIN, RefBackend, ref_nd_path  # noqa: E402
+from golden_cases import CASES, NSTEPS, ele_nd  # noqa: E402
+from modelspec import (CONCRETE02_CORE, CONCRETE02_COVER, ELASTIC, J2_STEEL, ND_3D, ND_PLANE_STRAIN, STEEL02,  # noqa: E402
+                       RefBackend, ref_nd_path, ref_uni_path)
 
 
 def material_paths():
@@ -30,6 +31,13 @@ def material_paths():
             key = f"{name}_{tname}"
             out[key + "_par"] = np.array(p); out[key + "_strain"] = strains; out[key + "_commit"] = commit
             out[key + "_stress"] = s; out[key + "_tangent"] = t
+    for name, (kind, p) in (("steel02", STEEL02), ("concrete02_core", CONCRETE02_CORE), ("concrete02_cover", CONCRETE02_COVER)):
+        n = 300
+        strains = np.cumsum(rng.normal(0, 6e-4, n)) - (0.002 if kind else 0.0)
+        commit = (rng.random(n) < 0.6).astype(np.int32)
+        s, t = ref_uni_path(kind, p, strains, commit)
+        out[name + "_par"] = np.array(p); out[name + "_strain"] = strains; out[name + "_commit"] = commit
+        out[name + "_stress"] = s; out[name + "_tangent"] = t
     np.savez_compressed(os.path.join(HERE, "material_paths.npz"), **out)
 
 
@@ -39,11 +47,11 @@ def model_case(name, spec, numberer, soe, scale, nsteps=NSTEPS):
     ids = R.ids()
     ptr, idx = R.csr()
     out = dict(ids=ids, ptr=ptr, idx=idx, numberer=numberer, soe=soe)
-    nd = 24 if spec.ndm == 3 else 8
+    nd = ele_nd(spec)
     _, fe = R.fe_ids(nd)
     out["fe_ids"] = fe
     for s in range(nsteps):
-        u = rng.normal(0, scale * (s + 1), (spec.nn, spec.ndf)); u[ids < 0] = 0
+        u = rng.normal(0, 1.0, (spec.nn, spec.ndf)) * np.asarray(scale) * (s + 1); u[ids < 0] = 0
         R.set_trial_disp(u); R.apply_load(0.25 * (s + 1))
         out[f"u{s}"] = u
         out[f"A{s}"] = R.form_tangent(); out[f"B{s}"] = R.form_unbalance()

@@ -1,5 +1,5 @@
 """The models behind tests/golden/*.npz (generated from the reference by tests/golden/make_golden.py)."""
-from modelspec import ELASTIC, J2_STEEL, brick_block, quad_plane
+from modelspec import ELASTIC, J2_STEEL, brick_block, frame2d, quad_plane
 
 # name -> (spec factory, numberer, soe, displacement scale)
 CASES = {
@@ -8,5 +8,13 @@ CASES = {
     "brick_elastic_rcm_csc": (lambda: brick_block(2, 3, 3, mat=ELASTIC, distort=0.3, seed=3), 1, 0, 2e-3),
     "quad_elastic_rcm_csc": (lambda: quad_plane(10, 4, mat=ELASTIC, distort=0.0, seed=4), 1, 0, 2e-2),
     "quad_j2_plain_csr": (lambda: quad_plane(6, 5, mat=J2_STEEL, lx=6.0, ly=5.0, distort=0.3, seed=5, body=(0.0, -0.02)), 0, 1, 2e-3),
+    # 2D RC frame: forceBeamColumn + fibre sections (Steel02, Concrete02); scale per dof (ux, uy, rz)
+    "frame2d_fiber_rcm_csc": (lambda: frame2d(2, 3, 2), 1, 0, (0.006, 0.003, 6e-5)),
+    "frame2d_fiber_plain_csr": (lambda: frame2d(3, 2, 1, nip=4), 0, 1, (0.008, 0.002, 5e-5)),
 }
 NSTEPS = 3
+
+
+def ele_nd(spec):
+    """dofs of one element of the (single-kind) model"""
+    return {0: 24, 1: 8, 2: 6}[spec.groups[0].kind]

@@ -23,7 +23,8 @@ ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libref_harness.so")
 
 MAT_ELASTIC, MAT_J2 = 0, 1
-ELE_BRICK, ELE_QUAD = 0, 1
+ELE_BRICK, ELE_QUAD, ELE_FBC2D = 0, 1, 2
+UNI_STEEL02, UNI_CONCRETE02 = 0, 1
 ND_3D, ND_PLANE_STRAIN = 0, 1
 NUMBERER_PLAIN, NUMBERER_RCM = 0, 1
 SOE_CSC, SOE_CSR = 0, 1
@@ -48,6 +49,8 @@ class ModelSpec:
     materials: list           # (tag, kind, params[<=8])
     groups: list = field(default_factory=list)
     loads: np.ndarray = None  # [nload, 1+ndf] (node tag, values...)
+    uniaxials: list = field(default_factory=list)   # (tag, kind, params)
+    sections: list = field(default_factory=list)    # (tag, y[nf], A[nf], uniaxial tags[nf])
 
     @property
     def nn(self):
@@ -128,6 +131,66 @@ def quad_plane(nx, ny, mat=ELASTIC, lx=40.0, ly=10.0, thick=1.0, distort=0.0, se
                                    np.ones(ne, np.int32), par)], loads)
 
 
+STEEL02 = (UNI_STEEL02, [60.0, 29000.0, 0.01, 18.0, 0.925, 0.15, 0.0, 1.0, 0.0, 1.0, 0.0])   # Fy E0 b R0 cR1 cR2 a1..a4 sigInit
+CONCRETE02_CORE = (UNI_CONCRETE02, [-6.0, -0.004, -5.0, -0.014, 0.1, 0.6, 300.0])            # fc epsc0 fcu epscu rat ft Ets
+CONCRETE02_COVER = (UNI_CONCRETE02, [-5.0, -0.002, 0.0, -0.006, 0.1, 0.5, 250.0])
+
+
+def rc_section(tag=1, h=24.0, b=15.0, cover=1.5, nf_core=10, nf_cover=2, As=0.6):
+    """the classic RC fibre section (OpenSees example 'RCFrameGravity'): confined core, unconfined cover,
+    three layers of steel -- as (y, A, uniaxial tag) fibres; uniaxial tags 1 core, 2 cover, 3 steel"""
+    y, A, m = [], [], []
+    y1, z1 = h / 2.0, b / 2.0
+    hc = h - 2 * cover
+    for i in range(nf_core):                      # core patch
+        y.append(-hc / 2 + (i + 0.5) * hc / nf_core); A.append((b - 2 * cover) * hc / nf_core); m.append(1)
+    for i in range(nf_core):                      # side cover
+        y.append(-hc / 2 + (i + 0.5) * hc / nf_core); A.append(2 * cover * hc / nf_core); m.append(2)
+    for sgn in (-1, 1):                           # top / bottom cover
+        for i in range(nf_cover):
+            y.append(sgn * (hc / 2 + (i + 0.5) * cover / nf_cover)); A.append(b * cover / nf_cover); m.append(2)
+    for yy, n in ((y1 - cover, 3), (0.0, 2), (-(y1 - cover), 3)):   # steel layers
+        for _ in range(n):
+            y.append(yy); A.append(As); m.append(3)
+    return (tag, np.array(y), np.array(A), np.array(m, np.int32))
+
+
+def frame2d(nbay=2, nstory=3, ndiv=2, nip=5, bay=360.0, story=144.0, max_iters=10, tol=1e-12, lateral=10.0, gravity=-60.0):
+    """2D RC moment frame of forceBeamColumn elements with fibre sections (Steel02 + Concrete02),
+    every member split in ndiv elements; bases fixed; gravity on the floor nodes + lateral load at the roof"""
+    pts = {}
+    def node(x, y):
+        key = (round(x, 6), round(y, 6))
+        if key not in pts:
+            pts[key] = len(pts) + 1
+        return pts[key]
+    conn = []
+    for i in range(nbay + 1):
+        for j in range(nstory):
+            for d in range(ndiv):
+                conn.append((node(i * bay, j * story + d * story / ndiv), node(i * bay, j * story + (d + 1) * story / ndiv)))
+    for j in range(1, nstory + 1):
+        for i in range(nbay):
+            for d in range(ndiv):
+                conn.append((node(i * bay + d * bay / ndiv, j * story), node(i * bay + (d + 1) * bay / ndiv, j * story)))
+    nn = len(pts)
+    crd = np.zeros((nn, 2))
+    for (x, y), t in pts.items():
+        crd[t - 1] = (x, y)
+    conn = np.array(conn, np.int32)
+    ne = len(conn)
+    par = np.zeros((ne, 8)); par[:, 0] = nip; par[:, 1] = max_iters; par[:, 2] = tol
+    fix = np.array([(t, d) for (x, y), t in pts.items() if y == 0.0 for d in range(3)], np.int32).reshape(-1, 2)
+    loads = []
+    for (x, y), t in pts.items():
+        if y > 0 and abs(y / story - round(y / story)) < 1e-9 and abs(x / bay - round(x / bay)) < 1e-9:
+            loads.append([t, lateral if (x == 0.0 and round(y / story) == nstory) else 0.0, gravity, 0.0])
+    return ModelSpec(2, 3, np.arange(1, nn + 1, dtype=np.int32), crd, fix, [],
+                     [ElementGroup(ELE_FBC2D, np.arange(1, ne + 1, dtype=np.int32), conn, np.ones(ne, np.int32), par)],
+                     np.array(loads), uniaxials=[(1, *CONCRETE02_CORE), (2, *CONCRETE02_COVER), (3, *STEEL02)],
+                     sections=[rc_section(1)])
+
+
 def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
@@ -152,10 +215,17 @@ class OracleBackend(_Backend):
         for tag, kind, p in spec.materials:
             pp = np.zeros(8); pp[:len(p)] = p
             assert L.orc_add_nd_material(self.h, tag, kind, _p(pp)) == 0
+        for tag, kind, p in spec.uniaxials:
+            pp = np.zeros(12); pp[:len(p)] = p
+            assert L.orc_add_uniaxial(self.h, tag, kind, _p(pp)) == 0
+        for tag, y, A, mt in spec.sections:
+            y, A, mt = np.ascontiguousarray(y, np.float64), np.ascontiguousarray(A, np.float64), np.ascontiguousarray(mt, np.int32)
+            assert L.orc_add_fiber_section(self.h, tag, len(y), _p(y), _p(A), _p(mt)) == 0
         for g in spec.groups:
             for i in range(len(g.tags)):
                 c = np.ascontiguousarray(g.conn[i], np.int32); pr = np.ascontiguousarray(g.par[i], np.float64)
-                assert L.orc_add_element(self.h, g.kind, int(g.tags[i]), _p(c), int(g.mat[i]), _p(pr)) == 0
+                rc = L.orc_add_element(self.h, g.kind, int(g.tags[i]), _p(c), int(g.mat[i]), _p(pr))
+                assert rc == 0, rc
         if spec.loads is not None:
             for row in spec.loads:
                 v = np.ascontiguousarray(row[1:], np.float64)
@@ -225,6 +295,24 @@ def have_ref():
     return os.path.exists(REF_SO)
 
 
+def oracle_uni_path(kind, p, strains, commit):
+    L = ctypes.CDLL(ORACLE_SO)
+    strains = np.ascontiguousarray(strains, np.float64); commit = np.ascontiguousarray(commit, np.int32)
+    pp = np.zeros(12); pp[:len(p)] = p
+    s = np.zeros(len(strains)); t = np.zeros(len(strains))
+    assert L.orc_uni_path(kind, _p(pp), len(strains), _p(strains), _p(commit), _p(s), _p(t)) == 0
+    return s, t
+
+
+def ref_uni_path(kind, p, strains, commit):
+    L = ctypes.CDLL(REF_SO)
+    strains = np.ascontiguousarray(strains, np.float64); commit = np.ascontiguousarray(commit, np.int32)
+    pp = np.zeros(12); pp[:len(p)] = p
+    s = np.zeros(len(strains)); t = np.zeros(len(strains))
+    assert L.ref_uni_path(kind, _p(pp), len(strains), _p(strains), _p(commit), _p(s), _p(t)) == 0
+    return s, t
+
+
 def ref_nd_path(kind, p, type_, strains, commit):
     L = ctypes.CDLL(REF_SO)
     order = 6 if type_ == ND_3D else 3
@@ -258,6 +346,14 @@ class RefBackend(_Backend):
             assert L.ref_add_nd_material(self.h, tag, kind, _p(pp)) == 0
         L.ref_add_quad.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_double,
                                    ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_void_p]
+        L.ref_add_force_beam2d.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_double]
+        for tag, kind, p in spec.uniaxials:
+            pp = np.zeros(12); pp[:len(p)] = p
+            assert L.ref_add_uniaxial(self.h, tag, kind, _p(pp)) == 0
+        for tag, y, A, mt in spec.sections:
+            y, A, mt = np.ascontiguousarray(y, np.float64), np.ascontiguousarray(A, np.float64), np.ascontiguousarray(mt, np.int32)
+            assert L.ref_add_fiber_section(self.h, tag, len(y), _p(y), _p(A), _p(mt)) == 0
         self.ele_tags = []
         for g in spec.groups:
             for i in range(len(g.tags)):
@@ -265,6 +361,9 @@ class RefBackend(_Backend):
                 if g.kind == ELE_BRICK:
                     b = np.ascontiguousarray(g.par[i, :3], np.float64)
                     assert L.ref_add_brick(self.h, int(g.tags[i]), _p(c), int(g.mat[i]), _p(b)) == 0
+                elif g.kind == ELE_FBC2D:
+                    assert L.ref_add_force_beam2d(self.h, int(g.tags[i]), _p(c), int(g.mat[i]), int(g.par[i, 0]),
+                                                  int(g.par[i, 1]), float(g.par[i, 2])) == 0
                 else:
                     b = np.ascontiguousarray(g.par[i, 4:6], np.float64)
                     assert L.ref_add_quad(self.h, int(g.tags[i]), _p(c), int(g.mat[i]), float(g.par[i, 0]),

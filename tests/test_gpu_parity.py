@@ -13,12 +13,13 @@ import numpy as np
 import pytest
 
 import xara_b200 as xb
-from golden_cases import CASES, NSTEPS
-from modelspec import ELASTIC, J2_STEEL, OracleBackend, brick_block, quad_plane
+from golden_cases import CASES, NSTEPS, ele_nd
+from modelspec import ELASTIC, J2_STEEL, OracleBackend, brick_block, frame2d, quad_plane
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 RTOL = 1e-12
+BEAM_RTOL = 1e-10
 
 
 def relerr(a, b):
@@ -31,15 +32,18 @@ def test_device_vs_golden_reference_vectors(name):
     g = np.load(os.path.join(GOLD, name + ".npz"))
     spec = mk()
     D = xb.DeviceModel.from_spec(spec, numberer, soe).to_device(0)
-    nd = 24 if spec.ndm == 3 else 8
+    nd = ele_nd(spec)
+    # the force-based beam iterates to |dW| < 1e-12 per element: its converged state, and with it
+    # K and R, is reproducible to the iteration tolerance, not to the last bit
+    tol = BEAM_RTOL if nd == 6 else RTOL
     for s in range(NSTEPS):
         D.set_trial_disp(g[f"u{s}"]); D.update(); D.apply_load(0.25 * (s + 1))
         A, B = D.form_tangent(), D.form_unbalance()
-        assert relerr(A, g[f"A{s}"]) < RTOL
-        assert relerr(B, g[f"B{s}"]) < RTOL
+        assert relerr(A, g[f"A{s}"]) < tol
+        assert relerr(B, g[f"B{s}"]) < tol
         for e in range(len(g[f"K{s}"])):
-            assert relerr(D.element_tangent(e, nd), g[f"K{s}"][e]) < RTOL
-            assert relerr(D.element_resid(e, nd), g[f"R{s}"][e]) < RTOL
+            assert relerr(D.element_tangent(e, nd), g[f"K{s}"][e]) < tol
+            assert relerr(D.element_resid(e, nd), g[f"R{s}"][e]) < tol
         D.commit()
 
 
@@ -98,23 +102,13 @@ def _newton(model, solve, nsteps, dlam, tol, max_iter, is_dev):
     return hist
 
 
-@pytest.mark.parametrize("shape", ["brick", "quad"])
-def test_newton_iteration_counts_match_oracle(shape):
+def _newton_counts_match(spec, nsteps, min_iters):
     """Static Newton (LoadControl, NormDispIncr) driven once by the oracle and once by the device:
     identical iteration counts per step and the same convergence history.  The tolerance is picked
     from a fixed list so that, in the oracle's own history, no deciding norm sits within 3x of it:
     an iteration count must not hinge on the last bits of a norm."""
     import scipy.sparse as sp
     import scipy.sparse.linalg as spla
-
-    def make():
-        if shape == "brick":
-            return brick_block(4, 4, 6, mat=J2_STEEL, lx=1.0, ly=1.0, lz=3.0, load=(1.2, 0.0, -0.5))
-        spec = quad_plane(16, 4, mat=J2_STEEL, lx=8.0, ly=2.0)
-        spec.loads[:, 1:] = [0.0, -10.0]
-        return spec
-
-    spec = make()
     O = OracleBackend(spec, 1, 1)
     ptr, idx = O.csr()
     neq = O.neq
@@ -125,19 +119,32 @@ def test_newton_iteration_counts_match_oracle(shape):
     best = None
     for tol in (1e-6, 3e-7, 1e-7, 3e-8, 1e-8, 3e-9, 1e-9):
         O = OracleBackend(spec, 1, 1); O._u = np.zeros((spec.nn, spec.ndf))
-        h = _newton(O, solve, 8, 1.0, tol, 25, False)
+        h = _newton(O, solve, nsteps, 1.0, tol, 25, False)
         margin = min(min(x[-2] / tol, tol / max(x[-1], 1e-300)) for x in h)
         if best is None or margin > best[0]:
             best = (margin, tol, h, O._u.copy())
     margin, tol, ho, uo = best
     assert margin >= 3.0, (margin, tol)
     D = xb.DeviceModel.from_spec(spec, 1, 1).to_device(0)
-    hd = _newton(D, solve, 8, 1.0, tol, 25, True)
+    hd = _newton(D, solve, nsteps, 1.0, tol, 25, True)
     assert [len(h) for h in ho] == [len(h) for h in hd]          # identical iteration counts
-    assert max(len(h) for h in ho) >= 6                            # the steps really go plastic
+    assert max(len(h) for h in ho) >= min_iters                    # the steps really go inelastic
     for a, b in zip(ho, hd):
-        assert np.allclose(a[:-1], b[:-1], rtol=1e-6, atol=1e-13)  # same convergence history
-    assert relerr(D.trial_disp(), uo) < 1e-9
+        assert np.allclose(a[:-1], b[:-1], rtol=1e-5, atol=1e-11)  # same convergence history
+    assert relerr(D.trial_disp(), uo) < 1e-8
+
+
+@pytest.mark.parametrize("shape", ["brick", "quad", "frame"])
+def test_newton_iteration_counts_match_oracle(shape):
+    if shape == "brick":
+        spec = brick_block(4, 4, 6, mat=J2_STEEL, lx=1.0, ly=1.0, lz=3.0, load=(1.2, 0.0, -0.5))
+        _newton_counts_match(spec, 8, 6)
+    elif shape == "quad":
+        spec = quad_plane(16, 4, mat=J2_STEEL, lx=8.0, ly=2.0)
+        spec.loads[:, 1:] = [0.0, -10.0]
+        _newton_counts_match(spec, 8, 6)
+    else:   # load-controlled pushover of the RC frame (forceBeamColumn, fibre sections)
+        _newton_counts_match(frame2d(2, 3, 2, lateral=22.0, gravity=-40.0), 5, 5)
 
 
 def test_revert_to_last_commit_and_incr():
@@ -317,3 +324,55 @@ def test_two_gpus_nccl_exchange_matches_single_gpu(tmp_path):
         d = np.load(out + f".{rank}.npz")
         assert np.array_equal(d["B"], Bg[d["rows"]])
         assert np.array_equal(d["A"], np.concatenate([Ag[gptr[q]:gptr[q + 1]] for q in d["rows"]]))
+
+
+def test_frame_fibre_beams_vs_oracle_history():
+    """forceBeamColumn + FiberSection2d (Steel02 / Concrete02): cyclic sway history with commits and a
+    revertToLastCommit, device against the oracle"""
+    spec = frame2d(3, 4, 2)
+    O = OracleBackend(spec, 1, 0)
+    D = xb.DeviceModel.from_spec(spec, 1, 0).to_device(0)
+    ids = O.ids()
+    assert relerr(D.form_tangent(), O.form_tangent()) < BEAM_RTOL          # initial (elastic) stiffness
+    y = spec.crd[:, 1] / spec.crd[:, 1].max()
+    rng = np.random.default_rng(3)
+    amp = [0.4, 1.2, 2.5, 1.0, -1.5, -3.0, 0.5, 3.5]                        # inches of roof drift, cycling
+    for s, a in enumerate(amp):
+        u = np.zeros((spec.nn, 3))
+        u[:, 0] = a * y ** 1.5; u[:, 1] = -0.01 * y; u[:, 2] = -1.5 * a * y ** 0.5 / spec.crd[:, 1].max()
+        u += rng.normal(0, 1.0, u.shape) * (2e-3, 1e-3, 2e-5)
+        u[ids < 0] = 0
+        assert O.set_trial_disp(u) == 0
+        D.set_trial_disp(u); D.update(); D.apply_load(0.1 * s); O.apply_load(0.1 * s)
+        assert relerr(D.form_tangent(), O.form_tangent()) < BEAM_RTOL
+        assert relerr(D.form_unbalance(), O.form_unbalance()) < BEAM_RTOL
+        if s == 4:
+            O.revert(); D.revert_to_last_commit()
+            assert relerr(D.form_tangent(), O.form_tangent()) < BEAM_RTOL
+            assert relerr(D.form_unbalance(), O.form_unbalance()) < BEAM_RTOL
+        else:
+            O.commit(); D.commit()
+    # the history went well past yield: the tangent is far from the initial one
+    D0 = xb.DeviceModel.from_spec(spec, 1, 0).to_device(0)
+    assert relerr(D.form_tangent(), D0.form_tangent()) > 0.05
+
+
+def test_partitioned_frame_matches_single_gpu():
+    spec_fn = lambda: frame2d(4, 5, 2)
+    spec = spec_fn()
+    G = xb.DeviceModel.from_spec(spec, 1, 0).to_device(0)
+    gptr, _ = G.pattern()
+    ranks = [xb.DeviceModel.from_spec(spec_fn(), 1, 0, 3, r).to_device(0) for r in range(3)]
+    y = spec.crd[:, 1] / spec.crd[:, 1].max()
+    for a in (0.8, 2.4):
+        u = np.zeros((spec.nn, 3)); u[:, 0] = a * y ** 1.5; u[:, 2] = -1.5 * a * y ** 0.5 / spec.crd[:, 1].max()
+        u[G.ids() < 0] = 0
+        G.set_trial_disp(u); G.update(); G.apply_load(1.0)
+        Ag, Bg = G.form_tangent(), G.form_unbalance()
+        for m, (A, B) in zip(ranks, _partitioned_pass(ranks, u, 1.0)):
+            rows = m.row_eqns()
+            assert np.array_equal(B, Bg[rows])
+            assert np.array_equal(A, np.concatenate([Ag[gptr[q]:gptr[q + 1]] for q in rows]))
+        G.commit()
+        for m in ranks:
+            m.commit()

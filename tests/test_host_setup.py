@@ -9,7 +9,7 @@ import pytest
 
 import xara_b200 as xb
 from golden_cases import CASES
-from modelspec import ELASTIC, J2_STEEL, OracleBackend, brick_block, quad_plane
+from modelspec import ELASTIC, J2_STEEL, OracleBackend, brick_block, frame2d, quad_plane
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -46,6 +46,7 @@ SPECS = {
     "brick_relabel": lambda: relabel(brick_block(3, 3, 3), 5),
     "quad_relabel": lambda: relabel(quad_plane(7, 4, distort=0.2), 6),
     "brick_sliver": lambda: brick_block(9, 1, 1),
+    "frame2d": lambda: frame2d(3, 4, 2),
 }
 
 
@@ -56,7 +57,7 @@ def test_numbering_pattern_scatter_bit_exact(name, numberer, soe):
     spec = SPECS[name]()
     O = OracleBackend(spec, numberer, soe)
     D = xb.DeviceModel.from_spec(spec, numberer, soe)
-    nd = 24 if spec.ndm == 3 else 8
+    nd = {0: 24, 1: 8, 2: 6}[spec.groups[0].kind]
     assert D.neq == O.neq and D.nnz == O.nnz
     assert np.array_equal(D.node_tags(), spec.node_tags)
     assert np.array_equal(D.ids(), O.ids())

@@ -9,9 +9,9 @@ import os
 import numpy as np
 import pytest
 
-from golden_cases import CASES, NSTEPS
+from golden_cases import CASES, NSTEPS, ele_nd
 from modelspec import (ELASTIC, J2_STEEL, MAT_ELASTIC, MAT_J2, ND_3D, ND_PLANE_STRAIN, OracleBackend, RefBackend,
-                       brick_block, have_ref, oracle_nd_path, quad_plane, ref_nd_path)
+                       brick_block, frame2d, have_ref, oracle_nd_path, oracle_uni_path, quad_plane, ref_nd_path)
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 RTOL = 1e-12
@@ -35,13 +35,22 @@ def test_material_paths_vs_golden(key, kind, type_):
         assert np.abs(g[key + "_tangent"] - el).max() > 1e-3 * np.abs(el).max()
 
 
+@pytest.mark.parametrize("key,kind", [("steel02", 0), ("concrete02_core", 1), ("concrete02_cover", 1)])
+def test_uniaxial_paths_vs_golden(key, kind):
+    g = np.load(os.path.join(GOLD, "material_paths.npz"))
+    s, t = oracle_uni_path(kind, g[key + "_par"], g[key + "_strain"], g[key + "_commit"])
+    assert close(s, g[key + "_stress"], 1e-12)
+    assert close(t, g[key + "_tangent"], 1e-11)       # Steel02's tangent goes through three pow() calls
+    assert len(np.unique(np.round(g[key + "_tangent"], 3))) > (20 if kind == 0 else 3)     # the path really cycles
+
+
 @pytest.mark.parametrize("name", list(CASES))
 def test_model_vs_golden(name):
     mk, numberer, soe, _ = CASES[name]
     g = np.load(os.path.join(GOLD, name + ".npz"))
     spec = mk()
     O = OracleBackend(spec, numberer, soe)
-    nd = 24 if spec.ndm == 3 else 8
+    nd = ele_nd(spec)
     assert np.array_equal(O.ids(), g["ids"])                       # bit-exact DOF numbering
     ptr, idx = O.csr()
     assert np.array_equal(ptr, g["ptr"]) and np.array_equal(idx, g["idx"])   # bit-exact pattern
@@ -99,17 +108,21 @@ def test_empty_and_constrained_edge_cases():
 @pytest.mark.parametrize("soe", [0, 1])
 def test_oracle_vs_live_reference(mat, numberer, soe):
     rng = np.random.default_rng(7)
-    for spec in (brick_block(3, 2, 2, mat=mat, distort=0.2, seed=11), quad_plane(5, 4, mat=mat, distort=0.2, seed=12)):
+    specs = [brick_block(3, 2, 2, mat=mat, distort=0.2, seed=11), quad_plane(5, 4, mat=mat, distort=0.2, seed=12)]
+    if mat is J2_STEEL:
+        specs.append(frame2d(2, 2, 2))
+    for spec in specs:
         O, R = OracleBackend(spec, numberer, soe), RefBackend(spec, numberer, soe)
         assert O.neq == R.neq and O.nnz == R.nnz
         assert np.array_equal(O.ids(), R.ids())
         assert all(np.array_equal(a, b) for a, b in zip(O.csr(), R.csr()))
         for s in range(3):
-            u = rng.normal(0, 2e-3 * (s + 1), (spec.nn, spec.ndf)); u[O.ids() < 0] = 0
+            sc = (0.02, 0.02, 2e-4) if spec.ndf == 3 and spec.ndm == 2 else 2e-3
+            u = rng.normal(0, 1.0, (spec.nn, spec.ndf)) * np.asarray(sc) * (s + 1); u[O.ids() < 0] = 0
             O.set_trial_disp(u); R.set_trial_disp(u)
             O.apply_load(0.3 * s); R.apply_load(0.3 * s)
-            assert close(O.form_tangent(), R.form_tangent())
-            assert close(O.form_unbalance(), R.form_unbalance())
+            assert close(O.form_tangent(), R.form_tangent(), 1e-11 if spec.ndf == 3 and spec.ndm == 2 else RTOL)
+            assert close(O.form_unbalance(), R.form_unbalance(), 1e-11 if spec.ndf == 3 and spec.ndm == 2 else RTOL)
             O.commit(); R.commit()
 
 

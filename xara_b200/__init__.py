@@ -28,11 +28,12 @@ import os
 import numpy as np
 
 __all__ = ["DeviceModel", "XaraB200Error", "lib", "LIB_PATH", "device_count", "comm_unique_id", "exchange_local",
-           "MAT_ELASTIC_ISOTROPIC", "MAT_J2PLASTICITY", "ELE_STDBRICK", "ELE_FOURNODEQUAD",
+           "MAT_ELASTIC_ISOTROPIC", "MAT_J2PLASTICITY", "ELE_STDBRICK", "ELE_FOURNODEQUAD", "ELE_FORCEBEAMCOLUMN2D", "UNI_STEEL02", "UNI_CONCRETE02",
            "NUMBERER_PLAIN", "NUMBERER_RCM", "SOE_SPARSE_GEN_COL", "SOE_SPARSE_GEN_ROW"]
 
 MAT_ELASTIC_ISOTROPIC, MAT_J2PLASTICITY = 0, 1
-ELE_STDBRICK, ELE_FOURNODEQUAD = 0, 1
+ELE_STDBRICK, ELE_FOURNODEQUAD, ELE_FORCEBEAMCOLUMN2D = 0, 1, 2
+UNI_STEEL02, UNI_CONCRETE02 = 0, 1
 NUMBERER_PLAIN, NUMBERER_RCM = 0, 1
 SOE_SPARSE_GEN_COL, SOE_SPARSE_GEN_ROW = 0, 1
 
@@ -59,6 +60,8 @@ def _load():
         "xb_add_nodes": (i32, [vp, i32, vp, vp]),
         "xb_add_sp": (i32, [vp, i32, vp, vp]),
         "xb_add_nd_material": (i32, [vp, i32, i32, vp, i32]),
+        "xb_add_uniaxial_material": (i32, [vp, i32, i32, vp, i32]),
+        "xb_add_fiber_section": (i32, [vp, i32, i32, vp, vp, vp]),
         "xb_add_elements": (i32, [vp, i32, i32, vp, vp, vp, vp, i32]),
         "xb_add_nodal_loads": (i32, [vp, i32, vp, vp]),
         "xb_setup": (i32, [vp, i32, i32]),
@@ -188,6 +191,14 @@ class DeviceModel:
         par = _f64(par)
         self._ck(lib.xb_add_nd_material(self._h, tag, kind, _ptr(par), len(par)))
 
+    def uniaxial_material(self, tag, kind, par):
+        par = _f64(par)
+        self._ck(lib.xb_add_uniaxial_material(self._h, tag, kind, _ptr(par), len(par)))
+
+    def fiber_section(self, tag, y, A, mat_tags):
+        y, A, mat_tags = _f64(y), _f64(A), _i32(mat_tags)
+        self._ck(lib.xb_add_fiber_section(self._h, tag, len(y), _ptr(y), _ptr(A), _ptr(mat_tags)))
+
     def add_elements(self, kind, tags, conn, mat_tags, par):
         tags, conn, mat_tags, par = _i32(tags), _i32(conn), _i32(mat_tags), _f64(par)
         assert par.ndim == 2 and len(par) == len(tags)
@@ -207,6 +218,10 @@ class DeviceModel:
             m.fix(spec.fix[:, 0], spec.fix[:, 1])
         for tag, kind, p in spec.materials:
             m.nd_material(tag, kind, p)
+        for tag, kind, p in getattr(spec, "uniaxials", []):
+            m.uniaxial_material(tag, kind, p)
+        for tag, y, A, mt in getattr(spec, "sections", []):
+            m.fiber_section(tag, y, A, mt)
         for g in spec.groups:
             m.add_elements(g.kind, g.tags, g.conn, g.mat, g.par)
         if spec.loads is not None and len(spec.loads):

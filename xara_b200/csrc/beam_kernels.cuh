@@ -1,0 +1,427 @@
+// Force-based beam-column with fibre sections on the device.
+//
+// Reference counterparts (under /root/reference/SRC):
+//   ForceBeamColumn2d::update / commitState / revertToLastCommit / getTangentStiff /
+//     getResistingForce                  element/Frame/Other/Force/ForceBeamColumn2d.cpp:559,276,310,400,523
+//   LinearCrdTransf2d (no offsets)       coordTransformation/LinearCrdTransf2d.cpp
+//   LobattoBeamIntegration               quadrature/Frame/LobattoBeamIntegration.cpp
+//   FiberSection2d::setTrialSectionDeformation / revertToLastCommit
+//                                        material/section/FiberSection2d.cpp:225,376
+//   SectionForceDeformation::getSectionFlexibility -> cmx_inv2   matrix/routines/invGL2.c
+//   Steel02::setTrialStrain              material/uniaxial/steel/Steel02.cpp:113
+//   Concrete02::setTrialStrain           material/uniaxial/concrete/Concrete02.cpp:167
+//
+// One thread per element.  All state is SoA over the element index (coalesced across the
+// threads of a warp): element state, per-section state, and per-fibre history with a fixed
+// record of XB_FIB_NV doubles (committed and trial copies in separate buffers, so that
+// commit / revert are plain device copies).
+#pragma once
+#include <cfloat>
+#include <cuda_runtime.h>
+
+namespace xbk {
+
+constexpr int XB_FIB_NV = 11;   // doubles per fibre record
+constexpr int XB_MAXSEC = 10;
+// Steel02 record:   0 epsmin 1 epsmax 2 epspl 3 epss0 4 sigs0 5 epsr 6 sigr 7 kon 8 e 9 sig 10 eps
+// Concrete02 record: 0 ecmin 1 dept 8 e 9 sig 10 eps
+
+struct BeamView {
+  long long n;                 // elements
+  int nip, nf, maxIters;
+  double tol;
+  const int* conn;             // [n][2]
+  const double* geo;           // [3][n]  L, cosTheta, sinTheta
+  // section template (shared by every section of every element of the group)
+  const double* fy;            // [nf] y - yBar
+  const double* fA;            // [nf]
+  const int* fkind;            // [nf] 0 Steel02, 1 Concrete02
+  const double* fpar;          // [nf][12] material parameters
+  const double* fs0;           // [4] initial section flexibility (column-major 2x2)
+  // element state, SoA [k][n]
+  double* Se;                  // [3][n]
+  double* kv;                  // [9][n] column-major
+  double* Sec;                 // committed
+  double* kvc;
+  int* iflag;                  // [n] initialFlag
+  // section state [i][k][n]
+  double* vs;                  // [nip][2][n]
+  double* fs;                  // [nip][4][n]
+  double* Ssr;                 // [nip][2][n]
+  double* vsc;                 // [nip][2][n] committed
+  // fibre records [ (i*nf+f)*NV + v ][n]
+  double* fc;                  // committed
+  double* ft;                  // trial
+  const long long* kdst;       // [n][2] slot of node a in KeN (or send buffer)
+  double* KeN;
+  double* sendK;
+  int cps;
+  double* Re;                  // [n][6]
+};
+
+__device__ __forceinline__ void lobatto_rule(int n, double* xi, double* wt) {
+  // LobattoBeamIntegration.cpp: the literals of getSectionLocations / getSectionWeights
+  const double X[11][10] = {{0},{0},{-1.0,1.0},{-1.0,0.0,1.0},{-1.0,-0.44721360,0.44721360,1.0},
+    {-1.0,-0.65465367,0.0,0.65465367,1.0},{-1.0,-0.7650553239,-0.2852315164,0.2852315164,0.7650553239,1.0},
+    {-1.0,-0.8302238962,-0.4688487934,0.0,0.4688487934,0.8302238962,1.0},
+    {-1.0,-0.8717401485,-0.5917001814,-0.2092992179,0.2092992179,0.5917001814,0.8717401485,1.0},
+    {-1.0,-0.8997579954,-0.6771862795,-0.3631174638,0.0,0.3631174638,0.6771862795,0.8997579954,1.0},
+    {-1.0,-0.9195339082,-0.7387738651,-0.4779249498,-0.1652789577,0.1652789577,0.4779249498,0.7387738651,0.9195339082,1.0}};
+  const double W[11][10] = {{0},{0},{1.0,1.0},{0.333333333333333,1.333333333333333,0.333333333333333},
+    {0.166666666666667,0.833333333333333,0.833333333333333,0.166666666666667},
+    {0.1,0.5444444444,0.7111111111,0.5444444444,0.1},
+    {0.06666666667,0.3784749562,0.5548583770,0.5548583770,0.3784749562,0.06666666667},
+    {0.04761904762,0.2768260473,0.4317453812,0.4876190476,0.4317453812,0.2768260473,0.04761904762},
+    {0.03571428571,0.2107042271,0.3411226924,0.4124587946,0.4124587946,0.3411226924,0.2107042271,0.03571428571},
+    {0.02777777778,0.1654953615,0.2745387125,0.3464285109,0.3715192743,0.3464285109,0.2745387125,0.1654953615,0.02777777778},
+    {0.02222222222,0.1333059908,0.2248893421,0.2920426836,0.3275397611,0.3275397611,0.2920426836,0.2248893421,0.1333059908,0.02222222222}};
+  for (int i = 0; i < n; i++) { xi[i] = 0.5 * (X[n][i] + 1.0); wt[i] = W[n][i] * 0.5; }
+}
+
+// Steel02::setTrialStrain.  C = committed record, T = trial record (both strided by n)
+__device__ __forceinline__ void steel02_trial(const double* __restrict__ p, const double* C, double* T, long long n,
+                                              double trialStrain, double& sig_o, double& e_o) {
+  const double Fy = p[0], E0 = p[1], b = p[2], R0 = p[3], cR1 = p[4], cR2 = p[5], a1 = p[6], a2 = p[7], a3 = p[8],
+               a4 = p[9], sigini = p[10];
+  const double Esh = b * E0, epsy = Fy / E0;
+  double eps = trialStrain;
+  if (sigini != 0.0) eps = trialStrain + sigini / E0;
+  const double epsP = C[10 * n], sigP = C[9 * n];
+  const double deps = eps - epsP;
+  double epsmin = C[0], epsmax = C[1 * n], epspl = C[2 * n], epss0 = C[3 * n], sigs0 = C[4 * n], epsr = C[5 * n],
+         sigr = C[6 * n];
+  int kon = (int)C[7 * n];
+  double sig, e;
+  bool done = false;
+  if (kon == 0 || kon == 3) {
+    if (fabs(deps) < 10.0 * DBL_EPSILON) {
+      e = E0; sig = sigini; kon = 3; done = true;
+    } else {
+      epsmax = epsy; epsmin = -epsy;
+      if (deps < 0.0) { kon = 2; epss0 = epsmin; sigs0 = -Fy; epspl = epsmin; }
+      else { kon = 1; epss0 = epsmax; sigs0 = Fy; epspl = epsmax; }
+    }
+  }
+  if (!done) {
+    if (kon == 2 && deps > 0.0) {
+      kon = 1; epsr = epsP; sigr = sigP;
+      if (epsP < epsmin) epsmin = epsP;
+      const double d1 = (epsmax - epsmin) / (2.0 * (a4 * epsy));
+      const double shft = 1.0 + a3 * pow(d1, 0.8);
+      epss0 = (Fy * shft - Esh * epsy * shft - sigr + E0 * epsr) / (E0 - Esh);
+      sigs0 = Fy * shft + Esh * (epss0 - epsy * shft);
+      epspl = epsmax;
+    } else if (kon == 1 && deps < 0.0) {
+      kon = 2; epsr = epsP; sigr = sigP;
+      if (epsP > epsmax) epsmax = epsP;
+      const double d1 = (epsmax - epsmin) / (2.0 * (a2 * epsy));
+      const double shft = 1.0 + a1 * pow(d1, 0.8);
+      epss0 = (-Fy * shft + Esh * epsy * shft - sigr + E0 * epsr) / (E0 - Esh);
+      sigs0 = -Fy * shft + Esh * (epss0 + epsy * shft);
+      epspl = epsmin;
+    }
+    const double xi = fabs((epspl - epss0) / epsy);
+    const double R = R0 * (1.0 - (cR1 * xi) / (cR2 + xi));
+    const double epsrat = (eps - epsr) / (epss0 - epsr);
+    const double dum1 = 1.0 + pow(fabs(epsrat), R);
+    const double dum2 = pow(dum1, (1 / R));
+    sig = b * epsrat + (1.0 - b) * epsrat / dum2;
+    sig = sig * (sigs0 - sigr) + sigr;
+    e = b + (1.0 - b) / (dum1 * dum2);
+    e = e * (sigs0 - sigr) / (epss0 - epsr);
+  }
+  T[0] = epsmin; T[1 * n] = epsmax; T[2 * n] = epspl; T[3 * n] = epss0; T[4 * n] = sigs0; T[5 * n] = epsr; T[6 * n] = sigr;
+  T[7 * n] = (double)kon; T[8 * n] = e; T[9 * n] = sig; T[10 * n] = eps;
+  sig_o = sig; e_o = e;
+}
+
+__device__ __forceinline__ void c02_tens(const double* p, double epsc, double& sigc, double& Ect) {
+  const double fc = p[0], epsc0 = p[1], ft = p[5], Ets = p[6];
+  const double Ec0 = 2.0 * fc / epsc0;
+  const double eps0 = ft / Ec0;
+  const double epsu = ft * (1.0 / Ets + 1.0 / Ec0);
+  if (epsc <= eps0) { sigc = epsc * Ec0; Ect = Ec0; }
+  else if (epsc <= epsu) { Ect = -Ets; sigc = ft - Ets * (epsc - eps0); }
+  else { Ect = 1.0e-10; sigc = 0.0; }
+}
+__device__ __forceinline__ void c02_compr(const double* p, double epsc, double& sigc, double& Ect) {
+  const double fc = p[0], epsc0 = p[1], fcu = p[2], epscu = p[3];
+  const double Ec0 = 2.0 * fc / epsc0;
+  const double ratLocal = epsc / epsc0;
+  if (epsc >= epsc0) { sigc = fc * ratLocal * (2.0 - ratLocal); Ect = Ec0 * (1.0 - ratLocal); }
+  else if (epsc > epscu) { sigc = (fcu - fc) * (epsc - epsc0) / (epscu - epsc0) + fc; Ect = (fcu - fc) / (epscu - epsc0); }
+  else { sigc = fcu; Ect = 1.0e-10; }
+}
+// Concrete02::setTrialStrain.  p = fc, epsc0, fcu, epscu (already made negative on the host), rat, ft, Ets
+__device__ __forceinline__ void concrete02_trial(const double* __restrict__ p, const double* C, double* T, long long n,
+                                                 double trialStrain, double& sig_o, double& e_o) {
+  const double fc = p[0], epsc0 = p[1], fcu = p[2], epscu = p[3], rat = p[4];
+  const double ec0 = fc * 2. / epsc0;
+  double ecmin = C[0], dept = C[1 * n];
+  const double epsP = C[10 * n], sigP = C[9 * n];
+  const double eps = trialStrain;
+  const double deps = eps - epsP;
+  // the early return keeps the previous TRIAL stress / tangent (Concrete02.cpp:183)
+  double sig = T[9 * n], e = T[8 * n];
+  if (!(fabs(deps) < DBL_EPSILON)) {
+    if (eps < ecmin) {
+      c02_compr(p, eps, sig, e);
+      ecmin = eps;
+    } else {
+      const double epsr = (fcu - rat * ec0 * epscu) / (ec0 * (1.0 - rat));
+      const double sigmr = ec0 * epsr;
+      double sigmm, dumy;
+      c02_compr(p, ecmin, sigmm, dumy);
+      const double er = (sigmm - sigmr) / (ecmin - epsr);
+      const double ept = ecmin - sigmm / er;
+      if (eps <= ept) {
+        const double sigmin = sigmm + er * (eps - ecmin);
+        const double sigmax = er * .5f * (eps - ept);
+        sig = sigP + ec0 * deps;
+        e = ec0;
+        if (sig <= sigmin) { sig = sigmin; e = er; }
+        if (sig >= sigmax) { sig = sigmax; e = 0.5 * er; }
+      } else {
+        const double epn = ept + dept;
+        double sicn;
+        if (eps <= epn) {
+          c02_tens(p, dept, sicn, e);
+          if (dept != 0.0) e = sicn / dept; else e = ec0;
+          sig = e * (eps - ept);
+        } else {
+          const double epstmp = eps - ept;
+          c02_tens(p, epstmp, sig, e);
+          dept = eps - ept;
+        }
+      }
+    }
+  }
+  T[0] = ecmin; T[1 * n] = dept; T[8 * n] = e; T[9 * n] = sig; T[10 * n] = eps;
+  sig_o = sig; e_o = e;
+}
+
+// FiberSection2d::setTrialSectionDeformation for section i of element e -> s[2], k[4] (column-major)
+__device__ __forceinline__ void section_trial(const BeamView& B, long long e, int i, const double* d, double* s, double* k) {
+  k[0] = k[1] = k[2] = k[3] = 0.0; s[0] = s[1] = 0.0;
+  const double d0 = d[0], d1 = d[1];
+  for (int f = 0; f < B.nf; f++) {
+    const double y = __ldg(B.fy + f), A = __ldg(B.fA + f);
+    const double strain = d0 - y * d1;
+    const size_t rec = ((size_t)(i * B.nf + f) * XB_FIB_NV) * B.n + e;
+    double stress, tangent;
+    if (__ldg(B.fkind + f) == 0) steel02_trial(B.fpar + f * 12, B.fc + rec, B.ft + rec, B.n, strain, stress, tangent);
+    else concrete02_trial(B.fpar + f * 12, B.fc + rec, B.ft + rec, B.n, strain, stress, tangent);
+    const double ks0 = tangent * A;
+    const double ks1 = ks0 * -y;
+    k[0] += ks0; k[1] += ks1; k[3] += ks1 * -y;
+    const double fs0 = stress * A;
+    s[0] += fs0; s[1] += fs0 * -y;
+  }
+  k[2] = k[1];
+}
+__device__ __forceinline__ void inv2(const double* a, double* ainv) {   // matrix/routines/invGL2.c
+  const double det = a[0] * a[3] - a[2] * a[1];
+  ainv[0] = a[3] / det; ainv[1] = -a[1] / det; ainv[2] = -a[2] / det; ainv[3] = a[0] / det;
+}
+__device__ __forceinline__ void inv3(const double* a, double* ainv) {   // matrix/routines/invGL3.c
+  const double* A = a - 4; double* I = ainv - 4;
+  const double det = A[4]*A[8]*A[12] - A[4]*A[11]*A[9] - A[7]*A[5]*A[12] + A[7]*A[11]*A[6] + A[10]*A[5]*A[9] - A[10]*A[8]*A[6];
+  double c[9];
+  c[0] =  A[8]*A[12] - A[11]*A[9];  c[3] = -(A[5]*A[12] - A[11]*A[6]); c[6] =  A[5]*A[9] - A[8]*A[6];
+  c[1] = -(A[7]*A[12] - A[10]*A[9]); c[4] =  A[4]*A[12] - A[10]*A[6];  c[7] = -(A[4]*A[9] - A[7]*A[6]);
+  c[2] =  A[7]*A[11] - A[10]*A[8];  c[5] = -(A[4]*A[11] - A[10]*A[5]); c[8] =  A[4]*A[8] - A[7]*A[5];
+  for (int i = 1; i <= 3; ++i) for (int j = 1; j <= 3; ++j) I[j + i * 3] = c[i + j * 3 - 4] / det;
+}
+__device__ __forceinline__ void crd2d_basic(double L, double cosT, double sinT, const double* ug, double* ub) {
+  const double oneOverL = 1.0 / L;
+  const double sl = sinT * oneOverL, cl = cosT * oneOverL;
+  ub[0] = -cosT * ug[0] - sinT * ug[1] + cosT * ug[3] + sinT * ug[4];
+  ub[1] = -sl * ug[0] + cl * ug[1] + ug[2] + sl * ug[3] - cl * ug[4];
+  ub[2] = ub[1] + ug[5] - ug[2];
+}
+
+// ForceBeamColumn2d::update (no element loads).  U = trial displacements, DU = Node::getIncrDeltaDisp
+__global__ void __launch_bounds__(64) fbc2d_update_kernel(BeamView B, const double* __restrict__ U,
+                                                          const double* __restrict__ DU, int* fail) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B.n) return;
+  const long long n = B.n;
+  const int nip = B.nip;
+  const double L = B.geo[e], cosT = B.geo[n + e], sinT = B.geo[2 * n + e];
+  double ug[6], dug[6];
+  for (int a = 0; a < 2; a++) {
+    const int nd = B.conn[e * 2 + a];
+    for (int j = 0; j < 3; j++) { ug[a * 3 + j] = U[(size_t)nd * 3 + j]; dug[a * 3 + j] = DU[(size_t)nd * 3 + j]; }
+  }
+  double v[3], dv[3], vin[3];
+  crd2d_basic(L, cosT, sinT, ug, v);
+  crd2d_basic(L, cosT, sinT, dug, dv);
+  const int initialFlag = B.iflag[e];
+  if (initialFlag != 0 && sqrt(dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]) <= DBL_EPSILON) return;
+  for (int i = 0; i < 3; i++) vin[i] = v[i] - dv[i];
+  double xi[XB_MAXSEC], wt[XB_MAXSEC];
+  lobatto_rule(nip, xi, wt);
+  double Se[3], kv[9];
+  for (int i = 0; i < 3; i++) Se[i] = B.Se[i * n + e];
+  for (int i = 0; i < 9; i++) kv[i] = B.kv[i * n + e];
+  double fs0[4];
+  for (int i = 0; i < 4; i++) fs0[i] = __ldg(B.fs0 + i);
+  double vr[3], f[9], dSe[3], SeTrial[3], kvTrial[9], dvTrial[3], dvToDo[3];
+  double vsSub[XB_MAXSEC][2], fsSub[XB_MAXSEC][4], SsrSub[XB_MAXSEC][2];
+  int numSubdivide = 1;
+  bool converged = false;
+  for (int i = 0; i < 3; i++) { dvToDo[i] = dv[i]; dvTrial[i] = dvToDo[i]; }
+  const double factor = 10;
+  const int maxSubdivisions = 4;
+  while (!converged && numSubdivide <= maxSubdivisions) {
+    for (int l = 0; l < 3; l++) {
+      for (int i = 0; i < 3; i++) SeTrial[i] = Se[i];
+      for (int i = 0; i < 9; i++) kvTrial[i] = kv[i];
+      for (int i = 0; i < nip; i++) {
+        for (int q = 0; q < 2; q++) { vsSub[i][q] = B.vs[(size_t)(i * 2 + q) * n + e]; SsrSub[i][q] = B.Ssr[(size_t)(i * 2 + q) * n + e]; }
+        for (int q = 0; q < 4; q++) fsSub[i][q] = B.fs[(size_t)(i * 4 + q) * n + e];
+      }
+      for (int i = 0; i < 3; i++) dSe[i] = 0.0;
+      for (int j = 0; j < 3; j++) for (int i = 0; i < 3; i++) dSe[i] += kvTrial[i + 3 * j] * dvTrial[j];
+      for (int i = 0; i < 3; i++) SeTrial[i] += dSe[i];
+      int numIters = B.maxIters;
+      if (l == 1) numIters = 10 * B.maxIters;
+      for (int j = 0; j < numIters; j++) {
+        for (int i = 0; i < 9; i++) f[i] = 0.0;
+        vr[0] = vr[1] = vr[2] = 0.0;
+        for (int i = 0; i < nip; i++) {
+          double Ss[2], dSs[2], dvs[2], fb[6], ssec[2], ksec[4];
+          const double xL = xi[i], xL1 = xL - 1.0, wtL = wt[i] * L;
+          Ss[0] = SeTrial[0];
+          Ss[1] = xL1 * SeTrial[1] + xL * SeTrial[2];
+          dSs[0] = Ss[0] - SsrSub[i][0]; dSs[1] = Ss[1] - SsrSub[i][1];
+          const bool initial = (l == 1) || (l == 2 && j == 0);
+          const double* fuse = initial ? fs0 : fsSub[i];
+          dvs[0] = 0.0; dvs[1] = 0.0;
+          for (int c = 0; c < 2; c++) for (int r = 0; r < 2; r++) dvs[r] += fuse[r + 2 * c] * dSs[c];
+          if (initialFlag != 0) { vsSub[i][0] += dvs[0]; vsSub[i][1] += dvs[1]; }
+          section_trial(B, e, i, vsSub[i], ssec, ksec);
+          SsrSub[i][0] = ssec[0]; SsrSub[i][1] = ssec[1];
+          inv2(ksec, fsSub[i]);
+          dSs[0] = Ss[0] - SsrSub[i][0]; dSs[1] = Ss[1] - SsrSub[i][1];
+          dvs[0] = 0.0; dvs[1] = 0.0;
+          for (int c = 0; c < 2; c++) for (int r = 0; r < 2; r++) dvs[r] += fsSub[i][r + 2 * c] * dSs[c];
+          for (int q = 0; q < 6; q++) fb[q] = 0.0;
+          const double* fSec = fsSub[i];
+          for (int jj = 0; jj < 2; jj++) fb[jj + 2 * 0] += fSec[jj + 2 * 0] * wtL;
+          for (int jj = 0; jj < 2; jj++) { const double tmp = fSec[jj + 2 * 1] * wtL; fb[jj + 2 * 1] += xL1 * tmp; fb[jj + 2 * 2] += xL * tmp; }
+          for (int jj = 0; jj < 3; jj++) f[0 + 3 * jj] += fb[0 + 2 * jj];
+          for (int jj = 0; jj < 3; jj++) { const double tmp = fb[1 + 2 * jj]; f[1 + 3 * jj] += xL1 * tmp; f[2 + 3 * jj] += xL * tmp; }
+          dvs[0] += vsSub[i][0]; dvs[1] += vsSub[i][1];
+          { const double dei = dvs[0] * wtL; vr[0] += dei; }
+          { const double dei = dvs[1] * wtL; vr[1] += xL1 * dei; vr[2] += xL * dei; }
+        }
+        inv3(f, kvTrial);
+        for (int i = 0; i < 3; i++) { dv[i] = vin[i]; dv[i] += dvTrial[i]; dv[i] -= vr[i]; }
+        for (int i = 0; i < 3; i++) dSe[i] = 0.0;
+        for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) dSe[r] += kvTrial[r + 3 * c] * dv[c];
+        double dW = 0.0;
+        for (int i = 0; i < 3; i++) dW += dv[i] * dSe[i];
+        for (int i = 0; i < 3; i++) SeTrial[i] += dSe[i];
+        if (fabs(dW) < B.tol) {
+          for (int i = 0; i < 3; i++) { dvToDo[i] -= dvTrial[i]; vin[i] += dvTrial[i]; }
+          if (sqrt(dvToDo[0] * dvToDo[0] + dvToDo[1] * dvToDo[1] + dvToDo[2] * dvToDo[2]) <= DBL_EPSILON) converged = true;
+          else { for (int i = 0; i < 3; i++) dvTrial[i] = dvToDo[i]; numSubdivide = 1; }
+          for (int i = 0; i < 3; i++) Se[i] = SeTrial[i];
+          for (int i = 0; i < 9; i++) kv[i] = kvTrial[i];
+          for (int i = 0; i < 3; i++) B.Se[i * n + e] = Se[i];
+          for (int i = 0; i < 9; i++) B.kv[i * n + e] = kv[i];
+          for (int i = 0; i < nip; i++) {
+            for (int q = 0; q < 2; q++) { B.vs[(size_t)(i * 2 + q) * n + e] = vsSub[i][q]; B.Ssr[(size_t)(i * 2 + q) * n + e] = SsrSub[i][q]; }
+            for (int q = 0; q < 4; q++) B.fs[(size_t)(i * 4 + q) * n + e] = fsSub[i][q];
+          }
+          j = numIters + 1; l = 3;
+        } else {
+          if (j == (numIters - 1) && (l == 2)) { for (int i = 0; i < 3; i++) dvTrial[i] /= factor; numSubdivide++; }
+        }
+      }
+    }
+  }
+  if (!converged) { atomicExch(fail, 2); return; }
+  B.iflag[e] = 1;
+}
+
+// getTangentStiff -> LinearCrdTransf2d::getGlobalStiffMatrix(kv); getResistingForce ->
+// getGlobalResistingForce(Se).  Rows of node a go to that node's slot (node-major storage).
+__global__ void __launch_bounds__(128) fbc2d_form_kernel(BeamView B, int want_k, int want_r, int transpose) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B.n) return;
+  const long long n = B.n;
+  const double L = B.geo[e], cosTheta = B.geo[n + e], sinTheta = B.geo[2 * n + e], oneOverL = 1.0 / L;
+  if (want_k) {
+    double kb[9];
+    for (int i = 0; i < 9; i++) kb[i] = B.kv[i * n + e];
+    const double kb00 = kb[0], kb10 = kb[1], kb20 = kb[2], kb01 = kb[3], kb11 = kb[4], kb21 = kb[5], kb02 = kb[6], kb12 = kb[7], kb22 = kb[8];
+    double tmp[3][6], kg[6][6];
+    const double sl = sinTheta * oneOverL, cl = cosTheta * oneOverL;
+    tmp[0][0] = -cosTheta * kb00 - sl * (kb01 + kb02); tmp[0][1] = -sinTheta * kb00 + cl * (kb01 + kb02);
+    tmp[0][2] = kb01; tmp[0][3] = -tmp[0][0]; tmp[0][4] = -tmp[0][1]; tmp[0][5] = kb02;
+    tmp[1][0] = -cosTheta * kb10 - sl * (kb11 + kb12); tmp[1][1] = -sinTheta * kb10 + cl * (kb11 + kb12);
+    tmp[1][2] = kb11; tmp[1][3] = -tmp[1][0]; tmp[1][4] = -tmp[1][1]; tmp[1][5] = kb12;
+    tmp[2][0] = -cosTheta * kb20 - sl * (kb21 + kb22); tmp[2][1] = -sinTheta * kb20 + cl * (kb21 + kb22);
+    tmp[2][2] = kb21; tmp[2][3] = -tmp[2][0]; tmp[2][4] = -tmp[2][1]; tmp[2][5] = kb22;
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+      kg[0][c] = -cosTheta * tmp[0][c] - sl * (tmp[1][c] + tmp[2][c]);
+      kg[1][c] = -sinTheta * tmp[0][c] + cl * (tmp[1][c] + tmp[2][c]);
+      kg[2][c] = tmp[1][c];
+      kg[3][c] = -kg[0][c]; kg[4][c] = -kg[1][c];
+      kg[5][c] = tmp[2][c];
+    }
+    for (int a = 0; a < 2; a++) {
+      const long long d = B.kdst[e * 2 + a];
+      double* base = d >= 0 ? B.KeN + d : B.sendK + (-d - 1);
+      for (int p = 0; p < 3; p++)
+        for (int c = 0; c < 6; c++) base[p * B.cps + c] = transpose ? kg[c][a * 3 + p] : kg[a * 3 + p][c];
+    }
+  }
+  if (want_r) {
+    const double q0 = B.Se[e], q1 = B.Se[n + e], q2 = B.Se[2 * n + e];
+    const double V = oneOverL * (q1 + q2);
+    const double pl[6] = {-q0, V, q1, q0, -V, q2};
+    double* R = B.Re + e * 6;
+    R[0] = cosTheta * pl[0] - sinTheta * pl[1];
+    R[1] = sinTheta * pl[0] + cosTheta * pl[1];
+    R[2] = pl[2];
+    R[3] = cosTheta * pl[3] - sinTheta * pl[4];
+    R[4] = sinTheta * pl[3] + cosTheta * pl[4];
+    R[5] = pl[5];
+  }
+}
+
+// ForceBeamColumn2d::revertToLastCommit: the fibre records have been copied back already
+// (committed -> trial); sections recompute (FiberSection2d::revertToLastCommit, then
+// setTrialSectionDeformation(vs)), element state back, initialFlag = 0.
+__global__ void __launch_bounds__(64) fbc2d_revert_kernel(BeamView B) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B.n) return;
+  const long long n = B.n;
+  for (int i = 0; i < B.nip; i++) {
+    double vs[2], s[2], k[4], fl[4];
+    for (int q = 0; q < 2; q++) { vs[q] = B.vsc[(size_t)(i * 2 + q) * n + e]; B.vs[(size_t)(i * 2 + q) * n + e] = vs[q]; }
+    section_trial(B, e, i, vs, s, k);
+    inv2(k, fl);
+    for (int q = 0; q < 2; q++) B.Ssr[(size_t)(i * 2 + q) * n + e] = s[q];
+    for (int q = 0; q < 4; q++) B.fs[(size_t)(i * 4 + q) * n + e] = fl[q];
+  }
+  for (int i = 0; i < 3; i++) B.Se[i * n + e] = B.Sec[i * n + e];
+  for (int i = 0; i < 9; i++) B.kv[i * n + e] = B.kvc[i * n + e];
+  B.iflag[e] = 0;
+}
+
+// Node::setTrialDisp bookkeeping: DU = Unew - U (incrDeltaDisp), U = Unew
+__global__ void set_disp_kernel(long long ndof, const double* __restrict__ Unew, double* __restrict__ U,
+                                double* __restrict__ DU) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ndof) return;
+  const double u = Unew[i];
+  DU[i] = u - U[i];
+  U[i] = u;
+}
+
+}  // namespace xbk

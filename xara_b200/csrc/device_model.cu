@@ -7,6 +7,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -15,6 +16,7 @@
 #include "../../include/xara_b200.h"
 #include "host_model.hpp"
 #include "kernels.cuh"
+#include "beam_kernels.cuh"
 
 using namespace xbk;
 
@@ -611,11 +613,13 @@ __global__ void __launch_bounds__(256) assemble_B_kernel(AsmView V, const double
 
 // AnalysisModel::incrDisp: trial += dU[id]
 __global__ void incr_disp_kernel(long long ndof, const int* __restrict__ id, const double* __restrict__ dU,
-                                 double* __restrict__ U) {
+                                 double* __restrict__ U, double* __restrict__ DU) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ndof) return;
   const int r = id[i];
-  if (r >= 0) U[i] += dU[r];
+  const double d = r >= 0 ? dU[r] : 0.0;   // Node::incrTrialDisp: trial += incr, incrDeltaDisp = incr
+  U[i] += d;
+  DU[i] = d;
 }
 
 // interface exchange, send side.  Element-tangent rows need no packing: the element kernel
@@ -637,9 +641,22 @@ static thread_local std::string g_err;
 
 struct DevGroup {
   GroupView v{};
+  BeamView b{};              // forceBeamColumn batches
   int kind = 0, mat_kind = 0, nip = 0, nst = 0, nd = 0;
   long long ngp = 0;
+  size_t fib_doubles = 0;    // size of one fibre-record buffer
 };
+
+// broadcast the initial fibre records (one per fibre of the section template) to every element
+__global__ void fiber_init_kernel(long long n, int nrec, const double* __restrict__ init_c,
+                                  const double* __restrict__ init_t, int nf_nv, double* fc, double* ft) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)nrec * n) return;
+  const long long r = i / n;                 // record*NV + v over all sections
+  const int within = (int)(r % nf_nv);       // same template for every section
+  fc[i] = init_c[within];
+  ft[i] = init_t[within];
+}
 
 struct xb_model {
   xb::HostModel h;
@@ -649,6 +666,8 @@ struct xb_model {
   bool own_stream = false;
   std::vector<DevGroup> dg;
   std::vector<void*> allocs;
+  double *dDU = nullptr, *dUin = nullptr;   // Node::getIncrDeltaDisp, staging for xb_set_trial_disp
+  bool has_beams = false;
   double *dX = nullptr, *dU = nullptr, *dUc = nullptr, *dKe = nullptr, *dRe = nullptr, *dA = nullptr,
          *dB = nullptr, *dLoad = nullptr, *dMpar = nullptr, *dTmp = nullptr;
   int* dId = nullptr;
@@ -767,6 +786,8 @@ void xb_model_destroy(xb_model* m) {
 int xb_add_nodes(xb_model* m, int n, const int* tags, const double* crd) { HOSTCALL(m->h.add_nodes(n, tags, crd)); }
 int xb_add_sp(xb_model* m, int n, const int* t, const int* d) { HOSTCALL(m->h.add_sp(n, t, d)); }
 int xb_add_nd_material(xb_model* m, int tag, int kind, const double* par, int npar) { HOSTCALL(m->h.add_material(tag, kind, par, npar)); }
+int xb_add_uniaxial_material(xb_model* m, int tag, int kind, const double* par, int npar) { HOSTCALL(m->h.add_uniaxial(tag, kind, par, npar)); }
+int xb_add_fiber_section(xb_model* m, int tag, int nf, const double* y, const double* A, const int* mt) { HOSTCALL(m->h.add_fiber_section(tag, nf, y, A, mt)); }
 int xb_add_elements(xb_model* m, int kind, int n, const int* tags, const int* conn, const int* mt, const double* par, int ps) {
   HOSTCALL(m->h.add_elements(kind, n, tags, conn, mt, par, ps));
 }
@@ -854,6 +875,9 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
   CU(dev_upload(m, &m->dX, h.crd));
   CU(dev_alloc(m, &m->dU, nn * h.ndf));
   CU(dev_alloc(m, &m->dUc, nn * h.ndf));
+  CU(dev_alloc(m, &m->dDU, nn * h.ndf));
+  CU(dev_alloc(m, &m->dUin, nn * h.ndf));
+  CU(cudaMemset(m->dDU, 0, sizeof(double) * std::max<size_t>(nn * h.ndf, 1)));
   CU(cudaMemset(m->dU, 0, sizeof(double) * std::max<size_t>(nn * h.ndf, 1)));
   CU(cudaMemset(m->dUc, 0, sizeof(double) * std::max<size_t>(nn * h.ndf, 1)));
   CU(dev_upload(m, &m->dId, h.id));
@@ -875,9 +899,83 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
   for (auto& g : h.groups) {
     const xb::EleKind& k = xb::ele_kind(g.kind);
     DevGroup d;
-    d.kind = g.kind; d.mat_kind = g.mat_kind; d.nip = k.nip; d.nst = k.nst; d.nd = k.nen * k.ndf;
-    d.ngp = g.n() * k.nip;
+    d.kind = g.kind; d.mat_kind = g.mat_kind; d.nip = k.nip ? k.nip : g.nip; d.nst = k.nst; d.nd = k.nen * k.ndf;
+    d.ngp = g.n() * d.nip;
     d.v.n = g.n();
+    if (g.kind == XB_ELE_FORCEBEAMCOLUMN2D) {
+      m->has_beams = true;
+      const xb::FiberSectionDef& sd = h.secs[g.sec];
+      const int nf = (int)sd.y.size();
+      const long long ne = g.n();
+      BeamView& b = d.b;
+      b.n = ne; b.nip = g.nip; b.nf = nf; b.maxIters = g.max_iters; b.tol = g.tol;
+      int* conn = nullptr;
+      CU(dev_upload(m, &conn, g.conn));
+      b.conn = conn;
+      // LinearCrdTransf2d::computeElemtLengthAndOrient (LinearCrdTransf2d.cpp)
+      std::vector<double> geo((size_t)3 * ne);
+      for (long long e = 0; e < ne; e++) {
+        const int a = g.conn[e * 2], c = g.conn[e * 2 + 1];
+        const double dx0 = h.crd[(size_t)c * 2] - h.crd[(size_t)a * 2], dx1 = h.crd[(size_t)c * 2 + 1] - h.crd[(size_t)a * 2 + 1];
+        const double L = std::sqrt(dx0 * dx0 + dx1 * dx1);
+        if (L == 0.0) return fail(XB_ERR_ARG, "forceBeamColumn: zero element length");
+        geo[e] = L; geo[ne + e] = dx0 / L; geo[2 * ne + e] = dx1 / L;
+      }
+      double* dgeo = nullptr; CU(dev_upload(m, &dgeo, geo)); b.geo = dgeo;
+      // section template + initial fibre records (Steel02::revertToStart, Concrete02 constructor)
+      std::vector<double> fy(nf), fA(sd.A), fpar((size_t)nf * 12), ic((size_t)nf * XB_FIB_NV, 0.0), it((size_t)nf * XB_FIB_NV, 0.0);
+      std::vector<int> fkind(nf);
+      double k0[4] = {0, 0, 0, 0};
+      for (int f = 0; f < nf; f++) {
+        const xb::Uniaxial& u = h.unis[sd.mat[f]];
+        fy[f] = sd.y[f] - sd.yBar; fkind[f] = u.kind;
+        std::memcpy(&fpar[(size_t)f * 12], u.par, sizeof(double) * 12);
+        double* C = &ic[(size_t)f * XB_FIB_NV]; double* T = &it[(size_t)f * XB_FIB_NV];
+        double E0;
+        if (u.kind == XB_UNI_STEEL02) {
+          const double Fy = u.par[0], sigini = u.par[10];
+          E0 = u.par[1];
+          C[0] = -(Fy / E0); C[1] = Fy / E0; C[7] = 0.0; C[8] = E0; C[9] = 0.0; C[10] = 0.0;
+          if (sigini != 0.0) { C[10] = sigini / E0; C[9] = sigini; }
+          T[8] = E0;
+        } else {
+          E0 = 2.0 * u.par[0] / u.par[1];
+          C[8] = E0; T[8] = E0;
+        }
+        // FiberSection2d::getInitialTangent (FiberSection2d.cpp:271)
+        const double ks0 = E0 * fA[f], ks1 = ks0 * -fy[f];
+        k0[0] += ks0; k0[1] += ks1; k0[3] += ks1 * -fy[f];
+      }
+      k0[2] = k0[1];
+      const double det = k0[0] * k0[3] - k0[2] * k0[1];
+      std::vector<double> fs0 = {k0[3] / det, -k0[1] / det, -k0[2] / det, k0[0] / det};
+      double *dfy = nullptr, *dfA = nullptr, *dfpar = nullptr, *dfs0 = nullptr, *dic = nullptr, *dit = nullptr; int* dfk = nullptr;
+      CU(dev_upload(m, &dfy, fy)); CU(dev_upload(m, &dfA, fA)); CU(dev_upload(m, &dfpar, fpar)); CU(dev_upload(m, &dfk, fkind));
+      CU(dev_upload(m, &dfs0, fs0)); CU(dev_upload(m, &dic, ic)); CU(dev_upload(m, &dit, it));
+      b.fy = dfy; b.fA = dfA; b.fkind = dfk; b.fpar = dfpar; b.fs0 = dfs0;
+      CU(dev_alloc(m, &b.Se, (size_t)3 * ne)); CU(dev_alloc(m, &b.kv, (size_t)9 * ne));
+      CU(dev_alloc(m, &b.Sec, (size_t)3 * ne)); CU(dev_alloc(m, &b.kvc, (size_t)9 * ne));
+      CU(dev_alloc(m, &b.iflag, (size_t)ne));
+      CU(dev_alloc(m, &b.vs, (size_t)g.nip * 2 * ne)); CU(dev_alloc(m, &b.vsc, (size_t)g.nip * 2 * ne));
+      CU(dev_alloc(m, &b.fs, (size_t)g.nip * 4 * ne)); CU(dev_alloc(m, &b.Ssr, (size_t)g.nip * 2 * ne));
+      for (double* q : {b.Se, b.Sec}) CU(cudaMemset(q, 0, sizeof(double) * 3 * ne));
+      for (double* q : {b.kv, b.kvc}) CU(cudaMemset(q, 0, sizeof(double) * 9 * ne));
+      for (double* q : {b.vs, b.vsc, b.Ssr}) CU(cudaMemset(q, 0, sizeof(double) * g.nip * 2 * ne));
+      CU(cudaMemset(b.fs, 0, sizeof(double) * g.nip * 4 * ne));
+      CU(cudaMemset(b.iflag, 0, sizeof(int) * ne));
+      d.fib_doubles = (size_t)g.nip * nf * XB_FIB_NV * ne;
+      CU(dev_alloc(m, &b.fc, d.fib_doubles)); CU(dev_alloc(m, &b.ft, d.fib_doubles));
+      {
+        const long long tot = (long long)g.nip * nf * XB_FIB_NV * ne;
+        fiber_init_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, m->stream>>>(ne, g.nip * nf * XB_FIB_NV, dic, dit, nf * XB_FIB_NV, b.fc, b.ft);
+        CU(cudaGetLastError());
+      }
+      long long* kdst = nullptr;
+      CU(dev_upload(m, &kdst, g.kdst));
+      b.kdst = kdst; b.KeN = m->dKe; b.cps = h.cp_stride; b.Re = m->dRe + g.re_off;
+      m->dg.push_back(d);
+      continue;
+    }
     int* conn = nullptr; int* mat = nullptr; double* par = nullptr;
     CU(dev_upload(m, &conn, g.conn));
     CU(dev_upload(m, &mat, g.mat));
@@ -919,7 +1017,7 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
     CU(dev_upload(m, &m->dPrDst, h.pr_dst));
   }
   a.recvK = m->dRecvK; a.recvR = m->dRecvR;
-  for (auto& d : m->dg) d.v.sendK = m->dSendK;
+  for (auto& d : m->dg) { d.v.sendK = m->dSendK; d.b.sendK = m->dSendK; }
   long long *ptr = nullptr, *n2e_ptr = nullptr, *roff = nullptr, *ncol_ptr = nullptr;
   unsigned short* cp = nullptr;
   CU(dev_upload(m, &ptr, h.ptr));
@@ -933,6 +1031,7 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
   // the state determination of an untouched model: J2Plasticity's constructor runs
   // plastic_integrator() on zero strain (J2Plasticity.cpp:105) so that getTangent()
   // is the elastic tangent before the first update; an update at U=0 reproduces that.
+  CU(cudaDeviceSynchronize());   // the memsets above ran on the legacy stream
   int rc = xb_update(m);
   if (rc < 0) return rc;
   CU(cudaStreamSynchronize(m->stream));
@@ -946,7 +1045,8 @@ static int check_fail_flag(xb_model* m) {
   CU(cudaStreamSynchronize(m->stream));
   if (f) {
     cudaMemsetAsync(m->dFail, 0, sizeof(int), m->stream);
-    return fail(XB_ERR_MATERIAL, "More than 25 iterations in J2-plasticity (J2Plasticity.cpp:296)");
+    return fail(XB_ERR_MATERIAL, f == 2 ? "ForceBeamColumn2d::update - failed to get compatible element forces & deformations (ForceBeamColumn2d.cpp:922)"
+                                        : "More than 25 iterations in J2-plasticity (J2Plasticity.cpp:296)");
   }
   return XB_OK;
 }
@@ -954,7 +1054,15 @@ static int check_fail_flag(xb_model* m) {
 int xb_set_trial_disp(xb_model* m, const double* u) {
   NEED_DEVICE();
   CU(cudaSetDevice(m->device));
-  CU(cudaMemcpyAsync(m->dU, u, sizeof(double) * m->h.nn() * m->h.ndf, cudaMemcpyHostToDevice, m->stream));
+  // Node::setTrialDisp also records incrDeltaDisp = new - previous trial (Node.cpp), which the
+  // force-based beam's state determination starts from
+  const long long ndof = (long long)m->h.nn() * m->h.ndf;
+  CU(cudaMemcpyAsync(m->dUin, u, sizeof(double) * ndof, cudaMemcpyHostToDevice, m->stream));
+  if (ndof) {
+    set_disp_kernel<<<(unsigned)((ndof + 255) / 256), 256, 0, m->stream>>>(ndof, m->dUin, m->dU, m->dDU);
+    m->launches++;
+  }
+  CU(cudaGetLastError());
   return XB_OK;
 }
 
@@ -963,7 +1071,7 @@ int xb_incr_trial_disp(xb_model* m, const double* dU) {
   CU(cudaSetDevice(m->device));
   CU(cudaMemcpyAsync(m->dTmp, dU, sizeof(double) * m->h.neq, cudaMemcpyHostToDevice, m->stream));
   const long long ndof = (long long)m->h.nn() * m->h.ndf;
-  incr_disp_kernel<<<(unsigned)((ndof + 255) / 256), 256, 0, m->stream>>>(ndof, m->dId, m->dTmp, m->dU);
+  incr_disp_kernel<<<(unsigned)((ndof + 255) / 256), 256, 0, m->stream>>>(ndof, m->dId, m->dTmp, m->dU, m->dDU);
   m->launches++;
   CU(cudaGetLastError());
   return XB_OK;
@@ -983,6 +1091,12 @@ int xb_update(xb_model* m) {
   long long bytes = 0;
   for (auto& d : m->dg) {
     if (d.v.n == 0) continue;
+    if (d.kind == XB_ELE_FORCEBEAMCOLUMN2D) {
+      fbc2d_update_kernel<<<(unsigned)((d.b.n + 63) / 64), 64, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
+      m->launches++;
+      bytes += (long long)d.b.n * d.b.nip * d.b.nf * XB_FIB_NV * 8 * 2;   // one section pass: records in, out
+      continue;
+    }
     const unsigned blocks = (unsigned)((d.ngp + 127) / 128);
     const bool j2 = d.mat_kind == XB_MAT_J2PLASTICITY;
     if (d.kind == XB_ELE_STDBRICK) {
@@ -1018,6 +1132,12 @@ int xb_form_element_tangents(xb_model* m) {
   long long bytes = 0;
   for (auto& d : m->dg) {
     if (d.v.n == 0) continue;
+    if (d.kind == XB_ELE_FORCEBEAMCOLUMN2D) {
+      fbc2d_form_kernel<<<(unsigned)((d.b.n + 127) / 128), 128, 0, m->stream>>>(d.b, 1, 0, transpose);
+      m->launches++;
+      bytes += d.b.n * (9 + 36) * 8;
+      continue;
+    }
     const bool j2 = d.mat_kind == XB_MAT_J2PLASTICITY;
     if (d.kind == XB_ELE_STDBRICK) {
       const unsigned blocks = (unsigned)((d.v.n + BT_ELEMS - 1) / BT_ELEMS);
@@ -1176,6 +1296,12 @@ int xb_form_element_resids(xb_model* m) {
   long long bytes = 0;
   for (auto& d : m->dg) {
     if (d.v.n == 0) continue;
+    if (d.kind == XB_ELE_FORCEBEAMCOLUMN2D) {
+      fbc2d_form_kernel<<<(unsigned)((d.b.n + 127) / 128), 128, 0, m->stream>>>(d.b, 0, 1, 0);
+      m->launches++;
+      bytes += d.b.n * (3 + 6) * 8;
+      continue;
+    }
     if (d.kind == XB_ELE_STDBRICK) {
       brick_resid_kernel<<<(unsigned)((d.ngp + 127) / 128), 128, 0, m->stream>>>(d.v, m->dX);
     } else {
@@ -1222,9 +1348,21 @@ int xb_commit(xb_model* m) {
   CU(cudaSetDevice(m->device));
   // J2Plasticity::commitState (J2Plasticity.cpp:538): epsilon_p_n = epsilon_p_nplus1, xi_n = xi_nplus1.
   // Every update rewrites the whole trial set, so committing is a buffer swap.
-  for (auto& d : m->dg)
-    if (d.mat_kind == XB_MAT_J2PLASTICITY) std::swap(d.v.hc, d.v.ht);
-  CU(cudaMemcpyAsync(m->dUc, m->dU, sizeof(double) * m->h.nn() * m->h.ndf, cudaMemcpyDeviceToDevice, m->stream));
+  for (auto& d : m->dg) {
+    if (d.kind == XB_ELE_FORCEBEAMCOLUMN2D) {
+      // ForceBeamColumn2d::commitState (ForceBeamColumn2d.cpp:276): vscommit = vs, sections (fibres)
+      // commit, kvcommit = kv, Secommit = Se.  The trial records must survive (Concrete02 keeps
+      // its last trial stress on a zero increment), so this is a copy, not a swap.
+      BeamView& b = d.b;
+      CU(cudaMemcpyAsync(b.fc, b.ft, sizeof(double) * d.fib_doubles, cudaMemcpyDeviceToDevice, m->stream));
+      CU(cudaMemcpyAsync(b.vsc, b.vs, sizeof(double) * b.nip * 2 * b.n, cudaMemcpyDeviceToDevice, m->stream));
+      CU(cudaMemcpyAsync(b.Sec, b.Se, sizeof(double) * 3 * b.n, cudaMemcpyDeviceToDevice, m->stream));
+      CU(cudaMemcpyAsync(b.kvc, b.kv, sizeof(double) * 9 * b.n, cudaMemcpyDeviceToDevice, m->stream));
+    } else if (d.mat_kind == XB_MAT_J2PLASTICITY) std::swap(d.v.hc, d.v.ht);
+  }
+  const size_t nb = sizeof(double) * m->h.nn() * m->h.ndf;
+  CU(cudaMemcpyAsync(m->dUc, m->dU, nb, cudaMemcpyDeviceToDevice, m->stream));
+  CU(cudaMemsetAsync(m->dDU, 0, std::max<size_t>(nb, 1), m->stream));   // Node::commitState: incrDeltaDisp = 0
   return XB_OK;
 }
 
@@ -1234,8 +1372,17 @@ int xb_revert_to_last_commit(xb_model* m) {
   // Node::revertToLastCommit restores the trial displacement; the material history is
   // untouched (J2Plasticity::revertToLastCommit is empty) and the next update rebuilds
   // the trial state from the committed one.
-  CU(cudaMemcpyAsync(m->dU, m->dUc, sizeof(double) * m->h.nn() * m->h.ndf, cudaMemcpyDeviceToDevice, m->stream));
-  return xb_update(m);
+  const size_t nb = sizeof(double) * m->h.nn() * m->h.ndf;
+  CU(cudaMemcpyAsync(m->dU, m->dUc, nb, cudaMemcpyDeviceToDevice, m->stream));
+  CU(cudaMemsetAsync(m->dDU, 0, std::max<size_t>(nb, 1), m->stream));
+  for (auto& d : m->dg)
+    if (d.kind == XB_ELE_FORCEBEAMCOLUMN2D && d.b.n) {
+      CU(cudaMemcpyAsync(d.b.ft, d.b.fc, sizeof(double) * d.fib_doubles, cudaMemcpyDeviceToDevice, m->stream));
+      fbc2d_revert_kernel<<<(unsigned)((d.b.n + 63) / 64), 64, 0, m->stream>>>(d.b);
+      m->launches++;
+    }
+  CU(cudaGetLastError());
+  return xb_update(m);   // Domain::revertToLastCommit ends with this->update() (Domain.cpp:1948)
 }
 
 int xb_synchronize(xb_model* m) {
@@ -1291,6 +1438,7 @@ int xb_get_gp_response(xb_model* m, long long e, int gpt, double* stress, double
   const int gi = m->h.fe_group[e];
   const xb::Group& g = m->h.groups[gi];
   const DevGroup& d = m->dg[gi];
+  if (d.kind == XB_ELE_FORCEBEAMCOLUMN2D) return fail(XB_ERR_UNSUPPORTED, "xb_get_gp_response: continuum elements only");
   if (gpt < 0 || gpt >= d.nip) return fail(XB_ERR_ARG, "gauss point out of range");
   const long long gp = (long long)m->h.fe_local[e] * d.nip + gpt;
   CU(cudaStreamSynchronize(m->stream));

@@ -12,8 +12,11 @@ namespace xb {
 
 static const EleKind kBrick{8, 3, 8, 6, 3};
 static const EleKind kQuad{4, 2, 4, 3, 3};  // par kept: thickness, b1, b2
+static const EleKind kBeam2d{2, 3, 0, 2, 3};  // nip is a property of the batch; par: nIP, maxIters, tol
 
-const EleKind& ele_kind(int kind) { return kind == XB_ELE_STDBRICK ? kBrick : kQuad; }
+const EleKind& ele_kind(int kind) {
+  return kind == XB_ELE_STDBRICK ? kBrick : (kind == XB_ELE_FOURNODEQUAD ? kQuad : kBeam2d);
+}
 
 int HostModel::add_nodes(int n, const int* tags, const double* c) {
   if (is_setup) { err = "xb_add_nodes after xb_setup"; return XB_ERR_STATE; }
@@ -45,12 +48,69 @@ int HostModel::add_material(int tag, int kind, const double* par, int npar) {
   return XB_OK;
 }
 
+int HostModel::add_uniaxial(int tag, int kind, const double* par, int npar) {
+  if (is_setup) { err = "xb_add_uniaxial_material after xb_setup"; return XB_ERR_STATE; }
+  const int need = kind == XB_UNI_STEEL02 ? 10 : (kind == XB_UNI_CONCRETE02 ? 7 : -1);
+  if (need < 0) { err = "xb_add_uniaxial_material: unknown kind"; return XB_ERR_ARG; }
+  if (npar < need || npar > 12) { err = "xb_add_uniaxial_material: wrong parameter count"; return XB_ERR_ARG; }
+  for (auto& u : unis) if (u.tag == tag) { err = "xb_add_uniaxial_material: duplicate tag"; return XB_ERR_ARG; }
+  Uniaxial u{};
+  u.tag = tag; u.kind = kind;
+  std::memcpy(u.par, par, sizeof(double) * npar);
+  if (kind == XB_UNI_CONCRETE02) {   // Concrete02.cpp:101-104: compression quantities are made negative
+    for (int i = 0; i < 4; i++) if (u.par[i] > 0) u.par[i] = -u.par[i];
+  }
+  unis.push_back(u);
+  return XB_OK;
+}
+
+int HostModel::add_fiber_section(int tag, int nf, const double* y, const double* A, const int* mat_tags) {
+  if (is_setup) { err = "xb_add_fiber_section after xb_setup"; return XB_ERR_STATE; }
+  if (nf <= 0) { err = "xb_add_fiber_section: no fibres"; return XB_ERR_ARG; }
+  for (auto& sdef : secs) if (sdef.tag == tag) { err = "xb_add_fiber_section: duplicate tag"; return XB_ERR_ARG; }
+  FiberSectionDef d;
+  d.tag = tag;
+  d.y.assign(y, y + nf); d.A.assign(A, A + nf); d.mat.resize(nf);
+  double ABar = 0.0, QzBar = 0.0;
+  for (int i = 0; i < nf; i++) {
+    d.mat[i] = -1;
+    for (size_t j = 0; j < unis.size(); j++) if (unis[j].tag == mat_tags[i]) d.mat[i] = (int)j;
+    if (d.mat[i] < 0) { err = "xb_add_fiber_section: unknown uniaxial material tag"; return XB_ERR_ARG; }
+    ABar += A[i]; QzBar += y[i] * A[i]; d.yBar = QzBar / ABar;     // FiberSection2d::addFiber, FiberSection2d.cpp:150-154
+  }
+  secs.push_back(std::move(d));
+  return XB_OK;
+}
+
 int HostModel::add_elements(int kind, int n, const int* tags, const int* conn, const int* mat_tags,
                             const double* par, int par_stride) {
   if (is_setup) { err = "xb_add_elements after xb_setup"; return XB_ERR_STATE; }
-  if (kind != XB_ELE_STDBRICK && kind != XB_ELE_FOURNODEQUAD) { err = "xb_add_elements: unknown kind"; return XB_ERR_ARG; }
+  if (kind != XB_ELE_STDBRICK && kind != XB_ELE_FOURNODEQUAD && kind != XB_ELE_FORCEBEAMCOLUMN2D) { err = "xb_add_elements: unknown kind"; return XB_ERR_ARG; }
   const EleKind& k = ele_kind(kind);
   if (k.ndf != ndf) { err = "xb_add_elements: element dofs per node differ from the model's ndf"; return XB_ERR_UNSUPPORTED; }
+  if (kind == XB_ELE_FORCEBEAMCOLUMN2D) {
+    if (ndm != 2 || par_stride < 3) { err = "forceBeamColumn (2D): ndm must be 2 and par = nIP, maxIters, tol"; return XB_ERR_ARG; }
+    Group g;
+    g.kind = kind; g.mat_kind = 0;
+    g.tag.assign(tags, tags + n);
+    g.conn.assign(conn, conn + (size_t)n * 2);
+    g.mat.assign(n, 0);
+    g.par.resize((size_t)n * k.npar);
+    for (int i = 0; i < n; i++) {
+      const double* p = par + (size_t)i * par_stride;
+      int sidx = -1;
+      for (size_t j = 0; j < secs.size(); j++) if (secs[j].tag == mat_tags[i]) sidx = (int)j;
+      if (sidx < 0) { err = "forceBeamColumn: unknown section tag"; return XB_ERR_ARG; }
+      if (i == 0) { g.sec = sidx; g.nip = (int)p[0]; g.max_iters = (int)p[1]; g.tol = p[2]; }
+      else if (sidx != g.sec || (int)p[0] != g.nip || (int)p[1] != g.max_iters || p[2] != g.tol) {
+        err = "forceBeamColumn: one section / nIP / maxIters / tol per xb_add_elements call"; return XB_ERR_UNSUPPORTED;
+      }
+      g.par[(size_t)i * 3] = p[0]; g.par[(size_t)i * 3 + 1] = p[1]; g.par[(size_t)i * 3 + 2] = p[2];
+    }
+    if (g.nip < 2 || g.nip > 10) { err = "forceBeamColumn: Lobatto integration takes 2..10 points"; return XB_ERR_ARG; }
+    if (n > 0) groups.push_back(std::move(g));
+    return XB_OK;
+  }
   if ((kind == XB_ELE_STDBRICK && (ndm != 3 || par_stride < 3)) ||
       (kind == XB_ELE_FOURNODEQUAD && (ndm != 2 || par_stride < 6))) {
     err = "xb_add_elements: ndm / par_stride do not fit the element kind"; return XB_ERR_ARG;
@@ -368,7 +428,10 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
   } else {
     lgroups.resize(groups.size());
     std::vector<std::vector<int>> keep(groups.size());   // batch index -> kept element indices
-    for (size_t gi = 0; gi < groups.size(); gi++) { lgroups[gi].kind = groups[gi].kind; lgroups[gi].mat_kind = groups[gi].mat_kind; }
+    for (size_t gi = 0; gi < groups.size(); gi++) {
+      lgroups[gi].kind = groups[gi].kind; lgroups[gi].mat_kind = groups[gi].mat_kind;
+      lgroups[gi].sec = groups[gi].sec; lgroups[gi].nip = groups[gi].nip; lgroups[gi].max_iters = groups[gi].max_iters; lgroups[gi].tol = groups[gi].tol;
+    }
     std::vector<std::vector<int>> newidx(groups.size());
     for (size_t gi = 0; gi < groups.size(); gi++) newidx[gi].assign(groups[gi].n(), -1);
     // kept elements of a batch keep their batch order
@@ -399,7 +462,7 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
     const EleKind& k = ele_kind(LG[gi].kind);
     const long long nd = k.nen * k.ndf;
     ke_off[gi] = ke_total; re_off[gi] = re_total; gp_off[gi] = ngp;
-    ke_total += LG[gi].n() * nd * nd; re_total += LG[gi].n() * nd; ngp += LG[gi].n() * k.nip;
+    ke_total += LG[gi].n() * nd * nd; re_total += LG[gi].n() * nd; ngp += LG[gi].n() * (k.nip ? k.nip : LG[gi].nip);
   }
 
   // ---- local node tables ----

@@ -34,6 +34,18 @@ struct Material {
   double par[8];
 };
 
+struct Uniaxial {
+  int tag, kind;
+  double par[12];
+};
+// section Fiber (FiberSection2d): fibres in the order they were added
+struct FiberSectionDef {
+  int tag = 0;
+  std::vector<double> y, A;
+  std::vector<int> mat;      // index into HostModel::unis
+  double yBar = 0.0;         // FiberSection2d::addFiber keeps QzBar/ABar up to date
+};
+
 // one xb_add_elements call: a homogeneous batch (one element kind, one material kind).
 // After setup() it holds only the elements of this rank's partition.
 struct Group {
@@ -42,6 +54,9 @@ struct Group {
   std::vector<int> conn;     // [n][nen] node TAGS until setup(), LOCAL node indices after
   std::vector<int> mat;      // [n] material index into HostModel::mats
   std::vector<double> par;   // [n][npar]
+  // forceBeamColumn batches: one fibre section, nIP Lobatto points, element iteration controls
+  int sec = -1, nip = 0, max_iters = 10;
+  double tol = 1e-12;
   std::vector<long long> kdst;  // [n][nen] where the rows of node a of element l go: >= 0 offset of the
                                 //   slot in the node-major buffer KeN (node owned here), < 0 offset
                                 //   -(x+1) in the send buffer (node owned by another rank)
@@ -67,6 +82,8 @@ struct HostModel {
   std::vector<double> crd;          // [nn][ndm]
   std::vector<int> sp_node, sp_dof; // fix
   std::vector<Material> mats;
+  std::vector<Uniaxial> unis;
+  std::vector<FiberSectionDef> secs;
   std::vector<Group> groups;
   std::vector<int> load_node;       // pending nodal loads (tags)
   std::vector<double> load_val;     // [nload][ndf]
@@ -127,6 +144,8 @@ struct HostModel {
   int add_nodes(int n, const int* tags, const double* c);
   int add_sp(int n, const int* tags, const int* dofs);
   int add_material(int tag, int kind, const double* par, int npar);
+  int add_uniaxial(int tag, int kind, const double* par, int npar);
+  int add_fiber_section(int tag, int nf, const double* y, const double* A, const int* mat_tags);
   int add_elements(int kind, int n, const int* tags, const int* conn, const int* mat_tags,
                    const double* par, int par_stride);
   int add_loads(int n, const int* tags, const double* vals);
