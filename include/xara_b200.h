@@ -98,6 +98,12 @@ int xb_add_elements(xb_model*, int kind, int n, const int* tags, const int* conn
  * values is [n][ndf]; loads on one node accumulate */
 int xb_add_nodal_loads(xb_model*, int n, const int* node_tags, const double* values);
 
+/* `mass` command: Node::setMass with a diagonal matrix (domain/node/Node.h:127); mass is [n][ndf].
+ * Element masses (material rho) are NOT on the device path: keep rho = 0 in transient models. */
+int xb_set_nodal_mass(xb_model*, int n, const int* node_tags, const double* mass);
+/* `rayleigh alphaM 0 0 0` on the nodes (Node::setRayleighDampingFactor): C_node = alphaM * M_node */
+int xb_set_rayleigh_alpha_m(xb_model*, double alphaM);
+
 /* ---- analysis set-up: BasicAnalysisBuilder::domainChanged (runtime/runtime/
  * BasicAnalysisBuilder.cpp:225): PlainHandler::handle (analysis/handler/PlainHandler.cpp:60),
  * numberDOF, AnalysisModel::getDOFGraph (analysis/model/AnalysisModel.cpp:286),
@@ -153,6 +159,18 @@ int xb_set_trial_disp(xb_model*, const double* u);
  * (the GLOBAL increment, also on a partitioned model) */
 int xb_incr_trial_disp(xb_model*, const double* dU);
 int xb_get_trial_disp(xb_model*, double* u);
+/* ---- transient analysis (analysis/integrator/Dynamic/Newmark.cpp, TransientIntegrator.cpp) ----
+ * c1,c2,c3 of Newmark::newStep (:117-140): formTangent gives c1*K + c2*C + c3*M with the
+ * DOF_Group (nodal mass) terms added first, formUnbalance gives P - M a - C v - R.  (1,0,0) = static. */
+int xb_set_transient_factors(xb_model*, double c1, double c2, double c3);
+/* Newmark::newStep predictor, displacement unknown (:150-160): V = a1*V + a2*A, A = a4*A + a3*V_old */
+int xb_newmark_predict(xb_model*, double a1, double a2, double a3, double a4);
+/* Newmark::update (:411) + AnalysisModel::setResponse: U += cu*dU[id], V += cv*dU[id], A += ca*dU[id];
+ * dU is the GLOBAL increment [neq] in host memory */
+int xb_incr_trial_response(xb_model*, const double* dU, double cu, double cv, double ca);
+/* AnalysisModel::setVel / setAccel and their read-back, [nn][ndf] host arrays */
+int xb_set_trial_vel_accel(xb_model*, const double* v, const double* a);
+int xb_get_trial_vel_accel(xb_model*, double* v, double* a);
 /* Domain::update -> Element::update -> NDMaterial::setTrialStrain for every Gauss point */
 int xb_update(xb_model*);
 /* AnalysisModel::applyLoadDomain(lambda) for the Linear-series pattern */

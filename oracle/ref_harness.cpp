@@ -71,6 +71,8 @@
 #include <SparseGenRowLinSolver.h>
 #include <SparseGenColLinSolver.h>
 #include <LoadControl.h>
+#include <Newmark.h>
+#include <TransientIntegrator.h>
 #include <DisplacementControl.h>
 #include <NewtonRaphson.h>
 #include <CTestNormDispIncr.h>
@@ -166,7 +168,9 @@ struct RefModel {
   const int* ptr() const { return rsoe ? rsoe->rowStartA : csoe->colStartA; }
   const int* idx() const { return rsoe ? rsoe->colA : csoe->rowA; }
   const double* A() const { return rsoe ? rsoe->A : csoe->A; }
-  StaticIntegrator* integ = nullptr;
+  IncrementalIntegrator* integ = nullptr;
+  StaticIntegrator* sinteg = nullptr;
+  TransientIntegrator* tinteg = nullptr;
   ConvergenceTest* test = nullptr;
   NewtonRaphson* algo = nullptr;
   int nloads = 0;
@@ -286,15 +290,79 @@ int ref_add_load(void* h, int nodeTag, const double* vals) {
 // restates BasicAnalysisBuilder::domainChanged (BasicAnalysisBuilder.cpp:225-300)
 // numberer: 0 Plain, 1 RCM.  integrator: LoadControl(dlambda).
 // soeKind: 0 SparseGenColLinSOE (CSC, the live "SparseGeneral" system), 1 SparseGenRowLinSOE (CSR)
+static int ref_setup_common(RefModel* m, int numberer, int soeKind, int testKind, double tol, int maxIter);
+
 int ref_setup(void* h, int numberer, int soeKind, double dlambda, int testKind, double tol, int maxIter) {
   RefModel* m = (RefModel*)h;
+  m->sinteg = new LoadControl(dlambda, 1, dlambda, dlambda);
+  m->integ = m->sinteg;
+  return ref_setup_common(m, numberer, soeKind, testKind, tol, maxIter);
+}
+
+// `mass` command: Node::setMass with a diagonal matrix (domain/node/Node.h:127)
+int ref_set_mass(void* h, int nodeTag, const double* mvals) {
+  RefModel* m = (RefModel*)h;
+  Node* n = m->domain->getNode(nodeTag);
+  if (!n) return -1;
+  Matrix M(m->ndf, m->ndf);
+  for (int i = 0; i < m->ndf; i++) M(i, i) = mvals[i];
+  return n->setMass(M);
+}
+// rayleigh alphaM 0 0 0 restricted to the nodes (Node::setRayleighDampingFactor)
+int ref_set_alphaM(void* h, double alphaM) {
+  RefModel* m = (RefModel*)h;
+  NodeIter& it = m->domain->getNodes(); Node* n;
+  while ((n = it()) != nullptr) n->setRayleighDampingFactor(alphaM);
+  return 0;
+}
+// integrator Newmark gamma beta (displacement form); analysis Transient
+int ref_setup_transient(void* h, int numberer, int soeKind, double gamma, double beta, int testKind, double tol, int maxIter) {
+  RefModel* m = (RefModel*)h;
+  m->tinteg = new Newmark(gamma, beta);
+  m->integ = m->tinteg;
+  return ref_setup_common(m, numberer, soeKind, testKind, tol, maxIter);
+}
+int ref_transient_new_step(void* h, double dt) { return ((RefModel*)h)->tinteg->newStep(dt); }
+int ref_transient_update(void* h, const double* dU) {
+  RefModel* m = (RefModel*)h;
+  Vector v(m->n());
+  for (int i = 0; i < m->n(); i++) v(i) = dU[i];
+  return m->tinteg->update(v);
+}
+int ref_get_vel_accel(void* h, int n, const int* tags, double* vel, double* acc) {
+  RefModel* m = (RefModel*)h;
+  for (int i = 0; i < n; i++) {
+    Node* nd = m->domain->getNode(tags[i]);
+    const Vector& v = nd->getTrialVel(); const Vector& a = nd->getTrialAccel();
+    for (int j = 0; j < m->ndf; j++) { vel[(size_t)i * m->ndf + j] = v(j); acc[(size_t)i * m->ndf + j] = a(j); }
+  }
+  return 0;
+}
+// BasicAnalysisBuilder::analyzeStep (BasicAnalysisBuilder.cpp:464): newStep(dT), solveCurrentStep, commit
+int ref_analyze_transient(void* h, int nsteps, double dt, int* iters, double* norms, int maxIter) {
+  RefModel* m = (RefModel*)h;
+  for (int s = 0; s < nsteps; s++) {
+    if (m->amodel->analysisStep(dt) < 0) return -2;
+    if (m->tinteg->newStep(dt) < 0) return -2;
+    int r = m->algo->solveCurrentStep();
+    iters[s] = m->test->getNumTests();
+    if (norms) {
+      const Vector& nv = m->test->getNorms();
+      for (int k = 0; k < maxIter && k < nv.Size(); k++) norms[(size_t)s * maxIter + k] = nv(k);
+    }
+    if (r < 0) { m->domain->revertToLastCommit(); m->tinteg->revertToLastStep(); return -3; }
+    if (m->tinteg->commit() < 0) return -4;
+  }
+  return 0;
+}
+
+static int ref_setup_common(RefModel* m, int numberer, int soeKind, int testKind, double tol, int maxIter) {
   m->amodel = new AnalysisModel();
   m->handler = new PlainHandler();
   if (numberer == 0) m->numberer = new PlainNumberer();
   else { RCM* rcm = new RCM(false); m->numberer = new DOF_Numberer(*rcm); }
   if (soeKind == 1) { m->rsoe = new RowSOE(*new HarnessRowSolver()); m->soe = m->rsoe; }
   else { m->csoe = new SparseGenColLinSOE(*new HarnessColSolver()); m->soe = m->csoe; }
-  m->integ = new LoadControl(dlambda, 1, dlambda, dlambda);
   if (testKind == 0) m->test = new CTestNormDispIncr(tol, maxIter, 0);
   else if (testKind == 1) m->test = new CTestNormUnbalance(tol, maxIter, 0);
   else m->test = new CTestEnergyIncr(tol, maxIter, 0);
@@ -420,15 +488,15 @@ int ref_analyze_static(void* h, int nsteps, int* iters, double* norms, int maxIt
   RefModel* m = (RefModel*)h;
   for (int s = 0; s < nsteps; s++) {
     if (m->amodel->analysisStep(0.0) < 0) return -2;
-    if (m->integ->newStep() < 0) return -2;
+    if (m->sinteg->newStep() < 0) return -2;
     int r = m->algo->solveCurrentStep();
     iters[s] = m->test->getNumTests();
     if (norms) {
       const Vector& nv = m->test->getNorms();
       for (int k = 0; k < maxIter && k < nv.Size(); k++) norms[(size_t)s * maxIter + k] = nv(k);
     }
-    if (r < 0) { m->domain->revertToLastCommit(); m->integ->revertToLastStep(); return -3; }
-    if (m->integ->commit() < 0) return -4;
+    if (r < 0) { m->domain->revertToLastCommit(); m->sinteg->revertToLastStep(); return -3; }
+    if (m->sinteg->commit() < 0) return -4;
   }
   return 0;
 }

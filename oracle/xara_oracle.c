@@ -829,6 +829,10 @@ typedef struct {
   int nn; int* node_tag; double* crd; /* [nn][ndm], ascending tag (MapOfTaggedObjects order, Domain.cpp:98) */
   double* trial; double* commit_disp; /* [nn][ndf] */
   double* incr;                       /* [nn][ndf] Node::getIncrDeltaDisp (Node.cpp:435) */
+  double* mass;                       /* [nn][ndf] diagonal of Node::mass (`mass` command) */
+  double* vel; double* acc; double* velc; double* accc;   /* trial / committed velocity, acceleration */
+  double alphaM;                      /* Node::setRayleighDampingFactor */
+  double c1, c2, c3;                  /* TransientIntegrator coefficients (Newmark.cpp:117-140); 1,0,0 = static */
   int nuni; int* uni_tag; int* uni_kind; double* uni_par;   /* uniaxial materials [nuni][12] */
   int nsec; OrcSecDef* sec;           /* fibre section definitions */
   double* load;                       /* [nn][ndf] reference nodal loads (pattern 1, Linear series) */
@@ -859,6 +863,10 @@ void* orc_model_new(int ndm, int ndf, int nn, const int* tags, const double* crd
   m->trial = (double*)calloc((size_t)nn * ndf, sizeof(double));
   m->commit_disp = (double*)calloc((size_t)nn * ndf, sizeof(double));
   m->incr = (double*)calloc((size_t)nn * ndf, sizeof(double));
+  m->mass = (double*)calloc((size_t)nn * ndf, sizeof(double));
+  m->vel = (double*)calloc((size_t)nn * ndf, sizeof(double)); m->acc = (double*)calloc((size_t)nn * ndf, sizeof(double));
+  m->velc = (double*)calloc((size_t)nn * ndf, sizeof(double)); m->accc = (double*)calloc((size_t)nn * ndf, sizeof(double));
+  m->c1 = 1.0; m->c2 = 0.0; m->c3 = 0.0;
   m->load = (double*)calloc((size_t)nn * ndf, sizeof(double));
   m->fixed = (int*)calloc((size_t)nn * ndf, sizeof(int));
   m->mat_tag = NULL; m->nmat = 0;
@@ -879,6 +887,30 @@ int orc_add_nd_material(void* h, int tag, int kind, const double* p) {
   memcpy(m->mat_par + 8 * m->nmat, p, sizeof(double) * (kind == ORC_MAT_J2 ? 7 : 3));
   m->nmat++; return 0;
 }
+/* ---- transient analysis (Newmark, displacement form; nodal masses, mass-proportional damping) ---- */
+int orc_set_mass(void* h, int nodeTag, const double* mv) {
+  OrcModel* m = (OrcModel*)h; int n = find_node(m, nodeTag); if (n < 0) return -1;
+  for (int i = 0; i < m->ndf; i++) m->mass[n * m->ndf + i] = mv[i];
+  return 0;
+}
+void orc_set_alphaM(void* h, double a) { ((OrcModel*)h)->alphaM = a; }
+void orc_set_transient(void* h, double c1, double c2, double c3) { OrcModel* m = (OrcModel*)h; m->c1 = c1; m->c2 = c2; m->c3 = c3; }
+/* Newmark::newStep, displacement unknown (Newmark.cpp:150-160): Udot = a1*Udot + a2*Udotdot(old),
+ * Udotdot = a4*Udotdot + a3*Udot(old); Vector::addVector(thisFact, other, otherFact) */
+void orc_newmark_predict(void* h, double a1, double a2, double a3, double a4) {
+  OrcModel* m = (OrcModel*)h;
+  for (int i = 0; i < m->nn * m->ndf; i++) {
+    if (m->id[i] < 0) continue;
+    double v0 = m->vel[i], ac0 = m->acc[i];
+    m->vel[i] = v0 * a1 + ac0 * a2;
+    m->acc[i] = ac0 * a4 + v0 * a3;
+  }
+}
+void orc_get_vel_accel(void* h, double* v, double* a) {
+  OrcModel* m = (OrcModel*)h;
+  memcpy(v, m->vel, sizeof(double) * m->nn * m->ndf); memcpy(a, m->acc, sizeof(double) * m->nn * m->ndf);
+}
+
 /* uniaxialMaterial Steel02 / Concrete02 ; section Fiber (fibers in the order given) */
 int orc_add_uniaxial(void* h, int tag, int kind, const double* p) {
   OrcModel* m = (OrcModel*)h;
@@ -1318,6 +1350,21 @@ int orc_set_trial_disp(void* h, const double* u) {
   for (int e = 0; e < m->ne; e++) rc |= ele_update(m, &m->ele[e]);
   return rc;
 }
+/* Newmark::update (Newmark.cpp:411-458): U += cu*dU, Udot += cv*dU, Udotdot += ca*dU by equation,
+ * AnalysisModel::setResponse -> Node::setTrialDisp/Vel/Accel, then updateDomain */
+int orc_incr_response(void* h, const double* dU, double cu, double cv, double ca) {
+  OrcModel* m = (OrcModel*)h; int rc = 0;
+  for (int i = 0; i < m->nn * m->ndf; i++) {
+    int r = m->id[i];
+    if (r < 0) { m->incr[i] = 0.0; continue; }
+    double d = dU[r];
+    double un = (cu == 1.0) ? m->trial[i] + d : m->trial[i] + d * cu;
+    m->incr[i] = un - m->trial[i]; m->trial[i] = un;
+    m->vel[i] += d * cv; m->acc[i] += d * ca;
+  }
+  for (int e = 0; e < m->ne; e++) rc |= ele_update(m, &m->ele[e]);
+  return rc;
+}
 void orc_apply_load(void* h, double lambda) { ((OrcModel*)h)->lambda = lambda; }
 
 /* Element::getTangentStiff / getResistingForce of FE element e (row-major) */
@@ -1341,6 +1388,19 @@ int orc_ele_resid(void* h, int e, double* R) {
 int orc_form_tangent(void* h, double* A) {
   OrcModel* m = (OrcModel*)h;
   memset(m->A, 0, sizeof(double) * m->nnz);
+  /* TransientIntegrator::formTangent (TransientIntegrator.cpp:89-97): DOF_Group tangents first,
+   * Newmark::formNodTangent: zeroTangent; addCtoTang(c2) (C = alphaM*M, Node::getDamp); addMtoTang(c3) */
+  if (m->c2 != 0.0 || m->c3 != 0.0)
+    for (int n = 0; n < m->nn; n++)
+      for (int j = 0; j < m->ndf; j++) {
+        int r = m->id[n * m->ndf + j];
+        if (r < 0) continue;
+        double t = 0.0;
+        t += (m->mass[n * m->ndf + j] * m->alphaM) * m->c2;
+        t += m->mass[n * m->ndf + j] * m->c3;
+        int k = soe_find(m, r, r);
+        m->A[k] += t;
+      }
   for (int e = 0; e < m->ne; e++) {
     OrcEle* el = &m->ele[e]; double K[576], R[24]; int ids[32];
     int nd_e = el->nen * el->ndf_e;
@@ -1348,7 +1408,9 @@ int orc_form_tangent(void* h, double* A) {
     else if (el->kind == ORC_ELE_QUAD) quad_form(m, el, 1, K, R);
     else beam_form(el->beam, K, R);
     int n = ele_ids(m, el, ids); (void)n;
-    for (int i = 0; i < nd_e; i++) for (int j = 0; j < nd_e; j++) K[i * nd_e + j] = 0.0 + K[i * nd_e + j];
+    /* FE_Element::addKtToTang(c1): theTangent->addMatrix(K, c1) on a zeroed matrix */
+    for (int i = 0; i < nd_e; i++) for (int j = 0; j < nd_e; j++)
+      K[i * nd_e + j] = (m->c1 == 1.0) ? 0.0 + K[i * nd_e + j] : 0.0 + K[i * nd_e + j] * m->c1;
     if (m->soe_kind == 1) {
       for (int i = 0; i < nd_e; i++) { int row = ids[i]; if (row < 0) continue;
         for (int j = 0; j < nd_e; j++) { int col = ids[j]; if (col < 0) continue;
@@ -1388,7 +1450,12 @@ int orc_form_unbalance(void* h, double* B) {
   for (int n = 0; n < m->nn; n++)
     for (int j = 0; j < m->ndf; j++) {
       int pos = m->id[n * m->ndf + j];
-      if (pos >= 0) m->B[pos] += 0.0 + m->load[n * m->ndf + j] * m->lambda;
+      if (pos < 0) continue;
+      /* Node::getUnbalancedLoadIncInertia (Node.cpp): P - M a - alphaM M v (static: c2 = c3 = 0 and v = a = 0) */
+      double ub = 0.0 + m->load[n * m->ndf + j] * m->lambda;
+      double ms = m->mass[n * m->ndf + j];
+      if (ms != 0.0) { ub -= ms * m->acc[n * m->ndf + j]; if (m->alphaM != 0.0) ub += ms * m->vel[n * m->ndf + j] * -m->alphaM; }
+      m->B[pos] += ub;
     }
   if (B) memcpy(B, m->B, sizeof(double) * m->neq);
   return 0;
@@ -1399,6 +1466,7 @@ int orc_commit(void* h) {
   OrcModel* m = (OrcModel*)h;
   memcpy(m->commit_disp, m->trial, sizeof(double) * m->nn * m->ndf);
   memset(m->incr, 0, sizeof(double) * m->nn * m->ndf);        /* Node::commitState */
+  memcpy(m->velc, m->vel, sizeof(double) * m->nn * m->ndf); memcpy(m->accc, m->acc, sizeof(double) * m->nn * m->ndf);
   for (int e = 0; e < m->ne; e++) {
     if (m->ele[e].kind == ORC_ELE_FBC2D) beam_commit(m->ele[e].beam);
     else for (int g = 0; g < m->ele[e].nip; g++) gp_commit(&m->ele[e].gp[g]);
@@ -1410,6 +1478,7 @@ int orc_revert(void* h) {
   /* Domain::revertToLastCommit (Domain.cpp:1925): nodes, elements, then update() */
   memcpy(m->trial, m->commit_disp, sizeof(double) * m->nn * m->ndf);
   memset(m->incr, 0, sizeof(double) * m->nn * m->ndf);
+  memcpy(m->vel, m->velc, sizeof(double) * m->nn * m->ndf); memcpy(m->acc, m->accc, sizeof(double) * m->nn * m->ndf);
   for (int e = 0; e < m->ne; e++) {
     if (m->ele[e].kind == ORC_ELE_FBC2D) beam_revert(m->ele[e].beam);
     else for (int g = 0; g < m->ele[e].nip; g++) gp_revert(&m->ele[e].gp[g]);

@@ -61,7 +61,33 @@ def model_case(name, spec, numberer, soe, scale, nsteps=NSTEPS):
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
 
 
+def transient_case(name, spec, mass, gamma, beta, dt, nsteps=3, niter=3):
+    """Newmark steps driven through the reference's own integrator: newStep, then `niter` Newton
+    iterations (formUnbalance, formTangent, solve, update) per step; everything recorded."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    R = RefBackend(spec, 1, 1, defer_setup=True)
+    R.set_mass(spec.node_tags, mass); R.setup_transient(1, 1, gamma, beta)
+    ptr, idx = R.csr(); neq = R.neq
+    out = dict(mass=mass, gamma=gamma, beta=beta, dt=dt, nsteps=nsteps, niter=niter, ids=R.ids(), ptr=ptr, idx=idx)
+    for s in range(nsteps):
+        assert R.new_step(dt) == 0
+        for it in range(niter):
+            B = R.form_unbalance(); A = R.form_tangent()
+            dU = spla.spsolve(sp.csr_matrix((A, idx, ptr), shape=(neq, neq)).tocsc(), B)
+            out[f"A{s}_{it}"] = A; out[f"B{s}_{it}"] = B; out[f"dU{s}_{it}"] = dU
+            R.transient_update(dU)
+        v, a = R.vel_accel()
+        out[f"v{s}"] = v; out[f"a{s}"] = a; out[f"u{s}"] = R.get_trial_disp()
+        R.commit()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+
+
 if __name__ == "__main__":
+    from golden_cases import TRANSIENT_CASES
+    for name, (mk, mass_fn, gamma, beta, dt) in TRANSIENT_CASES.items():
+        spec = mk()
+        transient_case(name, spec, mass_fn(spec), gamma, beta, dt)
     material_paths()
     for name, (mk, numberer, soe, scale) in CASES.items():
         model_case(name, mk(), numberer, soe, scale)

@@ -18,3 +18,26 @@ NSTEPS = 3
 def ele_nd(spec):
     """dofs of one element of the (single-kind) model"""
     return {0: 24, 1: 8, 2: 6}[spec.groups[0].kind]
+
+
+def _uniform_mass(val, rot=None):
+    def f(spec):
+        import numpy as np
+        m = np.full((spec.nn, spec.ndf), val)
+        if rot is not None:
+            m[:, 2] = rot
+        return m
+    return f
+
+
+# Newmark (displacement form) with nodal masses: name -> (spec factory, mass(spec), gamma, beta, dt)
+TRANSIENT_CASES = {
+    "newmark_brick_j2": (lambda: brick_block(3, 3, 4, mat=J2_STEEL, lz=3.0, load=(40.0, 0.0, -5.0)), _uniform_mass(0.05), 0.5, 0.25, 0.02),
+    "newmark_frame2d": (lambda: frame2d(2, 2, 2, lateral=30.0), _uniform_mass(0.05, 0.0), 0.5, 0.25, 0.02),
+}
+
+
+def newmark_coeffs(gamma, beta, dt):
+    """c1 c2 c3 and the predictor's a1..a4 of Newmark::newStep (displacement unknown)"""
+    return ((1.0, gamma / (beta * dt), 1.0 / (beta * dt * dt)),
+            (1.0 - gamma / beta, dt * (1.0 - 0.5 * gamma / beta), -1.0 / (beta * dt), 1.0 - 0.5 / beta))

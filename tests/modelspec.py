@@ -266,6 +266,34 @@ class OracleBackend(_Backend):
     def ele_resid(self, e, nd):
         R = np.zeros(nd); self.L.orc_ele_resid(self.h, e, _p(R)); return R
 
+    # ---- transient (Newmark, displacement form) ----
+    def set_mass(self, tags, mass):
+        for t, mv in zip(tags, np.ascontiguousarray(mass, np.float64)):
+            assert self.L.orc_set_mass(self.h, int(t), _p(np.ascontiguousarray(mv))) == 0
+
+    def set_transient(self, c1, c2, c3):
+        self.L.orc_set_transient.argtypes = [ctypes.c_void_p] + [ctypes.c_double] * 3
+        self.L.orc_set_transient(self.h, c1, c2, c3)
+
+    def newmark_predict(self, a1, a2, a3, a4):
+        self.L.orc_newmark_predict.argtypes = [ctypes.c_void_p] + [ctypes.c_double] * 4
+        self.L.orc_newmark_predict(self.h, a1, a2, a3, a4)
+
+    def incr_response(self, dU, cu, cv, ca):
+        dU = np.ascontiguousarray(dU, np.float64)
+        self.L.orc_incr_response.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_double] * 3
+        return self.L.orc_incr_response(self.h, _p(dU), cu, cv, ca)
+
+    def vel_accel(self):
+        v = np.zeros((self.spec.nn, self.spec.ndf)); a = np.zeros_like(v)
+        self.L.orc_get_vel_accel(self.h, _p(v), _p(a)); return v, a
+
+    def update(self):
+        return self.set_trial_disp(self.trial_disp())
+
+    def trial_disp(self):
+        raise NotImplementedError
+
     def commit(self):
         return self.L.orc_commit(self.h)
 
@@ -330,7 +358,7 @@ class RefBackend(_Backend):
     """The reference's own Domain / AnalysisModel / LinearSOE, through oracle/ref_harness.cpp."""
 
     def __init__(self, spec: ModelSpec, numberer=NUMBERER_PLAIN, soe=SOE_CSC, dlambda=1.0,
-                 test=0, tol=1e-8, max_iter=20):
+                 test=0, tol=1e-8, max_iter=20, defer_setup=False):
         L = ctypes.CDLL(REF_SO)
         self.L, self.spec = L, spec
         L.ref_model_new.restype = ctypes.c_void_p
@@ -374,6 +402,10 @@ class RefBackend(_Backend):
             for row in spec.loads:
                 v = np.ascontiguousarray(row[1:], np.float64)
                 assert L.ref_add_load(self.h, int(row[0]), _p(v)) == 0
+        self.ne = len(self.ele_tags)
+        self.max_iter = max_iter
+        if defer_setup:       # the caller picks the integrator (setup_transient)
+            return
         L.ref_setup.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,
                                 ctypes.c_double, ctypes.c_int]
         self.neq = L.ref_setup(self.h, numberer, soe, dlambda, test, tol, max_iter)
@@ -425,6 +457,36 @@ class RefBackend(_Backend):
 
     def revert(self):
         return self.L.ref_revert(self.h)
+
+    # ---- transient: the reference's own Newmark ----
+    def set_mass(self, tags, mass):
+        for t, mv in zip(tags, np.ascontiguousarray(mass, np.float64)):
+            assert self.L.ref_set_mass(self.h, int(t), _p(np.ascontiguousarray(mv))) == 0
+
+    def setup_transient(self, numberer, soe, gamma, beta, test=0, tol=1e-8, max_iter=20):
+        self.L.ref_setup_transient.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                               ctypes.c_int, ctypes.c_double, ctypes.c_int]
+        self.neq = self.L.ref_setup_transient(self.h, numberer, soe, gamma, beta, test, tol, max_iter)
+        assert self.neq >= 0
+        self.nnz = self.L.ref_nnz(self.h); self.max_iter = max_iter
+
+    def new_step(self, dt):
+        self.L.ref_transient_new_step.argtypes = [ctypes.c_void_p, ctypes.c_double]
+        return self.L.ref_transient_new_step(self.h, dt)
+
+    def transient_update(self, dU):
+        dU = np.ascontiguousarray(dU, np.float64)
+        return self.L.ref_transient_update(self.h, _p(dU))
+
+    def vel_accel(self):
+        v = np.zeros((self.spec.nn, self.spec.ndf)); a = np.zeros_like(v)
+        self.L.ref_get_vel_accel(self.h, self.spec.nn, _p(self.tags), _p(v), _p(a)); return v, a
+
+    def analyze_transient(self, nsteps, dt):
+        self.L.ref_analyze_transient.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        iters = np.zeros(nsteps, np.int32); norms = np.zeros((nsteps, self.max_iter))
+        rc = self.L.ref_analyze_transient(self.h, nsteps, dt, _p(iters), _p(norms), self.max_iter)
+        return rc, iters, norms
 
     def analyze_static(self, nsteps):
         iters = np.zeros(nsteps, np.int32); norms = np.zeros((nsteps, self.max_iter))

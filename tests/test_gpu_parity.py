@@ -376,3 +376,82 @@ def test_partitioned_frame_matches_single_gpu():
         G.commit()
         for m in ranks:
             m.commit()
+
+
+@pytest.mark.parametrize("name", ["newmark_brick_j2", "newmark_frame2d"])
+def test_newmark_device_vs_golden_reference_history(name):
+    """Newmark (displacement form, nodal masses): the device replays the history recorded from the
+    reference's own Newmark integrator -- c1 K + c3 M tangent, P - M a - R unbalance, predictor,
+    response update -- and matches A, B, velocities and accelerations."""
+    from golden_cases import TRANSIENT_CASES
+    from test_oracle import drive_transient_vs_golden
+    mk, *_ = TRANSIENT_CASES[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    spec = mk()
+    D = xb.DeviceModel(spec.ndm, spec.ndf)
+    D.add_nodes(spec.node_tags, spec.crd); D.fix(spec.fix[:, 0], spec.fix[:, 1])
+    for tag, kind, p in spec.materials:
+        D.nd_material(tag, kind, p)
+    for tag, kind, p in spec.uniaxials:
+        D.uniaxial_material(tag, kind, p)
+    for tag, y, A, mt in spec.sections:
+        D.fiber_section(tag, y, A, mt)
+    for grp in spec.groups:
+        D.add_elements(grp.kind, grp.tags, grp.conn, grp.mat, grp.par)
+    D.add_nodal_loads(spec.loads[:, 0].astype(np.int32), spec.loads[:, 1:])
+    D.set_mass(spec.node_tags, g["mass"])
+    D.setup(1, 1); D.to_device(0)
+    assert np.array_equal(D.ids(), g["ids"])
+    tol = BEAM_RTOL if spec.groups[0].kind == 2 else 1e-11
+
+    def check(A, Ag, B, Bg, bscale):
+        assert relerr(A, Ag) < tol
+        assert np.abs(B - Bg).max() <= tol * bscale
+
+    drive_transient_vs_golden(D, g, name, check)
+
+
+def test_newmark_time_history_counts_match_oracle():
+    """a transient run (Newmark average acceleration, nodal masses, alphaM damping) driven by the
+    oracle and by the device: same Newton iteration counts per step, same response"""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from golden_cases import newmark_coeffs
+    spec = brick_block(3, 3, 5, mat=J2_STEEL, lz=4.0, load=(60.0, 0.0, -10.0))
+    mass = np.full((spec.nn, 3), 0.02)
+    gamma, beta, dt, alphaM = 0.5, 0.25, 0.01, 0.8
+    (c1, c2, c3), (a1, a2, a3, a4) = newmark_coeffs(gamma, beta, dt)
+    O = OracleBackend(spec, 1, 1); O.set_mass(spec.node_tags, mass)
+    O.L.orc_set_alphaM.argtypes = [__import__("ctypes").c_void_p, __import__("ctypes").c_double]; O.L.orc_set_alphaM(O.h, alphaM)
+    D = xb.DeviceModel.from_spec(spec, 1, 1) if False else None
+    D = xb.DeviceModel(3, 3)
+    D.add_nodes(spec.node_tags, spec.crd); D.fix(spec.fix[:, 0], spec.fix[:, 1]); D.nd_material(1, *spec.materials[0][1:])
+    grp = spec.groups[0]; D.add_elements(grp.kind, grp.tags, grp.conn, grp.mat, grp.par)
+    D.add_nodal_loads(spec.loads[:, 0].astype(np.int32), spec.loads[:, 1:]); D.set_mass(spec.node_tags, mass)
+    D.set_rayleigh_alpha_m(alphaM); D.setup(1, 1); D.to_device(0)
+    ptr, idx = O.csr(); neq = O.neq
+
+    def run(M):
+        hist = []; t = 0.0
+        for s in range(12):
+            t += dt
+            M.set_transient(c1, c2, c3); M.newmark_predict(a1, a2, a3, a4)
+            M.apply_load(min(t, 0.06) / 0.06)                       # ramp, then hold: free vibration + yielding
+            M.incr_response(np.zeros(neq), 1.0, c2, c3)
+            B = M.form_unbalance(); norms = []
+            for it in range(20):
+                A = M.form_tangent()
+                dU = spla.spsolve(sp.csr_matrix((A, idx, ptr), shape=(neq, neq)).tocsc(), B)
+                M.incr_response(dU, 1.0, c2, c3)
+                B = M.form_unbalance()
+                norms.append(float(np.linalg.norm(dU)))
+                if norms[-1] <= 1e-9:
+                    break
+            hist.append(norms); M.commit()
+        return hist, M.vel_accel()
+
+    ho, (vo, ao) = run(O)
+    hd, (vd, ad) = run(D)
+    assert [len(h) for h in ho] == [len(h) for h in hd]
+    assert max(len(h) for h in ho) >= 3
+    assert relerr(vd, vo) < 1e-8 and relerr(ad, ao) < 1e-8

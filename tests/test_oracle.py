@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from golden_cases import CASES, NSTEPS, ele_nd
+from golden_cases import CASES, NSTEPS, TRANSIENT_CASES, ele_nd, newmark_coeffs
 from modelspec import (ELASTIC, J2_STEEL, MAT_ELASTIC, MAT_J2, ND_3D, ND_PLANE_STRAIN, OracleBackend, RefBackend,
                        brick_block, frame2d, have_ref, oracle_nd_path, oracle_uni_path, quad_plane, ref_nd_path)
 
@@ -137,3 +137,37 @@ def test_material_paths_vs_live_reference():
             so, to = oracle_nd_path(kind, p, type_, strains, commit)
             sr, tr = ref_nd_path(kind, p, type_, strains, commit)
             assert close(so, sr) and close(to, tr)
+
+
+def drive_transient_vs_golden(model, g, name, check, is_dev=False):
+    """replays the golden Newmark history (the reference's dU per iteration) through `model`"""
+    (c1, c2, c3), (a1, a2, a3, a4) = newmark_coeffs(float(g["gamma"]), float(g["beta"]), float(g["dt"]))
+    t = 0.0
+    neq = len(g["B0_0"])
+    for s in range(int(g["nsteps"])):
+        t += float(g["dt"])
+        model.set_transient(c1, c2, c3); model.newmark_predict(a1, a2, a3, a4); model.apply_load(t)
+        model.incr_response(np.zeros(neq), 1.0, c2, c3)          # newStep ends with updateDomain(time, dT)
+        for it in range(int(g["niter"])):
+            B = model.form_unbalance(); A = model.form_tangent()
+            check(A, g[f"A{s}_{it}"], B, g[f"B{s}_{it}"], np.abs(g[f"B{s}_0"]).max())
+            model.incr_response(g[f"dU{s}_{it}"], 1.0, c2, c3)
+        v, a = model.vel_accel()
+        assert close(v, g[f"v{s}"], 1e-11) and close(a, g[f"a{s}"], 1e-11)
+        model.commit()
+
+
+@pytest.mark.parametrize("name", list(TRANSIENT_CASES))
+def test_newmark_vs_golden(name):
+    mk, mass_fn, *_ = TRANSIENT_CASES[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    spec = mk()
+    O = OracleBackend(spec, 1, 1)
+    O.set_mass(spec.node_tags, g["mass"])
+    assert np.array_equal(O.ids(), g["ids"])
+
+    def check(A, Ag, B, Bg, bscale):
+        assert close(A, Ag, 1e-11)
+        assert np.abs(B - Bg).max() <= 1e-11 * bscale          # B -> 0 as Newton converges: scale by the step's first residual
+
+    drive_transient_vs_golden(O, g, name, check)

@@ -64,6 +64,13 @@ def _load():
         "xb_add_fiber_section": (i32, [vp, i32, i32, vp, vp, vp]),
         "xb_add_elements": (i32, [vp, i32, i32, vp, vp, vp, vp, i32]),
         "xb_add_nodal_loads": (i32, [vp, i32, vp, vp]),
+        "xb_set_nodal_mass": (i32, [vp, i32, vp, vp]),
+        "xb_set_rayleigh_alpha_m": (i32, [vp, f64]),
+        "xb_set_transient_factors": (i32, [vp, f64, f64, f64]),
+        "xb_newmark_predict": (i32, [vp, f64, f64, f64, f64]),
+        "xb_incr_trial_response": (i32, [vp, vp, f64, f64, f64]),
+        "xb_set_trial_vel_accel": (i32, [vp, vp, vp]),
+        "xb_get_trial_vel_accel": (i32, [vp, vp, vp]),
         "xb_setup": (i32, [vp, i32, i32]),
         "xb_setup_partitioned": (i32, [vp, i32, i32, i32, i32, vp]),
         "xb_num_rows": (i32, [vp]),
@@ -305,6 +312,30 @@ class DeviceModel:
 
     def trial_disp(self):
         u = np.zeros((self.nn, self.ndf)); self._ck(lib.xb_get_trial_disp(self._h, _ptr(u))); return u
+
+    # ---- transient (Newmark) ----
+    def set_mass(self, node_tags, mass):
+        """`mass` command, before setup(); mass is [n][ndf] (diagonal terms)"""
+        node_tags, mass = _i32(node_tags), _f64(mass)
+        self._ck(lib.xb_set_nodal_mass(self._h, len(node_tags), _ptr(node_tags), _ptr(mass)))
+
+    def set_rayleigh_alpha_m(self, alpha_m):
+        self._ck(lib.xb_set_rayleigh_alpha_m(self._h, float(alpha_m)))
+
+    def set_transient(self, c1, c2, c3):
+        self._ck(lib.xb_set_transient_factors(self._h, c1, c2, c3))
+
+    def newmark_predict(self, a1, a2, a3, a4):
+        self._ck(lib.xb_newmark_predict(self._h, a1, a2, a3, a4))
+
+    def incr_response(self, dU, cu, cv, ca):
+        dU = _f64(dU); assert dU.size == self.neq
+        self._ck(lib.xb_incr_trial_response(self._h, _ptr(dU), cu, cv, ca))
+        self._keep = dU
+
+    def vel_accel(self):
+        v = np.zeros((self.nn, self.ndf)); a = np.zeros((self.nn, self.ndf))
+        self._ck(lib.xb_get_trial_vel_accel(self._h, _ptr(v), _ptr(a))); return v, a
 
     def update(self):
         self._ck(lib.xb_update(self._h))

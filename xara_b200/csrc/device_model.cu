@@ -521,6 +521,13 @@ struct AsmView {
   const unsigned short* colpos;  // [*][cp_stride]
   const long long* ncol_ptr;  // [nn+1]
   const double* load;         // [nn][ndf]
+  // transient terms (TransientIntegrator::formTangent / formNodUnbalance): nodal mass diagonal,
+  // trial velocity / acceleration, Newmark's c1 c2 c3, Rayleigh alphaM.  Static: c1=1, c2=c3=0.
+  const double* mass;         // [nn][ndf]
+  const double* vel;          // [nn][ndf]
+  const double* acc;          // [nn][ndf]
+  const unsigned short* diagpos;  // [nn][ndf]
+  double c1, c2, c3, alphaM;
   const double* recvK;        // element-matrix rows received from other ranks (slots with koff < 0)
   const double* recvR;        // element-residual entries received from other ranks (roff < 0)
 };
@@ -548,6 +555,20 @@ __global__ void __launch_bounds__(256, 3) assemble_A_kernel(AsmView V, const dou
   if (t0 == t1) L = 1;  // a node with no element: its rows hold the (zero) diagonal only
   for (int c = lane; c < NDF * L; c += 32) acc[(c / L) * V.max_row + (c % L)] = 0.0;
   __syncwarp();
+  if ((V.c2 != 0.0 || V.c3 != 0.0) && lane < NDF) {
+    // the DOF_Group tangents are added before the elements' (TransientIntegrator.cpp:89-107):
+    // Newmark::formNodTangent = c2 * (alphaM * M) + c3 * M on the diagonal
+    const unsigned short dp = V.diagpos[n * NDF + lane];
+    if (dp != 0xFFFF) {
+      const double ms = V.mass[n * NDF + lane];
+      double t = 0.0;
+      t += (ms * V.alphaM) * V.c2;
+      t += ms * V.c3;
+      acc[lane * V.max_row + dp] = t;
+    }
+  }
+  __syncwarp();
+  const double c1 = V.c1;
   const int cps = V.cp_stride;
   const bool on = lane < cps;
   constexpr int CH = 4;  // slots in flight together; the node's slots are one contiguous stream
@@ -566,7 +587,7 @@ __global__ void __launch_bounds__(256, 3) assemble_A_kernel(AsmView V, const dou
     for (int c = 0; c < CH; c++) {   // FE_Element order: the order addA is called in
       if (pos[c] != 0xFFFF) {
 #pragma unroll
-        for (int p = 0; p < NDF; p++) acc[p * V.max_row + pos[c]] += v[c][p];
+        for (int p = 0; p < NDF; p++) acc[p * V.max_row + pos[c]] += (c1 == 1.0 ? v[c][p] : v[c][p] * c1);
       }
       __syncwarp();
     }
@@ -607,7 +628,11 @@ __global__ void __launch_bounds__(256) assemble_B_kernel(AsmView V, const double
     const long long ro = V.n2e_roff[t];
     acc += -(ro >= 0 ? Re[ro + p] : V.recvR[(-ro - 1) + p]);
   }
-  acc += V.load[i] * lambda;
+  // DOF_Group::getUnbalance: Node::getUnbalancedLoadIncInertia = P - M a - alphaM M v
+  double ub = V.load[i] * lambda;
+  const double ms = V.mass[i];
+  if (ms != 0.0) { ub -= ms * V.acc[i]; if (V.alphaM != 0.0) ub += ms * V.vel[i] * -V.alphaM; }
+  acc += ub;
   B[r] = acc;
 }
 
@@ -666,8 +691,11 @@ struct xb_model {
   bool own_stream = false;
   std::vector<DevGroup> dg;
   std::vector<void*> allocs;
+  double *dV = nullptr, *dAcc = nullptr, *dVc = nullptr, *dAc = nullptr, *dMass = nullptr;
+  unsigned short* dDiag = nullptr;
   double *dDU = nullptr, *dUin = nullptr;   // Node::getIncrDeltaDisp, staging for xb_set_trial_disp
   bool has_beams = false;
+  double alphaM = 0.0;      // Node::setRayleighDampingFactor
   double *dX = nullptr, *dU = nullptr, *dUc = nullptr, *dKe = nullptr, *dRe = nullptr, *dA = nullptr,
          *dB = nullptr, *dLoad = nullptr, *dMpar = nullptr, *dTmp = nullptr;
   int* dId = nullptr;
@@ -875,6 +903,12 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
   CU(dev_upload(m, &m->dX, h.crd));
   CU(dev_alloc(m, &m->dU, nn * h.ndf));
   CU(dev_alloc(m, &m->dUc, nn * h.ndf));
+  for (double** q : {&m->dV, &m->dAcc, &m->dVc, &m->dAc}) {
+    CU(dev_alloc(m, q, nn * h.ndf));
+    CU(cudaMemset(*q, 0, sizeof(double) * std::max<size_t>(nn * h.ndf, 1)));
+  }
+  CU(dev_upload(m, &m->dMass, h.mass));
+  CU(dev_upload(m, &m->dDiag, h.diagpos));
   CU(dev_alloc(m, &m->dDU, nn * h.ndf));
   CU(dev_alloc(m, &m->dUin, nn * h.ndf));
   CU(cudaMemset(m->dDU, 0, sizeof(double) * std::max<size_t>(nn * h.ndf, 1)));
@@ -1004,6 +1038,8 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
   AsmView& a = m->av;
   a.nn = (int)nn; a.ndf = h.ndf; a.cp_stride = h.cp_stride; a.max_row = std::max(h.max_row, 1);
   a.row_of = m->dRowOf; a.load = m->dLoad;
+  a.mass = m->dMass; a.vel = m->dV; a.acc = m->dAcc; a.diagpos = m->dDiag;
+  a.c1 = 1.0; a.c2 = 0.0; a.c3 = 0.0; a.alphaM = m->alphaM;
   if (h.nparts > 1) {
     CU(dev_alloc(m, &m->dSendK, (size_t)h.send_k_total));
     CU(dev_alloc(m, &m->dRecvK, (size_t)h.recv_k_total));
@@ -1074,6 +1110,76 @@ int xb_incr_trial_disp(xb_model* m, const double* dU) {
   incr_disp_kernel<<<(unsigned)((ndof + 255) / 256), 256, 0, m->stream>>>(ndof, m->dId, m->dTmp, m->dU, m->dDU);
   m->launches++;
   CU(cudaGetLastError());
+  return XB_OK;
+}
+
+// Newmark::newStep, displacement unknown (Newmark.cpp:150-160)
+__global__ void newmark_predict_kernel(long long ndof, const int* __restrict__ id, double a1, double a2, double a3,
+                                       double a4, double* __restrict__ V, double* __restrict__ A) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ndof || id[i] < 0) return;
+  const double v0 = V[i], ac0 = A[i];
+  V[i] = v0 * a1 + ac0 * a2;
+  A[i] = ac0 * a4 + v0 * a3;
+}
+// Newmark::update (Newmark.cpp:411-458) + AnalysisModel::setResponse
+__global__ void incr_response_kernel(long long ndof, const int* __restrict__ id, const double* __restrict__ dU,
+                                     double cu, double cv, double ca, double* __restrict__ U, double* __restrict__ DU,
+                                     double* __restrict__ V, double* __restrict__ A) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ndof) return;
+  const int r = id[i];
+  if (r < 0) { DU[i] = 0.0; return; }
+  const double d = dU[r];
+  const double u0 = U[i];
+  const double un = (cu == 1.0) ? u0 + d : u0 + d * cu;
+  DU[i] = un - u0; U[i] = un;
+  V[i] += d * cv; A[i] += d * ca;
+}
+
+int xb_set_nodal_mass(xb_model* m, int n, const int* tags, const double* mass) { HOSTCALL(m->h.add_mass(n, tags, mass)); }
+int xb_set_rayleigh_alpha_m(xb_model* m, double alphaM) {
+  if (!m) return fail(XB_ERR_ARG, "null model");
+  m->alphaM = alphaM; m->av.alphaM = alphaM;
+  return XB_OK;
+}
+int xb_set_transient_factors(xb_model* m, double c1, double c2, double c3) {
+  NEED_DEVICE();
+  m->av.c1 = c1; m->av.c2 = c2; m->av.c3 = c3;
+  return XB_OK;
+}
+int xb_newmark_predict(xb_model* m, double a1, double a2, double a3, double a4) {
+  NEED_DEVICE();
+  CU(cudaSetDevice(m->device));
+  const long long ndof = (long long)m->h.nn() * m->h.ndf;
+  if (ndof) { newmark_predict_kernel<<<(unsigned)((ndof + 255) / 256), 256, 0, m->stream>>>(ndof, m->dId, a1, a2, a3, a4, m->dV, m->dAcc); m->launches++; }
+  CU(cudaGetLastError());
+  return XB_OK;
+}
+int xb_incr_trial_response(xb_model* m, const double* dU, double cu, double cv, double ca) {
+  NEED_DEVICE();
+  CU(cudaSetDevice(m->device));
+  CU(cudaMemcpyAsync(m->dTmp, dU, sizeof(double) * m->h.neq, cudaMemcpyHostToDevice, m->stream));
+  const long long ndof = (long long)m->h.nn() * m->h.ndf;
+  if (ndof) { incr_response_kernel<<<(unsigned)((ndof + 255) / 256), 256, 0, m->stream>>>(ndof, m->dId, m->dTmp, cu, cv, ca, m->dU, m->dDU, m->dV, m->dAcc); m->launches++; }
+  CU(cudaGetLastError());
+  return XB_OK;
+}
+int xb_set_trial_vel_accel(xb_model* m, const double* v, const double* a) {
+  NEED_DEVICE();
+  CU(cudaSetDevice(m->device));
+  const size_t nb = sizeof(double) * m->h.nn() * m->h.ndf;
+  CU(cudaMemcpyAsync(m->dV, v, nb, cudaMemcpyHostToDevice, m->stream));
+  CU(cudaMemcpyAsync(m->dAcc, a, nb, cudaMemcpyHostToDevice, m->stream));
+  return XB_OK;
+}
+int xb_get_trial_vel_accel(xb_model* m, double* v, double* a) {
+  NEED_DEVICE();
+  CU(cudaSetDevice(m->device));
+  const size_t nb = sizeof(double) * m->h.nn() * m->h.ndf;
+  CU(cudaMemcpyAsync(v, m->dV, nb, cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaMemcpyAsync(a, m->dAcc, nb, cudaMemcpyDeviceToHost, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
   return XB_OK;
 }
 
@@ -1362,6 +1468,8 @@ int xb_commit(xb_model* m) {
   }
   const size_t nb = sizeof(double) * m->h.nn() * m->h.ndf;
   CU(cudaMemcpyAsync(m->dUc, m->dU, nb, cudaMemcpyDeviceToDevice, m->stream));
+  CU(cudaMemcpyAsync(m->dVc, m->dV, nb, cudaMemcpyDeviceToDevice, m->stream));
+  CU(cudaMemcpyAsync(m->dAc, m->dAcc, nb, cudaMemcpyDeviceToDevice, m->stream));
   CU(cudaMemsetAsync(m->dDU, 0, std::max<size_t>(nb, 1), m->stream));   // Node::commitState: incrDeltaDisp = 0
   return XB_OK;
 }
@@ -1374,6 +1482,8 @@ int xb_revert_to_last_commit(xb_model* m) {
   // the trial state from the committed one.
   const size_t nb = sizeof(double) * m->h.nn() * m->h.ndf;
   CU(cudaMemcpyAsync(m->dU, m->dUc, nb, cudaMemcpyDeviceToDevice, m->stream));
+  CU(cudaMemcpyAsync(m->dV, m->dVc, nb, cudaMemcpyDeviceToDevice, m->stream));
+  CU(cudaMemcpyAsync(m->dAcc, m->dAc, nb, cudaMemcpyDeviceToDevice, m->stream));
   CU(cudaMemsetAsync(m->dDU, 0, std::max<size_t>(nb, 1), m->stream));
   for (auto& d : m->dg)
     if (d.kind == XB_ELE_FORCEBEAMCOLUMN2D && d.b.n) {

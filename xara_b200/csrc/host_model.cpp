@@ -156,6 +156,13 @@ int HostModel::add_loads(int n, const int* tags, const double* vals) {
   return XB_OK;
 }
 
+int HostModel::add_mass(int n, const int* tags, const double* vals) {
+  if (is_setup) { err = "xb_set_nodal_mass after xb_setup"; return XB_ERR_STATE; }
+  mass_node.insert(mass_node.end(), tags, tags + n);
+  mass_val.insert(mass_val.end(), vals, vals + (size_t)n * ndf);
+  return XB_OK;
+}
+
 namespace {
 struct TagIndex {
   const std::vector<int>& tags;
@@ -270,6 +277,13 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
     int ix = nidx(load_node[i]);
     if (ix < 0) { err = "load references an unknown node tag"; return XB_ERR_ARG; }
     for (int j = 0; j < ndf; j++) gload[(size_t)ix * ndf + j] += load_val[i * ndf + j];
+  }
+
+  std::vector<double> gmass((size_t)n_nodes * ndf, 0.0);
+  for (size_t i = 0; i < mass_node.size(); i++) {
+    int ix = nidx(mass_node[i]);
+    if (ix < 0) { err = "mass references an unknown node tag"; return XB_ERR_ARG; }
+    for (int j = 0; j < ndf; j++) gmass[(size_t)ix * ndf + j] = mass_val[i * ndf + j];   // Node::setMass replaces
   }
 
   // ---- FE_Element order: Domain element map by ascending tag (PlainHandler.cpp:228-250) ----
@@ -466,14 +480,17 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
   }
 
   // ---- local node tables ----
-  id.resize((size_t)nl * ndf); load.resize((size_t)nl * ndf); owned.assign(nl, 0);
+  id.resize((size_t)nl * ndf); load.resize((size_t)nl * ndf); owned.assign(nl, 0); mass.resize((size_t)nl * ndf);
   {
     std::vector<int> t(nl); std::vector<double> c((size_t)nl * ndm);
     for (int i = 0; i < nl; i++) {
       const int n = lnode[i];
       t[i] = node_tag[n];
       std::memcpy(&c[(size_t)i * ndm], &crd[(size_t)n * ndm], sizeof(double) * ndm);
-      for (int j = 0; j < ndf; j++) { id[(size_t)i * ndf + j] = gid[(size_t)n * ndf + j]; load[(size_t)i * ndf + j] = gload[(size_t)n * ndf + j]; }
+      for (int j = 0; j < ndf; j++) {
+        id[(size_t)i * ndf + j] = gid[(size_t)n * ndf + j]; load[(size_t)i * ndf + j] = gload[(size_t)n * ndf + j];
+        mass[(size_t)i * ndf + j] = gmass[(size_t)n * ndf + j];
+      }
       owned[i] = owner[n] == rank;
     }
     node_tag.swap(t); crd.swap(c);
@@ -637,6 +654,20 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
       if (r < 0) continue;
       if (isolated) idx[ptr[r]] = id[(size_t)i * ndf + j];
       else std::copy(&ncol[ncol_ptr[i]], &ncol[ncol_ptr[i]] + L, &idx[ptr[r]]);
+    }
+  }
+
+  // position of every owned dof's own equation in its node's list (the diagonal entry of A)
+  diagpos.assign((size_t)nl * ndf, 0xFFFF);
+  for (int i = 0; i < nl; i++) {
+    if (!owned[i]) continue;
+    const int* cols = &ncol[ncol_ptr[i]];
+    const long long L = ncol_ptr[i + 1] - ncol_ptr[i];
+    const bool isolated = n2e_ptr[i + 1] == n2e_ptr[i];
+    for (int j = 0; j < ndf; j++) {
+      const int q = id[(size_t)i * ndf + j];
+      if (q < 0) continue;
+      diagpos[(size_t)i * ndf + j] = isolated ? 0 : (uint16_t)(std::lower_bound(cols, cols + L, q) - cols);
     }
   }
 

@@ -88,6 +88,10 @@ struct HostModel {
   std::vector<int> load_node;       // pending nodal loads (tags)
   std::vector<double> load_val;     // [nload][ndf]
   std::vector<double> load;         // [nn][ndf]
+  std::vector<int> mass_node;       // pending `mass` commands (tags)
+  std::vector<double> mass_val;     // [n][ndf]
+  std::vector<double> mass;         // [nn][ndf] diagonal of Node::mass
+  std::vector<uint16_t> diagpos;    // [nn][ndf] position of the dof's own equation in the node's column list
 
   // --- analysis (valid after setup) ---
   bool is_setup = false;
@@ -149,6 +153,7 @@ struct HostModel {
   int add_elements(int kind, int n, const int* tags, const int* conn, const int* mat_tags,
                    const double* par, int par_stride);
   int add_loads(int n, const int* tags, const double* vals);
+  int add_mass(int n, const int* tags, const double* vals);
   // part: nullptr (built-in recursive coordinate bisection) or [ne] ranks in FE order
   int setup(int numberer, int soe_kind, int nparts = 1, int rank = 0, const int* part = nullptr);
   long long nnz() const { return ptr.empty() ? 0 : ptr.back(); }
