@@ -328,10 +328,13 @@ class DeviceModel:
     def newmark_predict(self, a1, a2, a3, a4):
         self._ck(lib.xb_newmark_predict(self._h, a1, a2, a3, a4))
 
-    def incr_response(self, dU, cu, cv, ca):
+    def incr_response(self, dU, cu, cv, ca, update=True):
+        """Newmark::update: response increment, then (as the reference does) updateDomain"""
         dU = _f64(dU); assert dU.size == self.neq
         self._ck(lib.xb_incr_trial_response(self._h, _ptr(dU), cu, cv, ca))
         self._keep = dU
+        if update:
+            self.update()
 
     def vel_accel(self):
         v = np.zeros((self.nn, self.ndf)); a = np.zeros((self.nn, self.ndf))
