@@ -163,7 +163,9 @@ def ours_main(a):
     if world == 1 and a.gpus > 1:
         raise SystemExit("launch N > 1 with torch.distributed.run (see module docstring)")
     if world > 1:   # the host-side set-up is OpenMP-parallel: share the cores between the ranks
-        os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or world) // world)))
+        # (torchrun exports OMP_NUM_THREADS=1, which would serialise the set-up; must be set before
+        # libxara_b200.so brings libgomp in)
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or world) // world))
 
     import torch
     import torch.distributed as dist
