@@ -157,6 +157,11 @@ def workload_name(n):
 # our arm
 # ---------------------------------------------------------------------------------------
 def ours_main(a):
+    # stdout carries exactly one JSON line: libraries that chat on fd 1 (NCCL prints its version
+    # there) are pointed at stderr, the JSON goes out through a private copy of the original fd
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -311,7 +316,7 @@ def ours_main(a):
                 "formUnbalance_ms": ms_max["element_resid"] + ms_max["exchange_B"] + ms_max["assemble_B"],
                 "update_ms": ms_max["update"],
                 "gpu_launches": int(launches_all), "clocks": clk, "e2e": e2e, "roofline": roofline, "cpu_baseline": cb}
-        print(json.dumps(line), flush=True)
+        json_out.write(json.dumps(line) + "\n"); json_out.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -300,7 +300,7 @@ constexpr int BT_TILE = 24 * BT_TROW; // 600 doubles: = 8 mod 16, so two element
 constexpr int BT_WARP_DOUBLES = 4 * BT_TILE;   // >= 4*8*(BT_NSTR+BT_DSTR) = 1728
 template <int MATK>
 __global__ void __launch_bounds__(BT_ELEMS * 8, 2) brick_tangent_kernel(GroupView G, const double* __restrict__ X,
-                                                                        int transpose) {
+                                                                        int transpose, long long ebeg, long long eend) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -308,10 +308,11 @@ __global__ void __launch_bounds__(BT_ELEMS * 8, 2) brick_tangent_kernel(GroupVie
   double* wbase = smem + warp * BT_WARP_DOUBLES;
   double* sN = wbase;                              // [4][8 g][8 n][4]
   double* sD = wbase + 4 * 8 * BT_NSTR;            // [4][8 g][22]
-  const long long e0 = (long long)blockIdx.x * BT_ELEMS + warp * 4;   // first element of the warp
+  const long long e0 = ebeg + (long long)blockIdx.x * BT_ELEMS + warp * 4;   // first element of the warp
+  if (e0 >= eend) return;
   const long long e_raw = e0 + s;
-  const bool live = e_raw < G.n;
-  const long long e = live ? e_raw : G.n - 1;
+  const bool live = e_raw < eend;
+  const long long e = live ? e_raw : eend - 1;
   const long long ngp = G.n * 8;
   // destination of the rows of node k of element s (needed only in phase C: requested now)
   const long long dst_l = live ? __ldg(G.kdst + e * 8 + k) : 0;
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(BT_ELEMS * 8, 2) brick_tangent_kernel(GroupVie
   __syncwarp();
   // lane (s,k) fetches the destination of the rows of node k of element s; then the warp streams
   // its 4 x 8 node chunks (3 rows x 24 columns each) out, 24 consecutive doubles per row
-  const int nlive = (int)((G.n - e0) < 4 ? (G.n - e0) : 4);
+  const int nlive = (int)((eend - e0) < 4 ? (eend - e0) : 4);
   const int cps = G.cps;
 #pragma unroll
   for (int el = 0; el < 4; el++) {
@@ -538,11 +539,13 @@ struct AsmView {
 // Every entry of A is written exactly once, so no zeroA pass is needed.
 template <int NDF>
 __global__ void __launch_bounds__(256, 3) assemble_A_kernel(AsmView V, const double* __restrict__ KeN,
-                                                         double* __restrict__ A) {
+                                                            double* __restrict__ A, const int* __restrict__ perm,
+                                                            long long first, long long count) {
   extern __shared__ double sacc[];  // [warps][NDF][max_row]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long n = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-  if (n >= V.nn) return;
+  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (w >= count) return;
+  const long long n = __ldg(perm + first + w);   // owned nodes, ordered by the element range that completes them
   double* acc = sacc + (size_t)warp * NDF * V.max_row;
   // everything that does not depend on the element loop is requested up front
   const long long t0 = __ldg(V.n2e_ptr + n), t1 = __ldg(V.n2e_ptr + n + 1);
@@ -705,6 +708,11 @@ struct xb_model {
   double *dSendK = nullptr, *dRecvK = nullptr, *dSendR = nullptr, *dRecvR = nullptr;
   long long *dPrSrc = nullptr, *dPrDst = nullptr, *dUkSrc = nullptr, *dUkDst = nullptr;
   ncclComm_t comm = nullptr;
+  // pipelined formTangent
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_done = nullptr;
+  std::vector<cudaEvent_t> ev_chunk;
+  int* dPerm = nullptr;
   AsmView av{};
   double lambda = 0.0;
   long long launches = 0;
@@ -797,6 +805,10 @@ void xb_model_destroy(xb_model* m) {
   if (m->on_device) {
     cudaSetDevice(m->device);
     if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
+    if (m->stream2) cudaStreamDestroy(m->stream2);
+    if (m->ev_start) cudaEventDestroy(m->ev_start);
+    if (m->ev_done) cudaEventDestroy(m->ev_done);
+    for (auto e : m->ev_chunk) cudaEventDestroy(e);
     for (void* p : m->allocs) cudaFree(p);
     if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
   }
@@ -916,6 +928,12 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
   CU(cudaMemset(m->dUc, 0, sizeof(double) * std::max<size_t>(nn * h.ndf, 1)));
   CU(dev_upload(m, &m->dId, h.id));
   CU(dev_upload(m, &m->dRowOf, h.row_of));
+  CU(dev_upload(m, &m->dPerm, h.node_perm));
+  CU(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&m->ev_done, cudaEventDisableTiming));
+  m->ev_chunk.resize(h.nchunk);
+  for (auto& e : m->ev_chunk) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CU(dev_upload(m, &m->dLoad, h.load));
   std::vector<double> mp(h.mats.size() * 8);
   for (size_t i = 0; i < h.mats.size(); i++) std::memcpy(&mp[i * 8], h.mats[i].par, sizeof(double) * 8);
@@ -1231,41 +1249,55 @@ int xb_apply_load(xb_model* m, double lambda) {
 
 static int pack_for_peers(xb_model* m, int which);
 
-int xb_form_element_tangents(xb_model* m) {
-  NEED_DEVICE();
-  CU(cudaSetDevice(m->device));
+// element-tangent kernels of one batch over the element range [ebeg, eend) (bricks) on `st`
+static int launch_group_tangents(xb_model* m, DevGroup& d, long long ebeg, long long eend, cudaStream_t st) {
   const int transpose = m->h.soe_kind == XB_SOE_SPARSE_GEN_COL ? 1 : 0;
+  if (d.kind == XB_ELE_FORCEBEAMCOLUMN2D) {
+    fbc2d_form_kernel<<<(unsigned)((d.b.n + 127) / 128), 128, 0, st>>>(d.b, 1, 0, transpose);
+    m->launches++;
+    return XB_OK;
+  }
+  const bool j2 = d.mat_kind == XB_MAT_J2PLASTICITY;
+  if (d.kind == XB_ELE_STDBRICK) {
+    const unsigned blocks = (unsigned)((eend - ebeg + BT_ELEMS - 1) / BT_ELEMS);
+    const size_t sm = sizeof(double) * (BT_ELEMS / 4) * BT_WARP_DOUBLES;
+    if (j2) {
+      CU(cudaFuncSetAttribute(brick_tangent_kernel<XB_MAT_J2PLASTICITY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      brick_tangent_kernel<XB_MAT_J2PLASTICITY><<<blocks, BT_ELEMS * 8, sm, st>>>(d.v, m->dX, transpose, ebeg, eend);
+    } else {
+      CU(cudaFuncSetAttribute(brick_tangent_kernel<XB_MAT_ELASTIC_ISOTROPIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      brick_tangent_kernel<XB_MAT_ELASTIC_ISOTROPIC><<<blocks, BT_ELEMS * 8, sm, st>>>(d.v, m->dX, transpose, ebeg, eend);
+    }
+  } else {
+    const unsigned blocks = (unsigned)((d.v.n * 4 + 127) / 128);
+    if (j2) quad_tangent_kernel<XB_MAT_J2PLASTICITY><<<blocks, 128, 0, st>>>(d.v, m->dX, transpose);
+    else quad_tangent_kernel<XB_MAT_ELASTIC_ISOTROPIC><<<blocks, 128, 0, st>>>(d.v, m->dX, transpose);
+  }
+  m->launches++;
+  return XB_OK;
+}
+
+static void account_element_tangent_bytes(xb_model* m) {
   long long bytes = 0;
   for (auto& d : m->dg) {
     if (d.v.n == 0) continue;
-    if (d.kind == XB_ELE_FORCEBEAMCOLUMN2D) {
-      fbc2d_form_kernel<<<(unsigned)((d.b.n + 127) / 128), 128, 0, m->stream>>>(d.b, 1, 0, transpose);
-      m->launches++;
-      bytes += d.b.n * (9 + 36) * 8;
-      continue;
-    }
-    const bool j2 = d.mat_kind == XB_MAT_J2PLASTICITY;
-    if (d.kind == XB_ELE_STDBRICK) {
-      const unsigned blocks = (unsigned)((d.v.n + BT_ELEMS - 1) / BT_ELEMS);
-      const size_t sm = sizeof(double) * (BT_ELEMS / 4) * BT_WARP_DOUBLES;
-      if (j2) {
-        CU(cudaFuncSetAttribute(brick_tangent_kernel<XB_MAT_J2PLASTICITY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        brick_tangent_kernel<XB_MAT_J2PLASTICITY><<<blocks, BT_ELEMS * 8, sm, m->stream>>>(d.v, m->dX, transpose);
-      } else {
-        CU(cudaFuncSetAttribute(brick_tangent_kernel<XB_MAT_ELASTIC_ISOTROPIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        brick_tangent_kernel<XB_MAT_ELASTIC_ISOTROPIC><<<blocks, BT_ELEMS * 8, sm, m->stream>>>(d.v, m->dX, transpose);
-      }
-    } else {
-      const unsigned blocks = (unsigned)((d.v.n * 4 + 127) / 128);
-      if (j2) quad_tangent_kernel<XB_MAT_J2PLASTICITY><<<blocks, 128, 0, m->stream>>>(d.v, m->dX, transpose);
-      else quad_tangent_kernel<XB_MAT_ELASTIC_ISOTROPIC><<<blocks, 128, 0, m->stream>>>(d.v, m->dX, transpose);
-    }
-    m->launches++;
+    if (d.kind == XB_ELE_FORCEBEAMCOLUMN2D) { bytes += d.b.n * (9 + 36) * 8; continue; }
     // compact tangent + connectivity in, element matrix out
-    bytes += d.ngp * 8 * (j2 ? 8 : 0) + d.v.n * ((long long)d.nd * d.nd * 8 + (d.nd / m->h.ndf) * 4);
+    bytes += d.ngp * 8 * (d.mat_kind == XB_MAT_J2PLASTICITY ? 8 : 0) + d.v.n * ((long long)d.nd * d.nd * 8 + (d.nd / m->h.ndf) * 4);
   }
   bytes += (long long)m->h.nn() * m->h.ndm * 8;
   m->alg_bytes[3] = bytes;
+}
+
+int xb_form_element_tangents(xb_model* m) {
+  NEED_DEVICE();
+  CU(cudaSetDevice(m->device));
+  for (auto& d : m->dg) {
+    if (d.v.n == 0) continue;
+    int rc = launch_group_tangents(m, d, 0, d.v.n, m->stream);
+    if (rc < 0) return rc;
+  }
+  account_element_tangent_bytes(m);
   CU(cudaGetLastError());
   return pack_for_peers(m, 0);
 }
@@ -1347,33 +1379,28 @@ int xb_exchange_local(xb_model** ms, int n, int which) {
   return XB_OK;
 }
 
-int xb_assemble_tangent(xb_model* m, double* A) {
-  NEED_DEVICE();
-  CU(cudaSetDevice(m->device));
-  if (!m->h.uk_src.empty()) {   // rows received from other ranks -> their slots
-    const long long nch = (long long)m->h.uk_src.size();
-    unpack_rows_kernel<<<(unsigned)((nch * 32 + 255) / 256), 256, 0, m->stream>>>(nch, m->dUkSrc, m->dUkDst, m->h.chunk, m->dRecvK, m->dKe);
-    m->launches++;
+// assembly of the owned nodes node_perm[first, first+count) on `st`
+static int launch_assemble(xb_model* m, long long first, long long count, cudaStream_t st) {
+  if (count <= 0) return XB_OK;
+  const int warps = 8;
+  const size_t sm = sizeof(double) * warps * m->h.ndf * m->av.max_row;
+  if (sm > 200 * 1024) return fail(XB_ERR_UNSUPPORTED, "row too long for the node-owned assembly kernel");
+  const unsigned blocks = (unsigned)((count + warps - 1) / warps);
+  if (m->h.ndf == 3) {
+    CU(cudaFuncSetAttribute(assemble_A_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    assemble_A_kernel<3><<<blocks, warps * 32, sm, st>>>(m->av, m->dKe, m->dA, m->dPerm, first, count);
+  } else if (m->h.ndf == 2) {
+    CU(cudaFuncSetAttribute(assemble_A_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    assemble_A_kernel<2><<<blocks, warps * 32, sm, st>>>(m->av, m->dKe, m->dA, m->dPerm, first, count);
+  } else {
+    CU(cudaFuncSetAttribute(assemble_A_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    assemble_A_kernel<1><<<blocks, warps * 32, sm, st>>>(m->av, m->dKe, m->dA, m->dPerm, first, count);
   }
-  {
-    const int warps = 8;
-    const size_t sm = sizeof(double) * warps * m->h.ndf * m->av.max_row;
-    if (sm > 200 * 1024) return fail(XB_ERR_UNSUPPORTED, "row too long for the node-owned assembly kernel");
-    const unsigned blocks = (unsigned)((m->h.nn() + warps - 1) / warps);
-    if (blocks) {
-      if (m->h.ndf == 3) {
-        CU(cudaFuncSetAttribute(assemble_A_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        assemble_A_kernel<3><<<blocks, warps * 32, sm, m->stream>>>(m->av, m->dKe, m->dA);
-      } else if (m->h.ndf == 2) {
-        CU(cudaFuncSetAttribute(assemble_A_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        assemble_A_kernel<2><<<blocks, warps * 32, sm, m->stream>>>(m->av, m->dKe, m->dA);
-      } else {
-        CU(cudaFuncSetAttribute(assemble_A_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        assemble_A_kernel<1><<<blocks, warps * 32, sm, m->stream>>>(m->av, m->dKe, m->dA);
-      }
-      m->launches++;
-    }
-  }
+  m->launches++;
+  return XB_OK;
+}
+
+static int finish_tangent(xb_model* m, double* A) {
   // element matrices + per-(node,element) position map in, A out
   m->alg_bytes[4] = m->h.kn_total * 8 + (long long)m->h.colpos.size() * 2 + m->h.nnz() * 8;
   // compulsory traffic of formTangent as a whole: tangent data, connectivity, coordinates in, A out
@@ -1389,11 +1416,64 @@ int xb_assemble_tangent(xb_model* m, double* A) {
   return XB_OK;
 }
 
-int xb_form_tangent(xb_model* m, double* A) {
-  int rc = xb_form_element_tangents(m);
+static int unpack_received_rows(xb_model* m, cudaStream_t st) {
+  if (m->h.uk_src.empty()) return XB_OK;   // rows received from other ranks -> their slots
+  const long long nch = (long long)m->h.uk_src.size();
+  unpack_rows_kernel<<<(unsigned)((nch * 32 + 255) / 256), 256, 0, st>>>(nch, m->dUkSrc, m->dUkDst, m->h.chunk, m->dRecvK, m->dKe);
+  m->launches++;
+  return XB_OK;
+}
+
+int xb_assemble_tangent(xb_model* m, double* A) {
+  NEED_DEVICE();
+  CU(cudaSetDevice(m->device));
+  int rc = unpack_received_rows(m, m->stream);
   if (rc < 0) return rc;
-  if (m->h.nparts > 1 && (rc = xb_exchange(m, 0)) < 0) return rc;
-  return xb_assemble_tangent(m, A);
+  rc = launch_assemble(m, 0, (long long)m->h.node_perm.size(), m->stream);
+  if (rc < 0) return rc;
+  return finish_tangent(m, A);
+}
+
+// IncrementalIntegrator::formTangent.  Large single-batch models run it as a two-stream
+// pipeline: the element kernel works through consecutive element ranges on the model's stream
+// while a second stream assembles the nodes each finished range completes (the element kernel
+// is FP64/latency bound, the assembly HBM bound: together they fill the SMs better than in turn).
+// Nodes fed by other ranks wait for the exchange.  The result is identical: every row is still
+// accumulated in FE_Element order by one warp.
+int xb_form_tangent(xb_model* m, double* A) {
+  NEED_DEVICE();
+  CU(cudaSetDevice(m->device));
+  const int nc = m->h.nchunk;
+  if (nc <= 1 || m->dg.size() != 1 || m->dg[0].kind != XB_ELE_STDBRICK || !m->stream2) {
+    int rc = xb_form_element_tangents(m);
+    if (rc < 0) return rc;
+    if (m->h.nparts > 1 && (rc = xb_exchange(m, 0)) < 0) return rc;
+    return xb_assemble_tangent(m, A);
+  }
+  DevGroup& d = m->dg[0];
+  const long long per = (d.v.n + nc - 1) / nc;
+  CU(cudaEventRecord(m->ev_start, m->stream));
+  CU(cudaStreamWaitEvent(m->stream2, m->ev_start, 0));      // A and KeN are free once earlier work is done
+  for (int c = 0; c < nc; c++) {
+    const long long e0 = c * per, e1 = std::min<long long>(d.v.n, e0 + per);
+    int rc = launch_group_tangents(m, d, e0, e1, m->stream);
+    if (rc < 0) return rc;
+    CU(cudaEventRecord(m->ev_chunk[c], m->stream));
+    CU(cudaStreamWaitEvent(m->stream2, m->ev_chunk[c], 0));
+    rc = launch_assemble(m, m->h.chunk_node_ptr[c], m->h.chunk_node_ptr[c + 1] - m->h.chunk_node_ptr[c], m->stream2);
+    if (rc < 0) return rc;
+  }
+  account_element_tangent_bytes(m);
+  CU(cudaEventRecord(m->ev_done, m->stream2));
+  CU(cudaStreamWaitEvent(m->stream, m->ev_done, 0));
+  if (m->h.nparts > 1) {     // interface nodes: exchange, unpack, assemble on the main stream
+    int rc = xb_exchange(m, 0);
+    if (rc < 0) return rc;
+    if ((rc = unpack_received_rows(m, m->stream)) < 0) return rc;
+    rc = launch_assemble(m, m->h.chunk_node_ptr[nc], m->h.chunk_node_ptr[nc + 1] - m->h.chunk_node_ptr[nc], m->stream);
+    if (rc < 0) return rc;
+  }
+  return finish_tangent(m, A);
 }
 
 int xb_form_element_resids(xb_model* m) {

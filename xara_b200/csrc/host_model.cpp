@@ -691,6 +691,32 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
     }
   }
 
+  // ---- node order for the pipelined formTangent (single-batch models; else one range) ----
+  {
+    const std::vector<Group>& FG = nparts == 1 ? groups : lgroups;
+    nchunk = (FG.size() == 1 && ne >= 65536) ? 8 : 1;
+    const long long per = nchunk > 1 ? (ne + nchunk - 1) / nchunk : ne;
+    std::vector<int> ready(nl, -1);
+    for (int i = 0; i < nl; i++) {
+      if (!owned[i]) continue;
+      int rdy = 0;
+      for (long long t = n2e_ptr[i]; t < n2e_ptr[i + 1]; t++) {
+        const long long ge = n2e_fe[t];
+        if (part_fe[ge] != rank) { rdy = nchunk; break; }          // needs the interface exchange
+        const long long le = nparts == 1 ? ge : g_fe_to_local[ge];  // local FE index == index in the batch
+        const long long l = fe_local[le];
+        rdy = std::max(rdy, nchunk > 1 ? (int)(l / per) : 0);
+      }
+      ready[i] = rdy;
+    }
+    chunk_node_ptr.assign((size_t)nchunk + 2, 0);
+    for (int i = 0; i < nl; i++) if (ready[i] >= 0) chunk_node_ptr[ready[i] + 1]++;
+    for (int c = 0; c <= nchunk; c++) chunk_node_ptr[c + 1] += chunk_node_ptr[c];
+    node_perm.resize(chunk_node_ptr[nchunk + 1]);
+    std::vector<long long> fill(chunk_node_ptr.begin(), chunk_node_ptr.end() - 1);
+    for (int i = 0; i < nl; i++) if (ready[i] >= 0) node_perm[fill[ready[i]]++] = i;
+  }
+
   // ---- commit the local element groups ----
   if (nparts > 1) groups.swap(lgroups);
   for (size_t gi = 0; gi < groups.size(); gi++) { groups[gi].ke_off = ke_off[gi]; groups[gi].re_off = re_off[gi]; groups[gi].gp_off = gp_off[gi]; }

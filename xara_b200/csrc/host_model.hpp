@@ -131,6 +131,12 @@ struct HostModel {
   int cp_stride = 0;                // max nd over groups
   std::vector<uint16_t> colpos;     // [n2e_total][cp_stride]: position of local dof j's equation
                                     //   inside node n's column list, 0xFFFF if constrained
+  // pipelined formTangent: the elements are cut into `nchunk` consecutive ranges (per batch); a
+  // node can be assembled once the last range holding one of its elements is done.  node_perm
+  // lists the owned nodes by that range (nodes with rows from other ranks last: range nchunk).
+  int nchunk = 1;
+  std::vector<int> node_perm;       // [n_owned_nodes_with_rows]
+  std::vector<long long> chunk_node_ptr;   // [nchunk+2]
   int max_row = 0;                  // longest row
   long long ke_total = 0, re_total = 0, ngp = 0;
   int chunk = 0;                    // doubles per slot: ndf rows x cp_stride columns
