@@ -215,13 +215,26 @@ def ours_main(a):
         step()
     D.synchronize()
 
-    names = ["update", "element_resid", "exchange_B", "assemble_B", "element_tangent", "exchange_A", "assemble_A"]
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(8)] for _ in range(a.steps)]
+    # ---- the timed region: K passes of the hot path through the public calls ----
     clocks = ClockSampler(local); clocks.start()
     l0 = D.launch_count()
     barrier()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record(stream)
+    for k in range(a.steps):
+        step()
+    end.record(stream)
+    barrier()
+    D.synchronize()
+    total_ms = start.elapsed_time(end)
+    launches = D.launch_count() - l0
+    clk = clocks.stop()
+
+    # ---- the same K passes again with an event between the phases (formTangent un-pipelined here,
+    # so that each kernel's own duration is seen): per-kernel times for the roofline ----
+    names = ["update", "element_resid", "exchange_B", "assemble_B", "element_tangent", "exchange_A", "assemble_A"]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(8)] for _ in range(a.steps)]
+    barrier()
     for k in range(a.steps):
         e = ev[k]
         e[0].record(stream); D.update()
@@ -232,12 +245,8 @@ def ours_main(a):
         e[5].record(stream); D.exchange(0)
         e[6].record(stream); D.assemble_tangent()
         e[7].record(stream)
-    end.record(stream)
     barrier()
     D.synchronize()
-    total_ms = start.elapsed_time(end)
-    launches = D.launch_count() - l0
-    clk = clocks.stop()
     ms = {nm: float(np.mean([ev[k][i].elapsed_time(ev[k][i + 1]) for k in range(a.steps)])) for i, nm in enumerate(names)}
     if world > 1:   # time on the device, MAX over ranks
         t = torch.tensor([total_ms] + [ms[nm] for nm in names] + [float(launches)], device="cuda", dtype=torch.float64)
@@ -312,6 +321,8 @@ def ours_main(a):
                            "l2": "inputs larger than L2 (per GPU at N=1: state 7 GB, element matrices 19 GB, A 8 GB vs 126 MB)",
                            "setup_s": {"mesh": t_mesh, "host_setup": t_setup, "upload": t_upload}},
                 "kernel_ms": ms_max, "kernel_ms_rank0": ms,
+                "kernel_ms_note": "separate instrumented pass, formTangent's two kernels run back to back; in the timed "
+                                  "region xb_form_tangent overlaps them on two streams, so ms_per_step < sum(kernel_ms)",
                 "formTangent_ms": ms_max["element_tangent"] + ms_max["exchange_A"] + ms_max["assemble_A"],
                 "formUnbalance_ms": ms_max["element_resid"] + ms_max["exchange_B"] + ms_max["assemble_B"],
                 "update_ms": ms_max["update"],
