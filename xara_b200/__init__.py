@@ -37,7 +37,8 @@ UNI_STEEL02, UNI_CONCRETE02 = 0, 1
 NUMBERER_PLAIN, NUMBERER_RCM = 0, 1
 SOE_SPARSE_GEN_COL, SOE_SPARSE_GEN_ROW = 0, 1
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libxara_b200.so")
+# XARA_B200_LIB: an alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("XARA_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libxara_b200.so")
 
 
 class XaraB200Error(RuntimeError):

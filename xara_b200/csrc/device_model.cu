@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -17,6 +18,15 @@
 #include "host_model.hpp"
 #include "kernels.cuh"
 #include "beam_kernels.cuh"
+
+// assembly kernel tuning (measured on B200, n=128: CH=2/OCC=5 3.29 ms, CH=4/OCC=3 3.94 ms, CH=8/OCC=2 5.41 ms):
+// many warps with two node-slots in flight each beat few warps with many
+#ifndef XB_ASM_CH
+#define XB_ASM_CH 2
+#endif
+#ifndef XB_ASM_OCC
+#define XB_ASM_OCC 5
+#endif
 
 using namespace xbk;
 
@@ -427,6 +437,115 @@ __global__ void __launch_bounds__(BT_ELEMS * 8, 2) brick_tangent_kernel(GroupVie
   }
 }
 
+// The same element tangent for the column-compressed SOE (SparseGenColLinSOE, the reference's
+// live general sparse system): there the stored matrix is K^T, so the column block lane k owns is
+// exactly node k's slot (3 rows x 24 columns, contiguous).  No shared-memory tile is needed: the
+// lane streams its own slot out with 16-byte stores, and the 8 row blocks are done in two passes of
+// 4 (36 FP64 accumulators instead of 72 -> 3 CTAs per SM instead of 2; D*B_k is recomputed in the
+// second pass, +20 % FP64 work in the main loop).
+template <int MATK>
+__global__ void __launch_bounds__(BT_ELEMS * 8, 3) brick_tangent_csc_kernel(GroupView G, const double* __restrict__ X,
+                                                                            long long ebeg, long long eend) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int s = lane >> 3, k = lane & 7;
+  double* wbase = smem + warp * (4 * 8 * (BT_NSTR + BT_DSTR));
+  double* sN = wbase;
+  double* sD = wbase + 4 * 8 * BT_NSTR;
+  const long long e0 = ebeg + (long long)blockIdx.x * BT_ELEMS + warp * 4;
+  if (e0 >= eend) return;
+  const long long e_raw = e0 + s;
+  const bool live = e_raw < eend;
+  const long long e = live ? e_raw : eend - 1;
+  const long long ngp = G.n * 8;
+  const long long dst = __ldg(G.kdst + e * 8 + k);
+  {
+    const int* c = G.conn + e * 8;
+    double xl[3][8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      const int nd = __ldg(c + a);
+#pragma unroll
+      for (int d = 0; d < 3; d++) xl[d][a] = __ldg(X + (size_t)nd * 3 + d);
+    }
+    double shp[4][8], dvol;
+    brick_shp(k, xl, shp, dvol);
+    double* n = sN + (s * 8 + k) * BT_NSTR;
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      *reinterpret_cast<double2*>(n + a * 4) = make_double2(shp[0][a], shp[1][a]);
+      *reinterpret_cast<double2*>(n + a * 4 + 2) = make_double2(shp[2][a], 0.0);
+    }
+    double d21[22];
+    brick_D<MATK>(G, e, e * 8 + k, ngp, dvol, d21);
+    d21[21] = 0.0;
+    double* dd = sD + (s * 8 + k) * BT_DSTR;
+#pragma unroll
+    for (int i = 0; i < 11; i++) *reinterpret_cast<double2*>(dd + 2 * i) = make_double2(d21[2 * i], d21[2 * i + 1]);
+  }
+  __syncwarp();
+  double* base = (dst >= 0 ? G.KeN + dst : G.sendK + (-dst - 1));
+  const int cps = G.cps;
+#pragma unroll 1
+  for (int h = 0; h < 2; h++) {
+    double acc[4][3][3];
+#pragma unroll
+    for (int J = 0; J < 4; J++)
+#pragma unroll
+      for (int p = 0; p < 3; p++)
+#pragma unroll
+        for (int q = 0; q < 3; q++) acc[J][p][q] = 0.0;
+#pragma unroll 1
+    for (int g = 0; g < 8; g++) {
+      const double* n = sN + (s * 8 + g) * BT_NSTR;
+      const double* dp = sD + (s * 8 + g) * BT_DSTR;
+      const double2 nk = *reinterpret_cast<const double2*>(n + k * 4);
+      const double N1 = nk.x, N2 = nk.y, N3 = n[k * 4 + 2];
+      double d[22];
+#pragma unroll
+      for (int i = 0; i < 11; i++) {
+        const double2 t = *reinterpret_cast<const double2*>(dp + 2 * i);
+        d[2 * i] = t.x; d[2 * i + 1] = t.y;
+      }
+      double DB[6][3];
+#pragma unroll
+      for (int r = 0; r < 6; r++) {
+        const double dr0 = d[sym6(r, 0)], dr1 = d[sym6(r, 1)], dr2 = d[sym6(r, 2)], dr3 = d[sym6(r, 3)],
+                     dr4 = d[sym6(r, 4)], dr5 = d[sym6(r, 5)];
+        DB[r][0] = dr0 * N1 + dr3 * N2 + dr5 * N3;
+        DB[r][1] = dr1 * N2 + dr3 * N1 + dr4 * N3;
+        DB[r][2] = dr2 * N3 + dr4 * N2 + dr5 * N1;
+      }
+#pragma unroll
+      for (int J = 0; J < 4; J++) {
+        const double* mjp = n + (4 * h + J) * 4;
+        const double2 mj = *reinterpret_cast<const double2*>(mjp);
+        const double M1 = mj.x, M2 = mj.y, M3 = mjp[2];
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          acc[J][0][q] += M1 * DB[0][q] + M2 * DB[3][q] + M3 * DB[5][q];
+          acc[J][1][q] += M2 * DB[1][q] + M1 * DB[3][q] + M3 * DB[4][q];
+          acc[J][2][q] += M3 * DB[2][q] + M2 * DB[4][q] + M1 * DB[5][q];
+        }
+      }
+    }
+    // K(3J+p, 3k+q) is entry (row q, column 3J+p) of node k's slot: columns 12h .. 12h+11 of each row
+    if (live) {
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        double2* row = reinterpret_cast<double2*>(base + q * cps + 12 * h);
+        row[0] = make_double2(acc[0][0][q], acc[0][1][q]);
+        row[1] = make_double2(acc[0][2][q], acc[1][0][q]);
+        row[2] = make_double2(acc[1][1][q], acc[1][2][q]);
+        row[3] = make_double2(acc[2][0][q], acc[2][1][q]);
+        row[4] = make_double2(acc[2][2][q], acc[3][0][q]);
+        row[5] = make_double2(acc[3][1][q], acc[3][2][q]);
+      }
+    }
+  }
+}
+
 // FourNodeQuad::getTangentStiff (FourNodeQuad.cpp:226-281).  4 lanes per element, lane b
 // owns column block beta=b (8 rows x 2 columns); shape functions are recomputed per lane.
 template <int MATK>
@@ -538,7 +657,7 @@ struct AsmView {
 // the order IncrementalIntegrator::formTangent (IncrementalIntegrator.cpp:91-99) calls addA.
 // Every entry of A is written exactly once, so no zeroA pass is needed.
 template <int NDF>
-__global__ void __launch_bounds__(256, 3) assemble_A_kernel(AsmView V, const double* __restrict__ KeN,
+__global__ void __launch_bounds__(256, XB_ASM_OCC) assemble_A_kernel(AsmView V, const double* __restrict__ KeN,
                                                             double* __restrict__ A, const int* __restrict__ perm,
                                                             long long first, long long count) {
   extern __shared__ double sacc[];  // [warps][NDF][max_row]
@@ -574,7 +693,7 @@ __global__ void __launch_bounds__(256, 3) assemble_A_kernel(AsmView V, const dou
   const double c1 = V.c1;
   const int cps = V.cp_stride;
   const bool on = lane < cps;
-  constexpr int CH = 4;  // slots in flight together; the node's slots are one contiguous stream
+  constexpr int CH = XB_ASM_CH;  // slots in flight together; the node's slots are one contiguous stream
   for (long long tb = t0; tb < t1; tb += CH) {
     double v[CH][NDF];
     unsigned short pos[CH];
@@ -698,6 +817,7 @@ struct xb_model {
   unsigned short* dDiag = nullptr;
   double *dDU = nullptr, *dUin = nullptr;   // Node::getIncrDeltaDisp, staging for xb_set_trial_disp
   bool has_beams = false;
+  bool tile_kernel_for_csc = false;   // XB_TANGENT_TILE=1: keep the shared-tile kernel for the CSC layout too
   double alphaM = 0.0;      // Node::setRayleighDampingFactor
   double *dX = nullptr, *dU = nullptr, *dUc = nullptr, *dKe = nullptr, *dRe = nullptr, *dA = nullptr,
          *dB = nullptr, *dLoad = nullptr, *dMpar = nullptr, *dTmp = nullptr;
@@ -909,6 +1029,7 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
   if (cuda_stream) m->stream = (cudaStream_t)cuda_stream;
   else { CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking)); m->own_stream = true; }
   m->on_device = true;  // from here xb_model_destroy frees what was allocated
+  { const char* t = std::getenv("XB_TANGENT_TILE"); m->tile_kernel_for_csc = t && t[0] == '1'; }
 
   xb::HostModel& h = m->h;
   const size_t nn = h.nn();
@@ -1260,6 +1381,18 @@ static int launch_group_tangents(xb_model* m, DevGroup& d, long long ebeg, long 
   const bool j2 = d.mat_kind == XB_MAT_J2PLASTICITY;
   if (d.kind == XB_ELE_STDBRICK) {
     const unsigned blocks = (unsigned)((eend - ebeg + BT_ELEMS - 1) / BT_ELEMS);
+    if (transpose && m->h.cp_stride == 24 && !m->tile_kernel_for_csc) {
+      const size_t smc = sizeof(double) * (BT_ELEMS / 4) * (4 * 8 * (BT_NSTR + BT_DSTR));
+      if (j2) {
+        CU(cudaFuncSetAttribute(brick_tangent_csc_kernel<XB_MAT_J2PLASTICITY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc));
+        brick_tangent_csc_kernel<XB_MAT_J2PLASTICITY><<<blocks, BT_ELEMS * 8, smc, st>>>(d.v, m->dX, ebeg, eend);
+      } else {
+        CU(cudaFuncSetAttribute(brick_tangent_csc_kernel<XB_MAT_ELASTIC_ISOTROPIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc));
+        brick_tangent_csc_kernel<XB_MAT_ELASTIC_ISOTROPIC><<<blocks, BT_ELEMS * 8, smc, st>>>(d.v, m->dX, ebeg, eend);
+      }
+      m->launches++;
+      return XB_OK;
+    }
     const size_t sm = sizeof(double) * (BT_ELEMS / 4) * BT_WARP_DOUBLES;
     if (j2) {
       CU(cudaFuncSetAttribute(brick_tangent_kernel<XB_MAT_J2PLASTICITY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));

@@ -3,6 +3,7 @@
 #include "host_model.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -694,7 +695,11 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
   // ---- node order for the pipelined formTangent (single-batch models; else one range) ----
   {
     const std::vector<Group>& FG = nparts == 1 ? groups : lgroups;
-    nchunk = (FG.size() == 1 && ne >= 65536) ? 8 : 1;
+    // (measured on B200: the element kernel's 228 registers x 8 warps leave no room for assembly
+    //  CTAs to co-reside, so the pipeline buys nothing there; it stays opt-in: XB_PIPELINE=<ranges>)
+    const char* pl = std::getenv("XB_PIPELINE");
+    const int want = pl ? std::atoi(pl) : 1;
+    nchunk = (FG.size() == 1 && ne >= 65536 && want > 1 && want <= 64) ? want : 1;
     const long long per = nchunk > 1 ? (ne + nchunk - 1) / nchunk : ne;
     std::vector<int> ready(nl, -1);
     for (int i = 0; i < nl; i++) {
