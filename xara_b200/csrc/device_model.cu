@@ -817,7 +817,10 @@ struct xb_model {
   unsigned short* dDiag = nullptr;
   double *dDU = nullptr, *dUin = nullptr;   // Node::getIncrDeltaDisp, staging for xb_set_trial_disp
   bool has_beams = false;
-  bool tile_kernel_for_csc = false;   // XB_TANGENT_TILE=1: keep the shared-tile kernel for the CSC layout too
+  // XB_TANGENT_CSC=1 selects brick_tangent_csc_kernel (tile-free, two passes).  Measured on B200 at
+  // 4.1M elements: 12.1 ms against 10.6 ms for the shared-tile kernel -- its main loop turns
+  // shared-memory bound (D and N are re-read in the second pass) -- so it is not the default.
+  bool csc_direct_kernel = false;
   double alphaM = 0.0;      // Node::setRayleighDampingFactor
   double *dX = nullptr, *dU = nullptr, *dUc = nullptr, *dKe = nullptr, *dRe = nullptr, *dA = nullptr,
          *dB = nullptr, *dLoad = nullptr, *dMpar = nullptr, *dTmp = nullptr;
@@ -1029,7 +1032,7 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
   if (cuda_stream) m->stream = (cudaStream_t)cuda_stream;
   else { CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking)); m->own_stream = true; }
   m->on_device = true;  // from here xb_model_destroy frees what was allocated
-  { const char* t = std::getenv("XB_TANGENT_TILE"); m->tile_kernel_for_csc = t && t[0] == '1'; }
+  { const char* t = std::getenv("XB_TANGENT_CSC"); m->csc_direct_kernel = t && t[0] == '1'; }
 
   xb::HostModel& h = m->h;
   const size_t nn = h.nn();
@@ -1381,7 +1384,7 @@ static int launch_group_tangents(xb_model* m, DevGroup& d, long long ebeg, long 
   const bool j2 = d.mat_kind == XB_MAT_J2PLASTICITY;
   if (d.kind == XB_ELE_STDBRICK) {
     const unsigned blocks = (unsigned)((eend - ebeg + BT_ELEMS - 1) / BT_ELEMS);
-    if (transpose && m->h.cp_stride == 24 && !m->tile_kernel_for_csc) {
+    if (transpose && m->h.cp_stride == 24 && m->csc_direct_kernel) {
       const size_t smc = sizeof(double) * (BT_ELEMS / 4) * (4 * 8 * (BT_NSTR + BT_DSTR));
       if (j2) {
         CU(cudaFuncSetAttribute(brick_tangent_csc_kernel<XB_MAT_J2PLASTICITY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc));
