@@ -55,15 +55,44 @@ struct GroupView {
 // state determination: Element::update -> NDMaterial::setTrialStrain
 // =====================================================================================
 
+// residual of one brick from its 8 Gauss points (8 adjacent lanes): B^T sigma dvol - N b dvol,
+// summed by a fixed butterfly, lane a stores node a's three entries
+__device__ __forceinline__ void brick_resid_store(const GroupView& G, long long e, int g, bool live,
+                                                  const double (&shp)[4][8], double dvol, const double* sig) {
+  double st[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) st[i] = sig[i] * dvol;   // wg = 1 (Brick.cpp:61)
+  const double b0 = __ldg(G.par + e), b1 = __ldg(G.par + G.n + e), b2 = __ldg(G.par + 2 * G.n + e);
+  double r[24];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    r[3 * j + 0] = shp[0][j] * st[0] + shp[1][j] * st[3] + shp[2][j] * st[5] - dvol * b0 * shp[3][j];
+    r[3 * j + 1] = shp[1][j] * st[1] + shp[0][j] * st[3] + shp[2][j] * st[4] - dvol * b1 * shp[3][j];
+    r[3 * j + 2] = shp[2][j] * st[2] + shp[1][j] * st[4] + shp[0][j] * st[5] - dvol * b2 * shp[3][j];
+  }
+#pragma unroll
+  for (int i = 0; i < 24; i++) {
+    r[i] += __shfl_xor_sync(0xffffffffu, r[i], 1);
+    r[i] += __shfl_xor_sync(0xffffffffu, r[i], 2);
+    r[i] += __shfl_xor_sync(0xffffffffu, r[i], 4);
+  }
+  if (!live) return;
+  double* out = G.Re + e * 24;
+#pragma unroll
+  for (int a = 0; a < 8; a++)
+    if (g == a) { out[3 * a] = r[3 * a]; out[3 * a + 1] = r[3 * a + 1]; out[3 * a + 2] = r[3 * a + 2]; }
+}
+
 // Brick::update (Brick.cpp:718-840); one thread per Gauss point
 template <int MATK>
 __global__ void __launch_bounds__(128) brick_update_kernel(GroupView G, const double* __restrict__ X,
                                                            const double* __restrict__ U, int* fail) {
-  const long long gp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long gp_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long ngp = G.n * 8;
-  if (gp >= ngp) return;
+  const bool live = gp_raw < ngp;                 // dead lanes still take part in the shuffles below
+  const long long gp = live ? gp_raw : ngp - 1;
   const long long e = gp >> 3;
-  const int g = (int)(gp & 7);
+  const int g = (int)(gp_raw & 7);
   const int* c = G.conn + e * 8;
   double xl[3][8], ul[3][8];
 #pragma unroll
@@ -85,6 +114,7 @@ __global__ void __launch_bounds__(128) brick_update_kernel(GroupView G, const do
     s[5] += shp[2][j] * ul[0][j] + shp[0][j] * ul[2][j];
   }
   const double* p = G.mpar + (size_t)__ldg(G.mat + e) * 8;
+  double st[6];
   if (MATK == XB_MAT_J2PLASTICITY) {
     double par[7], epn[6], et[6];
 #pragma unroll
@@ -95,29 +125,39 @@ __global__ void __launch_bounds__(128) brick_update_kernel(GroupView G, const do
     et[0] = s[0]; et[1] = s[1]; et[2] = s[2]; et[3] = 0.50 * s[3]; et[4] = 0.50 * s[4]; et[5] = 0.50 * s[5];
     J2Result r;
     j2_integrate(par, et, epn, xin, 0.0, r);
-    if (r.fail) atomicExch(fail, 1);
+    if (r.fail && live) atomicExch(fail, 1);
+    if (live) {
 #pragma unroll
-    for (int i = 0; i < 6; i++) {
-      G.ht[(size_t)i * ngp + gp] = r.ep[i];
-      G.sig[(size_t)i * ngp + gp] = r.sig[i];
-      G.tan[(size_t)i * ngp + gp] = r.nrm[i];
+      for (int i = 0; i < 6; i++) {
+        G.ht[(size_t)i * ngp + gp] = r.ep[i];
+        G.sig[(size_t)i * ngp + gp] = r.sig[i];
+        G.tan[(size_t)i * ngp + gp] = r.nrm[i];
+      }
+      G.ht[(size_t)6 * ngp + gp] = r.xi;
+      G.tan[(size_t)6 * ngp + gp] = r.c2;
+      G.tan[(size_t)7 * ngp + gp] = r.c3;
     }
-    G.ht[(size_t)6 * ngp + gp] = r.xi;
-    G.tan[(size_t)6 * ngp + gp] = r.c2;
-    G.tan[(size_t)7 * ngp + gp] = r.c3;
+#pragma unroll
+    for (int i = 0; i < 6; i++) st[i] = r.sig[i];
   } else {
     const double E = __ldg(p), v = __ldg(p + 1);
     double mu2 = E / (1.0 + v);
     const double lam = v * mu2 / (1.0 - 2.0 * v);
     const double mu = 0.50 * mu2;
     mu2 += lam;
-    G.sig[(size_t)0 * ngp + gp] = mu2 * s[0] + lam * (s[1] + s[2]);
-    G.sig[(size_t)1 * ngp + gp] = mu2 * s[1] + lam * (s[0] + s[2]);
-    G.sig[(size_t)2 * ngp + gp] = mu2 * s[2] + lam * (s[0] + s[1]);
-    G.sig[(size_t)3 * ngp + gp] = mu * s[3];
-    G.sig[(size_t)4 * ngp + gp] = mu * s[4];
-    G.sig[(size_t)5 * ngp + gp] = mu * s[5];
+    st[0] = mu2 * s[0] + lam * (s[1] + s[2]);
+    st[1] = mu2 * s[1] + lam * (s[0] + s[2]);
+    st[2] = mu2 * s[2] + lam * (s[0] + s[1]);
+    st[3] = mu * s[3]; st[4] = mu * s[4]; st[5] = mu * s[5];
+    if (live) {
+#pragma unroll
+      for (int i = 0; i < 6; i++) G.sig[(size_t)i * ngp + gp] = st[i];
+    }
   }
+  // Element::getResistingForce needs nothing but the stresses just computed and the shape
+  // functions already at hand: form it here (Brick.cpp:843-1022 with tang_flag = 0), so that
+  // formUnbalance only has to assemble.
+  brick_resid_store(G, e, g, live, shp, xsj, st);
 }
 
 // FourNodeQuad::update (FourNodeQuad.cpp:190-222); one thread per Gauss point
@@ -183,49 +223,6 @@ __global__ void __launch_bounds__(128) quad_update_kernel(GroupView G, const dou
 // =====================================================================================
 // element residual: Element::getResistingForce
 // =====================================================================================
-
-// Brick::formResidAndTangent(tang_flag=0) (Brick.cpp:843-1022); thread per Gauss point,
-// the 8 points of an element sit in 8 adjacent lanes and are summed by a fixed butterfly.
-__global__ void __launch_bounds__(128) brick_resid_kernel(GroupView G, const double* __restrict__ X) {
-  const long long gp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long ngp = G.n * 8;
-  const bool live = gp < ngp;
-  const long long e = live ? (gp >> 3) : (ngp - 1) >> 3;
-  const int g = (int)(gp & 7);
-  const int* c = G.conn + e * 8;
-  double xl[3][8];
-#pragma unroll
-  for (int a = 0; a < 8; a++) {
-    const int nd = __ldg(c + a);
-#pragma unroll
-    for (int d = 0; d < 3; d++) xl[d][a] = __ldg(X + (size_t)nd * 3 + d);
-  }
-  double shp[4][8], dvol;
-  brick_shp(g, xl, shp, dvol);  // wg = 1 (Brick.cpp:61)
-  const long long gpc = live ? gp : ngp - 1;
-  double st[6];
-#pragma unroll
-  for (int i = 0; i < 6; i++) st[i] = G.sig[(size_t)i * ngp + gpc] * dvol;
-  const double b0 = __ldg(G.par + e), b1 = __ldg(G.par + G.n + e), b2 = __ldg(G.par + 2 * G.n + e);
-  double r[24];
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    r[3 * j + 0] = shp[0][j] * st[0] + shp[1][j] * st[3] + shp[2][j] * st[5] - dvol * b0 * shp[3][j];
-    r[3 * j + 1] = shp[1][j] * st[1] + shp[0][j] * st[3] + shp[2][j] * st[4] - dvol * b1 * shp[3][j];
-    r[3 * j + 2] = shp[2][j] * st[2] + shp[1][j] * st[4] + shp[0][j] * st[5] - dvol * b2 * shp[3][j];
-  }
-#pragma unroll
-  for (int i = 0; i < 24; i++) {
-    r[i] += __shfl_xor_sync(0xffffffffu, r[i], 1);
-    r[i] += __shfl_xor_sync(0xffffffffu, r[i], 2);
-    r[i] += __shfl_xor_sync(0xffffffffu, r[i], 4);
-  }
-  if (!live) return;
-  double* out = G.Re + e * 24;
-#pragma unroll
-  for (int a = 0; a < 8; a++)
-    if (g == a) { out[3 * a] = r[3 * a]; out[3 * a + 1] = r[3 * a + 1]; out[3 * a + 2] = r[3 * a + 2]; }
-}
 
 // FourNodeQuad::getResistingForce (FourNodeQuad.cpp:507-553); thread per element
 __global__ void __launch_bounds__(128) quad_resid_kernel(GroupView G, const double* __restrict__ X) {
@@ -1357,6 +1354,7 @@ int xb_update(xb_model* m) {
     m->launches++;
     // per Gauss point: committed history read (7) + trial history, stress, compact tangent written
     bytes += d.ngp * 8 * (j2 ? (7 + 7 + d.nst + 8) : d.nst);
+    if (d.kind == XB_ELE_STDBRICK) bytes += d.v.n * d.nd * 8;   // + the element residual it leaves behind
   }
   bytes += (long long)m->h.nn() * (m->h.ndm + m->h.ndf) * 8;  // coordinates + trial displacement, once
   for (auto& g : m->h.groups) bytes += (long long)g.conn.size() * 4;
@@ -1624,11 +1622,8 @@ int xb_form_element_resids(xb_model* m) {
       bytes += d.b.n * (3 + 6) * 8;
       continue;
     }
-    if (d.kind == XB_ELE_STDBRICK) {
-      brick_resid_kernel<<<(unsigned)((d.ngp + 127) / 128), 128, 0, m->stream>>>(d.v, m->dX);
-    } else {
-      quad_resid_kernel<<<(unsigned)((d.v.n + 127) / 128), 128, 0, m->stream>>>(d.v, m->dX);
-    }
+    if (d.kind == XB_ELE_STDBRICK) continue;   // brick_update_kernel already left Re (it is a function of the state only)
+    quad_resid_kernel<<<(unsigned)((d.v.n + 127) / 128), 128, 0, m->stream>>>(d.v, m->dX);
     m->launches++;
     bytes += d.ngp * 8 * d.nst + d.v.n * ((long long)d.nd * 8 + (d.nd / m->h.ndf) * 4);
   }
