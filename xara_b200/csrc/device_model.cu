@@ -70,17 +70,30 @@ __device__ __forceinline__ void brick_resid_store(const GroupView& G, long long 
     r[3 * j + 1] = shp[1][j] * st[1] + shp[0][j] * st[3] + shp[2][j] * st[4] - dvol * b1 * shp[3][j];
     r[3 * j + 2] = shp[2][j] * st[2] + shp[1][j] * st[4] + shp[0][j] * st[5] - dvol * b2 * shp[3][j];
   }
+  // reduce-scatter over the 8 lanes: each step halves what a lane keeps; lane g ends with node g
+  double k12[12], k6[6], k3[3];
+  const bool b4 = g & 4, b2 = g & 2, b1 = g & 1;
 #pragma unroll
-  for (int i = 0; i < 24; i++) {
-    r[i] += __shfl_xor_sync(0xffffffffu, r[i], 1);
-    r[i] += __shfl_xor_sync(0xffffffffu, r[i], 2);
-    r[i] += __shfl_xor_sync(0xffffffffu, r[i], 4);
+  for (int i = 0; i < 12; i++) {
+    const double send = b4 ? r[i] : r[12 + i];
+    const double recv = __shfl_xor_sync(0xffffffffu, send, 4);
+    k12[i] = (b4 ? r[12 + i] : r[i]) + recv;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    const double send = b2 ? k12[i] : k12[6 + i];
+    const double recv = __shfl_xor_sync(0xffffffffu, send, 2);
+    k6[i] = (b2 ? k12[6 + i] : k12[i]) + recv;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const double send = b1 ? k6[i] : k6[3 + i];
+    const double recv = __shfl_xor_sync(0xffffffffu, send, 1);
+    k3[i] = (b1 ? k6[3 + i] : k6[i]) + recv;
   }
   if (!live) return;
-  double* out = G.Re + e * 24;
-#pragma unroll
-  for (int a = 0; a < 8; a++)
-    if (g == a) { out[3 * a] = r[3 * a]; out[3 * a + 1] = r[3 * a + 1]; out[3 * a + 2] = r[3 * a + 2]; }
+  double* out = G.Re + e * 24 + 3 * g;
+  out[0] = k3[0]; out[1] = k3[1]; out[2] = k3[2];
 }
 
 // Brick::update (Brick.cpp:718-840); one thread per Gauss point
