@@ -72,24 +72,24 @@ __device__ __forceinline__ void brick_resid_store(const GroupView& G, long long 
   }
   // reduce-scatter over the 8 lanes: each step halves what a lane keeps; lane g ends with node g
   double k12[12], k6[6], k3[3];
-  const bool b4 = g & 4, b2 = g & 2, b1 = g & 1;
+  const bool hi4 = g & 4, hi2 = g & 2, hi1 = g & 1;
 #pragma unroll
   for (int i = 0; i < 12; i++) {
-    const double send = b4 ? r[i] : r[12 + i];
+    const double send = hi4 ? r[i] : r[12 + i];
     const double recv = __shfl_xor_sync(0xffffffffu, send, 4);
-    k12[i] = (b4 ? r[12 + i] : r[i]) + recv;
+    k12[i] = (hi4 ? r[12 + i] : r[i]) + recv;
   }
 #pragma unroll
   for (int i = 0; i < 6; i++) {
-    const double send = b2 ? k12[i] : k12[6 + i];
+    const double send = hi2 ? k12[i] : k12[6 + i];
     const double recv = __shfl_xor_sync(0xffffffffu, send, 2);
-    k6[i] = (b2 ? k12[6 + i] : k12[i]) + recv;
+    k6[i] = (hi2 ? k12[6 + i] : k12[i]) + recv;
   }
 #pragma unroll
   for (int i = 0; i < 3; i++) {
-    const double send = b1 ? k6[i] : k6[3 + i];
+    const double send = hi1 ? k6[i] : k6[3 + i];
     const double recv = __shfl_xor_sync(0xffffffffu, send, 1);
-    k3[i] = (b1 ? k6[3 + i] : k6[i]) + recv;
+    k3[i] = (hi1 ? k6[3 + i] : k6[i]) + recv;
   }
   if (!live) return;
   double* out = G.Re + e * 24 + 3 * g;
