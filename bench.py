@@ -76,10 +76,33 @@ class ClockSampler:
                 "samples": len(sm), "reasons": reasons}
 
 
-def workload_spec(n, z0=0, z1=None):
-    """n^3 J2 stdBrick block (z slab [z0,z1) of it), base fixed, top loaded."""
-    from modelspec import J2_STEEL, brick_block
+def workload_spec(n, workload="brick"):
+    """brick: n^3 J2 stdBrick block (BASELINE configs[2], the headline workload);
+    quad: n x n plane-strain ElasticIsotropic FourNodeQuad mesh (configs[1]);
+    frame: 2D RC frame of forceBeamColumn elements with Steel02/Concrete02 fibre sections, n bays x n storeys
+           (the 2D counterpart of configs[3])"""
+    from modelspec import ELASTIC, J2_STEEL, brick_block, frame2d, quad_plane
+    if workload == "quad":
+        return quad_plane(n, n, mat=(ELASTIC[0], [1000.0, 0.25, 0.0]), lx=float(n), ly=float(n))
+    if workload == "frame":
+        return frame2d(n, n, 2)
     return brick_block(n, n, n, mat=J2_STEEL)
+
+
+def displacement_field_for(spec, crd, workload):
+    if workload == "brick":
+        return displacement_field(crd)
+    if workload == "quad":
+        x, y = crd[:, 0], crd[:, 1]
+        u = np.empty_like(crd)
+        u[:, 0] = 1e-3 * (y * y / (1.0 + y.max()) + 0.3 * np.sin(0.07 * x) * y)
+        u[:, 1] = 1e-3 * (0.5 * x * y / (1.0 + x.max()))
+        return u
+    y = crd[:, 1] / crd[:, 1].max()                      # frame: sway with matching joint rotations
+    u = np.zeros((len(crd), 3))
+    a = 0.004 * crd[:, 1].max()
+    u[:, 0] = a * y ** 1.5; u[:, 1] = -0.01 * y; u[:, 2] = -1.5 * a * y ** 0.5 / crd[:, 1].max()
+    return u
 
 
 def displacement_field(crd, amp=4e-3):
@@ -149,7 +172,11 @@ def reference_main(a):
     print(json.dumps(line), flush=True)
 
 
-def workload_name(n):
+def workload_name(n, workload="brick"):
+    if workload == "quad":
+        return f"2D FourNodeQuad plane-strain ElasticIsotropic mesh {n}x{n} = {n * n} elements (BASELINE configs[1])"
+    if workload == "frame":
+        return f"2D RC frame {n} bays x {n} storeys, forceBeamColumn + fibre sections Steel02/Concrete02 (2D counterpart of BASELINE configs[3])"
     return f"3D stdBrick J2Plasticity block {n}x{n}x{n} = {n ** 3} elements (BASELINE configs[2])"
 
 
@@ -183,7 +210,7 @@ def ours_main(a):
 
     n = a.n
     t0 = time.time()
-    spec = workload_spec(n)
+    spec = workload_spec(n, a.workload)
     t_mesh = time.time() - t0
     t0 = time.time()
     D = xb.DeviceModel.from_spec(spec, xb.NUMBERER_PLAIN, xb.SOE_SPARSE_GEN_COL, world, rank)
@@ -198,8 +225,9 @@ def ours_main(a):
         D.comm_init(box[0])
     t_upload = time.time() - t0
     ids = D.ids()
-    u = displacement_field(spec.crd[D.node_tags() - 1]); u[ids < 0] = 0.0
-    ngp_global, ne_global = spec.ne * 8, spec.ne
+    u = displacement_field_for(spec, spec.crd[D.node_tags() - 1], a.workload); u[ids < 0] = 0.0
+    nip = {"brick": 8, "quad": 4, "frame": 5}[a.workload]
+    ngp_global, ne_global = spec.ne * nip, spec.ne
     del spec
     D.set_trial_disp(u); D.apply_load(1.0); D.synchronize()
 
@@ -262,6 +290,8 @@ def ours_main(a):
     # ---- roofline of the dominant kernel (this rank's launches), live numbers ----
     peak, peak_src = peaks()
     which = {"update": 0, "assemble_B": 1, "element_tangent": 3, "assemble_A": 4}
+    if a.workload != "brick":
+        which.pop("update", None) if False else None
     dom = max(which, key=lambda k: ms[k])
     alg = D.algorithmic_bytes(which[dom])
     achieved = alg / (ms[dom] * 1e-3) / 1e9
@@ -305,14 +335,14 @@ def ours_main(a):
                    "host buffers; every rank moves its own nodes' u in and its owned rows of A, B out (bytes summed over ranks)"}
 
     cb = None
-    if not a.no_cpu_baseline and world == 1:
+    if not a.no_cpu_baseline and world == 1 and a.workload == "brick":
         cb, _ = cpu_arm(a.cpu_steps, 1, 1, a.cpu_sample)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(n), "elements": int(ne_global), "gauss_points": int(ngp_global),
+                "config": {"workload": workload_name(n, a.workload), "elements": int(ne_global), "gauss_points": int(ngp_global),
                            "equations": int(D.neq), "rank0": {"elements": int(D.ne), "rows": int(D.nrows), "nnz": int(D.nnz),
                                                               "peers": [[int(r), int(c[0]), int(c[1])] for r, c in D.peers()]},
                            "partition": "none" if world == 1 else f"recursive coordinate bisection, {world} parts, "
@@ -340,6 +370,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=160, help="elements per side of the block (160 -> 4.096M)")
+    ap.add_argument("--workload", default="brick", choices=["brick", "quad", "frame"],
+                    help="brick = the headline workload; quad / frame = secondary lines (profiles/), n = cells per side")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=22, help="CPU arm sample: elements per side")
     ap.add_argument("--cpu-steps", type=int, default=3)
