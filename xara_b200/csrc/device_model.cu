@@ -556,6 +556,214 @@ __global__ void __launch_bounds__(BT_ELEMS * 8, 3) brick_tangent_csc_kernel(Grou
   }
 }
 
+// Third form of the same element tangent, the default: a persistent, software-pipelined kernel
+// that uses the symmetry of the material tangent (J2Plasticity's consistent tangent and the elastic
+// one are symmetric 6x6 matrices, so K_kJ = K_Jk^T).  Differences to brick_tangent_kernel:
+//   * each of the 8 lanes of an element forms only 5 (lanes 0-3) or 4 (lanes 4-7) of the 36
+//     distinct node-pair blocks, J = k, k+1, .., k+4 (mod 8): 45 FP64 accumulators instead of 72
+//     and 189 instead of 270 DFMA per lane and Gauss point;
+//   * a warp walks over its batches of 4 elements in a loop and requests the inputs of the NEXT
+//     batch (its node's coordinates, the Gauss point's compact tangent, the slot address) before
+//     the main loop of the current one, so that the global-load latency hides behind FP64 work;
+//   * a lane loads only its own node / Gauss point; the coordinates go round through shared memory;
+//   * the output tile is bank-conflict free for both orientations (row stride 26, element stride
+//     632 doubles) and leaves with all 32 lanes storing 16 bytes each.
+// The sum over the Gauss points of one entry keeps the reference's order (point 0..7); inside a
+// point the products are grouped as B_J^T (D B_k), the mirror image of Matrix::addMatrixTripleProduct's
+// (B_J^T D) B_k -- agreement with the reference is to rounding (1e-16 of the block norm), not bitwise,
+// which is what BASELINE.json's 1e-12 asks for; runs on any partition are bitwise identical.
+constexpr int BS_R = 26;                  // tile row stride (doubles)
+constexpr int BS_T = 24 * BS_R + 8;       // tile stride per element: = 8 mod 16
+constexpr int BS_SG = 98;                 // per Gauss point: shape-function gradients [3][4 elements][8 nodes] + pad
+constexpr int BS_DG = 90;                 // per Gauss point: [4 elements][22] packed D + pad
+constexpr int BS_XS = 26;                 // per element: nodal coordinates [8][3] + pad
+constexpr int BS_WARP = 4 * BS_T + 32;    // tile (aliases the three regions above) + 32 slot addresses
+static_assert(8 * BS_SG + 8 * BS_DG + 4 * BS_XS <= 4 * BS_T, "staging regions must fit under the tile");
+
+template <int MATK>
+__device__ __forceinline__ void brick_D_regs(double m0, double m1, const double* t, double dvol, double* d21) {
+  if (MATK == XB_MAT_J2PLASTICITY) {
+#pragma unroll
+    for (int a = 0; a < 6; a++)
+#pragma unroll
+      for (int b = a; b < 6; b++) d21[sym6(a, b)] = j2_tangent_entry(a, b, m0, m1, t, t[6], t[7]) * dvol;
+  } else {
+    double mu2 = m0 / (1.0 + m1);
+    const double lam = m1 * mu2 / (1.0 - 2.0 * m1);
+    const double mu = 0.50 * mu2;
+    mu2 += lam;
+#pragma unroll
+    for (int a = 0; a < 6; a++)
+#pragma unroll
+      for (int b = a; b < 6; b++)
+        d21[sym6(a, b)] = ((a < 3 && b < 3) ? (a == b ? mu2 : lam) : (a == b ? mu : 0.0)) * dvol;
+  }
+}
+
+template <int MATK>
+__global__ void __launch_bounds__(128, 2) brick_tangent_sym_kernel(GroupView G, const double* __restrict__ X,
+                                                                   int transpose, long long ebeg, long long eend) {
+  extern __shared__ __align__(16) double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = lane >> 3, k = lane & 7;
+  double* wbase = smem + warp * BS_WARP;
+  double* sN = wbase;
+  double* sD = wbase + 8 * BS_SG;
+  double* sX = sD + 8 * BS_DG;
+  long long* sDst = reinterpret_cast<long long*>(wbase + 4 * BS_T);
+  const long long ngp = G.n * 8;
+  const long long nb = (eend - ebeg + 3) >> 2;               // batches of 4 elements
+  const long long stride = (long long)gridDim.x * 4;
+  long long b = (long long)blockIdx.x * 4 + warp;
+  if (b >= nb) return;
+  const long long elast = eend - 1;
+
+  // stage 1 (indices) and stage 2 (values) of batch b; stage 1 of the batch after it
+  long long e = ebeg + b * 4 + s; if (e > elast) e = elast;
+  int nd = __ldg(G.conn + e * 8 + k), mi = __ldg(G.mat + e);
+  double cx[3], ct[8], cm0, cm1;
+  long long cdst;
+#pragma unroll
+  for (int d = 0; d < 3; d++) cx[d] = __ldg(X + (size_t)nd * 3 + d);
+  if (MATK == XB_MAT_J2PLASTICITY) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) ct[i] = G.tan[(size_t)i * ngp + e * 8 + k];
+  }
+  cdst = __ldg(G.kdst + e * 8 + k);
+  cm0 = __ldg(G.mpar + (size_t)mi * 8); cm1 = __ldg(G.mpar + (size_t)mi * 8 + 1);
+  long long en = ebeg + (b + stride) * 4 + s; if (en > elast) en = elast;
+  nd = __ldg(G.conn + en * 8 + k); mi = __ldg(G.mat + en);
+
+  for (;;) {
+    // ---- A: coordinates round the element, shape functions and D*dvol at the lane's Gauss point ----
+#pragma unroll
+    for (int d = 0; d < 3; d++) sX[s * BS_XS + k * 3 + d] = cx[d];
+    sDst[lane] = cdst;
+    __syncwarp();
+    {
+      double xl[3][8];
+#pragma unroll
+      for (int i = 0; i < 12; i++) {
+        const double2 v = *reinterpret_cast<const double2*>(sX + s * BS_XS + 2 * i);
+        xl[(2 * i) % 3][(2 * i) / 3] = v.x;
+        xl[(2 * i + 1) % 3][(2 * i + 1) / 3] = v.y;
+      }
+      double shp[4][8], dvol;
+      brick_shp(k, xl, shp, dvol);
+#pragma unroll
+      for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int a = 0; a < 8; a += 2)
+          *reinterpret_cast<double2*>(sN + k * BS_SG + (c * 4 + s) * 8 + a) = make_double2(shp[c][a], shp[c][a + 1]);
+      double d21[22];
+      brick_D_regs<MATK>(cm0, cm1, ct, dvol, d21);
+      d21[21] = 0.0;
+      double* dd = sD + k * BS_DG + s * 22;
+#pragma unroll
+      for (int i = 0; i < 11; i++) *reinterpret_cast<double2*>(dd + 2 * i) = make_double2(d21[2 * i], d21[2 * i + 1]);
+    }
+    // ---- request the next batch's inputs; they land while the main loop runs ----
+    const bool more = b + stride < nb;
+    if (more) {
+      e = en;
+#pragma unroll
+      for (int d = 0; d < 3; d++) cx[d] = __ldg(X + (size_t)nd * 3 + d);
+      if (MATK == XB_MAT_J2PLASTICITY) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) ct[i] = G.tan[(size_t)i * ngp + e * 8 + k];
+      }
+      cdst = __ldg(G.kdst + e * 8 + k);
+      cm0 = __ldg(G.mpar + (size_t)mi * 8); cm1 = __ldg(G.mpar + (size_t)mi * 8 + 1);
+      en = ebeg + (b + 2 * stride) * 4 + s; if (en > elast) en = elast;
+      nd = __ldg(G.conn + en * 8 + k); mi = __ldg(G.mat + en);
+    }
+    __syncwarp();
+    // ---- B: lane k accumulates the blocks K_Jk = sum_g B_J^T (D B_k), J = k .. k+4 (mod 8) ----
+    double acc[5][3][3];
+#pragma unroll
+    for (int t = 0; t < 5; t++)
+#pragma unroll
+      for (int p = 0; p < 3; p++)
+#pragma unroll
+        for (int q = 0; q < 3; q++) acc[t][p][q] = 0.0;
+#pragma unroll 1
+    for (int g = 0; g < 8; g++) {
+      const double* ng = sN + g * BS_SG + s * 8;
+      const double* dp = sD + g * BS_DG + s * 22;
+      double d[22];
+#pragma unroll
+      for (int i = 0; i < 11; i++) {
+        const double2 v = *reinterpret_cast<const double2*>(dp + 2 * i);
+        d[2 * i] = v.x; d[2 * i + 1] = v.y;
+      }
+      const double N1 = ng[k], N2 = ng[32 + k], N3 = ng[64 + k];
+      double DB[6][3];
+#pragma unroll
+      for (int r = 0; r < 6; r++) {
+        const double dr0 = d[sym6(r, 0)], dr1 = d[sym6(r, 1)], dr2 = d[sym6(r, 2)], dr3 = d[sym6(r, 3)],
+                     dr4 = d[sym6(r, 4)], dr5 = d[sym6(r, 5)];
+        DB[r][0] = dr0 * N1 + dr3 * N2 + dr5 * N3;
+        DB[r][1] = dr1 * N2 + dr3 * N1 + dr4 * N3;
+        DB[r][2] = dr2 * N3 + dr4 * N2 + dr5 * N1;
+      }
+#pragma unroll
+      for (int t = 0; t < 5; t++) {
+        const int J = (k + t) & 7;
+        const double M1 = ng[J], M2 = ng[32 + J], M3 = ng[64 + J];
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          acc[t][0][q] += M1 * DB[0][q] + M2 * DB[3][q] + M3 * DB[5][q];
+          acc[t][1][q] += M2 * DB[1][q] + M1 * DB[3][q] + M3 * DB[4][q];
+          acc[t][2][q] += M3 * DB[2][q] + M2 * DB[4][q] + M1 * DB[5][q];
+        }
+      }
+    }
+    __syncwarp();   // staging regions are dead: they become the output tile
+    // ---- C: both orientations of every block into the tile, then 16-byte stores to the node slots ----
+    {
+      double* tile = wbase + s * BS_T;
+#pragma unroll
+      for (int p = 0; p < 3; p++)
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+          tile[(3 * k + (transpose ? q : p)) * BS_R + 3 * k + (transpose ? p : q)] = acc[0][p][q];
+#pragma unroll
+      for (int t = 1; t < 5; t++) {
+        if (t == 4 && k >= 4) break;
+        const int J = (k + t) & 7;
+#pragma unroll
+        for (int p = 0; p < 3; p++)
+#pragma unroll
+          for (int q = 0; q < 3; q++) {
+            tile[(3 * J + p) * BS_R + 3 * k + q] = acc[t][p][q];
+            tile[(3 * k + q) * BS_R + 3 * J + p] = acc[t][p][q];
+          }
+      }
+    }
+    __syncwarp();
+    {
+      const long long rem = eend - (ebeg + b * 4);
+      const int nlive = rem < 4 ? (int)rem : 4;
+      const int cps = G.cps;
+      for (int el = 0; el < nlive; el++) {
+        const double* tile = wbase + el * BS_T;
+#pragma unroll
+        for (int it = 0; it < 9; it++) {
+          const int i = it * 32 + lane;            // double2 index inside the element: 8 nodes x 3 rows x 12
+          const int a = i / 36, row = i / 12, c2 = i - row * 12;
+          const long long dst = sDst[el * 8 + a];
+          const double2 v = *reinterpret_cast<const double2*>(tile + row * BS_R + 2 * c2);
+          double* out = (dst >= 0 ? G.KeN + dst : G.sendK + (-dst - 1)) + (row - 3 * a) * cps + 2 * c2;
+          *reinterpret_cast<double2*>(out) = v;
+        }
+      }
+    }
+    if (!more) break;
+    b += stride;
+    __syncwarp();
+  }
+}
+
 // FourNodeQuad::getTangentStiff (FourNodeQuad.cpp:226-281).  4 lanes per element, lane b
 // owns column block beta=b (8 rows x 2 columns); shape functions are recomputed per lane.
 template <int MATK>
@@ -831,6 +1039,8 @@ struct xb_model {
   // 4.1M elements: 12.1 ms against 10.6 ms for the shared-tile kernel -- its main loop turns
   // shared-memory bound (D and N are re-read in the second pass) -- so it is not the default.
   bool csc_direct_kernel = false;
+  int tangent_variant = 2;          // brick tangent kernel: 0 tile, 2 symmetric-pair persistent (XB_TANGENT=tile|sym)
+  int num_sms = 148;
   double alphaM = 0.0;      // Node::setRayleighDampingFactor
   double *dX = nullptr, *dU = nullptr, *dUc = nullptr, *dKe = nullptr, *dRe = nullptr, *dA = nullptr,
          *dB = nullptr, *dLoad = nullptr, *dMpar = nullptr, *dTmp = nullptr;
@@ -1043,6 +1253,8 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
   else { CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking)); m->own_stream = true; }
   m->on_device = true;  // from here xb_model_destroy frees what was allocated
   { const char* t = std::getenv("XB_TANGENT_CSC"); m->csc_direct_kernel = t && t[0] == '1'; }
+  { const char* t = std::getenv("XB_TANGENT"); if (t) m->tangent_variant = (t[0] == 't') ? 0 : 2; }
+  { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) m->num_sms = v; }
 
   xb::HostModel& h = m->h;
   const size_t nn = h.nn();
@@ -1404,6 +1616,24 @@ static int launch_group_tangents(xb_model* m, DevGroup& d, long long ebeg, long 
         CU(cudaFuncSetAttribute(brick_tangent_csc_kernel<XB_MAT_ELASTIC_ISOTROPIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc));
         brick_tangent_csc_kernel<XB_MAT_ELASTIC_ISOTROPIC><<<blocks, BT_ELEMS * 8, smc, st>>>(d.v, m->dX, ebeg, eend);
       }
+      m->launches++;
+      return XB_OK;
+    }
+    if (m->tangent_variant == 2 && (m->h.cp_stride % 2) == 0) {
+      const size_t sms = sizeof(double) * 4 * BS_WARP;
+      const long long nbat = (eend - ebeg + 3) / 4;
+      auto go = [&](auto kern) -> int {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sms));
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, sms));
+        if (per_sm < 1) per_sm = 1;
+        long long grid = (long long)per_sm * m->num_sms;
+        if (grid > (nbat + 3) / 4) grid = (nbat + 3) / 4;
+        kern<<<(unsigned)grid, 128, sms, st>>>(d.v, m->dX, transpose, ebeg, eend);
+        return XB_OK;
+      };
+      int rc = j2 ? go(brick_tangent_sym_kernel<XB_MAT_J2PLASTICITY>) : go(brick_tangent_sym_kernel<XB_MAT_ELASTIC_ISOTROPIC>);
+      if (rc < 0) return rc;
       m->launches++;
       return XB_OK;
     }
