@@ -97,8 +97,15 @@ __device__ __forceinline__ void brick_resid_store(const GroupView& G, long long 
 }
 
 // Brick::update (Brick.cpp:718-840); one thread per Gauss point
+constexpr int UPD_XS = 50;   // per element in shared memory: X[8][3], U[8][3] + pad
+#ifndef UPD_OCC
+#define UPD_OCC 4
+#endif
+#ifndef UPD_STASH
+#define UPD_STASH 0
+#endif
 template <int MATK>
-__global__ void __launch_bounds__(128) brick_update_kernel(GroupView G, const double* __restrict__ X,
+__global__ void __launch_bounds__(128, UPD_OCC) brick_update_kernel(GroupView G, const double* __restrict__ X,
                                                            const double* __restrict__ U, int* fail) {
   const long long gp_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long ngp = G.n * 8;
@@ -106,38 +113,72 @@ __global__ void __launch_bounds__(128) brick_update_kernel(GroupView G, const do
   const long long gp = live ? gp_raw : ngp - 1;
   const long long e = gp >> 3;
   const int g = (int)(gp_raw & 7);
-  const int* c = G.conn + e * 8;
-  double xl[3][8], ul[3][8];
+  // lane g fetches node g of its element (coordinates and trial displacements); the 8 lanes of
+  // the element exchange them through shared memory
+  __shared__ __align__(16) double sXU[16 * UPD_XS];
+  double* xu = sXU + (threadIdx.x >> 3) * UPD_XS;
+  {
+    const int nd = __ldg(G.conn + e * 8 + g);
 #pragma unroll
-  for (int a = 0; a < 8; a++) {
-    const int nd = __ldg(c + a);
-#pragma unroll
-    for (int d = 0; d < 3; d++) { xl[d][a] = __ldg(X + (size_t)nd * 3 + d); ul[d][a] = __ldg(U + (size_t)nd * 3 + d); }
+    for (int d = 0; d < 3; d++) {
+      xu[g * 3 + d] = __ldg(X + (size_t)nd * 3 + d);
+      xu[24 + g * 3 + d] = __ldg(U + (size_t)nd * 3 + d);
+    }
   }
+  // committed state of this Gauss point: requested before the shape functions are evaluated
+  double epn[6], xin = 0.0;
+  if (MATK == XB_MAT_J2PLASTICITY) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) epn[i] = G.hc[(size_t)i * ngp + gp];
+    xin = G.hc[(size_t)6 * ngp + gp];
+  }
+  __syncwarp();
   double shp[4][8], xsj;
-  brick_shp(g, xl, shp, xsj);
+  {
+    double xl[3][8];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      const double2 v = *reinterpret_cast<const double2*>(xu + 2 * i);
+      xl[(2 * i) % 3][(2 * i) / 3] = v.x;
+      xl[(2 * i + 1) % 3][(2 * i + 1) / 3] = v.y;
+    }
+    brick_shp(g, xl, shp, xsj);
+  }
   double s[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
   for (int j = 0; j < 8; j++) {
-    s[0] += shp[0][j] * ul[0][j];
-    s[1] += shp[1][j] * ul[1][j];
-    s[2] += shp[2][j] * ul[2][j];
-    s[3] += shp[1][j] * ul[0][j] + shp[0][j] * ul[1][j];
-    s[4] += shp[2][j] * ul[1][j] + shp[1][j] * ul[2][j];
-    s[5] += shp[2][j] * ul[0][j] + shp[0][j] * ul[2][j];
+    const double u0 = xu[24 + 3 * j], u1 = xu[25 + 3 * j], u2 = xu[26 + 3 * j];
+    s[0] += shp[0][j] * u0;
+    s[1] += shp[1][j] * u1;
+    s[2] += shp[2][j] * u2;
+    s[3] += shp[1][j] * u0 + shp[0][j] * u1;
+    s[4] += shp[2][j] * u1 + shp[1][j] * u2;
+    s[5] += shp[2][j] * u0 + shp[0][j] * u2;
   }
   const double* p = G.mpar + (size_t)__ldg(G.mat + e) * 8;
   double st[6];
   if (MATK == XB_MAT_J2PLASTICITY) {
-    double par[7], epn[6], et[6];
+    double par[7], et[6];
 #pragma unroll
     for (int i = 0; i < 7; i++) par[i] = __ldg(p + i);
-#pragma unroll
-    for (int i = 0; i < 6; i++) epn[i] = G.hc[(size_t)i * ngp + gp];
-    const double xin = G.hc[(size_t)6 * ngp + gp];
     et[0] = s[0]; et[1] = s[1]; et[2] = s[2]; et[3] = 0.50 * s[3]; et[4] = 0.50 * s[4]; et[5] = 0.50 * s[5];
+    // the shape functions are needed again for the residual: park them in shared memory while
+    // the return map runs (64 registers less over the longest-latency part of the kernel)
+#if UPD_STASH
+    __shared__ double sShp[32 * 128];
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+      for (int j = 0; j < 8; j++) sShp[(c * 8 + j) * 128 + threadIdx.x] = shp[c][j];
+#endif
     J2Result r;
     j2_integrate(par, et, epn, xin, 0.0, r);
+#if UPD_STASH
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+      for (int j = 0; j < 8; j++) shp[c][j] = sShp[(c * 8 + j) * 128 + threadIdx.x];
+#endif
     if (r.fail && live) atomicExch(fail, 1);
     if (live) {
 #pragma unroll
@@ -1052,7 +1093,8 @@ struct xb_model {
   long long *dPrSrc = nullptr, *dPrDst = nullptr, *dUkSrc = nullptr, *dUkDst = nullptr;
   ncclComm_t comm = nullptr;
   // pipelined formTangent
-  cudaStream_t stream2 = nullptr;
+  cudaStream_t stream2 = nullptr, stream3 = nullptr;   // assembly of finished ranges; copy-out of finished rows
+  std::vector<cudaEvent_t> ev_rows;
   cudaEvent_t ev_start = nullptr, ev_done = nullptr;
   std::vector<cudaEvent_t> ev_chunk;
   int* dPerm = nullptr;
@@ -1149,6 +1191,8 @@ void xb_model_destroy(xb_model* m) {
     cudaSetDevice(m->device);
     if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
     if (m->stream2) cudaStreamDestroy(m->stream2);
+    if (m->stream3) cudaStreamDestroy(m->stream3);
+    for (auto e : m->ev_rows) cudaEventDestroy(e);
     if (m->ev_start) cudaEventDestroy(m->ev_start);
     if (m->ev_done) cudaEventDestroy(m->ev_done);
     for (auto e : m->ev_chunk) cudaEventDestroy(e);
@@ -1278,6 +1322,9 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
   CU(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&m->ev_done, cudaEventDisableTiming));
+  CU(cudaStreamCreateWithFlags(&m->stream3, cudaStreamNonBlocking));
+  m->ev_rows.resize(h.nchunk);
+  for (auto& e : m->ev_rows) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   m->ev_chunk.resize(h.nchunk);
   for (auto& e : m->ev_chunk) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CU(dev_upload(m, &m->dLoad, h.load));
@@ -1821,7 +1868,9 @@ int xb_form_tangent(xb_model* m, double* A) {
   NEED_DEVICE();
   CU(cudaSetDevice(m->device));
   const int nc = m->h.nchunk;
-  if (nc <= 1 || m->dg.size() != 1 || m->dg[0].kind != XB_ELE_STDBRICK || !m->stream2) {
+  const bool stream_out = A != nullptr && m->h.rows_streamable && m->stream3;
+  if (nc <= 1 || m->dg.size() != 1 || m->dg[0].kind != XB_ELE_STDBRICK || !m->stream2 ||
+      !(stream_out || m->h.pipeline_forced)) {
     int rc = xb_form_element_tangents(m);
     if (rc < 0) return rc;
     if (m->h.nparts > 1 && (rc = xb_exchange(m, 0)) < 0) return rc;
@@ -1839,6 +1888,14 @@ int xb_form_tangent(xb_model* m, double* A) {
     CU(cudaStreamWaitEvent(m->stream2, m->ev_chunk[c], 0));
     rc = launch_assemble(m, m->h.chunk_node_ptr[c], m->h.chunk_node_ptr[c + 1] - m->h.chunk_node_ptr[c], m->stream2);
     if (rc < 0) return rc;
+    if (stream_out) {   // the rows this range completed leave for the host while the next range is formed
+      const long long a0 = m->h.chunk_a_ptr[c], a1 = m->h.chunk_a_ptr[c + 1];
+      if (a1 > a0) {
+        CU(cudaEventRecord(m->ev_rows[c], m->stream2));
+        CU(cudaStreamWaitEvent(m->stream3, m->ev_rows[c], 0));
+        CU(cudaMemcpyAsync(A + a0, m->dA + a0, sizeof(double) * (a1 - a0), cudaMemcpyDeviceToHost, m->stream3));
+      }
+    }
   }
   account_element_tangent_bytes(m);
   CU(cudaEventRecord(m->ev_done, m->stream2));
@@ -1849,6 +1906,15 @@ int xb_form_tangent(xb_model* m, double* A) {
     if ((rc = unpack_received_rows(m, m->stream)) < 0) return rc;
     rc = launch_assemble(m, m->h.chunk_node_ptr[nc], m->h.chunk_node_ptr[nc + 1] - m->h.chunk_node_ptr[nc], m->stream);
     if (rc < 0) return rc;
+  }
+  if (stream_out) {
+    const long long a0 = m->h.chunk_a_ptr[nc], a1 = m->h.chunk_a_ptr[nc + 1];   // rows of the interface nodes
+    int rc = finish_tangent(m, nullptr);
+    if (rc < 0) return rc;
+    if (a1 > a0) CU(cudaMemcpyAsync(A + a0, m->dA + a0, sizeof(double) * (a1 - a0), cudaMemcpyDeviceToHost, m->stream));
+    CU(cudaEventRecord(m->ev_done, m->stream3));
+    CU(cudaStreamWaitEvent(m->stream, m->ev_done, 0));
+    return check_fail_flag(m);
   }
   return finish_tangent(m, A);
 }

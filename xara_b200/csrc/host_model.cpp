@@ -697,8 +697,11 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
     const std::vector<Group>& FG = nparts == 1 ? groups : lgroups;
     // (measured on B200: the element kernel's 228 registers x 8 warps leave no room for assembly
     //  CTAs to co-reside, so the pipeline buys nothing there; it stays opt-in: XB_PIPELINE=<ranges>)
+    //  What the ranges do buy is the copy-out: with a host destination, xb_form_tangent sends the
+    //  rows of range c to the host while range c+1 is still being formed (chunk_a_ptr below).
     const char* pl = std::getenv("XB_PIPELINE");
-    const int want = pl ? std::atoi(pl) : 1;
+    const int want = pl ? std::atoi(pl) : 8;
+    pipeline_forced = pl != nullptr;
     nchunk = (FG.size() == 1 && ne >= 65536 && want > 1 && want <= 64) ? want : 1;
     const long long per = nchunk > 1 ? (ne + nchunk - 1) / nchunk : ne;
     std::vector<int> ready(nl, -1);
@@ -720,6 +723,23 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
     node_perm.resize(chunk_node_ptr[nchunk + 1]);
     std::vector<long long> fill(chunk_node_ptr.begin(), chunk_node_ptr.end() - 1);
     for (int i = 0; i < nl; i++) if (ready[i] >= 0) node_perm[fill[ready[i]]++] = i;
+    // rows each range completes: streamable when range c owns exactly the rows [r_c, r_{c+1}) of A
+    chunk_a_ptr.assign((size_t)nchunk + 2, 0);
+    rows_streamable = nchunk > 1;
+    int next_row = 0;
+    for (int c = 0; c <= nchunk && rows_streamable; c++) {
+      long long cnt = 0; int lo = nrows, hi = -1;
+      for (long long u = chunk_node_ptr[c]; u < chunk_node_ptr[c + 1]; u++)
+        for (int j = 0; j < ndf; j++) {
+          const int r = row_of[(size_t)node_perm[u] * ndf + j];
+          if (r < 0) continue;
+          cnt++; lo = std::min(lo, r); hi = std::max(hi, r);
+        }
+      if (cnt && (lo != next_row || hi - lo + 1 != cnt)) rows_streamable = false;
+      if (cnt) next_row = hi + 1;
+      chunk_a_ptr[c + 1] = ptr[next_row];
+    }
+    if (next_row != nrows) rows_streamable = false;
   }
 
   // ---- commit the local element groups ----
