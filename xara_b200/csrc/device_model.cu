@@ -25,7 +25,7 @@
 #define XB_ASM_CH 2
 #endif
 #ifndef XB_ASM_OCC
-#define XB_ASM_OCC 5
+#define XB_ASM_OCC 8
 #endif
 
 using namespace xbk;
@@ -753,9 +753,11 @@ __global__ void __launch_bounds__(128, 2) brick_tangent_sym_kernel(GroupView G, 
         const double M1 = ng[J], M2 = ng[32 + J], M3 = ng[64 + J];
 #pragma unroll
         for (int q = 0; q < 3; q++) {
-          acc[t][0][q] += M1 * DB[0][q] + M2 * DB[3][q] + M3 * DB[5][q];
-          acc[t][1][q] += M2 * DB[1][q] + M1 * DB[3][q] + M3 * DB[4][q];
-          acc[t][2][q] += M3 * DB[2][q] + M2 * DB[4][q] + M1 * DB[5][q];
+          // three chained FMAs per entry (the reference forms the 3x3 product first and then adds
+          // it: one more rounding and one more FP64 instruction per entry)
+          acc[t][0][q] = fma(M3, DB[5][q], fma(M2, DB[3][q], fma(M1, DB[0][q], acc[t][0][q])));
+          acc[t][1][q] = fma(M3, DB[4][q], fma(M1, DB[3][q], fma(M2, DB[1][q], acc[t][1][q])));
+          acc[t][2][q] = fma(M1, DB[5][q], fma(M2, DB[4][q], fma(M3, DB[2][q], acc[t][2][q])));
         }
       }
     }
@@ -917,43 +919,29 @@ struct AsmView {
 // Every entry of A is written exactly once, so no zeroA pass is needed.
 template <int NDF>
 __global__ void __launch_bounds__(256, XB_ASM_OCC) assemble_A_kernel(AsmView V, const double* __restrict__ KeN,
-                                                            double* __restrict__ A, const int* __restrict__ perm,
+                                                            double* __restrict__ A, const long long* __restrict__ task,
                                                             long long first, long long count) {
   extern __shared__ double sacc[];  // [warps][NDF][max_row]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (w >= count) return;
-  const long long n = __ldg(perm + first + w);   // owned nodes, ordered by the element range that completes them
   double* acc = sacc + (size_t)warp * NDF * V.max_row;
-  // everything that does not depend on the element loop is requested up front
-  const long long t0 = __ldg(V.n2e_ptr + n), t1 = __ldg(V.n2e_ptr + n + 1);
-  int L = (int)(__ldg(V.ncol_ptr + n + 1) - __ldg(V.ncol_ptr + n));
-  long long rowptr = -1;
-  if (lane < NDF) {
-    const int r = __ldg(V.row_of + n * NDF + lane);
-    if (r >= 0) rowptr = __ldg(V.ptr + r);
-  }
-  if (t0 == t1) L = 1;  // a node with no element: its rows hold the (zero) diagonal only
-  for (int c = lane; c < NDF * L; c += 32) acc[(c / L) * V.max_row + (c % L)] = 0.0;
-  __syncwarp();
-  if ((V.c2 != 0.0 || V.c3 != 0.0) && lane < NDF) {
-    // the DOF_Group tangents are added before the elements' (TransientIntegrator.cpp:89-107):
-    // Newmark::formNodTangent = c2 * (alphaM * M) + c3 * M on the diagonal
-    const unsigned short dp = V.diagpos[n * NDF + lane];
-    if (dp != 0xFFFF) {
-      const double ms = V.mass[n * NDF + lane];
-      double t = 0.0;
-      t += (ms * V.alphaM) * V.c2;
-      t += ms * V.c3;
-      acc[lane * V.max_row + dp] = t;
-    }
-  }
-  __syncwarp();
-  const double c1 = V.c1;
+  // one record per owned node, in the order the nodes are assembled (host_model.cpp, asm_task):
+  // first slot, slot count | row length << 32, node, A offset of each of its rows (-1: constrained)
+  constexpr int TW = 3 + NDF;
+  const long long word = lane < TW ? __ldg(task + (first + w) * TW + lane) : 0;
+  const long long t0 = __shfl_sync(0xffffffffu, word, 0);
+  const long long pk = __shfl_sync(0xffffffffu, word, 1);
+  const long long n = __shfl_sync(0xffffffffu, word, 2);
+  const int ns = (int)(pk & 0xffffffffll);
+  const int L = (int)(pk >> 32);
+  const long long t1 = t0 + ns;
   const int cps = V.cp_stride;
   const bool on = lane < cps;
   constexpr int CH = XB_ASM_CH;  // slots in flight together; the node's slots are one contiguous stream
-  for (long long tb = t0; tb < t1; tb += CH) {
+  const double c1 = V.c1;
+  long long tb = t0;
+  do {
     double v[CH][NDF];
     unsigned short pos[CH];
 #pragma unroll
@@ -964,6 +952,24 @@ __global__ void __launch_bounds__(256, XB_ASM_OCC) assemble_A_kernel(AsmView V, 
 #pragma unroll
       for (int p = 0; p < NDF; p++) v[c][p] = ok ? __ldg(KeN + (size_t)t * (NDF * cps) + p * cps + lane) : 0.0;
     }
+    if (tb == t0) {
+      // (the first slots are already on their way) clear the rows, then the DOF_Group tangents, which
+      // are added before the elements' (TransientIntegrator.cpp:89-107):
+      // Newmark::formNodTangent = c2 * (alphaM * M) + c3 * M on the diagonal
+      for (int c = lane; c < NDF * L; c += 32) acc[(c / L) * V.max_row + (c % L)] = 0.0;
+      __syncwarp();
+      if ((V.c2 != 0.0 || V.c3 != 0.0) && lane < NDF) {
+        const unsigned short dp = V.diagpos[n * NDF + lane];
+        if (dp != 0xFFFF) {
+          const double ms = V.mass[n * NDF + lane];
+          double t = 0.0;
+          t += (ms * V.alphaM) * V.c2;
+          t += ms * V.c3;
+          acc[lane * V.max_row + dp] = t;
+        }
+      }
+      __syncwarp();
+    }
 #pragma unroll
     for (int c = 0; c < CH; c++) {   // FE_Element order: the order addA is called in
       if (pos[c] != 0xFFFF) {
@@ -972,10 +978,11 @@ __global__ void __launch_bounds__(256, XB_ASM_OCC) assemble_A_kernel(AsmView V, 
       }
       __syncwarp();
     }
-  }
+    tb += CH;
+  } while (tb < t1);
 #pragma unroll
   for (int p = 0; p < NDF; p++) {
-    const long long rp = __shfl_sync(0xffffffffu, rowptr, p);
+    const long long rp = __shfl_sync(0xffffffffu, word, 3 + p);
     if (rp < 0) continue;
     double* out = A + rp;
     for (int c = lane; c < L; c += 32) out[c] = acc[p * V.max_row + c];
@@ -1097,7 +1104,7 @@ struct xb_model {
   std::vector<cudaEvent_t> ev_rows;
   cudaEvent_t ev_start = nullptr, ev_done = nullptr;
   std::vector<cudaEvent_t> ev_chunk;
-  int* dPerm = nullptr;
+  long long* dTask = nullptr;
   AsmView av{};
   double lambda = 0.0;
   long long launches = 0;
@@ -1318,7 +1325,7 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
   CU(cudaMemset(m->dUc, 0, sizeof(double) * std::max<size_t>(nn * h.ndf, 1)));
   CU(dev_upload(m, &m->dId, h.id));
   CU(dev_upload(m, &m->dRowOf, h.row_of));
-  CU(dev_upload(m, &m->dPerm, h.node_perm));
+  CU(dev_upload(m, &m->dTask, h.asm_task));
   CU(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&m->ev_done, cudaEventDisableTiming));
@@ -1812,13 +1819,13 @@ static int launch_assemble(xb_model* m, long long first, long long count, cudaSt
   const unsigned blocks = (unsigned)((count + warps - 1) / warps);
   if (m->h.ndf == 3) {
     CU(cudaFuncSetAttribute(assemble_A_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    assemble_A_kernel<3><<<blocks, warps * 32, sm, st>>>(m->av, m->dKe, m->dA, m->dPerm, first, count);
+    assemble_A_kernel<3><<<blocks, warps * 32, sm, st>>>(m->av, m->dKe, m->dA, m->dTask, first, count);
   } else if (m->h.ndf == 2) {
     CU(cudaFuncSetAttribute(assemble_A_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    assemble_A_kernel<2><<<blocks, warps * 32, sm, st>>>(m->av, m->dKe, m->dA, m->dPerm, first, count);
+    assemble_A_kernel<2><<<blocks, warps * 32, sm, st>>>(m->av, m->dKe, m->dA, m->dTask, first, count);
   } else {
     CU(cudaFuncSetAttribute(assemble_A_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    assemble_A_kernel<1><<<blocks, warps * 32, sm, st>>>(m->av, m->dKe, m->dA, m->dPerm, first, count);
+    assemble_A_kernel<1><<<blocks, warps * 32, sm, st>>>(m->av, m->dKe, m->dA, m->dTask, first, count);
   }
   m->launches++;
   return XB_OK;

@@ -723,6 +723,21 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
     node_perm.resize(chunk_node_ptr[nchunk + 1]);
     std::vector<long long> fill(chunk_node_ptr.begin(), chunk_node_ptr.end() - 1);
     for (int i = 0; i < nl; i++) if (ready[i] >= 0) node_perm[fill[ready[i]]++] = i;
+    // what the assembly warp of node_perm[u] needs, in one record (assemble_A_kernel)
+    const int TW = 3 + ndf;
+    asm_task.assign((size_t)node_perm.size() * TW, 0);
+    for (size_t u = 0; u < node_perm.size(); u++) {
+      const int i = node_perm[u];
+      long long* tk = &asm_task[u * TW];
+      const long long ns = n2e_ptr[i + 1] - n2e_ptr[i];
+      long long L = ncol_ptr[i + 1] - ncol_ptr[i];
+      if (ns == 0) L = 1;   // a node with no element: its rows hold the (zero) diagonal only
+      tk[0] = n2e_ptr[i]; tk[1] = ns | (L << 32); tk[2] = i;
+      for (int j = 0; j < ndf; j++) {
+        const int r = row_of[(size_t)i * ndf + j];
+        tk[3 + j] = r >= 0 ? ptr[r] : -1;
+      }
+    }
     // rows each range completes: streamable when range c owns exactly the rows [r_c, r_{c+1}) of A
     chunk_a_ptr.assign((size_t)nchunk + 2, 0);
     rows_streamable = nchunk > 1;

@@ -137,6 +137,7 @@ struct HostModel {
   int nchunk = 1;
   std::vector<int> node_perm;       // [n_owned_nodes_with_rows]
   std::vector<long long> chunk_node_ptr;   // [nchunk+2]
+  std::vector<long long> asm_task;         // [node_perm.size()][3+ndf] per-node record of the assembly kernel
   std::vector<long long> chunk_a_ptr;      // [nchunk+2] offsets in A of the rows each range completes
   bool rows_streamable = false;     // the ranges own consecutive row blocks of A (copy-out can follow them)
   bool pipeline_forced = false;     // XB_PIPELINE set: use the ranges also without a host destination
