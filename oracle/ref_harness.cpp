@@ -299,6 +299,16 @@ int ref_setup(void* h, int numberer, int soeKind, double dlambda, int testKind, 
   return ref_setup_common(m, numberer, soeKind, testKind, tol, maxIter);
 }
 
+// integrator DisplacementControl node dof incr (analysis/integrator/Static/DisplacementControl.cpp);
+// dof is 0-based here as inside the class (the Tcl command subtracts 1)
+int ref_setup_dispcontrol(void* h, int numberer, int soeKind, int node, int dof, double incr, int testKind, double tol, int maxIter) {
+  RefModel* m = (RefModel*)h;
+  m->sinteg = new DisplacementControl(node, dof, incr, m->domain, 1, incr, incr);
+  m->integ = m->sinteg;
+  return ref_setup_common(m, numberer, soeKind, testKind, tol, maxIter);
+}
+double ref_get_lambda(void* h) { return ((RefModel*)h)->amodel->getCurrentDomainTime(); }
+
 // `mass` command: Node::setMass with a diagonal matrix (domain/node/Node.h:127)
 int ref_set_mass(void* h, int nodeTag, const double* mvals) {
   RefModel* m = (RefModel*)h;
@@ -484,13 +494,18 @@ int ref_ele_resid(void* h, int tag, double* R) {
 // restates BasicAnalysisBuilder::analyzeStatic (BasicAnalysisBuilder.cpp:337-420):
 // newStep / solveCurrentStep / commit; iters[i] = Newton iterations of step i
 // (ConvergenceTest::getNumTests), norms[i*maxIter + k] = test norms.
+int ref_analyze_static_lam(void* h, int nsteps, int* iters, double* norms, int maxIter, double* lam);
 int ref_analyze_static(void* h, int nsteps, int* iters, double* norms, int maxIter) {
+  return ref_analyze_static_lam(h, nsteps, iters, norms, maxIter, nullptr);
+}
+int ref_analyze_static_lam(void* h, int nsteps, int* iters, double* norms, int maxIter, double* lam) {
   RefModel* m = (RefModel*)h;
   for (int s = 0; s < nsteps; s++) {
     if (m->amodel->analysisStep(0.0) < 0) return -2;
     if (m->sinteg->newStep() < 0) return -2;
     int r = m->algo->solveCurrentStep();
     iters[s] = m->test->getNumTests();
+    if (lam) lam[s] = m->amodel->getCurrentDomainTime();
     if (norms) {
       const Vector& nv = m->test->getNorms();
       for (int k = 0; k < maxIter && k < nv.Size(); k++) norms[(size_t)s * maxIter + k] = nv(k);

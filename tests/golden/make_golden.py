@@ -83,8 +83,28 @@ def transient_case(name, spec, mass, gamma, beta, dt, nsteps=3, niter=3):
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
 
 
+def dispcontrol_case(name, spec, numberer, soe, node, dof, incr, nsteps, tol, max_iter):
+    """the reference's StaticAnalysis loop with its own DisplacementControl, NewtonRaphson and
+    CTestNormDispIncr (ref_analyze_static_lam): iteration counts, test norms, load factors, final state"""
+    R = RefBackend(spec, defer_setup=True)
+    node = int(spec.node_tags[-1]) if node is None else node
+    R.setup_dispcontrol(numberer, soe, node, dof, incr, test=0, tol=tol, max_iter=max_iter)
+    rc, iters, norms, lam = R.analyze_static_lam(nsteps)
+    assert rc == 0, rc
+    # an iteration count must not hinge on the last bits of a norm: every deciding norm is >= 1.3x away
+    # from tol (two implementations that agree to 1e-10 cannot then disagree on a count)
+    for s in range(nsteps):
+        last = norms[s, iters[s] - 1]
+        assert last * 1.3 <= tol and (iters[s] == 1 or norms[s, iters[s] - 2] >= 1.3 * tol), (name, s, norms[s])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), iters=iters, norms=norms, lam=lam, u=R.get_trial_disp(),
+                        ids=R.ids(), node=node, dof=dof, incr=incr, tol=tol, max_iter=max_iter, numberer=numberer, soe=soe)
+    print(name, "iters", iters.tolist(), "lambda_end", lam[-1])
+
+
 if __name__ == "__main__":
-    from golden_cases import TRANSIENT_CASES
+    from golden_cases import DISPCONTROL_CASES, TRANSIENT_CASES
+    for name, (mk, *args) in DISPCONTROL_CASES.items():
+        dispcontrol_case(name, mk(), *args)
     for name, (mk, mass_fn, gamma, beta, dt) in TRANSIENT_CASES.items():
         spec = mk()
         transient_case(name, spec, mass_fn(spec), gamma, beta, dt)

@@ -1,5 +1,5 @@
 """The models behind tests/golden/*.npz (generated from the reference by tests/golden/make_golden.py)."""
-from modelspec import ELASTIC, J2_STEEL, brick_block, frame2d, quad_plane
+from modelspec import ELASTIC, J2_STEEL, brick_block, cantilever2d, frame2d, quad_plane
 
 # name -> (spec factory, numberer, soe, displacement scale)
 CASES = {
@@ -41,3 +41,13 @@ def newmark_coeffs(gamma, beta, dt):
     """c1 c2 c3 and the predictor's a1..a4 of Newmark::newStep (displacement unknown)"""
     return ((1.0, gamma / (beta * dt), 1.0 / (beta * dt * dt)),
             (1.0 - gamma / beta, dt * (1.0 - 0.5 * gamma / beta), -1.0 / (beta * dt), 1.0 - 0.5 / beta))
+
+
+# integrator DisplacementControl + Newton + NormDispIncr, run by the reference's own classes:
+# name -> (spec factory, numberer, soe, control node tag (None: last node), control dof, increment, steps, tol, max_iter)
+DISPCONTROL_CASES = {
+    # BASELINE configs[0]: the Ex2b cantilever pushover (to 5 % drift), with the RC fibre section
+    "dc_cantilever_fiber": (lambda: cantilever2d(ndiv=1), 0, 0, None, 0, 0.432, 50, 1e-8, 10),
+    # BASELINE configs[2] in small: J2 brick column pushed under displacement control
+    "dc_brick_j2": (lambda: brick_block(3, 3, 5, mat=J2_STEEL, lx=1.0, ly=1.0, lz=3.0, load=(1.0, 0.0, -0.3)), 1, 0, None, 0, 5e-3, 12, 3e-10, 15),
+}

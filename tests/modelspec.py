@@ -191,6 +191,69 @@ def frame2d(nbay=2, nstory=3, ndiv=2, nip=5, bay=360.0, story=144.0, max_iters=1
                      sections=[rc_section(1)])
 
 
+def cantilever2d(ndiv=1, nip=5, L=432.0, H=1.0, V=-100.0, max_iters=10, tol=1e-12):
+    """the reference's tests/Ex2b.Canti2D.InelasticSection.Push.py cantilever (BASELINE configs[0]) with
+    the RC fibre section of north_star (Steel02 + Concrete02): node 1 fixed, forceBeamColumn(s) up to the
+    free node, reference load (H lateral, V axial) at the top"""
+    nn = ndiv + 1
+    crd = np.zeros((nn, 2)); crd[:, 1] = np.linspace(0.0, L, nn)
+    conn = np.array([(i + 1, i + 2) for i in range(ndiv)], np.int32)
+    par = np.zeros((ndiv, 8)); par[:, 0] = nip; par[:, 1] = max_iters; par[:, 2] = tol
+    fix = np.array([(1, 0), (1, 1), (1, 2)], np.int32)
+    loads = np.array([[nn, H, V, 0.0]])
+    return ModelSpec(2, 3, np.arange(1, nn + 1, dtype=np.int32), crd, fix, [],
+                     [ElementGroup(ELE_FBC2D, np.arange(1, ndiv + 1, dtype=np.int32), conn, np.ones(ndiv, np.int32), par)],
+                     loads, uniaxials=[(1, *CONCRETE02_CORE), (2, *CONCRETE02_COVER), (3, *STEEL02)],
+                     sections=[rc_section(1)])
+
+
+def disp_control(model, solve, ctrl_eq, incr, nsteps, tol, max_iter, is_dev):
+    """StaticAnalysis with `integrator DisplacementControl node dof incr`, `algorithm Newton`,
+    `test NormDispIncr tol max_iter`, driven through any backend's update / form_* surface; the linear
+    solves go to `solve(A, b)`.  Follows DisplacementControl::domainChanged / newStep / update
+    (analysis/integrator/Static/DisplacementControl.cpp:352-366, 121-207, 210-266) and
+    NewtonRaphson::solveCurrentStep.  Returns (norm history per step, lambda per step)."""
+    def incr_disp(dU):
+        if is_dev:
+            model.incr_trial_disp(dU); model.update()
+        else:
+            u = model._u; ids = model.ids()
+            u[ids >= 0] += dU[ids[ids >= 0]]
+            model.set_trial_disp(u)
+    # domainChanged: phat = unbalance at lambda + 1 ("assumes unbalance at last was 0")
+    lam = 0.0
+    model.apply_load(lam + 1.0)
+    phat = model.form_unbalance().copy()
+    hist, lams = [], []
+    for _ in range(nsteps):
+        # newStep
+        A = model.form_tangent()
+        dUhat = solve(A, phat)
+        dlam = incr / dUhat[ctrl_eq]
+        lam += dlam
+        incr_disp(dUhat * dlam)
+        model.apply_load(lam)
+        # NewtonRaphson::solveCurrentStep
+        B = model.form_unbalance()
+        norms = []
+        for it in range(max_iter):
+            A = model.form_tangent()
+            dUbar = solve(A, B)
+            dUhat = solve(A, phat)               # update(): second solve with the reference load
+            dL = -dUbar[ctrl_eq] / dUhat[ctrl_eq]
+            dU = dUbar + dL * dUhat
+            lam += dL
+            incr_disp(dU)
+            model.apply_load(lam)
+            B = model.form_unbalance()
+            norms.append(float(np.linalg.norm(dU)))   # the integrator leaves deltaU in X for the test
+            if norms[-1] <= tol:
+                break
+        hist.append(norms); lams.append(lam)
+        model.commit()
+    return hist, np.array(lams)
+
+
 def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
@@ -492,3 +555,16 @@ class RefBackend(_Backend):
         iters = np.zeros(nsteps, np.int32); norms = np.zeros((nsteps, self.max_iter))
         rc = self.L.ref_analyze_static(self.h, nsteps, _p(iters), _p(norms), self.max_iter)
         return rc, iters, norms
+
+    # ---- the reference's own DisplacementControl ----
+    def setup_dispcontrol(self, numberer, soe, node, dof, incr, test=0, tol=1e-8, max_iter=20):
+        self.L.ref_setup_dispcontrol.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_int]
+        self.neq = self.L.ref_setup_dispcontrol(self.h, numberer, soe, node, dof, incr, test, tol, max_iter)
+        assert self.neq >= 0, self.neq
+        self.nnz = self.L.ref_nnz(self.h); self.max_iter = max_iter
+
+    def analyze_static_lam(self, nsteps):
+        iters = np.zeros(nsteps, np.int32); norms = np.zeros((nsteps, self.max_iter)); lam = np.zeros(nsteps)
+        rc = self.L.ref_analyze_static_lam(self.h, nsteps, _p(iters), _p(norms), self.max_iter, _p(lam))
+        return rc, iters, norms, lam

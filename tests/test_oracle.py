@@ -9,9 +9,9 @@ import os
 import numpy as np
 import pytest
 
-from golden_cases import CASES, NSTEPS, TRANSIENT_CASES, ele_nd, newmark_coeffs
+from golden_cases import CASES, DISPCONTROL_CASES, NSTEPS, TRANSIENT_CASES, ele_nd, newmark_coeffs
 from modelspec import (ELASTIC, J2_STEEL, MAT_ELASTIC, MAT_J2, ND_3D, ND_PLANE_STRAIN, OracleBackend, RefBackend,
-                       brick_block, frame2d, have_ref, oracle_nd_path, oracle_uni_path, quad_plane, ref_nd_path)
+                       brick_block, disp_control, frame2d, have_ref, oracle_nd_path, oracle_uni_path, quad_plane, ref_nd_path)
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 RTOL = 1e-12
@@ -171,3 +171,31 @@ def test_newmark_vs_golden(name):
         assert np.abs(B - Bg).max() <= 1e-11 * bscale          # B -> 0 as Newton converges: scale by the step's first residual
 
     drive_transient_vs_golden(O, g, name, check)
+
+
+@pytest.mark.parametrize("name", list(DISPCONTROL_CASES))
+def test_displacement_control_vs_golden(name):
+    """`integrator DisplacementControl` + Newton run by the reference's own classes (golden) against the
+    same algorithm driving the oracle's update / formUnbalance / formTangent: identical iteration
+    counts on every step, the same load-factor history and final displacements."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    mk, numberer, soe, node, dof, incr, nsteps, tol, max_iter = DISPCONTROL_CASES[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    spec = mk()
+    O = OracleBackend(spec, numberer, soe); O._u = np.zeros((spec.nn, spec.ndf))
+    ids = O.ids()
+    assert np.array_equal(ids, g["ids"])
+    ptr, idx = O.csr(); neq = O.neq
+
+    def solve(A, b):   # soe 0 is column-compressed: the stored pattern is that of A^T
+        M = sp.csr_matrix((A, idx, ptr), shape=(neq, neq))
+        return spla.spsolve((M.T if soe == 0 else M).tocsc(), b)
+
+    ctrl = ids[list(spec.node_tags).index(int(g["node"])), dof]
+    hist, lam = disp_control(O, solve, ctrl, incr, nsteps, tol, max_iter, False)
+    assert [len(h) for h in hist] == g["iters"].tolist()
+    assert close(lam, g["lam"], 1e-9)
+    assert close(O._u, g["u"], 1e-9)
+    for s, h in enumerate(hist):
+        assert np.allclose(h[:-1], g["norms"][s, :len(h) - 1], rtol=1e-5, atol=1e-12)
