@@ -49,9 +49,14 @@ enum {
   XB_ELE_STDBRICK = 0,    /* element/Brick/Brick.cpp, 8 nodes x 3 dof, 2x2x2 Gauss; par = b1,b2,b3 */
   XB_ELE_FOURNODEQUAD = 1,/* element/Plane/FourNodeQuad.cpp, 4 nodes x 2 dof, 2x2 Gauss;
                              par = thickness, type(0 PlaneStrain), pressure(=0), rho, b1, b2        */
-  XB_ELE_FORCEBEAMCOLUMN2D = 2 /* element/Frame/Other/Force/ForceBeamColumn2d.cpp, 2 nodes x 3 dof, Lobatto
+  XB_ELE_FORCEBEAMCOLUMN2D = 2,/* element/Frame/Other/Force/ForceBeamColumn2d.cpp, 2 nodes x 3 dof, Lobatto
                              integration, Linear transformation; mat_tags name the fibre section;
                              par = nIP, maxIters, tol (one section/nIP/maxIters/tol per call)          */
+  XB_ELE_FORCEBEAMCOLUMN3D = 3 /* `element forceBeamColumn` in a 3D model (runtime/commands/modeling/element/
+                             frames.cpp:333) = element/Frame/Other/Force/ForceBeamColumn3d.cpp, 2 nodes x 6 dof,
+                             Lobatto integration, `geomTransf Linear` (LinearCrdTransf3d, no offsets); mat_tags
+                             name a section added with xb_add_fiber_section3d;
+                             par = nIP, maxIters, tol, vecxz[3] (one section/nIP/maxIters/tol per call)  */
 };
 
 /* DOF numberers (analysis/numberer) */
@@ -89,6 +94,11 @@ int xb_add_uniaxial_material(xb_model*, int tag, int kind, const double* par, in
 /* section Fiber -> FiberSection2d (material/section/FiberSection2d.cpp:99 addFiber): nf fibres
  * (y, A, uniaxial material tag) in the order given; the centroid is computed as the command does */
 int xb_add_fiber_section(xb_model*, int tag, int nf, const double* y, const double* A, const int* mat_tags);
+/* section Fiber tag -GJ gj in a 3D model -> FiberSection3d (material/section/FiberSection3d.cpp:294 addFiber,
+ * runtime/commands/modeling/section.cpp:497): fibres (y, z, A, uniaxial tag), response P, Mz, My and an
+ * elastic torsion GJ */
+int xb_add_fiber_section3d(xb_model*, int tag, int nf, const double* y, const double* z, const double* A,
+                           const int* mat_tags, double GJ);
 /* Domain::addElement (Domain.cpp:442) for n elements of one kind; conn is [n][nen] node
  * tags, mat_tags [n], par [n][par_stride] (par_stride >= the kind's parameter count).
  * All materials referenced by one call must be of one nDMaterial kind. */

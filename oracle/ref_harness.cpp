@@ -45,6 +45,10 @@
 #include <Steel02.h>
 #include <Concrete02.h>
 #include <FiberSection2d.h>
+#include <FiberSection3d.h>
+#include <ElasticMaterial.h>
+#include <ForceBeamColumn3d.h>
+#include <LinearCrdTransf3d.h>
 #include <ForceBeamColumn2d.h>
 #include <LinearCrdTransf2d.h>
 #include <LobattoBeamIntegration.h>
@@ -158,6 +162,7 @@ struct RefModel {
   std::map<int, NDMaterial*> ndmats;
   std::map<int, UniaxialMaterial*> unimats;
   std::map<int, FiberSection2d*> sections2d;
+  std::map<int, FiberSection3d*> sections3d;
   AnalysisModel* amodel = nullptr;
   PlainHandler* handler = nullptr;
   DOF_Numberer* numberer = nullptr;
@@ -258,6 +263,29 @@ int ref_add_force_beam2d(void* h, int tag, const int* nd, int secTag, int nip, i
   LobattoBeamIntegration bi;
   LinearCrdTransf2d transf(tag);
   Element* e = new ForceBeamColumn2d(tag, nd[0], nd[1], nip, secs.data(), bi, transf, 0.0, maxIters, tol);
+  return m->domain->addElement(e) ? 0 : -1;
+}
+
+// section Fiber tag -GJ gj { fiber y z A mat ... } in a 3D model (runtime/commands/modeling/section.cpp:497):
+// FiberSection3d with an elastic torsion material, centroid computed
+int ref_add_fiber_section3d(void* h, int tag, int nf, const double* y, const double* z, const double* A, const int* matTags, double GJ) {
+  RefModel* m = (RefModel*)h;
+  ElasticMaterial torsion(0, GJ);
+  FiberSection3d* s = new FiberSection3d(tag, nf, torsion, true);
+  for (int i = 0; i < nf; i++)
+    if (s->addFiber(*m->unimats.at(matTags[i]), A[i], y[i], z[i]) < 0) return -1;
+  m->sections3d[tag] = s;
+  return 0;
+}
+// element forceBeamColumn (3D, frames.cpp:333 -> ForceBeamColumn3d): Lobatto integration,
+// geomTransf Linear with vecxz, nIP copies of one section
+int ref_add_force_beam3d(void* h, int tag, const int* nd, int secTag, int nip, int maxIters, double tol, const double* vecxz) {
+  RefModel* m = (RefModel*)h;
+  std::vector<SectionForceDeformation*> secs(nip, m->sections3d.at(secTag));
+  LobattoBeamIntegration bi;
+  Vector v(3); v(0) = vecxz[0]; v(1) = vecxz[1]; v(2) = vecxz[2];
+  LinearCrdTransf3d transf(tag, v);
+  Element* e = new ForceBeamColumn3d(tag, nd[0], nd[1], nip, secs.data(), bi, transf, 0.0, maxIters, tol);
   return m->domain->addElement(e) ? 0 : -1;
 }
 

@@ -20,7 +20,7 @@
 /* ------------------------------------------------------------------------ */
 /* material kinds / element kinds shared with tests (mirrors include/xara_b200.h) */
 enum { ORC_MAT_ELASTIC_ISOTROPIC = 0, ORC_MAT_J2 = 1 };
-enum { ORC_ELE_BRICK = 0, ORC_ELE_QUAD = 1, ORC_ELE_FBC2D = 2 };
+enum { ORC_ELE_BRICK = 0, ORC_ELE_QUAD = 1, ORC_ELE_FBC2D = 2, ORC_ELE_FBC3D = 3 };
 enum { ORC_UNI_STEEL02 = 0, ORC_UNI_CONCRETE02 = 1 };
 enum { ORC_ND_3D = 0, ORC_ND_PLANE_STRAIN = 1 };
 
@@ -808,6 +808,317 @@ static void beam_revert(OrcBeam* b) {
 }
 
 /* ======================================================================== */
+/* FiberSection3d (SRC/material/section/FiberSection3d.cpp), `section Fiber tag -GJ gj`: */
+/* code = P, MZ, MY, T; elastic torsion (ElasticMaterial GJ)                   */
+/* ======================================================================== */
+typedef struct {
+  int nf; double* y; double* z; double* A; OrcUni* mat; double yBar, zBar, GJ;
+  double e[4], s[4], k[16];    /* kData column-major 4x4 */
+} OrcSec3;
+
+/* FiberSection3d::setTrialSectionDeformation, FiberSection3d.cpp:422-475 */
+static int sec3_set_trial(OrcSec3* S, const double* d) {
+  for (int i = 0; i < 4; i++) { S->e[i] = d[i]; S->s[i] = 0.0; }
+  for (int i = 0; i < 16; i++) S->k[i] = 0.0;
+  const double e0 = d[0], e1 = d[1], e2 = d[2], e3 = d[3];
+  int res = 0;
+  for (int i = 0; i < S->nf; i++) {
+    const double y = S->y[i] - S->yBar, z = S->z[i] - S->zBar, A = S->A[i];
+    double strain = e0 - y * e1 + z * e2;
+    res += uni_set_trial(&S->mat[i], strain);
+    double tangent = S->mat[i].e, stress = S->mat[i].sig;
+    double EA = tangent * A;
+    S->k[0] += EA; S->k[1] += -y * EA; S->k[2] += z * EA;
+    S->k[5] += y * y * EA; S->k[10] += z * z * EA; S->k[6] += -y * z * EA;
+    double fs0 = stress * A;
+    S->s[0] += fs0; S->s[1] += -y * fs0; S->s[2] += z * fs0;
+  }
+  S->k[4] = S->k[1]; S->k[8] = S->k[2]; S->k[9] = S->k[6];
+  /* theTorsion->setTrial(e3, stress, tangent): ElasticMaterial */
+  S->s[3] = S->GJ * e3; S->k[15] = S->GJ;
+  return res;
+}
+/* FiberSection3d::revertToLastCommit, FiberSection3d.cpp:612-666 (sData[3] is left at 0) */
+static void sec3_revert(OrcSec3* S) {
+  for (int i = 0; i < 16; i++) S->k[i] = 0.0;
+  for (int i = 0; i < 4; i++) S->s[i] = 0.0;
+  for (int i = 0; i < S->nf; i++) {
+    const double y = S->y[i] - S->yBar, z = S->z[i] - S->zBar, A = S->A[i];
+    uni_revert(&S->mat[i]);
+    double value = S->mat[i].e * A, vas1 = -y * value, vas2 = z * value, vas1as2 = vas1 * z;
+    S->k[0] += value; S->k[1] += vas1; S->k[2] += vas2;
+    S->k[5] += vas1 * -y; S->k[6] += vas1as2; S->k[10] += vas2 * z;
+    double fs0 = S->mat[i].sig * A;
+    S->s[0] += fs0; S->s[1] += fs0 * -y; S->s[2] += fs0 * z;
+  }
+  S->k[4] = S->k[1]; S->k[8] = S->k[2]; S->k[9] = S->k[6];
+  S->k[15] = S->GJ;
+}
+/* SectionForceDeformation::getSectionFlexibility -> Matrix::Invert -> cmx_inv4 (matrix/routines/invGL4.c,
+ * a cofactor expansion).  ks is block diagonal here (P-Mz-My block, torsion): the cofactor
+ * expansion of the 4x4 reduces to that of the 3x3 block times k33 over det3*k33, so the block is
+ * inverted with the 3x3 cofactor formula and the torsion entry by division (same to rounding). */
+static void sec3_flex(const double* k, double* f) {
+  double a[9], ai[9];
+  for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) a[r + 3 * c] = k[r + 4 * c];
+  inv3(a, ai);
+  for (int i = 0; i < 16; i++) f[i] = 0.0;
+  for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) f[r + 4 * c] = ai[r + 3 * c];
+  f[15] = 1.0 / k[15];
+}
+static void sec3_initial_flex(const OrcSec3* S, double* f) {   /* FiberSection3d::getInitialTangent + Invert */
+  double k[16]; for (int i = 0; i < 16; i++) k[i] = 0.0;
+  for (int i = 0; i < S->nf; i++) {
+    const double y = S->y[i] - S->yBar, z = S->z[i] - S->zBar, A = S->A[i];
+    const double EA = uni_initial_tangent(&S->mat[i]) * A;
+    const double vas2 = z * EA;
+    k[0] += EA; k[1] += -y * EA; k[2] += z * EA; k[5] += y * y * EA; k[6] += -y * z * EA; k[10] += vas2 * z;
+  }
+  k[4] = k[1]; k[8] = k[2]; k[9] = k[6]; k[15] = S->GJ;
+  sec3_flex(k, f);
+}
+
+/* ======================================================================== */
+/* ForceBeamColumn3d (SRC/element/Frame/Other/Force/ForceBeamColumn3d.cpp)    */
+/* with LinearCrdTransf3d (no offsets) and LobattoBeamIntegration              */
+/* ======================================================================== */
+typedef struct {
+  int nip, maxIters; double tol;
+  OrcSec3 sec[ORC_MAXSEC];
+  double L, R[3][3];
+  int initialFlag;
+  double kv[36], Se[6], kvcommit[36], Secommit[6];       /* kv column-major 6x6 */
+  double fs[ORC_MAXSEC][16], vs[ORC_MAXSEC][4], Ssr[ORC_MAXSEC][4], vscommit[ORC_MAXSEC][4];
+} OrcBeam3;
+
+/* LinearCrdTransf3d::initialize -> computeElemtLengthAndOrient + getLocalAxes, LinearCrdTransf3d.cpp:203-330 */
+static int crd3d_init(OrcBeam3* b, const double* xi, const double* xj, const double* vecxz) {
+  double dx[3] = { xj[0] - xi[0], xj[1] - xi[1], xj[2] - xi[2] };
+  b->L = sqrt(dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2]);
+  if (b->L == 0.0) return -2;
+  for (int i = 0; i < 3; i++) b->R[0][i] = dx[i] / b->L;
+  const double* v = vecxz; const double* x = b->R[0];
+  double y[3] = { v[1] * x[2] - v[2] * x[1], v[2] * x[0] - v[0] * x[2], v[0] * x[1] - v[1] * x[0] };
+  double ynorm = sqrt(y[0] * y[0] + y[1] * y[1] + y[2] * y[2]);
+  if (ynorm == 0) return -3;
+  for (int i = 0; i < 3; i++) y[i] /= ynorm;
+  double z[3] = { x[1] * y[2] - x[2] * y[1], x[2] * y[0] - x[0] * y[2], x[0] * y[1] - x[1] * y[0] };
+  for (int i = 0; i < 3; i++) { b->R[1][i] = y[i]; b->R[2][i] = z[i]; }
+  return 0;
+}
+/* LinearCrdTransf3d::getBasicTrialDisp / getBasicIncrDeltaDisp, LinearCrdTransf3d.cpp:344-421 */
+static void crd3d_basic(const OrcBeam3* b, const double* ug, double* ub) {
+  double ul[12];
+  for (int blk = 0; blk < 4; blk++)
+    for (int r = 0; r < 3; r++)
+      ul[3 * blk + r] = b->R[r][0] * ug[3 * blk] + b->R[r][1] * ug[3 * blk + 1] + b->R[r][2] * ug[3 * blk + 2];
+  double oneOverL = 1.0 / b->L, tmp;
+  ub[0] = ul[6] - ul[0];
+  tmp = oneOverL * (ul[1] - ul[7]);
+  ub[1] = ul[5] + tmp; ub[2] = ul[11] + tmp;
+  tmp = oneOverL * (ul[8] - ul[2]);
+  ub[3] = ul[4] + tmp; ub[4] = ul[10] + tmp;
+  ub[5] = ul[9] - ul[3];
+}
+/* Matrix::Invert of the 6x6 element flexibility (cmx_inv6, matrix/routines/invGL6.c: a generated
+ * cofactor expansion).  The torsion row/column is uncoupled here; the 5x5 block is inverted by
+ * Gauss-Jordan elimination with partial pivoting -- agreement with the cofactor expansion is to
+ * rounding times the block's condition number. f, kv column-major 6x6. */
+static int inv6_flex(const double* f, double* kv) {
+  double a[5][10];
+  for (int r = 0; r < 5; r++) { for (int c = 0; c < 5; c++) { a[r][c] = f[r + 6 * c]; a[r][5 + c] = (r == c) ? 1.0 : 0.0; } }
+  for (int c = 0; c < 5; c++) {
+    int p = c; double big = fabs(a[c][c]);
+    for (int r = c + 1; r < 5; r++) if (fabs(a[r][c]) > big) { big = fabs(a[r][c]); p = r; }
+    if (big == 0.0) return -1;
+    if (p != c) for (int q = 0; q < 10; q++) { double t = a[c][q]; a[c][q] = a[p][q]; a[p][q] = t; }
+    double piv = 1.0 / a[c][c];
+    for (int q = 0; q < 10; q++) a[c][q] *= piv;
+    for (int r = 0; r < 5; r++) if (r != c) { double m = a[r][c]; if (m != 0.0) for (int q = 0; q < 10; q++) a[r][q] -= m * a[c][q]; }
+  }
+  for (int i = 0; i < 36; i++) kv[i] = 0.0;
+  for (int r = 0; r < 5; r++) for (int c = 0; c < 5; c++) kv[r + 6 * c] = a[r][5 + c];
+  kv[35] = 1.0 / f[35];
+  return 0;
+}
+static double norm6(const double* v) { double s = 0.0; for (int i = 0; i < 6; i++) s += v[i] * v[i]; return sqrt(s); }
+
+/* ForceBeamColumn3d::update, ForceBeamColumn3d.cpp:587-1056 (no element loads; isTorsion = true) */
+static int beam3_update(OrcBeam3* b, const double* ug, const double* dug) {
+  double v[6], dv[6], vin[6];
+  crd3d_basic(b, ug, v);
+  crd3d_basic(b, dug, dv);
+  if (b->initialFlag != 0 && norm6(dv) <= DBL_EPSILON) return 0;
+  for (int i = 0; i < 6; i++) vin[i] = v[i] - dv[i];
+  const double L = b->L;
+  double xi[ORC_MAXSEC], wt[ORC_MAXSEC];
+  lobatto(b->nip, xi, wt);
+  double vr[6], f[36], dSe[6], SeTrial[6], kvTrial[36], dvTrial[6], dvToDo[6];
+  double vsSub[ORC_MAXSEC][4], fsSub[ORC_MAXSEC][16], SsrSub[ORC_MAXSEC][4];
+  int numSubdivide = 1, converged = 0;
+  for (int i = 0; i < 6; i++) { dvToDo[i] = dv[i]; dvTrial[i] = dvToDo[i]; }
+  const double factor = 10.0;
+  const int maxSubdivisions = 10;
+  while (!converged && numSubdivide <= maxSubdivisions) {
+    for (int l = 0; l < 3; l++) {
+      memcpy(SeTrial, b->Se, sizeof SeTrial); memcpy(kvTrial, b->kv, sizeof kvTrial);
+      for (int i = 0; i < b->nip; i++) {
+        memcpy(vsSub[i], b->vs[i], sizeof vsSub[i]); memcpy(fsSub[i], b->fs[i], sizeof fsSub[i]);
+        memcpy(SsrSub[i], b->Ssr[i], sizeof SsrSub[i]);
+      }
+      for (int i = 0; i < 6; i++) dSe[i] = 0.0;
+      for (int j = 0; j < 6; j++) for (int i = 0; i < 6; i++) dSe[i] += kvTrial[i + 6 * j] * dvTrial[j];
+      for (int i = 0; i < 6; i++) SeTrial[i] += dSe[i];
+      int numIters = b->maxIters;
+      if (l == 1) numIters = 10 * b->maxIters;
+      for (int j = 0; j < numIters; j++) {
+        for (int i = 0; i < 36; i++) f[i] = 0.0;
+        for (int i = 0; i < 6; i++) vr[i] = 0.0;
+        for (int i = 0; i < b->nip; i++) {
+          OrcSec3* S = &b->sec[i];
+          double Ss[4], dSs[4], dvs[4], fb[24];   /* fb (4 x 6) column-major */
+          double xL = xi[i], xL1 = xL - 1.0, wtL = wt[i] * L;
+          Ss[0] = SeTrial[0];
+          Ss[1] = xL1 * SeTrial[1] + xL * SeTrial[2];
+          Ss[2] = xL1 * SeTrial[3] + xL * SeTrial[4];
+          Ss[3] = SeTrial[5];
+          for (int q = 0; q < 4; q++) dSs[q] = Ss[q] - SsrSub[i][q];
+          const double* fuse;
+          double fs0[16];
+          if (l == 0) fuse = fsSub[i];
+          else if (l == 2) { if (j == 0) { sec3_initial_flex(S, fs0); fuse = fs0; } else fuse = fsSub[i]; }
+          else { sec3_initial_flex(S, fs0); fuse = fs0; }
+          for (int q = 0; q < 4; q++) dvs[q] = 0.0;
+          for (int c = 0; c < 4; c++) for (int r = 0; r < 4; r++) dvs[r] += fuse[r + 4 * c] * dSs[c];
+          if (b->initialFlag != 0) for (int q = 0; q < 4; q++) vsSub[i][q] += dvs[q];
+          if (sec3_set_trial(S, vsSub[i]) < 0) return -1;
+          for (int q = 0; q < 4; q++) SsrSub[i][q] = S->s[q];
+          sec3_flex(S->k, fsSub[i]);
+          for (int q = 0; q < 4; q++) dSs[q] = Ss[q] - SsrSub[i][q];
+          for (int q = 0; q < 4; q++) dvs[q] = 0.0;
+          for (int c = 0; c < 4; c++) for (int r = 0; r < 4; r++) dvs[r] += fsSub[i][r + 4 * c] * dSs[c];
+          /* fb = fs * b * wtL ; code = {P, MZ, MY, T} */
+          for (int q = 0; q < 24; q++) fb[q] = 0.0;
+          const double* fSec = fsSub[i];
+          for (int jj = 0; jj < 4; jj++) fb[jj + 4 * 0] += fSec[jj + 4 * 0] * wtL;
+          for (int jj = 0; jj < 4; jj++) { double tmp = fSec[jj + 4 * 1] * wtL; fb[jj + 4 * 1] += xL1 * tmp; fb[jj + 4 * 2] += xL * tmp; }
+          for (int jj = 0; jj < 4; jj++) { double tmp = fSec[jj + 4 * 2] * wtL; fb[jj + 4 * 3] += xL1 * tmp; fb[jj + 4 * 4] += xL * tmp; }
+          for (int jj = 0; jj < 4; jj++) fb[jj + 4 * 5] += fSec[jj + 4 * 3] * wtL;
+          /* f += b^T fb */
+          for (int jj = 0; jj < 6; jj++) f[0 + 6 * jj] += fb[0 + 4 * jj];
+          for (int jj = 0; jj < 6; jj++) { double tmp = fb[1 + 4 * jj]; f[1 + 6 * jj] += xL1 * tmp; f[2 + 6 * jj] += xL * tmp; }
+          for (int jj = 0; jj < 6; jj++) { double tmp = fb[2 + 4 * jj]; f[3 + 6 * jj] += xL1 * tmp; f[4 + 6 * jj] += xL * tmp; }
+          for (int jj = 0; jj < 6; jj++) f[5 + 6 * jj] += fb[3 + 4 * jj];
+          /* vr += b^T (vs + dvs) wtL */
+          for (int q = 0; q < 4; q++) dvs[q] += vsSub[i][q];
+          { double dei = dvs[0] * wtL; vr[0] += dei; }
+          { double dei = dvs[1] * wtL; vr[1] += xL1 * dei; vr[2] += xL * dei; }
+          { double dei = dvs[2] * wtL; vr[3] += xL1 * dei; vr[4] += xL * dei; }
+          { double dei = dvs[3] * wtL; vr[5] += dei; }
+        }
+        if (inv6_flex(f, kvTrial) < 0) return -1;
+        for (int i = 0; i < 6; i++) { dv[i] = vin[i]; dv[i] += dvTrial[i]; dv[i] -= vr[i]; }
+        for (int i = 0; i < 6; i++) dSe[i] = 0.0;
+        for (int c = 0; c < 6; c++) for (int r = 0; r < 6; r++) dSe[r] += kvTrial[r + 6 * c] * dv[c];
+        double dW = 0.0;
+        for (int i = 0; i < 6; i++) dW += dv[i] * dSe[i];
+        for (int i = 0; i < 6; i++) SeTrial[i] += dSe[i];
+        if (fabs(dW) < b->tol) {
+          for (int i = 0; i < 6; i++) { dvToDo[i] -= dvTrial[i]; vin[i] += dvTrial[i]; }
+          if (norm6(dvToDo) <= DBL_EPSILON) converged = 1;
+          else { for (int i = 0; i < 6; i++) dvTrial[i] = dvToDo[i]; numSubdivide = 1; }
+          memcpy(b->kv, kvTrial, sizeof kvTrial); memcpy(b->Se, SeTrial, sizeof SeTrial);
+          for (int k = 0; k < b->nip; k++) {
+            memcpy(b->vs[k], vsSub[k], sizeof vsSub[k]); memcpy(b->fs[k], fsSub[k], sizeof fsSub[k]);
+            memcpy(b->Ssr[k], SsrSub[k], sizeof SsrSub[k]);
+          }
+          j = numIters + 1; l = 4;
+        } else {
+          if (j == (numIters - 1) && (l == 2)) { for (int i = 0; i < 6; i++) dvTrial[i] /= factor; numSubdivide++; }
+        }
+      }
+    }
+  }
+  if (!converged) return -1;
+  b->initialFlag = 1;
+  return 0;
+}
+
+/* LinearCrdTransf3d::getGlobalStiffMatrix (no offsets, :767-926) and getGlobalResistingForce (:699-765);
+ * K row-major 12x12 */
+static void beam3_form(const OrcBeam3* b, double* K, double* Rg) {
+  const double oneOverL = 1.0 / b->L;
+  const double (*R)[3] = b->R;
+  if (K) {
+    double kb[6][6], kl[12][12], tmp[12][12];
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) kb[i][j] = b->kv[i + 6 * j];
+    for (int i = 0; i < 6; i++) {
+      tmp[i][0] = -kb[i][0];
+      tmp[i][1] = oneOverL * (kb[i][1] + kb[i][2]);
+      tmp[i][2] = -oneOverL * (kb[i][3] + kb[i][4]);
+      tmp[i][3] = -kb[i][5];
+      tmp[i][4] = kb[i][3];
+      tmp[i][5] = kb[i][1];
+      tmp[i][6] = kb[i][0];
+      tmp[i][7] = -tmp[i][1];
+      tmp[i][8] = -tmp[i][2];
+      tmp[i][9] = kb[i][5];
+      tmp[i][10] = kb[i][4];
+      tmp[i][11] = kb[i][2];
+    }
+    for (int i = 0; i < 12; i++) {
+      kl[0][i] = -tmp[0][i];
+      kl[1][i] = oneOverL * (tmp[1][i] + tmp[2][i]);
+      kl[2][i] = -oneOverL * (tmp[3][i] + tmp[4][i]);
+      kl[3][i] = -tmp[5][i];
+      kl[4][i] = tmp[3][i];
+      kl[5][i] = tmp[1][i];
+      kl[6][i] = tmp[0][i];
+      kl[7][i] = -kl[1][i];
+      kl[8][i] = -kl[2][i];
+      kl[9][i] = tmp[5][i];
+      kl[10][i] = tmp[4][i];
+      kl[11][i] = tmp[2][i];
+    }
+    for (int m = 0; m < 12; m++)
+      for (int blk = 0; blk < 4; blk++)
+        for (int c = 0; c < 3; c++)
+          tmp[m][3 * blk + c] = kl[m][3 * blk] * R[0][c] + kl[m][3 * blk + 1] * R[1][c] + kl[m][3 * blk + 2] * R[2][c];
+    for (int m = 0; m < 12; m++)
+      for (int blk = 0; blk < 4; blk++)
+        for (int c = 0; c < 3; c++)
+          K[(3 * blk + c) * 12 + m] = R[0][c] * tmp[3 * blk][m] + R[1][c] * tmp[3 * blk + 1][m] + R[2][c] * tmp[3 * blk + 2][m];
+  }
+  const double* q = b->Se;
+  double pl[12];
+  pl[0] = -q[0]; pl[1] = oneOverL * (q[1] + q[2]); pl[2] = -oneOverL * (q[3] + q[4]); pl[3] = -q[5];
+  pl[4] = q[3]; pl[5] = q[1]; pl[6] = q[0]; pl[7] = -pl[1]; pl[8] = -pl[2]; pl[9] = q[5]; pl[10] = q[4]; pl[11] = q[2];
+  pl[0] += 0.0; pl[1] += 0.0; pl[7] += 0.0; pl[2] += 0.0; pl[8] += 0.0;     /* p0 = 0 */
+  for (int blk = 0; blk < 4; blk++)
+    for (int c = 0; c < 3; c++)
+      Rg[3 * blk + c] = R[0][c] * pl[3 * blk] + R[1][c] * pl[3 * blk + 1] + R[2][c] * pl[3 * blk + 2];
+}
+/* ForceBeamColumn3d::commitState / revertToLastCommit, ForceBeamColumn3d.cpp:279-345 */
+static void beam3_commit(OrcBeam3* b) {
+  for (int i = 0; i < b->nip; i++) {
+    memcpy(b->vscommit[i], b->vs[i], sizeof b->vs[i]);
+    for (int f = 0; f < b->sec[i].nf; f++) uni_commit(&b->sec[i].mat[f]);
+  }
+  memcpy(b->kvcommit, b->kv, sizeof b->kv); memcpy(b->Secommit, b->Se, sizeof b->Se);
+}
+static void beam3_revert(OrcBeam3* b) {
+  for (int i = 0; i < b->nip; i++) {
+    memcpy(b->vs[i], b->vscommit[i], sizeof b->vs[i]);
+    sec3_revert(&b->sec[i]);
+    sec3_set_trial(&b->sec[i], b->vs[i]);
+    for (int q = 0; q < 4; q++) b->Ssr[i][q] = b->sec[i].s[q];
+    sec3_flex(b->sec[i].k, b->fs[i]);
+  }
+  memcpy(b->Se, b->Secommit, sizeof b->Se); memcpy(b->kv, b->kvcommit, sizeof b->kv);
+  b->initialFlag = 0;
+}
+
+/* ======================================================================== */
 /* the model: Domain + AnalysisModel + LinearSOE flattened                    */
 /* ======================================================================== */
 typedef struct {
@@ -820,9 +1131,10 @@ typedef struct {
   OrcGP gp[8];
   int nip;
   OrcBeam* beam;     /* ORC_ELE_FBC2D */
+  OrcBeam3* beam3;   /* ORC_ELE_FBC3D */
 } OrcEle;
 
-typedef struct { int tag, nf; double* y; double* A; int* mat; } OrcSecDef;
+typedef struct { int tag, nf; double* y; double* z; double* A; int* mat; double GJ; } OrcSecDef;
 
 typedef struct {
   int ndm, ndf;
@@ -926,7 +1238,7 @@ int orc_add_fiber_section(void* h, int tag, int nf, const double* y, const doubl
   OrcModel* m = (OrcModel*)h;
   m->sec = (OrcSecDef*)realloc(m->sec, sizeof(OrcSecDef) * (m->nsec + 1));
   OrcSecDef* d = &m->sec[m->nsec];
-  d->tag = tag; d->nf = nf;
+  d->tag = tag; d->nf = nf; d->z = NULL; d->GJ = 0.0;
   d->y = (double*)malloc(sizeof(double) * nf); d->A = (double*)malloc(sizeof(double) * nf); d->mat = (int*)malloc(sizeof(int) * nf);
   memcpy(d->y, y, sizeof(double) * nf); memcpy(d->A, A, sizeof(double) * nf);
   for (int i = 0; i < nf; i++) {
@@ -935,6 +1247,16 @@ int orc_add_fiber_section(void* h, int tag, int nf, const double* y, const doubl
     if (d->mat[i] < 0) return -1;
   }
   m->nsec++; return 0;
+}
+/* section Fiber tag -GJ gj { fiber y z A mat ... } in a 3D model: FiberSection3d */
+int orc_add_fiber_section3d(void* h, int tag, int nf, const double* y, const double* z, const double* A, const int* matTags, double GJ) {
+  int rc = orc_add_fiber_section(h, tag, nf, y, A, matTags);
+  if (rc < 0) return rc;
+  OrcModel* m = (OrcModel*)h;
+  OrcSecDef* d = &m->sec[m->nsec - 1];
+  d->z = (double*)malloc(sizeof(double) * nf); memcpy(d->z, z, sizeof(double) * nf);
+  d->GJ = GJ;
+  return 0;
 }
 static int beam_update(OrcBeam* b, const double* ug, const double* dug);
 static int find_mat(const OrcModel* m, int tag) { for (int i = 0; i < m->nmat; i++) if (m->mat_tag[i] == tag) return i; return -1; }
@@ -946,9 +1268,38 @@ int orc_add_element(void* h, int kind, int tag, const int* nodeTags, int matTag,
   memset(e, 0, sizeof *e);
   e->kind = kind; e->tag = tag;
   e->nen = (kind == ORC_ELE_BRICK) ? 8 : (kind == ORC_ELE_QUAD ? 4 : 2);
-  e->ndf_e = (kind == ORC_ELE_BRICK) ? 3 : (kind == ORC_ELE_QUAD ? 2 : 3);
+  e->ndf_e = (kind == ORC_ELE_BRICK) ? 3 : (kind == ORC_ELE_QUAD ? 2 : (kind == ORC_ELE_FBC3D ? 6 : 3));
   e->nip = (kind == ORC_ELE_BRICK) ? 8 : 4;
   for (int i = 0; i < e->nen; i++) { e->node[i] = find_node(m, nodeTags[i]); if (e->node[i] < 0) return -1; }
+  if (kind == ORC_ELE_FBC3D) {
+    /* forceBeamColumn in a 3D model (ForceBeamColumn3d): matTag names the FiberSection3d;
+     * par = nIP, maxIters, tol, vecxz[3] of `geomTransf Linear`; Lobatto integration */
+    int sd = -1;
+    for (int i = 0; i < m->nsec; i++) if (m->sec[i].tag == matTag) sd = i;
+    if (sd < 0 || m->sec[sd].z == NULL) return -2;
+    OrcBeam3* b = (OrcBeam3*)calloc(1, sizeof(OrcBeam3));
+    b->nip = (int)par[0]; b->maxIters = (int)par[1]; b->tol = par[2];
+    if (b->nip < 2 || b->nip > ORC_MAXSEC) return -3;
+    const OrcSecDef* d = &m->sec[sd];
+    for (int i = 0; i < b->nip; i++) {
+      OrcSec3* S = &b->sec[i];
+      S->nf = d->nf; S->y = d->y; S->z = d->z; S->A = d->A; S->GJ = d->GJ;
+      S->mat = (OrcUni*)malloc(sizeof(OrcUni) * d->nf);
+      double ABar = 0.0, QzBar = 0.0, QyBar = 0.0;
+      for (int f = 0; f < d->nf; f++) {
+        uni_init(&S->mat[f], m->uni_kind[d->mat[f]], m->uni_par + 12 * d->mat[f]);
+        ABar += d->A[f]; QzBar += d->y[f] * d->A[f]; QyBar += d->z[f] * d->A[f];   /* FiberSection3d::addFiber */
+        S->yBar = QzBar / ABar; S->zBar = QyBar / ABar;
+      }
+    }
+    if (crd3d_init(b, m->crd + e->node[0] * 3, m->crd + e->node[1] * 3, par + 3) < 0) return -3;
+    e->beam3 = b; e->nip = b->nip; e->mat = sd;
+    memcpy(e->par, par, 8 * sizeof(double));
+    double ug[12], dug[12];   /* Domain::addElement calls element->update() (Domain.cpp:391) */
+    for (int a = 0; a < 2; a++) for (int j = 0; j < 6; j++) { ug[a * 6 + j] = m->trial[e->node[a] * 6 + j]; dug[a * 6 + j] = m->incr[e->node[a] * 6 + j]; }
+    if (beam3_update(b, ug, dug) < 0) return -4;
+    m->ne++; return 0;
+  }
   if (kind == ORC_ELE_FBC2D) {
     /* forceBeamColumn: matTag names the fibre section; par = nIP, maxIters, tol.
      * Lobatto integration, Linear transformation (no offsets). */
@@ -1339,6 +1690,11 @@ static void quad_form(OrcModel* m, OrcEle* el, int tang_flag, double* K, double*
 static int ele_update(OrcModel* m, OrcEle* el) {
   if (el->kind == ORC_ELE_BRICK) return brick_update(m, el);
   if (el->kind == ORC_ELE_QUAD) return quad_update(m, el);
+  if (el->kind == ORC_ELE_FBC3D) {
+    double ug[12], dug[12];
+    for (int a = 0; a < 2; a++) for (int j = 0; j < 6; j++) { ug[a * 6 + j] = m->trial[el->node[a] * 6 + j]; dug[a * 6 + j] = m->incr[el->node[a] * 6 + j]; }
+    return beam3_update(el->beam3, ug, dug);
+  }
   double ug[6], dug[6];
   for (int a = 0; a < 2; a++) for (int j = 0; j < 3; j++) { ug[a * 3 + j] = m->trial[el->node[a] * 3 + j]; dug[a * 3 + j] = m->incr[el->node[a] * 3 + j]; }
   return beam_update(el->beam, ug, dug);
@@ -1371,12 +1727,14 @@ void orc_apply_load(void* h, double lambda) { ((OrcModel*)h)->lambda = lambda; }
 int orc_ele_tangent(void* h, int e, double* K) {
   OrcModel* m = (OrcModel*)h; double R[24];
   if (m->ele[e].kind == ORC_ELE_FBC2D) { beam_form(m->ele[e].beam, K, R); return 6; }
+  if (m->ele[e].kind == ORC_ELE_FBC3D) { beam3_form(m->ele[e].beam3, K, R); return 12; }
   if (m->ele[e].kind == ORC_ELE_BRICK) { brick_form(m, &m->ele[e], 1, K, R); return 24; }
   quad_form(m, &m->ele[e], 1, K, R); return 8;
 }
 int orc_ele_resid(void* h, int e, double* R) {
   OrcModel* m = (OrcModel*)h;
   if (m->ele[e].kind == ORC_ELE_FBC2D) { beam_form(m->ele[e].beam, NULL, R); return 6; }
+  if (m->ele[e].kind == ORC_ELE_FBC3D) { beam3_form(m->ele[e].beam3, NULL, R); return 12; }
   if (m->ele[e].kind == ORC_ELE_BRICK) { brick_form(m, &m->ele[e], 0, NULL, R); return 24; }
   double K[64]; quad_form(m, &m->ele[e], 0, K, R); return 8;
 }
@@ -1406,6 +1764,7 @@ int orc_form_tangent(void* h, double* A) {
     int nd_e = el->nen * el->ndf_e;
     if (el->kind == ORC_ELE_BRICK) brick_form(m, el, 1, K, R);
     else if (el->kind == ORC_ELE_QUAD) quad_form(m, el, 1, K, R);
+    else if (el->kind == ORC_ELE_FBC3D) beam3_form(el->beam3, K, R);
     else beam_form(el->beam, K, R);
     int n = ele_ids(m, el, ids); (void)n;
     /* FE_Element::addKtToTang(c1): theTangent->addMatrix(K, c1) on a zeroed matrix */
@@ -1440,6 +1799,7 @@ int orc_form_unbalance(void* h, double* B) {
     int nd_e = el->nen * el->ndf_e;
     if (el->kind == ORC_ELE_BRICK) brick_form(m, el, 0, NULL, R);
     else if (el->kind == ORC_ELE_QUAD) quad_form(m, el, 0, K, R);
+    else if (el->kind == ORC_ELE_FBC3D) beam3_form(el->beam3, NULL, R);
     else beam_form(el->beam, NULL, R);
     ele_ids(m, el, ids);
     for (int i = 0; i < nd_e; i++) {
@@ -1469,6 +1829,7 @@ int orc_commit(void* h) {
   memcpy(m->velc, m->vel, sizeof(double) * m->nn * m->ndf); memcpy(m->accc, m->acc, sizeof(double) * m->nn * m->ndf);
   for (int e = 0; e < m->ne; e++) {
     if (m->ele[e].kind == ORC_ELE_FBC2D) beam_commit(m->ele[e].beam);
+    else if (m->ele[e].kind == ORC_ELE_FBC3D) beam3_commit(m->ele[e].beam3);
     else for (int g = 0; g < m->ele[e].nip; g++) gp_commit(&m->ele[e].gp[g]);
   }
   return 0;
@@ -1481,6 +1842,7 @@ int orc_revert(void* h) {
   memcpy(m->vel, m->velc, sizeof(double) * m->nn * m->ndf); memcpy(m->acc, m->accc, sizeof(double) * m->nn * m->ndf);
   for (int e = 0; e < m->ne; e++) {
     if (m->ele[e].kind == ORC_ELE_FBC2D) beam_revert(m->ele[e].beam);
+    else if (m->ele[e].kind == ORC_ELE_FBC3D) beam3_revert(m->ele[e].beam3);
     else for (int g = 0; g < m->ele[e].nip; g++) gp_revert(&m->ele[e].gp[g]);
   }
   int rc = 0;

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 import zlib  # noqa: E402
 
-from golden_cases import CASES, NSTEPS, ele_nd  # noqa: E402
+from golden_cases import CASES, NSTEPS, control_node, ele_nd  # noqa: E402
 from modelspec import (CONCRETE02_CORE, CONCRETE02_COVER, ELASTIC, J2_STEEL, ND_3D, ND_PLANE_STRAIN, STEEL02,  # noqa: E402
                        RefBackend, ref_nd_path, ref_uni_path)
 
@@ -87,7 +87,7 @@ def dispcontrol_case(name, spec, numberer, soe, node, dof, incr, nsteps, tol, ma
     """the reference's StaticAnalysis loop with its own DisplacementControl, NewtonRaphson and
     CTestNormDispIncr (ref_analyze_static_lam): iteration counts, test norms, load factors, final state"""
     R = RefBackend(spec, defer_setup=True)
-    node = int(spec.node_tags[-1]) if node is None else node
+    node = control_node(spec, node)
     R.setup_dispcontrol(numberer, soe, node, dof, incr, test=0, tol=tol, max_iter=max_iter)
     rc, iters, norms, lam = R.analyze_static_lam(nsteps)
     assert rc == 0, rc
@@ -102,13 +102,19 @@ def dispcontrol_case(name, spec, numberer, soe, node, dof, incr, nsteps, tol, ma
 
 
 if __name__ == "__main__":
+    # python tests/golden/make_golden.py [substring]: only the cases whose name contains it
     from golden_cases import DISPCONTROL_CASES, TRANSIENT_CASES
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
     for name, (mk, *args) in DISPCONTROL_CASES.items():
-        dispcontrol_case(name, mk(), *args)
+        if only in name:
+            dispcontrol_case(name, mk(), *args)
     for name, (mk, mass_fn, gamma, beta, dt) in TRANSIENT_CASES.items():
-        spec = mk()
-        transient_case(name, spec, mass_fn(spec), gamma, beta, dt)
-    material_paths()
+        if only in name:
+            spec = mk()
+            transient_case(name, spec, mass_fn(spec), gamma, beta, dt)
+    if only in "material_paths":
+        material_paths()
     for name, (mk, numberer, soe, scale) in CASES.items():
-        model_case(name, mk(), numberer, soe, scale)
+        if only in name:
+            model_case(name, mk(), numberer, soe, scale)
     print("golden fixtures written to", HERE)

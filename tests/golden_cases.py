@@ -1,5 +1,5 @@
 """The models behind tests/golden/*.npz (generated from the reference by tests/golden/make_golden.py)."""
-from modelspec import ELASTIC, J2_STEEL, brick_block, cantilever2d, frame2d, quad_plane
+from modelspec import ELASTIC, J2_STEEL, brick_block, cantilever2d, frame2d, frame3d, quad_plane
 
 # name -> (spec factory, numberer, soe, displacement scale)
 CASES = {
@@ -11,13 +11,16 @@ CASES = {
     # 2D RC frame: forceBeamColumn + fibre sections (Steel02, Concrete02); scale per dof (ux, uy, rz)
     "frame2d_fiber_rcm_csc": (lambda: frame2d(2, 3, 2), 1, 0, (0.006, 0.003, 6e-5)),
     "frame2d_fiber_plain_csr": (lambda: frame2d(3, 2, 1, nip=4), 0, 1, (0.008, 0.002, 5e-5)),
+    # 3D RC space frame: forceBeamColumn (ForceBeamColumn3d) + FiberSection3d; scale per dof (u, r)
+    "frame3d_fiber_rcm_csc": (lambda: frame3d(2, 1, 2, ndiv=1), 1, 0, (0.015, 0.015, 0.002, 1e-4, 1e-4, 1e-4)),
+    "frame3d_fiber_plain_csr": (lambda: frame3d(1, 2, 2, ndiv=2, nip=5), 0, 1, (0.005, 0.0075, 0.00075, 5e-5, 2.5e-5, 5e-5)),
 }
 NSTEPS = 3
 
 
 def ele_nd(spec):
     """dofs of one element of the (single-kind) model"""
-    return {0: 24, 1: 8, 2: 6}[spec.groups[0].kind]
+    return {0: 24, 1: 8, 2: 6, 3: 12}[spec.groups[0].kind]
 
 
 def _uniform_mass(val, rot=None):
@@ -25,7 +28,7 @@ def _uniform_mass(val, rot=None):
         import numpy as np
         m = np.full((spec.nn, spec.ndf), val)
         if rot is not None:
-            m[:, 2] = rot
+            m[:, spec.ndm:] = rot       # rotational dofs: rz in 2D, rx ry rz in 3D
         return m
     return f
 
@@ -34,6 +37,7 @@ def _uniform_mass(val, rot=None):
 TRANSIENT_CASES = {
     "newmark_brick_j2": (lambda: brick_block(3, 3, 4, mat=J2_STEEL, lz=3.0, load=(40.0, 0.0, -5.0)), _uniform_mass(0.05), 0.5, 0.25, 0.02),
     "newmark_frame2d": (lambda: frame2d(2, 2, 2, lateral=30.0), _uniform_mass(0.05, 0.0), 0.5, 0.25, 0.02),
+    "newmark_frame3d": (lambda: frame3d(1, 1, 2, ndiv=2, lateral=(25.0, 15.0)), _uniform_mass(0.05, 0.0), 0.5, 0.25, 0.02),
 }
 
 
@@ -49,5 +53,20 @@ DISPCONTROL_CASES = {
     # BASELINE configs[0]: the Ex2b cantilever pushover (to 5 % drift), with the RC fibre section
     "dc_cantilever_fiber": (lambda: cantilever2d(ndiv=1), 0, 0, None, 0, 0.432, 50, 1e-8, 10),
     # BASELINE configs[2] in small: J2 brick column pushed under displacement control
+    # 3D RC space frame pushed at a roof corner under displacement control (biaxial bending + torsion)
+    "dc_frame3d": (lambda: frame3d(1, 1, 2, ndiv=1, lateral=(1.0, 0.6), gravity=-2.0), 1, 0, "roof", 0, 0.25, 9, 3e-7, 12),
     "dc_brick_j2": (lambda: brick_block(3, 3, 5, mat=J2_STEEL, lx=1.0, ly=1.0, lz=3.0, load=(1.0, 0.0, -0.3)), 1, 0, None, 0, 5e-3, 12, 3e-10, 15),
 }
+
+
+def control_node(spec, node):
+    """control node of a DISPCONTROL case: None = the last node, "roof" = the loaded roof corner of a
+    space frame (x = y = 0 at the top), else the tag itself"""
+    import numpy as np
+    if node is None:
+        return int(spec.node_tags[-1])
+    if node == "roof":
+        c = spec.crd
+        top = np.where((c[:, 0] == 0.0) & (c[:, 1] == 0.0) & (c[:, 2] == c[:, 2].max()))[0]
+        return int(spec.node_tags[top[0]])
+    return int(node)

@@ -23,7 +23,7 @@ ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libref_harness.so")
 
 MAT_ELASTIC, MAT_J2 = 0, 1
-ELE_BRICK, ELE_QUAD, ELE_FBC2D = 0, 1, 2
+ELE_BRICK, ELE_QUAD, ELE_FBC2D, ELE_FBC3D = 0, 1, 2, 3
 UNI_STEEL02, UNI_CONCRETE02 = 0, 1
 ND_3D, ND_PLANE_STRAIN = 0, 1
 NUMBERER_PLAIN, NUMBERER_RCM = 0, 1
@@ -191,6 +191,77 @@ def frame2d(nbay=2, nstory=3, ndiv=2, nip=5, bay=360.0, story=144.0, max_iters=1
                      sections=[rc_section(1)])
 
 
+def rc_section3d(tag=1, h=24.0, b=18.0, cover=1.5, ny=6, nz=4, As=0.6, GJ=2.0e6):
+    """3D RC fibre section (`section Fiber tag -GJ gj`): confined core patch ny x nz, four cover strips,
+    eight bars -- as (tag, y, A, uniaxial tag, z, GJ); uniaxial tags 1 core, 2 cover, 3 steel"""
+    y, z, A, m = [], [], [], []
+    hc, bc = h - 2 * cover, b - 2 * cover
+    for i in range(ny):
+        for j in range(nz):
+            y.append(-hc / 2 + (i + 0.5) * hc / ny); z.append(-bc / 2 + (j + 0.5) * bc / nz)
+            A.append(hc * bc / (ny * nz)); m.append(1)
+    for sgn in (-1, 1):
+        for j in range(nz):       # top / bottom cover strips (full width split in nz)
+            y.append(sgn * (h - cover) / 2); z.append(-b / 2 + (j + 0.5) * b / nz); A.append(cover * b / nz); m.append(2)
+        for i in range(ny):       # side cover strips
+            y.append(-hc / 2 + (i + 0.5) * hc / ny); z.append(sgn * (b - cover) / 2); A.append(cover * hc / ny); m.append(2)
+    for yy in (-hc / 2, 0.0, hc / 2):
+        for zz in (-bc / 2, 0.0, bc / 2):
+            if yy == 0.0 and zz == 0.0:
+                continue
+            y.append(yy); z.append(zz); A.append(As); m.append(3)
+    return (tag, np.array(y), np.array(A), np.array(m, np.int32), np.array(z), GJ)
+
+
+def frame3d(nx=1, ny=1, nstory=2, ndiv=1, nip=4, bay=240.0, story=144.0, max_iters=10, tol=1e-12,
+            lateral=(8.0, 5.0), gravity=-40.0):
+    """3D RC space frame of forceBeamColumn elements (ForceBeamColumn3d, FiberSection3d: Steel02 + Concrete02):
+    columns on an (nx+1) x (ny+1) grid, beams in both directions at every floor; bases fixed; gravity on the
+    floor nodes, lateral loads (x, y) at the roof corner.  ndm 3, ndf 6."""
+    pts = {}
+    def node(x, y, z):
+        key = (round(x, 6), round(y, 6), round(z, 6))
+        if key not in pts:
+            pts[key] = len(pts) + 1
+        return pts[key]
+    conn, vec = [], []
+    for i in range(nx + 1):
+        for j in range(ny + 1):
+            for k in range(nstory):
+                for d in range(ndiv):
+                    conn.append((node(i * bay, j * bay, k * story + d * story / ndiv), node(i * bay, j * bay, k * story + (d + 1) * story / ndiv)))
+                    vec.append((1.0, 0.0, 0.0))          # columns: local x up, vecxz = global X
+    for k in range(1, nstory + 1):
+        for j in range(ny + 1):
+            for i in range(nx):
+                for d in range(ndiv):
+                    conn.append((node(i * bay + d * bay / ndiv, j * bay, k * story), node(i * bay + (d + 1) * bay / ndiv, j * bay, k * story)))
+                    vec.append((0.0, 0.0, 1.0))          # beams: vecxz = global Z
+        for i in range(nx + 1):
+            for j in range(ny):
+                for d in range(ndiv):
+                    conn.append((node(i * bay, j * bay + d * bay / ndiv, k * story), node(i * bay, j * bay + (d + 1) * bay / ndiv, k * story)))
+                    vec.append((0.0, 0.0, 1.0))
+    nn = len(pts)
+    crd = np.zeros((nn, 3))
+    for key, t in pts.items():
+        crd[t - 1] = key
+    conn = np.array(conn, np.int32)
+    ne = len(conn)
+    par = np.zeros((ne, 8)); par[:, 0] = nip; par[:, 1] = max_iters; par[:, 2] = tol; par[:, 3:6] = np.array(vec)
+    fix = np.array([(t, d) for (x, y, z), t in pts.items() if z == 0.0 for d in range(6)], np.int32).reshape(-1, 2)
+    loads = []
+    for (x, y, z), t in pts.items():
+        on_grid = abs(x / bay - round(x / bay)) < 1e-9 and abs(y / bay - round(y / bay)) < 1e-9
+        if z > 0 and abs(z / story - round(z / story)) < 1e-9 and on_grid:
+            top = round(z / story) == nstory and x == 0.0 and y == 0.0
+            loads.append([t, lateral[0] if top else 0.0, lateral[1] if top else 0.0, gravity, 0.0, 0.0, 0.0])
+    return ModelSpec(3, 6, np.arange(1, nn + 1, dtype=np.int32), crd, fix, [],
+                     [ElementGroup(ELE_FBC3D, np.arange(1, ne + 1, dtype=np.int32), conn, np.ones(ne, np.int32), par)],
+                     np.array(loads), uniaxials=[(1, *CONCRETE02_CORE), (2, *CONCRETE02_COVER), (3, *STEEL02)],
+                     sections=[rc_section3d(1)])
+
+
 def cantilever2d(ndiv=1, nip=5, L=432.0, H=1.0, V=-100.0, max_iters=10, tol=1e-12):
     """the reference's tests/Ex2b.Canti2D.InelasticSection.Push.py cantilever (BASELINE configs[0]) with
     the RC fibre section of north_star (Steel02 + Concrete02): node 1 fixed, forceBeamColumn(s) up to the
@@ -281,9 +352,16 @@ class OracleBackend(_Backend):
         for tag, kind, p in spec.uniaxials:
             pp = np.zeros(12); pp[:len(p)] = p
             assert L.orc_add_uniaxial(self.h, tag, kind, _p(pp)) == 0
-        for tag, y, A, mt in spec.sections:
+        L.orc_add_fiber_section3d.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double]
+        for sec in spec.sections:
+            tag, y, A, mt = sec[:4]
             y, A, mt = np.ascontiguousarray(y, np.float64), np.ascontiguousarray(A, np.float64), np.ascontiguousarray(mt, np.int32)
-            assert L.orc_add_fiber_section(self.h, tag, len(y), _p(y), _p(A), _p(mt)) == 0
+            if len(sec) == 6:     # 3D: (tag, y, A, mat, z, GJ)
+                z = np.ascontiguousarray(sec[4], np.float64)
+                assert L.orc_add_fiber_section3d(self.h, tag, len(y), _p(y), _p(z), _p(A), _p(mt), float(sec[5])) == 0
+            else:
+                assert L.orc_add_fiber_section(self.h, tag, len(y), _p(y), _p(A), _p(mt)) == 0
         for g in spec.groups:
             for i in range(len(g.tags)):
                 c = np.ascontiguousarray(g.conn[i], np.int32); pr = np.ascontiguousarray(g.par[i], np.float64)
@@ -442,9 +520,18 @@ class RefBackend(_Backend):
         for tag, kind, p in spec.uniaxials:
             pp = np.zeros(12); pp[:len(p)] = p
             assert L.ref_add_uniaxial(self.h, tag, kind, _p(pp)) == 0
-        for tag, y, A, mt in spec.sections:
+        L.ref_add_fiber_section3d.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double]
+        L.ref_add_force_beam3d.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_double, ctypes.c_void_p]
+        for sec in spec.sections:
+            tag, y, A, mt = sec[:4]
             y, A, mt = np.ascontiguousarray(y, np.float64), np.ascontiguousarray(A, np.float64), np.ascontiguousarray(mt, np.int32)
-            assert L.ref_add_fiber_section(self.h, tag, len(y), _p(y), _p(A), _p(mt)) == 0
+            if len(sec) == 6:
+                z = np.ascontiguousarray(sec[4], np.float64)
+                assert L.ref_add_fiber_section3d(self.h, tag, len(y), _p(y), _p(z), _p(A), _p(mt), float(sec[5])) == 0
+            else:
+                assert L.ref_add_fiber_section(self.h, tag, len(y), _p(y), _p(A), _p(mt)) == 0
         self.ele_tags = []
         for g in spec.groups:
             for i in range(len(g.tags)):
@@ -452,6 +539,10 @@ class RefBackend(_Backend):
                 if g.kind == ELE_BRICK:
                     b = np.ascontiguousarray(g.par[i, :3], np.float64)
                     assert L.ref_add_brick(self.h, int(g.tags[i]), _p(c), int(g.mat[i]), _p(b)) == 0
+                elif g.kind == ELE_FBC3D:
+                    vx = np.ascontiguousarray(g.par[i, 3:6], np.float64)
+                    assert L.ref_add_force_beam3d(self.h, int(g.tags[i]), _p(c), int(g.mat[i]), int(g.par[i, 0]),
+                                                  int(g.par[i, 1]), float(g.par[i, 2]), _p(vx)) == 0
                 elif g.kind == ELE_FBC2D:
                     assert L.ref_add_force_beam2d(self.h, int(g.tags[i]), _p(c), int(g.mat[i]), int(g.par[i, 0]),
                                                   int(g.par[i, 1]), float(g.par[i, 2])) == 0

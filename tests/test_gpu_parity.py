@@ -14,7 +14,7 @@ import pytest
 
 import xara_b200 as xb
 from golden_cases import CASES, NSTEPS, ele_nd
-from modelspec import ELASTIC, J2_STEEL, OracleBackend, brick_block, frame2d, quad_plane
+from modelspec import ELASTIC, J2_STEEL, OracleBackend, brick_block, frame2d, frame3d, quad_plane
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -35,7 +35,7 @@ def test_device_vs_golden_reference_vectors(name):
     nd = ele_nd(spec)
     # the force-based beam iterates to |dW| < 1e-12 per element: its converged state, and with it
     # K and R, is reproducible to the iteration tolerance, not to the last bit
-    tol = BEAM_RTOL if nd == 6 else RTOL
+    tol = BEAM_RTOL if nd in (6, 12) else RTOL
     for s in range(NSTEPS):
         D.set_trial_disp(g[f"u{s}"]); D.update(); D.apply_load(0.25 * (s + 1))
         A, B = D.form_tangent(), D.form_unbalance()
@@ -134,7 +134,7 @@ def _newton_counts_match(spec, nsteps, min_iters):
     assert relerr(D.trial_disp(), uo) < 1e-8
 
 
-@pytest.mark.parametrize("shape", ["brick", "quad", "frame"])
+@pytest.mark.parametrize("shape", ["brick", "quad", "frame", "frame3d"])
 def test_newton_iteration_counts_match_oracle(shape):
     if shape == "brick":
         spec = brick_block(4, 4, 6, mat=J2_STEEL, lx=1.0, ly=1.0, lz=3.0, load=(1.2, 0.0, -0.5))
@@ -143,8 +143,10 @@ def test_newton_iteration_counts_match_oracle(shape):
         spec = quad_plane(16, 4, mat=J2_STEEL, lx=8.0, ly=2.0)
         spec.loads[:, 1:] = [0.0, -10.0]
         _newton_counts_match(spec, 8, 6)
-    else:   # load-controlled pushover of the RC frame (forceBeamColumn, fibre sections)
+    elif shape == "frame":   # load-controlled pushover of the RC frame (forceBeamColumn, fibre sections)
         _newton_counts_match(frame2d(2, 3, 2, lateral=22.0, gravity=-40.0), 5, 5)
+    else:   # 3D space frame (ForceBeamColumn3d, FiberSection3d): biaxial push at a roof corner
+        _newton_counts_match(frame3d(1, 1, 2, ndiv=2, lateral=(20.0, 12.0), gravity=-40.0), 5, 5)
 
 
 def test_revert_to_last_commit_and_incr():
@@ -361,6 +363,66 @@ def test_frame_fibre_beams_vs_oracle_history():
     assert relerr(D.form_tangent(), D0.form_tangent()) > 0.05
 
 
+def test_frame3d_fibre_beams_vs_oracle_history():
+    """forceBeamColumn in 3D (ForceBeamColumn3d) + FiberSection3d (Steel02 / Concrete02, elastic torsion):
+    cyclic biaxial sway + twist history with commits and a revertToLastCommit, device against the oracle"""
+    spec = frame3d(2, 2, 3, ndiv=2)
+    O = OracleBackend(spec, 1, 0)
+    D = xb.DeviceModel.from_spec(spec, 1, 0).to_device(0)
+    ids = O.ids()
+    assert relerr(D.form_tangent(), O.form_tangent()) < BEAM_RTOL          # initial (elastic) stiffness
+    H = spec.crd[:, 2].max()
+    z = spec.crd[:, 2] / H
+    xc, yc = spec.crd[:, 0] - spec.crd[:, 0].mean(), spec.crd[:, 1] - spec.crd[:, 1].mean()
+    rng = np.random.default_rng(5)
+    amp = [0.2, 0.6, 1.2, 0.5, -0.7, -1.4, 0.3, 0.6]                        # inches of roof drift, cycling
+    for s, a in enumerate(amp):
+        th = 2e-3 * a * z                                                   # floor twist about the vertical axis
+        u = np.zeros((spec.nn, 6))
+        u[:, 0] = a * z ** 1.5 - th * yc; u[:, 1] = 0.6 * a * z ** 1.5 + th * xc; u[:, 2] = -0.01 * z
+        u[:, 3] = -0.6 * 1.5 * a * z ** 0.5 / H; u[:, 4] = 1.5 * a * z ** 0.5 / H; u[:, 5] = th
+        u += rng.normal(0, 1.0, u.shape) * (2e-3, 2e-3, 5e-4, 1e-5, 1e-5, 1e-5)
+        u[ids < 0] = 0
+        assert O.set_trial_disp(u) == 0
+        D.set_trial_disp(u); D.update(); D.apply_load(0.1 * s); O.apply_load(0.1 * s)
+        assert relerr(D.form_tangent(), O.form_tangent()) < BEAM_RTOL
+        assert relerr(D.form_unbalance(), O.form_unbalance()) < BEAM_RTOL
+        for e in (0, spec.groups[0].conn.shape[0] - 1):
+            assert relerr(D.element_tangent(e, 12), O.ele_tangent(e, 12)) < BEAM_RTOL
+            assert relerr(D.element_resid(e, 12), O.ele_resid(e, 12)) < BEAM_RTOL
+        if s == 4:
+            O.revert(); D.revert_to_last_commit()
+            assert relerr(D.form_tangent(), O.form_tangent()) < BEAM_RTOL
+            assert relerr(D.form_unbalance(), O.form_unbalance()) < BEAM_RTOL
+        else:
+            O.commit(); D.commit()
+    D0 = xb.DeviceModel.from_spec(spec, 1, 0).to_device(0)
+    assert relerr(D.form_tangent(), D0.form_tangent()) > 0.05              # well past yield
+
+
+def test_partitioned_frame3d_matches_single_gpu():
+    spec_fn = lambda: frame3d(3, 2, 3, ndiv=2)
+    spec = spec_fn()
+    G = xb.DeviceModel.from_spec(spec, 1, 1).to_device(0)
+    gptr, _ = G.pattern()
+    ranks = [xb.DeviceModel.from_spec(spec_fn(), 1, 1, 3, r).to_device(0) for r in range(3)]
+    H = spec.crd[:, 2].max()
+    z = spec.crd[:, 2] / H
+    for a in (0.6, 1.8):
+        u = np.zeros((spec.nn, 6)); u[:, 0] = a * z ** 1.5; u[:, 1] = 0.5 * a * z ** 1.5
+        u[:, 3] = -0.5 * 1.5 * a * z ** 0.5 / H; u[:, 4] = 1.5 * a * z ** 0.5 / H
+        u[G.ids() < 0] = 0
+        G.set_trial_disp(u); G.update(); G.apply_load(1.0)
+        Ag, Bg = G.form_tangent(), G.form_unbalance()
+        for m, (A, B) in zip(ranks, _partitioned_pass(ranks, u, 1.0)):
+            rows = m.row_eqns()
+            assert np.array_equal(B, Bg[rows])
+            assert np.array_equal(A, np.concatenate([Ag[gptr[q]:gptr[q + 1]] for q in rows]))
+        G.commit()
+        for m in ranks:
+            m.commit()
+
+
 def test_partitioned_frame_matches_single_gpu():
     spec_fn = lambda: frame2d(4, 5, 2)
     spec = spec_fn()
@@ -382,7 +444,7 @@ def test_partitioned_frame_matches_single_gpu():
             m.commit()
 
 
-@pytest.mark.parametrize("name", ["newmark_brick_j2", "newmark_frame2d"])
+@pytest.mark.parametrize("name", ["newmark_brick_j2", "newmark_frame2d", "newmark_frame3d"])
 def test_newmark_device_vs_golden_reference_history(name):
     """Newmark (displacement form, nodal masses): the device replays the history recorded from the
     reference's own Newmark integrator -- c1 K + c3 M tangent, P - M a - R unbalance, predictor,
@@ -392,21 +454,11 @@ def test_newmark_device_vs_golden_reference_history(name):
     mk, *_ = TRANSIENT_CASES[name]
     g = np.load(os.path.join(GOLD, name + ".npz"))
     spec = mk()
-    D = xb.DeviceModel(spec.ndm, spec.ndf)
-    D.add_nodes(spec.node_tags, spec.crd); D.fix(spec.fix[:, 0], spec.fix[:, 1])
-    for tag, kind, p in spec.materials:
-        D.nd_material(tag, kind, p)
-    for tag, kind, p in spec.uniaxials:
-        D.uniaxial_material(tag, kind, p)
-    for tag, y, A, mt in spec.sections:
-        D.fiber_section(tag, y, A, mt)
-    for grp in spec.groups:
-        D.add_elements(grp.kind, grp.tags, grp.conn, grp.mat, grp.par)
-    D.add_nodal_loads(spec.loads[:, 0].astype(np.int32), spec.loads[:, 1:])
+    D = xb.DeviceModel.from_spec(spec, setup=False)
     D.set_mass(spec.node_tags, g["mass"])
     D.setup(1, 1); D.to_device(0)
     assert np.array_equal(D.ids(), g["ids"])
-    tol = BEAM_RTOL if spec.groups[0].kind == 2 else 1e-11
+    tol = BEAM_RTOL if spec.groups[0].kind in (2, 3) else 1e-11
 
     def check(A, Ag, B, Bg, bscale):
         assert relerr(A, Ag) < tol

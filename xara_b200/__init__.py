@@ -63,6 +63,7 @@ def _load():
         "xb_add_nd_material": (i32, [vp, i32, i32, vp, i32]),
         "xb_add_uniaxial_material": (i32, [vp, i32, i32, vp, i32]),
         "xb_add_fiber_section": (i32, [vp, i32, i32, vp, vp, vp]),
+        "xb_add_fiber_section3d": (i32, [vp, i32, i32, vp, vp, vp, vp, f64]),
         "xb_add_elements": (i32, [vp, i32, i32, vp, vp, vp, vp, i32]),
         "xb_add_nodal_loads": (i32, [vp, i32, vp, vp]),
         "xb_set_nodal_mass": (i32, [vp, i32, vp, vp]),
@@ -207,6 +208,10 @@ class DeviceModel:
         y, A, mat_tags = _f64(y), _f64(A), _i32(mat_tags)
         self._ck(lib.xb_add_fiber_section(self._h, tag, len(y), _ptr(y), _ptr(A), _ptr(mat_tags)))
 
+    def fiber_section3d(self, tag, y, z, A, mat_tags, GJ):
+        y, z, A, mat_tags = _f64(y), _f64(z), _f64(A), _i32(mat_tags)
+        self._ck(lib.xb_add_fiber_section3d(self._h, tag, len(y), _ptr(y), _ptr(z), _ptr(A), _ptr(mat_tags), float(GJ)))
+
     def add_elements(self, kind, tags, conn, mat_tags, par):
         tags, conn, mat_tags, par = _i32(tags), _i32(conn), _i32(mat_tags), _f64(par)
         assert par.ndim == 2 and len(par) == len(tags)
@@ -218,8 +223,9 @@ class DeviceModel:
         self._ck(lib.xb_add_nodal_loads(self._h, len(node_tags), _ptr(node_tags), _ptr(values)))
 
     @classmethod
-    def from_spec(cls, spec, numberer=NUMBERER_PLAIN, soe=SOE_SPARSE_GEN_COL, nparts=1, rank=0, part=None):
-        """Build from a tests/modelspec.py ModelSpec (duck-typed)."""
+    def from_spec(cls, spec, numberer=NUMBERER_PLAIN, soe=SOE_SPARSE_GEN_COL, nparts=1, rank=0, part=None, setup=True):
+        """Build from a tests/modelspec.py ModelSpec (duck-typed); setup=False leaves xb_setup to the caller
+        (e.g. to add nodal masses first)."""
         m = cls(spec.ndm, spec.ndf)
         m.add_nodes(spec.node_tags, spec.crd)
         if len(spec.fix):
@@ -228,13 +234,17 @@ class DeviceModel:
             m.nd_material(tag, kind, p)
         for tag, kind, p in getattr(spec, "uniaxials", []):
             m.uniaxial_material(tag, kind, p)
-        for tag, y, A, mt in getattr(spec, "sections", []):
-            m.fiber_section(tag, y, A, mt)
+        for sec in getattr(spec, "sections", []):
+            if len(sec) == 6:      # 3D: (tag, y, A, mat, z, GJ)
+                m.fiber_section3d(sec[0], sec[1], sec[4], sec[2], sec[3], sec[5])
+            else:
+                m.fiber_section(*sec)
         for g in spec.groups:
             m.add_elements(g.kind, g.tags, g.conn, g.mat, g.par)
         if spec.loads is not None and len(spec.loads):
             m.add_nodal_loads(spec.loads[:, 0].astype(np.int32), spec.loads[:, 1:])
-        m.setup(numberer, soe, nparts, rank, part)
+        if setup:
+            m.setup(numberer, soe, nparts, rank, part)
         return m
 
     # ---- analysis set-up (host) ----

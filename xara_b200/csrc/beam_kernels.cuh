@@ -23,6 +23,7 @@ namespace xbk {
 
 constexpr int XB_FIB_NV = 11;   // doubles per fibre record
 constexpr int XB_MAXSEC = 10;
+constexpr int XB_FBC3D_MAX_PASSES = 20000;   // see fbc3d_update_kernel
 // Steel02 record:   0 epsmin 1 epsmax 2 epspl 3 epss0 4 sigs0 5 epsr 6 sigr 7 kon 8 e 9 sig 10 eps
 // Concrete02 record: 0 ecmin 1 dept 8 e 9 sig 10 eps
 
@@ -31,24 +32,27 @@ struct BeamView {
   int nip, nf, maxIters;
   double tol;
   const int* conn;             // [n][2]
-  const double* geo;           // [3][n]  L, cosTheta, sinTheta
+  const double* geo;           // 2D: [3][n]  L, cosTheta, sinTheta;  3D: [10][n]  L, R[3][3] row-major
+  int nb, ord;                 // basic dofs (3 | 6) and section order (2 | 4): sizes of the arrays below
   // section template (shared by every section of every element of the group)
   const double* fy;            // [nf] y - yBar
+  const double* fz;            // [nf] z - zBar (3D)
+  double GJ;                   // elastic torsion (3D)
   const double* fA;            // [nf]
   const int* fkind;            // [nf] 0 Steel02, 1 Concrete02
   const double* fpar;          // [nf][12] material parameters
-  const double* fs0;           // [4] initial section flexibility (column-major 2x2)
+  const double* fs0;           // [ord*ord] initial section flexibility (column-major)
   // element state, SoA [k][n]
-  double* Se;                  // [3][n]
-  double* kv;                  // [9][n] column-major
+  double* Se;                  // [nb][n]
+  double* kv;                  // [nb*nb][n] column-major
   double* Sec;                 // committed
   double* kvc;
   int* iflag;                  // [n] initialFlag
   // section state [i][k][n]
-  double* vs;                  // [nip][2][n]
-  double* fs;                  // [nip][4][n]
-  double* Ssr;                 // [nip][2][n]
-  double* vsc;                 // [nip][2][n] committed
+  double* vs;                  // [nip][ord][n]
+  double* fs;                  // [nip][ord*ord][n]
+  double* Ssr;                 // [nip][ord][n]
+  double* vsc;                 // [nip][ord][n] committed
   // fibre records [ (i*nf+f)*NV + v ][n]
   double* fc;                  // committed
   double* ft;                  // trial
@@ -56,7 +60,7 @@ struct BeamView {
   double* KeN;
   double* sendK;
   int cps;
-  double* Re;                  // [n][6]
+  double* Re;                  // [n][2*ndf]
 };
 
 __device__ __forceinline__ void lobatto_rule(int n, double* xi, double* wt) {
@@ -411,6 +415,289 @@ __global__ void __launch_bounds__(64) fbc2d_revert_kernel(BeamView B) {
   }
   for (int i = 0; i < 3; i++) B.Se[i * n + e] = B.Sec[i * n + e];
   for (int i = 0; i < 9; i++) B.kv[i * n + e] = B.kvc[i * n + e];
+  B.iflag[e] = 0;
+}
+
+// =====================================================================================
+// 3D: ForceBeamColumn3d + FiberSection3d (P, Mz, My, T with elastic torsion) + LinearCrdTransf3d
+//   ForceBeamColumn3d::update / commitState / revertToLastCommit / getTangentStiff / getResistingForce
+//                                         element/Frame/Other/Force/ForceBeamColumn3d.cpp:587,279,313,401,551
+//   LinearCrdTransf3d (no offsets)        coordTransformation/LinearCrdTransf3d.cpp:344,492,699,767
+//   FiberSection3d::setTrialSectionDeformation      material/section/FiberSection3d.cpp:422
+//   Matrix::Invert -> cmx_inv4 / cmx_inv6 (cofactor expansions, matrix/routines/invGL4.c, invGL6.c): the
+//   section stiffness and the element flexibility are block diagonal here (torsion uncoupled), so the
+//   P-Mz-My block goes through the 3x3 cofactor formula and the 5x5 block of the flexibility through
+//   Gauss-Jordan elimination with partial pivoting; agreement is to rounding x condition number.
+// =====================================================================================
+
+// FiberSection3d::setTrialSectionDeformation for section i of element e -> s[4], k[16] (column-major)
+__device__ __forceinline__ void section3_trial(const BeamView& B, long long e, int i, const double* d, double* s, double* k) {
+  for (int q = 0; q < 16; q++) k[q] = 0.0;
+  s[0] = s[1] = s[2] = 0.0;
+  const double e0 = d[0], e1 = d[1], e2 = d[2], e3 = d[3];
+  for (int f = 0; f < B.nf; f++) {
+    const double y = __ldg(B.fy + f), z = __ldg(B.fz + f), A = __ldg(B.fA + f);
+    const double strain = e0 - y * e1 + z * e2;
+    const size_t rec = ((size_t)(i * B.nf + f) * XB_FIB_NV) * B.n + e;
+    double stress, tangent;
+    if (__ldg(B.fkind + f) == 0) steel02_trial(B.fpar + f * 12, B.fc + rec, B.ft + rec, B.n, strain, stress, tangent);
+    else concrete02_trial(B.fpar + f * 12, B.fc + rec, B.ft + rec, B.n, strain, stress, tangent);
+    const double EA = tangent * A;
+    k[0] += EA; k[1] += -y * EA; k[2] += z * EA;
+    k[5] += y * y * EA; k[10] += z * z * EA; k[6] += -y * z * EA;
+    const double fs0 = stress * A;
+    s[0] += fs0; s[1] += -y * fs0; s[2] += z * fs0;
+  }
+  k[4] = k[1]; k[8] = k[2]; k[9] = k[6];
+  s[3] = B.GJ * e3; k[15] = B.GJ;
+}
+__device__ __forceinline__ void section3_flex(const double* k, double* f) {
+  double a[9], ai[9];
+  for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) a[r + 3 * c] = k[r + 4 * c];
+  inv3(a, ai);
+  for (int q = 0; q < 16; q++) f[q] = 0.0;
+  for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) f[r + 4 * c] = ai[r + 3 * c];
+  f[15] = 1.0 / k[15];
+}
+// inverse of the element flexibility (column-major 6x6, torsion uncoupled); false if singular
+__device__ __forceinline__ bool inv6_flex(const double* f, double* kv) {
+  double a[5][10];
+  for (int r = 0; r < 5; r++) for (int c = 0; c < 5; c++) { a[r][c] = f[r + 6 * c]; a[r][5 + c] = (r == c) ? 1.0 : 0.0; }
+  for (int c = 0; c < 5; c++) {
+    int p = c; double big = fabs(a[c][c]);
+    for (int r = c + 1; r < 5; r++) if (fabs(a[r][c]) > big) { big = fabs(a[r][c]); p = r; }
+    if (big == 0.0) return false;
+    if (p != c) for (int q = 0; q < 10; q++) { const double t = a[c][q]; a[c][q] = a[p][q]; a[p][q] = t; }
+    const double piv = 1.0 / a[c][c];
+    for (int q = 0; q < 10; q++) a[c][q] *= piv;
+    for (int r = 0; r < 5; r++) if (r != c) { const double mlt = a[r][c]; if (mlt != 0.0) for (int q = 0; q < 10; q++) a[r][q] -= mlt * a[c][q]; }
+  }
+  for (int q = 0; q < 36; q++) kv[q] = 0.0;
+  for (int r = 0; r < 5; r++) for (int c = 0; c < 5; c++) kv[r + 6 * c] = a[r][5 + c];
+  kv[35] = 1.0 / f[35];
+  return true;
+}
+__device__ __forceinline__ void crd3d_basic(double L, const double* R, const double* ug, double* ub) {
+  double ul[12];
+  for (int blk = 0; blk < 4; blk++)
+    for (int r = 0; r < 3; r++)
+      ul[3 * blk + r] = R[3 * r] * ug[3 * blk] + R[3 * r + 1] * ug[3 * blk + 1] + R[3 * r + 2] * ug[3 * blk + 2];
+  const double oneOverL = 1.0 / L;
+  double tmp;
+  ub[0] = ul[6] - ul[0];
+  tmp = oneOverL * (ul[1] - ul[7]);
+  ub[1] = ul[5] + tmp; ub[2] = ul[11] + tmp;
+  tmp = oneOverL * (ul[8] - ul[2]);
+  ub[3] = ul[4] + tmp; ub[4] = ul[10] + tmp;
+  ub[5] = ul[9] - ul[3];
+}
+__device__ __forceinline__ double norm6(const double* v) { double s = 0.0; for (int i = 0; i < 6; i++) s += v[i] * v[i]; return sqrt(s); }
+
+// ForceBeamColumn3d::update (no element loads).  U = trial displacements, DU = Node::getIncrDeltaDisp
+__global__ void __launch_bounds__(64) fbc3d_update_kernel(BeamView B, const double* __restrict__ U,
+                                                          const double* __restrict__ DU, int* fail) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B.n) return;
+  const long long n = B.n;
+  const int nip = B.nip;
+  double R[9];
+  const double L = B.geo[e];
+  for (int q = 0; q < 9; q++) R[q] = B.geo[(size_t)(1 + q) * n + e];
+  double ug[12], dug[12];
+  for (int a = 0; a < 2; a++) {
+    const int nd = B.conn[e * 2 + a];
+    for (int j = 0; j < 6; j++) { ug[a * 6 + j] = U[(size_t)nd * 6 + j]; dug[a * 6 + j] = DU[(size_t)nd * 6 + j]; }
+  }
+  double v[6], dv[6], vin[6];
+  crd3d_basic(L, R, ug, v);
+  crd3d_basic(L, R, dug, dv);
+  const int initialFlag = B.iflag[e];
+  if (initialFlag != 0 && norm6(dv) <= DBL_EPSILON) return;
+  for (int i = 0; i < 6; i++) vin[i] = v[i] - dv[i];
+  double xi[XB_MAXSEC], wt[XB_MAXSEC];
+  lobatto_rule(nip, xi, wt);
+  double Se[6], kv[36];
+  for (int i = 0; i < 6; i++) Se[i] = B.Se[i * n + e];
+  for (int i = 0; i < 36; i++) kv[i] = B.kv[i * n + e];
+  double fs0[16];
+  for (int i = 0; i < 16; i++) fs0[i] = __ldg(B.fs0 + i);
+  double vr[6], f[36], dSe[6], SeTrial[6], kvTrial[36], dvTrial[6], dvToDo[6];
+  double vsSub[XB_MAXSEC][4], fsSub[XB_MAXSEC][16], SsrSub[XB_MAXSEC][4];
+  int numSubdivide = 1;
+  bool converged = false;
+  for (int i = 0; i < 6; i++) { dvToDo[i] = dv[i]; dvTrial[i] = dvToDo[i]; }
+  const double factor = 10.0;
+  const int maxSubdivisions = 10;
+  // Device-only guard: every converged sub-step resets numSubdivide (as in the reference), so a
+  // diverging global iteration can ask for ~10^10 sub-steps; a kernel that long takes the context
+  // down.  Past XB_FBC3D_MAX_PASSES element iterations the update reports the reference's failure.
+  int passes = 0;
+  while (!converged && numSubdivide <= maxSubdivisions) {
+    for (int l = 0; l < 3; l++) {
+      for (int i = 0; i < 6; i++) SeTrial[i] = Se[i];
+      for (int i = 0; i < 36; i++) kvTrial[i] = kv[i];
+      for (int i = 0; i < nip; i++) {
+        for (int q = 0; q < 4; q++) { vsSub[i][q] = B.vs[(size_t)(i * 4 + q) * n + e]; SsrSub[i][q] = B.Ssr[(size_t)(i * 4 + q) * n + e]; }
+        for (int q = 0; q < 16; q++) fsSub[i][q] = B.fs[(size_t)(i * 16 + q) * n + e];
+      }
+      for (int i = 0; i < 6; i++) dSe[i] = 0.0;
+      for (int j = 0; j < 6; j++) for (int i = 0; i < 6; i++) dSe[i] += kvTrial[i + 6 * j] * dvTrial[j];
+      for (int i = 0; i < 6; i++) SeTrial[i] += dSe[i];
+      int numIters = B.maxIters;
+      if (l == 1) numIters = 10 * B.maxIters;
+      for (int j = 0; j < numIters; j++) {
+        if (++passes > XB_FBC3D_MAX_PASSES) { atomicExch(fail, 2); return; }
+        for (int i = 0; i < 36; i++) f[i] = 0.0;
+        for (int i = 0; i < 6; i++) vr[i] = 0.0;
+        for (int i = 0; i < nip; i++) {
+          double Ss[4], dSs[4], dvs[4], fb[24], ssec[4], ksec[16];
+          const double xL = xi[i], xL1 = xL - 1.0, wtL = wt[i] * L;
+          Ss[0] = SeTrial[0];
+          Ss[1] = xL1 * SeTrial[1] + xL * SeTrial[2];
+          Ss[2] = xL1 * SeTrial[3] + xL * SeTrial[4];
+          Ss[3] = SeTrial[5];
+          for (int q = 0; q < 4; q++) dSs[q] = Ss[q] - SsrSub[i][q];
+          const bool initial = (l == 1) || (l == 2 && j == 0);
+          const double* fuse = initial ? fs0 : fsSub[i];
+          for (int q = 0; q < 4; q++) dvs[q] = 0.0;
+          for (int c = 0; c < 4; c++) for (int r = 0; r < 4; r++) dvs[r] += fuse[r + 4 * c] * dSs[c];
+          if (initialFlag != 0) for (int q = 0; q < 4; q++) vsSub[i][q] += dvs[q];
+          section3_trial(B, e, i, vsSub[i], ssec, ksec);
+          for (int q = 0; q < 4; q++) SsrSub[i][q] = ssec[q];
+          section3_flex(ksec, fsSub[i]);
+          for (int q = 0; q < 4; q++) dSs[q] = Ss[q] - SsrSub[i][q];
+          for (int q = 0; q < 4; q++) dvs[q] = 0.0;
+          for (int c = 0; c < 4; c++) for (int r = 0; r < 4; r++) dvs[r] += fsSub[i][r + 4 * c] * dSs[c];
+          for (int q = 0; q < 24; q++) fb[q] = 0.0;
+          const double* fSec = fsSub[i];
+          for (int jj = 0; jj < 4; jj++) fb[jj + 4 * 0] += fSec[jj + 4 * 0] * wtL;
+          for (int jj = 0; jj < 4; jj++) { const double tmp = fSec[jj + 4 * 1] * wtL; fb[jj + 4 * 1] += xL1 * tmp; fb[jj + 4 * 2] += xL * tmp; }
+          for (int jj = 0; jj < 4; jj++) { const double tmp = fSec[jj + 4 * 2] * wtL; fb[jj + 4 * 3] += xL1 * tmp; fb[jj + 4 * 4] += xL * tmp; }
+          for (int jj = 0; jj < 4; jj++) fb[jj + 4 * 5] += fSec[jj + 4 * 3] * wtL;
+          for (int jj = 0; jj < 6; jj++) f[0 + 6 * jj] += fb[0 + 4 * jj];
+          for (int jj = 0; jj < 6; jj++) { const double tmp = fb[1 + 4 * jj]; f[1 + 6 * jj] += xL1 * tmp; f[2 + 6 * jj] += xL * tmp; }
+          for (int jj = 0; jj < 6; jj++) { const double tmp = fb[2 + 4 * jj]; f[3 + 6 * jj] += xL1 * tmp; f[4 + 6 * jj] += xL * tmp; }
+          for (int jj = 0; jj < 6; jj++) f[5 + 6 * jj] += fb[3 + 4 * jj];
+          for (int q = 0; q < 4; q++) dvs[q] += vsSub[i][q];
+          { const double dei = dvs[0] * wtL; vr[0] += dei; }
+          { const double dei = dvs[1] * wtL; vr[1] += xL1 * dei; vr[2] += xL * dei; }
+          { const double dei = dvs[2] * wtL; vr[3] += xL1 * dei; vr[4] += xL * dei; }
+          { const double dei = dvs[3] * wtL; vr[5] += dei; }
+        }
+        if (!inv6_flex(f, kvTrial)) { atomicExch(fail, 2); return; }
+        for (int i = 0; i < 6; i++) { dv[i] = vin[i]; dv[i] += dvTrial[i]; dv[i] -= vr[i]; }
+        for (int i = 0; i < 6; i++) dSe[i] = 0.0;
+        for (int c = 0; c < 6; c++) for (int r = 0; r < 6; r++) dSe[r] += kvTrial[r + 6 * c] * dv[c];
+        double dW = 0.0;
+        for (int i = 0; i < 6; i++) dW += dv[i] * dSe[i];
+        for (int i = 0; i < 6; i++) SeTrial[i] += dSe[i];
+        if (fabs(dW) < B.tol) {
+          for (int i = 0; i < 6; i++) { dvToDo[i] -= dvTrial[i]; vin[i] += dvTrial[i]; }
+          if (norm6(dvToDo) <= DBL_EPSILON) converged = true;
+          else { for (int i = 0; i < 6; i++) dvTrial[i] = dvToDo[i]; numSubdivide = 1; }
+          for (int i = 0; i < 6; i++) Se[i] = SeTrial[i];
+          for (int i = 0; i < 36; i++) kv[i] = kvTrial[i];
+          for (int i = 0; i < 6; i++) B.Se[i * n + e] = Se[i];
+          for (int i = 0; i < 36; i++) B.kv[i * n + e] = kv[i];
+          for (int i = 0; i < nip; i++) {
+            for (int q = 0; q < 4; q++) { B.vs[(size_t)(i * 4 + q) * n + e] = vsSub[i][q]; B.Ssr[(size_t)(i * 4 + q) * n + e] = SsrSub[i][q]; }
+            for (int q = 0; q < 16; q++) B.fs[(size_t)(i * 16 + q) * n + e] = fsSub[i][q];
+          }
+          j = numIters + 1; l = 4;
+        } else {
+          if (j == (numIters - 1) && (l == 2)) { for (int i = 0; i < 6; i++) dvTrial[i] /= factor; numSubdivide++; }
+        }
+      }
+    }
+  }
+  if (!converged) { atomicExch(fail, 2); return; }
+  B.iflag[e] = 1;
+}
+
+// getTangentStiff -> LinearCrdTransf3d::getGlobalStiffMatrix(kv); getResistingForce ->
+// getGlobalResistingForce(Se).  Rows of node a (6 of them) go to that node's slot.
+__global__ void __launch_bounds__(64) fbc3d_form_kernel(BeamView B, int want_k, int want_r, int transpose) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B.n) return;
+  const long long n = B.n;
+  const double L = B.geo[e], oneOverL = 1.0 / L;
+  double R[3][3];
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R[r][c] = B.geo[(size_t)(1 + 3 * r + c) * n + e];
+  if (want_k) {
+    double kb[6][6], kl[12][12], tmp[12][12];
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) kb[i][j] = B.kv[(size_t)(i + 6 * j) * n + e];
+    for (int i = 0; i < 6; i++) {
+      tmp[i][0] = -kb[i][0];
+      tmp[i][1] = oneOverL * (kb[i][1] + kb[i][2]);
+      tmp[i][2] = -oneOverL * (kb[i][3] + kb[i][4]);
+      tmp[i][3] = -kb[i][5];
+      tmp[i][4] = kb[i][3];
+      tmp[i][5] = kb[i][1];
+      tmp[i][6] = kb[i][0];
+      tmp[i][7] = -tmp[i][1];
+      tmp[i][8] = -tmp[i][2];
+      tmp[i][9] = kb[i][5];
+      tmp[i][10] = kb[i][4];
+      tmp[i][11] = kb[i][2];
+    }
+    for (int i = 0; i < 12; i++) {
+      kl[0][i] = -tmp[0][i];
+      kl[1][i] = oneOverL * (tmp[1][i] + tmp[2][i]);
+      kl[2][i] = -oneOverL * (tmp[3][i] + tmp[4][i]);
+      kl[3][i] = -tmp[5][i];
+      kl[4][i] = tmp[3][i];
+      kl[5][i] = tmp[1][i];
+      kl[6][i] = tmp[0][i];
+      kl[7][i] = -kl[1][i];
+      kl[8][i] = -kl[2][i];
+      kl[9][i] = tmp[5][i];
+      kl[10][i] = tmp[4][i];
+      kl[11][i] = tmp[2][i];
+    }
+    for (int m = 0; m < 12; m++)
+      for (int blk = 0; blk < 4; blk++)
+        for (int c = 0; c < 3; c++)
+          tmp[m][3 * blk + c] = kl[m][3 * blk] * R[0][c] + kl[m][3 * blk + 1] * R[1][c] + kl[m][3 * blk + 2] * R[2][c];
+    // kg(3 blk + c, m) = sum_r R[r][c] tmp[3 blk + r][m]; kl is free now: reuse it for kg
+    for (int m = 0; m < 12; m++)
+      for (int blk = 0; blk < 4; blk++)
+        for (int c = 0; c < 3; c++)
+          kl[3 * blk + c][m] = R[0][c] * tmp[3 * blk][m] + R[1][c] * tmp[3 * blk + 1][m] + R[2][c] * tmp[3 * blk + 2][m];
+    for (int a = 0; a < 2; a++) {
+      const long long d = B.kdst[e * 2 + a];
+      double* base = d >= 0 ? B.KeN + d : B.sendK + (-d - 1);
+      for (int p = 0; p < 6; p++)
+        for (int c = 0; c < 12; c++) base[p * B.cps + c] = transpose ? kl[c][a * 6 + p] : kl[a * 6 + p][c];
+    }
+  }
+  if (want_r) {
+    double q[6];
+    for (int i = 0; i < 6; i++) q[i] = B.Se[i * n + e];
+    double pl[12];
+    pl[0] = -q[0]; pl[1] = oneOverL * (q[1] + q[2]); pl[2] = -oneOverL * (q[3] + q[4]); pl[3] = -q[5];
+    pl[4] = q[3]; pl[5] = q[1]; pl[6] = q[0]; pl[7] = -pl[1]; pl[8] = -pl[2]; pl[9] = q[5]; pl[10] = q[4]; pl[11] = q[2];
+    double* Rg = B.Re + e * 12;
+    for (int blk = 0; blk < 4; blk++)
+      for (int c = 0; c < 3; c++)
+        Rg[3 * blk + c] = R[0][c] * pl[3 * blk] + R[1][c] * pl[3 * blk + 1] + R[2][c] * pl[3 * blk + 2];
+  }
+}
+
+// ForceBeamColumn3d::revertToLastCommit (fibre records already copied back, committed -> trial)
+__global__ void __launch_bounds__(64) fbc3d_revert_kernel(BeamView B) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B.n) return;
+  const long long n = B.n;
+  for (int i = 0; i < B.nip; i++) {
+    double vs[4], s[4], k[16], fl[16];
+    for (int q = 0; q < 4; q++) { vs[q] = B.vsc[(size_t)(i * 4 + q) * n + e]; B.vs[(size_t)(i * 4 + q) * n + e] = vs[q]; }
+    section3_trial(B, e, i, vs, s, k);
+    section3_flex(k, fl);
+    for (int q = 0; q < 4; q++) B.Ssr[(size_t)(i * 4 + q) * n + e] = s[q];
+    for (int q = 0; q < 16; q++) B.fs[(size_t)(i * 16 + q) * n + e] = fl[q];
+  }
+  for (int i = 0; i < 6; i++) B.Se[i * n + e] = B.Sec[i * n + e];
+  for (int i = 0; i < 36; i++) B.kv[i * n + e] = B.kvc[i * n + e];
   B.iflag[e] = 0;
 }
 

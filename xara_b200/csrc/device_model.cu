@@ -19,6 +19,8 @@
 #include "kernels.cuh"
 #include "beam_kernels.cuh"
 
+static inline bool is_beam(int kind) { return kind == XB_ELE_FORCEBEAMCOLUMN2D || kind == XB_ELE_FORCEBEAMCOLUMN3D; }
+
 // assembly kernel tuning (measured on B200, n=128: CH=2/OCC=5 3.29 ms, CH=4/OCC=3 3.94 ms, CH=8/OCC=2 5.41 ms):
 // many warps with two node-slots in flight each beat few warps with many
 #ifndef XB_ASM_CH
@@ -1186,7 +1188,7 @@ int xb_device_count(void) {
 }
 
 xb_model* xb_model_create(int ndm, int ndf) {
-  if (ndm < 2 || ndm > 3 || ndf < 1 || ndf > 3) { g_err = "xb_model_create: ndm in {2,3}, ndf in {1..3}"; return nullptr; }
+  if (ndm < 2 || ndm > 3 || ndf < 1 || (ndf > 3 && ndf != 6)) { g_err = "xb_model_create: ndm in {2,3}, ndf in {1,2,3,6}"; return nullptr; }
   xb_model* m = new xb_model;
   m->h.ndm = ndm; m->h.ndf = ndf;
   return m;
@@ -1222,6 +1224,7 @@ int xb_add_sp(xb_model* m, int n, const int* t, const int* d) { HOSTCALL(m->h.ad
 int xb_add_nd_material(xb_model* m, int tag, int kind, const double* par, int npar) { HOSTCALL(m->h.add_material(tag, kind, par, npar)); }
 int xb_add_uniaxial_material(xb_model* m, int tag, int kind, const double* par, int npar) { HOSTCALL(m->h.add_uniaxial(tag, kind, par, npar)); }
 int xb_add_fiber_section(xb_model* m, int tag, int nf, const double* y, const double* A, const int* mt) { HOSTCALL(m->h.add_fiber_section(tag, nf, y, A, mt)); }
+int xb_add_fiber_section3d(xb_model* m, int tag, int nf, const double* y, const double* z, const double* A, const int* mt, double GJ) { HOSTCALL(m->h.add_fiber_section3d(tag, nf, y, z, A, mt, GJ)); }
 int xb_add_elements(xb_model* m, int kind, int n, const int* tags, const int* conn, const int* mt, const double* par, int ps) {
   HOSTCALL(m->h.add_elements(kind, n, tags, conn, mt, par, ps));
 }
@@ -1354,33 +1357,56 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
     d.kind = g.kind; d.mat_kind = g.mat_kind; d.nip = k.nip ? k.nip : g.nip; d.nst = k.nst; d.nd = k.nen * k.ndf;
     d.ngp = g.n() * d.nip;
     d.v.n = g.n();
-    if (g.kind == XB_ELE_FORCEBEAMCOLUMN2D) {
+    if (is_beam(g.kind)) {
       m->has_beams = true;
+      const bool b3 = g.kind == XB_ELE_FORCEBEAMCOLUMN3D;
       const xb::FiberSectionDef& sd = h.secs[g.sec];
       const int nf = (int)sd.y.size();
       const long long ne = g.n();
       BeamView& b = d.b;
       b.n = ne; b.nip = g.nip; b.nf = nf; b.maxIters = g.max_iters; b.tol = g.tol;
+      b.nb = b3 ? 6 : 3; b.ord = b3 ? 4 : 2; b.GJ = sd.GJ;
+      const int nb = b.nb, ord = b.ord;
       int* conn = nullptr;
       CU(dev_upload(m, &conn, g.conn));
       b.conn = conn;
-      // LinearCrdTransf2d::computeElemtLengthAndOrient (LinearCrdTransf2d.cpp)
-      std::vector<double> geo((size_t)3 * ne);
+      std::vector<double> geo((size_t)(b3 ? 10 : 3) * ne);
       for (long long e = 0; e < ne; e++) {
         const int a = g.conn[e * 2], c = g.conn[e * 2 + 1];
-        const double dx0 = h.crd[(size_t)c * 2] - h.crd[(size_t)a * 2], dx1 = h.crd[(size_t)c * 2 + 1] - h.crd[(size_t)a * 2 + 1];
-        const double L = std::sqrt(dx0 * dx0 + dx1 * dx1);
-        if (L == 0.0) return fail(XB_ERR_ARG, "forceBeamColumn: zero element length");
-        geo[e] = L; geo[ne + e] = dx0 / L; geo[2 * ne + e] = dx1 / L;
+        if (!b3) {
+          // LinearCrdTransf2d::computeElemtLengthAndOrient (LinearCrdTransf2d.cpp)
+          const double dx0 = h.crd[(size_t)c * 2] - h.crd[(size_t)a * 2], dx1 = h.crd[(size_t)c * 2 + 1] - h.crd[(size_t)a * 2 + 1];
+          const double L = std::sqrt(dx0 * dx0 + dx1 * dx1);
+          if (L == 0.0) return fail(XB_ERR_ARG, "forceBeamColumn: zero element length");
+          geo[e] = L; geo[ne + e] = dx0 / L; geo[2 * ne + e] = dx1 / L;
+        } else {
+          // LinearCrdTransf3d::computeElemtLengthAndOrient + getLocalAxes (LinearCrdTransf3d.cpp:203-330):
+          // x = dx / L, y = vecxz ^ x (normalised), z = x ^ y
+          const double* xi = &h.crd[(size_t)a * 3]; const double* xj = &h.crd[(size_t)c * 3];
+          const double* v = &g.par[(size_t)e * 6 + 3];
+          const double dx[3] = {xj[0] - xi[0], xj[1] - xi[1], xj[2] - xi[2]};
+          const double L = std::sqrt(dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2]);
+          if (L == 0.0) return fail(XB_ERR_ARG, "forceBeamColumn: zero element length");
+          const double x[3] = {dx[0] / L, dx[1] / L, dx[2] / L};
+          double y[3] = {v[1] * x[2] - v[2] * x[1], v[2] * x[0] - v[0] * x[2], v[0] * x[1] - v[1] * x[0]};
+          const double ynorm = std::sqrt(y[0] * y[0] + y[1] * y[1] + y[2] * y[2]);
+          if (ynorm == 0) return fail(XB_ERR_ARG, "geomTransf Linear: vecxz parallel to the element axis (LinearCrdTransf3d.cpp:311)");
+          for (int i = 0; i < 3; i++) y[i] /= ynorm;
+          const double z[3] = {x[1] * y[2] - x[2] * y[1], x[2] * y[0] - x[0] * y[2], x[0] * y[1] - x[1] * y[0]};
+          geo[e] = L;
+          for (int i = 0; i < 3; i++) { geo[(size_t)(1 + i) * ne + e] = x[i]; geo[(size_t)(4 + i) * ne + e] = y[i]; geo[(size_t)(7 + i) * ne + e] = z[i]; }
+        }
       }
       double* dgeo = nullptr; CU(dev_upload(m, &dgeo, geo)); b.geo = dgeo;
       // section template + initial fibre records (Steel02::revertToStart, Concrete02 constructor)
-      std::vector<double> fy(nf), fA(sd.A), fpar((size_t)nf * 12), ic((size_t)nf * XB_FIB_NV, 0.0), it((size_t)nf * XB_FIB_NV, 0.0);
+      std::vector<double> fy(nf), fz(nf, 0.0), fA(sd.A), fpar((size_t)nf * 12), ic((size_t)nf * XB_FIB_NV, 0.0), it((size_t)nf * XB_FIB_NV, 0.0);
       std::vector<int> fkind(nf);
       double k0[4] = {0, 0, 0, 0};
+      double k3[16] = {0};   // FiberSection3d::getInitialTangent, column-major 4x4
       for (int f = 0; f < nf; f++) {
         const xb::Uniaxial& u = h.unis[sd.mat[f]];
         fy[f] = sd.y[f] - sd.yBar; fkind[f] = u.kind;
+        if (b3) fz[f] = sd.z[f] - sd.zBar;
         std::memcpy(&fpar[(size_t)f * 12], u.par, sizeof(double) * 12);
         double* C = &ic[(size_t)f * XB_FIB_NV]; double* T = &it[(size_t)f * XB_FIB_NV];
         double E0;
@@ -1397,23 +1423,42 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
         // FiberSection2d::getInitialTangent (FiberSection2d.cpp:271)
         const double ks0 = E0 * fA[f], ks1 = ks0 * -fy[f];
         k0[0] += ks0; k0[1] += ks1; k0[3] += ks1 * -fy[f];
+        if (b3) {   // FiberSection3d.cpp:478-520 (getInitialTangent): vas2 = z * EA, k22 += vas2 * z
+          const double y = fy[f], z = fz[f], EA = ks0, vas2 = z * EA;
+          k3[0] += EA; k3[1] += -y * EA; k3[2] += z * EA; k3[5] += y * y * EA; k3[6] += -y * z * EA; k3[10] += vas2 * z;
+        }
       }
       k0[2] = k0[1];
       const double det = k0[0] * k0[3] - k0[2] * k0[1];
       std::vector<double> fs0 = {k0[3] / det, -k0[1] / det, -k0[2] / det, k0[0] / det};
-      double *dfy = nullptr, *dfA = nullptr, *dfpar = nullptr, *dfs0 = nullptr, *dic = nullptr, *dit = nullptr; int* dfk = nullptr;
-      CU(dev_upload(m, &dfy, fy)); CU(dev_upload(m, &dfA, fA)); CU(dev_upload(m, &dfpar, fpar)); CU(dev_upload(m, &dfk, fkind));
+      if (b3) {
+        // SectionForceDeformation::getSectionFlexibility of the initial tangent: the P-Mz-My block through the
+        // 3x3 cofactor formula (invGL3.c), torsion by division -- as beam_kernels.cuh::section3_flex does
+        k3[4] = k3[1]; k3[8] = k3[2]; k3[9] = k3[6]; k3[15] = sd.GJ;
+        double a3[9], c3[9];
+        for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) a3[r + 3 * c] = k3[r + 4 * c];
+        auto A_ = [&](int i) { return a3[i - 4]; };   // invGL3.c indexes its 3x3 from 4
+        const double det3 = A_(4)*A_(8)*A_(12) - A_(4)*A_(11)*A_(9) - A_(7)*A_(5)*A_(12) + A_(7)*A_(11)*A_(6) + A_(10)*A_(5)*A_(9) - A_(10)*A_(8)*A_(6);
+        c3[0] =  A_(8)*A_(12) - A_(11)*A_(9);  c3[3] = -(A_(5)*A_(12) - A_(11)*A_(6)); c3[6] =  A_(5)*A_(9) - A_(8)*A_(6);
+        c3[1] = -(A_(7)*A_(12) - A_(10)*A_(9)); c3[4] =  A_(4)*A_(12) - A_(10)*A_(6);  c3[7] = -(A_(4)*A_(9) - A_(7)*A_(6));
+        c3[2] =  A_(7)*A_(11) - A_(10)*A_(8);  c3[5] = -(A_(4)*A_(11) - A_(10)*A_(5)); c3[8] =  A_(4)*A_(8) - A_(7)*A_(5);
+        fs0.assign(16, 0.0);
+        for (int i = 1; i <= 3; ++i) for (int j = 1; j <= 3; ++j) fs0[(j - 1) + 4 * (i - 1)] = c3[i + j * 3 - 4] / det3;
+        fs0[15] = 1.0 / k3[15];
+      }
+      double *dfy = nullptr, *dfz = nullptr, *dfA = nullptr, *dfpar = nullptr, *dfs0 = nullptr, *dic = nullptr, *dit = nullptr; int* dfk = nullptr;
+      CU(dev_upload(m, &dfy, fy)); CU(dev_upload(m, &dfz, fz)); CU(dev_upload(m, &dfA, fA)); CU(dev_upload(m, &dfpar, fpar)); CU(dev_upload(m, &dfk, fkind));
       CU(dev_upload(m, &dfs0, fs0)); CU(dev_upload(m, &dic, ic)); CU(dev_upload(m, &dit, it));
-      b.fy = dfy; b.fA = dfA; b.fkind = dfk; b.fpar = dfpar; b.fs0 = dfs0;
-      CU(dev_alloc(m, &b.Se, (size_t)3 * ne)); CU(dev_alloc(m, &b.kv, (size_t)9 * ne));
-      CU(dev_alloc(m, &b.Sec, (size_t)3 * ne)); CU(dev_alloc(m, &b.kvc, (size_t)9 * ne));
+      b.fy = dfy; b.fz = dfz; b.fA = dfA; b.fkind = dfk; b.fpar = dfpar; b.fs0 = dfs0;
+      CU(dev_alloc(m, &b.Se, (size_t)nb * ne)); CU(dev_alloc(m, &b.kv, (size_t)nb * nb * ne));
+      CU(dev_alloc(m, &b.Sec, (size_t)nb * ne)); CU(dev_alloc(m, &b.kvc, (size_t)nb * nb * ne));
       CU(dev_alloc(m, &b.iflag, (size_t)ne));
-      CU(dev_alloc(m, &b.vs, (size_t)g.nip * 2 * ne)); CU(dev_alloc(m, &b.vsc, (size_t)g.nip * 2 * ne));
-      CU(dev_alloc(m, &b.fs, (size_t)g.nip * 4 * ne)); CU(dev_alloc(m, &b.Ssr, (size_t)g.nip * 2 * ne));
-      for (double* q : {b.Se, b.Sec}) CU(cudaMemset(q, 0, sizeof(double) * 3 * ne));
-      for (double* q : {b.kv, b.kvc}) CU(cudaMemset(q, 0, sizeof(double) * 9 * ne));
-      for (double* q : {b.vs, b.vsc, b.Ssr}) CU(cudaMemset(q, 0, sizeof(double) * g.nip * 2 * ne));
-      CU(cudaMemset(b.fs, 0, sizeof(double) * g.nip * 4 * ne));
+      CU(dev_alloc(m, &b.vs, (size_t)g.nip * ord * ne)); CU(dev_alloc(m, &b.vsc, (size_t)g.nip * ord * ne));
+      CU(dev_alloc(m, &b.fs, (size_t)g.nip * ord * ord * ne)); CU(dev_alloc(m, &b.Ssr, (size_t)g.nip * ord * ne));
+      for (double* q : {b.Se, b.Sec}) CU(cudaMemset(q, 0, sizeof(double) * nb * ne));
+      for (double* q : {b.kv, b.kvc}) CU(cudaMemset(q, 0, sizeof(double) * nb * nb * ne));
+      for (double* q : {b.vs, b.vsc, b.Ssr}) CU(cudaMemset(q, 0, sizeof(double) * g.nip * ord * ne));
+      CU(cudaMemset(b.fs, 0, sizeof(double) * g.nip * ord * ord * ne));
       CU(cudaMemset(b.iflag, 0, sizeof(int) * ne));
       d.fib_doubles = (size_t)g.nip * nf * XB_FIB_NV * ne;
       CU(dev_alloc(m, &b.fc, d.fib_doubles)); CU(dev_alloc(m, &b.ft, d.fib_doubles));
@@ -1499,7 +1544,7 @@ static int check_fail_flag(xb_model* m) {
   CU(cudaStreamSynchronize(m->stream));
   if (f) {
     cudaMemsetAsync(m->dFail, 0, sizeof(int), m->stream);
-    return fail(XB_ERR_MATERIAL, f == 2 ? "ForceBeamColumn2d::update - failed to get compatible element forces & deformations (ForceBeamColumn2d.cpp:922)"
+    return fail(XB_ERR_MATERIAL, f == 2 ? "ForceBeamColumn2d/3d::update - failed to get compatible element forces & deformations (ForceBeamColumn2d.cpp:922, ForceBeamColumn3d.cpp:1047)"
                                         : "More than 25 iterations in J2-plasticity (J2Plasticity.cpp:296)");
   }
   return XB_OK;
@@ -1615,8 +1660,9 @@ int xb_update(xb_model* m) {
   long long bytes = 0;
   for (auto& d : m->dg) {
     if (d.v.n == 0) continue;
-    if (d.kind == XB_ELE_FORCEBEAMCOLUMN2D) {
-      fbc2d_update_kernel<<<(unsigned)((d.b.n + 63) / 64), 64, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
+    if (is_beam(d.kind)) {
+      if (d.kind == XB_ELE_FORCEBEAMCOLUMN3D) fbc3d_update_kernel<<<(unsigned)((d.b.n + 63) / 64), 64, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
+      else fbc2d_update_kernel<<<(unsigned)((d.b.n + 63) / 64), 64, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
       m->launches++;
       bytes += (long long)d.b.n * d.b.nip * d.b.nf * XB_FIB_NV * 8 * 2;   // one section pass: records in, out
       continue;
@@ -1653,8 +1699,9 @@ static int pack_for_peers(xb_model* m, int which);
 // element-tangent kernels of one batch over the element range [ebeg, eend) (bricks) on `st`
 static int launch_group_tangents(xb_model* m, DevGroup& d, long long ebeg, long long eend, cudaStream_t st) {
   const int transpose = m->h.soe_kind == XB_SOE_SPARSE_GEN_COL ? 1 : 0;
-  if (d.kind == XB_ELE_FORCEBEAMCOLUMN2D) {
-    fbc2d_form_kernel<<<(unsigned)((d.b.n + 127) / 128), 128, 0, st>>>(d.b, 1, 0, transpose);
+  if (is_beam(d.kind)) {
+    if (d.kind == XB_ELE_FORCEBEAMCOLUMN3D) fbc3d_form_kernel<<<(unsigned)((d.b.n + 63) / 64), 64, 0, st>>>(d.b, 1, 0, transpose);
+    else fbc2d_form_kernel<<<(unsigned)((d.b.n + 127) / 128), 128, 0, st>>>(d.b, 1, 0, transpose);
     m->launches++;
     return XB_OK;
   }
@@ -1712,7 +1759,7 @@ static void account_element_tangent_bytes(xb_model* m) {
   long long bytes = 0;
   for (auto& d : m->dg) {
     if (d.v.n == 0) continue;
-    if (d.kind == XB_ELE_FORCEBEAMCOLUMN2D) { bytes += d.b.n * (9 + 36) * 8; continue; }
+    if (is_beam(d.kind)) { bytes += d.b.n * (d.b.nb * d.b.nb + 4 * d.b.nb * d.b.nb) * 8; continue; }
     // compact tangent + connectivity in, element matrix out
     bytes += d.ngp * 8 * (d.mat_kind == XB_MAT_J2PLASTICITY ? 8 : 0) + d.v.n * ((long long)d.nd * d.nd * 8 + (d.nd / m->h.ndf) * 4);
   }
@@ -1820,6 +1867,9 @@ static int launch_assemble(xb_model* m, long long first, long long count, cudaSt
   if (m->h.ndf == 3) {
     CU(cudaFuncSetAttribute(assemble_A_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     assemble_A_kernel<3><<<blocks, warps * 32, sm, st>>>(m->av, m->dKe, m->dA, m->dTask, first, count);
+  } else if (m->h.ndf == 6) {
+    CU(cudaFuncSetAttribute(assemble_A_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    assemble_A_kernel<6><<<blocks, warps * 32, sm, st>>>(m->av, m->dKe, m->dA, m->dTask, first, count);
   } else if (m->h.ndf == 2) {
     CU(cudaFuncSetAttribute(assemble_A_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     assemble_A_kernel<2><<<blocks, warps * 32, sm, st>>>(m->av, m->dKe, m->dA, m->dTask, first, count);
@@ -1932,10 +1982,11 @@ int xb_form_element_resids(xb_model* m) {
   long long bytes = 0;
   for (auto& d : m->dg) {
     if (d.v.n == 0) continue;
-    if (d.kind == XB_ELE_FORCEBEAMCOLUMN2D) {
-      fbc2d_form_kernel<<<(unsigned)((d.b.n + 127) / 128), 128, 0, m->stream>>>(d.b, 0, 1, 0);
+    if (is_beam(d.kind)) {
+      if (d.kind == XB_ELE_FORCEBEAMCOLUMN3D) fbc3d_form_kernel<<<(unsigned)((d.b.n + 63) / 64), 64, 0, m->stream>>>(d.b, 0, 1, 0);
+      else fbc2d_form_kernel<<<(unsigned)((d.b.n + 127) / 128), 128, 0, m->stream>>>(d.b, 0, 1, 0);
       m->launches++;
-      bytes += d.b.n * (3 + 6) * 8;
+      bytes += d.b.n * (d.b.nb + 2 * d.b.nb) * 8;
       continue;
     }
     if (d.kind == XB_ELE_STDBRICK) continue;   // brick_update_kernel already left Re (it is a function of the state only)
@@ -1982,15 +2033,15 @@ int xb_commit(xb_model* m) {
   // J2Plasticity::commitState (J2Plasticity.cpp:538): epsilon_p_n = epsilon_p_nplus1, xi_n = xi_nplus1.
   // Every update rewrites the whole trial set, so committing is a buffer swap.
   for (auto& d : m->dg) {
-    if (d.kind == XB_ELE_FORCEBEAMCOLUMN2D) {
+    if (is_beam(d.kind)) {
       // ForceBeamColumn2d::commitState (ForceBeamColumn2d.cpp:276): vscommit = vs, sections (fibres)
       // commit, kvcommit = kv, Secommit = Se.  The trial records must survive (Concrete02 keeps
       // its last trial stress on a zero increment), so this is a copy, not a swap.
       BeamView& b = d.b;
       CU(cudaMemcpyAsync(b.fc, b.ft, sizeof(double) * d.fib_doubles, cudaMemcpyDeviceToDevice, m->stream));
-      CU(cudaMemcpyAsync(b.vsc, b.vs, sizeof(double) * b.nip * 2 * b.n, cudaMemcpyDeviceToDevice, m->stream));
-      CU(cudaMemcpyAsync(b.Sec, b.Se, sizeof(double) * 3 * b.n, cudaMemcpyDeviceToDevice, m->stream));
-      CU(cudaMemcpyAsync(b.kvc, b.kv, sizeof(double) * 9 * b.n, cudaMemcpyDeviceToDevice, m->stream));
+      CU(cudaMemcpyAsync(b.vsc, b.vs, sizeof(double) * b.nip * b.ord * b.n, cudaMemcpyDeviceToDevice, m->stream));
+      CU(cudaMemcpyAsync(b.Sec, b.Se, sizeof(double) * b.nb * b.n, cudaMemcpyDeviceToDevice, m->stream));
+      CU(cudaMemcpyAsync(b.kvc, b.kv, sizeof(double) * b.nb * b.nb * b.n, cudaMemcpyDeviceToDevice, m->stream));
     } else if (d.mat_kind == XB_MAT_J2PLASTICITY) std::swap(d.v.hc, d.v.ht);
   }
   const size_t nb = sizeof(double) * m->h.nn() * m->h.ndf;
@@ -2013,9 +2064,10 @@ int xb_revert_to_last_commit(xb_model* m) {
   CU(cudaMemcpyAsync(m->dAcc, m->dAc, nb, cudaMemcpyDeviceToDevice, m->stream));
   CU(cudaMemsetAsync(m->dDU, 0, std::max<size_t>(nb, 1), m->stream));
   for (auto& d : m->dg)
-    if (d.kind == XB_ELE_FORCEBEAMCOLUMN2D && d.b.n) {
+    if (is_beam(d.kind) && d.b.n) {
       CU(cudaMemcpyAsync(d.b.ft, d.b.fc, sizeof(double) * d.fib_doubles, cudaMemcpyDeviceToDevice, m->stream));
-      fbc2d_revert_kernel<<<(unsigned)((d.b.n + 63) / 64), 64, 0, m->stream>>>(d.b);
+      if (d.kind == XB_ELE_FORCEBEAMCOLUMN3D) fbc3d_revert_kernel<<<(unsigned)((d.b.n + 63) / 64), 64, 0, m->stream>>>(d.b);
+      else fbc2d_revert_kernel<<<(unsigned)((d.b.n + 63) / 64), 64, 0, m->stream>>>(d.b);
       m->launches++;
     }
   CU(cudaGetLastError());
@@ -2075,7 +2127,7 @@ int xb_get_gp_response(xb_model* m, long long e, int gpt, double* stress, double
   const int gi = m->h.fe_group[e];
   const xb::Group& g = m->h.groups[gi];
   const DevGroup& d = m->dg[gi];
-  if (d.kind == XB_ELE_FORCEBEAMCOLUMN2D) return fail(XB_ERR_UNSUPPORTED, "xb_get_gp_response: continuum elements only");
+  if (is_beam(d.kind)) return fail(XB_ERR_UNSUPPORTED, "xb_get_gp_response: continuum elements only");
   if (gpt < 0 || gpt >= d.nip) return fail(XB_ERR_ARG, "gauss point out of range");
   const long long gp = (long long)m->h.fe_local[e] * d.nip + gpt;
   CU(cudaStreamSynchronize(m->stream));

@@ -14,9 +14,10 @@ namespace xb {
 static const EleKind kBrick{8, 3, 8, 6, 3};
 static const EleKind kQuad{4, 2, 4, 3, 3};  // par kept: thickness, b1, b2
 static const EleKind kBeam2d{2, 3, 0, 2, 3};  // nip is a property of the batch; par: nIP, maxIters, tol
+static const EleKind kBeam3d{2, 6, 0, 4, 6};  // par: nIP, maxIters, tol, vecxz[3]
 
 const EleKind& ele_kind(int kind) {
-  return kind == XB_ELE_STDBRICK ? kBrick : (kind == XB_ELE_FOURNODEQUAD ? kQuad : kBeam2d);
+  return kind == XB_ELE_STDBRICK ? kBrick : (kind == XB_ELE_FOURNODEQUAD ? kQuad : (kind == XB_ELE_FORCEBEAMCOLUMN3D ? kBeam3d : kBeam2d));
 }
 
 int HostModel::add_nodes(int n, const int* tags, const double* c) {
@@ -83,14 +84,27 @@ int HostModel::add_fiber_section(int tag, int nf, const double* y, const double*
   return XB_OK;
 }
 
+int HostModel::add_fiber_section3d(int tag, int nf, const double* y, const double* z, const double* A, const int* mat_tags, double GJ) {
+  if (!z || !(GJ > 0.0)) { err = "xb_add_fiber_section3d: needs fibre z coordinates and GJ > 0 (section Fiber -GJ)"; return XB_ERR_ARG; }
+  int rc = add_fiber_section(tag, nf, y, A, mat_tags);
+  if (rc < 0) return rc;
+  FiberSectionDef& d = secs.back();
+  d.z.assign(z, z + nf); d.GJ = GJ; d.is3d = true;
+  double ABar = 0.0, QyBar = 0.0;
+  for (int i = 0; i < nf; i++) { ABar += A[i]; QyBar += z[i] * A[i]; d.zBar = QyBar / ABar; }   // FiberSection3d::addFiber, FiberSection3d.cpp:343-350
+  return XB_OK;
+}
+
 int HostModel::add_elements(int kind, int n, const int* tags, const int* conn, const int* mat_tags,
                             const double* par, int par_stride) {
   if (is_setup) { err = "xb_add_elements after xb_setup"; return XB_ERR_STATE; }
-  if (kind != XB_ELE_STDBRICK && kind != XB_ELE_FOURNODEQUAD && kind != XB_ELE_FORCEBEAMCOLUMN2D) { err = "xb_add_elements: unknown kind"; return XB_ERR_ARG; }
+  if (kind != XB_ELE_STDBRICK && kind != XB_ELE_FOURNODEQUAD && kind != XB_ELE_FORCEBEAMCOLUMN2D && kind != XB_ELE_FORCEBEAMCOLUMN3D) { err = "xb_add_elements: unknown kind"; return XB_ERR_ARG; }
   const EleKind& k = ele_kind(kind);
   if (k.ndf != ndf) { err = "xb_add_elements: element dofs per node differ from the model's ndf"; return XB_ERR_UNSUPPORTED; }
-  if (kind == XB_ELE_FORCEBEAMCOLUMN2D) {
-    if (ndm != 2 || par_stride < 3) { err = "forceBeamColumn (2D): ndm must be 2 and par = nIP, maxIters, tol"; return XB_ERR_ARG; }
+  if (kind == XB_ELE_FORCEBEAMCOLUMN2D || kind == XB_ELE_FORCEBEAMCOLUMN3D) {
+    const bool b3 = kind == XB_ELE_FORCEBEAMCOLUMN3D;
+    if (!b3 && (ndm != 2 || par_stride < 3)) { err = "forceBeamColumn (2D): ndm must be 2 and par = nIP, maxIters, tol"; return XB_ERR_ARG; }
+    if (b3 && (ndm != 3 || par_stride < 6)) { err = "forceBeamColumn (3D): ndm must be 3 and par = nIP, maxIters, tol, vecxz[3]"; return XB_ERR_ARG; }
     Group g;
     g.kind = kind; g.mat_kind = 0;
     g.tag.assign(tags, tags + n);
@@ -102,11 +116,12 @@ int HostModel::add_elements(int kind, int n, const int* tags, const int* conn, c
       int sidx = -1;
       for (size_t j = 0; j < secs.size(); j++) if (secs[j].tag == mat_tags[i]) sidx = (int)j;
       if (sidx < 0) { err = "forceBeamColumn: unknown section tag"; return XB_ERR_ARG; }
+      if (secs[sidx].is3d != b3) { err = "forceBeamColumn: a 3D element needs xb_add_fiber_section3d, a 2D one xb_add_fiber_section"; return XB_ERR_ARG; }
       if (i == 0) { g.sec = sidx; g.nip = (int)p[0]; g.max_iters = (int)p[1]; g.tol = p[2]; }
       else if (sidx != g.sec || (int)p[0] != g.nip || (int)p[1] != g.max_iters || p[2] != g.tol) {
         err = "forceBeamColumn: one section / nIP / maxIters / tol per xb_add_elements call"; return XB_ERR_UNSUPPORTED;
       }
-      g.par[(size_t)i * 3] = p[0]; g.par[(size_t)i * 3 + 1] = p[1]; g.par[(size_t)i * 3 + 2] = p[2];
+      for (int q = 0; q < k.npar; q++) g.par[(size_t)i * k.npar + q] = p[q];
     }
     if (g.nip < 2 || g.nip > 10) { err = "forceBeamColumn: Lobatto integration takes 2..10 points"; return XB_ERR_ARG; }
     if (n > 0) groups.push_back(std::move(g));
