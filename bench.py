@@ -80,12 +80,15 @@ def workload_spec(n, workload="brick"):
     """brick: n^3 J2 stdBrick block (BASELINE configs[2], the headline workload);
     quad: n x n plane-strain ElasticIsotropic FourNodeQuad mesh (configs[1]);
     frame: 2D RC frame of forceBeamColumn elements with Steel02/Concrete02 fibre sections, n bays x n storeys
-           (the 2D counterpart of configs[3])"""
-    from modelspec import ELASTIC, J2_STEEL, brick_block, frame2d, quad_plane
+           (the 2D counterpart of configs[3]);
+    frame3d: 3D RC space frame, forceBeamColumn (ForceBeamColumn3d) + FiberSection3d (configs[3])"""
+    from modelspec import ELASTIC, J2_STEEL, brick_block, frame2d, frame3d, quad_plane
     if workload == "quad":
         return quad_plane(n, n, mat=(ELASTIC[0], [1000.0, 0.25, 0.0]), lx=float(n), ly=float(n))
     if workload == "frame":
         return frame2d(n, n, 2)
+    if workload == "frame3d":   # n x n bays, 3.8 n storeys, 2 elements per member: n = 20 -> 194,712 elements
+        return frame3d(n, n, max(1, round(3.8 * n)), ndiv=2)
     return brick_block(n, n, n, mat=J2_STEEL)
 
 
@@ -97,6 +100,16 @@ def displacement_field_for(spec, crd, workload):
         u = np.empty_like(crd)
         u[:, 0] = 1e-3 * (y * y / (1.0 + y.max()) + 0.3 * np.sin(0.07 * x) * y)
         u[:, 1] = 1e-3 * (0.5 * x * y / (1.0 + x.max()))
+        return u
+    if workload == "frame3d":                            # biaxial sway with matching joint rotations + a floor twist
+        H = crd[:, 2].max()
+        z = crd[:, 2] / H
+        xc, yc = crd[:, 0] - crd[:, 0].mean(), crd[:, 1] - crd[:, 1].mean()
+        a = 0.002 * H
+        th = 1e-4 * z
+        u = np.zeros((len(crd), 6))
+        u[:, 0] = a * z ** 1.5 - th * yc; u[:, 1] = 0.6 * a * z ** 1.5 + th * xc; u[:, 2] = -0.01 * z
+        u[:, 3] = -0.6 * 1.5 * a * z ** 0.5 / H; u[:, 4] = 1.5 * a * z ** 0.5 / H; u[:, 5] = th
         return u
     y = crd[:, 1] / crd[:, 1].max()                      # frame: sway with matching joint rotations
     u = np.zeros((len(crd), 3))
@@ -176,7 +189,10 @@ def workload_name(n, workload="brick"):
     if workload == "quad":
         return f"2D FourNodeQuad plane-strain ElasticIsotropic mesh {n}x{n} = {n * n} elements (BASELINE configs[1])"
     if workload == "frame":
-        return f"2D RC frame {n} bays x {n} storeys, forceBeamColumn + fibre sections Steel02/Concrete02 (2D counterpart of BASELINE configs[3])"
+        return f"2D RC frame {n} bays x {n} storeys, forceBeamColumn + fibre sections Steel02/Concrete02, Newmark terms (2D counterpart of BASELINE configs[3])"
+    if workload == "frame3d":
+        return (f"3D RC space frame {n}x{n} bays x {max(1, round(3.8 * n))} storeys, forceBeamColumn (ForceBeamColumn3d) + FiberSection3d "
+                "Steel02/Concrete02, transient Newmark terms (BASELINE configs[3])")
     return f"3D stdBrick J2Plasticity block {n}x{n}x{n} = {n ** 3} elements (BASELINE configs[2])"
 
 
@@ -213,7 +229,16 @@ def ours_main(a):
     spec = workload_spec(n, a.workload)
     t_mesh = time.time() - t0
     t0 = time.time()
-    D = xb.DeviceModel.from_spec(spec, xb.NUMBERER_PLAIN, xb.SOE_SPARSE_GEN_COL, world, rank)
+    is_frame = a.workload in ("frame", "frame3d")
+    if is_frame:
+        # configs[3] is a transient Newmark run: nodal masses (translations), average acceleration, dt = 0.02:
+        # formTangent gives c1 K + c3 M, formUnbalance P - M a - R
+        D = xb.DeviceModel.from_spec(spec, setup=False)
+        mass = np.zeros((spec.nn, spec.ndf)); mass[:, :spec.ndm] = 0.05
+        D.set_mass(spec.node_tags, mass)
+        D.setup(xb.NUMBERER_PLAIN, xb.SOE_SPARSE_GEN_COL, world, rank)
+    else:
+        D = xb.DeviceModel.from_spec(spec, xb.NUMBERER_PLAIN, xb.SOE_SPARSE_GEN_COL, world, rank)
     t_setup = time.time() - t0
     stream = torch.cuda.Stream()          # a real (non-default) stream: the kernels and the events share it
     torch.cuda.set_stream(stream)
@@ -226,10 +251,15 @@ def ours_main(a):
     t_upload = time.time() - t0
     ids = D.ids()
     u = displacement_field_for(spec, spec.crd[D.node_tags() - 1], a.workload); u[ids < 0] = 0.0
-    nip = {"brick": 8, "quad": 4, "frame": 5}[a.workload]
+    nip = {"brick": 8, "quad": 4, "frame": 5, "frame3d": 4}[a.workload]
     ngp_global, ne_global = spec.ne * nip, spec.ne
     del spec
+    if is_frame:
+        gamma, beta, dt = 0.5, 0.25, 0.02
+        D.set_transient(1.0, gamma / (beta * dt), 1.0 / (beta * dt * dt))
     D.set_trial_disp(u); D.apply_load(1.0); D.synchronize()
+    u_alt = (u, 1.01 * u)
+    flip = [0]
 
     def barrier():
         if world > 1:
@@ -237,6 +267,9 @@ def ours_main(a):
         torch.cuda.synchronize()
 
     def step():
+        if is_frame:   # a force-based beam returns at once on a zero increment: alternate two trial fields
+            flip[0] ^= 1
+            D.set_trial_disp(u_alt[flip[0]])
         D.update(); D.form_unbalance(host=False); D.form_tangent(host=False)
 
     for _ in range(max(a.warmup, 3)):
@@ -265,6 +298,9 @@ def ours_main(a):
     barrier()
     for k in range(a.steps):
         e = ev[k]
+        if is_frame:
+            flip[0] ^= 1
+            D.set_trial_disp(u_alt[flip[0]])
         e[0].record(stream); D.update()
         e[1].record(stream); D.form_element_resids()
         e[2].record(stream); D.exchange(1)
@@ -373,7 +409,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=160, help="elements per side of the block (160 -> 4.096M)")
-    ap.add_argument("--workload", default="brick", choices=["brick", "quad", "frame"],
+    ap.add_argument("--workload", default="brick", choices=["brick", "quad", "frame", "frame3d"],
                     help="brick = the headline workload; quad / frame = secondary lines (profiles/), n = cells per side")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=22, help="CPU arm sample: elements per side")

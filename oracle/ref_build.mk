@@ -45,8 +45,16 @@ $(OBJ)/%.o: $(SRC)/%.c
 	@mkdir -p $(dir $@)
 	@$(CC) -O3 -march=haswell -ffloat-store -fPIC -w -I$(SRC)/matrix/routines -c $< -o $@ 2> $@.err || (echo "" | $(CC) -x c -c - -o $@)
 
+# ---- the reference's vendored METIS 4 (OTHER/METIS, plain C): graph/partitioner/Metis.cpp calls
+# METIS_PartGraphKway on the element graph; the partition tests feed its result to xb_setup_partitioned ----
+metis: $(OUT)/libmetis_ref.so
+$(OUT)/libmetis_ref.so: $(wildcard $(REF)/OTHER/METIS/*.c)
+	@mkdir -p $(OUT)
+	@echo "build $@"
+	@$(CC) -O2 -fPIC -shared -std=gnu89 -w -fcommon -I$(REF)/OTHER/METIS $^ -o $@ -lm
+
 # ---- the harness shared library the tests and the reference bench arm load ----
-harness: $(OUT)/libref_harness.so
+harness: $(OUT)/libref_harness.so $(OUT)/libmetis_ref.so
 $(OUT)/libref_harness.so: ref_harness.cpp ref_shims.cpp $(OUT)/libxara_ref.a
 	@echo "link $@"
 	@$(CXX) -std=c++17 -O2 -fPIC -w -D_LINUX -D_UNIX $(INCS) -shared ref_harness.cpp ref_shims.cpp \

@@ -21,6 +21,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libref_harness.so")
+METIS_SO = os.path.join(ROOT, "oracle", "_ref", "libmetis_ref.so")
 
 MAT_ELASTIC, MAT_J2 = 0, 1
 ELE_BRICK, ELE_QUAD, ELE_FBC2D, ELE_FBC3D = 0, 1, 2, 3
@@ -260,6 +261,63 @@ def frame3d(nx=1, ny=1, nstory=2, ndiv=1, nip=4, bay=240.0, story=144.0, max_ite
                      [ElementGroup(ELE_FBC3D, np.arange(1, ne + 1, dtype=np.int32), conn, np.ones(ne, np.int32), par)],
                      np.array(loads), uniaxials=[(1, *CONCRETE02_CORE), (2, *CONCRETE02_COVER), (3, *STEEL02)],
                      sections=[rc_section3d(1)])
+
+
+def soil_structure_block(nx=6, ny=6, nz=6, distort=0.0, seed=0):
+    """BASELINE configs[4] in small: a J2 soil block (material 1) with an ElasticIsotropic footing + pier
+    (material 2, stiff) embedded at the top centre -- two element batches whose FE_Element (tag) order
+    interleaves; loads on the pier top.  ndm 3, ndf 3, stdBrick throughout."""
+    spec = brick_block(nx, ny, nz, mat=J2_STEEL, distort=distort, seed=seed)
+    g = spec.groups[0]
+    e = np.arange(len(g.tags))
+    ex, ey, ez = e % nx, (e // nx) % ny, e // (nx * ny)
+    cx, cy = (nx - 1) / 2.0, (ny - 1) / 2.0
+    footing = (ez >= nz - 2) & (np.abs(ex - cx) <= nx / 4.0) & (np.abs(ey - cy) <= ny / 4.0)
+    pier = (ez >= nz - 3) & (np.abs(ex - cx) <= 0.5) & (np.abs(ey - cy) <= 0.5)
+    struct = footing | pier
+    mats = [(1, *J2_STEEL), (2, MAT_ELASTIC, [3.0e6, 0.2, 0.0])]
+    groups = [ElementGroup(ELE_BRICK, g.tags[~struct], g.conn[~struct], np.full((~struct).sum(), 1, np.int32), g.par[~struct]),
+              ElementGroup(ELE_BRICK, g.tags[struct], g.conn[struct], np.full(struct.sum(), 2, np.int32), g.par[struct])]
+    return ModelSpec(3, 3, spec.node_tags, spec.crd, spec.fix, mats, groups, spec.loads)
+
+
+def have_metis():
+    return os.path.exists(METIS_SO)
+
+
+def element_graph(spec):
+    """Domain::buildEleGraph (domain/domain/Domain.cpp:2410): one vertex per element in ascending tag order,
+    an edge between elements that share a node, adjacency sorted (Vertex::addEdge -> ID::insert)"""
+    tags = np.concatenate([g.tags for g in spec.groups])
+    order = np.argsort(tags, kind="stable")
+    conns = [c for g in spec.groups for c in g.conn]
+    node2e = {}
+    for v, k in enumerate(order):
+        for n in conns[k]:
+            node2e.setdefault(int(n), []).append(v)
+    adj = [set() for _ in order]
+    for es in node2e.values():
+        for a in es:
+            adj[a].update(es)
+    xadj, adjncy = [0], []
+    for v, s_ in enumerate(adj):
+        s_.discard(v)
+        adjncy.extend(sorted(s_)); xadj.append(len(adjncy))
+    return np.array(xadj, np.int32), np.array(adjncy, np.int32)
+
+
+def metis_partition(spec, nparts):
+    """what graph/partitioner/Metis.cpp:320 does for DomainPartitioner: METIS_PartGraphKway (METIS 4 from the
+    reference's OTHER/METIS, default options, no weights) on the element graph; part[e] in FE_Element order"""
+    L = ctypes.CDLL(METIS_SO)
+    xadj, adjncy = element_graph(spec)
+    n = ctypes.c_int(len(xadj) - 1); wf = ctypes.c_int(0); nf = ctypes.c_int(0); npart = ctypes.c_int(nparts)
+    options = (ctypes.c_int * 5)(0, 0, 0, 0, 0); edgecut = ctypes.c_int(0)
+    part = np.zeros(len(xadj) - 1, np.int32)
+    if nparts > 1:
+        L.METIS_PartGraphKway(ctypes.byref(n), _p(xadj), _p(adjncy), None, None, ctypes.byref(wf), ctypes.byref(nf),
+                              ctypes.byref(npart), options, ctypes.byref(edgecut), _p(part))
+    return part
 
 
 def cantilever2d(ndiv=1, nip=5, L=432.0, H=1.0, V=-100.0, max_iters=10, tol=1e-12):

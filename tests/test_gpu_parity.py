@@ -14,7 +14,8 @@ import pytest
 
 import xara_b200 as xb
 from golden_cases import CASES, NSTEPS, ele_nd
-from modelspec import ELASTIC, J2_STEEL, OracleBackend, brick_block, frame2d, frame3d, quad_plane
+from modelspec import (ELASTIC, J2_STEEL, OracleBackend, brick_block, frame2d, frame3d, have_metis, metis_partition,
+                       quad_plane, soil_structure_block)
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -282,6 +283,40 @@ def test_partitioned_quad_and_scattered_partition():
         rows = m.row_eqns(); ptr, _ = m.pattern()
         assert np.array_equal(B, Bg[rows])
         assert np.array_equal(A, np.concatenate([Ag[gptr[q]:gptr[q + 1]] for q in rows]))
+
+
+@pytest.mark.skipif(not have_metis(), reason="oracle/_ref/libmetis_ref.so not built (needs /root/reference)")
+@pytest.mark.parametrize("nparts", [4, 8])
+def test_soil_structure_metis_partition_reproduces_single_gpu(nparts):
+    """BASELINE configs[4] in small: a mixed mesh (J2 soil + elastic footing/pier: two element batches whose
+    FE order interleaves) split by METIS_PartGraphKway exactly as the reference's DomainPartitioner would
+    (reference's own METIS 4 on Domain::buildEleGraph's element graph).  The single-GPU result matches the
+    oracle; every rank's owned rows match the single-GPU rows bit for bit."""
+    rng = np.random.default_rng(8)
+    mk = lambda: soil_structure_block(8, 8, 6, distort=0.15, seed=4)
+    spec = mk()
+    part = metis_partition(spec, nparts)
+    assert np.bincount(part, minlength=nparts).min() > 0
+    G = xb.DeviceModel.from_spec(spec, 1, 0).to_device(0)
+    O = OracleBackend(spec, 1, 0)
+    gptr, _ = G.pattern()
+    ranks = [xb.DeviceModel.from_spec(mk(), 1, 0, nparts, r, part).to_device(0) for r in range(nparts)]
+    assert np.array_equal(ranks[0].partition(G.ne), part)
+    ids = G.ids()
+    for s in range(2):
+        u = rng.normal(0, 2e-3 * (s + 1), (spec.nn, 3)); u[ids < 0] = 0
+        lam = 0.5 * (s + 1)
+        G.set_trial_disp(u); G.update(); G.apply_load(lam)
+        Ag, Bg = G.form_tangent(), G.form_unbalance()
+        O.set_trial_disp(u); O.apply_load(lam)
+        assert relerr(Ag, O.form_tangent()) < RTOL and relerr(Bg, O.form_unbalance()) < RTOL
+        for m, (A, B) in zip(ranks, _partitioned_pass(ranks, u, lam)):
+            rows = m.row_eqns()
+            assert np.array_equal(B, Bg[rows])
+            assert np.array_equal(A, np.concatenate([Ag[gptr[q]:gptr[q + 1]] for q in rows]))
+        G.commit(); O.commit()
+        for m in ranks:
+            m.commit()
 
 
 NCCL_WORKER = r'''

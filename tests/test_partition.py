@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 import xara_b200 as xb
-from modelspec import ELASTIC, J2_STEEL, brick_block, quad_plane
+from modelspec import ELASTIC, J2_STEEL, brick_block, element_graph, have_metis, metis_partition, quad_plane, soil_structure_block
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -59,6 +59,25 @@ def test_quad_partition_and_user_partition():
     spec = brick_block(4, 4, 4)
     part = (np.arange(spec.ne) * 7 % 3).astype(np.int32)          # a deliberately scattered partition
     check_partition(lambda: brick_block(4, 4, 4), 3, 0, 1, part)
+
+
+@pytest.mark.skipif(not have_metis(), reason="oracle/_ref/libmetis_ref.so not built (needs /root/reference)")
+@pytest.mark.parametrize("nparts", [2, 5, 8])
+def test_metis_partition_of_mixed_mesh(nparts):
+    """a caller-supplied partition from the reference's own METIS (graph/partitioner/Metis.cpp:320 on
+    Domain::buildEleGraph's graph) over a two-batch soil + structure mesh"""
+    spec = soil_structure_block(7, 6, 6)
+    xadj, adjncy = element_graph(spec)
+    assert len(xadj) == spec.ne + 1 and xadj[1] - xadj[0] == 7          # a corner brick touches 7 others
+    part = metis_partition(spec, nparts)
+    counts = np.bincount(part, minlength=nparts)
+    assert counts.min() > 0 and counts.max() <= 1.2 * spec.ne / nparts + 1
+    ranks = check_partition(lambda: soil_structure_block(7, 6, 6), nparts, 1, 0, part)
+    # METIS keeps the parts compact: fewer interface rows than a round-robin split of the same mesh
+    rr = (np.arange(spec.ne) % nparts).astype(np.int32)
+    scattered = [xb.DeviceModel.from_spec(soil_structure_block(7, 6, 6), 1, 0, nparts, r, rr) for r in range(nparts)]
+    cut = lambda ms: sum(int(c[4]) for m in ms for _, c in m.peers())
+    assert cut(ranks) < 0.6 * cut(scattered)
 
 
 def test_rcb_is_balanced_and_compact():
