@@ -23,7 +23,10 @@ namespace xbk {
 
 constexpr int XB_FIB_NV = 11;   // doubles per fibre record
 constexpr int XB_MAXSEC = 10;
-constexpr int XB_FBC3D_MAX_PASSES = 20000;   // see fbc3d_update_kernel
+constexpr int XB_FBC3D_MAX_PASSES = 20000;
+#ifndef XB_FBC_SEC_OCC
+#define XB_FBC_SEC_OCC 6
+#endif   // see fbc3d_update_kernel
 // Steel02 record:   0 epsmin 1 epsmax 2 epspl 3 epss0 4 sigs0 5 epsr 6 sigr 7 kon 8 e 9 sig 10 eps
 // Concrete02 record: 0 ecmin 1 dept 8 e 9 sig 10 eps
 
@@ -83,18 +86,40 @@ __device__ __forceinline__ void lobatto_rule(int n, double* xi, double* wt) {
 }
 
 // Steel02::setTrialStrain.  C = committed record, T = trial record (both strided by n)
+// committed record of one fibre in registers (what the trial computation reads): c[0..10] as laid out above;
+// t8, t9 = the previous TRIAL tangent / stress (Concrete02 only)
+struct FibRec { double c[11]; double t8, t9; };
+__device__ __forceinline__ void fib_load(int kind, const double* C, const double* T, long long n, FibRec& r) {
+  if (kind == 0) {
+#pragma unroll
+    for (int v = 0; v < 8; v++) r.c[v] = C[(size_t)v * n];
+    r.c[9] = C[9 * n]; r.c[10] = C[10 * n];
+  } else {
+    r.c[0] = C[0]; r.c[1] = C[1 * n]; r.c[9] = C[9 * n]; r.c[10] = C[10 * n];
+    r.t8 = T[8 * n]; r.t9 = T[9 * n];
+  }
+}
+__device__ __forceinline__ void steel02_trial_r(const double* __restrict__ p, const FibRec& r, double* T, long long n,
+                                                double trialStrain, double& sig_o, double& e_o);
+__device__ __forceinline__ void concrete02_trial_r(const double* __restrict__ p, const FibRec& r, double* T, long long n,
+                                                   double trialStrain, double& sig_o, double& e_o);
 __device__ __forceinline__ void steel02_trial(const double* __restrict__ p, const double* C, double* T, long long n,
                                               double trialStrain, double& sig_o, double& e_o) {
+  FibRec r; fib_load(0, C, T, n, r);
+  steel02_trial_r(p, r, T, n, trialStrain, sig_o, e_o);
+}
+__device__ __forceinline__ void steel02_trial_r(const double* __restrict__ p, const FibRec& r, double* T, long long n,
+                                                double trialStrain, double& sig_o, double& e_o) {
   const double Fy = p[0], E0 = p[1], b = p[2], R0 = p[3], cR1 = p[4], cR2 = p[5], a1 = p[6], a2 = p[7], a3 = p[8],
                a4 = p[9], sigini = p[10];
   const double Esh = b * E0, epsy = Fy / E0;
   double eps = trialStrain;
   if (sigini != 0.0) eps = trialStrain + sigini / E0;
-  const double epsP = C[10 * n], sigP = C[9 * n];
+  const double epsP = r.c[10], sigP = r.c[9];
   const double deps = eps - epsP;
-  double epsmin = C[0], epsmax = C[1 * n], epspl = C[2 * n], epss0 = C[3 * n], sigs0 = C[4 * n], epsr = C[5 * n],
-         sigr = C[6 * n];
-  int kon = (int)C[7 * n];
+  double epsmin = r.c[0], epsmax = r.c[1], epspl = r.c[2], epss0 = r.c[3], sigs0 = r.c[4], epsr = r.c[5],
+         sigr = r.c[6];
+  int kon = (int)r.c[7];
   double sig, e;
   bool done = false;
   if (kon == 0 || kon == 3) {
@@ -159,14 +184,19 @@ __device__ __forceinline__ void c02_compr(const double* p, double epsc, double& 
 // Concrete02::setTrialStrain.  p = fc, epsc0, fcu, epscu (already made negative on the host), rat, ft, Ets
 __device__ __forceinline__ void concrete02_trial(const double* __restrict__ p, const double* C, double* T, long long n,
                                                  double trialStrain, double& sig_o, double& e_o) {
+  FibRec r; fib_load(1, C, T, n, r);
+  concrete02_trial_r(p, r, T, n, trialStrain, sig_o, e_o);
+}
+__device__ __forceinline__ void concrete02_trial_r(const double* __restrict__ p, const FibRec& r, double* T, long long n,
+                                                   double trialStrain, double& sig_o, double& e_o) {
   const double fc = p[0], epsc0 = p[1], fcu = p[2], epscu = p[3], rat = p[4];
   const double ec0 = fc * 2. / epsc0;
-  double ecmin = C[0], dept = C[1 * n];
-  const double epsP = C[10 * n], sigP = C[9 * n];
+  double ecmin = r.c[0], dept = r.c[1];
+  const double epsP = r.c[10], sigP = r.c[9];
   const double eps = trialStrain;
   const double deps = eps - epsP;
   // the early return keeps the previous TRIAL stress / tangent (Concrete02.cpp:183)
-  double sig = T[9 * n], e = T[8 * n];
+  double sig = r.t9, e = r.t8;
   if (!(fabs(deps) < DBL_EPSILON)) {
     if (eps < ecmin) {
       c02_compr(p, eps, sig, e);
@@ -430,7 +460,9 @@ __global__ void __launch_bounds__(64) fbc2d_revert_kernel(BeamView B) {
 //   Gauss-Jordan elimination with partial pivoting; agreement is to rounding x condition number.
 // =====================================================================================
 
-// FiberSection3d::setTrialSectionDeformation for section i of element e -> s[4], k[16] (column-major)
+// FiberSection3d::setTrialSectionDeformation for section i of element e -> s[4], k[16] (column-major).
+// (Requesting fibre f+1's record ahead of fibre f's update was tried: the extra live registers cost more
+// than the hidden latency gains, 3.5 vs 3.0 ms on the 195k-element frame.)
 __device__ __forceinline__ void section3_trial(const BeamView& B, long long e, int i, const double* d, double* s, double* k) {
   for (int q = 0; q < 16; q++) k[q] = 0.0;
   s[0] = s[1] = s[2] = 0.0;
@@ -612,6 +644,461 @@ __global__ void __launch_bounds__(64) fbc3d_update_kernel(BeamView B, const doub
   }
   if (!converged) { atomicExch(fail, 2); return; }
   B.iflag[e] = 1;
+}
+
+// ---- the same update with one LANE PER SECTION (G lanes per element, G = 4 | 8 | 16 >= nIP) ----
+// The thread-per-element form above keeps every section's state in per-thread arrays (4 KB of local
+// memory, 255 registers, one resident warp per scheduler) and walks nIP x nf fibres serially.  Here
+// lane i of an element's group owns section i: its deformation, flexibility and resisting force are
+// scalars in registers, the fibre loops of the sections run side by side, and the element-level
+// algebra (flexibility sum, 6x6 inverse, energy test) is done redundantly by the G lanes on values
+// summed over the group IN SECTION ORDER (shuffle from lane 0, 1, ..: the reference's f += .., vr += ..),
+// so the arithmetic -- and every convergence decision -- is that of the thread-per-element form.
+__constant__ double LOBATTO_X[11][10] = {{0},{0},{-1.0,1.0},{-1.0,0.0,1.0},{-1.0,-0.44721360,0.44721360,1.0},
+    {-1.0,-0.65465367,0.0,0.65465367,1.0},{-1.0,-0.7650553239,-0.2852315164,0.2852315164,0.7650553239,1.0},
+    {-1.0,-0.8302238962,-0.4688487934,0.0,0.4688487934,0.8302238962,1.0},
+    {-1.0,-0.8717401485,-0.5917001814,-0.2092992179,0.2092992179,0.5917001814,0.8717401485,1.0},
+    {-1.0,-0.8997579954,-0.6771862795,-0.3631174638,0.0,0.3631174638,0.6771862795,0.8997579954,1.0},
+    {-1.0,-0.9195339082,-0.7387738651,-0.4779249498,-0.1652789577,0.1652789577,0.4779249498,0.7387738651,0.9195339082,1.0}};
+__constant__ double LOBATTO_W[11][10] = {{0},{0},{1.0,1.0},{0.333333333333333,1.333333333333333,0.333333333333333},
+    {0.166666666666667,0.833333333333333,0.833333333333333,0.166666666666667},
+    {0.1,0.5444444444,0.7111111111,0.5444444444,0.1},
+    {0.06666666667,0.3784749562,0.5548583770,0.5548583770,0.3784749562,0.06666666667},
+    {0.04761904762,0.2768260473,0.4317453812,0.4876190476,0.4317453812,0.2768260473,0.04761904762},
+    {0.03571428571,0.2107042271,0.3411226924,0.4124587946,0.4124587946,0.3411226924,0.2107042271,0.03571428571},
+    {0.02777777778,0.1654953615,0.2745387125,0.3464285109,0.3715192743,0.3464285109,0.2745387125,0.1654953615,0.02777777778},
+    {0.02222222222,0.1333059908,0.2248893421,0.2920426836,0.3275397611,0.3275397611,0.2920426836,0.2248893421,0.1333059908,0.02222222222}};
+__device__ __forceinline__ double lobatto_x(int n, int i) { return 0.5 * (LOBATTO_X[n][i] + 1.0); }
+__device__ __forceinline__ double lobatto_w(int n, int i) { return LOBATTO_W[n][i] * 0.5; }
+// sum over the sections of an element in section order: lanes gbase .. gbase + nip - 1 of the warp
+__device__ __forceinline__ double group_sum_ordered(double x, unsigned gmask, int gbase, int nip) {
+  double s = __shfl_sync(gmask, x, gbase);
+  for (int k = 1; k < nip; k++) s += __shfl_sync(gmask, x, gbase + k);
+  return s;
+}
+// inv6_flex without dynamically indexed rows (everything stays in registers): f5 is the 5x5 block
+// (column-major, stride 5), f55 the torsion entry; same pivot choice and operation order as inv6_flex
+template <int C>
+__device__ __forceinline__ void gj5_step(double (&a)[5][10], bool& ok) {
+  // column C of the Gauss-Jordan elimination with partial pivoting; all indices are compile-time
+  int p = C; double big = fabs(a[C][C]);
+#pragma unroll
+  for (int r = C + 1; r < 5; r++) if (fabs(a[r][C]) > big) { big = fabs(a[r][C]); p = r; }
+  if (big == 0.0) ok = false;
+#pragma unroll
+  for (int r = C + 1; r < 5; r++) {
+    const bool sw = (p == r);
+#pragma unroll
+    for (int q = 0; q < 10; q++) { const double x = a[C][q], y = a[r][q]; a[C][q] = sw ? y : x; a[r][q] = sw ? x : y; }
+  }
+  const double piv = 1.0 / a[C][C];
+#pragma unroll
+  for (int q = 0; q < 10; q++) a[C][q] *= piv;
+#pragma unroll
+  for (int r = 0; r < 5; r++)
+    if (r != C) {
+      const double mlt = a[r][C];
+      if (mlt != 0.0) {
+#pragma unroll
+        for (int q = 0; q < 10; q++) a[r][q] -= mlt * a[C][q];
+      }
+    }
+}
+__device__ __forceinline__ bool inv5p1_flex(const double* f5, double f55, double* k5, double& k55) {
+  double a[5][10];
+#pragma unroll
+  for (int r = 0; r < 5; r++)
+#pragma unroll
+    for (int c = 0; c < 5; c++) { a[r][c] = f5[r + 5 * c]; a[r][5 + c] = (r == c) ? 1.0 : 0.0; }
+  bool ok = true;
+  gj5_step<0>(a, ok); gj5_step<1>(a, ok); gj5_step<2>(a, ok); gj5_step<3>(a, ok); gj5_step<4>(a, ok);
+#pragma unroll
+  for (int r = 0; r < 5; r++)
+#pragma unroll
+    for (int c = 0; c < 5; c++) k5[r + 5 * c] = a[r][5 + c];
+  k55 = 1.0 / f55;
+  return ok;
+}
+
+template <int G>
+__global__ void __launch_bounds__(128, XB_FBC_SEC_OCC) fbc3d_update_sec_kernel(BeamView B, const double* __restrict__ U,
+                                                               const double* __restrict__ DU, int* fail) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long e = tid / G;
+  const int i = (int)(tid - e * G);          // this lane's section
+  if (e >= B.n) return;                      // a whole group leaves together
+  const int lane = threadIdx.x & 31;
+  const int gbase = lane & ~(G - 1);
+  const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << gbase;
+  const long long n = B.n;
+  const int nip = B.nip;
+  const bool act = i < nip;
+  const int is = act ? i : 0;                // idle lanes shadow section 0's addresses, never store
+  double R[9];
+  const double L = B.geo[e];
+#pragma unroll
+  for (int q = 0; q < 9; q++) R[q] = B.geo[(size_t)(1 + q) * n + e];
+  double v[6], dv[6], vin[6];
+  {
+    double ug[12], dug[12];
+#pragma unroll
+    for (int a = 0; a < 2; a++) {
+      const int nd = B.conn[e * 2 + a];
+#pragma unroll
+      for (int j = 0; j < 6; j++) { ug[a * 6 + j] = U[(size_t)nd * 6 + j]; dug[a * 6 + j] = DU[(size_t)nd * 6 + j]; }
+    }
+    crd3d_basic(L, R, ug, v);
+    crd3d_basic(L, R, dug, dv);
+  }
+  const int initialFlag = B.iflag[e];
+  if (initialFlag != 0 && norm6(dv) <= DBL_EPSILON) return;
+#pragma unroll
+  for (int q = 0; q < 6; q++) vin[q] = v[q] - dv[q];
+  const double xL = lobatto_x(nip, is), xL1 = xL - 1.0, wtL = lobatto_w(nip, is) * L;
+  // initial section flexibility: 3x3 block (column-major, stride 3) + torsion
+  double f0[9], f0t;
+#pragma unroll
+  for (int c = 0; c < 3; c++)
+#pragma unroll
+    for (int r = 0; r < 3; r++) f0[r + 3 * c] = __ldg(B.fs0 + r + 4 * c);
+  f0t = __ldg(B.fs0 + 15);
+  double dvTrial[6], dvToDo[6];
+#pragma unroll
+  for (int q = 0; q < 6; q++) { dvToDo[q] = dv[q]; dvTrial[q] = dvToDo[q]; }
+  int numSubdivide = 1;
+  bool converged = false;
+  const double factor = 10.0;
+  const int maxSubdivisions = 10;
+  int passes = 0;
+  while (!converged && numSubdivide <= maxSubdivisions) {
+    for (int l = 0; l < 3; l++) {
+      double SeTrial[6], k5[25], k55;
+#pragma unroll
+      for (int q = 0; q < 6; q++) SeTrial[q] = B.Se[(size_t)q * n + e];
+#pragma unroll
+      for (int c = 0; c < 5; c++)
+#pragma unroll
+        for (int r = 0; r < 5; r++) k5[r + 5 * c] = B.kv[(size_t)(r + 6 * c) * n + e];
+      k55 = B.kv[(size_t)35 * n + e];
+      double vsS[4], SsrS[4], fsS[9], fsT;
+#pragma unroll
+      for (int q = 0; q < 4; q++) { vsS[q] = B.vs[(size_t)(is * 4 + q) * n + e]; SsrS[q] = B.Ssr[(size_t)(is * 4 + q) * n + e]; }
+#pragma unroll
+      for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) fsS[r + 3 * c] = B.fs[(size_t)(is * 16 + r + 4 * c) * n + e];
+      fsT = B.fs[(size_t)(is * 16 + 15) * n + e];
+      {
+        // SeTrial += kv * dvTrial: column by column, as Vector::addMatrixVector does; the torsion row and
+        // column of kv hold exact zeros off the diagonal
+        double dSe[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < 5; c++)
+#pragma unroll
+          for (int r = 0; r < 5; r++) dSe[r] += k5[r + 5 * c] * dvTrial[c];
+        dSe[5] += k55 * dvTrial[5];
+#pragma unroll
+        for (int q = 0; q < 6; q++) SeTrial[q] += dSe[q];
+      }
+      int numIters = B.maxIters;
+      if (l == 1) numIters = 10 * B.maxIters;
+      for (int j = 0; j < numIters; j++) {
+        if (++passes > XB_FBC3D_MAX_PASSES) { if (i == 0) atomicExch(fail, 2); return; }
+        double fl5[25], fl55 = 0.0, vrl[6];
+#pragma unroll
+        for (int q = 0; q < 25; q++) fl5[q] = 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; q++) vrl[q] = 0.0;
+        if (act) {
+          double Ss[4], dSs[4], dvs[4], ssec[4], ksec[16];
+          Ss[0] = SeTrial[0];
+          Ss[1] = xL1 * SeTrial[1] + xL * SeTrial[2];
+          Ss[2] = xL1 * SeTrial[3] + xL * SeTrial[4];
+          Ss[3] = SeTrial[5];
+#pragma unroll
+          for (int q = 0; q < 4; q++) dSs[q] = Ss[q] - SsrS[q];
+          const bool initial = (l == 1) || (l == 2 && j == 0);
+          // dvs = fs * dSs (Vector::addMatrixVector, column by column; the zero couplings of the torsion
+          // row / column add exact zeros in the reference)
+#pragma unroll
+          for (int q = 0; q < 4; q++) dvs[q] = 0.0;
+#pragma unroll
+          for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int r = 0; r < 3; r++) dvs[r] += (initial ? f0[r + 3 * c] : fsS[r + 3 * c]) * dSs[c];
+          dvs[3] += (initial ? f0t : fsT) * dSs[3];
+          if (initialFlag != 0) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) vsS[q] += dvs[q];
+          }
+          section3_trial(B, e, i, vsS, ssec, ksec);
+#pragma unroll
+          for (int q = 0; q < 4; q++) SsrS[q] = ssec[q];
+          {
+            double a3[9];
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+              for (int r = 0; r < 3; r++) a3[r + 3 * c] = ksec[r + 4 * c];
+            inv3(a3, fsS);
+            fsT = 1.0 / ksec[15];
+          }
+#pragma unroll
+          for (int q = 0; q < 4; q++) dSs[q] = Ss[q] - SsrS[q];
+#pragma unroll
+          for (int q = 0; q < 4; q++) dvs[q] = 0.0;
+#pragma unroll
+          for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int r = 0; r < 3; r++) dvs[r] += fsS[r + 3 * c] * dSs[c];
+          dvs[3] += fsT * dSs[3];
+          // fb = fs * b * wtL (4 x 6, only the P-Mz-My rows x the 5 flexural / axial columns are non-zero,
+          // plus the torsion entry); this section's addend to f = b^T fb
+          double fb[3][5];
+#pragma unroll
+          for (int r = 0; r < 3; r++) {
+            fb[r][0] = fsS[r + 3 * 0] * wtL;
+            { const double tmp = fsS[r + 3 * 1] * wtL; fb[r][1] = xL1 * tmp; fb[r][2] = xL * tmp; }
+            { const double tmp = fsS[r + 3 * 2] * wtL; fb[r][3] = xL1 * tmp; fb[r][4] = xL * tmp; }
+          }
+#pragma unroll
+          for (int c = 0; c < 5; c++) {
+            fl5[0 + 5 * c] = fb[0][c];
+            { const double tmp = fb[1][c]; fl5[1 + 5 * c] = xL1 * tmp; fl5[2 + 5 * c] = xL * tmp; }
+            { const double tmp = fb[2][c]; fl5[3 + 5 * c] = xL1 * tmp; fl5[4 + 5 * c] = xL * tmp; }
+          }
+          fl55 = fsT * wtL;
+#pragma unroll
+          for (int q = 0; q < 4; q++) dvs[q] += vsS[q];
+          { const double dei = dvs[0] * wtL; vrl[0] = dei; }
+          { const double dei = dvs[1] * wtL; vrl[1] = xL1 * dei; vrl[2] = xL * dei; }
+          { const double dei = dvs[2] * wtL; vrl[3] = xL1 * dei; vrl[4] = xL * dei; }
+          { const double dei = dvs[3] * wtL; vrl[5] = dei; }
+        }
+        double f5[25], f55, vr[6];
+#pragma unroll
+        for (int q = 0; q < 25; q++) f5[q] = group_sum_ordered(fl5[q], gmask, gbase, nip);
+        f55 = group_sum_ordered(fl55, gmask, gbase, nip);
+#pragma unroll
+        for (int q = 0; q < 6; q++) vr[q] = group_sum_ordered(vrl[q], gmask, gbase, nip);
+        if (!inv5p1_flex(f5, f55, k5, k55)) { if (i == 0) atomicExch(fail, 2); return; }
+#pragma unroll
+        for (int q = 0; q < 6; q++) { dv[q] = vin[q]; dv[q] += dvTrial[q]; dv[q] -= vr[q]; }
+        double dSe[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < 5; c++)
+#pragma unroll
+          for (int r = 0; r < 5; r++) dSe[r] += k5[r + 5 * c] * dv[c];
+        dSe[5] += k55 * dv[5];
+        double dW = 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; q++) dW += dv[q] * dSe[q];
+#pragma unroll
+        for (int q = 0; q < 6; q++) SeTrial[q] += dSe[q];
+        if (fabs(dW) < B.tol) {
+#pragma unroll
+          for (int q = 0; q < 6; q++) { dvToDo[q] -= dvTrial[q]; vin[q] += dvTrial[q]; }
+          if (norm6(dvToDo) <= DBL_EPSILON) converged = true;
+          else {
+#pragma unroll
+            for (int q = 0; q < 6; q++) dvTrial[q] = dvToDo[q];
+            numSubdivide = 1;
+          }
+          if (i == 0) {
+#pragma unroll
+            for (int q = 0; q < 6; q++) B.Se[(size_t)q * n + e] = SeTrial[q];
+#pragma unroll
+            for (int c = 0; c < 5; c++)
+#pragma unroll
+              for (int r = 0; r < 5; r++) B.kv[(size_t)(r + 6 * c) * n + e] = k5[r + 5 * c];
+            B.kv[(size_t)35 * n + e] = k55;
+          }
+          if (act) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) { B.vs[(size_t)(i * 4 + q) * n + e] = vsS[q]; B.Ssr[(size_t)(i * 4 + q) * n + e] = SsrS[q]; }
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+              for (int r = 0; r < 3; r++) B.fs[(size_t)(i * 16 + r + 4 * c) * n + e] = fsS[r + 3 * c];
+            B.fs[(size_t)(i * 16 + 15) * n + e] = fsT;
+          }
+          // the next l iteration (if any) re-reads the state just stored: make it visible to the group
+          __syncwarp(gmask);
+          j = numIters + 1; l = 4;
+        } else {
+          if (j == (numIters - 1) && (l == 2)) {
+#pragma unroll
+            for (int q = 0; q < 6; q++) dvTrial[q] /= factor;
+            numSubdivide++;
+          }
+        }
+      }
+    }
+  }
+  if (!converged) { if (i == 0) atomicExch(fail, 2); return; }
+  if (i == 0) B.iflag[e] = 1;
+}
+
+// ForceBeamColumn2d::update with one lane per section (see fbc3d_update_sec_kernel)
+template <int G>
+__global__ void __launch_bounds__(128, XB_FBC_SEC_OCC) fbc2d_update_sec_kernel(BeamView B, const double* __restrict__ U,
+                                                                               const double* __restrict__ DU, int* fail) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long e = tid / G;
+  const int i = (int)(tid - e * G);
+  if (e >= B.n) return;
+  const int lane = threadIdx.x & 31;
+  const int gbase = lane & ~(G - 1);
+  const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << gbase;
+  const long long n = B.n;
+  const int nip = B.nip;
+  const bool act = i < nip;
+  const int is = act ? i : 0;
+  const double L = B.geo[e], cosT = B.geo[n + e], sinT = B.geo[2 * n + e];
+  double v[3], dv[3], vin[3];
+  {
+    double ug[6], dug[6];
+#pragma unroll
+    for (int a = 0; a < 2; a++) {
+      const int nd = B.conn[e * 2 + a];
+#pragma unroll
+      for (int j = 0; j < 3; j++) { ug[a * 3 + j] = U[(size_t)nd * 3 + j]; dug[a * 3 + j] = DU[(size_t)nd * 3 + j]; }
+    }
+    crd2d_basic(L, cosT, sinT, ug, v);
+    crd2d_basic(L, cosT, sinT, dug, dv);
+  }
+  const int initialFlag = B.iflag[e];
+  if (initialFlag != 0 && sqrt(dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]) <= DBL_EPSILON) return;
+#pragma unroll
+  for (int q = 0; q < 3; q++) vin[q] = v[q] - dv[q];
+  const double xL = lobatto_x(nip, is), xL1 = xL - 1.0, wtL = lobatto_w(nip, is) * L;
+  double f0[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) f0[q] = __ldg(B.fs0 + q);
+  double dvTrial[3], dvToDo[3];
+#pragma unroll
+  for (int q = 0; q < 3; q++) { dvToDo[q] = dv[q]; dvTrial[q] = dvToDo[q]; }
+  int numSubdivide = 1;
+  bool converged = false;
+  const double factor = 10;
+  const int maxSubdivisions = 4;
+  while (!converged && numSubdivide <= maxSubdivisions) {
+    for (int l = 0; l < 3; l++) {
+      double SeTrial[3], kvTrial[9];
+#pragma unroll
+      for (int q = 0; q < 3; q++) SeTrial[q] = B.Se[(size_t)q * n + e];
+#pragma unroll
+      for (int q = 0; q < 9; q++) kvTrial[q] = B.kv[(size_t)q * n + e];
+      double vsS[2], SsrS[2], fsS[4];
+#pragma unroll
+      for (int q = 0; q < 2; q++) { vsS[q] = B.vs[(size_t)(is * 2 + q) * n + e]; SsrS[q] = B.Ssr[(size_t)(is * 2 + q) * n + e]; }
+#pragma unroll
+      for (int q = 0; q < 4; q++) fsS[q] = B.fs[(size_t)(is * 4 + q) * n + e];
+      {
+        double dSe[3] = {0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+          for (int r = 0; r < 3; r++) dSe[r] += kvTrial[r + 3 * c] * dvTrial[c];
+#pragma unroll
+        for (int q = 0; q < 3; q++) SeTrial[q] += dSe[q];
+      }
+      int numIters = B.maxIters;
+      if (l == 1) numIters = 10 * B.maxIters;
+      for (int j = 0; j < numIters; j++) {
+        double fl[9], vrl[3];
+#pragma unroll
+        for (int q = 0; q < 9; q++) fl[q] = 0.0;
+        vrl[0] = vrl[1] = vrl[2] = 0.0;
+        if (act) {
+          double Ss[2], dSs[2], dvs[2], fb[6], ssec[2], ksec[4];
+          Ss[0] = SeTrial[0];
+          Ss[1] = xL1 * SeTrial[1] + xL * SeTrial[2];
+          dSs[0] = Ss[0] - SsrS[0]; dSs[1] = Ss[1] - SsrS[1];
+          const bool initial = (l == 1) || (l == 2 && j == 0);
+          dvs[0] = 0.0; dvs[1] = 0.0;
+#pragma unroll
+          for (int c = 0; c < 2; c++)
+#pragma unroll
+            for (int r = 0; r < 2; r++) dvs[r] += (initial ? f0[r + 2 * c] : fsS[r + 2 * c]) * dSs[c];
+          if (initialFlag != 0) { vsS[0] += dvs[0]; vsS[1] += dvs[1]; }
+          section_trial(B, e, i, vsS, ssec, ksec);
+          SsrS[0] = ssec[0]; SsrS[1] = ssec[1];
+          inv2(ksec, fsS);
+          dSs[0] = Ss[0] - SsrS[0]; dSs[1] = Ss[1] - SsrS[1];
+          dvs[0] = 0.0; dvs[1] = 0.0;
+#pragma unroll
+          for (int c = 0; c < 2; c++)
+#pragma unroll
+            for (int r = 0; r < 2; r++) dvs[r] += fsS[r + 2 * c] * dSs[c];
+          // fb = fs * b * wtL (2 x 3), this section's addend to f = b^T fb
+#pragma unroll
+          for (int jj = 0; jj < 2; jj++) {
+            fb[jj + 2 * 0] = fsS[jj + 2 * 0] * wtL;
+            const double tmp = fsS[jj + 2 * 1] * wtL; fb[jj + 2 * 1] = xL1 * tmp; fb[jj + 2 * 2] = xL * tmp;
+          }
+#pragma unroll
+          for (int jj = 0; jj < 3; jj++) {
+            fl[0 + 3 * jj] = fb[0 + 2 * jj];
+            const double tmp = fb[1 + 2 * jj]; fl[1 + 3 * jj] = xL1 * tmp; fl[2 + 3 * jj] = xL * tmp;
+          }
+          dvs[0] += vsS[0]; dvs[1] += vsS[1];
+          { const double dei = dvs[0] * wtL; vrl[0] = dei; }
+          { const double dei = dvs[1] * wtL; vrl[1] = xL1 * dei; vrl[2] = xL * dei; }
+        }
+        double f[9], vr[3];
+#pragma unroll
+        for (int q = 0; q < 9; q++) f[q] = group_sum_ordered(fl[q], gmask, gbase, nip);
+#pragma unroll
+        for (int q = 0; q < 3; q++) vr[q] = group_sum_ordered(vrl[q], gmask, gbase, nip);
+        inv3(f, kvTrial);
+#pragma unroll
+        for (int q = 0; q < 3; q++) { dv[q] = vin[q]; dv[q] += dvTrial[q]; dv[q] -= vr[q]; }
+        double dSe[3] = {0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+          for (int r = 0; r < 3; r++) dSe[r] += kvTrial[r + 3 * c] * dv[c];
+        double dW = 0.0;
+#pragma unroll
+        for (int q = 0; q < 3; q++) dW += dv[q] * dSe[q];
+#pragma unroll
+        for (int q = 0; q < 3; q++) SeTrial[q] += dSe[q];
+        if (fabs(dW) < B.tol) {
+#pragma unroll
+          for (int q = 0; q < 3; q++) { dvToDo[q] -= dvTrial[q]; vin[q] += dvTrial[q]; }
+          if (sqrt(dvToDo[0] * dvToDo[0] + dvToDo[1] * dvToDo[1] + dvToDo[2] * dvToDo[2]) <= DBL_EPSILON) converged = true;
+          else {
+#pragma unroll
+            for (int q = 0; q < 3; q++) dvTrial[q] = dvToDo[q];
+            numSubdivide = 1;
+          }
+          if (i == 0) {
+#pragma unroll
+            for (int q = 0; q < 3; q++) B.Se[(size_t)q * n + e] = SeTrial[q];
+#pragma unroll
+            for (int q = 0; q < 9; q++) B.kv[(size_t)q * n + e] = kvTrial[q];
+          }
+          if (act) {
+#pragma unroll
+            for (int q = 0; q < 2; q++) { B.vs[(size_t)(i * 2 + q) * n + e] = vsS[q]; B.Ssr[(size_t)(i * 2 + q) * n + e] = SsrS[q]; }
+#pragma unroll
+            for (int q = 0; q < 4; q++) B.fs[(size_t)(i * 4 + q) * n + e] = fsS[q];
+          }
+          __syncwarp(gmask);
+          j = numIters + 1; l = 3;
+        } else {
+          if (j == (numIters - 1) && (l == 2)) {
+#pragma unroll
+            for (int q = 0; q < 3; q++) dvTrial[q] /= factor;
+            numSubdivide++;
+          }
+        }
+      }
+    }
+  }
+  if (!converged) { if (i == 0) atomicExch(fail, 2); return; }
+  if (i == 0) B.iflag[e] = 1;
 }
 
 // getTangentStiff -> LinearCrdTransf3d::getGlobalStiffMatrix(kv); getResistingForce ->

@@ -1661,8 +1661,23 @@ int xb_update(xb_model* m) {
   for (auto& d : m->dg) {
     if (d.v.n == 0) continue;
     if (is_beam(d.kind)) {
-      if (d.kind == XB_ELE_FORCEBEAMCOLUMN3D) fbc3d_update_kernel<<<(unsigned)((d.b.n + 63) / 64), 64, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
-      else fbc2d_update_kernel<<<(unsigned)((d.b.n + 63) / 64), 64, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
+      if (d.kind == XB_ELE_FORCEBEAMCOLUMN3D) {
+        // default: one lane per section (G lanes per element); XB_BEAM=element selects the thread-per-element form
+        static const bool per_element = [] { const char* v = getenv("XB_BEAM"); return v && !strcmp(v, "element"); }();
+        const long long nb = d.b.n;
+        if (per_element) fbc3d_update_kernel<<<(unsigned)((nb + 63) / 64), 64, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
+        else if (d.b.nip <= 4) fbc3d_update_sec_kernel<4><<<(unsigned)((nb * 4 + 127) / 128), 128, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
+        else if (d.b.nip <= 8) fbc3d_update_sec_kernel<8><<<(unsigned)((nb * 8 + 127) / 128), 128, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
+        else fbc3d_update_sec_kernel<16><<<(unsigned)((nb * 16 + 127) / 128), 128, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
+      }
+      else {
+        static const bool per_element = [] { const char* v = getenv("XB_BEAM"); return v && !strcmp(v, "element"); }();
+        const long long nb = d.b.n;
+        if (per_element) fbc2d_update_kernel<<<(unsigned)((nb + 63) / 64), 64, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
+        else if (d.b.nip <= 4) fbc2d_update_sec_kernel<4><<<(unsigned)((nb * 4 + 127) / 128), 128, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
+        else if (d.b.nip <= 8) fbc2d_update_sec_kernel<8><<<(unsigned)((nb * 8 + 127) / 128), 128, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
+        else fbc2d_update_sec_kernel<16><<<(unsigned)((nb * 16 + 127) / 128), 128, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
+      }
       m->launches++;
       bytes += (long long)d.b.n * d.b.nip * d.b.nf * XB_FIB_NV * 8 * 2;   // one section pass: records in, out
       continue;
