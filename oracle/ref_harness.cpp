@@ -209,7 +209,7 @@ int ref_add_nd_material(void* h, int tag, int kind, const double* p) {
   RefModel* m = (RefModel*)h;
   NDMaterial* mat = nullptr;
   if (kind == 0) mat = new ElasticIsotropicMaterial(tag, p[0], p[1], p[2]);
-  else if (kind == 1) mat = new J2Plasticity(tag, 0, p[0], p[1], p[2], p[3], p[4], p[5], p[6], 0.0);
+  else if (kind == 1) mat = new J2Plasticity(tag, 0, p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7]);   // p[7] = rho
   if (!mat) return -1;
   m->ndmats[tag] = mat;
   return 0;
@@ -352,6 +352,10 @@ int ref_set_alphaM(void* h, double alphaM) {
   NodeIter& it = m->domain->getNodes(); Node* n;
   while ((n = it()) != nullptr) n->setRayleighDampingFactor(alphaM);
   return 0;
+}
+// `rayleigh alphaM betaK betaKinit betaKcomm` (Domain::setRayleighDampingFactors, Domain.cpp:1858)
+int ref_set_rayleigh(void* h, double alphaM, double betaK, double betaK0, double betaKc) {
+  return ((RefModel*)h)->domain->setRayleighDampingFactors(alphaM, betaK, betaK0, betaKc);
 }
 // integrator Newmark gamma beta (displacement form); analysis Transient
 int ref_setup_transient(void* h, int numberer, int soeKind, double gamma, double beta, int testKind, double tol, int maxIter) {

@@ -264,14 +264,40 @@ static void el_get_stress(const OrcElastic* m, int type, double* s) {
 /* one integration point of either kind */
 typedef struct {
   int kind, type;
+  double rho;        /* NDMaterial::getRho: J2Plasticity's rho (par[7]), ElasticIsotropicMaterial's rho (par[2]) */
   union { OrcJ2 j2; OrcElastic el; } u;
 } OrcGP;
 
 static void gp_init(OrcGP* g, int kind, int type, const double* p) {
   memset(g, 0, sizeof *g);
   g->kind = kind; g->type = type;
-  if (kind == ORC_MAT_J2) j2_init(&g->u.j2, p);
-  else { g->u.el.E = p[0]; g->u.el.v = p[1]; }
+  if (kind == ORC_MAT_J2) { j2_init(&g->u.j2, p); g->rho = p[7]; }
+  else { g->u.el.E = p[0]; g->u.el.v = p[1]; g->rho = p[2]; }
+}
+/* J2Plasticity::doInitialTangent (J2Plasticity.cpp:398-421) through J2ThreeDimensional::getInitialTangent
+ * (J2ThreeDimensional.cpp:237) / J2PlaneStrain::getInitialTangent; elastic: the tangent itself */
+static double j2_initial_entry(const OrcJ2* m, int i, int j, int k, int l) {
+  double t = m->bulk * IbunI(i, j, k, l);
+  t += (2.0 * m->shear) * IIdev(i, j, k, l);
+  return t;
+}
+static void el_get_tangent(const OrcElastic* m, int type, double* D);
+static void gp_get_initial_tangent(const OrcGP* g, double* D) {
+  if (g->kind != ORC_MAT_J2) { el_get_tangent(&g->u.el, g->type, D); return; }
+  const OrcJ2* m = &g->u.j2;
+  if (g->type == ORC_ND_3D) {
+    for (int ii = 0; ii < 6; ii++)
+      for (int jj = 0; jj < 6; jj++) {
+        int i, j, k, l;
+        j2_index_map(ii, &i, &j); j2_index_map(jj, &k, &l);
+        D[ii * 6 + jj] = j2_initial_entry(m, i, j, k, l);
+      }
+  } else {
+    D[0] = j2_initial_entry(m, 0, 0, 0, 0); D[4] = j2_initial_entry(m, 1, 1, 1, 1); D[8] = j2_initial_entry(m, 0, 1, 0, 1);
+    D[1] = j2_initial_entry(m, 0, 0, 1, 1); D[3] = j2_initial_entry(m, 1, 1, 0, 0);
+    D[2] = j2_initial_entry(m, 0, 0, 0, 1); D[6] = j2_initial_entry(m, 0, 1, 0, 0);
+    D[5] = j2_initial_entry(m, 1, 1, 0, 1); D[7] = j2_initial_entry(m, 0, 1, 1, 1);
+  }
 }
 static int gp_set_trial_strain(OrcGP* g, const double* e) {
   int n = (g->type == ORC_ND_3D) ? 6 : 3;
@@ -1132,6 +1158,7 @@ typedef struct {
   int nip;
   OrcBeam* beam;     /* ORC_ELE_FBC2D */
   OrcBeam3* beam3;   /* ORC_ELE_FBC3D */
+  double* Kc;        /* Element::Kc (committed tangent), row-major nd x nd; allocated while betaKc != 0 */
 } OrcEle;
 
 typedef struct { int tag, nf; double* y; double* z; double* A; int* mat; double GJ; } OrcSecDef;
@@ -1144,6 +1171,7 @@ typedef struct {
   double* mass;                       /* [nn][ndf] diagonal of Node::mass (`mass` command) */
   double* vel; double* acc; double* velc; double* accc;   /* trial / committed velocity, acceleration */
   double alphaM;                      /* Node::setRayleighDampingFactor */
+  double e_alphaM, betaK, betaK0, betaKc;   /* Element::setRayleighDampingFactors (Domain::setRayleighDampingFactors) */
   double c1, c2, c3;                  /* TransientIntegrator coefficients (Newmark.cpp:117-140); 1,0,0 = static */
   int nuni; int* uni_tag; int* uni_kind; double* uni_par;   /* uniaxial materials [nuni][12] */
   int nsec; OrcSecDef* sec;           /* fibre section definitions */
@@ -1196,7 +1224,7 @@ int orc_add_nd_material(void* h, int tag, int kind, const double* p) {
   m->mat_par = (double*)realloc(m->mat_par, sizeof(double) * 8 * (m->nmat + 1));
   m->mat_tag[m->nmat] = tag; m->mat_kind[m->nmat] = kind;
   memset(m->mat_par + 8 * m->nmat, 0, 8 * sizeof(double));
-  memcpy(m->mat_par + 8 * m->nmat, p, sizeof(double) * (kind == ORC_MAT_J2 ? 7 : 3));
+  memcpy(m->mat_par + 8 * m->nmat, p, sizeof(double) * (kind == ORC_MAT_J2 ? 8 : 3));   /* J2: ..., eta, rho */
   m->nmat++; return 0;
 }
 /* ---- transient analysis (Newmark, displacement form; nodal masses, mass-proportional damping) ---- */
@@ -1543,7 +1571,10 @@ static void brick_form(OrcModel* m, OrcEle* el, int tang_flag, double* K, double
     double stress[6], dd[36];
     gp_get_stress(&el->gp[g], stress);
     for (int i = 0; i < 6; i++) stress[i] *= dvol[g];
-    if (tang_flag) { gp_get_tangent(&el->gp[g], dd); for (int i = 0; i < 36; i++) dd[i] *= dvol[g]; }
+    if (tang_flag) {   /* 2: Brick::getInitialStiff (Brick.cpp:324), the same loops on getInitialTangent() */
+      if (tang_flag == 2) gp_get_initial_tangent(&el->gp[g], dd); else gp_get_tangent(&el->gp[g], dd);
+      for (int i = 0; i < 36; i++) dd[i] *= dvol[g];
+    }
     int jj = 0;
     for (int j = 0; j < 8; j++) {
       double b00 = shp[0][j], b11 = shp[1][j], b22 = shp[2][j], b30 = shp[1][j], b31 = shp[0][j],
@@ -1654,7 +1685,8 @@ static void quad_form(OrcModel* m, OrcEle* el, int tang_flag, double* K, double*
     for (int i = 0; i < 4; i++) {
       double shp[3][4]; double dvol = quad_shape(m, el, quad_pts[i][0], quad_pts[i][1], shp);
       dvol *= (thickness * quad_wts[i]);
-      double D[9]; gp_get_tangent(&el->gp[i], D);
+      double D[9];
+      if (tang_flag == 2) gp_get_initial_tangent(&el->gp[i], D); else gp_get_tangent(&el->gp[i], D);   /* 2: getInitialStiff */
       const double D00 = D[0], D01 = D[1], D02 = D[2], D10 = D[3], D11 = D[4], D12 = D[5], D20 = D[6], D21 = D[7], D22 = D[8];
       double DB[3][2];
       for (int alpha = 0, ia = 0; alpha < 4; alpha++, ia += 2)
@@ -1724,6 +1756,191 @@ int orc_incr_response(void* h, const double* dU, double cu, double cv, double ca
 void orc_apply_load(void* h, double lambda) { ((OrcModel*)h)->lambda = lambda; }
 
 /* Element::getTangentStiff / getResistingForce of FE element e (row-major) */
+
+/* ======================================================================== */
+/* Rayleigh damping and element masses: Element::getDamp / getRayleighDampingForces (element/Element.cpp:182,284), */
+/* Brick::formInertiaTerms (Brick.cpp:595), FourNodeQuad::getMass (FourNodeQuad.cpp:387),                           */
+/* getResistingForceIncInertia of each element, getInitialStiff of each element                                    */
+/* ======================================================================== */
+static int ele_nd(const OrcEle* el) { return el->nen * el->ndf_e; }
+
+/* ForceBeamColumn2d::getInitialFlexibility + Matrix::Invert (ForceBeamColumn2d.cpp getInitialStiff) */
+static void beam_initial_kv(const OrcBeam* b, double* kv0) {
+  double xi[ORC_MAXSEC], wt[ORC_MAXSEC], f[9];
+  lobatto(b->nip, xi, wt);
+  for (int i = 0; i < 9; i++) f[i] = 0.0;
+  for (int i = 0; i < b->nip; i++) {
+    double fSec[4], fb[6];
+    sec_initial_flex(&b->sec[i], fSec);
+    double xL = xi[i], xL1 = xL - 1.0, wtL = wt[i] * b->L;
+    for (int q = 0; q < 6; q++) fb[q] = 0.0;
+    for (int jj = 0; jj < 2; jj++) fb[jj + 2 * 0] += fSec[jj + 2 * 0] * wtL;
+    for (int jj = 0; jj < 2; jj++) { double tmp = fSec[jj + 2 * 1] * wtL; fb[jj + 2 * 1] += xL1 * tmp; fb[jj + 2 * 2] += xL * tmp; }
+    for (int jj = 0; jj < 3; jj++) f[0 + 3 * jj] += fb[0 + 2 * jj];
+    for (int jj = 0; jj < 3; jj++) { double tmp = fb[1 + 2 * jj]; f[1 + 3 * jj] += xL1 * tmp; f[2 + 3 * jj] += xL * tmp; }
+  }
+  inv3(f, kv0);
+}
+/* ForceBeamColumn3d::getInitialFlexibility (ForceBeamColumn3d.cpp:2003) + Matrix::Invert */
+static void beam3_initial_kv(const OrcBeam3* b, double* kv0) {
+  double xi[ORC_MAXSEC], wt[ORC_MAXSEC], f[36];
+  lobatto(b->nip, xi, wt);
+  for (int i = 0; i < 36; i++) f[i] = 0.0;
+  for (int i = 0; i < b->nip; i++) {
+    double fSec[16], fb[24];
+    sec3_initial_flex(&b->sec[i], fSec);
+    double xL = xi[i], xL1 = xL - 1.0, wtL = wt[i] * b->L;
+    for (int q = 0; q < 24; q++) fb[q] = 0.0;
+    for (int jj = 0; jj < 4; jj++) fb[jj + 4 * 0] += fSec[jj + 4 * 0] * wtL;
+    for (int jj = 0; jj < 4; jj++) { double tmp = fSec[jj + 4 * 1] * wtL; fb[jj + 4 * 1] += xL1 * tmp; fb[jj + 4 * 2] += xL * tmp; }
+    for (int jj = 0; jj < 4; jj++) { double tmp = fSec[jj + 4 * 2] * wtL; fb[jj + 4 * 3] += xL1 * tmp; fb[jj + 4 * 4] += xL * tmp; }
+    for (int jj = 0; jj < 4; jj++) fb[jj + 4 * 5] += fSec[jj + 4 * 3] * wtL;
+    for (int jj = 0; jj < 6; jj++) f[0 + 6 * jj] += fb[0 + 4 * jj];
+    for (int jj = 0; jj < 6; jj++) { double tmp = fb[1 + 4 * jj]; f[1 + 6 * jj] += xL1 * tmp; f[2 + 6 * jj] += xL * tmp; }
+    for (int jj = 0; jj < 6; jj++) { double tmp = fb[2 + 4 * jj]; f[3 + 6 * jj] += xL1 * tmp; f[4 + 6 * jj] += xL * tmp; }
+    for (int jj = 0; jj < 6; jj++) f[5 + 6 * jj] += fb[3 + 4 * jj];
+  }
+  inv6_flex(f, kv0);
+}
+
+/* Element::getTangentStiff (which = 1) / getInitialStiff (which = 2), row-major nd x nd */
+static void ele_K(OrcModel* m, OrcEle* el, int which, double* K) {
+  double R[24];
+  if (el->kind == ORC_ELE_BRICK) brick_form(m, el, which, K, R);
+  else if (el->kind == ORC_ELE_QUAD) quad_form(m, el, which, K, R);
+  else if (el->kind == ORC_ELE_FBC2D) {
+    if (which == 1) beam_form(el->beam, K, R);
+    else { OrcBeam t = *el->beam; beam_initial_kv(el->beam, t.kv); beam_form(&t, K, R); }
+  } else {
+    if (which == 1) beam3_form(el->beam3, K, R);
+    else { OrcBeam3 t = *el->beam3; beam3_initial_kv(el->beam3, t.kv); beam3_form(&t, K, R); }
+  }
+}
+
+/* Element::getMass: Brick::formInertiaTerms(1) (consistent), FourNodeQuad::getMass (lumped, material rho;
+ * the element's own rho parameter must be 0), force beams with rho = 0 (zero matrix).
+ * inertia != NULL: also the addend of formInertiaTerms to the residual (brick), row-major M. */
+static void ele_M(OrcModel* m, OrcEle* el, double* M, double* inertia) {
+  const int nd = ele_nd(el);
+  for (int i = 0; i < nd * nd; i++) M[i] = 0.0;
+  if (inertia) for (int i = 0; i < nd; i++) inertia[i] = 0.0;
+  if (el->kind == ORC_ELE_BRICK) {
+    double xl[3][8];
+    for (int i = 0; i < 8; i++) for (int d = 0; d < 3; d++) xl[d][i] = m->crd[el->node[i] * 3 + d];
+    const double one_over_root3 = 1.0 / sqrt(3.0);
+    const double sg[2] = { -one_over_root3, one_over_root3 };
+    double Shape[8][4][8], dvol[8];
+    int count = 0;
+    for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) for (int k = 0; k < 2; k++) {
+      double gp[3] = { sg[i], sg[j], sg[k] }, xsj;
+      shp3d(gp, &xsj, Shape[count], xl);
+      dvol[count] = 1.0 * xsj;
+      count++;
+    }
+    for (int i = 0; i < 8; i++) {
+      double (*shp)[8] = Shape[i];
+      double momentum[3] = {0.0, 0.0, 0.0};
+      for (int j = 0; j < 8; j++) {
+        const double* a = m->acc + (size_t)el->node[j] * m->ndf;
+        for (int p = 0; p < 3; p++) momentum[p] += a[p] * shp[3][j];      /* Vector::addVector(1.0, accel, shp) */
+      }
+      const double rho = el->gp[i].rho;
+      for (int p = 0; p < 3; p++) momentum[p] *= rho;
+      int jj = 0;
+      for (int j = 0; j < 8; j++) {
+        double temp = shp[3][j] * dvol[i];
+        if (inertia) for (int p = 0; p < 3; p++) inertia[jj + p] += temp * momentum[p];
+        temp *= rho;
+        int kk = 0;
+        for (int k = 0; k < 8; k++) {
+          const double massJK = temp * shp[3][k];
+          for (int p = 0; p < 3; p++) M[(jj + p) * 24 + kk + p] += massJK;
+          kk += 3;
+        }
+        jj += 3;
+      }
+    }
+  } else if (el->kind == ORC_ELE_QUAD) {
+    double rhoi[4], sum = 0.0;
+    for (int i = 0; i < 4; i++) { rhoi[i] = el->gp[i].rho; sum += rhoi[i]; }
+    if (sum == 0.0) return;
+    for (int i = 0; i < 4; i++) {
+      double shp[3][4];
+      double rhodvol = quad_shape(m, el, quad_pts[i][0], quad_pts[i][1], shp);
+      rhodvol *= (rhoi[i] * el->par[0] * quad_wts[i]);
+      for (int alpha = 0, ia = 0; alpha < 4; alpha++, ia++) {
+        const double Nrho = shp[2][alpha] * rhodvol;
+        M[ia * 8 + ia] += Nrho;
+        ia++;
+        M[ia * 8 + ia] += Nrho;
+      }
+    }
+  }
+}
+
+/* Element::getDamp (Element.cpp:182): alphaM M + betaK Kt + betaK0 K0 + betaKc Kc, accumulated in that order */
+static void ele_damp(OrcModel* m, OrcEle* el, double* D) {
+  const int nd = ele_nd(el), n2 = nd * nd;
+  double T[576];
+  for (int i = 0; i < n2; i++) D[i] = 0.0;
+  if (m->e_alphaM != 0.0) { ele_M(m, el, T, NULL); for (int i = 0; i < n2; i++) D[i] = T[i] * m->e_alphaM; }
+  if (m->betaK != 0.0) { ele_K(m, el, 1, T); for (int i = 0; i < n2; i++) D[i] += T[i] * m->betaK; }
+  if (m->betaK0 != 0.0) { ele_K(m, el, 2, T); for (int i = 0; i < n2; i++) D[i] += T[i] * m->betaK0; }
+  if (m->betaKc != 0.0 && el->Kc) { for (int i = 0; i < n2; i++) D[i] += el->Kc[i] * m->betaKc; }
+}
+static int any_rayleigh(const OrcModel* m) { return m->e_alphaM != 0.0 || m->betaK != 0.0 || m->betaK0 != 0.0 || m->betaKc != 0.0; }
+
+/* Element::getResistingForceIncInertia as each element implements it (Brick.cpp:568, FourNodeQuad.cpp:556,
+ * ForceBeamColumn2d/3d with rho = 0).  R holds getResistingForce on entry. */
+static void ele_add_inertia_and_damping(OrcModel* m, OrcEle* el, double* R) {
+  const int nd = ele_nd(el);
+  double M[576], D[576], F[24], v[24];
+  int add_damp = 0;
+  if (el->kind == ORC_ELE_BRICK) {
+    double inertia[24], sum = 0.0;
+    for (int i = 0; i < 8; i++) sum += fabs(el->gp[i].rho);
+    if (sum != 0.0) {                                      /* rho = 0: formInertiaTerms adds exact zeros */
+      ele_M(m, el, M, inertia);
+      for (int i = 0; i < nd; i++) R[i] += inertia[i];     /* formInertiaTerms adds into resid */
+    }
+    add_damp = any_rayleigh(m);
+  } else if (el->kind == ORC_ELE_QUAD) {
+    double sum = 0.0;
+    for (int i = 0; i < 4; i++) sum += el->gp[i].rho;
+    if (sum == 0.0) add_damp = (m->betaK != 0.0 || m->betaK0 != 0.0 || m->betaKc != 0.0);
+    else {
+      ele_M(m, el, M, NULL);
+      for (int a = 0; a < 4; a++) for (int p = 0; p < 2; p++) {
+        const int i = 2 * a + p;
+        R[i] += M[i * 8 + i] * m->acc[(size_t)el->node[a] * m->ndf + p];
+      }
+      add_damp = any_rayleigh(m);
+    }
+  } else add_damp = (m->betaK != 0.0 || m->betaK0 != 0.0 || m->betaKc != 0.0);
+  if (!add_damp) return;
+  /* Element::getRayleighDampingForces: F = D v, column by column (Vector::addMatrixVector(0.0, D, v, 1.0)) */
+  ele_damp(m, el, D);
+  for (int a = 0; a < el->nen; a++) for (int p = 0; p < el->ndf_e; p++) v[a * el->ndf_e + p] = m->vel[(size_t)el->node[a] * m->ndf + p];
+  for (int i = 0; i < nd; i++) F[i] = 0.0;
+  for (int j = 0; j < nd; j++) { const double vj = v[j]; for (int i = 0; i < nd; i++) F[i] += D[i * nd + j] * vj; }
+  for (int i = 0; i < nd; i++) R[i] += F[i];
+}
+
+/* `rayleigh alphaM betaK betaKinit betaKcomm` = Domain::setRayleighDampingFactors (Domain.cpp:1858): every
+ * element (Element::setRayleighDampingFactors: Kc = copy of the current tangent when betaKc != 0) and every node */
+int orc_set_rayleigh(void* h, double alphaM, double betaK, double betaK0, double betaKc) {
+  OrcModel* m = (OrcModel*)h;
+  m->e_alphaM = alphaM; m->betaK = betaK; m->betaK0 = betaK0; m->betaKc = betaKc;
+  m->alphaM = alphaM;
+  for (int e = 0; e < m->ne; e++) {
+    OrcEle* el = &m->ele[e];
+    if (betaKc != 0.0) {
+      if (!el->Kc) { el->Kc = (double*)malloc(sizeof(double) * 576); ele_K(m, el, 1, el->Kc); }
+    } else if (el->Kc) { free(el->Kc); el->Kc = NULL; }
+  }
+  return 0;
+}
+
 int orc_ele_tangent(void* h, int e, double* K) {
   OrcModel* m = (OrcModel*)h; double R[24];
   if (m->ele[e].kind == ORC_ELE_FBC2D) { beam_form(m->ele[e].beam, K, R); return 6; }
@@ -1770,6 +1987,16 @@ int orc_form_tangent(void* h, double* A) {
     /* FE_Element::addKtToTang(c1): theTangent->addMatrix(K, c1) on a zeroed matrix */
     for (int i = 0; i < nd_e; i++) for (int j = 0; j < nd_e; j++)
       K[i * nd_e + j] = (m->c1 == 1.0) ? 0.0 + K[i * nd_e + j] : 0.0 + K[i * nd_e + j] * m->c1;
+    /* Newmark::formEleTangent (Newmark.cpp:262): addCtoTang(c2) -> += getDamp() * c2, addMtoTang(c3) -> += getMass() * c3
+     * (FE_Element.cpp:279,292); both add exact zeros when the element has neither damping factors nor mass */
+    if (m->c2 != 0.0 && any_rayleigh(m)) {
+      double D[576]; ele_damp(m, el, D);
+      for (int i = 0; i < nd_e * nd_e; i++) K[i] += D[i] * m->c2;
+    }
+    if (m->c3 != 0.0 && (el->kind == ORC_ELE_BRICK || el->kind == ORC_ELE_QUAD)) {
+      double M[576]; ele_M(m, el, M, NULL);
+      for (int i = 0; i < nd_e * nd_e; i++) K[i] += M[i] * m->c3;
+    }
     if (m->soe_kind == 1) {
       for (int i = 0; i < nd_e; i++) { int row = ids[i]; if (row < 0) continue;
         for (int j = 0; j < nd_e; j++) { int col = ids[j]; if (col < 0) continue;
@@ -1801,6 +2028,9 @@ int orc_form_unbalance(void* h, double* B) {
     else if (el->kind == ORC_ELE_QUAD) quad_form(m, el, 0, K, R);
     else if (el->kind == ORC_ELE_FBC3D) beam3_form(el->beam3, NULL, R);
     else beam_form(el->beam, NULL, R);
+    /* TransientIntegrator::formEleResidual -> addRIncInertiaToResidual -> getResistingForceIncInertia; with
+     * zero velocities / accelerations (static analysis) the extra terms are exact zeros */
+    ele_add_inertia_and_damping(m, el, R);
     ele_ids(m, el, ids);
     for (int i = 0; i < nd_e; i++) {
       double res = 0.0 * 1.0 + R[i] * -1.0;   /* Vector::addVector(1.0, R, -1.0) on a zeroed residual */
@@ -1828,6 +2058,7 @@ int orc_commit(void* h) {
   memset(m->incr, 0, sizeof(double) * m->nn * m->ndf);        /* Node::commitState */
   memcpy(m->velc, m->vel, sizeof(double) * m->nn * m->ndf); memcpy(m->accc, m->acc, sizeof(double) * m->nn * m->ndf);
   for (int e = 0; e < m->ne; e++) {
+    if (m->ele[e].Kc) ele_K(m, &m->ele[e], 1, m->ele[e].Kc);   /* Element::commitState: *Kc = getTangentStiff(), before the materials commit */
     if (m->ele[e].kind == ORC_ELE_FBC2D) beam_commit(m->ele[e].beam);
     else if (m->ele[e].kind == ORC_ELE_FBC3D) beam3_commit(m->ele[e].beam3);
     else for (int g = 0; g < m->ele[e].nip; g++) gp_commit(&m->ele[e].gp[g]);

@@ -61,15 +61,20 @@ def model_case(name, spec, numberer, soe, scale, nsteps=NSTEPS):
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
 
 
-def transient_case(name, spec, mass, gamma, beta, dt, nsteps=3, niter=3):
+def transient_case(name, spec, mass, gamma, beta, dt, nsteps=3, niter=3, rayleigh=None):
     """Newmark steps driven through the reference's own integrator: newStep, then `niter` Newton
     iterations (formUnbalance, formTangent, solve, update) per step; everything recorded."""
     import scipy.sparse as sp
     import scipy.sparse.linalg as spla
     R = RefBackend(spec, 1, 1, defer_setup=True)
-    R.set_mass(spec.node_tags, mass); R.setup_transient(1, 1, gamma, beta)
+    R.set_mass(spec.node_tags, mass)
+    if rayleigh is not None:
+        R.set_rayleigh(*rayleigh)
+    R.setup_transient(1, 1, gamma, beta)
     ptr, idx = R.csr(); neq = R.neq
     out = dict(mass=mass, gamma=gamma, beta=beta, dt=dt, nsteps=nsteps, niter=niter, ids=R.ids(), ptr=ptr, idx=idx)
+    if rayleigh is not None:
+        out["rayleigh"] = np.array(rayleigh)
     for s in range(nsteps):
         assert R.new_step(dt) == 0
         for it in range(niter):
@@ -103,8 +108,12 @@ def dispcontrol_case(name, spec, numberer, soe, node, dof, incr, nsteps, tol, ma
 
 if __name__ == "__main__":
     # python tests/golden/make_golden.py [substring]: only the cases whose name contains it
-    from golden_cases import DISPCONTROL_CASES, TRANSIENT_CASES
+    from golden_cases import DISPCONTROL_CASES, RAYLEIGH_CASES, TRANSIENT_CASES
     only = sys.argv[1] if len(sys.argv) > 1 else ""
+    for name, (mk, mass_fn, gamma, beta, dt, ray) in RAYLEIGH_CASES.items():
+        if only in name:
+            spec = mk()
+            transient_case(name, spec, mass_fn(spec), gamma, beta, dt, rayleigh=ray)
     for name, (mk, *args) in DISPCONTROL_CASES.items():
         if only in name:
             dispcontrol_case(name, mk(), *args)

@@ -41,6 +41,20 @@ TRANSIENT_CASES = {
 }
 
 
+# the same with `rayleigh alphaM betaK betaKinit betaKcomm` on elements and nodes, and element masses from the
+# material density (stdBrick: consistent, FourNodeQuad: lumped): name -> (spec, mass(spec), gamma, beta, dt, rayleigh)
+J2_STEEL_RHO = (J2_STEEL[0], J2_STEEL[1] + [2.0e-3])
+RAYLEIGH = (0.3, 0.002, 0.001, 0.0015)
+RAYLEIGH_CASES = {
+    "rayleigh_brick_j2": (lambda: brick_block(3, 3, 4, mat=J2_STEEL_RHO, lz=3.0, load=(40.0, 0.0, -5.0), distort=0.2, seed=6),
+                          _uniform_mass(0.05), 0.5, 0.25, 0.02, RAYLEIGH),
+    "rayleigh_quad_j2": (lambda: quad_plane(6, 4, mat=J2_STEEL_RHO, lx=6.0, ly=4.0, distort=0.2, seed=7),
+                         _uniform_mass(0.05), 0.5, 0.25, 0.02, RAYLEIGH),
+    "rayleigh_frame2d": (lambda: frame2d(2, 2, 2, lateral=30.0), _uniform_mass(0.05, 0.0), 0.5, 0.25, 0.02, RAYLEIGH),
+    "rayleigh_frame3d": (lambda: frame3d(1, 1, 2, ndiv=2, lateral=(25.0, 15.0)), _uniform_mass(0.05, 0.0), 0.5, 0.25, 0.02, RAYLEIGH),
+}
+
+
 def newmark_coeffs(gamma, beta, dt):
     """c1 c2 c3 and the predictor's a1..a4 of Newmark::newStep (displacement unknown)"""
     return ((1.0, gamma / (beta * dt), 1.0 / (beta * dt * dt)),

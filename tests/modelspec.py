@@ -470,6 +470,10 @@ class OracleBackend(_Backend):
         for t, mv in zip(tags, np.ascontiguousarray(mass, np.float64)):
             assert self.L.orc_set_mass(self.h, int(t), _p(np.ascontiguousarray(mv))) == 0
 
+    def set_rayleigh(self, alphaM, betaK, betaK0, betaKc):
+        self.L.orc_set_rayleigh.argtypes = [ctypes.c_void_p] + [ctypes.c_double] * 4
+        assert self.L.orc_set_rayleigh(self.h, alphaM, betaK, betaK0, betaKc) == 0
+
     def set_transient(self, c1, c2, c3):
         self.L.orc_set_transient.argtypes = [ctypes.c_void_p] + [ctypes.c_double] * 3
         self.L.orc_set_transient(self.h, c1, c2, c3)
@@ -674,6 +678,10 @@ class RefBackend(_Backend):
     def set_mass(self, tags, mass):
         for t, mv in zip(tags, np.ascontiguousarray(mass, np.float64)):
             assert self.L.ref_set_mass(self.h, int(t), _p(np.ascontiguousarray(mv))) == 0
+
+    def set_rayleigh(self, alphaM, betaK, betaK0, betaKc):
+        self.L.ref_set_rayleigh.argtypes = [ctypes.c_void_p] + [ctypes.c_double] * 4
+        assert self.L.ref_set_rayleigh(self.h, alphaM, betaK, betaK0, betaKc) == 0
 
     def setup_transient(self, numberer, soe, gamma, beta, test=0, tol=1e-8, max_iter=20):
         self.L.ref_setup_transient.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,

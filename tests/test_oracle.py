@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from golden_cases import CASES, DISPCONTROL_CASES, NSTEPS, TRANSIENT_CASES, ele_nd, newmark_coeffs
+from golden_cases import CASES, DISPCONTROL_CASES, NSTEPS, RAYLEIGH_CASES, TRANSIENT_CASES, ele_nd, newmark_coeffs
 from modelspec import (ELASTIC, J2_STEEL, MAT_ELASTIC, MAT_J2, ND_3D, ND_PLANE_STRAIN, OracleBackend, RefBackend,
                        brick_block, disp_control, frame2d, frame3d, have_ref, oracle_nd_path, oracle_uni_path, quad_plane, ref_nd_path)
 
@@ -146,6 +146,8 @@ def drive_transient_vs_golden(model, g, name, check, is_dev=False):
     (c1, c2, c3), (a1, a2, a3, a4) = newmark_coeffs(float(g["gamma"]), float(g["beta"]), float(g["dt"]))
     t = 0.0
     neq = len(g["B0_0"])
+    if "rayleigh" in g:          # `rayleigh` command before the analysis: elements (Kc = current tangent) and nodes
+        model.set_rayleigh(*[float(x) for x in g["rayleigh"]])
     for s in range(int(g["nsteps"])):
         t += float(g["dt"])
         model.set_transient(c1, c2, c3); model.newmark_predict(a1, a2, a3, a4); model.apply_load(t)
@@ -159,9 +161,9 @@ def drive_transient_vs_golden(model, g, name, check, is_dev=False):
         model.commit()
 
 
-@pytest.mark.parametrize("name", list(TRANSIENT_CASES))
+@pytest.mark.parametrize("name", list(TRANSIENT_CASES) + list(RAYLEIGH_CASES))
 def test_newmark_vs_golden(name):
-    mk, mass_fn, *_ = TRANSIENT_CASES[name]
+    mk, mass_fn, *_ = {**TRANSIENT_CASES, **RAYLEIGH_CASES}[name]
     g = np.load(os.path.join(GOLD, name + ".npz"))
     spec = mk()
     O = OracleBackend(spec, 1, 1)
