@@ -109,10 +109,18 @@ int xb_add_elements(xb_model*, int kind, int n, const int* tags, const int* conn
 int xb_add_nodal_loads(xb_model*, int n, const int* node_tags, const double* values);
 
 /* `mass` command: Node::setMass with a diagonal matrix (domain/node/Node.h:127); mass is [n][ndf].
- * Element masses (material rho) are NOT on the device path: keep rho = 0 in transient models. */
+ * Element masses come from the nDMaterial density (J2Plasticity par[7], ElasticIsotropic par[2]): stdBrick forms
+ * the consistent mass (Brick::formInertiaTerms, Brick.cpp:595), FourNodeQuad the lumped one (FourNodeQuad.cpp:387,
+ * the element's own rho parameter must stay 0); force beam-columns carry no element mass (rho = 0). */
 int xb_set_nodal_mass(xb_model*, int n, const int* node_tags, const double* mass);
 /* `rayleigh alphaM 0 0 0` on the nodes (Node::setRayleighDampingFactor): C_node = alphaM * M_node */
 int xb_set_rayleigh_alpha_m(xb_model*, double alphaM);
+/* `rayleigh alphaM betaK betaKinit betaKcomm` = Domain::setRayleighDampingFactors (domain/domain/Domain.cpp:1858):
+ * every element (Element::setRayleighDampingFactors, element/Element.cpp:110; Kc is set to the current tangent
+ * when betaKcomm != 0 and refreshed at every commit) and every node.  With transient factors (c1,c2,c3) the
+ * element tangent becomes c1 Kt + c2 (alphaM M + betaK Kt + betaK0 K0 + betaKc Kc) + c3 M and the element
+ * residual getResistingForceIncInertia = R + M a + C v.  Any time before or after xb_device_init. */
+int xb_set_rayleigh(xb_model*, double alphaM, double betaK, double betaK0, double betaKc);
 
 /* ---- analysis set-up: BasicAnalysisBuilder::domainChanged (runtime/runtime/
  * BasicAnalysisBuilder.cpp:225): PlainHandler::handle (analysis/handler/PlainHandler.cpp:60),

@@ -1246,6 +1246,11 @@ void orc_newmark_predict(void* h, double a1, double a2, double a3, double a4) {
     m->acc[i] = ac0 * a4 + v0 * a3;
   }
 }
+/* AnalysisModel::setVel / setAccel: trial velocities and accelerations, [nn][ndf] */
+void orc_set_vel_accel(void* h, const double* v, const double* a) {
+  OrcModel* m = (OrcModel*)h;
+  memcpy(m->vel, v, sizeof(double) * m->nn * m->ndf); memcpy(m->acc, a, sizeof(double) * m->nn * m->ndf);
+}
 void orc_get_vel_accel(void* h, double* v, double* a) {
   OrcModel* m = (OrcModel*)h;
   memcpy(v, m->vel, sizeof(double) * m->nn * m->ndf); memcpy(a, m->acc, sizeof(double) * m->nn * m->ndf);

@@ -487,6 +487,10 @@ class OracleBackend(_Backend):
         self.L.orc_incr_response.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_double] * 3
         return self.L.orc_incr_response(self.h, _p(dU), cu, cv, ca)
 
+    def set_vel_accel(self, v, a):
+        v, a = np.ascontiguousarray(v, np.float64), np.ascontiguousarray(a, np.float64)
+        self.L.orc_set_vel_accel(self.h, _p(v), _p(a))
+
     def vel_accel(self):
         v = np.zeros((self.spec.nn, self.spec.ndf)); a = np.zeros_like(v)
         self.L.orc_get_vel_accel(self.h, _p(v), _p(a)); return v, a

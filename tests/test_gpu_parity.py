@@ -479,14 +479,17 @@ def test_partitioned_frame_matches_single_gpu():
             m.commit()
 
 
-@pytest.mark.parametrize("name", ["newmark_brick_j2", "newmark_frame2d", "newmark_frame3d"])
+@pytest.mark.parametrize("name", ["newmark_brick_j2", "newmark_frame2d", "newmark_frame3d", "rayleigh_brick_j2",
+                                  "rayleigh_quad_j2", "rayleigh_frame2d", "rayleigh_frame3d"])
 def test_newmark_device_vs_golden_reference_history(name):
     """Newmark (displacement form, nodal masses): the device replays the history recorded from the
     reference's own Newmark integrator -- c1 K + c3 M tangent, P - M a - R unbalance, predictor,
-    response update -- and matches A, B, velocities and accelerations."""
-    from golden_cases import TRANSIENT_CASES
+    response update -- and matches A, B, velocities and accelerations.  The rayleigh_* histories add
+    `rayleigh alphaM betaK betaKinit betaKcomm` and element masses from the material density: element tangent
+    c1 Kt + c2 (alphaM M + betaK Kt + betaK0 K0 + betaKc Kc) + c3 M, residual getResistingForceIncInertia."""
+    from golden_cases import RAYLEIGH_CASES, TRANSIENT_CASES
     from test_oracle import drive_transient_vs_golden
-    mk, *_ = TRANSIENT_CASES[name]
+    mk, *_ = {**TRANSIENT_CASES, **RAYLEIGH_CASES}[name]
     g = np.load(os.path.join(GOLD, name + ".npz"))
     spec = mk()
     D = xb.DeviceModel.from_spec(spec, setup=False)
@@ -500,6 +503,43 @@ def test_newmark_device_vs_golden_reference_history(name):
         assert np.abs(B - Bg).max() <= tol * bscale
 
     drive_transient_vs_golden(D, g, name, check)
+
+
+def test_partitioned_rayleigh_transient_matches_single_gpu():
+    """damping and element-mass terms on a partitioned model: interface rows (tangent, mass, damping forces)
+    travel like the static ones, owned rows are bitwise those of the single-GPU run"""
+    from golden_cases import J2_STEEL_RHO, RAYLEIGH, newmark_coeffs
+    mk = lambda: brick_block(5, 4, 6, mat=J2_STEEL_RHO, distort=0.2, seed=11)
+    spec = mk()
+    (c1, c2, c3), _ = newmark_coeffs(0.5, 0.25, 0.02)
+    rng = np.random.default_rng(12)
+
+    def prep(D):
+        D.to_device(0); D.set_rayleigh(*RAYLEIGH); D.set_transient(c1, c2, c3)
+        return D
+
+    G = prep(xb.DeviceModel.from_spec(spec, 1, 0))
+    O = OracleBackend(spec, 1, 0); O.set_rayleigh(*RAYLEIGH); O.set_transient(c1, c2, c3)
+    gptr, _ = G.pattern()
+    ranks = [prep(xb.DeviceModel.from_spec(mk(), 1, 0, 3, r)) for r in range(3)]
+    ids = G.ids()
+    for s in range(2):
+        u = rng.normal(0, 2e-3 * (s + 1), (spec.nn, 3)); u[ids < 0] = 0
+        v = rng.normal(0, 0.05, (spec.nn, 3)); v[ids < 0] = 0
+        a = rng.normal(0, 2.0, (spec.nn, 3)); a[ids < 0] = 0
+        G.set_trial_disp(u); G.set_vel_accel(v, a); G.update(); G.apply_load(0.5)
+        Ag, Bg = G.form_tangent(), G.form_unbalance()
+        O.set_trial_disp(u); O.set_vel_accel(v, a); O.apply_load(0.5)
+        assert relerr(Ag, O.form_tangent()) < 1e-11 and relerr(Bg, O.form_unbalance()) < 1e-11
+        for m in ranks:
+            m.set_vel_accel(v[m.node_tags() - 1], a[m.node_tags() - 1])
+        for m, (A, B) in zip(ranks, _partitioned_pass(ranks, u, 0.5)):
+            rows = m.row_eqns()
+            assert np.array_equal(B, Bg[rows])
+            assert np.array_equal(A, np.concatenate([Ag[gptr[q]:gptr[q + 1]] for q in rows]))
+        G.commit(); O.commit()
+        for m in ranks:
+            m.commit()
 
 
 def test_newmark_time_history_counts_match_oracle():

@@ -68,6 +68,7 @@ def _load():
         "xb_add_nodal_loads": (i32, [vp, i32, vp, vp]),
         "xb_set_nodal_mass": (i32, [vp, i32, vp, vp]),
         "xb_set_rayleigh_alpha_m": (i32, [vp, f64]),
+        "xb_set_rayleigh": (i32, [vp, f64, f64, f64, f64]),
         "xb_set_transient_factors": (i32, [vp, f64, f64, f64]),
         "xb_newmark_predict": (i32, [vp, f64, f64, f64, f64]),
         "xb_incr_trial_response": (i32, [vp, vp, f64, f64, f64]),
@@ -333,6 +334,10 @@ class DeviceModel:
     def set_rayleigh_alpha_m(self, alpha_m):
         self._ck(lib.xb_set_rayleigh_alpha_m(self._h, float(alpha_m)))
 
+    def set_rayleigh(self, alpha_m, beta_k, beta_k0, beta_kc):
+        """`rayleigh alphaM betaK betaKinit betaKcomm` on every element and node"""
+        self._ck(lib.xb_set_rayleigh(self._h, float(alpha_m), float(beta_k), float(beta_k0), float(beta_kc)))
+
     def set_transient(self, c1, c2, c3):
         self._ck(lib.xb_set_transient_factors(self._h, c1, c2, c3))
 
@@ -346,6 +351,11 @@ class DeviceModel:
         self._keep = dU
         if update:
             self.update()
+
+    def set_vel_accel(self, v, a):
+        """AnalysisModel::setVel / setAccel: trial velocities and accelerations of this rank's nodes, [nn][ndf]"""
+        v, a = _f64(v), _f64(a)
+        self._ck(lib.xb_set_trial_vel_accel(self._h, _ptr(v), _ptr(a)))
 
     def vel_accel(self):
         v = np.zeros((self.nn, self.ndf)); a = np.zeros((self.nn, self.ndf))

@@ -64,6 +64,17 @@ struct BeamView {
   double* sendK;
   int cps;
   double* Re;                  // [n][2*ndf]
+  // Rayleigh damping (Element::getDamp): initial stiffness kv0 = inverse of the initial flexibility
+  // (getInitialStiff), Kc = kv at the last commit (Element::commitState); both basic, column-major [nb*nb][n]
+  double* kv0;
+  double* kvK;
+};
+
+// transient coefficients handed to the form kernels (see TanCoef / DynCoef in device_model.cu)
+struct BeamDyn {
+  int k_on; double at, a0, ac;         // tangent: at kv + a0 kv0 + ac kvK
+  int r_on; double bK, bK0, bKc;       // resisting force: + T^T (bK kv + bK0 kv0 + bKc kvK) T v
+  const double* V;                     // trial velocities [nn][ndf]
 };
 
 __device__ __forceinline__ void lobatto_rule(int n, double* xi, double* wt) {
@@ -382,7 +393,7 @@ __global__ void __launch_bounds__(64) fbc2d_update_kernel(BeamView B, const doub
 
 // getTangentStiff -> LinearCrdTransf2d::getGlobalStiffMatrix(kv); getResistingForce ->
 // getGlobalResistingForce(Se).  Rows of node a go to that node's slot (node-major storage).
-__global__ void __launch_bounds__(128) fbc2d_form_kernel(BeamView B, int want_k, int want_r, int transpose) {
+__global__ void __launch_bounds__(128) fbc2d_form_kernel(BeamView B, int want_k, int want_r, int transpose, BeamDyn dy) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= B.n) return;
   const long long n = B.n;
@@ -390,6 +401,14 @@ __global__ void __launch_bounds__(128) fbc2d_form_kernel(BeamView B, int want_k,
   if (want_k) {
     double kb[9];
     for (int i = 0; i < 9; i++) kb[i] = B.kv[i * n + e];
+    if (dy.k_on) {
+      for (int i = 0; i < 9; i++) {
+        double t = dy.at * kb[i];
+        if (dy.a0 != 0.0) t += dy.a0 * B.kv0[i * n + e];
+        if (dy.ac != 0.0) t += dy.ac * B.kvK[i * n + e];
+        kb[i] = t;
+      }
+    }
     const double kb00 = kb[0], kb10 = kb[1], kb20 = kb[2], kb01 = kb[3], kb11 = kb[4], kb21 = kb[5], kb02 = kb[6], kb12 = kb[7], kb22 = kb[8];
     double tmp[3][6], kg[6][6];
     const double sl = sinTheta * oneOverL, cl = cosTheta * oneOverL;
@@ -415,7 +434,25 @@ __global__ void __launch_bounds__(128) fbc2d_form_kernel(BeamView B, int want_k,
     }
   }
   if (want_r) {
-    const double q0 = B.Se[e], q1 = B.Se[n + e], q2 = B.Se[2 * n + e];
+    double q0 = B.Se[e], q1 = B.Se[n + e], q2 = B.Se[2 * n + e];
+    if (dy.r_on) {
+      // Element::getRayleighDampingForces with stiffness-proportional terms: T^T [kd (T v)], kd basic
+      double vg[6], vb[3];
+      for (int a = 0; a < 2; a++) {
+        const int nd = B.conn[e * 2 + a];
+        for (int j = 0; j < 3; j++) vg[a * 3 + j] = dy.V[(size_t)nd * 3 + j];
+      }
+      crd2d_basic(L, cosTheta, sinTheta, vg, vb);
+      double qd[3] = {0, 0, 0};
+      for (int c = 0; c < 3; c++)
+        for (int r = 0; r < 3; r++) {
+          double kd = dy.bK * B.kv[(r + 3 * c) * n + e];
+          if (dy.bK0 != 0.0) kd += dy.bK0 * B.kv0[(r + 3 * c) * n + e];
+          if (dy.bKc != 0.0) kd += dy.bKc * B.kvK[(r + 3 * c) * n + e];
+          qd[r] += kd * vb[c];
+        }
+      q0 += qd[0]; q1 += qd[1]; q2 += qd[2];
+    }
     const double V = oneOverL * (q1 + q2);
     const double pl[6] = {-q0, V, q1, q0, -V, q2};
     double* R = B.Re + e * 6;
@@ -1103,7 +1140,7 @@ __global__ void __launch_bounds__(128, XB_FBC_SEC_OCC) fbc2d_update_sec_kernel(B
 
 // getTangentStiff -> LinearCrdTransf3d::getGlobalStiffMatrix(kv); getResistingForce ->
 // getGlobalResistingForce(Se).  Rows of node a (6 of them) go to that node's slot.
-__global__ void __launch_bounds__(64) fbc3d_form_kernel(BeamView B, int want_k, int want_r, int transpose) {
+__global__ void __launch_bounds__(64) fbc3d_form_kernel(BeamView B, int want_k, int want_r, int transpose, BeamDyn dy) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= B.n) return;
   const long long n = B.n;
@@ -1113,6 +1150,14 @@ __global__ void __launch_bounds__(64) fbc3d_form_kernel(BeamView B, int want_k, 
   if (want_k) {
     double kb[6][6], kl[12][12], tmp[12][12];
     for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) kb[i][j] = B.kv[(size_t)(i + 6 * j) * n + e];
+    if (dy.k_on) {
+      for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) {
+        double t = dy.at * kb[i][j];
+        if (dy.a0 != 0.0) t += dy.a0 * B.kv0[(size_t)(i + 6 * j) * n + e];
+        if (dy.ac != 0.0) t += dy.ac * B.kvK[(size_t)(i + 6 * j) * n + e];
+        kb[i][j] = t;
+      }
+    }
     for (int i = 0; i < 6; i++) {
       tmp[i][0] = -kb[i][0];
       tmp[i][1] = oneOverL * (kb[i][1] + kb[i][2]);
@@ -1160,6 +1205,24 @@ __global__ void __launch_bounds__(64) fbc3d_form_kernel(BeamView B, int want_k, 
   if (want_r) {
     double q[6];
     for (int i = 0; i < 6; i++) q[i] = B.Se[i * n + e];
+    if (dy.r_on) {
+      double vg[12], vb[6], Rf[9];
+      for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) Rf[3 * r + c] = R[r][c];
+      for (int a = 0; a < 2; a++) {
+        const int nd = B.conn[e * 2 + a];
+        for (int j = 0; j < 6; j++) vg[a * 6 + j] = dy.V[(size_t)nd * 6 + j];
+      }
+      crd3d_basic(L, Rf, vg, vb);
+      double qd[6] = {0, 0, 0, 0, 0, 0};
+      for (int c = 0; c < 6; c++)
+        for (int r = 0; r < 6; r++) {
+          double kd = dy.bK * B.kv[(size_t)(r + 6 * c) * n + e];
+          if (dy.bK0 != 0.0) kd += dy.bK0 * B.kv0[(size_t)(r + 6 * c) * n + e];
+          if (dy.bKc != 0.0) kd += dy.bKc * B.kvK[(size_t)(r + 6 * c) * n + e];
+          qd[r] += kd * vb[c];
+        }
+      for (int i = 0; i < 6; i++) q[i] += qd[i];
+    }
     double pl[12];
     pl[0] = -q[0]; pl[1] = oneOverL * (q[1] + q[2]); pl[2] = -oneOverL * (q[3] + q[4]); pl[3] = -q[5];
     pl[4] = q[3]; pl[5] = q[1]; pl[6] = q[0]; pl[7] = -pl[1]; pl[8] = -pl[2]; pl[9] = q[5]; pl[10] = q[4]; pl[11] = q[2];
@@ -1186,6 +1249,56 @@ __global__ void __launch_bounds__(64) fbc3d_revert_kernel(BeamView B) {
   for (int i = 0; i < 6; i++) B.Se[i * n + e] = B.Sec[i * n + e];
   for (int i = 0; i < 36; i++) B.kv[i * n + e] = B.kvc[i * n + e];
   B.iflag[e] = 0;
+}
+
+// ForceBeamColumn2d/3d::getInitialStiff in basic coordinates: the inverse of the initial flexibility
+// sum_i b_i^T fs0 b_i w_i L (getInitialFlexibility); thread per element, run once when betaK0 is first set
+__global__ void fbc_kv0_kernel(BeamView B) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B.n) return;
+  const long long n = B.n;
+  const double L = B.geo[e];
+  if (B.nb == 3) {
+    double f[9], k0[9], fS[4];
+    for (int q = 0; q < 9; q++) f[q] = 0.0;
+    for (int q = 0; q < 4; q++) fS[q] = __ldg(B.fs0 + q);
+    for (int i = 0; i < B.nip; i++) {
+      const double xL = lobatto_x(B.nip, i), xL1 = xL - 1.0, wtL = lobatto_w(B.nip, i) * L;
+      double fb[6];
+      for (int q = 0; q < 6; q++) fb[q] = 0.0;
+      for (int jj = 0; jj < 2; jj++) fb[jj + 2 * 0] += fS[jj + 2 * 0] * wtL;
+      for (int jj = 0; jj < 2; jj++) { const double tmp = fS[jj + 2 * 1] * wtL; fb[jj + 2 * 1] += xL1 * tmp; fb[jj + 2 * 2] += xL * tmp; }
+      for (int jj = 0; jj < 3; jj++) f[0 + 3 * jj] += fb[0 + 2 * jj];
+      for (int jj = 0; jj < 3; jj++) { const double tmp = fb[1 + 2 * jj]; f[1 + 3 * jj] += xL1 * tmp; f[2 + 3 * jj] += xL * tmp; }
+    }
+    inv3(f, k0);
+    for (int q = 0; q < 9; q++) B.kv0[(size_t)q * n + e] = k0[q];
+  } else {
+    double f5[25], f55 = 0.0, k5[25], k55;
+    for (int q = 0; q < 25; q++) f5[q] = 0.0;
+    double fS[9];
+    for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) fS[r + 3 * c] = __ldg(B.fs0 + r + 4 * c);
+    const double fT = __ldg(B.fs0 + 15);
+    for (int i = 0; i < B.nip; i++) {
+      const double xL = lobatto_x(B.nip, i), xL1 = xL - 1.0, wtL = lobatto_w(B.nip, i) * L;
+      double fb[3][5];
+      for (int r = 0; r < 3; r++) {
+        fb[r][0] = fS[r + 3 * 0] * wtL;
+        { const double tmp = fS[r + 3 * 1] * wtL; fb[r][1] = xL1 * tmp; fb[r][2] = xL * tmp; }
+        { const double tmp = fS[r + 3 * 2] * wtL; fb[r][3] = xL1 * tmp; fb[r][4] = xL * tmp; }
+      }
+      for (int c = 0; c < 5; c++) {
+        f5[0 + 5 * c] += fb[0][c];
+        { const double tmp = fb[1][c]; f5[1 + 5 * c] += xL1 * tmp; f5[2 + 5 * c] += xL * tmp; }
+        { const double tmp = fb[2][c]; f5[3 + 5 * c] += xL1 * tmp; f5[4 + 5 * c] += xL * tmp; }
+      }
+      f55 += fT * wtL;
+    }
+    inv5p1_flex(f5, f55, k5, k55);
+    for (int q = 0; q < 36; q++) B.kv0[(size_t)q * n + e] = 0.0;
+    for (int c = 0; c < 5; c++) for (int r = 0; r < 5; r++) B.kv0[(size_t)(r + 6 * c) * n + e] = k5[r + 5 * c];
+    B.kv0[(size_t)35 * n + e] = k55;
+  }
 }
 
 // Node::setTrialDisp bookkeeping: DU = Unew - U (incrDeltaDisp), U = Unew

@@ -46,12 +46,22 @@ struct GroupView {
   double* ht;           // J2: trial     epsilon_p (6) + xi   [7][ngp]
   double* sig;          // stress                              [nst][ngp]
   double* tan;          // J2: normal (6), c2, c3              [8][ngp]
+  double* tanc;         // the same at the last commit (Element::Kc, Rayleigh betaKc); null until `rayleigh` asks for it
   const long long* kdst;  // [n][nen] destination of the rows of node a: >= 0 in KeN, < 0 -(x+1) in sendK
   double* KeN;          // node-major element-tangent rows of the owned nodes
   double* sendK;        // rows for nodes other ranks own (interface exchange send buffer)
   int cps;              // columns per row in a slot (cp_stride)
   double* Re;           // [n][nd]
 };
+
+// Transient analysis with element damping / mass.  FE_Element::getTangent under Newmark::formEleTangent
+// (Newmark.cpp:262) is c1 Kt + c2 (alphaM M + betaK Kt + betaK0 K0 + betaKc Kc) + c3 M (Element::getDamp,
+// element/Element.cpp:182).  K is linear in the material tangent, so the element kernels form
+//   at Kt + a0 K0 + ac Kc + cM M,   at = c1 + c2 betaK, a0 = c2 betaK0, ac = c2 betaKc, cM = c2 alphaM + c3
+// (same terms, summed in another order: agreement with the reference is to rounding).  on = 0: static path.
+struct TanCoef { int on; double at, a0, ac, cM; };
+// Element::getResistingForceIncInertia: R + M a + (alphaM M + betaK Kt + betaK0 K0 + betaKc Kc) v
+struct DynCoef { int on; double aM, bK, bK0, bKc; };
 
 // =====================================================================================
 // state determination: Element::update -> NDMaterial::setTrialStrain
@@ -216,6 +226,175 @@ __global__ void __launch_bounds__(128, UPD_OCC) brick_update_kernel(GroupView G,
   brick_resid_store(G, e, g, live, shp, xsj, st);
 }
 
+// Brick::getResistingForceIncInertia (Brick.cpp:568): resid + formInertiaTerms (consistent mass, M a) +
+// Element::getRayleighDampingForces (D v).  One thread per Gauss point, as brick_update_kernel: the point's
+// share of  B^T [(betaK Dt + betaK0 D0 + betaKc Dc)(B v)] dvol + N rho (N a + alphaM N v) dvol  is summed over the
+// element's 8 lanes and added to the static residual the update kernel left in G.Re; the total goes to Rt.
+constexpr int DYN_XS = 74;   // per element in shared memory: X, V, A [8][3] each + pad
+template <int MATK>
+__global__ void __launch_bounds__(128) brick_dyn_resid_kernel(GroupView G, const double* __restrict__ X,
+                                                              const double* __restrict__ V, const double* __restrict__ A,
+                                                              DynCoef dc, double* __restrict__ Rt) {
+  const long long gp_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long ngp = G.n * 8;
+  const bool live = gp_raw < ngp;
+  const long long gp = live ? gp_raw : ngp - 1;
+  const long long e = gp >> 3;
+  const int g = (int)(gp_raw & 7);
+  __shared__ __align__(16) double sX[16 * DYN_XS];
+  double* xu = sX + (threadIdx.x >> 3) * DYN_XS;
+  {
+    const int nd = __ldg(G.conn + e * 8 + g);
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      xu[g * 3 + d] = __ldg(X + (size_t)nd * 3 + d);
+      xu[24 + g * 3 + d] = __ldg(V + (size_t)nd * 3 + d);
+      xu[48 + g * 3 + d] = __ldg(A + (size_t)nd * 3 + d);
+    }
+  }
+  __syncwarp();
+  double shp[4][8], dvol;
+  {
+    double xl[3][8];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      const double2 v = *reinterpret_cast<const double2*>(xu + 2 * i);
+      xl[(2 * i) % 3][(2 * i) / 3] = v.x;
+      xl[(2 * i + 1) % 3][(2 * i + 1) / 3] = v.y;
+    }
+    brick_shp(g, xl, shp, dvol);
+  }
+  // strain rate B v (engineering shears) and the accelerations / velocities interpolated at the point
+  double er[6] = {0, 0, 0, 0, 0, 0}, w[3] = {0, 0, 0};
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const double v0 = xu[24 + 3 * j], v1 = xu[25 + 3 * j], v2 = xu[26 + 3 * j];
+    er[0] += shp[0][j] * v0;
+    er[1] += shp[1][j] * v1;
+    er[2] += shp[2][j] * v2;
+    er[3] += shp[1][j] * v0 + shp[0][j] * v1;
+    er[4] += shp[2][j] * v1 + shp[1][j] * v2;
+    er[5] += shp[2][j] * v0 + shp[0][j] * v2;
+    w[0] += shp[3][j] * (xu[48 + 3 * j] + dc.aM * v0);
+    w[1] += shp[3][j] * (xu[49 + 3 * j] + dc.aM * v1);
+    w[2] += shp[3][j] * (xu[50 + 3 * j] + dc.aM * v2);
+  }
+  const double* p = G.mpar + (size_t)__ldg(G.mat + e) * 8;
+  const double rho = __ldg(p + (MATK == XB_MAT_J2PLASTICITY ? 7 : 2));
+  double sd[6] = {0, 0, 0, 0, 0, 0};
+  if (dc.bK != 0.0 || dc.bK0 != 0.0 || dc.bKc != 0.0) {
+    if (MATK == XB_MAT_J2PLASTICITY) {
+      const double bulk = __ldg(p), shear = __ldg(p + 1);
+      double n[6], nc[6] = {0, 0, 0, 0, 0, 0}, z[6] = {0, 0, 0, 0, 0, 0}, c2c = 0.0, c3c = 0.0;
+#pragma unroll
+      for (int q = 0; q < 6; q++) n[q] = G.tan[(size_t)q * ngp + gp];
+      const double c2 = G.tan[(size_t)6 * ngp + gp], c3 = G.tan[(size_t)7 * ngp + gp];
+      if (dc.bKc != 0.0) {
+#pragma unroll
+        for (int q = 0; q < 6; q++) nc[q] = G.tanc[(size_t)q * ngp + gp];
+        c2c = G.tanc[(size_t)6 * ngp + gp]; c3c = G.tanc[(size_t)7 * ngp + gp];
+      }
+#pragma unroll
+      for (int a = 0; a < 6; a++)
+#pragma unroll
+        for (int b = 0; b < 6; b++)
+          sd[a] += (dc.bK * j2_tangent_entry(a, b, bulk, shear, n, c2, c3) + dc.bK0 * j2_tangent_entry(a, b, bulk, shear, z, 0.0, 0.0) +
+                    dc.bKc * j2_tangent_entry(a, b, bulk, shear, nc, c2c, c3c)) * er[b];
+    } else {
+      const double E = __ldg(p), v = __ldg(p + 1);
+      double mu2 = E / (1.0 + v);
+      const double lam = v * mu2 / (1.0 - 2.0 * v);
+      const double mu = 0.50 * mu2;
+      mu2 += lam;
+      const double f = dc.bK + dc.bK0 + dc.bKc;
+      sd[0] = f * (mu2 * er[0] + lam * (er[1] + er[2]));
+      sd[1] = f * (mu2 * er[1] + lam * (er[0] + er[2]));
+      sd[2] = f * (mu2 * er[2] + lam * (er[0] + er[1]));
+      sd[3] = f * (mu * er[3]); sd[4] = f * (mu * er[4]); sd[5] = f * (mu * er[5]);
+    }
+  }
+  double st[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) st[i] = sd[i] * dvol;
+  const double m0 = rho * w[0] * dvol, m1 = rho * w[1] * dvol, m2 = rho * w[2] * dvol;
+  double r[24];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    r[3 * j + 0] = shp[0][j] * st[0] + shp[1][j] * st[3] + shp[2][j] * st[5] + m0 * shp[3][j];
+    r[3 * j + 1] = shp[1][j] * st[1] + shp[0][j] * st[3] + shp[2][j] * st[4] + m1 * shp[3][j];
+    r[3 * j + 2] = shp[2][j] * st[2] + shp[1][j] * st[4] + shp[0][j] * st[5] + m2 * shp[3][j];
+  }
+  double k12[12], k6[6], k3[3];
+  const bool hi4 = g & 4, hi2 = g & 2, hi1 = g & 1;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    const double send = hi4 ? r[i] : r[12 + i];
+    const double recv = __shfl_xor_sync(0xffffffffu, send, 4);
+    k12[i] = (hi4 ? r[12 + i] : r[i]) + recv;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    const double send = hi2 ? k12[i] : k12[6 + i];
+    const double recv = __shfl_xor_sync(0xffffffffu, send, 2);
+    k6[i] = (hi2 ? k12[6 + i] : k12[i]) + recv;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const double send = hi1 ? k6[i] : k6[3 + i];
+    const double recv = __shfl_xor_sync(0xffffffffu, send, 1);
+    k3[i] = (hi1 ? k6[3 + i] : k6[i]) + recv;
+  }
+  if (!live) return;
+  const double* in = G.Re + e * 24 + 3 * g;
+  double* out = Rt + e * 24 + 3 * g;
+  out[0] = in[0] + k3[0]; out[1] = in[1] + k3[1]; out[2] = in[2] + k3[2];
+}
+
+// Brick::formInertiaTerms(tangFlag = 1): the consistent mass sum_g rho N_j N_k dvol on the three dofs of every
+// node pair, times cM = c2 alphaM + c3, added to the element tangent already in the node slots.  8 lanes per
+// element: lane k evaluates Gauss point k, then owns column node k.
+__global__ void __launch_bounds__(128) brick_mass_add_kernel(GroupView G, const double* __restrict__ X, int rho_idx, double cM) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long tot = G.n * 8;
+  const bool live = t < tot;
+  const long long e = live ? t >> 3 : G.n - 1;
+  const int k = (int)(t & 7);
+  double xl[3][8];
+#pragma unroll
+  for (int a = 0; a < 8; a++) {
+    const int nd = __ldg(G.conn + e * 8 + a);
+#pragma unroll
+    for (int d = 0; d < 3; d++) xl[d][a] = __ldg(X + (size_t)nd * 3 + d);
+  }
+  double shp[4][8], dvol;
+  brick_shp(k, xl, shp, dvol);
+  const double rho = __ldg(G.mpar + (size_t)__ldg(G.mat + e) * 8 + rho_idx);
+  const double rd = rho * dvol;
+  double mk[8] = {0, 0, 0, 0, 0, 0, 0, 0};    // m_jk for this lane's column node k
+#pragma unroll
+  for (int g = 0; g < 8; g++) {
+    const int src = (threadIdx.x & 24) | g;     // lane of Gauss point g of this element
+    const double rdg = __shfl_sync(0xffffffffu, rd, src);
+    double ng[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) ng[j] = __shfl_sync(0xffffffffu, shp[3][j], src);
+    double nk = ng[0];
+#pragma unroll
+    for (int j = 1; j < 8; j++) if (k == j) nk = ng[j];
+#pragma unroll
+    for (int j = 0; j < 8; j++) mk[j] += (ng[j] * rdg) * nk;
+  }
+  if (!live) return;
+  const int cps = G.cps;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const long long d = __ldg(G.kdst + e * 8 + j);
+    double* base = d >= 0 ? G.KeN + d : G.sendK + (-d - 1);
+#pragma unroll
+    for (int pdof = 0; pdof < 3; pdof++) base[pdof * cps + 3 * k + pdof] += cM * mk[j];
+  }
+}
+
 // FourNodeQuad::update (FourNodeQuad.cpp:190-222); one thread per Gauss point
 template <int MATK>
 __global__ void __launch_bounds__(128) quad_update_kernel(GroupView G, const double* __restrict__ X,
@@ -281,7 +460,9 @@ __global__ void __launch_bounds__(128) quad_update_kernel(GroupView G, const dou
 // =====================================================================================
 
 // FourNodeQuad::getResistingForce (FourNodeQuad.cpp:507-553); thread per element
-__global__ void __launch_bounds__(128) quad_resid_kernel(GroupView G, const double* __restrict__ X) {
+template <int MATK>
+__global__ void __launch_bounds__(128) quad_resid_kernel(GroupView G, const double* __restrict__ X, DynCoef dc,
+                                                         const double* __restrict__ V, const double* __restrict__ A) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= G.n) return;
   const long long ngp = G.n * 4;
@@ -294,20 +475,84 @@ __global__ void __launch_bounds__(128) quad_resid_kernel(GroupView G, const doub
   }
   const double th = __ldg(G.par + e), b0 = __ldg(G.par + G.n + e), b1 = __ldg(G.par + 2 * G.n + e);
   double P[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // FourNodeQuad::getResistingForceIncInertia (FourNodeQuad.cpp:556): P + M a (lumped) + D v
+  double vel[4][2], md[4] = {0, 0, 0, 0};
+  const double* p = G.mpar + (size_t)__ldg(G.mat + e) * 8;
+  const double rho = dc.on ? __ldg(p + (MATK == XB_MAT_J2PLASTICITY ? 7 : 2)) : 0.0;
+  const bool stiff_damp = dc.on && (dc.bK != 0.0 || dc.bK0 != 0.0 || dc.bKc != 0.0);
+  if (dc.on) {
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const int nd = __ldg(c + a);
+      vel[a][0] = __ldg(V + (size_t)nd * 2); vel[a][1] = __ldg(V + (size_t)nd * 2 + 1);
+    }
+  }
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     double xi, eta, shp[3][4];
     quad_point(i, xi, eta);
     double dvol = quad_shp(xi, eta, xc, shp);
     dvol *= th;
-    const double s0 = G.sig[(size_t)0 * ngp + e * 4 + i], s1 = G.sig[(size_t)1 * ngp + e * 4 + i],
-                 s2 = G.sig[(size_t)2 * ngp + e * 4 + i];
+    double s0 = G.sig[(size_t)0 * ngp + e * 4 + i], s1 = G.sig[(size_t)1 * ngp + e * 4 + i],
+           s2 = G.sig[(size_t)2 * ngp + e * 4 + i];
+    if (dc.on) {
+#pragma unroll
+      for (int a = 0; a < 4; a++) md[a] += shp[2][a] * (dvol * rho);
+    }
+    if (stiff_damp) {
+      // (betaK Kt + betaK0 K0 + betaKc Kc) v = B^T [(betaK Dt + betaK0 D0 + betaKc Dc) (B v)] dvol: a stress-like term
+      double er[3] = {0, 0, 0};
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        er[0] += shp[0][b] * vel[b][0];
+        er[1] += shp[1][b] * vel[b][1];
+        er[2] += shp[0][b] * vel[b][1] + shp[1][b] * vel[b][0];
+      }
+      double D[6];   // 00 01 02 11 12 22 over (xx, yy, xy)
+      if (MATK == XB_MAT_J2PLASTICITY) {
+        const double bulk = __ldg(p), shear = __ldg(p + 1);
+        const long long gp = e * 4 + i;
+        double n[6], nc[6] = {0, 0, 0, 0, 0, 0}, z[6] = {0, 0, 0, 0, 0, 0}, c2c = 0.0, c3c = 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; q++) n[q] = G.tan[(size_t)q * ngp + gp];
+        const double c2 = G.tan[(size_t)6 * ngp + gp], c3 = G.tan[(size_t)7 * ngp + gp];
+        if (dc.bKc != 0.0) {
+#pragma unroll
+          for (int q = 0; q < 6; q++) nc[q] = G.tanc[(size_t)q * ngp + gp];
+          c2c = G.tanc[(size_t)6 * ngp + gp]; c3c = G.tanc[(size_t)7 * ngp + gp];
+        }
+        const int ia[6] = {0, 0, 0, 1, 1, 3}, ib[6] = {0, 1, 3, 1, 3, 3};
+#pragma unroll
+        for (int q = 0; q < 6; q++)
+          D[q] = dc.bK * j2_tangent_entry(ia[q], ib[q], bulk, shear, n, c2, c3) +
+                 dc.bK0 * j2_tangent_entry(ia[q], ib[q], bulk, shear, z, 0.0, 0.0) +
+                 dc.bKc * j2_tangent_entry(ia[q], ib[q], bulk, shear, nc, c2c, c3c);
+      } else {
+        const double E = __ldg(p), v = __ldg(p + 1);
+        const double mu2 = E / (1.0 + v);
+        const double lam = v * mu2 / (1.0 - 2.0 * v);
+        const double mu = 0.50 * mu2;
+        const double f = dc.bK + dc.bK0 + dc.bKc;
+        D[0] = f * (mu2 + lam); D[1] = f * lam; D[2] = 0.0; D[3] = f * (mu2 + lam); D[4] = 0.0; D[5] = f * mu;
+      }
+      s0 += D[0] * er[0] + D[1] * er[1] + D[2] * er[2];
+      s1 += D[1] * er[0] + D[3] * er[1] + D[4] * er[2];
+      s2 += D[2] * er[0] + D[4] * er[1] + D[5] * er[2];
+    }
 #pragma unroll
     for (int a = 0; a < 4; a++) {
       P[2 * a] += dvol * (shp[0][a] * s0 + shp[1][a] * s2);
       P[2 * a + 1] += dvol * (shp[1][a] * s1 + shp[0][a] * s2);
       P[2 * a] -= dvol * (shp[2][a] * b0);
       P[2 * a + 1] -= dvol * (shp[2][a] * b1);
+    }
+  }
+  if (dc.on && rho != 0.0) {
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const int nd = __ldg(c + a);
+#pragma unroll
+      for (int q = 0; q < 2; q++) P[2 * a + q] += md[a] * (__ldg(A + (size_t)nd * 2 + q) + dc.aM * vel[a][q]);
     }
   }
   double* out = G.Re + e * 8;
@@ -645,7 +890,11 @@ __device__ __forceinline__ void brick_D_regs(double m0, double m1, const double*
 
 template <int MATK>
 __global__ void __launch_bounds__(128, 2) brick_tangent_sym_kernel(GroupView G, const double* __restrict__ X,
-                                                                   int transpose, long long ebeg, long long eend) {
+                                                                   int transpose, long long ebeg, long long eend,
+                                                                   const double* __restrict__ tsrc, int tzero,
+                                                                   double scale, int accum) {
+  // tsrc: compact tangent to use (G.tan: current, G.tanc: committed); tzero: none, i.e. the initial (elastic)
+  // tangent; scale multiplies the matrix; accum adds to what the slots hold.  Static analysis: (G.tan, 0, 1, 0).
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = lane >> 3, k = lane & 7;
@@ -670,7 +919,7 @@ __global__ void __launch_bounds__(128, 2) brick_tangent_sym_kernel(GroupView G, 
   for (int d = 0; d < 3; d++) cx[d] = __ldg(X + (size_t)nd * 3 + d);
   if (MATK == XB_MAT_J2PLASTICITY) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) ct[i] = G.tan[(size_t)i * ngp + e * 8 + k];
+    for (int i = 0; i < 8; i++) ct[i] = tzero ? 0.0 : tsrc[(size_t)i * ngp + e * 8 + k];
   }
   cdst = __ldg(G.kdst + e * 8 + k);
   cm0 = __ldg(G.mpar + (size_t)mi * 8); cm1 = __ldg(G.mpar + (size_t)mi * 8 + 1);
@@ -699,7 +948,7 @@ __global__ void __launch_bounds__(128, 2) brick_tangent_sym_kernel(GroupView G, 
         for (int a = 0; a < 8; a += 2)
           *reinterpret_cast<double2*>(sN + k * BS_SG + (c * 4 + s) * 8 + a) = make_double2(shp[c][a], shp[c][a + 1]);
       double d21[22];
-      brick_D_regs<MATK>(cm0, cm1, ct, dvol, d21);
+      brick_D_regs<MATK>(cm0, cm1, ct, dvol * scale, d21);
       d21[21] = 0.0;
       double* dd = sD + k * BS_DG + s * 22;
 #pragma unroll
@@ -713,7 +962,7 @@ __global__ void __launch_bounds__(128, 2) brick_tangent_sym_kernel(GroupView G, 
       for (int d = 0; d < 3; d++) cx[d] = __ldg(X + (size_t)nd * 3 + d);
       if (MATK == XB_MAT_J2PLASTICITY) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) ct[i] = G.tan[(size_t)i * ngp + e * 8 + k];
+        for (int i = 0; i < 8; i++) ct[i] = tzero ? 0.0 : tsrc[(size_t)i * ngp + e * 8 + k];
       }
       cdst = __ldg(G.kdst + e * 8 + k);
       cm0 = __ldg(G.mpar + (size_t)mi * 8); cm1 = __ldg(G.mpar + (size_t)mi * 8 + 1);
@@ -797,8 +1046,9 @@ __global__ void __launch_bounds__(128, 2) brick_tangent_sym_kernel(GroupView G, 
           const int i = it * 32 + lane;            // double2 index inside the element: 8 nodes x 3 rows x 12
           const int a = i / 36, row = i / 12, c2 = i - row * 12;
           const long long dst = sDst[el * 8 + a];
-          const double2 v = *reinterpret_cast<const double2*>(tile + row * BS_R + 2 * c2);
+          double2 v = *reinterpret_cast<const double2*>(tile + row * BS_R + 2 * c2);
           double* out = (dst >= 0 ? G.KeN + dst : G.sendK + (-dst - 1)) + (row - 3 * a) * cps + 2 * c2;
+          if (accum) { const double2 o = *reinterpret_cast<const double2*>(out); v.x += o.x; v.y += o.y; }
           *reinterpret_cast<double2*>(out) = v;
         }
       }
@@ -813,7 +1063,7 @@ __global__ void __launch_bounds__(128, 2) brick_tangent_sym_kernel(GroupView G, 
 // owns column block beta=b (8 rows x 2 columns); shape functions are recomputed per lane.
 template <int MATK>
 __global__ void __launch_bounds__(128) quad_tangent_kernel(GroupView G, const double* __restrict__ X,
-                                                           int transpose) {
+                                                           int transpose, TanCoef tc) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long e = t >> 2;
   const int beta = (int)(t & 3);
@@ -829,6 +1079,7 @@ __global__ void __launch_bounds__(128) quad_tangent_kernel(GroupView G, const do
   const double th = __ldg(G.par + e);
   const double* p = G.mpar + (size_t)__ldg(G.mat + e) * 8;
   double K[8][2];
+  double mdiag = 0.0;
 #pragma unroll
   for (int i = 0; i < 8; i++) K[i][0] = K[i][1] = 0.0;
 #pragma unroll
@@ -849,6 +1100,20 @@ __global__ void __launch_bounds__(128) quad_tangent_kernel(GroupView G, const do
       D00 = j2_tangent_entry(0, 0, bulk, shear, n, c2, c3); D01 = j2_tangent_entry(0, 1, bulk, shear, n, c2, c3);
       D02 = j2_tangent_entry(0, 3, bulk, shear, n, c2, c3); D11 = j2_tangent_entry(1, 1, bulk, shear, n, c2, c3);
       D12 = j2_tangent_entry(1, 3, bulk, shear, n, c2, c3); D22 = j2_tangent_entry(3, 3, bulk, shear, n, c2, c3);
+      if (tc.on) {   // at Dt + a0 D0 + ac Dc
+        double z[6] = {0, 0, 0, 0, 0, 0}, nc[6] = {0, 0, 0, 0, 0, 0}, c2c = 0.0, c3c = 0.0;
+        if (tc.ac != 0.0) {
+#pragma unroll
+          for (int q = 0; q < 6; q++) nc[q] = G.tanc[(size_t)q * ngp + gp];
+          c2c = G.tanc[(size_t)6 * ngp + gp]; c3c = G.tanc[(size_t)7 * ngp + gp];
+        }
+        D00 = tc.at * D00 + tc.a0 * j2_tangent_entry(0, 0, bulk, shear, z, 0.0, 0.0) + tc.ac * j2_tangent_entry(0, 0, bulk, shear, nc, c2c, c3c);
+        D01 = tc.at * D01 + tc.a0 * j2_tangent_entry(0, 1, bulk, shear, z, 0.0, 0.0) + tc.ac * j2_tangent_entry(0, 1, bulk, shear, nc, c2c, c3c);
+        D02 = tc.at * D02 + tc.a0 * j2_tangent_entry(0, 3, bulk, shear, z, 0.0, 0.0) + tc.ac * j2_tangent_entry(0, 3, bulk, shear, nc, c2c, c3c);
+        D11 = tc.at * D11 + tc.a0 * j2_tangent_entry(1, 1, bulk, shear, z, 0.0, 0.0) + tc.ac * j2_tangent_entry(1, 1, bulk, shear, nc, c2c, c3c);
+        D12 = tc.at * D12 + tc.a0 * j2_tangent_entry(1, 3, bulk, shear, z, 0.0, 0.0) + tc.ac * j2_tangent_entry(1, 3, bulk, shear, nc, c2c, c3c);
+        D22 = tc.at * D22 + tc.a0 * j2_tangent_entry(3, 3, bulk, shear, z, 0.0, 0.0) + tc.ac * j2_tangent_entry(3, 3, bulk, shear, nc, c2c, c3c);
+      }
       D10 = D01; D20 = D02; D21 = D12;
     } else {
       const double E = __ldg(p), v = __ldg(p + 1);
@@ -856,10 +1121,13 @@ __global__ void __launch_bounds__(128) quad_tangent_kernel(GroupView G, const do
       const double lam = v * mu2 / (1.0 - 2.0 * v);
       const double mu = 0.50 * mu2;
       D00 = D11 = mu2 + lam; D01 = D10 = lam; D22 = mu; D02 = D20 = D12 = D21 = 0.0;
+      if (tc.on) { const double f = tc.at + tc.a0 + tc.ac; D00 *= f; D11 *= f; D01 *= f; D10 *= f; D22 *= f; }
     }
-    double sb0 = shp[0][0], sb1 = shp[1][0];
+    double sb0 = shp[0][0], sb1 = shp[1][0], sb2 = shp[2][0];
 #pragma unroll
-    for (int b = 1; b < 4; b++) if (beta == b) { sb0 = shp[0][b]; sb1 = shp[1][b]; }
+    for (int b = 1; b < 4; b++) if (beta == b) { sb0 = shp[0][b]; sb1 = shp[1][b]; sb2 = shp[2][b]; }
+    // FourNodeQuad::getMass (FourNodeQuad.cpp:387): lumped, N_beta rho dvol on both dofs of node beta
+    if (tc.on) mdiag += sb2 * (dvol * __ldg(p + (MATK == XB_MAT_J2PLASTICITY ? 7 : 2)));
     const double DB00 = dvol * (D00 * sb0 + D02 * sb1), DB10 = dvol * (D10 * sb0 + D12 * sb1),
                  DB20 = dvol * (D20 * sb0 + D22 * sb1), DB01 = dvol * (D01 * sb1 + D02 * sb0),
                  DB11 = dvol * (D11 * sb1 + D12 * sb0), DB21 = dvol * (D21 * sb1 + D22 * sb0);
@@ -870,6 +1138,10 @@ __global__ void __launch_bounds__(128) quad_tangent_kernel(GroupView G, const do
       K[2 * a + 1][0] += shp[1][a] * DB10 + shp[0][a] * DB20;
       K[2 * a + 1][1] += shp[1][a] * DB11 + shp[0][a] * DB21;
     }
+  }
+  if (tc.on && tc.cM != 0.0) {
+#pragma unroll
+    for (int b = 0; b < 4; b++) if (beta == b) { K[2 * b][0] += tc.cM * mdiag; K[2 * b + 1][1] += tc.cM * mdiag; }
   }
   // rows of node a go to that node's slot (node-major storage) or to the send buffer
   const int cps = G.cps;
@@ -1058,7 +1330,8 @@ struct DevGroup {
   GroupView v{};
   BeamView b{};              // forceBeamColumn batches
   int kind = 0, mat_kind = 0, nip = 0, nst = 0, nd = 0;
-  long long ngp = 0;
+  long long ngp = 0, re_off = 0;
+  bool has_rho = false;      // some material of the batch has a density (element mass)
   size_t fib_doubles = 0;    // size of one fibre-record buffer
 };
 
@@ -1092,6 +1365,11 @@ struct xb_model {
   int tangent_variant = 2;          // brick tangent kernel: 0 tile, 2 symmetric-pair persistent (XB_TANGENT=tile|sym)
   int num_sms = 148;
   double alphaM = 0.0;      // Node::setRayleighDampingFactor
+  // Element::setRayleighDampingFactors (`rayleigh alphaM betaK betaKinit betaKcomm`) and element masses
+  double rayM = 0.0, rayK = 0.0, rayK0 = 0.0, rayKc = 0.0;
+  bool any_rho = false;
+  double* dRt = nullptr;    // element resisting forces including inertia and damping (getResistingForceIncInertia)
+  double* dRsrc = nullptr;  // what formUnbalance assembles: dRe, or dRt once damping / element mass is in play
   double *dX = nullptr, *dU = nullptr, *dUc = nullptr, *dKe = nullptr, *dRe = nullptr, *dA = nullptr,
          *dB = nullptr, *dLoad = nullptr, *dMpar = nullptr, *dTmp = nullptr;
   int* dId = nullptr;
@@ -1114,6 +1392,10 @@ struct xb_model {
 };
 
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+extern "C" {
+static int apply_rayleigh(xb_model* m);
+static bool any_rayleigh(const xb_model* m);
+}
 #define CU(x)                                                                         \
   do {                                                                                \
     cudaError_t _e = (x);                                                             \
@@ -1470,6 +1752,7 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
       long long* kdst = nullptr;
       CU(dev_upload(m, &kdst, g.kdst));
       b.kdst = kdst; b.KeN = m->dKe; b.cps = h.cp_stride; b.Re = m->dRe + g.re_off;
+      d.re_off = g.re_off;
       m->dg.push_back(d);
       continue;
     }
@@ -1495,6 +1778,9 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
     CU(dev_upload(m, &kdst, g.kdst));
     d.v.kdst = kdst; d.v.KeN = m->dKe; d.v.cps = h.cp_stride;
     d.v.Re = m->dRe + g.re_off;
+    d.re_off = g.re_off;
+    for (int mi : g.mat) if (h.mats[mi].par[g.mat_kind == XB_MAT_J2PLASTICITY ? 7 : 2] != 0.0) { d.has_rho = true; break; }
+    if (d.has_rho) m->any_rho = true;
     m->dg.push_back(d);
   }
 
@@ -1531,7 +1817,10 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
   // plastic_integrator() on zero strain (J2Plasticity.cpp:105) so that getTangent()
   // is the elastic tangent before the first update; an update at U=0 reproduces that.
   CU(cudaDeviceSynchronize());   // the memsets above ran on the legacy stream
+  m->dRsrc = m->dRe;
   int rc = xb_update(m);
+  if (rc < 0) return rc;
+  rc = apply_rayleigh(m);           // element masses, or a `rayleigh` given before the model went to the device
   if (rc < 0) return rc;
   CU(cudaStreamSynchronize(m->stream));
   m->launches = 0;
@@ -1606,6 +1895,50 @@ int xb_set_rayleigh_alpha_m(xb_model* m, double alphaM) {
   m->alphaM = alphaM; m->av.alphaM = alphaM;
   return XB_OK;
 }
+// device side of `rayleigh`: buffers the damping terms need, sized on first use
+static int apply_rayleigh(xb_model* m) {
+  if (!m->on_device) return XB_OK;
+  CU(cudaSetDevice(m->device));
+  const bool dyn = any_rayleigh(m) || m->any_rho;
+  if (dyn && !m->dRt) {
+    CU(dev_alloc(m, &m->dRt, (size_t)std::max<long long>(m->h.re_total, 1)));
+    CU(cudaMemsetAsync(m->dRt, 0, sizeof(double) * std::max<long long>(m->h.re_total, 1), m->stream));
+  }
+  m->dRsrc = dyn ? m->dRt : m->dRe;
+  for (auto& d : m->dg) {
+    if (d.v.n == 0) continue;
+    if (is_beam(d.kind)) {
+      BeamView& b = d.b;
+      const size_t nk = (size_t)b.nb * b.nb * b.n;
+      b.Re = m->dRsrc + d.re_off;
+      if (m->rayK0 != 0.0 && !b.kv0) {   // Element::getInitialStiff, formed once
+        CU(dev_alloc(m, &b.kv0, nk));
+        fbc_kv0_kernel<<<(unsigned)((b.n + 127) / 128), 128, 0, m->stream>>>(b);
+        m->launches++;
+      }
+      if (m->rayKc != 0.0 && !b.kvK) {   // Element::setRayleighDampingFactors: Kc = new Matrix(getTangentStiff())
+        CU(dev_alloc(m, &b.kvK, nk));
+        CU(cudaMemcpyAsync(b.kvK, b.kv, sizeof(double) * nk, cudaMemcpyDeviceToDevice, m->stream));
+      }
+      continue;
+    }
+    if (d.kind != XB_ELE_STDBRICK) d.v.Re = m->dRsrc + d.re_off;   // bricks: the update kernel keeps writing dRe
+    if (m->rayKc != 0.0 && d.mat_kind == XB_MAT_J2PLASTICITY && !d.v.tanc) {
+      CU(dev_alloc(m, &d.v.tanc, (size_t)8 * d.ngp));
+      CU(cudaMemcpyAsync(d.v.tanc, d.v.tan, sizeof(double) * 8 * d.ngp, cudaMemcpyDeviceToDevice, m->stream));
+    }
+  }
+  CU(cudaGetLastError());
+  return XB_OK;
+}
+
+int xb_set_rayleigh(xb_model* m, double alphaM, double betaK, double betaK0, double betaKc) {
+  if (!m) return fail(XB_ERR_ARG, "null model");
+  m->rayM = alphaM; m->rayK = betaK; m->rayK0 = betaK0; m->rayKc = betaKc;
+  m->alphaM = alphaM; m->av.alphaM = alphaM;      // Domain::setRayleighDampingFactors also sets every node's factor
+  return apply_rayleigh(m);
+}
+
 int xb_set_transient_factors(xb_model* m, double c1, double c2, double c3) {
   NEED_DEVICE();
   m->av.c1 = c1; m->av.c2 = c2; m->av.c3 = c3;
@@ -1711,16 +2044,44 @@ int xb_apply_load(xb_model* m, double lambda) {
 
 static int pack_for_peers(xb_model* m, int which);
 
+static bool any_rayleigh(const xb_model* m) { return m->rayM != 0.0 || m->rayK != 0.0 || m->rayK0 != 0.0 || m->rayKc != 0.0; }
+static TanCoef tan_coef(const xb_model* m) {
+  const AsmView& a = m->av;
+  TanCoef t{0, 1.0, 0.0, 0.0, 0.0};
+  if ((a.c2 != 0.0 && any_rayleigh(m)) || (a.c3 != 0.0 && m->any_rho)) {
+    t.on = 1; t.at = a.c1 + a.c2 * m->rayK; t.a0 = a.c2 * m->rayK0; t.ac = a.c2 * m->rayKc; t.cM = a.c2 * m->rayM + a.c3;
+  }
+  return t;
+}
+static DynCoef dyn_coef(const xb_model* m) {
+  DynCoef d{0, 0.0, 0.0, 0.0, 0.0};
+  if (any_rayleigh(m) || m->any_rho) { d.on = 1; d.aM = m->rayM; d.bK = m->rayK; d.bK0 = m->rayK0; d.bKc = m->rayKc; }
+  return d;
+}
+static BeamDyn beam_dyn(const xb_model* m) {
+  const TanCoef t = tan_coef(m);
+  BeamDyn b{};
+  b.k_on = t.on; b.at = t.at; b.a0 = t.a0; b.ac = t.ac;
+  b.r_on = (m->rayK != 0.0 || m->rayK0 != 0.0 || m->rayKc != 0.0) ? 1 : 0;
+  b.bK = m->rayK; b.bK0 = m->rayK0; b.bKc = m->rayKc; b.V = m->dV;
+  return b;
+}
+
 // element-tangent kernels of one batch over the element range [ebeg, eend) (bricks) on `st`
 static int launch_group_tangents(xb_model* m, DevGroup& d, long long ebeg, long long eend, cudaStream_t st) {
   const int transpose = m->h.soe_kind == XB_SOE_SPARSE_GEN_COL ? 1 : 0;
+  const TanCoef tc = tan_coef(m);
   if (is_beam(d.kind)) {
-    if (d.kind == XB_ELE_FORCEBEAMCOLUMN3D) fbc3d_form_kernel<<<(unsigned)((d.b.n + 63) / 64), 64, 0, st>>>(d.b, 1, 0, transpose);
-    else fbc2d_form_kernel<<<(unsigned)((d.b.n + 127) / 128), 128, 0, st>>>(d.b, 1, 0, transpose);
+    if (d.kind == XB_ELE_FORCEBEAMCOLUMN3D) fbc3d_form_kernel<<<(unsigned)((d.b.n + 63) / 64), 64, 0, st>>>(d.b, 1, 0, transpose, beam_dyn(m));
+    else fbc2d_form_kernel<<<(unsigned)((d.b.n + 127) / 128), 128, 0, st>>>(d.b, 1, 0, transpose, beam_dyn(m));
     m->launches++;
     return XB_OK;
   }
   const bool j2 = d.mat_kind == XB_MAT_J2PLASTICITY;
+  if (d.kind == XB_ELE_STDBRICK && tc.on && !(m->tangent_variant == 2 && (m->h.cp_stride % 2) == 0 && !m->csc_direct_kernel))
+    return fail(XB_ERR_UNSUPPORTED, "Rayleigh damping / element mass need the default (symmetric-pair) brick tangent kernel");
+  if (d.kind == XB_ELE_STDBRICK && tc.on && (ebeg != 0 || eend != d.v.n))
+    return fail(XB_ERR_UNSUPPORTED, "Rayleigh damping / element mass: XB_PIPELINE must be off");
   if (d.kind == XB_ELE_STDBRICK) {
     const unsigned blocks = (unsigned)((eend - ebeg + BT_ELEMS - 1) / BT_ELEMS);
     if (transpose && m->h.cp_stride == 24 && m->csc_direct_kernel) {
@@ -1745,12 +2106,22 @@ static int launch_group_tangents(xb_model* m, DevGroup& d, long long ebeg, long 
         if (per_sm < 1) per_sm = 1;
         long long grid = (long long)per_sm * m->num_sms;
         if (grid > (nbat + 3) / 4) grid = (nbat + 3) / 4;
-        kern<<<(unsigned)grid, 128, sms, st>>>(d.v, m->dX, transpose, ebeg, eend);
+        // static analysis, or a transient one without element damping / mass: one pass on the current tangent.
+        // Otherwise (c1 + c2 betaK) Kt + c2 betaK0 K0 + c2 betaKc Kc, one pass per term (K is linear in D).
+        if (!tc.on) { kern<<<(unsigned)grid, 128, sms, st>>>(d.v, m->dX, transpose, ebeg, eend, d.v.tan, 0, 1.0, 0); return XB_OK; }
+        if (!j2) { kern<<<(unsigned)grid, 128, sms, st>>>(d.v, m->dX, transpose, ebeg, eend, d.v.tan, 0, tc.at + tc.a0 + tc.ac, 0); return XB_OK; }
+        kern<<<(unsigned)grid, 128, sms, st>>>(d.v, m->dX, transpose, ebeg, eend, d.v.tan, 0, tc.at, 0);
+        if (tc.a0 != 0.0) { kern<<<(unsigned)grid, 128, sms, st>>>(d.v, m->dX, transpose, ebeg, eend, d.v.tan, 1, tc.a0, 1); m->launches++; }
+        if (tc.ac != 0.0) { kern<<<(unsigned)grid, 128, sms, st>>>(d.v, m->dX, transpose, ebeg, eend, d.v.tanc, 0, tc.ac, 1); m->launches++; }
         return XB_OK;
       };
       int rc = j2 ? go(brick_tangent_sym_kernel<XB_MAT_J2PLASTICITY>) : go(brick_tangent_sym_kernel<XB_MAT_ELASTIC_ISOTROPIC>);
       if (rc < 0) return rc;
       m->launches++;
+      if (tc.on && tc.cM != 0.0 && d.has_rho) {
+        brick_mass_add_kernel<<<(unsigned)((d.v.n * 8 + 127) / 128), 128, 0, st>>>(d.v, m->dX, j2 ? 7 : 2, tc.cM);
+        m->launches++;
+      }
       return XB_OK;
     }
     const size_t sm = sizeof(double) * (BT_ELEMS / 4) * BT_WARP_DOUBLES;
@@ -1763,8 +2134,8 @@ static int launch_group_tangents(xb_model* m, DevGroup& d, long long ebeg, long 
     }
   } else {
     const unsigned blocks = (unsigned)((d.v.n * 4 + 127) / 128);
-    if (j2) quad_tangent_kernel<XB_MAT_J2PLASTICITY><<<blocks, 128, 0, st>>>(d.v, m->dX, transpose);
-    else quad_tangent_kernel<XB_MAT_ELASTIC_ISOTROPIC><<<blocks, 128, 0, st>>>(d.v, m->dX, transpose);
+    if (j2) quad_tangent_kernel<XB_MAT_J2PLASTICITY><<<blocks, 128, 0, st>>>(d.v, m->dX, transpose, tc);
+    else quad_tangent_kernel<XB_MAT_ELASTIC_ISOTROPIC><<<blocks, 128, 0, st>>>(d.v, m->dX, transpose, tc);
   }
   m->launches++;
   return XB_OK;
@@ -1801,7 +2172,7 @@ static int pack_for_peers(xb_model* m, int which) {
   if (which == 0) return XB_OK;   // tangent rows were written into the send buffer by the element kernel
   const long long nch = (long long)m->h.pr_src.size();
   if (nch == 0) return XB_OK;
-  pack_resid_kernel<<<(unsigned)((nch * m->h.ndf + 255) / 256), 256, 0, m->stream>>>(nch, m->dPrSrc, m->dPrDst, m->h.ndf, m->dRe, m->dSendR);
+  pack_resid_kernel<<<(unsigned)((nch * m->h.ndf + 255) / 256), 256, 0, m->stream>>>(nch, m->dPrSrc, m->dPrDst, m->h.ndf, m->dRsrc, m->dSendR);
   m->launches++;
   CU(cudaGetLastError());
   return XB_OK;
@@ -1879,18 +2250,20 @@ static int launch_assemble(xb_model* m, long long first, long long count, cudaSt
   const size_t sm = sizeof(double) * warps * m->h.ndf * m->av.max_row;
   if (sm > 200 * 1024) return fail(XB_ERR_UNSUPPORTED, "row too long for the node-owned assembly kernel");
   const unsigned blocks = (unsigned)((count + warps - 1) / warps);
+  AsmView av = m->av;
+  if (tan_coef(m).on) av.c1 = 1.0;   // the element kernels already folded c1 (and the damping / mass terms) in
   if (m->h.ndf == 3) {
     CU(cudaFuncSetAttribute(assemble_A_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    assemble_A_kernel<3><<<blocks, warps * 32, sm, st>>>(m->av, m->dKe, m->dA, m->dTask, first, count);
+    assemble_A_kernel<3><<<blocks, warps * 32, sm, st>>>(av, m->dKe, m->dA, m->dTask, first, count);
   } else if (m->h.ndf == 6) {
     CU(cudaFuncSetAttribute(assemble_A_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    assemble_A_kernel<6><<<blocks, warps * 32, sm, st>>>(m->av, m->dKe, m->dA, m->dTask, first, count);
+    assemble_A_kernel<6><<<blocks, warps * 32, sm, st>>>(av, m->dKe, m->dA, m->dTask, first, count);
   } else if (m->h.ndf == 2) {
     CU(cudaFuncSetAttribute(assemble_A_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    assemble_A_kernel<2><<<blocks, warps * 32, sm, st>>>(m->av, m->dKe, m->dA, m->dTask, first, count);
+    assemble_A_kernel<2><<<blocks, warps * 32, sm, st>>>(av, m->dKe, m->dA, m->dTask, first, count);
   } else {
     CU(cudaFuncSetAttribute(assemble_A_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    assemble_A_kernel<1><<<blocks, warps * 32, sm, st>>>(m->av, m->dKe, m->dA, m->dTask, first, count);
+    assemble_A_kernel<1><<<blocks, warps * 32, sm, st>>>(av, m->dKe, m->dA, m->dTask, first, count);
   }
   m->launches++;
   return XB_OK;
@@ -1995,17 +2368,28 @@ int xb_form_element_resids(xb_model* m) {
   NEED_DEVICE();
   CU(cudaSetDevice(m->device));
   long long bytes = 0;
+  const DynCoef dc = dyn_coef(m);
   for (auto& d : m->dg) {
     if (d.v.n == 0) continue;
     if (is_beam(d.kind)) {
-      if (d.kind == XB_ELE_FORCEBEAMCOLUMN3D) fbc3d_form_kernel<<<(unsigned)((d.b.n + 63) / 64), 64, 0, m->stream>>>(d.b, 0, 1, 0);
-      else fbc2d_form_kernel<<<(unsigned)((d.b.n + 127) / 128), 128, 0, m->stream>>>(d.b, 0, 1, 0);
+      if (d.kind == XB_ELE_FORCEBEAMCOLUMN3D) fbc3d_form_kernel<<<(unsigned)((d.b.n + 63) / 64), 64, 0, m->stream>>>(d.b, 0, 1, 0, beam_dyn(m));
+      else fbc2d_form_kernel<<<(unsigned)((d.b.n + 127) / 128), 128, 0, m->stream>>>(d.b, 0, 1, 0, beam_dyn(m));
       m->launches++;
       bytes += d.b.n * (d.b.nb + 2 * d.b.nb) * 8;
       continue;
     }
-    if (d.kind == XB_ELE_STDBRICK) continue;   // brick_update_kernel already left Re (it is a function of the state only)
-    quad_resid_kernel<<<(unsigned)((d.v.n + 127) / 128), 128, 0, m->stream>>>(d.v, m->dX);
+    if (d.kind == XB_ELE_STDBRICK) {   // brick_update_kernel already left Re (it is a function of the state only)
+      if (dc.on) {   // + inertia and damping forces -> dRt
+        double* rt = m->dRt + d.re_off;
+        const unsigned blocks = (unsigned)((d.ngp + 127) / 128);
+        if (d.mat_kind == XB_MAT_J2PLASTICITY) brick_dyn_resid_kernel<XB_MAT_J2PLASTICITY><<<blocks, 128, 0, m->stream>>>(d.v, m->dX, m->dV, m->dAcc, dc, rt);
+        else brick_dyn_resid_kernel<XB_MAT_ELASTIC_ISOTROPIC><<<blocks, 128, 0, m->stream>>>(d.v, m->dX, m->dV, m->dAcc, dc, rt);
+        m->launches++;
+      }
+      continue;
+    }
+    if (d.mat_kind == XB_MAT_J2PLASTICITY) quad_resid_kernel<XB_MAT_J2PLASTICITY><<<(unsigned)((d.v.n + 127) / 128), 128, 0, m->stream>>>(d.v, m->dX, dc, m->dV, m->dAcc);
+    else quad_resid_kernel<XB_MAT_ELASTIC_ISOTROPIC><<<(unsigned)((d.v.n + 127) / 128), 128, 0, m->stream>>>(d.v, m->dX, dc, m->dV, m->dAcc);
     m->launches++;
     bytes += d.ngp * 8 * d.nst + d.v.n * ((long long)d.nd * 8 + (d.nd / m->h.ndf) * 4);
   }
@@ -2020,7 +2404,7 @@ int xb_assemble_unbalance(xb_model* m, double* B) {
   CU(cudaSetDevice(m->device));
   const long long ndof = (long long)m->h.nn() * m->h.ndf;
   if (ndof) {
-    assemble_B_kernel<<<(unsigned)((ndof + 255) / 256), 256, 0, m->stream>>>(m->av, m->dRe, m->lambda, m->dB);
+    assemble_B_kernel<<<(unsigned)((ndof + 255) / 256), 256, 0, m->stream>>>(m->av, m->dRsrc, m->lambda, m->dB);
     m->launches++;
   }
   long long bytes = (long long)m->h.nrows * 8 + (long long)m->h.nn() * (m->h.ndm + m->h.ndf) * 8;
@@ -2057,7 +2441,12 @@ int xb_commit(xb_model* m) {
       CU(cudaMemcpyAsync(b.vsc, b.vs, sizeof(double) * b.nip * b.ord * b.n, cudaMemcpyDeviceToDevice, m->stream));
       CU(cudaMemcpyAsync(b.Sec, b.Se, sizeof(double) * b.nb * b.n, cudaMemcpyDeviceToDevice, m->stream));
       CU(cudaMemcpyAsync(b.kvc, b.kv, sizeof(double) * b.nb * b.nb * b.n, cudaMemcpyDeviceToDevice, m->stream));
-    } else if (d.mat_kind == XB_MAT_J2PLASTICITY) std::swap(d.v.hc, d.v.ht);
+      // Element::commitState: *Kc = getTangentStiff()
+      if (b.kvK) CU(cudaMemcpyAsync(b.kvK, b.kv, sizeof(double) * b.nb * b.nb * b.n, cudaMemcpyDeviceToDevice, m->stream));
+    } else if (d.mat_kind == XB_MAT_J2PLASTICITY) {
+      if (d.v.tanc) CU(cudaMemcpyAsync(d.v.tanc, d.v.tan, sizeof(double) * 8 * d.ngp, cudaMemcpyDeviceToDevice, m->stream));
+      std::swap(d.v.hc, d.v.ht);
+    }
   }
   const size_t nb = sizeof(double) * m->h.nn() * m->h.ndf;
   CU(cudaMemcpyAsync(m->dUc, m->dU, nb, cudaMemcpyDeviceToDevice, m->stream));
@@ -2131,7 +2520,9 @@ int xb_get_element_resid(xb_model* m, long long e, double* R) {
   const xb::EleKind& k = xb::ele_kind(g.kind);
   const int nd = k.nen * k.ndf;
   CU(cudaStreamSynchronize(m->stream));
-  CU(cudaMemcpy(R, m->dRe + g.re_off + (long long)m->h.fe_local[e] * nd, sizeof(double) * nd, cudaMemcpyDeviceToHost));
+  // Element::getResistingForce; once damping / element mass is on, quads and beams leave getResistingForceIncInertia here
+  const double* src = g.kind == XB_ELE_STDBRICK ? m->dRe : m->dRsrc;
+  CU(cudaMemcpy(R, src + g.re_off + (long long)m->h.fe_local[e] * nd, sizeof(double) * nd, cudaMemcpyDeviceToHost));
   return nd;
 }
 
