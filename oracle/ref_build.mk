@@ -54,7 +54,15 @@ $(OUT)/libmetis_ref.so: $(wildcard $(REF)/OTHER/METIS/*.c)
 	@$(CC) -O2 -fPIC -shared -std=gnu89 -w -fcommon -I$(REF)/OTHER/METIS $^ -o $@ -lm
 
 # ---- the harness shared library the tests and the reference bench arm load ----
-harness: $(OUT)/libref_harness.so $(OUT)/libmetis_ref.so
+harness: $(OUT)/libref_harness.so $(OUT)/libmetis_ref.so $(OUT)/libref_glue.so
+
+# ---- the reference-side binding of INTEGRATION.md, built for real: the reference's own Newton loop on top of
+# the C ABI (tests only; links the product library, so it is kept apart from the harness the CPU arm loads) ----
+XB_DIR := ../xara_b200
+$(OUT)/libref_glue.so: ref_glue.cpp ref_harness.cpp ref_shims.cpp ../include/xara_b200.h $(OUT)/libxara_ref.a
+	@echo "link $@"
+	@$(CXX) -std=c++17 -O2 -fPIC -w -D_LINUX -D_UNIX $(INCS) -shared ref_glue.cpp ref_shims.cpp \
+	    -o $@ $(OUT)/libxara_ref.a -L$(XB_DIR) -lxara_b200 -Wl,-rpath,'$$ORIGIN/../../xara_b200' -Wl,--no-undefined
 $(OUT)/libref_harness.so: ref_harness.cpp ref_shims.cpp $(OUT)/libxara_ref.a
 	@echo "link $@"
 	@$(CXX) -std=c++17 -O2 -fPIC -w -D_LINUX -D_UNIX $(INCS) -shared ref_harness.cpp ref_shims.cpp \

@@ -1,0 +1,224 @@
+// TEST INFRASTRUCTURE ONLY -- the reference-side binding of INTEGRATION.md, built for real.
+//
+// The reference's OWN analysis objects (AnalysisModel, PlainHandler, numberer, SparseGenCol/Row
+// LinearSOE + solver, NewtonRaphson, CTestNormDispIncr, LoadControl::newStep) run a static analysis
+// in which only the three loops of the hot path are replaced by calls through the C ABI of
+// include/xara_b200.h:
+//     IncrementalIntegrator::formTangent   -> xb_form_tangent   (A lands in the SOE's own array)
+//     StaticIntegrator::formUnbalance      -> xb_apply_load + xb_form_unbalance
+//     LoadControl::update -> updateDomain  -> xb_incr_trial_disp + xb_update
+//     IncrementalIntegrator::commit        -> xb_commit (+ the reference's own commitDomain for the nodes)
+// The device model is read OUT OF THE REFERENCE'S Domain (nodes, SP constraints, Brick / FourNodeQuad
+// elements and their J2Plasticity / ElasticIsotropic materials, nodal loads): no script or model
+// command changes.  tests/test_gpu_parity.py compares the iteration counts and norms of this run
+// with those of the unmodified reference run -- the reference's own convergence test decides both.
+//
+// Built by oracle/ref_build.mk into oracle/_ref/libref_glue.so (links libxara_ref.a and
+// xara_b200/libxara_b200.so).  It re-uses the harness (model building through the reference's
+// classes) by including its translation unit; private members the glue has to read (element
+// connectivity, material parameters -- a maintainer would add accessors) are opened for this
+// translation unit only.
+#include <array>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#define private public
+#define protected public
+#include <LoadControl.h>               // before the harness: it drops the defines half way through its own includes
+#include <Brick.h>
+#include <FourNodeQuad.h>
+#include <J2Plasticity.h>
+#include <ElasticIsotropicMaterial.h>
+#include "ref_harness.cpp"
+#undef private
+#undef protected
+#include <SP_ConstraintIter.h>
+#include <LoadPatternIter.h>
+#include <NodalLoadIter.h>
+
+#include "../include/xara_b200.h"
+
+namespace {
+
+struct Glue {
+  xb_model* x = nullptr;
+  std::string err;
+};
+std::map<void*, Glue> g_glue;
+
+// INTEGRATION.md "B200Assembler::domainChanged": the Domain -> xb_model
+int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
+  Domain* dom = m->domain;
+  xb_model* x = xb_model_create(m->ndm, m->ndf);
+  if (!x) { G.err = xb_last_error(); return -1; }
+  G.x = x;
+  // 1. nodes in Domain order
+  std::vector<int> tags; std::vector<double> crd;
+  { NodeIter& ni = dom->getNodes(); Node* nd;
+    while ((nd = ni()) != nullptr) {
+      tags.push_back(nd->getTag());
+      const Vector& c = nd->getCrds();
+      for (int d = 0; d < m->ndm; d++) crd.push_back(c(d));
+    } }
+  if (xb_add_nodes(x, (int)tags.size(), tags.data(), crd.data()) < 0) { G.err = xb_last_error(); return -2; }
+  // 2. SP constraints
+  std::vector<int> spn, spd;
+  { SP_ConstraintIter& si = dom->getDomainAndLoadPatternSPs(); SP_Constraint* sp;
+    while ((sp = si()) != nullptr) { spn.push_back(sp->getNodeTag()); spd.push_back(sp->getDOF_Number()); } }
+  if (!spn.empty() && xb_add_sp(x, (int)spn.size(), spn.data(), spd.data()) < 0) { G.err = xb_last_error(); return -3; }
+  // 3. materials and elements, one batch per (element class, material kind)
+  struct Batch { std::vector<int> tag, conn, mat; std::vector<double> par; };
+  std::map<std::pair<int, int>, Batch> batches;     // (xb element kind, xb material kind)
+  std::map<int, int> mats_done;
+  auto material = [&](NDMaterial* nm, int& kind) -> int {
+    double p[8] = {0, 0, 0, 0, 0, 0, 0, 0}; int np = 0;
+    if (auto* j = dynamic_cast<J2Plasticity*>(nm)) {
+      kind = XB_MAT_J2PLASTICITY;
+      p[0] = j->bulk; p[1] = j->shear; p[2] = j->sigma_0; p[3] = j->sigma_infty; p[4] = j->delta; p[5] = j->Hard; p[6] = j->eta; p[7] = j->rho; np = 8;
+    } else if (auto* e = dynamic_cast<ElasticIsotropicMaterial*>(nm)) {
+      kind = XB_MAT_ELASTIC_ISOTROPIC; p[0] = e->E; p[1] = e->v; p[2] = e->rho; np = 3;
+    } else return -1;
+    const int tag = nm->getTag();            // getCopy keeps the tag of the nDMaterial command
+    if (!mats_done.count(tag)) {
+      if (xb_add_nd_material(x, tag, kind, p, np) < 0) return -2;
+      mats_done[tag] = kind;
+    }
+    return tag;
+  };
+  { ElementIter& ei = dom->getElements(); Element* el;
+    while ((el = ei()) != nullptr) {
+      int mk = 0;
+      if (auto* b = dynamic_cast<Brick*>(el)) {
+        const int mt = material(b->materialPointers[0], mk);
+        if (mt < 0) { G.err = "glue: unsupported nDMaterial in a Brick"; return -4; }
+        Batch& B = batches[{XB_ELE_STDBRICK, mk}];
+        B.tag.push_back(el->getTag()); B.mat.push_back(mt);
+        for (int a = 0; a < 8; a++) B.conn.push_back(b->connectedExternalNodes(a));
+        for (int d = 0; d < 3; d++) B.par.push_back(b->b[d]);
+      } else if (auto* q = dynamic_cast<FourNodeQuad*>(el)) {
+        const int mt = material(q->theMaterial[0], mk);
+        if (mt < 0) { G.err = "glue: unsupported nDMaterial in a FourNodeQuad"; return -4; }
+        Batch& B = batches[{XB_ELE_FOURNODEQUAD, mk}];
+        B.tag.push_back(el->getTag()); B.mat.push_back(mt);
+        for (int a = 0; a < 4; a++) B.conn.push_back(q->connectedExternalNodes(a));
+        const double par[6] = {q->thickness, 0.0, q->pressure, q->rho, q->b[0], q->b[1]};
+        B.par.insert(B.par.end(), par, par + 6);
+      } else { G.err = "glue: element class outside the device path (keep the CPU integrator)"; return -5; }
+    } }
+  for (auto& kv : batches) {
+    Batch& B = kv.second;
+    const int stride = kv.first.first == XB_ELE_STDBRICK ? 3 : 6;
+    if (xb_add_elements(x, kv.first.first, (int)B.tag.size(), B.tag.data(), B.conn.data(), B.mat.data(), B.par.data(), stride) < 0) {
+      G.err = xb_last_error(); return -6;
+    }
+  }
+  // 4. nodal loads of the load patterns (Linear series)
+  { LoadPatternIter& pi = dom->getLoadPatterns(); LoadPattern* lp;
+    while ((lp = pi()) != nullptr) {
+      NodalLoadIter& li = lp->getNodalLoads(); NodalLoad* nl;
+      while ((nl = li()) != nullptr) {
+        int type; const Vector& v = nl->getData(type);
+        std::vector<double> vals(m->ndf, 0.0);
+        for (int d = 0; d < m->ndf && d < v.Size(); d++) vals[d] = v(d);
+        const int nt = nl->getNodeTag();
+        if (xb_add_nodal_loads(x, 1, &nt, vals.data()) < 0) { G.err = xb_last_error(); return -7; }
+      }
+    } }
+  // 5. the same numberer / SOE as the analysis; the numbering must be the reference's own
+  const int neq = xb_setup(x, numberer, soeKind);
+  if (neq < 0) { G.err = xb_last_error(); return -8; }
+  if (neq != m->soe->getNumEqn()) { G.err = "glue: equation count differs from the reference's"; return -9; }
+  std::vector<int> xt(tags.size()), ids(tags.size() * m->ndf);
+  xb_get_node_tags(x, xt.data()); xb_get_ids(x, ids.data());
+  for (size_t i = 0; i < xt.size(); i++) {
+    const ID& rid = dom->getNode(xt[i])->getDOF_GroupPtr()->getID();
+    for (int d = 0; d < m->ndf; d++)
+      if (rid(d) != ids[i * m->ndf + d]) { G.err = "glue: DOF numbering differs from the reference's"; return -10; }
+  }
+  if (xb_device_init(x, device, nullptr) < 0) { G.err = xb_last_error(); return -11; }
+  return neq;
+}
+
+// INTEGRATION.md "B200LoadControl"
+class B200LoadControl : public LoadControl {
+ public:
+  B200LoadControl(double dl) : LoadControl(dl, 1, dl, dl) {}
+  xb_model* x = nullptr;
+  RefModel* rm = nullptr;
+  long calls[4] = {0, 0, 0, 0};
+  double* soeA() { return rm->rsoe ? rm->rsoe->A : rm->csoe->A; }
+  Vector& soeB() { return rm->rsoe ? rm->rsoe->B : rm->csoe->B; }
+
+  int formTangent(int statFlag) override {
+    if (statFlag != CURRENT_TANGENT) return LoadControl::formTangent(statFlag);
+    statusFlag = statFlag;
+    this->getLinearSOE()->zeroA();              // resets the solver's "factored" flag; every entry is overwritten below
+    calls[0]++;
+    return xb_form_tangent(x, soeA());
+  }
+  int formTangent(int statFlag, double iFactor, double cFactor) override {
+    if (statFlag != CURRENT_TANGENT) return LoadControl::formTangent(statFlag, iFactor, cFactor);
+    return this->formTangent(statFlag);
+  }
+  // StaticIntegrator::formUnbalance is final: zeroB(); formElementResidual(); formNodalUnbalance()
+  int formElementResidual() override {
+    calls[1]++;
+    if (xb_apply_load(x, this->getAnalysisModel()->getCurrentDomainTime()) < 0) return -1;
+    Vector& B = soeB();
+    return xb_form_unbalance(x, &B(0));         // elements and nodal loads, the whole right-hand side
+  }
+  int formNodalUnbalance() override { return 0; }
+  int update(const Vector& dU) override {
+    AnalysisModel* am = this->getAnalysisModel();
+    LinearSOE* soe = this->getLinearSOE();
+    am->incrDisp(dU);                            // the reference's nodes follow (recorders read them); no Element::update
+    calls[2]++;
+    std::vector<double> du(dU.Size());
+    for (int i = 0; i < dU.Size(); i++) du[i] = dU(i);
+    if (xb_incr_trial_disp(x, du.data()) < 0 || xb_update(x) < 0) return -1;
+    soe->setX(dU);
+    numIncrLastStep++;
+    return 0;
+  }
+  int commit() override {
+    calls[3]++;
+    if (xb_commit(x) < 0) return -1;
+    return LoadControl::commit();
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+// analysis set-up as ref_setup, with the device-backed LoadControl; returns numEqn
+int glue_setup_loadcontrol(void* h, int numberer, int soeKind, double dlambda, int testKind, double tol, int maxIter, int device) {
+  RefModel* m = (RefModel*)h;
+  B200LoadControl* li = new B200LoadControl(dlambda);
+  m->sinteg = li; m->integ = li;
+  const int neq = ref_setup_common(m, numberer, soeKind, testKind, tol, maxIter);
+  if (neq < 0) return neq;
+  Glue& G = g_glue[h];
+  const int rc = domain_to_xb(m, numberer, soeKind, device, G);
+  if (rc < 0) { fprintf(stderr, "glue: %s\n", G.err.c_str()); return -100 + rc; }
+  li->x = G.x; li->rm = m;
+  return neq;
+}
+const char* glue_last_error(void* h) { return g_glue[h].err.c_str(); }
+// how often the reference's algorithm went through each replaced loop: formTangent, formUnbalance, update, commit
+void glue_call_counts(void* h, long* out) {
+  B200LoadControl* li = dynamic_cast<B200LoadControl*>(((RefModel*)h)->sinteg);
+  for (int i = 0; i < 4; i++) out[i] = li ? li->calls[i] : -1;
+}
+long long glue_launch_count(void* h) { return xb_launch_count(g_glue[h].x); }
+// trial displacements of the device model, [nn][ndf] in Domain order
+int glue_get_trial_disp(void* h, double* u) { return xb_get_trial_disp(g_glue[h].x, u); }
+
+}  // extern "C"

@@ -1,0 +1,2 @@
+#!/bin/bash
+timeout 1200 python -m pytest tests -m gpu -x -q -k "reference_newton_loop" 2>&1 | tail -25

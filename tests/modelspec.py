@@ -22,6 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libref_harness.so")
 METIS_SO = os.path.join(ROOT, "oracle", "_ref", "libmetis_ref.so")
+GLUE_SO = os.path.join(ROOT, "oracle", "_ref", "libref_glue.so")
 
 MAT_ELASTIC, MAT_J2 = 0, 1
 ELE_BRICK, ELE_QUAD, ELE_FBC2D, ELE_FBC3D = 0, 1, 2, 3
@@ -279,6 +280,10 @@ def soil_structure_block(nx=6, ny=6, nz=6, distort=0.0, seed=0):
     groups = [ElementGroup(ELE_BRICK, g.tags[~struct], g.conn[~struct], np.full((~struct).sum(), 1, np.int32), g.par[~struct]),
               ElementGroup(ELE_BRICK, g.tags[struct], g.conn[struct], np.full(struct.sum(), 2, np.int32), g.par[struct])]
     return ModelSpec(3, 3, spec.node_tags, spec.crd, spec.fix, mats, groups, spec.loads)
+
+
+def have_glue():
+    return os.path.exists(GLUE_SO)
 
 
 def have_metis():
@@ -565,8 +570,8 @@ class RefBackend(_Backend):
     """The reference's own Domain / AnalysisModel / LinearSOE, through oracle/ref_harness.cpp."""
 
     def __init__(self, spec: ModelSpec, numberer=NUMBERER_PLAIN, soe=SOE_CSC, dlambda=1.0,
-                 test=0, tol=1e-8, max_iter=20, defer_setup=False):
-        L = ctypes.CDLL(REF_SO)
+                 test=0, tol=1e-8, max_iter=20, defer_setup=False, so=None):
+        L = ctypes.CDLL(so or REF_SO)
         self.L, self.spec = L, spec
         L.ref_model_new.restype = ctypes.c_void_p
         self.h = ctypes.c_void_p(L.ref_model_new(spec.ndm, spec.ndf))
@@ -682,6 +687,27 @@ class RefBackend(_Backend):
     def set_mass(self, tags, mass):
         for t, mv in zip(tags, np.ascontiguousarray(mass, np.float64)):
             assert self.L.ref_set_mass(self.h, int(t), _p(np.ascontiguousarray(mv))) == 0
+
+    # ---- the reference's own analysis loop on top of the device path (oracle/ref_glue.cpp, so=GLUE_SO) ----
+    def setup_glue_loadcontrol(self, numberer, soe, dlambda, test=0, tol=1e-8, max_iter=20, device=0):
+        self.L.glue_setup_loadcontrol.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,
+                                                  ctypes.c_double, ctypes.c_int, ctypes.c_int]
+        self.neq = self.L.glue_setup_loadcontrol(self.h, numberer, soe, dlambda, test, tol, max_iter, device)
+        if self.neq < 0:
+            self.L.glue_last_error.restype = ctypes.c_char_p; self.L.glue_last_error.argtypes = [ctypes.c_void_p]
+            raise RuntimeError(f"glue set-up failed ({self.neq}): {self.L.glue_last_error(self.h).decode()}")
+        self.nnz = self.L.ref_nnz(self.h); self.max_iter = max_iter
+
+    def glue_counts(self):
+        c = (ctypes.c_long * 4)(); self.L.glue_call_counts.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        self.L.glue_call_counts(self.h, c)
+        self.L.glue_launch_count.restype = ctypes.c_longlong; self.L.glue_launch_count.argtypes = [ctypes.c_void_p]
+        return list(c), int(self.L.glue_launch_count(self.h))
+
+    def glue_trial_disp(self):
+        u = np.zeros((self.spec.nn, self.spec.ndf)); self.L.glue_get_trial_disp.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        assert self.L.glue_get_trial_disp(self.h, _p(u)) >= 0
+        return u
 
     def set_rayleigh(self, alphaM, betaK, betaK0, betaKc):
         self.L.ref_set_rayleigh.argtypes = [ctypes.c_void_p] + [ctypes.c_double] * 4

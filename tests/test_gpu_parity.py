@@ -14,7 +14,7 @@ import pytest
 
 import xara_b200 as xb
 from golden_cases import CASES, NSTEPS, ele_nd
-from modelspec import (ELASTIC, J2_STEEL, OracleBackend, brick_block, frame2d, frame3d, have_metis, metis_partition,
+from modelspec import (ELASTIC, J2_STEEL, OracleBackend, brick_block, frame2d, frame3d, have_glue, have_metis, have_ref, metis_partition,
                        quad_plane, soil_structure_block)
 
 pytestmark = pytest.mark.gpu
@@ -148,6 +148,47 @@ def test_newton_iteration_counts_match_oracle(shape):
         _newton_counts_match(frame2d(2, 3, 2, lateral=22.0, gravity=-40.0), 5, 5)
     else:   # 3D space frame (ForceBeamColumn3d, FiberSection3d): biaxial push at a roof corner
         _newton_counts_match(frame3d(1, 1, 2, ndiv=2, lateral=(20.0, 12.0), gravity=-40.0), 5, 5)
+
+
+@pytest.mark.skipif(not (have_ref() and have_glue()), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("shape,numberer,soe", [("brick", 1, 0), ("quad", 0, 1), ("mixed", 1, 1)])
+def test_reference_newton_loop_drives_device_path(shape, numberer, soe):
+    """The drop-in, end to end: the REFERENCE'S OWN StaticAnalysis objects (AnalysisModel, PlainHandler, numberer,
+    SparseGenCol/Row SOE and solver, NewtonRaphson, CTestNormDispIncr, LoadControl::newStep) run a load-controlled
+    Newton analysis twice on the same Domain description -- once unmodified on the CPU, once with the integrator
+    of INTEGRATION.md (oracle/ref_glue.cpp) that reads the model out of the Domain and routes formTangent /
+    formUnbalance / update / commit through the C ABI to the device.  Same iteration count on every step (decided
+    by the reference's own convergence test), same norms, same final displacements."""
+    from modelspec import GLUE_SO, RefBackend
+    if shape == "brick":
+        mk = lambda: brick_block(4, 4, 6, mat=J2_STEEL, lx=1.0, ly=1.0, lz=3.0, load=(1.2, 0.0, -0.5))
+    elif shape == "quad":
+        def mk():
+            sp = quad_plane(16, 4, mat=J2_STEEL, lx=8.0, ly=2.0); sp.loads[:, 1:] = [0.0, -10.0]; return sp
+    else:
+        def mk():   # soil (J2) + footing (elastic): two element batches, loaded well past first yield
+            sp = soil_structure_block(5, 5, 5, distort=0.1, seed=2); sp.loads[:, 1:] *= 12.0; return sp
+    nsteps, dl, max_iter = 8, 1.0 / 8, 25
+    best = None
+    for tol in (1e-6, 1e-7, 1e-8, 1e-9):          # a tolerance no deciding norm sits within 3x of
+        C = RefBackend(mk(), numberer, soe, dlambda=dl, test=0, tol=tol, max_iter=max_iter)
+        rc, iters, norms = C.analyze_static(nsteps)
+        assert rc == 0
+        margin = min(min(norms[s, iters[s] - 2] / tol if iters[s] > 1 else 1e9, tol / max(norms[s, iters[s] - 1], 1e-300)) for s in range(nsteps))
+        if best is None or margin > best[0]:
+            best = (margin, tol, iters.copy(), norms.copy(), C.get_trial_disp())
+    margin, tol, it_cpu, nm_cpu, u_cpu = best
+    assert margin >= 3.0 and it_cpu.max() >= 4
+    D = RefBackend(mk(), defer_setup=True, so=GLUE_SO)
+    D.setup_glue_loadcontrol(numberer, soe, dl, test=0, tol=tol, max_iter=max_iter)
+    rc, it_dev, nm_dev = D.analyze_static(nsteps)
+    assert rc == 0
+    assert it_dev.tolist() == it_cpu.tolist()                       # identical Newton iteration counts
+    for s in range(nsteps):
+        assert np.allclose(nm_dev[s, :it_dev[s] - 1], nm_cpu[s, :it_cpu[s] - 1], rtol=1e-5, atol=1e-11)
+    assert relerr(D.glue_trial_disp(), u_cpu) < 1e-8
+    calls, launches = D.glue_counts()
+    assert calls[0] == it_cpu.sum() and calls[3] == nsteps and launches > 0     # the device did the work
 
 
 def test_revert_to_last_commit_and_incr():

@@ -888,11 +888,15 @@ __device__ __forceinline__ void brick_D_regs(double m0, double m1, const double*
   }
 }
 
-template <int MATK>
+template <int MATK, int DYN>
 __global__ void __launch_bounds__(128, 2) brick_tangent_sym_kernel(GroupView G, const double* __restrict__ X,
                                                                    int transpose, long long ebeg, long long eend,
-                                                                   const double* __restrict__ tsrc, int tzero,
-                                                                   double scale, int accum) {
+                                                                   const double* __restrict__ tsrc_, int tzero_,
+                                                                   double scale_, int accum_) {
+  // DYN = 0 (static analysis): the arguments are compile-time constants, nothing is paid for them
+  const double* __restrict__ tsrc = DYN ? tsrc_ : G.tan;
+  const int tzero = DYN ? tzero_ : 0, accum = DYN ? accum_ : 0;
+  const double scale = DYN ? scale_ : 1.0;
   // tsrc: compact tangent to use (G.tan: current, G.tanc: committed); tzero: none, i.e. the initial (elastic)
   // tangent; scale multiplies the matrix; accum adds to what the slots hold.  Static analysis: (G.tan, 0, 1, 0).
   extern __shared__ __align__(16) double smem[];
@@ -2115,7 +2119,8 @@ static int launch_group_tangents(xb_model* m, DevGroup& d, long long ebeg, long 
         if (tc.ac != 0.0) { kern<<<(unsigned)grid, 128, sms, st>>>(d.v, m->dX, transpose, ebeg, eend, d.v.tanc, 0, tc.ac, 1); m->launches++; }
         return XB_OK;
       };
-      int rc = j2 ? go(brick_tangent_sym_kernel<XB_MAT_J2PLASTICITY>) : go(brick_tangent_sym_kernel<XB_MAT_ELASTIC_ISOTROPIC>);
+      int rc = tc.on ? (j2 ? go(brick_tangent_sym_kernel<XB_MAT_J2PLASTICITY, 1>) : go(brick_tangent_sym_kernel<XB_MAT_ELASTIC_ISOTROPIC, 1>))
+                     : (j2 ? go(brick_tangent_sym_kernel<XB_MAT_J2PLASTICITY, 0>) : go(brick_tangent_sym_kernel<XB_MAT_ELASTIC_ISOTROPIC, 0>));
       if (rc < 0) return rc;
       m->launches++;
       if (tc.on && tc.cM != 0.0 && d.has_rho) {
