@@ -32,6 +32,9 @@
 #define private public
 #define protected public
 #include <LoadControl.h>               // before the harness: it drops the defines half way through its own includes
+#include <Newmark.h>
+#include <Node.h>
+#include <Element.h>
 #include <Brick.h>
 #include <FourNodeQuad.h>
 #include <J2Plasticity.h>
@@ -131,6 +134,22 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
         if (xb_add_nodal_loads(x, 1, &nt, vals.data()) < 0) { G.err = xb_last_error(); return -7; }
       }
     } }
+  // 4b. `mass` command (Node::getMass, diagonal) and `rayleigh` (Element / Node factors)
+  { std::vector<int> mt; std::vector<double> mv;
+    NodeIter& ni = dom->getNodes(); Node* nd;
+    while ((nd = ni()) != nullptr) {
+      const Matrix& M = nd->getMass();
+      bool any = false;
+      for (int d = 0; d < m->ndf && d < M.noRows(); d++) if (M(d, d) != 0.0) any = true;
+      if (!any) continue;
+      mt.push_back(nd->getTag());
+      for (int d = 0; d < m->ndf; d++) mv.push_back(d < M.noRows() ? M(d, d) : 0.0);
+    }
+    if (!mt.empty() && xb_set_nodal_mass(x, (int)mt.size(), mt.data(), mv.data()) < 0) { G.err = xb_last_error(); return -7; } }
+  { ElementIter& ei = dom->getElements(); Element* el = ei();
+    if (el && (el->alphaM != 0.0 || el->betaK != 0.0 || el->betaK0 != 0.0 || el->betaKc != 0.0))
+      if (xb_set_rayleigh(x, el->alphaM, el->betaK, el->betaK0, el->betaKc) < 0) { G.err = xb_last_error(); return -7; }
+    while (el) el = ei(); }   // drain the iterator
   // 5. the same numberer / SOE as the analysis; the numbering must be the reference's own
   const int neq = xb_setup(x, numberer, soeKind);
   if (neq < 0) { G.err = xb_last_error(); return -8; }
@@ -194,9 +213,85 @@ class B200LoadControl : public LoadControl {
   }
 };
 
+// the transient counterpart: Newmark (displacement unknown).  newStep / update keep the reference's own U, Udot,
+// Udotdot vectors and its nodes up to date (AnalysisModel::setVel / setAccel / setResponse are node-level), and
+// replace AnalysisModel::updateDomain -> Domain::update, formTangent and formUnbalance.
+class B200Newmark : public Newmark {
+ public:
+  B200Newmark(double g, double b) : Newmark(g, b) {}
+  xb_model* x = nullptr;
+  RefModel* rm = nullptr;
+  long calls[4] = {0, 0, 0, 0};
+  double* soeA() { return rm->rsoe ? rm->rsoe->A : rm->csoe->A; }
+  Vector& soeB() { return rm->rsoe ? rm->rsoe->B : rm->csoe->B; }
+
+  int newStep(double deltaT) override {                 // Newmark::newStep (Newmark.cpp:105), unknown = Displacement
+    if (deltaT <= 0.0 || beta == 0 || U == nullptr || unknown != 1) return -1;
+    AnalysisModel* theModel = this->getAnalysisModel();
+    c1 = 1.0; c2 = gamma / (beta * deltaT); c3 = 1.0 / (beta * deltaT * deltaT);
+    (*Ut) = *U; (*Utdot) = *Udot; (*Utdotdot) = *Udotdot;
+    const double a1 = (1.0 - gamma / beta), a2 = deltaT * (1.0 - 0.5 * gamma / beta);
+    Udot->addVector(a1, *Utdotdot, a2);
+    const double a3 = -1.0 / (beta * deltaT), a4 = 1.0 - 0.5 / beta;
+    Udotdot->addVector(a4, *Utdot, a3);
+    theModel->setVel(*Udot);
+    theModel->setAccel(*Udotdot);
+    double time = theModel->getCurrentDomainTime();
+    time += deltaT;
+    theModel->applyLoadDomain(time);                    // in place of updateDomain(time, dT): loads on the reference's nodes ...
+    if (xb_set_transient_factors(x, c1, c2, c3) < 0 || xb_newmark_predict(x, a1, a2, a3, a4) < 0 ||
+        xb_apply_load(x, time) < 0 || xb_update(x) < 0) return -2;   // ... and Domain::update on the device
+    return 0;
+  }
+  int update(const Vector& deltaU) override {           // Newmark::update (Newmark.cpp:411)
+    AnalysisModel* theModel = this->getAnalysisModel();
+    (*U) += deltaU;
+    Udot->addVector(1.0, deltaU, c2);
+    Udotdot->addVector(1.0, deltaU, c3);
+    theModel->setResponse(*U, *Udot, *Udotdot);
+    calls[2]++;
+    std::vector<double> du(deltaU.Size());
+    for (int i = 0; i < deltaU.Size(); i++) du[i] = deltaU(i);
+    if (xb_incr_trial_response(x, du.data(), 1.0, c2, c3) < 0 || xb_update(x) < 0) return -1;
+    return 0;
+  }
+  int formTangent(int statFlag) override {              // TransientIntegrator::formTangent (TransientIntegrator.cpp:61)
+    if (statFlag != CURRENT_TANGENT) return Newmark::formTangent(statFlag);
+    statusFlag = statFlag;
+    this->getLinearSOE()->zeroA();
+    calls[0]++;
+    return xb_form_tangent(x, soeA());
+  }
+  int formUnbalance() override {                        // TransientIntegrator::formUnbalance (:114)
+    calls[1]++;
+    this->getLinearSOE()->zeroB();
+    Vector& B = soeB();
+    return xb_form_unbalance(x, &B(0));
+  }
+  int commit() override {
+    calls[3]++;
+    if (xb_commit(x) < 0) return -1;
+    return Newmark::commit();
+  }
+};
+
 }  // namespace
 
 extern "C" {
+
+// analysis set-up as ref_setup_transient, with the device-backed Newmark; returns numEqn
+int glue_setup_newmark(void* h, int numberer, int soeKind, double gamma, double beta, int testKind, double tol, int maxIter, int device) {
+  RefModel* m = (RefModel*)h;
+  B200Newmark* ni = new B200Newmark(gamma, beta);
+  m->tinteg = ni; m->integ = ni;
+  const int neq = ref_setup_common(m, numberer, soeKind, testKind, tol, maxIter);
+  if (neq < 0) return neq;
+  Glue& G = g_glue[h];
+  const int rc = domain_to_xb(m, numberer, soeKind, device, G);
+  if (rc < 0) { fprintf(stderr, "glue: %s\n", G.err.c_str()); return -100 + rc; }
+  ni->x = G.x; ni->rm = m;
+  return neq;
+}
 
 // analysis set-up as ref_setup, with the device-backed LoadControl; returns numEqn
 int glue_setup_loadcontrol(void* h, int numberer, int soeKind, double dlambda, int testKind, double tol, int maxIter, int device) {
@@ -215,7 +310,8 @@ const char* glue_last_error(void* h) { return g_glue[h].err.c_str(); }
 // how often the reference's algorithm went through each replaced loop: formTangent, formUnbalance, update, commit
 void glue_call_counts(void* h, long* out) {
   B200LoadControl* li = dynamic_cast<B200LoadControl*>(((RefModel*)h)->sinteg);
-  for (int i = 0; i < 4; i++) out[i] = li ? li->calls[i] : -1;
+  B200Newmark* ni = dynamic_cast<B200Newmark*>(((RefModel*)h)->tinteg);
+  for (int i = 0; i < 4; i++) out[i] = li ? li->calls[i] : (ni ? ni->calls[i] : -1);
 }
 long long glue_launch_count(void* h) { return xb_launch_count(g_glue[h].x); }
 // trial displacements of the device model, [nn][ndf] in Domain order

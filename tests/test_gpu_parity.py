@@ -191,6 +191,55 @@ def test_reference_newton_loop_drives_device_path(shape, numberer, soe):
     assert calls[0] == it_cpu.sum() and calls[3] == nsteps and launches > 0     # the device did the work
 
 
+@pytest.mark.skipif(not (have_ref() and have_glue()), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("shape", ["brick", "quad"])
+def test_reference_newmark_loop_drives_device_path(shape):
+    """The transient drop-in: the reference's own Newmark bookkeeping (U, Udot, Udotdot, predictor), NewtonRaphson and
+    convergence test, with newStep / update / formTangent / formUnbalance / commit of the integrator routed to the
+    device (oracle/ref_glue.cpp, B200Newmark).  Nodal masses, `rayleigh` factors and the material density are read
+    out of the reference's Domain.  Same iteration counts, norms, displacements, velocities and accelerations as
+    the unmodified reference run."""
+    from golden_cases import J2_STEEL_RHO, RAYLEIGH
+    from modelspec import GLUE_SO, RefBackend
+    if shape == "brick":
+        mk = lambda: brick_block(3, 3, 4, mat=J2_STEEL_RHO, lz=3.0, load=(240.0, 0.0, -30.0), distort=0.15, seed=3)
+    else:
+        def mk():
+            sp = quad_plane(12, 4, mat=J2_STEEL_RHO, lx=6.0, ly=2.0, distort=0.1, seed=4); sp.loads[:, 1:] = [0.0, -260.0]; return sp
+    nsteps, dt, gamma, beta, max_iter = 8, 0.02, 0.5, 0.25, 25
+
+    def build(so=None):
+        spec = mk()
+        R = RefBackend(spec, defer_setup=True, so=so)
+        mass = np.zeros((spec.nn, spec.ndf)); mass[:] = 0.05
+        R.set_mass(spec.node_tags, mass); R.set_rayleigh(*RAYLEIGH)
+        return R
+
+    # stiffness-proportional damping on the CURRENT tangent makes Newton converge linearly here (6-8 iterations a
+    # step): pick the tolerance that no deciding norm sits close to (the two runs agree to ~1e-6 in every norm)
+    best = None
+    for tol in (1e-8, 3e-9, 1e-9, 3e-10, 1e-10):
+        C = build(); C.setup_transient(1, 1, gamma, beta, test=0, tol=tol, max_iter=max_iter)
+        rc, it_cpu, nm_cpu = C.analyze_transient(nsteps, dt)
+        assert rc == 0
+        margin = min(min(nm_cpu[s, it_cpu[s] - 2] / tol if it_cpu[s] > 1 else 1e9, tol / max(nm_cpu[s, it_cpu[s] - 1], 1e-300)) for s in range(nsteps))
+        if best is None or margin > best[0]:
+            best = (margin, tol, it_cpu.copy(), nm_cpu.copy(), C)
+    margin, tol, it_cpu, nm_cpu, C = best
+    assert margin >= 1.3 and it_cpu.max() >= 3, (margin, tol)
+    D = build(GLUE_SO); D.setup_glue_newmark(1, 1, gamma, beta, test=0, tol=tol, max_iter=max_iter)
+    rc, it_dev, nm_dev = D.analyze_transient(nsteps, dt)
+    assert rc == 0
+    assert it_dev.tolist() == it_cpu.tolist()
+    for s in range(nsteps):
+        assert np.allclose(nm_dev[s, :it_dev[s] - 1], nm_cpu[s, :it_cpu[s] - 1], rtol=1e-5, atol=1e-12)
+    assert relerr(D.glue_trial_disp(), C.get_trial_disp()) < 1e-8
+    vc, ac = C.vel_accel(); vd, ad = D.vel_accel()       # the reference's nodes, driven by the device path's solution
+    assert relerr(vd, vc) < 1e-7 and relerr(ad, ac) < 1e-7
+    calls, launches = D.glue_counts()
+    assert calls[0] == it_cpu.sum() and calls[3] == nsteps and launches > 0
+
+
 def test_revert_to_last_commit_and_incr():
     rng = np.random.default_rng(0)
     spec = brick_block(3, 3, 3, distort=0.1)
