@@ -33,8 +33,19 @@
 #define protected public
 #include <LoadControl.h>               // before the harness: it drops the defines half way through its own includes
 #include <Newmark.h>
+#include <DisplacementControl.h>
 #include <Node.h>
 #include <Element.h>
+#include <ForceBeamColumn2d.h>
+#include <ForceBeamColumn3d.h>
+#include <FiberSection2d.h>
+#include <FiberSection3d.h>
+#include <Steel02.h>
+#include <Concrete02.h>
+#include <ElasticMaterial.h>
+#include <LinearCrdTransf2d.h>
+#include <LinearCrdTransf3d.h>
+#include <LobattoBeamIntegration.h>
 #include <Brick.h>
 #include <FourNodeQuad.h>
 #include <J2Plasticity.h>
@@ -79,7 +90,9 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
   // 3. materials and elements, one batch per (element class, material kind)
   struct Batch { std::vector<int> tag, conn, mat; std::vector<double> par; };
   std::map<std::pair<int, int>, Batch> batches;     // (xb element kind, xb material kind)
-  std::map<int, int> mats_done;
+  std::map<int, int> mats_done, secs_done, unis_done;
+  struct BeamKey { int sec, nip, mi; double tol; bool is3; };
+  std::vector<BeamKey> beam_keys;
   auto material = [&](NDMaterial* nm, int& kind) -> int {
     double p[8] = {0, 0, 0, 0, 0, 0, 0, 0}; int np = 0;
     if (auto* j = dynamic_cast<J2Plasticity*>(nm)) {
@@ -113,11 +126,78 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
         for (int a = 0; a < 4; a++) B.conn.push_back(q->connectedExternalNodes(a));
         const double par[6] = {q->thickness, 0.0, q->pressure, q->rho, q->b[0], q->b[1]};
         B.par.insert(B.par.end(), par, par + 6);
+      } else if (dynamic_cast<ForceBeamColumn2d*>(el) || dynamic_cast<ForceBeamColumn3d*>(el)) {
+        // forceBeamColumn with nIP copies of one fibre section (Steel02 / Concrete02 fibres), Lobatto integration,
+        // geomTransf Linear without joint offsets
+        auto* b2 = dynamic_cast<ForceBeamColumn2d*>(el); auto* b3 = dynamic_cast<ForceBeamColumn3d*>(el);
+        const int nsec = b2 ? b2->numSections : b3->numSections;
+        SectionForceDeformation** secs = b2 ? b2->sections : b3->sections;
+        BeamIntegration* bi = b2 ? b2->beamIntegr : b3->beamIntegr;
+        CrdTransf* ct = b2 ? b2->crdTransf : b3->crdTransf;
+        if (!dynamic_cast<LobattoBeamIntegration*>(bi)) { G.err = "glue: beam integration other than Lobatto"; return -5; }
+        if ((b2 ? b2->rho : b3->rho) != 0.0) { G.err = "glue: forceBeamColumn with element mass"; return -5; }
+        for (int i = 1; i < nsec; i++) if (secs[i]->getTag() != secs[0]->getTag()) { G.err = "glue: sections of one element differ"; return -5; }
+        const int stag = secs[0]->getTag();
+        if (!secs_done.count(stag)) {
+          auto uniaxial = [&](UniaxialMaterial* um) -> int {
+            const int t = um->getTag();
+            if (unis_done.count(t)) return t;
+            double p[12] = {0}; int kind, np;
+            if (auto* s2 = dynamic_cast<Steel02*>(um)) {
+              kind = XB_UNI_STEEL02; np = 11;
+              const double q[11] = {s2->Fy, s2->E0, s2->b, s2->R0, s2->cR1, s2->cR2, s2->a1, s2->a2, s2->a3, s2->a4, s2->sigini};
+              std::memcpy(p, q, sizeof q);
+            } else if (auto* c2 = dynamic_cast<Concrete02*>(um)) {
+              kind = XB_UNI_CONCRETE02; np = 7;
+              const double q[7] = {c2->fc, c2->epsc0, c2->fcu, c2->epscu, c2->rat, c2->ft, c2->Ets};
+              std::memcpy(p, q, sizeof q);
+            } else return -1;
+            if (xb_add_uniaxial_material(x, t, kind, p, np) < 0) return -1;
+            unis_done[t] = 1;
+            return t;
+          };
+          std::vector<double> y, z, A; std::vector<int> mt;
+          if (auto* f2 = dynamic_cast<FiberSection2d*>(secs[0])) {
+            for (int f = 0; f < f2->numFibers; f++) {
+              y.push_back(f2->matData[2 * f]); A.push_back(f2->matData[2 * f + 1]);
+              const int t = uniaxial(f2->theMaterials[f]); if (t < 0) { G.err = "glue: unsupported fibre material"; return -5; }
+              mt.push_back(t);
+            }
+            if (xb_add_fiber_section(x, stag, (int)y.size(), y.data(), A.data(), mt.data()) < 0) { G.err = xb_last_error(); return -6; }
+          } else if (auto* f3 = dynamic_cast<FiberSection3d*>(secs[0])) {
+            for (int f = 0; f < f3->numFibers; f++) {
+              y.push_back(f3->matData[3 * f]); z.push_back(f3->matData[3 * f + 1]); A.push_back(f3->matData[3 * f + 2]);
+              const int t = uniaxial(f3->theMaterials[f]); if (t < 0) { G.err = "glue: unsupported fibre material"; return -5; }
+              mt.push_back(t);
+            }
+            auto* tor = dynamic_cast<ElasticMaterial*>(f3->theTorsion);
+            if (!tor) { G.err = "glue: torsion other than an ElasticMaterial"; return -5; }
+            if (xb_add_fiber_section3d(x, stag, (int)y.size(), y.data(), z.data(), A.data(), mt.data(), tor->getInitialTangent()) < 0) { G.err = xb_last_error(); return -6; }
+          } else { G.err = "glue: section other than a fibre section"; return -5; }
+          secs_done[stag] = 1;
+        }
+        // one batch per (section, nIP, maxIters, tol): key them through the map's second index
+        const int maxIters = b2 ? b2->maxIters : b3->maxIters; const double tol = b2 ? b2->tol : b3->tol;
+        int key = -1;
+        for (size_t q = 0; q < beam_keys.size(); q++)
+          if (beam_keys[q].sec == stag && beam_keys[q].nip == nsec && beam_keys[q].mi == maxIters && beam_keys[q].tol == tol && beam_keys[q].is3 == (b3 != nullptr)) key = (int)q;
+        if (key < 0) { beam_keys.push_back({stag, nsec, maxIters, tol, b3 != nullptr}); key = (int)beam_keys.size() - 1; }
+        Batch& B = batches[{b3 ? XB_ELE_FORCEBEAMCOLUMN3D : XB_ELE_FORCEBEAMCOLUMN2D, 1000 + key}];
+        B.tag.push_back(el->getTag()); B.mat.push_back(stag);
+        const ID& en = el->getExternalNodes();
+        B.conn.push_back(en(0)); B.conn.push_back(en(1));
+        B.par.push_back(nsec); B.par.push_back(maxIters); B.par.push_back(tol);
+        if (b3) {   // the local z axis serves as vecxz: y = z ^ x, so the same triad comes out
+          Vector xa(3), ya(3), za(3);
+          ct->getLocalAxes(xa, ya, za);
+          for (int d = 0; d < 3; d++) B.par.push_back(za(d));
+        }
       } else { G.err = "glue: element class outside the device path (keep the CPU integrator)"; return -5; }
     } }
   for (auto& kv : batches) {
     Batch& B = kv.second;
-    const int stride = kv.first.first == XB_ELE_STDBRICK ? 3 : 6;
+    const int ek = kv.first.first;
+    const int stride = ek == XB_ELE_STDBRICK ? 3 : (ek == XB_ELE_FORCEBEAMCOLUMN2D ? 3 : 6);
     if (xb_add_elements(x, kv.first.first, (int)B.tag.size(), B.tag.data(), B.conn.data(), B.mat.data(), B.par.data(), stride) < 0) {
       G.err = xb_last_error(); return -6;
     }
@@ -213,6 +293,98 @@ class B200LoadControl : public LoadControl {
   }
 };
 
+// `integrator DisplacementControl`: newStep / update as DisplacementControl.cpp:121,210 (no sensitivities), with
+// AnalysisModel::updateDomain replaced; the two solves per iteration stay in the reference's SOE
+class B200DisplacementControl : public DisplacementControl {
+ public:
+  B200DisplacementControl(int node, int dof, double incr, Domain* d) : DisplacementControl(node, dof, incr, d, 1, incr, incr) {}
+  xb_model* x = nullptr;
+  RefModel* rm = nullptr;
+  long calls[4] = {0, 0, 0, 0};
+  double* soeA() { return rm->rsoe ? rm->rsoe->A : rm->csoe->A; }
+  Vector& soeB() { return rm->rsoe ? rm->rsoe->B : rm->csoe->B; }
+  int push(const Vector& dU, double lambda) {          // incrDisp + applyLoadDomain + updateDomain
+    AnalysisModel* am = this->getAnalysisModel();
+    am->incrDisp(dU);
+    am->applyLoadDomain(lambda);
+    std::vector<double> du(dU.Size());
+    for (int i = 0; i < dU.Size(); i++) du[i] = dU(i);
+    if (xb_incr_trial_disp(x, du.data()) < 0 || xb_apply_load(x, lambda) < 0 || xb_update(x) < 0) return -1;
+    return 0;
+  }
+  int newStep() override {
+    if (theDofID == -1) return -1;
+    AnalysisModel* theModel = this->getAnalysisModel();
+    LinearSOE* theLinSOE = this->getLinearSOE();
+    double factor = pow(specNumIncrStep / numIncrLastStep, 1.0);
+    theIncrement *= factor;
+    if (theIncrement < minIncrement) theIncrement = minIncrement;
+    else if (theIncrement > maxIncrement) theIncrement = maxIncrement;
+    currentLambda = theModel->getCurrentDomainTime();
+    this->formTangent(tangFlag);
+    theLinSOE->setB(*phat);
+    if (theLinSOE->solve() < 0) return -1;
+    (*deltaUhat) = theLinSOE->getX();
+    const double dUahat = (*deltaUhat)(theDofID);
+    if (dUahat == 0.0) return -1;
+    const double dlambda = theIncrement / dUahat;
+    deltaLambdaStep = dlambda;
+    currentLambda += dlambda;
+    (*deltaU) = *deltaUhat;
+    (*deltaU) *= dlambda;
+    (*deltaUstep) = (*deltaU);
+    if (push(*deltaU, currentLambda) < 0) return -1;
+    numIncrLastStep = 0;
+    return 0;
+  }
+  int update(const Vector& dU) override {
+    if (theDofID == -1) return -1;
+    LinearSOE* theLinSOE = this->getLinearSOE();
+    (*deltaUbar) = dU;
+    const double dUabar = (*deltaUbar)(theDofID);
+    theLinSOE->setB(*phat);
+    theLinSOE->solve();
+    (*deltaUhat) = theLinSOE->getX();
+    const double dUahat = (*deltaUhat)(theDofID);
+    if (dUahat == 0.0) return -1;
+    dLambda = -dUabar / dUahat;
+    (*deltaU) = (*deltaUbar);
+    deltaU->addVector(1.0, *deltaUhat, dLambda);
+    (*deltaUstep) += *deltaU;
+    deltaLambdaStep += dLambda;
+    currentLambda += dLambda;
+    calls[2]++;
+    if (push(*deltaU, currentLambda) < 0) return -1;
+    theLinSOE->setX(*deltaU);
+    numIncrLastStep++;
+    return 0;
+  }
+  int formTangent(int statFlag) override {
+    if (!x || statFlag != CURRENT_TANGENT) return DisplacementControl::formTangent(statFlag);
+    statusFlag = statFlag;
+    this->getLinearSOE()->zeroA();
+    calls[0]++;
+    return xb_form_tangent(x, soeA());
+  }
+  int formTangent(int statFlag, double iFactor, double cFactor) override {
+    if (!x || statFlag != CURRENT_TANGENT) return DisplacementControl::formTangent(statFlag, iFactor, cFactor);
+    return this->formTangent(statFlag);
+  }
+  int formElementResidual() override {
+    if (!x) return DisplacementControl::formElementResidual();   // domainChanged before the device model exists
+    calls[1]++;
+    if (xb_apply_load(x, this->getAnalysisModel()->getCurrentDomainTime()) < 0) return -1;
+    Vector& B = soeB();
+    return xb_form_unbalance(x, &B(0));
+  }
+  int formNodalUnbalance() override { return x ? 0 : DisplacementControl::formNodalUnbalance(); }
+  int commit() override {
+    calls[3]++;
+    if (xb_commit(x) < 0) return -1;
+    return DisplacementControl::commit();
+  }
+};
+
 // the transient counterpart: Newmark (displacement unknown).  newStep / update keep the reference's own U, Udot,
 // Udotdot vectors and its nodes up to date (AnalysisModel::setVel / setAccel / setResponse are node-level), and
 // replace AnalysisModel::updateDomain -> Domain::update, formTangent and formUnbalance.
@@ -279,6 +451,20 @@ class B200Newmark : public Newmark {
 
 extern "C" {
 
+// analysis set-up as ref_setup_dispcontrol, with the device-backed DisplacementControl; returns numEqn
+int glue_setup_dispcontrol(void* h, int numberer, int soeKind, int node, int dof, double incr, int testKind, double tol, int maxIter, int device) {
+  RefModel* m = (RefModel*)h;
+  B200DisplacementControl* li = new B200DisplacementControl(node, dof, incr, m->domain);
+  m->sinteg = li; m->integ = li;
+  const int neq = ref_setup_common(m, numberer, soeKind, testKind, tol, maxIter);
+  if (neq < 0) return neq;
+  Glue& G = g_glue[h];
+  const int rc = domain_to_xb(m, numberer, soeKind, device, G);
+  if (rc < 0) { fprintf(stderr, "glue: %s\n", G.err.c_str()); return -100 + rc; }
+  li->x = G.x; li->rm = m;
+  if (li->domainChanged() < 0) return -200;      // the reference load vector phat, now through the device path
+  return neq;
+}
 // analysis set-up as ref_setup_transient, with the device-backed Newmark; returns numEqn
 int glue_setup_newmark(void* h, int numberer, int soeKind, double gamma, double beta, int testKind, double tol, int maxIter, int device) {
   RefModel* m = (RefModel*)h;
@@ -311,7 +497,8 @@ const char* glue_last_error(void* h) { return g_glue[h].err.c_str(); }
 void glue_call_counts(void* h, long* out) {
   B200LoadControl* li = dynamic_cast<B200LoadControl*>(((RefModel*)h)->sinteg);
   B200Newmark* ni = dynamic_cast<B200Newmark*>(((RefModel*)h)->tinteg);
-  for (int i = 0; i < 4; i++) out[i] = li ? li->calls[i] : (ni ? ni->calls[i] : -1);
+  B200DisplacementControl* di = dynamic_cast<B200DisplacementControl*>(((RefModel*)h)->sinteg);
+  for (int i = 0; i < 4; i++) out[i] = li ? li->calls[i] : (ni ? ni->calls[i] : (di ? di->calls[i] : -1));
 }
 long long glue_launch_count(void* h) { return xb_launch_count(g_glue[h].x); }
 // trial displacements of the device model, [nn][ndf] in Domain order

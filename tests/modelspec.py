@@ -707,6 +707,15 @@ class RefBackend(_Backend):
             raise RuntimeError(f"glue set-up failed ({self.neq}): {self.L.glue_last_error(self.h).decode()}")
         self.nnz = self.L.ref_nnz(self.h); self.max_iter = max_iter
 
+    def setup_glue_dispcontrol(self, numberer, soe, node, dof, incr, test=0, tol=1e-8, max_iter=20, device=0):
+        self.L.glue_setup_dispcontrol.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                  ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int]
+        self.neq = self.L.glue_setup_dispcontrol(self.h, numberer, soe, node, dof, incr, test, tol, max_iter, device)
+        if self.neq < 0:
+            self.L.glue_last_error.restype = ctypes.c_char_p; self.L.glue_last_error.argtypes = [ctypes.c_void_p]
+            raise RuntimeError(f"glue set-up failed ({self.neq}): {self.L.glue_last_error(self.h).decode()}")
+        self.nnz = self.L.ref_nnz(self.h); self.max_iter = max_iter
+
     def glue_counts(self):
         c = (ctypes.c_long * 4)(); self.L.glue_call_counts.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         self.L.glue_call_counts(self.h, c)

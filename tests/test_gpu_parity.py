@@ -240,6 +240,68 @@ def test_reference_newmark_loop_drives_device_path(shape):
     assert calls[0] == it_cpu.sum() and calls[3] == nsteps and launches > 0
 
 
+@pytest.mark.skipif(not have_glue(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("name", ["dc_cantilever_fiber", "dc_frame3d", "dc_brick_j2"])
+def test_reference_displacement_control_drives_device_path(name):
+    """BASELINE configs[0] (the Ex2b cantilever pushover with the RC fibre section), the 3D space-frame pushover and
+    the J2 brick column: the reference's own DisplacementControl + NewtonRaphson + CTestNormDispIncr objects, with the
+    integrator's model-facing calls routed to the device (B200DisplacementControl in oracle/ref_glue.cpp; frames, fibre
+    sections and uniaxial materials read out of the reference's Domain).  Checked against the history the UNMODIFIED
+    reference produced (tests/golden/dc_*.npz): identical iteration counts, load factors, displacements."""
+    from golden_cases import DISPCONTROL_CASES
+    from modelspec import GLUE_SO, RefBackend
+    mk, numberer, soe, node, dof, incr, nsteps, tol, max_iter = DISPCONTROL_CASES[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    D = RefBackend(mk(), defer_setup=True, so=GLUE_SO)
+    D.setup_glue_dispcontrol(numberer, soe, int(g["node"]), dof, incr, test=0, tol=tol, max_iter=max_iter)
+    rc, iters, norms, lam = D.analyze_static_lam(nsteps)
+    assert rc == 0
+    assert iters.tolist() == g["iters"].tolist()
+    assert relerr(lam, g["lam"]) < 1e-8
+    assert relerr(D.glue_trial_disp(), g["u"]) < 1e-8
+    for s in range(nsteps):
+        assert np.allclose(norms[s, :iters[s] - 1], g["norms"][s, :iters[s] - 1], rtol=1e-5, atol=1e-12)
+    calls, launches = D.glue_counts()
+    assert calls[3] == nsteps and launches > 0
+
+
+@pytest.mark.skipif(not (have_ref() and have_glue()), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("shape", ["frame2d", "frame3d"])
+def test_reference_newmark_loop_drives_device_frames(shape):
+    """BASELINE configs[3] in small: RC frames of forceBeamColumn elements (Steel02 / Concrete02 fibre sections),
+    transient Newmark with nodal masses and Rayleigh damping, run by the reference's own objects on the CPU and
+    with the device-backed integrator: same iteration counts and responses."""
+    from golden_cases import RAYLEIGH
+    from modelspec import GLUE_SO, RefBackend
+    mk = (lambda: frame2d(2, 2, 2, lateral=30.0)) if shape == "frame2d" else (lambda: frame3d(1, 1, 2, ndiv=2, lateral=(25.0, 15.0)))
+    nsteps, dt, gamma, beta, max_iter = 6, 0.02, 0.5, 0.25, 25
+
+    def build(so=None):
+        spec = mk()
+        R = RefBackend(spec, defer_setup=True, so=so)
+        mass = np.zeros((spec.nn, spec.ndf)); mass[:, :spec.ndm] = 0.05
+        R.set_mass(spec.node_tags, mass); R.set_rayleigh(*RAYLEIGH)
+        return R
+
+    best = None
+    for tol in (1e-7, 1e-8, 1e-9, 1e-10):
+        C = build(); C.setup_transient(1, 1, gamma, beta, test=0, tol=tol, max_iter=max_iter)
+        rc, it_cpu, nm_cpu = C.analyze_transient(nsteps, dt)
+        assert rc == 0
+        margin = min(min(nm_cpu[s, it_cpu[s] - 2] / tol if it_cpu[s] > 1 else 1e9, tol / max(nm_cpu[s, it_cpu[s] - 1], 1e-300)) for s in range(nsteps))
+        if best is None or margin > best[0]:
+            best = (margin, tol, it_cpu.copy(), nm_cpu.copy(), C)
+    margin, tol, it_cpu, nm_cpu, C = best
+    assert margin >= 1.5, (margin, tol)
+    D = build(GLUE_SO); D.setup_glue_newmark(1, 1, gamma, beta, test=0, tol=tol, max_iter=max_iter)
+    rc, it_dev, nm_dev = D.analyze_transient(nsteps, dt)
+    assert rc == 0
+    assert it_dev.tolist() == it_cpu.tolist()
+    assert relerr(D.glue_trial_disp(), C.get_trial_disp()) < 1e-7
+    vc, ac = C.vel_accel(); vd, ad = D.vel_accel()
+    assert relerr(vd, vc) < 1e-6 and relerr(ad, ac) < 1e-6
+
+
 def test_revert_to_last_commit_and_incr():
     rng = np.random.default_rng(0)
     spec = brick_block(3, 3, 3, distort=0.1)
