@@ -332,8 +332,17 @@ def ours_main(a):
     alg = D.algorithmic_bytes(which[dom])
     achieved = alg / (ms[dom] * 1e-3) / 1e9
     path_alg = D.algorithmic_bytes(0) + D.algorithmic_bytes(1) + D.algorithmic_bytes(2)
+    # DRAM traffic of that kernel from the committed `ncu --set full` capture (profiles/ncu_traffic.json, taken on a
+    # smaller block of the same workload), scaled to this rank's element count: per launch, like `achieved`
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if a.workload == "brick" and os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if dom in tj.get("kernels", {}):
+            traffic = tj["kernels"][dom]["dram_bytes_per_launch"] * (float(D.ne) / tj["elements"])
+            traffic_src = tj["source"]
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms[dom],
                 "path": {"algorithmic_bytes_per_step": path_alg, "achieved": path_alg / (ms_per_step * 1e-3) / 1e9,
                          "frac": path_alg / (ms_per_step * 1e-3) / 1e9 / peak,
@@ -341,7 +350,7 @@ def ours_main(a):
                                  "out) over the whole step; the element-matrix round trip through HBM is overhead here"}}
 
     # ---- end to end through the C-ABI with HOST buffers (pinned), copies inside the timed region ----
-    e2e_steps = max(1, min(a.steps, a.e2e_steps))
+    e2e_steps = max(1, min(a.steps, a.e2e_steps)) if a.e2e_steps > 0 else 0
     # two trial fields, alternated, so that every e2e step is a genuine state determination (a force-based
     # beam returns at once when the displacement increment is zero)
     u_pin = torch.empty(u.size, dtype=torch.float64, pin_memory=True); u_pin.numpy()[:] = u.ravel()
@@ -353,7 +362,8 @@ def ours_main(a):
     def e2e_step(i):
         D.set_trial_disp(uns[i % 2]); D.update(); D.form_unbalance(out=Bn); D.form_tangent(out=An)
 
-    e2e_step(1)
+    if e2e_steps:
+        e2e_step(1)
     barrier()
     s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s2.record(stream)
@@ -361,13 +371,13 @@ def ours_main(a):
         e2e_step(i)
     e2.record(stream)
     barrier()
-    e2e_ms = s2.elapsed_time(e2) / e2e_steps
+    e2e_ms = s2.elapsed_time(e2) / max(e2e_steps, 1)
     h2d, d2h = float(u.size * 8), float((D.nnz + D.nrows) * 8)
     if world > 1:
         t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_ms = float(t[0])
         t = torch.tensor([h2d, d2h], device="cuda", dtype=torch.float64); dist.all_reduce(t); h2d, d2h = float(t[0]), float(t[1])
     checksum = float(An[:1000].sum() + Bn[:1000].sum())
-    e2e = {"value": ngp_global / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+    e2e = None if not e2e_steps else {"value": ngp_global / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "steps": e2e_steps, "result_checksum_rank0": checksum,
            "note": "xb_set_trial_disp(host u) + xb_update + xb_form_unbalance(host B) + xb_form_tangent(host A), pinned "
@@ -411,7 +421,7 @@ def main():
     ap.add_argument("--n", type=int, default=160, help="elements per side of the block (160 -> 4.096M)")
     ap.add_argument("--workload", default="brick", choices=["brick", "quad", "frame", "frame3d"],
                     help="brick = the headline workload; quad / frame = secondary lines (profiles/), n = cells per side")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=3, help="0 skips the end-to-end leg (profiling runs only)")
     ap.add_argument("--cpu-sample", type=int, default=22, help="CPU arm sample: elements per side")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
