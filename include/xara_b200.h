@@ -87,6 +87,12 @@ void xb_model_destroy(xb_model*);
 int xb_add_nodes(xb_model*, int n, const int* tags, const double* crd);
 /* Domain::addSP_Constraint (Domain.cpp:636) -- homogeneous `fix`; dof is 0-based */
 int xb_add_sp(xb_model*, int n, const int* node_tags, const int* dofs);
+/* Domain::addMP_Constraint (Domain.cpp:739) for `equalDOF rNode cNode dofs...`
+ * (runtime/commands/domain/constraint.cpp): an MP_Constraint with an identity constraint matrix, the only kind
+ * PlainHandler accepts (PlainHandler.cpp:129-176).  The n (0-based) dofs of the constrained node take the
+ * equation numbers of the same dofs of the retained node (PlainNumberer.cpp:111-142, DOF_Numberer.cpp:151-190).
+ * Chains (a retained dof that is itself constrained) and partitioned models return XB_ERR_UNSUPPORTED at set-up. */
+int xb_add_equal_dof(xb_model*, int retained_node_tag, int constrained_node_tag, int n, const int* dofs);
 /* OPS nDMaterial command; par has npar doubles in the order listed at the kind */
 int xb_add_nd_material(xb_model*, int tag, int kind, const double* par, int npar);
 /* uniaxialMaterial Steel02 | Concrete02 (runtime/commands/modeling/uniaxial.cpp) */

@@ -54,6 +54,8 @@
 #undef private
 #undef protected
 #include <SP_ConstraintIter.h>
+#include <MP_Constraint.h>
+#include <MP_ConstraintIter.h>
 #include <LoadPatternIter.h>
 #include <NodalLoadIter.h>
 
@@ -87,6 +89,20 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
   { SP_ConstraintIter& si = dom->getDomainAndLoadPatternSPs(); SP_Constraint* sp;
     while ((sp = si()) != nullptr) { spn.push_back(sp->getNodeTag()); spd.push_back(sp->getDOF_Number()); } }
   if (!spn.empty() && xb_add_sp(x, (int)spn.size(), spn.data(), spd.data()) < 0) { G.err = xb_last_error(); return -3; }
+  // 2b. MP constraints: `equalDOF` only (identity constraint matrix on the same dofs -- what PlainHandler accepts)
+  { MP_ConstraintIter& mi = dom->getMPs(); MP_Constraint* mp;
+    while ((mp = mi()) != nullptr) {
+      const ID& cd = mp->getConstrainedDOFs(); const ID& rd = mp->getRetainedDOFs(); const Matrix& C = mp->getConstraint();
+      bool ident = cd.Size() == rd.Size() && C.noRows() == cd.Size() && C.noCols() == cd.Size() && !mp->isTimeVarying();
+      for (int i = 0; ident && i < cd.Size(); i++) {
+        if (cd(i) != rd(i)) ident = false;
+        for (int j = 0; ident && j < cd.Size(); j++) if (C(i, j) != (i == j ? 1.0 : 0.0)) ident = false;
+      }
+      if (!ident) { G.err = "MP_Constraint that is not an equalDOF: outside the device path"; return -3; }
+      std::vector<int> dofs(cd.Size());
+      for (int i = 0; i < cd.Size(); i++) dofs[i] = cd(i);
+      if (xb_add_equal_dof(x, mp->getNodeRetained(), mp->getNodeConstrained(), (int)dofs.size(), dofs.data()) < 0) { G.err = xb_last_error(); return -3; }
+    } }
   // 3. materials and elements, one batch per (element class, material kind)
   struct Batch { std::vector<int> tag, conn, mat; std::vector<double> par; };
   std::map<std::pair<int, int>, Batch> batches;     // (xb element kind, xb material kind)

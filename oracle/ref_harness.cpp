@@ -203,6 +203,16 @@ int ref_fix(void* h, int nodeTag, int dof) {
   return m->domain->addSP_Constraint(sp) ? 0 : -1;
 }
 
+// `equalDOF rNode cNode dofs...` (runtime/commands/domain/constraint.cpp: MP_Constraint with an identity Ccr)
+int ref_equal_dof(void* h, int rTag, int cTag, int n, const int* dofs) {
+  RefModel* m = (RefModel*)h;
+  Matrix Ccr(n, n);
+  ID rcDOF(n);
+  for (int i = 0; i < n; i++) { Ccr(i, i) = 1.0; rcDOF(i) = dofs[i]; }
+  MP_Constraint* mp = new MP_Constraint(rTag, cTag, Ccr, rcDOF, rcDOF);
+  return m->domain->addMP_Constraint(mp) ? 0 : -1;
+}
+
 // kind 0: ElasticIsotropic (E, nu, rho)        -- runtime/commands/modeling/nDMaterial.cpp
 // kind 1: J2Plasticity (K,G,sig0,sigInf,delta,H,eta) -- commands/modeling/material/plastic.cpp:927
 int ref_add_nd_material(void* h, int tag, int kind, const double* p) {

@@ -1177,6 +1177,7 @@ typedef struct {
   int nsec; OrcSecDef* sec;           /* fibre section definitions */
   double* load;                       /* [nn][ndf] reference nodal loads (pattern 1, Linear series) */
   int* fixed;                         /* [nn][ndf] 1 when an SP_Constraint holds the dof */
+  int nmp; int* mp;                   /* equalDOF: (retained node, constrained node, dof) index triples */
   int nmat; int* mat_tag; int* mat_kind; double* mat_par; /* [nmat][8] */
   int ne, ecap; OrcEle* ele;          /* ascending element tag after setup */
   /* analysis side */
@@ -1217,6 +1218,18 @@ int orc_fix(void* h, int nodeTag, int dof) {
   if (n < 0 || dof < 0 || dof >= m->ndf) return -1;
   m->fixed[n * m->ndf + dof] = 1; return 0;
 }
+/* `equalDOF rNode cNode dofs...`: an MP_Constraint with an identity constraint matrix (same dofs on both nodes);
+ * PlainHandler gives the constrained dofs id -4 (PlainHandler.cpp:129-176), the numberer then hands them the
+ * retained dof's equation (PlainNumberer.cpp:111-142, DOF_Numberer.cpp:151-190) */
+int orc_equal_dof(void* h, int rTag, int cTag, int n, const int* dofs) {
+  OrcModel* m = (OrcModel*)h;
+  int r = find_node(m, rTag), c = find_node(m, cTag);
+  if (r < 0 || c < 0) return -1;
+  m->mp = (int*)realloc(m->mp, sizeof(int) * 3 * (m->nmp + n));
+  for (int i = 0; i < n; i++) { m->mp[3 * m->nmp] = r; m->mp[3 * m->nmp + 1] = c; m->mp[3 * m->nmp + 2] = dofs[i]; m->nmp++; }
+  return 0;
+}
+
 int orc_add_nd_material(void* h, int tag, int kind, const double* p) {
   OrcModel* m = (OrcModel*)h;
   m->mat_tag = (int*)realloc(m->mat_tag, sizeof(int) * (m->nmat + 1));
@@ -1403,6 +1416,10 @@ int orc_setup(void* h, int numberer, int soe_kind) {
   qsort(m->ele, m->ne, sizeof(OrcEle), cmp_ele); /* Domain element map iterates by tag */
   m->id = (int*)malloc(sizeof(int) * nn * ndf);
   for (int i = 0; i < nn * ndf; i++) m->id[i] = m->fixed[i] ? -1 : -2;
+  for (int i = 0; i < m->nmp; i++) {       /* PlainHandler: -4 unless the dof is already constrained (then a warning) */
+    int* idc = &m->id[m->mp[3 * i + 1] * ndf + m->mp[3 * i + 2]];
+    if (*idc == -2) *idc = -4;
+  }
 
   int* order = (int*)malloc(sizeof(int) * nn);
   if (numberer == 0) {
@@ -1448,6 +1465,10 @@ int orc_setup(void* h, int numberer, int soe_kind) {
   }
   free(order);
   m->neq = eqn;
+  for (int i = 0; i < m->nmp; i++) {       /* the numberer's last pass: -4 -> the retained dof's id */
+    int* idc = &m->id[m->mp[3 * i + 1] * ndf + m->mp[3 * i + 2]];
+    if (*idc == -4) *idc = m->id[m->mp[3 * i] * ndf + m->mp[3 * i + 2]];
+  }
 
   /* DOF graph: per equation a sorted adjacency (Vertex::addEdge skips self) */
   IntSet* adj = (IntSet*)calloc(eqn > 0 ? eqn : 1, sizeof(IntSet));

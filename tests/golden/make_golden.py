@@ -15,7 +15,7 @@ import zlib  # noqa: E402
 
 from golden_cases import CASES, NSTEPS, control_node, ele_nd  # noqa: E402
 from modelspec import (CONCRETE02_CORE, CONCRETE02_COVER, ELASTIC, J2_STEEL, ND_3D, ND_PLANE_STRAIN, STEEL02,  # noqa: E402
-                       RefBackend, ref_nd_path, ref_uni_path)
+                       RefBackend, ref_nd_path, ref_uni_path, tie)
 
 
 def material_paths():
@@ -52,6 +52,7 @@ def model_case(name, spec, numberer, soe, scale, nsteps=NSTEPS):
     out["fe_ids"] = fe
     for s in range(nsteps):
         u = rng.normal(0, 1.0, (spec.nn, spec.ndf)) * np.asarray(scale) * (s + 1); u[ids < 0] = 0
+        tie(spec, u)
         R.set_trial_disp(u); R.apply_load(0.25 * (s + 1))
         out[f"u{s}"] = u
         out[f"A{s}"] = R.form_tangent(); out[f"B{s}"] = R.form_unbalance()

@@ -1,5 +1,6 @@
 """The models behind tests/golden/*.npz (generated from the reference by tests/golden/make_golden.py)."""
-from modelspec import ELASTIC, J2_STEEL, brick_block, cantilever2d, frame2d, frame3d, quad_plane
+from modelspec import (ELASTIC, J2_STEEL, brick_block, brick_periodic_equaldof, cantilever2d, frame2d, frame2d_diaphragm_equaldof,
+                       frame3d, quad_plane, soil_column_equaldof)
 
 # name -> (spec factory, numberer, soe, displacement scale)
 CASES = {
@@ -14,6 +15,14 @@ CASES = {
     # 3D RC space frame: forceBeamColumn (ForceBeamColumn3d) + FiberSection3d; scale per dof (u, r)
     "frame3d_fiber_rcm_csc": (lambda: frame3d(2, 1, 2, ndiv=1), 1, 0, (0.015, 0.015, 0.002, 1e-4, 1e-4, 1e-4)),
     "frame3d_fiber_plain_csr": (lambda: frame3d(1, 2, 2, ndiv=2, nip=5), 0, 1, (0.005, 0.0075, 0.00075, 5e-5, 2.5e-5, 5e-5)),
+    # MP constraints (`equalDOF`, PlainHandler's -4 ids): tied dofs inside one element / across elements / onto a
+    # fixed dof / several constrained dofs on one retained dof
+    "equaldof_soilcolumn_plain_csc": (lambda: soil_column_equaldof(8), 0, 0, 2e-3),
+    "equaldof_soilcolumn_rcm_csr": (lambda: soil_column_equaldof(5, mat=ELASTIC, seed=23), 1, 1, 2e-2),
+    "equaldof_brick_rcm_csc": (lambda: brick_periodic_equaldof(3, 3, 2), 1, 0, 2e-3),
+    "equaldof_brick_plain_csr": (lambda: brick_periodic_equaldof(2, 3, 3, dofs=(0, 1, 2), seed=24), 0, 1, 2e-3),
+    "equaldof_frame2d_rcm_csc": (lambda: frame2d_diaphragm_equaldof(2, 2, 1), 1, 0, (0.006, 0.003, 6e-5)),
+    "equaldof_frame2d_plain_csr": (lambda: frame2d_diaphragm_equaldof(3, 2, 2, nip=4), 0, 1, (0.008, 0.002, 5e-5)),
 }
 NSTEPS = 3
 
@@ -52,6 +61,9 @@ RAYLEIGH_CASES = {
                          _uniform_mass(0.05), 0.5, 0.25, 0.02, RAYLEIGH),
     "rayleigh_frame2d": (lambda: frame2d(2, 2, 2, lateral=30.0), _uniform_mass(0.05, 0.0), 0.5, 0.25, 0.02, RAYLEIGH),
     "rayleigh_frame3d": (lambda: frame3d(1, 1, 2, ndiv=2, lateral=(25.0, 15.0)), _uniform_mass(0.05, 0.0), 0.5, 0.25, 0.02, RAYLEIGH),
+    # with `equalDOF`: the nodal masses / nodal unbalance of every dof on a shared equation, in DOF_Group order
+    "rayleigh_soilcolumn_equaldof": (lambda: soil_column_equaldof(6, mat=J2_STEEL_RHO), _uniform_mass(0.05), 0.5, 0.25, 0.02, RAYLEIGH),
+    "rayleigh_frame2d_equaldof": (lambda: frame2d_diaphragm_equaldof(2, 2, 1, lateral=30.0), _uniform_mass(0.05, 0.0), 0.5, 0.25, 0.02, RAYLEIGH),
 }
 
 

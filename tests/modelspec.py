@@ -52,6 +52,7 @@ class ModelSpec:
     groups: list = field(default_factory=list)
     loads: np.ndarray = None  # [nload, 1+ndf] (node tag, values...)
     uniaxials: list = field(default_factory=list)   # (tag, kind, params)
+    equal_dofs: list = field(default_factory=list)  # `equalDOF`: (retained node tag, constrained node tag, [dofs], 0-based)
     sections: list = field(default_factory=list)    # (tag, y[nf], A[nf], uniaxial tags[nf])
 
     @property
@@ -282,6 +283,54 @@ def soil_structure_block(nx=6, ny=6, nz=6, distort=0.0, seed=0):
     return ModelSpec(3, 3, spec.node_tags, spec.crd, spec.fix, mats, groups, spec.loads)
 
 
+def tie(spec, u):
+    """make a nodal field consistent with the model's `equalDOF`s: constrained dofs take the retained dof's value"""
+    if not spec.equal_dofs:
+        return u
+    ix = {int(t): i for i, t in enumerate(spec.node_tags)}
+    for r, c, dofs in spec.equal_dofs:
+        u[ix[int(c)], list(dofs)] = u[ix[int(r)], list(dofs)]
+    return u
+
+
+def soil_column_equaldof(ny=8, mat=J2_STEEL, distort=0.15, seed=21):
+    """the classic site-response column: one FourNodeQuad wide, base fixed, the left and right node of every
+    level tied with `equalDOF` in both dofs (periodic boundary) -- tied dofs sit in the SAME element"""
+    spec = quad_plane(1, ny, mat=mat, lx=1.0, ly=float(ny), distort=distort, seed=seed, body=(0.0, -0.02))
+    spec.fix = np.array([(t, d) for t in (1, 2) for d in range(2)], np.int32)
+    spec.equal_dofs = [(1 + 2 * j, 2 + 2 * j, [0, 1]) for j in range(1, ny + 1)]
+    spec.loads = np.array([[1 + 2 * ny, 2.0, -1.0], [2 + 2 * ny, 0.5, 0.25], [1 + 2 * (ny // 2), 1.0, 0.0]])
+    return spec
+
+
+def brick_periodic_equaldof(nx=3, ny=3, nz=2, mat=J2_STEEL, dofs=(0, 2), distort=0.2, seed=22):
+    """a stdBrick block whose x = lx face follows its x = 0 face in `dofs` (partial tie, nodes in different
+    elements), plus one interior pair tied in all three dofs and one tie onto a fixed node"""
+    spec = brick_block(nx, ny, nz, mat=mat, distort=distort, seed=seed, body=(0.0, 0.0, -0.01))
+    def nid(i, j, k):
+        return i + (nx + 1) * (j + (ny + 1) * k) + 1
+    eq = [(nid(0, j, k), nid(nx, j, k), list(dofs)) for k in range(1, nz + 1) for j in range(ny + 1)]
+    eq.append((nid(1, 1, 1), nid(nx - 1, ny - 1, nz), [0, 1, 2]))   # far-apart interior / top nodes
+    eq.append((nid(1, 0, 0), nid(1, 0, 1), [1]))              # retained dof is fixed: the tied dof is fixed too
+    spec.equal_dofs = eq
+    return spec
+
+
+def frame2d_diaphragm_equaldof(nbay=2, nstory=2, ndiv=1, **kw):
+    """2D RC frame with every floor's column-line nodes tied to the first one in ux (rigid diaphragm, the usual
+    `equalDOF $master $slave 1`): one retained dof with several constrained ones, both ends of a girder on one equation"""
+    spec = frame2d(nbay, nstory, ndiv, **kw)
+    bay, story = 360.0, 144.0
+    eq = []
+    for j in range(1, nstory + 1):
+        line = [int(spec.node_tags[i]) for i in range(spec.nn)
+                if abs(spec.crd[i, 1] - j * story) < 1e-9 and abs(spec.crd[i, 0] / bay - round(spec.crd[i, 0] / bay)) < 1e-9]
+        line.sort(key=lambda t: spec.crd[t - 1, 0])
+        eq += [(line[0], t, [0]) for t in line[1:]]
+    spec.equal_dofs = eq
+    return spec
+
+
 def have_glue():
     return os.path.exists(GLUE_SO)
 
@@ -409,6 +458,9 @@ class OracleBackend(_Backend):
         assert self.h, "node tags must ascend"
         for t, d in spec.fix:
             assert L.orc_fix(self.h, int(t), int(d)) == 0
+        for r, c, dofs in spec.equal_dofs:
+            d = np.ascontiguousarray(dofs, np.int32)
+            assert L.orc_equal_dof(self.h, int(r), int(c), len(d), _p(d)) == 0
         for tag, kind, p in spec.materials:
             pp = np.zeros(8); pp[:len(p)] = p
             assert L.orc_add_nd_material(self.h, tag, kind, _p(pp)) == 0
@@ -581,6 +633,9 @@ class RefBackend(_Backend):
             assert L.ref_add_node(self.h, int(t), _p(xx)) == 0
         for t, d in spec.fix:
             assert L.ref_fix(self.h, int(t), int(d)) == 0
+        for r, c, dofs in spec.equal_dofs:
+            d = np.ascontiguousarray(dofs, np.int32)
+            assert L.ref_equal_dof(self.h, int(r), int(c), len(d), _p(d)) == 0
         for tag, kind, p in spec.materials:
             pp = np.zeros(8); pp[:len(p)] = p
             assert L.ref_add_nd_material(self.h, tag, kind, _p(pp)) == 0

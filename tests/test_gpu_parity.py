@@ -14,8 +14,8 @@ import pytest
 
 import xara_b200 as xb
 from golden_cases import CASES, NSTEPS, ele_nd
-from modelspec import (ELASTIC, J2_STEEL, OracleBackend, brick_block, frame2d, frame3d, have_glue, have_metis, have_ref, metis_partition,
-                       quad_plane, soil_structure_block)
+from modelspec import (ELASTIC, J2_STEEL, OracleBackend, brick_block, brick_periodic_equaldof, frame2d, frame2d_diaphragm_equaldof, frame3d,
+                       have_glue, have_metis, have_ref, metis_partition, quad_plane, soil_column_equaldof, soil_structure_block, tie)
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -71,6 +71,46 @@ def test_device_vs_oracle_load_history(mat, shape, numberer, soe):
         for e in (0, O.ne // 2, O.ne - 1):
             assert relerr(D.element_tangent(e, nd), O.ele_tangent(e, nd)) < RTOL
             assert relerr(D.element_resid(e, nd), O.ele_resid(e, nd)) < RTOL
+        if s % 2 == 0:
+            O.commit(); D.commit()
+
+
+@pytest.mark.parametrize("shape", ["soilcolumn", "brick", "brick_elastic", "frame2d"])
+@pytest.mark.parametrize("numberer,soe", [(0, 0), (1, 1), (1, 0)])
+def test_device_vs_oracle_load_history_equaldof(shape, numberer, soe):
+    """`equalDOF` (MP_Constraint, PlainHandler's -4 ids): constrained dofs share the retained dof's equation.  Rows fed
+    by several nodes, two dofs of one element on one equation, ties onto fixed dofs; A and B against the oracle over a
+    load history with commits, plus the nodal-mass terms of a transient tangent on the shared rows."""
+    rng = np.random.default_rng(43)
+    if shape == "soilcolumn":
+        spec, sc = soil_column_equaldof(40, distort=0.2, seed=31), 2e-3
+    elif shape == "brick":
+        spec, sc = brick_periodic_equaldof(5, 4, 3, seed=32), 1.5e-3
+    elif shape == "brick_elastic":
+        spec, sc = brick_periodic_equaldof(3, 5, 4, mat=ELASTIC, dofs=(0, 1, 2), seed=33), 1.5e-3
+    else:
+        spec, sc = frame2d_diaphragm_equaldof(3, 4, 2), np.array((0.006, 0.003, 6e-5))
+    beam = spec.groups[0].kind in (2, 3)
+    tol = BEAM_RTOL if beam else RTOL
+    mass = rng.uniform(0.01, 0.1, (spec.nn, spec.ndf))
+    O = OracleBackend(spec, numberer, soe); O.set_mass(spec.node_tags, mass)
+    D = xb.DeviceModel.from_spec(spec, setup=False); D.set_mass(spec.node_tags, mass); D.setup(numberer, soe); D.to_device(0)
+    ids = O.ids()
+    assert np.array_equal(D.ids(), ids)
+    assert (np.bincount(ids[ids >= 0]) > 1).sum() >= 4          # equations really are shared
+    assert relerr(D.form_tangent(), O.form_tangent()) < tol
+    for s in range(5):
+        u = rng.normal(0, 1.0, (spec.nn, spec.ndf)) * sc * (s + 1); u[ids < 0] = 0
+        tie(spec, u)
+        O.set_trial_disp(u); D.set_trial_disp(u); D.update()
+        O.apply_load(0.2 * s); D.apply_load(0.2 * s)
+        if s == 3:      # Newmark terms: c1 K + c3 M (+ alphaM c2 M), P - M a - alphaM M v - R
+            v, a = rng.normal(0, 1.0, (2, spec.nn, spec.ndf)); v[ids < 0] = 0; a[ids < 0] = 0
+            tie(spec, v); tie(spec, a)
+            for m in (O, D):
+                m.set_rayleigh(0.3, 0.0, 0.0, 0.0); m.set_transient(1.0, 50.0, 1.0e4); m.set_vel_accel(v, a)
+        assert relerr(D.form_tangent(), O.form_tangent()) < tol
+        assert relerr(D.form_unbalance(), O.form_unbalance()) < tol
         if s % 2 == 0:
             O.commit(); D.commit()
 
@@ -135,9 +175,15 @@ def _newton_counts_match(spec, nsteps, min_iters):
     assert relerr(D.trial_disp(), uo) < 1e-8
 
 
-@pytest.mark.parametrize("shape", ["brick", "quad", "frame", "frame3d"])
+@pytest.mark.parametrize("shape", ["brick", "quad", "frame", "frame3d", "soilcolumn_equaldof", "frame_equaldof"])
 def test_newton_iteration_counts_match_oracle(shape):
-    if shape == "brick":
+    if shape == "soilcolumn_equaldof":      # sheared soil column with tied (periodic) sides
+        spec = soil_column_equaldof(12, mat=J2_STEEL, distort=0.1)
+        spec.loads = np.array([[1 + 2 * 12, 22.0, -3.0], [1 + 2 * 6, 10.0, 0.0]])
+        _newton_counts_match(spec, 8, 6)
+    elif shape == "frame_equaldof":         # RC frame with rigid-diaphragm ties
+        _newton_counts_match(frame2d_diaphragm_equaldof(2, 3, 2, lateral=22.0, gravity=-40.0), 5, 4)
+    elif shape == "brick":
         spec = brick_block(4, 4, 6, mat=J2_STEEL, lx=1.0, ly=1.0, lz=3.0, load=(1.2, 0.0, -0.5))
         _newton_counts_match(spec, 8, 6)
     elif shape == "quad":
@@ -151,7 +197,8 @@ def test_newton_iteration_counts_match_oracle(shape):
 
 
 @pytest.mark.skipif(not (have_ref() and have_glue()), reason="oracle/_ref not built (needs /root/reference)")
-@pytest.mark.parametrize("shape,numberer,soe", [("brick", 1, 0), ("quad", 0, 1), ("mixed", 1, 1)])
+@pytest.mark.parametrize("shape,numberer,soe", [("brick", 1, 0), ("quad", 0, 1), ("mixed", 1, 1), ("soilcolumn_equaldof", 1, 0),
+                                                ("soilcolumn_equaldof", 0, 1)])
 def test_reference_newton_loop_drives_device_path(shape, numberer, soe):
     """The drop-in, end to end: the REFERENCE'S OWN StaticAnalysis objects (AnalysisModel, PlainHandler, numberer,
     SparseGenCol/Row SOE and solver, NewtonRaphson, CTestNormDispIncr, LoadControl::newStep) run a load-controlled
@@ -165,6 +212,10 @@ def test_reference_newton_loop_drives_device_path(shape, numberer, soe):
     elif shape == "quad":
         def mk():
             sp = quad_plane(16, 4, mat=J2_STEEL, lx=8.0, ly=2.0); sp.loads[:, 1:] = [0.0, -10.0]; return sp
+    elif shape == "soilcolumn_equaldof":
+        def mk():   # MP_Constraints read out of the Domain (`equalDOF`): sheared soil column with tied sides
+            sp = soil_column_equaldof(12, mat=J2_STEEL, distort=0.1)
+            sp.loads = np.array([[1 + 2 * 12, 22.0 * 8, -3.0 * 8], [1 + 2 * 6, 10.0 * 8, 0.0]]); return sp
     else:
         def mk():   # soil (J2) + footing (elastic): two element batches, loaded well past first yield
             sp = soil_structure_block(5, 5, 5, distort=0.1, seed=2); sp.loads[:, 1:] *= 12.0; return sp
@@ -632,7 +683,8 @@ def test_partitioned_frame_matches_single_gpu():
 
 
 @pytest.mark.parametrize("name", ["newmark_brick_j2", "newmark_frame2d", "newmark_frame3d", "rayleigh_brick_j2",
-                                  "rayleigh_quad_j2", "rayleigh_frame2d", "rayleigh_frame3d"])
+                                  "rayleigh_quad_j2", "rayleigh_frame2d", "rayleigh_frame3d",
+                                  "rayleigh_soilcolumn_equaldof", "rayleigh_frame2d_equaldof"])
 def test_newmark_device_vs_golden_reference_history(name):
     """Newmark (displacement form, nodal masses): the device replays the history recorded from the
     reference's own Newmark integrator -- c1 K + c3 M tangent, P - M a - R unbalance, predictor,

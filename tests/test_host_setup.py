@@ -9,7 +9,8 @@ import pytest
 
 import xara_b200 as xb
 from golden_cases import CASES
-from modelspec import ELASTIC, J2_STEEL, OracleBackend, brick_block, frame2d, quad_plane
+from modelspec import (ELASTIC, J2_STEEL, OracleBackend, brick_block, brick_periodic_equaldof, frame2d, frame2d_diaphragm_equaldof,
+                       quad_plane, soil_column_equaldof)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -47,6 +48,10 @@ SPECS = {
     "quad_relabel": lambda: relabel(quad_plane(7, 4, distort=0.2), 6),
     "brick_sliver": lambda: brick_block(9, 1, 1),
     "frame2d": lambda: frame2d(3, 4, 2),
+    # `equalDOF` (MP_Constraint with an identity matrix): constrained dofs share the retained dof's equation
+    "soilcolumn_equaldof": lambda: soil_column_equaldof(7),
+    "brick_equaldof": lambda: brick_periodic_equaldof(3, 2, 3),
+    "frame2d_equaldof": lambda: frame2d_diaphragm_equaldof(3, 3, 2),
 }
 
 
@@ -124,6 +129,38 @@ def test_no_cpu_fallback_without_device():
         D.to_device(0)
     with pytest.raises(xb.XaraB200Error):
         D.form_tangent()
+
+
+def test_equal_dof_edge_cases():
+    # a retained node with no element of its own, a constrained node tied onto a fixed dof, and refusals
+    spec = brick_block(2, 1, 1)
+    spec.node_tags = np.append(spec.node_tags, 100).astype(np.int32)
+    spec.crd = np.vstack([spec.crd, [5.0, 5.0, 5.0]])
+    spec.equal_dofs = [(100, int(spec.node_tags[-2]), [0, 2]), (1, int(spec.node_tags[-3]), [1])]   # node 1 is fixed
+    for numberer in (0, 1):
+        for soe in (0, 1):
+            O = OracleBackend(spec, numberer, soe); D = xb.DeviceModel.from_spec(spec, numberer, soe)
+            ids = D.ids()
+            assert np.array_equal(ids, O.ids())
+            assert np.array_equal(ids[-1, [0, 2]], ids[-2, [0, 2]]) and ids[-3, 1] == -1
+            assert all(np.array_equal(a, b) for a, b in zip(D.pattern(), O.csr()))
+            sm = D.scatter_map(0, D.ne, 24)
+            for e in range(D.ne):
+                assert np.array_equal(sm[e], O.scatter_map(e, 24))
+    chain = brick_block(2, 1, 1)
+    chain.equal_dofs = [(7, 8, [0]), (8, 9, [0])]            # node 8's dof is retained AND constrained
+    with pytest.raises(xb.XaraB200Error):
+        xb.DeviceModel.from_spec(chain, 0, 0)
+    part = brick_block(4, 1, 1)
+    part.equal_dofs = [(9, 10, [0])]
+    with pytest.raises(xb.XaraB200Error):                    # equalDOF on a partitioned model: refused, not approximated
+        xb.DeviceModel.from_spec(part, 0, 0, nparts=2, rank=0)
+    m = xb.DeviceModel(3, 3)
+    m.add_nodes([1, 2], np.zeros((2, 3)))
+    with pytest.raises(xb.XaraB200Error):
+        m.equal_dof(1, 1, [0])
+    with pytest.raises(xb.XaraB200Error):
+        m.equal_dof(1, 2, [3])
 
 
 def test_all_fixed_and_isolated_nodes():

@@ -11,7 +11,8 @@ import pytest
 
 from golden_cases import CASES, DISPCONTROL_CASES, NSTEPS, RAYLEIGH_CASES, TRANSIENT_CASES, ele_nd, newmark_coeffs
 from modelspec import (ELASTIC, J2_STEEL, MAT_ELASTIC, MAT_J2, ND_3D, ND_PLANE_STRAIN, OracleBackend, RefBackend,
-                       brick_block, disp_control, frame2d, frame3d, have_ref, oracle_nd_path, oracle_uni_path, quad_plane, ref_nd_path)
+                       brick_block, brick_periodic_equaldof, disp_control, frame2d, frame2d_diaphragm_equaldof, frame3d, have_ref,
+                       oracle_nd_path, oracle_uni_path, quad_plane, ref_nd_path, soil_column_equaldof, tie)
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 RTOL = 1e-12
@@ -112,6 +113,8 @@ def test_oracle_vs_live_reference(mat, numberer, soe):
     if mat is J2_STEEL:
         specs.append(frame2d(2, 2, 2))
         specs.append(frame3d(1, 1, 2))
+        specs.append(frame2d_diaphragm_equaldof(2, 2, 1))
+    specs += [soil_column_equaldof(5, mat=mat), brick_periodic_equaldof(2, 2, 2, mat=mat)]     # `equalDOF`
     for spec in specs:
         beam = spec.groups[0].kind in (2, 3)
         O, R = OracleBackend(spec, numberer, soe), RefBackend(spec, numberer, soe)
@@ -121,6 +124,7 @@ def test_oracle_vs_live_reference(mat, numberer, soe):
         for s in range(3):
             sc = (0.02, 0.02, 2e-4) if spec.groups[0].kind == 2 else ((0.015, 0.015, 0.003, 1e-4, 1e-4, 1e-4) if beam else 2e-3)
             u = rng.normal(0, 1.0, (spec.nn, spec.ndf)) * np.asarray(sc) * (s + 1); u[O.ids() < 0] = 0
+            tie(spec, u)
             O.set_trial_disp(u); R.set_trial_disp(u)
             O.apply_load(0.3 * s); R.apply_load(0.3 * s)
             assert close(O.form_tangent(), R.form_tangent(), 1e-11 if beam else RTOL)

@@ -60,6 +60,7 @@ def _load():
         "xb_model_destroy": (None, [vp]),
         "xb_add_nodes": (i32, [vp, i32, vp, vp]),
         "xb_add_sp": (i32, [vp, i32, vp, vp]),
+        "xb_add_equal_dof": (i32, [vp, i32, i32, i32, vp]),
         "xb_add_nd_material": (i32, [vp, i32, i32, vp, i32]),
         "xb_add_uniaxial_material": (i32, [vp, i32, i32, vp, i32]),
         "xb_add_fiber_section": (i32, [vp, i32, i32, vp, vp, vp]),
@@ -197,6 +198,10 @@ class DeviceModel:
         node_tags, dofs = _i32(node_tags), _i32(dofs)
         self._ck(lib.xb_add_sp(self._h, len(node_tags), _ptr(node_tags), _ptr(dofs)))
 
+    def equal_dof(self, retained_tag, constrained_tag, dofs):
+        dofs = np.ascontiguousarray(dofs, np.int32)
+        self._ck(lib.xb_add_equal_dof(self._h, int(retained_tag), int(constrained_tag), len(dofs), _ptr(dofs)))
+
     def nd_material(self, tag, kind, par):
         par = _f64(par)
         self._ck(lib.xb_add_nd_material(self._h, tag, kind, _ptr(par), len(par)))
@@ -231,6 +236,8 @@ class DeviceModel:
         m.add_nodes(spec.node_tags, spec.crd)
         if len(spec.fix):
             m.fix(spec.fix[:, 0], spec.fix[:, 1])
+        for r, c, dofs in getattr(spec, "equal_dofs", []):
+            m.equal_dof(r, c, dofs)
         for tag, kind, p in spec.materials:
             m.nd_material(tag, kind, p)
         for tag, kind, p in getattr(spec, "uniaxials", []):

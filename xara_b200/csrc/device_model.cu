@@ -1189,13 +1189,25 @@ struct AsmView {
   double c1, c2, c3, alphaM;
   const double* recvK;        // element-matrix rows received from other ranks (slots with koff < 0)
   const double* recvR;        // element-residual entries received from other ranks (roff < 0)
+  // MP constraints (equalDOF): equations shared by several (node, dof) are assembled by row (host_model.hpp, irr_*)
+  int max_dup, nirr, irr_max_row;
+  const int* irr_row;             // [nirr] local row
+  const long long* irr_ptr;       // [nirr+1] -> contributions in (FE_Element, element dof) order
+  const long long* irr_src;       // [*] offset of the element-matrix row in KeN
+  const long long* irr_roff;      // [*] offset of the element-residual entry in Re
+  const unsigned short* irr_cp;   // [*][cp_stride] column position | duplicate rank << 13
+  const long long* irr_own_ptr;   // [nirr+1] -> (node, dof) pairs on the equation, DOF_Group order
+  const int* irr_own;             // [*] node * ndf + dof
+  const unsigned short* irr_diag; // [nirr]
 };
 
 // One warp per node.  The node's equations own rows (CSR) / columns (CSC) that share one
 // column list; contributions of the adjacent elements are added in FE_Element order, i.e.
 // the order IncrementalIntegrator::formTangent (IncrementalIntegrator.cpp:91-99) calls addA.
 // Every entry of A is written exactly once, so no zeroA pass is needed.
-template <int NDF>
+// MP: with `equalDOF` two dofs of one element may sit on one equation; a position then carries the duplicate's
+// rank in its top 3 bits and the ranks are added in turn (the order addA meets them, SparseGenColLinSOE.cpp:264).
+template <int NDF, bool MP = false>
 __global__ void __launch_bounds__(256, XB_ASM_OCC) assemble_A_kernel(AsmView V, const double* __restrict__ KeN,
                                                             double* __restrict__ A, const long long* __restrict__ task,
                                                             long long first, long long count) {
@@ -1250,11 +1262,21 @@ __global__ void __launch_bounds__(256, XB_ASM_OCC) assemble_A_kernel(AsmView V, 
     }
 #pragma unroll
     for (int c = 0; c < CH; c++) {   // FE_Element order: the order addA is called in
-      if (pos[c] != 0xFFFF) {
+      if (!MP) {
+        if (pos[c] != 0xFFFF) {
 #pragma unroll
-        for (int p = 0; p < NDF; p++) acc[p * V.max_row + pos[c]] += (c1 == 1.0 ? v[c][p] : v[c][p] * c1);
+          for (int p = 0; p < NDF; p++) acc[p * V.max_row + pos[c]] += (c1 == 1.0 ? v[c][p] : v[c][p] * c1);
+        }
+        __syncwarp();
+      } else {
+        for (int r = 0; r <= V.max_dup; r++) {
+          if (pos[c] != 0xFFFF && (pos[c] >> 13) == r) {
+#pragma unroll
+            for (int p = 0; p < NDF; p++) acc[p * V.max_row + (pos[c] & 0x1FFF)] += (c1 == 1.0 ? v[c][p] : v[c][p] * c1);
+          }
+          __syncwarp();
+        }
       }
-      __syncwarp();
     }
     tb += CH;
   } while (tb < t1);
@@ -1265,6 +1287,66 @@ __global__ void __launch_bounds__(256, XB_ASM_OCC) assemble_A_kernel(AsmView V, 
     double* out = A + rp;
     for (int c = lane; c < L; c += 32) out[c] = acc[p * V.max_row + c];
   }
+}
+
+// Shared equations (equalDOF): one warp per row.  DOF_Group tangents first, in DOF_Group order
+// (TransientIntegrator.cpp:89-107), then the element-matrix rows of every (node, dof) on the equation in
+// (FE_Element, element dof) order -- the order SparseGenColLinSOE::addA / SparseGenRowLinSOE::addA meet them.
+__global__ void __launch_bounds__(256) assemble_A_irr_kernel(AsmView V, const double* __restrict__ KeN, double* __restrict__ A) {
+  extern __shared__ double sacc[];  // [warps][irr_max_row]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (w >= V.nirr) return;
+  double* acc = sacc + (size_t)warp * V.irr_max_row;
+  const int row = V.irr_row[w];
+  const long long a0 = V.ptr[row];
+  const int L = (int)(V.ptr[row + 1] - a0);
+  for (int c = lane; c < L; c += 32) acc[c] = 0.0;
+  __syncwarp();
+  if ((V.c2 != 0.0 || V.c3 != 0.0) && lane == 0) {
+    const unsigned short dp = V.irr_diag[w];
+    for (long long o = V.irr_own_ptr[w]; o < V.irr_own_ptr[w + 1]; o++) {
+      const double ms = V.mass[V.irr_own[o]];
+      double t = 0.0;
+      t += (ms * V.alphaM) * V.c2;
+      t += ms * V.c3;
+      acc[dp] += t;
+    }
+  }
+  __syncwarp();
+  const int cps = V.cp_stride;
+  const double c1 = V.c1;
+  for (long long k = V.irr_ptr[w]; k < V.irr_ptr[w + 1]; k++) {
+    const long long src = V.irr_src[k];
+    for (int l0 = 0; l0 < cps; l0 += 32) {      // cp_stride <= 32 for every element kind here; kept general
+      const int l = l0 + lane;
+      const unsigned short pos = l < cps ? V.irr_cp[(size_t)k * cps + l] : (unsigned short)0xFFFF;
+      const double v = pos != 0xFFFF ? KeN[src + l] : 0.0;
+      for (int r = 0; r <= V.max_dup; r++) {
+        if (pos != 0xFFFF && (pos >> 13) == r) acc[pos & 0x1FFF] += (c1 == 1.0 ? v : v * c1);
+        __syncwarp();
+      }
+    }
+  }
+  for (int c = lane; c < L; c += 32) A[a0 + c] = acc[c];
+}
+
+// formUnbalance for the shared equations: element residual entries in (FE_Element, element dof) order, then the
+// nodal unbalance of every (node, dof) on the equation in DOF_Group order.  One thread per row.
+__global__ void __launch_bounds__(128) assemble_B_irr_kernel(AsmView V, const double* __restrict__ Re, double lambda,
+                                                             double* __restrict__ B) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= V.nirr) return;
+  double acc = 0.0;
+  for (long long k = V.irr_ptr[w]; k < V.irr_ptr[w + 1]; k++) acc += -Re[V.irr_roff[k]];
+  for (long long o = V.irr_own_ptr[w]; o < V.irr_own_ptr[w + 1]; o++) {
+    const int i = V.irr_own[o];
+    double ub = V.load[i] * lambda;
+    const double ms = V.mass[i];
+    if (ms != 0.0) { ub -= ms * V.acc[i]; if (V.alphaM != 0.0) ub += ms * V.vel[i] * -V.alphaM; }
+    acc += ub;
+  }
+  B[V.irr_row[w]] = acc;
 }
 
 // interface exchange, receive side: rows that arrived from other ranks go to their slots
@@ -1507,6 +1589,7 @@ void xb_model_destroy(xb_model* m) {
 
 int xb_add_nodes(xb_model* m, int n, const int* tags, const double* crd) { HOSTCALL(m->h.add_nodes(n, tags, crd)); }
 int xb_add_sp(xb_model* m, int n, const int* t, const int* d) { HOSTCALL(m->h.add_sp(n, t, d)); }
+int xb_add_equal_dof(xb_model* m, int r, int c, int n, const int* dofs) { HOSTCALL(m->h.add_equal_dof(r, c, n, dofs)); }
 int xb_add_nd_material(xb_model* m, int tag, int kind, const double* par, int npar) { HOSTCALL(m->h.add_material(tag, kind, par, npar)); }
 int xb_add_uniaxial_material(xb_model* m, int tag, int kind, const double* par, int npar) { HOSTCALL(m->h.add_uniaxial(tag, kind, par, npar)); }
 int xb_add_fiber_section(xb_model* m, int tag, int nf, const double* y, const double* A, const int* mt) { HOSTCALL(m->h.add_fiber_section(tag, nf, y, A, mt)); }
@@ -1613,7 +1696,7 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
   CU(cudaMemset(m->dU, 0, sizeof(double) * std::max<size_t>(nn * h.ndf, 1)));
   CU(cudaMemset(m->dUc, 0, sizeof(double) * std::max<size_t>(nn * h.ndf, 1)));
   CU(dev_upload(m, &m->dId, h.id));
-  CU(dev_upload(m, &m->dRowOf, h.row_of));
+  CU(dev_upload(m, &m->dRowOf, h.row_of_dev));   // shared equations (equalDOF) are assembled by row
   CU(dev_upload(m, &m->dTask, h.asm_task));
   CU(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming));
@@ -1816,6 +1899,22 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
   CU(dev_upload(m, &ncol_ptr, h.ncol_ptr));
   a.ptr = ptr; a.n2e_ptr = n2e_ptr; a.n2e_roff = roff; a.colpos = cp;
   a.ncol_ptr = ncol_ptr;
+  a.max_dup = h.max_dup; a.nirr = (int)h.irr_row.size(); a.irr_max_row = std::max(h.irr_max_row, 1);
+  if (a.nirr) {
+    int *irow = nullptr, *iown = nullptr;
+    long long *iptr = nullptr, *isrc = nullptr, *iroff = nullptr, *ioptr = nullptr;
+    unsigned short *icp = nullptr, *idiag = nullptr;
+    CU(dev_upload(m, &irow, h.irr_row));
+    CU(dev_upload(m, &iptr, h.irr_ptr));
+    CU(dev_upload(m, &isrc, h.irr_src));
+    CU(dev_upload(m, &iroff, h.irr_roff));
+    CU(dev_upload(m, &icp, h.irr_cp));
+    CU(dev_upload(m, &ioptr, h.irr_own_ptr));
+    CU(dev_upload(m, &iown, h.irr_own));
+    CU(dev_upload(m, &idiag, h.irr_diag));
+    a.irr_row = irow; a.irr_ptr = iptr; a.irr_src = isrc; a.irr_roff = iroff; a.irr_cp = icp;
+    a.irr_own_ptr = ioptr; a.irr_own = iown; a.irr_diag = idiag;
+  }
 
   // the state determination of an untouched model: J2Plasticity's constructor runs
   // plastic_integrator() on zero strain (J2Plasticity.cpp:105) so that getTangent()
@@ -2257,6 +2356,24 @@ static int launch_assemble(xb_model* m, long long first, long long count, cudaSt
   const unsigned blocks = (unsigned)((count + warps - 1) / warps);
   AsmView av = m->av;
   if (tan_coef(m).on) av.c1 = 1.0;   // the element kernels already folded c1 (and the damping / mass terms) in
+  if (av.max_dup > 0 || av.nirr > 0) {   // equalDOF: ranked additions, then the shared rows
+#define XB_ASM_MP(N)                                                                                             \
+    case N:                                                                                                      \
+      CU(cudaFuncSetAttribute(assemble_A_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+      assemble_A_kernel<N, true><<<blocks, warps * 32, sm, st>>>(av, m->dKe, m->dA, m->dTask, first, count);      \
+      break;
+    switch (m->h.ndf) { XB_ASM_MP(1) XB_ASM_MP(2) XB_ASM_MP(3) XB_ASM_MP(6) default: return fail(XB_ERR_UNSUPPORTED, "ndf"); }
+#undef XB_ASM_MP
+    m->launches++;
+    if (av.nirr > 0) {
+      const size_t smi = sizeof(double) * warps * av.irr_max_row;
+      if (smi > 200 * 1024) return fail(XB_ERR_UNSUPPORTED, "shared equation row too long");
+      CU(cudaFuncSetAttribute(assemble_A_irr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smi));
+      assemble_A_irr_kernel<<<(unsigned)((av.nirr + warps - 1) / warps), warps * 32, smi, st>>>(av, m->dKe, m->dA);
+      m->launches++;
+    }
+    return XB_OK;
+  }
   if (m->h.ndf == 3) {
     CU(cudaFuncSetAttribute(assemble_A_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     assemble_A_kernel<3><<<blocks, warps * 32, sm, st>>>(av, m->dKe, m->dA, m->dTask, first, count);
@@ -2410,6 +2527,10 @@ int xb_assemble_unbalance(xb_model* m, double* B) {
   const long long ndof = (long long)m->h.nn() * m->h.ndf;
   if (ndof) {
     assemble_B_kernel<<<(unsigned)((ndof + 255) / 256), 256, 0, m->stream>>>(m->av, m->dRsrc, m->lambda, m->dB);
+    m->launches++;
+  }
+  if (m->av.nirr > 0) {
+    assemble_B_irr_kernel<<<(unsigned)((m->av.nirr + 127) / 128), 128, 0, m->stream>>>(m->av, m->dRsrc, m->lambda, m->dB);
     m->launches++;
   }
   long long bytes = (long long)m->h.nrows * 8 + (long long)m->h.nn() * (m->h.ndm + m->h.ndf) * 8;

@@ -95,6 +95,31 @@ int HostModel::add_fiber_section3d(int tag, int nf, const double* y, const doubl
   return XB_OK;
 }
 
+// element dofs of one slot that land on the same column (tied dofs inside one element): the k-th of them, in
+// element dof order, carries rank k in the top 3 bits of its position; the assembly adds rank 0, then 1, ...
+// (the order addA meets them).  Returns false when more than 8 share a column.
+static bool dup_ranks(uint16_t* cp, int n) {
+  bool ok = true;
+  for (int i = 0; i < n; i++) {
+    if (cp[i] == 0xFFFF) continue;
+    int rank = 0;
+    for (int j = 0; j < i; j++) if (cp[j] != 0xFFFF && (cp[j] & 0x1FFF) == cp[i]) rank++;
+    if (rank > 7) { ok = false; rank = 7; }
+    cp[i] = (uint16_t)(cp[i] | (rank << 13));
+  }
+  return ok;
+}
+
+int HostModel::add_equal_dof(int r_tag, int c_tag, int n, const int* dofs) {
+  if (is_setup) { err = "xb_add_equal_dof after xb_setup"; return XB_ERR_STATE; }
+  if (r_tag == c_tag || n < 1) { err = "xb_add_equal_dof: retained and constrained node must differ, n >= 1"; return XB_ERR_ARG; }
+  for (int i = 0; i < n; i++) {
+    if (dofs[i] < 0 || dofs[i] >= ndf) { err = "xb_add_equal_dof: dof out of range"; return XB_ERR_ARG; }
+    mp_r.push_back(r_tag); mp_c.push_back(c_tag); mp_dof.push_back(dofs[i]);
+  }
+  return XB_OK;
+}
+
 int HostModel::add_elements(int kind, int n, const int* tags, const int* conn, const int* mat_tags,
                             const double* par, int par_stride) {
   if (is_setup) { err = "xb_add_elements after xb_setup"; return XB_ERR_STATE; }
@@ -288,6 +313,21 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
     if (ix < 0) { err = "fix references an unknown node tag"; return XB_ERR_ARG; }
     gid[(size_t)ix * ndf + sp_dof[i]] = -1;
   }
+  // MP_Constraints with an identity matrix (equalDOF): constrained dofs get -4 unless already constrained
+  // (PlainHandler.cpp:129-176 warns and keeps the SP)
+  const bool have_mp = !mp_r.empty();
+  std::vector<int> mp_ri(mp_r.size()), mp_ci(mp_r.size());
+  if (have_mp && nparts > 1) { err = "MP constraints (equalDOF) on a partitioned model are outside the device path"; return XB_ERR_UNSUPPORTED; }
+  for (size_t i = 0; i < mp_r.size(); i++) {
+    mp_ri[i] = nidx(mp_r[i]); mp_ci[i] = nidx(mp_c[i]);
+    if (mp_ri[i] < 0 || mp_ci[i] < 0) { err = "equalDOF references an unknown node tag"; return XB_ERR_ARG; }
+  }
+  for (size_t i = 0; i < mp_r.size(); i++) {
+    int& idc = gid[(size_t)mp_ci[i] * ndf + mp_dof[i]];
+    if (idc == -2) idc = -4;
+  }
+  for (size_t i = 0; i < mp_r.size(); i++)
+    if (gid[(size_t)mp_ri[i] * ndf + mp_dof[i]] == -4) { err = "equalDOF: a retained dof is itself constrained by another equalDOF"; return XB_ERR_UNSUPPORTED; }
   std::vector<double> gload((size_t)n_nodes * ndf, 0.0);
   for (size_t i = 0; i < load_node.size(); i++) {
     int ix = nidx(load_node[i]);
@@ -394,6 +434,14 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
   }
   neq = eqn;
   { std::vector<int>().swap(order); }
+  // the numberer's last pass (PlainNumberer.cpp:111-142, DOF_Numberer.cpp:151-190): -4 -> the retained dof's id
+  std::vector<uint8_t> gshared(have_mp ? (size_t)n_nodes * ndf : 0, 0);   // (node, dof) on an equation several dofs share
+  for (size_t i = 0; i < mp_r.size(); i++) {
+    int& idc = gid[(size_t)mp_ci[i] * ndf + mp_dof[i]];
+    if (idc != -4) continue;
+    idc = gid[(size_t)mp_ri[i] * ndf + mp_dof[i]];
+    if (idc >= 0) { gshared[(size_t)mp_ci[i] * ndf + mp_dof[i]] = 1; gshared[(size_t)mp_ri[i] * ndf + mp_dof[i]] = 1; }
+  }
 
   // ---- element partition and node ownership (DomainPartitioner's role; the numbering above
   // is untouched, so every rank's rows are rows of the one global system) ----
@@ -516,6 +564,7 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
   for (int i = 0; i < nl; i++) if (owned[i])
     for (int j = 0; j < ndf; j++) if (id[(size_t)i * ndf + j] >= 0) row_geq.push_back(id[(size_t)i * ndf + j]);
   std::sort(row_geq.begin(), row_geq.end());
+  if (have_mp) row_geq.erase(std::unique(row_geq.begin(), row_geq.end()), row_geq.end());
   nrows = (int)row_geq.size();
   row_of.assign((size_t)nl * ndf, -1);
   for (int i = 0; i < nl; i++) if (owned[i])
@@ -623,7 +672,13 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
       if (!owned[i]) continue;
       G.nbrs(lnode[i], tmp);
       long long c = 0;
-      for (int w : tmp) for (int j = 0; j < ndf; j++) if (gid[(size_t)w * ndf + j] >= 0) c++;
+      if (!have_mp) { for (int w : tmp) for (int j = 0; j < ndf; j++) if (gid[(size_t)w * ndf + j] >= 0) c++; }
+      else {   // tied dofs put one equation under several neighbours: count distinct equations
+        std::vector<int> q;
+        for (int w : tmp) for (int j = 0; j < ndf; j++) if (gid[(size_t)w * ndf + j] >= 0) q.push_back(gid[(size_t)w * ndf + j]);
+        std::sort(q.begin(), q.end());
+        c = (long long)(std::unique(q.begin(), q.end()) - q.begin());
+      }
       ncol_ptr[i + 1] = c;
     }
   }
@@ -639,12 +694,45 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
       G.nbrs(lnode[i], tmp);
       int* out = &ncol[ncol_ptr[i]];
       long long c = 0;
-      for (int w : tmp) for (int j = 0; j < ndf; j++) { int q = gid[(size_t)w * ndf + j]; if (q >= 0) out[c++] = q; }
-      std::sort(out, out + c);
-      if (c >= 0xFFFF) too_long++;
+      if (!have_mp) {
+        for (int w : tmp) for (int j = 0; j < ndf; j++) { int q = gid[(size_t)w * ndf + j]; if (q >= 0) out[c++] = q; }
+        std::sort(out, out + c);
+      } else {
+        std::vector<int> q;
+        for (int w : tmp) for (int j = 0; j < ndf; j++) if (gid[(size_t)w * ndf + j] >= 0) q.push_back(gid[(size_t)w * ndf + j]);
+        std::sort(q.begin(), q.end());
+        q.erase(std::unique(q.begin(), q.end()), q.end());
+        c = (long long)q.size();
+        std::copy(q.begin(), q.end(), out);
+      }
+      if (c >= (have_mp ? 0x1FFF : 0xFFFF)) too_long++;   // with MP constraints 3 bits of a position carry the duplicate rank
     }
   }
-  if (too_long) { err = "a node couples with more than 65534 equations"; return XB_ERR_UNSUPPORTED; }
+  if (too_long) { err = "a node couples with more than 65534 equations (8190 with MP constraints)"; return XB_ERR_UNSUPPORTED; }
+
+  // shared rows: the union of the column lists of every node with a dof on the equation
+  row_of_dev = row_of;
+  std::vector<std::vector<int>> irr_cols;
+  irr_row.clear(); irr_own_ptr.assign(1, 0); irr_own.clear();
+  if (have_mp) {
+    std::vector<std::pair<int, int>> own;     // (row, node*ndf+dof), DOF_Group (node) order
+    for (int i = 0; i < nl; i++) for (int j = 0; j < ndf; j++)
+      if (gshared[(size_t)lnode[i] * ndf + j]) { own.push_back({row_of[(size_t)i * ndf + j], i * ndf + j}); row_of_dev[(size_t)i * ndf + j] = -1; }
+    std::stable_sort(own.begin(), own.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first < b.first; });
+    for (size_t u = 0; u < own.size(); u++) {
+      if (u == 0 || own[u].first != own[u - 1].first) {
+        if (u) irr_own_ptr.push_back((long long)irr_own.size());
+        irr_row.push_back(own[u].first); irr_cols.emplace_back();
+      }
+      irr_own.push_back(own[u].second);
+      const int i = own[u].second / ndf;
+      std::vector<int>& cl = irr_cols.back();
+      if (n2e_ptr[i + 1] == n2e_ptr[i]) cl.push_back(id[own[u].second]);
+      else cl.insert(cl.end(), &ncol[ncol_ptr[i]], &ncol[ncol_ptr[i + 1]]);
+    }
+    if (!own.empty()) irr_own_ptr.push_back((long long)irr_own.size());
+    for (auto& cl : irr_cols) { std::sort(cl.begin(), cl.end()); cl.erase(std::unique(cl.begin(), cl.end()), cl.end()); }
+  }
 
   ptr.assign((size_t)nrows + 1, 0);
   max_row = 0;
@@ -652,10 +740,19 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
     if (!owned[i]) continue;
     long long L = ncol_ptr[i + 1] - ncol_ptr[i];
     bool isolated = n2e_ptr[i + 1] == n2e_ptr[i];
+    // the assembly task of a node accumulates over the node's whole column list even when every one of its
+    // rows is a shared (equalDOF) row: size the accumulator for the list, not for the rows it writes
+    max_row = std::max<long long>(max_row, isolated ? 1 : L);
     for (int j = 0; j < ndf; j++) {
-      int r = row_of[(size_t)i * ndf + j];
-      if (r >= 0) { ptr[r + 1] = isolated ? 1 : L; max_row = std::max<long long>(max_row, ptr[r + 1]); }
+      int r = row_of_dev[(size_t)i * ndf + j];
+      if (r >= 0) ptr[r + 1] = isolated ? 1 : L;
     }
+  }
+  irr_max_row = 0;
+  for (size_t w = 0; w < irr_row.size(); w++) {
+    ptr[irr_row[w] + 1] = (long long)irr_cols[w].size();
+    irr_max_row = std::max<int>(irr_max_row, (int)irr_cols[w].size());
+    if (irr_cols[w].size() >= 0x1FFF) { err = "a shared equation couples with more than 8190 equations"; return XB_ERR_UNSUPPORTED; }
   }
   for (int r = 0; r < nrows; r++) ptr[r + 1] += ptr[r];
   const long long nz = ptr[nrows];
@@ -666,12 +763,13 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
     long long L = ncol_ptr[i + 1] - ncol_ptr[i];
     bool isolated = n2e_ptr[i + 1] == n2e_ptr[i];
     for (int j = 0; j < ndf; j++) {
-      int r = row_of[(size_t)i * ndf + j];
+      int r = row_of_dev[(size_t)i * ndf + j];
       if (r < 0) continue;
       if (isolated) idx[ptr[r]] = id[(size_t)i * ndf + j];
       else std::copy(&ncol[ncol_ptr[i]], &ncol[ncol_ptr[i]] + L, &idx[ptr[r]]);
     }
   }
+  for (size_t w = 0; w < irr_row.size(); w++) std::copy(irr_cols[w].begin(), irr_cols[w].end(), &idx[ptr[irr_row[w]]]);
 
   // position of every owned dof's own equation in its node's list (the diagonal entry of A)
   diagpos.assign((size_t)nl * ndf, 0xFFFF);
@@ -682,7 +780,7 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
     const bool isolated = n2e_ptr[i + 1] == n2e_ptr[i];
     for (int j = 0; j < ndf; j++) {
       const int q = id[(size_t)i * ndf + j];
-      if (q < 0) continue;
+      if (q < 0 || row_of_dev[(size_t)i * ndf + j] < 0) continue;    // shared rows: irr_diag
       diagpos[(size_t)i * ndf + j] = isolated ? 0 : (uint16_t)(std::lower_bound(cols, cols + L, q) - cols);
     }
   }
@@ -704,7 +802,43 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
           const int* it = std::lower_bound(cols, cols + L, q);
           cp[a * k->ndf + j] = (uint16_t)(it - cols);
         }
+      if (have_mp) dup_ranks(cp, k->nen * k->ndf);
     }
+  }
+  // shared rows: their contributions in (FE_Element, element dof) order -- the order addA / addB see them
+  irr_ptr.assign(1, 0); irr_src.clear(); irr_roff.clear(); irr_cp.clear(); irr_diag.clear();
+  for (size_t w = 0; w < irr_row.size(); w++) {
+    const std::vector<int>& cl = irr_cols[w];
+    struct Ent { long long fe; int dof; long long t; int j; };
+    std::vector<Ent> ents;
+    for (long long o = irr_own_ptr[w]; o < irr_own_ptr[w + 1]; o++) {
+      const int i = irr_own[o] / ndf, j = irr_own[o] % ndf;
+      for (long long t = n2e_ptr[i]; t < n2e_ptr[i + 1]; t++) ents.push_back({n2e_fe[t], n2e_loc[t] * ndf + j, t, j});
+    }
+    std::sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.fe != b.fe ? a.fe < b.fe : a.dof < b.dof; });
+    for (const Ent& en : ents) {
+      const EleKind* k; const int* c = G.conn_of(en.fe, &k);
+      irr_src.push_back(en.t * chunk + (long long)en.j * cp_stride);
+      irr_roff.push_back(n2e_roff[en.t] + en.j);
+      const size_t base = irr_cp.size();
+      irr_cp.resize(base + cp_stride, 0xFFFF);
+      for (int a = 0; a < k->nen; a++)
+        for (int j = 0; j < k->ndf; j++) {
+          const int q = gid[(size_t)c[a] * ndf + j];
+          if (q < 0) continue;
+          irr_cp[base + a * k->ndf + j] = (uint16_t)(std::lower_bound(cl.begin(), cl.end(), q) - cl.begin());
+        }
+      dup_ranks(&irr_cp[base], k->nen * k->ndf);
+    }
+    irr_ptr.push_back((long long)irr_src.size());
+    irr_diag.push_back((uint16_t)(std::lower_bound(cl.begin(), cl.end(), row_geq[irr_row[w]]) - cl.begin()));
+  }
+
+  max_dup = 0;
+  if (have_mp) {
+    for (uint16_t v : colpos) if (v != 0xFFFF) max_dup = std::max(max_dup, (int)(v >> 13));
+    for (uint16_t v : irr_cp) if (v != 0xFFFF) max_dup = std::max(max_dup, (int)(v >> 13));
+    // 0xFFFF is "no column"; a real position never reaches 0x1FFF here, so rank 7 + position 0x1FFF cannot occur
   }
 
   // ---- node order for the pipelined formTangent (single-batch models; else one range) ----
@@ -717,7 +851,7 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
     const char* pl = std::getenv("XB_PIPELINE");
     const int want = pl ? std::atoi(pl) : 8;
     pipeline_forced = pl != nullptr;
-    nchunk = (FG.size() == 1 && ne >= 65536 && want > 1 && want <= 64) ? want : 1;
+    nchunk = (FG.size() == 1 && ne >= 65536 && want > 1 && want <= 64 && !have_mp) ? want : 1;
     const long long per = nchunk > 1 ? (ne + nchunk - 1) / nchunk : ne;
     std::vector<int> ready(nl, -1);
     for (int i = 0; i < nl; i++) {
@@ -749,7 +883,7 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
       if (ns == 0) L = 1;   // a node with no element: its rows hold the (zero) diagonal only
       tk[0] = n2e_ptr[i]; tk[1] = ns | (L << 32); tk[2] = i;
       for (int j = 0; j < ndf; j++) {
-        const int r = row_of[(size_t)i * ndf + j];
+        const int r = row_of_dev[(size_t)i * ndf + j];
         tk[3 + j] = r >= 0 ? ptr[r] : -1;
       }
     }
@@ -761,7 +895,7 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
       long long cnt = 0; int lo = nrows, hi = -1;
       for (long long u = chunk_node_ptr[c]; u < chunk_node_ptr[c + 1]; u++)
         for (int j = 0; j < ndf; j++) {
-          const int r = row_of[(size_t)node_perm[u] * ndf + j];
+          const int r = row_of_dev[(size_t)node_perm[u] * ndf + j];
           if (r < 0) continue;
           cnt++; lo = std::min(lo, r); hi = std::max(hi, r);
         }
@@ -787,23 +921,23 @@ int HostModel::scatter_map(long long e0, long long e1, long long* map) const {
     const int nd = k.nen * k.ndf;
     const int* c = &g.conn[(size_t)fe_local[e] * k.nen];   // local node indices
     long long* out = map + (e - e0) * nd * nd;
-    const long long ge = fe_global[e];
-    // the slot of (node c[a], element e) on the rank owning that node
-    std::vector<long long> slot(k.nen);
-    for (int a = 0; a < k.nen; a++) {
-      slot[a] = -1;
-      for (long long t = n2e_ptr[c[a]]; t < n2e_ptr[c[a] + 1]; t++)
-        if (n2e_fe[t] == ge && n2e_loc[t] == a) { slot[a] = t; break; }
-    }
     for (int i = 0; i < nd; i++)
       for (int j = 0; j < nd; j++) {
         // CSR: entry (i,j) -> row id(i), column id(j).  CSC: entry (i,j) -> column id(j), row id(i).
-        int ownerdof = soe_kind == XB_SOE_SPARSE_GEN_ROW ? i : j;
-        int other = soe_kind == XB_SOE_SPARSE_GEN_ROW ? j : i;
-        int ro = row_of[(size_t)c[ownerdof / k.ndf] * ndf + ownerdof % k.ndf];
-        long long sl = slot[ownerdof / k.ndf];
-        uint16_t cp = sl < 0 ? (uint16_t)0xFFFF : colpos[(size_t)sl * cp_stride + other];
-        out[i * nd + j] = (ro < 0 || cp == 0xFFFF) ? -1 : ptr[ro] + cp;
+        // The location is where the assembly kernels put it: the owned row of the major equation, at the
+        // position of the minor equation in that row's (sorted) column list.
+        const int majordof = soe_kind == XB_SOE_SPARSE_GEN_ROW ? i : j;
+        const int minordof = soe_kind == XB_SOE_SPARSE_GEN_ROW ? j : i;
+        const int qmaj = id[(size_t)c[majordof / k.ndf] * ndf + majordof % k.ndf];
+        const int qmin = id[(size_t)c[minordof / k.ndf] * ndf + minordof % k.ndf];
+        out[i * nd + j] = -1;
+        if (qmaj < 0 || qmin < 0) continue;
+        const auto rit = std::lower_bound(row_geq.begin(), row_geq.end(), qmaj);
+        if (rit == row_geq.end() || *rit != qmaj) continue;                     // a row another rank owns
+        const long long r = rit - row_geq.begin();
+        const int* b = &idx[ptr[r]]; const int* en = &idx[ptr[r + 1]];
+        const int* it = std::lower_bound(b, en, qmin);
+        if (it != en && *it == qmin) out[i * nd + j] = ptr[r] + (it - b);
       }
   }
   return XB_OK;

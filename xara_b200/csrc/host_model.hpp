@@ -106,6 +106,22 @@ struct HostModel {
   long long ne_global = 0;
   std::vector<int> id;              // [nn][ndf] GLOBAL DOF_Group ids of the local nodes
   std::vector<int> row_of;          // [nn][ndf] local row of an owned free dof, else -1
+  // ---- MP constraints (`equalDOF`): PlainHandler's -4 ids.  A tied dof shares the retained dof's equation, so
+  // that row gathers from the elements of several nodes and has its own column list: "shared rows" are kept out
+  // of the per-node assembly tasks (row_of_dev = -1, task row offset = -1) and assembled by row (irr_*).
+  std::vector<int> mp_r, mp_c, mp_dof;       // retained / constrained node tag, dof
+  std::vector<int> row_of_dev;               // row_of with the dofs of shared equations set to -1
+  int max_dup = 0;                           // most element dofs of ONE element on one equation, minus 1 (colpos rank bits)
+  int irr_max_row = 0;
+  std::vector<int> irr_row;                  // [nirr] local row
+  std::vector<long long> irr_ptr;            // [nirr+1] -> entries, in (FE_Element, element dof) order = addA / addB order
+  std::vector<long long> irr_src;            // [*] offset of the element-matrix row in KeN
+  std::vector<long long> irr_roff;           // [*] offset of the element-residual entry in Re
+  std::vector<uint16_t> irr_cp;              // [*][cp_stride] column positions in the row's own list (+ rank bits)
+  std::vector<long long> irr_own_ptr;        // [nirr+1] -> owners
+  std::vector<int> irr_own;                  // [*] node * ndf + dof of every (node, dof) on the equation, DOF_Group order
+  std::vector<uint16_t> irr_diag;            // [nirr] position of the equation in its own row
+  int add_equal_dof(int r_tag, int c_tag, int n, const int* dofs);
   std::vector<uint8_t> owned;       // [nn] this rank owns the node's equations
   int nrows = 0;                    // owned equations (== neq when nparts == 1)
   std::vector<int> row_geq;         // [nrows] their global numbers, ascending
