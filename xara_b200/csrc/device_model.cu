@@ -144,6 +144,13 @@ __global__ void __launch_bounds__(128, UPD_OCC) brick_update_kernel(GroupView G,
     for (int i = 0; i < 6; i++) epn[i] = G.hc[(size_t)i * ngp + gp];
     xin = G.hc[(size_t)6 * ngp + gp];
   }
+  // ... and so are the material's parameters (a dependent load: material index, then the record)
+  const double* p = G.mpar + (size_t)__ldg(G.mat + e) * 8;
+  double par[7];
+  if (MATK == XB_MAT_J2PLASTICITY) {
+#pragma unroll
+    for (int i = 0; i < 7; i++) par[i] = __ldg(p + i);
+  }
   __syncwarp();
   double shp[4][8], xsj;
   {
@@ -167,12 +174,9 @@ __global__ void __launch_bounds__(128, UPD_OCC) brick_update_kernel(GroupView G,
     s[4] += shp[2][j] * u1 + shp[1][j] * u2;
     s[5] += shp[2][j] * u0 + shp[0][j] * u2;
   }
-  const double* p = G.mpar + (size_t)__ldg(G.mat + e) * 8;
   double st[6];
   if (MATK == XB_MAT_J2PLASTICITY) {
-    double par[7], et[6];
-#pragma unroll
-    for (int i = 0; i < 7; i++) par[i] = __ldg(p + i);
+    double et[6];
     et[0] = s[0]; et[1] = s[1]; et[2] = s[2]; et[3] = 0.50 * s[3]; et[4] = 0.50 * s[4]; et[5] = 0.50 * s[5];
     // the shape functions are needed again for the residual: park them in shared memory while
     // the return map runs (64 registers less over the longest-latency part of the kernel)
@@ -888,8 +892,14 @@ __device__ __forceinline__ void brick_D_regs(double m0, double m1, const double*
   }
 }
 
-template <int MATK, int DYN>
-__global__ void __launch_bounds__(128, 2) brick_tangent_sym_kernel(GroupView G, const double* __restrict__ X,
+// NW warps per CTA: 4 fills the register file with two CTAs per SM (8 warps x 254 registers); 3 leaves a quarter of
+// it free, so that CTAs of the (HBM-bound) assembly kernel can run beside this (FP64-bound) one -- used by the
+// pipelined xb_form_tangent, where the assembly of one element range overlaps the tangents of the next.
+#ifndef XB_STORE_V2
+#define XB_STORE_V2 1
+#endif
+template <int MATK, int DYN, int NW = 4>
+__global__ void __launch_bounds__(NW * 32, 2) brick_tangent_sym_kernel(GroupView G, const double* __restrict__ X,
                                                                    int transpose, long long ebeg, long long eend,
                                                                    const double* __restrict__ tsrc_, int tzero_,
                                                                    double scale_, int accum_) {
@@ -909,10 +919,18 @@ __global__ void __launch_bounds__(128, 2) brick_tangent_sym_kernel(GroupView G, 
   long long* sDst = reinterpret_cast<long long*>(wbase + 4 * BS_T);
   const long long ngp = G.n * 8;
   const long long nb = (eend - ebeg + 3) >> 2;               // batches of 4 elements
-  const long long stride = (long long)gridDim.x * 4;
-  long long b = (long long)blockIdx.x * 4 + warp;
+  const long long stride = (long long)gridDim.x * NW;
+  long long b = (long long)blockIdx.x * NW + warp;
   if (b >= nb) return;
   const long long elast = eend - 1;
+#if XB_STORE_V2
+  unsigned cpk[9];      // store loop: tile offset | node << 10 | offset in the node's slot << 13 (doubles)
+#pragma unroll
+  for (int it = 0; it < 9; it++) {
+    const int i = it * 32 + lane, a = i / 36, row = i / 12, c2 = i - row * 12;
+    cpk[it] = (unsigned)(row * BS_R + 2 * c2) | ((unsigned)a << 10) | ((unsigned)(2 * (i - 36 * a)) << 13);
+  }
+#endif
 
   // stage 1 (indices) and stage 2 (values) of batch b; stage 1 of the batch after it
   long long e = ebeg + b * 4 + s; if (e > elast) e = elast;
@@ -934,7 +952,11 @@ __global__ void __launch_bounds__(128, 2) brick_tangent_sym_kernel(GroupView G, 
     // ---- A: coordinates round the element, shape functions and D*dvol at the lane's Gauss point ----
 #pragma unroll
     for (int d = 0; d < 3; d++) sX[s * BS_XS + k * 3 + d] = cx[d];
+#if XB_STORE_V2
+    sDst[lane] = reinterpret_cast<long long>(cdst >= 0 ? G.KeN + cdst : G.sendK + (-cdst - 1));
+#else
     sDst[lane] = cdst;
+#endif
     __syncwarp();
     {
       double xl[3][8];
@@ -1039,6 +1061,27 @@ __global__ void __launch_bounds__(128, 2) brick_tangent_sym_kernel(GroupView G, 
       }
     }
     __syncwarp();
+#if XB_STORE_V2
+    {
+      // the element's 8 x 3 rows are 288 double2; lane handles i = it * 32 + lane: node a = i / 36, and inside
+      // the node's slot (3 rows of cps = 24 doubles, contiguous) double2 number i - 36 a.  (a, tile offset, slot
+      // offset) depend on (it, lane) only and sit packed in 9 registers; sDst holds resolved slot pointers.
+      const long long rem = eend - (ebeg + b * 4);
+      const int nlive = rem < 4 ? (int)rem : 4;
+      for (int el = 0; el < nlive; el++) {
+        const double* tile = wbase + el * BS_T;
+        double* const* dsts = reinterpret_cast<double* const*>(sDst) + el * 8;
+#pragma unroll
+        for (int it = 0; it < 9; it++) {
+          const unsigned pk = cpk[it];
+          double2 v = *reinterpret_cast<const double2*>(tile + (pk & 1023u));
+          double* out = dsts[(pk >> 10) & 7u] + (pk >> 13);
+          if (accum) { const double2 o = *reinterpret_cast<const double2*>(out); v.x += o.x; v.y += o.y; }
+          *reinterpret_cast<double2*>(out) = v;
+        }
+      }
+    }
+#else
     {
       const long long rem = eend - (ebeg + b * 4);
       const int nlive = rem < 4 ? (int)rem : 4;
@@ -1057,6 +1100,7 @@ __global__ void __launch_bounds__(128, 2) brick_tangent_sym_kernel(GroupView G, 
         }
       }
     }
+#endif
     if (!more) break;
     b += stride;
     __syncwarp();
@@ -1207,7 +1251,10 @@ struct AsmView {
 // Every entry of A is written exactly once, so no zeroA pass is needed.
 // MP: with `equalDOF` two dofs of one element may sit on one equation; a position then carries the duplicate's
 // rank in its top 3 bits and the ranks are added in turn (the order addA meets them, SparseGenColLinSOE.cpp:264).
-template <int NDF, bool MP = false>
+// SL: element kinds with few dofs (cp_stride <= 16: quads 8, 2D beams 6, 3D beams 12) would leave most of a warp
+// idle at one lane per element dof, so SL = 4 or 2 consecutive slots are LOADED side by side (lane = slot * 32/SL +
+// dof) and then ADDED one after the other -- the order of additions stays the FE_Element order.
+template <int NDF, bool MP = false, int SL = 1>
 __global__ void __launch_bounds__(256, XB_ASM_OCC) assemble_A_kernel(AsmView V, const double* __restrict__ KeN,
                                                             double* __restrict__ A, const long long* __restrict__ task,
                                                             long long first, long long count) {
@@ -1227,8 +1274,11 @@ __global__ void __launch_bounds__(256, XB_ASM_OCC) assemble_A_kernel(AsmView V, 
   const int L = (int)(pk >> 32);
   const long long t1 = t0 + ns;
   const int cps = V.cp_stride;
-  const bool on = lane < cps;
-  constexpr int CH = XB_ASM_CH;  // slots in flight together; the node's slots are one contiguous stream
+  constexpr int LW = 32 / SL;                       // lanes per slot
+  const int sub = SL == 1 ? 0 : lane / LW;          // which of the SL side-by-side slots
+  const int j = SL == 1 ? lane : lane % LW;         // element dof
+  const bool on = j < cps;
+  constexpr int CH = XB_ASM_CH;  // slot groups in flight together; the node's slots are one contiguous stream
   const double c1 = V.c1;
   long long tb = t0;
   do {
@@ -1236,11 +1286,11 @@ __global__ void __launch_bounds__(256, XB_ASM_OCC) assemble_A_kernel(AsmView V, 
     unsigned short pos[CH];
 #pragma unroll
     for (int c = 0; c < CH; c++) {
-      const long long t = tb + c;
+      const long long t = tb + c * SL + sub;
       const bool ok = on && t < t1;
-      pos[c] = ok ? __ldg(V.colpos + (size_t)t * cps + lane) : (unsigned short)0xFFFF;
+      pos[c] = ok ? __ldg(V.colpos + (size_t)t * cps + j) : (unsigned short)0xFFFF;
 #pragma unroll
-      for (int p = 0; p < NDF; p++) v[c][p] = ok ? __ldg(KeN + (size_t)t * (NDF * cps) + p * cps + lane) : 0.0;
+      for (int p = 0; p < NDF; p++) v[c][p] = ok ? __ldg(KeN + (size_t)t * (NDF * cps) + p * cps + j) : 0.0;
     }
     if (tb == t0) {
       // (the first slots are already on their way) clear the rows, then the DOF_Group tangents, which
@@ -1262,23 +1312,27 @@ __global__ void __launch_bounds__(256, XB_ASM_OCC) assemble_A_kernel(AsmView V, 
     }
 #pragma unroll
     for (int c = 0; c < CH; c++) {   // FE_Element order: the order addA is called in
-      if (!MP) {
-        if (pos[c] != 0xFFFF) {
 #pragma unroll
-          for (int p = 0; p < NDF; p++) acc[p * V.max_row + pos[c]] += (c1 == 1.0 ? v[c][p] : v[c][p] * c1);
-        }
-        __syncwarp();
-      } else {
-        for (int r = 0; r <= V.max_dup; r++) {
-          if (pos[c] != 0xFFFF && (pos[c] >> 13) == r) {
+      for (int sl = 0; sl < SL; sl++) {
+        const bool mine = (SL == 1 || sub == sl) && pos[c] != 0xFFFF;
+        if (!MP) {
+          if (mine) {
 #pragma unroll
-            for (int p = 0; p < NDF; p++) acc[p * V.max_row + (pos[c] & 0x1FFF)] += (c1 == 1.0 ? v[c][p] : v[c][p] * c1);
+            for (int p = 0; p < NDF; p++) acc[p * V.max_row + pos[c]] += (c1 == 1.0 ? v[c][p] : v[c][p] * c1);
           }
           __syncwarp();
+        } else {
+          for (int r = 0; r <= V.max_dup; r++) {
+            if (mine && (pos[c] >> 13) == r) {
+#pragma unroll
+              for (int p = 0; p < NDF; p++) acc[p * V.max_row + (pos[c] & 0x1FFF)] += (c1 == 1.0 ? v[c][p] : v[c][p] * c1);
+            }
+            __syncwarp();
+          }
         }
       }
     }
-    tb += CH;
+    tb += CH * SL;
   } while (tb < t1);
 #pragma unroll
   for (int p = 0; p < NDF; p++) {
@@ -1469,7 +1523,12 @@ struct xb_model {
   cudaStream_t stream2 = nullptr, stream3 = nullptr;   // assembly of finished ranges; copy-out of finished rows
   std::vector<cudaEvent_t> ev_rows;
   cudaEvent_t ev_start = nullptr, ev_done = nullptr;
-  std::vector<cudaEvent_t> ev_chunk;
+  std::vector<cudaEvent_t> ev_chunk, ev_asm;
+  bool tiled_on = true;             // XB_TILED_RUN=0: keep the tiled storage order but run formTangent in one piece
+  int tile_ahead = 2;               // XB_AHEAD: tiles the element kernel may run in front of the assembly
+  int tan_per_sm = 0;               // occupancy of the brick tangent kernel (cached)
+  const void* tan_kern = nullptr;
+  int tan_warps = 4;                // XB_TAN_WARPS=3: the ranged tangent launches leave room for assembly CTAs
   long long* dTask = nullptr;
   AsmView av{};
   double lambda = 0.0;
@@ -1573,6 +1632,7 @@ void xb_model_destroy(xb_model* m) {
     if (m->ev_start) cudaEventDestroy(m->ev_start);
     if (m->ev_done) cudaEventDestroy(m->ev_done);
     for (auto e : m->ev_chunk) cudaEventDestroy(e);
+    for (auto e : m->ev_asm) cudaEventDestroy(e);
     for (void* p : m->allocs) cudaFree(p);
     if (m->own_stream && m->stream) cudaStreamDestroy(m->stream);
   }
@@ -1706,6 +1766,13 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
   for (auto& e : m->ev_rows) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   m->ev_chunk.resize(h.nchunk);
   for (auto& e : m->ev_chunk) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  if (const char* t = std::getenv("XB_TAN_WARPS")) m->tan_warps = std::atoi(t) == 3 ? 3 : 4;
+  if (h.tiled) {
+    m->ev_asm.resize(h.nchunk);
+    for (auto& e : m->ev_asm) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (const char* t = std::getenv("XB_TILED_RUN")) m->tiled_on = std::atoi(t) != 0;
+    if (const char* t = std::getenv("XB_AHEAD")) m->tile_ahead = std::max(0, std::atoi(t));
+  }
   CU(dev_upload(m, &m->dLoad, h.load));
   std::vector<double> mp(h.mats.size() * 8);
   for (size_t i = 0; i < h.mats.size(); i++) std::memcpy(&mp[i * 8], h.mats[i].par, sizeof(double) * 8);
@@ -2199,27 +2266,36 @@ static int launch_group_tangents(xb_model* m, DevGroup& d, long long ebeg, long 
       m->launches++;
       return XB_OK;
     }
-    if (m->tangent_variant == 2 && (m->h.cp_stride % 2) == 0) {
-      const size_t sms = sizeof(double) * 4 * BS_WARP;
+    if (m->tangent_variant == 2 && m->h.cp_stride == 24) {   // (a node slot is 3 contiguous rows of 24)
+      // NW = 3 only where the assembly runs beside it (pipelined formTangent of a static analysis)
+      const int nw = (!tc.on && m->tan_warps == 3 && (ebeg != 0 || eend != d.v.n)) ? 3 : 4;
+      const size_t sms = sizeof(double) * nw * BS_WARP;
       const long long nbat = (eend - ebeg + 3) / 4;
       auto go = [&](auto kern) -> int {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sms));
-        int per_sm = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, sms));
-        if (per_sm < 1) per_sm = 1;
+        int per_sm = m->tan_per_sm;
+        if (per_sm == 0 || (const void*)kern != m->tan_kern) {   // once per kernel: these two calls cost more than a launch
+          CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sms));
+          // the same L1 / shared-memory split as the assembly kernel: CTAs of two kernels share an SM only then
+          CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+          CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nw * 32, sms));
+          if (per_sm < 1) per_sm = 1;
+          m->tan_per_sm = per_sm; m->tan_kern = (const void*)kern;
+        }
         long long grid = (long long)per_sm * m->num_sms;
-        if (grid > (nbat + 3) / 4) grid = (nbat + 3) / 4;
+        if (grid > (nbat + nw - 1) / nw) grid = (nbat + nw - 1) / nw;
+        const unsigned nt = (unsigned)nw * 32;
         // static analysis, or a transient one without element damping / mass: one pass on the current tangent.
         // Otherwise (c1 + c2 betaK) Kt + c2 betaK0 K0 + c2 betaKc Kc, one pass per term (K is linear in D).
-        if (!tc.on) { kern<<<(unsigned)grid, 128, sms, st>>>(d.v, m->dX, transpose, ebeg, eend, d.v.tan, 0, 1.0, 0); return XB_OK; }
-        if (!j2) { kern<<<(unsigned)grid, 128, sms, st>>>(d.v, m->dX, transpose, ebeg, eend, d.v.tan, 0, tc.at + tc.a0 + tc.ac, 0); return XB_OK; }
-        kern<<<(unsigned)grid, 128, sms, st>>>(d.v, m->dX, transpose, ebeg, eend, d.v.tan, 0, tc.at, 0);
-        if (tc.a0 != 0.0) { kern<<<(unsigned)grid, 128, sms, st>>>(d.v, m->dX, transpose, ebeg, eend, d.v.tan, 1, tc.a0, 1); m->launches++; }
-        if (tc.ac != 0.0) { kern<<<(unsigned)grid, 128, sms, st>>>(d.v, m->dX, transpose, ebeg, eend, d.v.tanc, 0, tc.ac, 1); m->launches++; }
+        if (!tc.on) { kern<<<(unsigned)grid, nt, sms, st>>>(d.v, m->dX, transpose, ebeg, eend, d.v.tan, 0, 1.0, 0); return XB_OK; }
+        if (!j2) { kern<<<(unsigned)grid, nt, sms, st>>>(d.v, m->dX, transpose, ebeg, eend, d.v.tan, 0, tc.at + tc.a0 + tc.ac, 0); return XB_OK; }
+        kern<<<(unsigned)grid, nt, sms, st>>>(d.v, m->dX, transpose, ebeg, eend, d.v.tan, 0, tc.at, 0);
+        if (tc.a0 != 0.0) { kern<<<(unsigned)grid, nt, sms, st>>>(d.v, m->dX, transpose, ebeg, eend, d.v.tan, 1, tc.a0, 1); m->launches++; }
+        if (tc.ac != 0.0) { kern<<<(unsigned)grid, nt, sms, st>>>(d.v, m->dX, transpose, ebeg, eend, d.v.tanc, 0, tc.ac, 1); m->launches++; }
         return XB_OK;
       };
       int rc = tc.on ? (j2 ? go(brick_tangent_sym_kernel<XB_MAT_J2PLASTICITY, 1>) : go(brick_tangent_sym_kernel<XB_MAT_ELASTIC_ISOTROPIC, 1>))
-                     : (j2 ? go(brick_tangent_sym_kernel<XB_MAT_J2PLASTICITY, 0>) : go(brick_tangent_sym_kernel<XB_MAT_ELASTIC_ISOTROPIC, 0>));
+                     : (nw == 3 ? (j2 ? go(brick_tangent_sym_kernel<XB_MAT_J2PLASTICITY, 0, 3>) : go(brick_tangent_sym_kernel<XB_MAT_ELASTIC_ISOTROPIC, 0, 3>))
+                                : (j2 ? go(brick_tangent_sym_kernel<XB_MAT_J2PLASTICITY, 0>) : go(brick_tangent_sym_kernel<XB_MAT_ELASTIC_ISOTROPIC, 0>)));
       if (rc < 0) return rc;
       m->launches++;
       if (tc.on && tc.cM != 0.0 && d.has_rho) {
@@ -2356,38 +2432,36 @@ static int launch_assemble(xb_model* m, long long first, long long count, cudaSt
   const unsigned blocks = (unsigned)((count + warps - 1) / warps);
   AsmView av = m->av;
   if (tan_coef(m).on) av.c1 = 1.0;   // the element kernels already folded c1 (and the damping / mass terms) in
-  if (av.max_dup > 0 || av.nirr > 0) {   // equalDOF: ranked additions, then the shared rows
-#define XB_ASM_MP(N)                                                                                             \
-    case N:                                                                                                      \
-      CU(cudaFuncSetAttribute(assemble_A_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
-      assemble_A_kernel<N, true><<<blocks, warps * 32, sm, st>>>(av, m->dKe, m->dA, m->dTask, first, count);      \
-      break;
-    switch (m->h.ndf) { XB_ASM_MP(1) XB_ASM_MP(2) XB_ASM_MP(3) XB_ASM_MP(6) default: return fail(XB_ERR_UNSUPPORTED, "ndf"); }
-#undef XB_ASM_MP
-    m->launches++;
-    if (av.nirr > 0) {
-      const size_t smi = sizeof(double) * warps * av.irr_max_row;
-      if (smi > 200 * 1024) return fail(XB_ERR_UNSUPPORTED, "shared equation row too long");
-      CU(cudaFuncSetAttribute(assemble_A_irr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smi));
-      assemble_A_irr_kernel<<<(unsigned)((av.nirr + warps - 1) / warps), warps * 32, smi, st>>>(av, m->dKe, m->dA);
-      m->launches++;
+  // the function attribute is the function's, not the model's: only ever raise it (per device)
+  auto go = [&](auto kern, size_t* attr) -> int {
+    if (sm > attr[m->device & 63]) {
+      CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      attr[m->device & 63] = sm;
     }
+    kern<<<blocks, warps * 32, sm, st>>>(av, m->dKe, m->dA, m->dTask, first, count);
+    m->launches++;
     return XB_OK;
+  };
+  const bool mp = av.max_dup > 0 || av.nirr > 0;     // equalDOF: ranked additions, then the shared rows
+  const int cps = m->h.cp_stride;
+  const int sl = cps <= 8 ? 4 : (cps <= 16 ? 2 : 1);  // slots loaded side by side (assemble_A_kernel, SL)
+  static size_t attr[16][64] = {{0}};
+  int rc = XB_ERR_UNSUPPORTED;
+#define XB_ASM_CASE(N, S, I)                                                             \
+  if (m->h.ndf == N && sl == S)                                                          \
+    rc = mp ? go(assemble_A_kernel<N, true, S>, attr[2 * I + 1]) : go(assemble_A_kernel<N, false, S>, attr[2 * I]);
+  XB_ASM_CASE(3, 1, 0) XB_ASM_CASE(3, 4, 1) XB_ASM_CASE(2, 4, 2) XB_ASM_CASE(6, 2, 3)
+  XB_ASM_CASE(1, 4, 4) XB_ASM_CASE(2, 1, 5) XB_ASM_CASE(6, 1, 6) XB_ASM_CASE(3, 2, 7)
+#undef XB_ASM_CASE
+  if (rc == XB_ERR_UNSUPPORTED) return fail(rc, "assembly kernel: no instance for this (ndf, dofs per element)");
+  if (rc < 0) return rc;
+  if (av.nirr > 0) {
+    const size_t smi = sizeof(double) * warps * av.irr_max_row;
+    if (smi > 200 * 1024) return fail(XB_ERR_UNSUPPORTED, "shared equation row too long");
+    CU(cudaFuncSetAttribute(assemble_A_irr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smi));
+    assemble_A_irr_kernel<<<(unsigned)((av.nirr + warps - 1) / warps), warps * 32, smi, st>>>(av, m->dKe, m->dA);
+    m->launches++;
   }
-  if (m->h.ndf == 3) {
-    CU(cudaFuncSetAttribute(assemble_A_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    assemble_A_kernel<3><<<blocks, warps * 32, sm, st>>>(av, m->dKe, m->dA, m->dTask, first, count);
-  } else if (m->h.ndf == 6) {
-    CU(cudaFuncSetAttribute(assemble_A_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    assemble_A_kernel<6><<<blocks, warps * 32, sm, st>>>(av, m->dKe, m->dA, m->dTask, first, count);
-  } else if (m->h.ndf == 2) {
-    CU(cudaFuncSetAttribute(assemble_A_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    assemble_A_kernel<2><<<blocks, warps * 32, sm, st>>>(av, m->dKe, m->dA, m->dTask, first, count);
-  } else {
-    CU(cudaFuncSetAttribute(assemble_A_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    assemble_A_kernel<1><<<blocks, warps * 32, sm, st>>>(av, m->dKe, m->dA, m->dTask, first, count);
-  }
-  m->launches++;
   return XB_OK;
 }
 
@@ -2435,9 +2509,11 @@ int xb_form_tangent(xb_model* m, double* A) {
   NEED_DEVICE();
   CU(cudaSetDevice(m->device));
   const int nc = m->h.nchunk;
+  const bool tiled = m->h.tiled && m->tiled_on;
   const bool stream_out = A != nullptr && m->h.rows_streamable && m->stream3;
-  if (nc <= 1 || m->dg.size() != 1 || m->dg[0].kind != XB_ELE_STDBRICK || !m->stream2 ||
-      !(stream_out || m->h.pipeline_forced)) {
+  // element damping / mass terms take several passes over the whole batch: no ranges then
+  if (nc <= 1 || m->dg.size() != 1 || m->dg[0].kind != XB_ELE_STDBRICK || !m->stream2 || tan_coef(m).on ||
+      (m->h.tiled && !m->tiled_on) || !(stream_out || m->h.pipeline_forced || tiled)) {
     int rc = xb_form_element_tangents(m);
     if (rc < 0) return rc;
     if (m->h.nparts > 1 && (rc = xb_exchange(m, 0)) < 0) return rc;
@@ -2445,21 +2521,41 @@ int xb_form_tangent(xb_model* m, double* A) {
   }
   DevGroup& d = m->dg[0];
   const long long per = (d.v.n + nc - 1) / nc;
+  // ranges that complete a contiguous block of rows of A (the unit of the copy-out): a range itself, or -- tiled --
+  // the FE-order slice its tile belongs to
+  const int ng = tiled ? m->h.nsuper : nc;
   CU(cudaEventRecord(m->ev_start, m->stream));
   CU(cudaStreamWaitEvent(m->stream2, m->ev_start, 0));      // A and KeN are free once earlier work is done
   for (int c = 0; c < nc; c++) {
-    const long long e0 = c * per, e1 = std::min<long long>(d.v.n, e0 + per);
+    const long long e0 = tiled ? m->h.tile_ptr[c] : c * per;
+    const long long e1 = tiled ? m->h.tile_ptr[c + 1] : std::min<long long>(d.v.n, e0 + per);
+    // tiled: the element kernel runs at most `ahead` tiles in front of the assembly, so that the rows a tile
+    // wrote are still in L2 when its nodes are assembled
+    const bool same = tiled && m->tile_ahead == 0;     // one stream: tangent, assembly, tangent, ... back to back
+    if (tiled && !same && c >= m->tile_ahead) CU(cudaStreamWaitEvent(m->stream, m->ev_asm[c - m->tile_ahead], 0));
     int rc = launch_group_tangents(m, d, e0, e1, m->stream);
     if (rc < 0) return rc;
-    CU(cudaEventRecord(m->ev_chunk[c], m->stream));
-    CU(cudaStreamWaitEvent(m->stream2, m->ev_chunk[c], 0));
-    rc = launch_assemble(m, m->h.chunk_node_ptr[c], m->h.chunk_node_ptr[c + 1] - m->h.chunk_node_ptr[c], m->stream2);
-    if (rc < 0) return rc;
-    if (stream_out) {   // the rows this range completed leave for the host while the next range is formed
-      const long long a0 = m->h.chunk_a_ptr[c], a1 = m->h.chunk_a_ptr[c + 1];
+    if (same) {
+      rc = launch_assemble(m, m->h.chunk_node_ptr[c], m->h.chunk_node_ptr[c + 1] - m->h.chunk_node_ptr[c], m->stream);
+      if (rc < 0) return rc;
+      if (c + 1 == nc || m->h.tile_super[c + 1] != m->h.tile_super[c]) {
+        CU(cudaEventRecord(m->ev_chunk[c], m->stream));
+        CU(cudaStreamWaitEvent(m->stream2, m->ev_chunk[c], 0));
+      }
+    } else {
+      CU(cudaEventRecord(m->ev_chunk[c], m->stream));
+      CU(cudaStreamWaitEvent(m->stream2, m->ev_chunk[c], 0));
+      rc = launch_assemble(m, m->h.chunk_node_ptr[c], m->h.chunk_node_ptr[c + 1] - m->h.chunk_node_ptr[c], m->stream2);
+      if (rc < 0) return rc;
+      if (tiled) CU(cudaEventRecord(m->ev_asm[c], m->stream2));
+    }
+    const int gI = tiled ? m->h.tile_super[c] : c;
+    const bool last_of_group = !tiled || c + 1 == nc || m->h.tile_super[c + 1] != gI;
+    if (stream_out && last_of_group) {   // the rows this range completed leave for the host while the next one is formed
+      const long long a0 = m->h.chunk_a_ptr[gI], a1 = m->h.chunk_a_ptr[gI + 1];
       if (a1 > a0) {
-        CU(cudaEventRecord(m->ev_rows[c], m->stream2));
-        CU(cudaStreamWaitEvent(m->stream3, m->ev_rows[c], 0));
+        CU(cudaEventRecord(m->ev_rows[gI], m->stream2));
+        CU(cudaStreamWaitEvent(m->stream3, m->ev_rows[gI], 0));
         CU(cudaMemcpyAsync(A + a0, m->dA + a0, sizeof(double) * (a1 - a0), cudaMemcpyDeviceToHost, m->stream3));
       }
     }
@@ -2475,7 +2571,7 @@ int xb_form_tangent(xb_model* m, double* A) {
     if (rc < 0) return rc;
   }
   if (stream_out) {
-    const long long a0 = m->h.chunk_a_ptr[nc], a1 = m->h.chunk_a_ptr[nc + 1];   // rows of the interface nodes
+    const long long a0 = m->h.chunk_a_ptr[ng], a1 = m->h.chunk_a_ptr[ng + 1];   // rows of the interface nodes
     int rc = finish_tangent(m, nullptr);
     if (rc < 0) return rc;
     if (a1 > a0) CU(cudaMemcpyAsync(A + a0, m->dA + a0, sizeof(double) * (a1 - a0), cudaMemcpyDeviceToHost, m->stream));

@@ -306,6 +306,61 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
   }
   if (bad) { err = "element references an unknown node tag"; return XB_ERR_ARG; }
 
+  // ---- storage order of a large brick batch: FE-order slices > spatial tiles (see host_model.hpp, `tiled`) ----
+  tiled = false; tile_ptr.clear(); tile_super.clear(); nsuper = 1;
+  {
+    // opt-in (XB_TILE=<elements per tile>, e.g. 9472 = 2 batches of 4 per warp of the persistent tangent kernel):
+    // measured on B200 it does not pay -- see DESIGN.md, "what was tried"
+    const char* tl = std::getenv("XB_TILE");
+    const long long target = tl ? std::atoll(tl) : 0;
+    const char* pl = std::getenv("XB_PIPELINE");
+    const int want = pl ? std::atoi(pl) : 8;
+    if (nparts == 1 && groups.size() == 1 && groups[0].kind == XB_ELE_STDBRICK && groups[0].n() >= 65536 && target >= 256 &&
+        want >= 1 && want <= 64 && mp_r.empty()) {
+      Group& g = groups[0];
+      const long long n = g.n();
+      std::vector<long long> byTag(n);
+      std::iota(byTag.begin(), byTag.end(), 0LL);
+      if (!std::is_sorted(g.tag.begin(), g.tag.end()))
+        std::sort(byTag.begin(), byTag.end(), [&](long long a, long long b) { return g.tag[a] < g.tag[b]; });
+      std::vector<double> cen((size_t)n * 3, 0.0);
+#pragma omp parallel for schedule(static)
+      for (long long e = 0; e < n; e++)
+        for (int a = 0; a < 8; a++)
+          for (int d = 0; d < ndm; d++) cen[e * 3 + d] += crd[(size_t)g.conn[e * 8 + a] * ndm + d];
+      nsuper = want;
+      const long long per = (n + nsuper - 1) / nsuper;
+      std::vector<int> leaf(n, 0);
+      tile_ptr.push_back(0);
+      for (int sidx = 0; sidx < nsuper; sidx++) {
+        const long long lo = std::min(n, sidx * per), hi = std::min(n, lo + per);
+        if (hi <= lo) continue;
+        const int np = (int)((hi - lo + target - 1) / target);
+        rcb(byTag, lo, hi, np, 0, cen.data(), ndm, leaf);     // reorders byTag[lo, hi) tile by tile
+        for (int q = 0; q < np; q++) {
+          // rcb's split points: part q of np over [lo, hi) -- recover the boundaries by counting
+          tile_super.push_back(sidx);
+        }
+        std::vector<long long> cnt(np, 0);
+        for (long long i = lo; i < hi; i++) cnt[leaf[byTag[i]]]++;
+        for (int q = 0; q < np; q++) tile_ptr.push_back(tile_ptr.back() + cnt[q]);
+      }
+      // the new storage order
+      std::vector<int> tag2(n), conn2((size_t)n * 8), mat2(n);
+      const int npar = ele_kind(g.kind).npar;
+      std::vector<double> par2((size_t)n * npar);
+#pragma omp parallel for schedule(static)
+      for (long long i = 0; i < n; i++) {
+        const long long o = byTag[i];
+        tag2[i] = g.tag[o]; mat2[i] = g.mat[o];
+        std::memcpy(&conn2[(size_t)i * 8], &g.conn[(size_t)o * 8], sizeof(int) * 8);
+        std::memcpy(&par2[(size_t)i * npar], &g.par[(size_t)o * npar], sizeof(double) * npar);
+      }
+      g.tag.swap(tag2); g.conn.swap(conn2); g.mat.swap(mat2); g.par.swap(par2);
+      tiled = true;
+    }
+  }
+
   // ---- PlainHandler::handle: every dof -2 (free) unless an SP_Constraint sets -1 ----
   std::vector<int> gid((size_t)n_nodes * ndf, -2);
   for (size_t i = 0; i < sp_node.size(); i++) {
@@ -852,7 +907,13 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
     const int want = pl ? std::atoi(pl) : 8;
     pipeline_forced = pl != nullptr;
     nchunk = (FG.size() == 1 && ne >= 65536 && want > 1 && want <= 64 && !have_mp) ? want : 1;
+    if (tiled) nchunk = (int)tile_super.size();
     const long long per = nchunk > 1 ? (ne + nchunk - 1) / nchunk : ne;
+    std::vector<int> tile_of;
+    if (tiled) {
+      tile_of.resize(ne);
+      for (int c = 0; c < nchunk; c++) for (long long l = tile_ptr[c]; l < tile_ptr[c + 1]; l++) tile_of[l] = c;
+    }
     std::vector<int> ready(nl, -1);
     for (int i = 0; i < nl; i++) {
       if (!owned[i]) continue;
@@ -862,7 +923,7 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
         if (part_fe[ge] != rank) { rdy = nchunk; break; }          // needs the interface exchange
         const long long le = nparts == 1 ? ge : g_fe_to_local[ge];  // local FE index == index in the batch
         const long long l = fe_local[le];
-        rdy = std::max(rdy, nchunk > 1 ? (int)(l / per) : 0);
+        rdy = std::max(rdy, tiled ? tile_of[l] : (nchunk > 1 ? (int)(l / per) : 0));
       }
       ready[i] = rdy;
     }
@@ -887,21 +948,25 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
         tk[3 + j] = r >= 0 ? ptr[r] : -1;
       }
     }
-    // rows each range completes: streamable when range c owns exactly the rows [r_c, r_{c+1}) of A
-    chunk_a_ptr.assign((size_t)nchunk + 2, 0);
+    // rows each range completes: streamable when range c owns exactly the rows [r_c, r_{c+1}) of A.  Tiled: the
+    // unit is the super-range (FE-order slice) -- its tiles complete rows in spatial, not row, order.
+    const int ng = tiled ? nsuper : nchunk;
+    auto group_of = [&](int c) { return c >= nchunk ? ng : (tiled ? tile_super[c] : c); };
+    chunk_a_ptr.assign((size_t)ng + 2, 0);
     rows_streamable = nchunk > 1;
     int next_row = 0;
-    for (int c = 0; c <= nchunk && rows_streamable; c++) {
+    for (int gI = 0, c = 0; gI <= ng && rows_streamable; gI++) {
       long long cnt = 0; int lo = nrows, hi = -1;
-      for (long long u = chunk_node_ptr[c]; u < chunk_node_ptr[c + 1]; u++)
-        for (int j = 0; j < ndf; j++) {
-          const int r = row_of_dev[(size_t)node_perm[u] * ndf + j];
-          if (r < 0) continue;
-          cnt++; lo = std::min(lo, r); hi = std::max(hi, r);
-        }
+      for (; c <= nchunk && group_of(c) == gI; c++)
+        for (long long u = chunk_node_ptr[c]; u < chunk_node_ptr[c + 1]; u++)
+          for (int j = 0; j < ndf; j++) {
+            const int r = row_of_dev[(size_t)node_perm[u] * ndf + j];
+            if (r < 0) continue;
+            cnt++; lo = std::min(lo, r); hi = std::max(hi, r);
+          }
       if (cnt && (lo != next_row || hi - lo + 1 != cnt)) rows_streamable = false;
       if (cnt) next_row = hi + 1;
-      chunk_a_ptr[c + 1] = ptr[next_row];
+      chunk_a_ptr[gI + 1] = ptr[next_row];
     }
     if (next_row != nrows) rows_streamable = false;
   }

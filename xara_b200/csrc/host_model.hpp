@@ -161,6 +161,15 @@ struct HostModel {
   std::vector<long long> chunk_a_ptr;      // [nchunk+2] offsets in A of the rows each range completes
   bool rows_streamable = false;     // the ranges own consecutive row blocks of A (copy-out can follow them)
   bool pipeline_forced = false;     // XB_PIPELINE set: use the ranges also without a host destination
+  // tiled formTangent (large single-batch brick models, one rank): at set-up the batch's STORAGE order (not the
+  // FE_Element order, which is by tag) becomes  super-range (FE-order slices, so that finished rows of A can leave
+  // for the host in order) > spatial tile (recursive coordinate bisection of the slice, <= tile_target elements).
+  // A range of the pipeline is then one tile: its element rows (~40 MB) are still in L2 when the nodes the tile
+  // completes are assembled, so most of the element-matrix round trip never reaches HBM.
+  bool tiled = false;
+  std::vector<long long> tile_ptr;  // [nchunk+1] storage index where each tile starts
+  std::vector<int> tile_super;      // [nchunk] super-range of a tile
+  int nsuper = 1;
   int max_row = 0;                  // longest row
   long long ke_total = 0, re_total = 0, ngp = 0;
   int chunk = 0;                    // doubles per slot: ndf rows x cp_stride columns
