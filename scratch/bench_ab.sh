@@ -1,7 +1,6 @@
 #!/bin/bash
 cd /root/repo
-
-for lib in libxara_b200.so libxara_b200_v0.so libxara_b200_v1.so libxara_b200.so; do
+for lib in libxara_b200_v0.so libxara_b200.so; do
 echo "== $lib"
 XARA_B200_LIB=/root/repo/xara_b200/$lib python bench.py --n 128 --steps 10 --warmup 3 --e2e-steps 0 --no-cpu-baseline 2>gpurun_out/bq.err | python -c "
 import json,sys

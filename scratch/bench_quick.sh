@@ -1,7 +1,9 @@
 #!/bin/bash
 cd /root/repo
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python bench.py --steps 10 --warmup 3 --e2e-steps 0 --no-cpu-baseline 2>gpurun_out/bq.err | python -c "
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for i in 1 2; do
+python bench.py --n 128 --steps 10 --warmup 3 --e2e-steps 0 --no-cpu-baseline 2>gpurun_out/bq.err | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 print('ms/step',round(d['ms_per_step'],3),'ft_call',round(d['formTangent_call_ms'],3),'kernels',{k:round(v,3) for k,v in d['kernel_ms'].items() if v>0.01}, 'launches', d['gpu_launches'], d['clocks'])" || tail -5 gpurun_out/bq.err
+done

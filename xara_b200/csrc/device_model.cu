@@ -871,7 +871,10 @@ constexpr int BS_DG = 90;                 // per Gauss point: [4 elements][22] p
 constexpr int BS_XS = 26;                 // per element: nodal coordinates [8][3] + pad
 constexpr int BS_WARP = 4 * BS_T + 32;    // tile (aliases the three regions above) + 32 slot addresses
 static_assert(8 * BS_SG + 8 * BS_DG + 4 * BS_XS <= 4 * BS_T, "staging regions must fit under the tile");
-static_assert(16 * BS_SG + 8 * 16 + 4 * BS_XS <= 4 * BS_T, "staging regions (rank-1 form) must fit under the tile");
+constexpr int BS_GV = 4 * 8 * 6 + 2;      // rank-1 form, per Gauss point: [4 elements][8 nodes][g0 g1 g2 v0 v1 v2] + pad
+                                          // (= 2 mod 16: the 8 lanes of an element, one Gauss point each, write 16-byte
+                                          //  pieces to 8 different bank groups; node records are 48 B apart: reads too)
+static_assert(8 * BS_GV + 8 * 16 + 4 * BS_XS <= 4 * BS_T, "staging regions (rank-1 form) must fit under the tile");
 // XB_TAN_RANK1: the J2 / elastic tangent is  D = alpha I(x)I + beta Isym + gamma n(x)n  (J2Plasticity.cpp:370-383:
 // beta = 2G + c3, alpha = K - beta/3, gamma = c2 - c3; elastic: alpha = lambda, beta = 2 mu, gamma = 0), hence
 //   B_J^T D B_k = alpha g_J g_k^T + beta/2 (g_k g_J^T + (g_J.g_k) I) + gamma v_J v_k^T,   g = grad N, v_J = B_J^T n:
@@ -928,8 +931,7 @@ __global__ void __launch_bounds__(NW * 32, 2) brick_tangent_sym_kernel(GroupView
   double* wbase = smem + warp * BS_WARP;
   double* sN = wbase;
 #if XB_TAN_RANK1
-  double* sV = wbase + 8 * BS_SG;          // B_J^T n per Gauss point, laid out like sN
-  double* sC = sV + 8 * BS_SG;             // per Gauss point: [4 elements][alpha, beta/2, gamma, -] * dvol
+  double* sC = wbase + 8 * BS_GV;          // per Gauss point: [4 elements][alpha, beta/2, gamma, -] * dvol
   double* sX = sC + 8 * 16;
 #else
   double* sD = wbase + 8 * BS_SG;
@@ -987,35 +989,32 @@ __global__ void __launch_bounds__(NW * 32, 2) brick_tangent_sym_kernel(GroupView
       }
       double shp[4][8], dvol;
       brick_shp(k, xl, shp, dvol);
-#pragma unroll
-      for (int c = 0; c < 3; c++)
-#pragma unroll
-        for (int a = 0; a < 8; a += 2)
-          *reinterpret_cast<double2*>(sN + k * BS_SG + (c * 4 + s) * 8 + a) = make_double2(shp[c][a], shp[c][a + 1]);
 #if XB_TAN_RANK1
       {
         const double dv = dvol * scale;
         double ca, cb, cg = 0.0;
+        double* rec = sN + k * BS_GV + s * 48;     // this Gauss point, this element: 8 node records
         if (MATK == XB_MAT_J2PLASTICITY) {
           const double beta = 2.0 * cm1 + ct[7];
           ca = (cm0 - beta * (1.0 / 3.0)) * dv; cb = (0.5 * beta) * dv; cg = (ct[6] - ct[7]) * dv;
 #pragma unroll
-          for (int a = 0; a < 8; a += 2) {
-            double v0[2], v1[2], v2[2];
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-              const double gx = shp[0][a + h], gy = shp[1][a + h], gz = shp[2][a + h];
-              v0[h] = gx * ct[0] + gy * ct[3] + gz * ct[5];
-              v1[h] = gy * ct[1] + gx * ct[3] + gz * ct[4];
-              v2[h] = gz * ct[2] + gy * ct[4] + gx * ct[5];
-            }
-            *reinterpret_cast<double2*>(sV + k * BS_SG + (0 * 4 + s) * 8 + a) = make_double2(v0[0], v0[1]);
-            *reinterpret_cast<double2*>(sV + k * BS_SG + (1 * 4 + s) * 8 + a) = make_double2(v1[0], v1[1]);
-            *reinterpret_cast<double2*>(sV + k * BS_SG + (2 * 4 + s) * 8 + a) = make_double2(v2[0], v2[1]);
+          for (int a = 0; a < 8; a++) {
+            const double gx = shp[0][a], gy = shp[1][a], gz = shp[2][a];
+            const double v0 = gx * ct[0] + gy * ct[3] + gz * ct[5];     // v = B_a^T n
+            const double v1 = gy * ct[1] + gx * ct[3] + gz * ct[4];
+            const double v2 = gz * ct[2] + gy * ct[4] + gx * ct[5];
+            *reinterpret_cast<double2*>(rec + a * 6) = make_double2(gx, gy);
+            *reinterpret_cast<double2*>(rec + a * 6 + 2) = make_double2(gz, v0);
+            *reinterpret_cast<double2*>(rec + a * 6 + 4) = make_double2(v1, v2);
           }
         } else {
           const double mu2 = cm0 / (1.0 + cm1);
           ca = (cm1 * mu2 / (1.0 - 2.0 * cm1)) * dv; cb = (0.50 * mu2) * dv;
+#pragma unroll
+          for (int a = 0; a < 8; a++) {
+            *reinterpret_cast<double2*>(rec + a * 6) = make_double2(shp[0][a], shp[1][a]);
+            rec[a * 6 + 2] = shp[2][a];
+          }
         }
         double* cc = sC + k * 16 + s * 4;
         *reinterpret_cast<double2*>(cc) = make_double2(ca, cb);
@@ -1023,6 +1022,11 @@ __global__ void __launch_bounds__(NW * 32, 2) brick_tangent_sym_kernel(GroupView
       }
     }
 #else
+#pragma unroll
+      for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int a = 0; a < 8; a += 2)
+          *reinterpret_cast<double2*>(sN + k * BS_SG + (c * 4 + s) * 8 + a) = make_double2(shp[c][a], shp[c][a + 1]);
       double d21[22];
       brick_D_regs<MATK>(cm0, cm1, ct, dvol * scale, d21);
       d21[21] = 0.0;
@@ -1059,36 +1063,43 @@ __global__ void __launch_bounds__(NW * 32, 2) brick_tangent_sym_kernel(GroupView
 #pragma unroll g_unroll
     for (int g = 0; g < 8; g++) {
 #if XB_TAN_RANK1
-      const double* ng = sN + g * BS_SG + s * 8;
-      const double* vg = sV + g * BS_SG + s * 8;
+      const double* rec = sN + g * BS_GV + s * 48;
       const double2 cab = *reinterpret_cast<const double2*>(sC + g * 16 + s * 4);
-      const double g0 = ng[k], g1 = ng[32 + k], g2 = ng[64 + k];
-      const double ak[3] = {cab.x * g0, cab.x * g1, cab.x * g2};      // alpha g_k
-      const double bk[3] = {cab.y * g0, cab.y * g1, cab.y * g2};      // beta/2 g_k
-      double wk[3] = {0.0, 0.0, 0.0};                                   // gamma v_k
+      const double2 k01 = *reinterpret_cast<const double2*>(rec + k * 6);
+      const double2 k23 = *reinterpret_cast<const double2*>(rec + k * 6 + 2);
+      const double ak[3] = {cab.x * k01.x, cab.x * k01.y, cab.x * k23.x};      // alpha g_k
+      const double bk[3] = {cab.y * k01.x, cab.y * k01.y, cab.y * k23.x};      // beta/2 g_k
+      double wk[3] = {0.0, 0.0, 0.0};                                            // gamma v_k
       if (MATK == XB_MAT_J2PLASTICITY) {
         const double cg = sC[g * 16 + s * 4 + 2];
-        wk[0] = cg * vg[k]; wk[1] = cg * vg[32 + k]; wk[2] = cg * vg[64 + k];
+        const double2 k45 = *reinterpret_cast<const double2*>(rec + k * 6 + 4);
+        wk[0] = cg * k23.y; wk[1] = cg * k45.x; wk[2] = cg * k45.y;
       }
 #pragma unroll
       for (int t = 0; t < 5; t++) {
         const int J = (k + t) & 7;
-        const double gJ[3] = {ng[J], ng[32 + J], ng[64 + J]};
-        const double sd = fma(gJ[2], bk[2], fma(gJ[1], bk[1], gJ[0] * bk[0]));
+        const double2 j01 = *reinterpret_cast<const double2*>(rec + J * 6);
         if (MATK == XB_MAT_J2PLASTICITY) {
-          const double vJ[3] = {vg[J], vg[32 + J], vg[64 + J]};
+          const double2 j23 = *reinterpret_cast<const double2*>(rec + J * 6 + 2);
+          const double2 j45 = *reinterpret_cast<const double2*>(rec + J * 6 + 4);
+          const double gJ[3] = {j01.x, j01.y, j23.x};
+          const double vJ[3] = {j23.y, j45.x, j45.y};
+          const double sd = fma(gJ[2], bk[2], fma(gJ[1], bk[1], gJ[0] * bk[0]));
 #pragma unroll
           for (int p = 0; p < 3; p++)
 #pragma unroll
             for (int q = 0; q < 3; q++)
               acc[t][p][q] = fma(vJ[p], wk[q], fma(bk[p], gJ[q], fma(gJ[p], ak[q], acc[t][p][q])));
+          acc[t][0][0] += sd; acc[t][1][1] += sd; acc[t][2][2] += sd;
         } else {
+          const double gJ[3] = {j01.x, j01.y, rec[J * 6 + 2]};
+          const double sd = fma(gJ[2], bk[2], fma(gJ[1], bk[1], gJ[0] * bk[0]));
 #pragma unroll
           for (int p = 0; p < 3; p++)
 #pragma unroll
             for (int q = 0; q < 3; q++) acc[t][p][q] = fma(bk[p], gJ[q], fma(gJ[p], ak[q], acc[t][p][q]));
+          acc[t][0][0] += sd; acc[t][1][1] += sd; acc[t][2][2] += sd;
         }
-        acc[t][0][0] += sd; acc[t][1][1] += sd; acc[t][2][2] += sd;
       }
     }
 #else
@@ -1158,13 +1169,26 @@ __global__ void __launch_bounds__(NW * 32, 2) brick_tangent_sym_kernel(GroupView
       for (int el = 0; el < nlive; el++) {
         const double* tile = wbase + el * BS_T;
         double* const* dsts = reinterpret_cast<double* const*>(sDst) + el * 8;
+        // all shared-memory reads of the element first, then the stores: a slot pointer read from shared memory
+        // could itself point into shared memory as far as the compiler knows, so loads placed after a store wait for it
+        double2 v[9];
+        double* out[9];
 #pragma unroll
         for (int it = 0; it < 9; it++) {
           const unsigned pk = cpk[it];
-          double2 v = *reinterpret_cast<const double2*>(tile + (pk & 1023u));
-          double* out = dsts[(pk >> 10) & 7u] + (pk >> 13);
-          if (accum) { const double2 o = *reinterpret_cast<const double2*>(out); v.x += o.x; v.y += o.y; }
-          *reinterpret_cast<double2*>(out) = v;
+          v[it] = *reinterpret_cast<const double2*>(tile + (pk & 1023u));
+          out[it] = dsts[(pk >> 10) & 7u] + (pk >> 13);
+        }
+        if (accum) {
+#pragma unroll
+          for (int it = 0; it < 9; it++) { const double2 o = *reinterpret_cast<const double2*>(out[it]); v[it].x += o.x; v[it].y += o.y; }
+        }
+#pragma unroll
+        for (int it = 0; it < 9; it++) {
+#ifdef XB_TAN_NOSTORE   // diagnostic build: everything but the global stores (the condition never holds)
+          if (v[it].x == 1.2345e300)
+#endif
+          *reinterpret_cast<double2*>(out[it]) = v[it];
         }
       }
     }
