@@ -871,16 +871,19 @@ constexpr int BS_DG = 90;                 // per Gauss point: [4 elements][22] p
 constexpr int BS_XS = 26;                 // per element: nodal coordinates [8][3] + pad
 constexpr int BS_WARP = 4 * BS_T + 32;    // tile (aliases the three regions above) + 32 slot addresses
 static_assert(8 * BS_SG + 8 * BS_DG + 4 * BS_XS <= 4 * BS_T, "staging regions must fit under the tile");
-constexpr int BS_GV = 4 * 8 * 6 + 2;      // rank-1 form, per Gauss point: [4 elements][8 nodes][g0 g1 g2 v0 v1 v2] + pad
-                                          // (= 2 mod 16: the 8 lanes of an element, one Gauss point each, write 16-byte
-                                          //  pieces to 8 different bank groups; node records are 48 B apart: reads too)
-static_assert(8 * BS_GV + 8 * 16 + 4 * BS_XS <= 4 * BS_T, "staging regions (rank-1 form) must fit under the tile");
+constexpr int BS_GV = 4 * 8 * 3 + 2;      // rank-1 form, per Gauss point: [4 elements][8 nodes][grad N] + pad (= 2 mod 16: the 8 lanes
+                                          //  of an element, one Gauss point each, write 16-byte pieces to 8 different bank groups;
+                                          //  the 24-byte node records are read with 8-byte loads, conflict-free per half warp)
+constexpr int BS_CN = 4 * 10;             // per Gauss point: [4 elements][alpha, beta/2, gamma (x dvol), n[6], -]
+static_assert(8 * BS_GV + 8 * BS_CN + 4 * BS_XS <= 4 * BS_T, "staging regions (rank-1 form) must fit under the tile");
 // XB_TAN_RANK1: the J2 / elastic tangent is  D = alpha I(x)I + beta Isym + gamma n(x)n  (J2Plasticity.cpp:370-383:
 // beta = 2G + c3, alpha = K - beta/3, gamma = c2 - c3; elastic: alpha = lambda, beta = 2 mu, gamma = 0), hence
-//   B_J^T D B_k = alpha g_J g_k^T + beta/2 (g_k g_J^T + (g_J.g_k) I) + gamma v_J v_k^T,   g = grad N, v_J = B_J^T n:
-// 33 FP64 operations per node pair and Gauss point instead of 27 + the 54 of D B_k shared by 4.5 pairs, and no 6x6 D
-// to build -- 15 % fewer FP64 instructions in a kernel that is bound by the FP64 pipe.  Same tangent, different
-// grouping of the products: agreement with the reference stays at rounding level (1e-15 of the block norm).
+//   B_J^T D B_k = alpha g_J g_k^T + beta/2 (g_k g_J^T + (g_J.g_k) I) + gamma v_J v_k^T,   g = grad N, v_J = B_J^T n = n g_J
+// (n as the symmetric 3x3 normal tensor).  ncu shows the kernel bound by the L1 / shared-memory data pipe (82 % of its
+// wavefront rate; FP64 pipe 51 %), so the form that moves the fewest shared-memory bytes wins: a node's record per
+// Gauss point is grad N alone (24 B instead of the 6x6 D per point plus gradients), v_J is recomputed from it (9 FP64
+// operations), and n comes as one broadcast read per element.  Same tangent, different grouping of the products:
+// agreement with the reference stays at rounding level (1e-15 of the block norm).
 #ifndef XB_TAN_RANK1
 #define XB_TAN_RANK1 1
 #endif
@@ -931,8 +934,8 @@ __global__ void __launch_bounds__(NW * 32, 2) brick_tangent_sym_kernel(GroupView
   double* wbase = smem + warp * BS_WARP;
   double* sN = wbase;
 #if XB_TAN_RANK1
-  double* sC = wbase + 8 * BS_GV;          // per Gauss point: [4 elements][alpha, beta/2, gamma, -] * dvol
-  double* sX = sC + 8 * 16;
+  double* sC = wbase + 8 * BS_GV;          // per Gauss point: [4 elements][alpha, beta/2, gamma (x dvol), n[6], -]
+  double* sX = sC + 8 * BS_CN;
 #else
   double* sD = wbase + 8 * BS_SG;
   double* sX = sD + 8 * BS_DG;
@@ -993,30 +996,23 @@ __global__ void __launch_bounds__(NW * 32, 2) brick_tangent_sym_kernel(GroupView
       {
         const double dv = dvol * scale;
         double ca, cb, cg = 0.0;
-        double* rec = sN + k * BS_GV + s * 48;     // this Gauss point, this element: 8 node records
+        double* rec = sN + k * BS_GV + s * 24;     // this Gauss point, this element: 8 node records (grad N)
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+          const int a0 = (2 * i) / 3, c0 = (2 * i) % 3, a1 = (2 * i + 1) / 3, c1 = (2 * i + 1) % 3;
+          *reinterpret_cast<double2*>(rec + 2 * i) = make_double2(shp[c0][a0], shp[c1][a1]);
+        }
+        double* cc = sC + k * BS_CN + s * 10;
         if (MATK == XB_MAT_J2PLASTICITY) {
           const double beta = 2.0 * cm1 + ct[7];
           ca = (cm0 - beta * (1.0 / 3.0)) * dv; cb = (0.5 * beta) * dv; cg = (ct[6] - ct[7]) * dv;
-#pragma unroll
-          for (int a = 0; a < 8; a++) {
-            const double gx = shp[0][a], gy = shp[1][a], gz = shp[2][a];
-            const double v0 = gx * ct[0] + gy * ct[3] + gz * ct[5];     // v = B_a^T n
-            const double v1 = gy * ct[1] + gx * ct[3] + gz * ct[4];
-            const double v2 = gz * ct[2] + gy * ct[4] + gx * ct[5];
-            *reinterpret_cast<double2*>(rec + a * 6) = make_double2(gx, gy);
-            *reinterpret_cast<double2*>(rec + a * 6 + 2) = make_double2(gz, v0);
-            *reinterpret_cast<double2*>(rec + a * 6 + 4) = make_double2(v1, v2);
-          }
+          *reinterpret_cast<double2*>(cc + 4) = make_double2(ct[0], ct[1]);
+          *reinterpret_cast<double2*>(cc + 6) = make_double2(ct[2], ct[3]);
+          *reinterpret_cast<double2*>(cc + 8) = make_double2(ct[4], ct[5]);
         } else {
           const double mu2 = cm0 / (1.0 + cm1);
           ca = (cm1 * mu2 / (1.0 - 2.0 * cm1)) * dv; cb = (0.50 * mu2) * dv;
-#pragma unroll
-          for (int a = 0; a < 8; a++) {
-            *reinterpret_cast<double2*>(rec + a * 6) = make_double2(shp[0][a], shp[1][a]);
-            rec[a * 6 + 2] = shp[2][a];
-          }
         }
-        double* cc = sC + k * 16 + s * 4;
         *reinterpret_cast<double2*>(cc) = make_double2(ca, cb);
         cc[2] = cg;
       }
@@ -1063,43 +1059,51 @@ __global__ void __launch_bounds__(NW * 32, 2) brick_tangent_sym_kernel(GroupView
 #pragma unroll g_unroll
     for (int g = 0; g < 8; g++) {
 #if XB_TAN_RANK1
-      const double* rec = sN + g * BS_GV + s * 48;
-      const double2 cab = *reinterpret_cast<const double2*>(sC + g * 16 + s * 4);
-      const double2 k01 = *reinterpret_cast<const double2*>(rec + k * 6);
-      const double2 k23 = *reinterpret_cast<const double2*>(rec + k * 6 + 2);
-      const double ak[3] = {cab.x * k01.x, cab.x * k01.y, cab.x * k23.x};      // alpha g_k
-      const double bk[3] = {cab.y * k01.x, cab.y * k01.y, cab.y * k23.x};      // beta/2 g_k
-      double wk[3] = {0.0, 0.0, 0.0};                                            // gamma v_k
+      const double* rec = sN + g * BS_GV + s * 24;
+      const double* cc = sC + g * BS_CN + s * 10;
+      const double2 cab = *reinterpret_cast<const double2*>(cc);
+      const double gk[3] = {rec[k * 3], rec[k * 3 + 1], rec[k * 3 + 2]};
+      const double ak[3] = {cab.x * gk[0], cab.x * gk[1], cab.x * gk[2]};      // alpha g_k
+      const double bk[3] = {cab.y * gk[0], cab.y * gk[1], cab.y * gk[2]};      // beta/2 g_k
+      double n0 = 0, n1 = 0, n2 = 0, n3 = 0, n4 = 0, n5 = 0, vk[3] = {0, 0, 0}, wk[3] = {0, 0, 0};
       if (MATK == XB_MAT_J2PLASTICITY) {
-        const double cg = sC[g * 16 + s * 4 + 2];
-        const double2 k45 = *reinterpret_cast<const double2*>(rec + k * 6 + 4);
-        wk[0] = cg * k23.y; wk[1] = cg * k45.x; wk[2] = cg * k45.y;
+        const double cg = cc[2];
+        const double2 n01 = *reinterpret_cast<const double2*>(cc + 4), n23 = *reinterpret_cast<const double2*>(cc + 6),
+                      n45 = *reinterpret_cast<const double2*>(cc + 8);
+        n0 = n01.x; n1 = n01.y; n2 = n23.x; n3 = n23.y; n4 = n45.x; n5 = n45.y;
+        vk[0] = gk[0] * n0 + gk[1] * n3 + gk[2] * n5;                            // v = B^T n (components 00 11 22 01 12 20)
+        vk[1] = gk[1] * n1 + gk[0] * n3 + gk[2] * n4;
+        vk[2] = gk[2] * n2 + gk[1] * n4 + gk[0] * n5;
+        wk[0] = cg * vk[0]; wk[1] = cg * vk[1]; wk[2] = cg * vk[2];              // gamma v_k
       }
 #pragma unroll
       for (int t = 0; t < 5; t++) {
         const int J = (k + t) & 7;
-        const double2 j01 = *reinterpret_cast<const double2*>(rec + J * 6);
+        double gJ[3], vJ[3];
+        if (t == 0) {
+          gJ[0] = gk[0]; gJ[1] = gk[1]; gJ[2] = gk[2]; vJ[0] = vk[0]; vJ[1] = vk[1]; vJ[2] = vk[2];
+        } else {
+          gJ[0] = rec[J * 3]; gJ[1] = rec[J * 3 + 1]; gJ[2] = rec[J * 3 + 2];
+          if (MATK == XB_MAT_J2PLASTICITY) {
+            vJ[0] = gJ[0] * n0 + gJ[1] * n3 + gJ[2] * n5;
+            vJ[1] = gJ[1] * n1 + gJ[0] * n3 + gJ[2] * n4;
+            vJ[2] = gJ[2] * n2 + gJ[1] * n4 + gJ[0] * n5;
+          }
+        }
+        const double sd = fma(gJ[2], bk[2], fma(gJ[1], bk[1], gJ[0] * bk[0]));
         if (MATK == XB_MAT_J2PLASTICITY) {
-          const double2 j23 = *reinterpret_cast<const double2*>(rec + J * 6 + 2);
-          const double2 j45 = *reinterpret_cast<const double2*>(rec + J * 6 + 4);
-          const double gJ[3] = {j01.x, j01.y, j23.x};
-          const double vJ[3] = {j23.y, j45.x, j45.y};
-          const double sd = fma(gJ[2], bk[2], fma(gJ[1], bk[1], gJ[0] * bk[0]));
 #pragma unroll
           for (int p = 0; p < 3; p++)
 #pragma unroll
             for (int q = 0; q < 3; q++)
               acc[t][p][q] = fma(vJ[p], wk[q], fma(bk[p], gJ[q], fma(gJ[p], ak[q], acc[t][p][q])));
-          acc[t][0][0] += sd; acc[t][1][1] += sd; acc[t][2][2] += sd;
         } else {
-          const double gJ[3] = {j01.x, j01.y, rec[J * 6 + 2]};
-          const double sd = fma(gJ[2], bk[2], fma(gJ[1], bk[1], gJ[0] * bk[0]));
 #pragma unroll
           for (int p = 0; p < 3; p++)
 #pragma unroll
             for (int q = 0; q < 3; q++) acc[t][p][q] = fma(bk[p], gJ[q], fma(gJ[p], ak[q], acc[t][p][q]));
-          acc[t][0][0] += sd; acc[t][1][1] += sd; acc[t][2][2] += sd;
         }
+        acc[t][0][0] += sd; acc[t][1][1] += sd; acc[t][2][2] += sd;
       }
     }
 #else
