@@ -850,73 +850,40 @@ __global__ void __launch_bounds__(BT_ELEMS * 8, 3) brick_tangent_csc_kernel(Grou
 
 // Third form of the same element tangent, the default: a persistent, software-pipelined kernel
 // that uses the symmetry of the material tangent (J2Plasticity's consistent tangent and the elastic
-// one are symmetric 6x6 matrices, so K_kJ = K_Jk^T).  Differences to brick_tangent_kernel:
+// one are symmetric 6x6 matrices, so K_kJ = K_Jk^T) and its structure.  Differences to brick_tangent_kernel:
 //   * each of the 8 lanes of an element forms only 5 (lanes 0-3) or 4 (lanes 4-7) of the 36
-//     distinct node-pair blocks, J = k, k+1, .., k+4 (mod 8): 45 FP64 accumulators instead of 72
-//     and 189 instead of 270 DFMA per lane and Gauss point;
+//     distinct node-pair blocks, J = k, k+1, .., k+4 (mod 8): 45 FP64 accumulators instead of 72;
+//   * the J2 / elastic tangent is  D = alpha I(x)I + beta Isym + gamma n(x)n  (J2Plasticity.cpp:370-383:
+//     beta = 2G + c3, alpha = K - beta/3, gamma = c2 - c3; elastic: alpha = lambda, beta = 2 mu, gamma = 0), hence
+//       B_J^T D B_k = alpha g_J g_k^T + beta/2 (g_k g_J^T + (g_J.g_k) I) + gamma v_J v_k^T,  g = grad N, v_J = B_J^T n = n g_J
+//     (n as the symmetric 3x3 normal tensor): no 6x6 D is built, a node's record per Gauss point in shared memory
+//     is grad N alone (24 B), v_J is recomputed from it (9 FP64 operations) and n comes as one broadcast read per
+//     element.  219 FP64 instructions per lane and Gauss point (the D B_k form: 189, but 80 instead of 37
+//     shared-memory wavefronts); ncu: FP64 pipe ~64 % of the measured DFMA rate, L1/shared data pipe 60-80 %;
 //   * a warp walks over its batches of 4 elements in a loop and requests the inputs of the NEXT
 //     batch (its node's coordinates, the Gauss point's compact tangent, the slot address) before
 //     the main loop of the current one, so that the global-load latency hides behind FP64 work;
 //   * a lane loads only its own node / Gauss point; the coordinates go round through shared memory;
 //   * the output tile is bank-conflict free for both orientations (row stride 26, element stride
-//     632 doubles) and leaves with all 32 lanes storing 16 bytes each.
-// The sum over the Gauss points of one entry keeps the reference's order (point 0..7); inside a
-// point the products are grouped as B_J^T (D B_k), the mirror image of Matrix::addMatrixTripleProduct's
-// (B_J^T D) B_k -- agreement with the reference is to rounding (1e-16 of the block norm), not bitwise,
-// which is what BASELINE.json's 1e-12 asks for; runs on any partition are bitwise identical.
+//     632 doubles) and leaves with all 32 lanes storing 16 bytes each; the store loop's (node, tile offset, slot
+//     offset) triples depend on (iteration, lane) only and sit packed in 9 registers.
+// The sum over the Gauss points of one entry keeps the reference's order (point 0..7); inside a point the
+// products are grouped differently from Matrix::addMatrixTripleProduct's (B_J^T D) B_k -- agreement with the
+// reference is to rounding (1e-15 of the block norm), not bitwise, which is what BASELINE.json's 1e-12 asks
+// for; runs on any partition are bitwise identical.
 constexpr int BS_R = 26;                  // tile row stride (doubles)
 constexpr int BS_T = 24 * BS_R + 8;       // tile stride per element: = 8 mod 16
-constexpr int BS_SG = 98;                 // per Gauss point: shape-function gradients [3][4 elements][8 nodes] + pad
-constexpr int BS_DG = 90;                 // per Gauss point: [4 elements][22] packed D + pad
 constexpr int BS_XS = 26;                 // per element: nodal coordinates [8][3] + pad
-constexpr int BS_WARP = 4 * BS_T + 32;    // tile (aliases the three regions above) + 32 slot addresses
-static_assert(8 * BS_SG + 8 * BS_DG + 4 * BS_XS <= 4 * BS_T, "staging regions must fit under the tile");
-constexpr int BS_GV = 4 * 8 * 3 + 2;      // rank-1 form, per Gauss point: [4 elements][8 nodes][grad N] + pad (= 2 mod 16: the 8 lanes
-                                          //  of an element, one Gauss point each, write 16-byte pieces to 8 different bank groups;
+constexpr int BS_WARP = 4 * BS_T + 32;    // tile (aliases the staging regions below) + 32 slot addresses
+constexpr int BS_GV = 4 * 8 * 3 + 2;      // per Gauss point: [4 elements][8 nodes][grad N] + pad (= 2 mod 16: the 8 lanes of an
+                                          //  element, one Gauss point each, write 16-byte pieces to 8 different bank groups;
                                           //  the 24-byte node records are read with 8-byte loads, conflict-free per half warp)
 constexpr int BS_CN = 4 * 10;             // per Gauss point: [4 elements][alpha, beta/2, gamma (x dvol), n[6], -]
-static_assert(8 * BS_GV + 8 * BS_CN + 4 * BS_XS <= 4 * BS_T, "staging regions (rank-1 form) must fit under the tile");
-// XB_TAN_RANK1: the J2 / elastic tangent is  D = alpha I(x)I + beta Isym + gamma n(x)n  (J2Plasticity.cpp:370-383:
-// beta = 2G + c3, alpha = K - beta/3, gamma = c2 - c3; elastic: alpha = lambda, beta = 2 mu, gamma = 0), hence
-//   B_J^T D B_k = alpha g_J g_k^T + beta/2 (g_k g_J^T + (g_J.g_k) I) + gamma v_J v_k^T,   g = grad N, v_J = B_J^T n = n g_J
-// (n as the symmetric 3x3 normal tensor).  ncu shows the kernel bound by the L1 / shared-memory data pipe (82 % of its
-// wavefront rate; FP64 pipe 51 %), so the form that moves the fewest shared-memory bytes wins: a node's record per
-// Gauss point is grad N alone (24 B instead of the 6x6 D per point plus gradients), v_J is recomputed from it (9 FP64
-// operations), and n comes as one broadcast read per element.  Same tangent, different grouping of the products:
-// agreement with the reference stays at rounding level (1e-15 of the block norm).
-#ifndef XB_TAN_RANK1
-#define XB_TAN_RANK1 1
-#endif
-#ifndef XB_TAN_GUNROLL
-#define XB_TAN_GUNROLL 1
-#endif
-
-template <int MATK>
-__device__ __forceinline__ void brick_D_regs(double m0, double m1, const double* t, double dvol, double* d21) {
-  if (MATK == XB_MAT_J2PLASTICITY) {
-#pragma unroll
-    for (int a = 0; a < 6; a++)
-#pragma unroll
-      for (int b = a; b < 6; b++) d21[sym6(a, b)] = j2_tangent_entry(a, b, m0, m1, t, t[6], t[7]) * dvol;
-  } else {
-    double mu2 = m0 / (1.0 + m1);
-    const double lam = m1 * mu2 / (1.0 - 2.0 * m1);
-    const double mu = 0.50 * mu2;
-    mu2 += lam;
-#pragma unroll
-    for (int a = 0; a < 6; a++)
-#pragma unroll
-      for (int b = a; b < 6; b++)
-        d21[sym6(a, b)] = ((a < 3 && b < 3) ? (a == b ? mu2 : lam) : (a == b ? mu : 0.0)) * dvol;
-  }
-}
+static_assert(8 * BS_GV + 8 * BS_CN + 4 * BS_XS <= 4 * BS_T, "staging regions must fit under the tile");
 
 // NW warps per CTA: 4 fills the register file with two CTAs per SM (8 warps x 254 registers); 3 leaves a quarter of
 // it free, so that CTAs of the (HBM-bound) assembly kernel can run beside this (FP64-bound) one -- used by the
 // pipelined xb_form_tangent, where the assembly of one element range overlaps the tangents of the next.
-#ifndef XB_STORE_V2
-#define XB_STORE_V2 1
-#endif
 template <int MATK, int DYN, int NW = 4>
 __global__ void __launch_bounds__(NW * 32, 2) brick_tangent_sym_kernel(GroupView G, const double* __restrict__ X,
                                                                    int transpose, long long ebeg, long long eend,
@@ -933,13 +900,8 @@ __global__ void __launch_bounds__(NW * 32, 2) brick_tangent_sym_kernel(GroupView
   const int s = lane >> 3, k = lane & 7;
   double* wbase = smem + warp * BS_WARP;
   double* sN = wbase;
-#if XB_TAN_RANK1
   double* sC = wbase + 8 * BS_GV;          // per Gauss point: [4 elements][alpha, beta/2, gamma (x dvol), n[6], -]
   double* sX = sC + 8 * BS_CN;
-#else
-  double* sD = wbase + 8 * BS_SG;
-  double* sX = sD + 8 * BS_DG;
-#endif
   long long* sDst = reinterpret_cast<long long*>(wbase + 4 * BS_T);
   const long long ngp = G.n * 8;
   const long long nb = (eend - ebeg + 3) >> 2;               // batches of 4 elements
@@ -947,14 +909,12 @@ __global__ void __launch_bounds__(NW * 32, 2) brick_tangent_sym_kernel(GroupView
   long long b = (long long)blockIdx.x * NW + warp;
   if (b >= nb) return;
   const long long elast = eend - 1;
-#if XB_STORE_V2
   unsigned cpk[9];      // store loop: tile offset | node << 10 | offset in the node's slot << 13 (doubles)
 #pragma unroll
   for (int it = 0; it < 9; it++) {
     const int i = it * 32 + lane, a = i / 36, row = i / 12, c2 = i - row * 12;
     cpk[it] = (unsigned)(row * BS_R + 2 * c2) | ((unsigned)a << 10) | ((unsigned)(2 * (i - 36 * a)) << 13);
   }
-#endif
 
   // stage 1 (indices) and stage 2 (values) of batch b; stage 1 of the batch after it
   long long e = ebeg + b * 4 + s; if (e > elast) e = elast;
@@ -976,11 +936,7 @@ __global__ void __launch_bounds__(NW * 32, 2) brick_tangent_sym_kernel(GroupView
     // ---- A: coordinates round the element, shape functions and D*dvol at the lane's Gauss point ----
 #pragma unroll
     for (int d = 0; d < 3; d++) sX[s * BS_XS + k * 3 + d] = cx[d];
-#if XB_STORE_V2
     sDst[lane] = reinterpret_cast<long long>(cdst >= 0 ? G.KeN + cdst : G.sendK + (-cdst - 1));
-#else
-    sDst[lane] = cdst;
-#endif
     __syncwarp();
     {
       double xl[3][8];
@@ -992,7 +948,6 @@ __global__ void __launch_bounds__(NW * 32, 2) brick_tangent_sym_kernel(GroupView
       }
       double shp[4][8], dvol;
       brick_shp(k, xl, shp, dvol);
-#if XB_TAN_RANK1
       {
         const double dv = dvol * scale;
         double ca, cb, cg = 0.0;
@@ -1017,20 +972,6 @@ __global__ void __launch_bounds__(NW * 32, 2) brick_tangent_sym_kernel(GroupView
         cc[2] = cg;
       }
     }
-#else
-#pragma unroll
-      for (int c = 0; c < 3; c++)
-#pragma unroll
-        for (int a = 0; a < 8; a += 2)
-          *reinterpret_cast<double2*>(sN + k * BS_SG + (c * 4 + s) * 8 + a) = make_double2(shp[c][a], shp[c][a + 1]);
-      double d21[22];
-      brick_D_regs<MATK>(cm0, cm1, ct, dvol * scale, d21);
-      d21[21] = 0.0;
-      double* dd = sD + k * BS_DG + s * 22;
-#pragma unroll
-      for (int i = 0; i < 11; i++) *reinterpret_cast<double2*>(dd + 2 * i) = make_double2(d21[2 * i], d21[2 * i + 1]);
-    }
-#endif
     // ---- request the next batch's inputs; they land while the main loop runs ----
     const bool more = b + stride < nb;
     if (more) {
@@ -1055,10 +996,8 @@ __global__ void __launch_bounds__(NW * 32, 2) brick_tangent_sym_kernel(GroupView
       for (int p = 0; p < 3; p++)
 #pragma unroll
         for (int q = 0; q < 3; q++) acc[t][p][q] = 0.0;
-    constexpr int g_unroll = XB_TAN_GUNROLL;
-#pragma unroll g_unroll
+#pragma unroll 1
     for (int g = 0; g < 8; g++) {
-#if XB_TAN_RANK1
       const double* rec = sN + g * BS_GV + s * 24;
       const double* cc = sC + g * BS_CN + s * 10;
       const double2 cab = *reinterpret_cast<const double2*>(cc);
@@ -1106,40 +1045,6 @@ __global__ void __launch_bounds__(NW * 32, 2) brick_tangent_sym_kernel(GroupView
         acc[t][0][0] += sd; acc[t][1][1] += sd; acc[t][2][2] += sd;
       }
     }
-#else
-      const double* ng = sN + g * BS_SG + s * 8;
-      const double* dp = sD + g * BS_DG + s * 22;
-      double d[22];
-#pragma unroll
-      for (int i = 0; i < 11; i++) {
-        const double2 v = *reinterpret_cast<const double2*>(dp + 2 * i);
-        d[2 * i] = v.x; d[2 * i + 1] = v.y;
-      }
-      const double N1 = ng[k], N2 = ng[32 + k], N3 = ng[64 + k];
-      double DB[6][3];
-#pragma unroll
-      for (int r = 0; r < 6; r++) {
-        const double dr0 = d[sym6(r, 0)], dr1 = d[sym6(r, 1)], dr2 = d[sym6(r, 2)], dr3 = d[sym6(r, 3)],
-                     dr4 = d[sym6(r, 4)], dr5 = d[sym6(r, 5)];
-        DB[r][0] = dr0 * N1 + dr3 * N2 + dr5 * N3;
-        DB[r][1] = dr1 * N2 + dr3 * N1 + dr4 * N3;
-        DB[r][2] = dr2 * N3 + dr4 * N2 + dr5 * N1;
-      }
-#pragma unroll
-      for (int t = 0; t < 5; t++) {
-        const int J = (k + t) & 7;
-        const double M1 = ng[J], M2 = ng[32 + J], M3 = ng[64 + J];
-#pragma unroll
-        for (int q = 0; q < 3; q++) {
-          // three chained FMAs per entry (the reference forms the 3x3 product first and then adds
-          // it: one more rounding and one more FP64 instruction per entry)
-          acc[t][0][q] = fma(M3, DB[5][q], fma(M2, DB[3][q], fma(M1, DB[0][q], acc[t][0][q])));
-          acc[t][1][q] = fma(M3, DB[4][q], fma(M1, DB[3][q], fma(M2, DB[1][q], acc[t][1][q])));
-          acc[t][2][q] = fma(M1, DB[5][q], fma(M2, DB[4][q], fma(M3, DB[2][q], acc[t][2][q])));
-        }
-      }
-    }
-#endif
     __syncwarp();   // staging regions are dead: they become the output tile
     // ---- C: both orientations of every block into the tile, then 16-byte stores to the node slots ----
     {
@@ -1163,7 +1068,6 @@ __global__ void __launch_bounds__(NW * 32, 2) brick_tangent_sym_kernel(GroupView
       }
     }
     __syncwarp();
-#if XB_STORE_V2
     {
       // the element's 8 x 3 rows are 288 double2; lane handles i = it * 32 + lane: node a = i / 36, and inside
       // the node's slot (3 rows of cps = 24 doubles, contiguous) double2 number i - 36 a.  (a, tile offset, slot
@@ -1189,33 +1093,10 @@ __global__ void __launch_bounds__(NW * 32, 2) brick_tangent_sym_kernel(GroupView
         }
 #pragma unroll
         for (int it = 0; it < 9; it++) {
-#ifdef XB_TAN_NOSTORE   // diagnostic build: everything but the global stores (the condition never holds)
-          if (v[it].x == 1.2345e300)
-#endif
           *reinterpret_cast<double2*>(out[it]) = v[it];
         }
       }
     }
-#else
-    {
-      const long long rem = eend - (ebeg + b * 4);
-      const int nlive = rem < 4 ? (int)rem : 4;
-      const int cps = G.cps;
-      for (int el = 0; el < nlive; el++) {
-        const double* tile = wbase + el * BS_T;
-#pragma unroll
-        for (int it = 0; it < 9; it++) {
-          const int i = it * 32 + lane;            // double2 index inside the element: 8 nodes x 3 rows x 12
-          const int a = i / 36, row = i / 12, c2 = i - row * 12;
-          const long long dst = sDst[el * 8 + a];
-          double2 v = *reinterpret_cast<const double2*>(tile + row * BS_R + 2 * c2);
-          double* out = (dst >= 0 ? G.KeN + dst : G.sendK + (-dst - 1)) + (row - 3 * a) * cps + 2 * c2;
-          if (accum) { const double2 o = *reinterpret_cast<const double2*>(out); v.x += o.x; v.y += o.y; }
-          *reinterpret_cast<double2*>(out) = v;
-        }
-      }
-    }
-#endif
     if (!more) break;
     b += stride;
     __syncwarp();
