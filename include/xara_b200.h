@@ -91,7 +91,8 @@ int xb_add_sp(xb_model*, int n, const int* node_tags, const int* dofs);
  * (runtime/commands/domain/constraint.cpp): an MP_Constraint with an identity constraint matrix, the only kind
  * PlainHandler accepts (PlainHandler.cpp:129-176).  The n (0-based) dofs of the constrained node take the
  * equation numbers of the same dofs of the retained node (PlainNumberer.cpp:111-142, DOF_Numberer.cpp:151-190).
- * Chains (a retained dof that is itself constrained) and partitioned models return XB_ERR_UNSUPPORTED at set-up. */
+ * On a partitioned model the nodes of a tie group are owned by one rank (the lowest owner in the group).
+ * Chains (a retained dof that is itself constrained) return XB_ERR_UNSUPPORTED at set-up. */
 int xb_add_equal_dof(xb_model*, int retained_node_tag, int constrained_node_tag, int n, const int* dofs);
 /* OPS nDMaterial command; par has npar doubles in the order listed at the kind */
 int xb_add_nd_material(xb_model*, int tag, int kind, const double* par, int npar);

@@ -506,6 +506,48 @@ def test_partitioned_ranks_reproduce_single_gpu_bitwise(nparts, numberer, soe):
             m.commit()
 
 
+@pytest.mark.parametrize("shape,nparts", [("brick", 3), ("soilcolumn", 2), ("frame2d", 4)])
+def test_partitioned_equal_dof_reproduces_single_gpu_bitwise(shape, nparts):
+    """`equalDOF` across ranks: the tie group's rank assembles the shared rows from its own element rows and the ones
+    it receives, in global (FE_Element, element dof) order -- the same bits as the single-GPU run."""
+    rng = np.random.default_rng(8)
+    if shape == "brick":
+        mk, sc = (lambda: brick_periodic_equaldof(6, 4, 3, seed=41)), 2e-3
+    elif shape == "soilcolumn":
+        mk, sc = (lambda: soil_column_equaldof(24, seed=42)), 2e-3
+    else:
+        mk, sc = (lambda: frame2d_diaphragm_equaldof(4, 3, 2)), np.array((0.006, 0.003, 6e-5))
+    spec = mk()
+    mass = rng.uniform(0.01, 0.1, (spec.nn, spec.ndf))
+
+    def build(*part):
+        m = xb.DeviceModel.from_spec(mk(), setup=False); m.set_mass(spec.node_tags, mass); m.setup(1, 0, *part)
+        return m.to_device(0)
+    G = build()
+    gptr, _ = G.pattern()
+    ranks = [build(nparts, r) for r in range(nparts)]
+    assert sorted(np.concatenate([m.row_eqns() for m in ranks]).tolist()) == list(range(G.neq))
+    ids = G.ids()
+    for s in range(3):
+        u = rng.normal(0, 1.0, (spec.nn, spec.ndf)) * sc * (s + 1); u[ids < 0] = 0
+        tie(spec, u)
+        if s == 2:     # transient terms: nodal masses of every dof on a shared equation
+            for m in [G] + ranks:
+                m.set_transient(1.0, 40.0, 8.0e3)
+        lam = 0.4 * s
+        G.set_trial_disp(u); G.update(); G.apply_load(lam)
+        Ag, Bg = G.form_tangent(), G.form_unbalance()
+        for m, (A, B) in zip(ranks, _partitioned_pass(ranks, u, lam)):
+            rows = m.row_eqns()
+            assert np.array_equal(B, Bg[rows])
+            ptr, _ = m.pattern()
+            for lr, q in enumerate(rows):
+                assert np.array_equal(A[ptr[lr]:ptr[lr + 1]], Ag[gptr[q]:gptr[q + 1]])
+        G.commit()
+        for m in ranks:
+            m.commit()
+
+
 def test_partitioned_quad_and_scattered_partition():
     rng = np.random.default_rng(6)
     mk = lambda: quad_plane(12, 9, mat=J2_STEEL, lx=12.0, ly=9.0, distort=0.2, seed=2)

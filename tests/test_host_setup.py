@@ -151,10 +151,6 @@ def test_equal_dof_edge_cases():
     chain.equal_dofs = [(7, 8, [0]), (8, 9, [0])]            # node 8's dof is retained AND constrained
     with pytest.raises(xb.XaraB200Error):
         xb.DeviceModel.from_spec(chain, 0, 0)
-    part = brick_block(4, 1, 1)
-    part.equal_dofs = [(9, 10, [0])]
-    with pytest.raises(xb.XaraB200Error):                    # equalDOF on a partitioned model: refused, not approximated
-        xb.DeviceModel.from_spec(part, 0, 0, nparts=2, rank=0)
     m = xb.DeviceModel(3, 3)
     m.add_nodes([1, 2], np.zeros((2, 3)))
     with pytest.raises(xb.XaraB200Error):

@@ -12,7 +12,8 @@ import numpy as np
 import pytest
 
 import xara_b200 as xb
-from modelspec import ELASTIC, J2_STEEL, brick_block, element_graph, have_metis, metis_partition, quad_plane, soil_structure_block
+from modelspec import (ELASTIC, J2_STEEL, brick_block, brick_periodic_equaldof, element_graph, frame2d_diaphragm_equaldof, have_metis,
+                       metis_partition, quad_plane, soil_column_equaldof, soil_structure_block)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -59,6 +60,24 @@ def test_quad_partition_and_user_partition():
     spec = brick_block(4, 4, 4)
     part = (np.arange(spec.ne) * 7 % 3).astype(np.int32)          # a deliberately scattered partition
     check_partition(lambda: brick_block(4, 4, 4), 3, 0, 1, part)
+
+
+@pytest.mark.parametrize("nparts", [2, 3, 5])
+def test_equal_dof_partition(nparts):
+    """`equalDOF` on a partitioned model: the nodes of a tie group go to one rank, which owns the shared equations (once)
+    and receives the element rows of the tied nodes it holds no element of through the ordinary exchange"""
+    check_partition(lambda: brick_periodic_equaldof(5, 4, 3), nparts, 1, 0)      # x = 0 and x = lx faces: different ranks
+    check_partition(lambda: soil_column_equaldof(16), nparts, 0, 1)
+    check_partition(lambda: frame2d_diaphragm_equaldof(4, 3, 2), nparts, 1, 1)
+    spec = brick_periodic_equaldof(4, 3, 3)
+    part = (np.arange(spec.ne) * 5 % nparts).astype(np.int32)                     # scattered: tie groups span many ranks
+    ranks = check_partition(lambda: brick_periodic_equaldof(4, 3, 3), nparts, 0, 0, part)
+    # a shared equation is owned exactly once although several (node, dof) carry it
+    ids = xb.DeviceModel.from_spec(spec, 0, 0).ids()
+    shared = np.where(np.bincount(ids[ids >= 0]) > 1)[0]
+    assert len(shared) >= 10
+    owners = [sum(int(q in set(m.row_eqns().tolist())) for m in ranks) for q in shared[:20]]
+    assert owners == [1] * len(owners)
 
 
 @pytest.mark.skipif(not have_metis(), reason="oracle/_ref/libmetis_ref.so not built (needs /root/reference)")

@@ -1392,7 +1392,10 @@ __global__ void __launch_bounds__(128) assemble_B_irr_kernel(AsmView V, const do
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= V.nirr) return;
   double acc = 0.0;
-  for (long long k = V.irr_ptr[w]; k < V.irr_ptr[w + 1]; k++) acc += -Re[V.irr_roff[k]];
+  for (long long k = V.irr_ptr[w]; k < V.irr_ptr[w + 1]; k++) {
+    const long long ro = V.irr_roff[k];
+    acc += -(ro >= 0 ? Re[ro] : V.recvR[-ro - 1]);
+  }
   for (long long o = V.irr_own_ptr[w]; o < V.irr_own_ptr[w + 1]; o++) {
     const int i = V.irr_own[o];
     double ub = V.load[i] * lambda;

@@ -372,7 +372,6 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
   // (PlainHandler.cpp:129-176 warns and keeps the SP)
   const bool have_mp = !mp_r.empty();
   std::vector<int> mp_ri(mp_r.size()), mp_ci(mp_r.size());
-  if (have_mp && nparts > 1) { err = "MP constraints (equalDOF) on a partitioned model are outside the device path"; return XB_ERR_UNSUPPORTED; }
   for (size_t i = 0; i < mp_r.size(); i++) {
     mp_ri[i] = nidx(mp_r[i]); mp_ci[i] = nidx(mp_c[i]);
     if (mp_ri[i] < 0 || mp_ci[i] < 0) { err = "equalDOF references an unknown node tag"; return XB_ERR_ARG; }
@@ -529,6 +528,22 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
       int o = nparts;
       for (long long t = G.n2e_ptr[n]; t < G.n2e_ptr[n + 1]; t++) o = std::min(o, part_fe[G.n2e_fe[t]]);
       owner[n] = (o == nparts) ? 0 : o;
+    }
+    // nodes tied by an equalDOF share equations: they go to ONE rank (the lowest owner of the tie group), which then
+    // holds every slot that feeds a shared row -- local ones, and remote ones through the ordinary exchange
+    if (have_mp) {
+      std::vector<int> root(n_nodes);
+      std::iota(root.begin(), root.end(), 0);
+      auto find = [&](int x) { while (root[x] != x) { root[x] = root[root[x]]; x = root[x]; } return x; };
+      for (size_t i = 0; i < mp_ri.size(); i++) {
+        const int a = find(mp_ri[i]), b = find(mp_ci[i]);
+        if (a != b) root[std::max(a, b)] = std::min(a, b);
+      }
+      std::vector<int> gown(n_nodes, nparts);
+      for (size_t i = 0; i < mp_ri.size(); i++)
+        for (int x : {mp_ri[i], mp_ci[i]}) { const int r = find(x); gown[r] = std::min(gown[r], owner[x]); }
+      for (size_t i = 0; i < mp_ri.size(); i++)
+        for (int x : {mp_ri[i], mp_ci[i]}) owner[x] = gown[find(x)];
     }
   }
 
@@ -772,7 +787,7 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
   if (have_mp) {
     std::vector<std::pair<int, int>> own;     // (row, node*ndf+dof), DOF_Group (node) order
     for (int i = 0; i < nl; i++) for (int j = 0; j < ndf; j++)
-      if (gshared[(size_t)lnode[i] * ndf + j]) { own.push_back({row_of[(size_t)i * ndf + j], i * ndf + j}); row_of_dev[(size_t)i * ndf + j] = -1; }
+      if (owned[i] && gshared[(size_t)lnode[i] * ndf + j]) { own.push_back({row_of[(size_t)i * ndf + j], i * ndf + j}); row_of_dev[(size_t)i * ndf + j] = -1; }
     std::stable_sort(own.begin(), own.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first < b.first; });
     for (size_t u = 0; u < own.size(); u++) {
       if (u == 0 || own[u].first != own[u - 1].first) {
@@ -874,7 +889,7 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
     for (const Ent& en : ents) {
       const EleKind* k; const int* c = G.conn_of(en.fe, &k);
       irr_src.push_back(en.t * chunk + (long long)en.j * cp_stride);
-      irr_roff.push_back(n2e_roff[en.t] + en.j);
+      irr_roff.push_back(n2e_roff[en.t] >= 0 ? n2e_roff[en.t] + en.j : n2e_roff[en.t] - en.j);   // < 0: -(offset in recvR + 1)
       const size_t base = irr_cp.size();
       irr_cp.resize(base + cp_stride, 0xFFFF);
       for (int a = 0; a < k->nen; a++)
