@@ -22,7 +22,7 @@
 enum { ORC_MAT_ELASTIC_ISOTROPIC = 0, ORC_MAT_J2 = 1 };
 enum { ORC_ELE_BRICK = 0, ORC_ELE_QUAD = 1, ORC_ELE_FBC2D = 2, ORC_ELE_FBC3D = 3 };
 enum { ORC_UNI_STEEL02 = 0, ORC_UNI_CONCRETE02 = 1 };
-enum { ORC_ND_3D = 0, ORC_ND_PLANE_STRAIN = 1 };
+enum { ORC_ND_3D = 0, ORC_ND_PLANE_STRAIN = 1, ORC_ND_PLANE_STRESS = 2 };  /* PLANE_STRESS: ElasticIsotropic only */
 
 /* ======================================================================== */
 /* J2Plasticity  (SRC/material/plastic/J2Plasticity.cpp)                     */
@@ -229,6 +229,14 @@ static void el_get_tangent(const OrcElastic* m, int type, double* D) {
   double mu2 = m->E / (1.0 + m->v);
   double lam = m->v * mu2 / (1.0 - 2.0 * m->v);
   double mu = 0.50 * mu2;
+  if (type == ORC_ND_PLANE_STRESS) {   /* ElasticIsotropicPlaneStress2D::getInitialTangent (material/elastic/ElasticIsotropicPlaneStress2D.cpp) */
+    double d00 = m->E / (1.0 - m->v * m->v);
+    double d01 = m->v * d00;
+    double d22 = 0.5 * (d00 - d01);
+    memset(D, 0, 9 * sizeof(double));
+    D[0] = D[4] = d00; D[1] = D[3] = d01; D[8] = d22;
+    return;
+  }
   if (type == ORC_ND_3D) {
     memset(D, 0, 36 * sizeof(double));
     mu2 += lam;
@@ -248,6 +256,15 @@ static void el_get_stress(const OrcElastic* m, int type, double* s) {
   double mu = 0.50 * mu2;
   mu2 += lam;
   const double* e = m->epsilon;
+  if (type == ORC_ND_PLANE_STRESS) {   /* ElasticIsotropicPlaneStress2D::getStress */
+    double d00 = m->E / (1.0 - m->v * m->v);
+    double d01 = m->v * d00;
+    double d22 = 0.5 * (d00 - d01);
+    s[0] = d00 * e[0] + d01 * e[1];
+    s[1] = d01 * e[0] + d00 * e[1];
+    s[2] = d22 * e[2];
+    return;
+  }
   if (type == ORC_ND_3D) {
     s[0] = mu2 * e[0] + lam * (e[1] + e[2]);
     s[1] = mu2 * e[1] + lam * (e[0] + e[2]);
@@ -1380,7 +1397,8 @@ int orc_add_element(void* h, int kind, int tag, const int* nodeTags, int matTag,
   }
   e->mat = find_mat(m, matTag); if (e->mat < 0) return -2;
   memcpy(e->par, par, 8 * sizeof(double));
-  int type = (kind == ORC_ELE_BRICK) ? ORC_ND_3D : ORC_ND_PLANE_STRAIN;
+  int type = (kind == ORC_ELE_BRICK) ? ORC_ND_3D : ((int)par[1] == 1 ? ORC_ND_PLANE_STRESS : ORC_ND_PLANE_STRAIN);
+  if (type == ORC_ND_PLANE_STRESS && m->mat_kind[e->mat] != ORC_MAT_ELASTIC_ISOTROPIC) return -5;   /* J2PlaneStress: another return map */
   for (int i = 0; i < e->nip; i++) gp_init(&e->gp[i], m->mat_kind[e->mat], type, m->mat_par + 8 * e->mat);
   m->ne++; return 0;
 }
@@ -1703,7 +1721,7 @@ static int quad_update(OrcModel* m, OrcEle* el) {
   return ret;
 }
 /* FourNodeQuad::getTangentStiff (FourNodeQuad.cpp:226-281), getResistingForce (507-553);
- * pressure load and Q (element loads) are zero in the hot path models. */
+ * with the surface pressure load; Q (element loads) is zero in the hot path models. */
 static void quad_form(OrcModel* m, OrcEle* el, int tang_flag, double* K, double* P) {
   double thickness = el->par[0];
   if (tang_flag) {
@@ -1741,6 +1759,19 @@ static void quad_form(OrcModel* m, OrcEle* el, int tang_flag, double* K, double*
       P[ia]     -= dvol * (shp[2][alpha] * el->par[4]);
       P[ia + 1] -= dvol * (shp[2][alpha] * el->par[5]);
     }
+  }
+  /* surface pressure: FourNodeQuad::setPressureLoadAtNodes (FourNodeQuad.cpp:1206-1264), P = P - pressureLoad (:542-546) */
+  if (el->par[2] != 0.0) {
+    double pl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const double po2 = el->par[2] / 2.0;
+    for (int a = 0; a < 4; a++) {
+      int b = (a + 1) & 3;
+      const double* xa = m->crd + (size_t)el->node[a] * m->ndm; const double* xb = m->crd + (size_t)el->node[b] * m->ndm;
+      double dx = xb[0] - xa[0], dy = xb[1] - xa[1];
+      pl[2 * a] += po2 * dy; pl[2 * b] += po2 * dy;
+      pl[2 * a + 1] += po2 * -dx; pl[2 * b + 1] += po2 * -dx;
+    }
+    for (int i = 0; i < 8; i++) P[i] += pl[i] * -1.0;
   }
 }
 

@@ -331,6 +331,15 @@ def frame2d_diaphragm_equaldof(nbay=2, nstory=2, ndiv=1, **kw):
     return spec
 
 
+def quad_plane_stress_pressure(nx=8, ny=5, type_=1, pressure=3.0, distort=0.2, seed=31, mat=ELASTIC):
+    """FourNodeQuad wall, `PlaneStress` (ElasticIsotropicPlaneStress2D) or PlaneStrain, with the element's surface
+    pressure argument set (FourNodeQuad::setPressureLoadAtNodes): par = thickness, type, pressure, rho, b1, b2"""
+    spec = quad_plane(nx, ny, mat=mat, lx=float(nx), ly=float(ny), thick=0.4, distort=distort, seed=seed, body=(0.01, -0.03))
+    spec.groups[0].par[:, 1] = type_
+    spec.groups[0].par[:, 2] = pressure * (1.0 + 0.1 * np.arange(spec.ne))      # a different pressure on every element
+    return spec
+
+
 def have_glue():
     return os.path.exists(GLUE_SO)
 

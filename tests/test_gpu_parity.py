@@ -761,7 +761,7 @@ def test_partitioned_frame_matches_single_gpu():
 
 @pytest.mark.parametrize("name", ["newmark_brick_j2", "newmark_frame2d", "newmark_frame3d", "rayleigh_brick_j2",
                                   "rayleigh_quad_j2", "rayleigh_frame2d", "rayleigh_frame3d",
-                                  "rayleigh_soilcolumn_equaldof", "rayleigh_frame2d_equaldof"])
+                                  "rayleigh_soilcolumn_equaldof", "rayleigh_frame2d_equaldof", "rayleigh_quad_planestress"])
 def test_newmark_device_vs_golden_reference_history(name):
     """Newmark (displacement form, nodal masses): the device replays the history recorded from the
     reference's own Newmark integrator -- c1 K + c3 M tangent, P - M a - R unbalance, predictor,

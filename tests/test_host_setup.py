@@ -151,6 +151,9 @@ def test_equal_dof_edge_cases():
     chain.equal_dofs = [(7, 8, [0]), (8, 9, [0])]            # node 8's dof is retained AND constrained
     with pytest.raises(xb.XaraB200Error):
         xb.DeviceModel.from_spec(chain, 0, 0)
+    from modelspec import quad_plane_stress_pressure
+    with pytest.raises(xb.XaraB200Error):      # J2Plasticity's PlaneStress copy (J2PlaneStress) is not on the device path
+        xb.DeviceModel.from_spec(quad_plane_stress_pressure(3, 3, 1, 1.0, mat=J2_STEEL), 0, 0)
     m = xb.DeviceModel(3, 3)
     m.add_nodes([1, 2], np.zeros((2, 3)))
     with pytest.raises(xb.XaraB200Error):

@@ -12,7 +12,7 @@ import pytest
 from golden_cases import CASES, DISPCONTROL_CASES, NSTEPS, RAYLEIGH_CASES, TRANSIENT_CASES, ele_nd, newmark_coeffs
 from modelspec import (ELASTIC, J2_STEEL, MAT_ELASTIC, MAT_J2, ND_3D, ND_PLANE_STRAIN, OracleBackend, RefBackend,
                        brick_block, brick_periodic_equaldof, disp_control, frame2d, frame2d_diaphragm_equaldof, frame3d, have_ref,
-                       oracle_nd_path, oracle_uni_path, quad_plane, ref_nd_path, soil_column_equaldof, tie)
+                       oracle_nd_path, oracle_uni_path, quad_plane, quad_plane_stress_pressure, ref_nd_path, soil_column_equaldof, tie)
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 RTOL = 1e-12
@@ -115,6 +115,7 @@ def test_oracle_vs_live_reference(mat, numberer, soe):
         specs.append(frame3d(1, 1, 2))
         specs.append(frame2d_diaphragm_equaldof(2, 2, 1))
     specs += [soil_column_equaldof(5, mat=mat), brick_periodic_equaldof(2, 2, 2, mat=mat)]     # `equalDOF`
+    specs.append(quad_plane_stress_pressure(5, 3, 1 if mat is ELASTIC else 0, 1.5, mat=mat))      # PlaneStress (elastic), pressure
     for spec in specs:
         beam = spec.groups[0].kind in (2, 3)
         O, R = OracleBackend(spec, numberer, soe), RefBackend(spec, numberer, soe)

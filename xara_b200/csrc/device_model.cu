@@ -108,6 +108,22 @@ __device__ __forceinline__ void brick_resid_store(const GroupView& G, long long 
   out[0] = k3[0]; out[1] = k3[1]; out[2] = k3[2];
 }
 
+// Elastic plane tangent of a FourNodeQuad's material copy: ElasticIsotropicPlaneStrain2D (…PlaneStrain2D.cpp:100-131)
+// or, ps != 0, ElasticIsotropicPlaneStress2D (…PlaneStress2D.cpp getStress / getInitialTangent): D = [d00 d01 0; d01 d00 0; 0 0 d22]
+__device__ __forceinline__ void quad_elastic_D(double E, double v, bool ps, double& d00, double& d01, double& d22) {
+  if (ps) {
+    d00 = E / (1.0 - v * v);
+    d01 = v * d00;
+    d22 = 0.5 * (d00 - d01);
+  } else {
+    double mu2 = E / (1.0 + v);
+    const double lam = v * mu2 / (1.0 - 2.0 * v);
+    const double mu = 0.50 * mu2;
+    mu2 += lam;
+    d00 = mu2; d01 = lam; d22 = mu;
+  }
+}
+
 // Brick::update (Brick.cpp:718-840); one thread per Gauss point
 constexpr int UPD_XS = 50;   // per element in shared memory: X[8][3], U[8][3] + pad
 #ifndef UPD_OCC
@@ -448,14 +464,11 @@ __global__ void __launch_bounds__(128) quad_update_kernel(GroupView G, const dou
     G.sig[(size_t)1 * ngp + gp] = r.sig[1];
     G.sig[(size_t)2 * ngp + gp] = r.sig[3];
   } else {
-    const double E = __ldg(p), v = __ldg(p + 1);
-    double mu2 = E / (1.0 + v);
-    const double lam = v * mu2 / (1.0 - 2.0 * v);
-    const double mu = 0.50 * mu2;
-    mu2 += lam;
-    G.sig[(size_t)0 * ngp + gp] = mu2 * eps[0] + lam * eps[1];
-    G.sig[(size_t)1 * ngp + gp] = lam * eps[0] + mu2 * eps[1];
-    G.sig[(size_t)2 * ngp + gp] = mu * eps[2];
+    double d00, d01, d22;
+    quad_elastic_D(__ldg(p), __ldg(p + 1), __ldg(G.par + 3 * G.n + e) != 0.0, d00, d01, d22);
+    G.sig[(size_t)0 * ngp + gp] = d00 * eps[0] + d01 * eps[1];
+    G.sig[(size_t)1 * ngp + gp] = d01 * eps[0] + d00 * eps[1];
+    G.sig[(size_t)2 * ngp + gp] = d22 * eps[2];
   }
 }
 
@@ -532,12 +545,10 @@ __global__ void __launch_bounds__(128) quad_resid_kernel(GroupView G, const doub
                  dc.bK0 * j2_tangent_entry(ia[q], ib[q], bulk, shear, z, 0.0, 0.0) +
                  dc.bKc * j2_tangent_entry(ia[q], ib[q], bulk, shear, nc, c2c, c3c);
       } else {
-        const double E = __ldg(p), v = __ldg(p + 1);
-        const double mu2 = E / (1.0 + v);
-        const double lam = v * mu2 / (1.0 - 2.0 * v);
-        const double mu = 0.50 * mu2;
+        double d00, d01, d22;
+        quad_elastic_D(__ldg(p), __ldg(p + 1), __ldg(G.par + 3 * G.n + e) != 0.0, d00, d01, d22);
         const double f = dc.bK + dc.bK0 + dc.bKc;
-        D[0] = f * (mu2 + lam); D[1] = f * lam; D[2] = 0.0; D[3] = f * (mu2 + lam); D[4] = 0.0; D[5] = f * mu;
+        D[0] = f * d00; D[1] = f * d01; D[2] = 0.0; D[3] = f * d00; D[4] = 0.0; D[5] = f * d22;
       }
       s0 += D[0] * er[0] + D[1] * er[1] + D[2] * er[2];
       s1 += D[1] * er[0] + D[3] * er[1] + D[4] * er[2];
@@ -550,6 +561,21 @@ __global__ void __launch_bounds__(128) quad_resid_kernel(GroupView G, const doub
       P[2 * a] -= dvol * (shp[2][a] * b0);
       P[2 * a + 1] -= dvol * (shp[2][a] * b1);
     }
+  }
+  // surface pressure (FourNodeQuad::setPressureLoadAtNodes, FourNodeQuad.cpp:1206-1264; subtracted at :542-546)
+  const double pressure = __ldg(G.par + 4 * G.n + e);
+  if (pressure != 0.0) {
+    double pl[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const double po2 = pressure / 2.0;
+#pragma unroll
+    for (int a = 0; a < 4; a++) {       // side a -> a+1
+      const int b = (a + 1) & 3;
+      const double dx = xc[b][0] - xc[a][0], dy = xc[b][1] - xc[a][1];
+      pl[2 * a] += po2 * dy; pl[2 * b] += po2 * dy;
+      pl[2 * a + 1] += po2 * -dx; pl[2 * b + 1] += po2 * -dx;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) P[i] += pl[i] * -1.0;
   }
   if (dc.on && rho != 0.0) {
 #pragma unroll
@@ -1160,11 +1186,9 @@ __global__ void __launch_bounds__(128) quad_tangent_kernel(GroupView G, const do
       }
       D10 = D01; D20 = D02; D21 = D12;
     } else {
-      const double E = __ldg(p), v = __ldg(p + 1);
-      const double mu2 = E / (1.0 + v);
-      const double lam = v * mu2 / (1.0 - 2.0 * v);
-      const double mu = 0.50 * mu2;
-      D00 = D11 = mu2 + lam; D01 = D10 = lam; D22 = mu; D02 = D20 = D12 = D21 = 0.0;
+      double d00, d01, d22;
+      quad_elastic_D(__ldg(p), __ldg(p + 1), __ldg(G.par + 3 * G.n + e) != 0.0, d00, d01, d22);
+      D00 = D11 = d00; D01 = D10 = d01; D22 = d22; D02 = D20 = D12 = D21 = 0.0;
       if (tc.on) { const double f = tc.at + tc.a0 + tc.ac; D00 *= f; D11 *= f; D01 *= f; D10 *= f; D22 *= f; }
     }
     double sb0 = shp[0][0], sb1 = shp[1][0], sb2 = shp[2][0];
@@ -2774,6 +2798,10 @@ int xb_get_gp_response(xb_model* m, long long e, int gpt, double* stress, double
         int A6 = d.nst == 6 ? a : map3[a], B6 = d.nst == 6 ? b : map3[b];
         tangent[a * d.nst + b] = j2_tangent_entry(A6, B6, p[0], p[1], t, t[6], t[7]);
       }
+  } else if (d.kind == XB_ELE_FOURNODEQUAD && g.par[(size_t)m->h.fe_local[e] * 5 + 3] != 0.0) {   // PlaneStress
+    const double d00 = p[0] / (1.0 - p[1] * p[1]), d01 = p[1] * d00, d22 = 0.5 * (d00 - d01);
+    const double D[9] = {d00, d01, 0, d01, d00, 0, 0, 0, d22};
+    for (int i = 0; i < 9; i++) tangent[i] = D[i];
   } else {
     double mu2 = p[0] / (1.0 + p[1]);
     const double lam = p[1] * mu2 / (1.0 - 2.0 * p[1]);

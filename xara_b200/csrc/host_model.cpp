@@ -12,7 +12,7 @@
 namespace xb {
 
 static const EleKind kBrick{8, 3, 8, 6, 3};
-static const EleKind kQuad{4, 2, 4, 3, 3};  // par kept: thickness, b1, b2
+static const EleKind kQuad{4, 2, 4, 3, 5};  // par kept: thickness, b1, b2, type (0 PlaneStrain, 1 PlaneStress), pressure
 static const EleKind kBeam2d{2, 3, 0, 2, 3};  // nip is a property of the batch; par: nIP, maxIters, tol
 static const EleKind kBeam3d{2, 6, 0, 4, 6};  // par: nIP, maxIters, tol, vecxz[3]
 
@@ -180,9 +180,10 @@ int HostModel::add_elements(int kind, int n, const int* tags, const int* conn, c
     double* q = &g.par[(size_t)i * k.npar];
     if (kind == XB_ELE_STDBRICK) { q[0] = p[0]; q[1] = p[1]; q[2] = p[2]; }
     else {
-      if ((int)p[1] != 0) { err = "FourNodeQuad: only PlaneStrain on the device path"; return XB_ERR_UNSUPPORTED; }
-      if (p[2] != 0.0) { err = "FourNodeQuad: surface pressure not on the device path"; return XB_ERR_UNSUPPORTED; }
-      q[0] = p[0]; q[1] = p[4]; q[2] = p[5];
+      if ((int)p[1] != 0 && (int)p[1] != 1) { err = "FourNodeQuad: type is 0 (PlaneStrain) or 1 (PlaneStress)"; return XB_ERR_ARG; }
+      // J2Plasticity's PlaneStress copy is a different class (J2PlaneStress: its own return map), not on the device path
+      if ((int)p[1] == 1 && mats[last_idx].kind != XB_MAT_ELASTIC_ISOTROPIC) { err = "FourNodeQuad PlaneStress: ElasticIsotropic only on the device path"; return XB_ERR_UNSUPPORTED; }
+      q[0] = p[0]; q[1] = p[4]; q[2] = p[5]; q[3] = (double)(int)p[1]; q[4] = p[2];
     }
   }
   g.mat_kind = mk < 0 ? 0 : mk;
