@@ -140,7 +140,10 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
         Batch& B = batches[{XB_ELE_FOURNODEQUAD, mk}];
         B.tag.push_back(el->getTag()); B.mat.push_back(mt);
         for (int a = 0; a < 4; a++) B.conn.push_back(q->connectedExternalNodes(a));
-        const double par[6] = {q->thickness, 0.0, q->pressure, q->rho, q->b[0], q->b[1]};
+        const char* ty = q->theMaterial[0]->getType();        // the copy FourNodeQuad asked for: "PlaneStrain" | "PlaneStress"
+        const bool pstress = std::strcmp(ty, "PlaneStress") == 0;
+        if (!pstress && std::strcmp(ty, "PlaneStrain") != 0) { G.err = "glue: FourNodeQuad material copy is neither PlaneStrain nor PlaneStress"; return -4; }
+        const double par[6] = {q->thickness, pstress ? 1.0 : 0.0, q->pressure, q->rho, q->b[0], q->b[1]};
         B.par.insert(B.par.end(), par, par + 6);
       } else if (dynamic_cast<ForceBeamColumn2d*>(el) || dynamic_cast<ForceBeamColumn3d*>(el)) {
         // forceBeamColumn with nIP copies of one fibre section (Steel02 / Concrete02 fibres), Lobatto integration,

@@ -15,7 +15,8 @@ import pytest
 import xara_b200 as xb
 from golden_cases import CASES, NSTEPS, ele_nd
 from modelspec import (ELASTIC, J2_STEEL, OracleBackend, brick_block, brick_periodic_equaldof, frame2d, frame2d_diaphragm_equaldof, frame3d,
-                       have_glue, have_metis, have_ref, metis_partition, quad_plane, soil_column_equaldof, soil_structure_block, tie)
+                       have_glue, have_metis, have_ref, metis_partition, quad_plane, quad_plane_stress_pressure, soil_column_equaldof,
+                       soil_structure_block, tie)
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -240,6 +241,23 @@ def test_reference_newton_loop_drives_device_path(shape, numberer, soe):
     assert relerr(D.glue_trial_disp(), u_cpu) < 1e-8
     calls, launches = D.glue_counts()
     assert calls[0] == it_cpu.sum() and calls[3] == nsteps and launches > 0     # the device did the work
+
+
+@pytest.mark.skipif(not (have_ref() and have_glue()), reason="oracle/_ref not built (needs /root/reference)")
+def test_reference_loop_reads_plane_stress_and_pressure_out_of_the_domain():
+    """FourNodeQuad with the PlaneStress material copy and a surface pressure: the glue reads both out of the reference's
+    Domain (theMaterial[0]->getType(), pressure); the reference's own analysis on CPU and on the device path agree."""
+    from modelspec import GLUE_SO, RefBackend
+    mk = lambda: quad_plane_stress_pressure(10, 6, 1, 4.0)
+    C = RefBackend(mk(), 1, 0, dlambda=0.5, test=0, tol=1e-9, max_iter=10)
+    rc, it_cpu, nm_cpu = C.analyze_static(2)
+    assert rc == 0
+    D = RefBackend(mk(), defer_setup=True, so=GLUE_SO)
+    D.setup_glue_loadcontrol(1, 0, 0.5, test=0, tol=1e-9, max_iter=10)
+    rc, it_dev, nm_dev = D.analyze_static(2)
+    assert rc == 0 and it_dev.tolist() == it_cpu.tolist()
+    u_cpu = C.get_trial_disp()
+    assert np.abs(u_cpu).max() > 1e-3 and relerr(D.glue_trial_disp(), u_cpu) < 1e-9
 
 
 @pytest.mark.skipif(not (have_ref() and have_glue()), reason="oracle/_ref not built (needs /root/reference)")
