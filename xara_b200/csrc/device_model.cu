@@ -907,9 +907,7 @@ constexpr int BS_GV = 4 * 8 * 3 + 2;      // per Gauss point: [4 elements][8 nod
 constexpr int BS_CN = 4 * 10;             // per Gauss point: [4 elements][alpha, beta/2, gamma (x dvol), n[6], -]
 static_assert(8 * BS_GV + 8 * BS_CN + 4 * BS_XS <= 4 * BS_T, "staging regions must fit under the tile");
 
-// NW warps per CTA: 4 fills the register file with two CTAs per SM (8 warps x 254 registers); 3 leaves a quarter of
-// it free, so that CTAs of the (HBM-bound) assembly kernel can run beside this (FP64-bound) one -- used by the
-// pipelined xb_form_tangent, where the assembly of one element range overlaps the tangents of the next.
+// NW warps per CTA: 4 fills the register file with two CTAs per SM (8 warps x 240-250 registers).
 template <int MATK, int DYN, int NW = 4>
 __global__ void __launch_bounds__(NW * 32, 2) brick_tangent_sym_kernel(GroupView G, const double* __restrict__ X,
                                                                    int transpose, long long ebeg, long long eend,
@@ -1555,7 +1553,6 @@ struct xb_model {
   int tile_ahead = 2;               // XB_AHEAD: tiles the element kernel may run in front of the assembly
   int tan_per_sm = 0;               // occupancy of the brick tangent kernel (cached)
   const void* tan_kern = nullptr;
-  int tan_warps = 4;                // XB_TAN_WARPS=3: the ranged tangent launches leave room for assembly CTAs
   long long* dTask = nullptr;
   AsmView av{};
   double lambda = 0.0;
@@ -1793,7 +1790,6 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
   for (auto& e : m->ev_rows) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   m->ev_chunk.resize(h.nchunk);
   for (auto& e : m->ev_chunk) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  if (const char* t = std::getenv("XB_TAN_WARPS")) m->tan_warps = std::atoi(t) == 3 ? 3 : 4;
   if (h.tiled) {
     m->ev_asm.resize(h.nchunk);
     for (auto& e : m->ev_asm) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -2294,16 +2290,13 @@ static int launch_group_tangents(xb_model* m, DevGroup& d, long long ebeg, long 
       return XB_OK;
     }
     if (m->tangent_variant == 2 && m->h.cp_stride == 24) {   // (a node slot is 3 contiguous rows of 24)
-      // NW = 3 only where the assembly runs beside it (pipelined formTangent of a static analysis)
-      const int nw = (!tc.on && m->tan_warps == 3 && (ebeg != 0 || eend != d.v.n)) ? 3 : 4;
+      constexpr int nw = 4;   // warps per CTA (a 3-warp variant that left room for assembly CTAs bought nothing: DESIGN.md)
       const size_t sms = sizeof(double) * nw * BS_WARP;
       const long long nbat = (eend - ebeg + 3) / 4;
       auto go = [&](auto kern) -> int {
         int per_sm = m->tan_per_sm;
         if (per_sm == 0 || (const void*)kern != m->tan_kern) {   // once per kernel: these two calls cost more than a launch
           CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sms));
-          // the same L1 / shared-memory split as the assembly kernel: CTAs of two kernels share an SM only then
-          CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
           CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nw * 32, sms));
           if (per_sm < 1) per_sm = 1;
           m->tan_per_sm = per_sm; m->tan_kern = (const void*)kern;
@@ -2321,8 +2314,7 @@ static int launch_group_tangents(xb_model* m, DevGroup& d, long long ebeg, long 
         return XB_OK;
       };
       int rc = tc.on ? (j2 ? go(brick_tangent_sym_kernel<XB_MAT_J2PLASTICITY, 1>) : go(brick_tangent_sym_kernel<XB_MAT_ELASTIC_ISOTROPIC, 1>))
-                     : (nw == 3 ? (j2 ? go(brick_tangent_sym_kernel<XB_MAT_J2PLASTICITY, 0, 3>) : go(brick_tangent_sym_kernel<XB_MAT_ELASTIC_ISOTROPIC, 0, 3>))
-                                : (j2 ? go(brick_tangent_sym_kernel<XB_MAT_J2PLASTICITY, 0>) : go(brick_tangent_sym_kernel<XB_MAT_ELASTIC_ISOTROPIC, 0>)));
+                     : (j2 ? go(brick_tangent_sym_kernel<XB_MAT_J2PLASTICITY, 0>) : go(brick_tangent_sym_kernel<XB_MAT_ELASTIC_ISOTROPIC, 0>));
       if (rc < 0) return rc;
       m->launches++;
       if (tc.on && tc.cM != 0.0 && d.has_rho) {
