@@ -451,8 +451,9 @@ def test_tiled_form_tangent_matches_oracle_and_untiled_bitwise(monkeypatch):
     O.set_trial_disp(u); O.apply_load(0.7)
     Ao, Bo = O.form_tangent(), O.form_unbalance()
     res = {}
-    for tile in ("0", "2048", "9472"):
-        monkeypatch.setenv("XB_TILE", tile)
+    for tile in ("0", "2048", "9472", "fused"):
+        monkeypatch.setenv("XB_TILE", "2048" if tile == "fused" else tile)
+        monkeypatch.setenv("XB_FUSED", "1" if tile == "fused" else "0")
         D = xb.DeviceModel.from_spec(spec, 1, 0).to_device(0)
         assert np.array_equal(D.ids(), ids) and np.array_equal(D.element_tags(), O.fe_ids(24)[0])
         D.set_trial_disp(u); D.update(); D.apply_load(0.7)
@@ -466,7 +467,7 @@ def test_tiled_form_tangent_matches_oracle_and_untiled_bitwise(monkeypatch):
         D.commit()
         D.set_trial_disp(1.5 * u); D.update()
         res[tile] = (A, B, D.form_tangent(host=True), D.form_unbalance())
-    for tile in ("2048", "9472"):
+    for tile in ("2048", "9472", "fused"):
         for x, y in zip(res["0"], res[tile]):
             assert np.array_equal(x, y)
 

@@ -907,30 +907,29 @@ constexpr int BS_GV = 4 * 8 * 3 + 2;      // per Gauss point: [4 elements][8 nod
 constexpr int BS_CN = 4 * 10;             // per Gauss point: [4 elements][alpha, beta/2, gamma (x dvol), n[6], -]
 static_assert(8 * BS_GV + 8 * BS_CN + 4 * BS_XS <= 4 * BS_T, "staging regions must fit under the tile");
 
-// NW warps per CTA: 4 fills the register file with two CTAs per SM (8 warps x 240-250 registers).
-template <int MATK, int DYN, int NW = 4>
-__global__ void __launch_bounds__(NW * 32, 2) brick_tangent_sym_kernel(GroupView G, const double* __restrict__ X,
-                                                                   int transpose, long long ebeg, long long eend,
-                                                                   const double* __restrict__ tsrc_, int tzero_,
-                                                                   double scale_, int accum_) {
+// The work of warp `wid` of `nwarps` on the elements [ebeg, eend): batches wid, wid + nwarps, ... of 4 elements;
+// wbase: the warp's BS_WARP doubles of shared memory.
+template <int MATK, int DYN>
+__device__ __forceinline__ void brick_tangent_sym_range(const GroupView& G, const double* __restrict__ X,
+                                                        int transpose, long long ebeg, long long eend,
+                                                        const double* __restrict__ tsrc_, int tzero_,
+                                                        double scale_, int accum_, double* wbase, long long wid, long long nwarps) {
   // DYN = 0 (static analysis): the arguments are compile-time constants, nothing is paid for them
   const double* __restrict__ tsrc = DYN ? tsrc_ : G.tan;
   const int tzero = DYN ? tzero_ : 0, accum = DYN ? accum_ : 0;
   const double scale = DYN ? scale_ : 1.0;
   // tsrc: compact tangent to use (G.tan: current, G.tanc: committed); tzero: none, i.e. the initial (elastic)
   // tangent; scale multiplies the matrix; accum adds to what the slots hold.  Static analysis: (G.tan, 0, 1, 0).
-  extern __shared__ __align__(16) double smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31;
   const int s = lane >> 3, k = lane & 7;
-  double* wbase = smem + warp * BS_WARP;
   double* sN = wbase;
   double* sC = wbase + 8 * BS_GV;          // per Gauss point: [4 elements][alpha, beta/2, gamma (x dvol), n[6], -]
   double* sX = sC + 8 * BS_CN;
   long long* sDst = reinterpret_cast<long long*>(wbase + 4 * BS_T);
   const long long ngp = G.n * 8;
   const long long nb = (eend - ebeg + 3) >> 2;               // batches of 4 elements
-  const long long stride = (long long)gridDim.x * NW;
-  long long b = (long long)blockIdx.x * NW + warp;
+  const long long stride = nwarps;
+  long long b = wid;
   if (b >= nb) return;
   const long long elast = eend - 1;
   unsigned cpk[9];      // store loop: tile offset | node << 10 | offset in the node's slot << 13 (doubles)
@@ -1127,6 +1126,18 @@ __global__ void __launch_bounds__(NW * 32, 2) brick_tangent_sym_kernel(GroupView
   }
 }
 
+// NW warps per CTA: 4 fills the register file with two CTAs per SM (8 warps x 240-250 registers).
+template <int MATK, int DYN, int NW = 4>
+__global__ void __launch_bounds__(NW * 32, 2) brick_tangent_sym_kernel(GroupView G, const double* __restrict__ X,
+                                                                   int transpose, long long ebeg, long long eend,
+                                                                   const double* __restrict__ tsrc_, int tzero_,
+                                                                   double scale_, int accum_) {
+  extern __shared__ __align__(16) double smem[];
+  const int warp = threadIdx.x >> 5;
+  brick_tangent_sym_range<MATK, DYN>(G, X, transpose, ebeg, eend, tsrc_, tzero_, scale_, accum_, smem + warp * BS_WARP,
+                                     (long long)blockIdx.x * NW + warp, (long long)gridDim.x * NW);
+}
+
 // FourNodeQuad::getTangentStiff (FourNodeQuad.cpp:226-281).  4 lanes per element, lane b
 // owns column block beta=b (8 rows x 2 columns); shape functions are recomputed per lane.
 template <int MATK>
@@ -1276,19 +1287,15 @@ struct AsmView {
 // SL: element kinds with few dofs (cp_stride <= 16: quads 8, 2D beams 6, 3D beams 12) would leave most of a warp
 // idle at one lane per element dof, so SL = 4 or 2 consecutive slots are LOADED side by side (lane = slot * 32/SL +
 // dof) and then ADDED one after the other -- the order of additions stays the FE_Element order.
-template <int NDF, bool MP = false, int SL = 1>
-__global__ void __launch_bounds__(256, XB_ASM_OCC) assemble_A_kernel(AsmView V, const double* __restrict__ KeN,
-                                                            double* __restrict__ A, const long long* __restrict__ task,
-                                                            long long first, long long count) {
-  extern __shared__ double sacc[];  // [warps][NDF][max_row]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-  if (w >= count) return;
-  double* acc = sacc + (size_t)warp * NDF * V.max_row;
+// CG: the element rows were written earlier in the SAME kernel launch (fused formTangent): read them with ld.global.cg
+template <int NDF, bool MP, int SL, bool CG, int CHN = XB_ASM_CH>
+__device__ __forceinline__ void assemble_A_node(const AsmView& V, const double* __restrict__ KeN, double* __restrict__ A,
+                                                const long long* __restrict__ task, long long u, double* acc) {
+  const int lane = threadIdx.x & 31;
   // one record per owned node, in the order the nodes are assembled (host_model.cpp, asm_task):
   // first slot, slot count | row length << 32, node, A offset of each of its rows (-1: constrained)
   constexpr int TW = 3 + NDF;
-  const long long word = lane < TW ? __ldg(task + (first + w) * TW + lane) : 0;
+  const long long word = lane < TW ? __ldg(task + u * TW + lane) : 0;
   const long long t0 = __shfl_sync(0xffffffffu, word, 0);
   const long long pk = __shfl_sync(0xffffffffu, word, 1);
   const long long n = __shfl_sync(0xffffffffu, word, 2);
@@ -1300,7 +1307,7 @@ __global__ void __launch_bounds__(256, XB_ASM_OCC) assemble_A_kernel(AsmView V, 
   const int sub = SL == 1 ? 0 : lane / LW;          // which of the SL side-by-side slots
   const int j = SL == 1 ? lane : lane % LW;         // element dof
   const bool on = j < cps;
-  constexpr int CH = XB_ASM_CH;  // slot groups in flight together; the node's slots are one contiguous stream
+  constexpr int CH = CHN;  // slot groups in flight together; the node's slots are one contiguous stream
   const double c1 = V.c1;
   long long tb = t0;
   do {
@@ -1312,7 +1319,10 @@ __global__ void __launch_bounds__(256, XB_ASM_OCC) assemble_A_kernel(AsmView V, 
       const bool ok = on && t < t1;
       pos[c] = ok ? __ldg(V.colpos + (size_t)t * cps + j) : (unsigned short)0xFFFF;
 #pragma unroll
-      for (int p = 0; p < NDF; p++) v[c][p] = ok ? __ldg(KeN + (size_t)t * (NDF * cps) + p * cps + j) : 0.0;
+      for (int p = 0; p < NDF; p++) {
+        const double* src = KeN + (size_t)t * (NDF * cps) + p * cps + j;
+        v[c][p] = ok ? (CG ? __ldcg(src) : __ldg(src)) : 0.0;
+      }
     }
     if (tb == t0) {
       // (the first slots are already on their way) clear the rows, then the DOF_Group tangents, which
@@ -1362,6 +1372,61 @@ __global__ void __launch_bounds__(256, XB_ASM_OCC) assemble_A_kernel(AsmView V, 
     if (rp < 0) continue;
     double* out = A + rp;
     for (int c = lane; c < L; c += 32) out[c] = acc[p * V.max_row + c];
+  }
+}
+
+template <int NDF, bool MP = false, int SL = 1>
+__global__ void __launch_bounds__(256, XB_ASM_OCC) assemble_A_kernel(AsmView V, const double* __restrict__ KeN,
+                                                            double* __restrict__ A, const long long* __restrict__ task,
+                                                            long long first, long long count) {
+  extern __shared__ double sacc[];  // [warps][NDF][max_row]
+  const int warp = threadIdx.x >> 5;
+  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (w >= count) return;
+  assemble_A_node<NDF, MP, SL, false>(V, KeN, A, task, first + w, sacc + (size_t)warp * NDF * V.max_row);
+}
+
+// formTangent of a tiled brick batch in ONE persistent launch (host_model.hpp, `tiled`).  Every warp alternates between
+// its share of the element tangents of tile t and its share of the nodes tile t-1 completed; a counter per tile
+// (one count per warp) tells when a tile's rows are all written.  A tile's rows (~44 MB) are read back out of L2,
+// and the two CTAs of an SM drift apart, so that the FP64/latency-bound and the HBM-bound phase overlap.
+// All CTAs must be resident (the grid is occupancy x SMs): a warp waits for tile t-1 only after finishing its own share
+// of tile t, and no warp waits before contributing to every tile up to the one it waits for, so there is no cycle.
+template <int MATK>
+__global__ void __launch_bounds__(128, 2) brick_form_tangent_fused_kernel(GroupView G, const double* __restrict__ X, int transpose,
+                                                                          AsmView V, const double* __restrict__ KeN,
+                                                                          double* __restrict__ A, const long long* __restrict__ task,
+                                                                          const long long* __restrict__ tile_ptr,
+                                                                          const long long* __restrict__ node_ptr,
+                                                                          unsigned* done, int ntiles) {
+  extern __shared__ __align__(16) double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* wbase = smem + warp * BS_WARP;
+  const long long wid = (long long)blockIdx.x * 4 + warp, nw = (long long)gridDim.x * 4;
+  for (int t = 0; t <= ntiles; t++) {
+    if (t < ntiles) {
+      brick_tangent_sym_range<MATK, 0>(G, X, transpose, __ldg(tile_ptr + t), __ldg(tile_ptr + t + 1), G.tan, 0, 1.0, 0, wbase, wid, nw);
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) atomicAdd(done + t, 1u);
+    }
+    if (t >= 1) {
+      const long long n0 = __ldg(node_ptr + t - 1), n1 = __ldg(node_ptr + t);
+      if (n0 + wid < n1) {
+        if (lane == 0) {
+          unsigned seen;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(done + t - 1) : "memory");
+            if (seen < (unsigned)nw) __nanosleep(64);
+          } while (seen < (unsigned)nw);
+        }
+        __syncwarp();
+        for (long long u = n0 + wid; u < n1; u += nw) {
+          assemble_A_node<3, false, 1, true, 8>(V, KeN, A, task, u, wbase);   // 8 slots (a brick node) in flight: 8 warps / SM only
+          __syncwarp();
+        }
+      }
+    }
   }
 }
 
@@ -1550,6 +1615,10 @@ struct xb_model {
   cudaEvent_t ev_start = nullptr, ev_done = nullptr;
   std::vector<cudaEvent_t> ev_chunk, ev_asm;
   bool tiled_on = true;             // XB_TILED_RUN=0: keep the tiled storage order but run formTangent in one piece
+  bool fused_on = false;            // XB_FUSED=1: tiled formTangent as ONE persistent launch (brick_form_tangent_fused_kernel)
+  long long *dTilePtr = nullptr, *dNodePtr = nullptr;
+  unsigned* dDone = nullptr;
+  int fused_grid = 0;
   int tile_ahead = 2;               // XB_AHEAD: tiles the element kernel may run in front of the assembly
   int tan_per_sm = 0;               // occupancy of the brick tangent kernel (cached)
   const void* tan_kern = nullptr;
@@ -1795,6 +1864,12 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
     for (auto& e : m->ev_asm) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     if (const char* t = std::getenv("XB_TILED_RUN")) m->tiled_on = std::atoi(t) != 0;
     if (const char* t = std::getenv("XB_AHEAD")) m->tile_ahead = std::max(0, std::atoi(t));
+    if (const char* t = std::getenv("XB_FUSED")) m->fused_on = std::atoi(t) != 0;
+    if (m->fused_on) {
+      CU(dev_upload(m, &m->dTilePtr, h.tile_ptr));
+      CU(dev_upload(m, &m->dNodePtr, h.chunk_node_ptr));
+      CU(dev_alloc(m, &m->dDone, (size_t)h.nchunk + 1));
+    }
   }
   CU(dev_upload(m, &m->dLoad, h.load));
   std::vector<double> mp(h.mats.size() * 8);
@@ -2539,6 +2614,27 @@ int xb_form_tangent(xb_model* m, double* A) {
     return xb_assemble_tangent(m, A);
   }
   DevGroup& d = m->dg[0];
+  if (tiled && m->fused_on && m->h.ndf == 3 && m->h.cp_stride == 24 && m->av.max_dup == 0 && m->av.nirr == 0 &&
+      (size_t)3 * m->av.max_row <= (size_t)BS_WARP) {
+    const bool j2 = d.mat_kind == XB_MAT_J2PLASTICITY;
+    const size_t sms = sizeof(double) * 4 * BS_WARP;
+    auto kern = j2 ? brick_form_tangent_fused_kernel<XB_MAT_J2PLASTICITY> : brick_form_tangent_fused_kernel<XB_MAT_ELASTIC_ISOTROPIC>;
+    if (m->fused_grid == 0) {
+      int per_sm = 0;
+      CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sms));
+      CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, sms));
+      if (per_sm < 1) return fail(XB_ERR_CUDA, "fused formTangent kernel does not fit an SM");
+      m->fused_grid = per_sm * m->num_sms;     // every CTA resident: the kernel's warps wait for one another
+    }
+    CU(cudaMemsetAsync(m->dDone, 0, sizeof(unsigned) * ((size_t)nc + 1), m->stream));
+    const int transpose = m->h.soe_kind == XB_SOE_SPARSE_GEN_COL ? 1 : 0;
+    AsmView av = m->av;
+    kern<<<(unsigned)m->fused_grid, 128, sms, m->stream>>>(d.v, m->dX, transpose, av, m->dKe, m->dA, m->dTask, m->dTilePtr,
+                                                            m->dNodePtr, m->dDone, nc);
+    m->launches++;
+    account_element_tangent_bytes(m);
+    return finish_tangent(m, A);
+  }
   const long long per = (d.v.n + nc - 1) / nc;
   // ranges that complete a contiguous block of rows of A (the unit of the copy-out): a range itself, or -- tiled --
   // the FE-order slice its tile belongs to
