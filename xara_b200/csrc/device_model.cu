@@ -2,6 +2,7 @@
 // formation and deterministic CSR/CSC assembly, plus the C-ABI of include/xara_b200.h.
 // Compiled for sm_100a only; there is no CPU fallback anywhere in this file.
 #include <cuda_runtime.h>
+#include <cuda_pipeline.h>
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -1392,6 +1393,81 @@ __global__ void __launch_bounds__(256, XB_ASM_OCC) assemble_A_kernel(AsmView V, 
 // and the two CTAs of an SM drift apart, so that the FP64/latency-bound and the HBM-bound phase overlap.
 // All CTAs must be resident (the grid is occupancy x SMs): a warp waits for tile t-1 only after finishing its own share
 // of tile t, and no warp waits before contributing to every tile up to the one it waits for, so there is no cycle.
+// Assembly phase of the fused kernel: a warp takes its nodes four at a time.  The four task records come with one
+// load; a node's slots are ONE contiguous stream in KeN (and in colpos), so they are fetched with 16-byte asynchronous
+// copies into the warp's shared memory -- no registers, all four nodes in flight together -- and then added row by
+// row, slot by slot (FE_Element order), into the accumulator.  Static analysis only (c1 = 1, no DOF_Group terms);
+// a node with more than 8 slots takes the direct path.
+constexpr int FA_G = 4;                               // nodes in flight per warp
+constexpr int FA_ROWS = 8 * 72;                       // doubles per node: 8 slots x 3 rows x 24
+constexpr int FA_POS = 8 * 24 / 4;                    // doubles per node holding 8 x 24 uint16 positions
+constexpr int FA_ACC = 448;                           // accumulator: 3 rows x max_row (<= 149)
+constexpr int FUSED_WARP = FA_G * (FA_ROWS + FA_POS) + FA_ACC;   // 2944 doubles = 23 KB per warp
+static_assert(FUSED_WARP >= BS_WARP, "the tangent phase uses the same shared memory");
+
+__device__ __forceinline__ void fused_assemble_group(const AsmView& V, const double* __restrict__ KeN, double* __restrict__ A,
+                                                     const long long* __restrict__ task, long long u0, long long ustride,
+                                                     long long uend, double* wbase) {
+  const int lane = threadIdx.x & 31;
+  const int q_of = lane >> 3, w_of = lane & 7;
+  const long long uq = u0 + q_of * ustride;
+  const long long word = (w_of < 6 && uq < uend) ? __ldg(task + uq * 6 + w_of) : 0;
+  double* rows = wbase;
+  unsigned short* spos = reinterpret_cast<unsigned short*>(wbase + FA_G * FA_ROWS);
+  double* acc = wbase + FA_G * (FA_ROWS + FA_POS);
+  long long t0[FA_G]; int ns[FA_G], L[FA_G];
+#pragma unroll
+  for (int q = 0; q < FA_G; q++) {
+    t0[q] = __shfl_sync(0xffffffffu, word, q * 8);
+    const long long pk = __shfl_sync(0xffffffffu, word, q * 8 + 1);
+    ns[q] = (u0 + q * ustride < uend) ? (int)(pk & 0xffffffffll) : -1;     // -1: no such node
+    L[q] = (int)(pk >> 32);
+    if (ns[q] > 0 && ns[q] <= 8) {
+      const double* src = KeN + (size_t)t0[q] * 72;
+      double* dst = rows + q * FA_ROWS;
+      for (int i = lane; i < ns[q] * 36; i += 32) __pipeline_memcpy_async(dst + 2 * i, src + 2 * i, 16);
+      const unsigned short* psrc = V.colpos + (size_t)t0[q] * 24;
+      unsigned short* pdst = spos + q * (8 * 24);
+      for (int i = lane; i < ns[q] * 3; i += 32) __pipeline_memcpy_async(pdst + 8 * i, psrc + 8 * i, 16);
+    }
+  }
+  __pipeline_commit();
+  __pipeline_wait_prior(0);
+  __syncwarp();
+#pragma unroll 1
+  for (int q = 0; q < FA_G; q++) {
+    if (ns[q] < 0) break;
+    if (ns[q] > 8) {       // rare: more than 8 elements at a node
+      assemble_A_node<3, false, 1, true>(V, KeN, A, task, u0 + q * ustride, acc);
+      __syncwarp();
+      continue;
+    }
+    const int Lq = ns[q] == 0 ? 1 : L[q];
+    for (int c = lane; c < 3 * Lq; c += 32) acc[(c / Lq) * V.max_row + (c % Lq)] = 0.0;
+    __syncwarp();
+    const double* r = rows + q * FA_ROWS;
+    const unsigned short* ps = spos + q * (8 * 24);
+    for (int c = 0; c < ns[q]; c++) {          // FE_Element order: the order addA is called in
+      if (lane < 24) {
+        const unsigned short pos = ps[c * 24 + lane];
+        if (pos != 0xFFFF) {
+#pragma unroll
+          for (int p = 0; p < 3; p++) acc[p * V.max_row + pos] += r[c * 72 + p * 24 + lane];
+        }
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int p = 0; p < 3; p++) {
+      const long long rp = __shfl_sync(0xffffffffu, word, q * 8 + 3 + p);
+      if (rp < 0) continue;
+      double* out = A + rp;
+      for (int c = lane; c < Lq; c += 32) out[c] = acc[p * V.max_row + c];
+    }
+    __syncwarp();
+  }
+}
+
 template <int MATK>
 __global__ void __launch_bounds__(128, 2) brick_form_tangent_fused_kernel(GroupView G, const double* __restrict__ X, int transpose,
                                                                           AsmView V, const double* __restrict__ KeN,
@@ -1401,7 +1477,7 @@ __global__ void __launch_bounds__(128, 2) brick_form_tangent_fused_kernel(GroupV
                                                                           unsigned* done, int ntiles) {
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* wbase = smem + warp * BS_WARP;
+  double* wbase = smem + warp * FUSED_WARP;
   const long long wid = (long long)blockIdx.x * 4 + warp, nw = (long long)gridDim.x * 4;
   for (int t = 0; t <= ntiles; t++) {
     if (t < ntiles) {
@@ -1421,8 +1497,8 @@ __global__ void __launch_bounds__(128, 2) brick_form_tangent_fused_kernel(GroupV
           } while (seen < (unsigned)nw);
         }
         __syncwarp();
-        for (long long u = n0 + wid; u < n1; u += nw) {
-          assemble_A_node<3, false, 1, true, 8>(V, KeN, A, task, u, wbase);   // 8 slots (a brick node) in flight: 8 warps / SM only
+        for (long long u = n0 + wid; u < n1; u += FA_G * nw) {
+          fused_assemble_group(V, KeN, A, task, u, nw, n1, wbase);
           __syncwarp();
         }
       }
@@ -2615,9 +2691,9 @@ int xb_form_tangent(xb_model* m, double* A) {
   }
   DevGroup& d = m->dg[0];
   if (tiled && m->fused_on && m->h.ndf == 3 && m->h.cp_stride == 24 && m->av.max_dup == 0 && m->av.nirr == 0 &&
-      (size_t)3 * m->av.max_row <= (size_t)BS_WARP) {
+      3 * m->av.max_row <= FA_ACC && m->av.c1 == 1.0 && m->av.c2 == 0.0 && m->av.c3 == 0.0) {
     const bool j2 = d.mat_kind == XB_MAT_J2PLASTICITY;
-    const size_t sms = sizeof(double) * 4 * BS_WARP;
+    const size_t sms = sizeof(double) * 4 * FUSED_WARP;
     auto kern = j2 ? brick_form_tangent_fused_kernel<XB_MAT_J2PLASTICITY> : brick_form_tangent_fused_kernel<XB_MAT_ELASTIC_ISOTROPIC>;
     if (m->fused_grid == 0) {
       int per_sm = 0;
