@@ -478,9 +478,13 @@ __global__ void __launch_bounds__(128) quad_update_kernel(GroupView G, const dou
 // =====================================================================================
 
 // FourNodeQuad::getResistingForce (FourNodeQuad.cpp:507-553); thread per element
-template <int MATK>
-__global__ void __launch_bounds__(128) quad_resid_kernel(GroupView G, const double* __restrict__ X, DynCoef dc,
+// DYN = 0 (static analysis): the inertia / damping terms are compiled out (154 -> far fewer registers: the kernel is
+// latency-bound and lives on occupancy)
+template <int MATK, int DYN>
+__global__ void __launch_bounds__(128, DYN ? 1 : 5) quad_resid_kernel(GroupView G, const double* __restrict__ X, DynCoef dc_,
                                                          const double* __restrict__ V, const double* __restrict__ A) {
+  DynCoef dc = dc_;
+  if (!DYN) { dc.on = 0; dc.aM = dc.bK = dc.bK0 = dc.bKc = 0.0; }
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= G.n) return;
   const long long ngp = G.n * 4;
@@ -496,9 +500,9 @@ __global__ void __launch_bounds__(128) quad_resid_kernel(GroupView G, const doub
   // FourNodeQuad::getResistingForceIncInertia (FourNodeQuad.cpp:556): P + M a (lumped) + D v
   double vel[4][2], md[4] = {0, 0, 0, 0};
   const double* p = G.mpar + (size_t)__ldg(G.mat + e) * 8;
-  const double rho = dc.on ? __ldg(p + (MATK == XB_MAT_J2PLASTICITY ? 7 : 2)) : 0.0;
-  const bool stiff_damp = dc.on && (dc.bK != 0.0 || dc.bK0 != 0.0 || dc.bKc != 0.0);
-  if (dc.on) {
+  const double rho = (DYN && dc.on) ? __ldg(p + (MATK == XB_MAT_J2PLASTICITY ? 7 : 2)) : 0.0;
+  const bool stiff_damp = DYN && dc.on && (dc.bK != 0.0 || dc.bK0 != 0.0 || dc.bKc != 0.0);
+  if (DYN && dc.on) {
 #pragma unroll
     for (int a = 0; a < 4; a++) {
       const int nd = __ldg(c + a);
@@ -513,7 +517,7 @@ __global__ void __launch_bounds__(128) quad_resid_kernel(GroupView G, const doub
     dvol *= th;
     double s0 = G.sig[(size_t)0 * ngp + e * 4 + i], s1 = G.sig[(size_t)1 * ngp + e * 4 + i],
            s2 = G.sig[(size_t)2 * ngp + e * 4 + i];
-    if (dc.on) {
+    if (DYN && dc.on) {
 #pragma unroll
       for (int a = 0; a < 4; a++) md[a] += shp[2][a] * (dvol * rho);
     }
@@ -578,7 +582,7 @@ __global__ void __launch_bounds__(128) quad_resid_kernel(GroupView G, const doub
 #pragma unroll
     for (int i = 0; i < 8; i++) P[i] += pl[i] * -1.0;
   }
-  if (dc.on && rho != 0.0) {
+  if (DYN && dc.on && rho != 0.0) {
 #pragma unroll
     for (int a = 0; a < 4; a++) {
       const int nd = __ldg(c + a);
@@ -1141,9 +1145,9 @@ __global__ void __launch_bounds__(NW * 32, 2) brick_tangent_sym_kernel(GroupView
 
 // FourNodeQuad::getTangentStiff (FourNodeQuad.cpp:226-281).  4 lanes per element, lane b
 // owns column block beta=b (8 rows x 2 columns); shape functions are recomputed per lane.
-template <int MATK>
-__global__ void __launch_bounds__(128) quad_tangent_kernel(GroupView G, const double* __restrict__ X,
-                                                           int transpose, TanCoef tc) {
+template <int MATK, int DYN>
+__global__ void __launch_bounds__(128, DYN ? 1 : 5) quad_tangent_kernel(GroupView G, const double* __restrict__ X,
+                                                                     int transpose, TanCoef tc) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long e = t >> 2;
   const int beta = (int)(t & 3);
@@ -1180,7 +1184,7 @@ __global__ void __launch_bounds__(128) quad_tangent_kernel(GroupView G, const do
       D00 = j2_tangent_entry(0, 0, bulk, shear, n, c2, c3); D01 = j2_tangent_entry(0, 1, bulk, shear, n, c2, c3);
       D02 = j2_tangent_entry(0, 3, bulk, shear, n, c2, c3); D11 = j2_tangent_entry(1, 1, bulk, shear, n, c2, c3);
       D12 = j2_tangent_entry(1, 3, bulk, shear, n, c2, c3); D22 = j2_tangent_entry(3, 3, bulk, shear, n, c2, c3);
-      if (tc.on) {   // at Dt + a0 D0 + ac Dc
+      if (DYN && tc.on) {   // at Dt + a0 D0 + ac Dc
         double z[6] = {0, 0, 0, 0, 0, 0}, nc[6] = {0, 0, 0, 0, 0, 0}, c2c = 0.0, c3c = 0.0;
         if (tc.ac != 0.0) {
 #pragma unroll
@@ -1199,13 +1203,13 @@ __global__ void __launch_bounds__(128) quad_tangent_kernel(GroupView G, const do
       double d00, d01, d22;
       quad_elastic_D(__ldg(p), __ldg(p + 1), __ldg(G.par + 3 * G.n + e) != 0.0, d00, d01, d22);
       D00 = D11 = d00; D01 = D10 = d01; D22 = d22; D02 = D20 = D12 = D21 = 0.0;
-      if (tc.on) { const double f = tc.at + tc.a0 + tc.ac; D00 *= f; D11 *= f; D01 *= f; D10 *= f; D22 *= f; }
+      if (DYN && tc.on) { const double f = tc.at + tc.a0 + tc.ac; D00 *= f; D11 *= f; D01 *= f; D10 *= f; D22 *= f; }
     }
     double sb0 = shp[0][0], sb1 = shp[1][0], sb2 = shp[2][0];
 #pragma unroll
     for (int b = 1; b < 4; b++) if (beta == b) { sb0 = shp[0][b]; sb1 = shp[1][b]; sb2 = shp[2][b]; }
     // FourNodeQuad::getMass (FourNodeQuad.cpp:387): lumped, N_beta rho dvol on both dofs of node beta
-    if (tc.on) mdiag += sb2 * (dvol * __ldg(p + (MATK == XB_MAT_J2PLASTICITY ? 7 : 2)));
+    if (DYN && tc.on) mdiag += sb2 * (dvol * __ldg(p + (MATK == XB_MAT_J2PLASTICITY ? 7 : 2)));
     const double DB00 = dvol * (D00 * sb0 + D02 * sb1), DB10 = dvol * (D10 * sb0 + D12 * sb1),
                  DB20 = dvol * (D20 * sb0 + D22 * sb1), DB01 = dvol * (D01 * sb1 + D02 * sb0),
                  DB11 = dvol * (D11 * sb1 + D12 * sb0), DB21 = dvol * (D21 * sb1 + D22 * sb0);
@@ -1217,7 +1221,7 @@ __global__ void __launch_bounds__(128) quad_tangent_kernel(GroupView G, const do
       K[2 * a + 1][1] += shp[1][a] * DB11 + shp[0][a] * DB21;
     }
   }
-  if (tc.on && tc.cM != 0.0) {
+  if (DYN && tc.on && tc.cM != 0.0) {
 #pragma unroll
     for (int b = 0; b < 4; b++) if (beta == b) { K[2 * b][0] += tc.cM * mdiag; K[2 * b + 1][1] += tc.cM * mdiag; }
   }
@@ -1347,6 +1351,7 @@ __device__ __forceinline__ void assemble_A_node(const AsmView& V, const double* 
     for (int c = 0; c < CH; c++) {   // FE_Element order: the order addA is called in
 #pragma unroll
       for (int sl = 0; sl < SL; sl++) {
+        if (SL > 1 && tb + c * SL + sl >= t1) break;     // (warp-uniform) no such slot
         const bool mine = (SL == 1 || sub == sl) && pos[c] != 0xFFFF;
         if (!MP) {
           if (mine) {
@@ -2484,8 +2489,13 @@ static int launch_group_tangents(xb_model* m, DevGroup& d, long long ebeg, long 
     }
   } else {
     const unsigned blocks = (unsigned)((d.v.n * 4 + 127) / 128);
-    if (j2) quad_tangent_kernel<XB_MAT_J2PLASTICITY><<<blocks, 128, 0, st>>>(d.v, m->dX, transpose, tc);
-    else quad_tangent_kernel<XB_MAT_ELASTIC_ISOTROPIC><<<blocks, 128, 0, st>>>(d.v, m->dX, transpose, tc);
+    if (tc.on) {
+      if (j2) quad_tangent_kernel<XB_MAT_J2PLASTICITY, 1><<<blocks, 128, 0, st>>>(d.v, m->dX, transpose, tc);
+      else quad_tangent_kernel<XB_MAT_ELASTIC_ISOTROPIC, 1><<<blocks, 128, 0, st>>>(d.v, m->dX, transpose, tc);
+    } else {
+      if (j2) quad_tangent_kernel<XB_MAT_J2PLASTICITY, 0><<<blocks, 128, 0, st>>>(d.v, m->dX, transpose, tc);
+      else quad_tangent_kernel<XB_MAT_ELASTIC_ISOTROPIC, 0><<<blocks, 128, 0, st>>>(d.v, m->dX, transpose, tc);
+    }
   }
   m->launches++;
   return XB_OK;
@@ -2797,8 +2807,17 @@ int xb_form_element_resids(xb_model* m) {
       }
       continue;
     }
-    if (d.mat_kind == XB_MAT_J2PLASTICITY) quad_resid_kernel<XB_MAT_J2PLASTICITY><<<(unsigned)((d.v.n + 127) / 128), 128, 0, m->stream>>>(d.v, m->dX, dc, m->dV, m->dAcc);
-    else quad_resid_kernel<XB_MAT_ELASTIC_ISOTROPIC><<<(unsigned)((d.v.n + 127) / 128), 128, 0, m->stream>>>(d.v, m->dX, dc, m->dV, m->dAcc);
+    {
+      const unsigned qb = (unsigned)((d.v.n + 127) / 128);
+      const bool qj2 = d.mat_kind == XB_MAT_J2PLASTICITY;
+      if (dc.on) {
+        if (qj2) quad_resid_kernel<XB_MAT_J2PLASTICITY, 1><<<qb, 128, 0, m->stream>>>(d.v, m->dX, dc, m->dV, m->dAcc);
+        else quad_resid_kernel<XB_MAT_ELASTIC_ISOTROPIC, 1><<<qb, 128, 0, m->stream>>>(d.v, m->dX, dc, m->dV, m->dAcc);
+      } else {
+        if (qj2) quad_resid_kernel<XB_MAT_J2PLASTICITY, 0><<<qb, 128, 0, m->stream>>>(d.v, m->dX, dc, m->dV, m->dAcc);
+        else quad_resid_kernel<XB_MAT_ELASTIC_ISOTROPIC, 0><<<qb, 128, 0, m->stream>>>(d.v, m->dX, dc, m->dV, m->dAcc);
+      }
+    }
     m->launches++;
     bytes += d.ngp * 8 * d.nst + d.v.n * ((long long)d.nd * 8 + (d.nd / m->h.ndf) * 4);
   }
