@@ -1333,7 +1333,9 @@ __device__ __forceinline__ void assemble_A_node(const AsmView& V, const double* 
       // (the first slots are already on their way) clear the rows, then the DOF_Group tangents, which
       // are added before the elements' (TransientIntegrator.cpp:89-107):
       // Newmark::formNodTangent = c2 * (alphaM * M) + c3 * M on the diagonal
-      for (int c = lane; c < NDF * L; c += 32) acc[(c / L) * V.max_row + (c % L)] = 0.0;
+#pragma unroll
+      for (int p = 0; p < NDF; p++)
+        for (int c = lane; c < L; c += 32) acc[p * V.max_row + c] = 0.0;     // (no division by the run-time L)
       __syncwarp();
       if ((V.c2 != 0.0 || V.c3 != 0.0) && lane < NDF) {
         const unsigned short dp = V.diagpos[n * NDF + lane];
