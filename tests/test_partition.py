@@ -119,10 +119,11 @@ import os, sys
 sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
 import numpy as np, torch, torch.distributed as dist
 import xara_b200 as xb
-from modelspec import brick_block
+from modelspec import brick_block, brick_periodic_equaldof
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
 rank = dist.get_rank()
-m = xb.DeviceModel.from_spec(brick_block(6, 5, 4, distort=0.1), 1, 0, 2, rank)
+mk = brick_periodic_equaldof if sys.argv[2] == "equaldof" else (lambda nx, ny, nz: brick_block(nx, ny, nz, distort=0.1))
+m = xb.DeviceModel.from_spec(mk(6, 5, 4), 1, 0, 2, rank)
 # every rank computed the same global numbering and partition
 part = torch.from_numpy(m.partition(120).astype(np.int64)); ref = part.clone(); dist.broadcast(ref, 0)
 assert torch.equal(part, ref)
@@ -140,12 +141,13 @@ dist.barrier(); print("rank", rank, "ok", m.nrows, m.ne, c.tolist())
 '''
 
 
-def test_two_ranks_over_gloo(tmp_path):
+@pytest.mark.parametrize("model", ["plain", "equaldof"])
+def test_two_ranks_over_gloo(tmp_path, model):
     import socket
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     script = tmp_path / "worker.py"
     script.write_text(WORKER.format(root=ROOT, port=port))
-    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), model], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                               text=True) for r in range(2)]
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for p, o in zip(procs, outs):
