@@ -57,9 +57,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.p.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """samples taken between t0 and t1 (the timed region, with 0.1 s of margin); a region shorter than the
+        sampling period falls back on the sample closest to it"""
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -68,10 +70,15 @@ class ClockSampler:
             self.p.wait(timeout=2)
         except Exception:
             self.p.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = [(t, r) for t, r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        if t0 is not None and rows:
+            inside = [(t, r) for t, r in rows if t0 - 0.1 <= t <= t1 + 0.1]
+            rows = inside or [min(rows, key=lambda tr: abs(tr[0] - 0.5 * (t0 + t1)))]
+        rows = [r for _, r in rows]
+        sm = [float(r[1]) for r in rows]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in rows for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": reasons}
 
@@ -249,6 +256,11 @@ def ours_main(a):
         dist.broadcast_object_list(box, 0)
         D.comm_init(box[0])
     t_upload = time.time() - t0
+    # clocks / throttle reasons: ONE nvidia-smi loop (rank 0's GPU), started well before the warm-up so that its NVML
+    # set-up is over when the timed region begins (eight of them starting inside a 20 ms region showed as jitter)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     ids = D.ids()
     u = displacement_field_for(spec, spec.crd[D.node_tags() - 1], a.workload); u[ids < 0] = 0.0
     nip = {"brick": 8, "quad": 4, "frame": 5, "frame3d": 4}[a.workload]
@@ -277,9 +289,9 @@ def ours_main(a):
     D.synchronize()
 
     # ---- the timed region: K passes of the hot path through the public calls ----
-    clocks = ClockSampler(local); clocks.start()
     l0 = D.launch_count()
     barrier()
+    t_wall0 = time.time()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record(stream)
     for k in range(a.steps):
@@ -287,9 +299,10 @@ def ours_main(a):
     end.record(stream)
     barrier()
     D.synchronize()
+    t_wall1 = time.time()
     total_ms = start.elapsed_time(end)
     launches = D.launch_count() - l0
-    clk = clocks.stop()
+    clk = clocks.stop(t_wall0, t_wall1)
 
     # ---- the same K passes again with an event between the phases (formTangent un-pipelined here,
     # so that each kernel's own duration is seen): per-kernel times for the roofline ----
