@@ -48,8 +48,8 @@ enum {
 enum {
   XB_ELE_STDBRICK = 0,    /* element/Brick/Brick.cpp, 8 nodes x 3 dof, 2x2x2 Gauss; par = b1,b2,b3 */
   XB_ELE_FOURNODEQUAD = 1,/* element/Plane/FourNodeQuad.cpp, 4 nodes x 2 dof, 2x2 Gauss;
-                             par = thickness, type (0 PlaneStrain, 1 PlaneStress: ElasticIsotropic only --
-                             J2Plasticity's PlaneStress copy is another class), surface pressure
+                             par = thickness, type (0 PlaneStrain, 1 PlaneStress; with J2Plasticity the copy is
+                             J2PlaneStrain / J2PlaneStress: one type per xb_add_elements call), surface pressure
                              (setPressureLoadAtNodes, FourNodeQuad.cpp:1206), rho (unused: the material's), b1, b2 */
   XB_ELE_FORCEBEAMCOLUMN2D = 2,/* element/Frame/Other/Force/ForceBeamColumn2d.cpp, 2 nodes x 3 dof, Lobatto
                              integration, Linear transformation; mat_tags name the fibre section;

@@ -22,7 +22,7 @@
 enum { ORC_MAT_ELASTIC_ISOTROPIC = 0, ORC_MAT_J2 = 1 };
 enum { ORC_ELE_BRICK = 0, ORC_ELE_QUAD = 1, ORC_ELE_FBC2D = 2, ORC_ELE_FBC3D = 3 };
 enum { ORC_UNI_STEEL02 = 0, ORC_UNI_CONCRETE02 = 1 };
-enum { ORC_ND_3D = 0, ORC_ND_PLANE_STRAIN = 1, ORC_ND_PLANE_STRESS = 2 };  /* PLANE_STRESS: ElasticIsotropic only */
+enum { ORC_ND_3D = 0, ORC_ND_PLANE_STRAIN = 1, ORC_ND_PLANE_STRESS = 2 };
 
 /* ======================================================================== */
 /* J2Plasticity  (SRC/material/plastic/J2Plasticity.cpp)                     */
@@ -34,6 +34,7 @@ typedef struct {
   double epsilon_p_n[3][3], epsilon_p_nplus1[3][3], xi_n, xi_nplus1;
   /* response, J2Plasticity.h:139-144 */
   double stress[3][3], tangent[3][3][3][3], strain[3][3];
+  double commitEps22;   /* J2PlaneStress (material/Plane/J2PlaneStress.h): the out-of-plane strain at the last commit */
 } OrcJ2;
 
 /* SRC/matrix/identity.h: rank-4 I (x) I and the deviatoric projector */
@@ -176,12 +177,40 @@ static void j2_init(OrcJ2* m, const double* p) {
 /* J2ThreeDimensional::setTrialStrain (J2ThreeDimensional.cpp:118-136) and
  * J2PlaneStrain::setTrialStrain (material/Plane/J2PlaneStrain.cpp:80-92) */
 static int j2_set_trial_strain(OrcJ2* m, int type, const double* e, double dt) {
-  memset(m->strain, 0, sizeof m->strain);
+  if (type != ORC_ND_PLANE_STRESS) memset(m->strain, 0, sizeof m->strain);
   if (type == ORC_ND_3D) {
     m->strain[0][0] = e[0]; m->strain[1][1] = e[1]; m->strain[2][2] = e[2];
     m->strain[0][1] = 0.50 * e[3]; m->strain[1][0] = m->strain[0][1];
     m->strain[1][2] = 0.50 * e[4]; m->strain[2][1] = m->strain[1][2];
     m->strain[2][0] = 0.50 * e[5]; m->strain[0][2] = m->strain[2][0];
+  } else if (type == ORC_ND_PLANE_STRESS) {
+    /* J2PlaneStress::setTrialStrain (material/Plane/J2PlaneStress.cpp:123-180): the out-of-plane strain of the LAST
+     * TRIAL is kept, then iterated until sigma_22 = 0 (|sigma_22| <= 1e-8 sigma_0, at most 26 integrator calls; the
+     * integrator's return value is not looked at); the tangent is condensed in place */
+    const double tolerance = 1.0e-8 * m->sigma_0;
+    const int max_iterations = 25;
+    int iteration_counter = 0;
+    const double eps22 = m->strain[2][2];
+    memset(m->strain, 0, sizeof m->strain);
+    m->strain[0][0] = e[0]; m->strain[1][1] = e[1];
+    m->strain[0][1] = 0.50 * e[2]; m->strain[1][0] = m->strain[0][1];
+    m->strain[2][2] = eps22;
+    do {
+      j2_plastic_integrator(m, dt);
+      m->strain[2][2] -= m->stress[2][2] / m->tangent[2][2][2][2];
+      iteration_counter++;
+      if (iteration_counter > max_iterations) break;
+    } while (fabs(m->stress[2][2]) > tolerance);
+    static const int PI[3] = {0, 1, 0}, PJ[3] = {0, 1, 1};
+    for (int ii = 0; ii < 3; ii++)
+      for (int jj = 0; jj < 3; jj++) {
+        const int i = PI[ii], j = PJ[ii], k = PI[jj], l = PJ[jj];
+        m->tangent[i][j][k][l] -= m->tangent[i][j][2][2] * m->tangent[2][2][k][l] / m->tangent[2][2][2][2];
+        m->tangent[j][i][k][l] = m->tangent[i][j][k][l];
+        m->tangent[i][j][l][k] = m->tangent[i][j][k][l];
+        m->tangent[j][i][l][k] = m->tangent[i][j][k][l];
+      }
+    return 0;
   } else {
     m->strain[0][0] = e[0]; m->strain[1][1] = e[1];
     m->strain[0][1] = 0.50 * e[2]; m->strain[1][0] = m->strain[0][1];
@@ -329,13 +358,14 @@ static void gp_get_tangent(const OrcGP* g, double* D) {
   if (g->kind == ORC_MAT_J2) j2_get_tangent(&g->u.j2, g->type, D); else el_get_tangent(&g->u.el, g->type, D);
 }
 static void gp_commit(OrcGP* g) {
-  if (g->kind == ORC_MAT_J2) j2_commit(&g->u.j2);
+  if (g->kind == ORC_MAT_J2) { j2_commit(&g->u.j2); if (g->type == ORC_ND_PLANE_STRESS) g->u.j2.commitEps22 = g->u.j2.strain[2][2]; }   /* J2PlaneStress::commitState */
   else memcpy(g->u.el.Cepsilon, g->u.el.epsilon, sizeof g->u.el.epsilon);
 }
 static void gp_revert(OrcGP* g) {
   /* J2Plasticity::revertToLastCommit is a no-op (J2Plasticity.cpp:546-550);
    * ElasticIsotropicThreeDimensional.cpp:139-144 restores epsilon */
   if (g->kind != ORC_MAT_J2) memcpy(g->u.el.epsilon, g->u.el.Cepsilon, sizeof g->u.el.epsilon);
+  else if (g->type == ORC_ND_PLANE_STRESS) g->u.j2.strain[2][2] = g->u.j2.commitEps22;   /* J2PlaneStress::revertToLastCommit */
 }
 
 /* material-level strain path; mirrors ref_nd_path in ref_harness.cpp */
@@ -1324,6 +1354,7 @@ int orc_add_fiber_section3d(void* h, int tag, int nf, const double* y, const dou
 static int beam_update(OrcBeam* b, const double* ug, const double* dug);
 static int find_mat(const OrcModel* m, int tag) { for (int i = 0; i < m->nmat; i++) if (m->mat_tag[i] == tag) return i; return -1; }
 
+static int quad_update(OrcModel* m, OrcEle* el);
 int orc_add_element(void* h, int kind, int tag, const int* nodeTags, int matTag, const double* par) {
   OrcModel* m = (OrcModel*)h;
   if (m->ne == m->ecap) { m->ecap = m->ecap ? 2 * m->ecap : 64; m->ele = (OrcEle*)realloc(m->ele, sizeof(OrcEle) * m->ecap); }
@@ -1398,8 +1429,9 @@ int orc_add_element(void* h, int kind, int tag, const int* nodeTags, int matTag,
   e->mat = find_mat(m, matTag); if (e->mat < 0) return -2;
   memcpy(e->par, par, 8 * sizeof(double));
   int type = (kind == ORC_ELE_BRICK) ? ORC_ND_3D : ((int)par[1] == 1 ? ORC_ND_PLANE_STRESS : ORC_ND_PLANE_STRAIN);
-  if (type == ORC_ND_PLANE_STRESS && m->mat_kind[e->mat] != ORC_MAT_ELASTIC_ISOTROPIC) return -5;   /* J2PlaneStress: another return map */
   for (int i = 0; i < e->nip; i++) gp_init(&e->gp[i], m->mat_kind[e->mat], type, m->mat_par + 8 * e->mat);
+  /* Domain::addElement calls element->update() (Domain.cpp:391): J2PlaneStress condenses its tangent there */
+  if (type == ORC_ND_PLANE_STRESS && m->mat_kind[e->mat] == ORC_MAT_J2) quad_update(m, e);
   m->ne++; return 0;
 }
 int orc_add_load(void* h, int nodeTag, const double* v) {

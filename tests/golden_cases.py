@@ -25,6 +25,7 @@ CASES = {
     "equaldof_frame2d_plain_csr": (lambda: frame2d_diaphragm_equaldof(3, 2, 2, nip=4), 0, 1, (0.008, 0.002, 5e-5)),
     # FourNodeQuad with the PlaneStress material copy (ElasticIsotropicPlaneStress2D) and surface pressure
     "quad_planestress_pressure_rcm_csc": (lambda: quad_plane_stress_pressure(8, 5, 1, 3.0), 1, 0, 2e-2),
+    "quad_planestress_j2_rcm_csr": (lambda: quad_plane_stress_pressure(6, 4, 1, -2.0, mat=J2_STEEL, seed=35), 1, 1, 2e-3),
     "quad_planestrain_pressure_j2_plain_csr": (lambda: quad_plane_stress_pressure(6, 4, 0, -2.0, mat=J2_STEEL, seed=32), 0, 1, 2e-3),
 }
 NSTEPS = 3
@@ -64,6 +65,7 @@ RAYLEIGH_CASES = {
                          _uniform_mass(0.05), 0.5, 0.25, 0.02, RAYLEIGH),
     "rayleigh_frame2d": (lambda: frame2d(2, 2, 2, lateral=30.0), _uniform_mass(0.05, 0.0), 0.5, 0.25, 0.02, RAYLEIGH),
     "rayleigh_frame3d": (lambda: frame3d(1, 1, 2, ndiv=2, lateral=(25.0, 15.0)), _uniform_mass(0.05, 0.0), 0.5, 0.25, 0.02, RAYLEIGH),
+    "rayleigh_quad_planestress_j2": (lambda: quad_plane_stress_pressure(6, 4, 1, 2.5, mat=J2_STEEL_RHO, seed=36), _uniform_mass(0.05), 0.5, 0.25, 0.02, RAYLEIGH),
     "rayleigh_quad_planestress": (lambda: quad_plane_stress_pressure(6, 4, 1, 2.5, seed=33), _uniform_mass(0.05), 0.5, 0.25, 0.02, RAYLEIGH),
     # with `equalDOF`: the nodal masses / nodal unbalance of every dof on a shared equation, in DOF_Group order
     "rayleigh_soilcolumn_equaldof": (lambda: soil_column_equaldof(6, mat=J2_STEEL_RHO), _uniform_mass(0.05), 0.5, 0.25, 0.02, RAYLEIGH),

@@ -27,7 +27,7 @@ GLUE_SO = os.path.join(ROOT, "oracle", "_ref", "libref_glue.so")
 MAT_ELASTIC, MAT_J2 = 0, 1
 ELE_BRICK, ELE_QUAD, ELE_FBC2D, ELE_FBC3D = 0, 1, 2, 3
 UNI_STEEL02, UNI_CONCRETE02 = 0, 1
-ND_3D, ND_PLANE_STRAIN = 0, 1
+ND_3D, ND_PLANE_STRAIN, ND_PLANE_STRESS = 0, 1, 2
 NUMBERER_PLAIN, NUMBERER_RCM = 0, 1
 SOE_CSC, SOE_CSR = 0, 1
 
@@ -621,7 +621,7 @@ def ref_nd_path(kind, p, type_, strains, commit):
     commit = np.ascontiguousarray(commit, np.int32)
     pp = np.zeros(8); pp[:len(p)] = p
     s = np.zeros((n, order)); t = np.zeros((n, order, order))
-    name = b"ThreeDimensional" if type_ == ND_3D else b"PlaneStrain"
+    name = {ND_3D: b"ThreeDimensional", ND_PLANE_STRAIN: b"PlaneStrain", ND_PLANE_STRESS: b"PlaneStress"}[type_]
     r = L.ref_nd_path(kind, _p(pp), name, n, _p(strains), _p(commit), _p(s), _p(t))
     assert r == order, r
     return s, t

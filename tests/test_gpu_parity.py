@@ -389,6 +389,34 @@ def test_revert_to_last_commit_and_incr():
     assert relerr(D.trial_disp(), u3) < 1e-15
 
 
+def test_j2_plane_stress_quads_history_and_revert():
+    """FourNodeQuad with J2Plasticity's PlaneStress copy (J2PlaneStress): the out-of-plane strain is a state of its own --
+    every trial starts from the LAST TRIAL's value, commit stores it, revertToLastCommit restores it -- and the
+    iteration on sigma_22 = 0 stops at 1e-8 sigma_0, so device and oracle agree to 1e-12 only if they make the same
+    sequence of integrator calls.  Uncommitted trials, commits and a revert in between."""
+    rng = np.random.default_rng(9)
+    spec = quad_plane_stress_pressure(7, 5, 1, 1.5, mat=J2_STEEL, seed=37)
+    O = OracleBackend(spec, 1, 0); D = xb.DeviceModel.from_spec(spec, 1, 0).to_device(0)
+    ids = O.ids()
+    assert relerr(D.form_tangent(), O.form_tangent()) < RTOL          # condensed elastic tangent of the untouched model
+    for s in range(6):
+        u = rng.normal(0, 2e-3 * (s + 1), (spec.nn, 2)); u[ids < 0] = 0
+        O.set_trial_disp(u); D.set_trial_disp(u); D.update()
+        O.apply_load(0.2 * s); D.apply_load(0.2 * s)
+        assert relerr(D.form_tangent(), O.form_tangent()) < RTOL
+        assert relerr(D.form_unbalance(), O.form_unbalance()) < RTOL
+        for e in (0, O.ne - 1):
+            assert relerr(D.element_tangent(e, 8), O.ele_tangent(e, 8)) < RTOL
+        if s in (1, 4):
+            O.commit(); D.commit()
+        if s == 3:
+            O.revert(); D.revert_to_last_commit()
+            assert relerr(D.form_tangent(), O.form_tangent()) < RTOL
+            assert relerr(D.form_unbalance(), O.form_unbalance()) < RTOL
+    sg, tg = D.gp_response(3, 2, 3)                                   # the condensed tangent: symmetric, plane-stress soft
+    assert np.allclose(tg, tg.T, rtol=0, atol=1e-9 * np.abs(tg).max()) and np.isfinite(sg).all()
+
+
 def test_full_size_properties_brick():
     """A 200k-element J2 block (too large for the oracle in seconds): properties that do not
     depend on size -- symmetry of A, rigid-body null space of the elastic operator, row sums of
@@ -780,7 +808,8 @@ def test_partitioned_frame_matches_single_gpu():
 
 @pytest.mark.parametrize("name", ["newmark_brick_j2", "newmark_frame2d", "newmark_frame3d", "rayleigh_brick_j2",
                                   "rayleigh_quad_j2", "rayleigh_frame2d", "rayleigh_frame3d",
-                                  "rayleigh_soilcolumn_equaldof", "rayleigh_frame2d_equaldof", "rayleigh_quad_planestress"])
+                                  "rayleigh_soilcolumn_equaldof", "rayleigh_frame2d_equaldof", "rayleigh_quad_planestress",
+                                  "rayleigh_quad_planestress_j2"])
 def test_newmark_device_vs_golden_reference_history(name):
     """Newmark (displacement form, nodal masses): the device replays the history recorded from the
     reference's own Newmark integrator -- c1 K + c3 M tangent, P - M a - R unbalance, predictor,

@@ -152,8 +152,10 @@ def test_equal_dof_edge_cases():
     with pytest.raises(xb.XaraB200Error):
         xb.DeviceModel.from_spec(chain, 0, 0)
     from modelspec import quad_plane_stress_pressure
-    with pytest.raises(xb.XaraB200Error):      # J2Plasticity's PlaneStress copy (J2PlaneStress) is not on the device path
-        xb.DeviceModel.from_spec(quad_plane_stress_pressure(3, 3, 1, 1.0, mat=J2_STEEL), 0, 0)
+    mixed = quad_plane_stress_pressure(3, 3, 1, 1.0, mat=J2_STEEL)
+    mixed.groups[0].par[::2, 1] = 0
+    with pytest.raises(xb.XaraB200Error):      # J2 quads: one plane type per batch (J2PlaneStress keeps a state of its own)
+        xb.DeviceModel.from_spec(mixed, 0, 0)
     m = xb.DeviceModel(3, 3)
     m.add_nodes([1, 2], np.zeros((2, 3)))
     with pytest.raises(xb.XaraB200Error):

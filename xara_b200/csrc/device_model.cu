@@ -125,6 +125,37 @@ __device__ __forceinline__ void quad_elastic_D(double E, double v, bool ps, doub
   }
 }
 
+// J2PlaneStress (material/Plane/J2PlaneStress.cpp:158-178): the 3D consistent tangent condensed on sigma_22 = 0,
+// entries (00,11,01) x (00,11,01) in the order D00 D01 D02 D11 D12 D22
+__device__ __forceinline__ void j2_plane_stress_D(double bulk, double shear, const double* n, double c2, double c3, double* D) {
+  const int ia[6] = {0, 0, 0, 1, 1, 3}, ib[6] = {0, 1, 3, 1, 3, 3};
+  const double t22 = j2_tangent_entry(2, 2, bulk, shear, n, c2, c3);
+#pragma unroll
+  for (int q = 0; q < 6; q++) {
+    double t = j2_tangent_entry(ia[q], ib[q], bulk, shear, n, c2, c3);
+    t -= j2_tangent_entry(ia[q], 2, bulk, shear, n, c2, c3) * j2_tangent_entry(2, ib[q], bulk, shear, n, c2, c3) / t22;
+    D[q] = t;
+  }
+}
+
+// Material tangent of a quad's J2 Gauss point, entries D00 D01 D02 D11 D12 D22 over (00, 11, 01), from the stored form:
+// the compact (normal, c2, c3) of J2PlaneStrain (J2PlaneStrain.cpp:127-146), or -- ps -- J2PlaneStress's condensed tangent
+__device__ __forceinline__ void quad_j2_D6(const double* __restrict__ tan, long long gp, long long ngp, bool ps,
+                                           double bulk, double shear, double* D) {
+  if (ps) {
+#pragma unroll
+    for (int q = 0; q < 6; q++) D[q] = tan[(size_t)q * ngp + gp];
+  } else {
+    double n[6];
+#pragma unroll
+    for (int q = 0; q < 6; q++) n[q] = tan[(size_t)q * ngp + gp];
+    const double c2 = tan[(size_t)6 * ngp + gp], c3 = tan[(size_t)7 * ngp + gp];
+    const int ia[6] = {0, 0, 0, 1, 1, 3}, ib[6] = {0, 1, 3, 1, 3, 3};
+#pragma unroll
+    for (int q = 0; q < 6; q++) D[q] = j2_tangent_entry(ia[q], ib[q], bulk, shear, n, c2, c3);
+  }
+}
+
 // Brick::update (Brick.cpp:718-840); one thread per Gauss point
 constexpr int UPD_XS = 50;   // per element in shared memory: X[8][3], U[8][3] + pad
 #ifndef UPD_OCC
@@ -451,16 +482,40 @@ __global__ void __launch_bounds__(128) quad_update_kernel(GroupView G, const dou
 #pragma unroll
     for (int i = 0; i < 6; i++) epn[i] = G.hc[(size_t)i * ngp + gp];
     const double xin = G.hc[(size_t)6 * ngp + gp];
-    // J2PlaneStrain::setTrialStrain (material/Plane/J2PlaneStrain.cpp:80-92)
-    et[0] = eps[0]; et[1] = eps[1]; et[2] = 0.0; et[3] = 0.50 * eps[2]; et[4] = 0.0; et[5] = 0.0;
     J2Result r;
-    j2_integrate(par, et, epn, xin, 0.0, r);
-    if (r.fail) atomicExch(fail, 1);
+    if (__ldg(G.par + 3 * G.n + e) != 0.0) {
+      // J2PlaneStress::setTrialStrain (material/Plane/J2PlaneStress.cpp:123-180): the out-of-plane strain of the last
+      // TRIAL (kept in row 6 of `tan`; row 7 holds the committed one) is iterated until sigma_22 = 0; the
+      // integrator's return value is not looked at there; rows 0-5 of `tan` take the condensed tangent
+      double e22 = G.tan[(size_t)6 * ngp + gp];
+      const double tol = 1.0e-8 * par[2];
+      int it = 0;
+      double s22;
+      do {
+        et[0] = eps[0]; et[1] = eps[1]; et[2] = e22; et[3] = 0.50 * eps[2]; et[4] = 0.0; et[5] = 0.0;
+        j2_integrate(par, et, epn, xin, 0.0, r);
+        s22 = r.sig[2];
+        e22 -= s22 / j2_tangent_entry(2, 2, par[0], par[1], r.nrm, r.c2, r.c3);
+        it++;
+        if (it > 25) break;
+      } while (fabs(s22) > tol);
+      double D[6];
+      j2_plane_stress_D(par[0], par[1], r.nrm, r.c2, r.c3, D);
 #pragma unroll
-    for (int i = 0; i < 6; i++) { G.ht[(size_t)i * ngp + gp] = r.ep[i]; G.tan[(size_t)i * ngp + gp] = r.nrm[i]; }
-    G.ht[(size_t)6 * ngp + gp] = r.xi;
-    G.tan[(size_t)6 * ngp + gp] = r.c2;
-    G.tan[(size_t)7 * ngp + gp] = r.c3;
+      for (int i = 0; i < 6; i++) { G.ht[(size_t)i * ngp + gp] = r.ep[i]; G.tan[(size_t)i * ngp + gp] = D[i]; }
+      G.ht[(size_t)6 * ngp + gp] = r.xi;
+      G.tan[(size_t)6 * ngp + gp] = e22;
+    } else {
+      // J2PlaneStrain::setTrialStrain (material/Plane/J2PlaneStrain.cpp:80-92)
+      et[0] = eps[0]; et[1] = eps[1]; et[2] = 0.0; et[3] = 0.50 * eps[2]; et[4] = 0.0; et[5] = 0.0;
+      j2_integrate(par, et, epn, xin, 0.0, r);
+      if (r.fail) atomicExch(fail, 1);
+#pragma unroll
+      for (int i = 0; i < 6; i++) { G.ht[(size_t)i * ngp + gp] = r.ep[i]; G.tan[(size_t)i * ngp + gp] = r.nrm[i]; }
+      G.ht[(size_t)6 * ngp + gp] = r.xi;
+      G.tan[(size_t)6 * ngp + gp] = r.c2;
+      G.tan[(size_t)7 * ngp + gp] = r.c3;
+    }
     G.sig[(size_t)0 * ngp + gp] = r.sig[0];
     G.sig[(size_t)1 * ngp + gp] = r.sig[1];
     G.sig[(size_t)2 * ngp + gp] = r.sig[3];
@@ -534,21 +589,14 @@ __global__ void __launch_bounds__(128, DYN ? 1 : 5) quad_resid_kernel(GroupView 
       if (MATK == XB_MAT_J2PLASTICITY) {
         const double bulk = __ldg(p), shear = __ldg(p + 1);
         const long long gp = e * 4 + i;
-        double n[6], nc[6] = {0, 0, 0, 0, 0, 0}, z[6] = {0, 0, 0, 0, 0, 0}, c2c = 0.0, c3c = 0.0;
-#pragma unroll
-        for (int q = 0; q < 6; q++) n[q] = G.tan[(size_t)q * ngp + gp];
-        const double c2 = G.tan[(size_t)6 * ngp + gp], c3 = G.tan[(size_t)7 * ngp + gp];
-        if (dc.bKc != 0.0) {
-#pragma unroll
-          for (int q = 0; q < 6; q++) nc[q] = G.tanc[(size_t)q * ngp + gp];
-          c2c = G.tanc[(size_t)6 * ngp + gp]; c3c = G.tanc[(size_t)7 * ngp + gp];
-        }
+        const bool ps = __ldg(G.par + 3 * G.n + e) != 0.0;
+        double Dt[6], Dc[6] = {0, 0, 0, 0, 0, 0}, z[6] = {0, 0, 0, 0, 0, 0};
+        quad_j2_D6(G.tan, gp, ngp, ps, bulk, shear, Dt);
+        if (dc.bKc != 0.0) quad_j2_D6(G.tanc, gp, ngp, ps, bulk, shear, Dc);
         const int ia[6] = {0, 0, 0, 1, 1, 3}, ib[6] = {0, 1, 3, 1, 3, 3};
 #pragma unroll
-        for (int q = 0; q < 6; q++)
-          D[q] = dc.bK * j2_tangent_entry(ia[q], ib[q], bulk, shear, n, c2, c3) +
-                 dc.bK0 * j2_tangent_entry(ia[q], ib[q], bulk, shear, z, 0.0, 0.0) +
-                 dc.bKc * j2_tangent_entry(ia[q], ib[q], bulk, shear, nc, c2c, c3c);
+        for (int q = 0; q < 6; q++)   // (J2PlaneStress::getInitialTangent hands out the uncondensed elastic entries)
+          D[q] = dc.bK * Dt[q] + dc.bK0 * j2_tangent_entry(ia[q], ib[q], bulk, shear, z, 0.0, 0.0) + dc.bKc * Dc[q];
       } else {
         double d00, d01, d22;
         quad_elastic_D(__ldg(p), __ldg(p + 1), __ldg(G.par + 3 * G.n + e) != 0.0, d00, d01, d22);
@@ -1176,28 +1224,18 @@ __global__ void __launch_bounds__(128, DYN ? 1 : 5) quad_tangent_kernel(GroupVie
     if (MATK == XB_MAT_J2PLASTICITY) {
       const double bulk = __ldg(p), shear = __ldg(p + 1);
       const long long gp = e * 4 + i;
-      double n[6];
-#pragma unroll
-      for (int q = 0; q < 6; q++) n[q] = G.tan[(size_t)q * ngp + gp];
-      const double c2 = G.tan[(size_t)6 * ngp + gp], c3 = G.tan[(size_t)7 * ngp + gp];
-      // J2PlaneStrain::getTangent (material/Plane/J2PlaneStrain.cpp:127-146): rows/cols (00,11,01)
-      D00 = j2_tangent_entry(0, 0, bulk, shear, n, c2, c3); D01 = j2_tangent_entry(0, 1, bulk, shear, n, c2, c3);
-      D02 = j2_tangent_entry(0, 3, bulk, shear, n, c2, c3); D11 = j2_tangent_entry(1, 1, bulk, shear, n, c2, c3);
-      D12 = j2_tangent_entry(1, 3, bulk, shear, n, c2, c3); D22 = j2_tangent_entry(3, 3, bulk, shear, n, c2, c3);
+      const bool ps = __ldg(G.par + 3 * G.n + e) != 0.0;
+      double Dt[6];
+      quad_j2_D6(G.tan, gp, ngp, ps, bulk, shear, Dt);
       if (DYN && tc.on) {   // at Dt + a0 D0 + ac Dc
-        double z[6] = {0, 0, 0, 0, 0, 0}, nc[6] = {0, 0, 0, 0, 0, 0}, c2c = 0.0, c3c = 0.0;
-        if (tc.ac != 0.0) {
+        double z[6] = {0, 0, 0, 0, 0, 0}, Dc[6] = {0, 0, 0, 0, 0, 0};
+        if (tc.ac != 0.0) quad_j2_D6(G.tanc, gp, ngp, ps, bulk, shear, Dc);
+        const int ia[6] = {0, 0, 0, 1, 1, 3}, ib[6] = {0, 1, 3, 1, 3, 3};
 #pragma unroll
-          for (int q = 0; q < 6; q++) nc[q] = G.tanc[(size_t)q * ngp + gp];
-          c2c = G.tanc[(size_t)6 * ngp + gp]; c3c = G.tanc[(size_t)7 * ngp + gp];
-        }
-        D00 = tc.at * D00 + tc.a0 * j2_tangent_entry(0, 0, bulk, shear, z, 0.0, 0.0) + tc.ac * j2_tangent_entry(0, 0, bulk, shear, nc, c2c, c3c);
-        D01 = tc.at * D01 + tc.a0 * j2_tangent_entry(0, 1, bulk, shear, z, 0.0, 0.0) + tc.ac * j2_tangent_entry(0, 1, bulk, shear, nc, c2c, c3c);
-        D02 = tc.at * D02 + tc.a0 * j2_tangent_entry(0, 3, bulk, shear, z, 0.0, 0.0) + tc.ac * j2_tangent_entry(0, 3, bulk, shear, nc, c2c, c3c);
-        D11 = tc.at * D11 + tc.a0 * j2_tangent_entry(1, 1, bulk, shear, z, 0.0, 0.0) + tc.ac * j2_tangent_entry(1, 1, bulk, shear, nc, c2c, c3c);
-        D12 = tc.at * D12 + tc.a0 * j2_tangent_entry(1, 3, bulk, shear, z, 0.0, 0.0) + tc.ac * j2_tangent_entry(1, 3, bulk, shear, nc, c2c, c3c);
-        D22 = tc.at * D22 + tc.a0 * j2_tangent_entry(3, 3, bulk, shear, z, 0.0, 0.0) + tc.ac * j2_tangent_entry(3, 3, bulk, shear, nc, c2c, c3c);
+        for (int q = 0; q < 6; q++)
+          Dt[q] = tc.at * Dt[q] + tc.a0 * j2_tangent_entry(ia[q], ib[q], bulk, shear, z, 0.0, 0.0) + tc.ac * Dc[q];
       }
+      D00 = Dt[0]; D01 = Dt[1]; D02 = Dt[2]; D11 = Dt[3]; D12 = Dt[4]; D22 = Dt[5];
       D10 = D01; D20 = D02; D21 = D12;
     } else {
       double d00, d01, d22;
@@ -1641,6 +1679,7 @@ static thread_local std::string g_err;
 
 struct DevGroup {
   GroupView v{};
+  bool j2ps = false;    // quads with J2PlaneStress: rows 6 / 7 of `tan` are the trial / committed out-of-plane strain
   BeamView b{};              // forceBeamColumn batches
   int kind = 0, mat_kind = 0, nip = 0, nst = 0, nd = 0;
   long long ngp = 0, re_off = 0;
@@ -1972,6 +2011,7 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
     const xb::EleKind& k = xb::ele_kind(g.kind);
     DevGroup d;
     d.kind = g.kind; d.mat_kind = g.mat_kind; d.nip = k.nip ? k.nip : g.nip; d.nst = k.nst; d.nd = k.nen * k.ndf;
+    d.j2ps = g.kind == XB_ELE_FOURNODEQUAD && g.mat_kind == XB_MAT_J2PLASTICITY && g.j2_plane_stress;
     d.ngp = g.n() * d.nip;
     d.v.n = g.n();
     if (is_beam(g.kind)) {
@@ -2878,6 +2918,8 @@ int xb_commit(xb_model* m) {
       // Element::commitState: *Kc = getTangentStiff()
       if (b.kvK) CU(cudaMemcpyAsync(b.kvK, b.kv, sizeof(double) * b.nb * b.nb * b.n, cudaMemcpyDeviceToDevice, m->stream));
     } else if (d.mat_kind == XB_MAT_J2PLASTICITY) {
+      // J2PlaneStress::commitState: commitEps22 = strain(2,2)
+      if (d.j2ps) CU(cudaMemcpyAsync(d.v.tan + (size_t)7 * d.ngp, d.v.tan + (size_t)6 * d.ngp, sizeof(double) * d.ngp, cudaMemcpyDeviceToDevice, m->stream));
       if (d.v.tanc) CU(cudaMemcpyAsync(d.v.tanc, d.v.tan, sizeof(double) * 8 * d.ngp, cudaMemcpyDeviceToDevice, m->stream));
       std::swap(d.v.hc, d.v.ht);
     }
@@ -2901,6 +2943,8 @@ int xb_revert_to_last_commit(xb_model* m) {
   CU(cudaMemcpyAsync(m->dV, m->dVc, nb, cudaMemcpyDeviceToDevice, m->stream));
   CU(cudaMemcpyAsync(m->dAcc, m->dAc, nb, cudaMemcpyDeviceToDevice, m->stream));
   CU(cudaMemsetAsync(m->dDU, 0, std::max<size_t>(nb, 1), m->stream));
+  for (auto& d : m->dg)   // J2PlaneStress::revertToLastCommit: strain(2,2) = commitEps22
+    if (d.j2ps && d.ngp) CU(cudaMemcpyAsync(d.v.tan + (size_t)6 * d.ngp, d.v.tan + (size_t)7 * d.ngp, sizeof(double) * d.ngp, cudaMemcpyDeviceToDevice, m->stream));
   for (auto& d : m->dg)
     if (is_beam(d.kind) && d.b.n) {
       CU(cudaMemcpyAsync(d.b.ft, d.b.fc, sizeof(double) * d.fib_doubles, cudaMemcpyDeviceToDevice, m->stream));
@@ -2978,6 +3022,11 @@ int xb_get_gp_response(xb_model* m, long long e, int gpt, double* stress, double
   if (g.mat_kind == XB_MAT_J2PLASTICITY) {
     double t[8];
     for (int i = 0; i < 8; i++) CU(cudaMemcpy(t + i, d.v.tan + (size_t)i * d.ngp + gp, sizeof(double), cudaMemcpyDeviceToHost));
+    if (d.j2ps) {   // rows 0-5: the condensed tangent D00 D01 D02 D11 D12 D22
+      const double D[9] = {t[0], t[1], t[2], t[1], t[3], t[4], t[2], t[4], t[5]};
+      for (int i = 0; i < 9; i++) tangent[i] = D[i];
+      return d.nst;
+    }
     for (int a = 0; a < d.nst; a++)
       for (int b = 0; b < d.nst; b++) {
         int A6 = d.nst == 6 ? a : map3[a], B6 = d.nst == 6 ? b : map3[b];

@@ -181,8 +181,12 @@ int HostModel::add_elements(int kind, int n, const int* tags, const int* conn, c
     if (kind == XB_ELE_STDBRICK) { q[0] = p[0]; q[1] = p[1]; q[2] = p[2]; }
     else {
       if ((int)p[1] != 0 && (int)p[1] != 1) { err = "FourNodeQuad: type is 0 (PlaneStrain) or 1 (PlaneStress)"; return XB_ERR_ARG; }
-      // J2Plasticity's PlaneStress copy is a different class (J2PlaneStress: its own return map), not on the device path
-      if ((int)p[1] == 1 && mats[last_idx].kind != XB_MAT_ELASTIC_ISOTROPIC) { err = "FourNodeQuad PlaneStress: ElasticIsotropic only on the device path"; return XB_ERR_UNSUPPORTED; }
+      // J2Plasticity's PlaneStress copy is another class (J2PlaneStress) with a state of its own (the out-of-plane strain):
+      // one plane type per batch of J2 quads, so that the batch's commit / revert can treat that state as a block
+      if (mats[last_idx].kind == XB_MAT_J2PLASTICITY) {
+        if (i == 0) g.j2_plane_stress = (int)p[1] == 1;
+        else if (g.j2_plane_stress != ((int)p[1] == 1)) { err = "FourNodeQuad with J2Plasticity: one plane type (PlaneStrain | PlaneStress) per xb_add_elements call"; return XB_ERR_UNSUPPORTED; }
+      }
       q[0] = p[0]; q[1] = p[4]; q[2] = p[5]; q[3] = (double)(int)p[1]; q[4] = p[2];
     }
   }
@@ -578,7 +582,7 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
     lgroups.resize(groups.size());
     std::vector<std::vector<int>> keep(groups.size());   // batch index -> kept element indices
     for (size_t gi = 0; gi < groups.size(); gi++) {
-      lgroups[gi].kind = groups[gi].kind; lgroups[gi].mat_kind = groups[gi].mat_kind;
+      lgroups[gi].kind = groups[gi].kind; lgroups[gi].mat_kind = groups[gi].mat_kind; lgroups[gi].j2_plane_stress = groups[gi].j2_plane_stress;
       lgroups[gi].sec = groups[gi].sec; lgroups[gi].nip = groups[gi].nip; lgroups[gi].max_iters = groups[gi].max_iters; lgroups[gi].tol = groups[gi].tol;
     }
     std::vector<std::vector<int>> newidx(groups.size());

@@ -61,6 +61,7 @@ struct Group {
   // forceBeamColumn batches: one fibre section, nIP Lobatto points, element iteration controls
   int sec = -1, nip = 0, max_iters = 10;
   double tol = 1e-12;
+  bool j2_plane_stress = false;   // FourNodeQuad batch whose J2Plasticity copies are J2PlaneStress
   std::vector<long long> kdst;  // [n][nen] where the rows of node a of element l go: >= 0 offset of the
                                 //   slot in the node-major buffer KeN (node owned here), < 0 offset
                                 //   -(x+1) in the send buffer (node owned by another rank)
