@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from golden_cases import CASES, DISPCONTROL_CASES, NSTEPS, RAYLEIGH_CASES, TRANSIENT_CASES, ele_nd, newmark_coeffs
-from modelspec import (ELASTIC, J2_STEEL, MAT_ELASTIC, MAT_J2, ND_3D, ND_PLANE_STRAIN, OracleBackend, RefBackend,
+from modelspec import (ELASTIC, J2_STEEL, MAT_ELASTIC, MAT_J2, ND_3D, ND_PLANE_STRAIN, ND_PLANE_STRESS, OracleBackend, RefBackend,
                        brick_block, brick_periodic_equaldof, disp_control, frame2d, frame2d_diaphragm_equaldof, frame3d, have_ref,
                        oracle_nd_path, oracle_uni_path, quad_plane, quad_plane_stress_pressure, ref_nd_path, soil_column_equaldof, tie)
 
@@ -144,6 +144,15 @@ def test_material_paths_vs_live_reference():
             so, to = oracle_nd_path(kind, p, type_, strains, commit)
             sr, tr = ref_nd_path(kind, p, type_, strains, commit)
             assert close(so, sr) and close(to, tr)
+    # the PlaneStress copies: ElasticIsotropicPlaneStress2D, and J2PlaneStress with its trial-to-trial out-of-plane strain
+    for kind, p in (J2_STEEL, ELASTIC):
+        strains = np.cumsum(rng.normal(0, 6e-4, (200, 3)), axis=0)
+        commit = (rng.random(200) < 0.6).astype(np.int32)
+        so, to = oracle_nd_path(kind, p, ND_PLANE_STRESS, strains, commit)
+        sr, tr = ref_nd_path(kind, p, ND_PLANE_STRESS, strains, commit)
+        assert close(so, sr) and close(to, tr)
+        if kind == MAT_J2:
+            assert len(np.unique(np.round(tr[:, 0, 0], 1))) > 50           # the path really goes plastic
 
 
 def drive_transient_vs_golden(model, g, name, check, is_dev=False):
