@@ -226,7 +226,8 @@ int xb_comm_init(xb_model*, const char* id128);
 int xb_exchange(xb_model*, int which);
 /* the same exchange between n models (ranks 0..n-1) living in one process: plain device copies */
 int xb_exchange_local(xb_model** models, int n, int which);
-/* Domain::commit / Domain::revertToLastCommit */
+/* Domain::commit (Domain.cpp:1895) / Domain::revertToLastCommit (Domain.cpp:1925): the revert also puts the load
+ * factor of the last commit back (currentTime = committedTime; applyLoad) and ends with an update */
 int xb_commit(xb_model*);
 int xb_revert_to_last_commit(xb_model*);
 /* blocks until the model's stream is idle; surfaces asynchronous errors */

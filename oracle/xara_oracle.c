@@ -1232,7 +1232,7 @@ typedef struct {
   int soe_kind;                       /* 0 SparseGenCol (CSC), 1 SparseGenRow (CSR) */
   int* ptr; int* idx; int nnz;        /* colStartA/rowA or rowStartA/colA */
   double* A; double* B;
-  double lambda;
+  double lambda, lambda_c;   /* load factor (Domain::currentTime under LoadControl) and its committed value */
 } OrcModel;
 
 static int find_node(const OrcModel* m, int tag) {
@@ -2143,6 +2143,7 @@ int orc_form_unbalance(void* h, double* B) {
 /* Domain::commit -> Element::commitState -> material commitState; nodes commit trial */
 int orc_commit(void* h) {
   OrcModel* m = (OrcModel*)h;
+  m->lambda_c = m->lambda;                                    /* Domain::commit: committedTime = currentTime */
   memcpy(m->commit_disp, m->trial, sizeof(double) * m->nn * m->ndf);
   memset(m->incr, 0, sizeof(double) * m->nn * m->ndf);        /* Node::commitState */
   memcpy(m->velc, m->vel, sizeof(double) * m->nn * m->ndf); memcpy(m->accc, m->acc, sizeof(double) * m->nn * m->ndf);
@@ -2156,7 +2157,8 @@ int orc_commit(void* h) {
 }
 int orc_revert(void* h) {
   OrcModel* m = (OrcModel*)h;
-  /* Domain::revertToLastCommit (Domain.cpp:1925): nodes, elements, then update() */
+  /* Domain::revertToLastCommit (Domain.cpp:1925): nodes, elements, currentTime = committedTime + applyLoad, then update() */
+  m->lambda = m->lambda_c;
   memcpy(m->trial, m->commit_disp, sizeof(double) * m->nn * m->ndf);
   memset(m->incr, 0, sizeof(double) * m->nn * m->ndf);
   memcpy(m->vel, m->velc, sizeof(double) * m->nn * m->ndf); memcpy(m->acc, m->accc, sizeof(double) * m->nn * m->ndf);

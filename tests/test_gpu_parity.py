@@ -377,10 +377,10 @@ def test_revert_to_last_commit_and_incr():
     O = OracleBackend(spec, 0, 1); D = xb.DeviceModel.from_spec(spec, 0, 1).to_device(0)
     ids = O.ids()
     u1 = rng.normal(0, 4e-3, (spec.nn, 3)); u1[ids < 0] = 0
-    O.set_trial_disp(u1); D.set_trial_disp(u1); D.update(); O.commit(); D.commit()
+    O.set_trial_disp(u1); D.set_trial_disp(u1); D.update(); O.apply_load(0.5); D.apply_load(0.5); O.commit(); D.commit()
     u2 = u1 + rng.normal(0, 4e-3, (spec.nn, 3)); u2[ids < 0] = 0
-    O.set_trial_disp(u2); D.set_trial_disp(u2); D.update()
-    O.revert(); O.set_trial_disp(u1); D.revert_to_last_commit()
+    O.set_trial_disp(u2); D.set_trial_disp(u2); D.update(); O.apply_load(0.9); D.apply_load(0.9)
+    O.revert(); D.revert_to_last_commit()            # Domain::revertToLastCommit: also the committed load factor (0.5)
     assert relerr(D.trial_disp(), u1) == 0.0
     assert relerr(D.form_unbalance(), O.form_unbalance()) < RTOL
     dU = rng.normal(0, 1e-3, O.neq)

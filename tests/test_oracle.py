@@ -134,6 +134,25 @@ def test_oracle_vs_live_reference(mat, numberer, soe):
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+def test_revert_to_last_commit_vs_live_reference():
+    """Domain::revertToLastCommit (Domain.cpp:1925): nodes and elements go back, the load factor of the last commit is
+    applied again, then update() -- incl. J2PlaneStress's out-of-plane strain and the force beams' section state"""
+    rng = np.random.default_rng(0)
+    for spec, sc in ((brick_block(3, 3, 3, distort=0.1), 4e-3), (frame2d(2, 2, 2), np.array((0.006, 0.003, 6e-5))),
+                     (quad_plane_stress_pressure(5, 4, 1, 1.5, mat=J2_STEEL), 3e-3)):
+        O, R = OracleBackend(spec, 0, 1), RefBackend(spec, 0, 1)
+        ids = O.ids()
+        u1 = rng.normal(0, 1, (spec.nn, spec.ndf)) * sc; u1[ids < 0] = 0
+        u2 = u1 + rng.normal(0, 1, (spec.nn, spec.ndf)) * sc; u2[ids < 0] = 0
+        for m in (O, R):
+            m.set_trial_disp(u1); m.apply_load(0.5); m.commit()
+            m.set_trial_disp(u2); m.apply_load(0.9); m.revert()
+        tol = 1e-11 if spec.groups[0].kind == 2 else RTOL
+        assert close(O.form_unbalance(), R.form_unbalance(), tol)        # lambda = 0.5 again
+        assert close(O.form_tangent(), R.form_tangent(), tol)
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
 def test_material_paths_vs_live_reference():
     rng = np.random.default_rng(3)
     for kind, p in (J2_STEEL, ELASTIC):

@@ -1746,7 +1746,7 @@ struct xb_model {
   const void* tan_kern = nullptr;
   long long* dTask = nullptr;
   AsmView av{};
-  double lambda = 0.0;
+  double lambda = 0.0, lambda_c = 0.0;   // load factor (Domain::currentTime under LoadControl) and its committed value
   long long launches = 0;
   long long alg_bytes[6] = {0, 0, 0, 0, 0, 0};
 };
@@ -2903,6 +2903,7 @@ int xb_form_unbalance(xb_model* m, double* B) {
 int xb_commit(xb_model* m) {
   NEED_DEVICE();
   CU(cudaSetDevice(m->device));
+  m->lambda_c = m->lambda;   // Domain::commit (Domain.cpp:1911): committedTime = currentTime
   // J2Plasticity::commitState (J2Plasticity.cpp:538): epsilon_p_n = epsilon_p_nplus1, xi_n = xi_nplus1.
   // Every update rewrites the whole trial set, so committing is a buffer swap.
   for (auto& d : m->dg) {
@@ -2935,6 +2936,7 @@ int xb_commit(xb_model* m) {
 int xb_revert_to_last_commit(xb_model* m) {
   NEED_DEVICE();
   CU(cudaSetDevice(m->device));
+  m->lambda = m->lambda_c;   // Domain::revertToLastCommit (Domain.cpp:1942-1947): currentTime = committedTime, applyLoad
   // Node::revertToLastCommit restores the trial displacement; the material history is
   // untouched (J2Plasticity::revertToLastCommit is empty) and the next update rebuilds
   // the trial state from the committed one.
