@@ -9,7 +9,7 @@ import pytest
 
 import xara_b200 as xb
 from golden_cases import CASES
-from modelspec import (ELASTIC, J2_STEEL, OracleBackend, brick_block, brick_periodic_equaldof, frame2d, frame2d_diaphragm_equaldof,
+from modelspec import (ELASTIC, J2_STEEL, OracleBackend, RefBackend, have_ref, brick_block, brick_periodic_equaldof, frame2d, frame2d_diaphragm_equaldof,
                        quad_plane, soil_column_equaldof)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -162,6 +162,44 @@ def test_equal_dof_edge_cases():
         m.equal_dof(1, 1, [0])
     with pytest.raises(xb.XaraB200Error):
         m.equal_dof(1, 2, [3])
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_ragged_random_meshes_bit_exact(seed):
+    """ragged input: a random subset of a brick block's elements (holes, nodes left without any element, disconnected
+    pieces), random extra fixes, random `equalDOF` ties (free-to-free, onto fixed dofs, onto element-less nodes), shuffled
+    element order and gappy tags -- numbering, pattern and scatter maps stay bit-exact against the oracle"""
+    rng = np.random.default_rng(100 + seed)
+    spec = brick_block(4, 3, 3, distort=0.1, seed=seed)
+    g = spec.groups[0]
+    keep = rng.random(spec.ne) < rng.uniform(0.35, 0.9)
+    keep[rng.integers(spec.ne)] = True
+    order = rng.permutation(np.where(keep)[0])
+    g.tags, g.conn, g.mat, g.par = (g.tags[order] * 5 + 2).astype(np.int32), g.conn[order], g.mat[order], g.par[order]
+    have = {(int(t), int(d)) for t, d in spec.fix}
+    extra = [(int(t), int(rng.integers(3))) for t in rng.choice(spec.node_tags, 4, replace=False)]
+    spec.fix = np.vstack([spec.fix, [td for td in extra if td not in have]]).astype(np.int32)
+    if seed % 3:        # ties: distinct retained / constrained nodes, no chains
+        nodes = rng.choice(spec.node_tags, 8, replace=False)
+        spec.equal_dofs = [(int(nodes[2 * i]), int(nodes[2 * i + 1]), sorted(rng.choice(3, rng.integers(1, 4), replace=False).tolist()))
+                           for i in range(4)]
+    for numberer in (0, 1):
+        for soe in (0, 1):
+            O = OracleBackend(spec, numberer, soe)
+            D = xb.DeviceModel.from_spec(spec, numberer, soe)
+            assert D.neq == O.neq and D.nnz == O.nnz
+            assert np.array_equal(D.ids(), O.ids())
+            assert all(np.array_equal(a, b) for a, b in zip(D.pattern(), O.csr()))
+            assert np.array_equal(D.element_tags(), O.fe_ids(24)[0])
+            sm = D.scatter_map(0, D.ne, 24)
+            for e in range(D.ne):
+                assert np.array_equal(sm[e], O.scatter_map(e, 24))
+            fixed = {(int(t), int(d)) for t, d in spec.fix}
+            quiet = not any((c, d) in fixed for _, c, dofs in spec.equal_dofs for d in dofs)   # (the reference warns on those)
+            if have_ref() and soe == 1 and quiet:   # ... and the oracle against the reference's own handler / numberer / SOE
+                R = RefBackend(spec, numberer, soe)
+                assert np.array_equal(O.ids(), R.ids())
+                assert all(np.array_equal(a, b) for a, b in zip(O.csr(), R.csr()))
 
 
 def test_all_fixed_and_isolated_nodes():
