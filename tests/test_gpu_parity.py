@@ -389,6 +389,26 @@ def test_revert_to_last_commit_and_incr():
     assert relerr(D.trial_disp(), u3) < 1e-15
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_ragged_random_meshes_device_vs_oracle(seed):
+    """the ragged meshes of tests/test_host_setup.py (holes, nodes without elements, disconnected pieces, extra fixes,
+    `equalDOF` ties, shuffled elements) through the device path: A and B against the oracle over a short history"""
+    from test_host_setup import ragged_spec
+    rng = np.random.default_rng(500 + seed)
+    spec = ragged_spec(seed)
+    for numberer, soe in ((0, 0), (1, 1)):
+        O = OracleBackend(spec, numberer, soe); D = xb.DeviceModel.from_spec(spec, numberer, soe).to_device(0)
+        ids = O.ids()
+        for s in range(3):
+            u = rng.normal(0, 2e-3 * (s + 1), (spec.nn, 3)); u[ids < 0] = 0
+            tie(spec, u)
+            O.set_trial_disp(u); D.set_trial_disp(u); D.update()
+            O.apply_load(0.3 * s); D.apply_load(0.3 * s)
+            assert relerr(D.form_tangent(), O.form_tangent()) < RTOL
+            assert relerr(D.form_unbalance(), O.form_unbalance()) < RTOL
+            O.commit(); D.commit()
+
+
 def test_j2_plane_stress_quads_history_and_revert():
     """FourNodeQuad with J2Plasticity's PlaneStress copy (J2PlaneStress): the out-of-plane strain is a state of its own --
     every trial starts from the LAST TRIAL's value, commit stores it, revertToLastCommit restores it -- and the
