@@ -230,6 +230,9 @@ int xb_exchange_local(xb_model** models, int n, int which);
  * factor of the last commit back (currentTime = committedTime; applyLoad) and ends with an update */
 int xb_commit(xb_model*);
 int xb_revert_to_last_commit(xb_model*);
+/* Domain::revertToStart (Domain.cpp:1951, the `reset` command): every node, material, section and element back to its
+ * initial state, time and load factor 0, then an update; Element::Kc is left as it is (as in the reference) */
+int xb_revert_to_start(xb_model*);
 /* blocks until the model's stream is idle; surfaces asynchronous errors */
 int xb_synchronize(xb_model*);
 

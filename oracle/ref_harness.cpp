@@ -515,6 +515,7 @@ int ref_form_unbalance(void* h, double* B) {
 
 int ref_commit(void* h) { return ((RefModel*)h)->domain->commit(); }
 int ref_revert(void* h) { return ((RefModel*)h)->domain->revertToLastCommit(); }
+int ref_revert_to_start(void* h) { return ((RefModel*)h)->domain->revertToStart(); }
 
 // element level: Element::getTangentStiff / getResistingForce
 int ref_ele_tangent(void* h, int tag, double* K) {

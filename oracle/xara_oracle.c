@@ -1354,6 +1354,48 @@ int orc_add_fiber_section3d(void* h, int tag, int nf, const double* y, const dou
 static int beam_update(OrcBeam* b, const double* ug, const double* dug);
 static int find_mat(const OrcModel* m, int tag) { for (int i = 0; i < m->nmat; i++) if (m->mat_tag[i] == tag) return i; return -1; }
 
+/* a fresh OrcBeam3 for element e: sections with their fibres in the initial state, transformation, zero element state */
+static OrcBeam3* beam3_build(OrcModel* m, OrcEle* e, int sd, const double* par) {
+  OrcBeam3* b = (OrcBeam3*)calloc(1, sizeof(OrcBeam3));
+  b->nip = (int)par[0]; b->maxIters = (int)par[1]; b->tol = par[2];
+  if (b->nip < 2 || b->nip > ORC_MAXSEC) return NULL;
+  const OrcSecDef* d = &m->sec[sd];
+  for (int i = 0; i < b->nip; i++) {
+    OrcSec3* S = &b->sec[i];
+    S->nf = d->nf; S->y = d->y; S->z = d->z; S->A = d->A; S->GJ = d->GJ;
+    S->mat = (OrcUni*)malloc(sizeof(OrcUni) * d->nf);
+    double ABar = 0.0, QzBar = 0.0, QyBar = 0.0;
+    for (int f = 0; f < d->nf; f++) {
+      uni_init(&S->mat[f], m->uni_kind[d->mat[f]], m->uni_par + 12 * d->mat[f]);
+      ABar += d->A[f]; QzBar += d->y[f] * d->A[f]; QyBar += d->z[f] * d->A[f];   /* FiberSection3d::addFiber */
+      S->yBar = QzBar / ABar; S->zBar = QyBar / ABar;
+    }
+  }
+  if (crd3d_init(b, m->crd + e->node[0] * 3, m->crd + e->node[1] * 3, par + 3) < 0) return NULL;
+  return b;
+}
+/* a fresh OrcBeam for element e: sections with their fibres in the initial state, transformation, zero element state */
+static OrcBeam* beam2_build(OrcModel* m, OrcEle* e, int sd, const double* par) {
+  OrcBeam* b = (OrcBeam*)calloc(1, sizeof(OrcBeam));
+  b->nip = (int)par[0]; b->maxIters = (int)par[1]; b->tol = par[2];
+  if (b->nip < 2 || b->nip > ORC_MAXSEC) return NULL;
+  const OrcSecDef* d = &m->sec[sd];
+  for (int i = 0; i < b->nip; i++) {
+    OrcSec* S = &b->sec[i];
+    S->nf = d->nf; S->y = d->y; S->A = d->A;
+    S->mat = (OrcUni*)malloc(sizeof(OrcUni) * d->nf);
+    double ABar = 0.0, QzBar = 0.0;
+    for (int f = 0; f < d->nf; f++) {
+      uni_init(&S->mat[f], m->uni_kind[d->mat[f]], m->uni_par + 12 * d->mat[f]);
+      ABar += d->A[f]; QzBar += d->y[f] * d->A[f]; S->yBar = QzBar / ABar;   /* FiberSection2d::addFiber */
+    }
+  }
+  /* LinearCrdTransf2d::computeElemtLengthAndOrient */
+  double dx0 = m->crd[e->node[1] * 2] - m->crd[e->node[0] * 2], dx1 = m->crd[e->node[1] * 2 + 1] - m->crd[e->node[0] * 2 + 1];
+  b->L = sqrt(dx0 * dx0 + dx1 * dx1);
+  b->cosTheta = dx0 / b->L; b->sinTheta = dx1 / b->L;
+  return b;
+}
 static int quad_update(OrcModel* m, OrcEle* el);
 int orc_add_element(void* h, int kind, int tag, const int* nodeTags, int matTag, const double* par) {
   OrcModel* m = (OrcModel*)h;
@@ -1371,22 +1413,8 @@ int orc_add_element(void* h, int kind, int tag, const int* nodeTags, int matTag,
     int sd = -1;
     for (int i = 0; i < m->nsec; i++) if (m->sec[i].tag == matTag) sd = i;
     if (sd < 0 || m->sec[sd].z == NULL) return -2;
-    OrcBeam3* b = (OrcBeam3*)calloc(1, sizeof(OrcBeam3));
-    b->nip = (int)par[0]; b->maxIters = (int)par[1]; b->tol = par[2];
-    if (b->nip < 2 || b->nip > ORC_MAXSEC) return -3;
-    const OrcSecDef* d = &m->sec[sd];
-    for (int i = 0; i < b->nip; i++) {
-      OrcSec3* S = &b->sec[i];
-      S->nf = d->nf; S->y = d->y; S->z = d->z; S->A = d->A; S->GJ = d->GJ;
-      S->mat = (OrcUni*)malloc(sizeof(OrcUni) * d->nf);
-      double ABar = 0.0, QzBar = 0.0, QyBar = 0.0;
-      for (int f = 0; f < d->nf; f++) {
-        uni_init(&S->mat[f], m->uni_kind[d->mat[f]], m->uni_par + 12 * d->mat[f]);
-        ABar += d->A[f]; QzBar += d->y[f] * d->A[f]; QyBar += d->z[f] * d->A[f];   /* FiberSection3d::addFiber */
-        S->yBar = QzBar / ABar; S->zBar = QyBar / ABar;
-      }
-    }
-    if (crd3d_init(b, m->crd + e->node[0] * 3, m->crd + e->node[1] * 3, par + 3) < 0) return -3;
+    OrcBeam3* b = beam3_build(m, e, sd, par);
+    if (!b) return -3;
     e->beam3 = b; e->nip = b->nip; e->mat = sd;
     memcpy(e->par, par, 8 * sizeof(double));
     double ug[12], dug[12];   /* Domain::addElement calls element->update() (Domain.cpp:391) */
@@ -1400,24 +1428,8 @@ int orc_add_element(void* h, int kind, int tag, const int* nodeTags, int matTag,
     int sd = -1;
     for (int i = 0; i < m->nsec; i++) if (m->sec[i].tag == matTag) sd = i;
     if (sd < 0) return -2;
-    OrcBeam* b = (OrcBeam*)calloc(1, sizeof(OrcBeam));
-    b->nip = (int)par[0]; b->maxIters = (int)par[1]; b->tol = par[2];
-    if (b->nip < 2 || b->nip > ORC_MAXSEC) return -3;
-    const OrcSecDef* d = &m->sec[sd];
-    for (int i = 0; i < b->nip; i++) {
-      OrcSec* S = &b->sec[i];
-      S->nf = d->nf; S->y = d->y; S->A = d->A;
-      S->mat = (OrcUni*)malloc(sizeof(OrcUni) * d->nf);
-      double ABar = 0.0, QzBar = 0.0;
-      for (int f = 0; f < d->nf; f++) {
-        uni_init(&S->mat[f], m->uni_kind[d->mat[f]], m->uni_par + 12 * d->mat[f]);
-        ABar += d->A[f]; QzBar += d->y[f] * d->A[f]; S->yBar = QzBar / ABar;   /* FiberSection2d::addFiber */
-      }
-    }
-    /* LinearCrdTransf2d::computeElemtLengthAndOrient */
-    double dx0 = m->crd[e->node[1] * 2] - m->crd[e->node[0] * 2], dx1 = m->crd[e->node[1] * 2 + 1] - m->crd[e->node[0] * 2 + 1];
-    b->L = sqrt(dx0 * dx0 + dx1 * dx1);
-    b->cosTheta = dx0 / b->L; b->sinTheta = dx1 / b->L;
+    OrcBeam* b = beam2_build(m, e, sd, par);
+    if (!b) return -3;
     e->beam = b; e->nip = b->nip; e->mat = sd;
     memcpy(e->par, par, 8 * sizeof(double));
     /* Domain::addElement calls element->update() (Domain.cpp:391) */
@@ -2155,6 +2167,42 @@ int orc_commit(void* h) {
   }
   return 0;
 }
+/* Domain::revertToStart (Domain.cpp:1951, the `reset` command): nodes and elements back to their initial state
+ * (Node::revertToStart; Brick / FourNodeQuad -> NDMaterial::revertToStart: J2Plasticity.cpp:532 zero(), J2PlaneStress also
+ * commitEps22 = 0; ForceBeamColumn2d.cpp:344 / 3d: sections, fs, vs, Ssr, Se, kv zero, initialFlag = 0), time and
+ * load factor 0, applyLoad(0), update().  Element::Kc (Rayleigh betaKc) is NOT reset by the reference. */
+int orc_revert_to_start(void* h) {
+  OrcModel* m = (OrcModel*)h;
+  const size_t nb = sizeof(double) * m->nn * m->ndf;
+  memset(m->trial, 0, nb); memset(m->commit_disp, 0, nb); memset(m->incr, 0, nb);
+  memset(m->vel, 0, nb); memset(m->velc, 0, nb); memset(m->acc, 0, nb); memset(m->accc, 0, nb);
+  m->lambda = m->lambda_c = 0.0;
+  for (int e = 0; e < m->ne; e++) {
+    OrcEle* el = &m->ele[e];
+    if (el->kind == ORC_ELE_FBC2D) {
+      for (int i = 0; i < el->beam->nip; i++) free(el->beam->sec[i].mat);
+      free(el->beam);
+      el->beam = beam2_build(m, el, el->mat, el->par);
+    } else if (el->kind == ORC_ELE_FBC3D) {
+      for (int i = 0; i < el->beam3->nip; i++) free(el->beam3->sec[i].mat);
+      free(el->beam3);
+      el->beam3 = beam3_build(m, el, el->mat, el->par);
+    } else {
+      for (int g = 0; g < el->nip; g++) {
+        OrcGP* gp = &el->gp[g];
+        if (gp->kind == ORC_MAT_J2) {   /* J2Plasticity::zero: history, stress, strain (the tangent stays until the update) */
+          j2_zero(&gp->u.j2);
+          memset(gp->u.j2.stress, 0, sizeof gp->u.j2.stress); memset(gp->u.j2.strain, 0, sizeof gp->u.j2.strain);
+          gp->u.j2.commitEps22 = 0.0;
+        } else { memset(gp->u.el.epsilon, 0, sizeof gp->u.el.epsilon); memset(gp->u.el.Cepsilon, 0, sizeof gp->u.el.Cepsilon); }
+      }
+    }
+  }
+  int rc = 0;
+  for (int e = 0; e < m->ne; e++) rc |= ele_update(m, &m->ele[e]);
+  return rc;
+}
+
 int orc_revert(void* h) {
   OrcModel* m = (OrcModel*)h;
   /* Domain::revertToLastCommit (Domain.cpp:1925): nodes, elements, currentTime = committedTime + applyLoad, then update() */

@@ -573,6 +573,9 @@ class OracleBackend(_Backend):
     def revert(self):
         return self.L.orc_revert(self.h)
 
+    def revert_to_start(self):
+        return self.L.orc_revert_to_start(self.h)
+
     def __del__(self):
         try:
             self.L.orc_model_free(self.h)
@@ -746,6 +749,9 @@ class RefBackend(_Backend):
 
     def revert(self):
         return self.L.ref_revert(self.h)
+
+    def revert_to_start(self):
+        return self.L.ref_revert_to_start(self.h)
 
     # ---- transient: the reference's own Newmark ----
     def set_mass(self, tags, mass):

@@ -409,6 +409,33 @@ def test_ragged_random_meshes_device_vs_oracle(seed):
             O.commit(); D.commit()
 
 
+@pytest.mark.parametrize("shape", ["brick", "quad_ps_j2", "frame2d", "frame3d"])
+def test_revert_to_start(shape):
+    """Domain::revertToStart (the `reset` command): after a committed plastic history the model is back at its initial
+    state (bitwise the initial A), and the next step matches the oracle (which is pinned to the reference's revertToStart)"""
+    rng = np.random.default_rng(2)
+    spec, sc = {"brick": (brick_block(3, 3, 3, distort=0.1), 4e-3),
+                "quad_ps_j2": (quad_plane_stress_pressure(5, 4, 1, 1.5, mat=J2_STEEL), 3e-3),
+                "frame2d": (frame2d(2, 2, 2), np.array((0.006, 0.003, 6e-5))),
+                "frame3d": (frame3d(1, 1, 2), np.array((0.015, 0.015, 0.003, 1e-4, 1e-4, 1e-4)))}[shape]
+    tol = BEAM_RTOL if shape.startswith("frame") else RTOL
+    O = OracleBackend(spec, 1, 1); D = xb.DeviceModel.from_spec(spec, 1, 1).to_device(0)
+    ids = O.ids()
+    A0, B0 = D.form_tangent().copy(), D.form_unbalance().copy()
+    for s in range(3):
+        u = rng.normal(0, 1, (spec.nn, spec.ndf)) * sc * (s + 1); u[ids < 0] = 0
+        O.set_trial_disp(u); D.set_trial_disp(u); D.update()
+        O.apply_load(0.4 * (s + 1)); D.apply_load(0.4 * (s + 1)); O.commit(); D.commit()
+    assert relerr(D.form_tangent(), A0) > 1e-3                     # the history left its mark
+    O.revert_to_start(); D.revert_to_start()
+    assert np.array_equal(D.form_tangent(), A0) and np.array_equal(D.form_unbalance(), B0)
+    assert relerr(D.form_tangent(), O.form_tangent()) < tol and np.abs(D.trial_disp()).max() == 0.0
+    u = rng.normal(0, 1, (spec.nn, spec.ndf)) * sc; u[ids < 0] = 0
+    O.set_trial_disp(u); D.set_trial_disp(u); D.update(); O.apply_load(0.3); D.apply_load(0.3)
+    assert relerr(D.form_tangent(), O.form_tangent()) < tol
+    assert relerr(D.form_unbalance(), O.form_unbalance()) < tol
+
+
 def test_j2_plane_stress_quads_history_and_revert():
     """FourNodeQuad with J2Plasticity's PlaneStress copy (J2PlaneStress): the out-of-plane strain is a state of its own --
     every trial starts from the LAST TRIAL's value, commit stores it, revertToLastCommit restores it -- and the

@@ -153,6 +153,33 @@ def test_revert_to_last_commit_vs_live_reference():
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+def test_revert_to_start_vs_live_reference():
+    """Domain::revertToStart (Domain.cpp:1951): after a committed history every element kind is back at its initial
+    state -- bitwise the initial A -- and the next step agrees with the reference"""
+    rng = np.random.default_rng(2)
+    cases = [(brick_block(3, 3, 3, distort=0.1), 4e-3), (quad_plane(5, 4, mat=J2_STEEL, lx=5.0, ly=4.0, distort=0.2), 3e-3),
+             (quad_plane_stress_pressure(5, 4, 1, 1.5, mat=J2_STEEL), 3e-3), (quad_plane_stress_pressure(5, 4, 1, 1.5), 2e-2),
+             (frame2d(2, 2, 2), np.array((0.006, 0.003, 6e-5))), (frame3d(1, 1, 2), np.array((0.015, 0.015, 0.003, 1e-4, 1e-4, 1e-4)))]
+    for spec, sc in cases:
+        tol = 1e-11 if spec.groups[0].kind in (2, 3) else RTOL
+        O, R = OracleBackend(spec, 1, 1), RefBackend(spec, 1, 1)
+        ids = O.ids()
+        A0 = O.form_tangent().copy()
+        for s in range(3):
+            u = rng.normal(0, 1, (spec.nn, spec.ndf)) * sc * (s + 1); u[ids < 0] = 0
+            for m in (O, R):
+                m.set_trial_disp(u); m.apply_load(0.4 * (s + 1)); m.commit()
+        for m in (O, R):
+            m.revert_to_start()
+        assert np.array_equal(O.form_tangent(), A0)
+        assert close(O.form_tangent(), R.form_tangent(), tol) and np.abs(O.form_unbalance() - R.form_unbalance()).max() < 1e-12
+        u = rng.normal(0, 1, (spec.nn, spec.ndf)) * sc; u[ids < 0] = 0
+        for m in (O, R):
+            m.set_trial_disp(u); m.apply_load(0.3)
+        assert close(O.form_tangent(), R.form_tangent(), tol) and close(O.form_unbalance(), R.form_unbalance(), tol)
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
 def test_material_paths_vs_live_reference():
     rng = np.random.default_rng(3)
     for kind, p in (J2_STEEL, ELASTIC):

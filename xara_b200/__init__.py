@@ -110,6 +110,7 @@ def _load():
         "xb_assemble_unbalance": (i32, [vp, vp]),
         "xb_commit": (i32, [vp]),
         "xb_revert_to_last_commit": (i32, [vp]),
+        "xb_revert_to_start": (i32, [vp]),
         "xb_synchronize": (i32, [vp]),
         "xb_device_A": (vp, [vp]),
         "xb_device_B": (vp, [vp]),
@@ -402,6 +403,9 @@ class DeviceModel:
 
     def commit(self):
         self._ck(lib.xb_commit(self._h))
+
+    def revert_to_start(self):
+        self._ck(lib.xb_revert_to_start(self._h))
 
     def revert_to_last_commit(self):
         self._ck(lib.xb_revert_to_last_commit(self._h))

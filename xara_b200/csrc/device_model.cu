@@ -1679,6 +1679,8 @@ static thread_local std::string g_err;
 
 struct DevGroup {
   GroupView v{};
+  const double *fib_ic = nullptr, *fib_it = nullptr;   // beams: initial committed / trial fibre records of one section
+  int fib_nrec = 0, fib_per_sec = 0, beam_ord = 0;
   bool j2ps = false;    // quads with J2PlaneStress: rows 6 / 7 of `tan` are the trial / committed out-of-plane strain
   BeamView b{};              // forceBeamColumn batches
   int kind = 0, mat_kind = 0, nip = 0, nst = 0, nd = 0;
@@ -2123,6 +2125,7 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
         const long long tot = (long long)g.nip * nf * XB_FIB_NV * ne;
         fiber_init_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, m->stream>>>(ne, g.nip * nf * XB_FIB_NV, dic, dit, nf * XB_FIB_NV, b.fc, b.ft);
         CU(cudaGetLastError());
+        d.fib_ic = dic; d.fib_it = dit; d.fib_nrec = g.nip * nf * XB_FIB_NV; d.fib_per_sec = nf * XB_FIB_NV; d.beam_ord = ord;
       }
       long long* kdst = nullptr;
       CU(dev_upload(m, &kdst, g.kdst));
@@ -2956,6 +2959,39 @@ int xb_revert_to_last_commit(xb_model* m) {
     }
   CU(cudaGetLastError());
   return xb_update(m);   // Domain::revertToLastCommit ends with this->update() (Domain.cpp:1948)
+}
+
+// Domain::revertToStart (Domain.cpp:1951, the `reset` command): nodes, materials, sections and elements back to their
+// initial state (Node::revertToStart; J2Plasticity.cpp:532 zero(), J2PlaneStress also commitEps22 = 0;
+// ForceBeamColumn2d.cpp:344 / 3d: sections, fs, vs, Ssr, Se, kv zero, initialFlag = 0), time and load factor 0, update().
+// Element::Kc (Rayleigh betaKc: `tanc`, `kvK`) is not reset by the reference either.
+int xb_revert_to_start(xb_model* m) {
+  NEED_DEVICE();
+  CU(cudaSetDevice(m->device));
+  const size_t nb = sizeof(double) * std::max<size_t>((size_t)m->h.nn() * m->h.ndf, 1);
+  for (double* q : {m->dU, m->dUc, m->dV, m->dVc, m->dAcc, m->dAc, m->dDU}) CU(cudaMemsetAsync(q, 0, nb, m->stream));
+  m->lambda = m->lambda_c = 0.0;
+  for (auto& d : m->dg) {
+    if (is_beam(d.kind)) {
+      BeamView& b = d.b;
+      if (b.n == 0) continue;
+      const size_t ne = (size_t)b.n, ord = (size_t)d.beam_ord;
+      for (double* q : {b.Se, b.Sec}) CU(cudaMemsetAsync(q, 0, sizeof(double) * b.nb * ne, m->stream));
+      for (double* q : {b.kv, b.kvc}) CU(cudaMemsetAsync(q, 0, sizeof(double) * b.nb * b.nb * ne, m->stream));
+      for (double* q : {b.vs, b.vsc, b.Ssr}) CU(cudaMemsetAsync(q, 0, sizeof(double) * b.nip * ord * ne, m->stream));
+      CU(cudaMemsetAsync(b.fs, 0, sizeof(double) * b.nip * ord * ord * ne, m->stream));
+      CU(cudaMemsetAsync(b.iflag, 0, sizeof(int) * ne, m->stream));
+      const long long tot = (long long)d.fib_nrec * b.n;
+      fiber_init_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, m->stream>>>(b.n, d.fib_nrec, d.fib_ic, d.fib_it, d.fib_per_sec, b.fc, b.ft);
+      m->launches++;
+    } else if (d.mat_kind == XB_MAT_J2PLASTICITY && d.ngp) {
+      CU(cudaMemsetAsync(d.v.hc, 0, sizeof(double) * 7 * d.ngp, m->stream));
+      CU(cudaMemsetAsync(d.v.ht, 0, sizeof(double) * 7 * d.ngp, m->stream));
+      CU(cudaMemsetAsync(d.v.tan, 0, sizeof(double) * 8 * d.ngp, m->stream));     // incl. J2PlaneStress's out-of-plane strains
+    }
+  }
+  CU(cudaGetLastError());
+  return xb_update(m);
 }
 
 int xb_synchronize(xb_model* m) {
