@@ -144,17 +144,16 @@ dist.barrier(); print("rank", rank, "ok", m.nrows, m.ne, c.tolist())
 @pytest.mark.parametrize("model", ["plain", "equaldof"])
 def test_two_ranks_over_gloo(tmp_path, model):
     import socket
-    for attempt in range(2):      # the probed port can be taken between the probe and the rendezvous: try once more
+    for attempt in range(2):      # the rendezvous of two fresh processes can fail for reasons of its own (port taken
+                                  # between probe and bind, a slow start): try once more
         s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
         script = tmp_path / f"worker{attempt}.py"
         script.write_text(WORKER.format(root=ROOT, port=port))
         procs = [subprocess.Popen([sys.executable, str(script), str(r), model], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                                   text=True) for r in range(2)]
         outs = [p.communicate(timeout=240)[0] for p in procs]
-        if all(p.returncode == 0 for p in procs) or attempt == 1:
-            break
-        if not any("Address already in use" in o or "connect" in o.lower() or "timed out" in o.lower() for o in outs):
-            break                 # a genuine failure: report it
+        if all(p.returncode == 0 for p in procs):
+            break                 # (a genuine failure fails twice and is reported below)
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
