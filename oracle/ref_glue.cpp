@@ -310,6 +310,13 @@ class B200LoadControl : public LoadControl {
     if (xb_commit(x) < 0) return -1;
     return LoadControl::commit();
   }
+  // a failed step: BasicAnalysisBuilder::analyzeStatic / analyzeTransient call Domain::revertToLastCommit and then this
+  // (BasicAnalysisBuilder.cpp:372-413, 488-519); the device state goes back with it
+  int revertToLastStep() override {
+    const int rc = LoadControl::revertToLastStep();
+    if (x && xb_revert_to_last_commit(x) < 0) return -1;
+    return rc;
+  }
 };
 
 // `integrator DisplacementControl`: newStep / update as DisplacementControl.cpp:121,210 (no sensitivities), with
@@ -402,6 +409,13 @@ class B200DisplacementControl : public DisplacementControl {
     if (xb_commit(x) < 0) return -1;
     return DisplacementControl::commit();
   }
+  // a failed step: BasicAnalysisBuilder::analyzeStatic / analyzeTransient call Domain::revertToLastCommit and then this
+  // (BasicAnalysisBuilder.cpp:372-413, 488-519); the device state goes back with it
+  int revertToLastStep() override {
+    const int rc = DisplacementControl::revertToLastStep();
+    if (x && xb_revert_to_last_commit(x) < 0) return -1;
+    return rc;
+  }
 };
 
 // the transient counterpart: Newmark (displacement unknown).  newStep / update keep the reference's own U, Udot,
@@ -463,6 +477,13 @@ class B200Newmark : public Newmark {
     calls[3]++;
     if (xb_commit(x) < 0) return -1;
     return Newmark::commit();
+  }
+  // a failed step: BasicAnalysisBuilder::analyzeStatic / analyzeTransient call Domain::revertToLastCommit and then this
+  // (BasicAnalysisBuilder.cpp:372-413, 488-519); the device state goes back with it
+  int revertToLastStep() override {
+    const int rc = Newmark::revertToLastStep();
+    if (x && xb_revert_to_last_commit(x) < 0) return -1;
+    return rc;
   }
 };
 

@@ -244,6 +244,24 @@ def test_reference_newton_loop_drives_device_path(shape, numberer, soe):
 
 
 @pytest.mark.skipif(not (have_ref() and have_glue()), reason="oracle/_ref not built (needs /root/reference)")
+def test_reference_failed_step_reverts_the_device_state():
+    """A step that does not converge (3 iterations allowed, the plastic steps need more): the reference's analysis loop
+    calls Domain::revertToLastCommit and the integrator's revertToLastStep -- same failing step, same iteration counts,
+    and the DEVICE state is back at the last commit, like the reference's Domain"""
+    from modelspec import GLUE_SO, RefBackend
+    mk = lambda: brick_block(4, 4, 6, mat=J2_STEEL, lx=1.0, ly=1.0, lz=3.0, load=(1.2, 0.0, -0.5))
+    C = RefBackend(mk(), 1, 0, dlambda=1.0 / 8, test=0, tol=1e-8, max_iter=3)
+    rc_cpu, it_cpu, _ = C.analyze_static(8)
+    assert rc_cpu == -3 and it_cpu[:5].tolist() == [2, 2, 2, 2, 2]          # steps 1-5 converge, step 6 fails
+    D = RefBackend(mk(), defer_setup=True, so=GLUE_SO)
+    D.setup_glue_loadcontrol(1, 0, 1.0 / 8, test=0, tol=1e-8, max_iter=3)
+    rc_dev, it_dev, _ = D.analyze_static(8)
+    assert rc_dev == -3 and it_dev.tolist() == it_cpu.tolist()
+    u_cpu = C.get_trial_disp()                                               # the state of the last commit (step 5)
+    assert np.abs(u_cpu).max() > 1e-3 and relerr(D.glue_trial_disp(), u_cpu) < 1e-9
+
+
+@pytest.mark.skipif(not (have_ref() and have_glue()), reason="oracle/_ref not built (needs /root/reference)")
 def test_reference_loop_reads_plane_stress_and_pressure_out_of_the_domain():
     """FourNodeQuad with the PlaneStress material copy and a surface pressure: the glue reads both out of the reference's
     Domain (theMaterial[0]->getType(), pressure); the reference's own analysis on CPU and on the device path agree."""
