@@ -251,6 +251,9 @@ def ours_main(a):
     torch.cuda.set_stream(stream)
     t0 = time.time()
     D.to_device(local, stream=stream.cuda_stream)
+    for kv in a.opt:          # run-time tuning options (xb_set_option): results do not depend on them
+        k, v = kv.split("=")
+        D.set_option(k, int(v))
     if world > 1:
         box = [xb.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, 0)
@@ -448,6 +451,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=22, help="CPU arm sample: elements per side")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="name=value for xb_set_option (kernel tuning experiments)")
     a = ap.parse_args()
     if a.n is None:
         a.n = {"brick": 160, "quad": 1000, "frame": 200, "frame3d": 20}[a.workload]

@@ -14,6 +14,7 @@ import pytest
 
 import xara_b200 as xb
 from golden_cases import CASES, NSTEPS, ele_nd
+from r1_bits_cases import CASES as R1_CASES, run_case as r1_run_case
 from modelspec import (ELASTIC, J2_STEEL, OracleBackend, brick_block, brick_periodic_equaldof, frame2d, frame2d_diaphragm_equaldof, frame3d,
                        have_glue, have_metis, have_ref, metis_partition, quad_plane, quad_plane_stress_pressure, soil_column_equaldof,
                        soil_structure_block, tie)
@@ -529,10 +530,20 @@ def test_full_size_properties_brick():
     assert np.abs(B - P).max() < 1e-12 * max(np.abs(P).max(), 1.0)
 
 
-def test_tiled_form_tangent_matches_oracle_and_untiled_bitwise(monkeypatch):
-    """Large brick batches are stored tile by tile (FE-order slices > spatial tiles) and formTangent runs as an element
-    -> assembly pipeline over the tiles.  Element tags arrive shuffled; DOF numbers, pattern and FE order are the
-    reference's all the same, A matches the oracle, and equals the untiled run bit for bit."""
+@pytest.mark.parametrize("name", list(R1_CASES))
+def test_tangent_and_unbalance_bits_equal_round1(name):
+    """formTangent through symmetric element records + the gathered assembly reproduces the round-1 device path (node-major
+    element rows) BIT FOR BIT: same block values, same FE_Element order of additions.  The digests were taken on a B200
+    with the round-1 library (tests/golden/make_r1_bits.py)."""
+    import json
+    with open(os.path.join(GOLD, "r1_tangent_bits.json")) as f:
+        want = json.load(f)[name]
+    assert r1_run_case(xb, name) == want
+
+
+def test_shuffled_tags_and_tangent_options_bitwise():
+    """Element tags arrive shuffled; DOF numbers, pattern and FE order are the reference's all the same and A matches the
+    oracle.  The run-time options (tangent kernel variant, ranged formTangent, block-row or gathered assembly) do not change a bit."""
     spec = brick_block(48, 40, 36, mat=J2_STEEL, distort=0.2, seed=3)
     g = spec.groups[0]
     p = np.random.default_rng(0).permutation(len(g.tags))
@@ -544,24 +555,24 @@ def test_tiled_form_tangent_matches_oracle_and_untiled_bitwise(monkeypatch):
     O.set_trial_disp(u); O.apply_load(0.7)
     Ao, Bo = O.form_tangent(), O.form_unbalance()
     res = {}
-    for tile in ("0", "2048", "9472", "fused"):
-        monkeypatch.setenv("XB_TILE", "2048" if tile == "fused" else tile)
-        monkeypatch.setenv("XB_FUSED", "1" if tile == "fused" else "0")
+    for opt in ((0, 0, 1), (1, 0, 0), (2, 1, 1), (3, 1, 0)):
         D = xb.DeviceModel.from_spec(spec, 1, 0).to_device(0)
+        D.set_option("tangent_variant", opt[0]).set_option("ranged_tangent", opt[1]).set_option("block_assembly", opt[2])
         assert np.array_equal(D.ids(), ids) and np.array_equal(D.element_tags(), O.fe_ids(24)[0])
         D.set_trial_disp(u); D.update(); D.apply_load(0.7)
         A = D.form_tangent(); B = D.form_unbalance()
         assert relerr(A, Ao) < RTOL and relerr(B, Bo) < RTOL
-        for e in (0, 1234, O.ne - 1):          # FE-order accessors see through the storage permutation
+        for e in (0, 1234, O.ne - 1):          # FE-order accessors see through the storage order
             assert relerr(D.element_tangent(e, 24), O.ele_tangent(e, 24)) < RTOL
             assert relerr(D.element_resid(e, 24), O.ele_resid(e, 24)) < RTOL
         D.form_element_tangents(); A3 = np.empty(D.nnz); D.assemble_tangent(A3); D.synchronize()
         assert np.array_equal(A, A3)
+        A4 = D.form_tangent(host=False); D.synchronize()
         D.commit()
         D.set_trial_disp(1.5 * u); D.update()
-        res[tile] = (A, B, D.form_tangent(host=True), D.form_unbalance())
-    for tile in ("2048", "9472", "fused"):
-        for x, y in zip(res["0"], res[tile]):
+        res[opt] = (A, B, D.form_tangent(host=True), D.form_unbalance())
+    for opt in ((1, 0, 0), (2, 1, 1), (3, 1, 0)):
+        for x, y in zip(res[(0, 0, 1)], res[opt]):
             assert np.array_equal(x, y)
 
 

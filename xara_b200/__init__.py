@@ -119,6 +119,7 @@ def _load():
         "xb_get_element_resid": (i32, [vp, i64, vp]),
         "xb_get_gp_response": (i32, [vp, i64, i32, vp, vp]),
         "xb_launch_count": (i64, [vp]),
+        "xb_set_option": (i32, [vp, ctypes.c_char_p, i32]),
         "xb_algorithmic_bytes": (i64, [vp, i32]),
     }
     for name, (res, args) in sig.items():
@@ -425,6 +426,11 @@ class DeviceModel:
 
     def launch_count(self):
         return lib.xb_launch_count(self._h)
+
+    def set_option(self, name: str, value: int):
+        """run-time tuning (include/xara_b200.h, xb_set_option); results do not depend on it"""
+        self._ck(lib.xb_set_option(self._h, name.encode(), int(value)))
+        return self
 
     def algorithmic_bytes(self, which):
         return lib.xb_algorithmic_bytes(self._h, which)

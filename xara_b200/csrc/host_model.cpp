@@ -311,61 +311,6 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
   }
   if (bad) { err = "element references an unknown node tag"; return XB_ERR_ARG; }
 
-  // ---- storage order of a large brick batch: FE-order slices > spatial tiles (see host_model.hpp, `tiled`) ----
-  tiled = false; tile_ptr.clear(); tile_super.clear(); nsuper = 1;
-  {
-    // opt-in (XB_TILE=<elements per tile>, e.g. 9472 = 2 batches of 4 per warp of the persistent tangent kernel):
-    // measured on B200 it does not pay -- see DESIGN.md, "what was tried"
-    const char* tl = std::getenv("XB_TILE");
-    const long long target = tl ? std::atoll(tl) : 0;
-    const char* pl = std::getenv("XB_PIPELINE");
-    const int want = pl ? std::atoi(pl) : 8;
-    if (nparts == 1 && groups.size() == 1 && groups[0].kind == XB_ELE_STDBRICK && groups[0].n() >= 65536 && target >= 256 &&
-        want >= 1 && want <= 64 && mp_r.empty()) {
-      Group& g = groups[0];
-      const long long n = g.n();
-      std::vector<long long> byTag(n);
-      std::iota(byTag.begin(), byTag.end(), 0LL);
-      if (!std::is_sorted(g.tag.begin(), g.tag.end()))
-        std::sort(byTag.begin(), byTag.end(), [&](long long a, long long b) { return g.tag[a] < g.tag[b]; });
-      std::vector<double> cen((size_t)n * 3, 0.0);
-#pragma omp parallel for schedule(static)
-      for (long long e = 0; e < n; e++)
-        for (int a = 0; a < 8; a++)
-          for (int d = 0; d < ndm; d++) cen[e * 3 + d] += crd[(size_t)g.conn[e * 8 + a] * ndm + d];
-      nsuper = want;
-      const long long per = (n + nsuper - 1) / nsuper;
-      std::vector<int> leaf(n, 0);
-      tile_ptr.push_back(0);
-      for (int sidx = 0; sidx < nsuper; sidx++) {
-        const long long lo = std::min(n, sidx * per), hi = std::min(n, lo + per);
-        if (hi <= lo) continue;
-        const int np = (int)((hi - lo + target - 1) / target);
-        rcb(byTag, lo, hi, np, 0, cen.data(), ndm, leaf);     // reorders byTag[lo, hi) tile by tile
-        for (int q = 0; q < np; q++) {
-          // rcb's split points: part q of np over [lo, hi) -- recover the boundaries by counting
-          tile_super.push_back(sidx);
-        }
-        std::vector<long long> cnt(np, 0);
-        for (long long i = lo; i < hi; i++) cnt[leaf[byTag[i]]]++;
-        for (int q = 0; q < np; q++) tile_ptr.push_back(tile_ptr.back() + cnt[q]);
-      }
-      // the new storage order
-      std::vector<int> tag2(n), conn2((size_t)n * 8), mat2(n);
-      const int npar = ele_kind(g.kind).npar;
-      std::vector<double> par2((size_t)n * npar);
-#pragma omp parallel for schedule(static)
-      for (long long i = 0; i < n; i++) {
-        const long long o = byTag[i];
-        tag2[i] = g.tag[o]; mat2[i] = g.mat[o];
-        std::memcpy(&conn2[(size_t)i * 8], &g.conn[(size_t)o * 8], sizeof(int) * 8);
-        std::memcpy(&par2[(size_t)i * npar], &g.par[(size_t)o * npar], sizeof(double) * npar);
-      }
-      g.tag.swap(tag2); g.conn.swap(conn2); g.mat.swap(mat2); g.par.swap(par2);
-      tiled = true;
-    }
-  }
-
   // ---- PlainHandler::handle: every dof -2 (free) unless an SP_Constraint sets -1 ----
   std::vector<int> gid((size_t)n_nodes * ndf, -2);
   for (size_t i = 0; i < sp_node.size(); i++) {
@@ -609,13 +554,18 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
   }
   const std::vector<Group>& LG = nparts == 1 ? groups : lgroups;
   // offsets of the local element matrices / residuals
-  std::vector<long long> ke_off(LG.size()), re_off(LG.size()), gp_off(LG.size());
-  ke_total = re_total = ngp = 0;
+  std::vector<long long> ke_off(LG.size()), re_off(LG.size()), gp_off(LG.size()), rec_off(LG.size(), 0);
+  ke_total = re_total = ngp = rec_total = 0;
+  // stdBrick tangents are kept as symmetric element records and gathered by the assembly (brick_rec.hpp).  A model
+  // with ndf = 3 in 3D holds no other element kind here, so this is the only brick path.
+  rec_mode = !groups.empty() && ndf == 3 && cp_stride == 24;     // (the global batches: the same answer on every rank)
+  for (const Group& g : groups) if (g.kind != XB_ELE_STDBRICK) rec_mode = false;
   for (size_t gi = 0; gi < LG.size(); gi++) {
     const EleKind& k = ele_kind(LG[gi].kind);
     const long long nd = k.nen * k.ndf;
-    ke_off[gi] = ke_total; re_off[gi] = re_total; gp_off[gi] = ngp;
+    ke_off[gi] = ke_total; re_off[gi] = re_total; gp_off[gi] = ngp; rec_off[gi] = rec_total;
     ke_total += LG[gi].n() * nd * nd; re_total += LG[gi].n() * nd; ngp += LG[gi].n() * (k.nip ? k.nip : LG[gi].nip);
+    if (rec_mode) rec_total += LG[gi].n() * kBrickRec;
   }
 
   // ---- local node tables ----
@@ -655,11 +605,12 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
   const long long n2e_total = n2e_ptr[nl];
   n2e_koff.resize(n2e_total); n2e_roff.resize(n2e_total); n2e_nd.resize(n2e_total);
   n2e_fe.resize(n2e_total); n2e_loc.resize(n2e_total);
-  // node-major storage of the element-tangent rows: slot u lives at KeN[u*chunk]
+  // node-major storage of the element-tangent rows: slot u lives at KeN[u*chunk] (record models: no KeN, n2e_ksrc)
   chunk = ndf * cp_stride;
-  kn_total = n2e_total * chunk;
+  kn_total = rec_mode ? 0 : n2e_total * chunk;
+  n2e_ksrc.assign(rec_mode ? n2e_total : 0, 0);
   std::vector<Group>& WG = nparts == 1 ? groups : lgroups;   // the local groups being built
-  for (auto& g : WG) g.kdst.assign((size_t)g.n() * ele_kind(g.kind).nen, 0);
+  for (auto& g : WG) g.kdst.assign(rec_mode ? 0 : (size_t)g.n() * ele_kind(g.kind).nen, 0);
   // receive-buffer layout: per source rank, chunks in (owned node ascending, FE order)
   std::vector<long long> rk(nparts, 0), rr(nparts, 0), rc(nparts, 0);
   std::vector<std::vector<long long>> in_kdst(nparts);
@@ -676,10 +627,12 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
       if (src == rank) {
         const int gi = G.fe_group[e];
         const long long l = nparts == 1 ? G.fe_local[e] : fe_local[g_fe_to_local[e]];
-        WG[gi].kdst[(size_t)l * k->nen + a] = u * chunk;
+        if (rec_mode) n2e_ksrc[u] = brick_rec_desc(rec_off[gi] + l * kBrickRec, a);
+        else WG[gi].kdst[(size_t)l * k->nen + a] = u * chunk;
         n2e_roff[u] = re_off[gi] + l * nd + (long long)a * k->ndf;
       } else {
-        in_kdst[src].push_back(u * chunk);
+        if (rec_mode) n2e_ksrc[u] = rk[src];   // relative to that peer's block of the receive buffer, fixed below
+        else in_kdst[src].push_back(u * chunk);
         n2e_roff[u] = rr[src];      // relative to that peer's block, fixed below
         rk[src] += chunk; rr[src] += k->ndf; rc[src]++;
       }
@@ -706,19 +659,22 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
       }
     }
   }
-  peers.clear(); pr_src.clear(); pr_dst.clear(); uk_src.clear(); uk_dst.clear();
+  peers.clear(); pr_src.clear(); pr_dst.clear(); uk_src.clear(); uk_dst.clear(); pk_src.clear();
   send_k_total = recv_k_total = send_r_total = recv_r_total = 0;
-  std::vector<long long> recv_r_base(nparts, 0);
+  std::vector<long long> recv_r_base(nparts, 0), recv_k_base(nparts, 0);
   for (int s = 0; s < nparts; s++) {
     if (s == rank || (sc[s] == 0 && rc[s] == 0)) continue;
     Peer p; p.rank = s;
     p.send_k = sk[s]; p.send_r = sr[s]; p.recv_k = rk[s]; p.recv_r = rr[s];
     p.chunks_out = sc[s]; p.chunks_in = rc[s];
     p.send_k_base = send_k_total; p.send_r_base = send_r_total; p.recv_k_base = recv_k_total; p.recv_r_base = recv_r_total;
-    recv_r_base[s] = recv_r_total;
+    recv_r_base[s] = recv_r_total; recv_k_base[s] = recv_k_total;
     long long dk = send_k_total, dr = send_r_total;
     for (const Out& o : outs[s]) {
-      WG[o.gi].kdst[(size_t)o.l * o.nen + o.a] = -(dk + 1);     // the element kernel writes straight into the send buffer
+      // the element kernel writes straight into the send buffer; record models gather the rows out of the record
+      // (pack_rows_rec_kernel: chunk c of the send buffer <- pk_src[c])
+      if (rec_mode) pk_src.push_back(brick_rec_desc(rec_off[o.gi] + o.l * kBrickRec, o.a));
+      else WG[o.gi].kdst[(size_t)o.l * o.nen + o.a] = -(dk + 1);
       pr_src.push_back(o.rsrc); pr_dst.push_back(dr);
       dk += chunk; dr += ndf;
     }
@@ -731,7 +687,10 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
   if (nparts > 1)
     for (long long u = 0; u < n2e_total; u++) {
       const int src = part_fe[n2e_fe[u]];
-      if (src != rank) n2e_roff[u] = -(recv_r_base[src] + n2e_roff[u] + 1);
+      if (src != rank) {
+        n2e_roff[u] = -(recv_r_base[src] + n2e_roff[u] + 1);
+        if (rec_mode) n2e_ksrc[u] = dense_rows_desc(recv_k_base[src] + n2e_ksrc[u]);
+      }
     }
 
   // ---- DOF graph -> sparse pattern of the owned rows.  Every free dof of node n is coupled
@@ -893,7 +852,8 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
     std::sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.fe != b.fe ? a.fe < b.fe : a.dof < b.dof; });
     for (const Ent& en : ents) {
       const EleKind* k; const int* c = G.conn_of(en.fe, &k);
-      irr_src.push_back(en.t * chunk + (long long)en.j * cp_stride);
+      // the element-matrix row: dense in KeN, or -- record models -- the slot's descriptor and the dof (descriptor * 4 + dof)
+      irr_src.push_back(rec_mode ? n2e_ksrc[en.t] * 4 + en.j : en.t * chunk + (long long)en.j * cp_stride);
       irr_roff.push_back(n2e_roff[en.t] >= 0 ? n2e_roff[en.t] + en.j : n2e_roff[en.t] - en.j);   // < 0: -(offset in recvR + 1)
       const size_t base = irr_cp.size();
       irr_cp.resize(base + cp_stride, 0xFFFF);
@@ -916,24 +876,14 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
     // 0xFFFF is "no column"; a real position never reaches 0x1FFF here, so rank 7 + position 0x1FFF cannot occur
   }
 
-  // ---- node order for the pipelined formTangent (single-batch models; else one range) ----
+  // ---- node order for the ranged formTangent (single-batch models; else one range) ----
   {
     const std::vector<Group>& FG = nparts == 1 ? groups : lgroups;
-    // (measured on B200: the element kernel's 228 registers x 8 warps leave no room for assembly
-    //  CTAs to co-reside, so the pipeline buys nothing there; it stays opt-in: XB_PIPELINE=<ranges>)
-    //  What the ranges do buy is the copy-out: with a host destination, xb_form_tangent sends the
-    //  rows of range c to the host while range c+1 is still being formed (chunk_a_ptr below).
-    const char* pl = std::getenv("XB_PIPELINE");
-    const int want = pl ? std::atoi(pl) : 8;
-    pipeline_forced = pl != nullptr;
-    nchunk = (FG.size() == 1 && ne >= 65536 && want > 1 && want <= 64 && !have_mp) ? want : 1;
-    if (tiled) nchunk = (int)tile_super.size();
+    // With a host destination, xb_form_tangent sends the rows of range c to the host while range c+1 is still
+    // being formed (chunk_a_ptr below); the element kernel and the assembly of the previous range also share the SMs.
+    const int want = 8;
+    nchunk = (FG.size() == 1 && ne >= 65536 && !have_mp) ? want : 1;
     const long long per = nchunk > 1 ? (ne + nchunk - 1) / nchunk : ne;
-    std::vector<int> tile_of;
-    if (tiled) {
-      tile_of.resize(ne);
-      for (int c = 0; c < nchunk; c++) for (long long l = tile_ptr[c]; l < tile_ptr[c + 1]; l++) tile_of[l] = c;
-    }
     std::vector<int> ready(nl, -1);
     for (int i = 0; i < nl; i++) {
       if (!owned[i]) continue;
@@ -943,7 +893,7 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
         if (part_fe[ge] != rank) { rdy = nchunk; break; }          // needs the interface exchange
         const long long le = nparts == 1 ? ge : g_fe_to_local[ge];  // local FE index == index in the batch
         const long long l = fe_local[le];
-        rdy = std::max(rdy, tiled ? tile_of[l] : (nchunk > 1 ? (int)(l / per) : 0));
+        rdy = std::max(rdy, nchunk > 1 ? (int)(l / per) : 0);
       }
       ready[i] = rdy;
     }
@@ -953,6 +903,35 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
     node_perm.resize(chunk_node_ptr[nchunk + 1]);
     std::vector<long long> fill(chunk_node_ptr.begin(), chunk_node_ptr.end() - 1);
     for (int i = 0; i < nl; i++) if (ready[i] >= 0) node_perm[fill[ready[i]]++] = i;
+    if (rec_mode) {
+      // Morton order of the node coordinates inside every range (one cell size for all axes, 16 bits each): the
+      // eight nodes of an element are assembled close together in time, so its record is read from HBM once
+      double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+      for (int i = 0; i < nl; i++)
+        for (int d = 0; d < ndm; d++) { lo[d] = std::min(lo[d], crd[(size_t)i * ndm + d]); hi[d] = std::max(hi[d], crd[(size_t)i * ndm + d]); }
+      double ext = 0.0;
+      for (int d = 0; d < ndm; d++) ext = std::max(ext, hi[d] - lo[d]);
+      const double inv = ext > 0.0 ? 65535.0 / ext : 0.0;
+      auto spread = [](uint64_t v) {   // 16 bits -> every third bit
+        v &= 0xFFFF;
+        v = (v | (v << 32)) & 0x1F00000000FFFFull;
+        v = (v | (v << 16)) & 0x1F0000FF0000FFull;
+        v = (v | (v << 8)) & 0x100F00F00F00F00Full;
+        v = (v | (v << 4)) & 0x10C30C30C30C30C3ull;
+        v = (v | (v << 2)) & 0x1249249249249249ull;
+        return v;
+      };
+      std::vector<std::pair<uint64_t, int>> keyed(node_perm.size());
+#pragma omp parallel for schedule(static)
+      for (long long u = 0; u < (long long)node_perm.size(); u++) {
+        const int i = node_perm[u];
+        uint64_t key = 0;
+        for (int d = 0; d < ndm; d++) key |= spread((uint64_t)((crd[(size_t)i * ndm + d] - lo[d]) * inv)) << d;
+        keyed[u] = {key, i};
+      }
+      for (int c = 0; c <= nchunk; c++) std::sort(keyed.begin() + chunk_node_ptr[c], keyed.begin() + chunk_node_ptr[c + 1]);
+      for (size_t u = 0; u < node_perm.size(); u++) node_perm[u] = keyed[u].second;
+    }
     // what the assembly warp of node_perm[u] needs, in one record (assemble_A_kernel)
     const int TW = 3 + ndf;
     asm_task.assign((size_t)node_perm.size() * TW, 0);
@@ -968,10 +947,81 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
         tk[3 + j] = r >= 0 ? ptr[r] : -1;
       }
     }
-    // rows each range completes: streamable when range c owns exactly the rows [r_c, r_{c+1}) of A.  Tiled: the
-    // unit is the super-range (FE-order slice) -- its tiles complete rows in spatial, not row, order.
-    const int ng = tiled ? nsuper : nchunk;
-    auto group_of = [&](int c) { return c >= nchunk ? ng : (tiled ? tile_super[c] : c); };
+    // ---- block-row assembly maps of a record model (host_model.hpp, blocks_ok) ----
+    blocks_ok = rec_mode && !have_mp;
+    nb_ptr.clear(); nb_info.clear(); inv_ptr.clear(); nb_inv.clear(); asm_task8.clear();
+    if (blocks_ok) {
+      nb_ptr.assign((size_t)nl + 1, 0); inv_ptr.assign((size_t)nl + 1, 0);
+#pragma omp parallel
+      {
+        std::vector<int> tmp;
+#pragma omp for schedule(dynamic, 4096)
+        for (int i = 0; i < nl; i++) {
+          if (!owned[i] || n2e_ptr[i + 1] == n2e_ptr[i]) continue;
+          G.nbrs(lnode[i], tmp);
+          nb_ptr[i + 1] = (long long)tmp.size();
+          inv_ptr[i + 1] = (long long)tmp.size() * ((n2e_ptr[i + 1] - n2e_ptr[i] + 7) / 8);
+        }
+      }
+      for (int i = 0; i < nl; i++) { nb_ptr[i + 1] += nb_ptr[i]; inv_ptr[i + 1] += inv_ptr[i]; }
+      nb_info.assign((size_t)nb_ptr[nl], 0); nb_inv.assign((size_t)inv_ptr[nl], ~0ull);
+      std::vector<int> self(nl, 0);
+      long long bad_nodes = 0;
+#pragma omp parallel
+      {
+        std::vector<int> tmp;
+#pragma omp for schedule(dynamic, 4096) reduction(+ : bad_nodes)
+        for (int i = 0; i < nl; i++) {
+          if (nb_ptr[i + 1] == nb_ptr[i]) continue;
+          G.nbrs(lnode[i], tmp);
+          const int nnb = (int)tmp.size();
+          const int* cols = &ncol[ncol_ptr[i]];
+          const long long L = ncol_ptr[i + 1] - ncol_ptr[i];
+          if (nnb > 0xFFFF || L >= 0x1FFF) { bad_nodes++; continue; }
+          for (int mI = 0; mI < nnb; mI++) {
+            const int w = tmp[mI];
+            if (w == lnode[i]) self[i] = mI;
+            int mask = 0, first = -1, prev = -1;
+            for (int j = 0; j < ndf; j++) {
+              const int q = gid[(size_t)w * ndf + j];
+              if (q < 0) continue;
+              const int pos = (int)(std::lower_bound(cols, cols + L, q) - cols);
+              if (first < 0) first = pos;
+              else if (pos != prev + 1) bad_nodes++;     // (cannot happen without MP constraints)
+              prev = pos; mask |= 1 << j;
+            }
+            nb_info[nb_ptr[i] + mI] = (uint16_t)((first < 0 ? 0 : first) | (mask << 13));
+          }
+          const long long ns = n2e_ptr[i + 1] - n2e_ptr[i];
+          for (long long sI = 0; sI < ns; sI++) {
+            const EleKind* k; const int* c = G.conn_of(n2e_fe[n2e_ptr[i] + sI], &k);
+            for (int a = 0; a < k->nen; a++) {
+              const int mI = (int)(std::lower_bound(tmp.begin(), tmp.end(), c[a]) - tmp.begin());
+              uint64_t& wd = nb_inv[inv_ptr[i] + (sI / 8) * nnb + mI];
+              const int sh = 8 * (int)(sI % 8);
+              wd = (wd & ~(0xFFull << sh)) | ((uint64_t)a << sh);
+            }
+          }
+        }
+      }
+      if (bad_nodes) { blocks_ok = false; nb_ptr.clear(); nb_info.clear(); inv_ptr.clear(); nb_inv.clear(); }
+      else {
+        asm_task8.assign((size_t)node_perm.size() * 8, 0);
+        for (size_t u = 0; u < node_perm.size(); u++) {
+          const int i = node_perm[u];
+          long long* tk = &asm_task8[u * 8];
+          const long long ns = n2e_ptr[i + 1] - n2e_ptr[i];
+          tk[0] = n2e_ptr[i];
+          tk[1] = ns | ((nb_ptr[i + 1] - nb_ptr[i]) << 16) | ((long long)self[i] << 32);
+          tk[2] = i;
+          for (int j = 0; j < 3; j++) { const int r = row_of_dev[(size_t)i * ndf + j]; tk[3 + j] = r >= 0 ? ptr[r] : -1; }
+          tk[6] = inv_ptr[i]; tk[7] = nb_ptr[i];
+        }
+      }
+    }
+    // rows each range completes: streamable when range c owns exactly the rows [r_c, r_{c+1}) of A
+    const int ng = nchunk;
+    auto group_of = [&](int c) { return c; };
     chunk_a_ptr.assign((size_t)ng + 2, 0);
     rows_streamable = nchunk > 1;
     int next_row = 0;
@@ -993,7 +1043,7 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
 
   // ---- commit the local element groups ----
   if (nparts > 1) groups.swap(lgroups);
-  for (size_t gi = 0; gi < groups.size(); gi++) { groups[gi].ke_off = ke_off[gi]; groups[gi].re_off = re_off[gi]; groups[gi].gp_off = gp_off[gi]; }
+  for (size_t gi = 0; gi < groups.size(); gi++) { groups[gi].ke_off = ke_off[gi]; groups[gi].rec_off = rec_off[gi]; groups[gi].re_off = re_off[gi]; groups[gi].gp_off = gp_off[gi]; }
   is_setup = true;
   return neq;
 }

@@ -18,6 +18,8 @@
 #include <string>
 #include <vector>
 
+#include "brick_rec.hpp"
+
 namespace xb {
 
 struct EleKind {
@@ -64,7 +66,9 @@ struct Group {
   bool j2_plane_stress = false;   // FourNodeQuad batch whose J2Plasticity copies are J2PlaneStress
   std::vector<long long> kdst;  // [n][nen] where the rows of node a of element l go: >= 0 offset of the
                                 //   slot in the node-major buffer KeN (node owned here), < 0 offset
-                                //   -(x+1) in the send buffer (node owned by another rank)
+                                //   -(x+1) in the send buffer (node owned by another rank).  Empty for stdBrick
+                                //   batches: their tangents are kept as symmetric element records (rec_off)
+  long long rec_off = 0;     // stdBrick: offset (doubles) of the batch's first element record (brick_rec.hpp)
   long long ke_off = 0;      // (legacy element-major offset; sizes the residual bookkeeping)
   long long re_off = 0;      // offset (doubles) of this group's element residuals
   long long gp_off = 0;      // first Gauss point (for reporting)
@@ -142,6 +146,24 @@ struct HostModel {
   std::vector<long long> n2e_ptr;   // [nn+1]
   std::vector<long long> n2e_koff;  // [*] offset of the slot in KeN (= slot index * chunk)
   std::vector<long long> n2e_roff;  // [*] offset in Re of entry (a*ndf)
+  // record models (stdBrick, see brick_rec.hpp): where the slot's rows come from.  offset << 4 | local node << 1 | 1:
+  // gathered from the element record at `offset` (doubles); offset << 4 | 0: ndf dense rows of cp_stride columns at
+  // `offset` of the receive buffer (the element lives on another rank).  Empty otherwise (slot u = KeN[u * chunk]).
+  std::vector<long long> n2e_ksrc;
+  bool rec_mode = false;            // every batch is stdBrick: element records + gathered assembly
+  long long rec_total = 0;          // doubles of element records
+  std::vector<long long> pk_src;    // record models: outgoing row chunk c (send buffer offset c * chunk) <- record descriptor
+  // Record models without MP constraints: the block-row form of the assembly (assemble_A_blocks_kernel).  The free dofs
+  // of a node carry consecutive equation numbers, so the columns of node n's rows are runs of <= 3 positions, one run
+  // per neighbour node m (nodes sharing an element with n, ascending node index): lane m of the node's warp owns the
+  // 3x3 block A(n, m) and sums the element blocks K_(J,K) of every slot in FE_Element order.
+  bool blocks_ok = false;
+  std::vector<long long> nb_ptr;    // [nn+1] neighbours of the owned nodes
+  std::vector<uint16_t> nb_info;    // [*] first column position (13 bits) | free-dof mask << 13 of neighbour m
+  std::vector<long long> inv_ptr;   // [nn+1] -> nb_inv, in 8-byte words: ceil(slots / 8) x neighbours per node
+  std::vector<uint64_t> nb_inv;     // [*] byte s of word (g, m): local node of neighbour m in slot 8 g + s, 0xFF if not in it
+  std::vector<long long> asm_task8; // [node_perm.size()][8]: first slot, slots | neighbours << 16 | own neighbour index << 32,
+                                    //   node, A offset of its 3 rows (-1: constrained), offset in nb_inv, offset in nb_info
   std::vector<uint8_t> n2e_nd;      // [*] nd = nen*ndf of that element
   std::vector<long long> n2e_fe;    // [*] GLOBAL FE index
   std::vector<uint8_t> n2e_loc;     // [*] local node a
@@ -152,25 +174,17 @@ struct HostModel {
   int cp_stride = 0;                // max nd over groups
   std::vector<uint16_t> colpos;     // [n2e_total][cp_stride]: position of local dof j's equation
                                     //   inside node n's column list, 0xFFFF if constrained
-  // pipelined formTangent: the elements are cut into `nchunk` consecutive ranges (per batch); a
+  // ranged formTangent: the elements are cut into `nchunk` consecutive ranges (per batch); a
   // node can be assembled once the last range holding one of its elements is done.  node_perm
-  // lists the owned nodes by that range (nodes with rows from other ranks last: range nchunk).
+  // lists the owned nodes by that range (nodes with rows from other ranks last: range nchunk);
+  // record models: inside a range in Morton order of the node coordinates, so that the records a
+  // node gathers from are still in L2 when its neighbours ask for them.
   int nchunk = 1;
   std::vector<int> node_perm;       // [n_owned_nodes_with_rows]
   std::vector<long long> chunk_node_ptr;   // [nchunk+2]
   std::vector<long long> asm_task;         // [node_perm.size()][3+ndf] per-node record of the assembly kernel
   std::vector<long long> chunk_a_ptr;      // [nchunk+2] offsets in A of the rows each range completes
   bool rows_streamable = false;     // the ranges own consecutive row blocks of A (copy-out can follow them)
-  bool pipeline_forced = false;     // XB_PIPELINE set: use the ranges also without a host destination
-  // tiled formTangent (large single-batch brick models, one rank): at set-up the batch's STORAGE order (not the
-  // FE_Element order, which is by tag) becomes  super-range (FE-order slices, so that finished rows of A can leave
-  // for the host in order) > spatial tile (recursive coordinate bisection of the slice, <= tile_target elements).
-  // A range of the pipeline is then one tile: its element rows (~40 MB) are still in L2 when the nodes the tile
-  // completes are assembled, so most of the element-matrix round trip never reaches HBM.
-  bool tiled = false;
-  std::vector<long long> tile_ptr;  // [nchunk+1] storage index where each tile starts
-  std::vector<int> tile_super;      // [nchunk] super-range of a tile
-  int nsuper = 1;
   int max_row = 0;                  // longest row
   long long ke_total = 0, re_total = 0, ngp = 0;
   int chunk = 0;                    // doubles per slot: ndf rows x cp_stride columns
