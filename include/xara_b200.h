@@ -249,10 +249,10 @@ int xb_get_element_resid(xb_model*, long long e, double* R);
 int xb_get_gp_response(xb_model*, long long e, int g, double* stress, double* tangent);
 
 /* Run-time tuning of the device path; the results are bit-for-bit the same under every setting.
- *   "tangent_passes"  1 | 2 (default 2): the stdBrick tangent kernel accumulates its node-pair blocks in one pass
- *                     (45 FP64 accumulators, 8 warps per SM) or two (27 + 18, 12 warps per SM)
- *   "ranged_tangent"  0 | 1 (default 0): run xb_form_tangent of a large single-batch brick model range by range on
+ *   "ranged_tangent"  0 | 1 (default 1): run xb_form_tangent of a large single-batch brick model range by range on
  *                     two streams also when A stays on the device (with a host destination it always does)
+ *   "fast_assembly"   0 | 1 (default 1): plain brick models (no MP constraints, rows <= 96 entries, <= 32 elements per
+ *                     node) take the hand-tuned record assembly kernel; 0 forces the generic one
  * Returns XB_ERR_ARG for an unknown name or value. */
 int xb_set_option(xb_model*, const char* name, int value);
 

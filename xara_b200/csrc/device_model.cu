@@ -664,8 +664,8 @@ __global__ void __launch_bounds__(128, DYN ? 1 : 5) quad_resid_kernel(GroupView 
 //     (n as the symmetric 3x3 normal tensor): no 6x6 D is built, a node's record per Gauss point in shared memory
 //     is grad N alone (24 B), v_J is recomputed from it (9 FP64 operations) and n comes as one broadcast read per
 //     element.  219 FP64 instructions per lane and Gauss point;
-//   * NPASS = 2: the blocks are accumulated in two passes over the Gauss points (t = 0,1,2 then t = 3,4: 27 + 18
-//     FP64 accumulators instead of 45), which brings the kernel from 2 to 3 CTAs per SM;
+//   * (NPASS = 2 accumulates the blocks in two passes over the Gauss points, t = 0,1,2 then t = 3,4: 27 + 18 FP64
+//     accumulators instead of 45 and room for 12 warps per SM -- measured slower, see below; NPASS = 1 is what runs);
 //   * a warp walks over its batches of 4 elements in a loop and requests the inputs of the NEXT batch (its node's
 //     coordinates, the Gauss point's compact tangent) before the main loop of the current one, so that the
 //     global-load latency hides behind FP64 work;
@@ -893,8 +893,10 @@ __device__ __forceinline__ void brick_tangent_rec_range(const GroupView& G, cons
   __syncwarp();
 }
 
-// Two CTAs per SM.  NPASS = 1: 4 warps per CTA (8 warps x ~240 registers fill the register file); NPASS = 2: 6 warps
-// per CTA at <= 168 registers (12 warps per SM, three per scheduler; their shared memory is exactly the SM's 228 KB).
+// Two CTAs of NW = 4 warps per SM: 8 warps x 222 registers fill the register file.  Measured on B200 (2.1 M elements):
+// one pass / 4 warps 2.62 ms; two passes (27 + 18 accumulators) at 4 warps and 192 registers 2.92 ms, at 6 warps and
+// 168 registers (12 warps per SM, 32 bytes of spills) 3.09 ms -- the second pass repeats the per-point set-up (+8 % FP64
+// work) and more warps do not buy it back, so the one-pass form is the only one kept.
 template <int MATK, int DYN, int NPASS, int NW>
 __global__ void __launch_bounds__(NW * 32, 2) brick_tangent_rec_kernel(GroupView G, const double* __restrict__ X,
                                                                    long long ebeg, long long eend,
@@ -905,18 +907,6 @@ __global__ void __launch_bounds__(NW * 32, 2) brick_tangent_rec_kernel(GroupView
   brick_tangent_rec_range<MATK, DYN, NPASS>(G, X, ebeg, eend, tsrc_, tzero_, scale_, accum_, smem + warp * BS_WARP,
                                             (long long)blockIdx.x * NW + warp, (long long)gridDim.x * NW);
 }
-// 5 warps per CTA, two CTAs per SM: 200 registers (ptxas rounds the launch-bounds limit of 204 down to 168)
-template <int MATK, int DYN, int NPASS>
-__global__ void __maxnreg__(200) brick_tangent_rec5_kernel(GroupView G, const double* __restrict__ X,
-                                                           long long ebeg, long long eend,
-                                                           const double* __restrict__ tsrc_, int tzero_,
-                                                           double scale_, int accum_) {
-  extern __shared__ __align__(16) double smem[];
-  const int warp = threadIdx.x >> 5;
-  brick_tangent_rec_range<MATK, DYN, NPASS>(G, X, ebeg, eend, tsrc_, tzero_, scale_, accum_, smem + warp * BS_WARP,
-                                            (long long)blockIdx.x * 5 + warp, (long long)gridDim.x * 5);
-}
-
 // FourNodeQuad::getTangentStiff (FourNodeQuad.cpp:226-281).  4 lanes per element, lane b
 // owns column block beta=b (8 rows x 2 columns); shape functions are recomputed per lane.
 template <int MATK, int DYN>
@@ -1038,8 +1028,8 @@ struct AsmView {
   // record models (stdBrick: brick_rec.hpp): a slot's rows are gathered from the element's symmetric record
   const long long* n2e_ksrc;  // [*] slot descriptor: offset << 4 | local node << 1 | 1 (record), offset << 4 (dense rows in recvK)
   const double* rec;          // element records
-  const unsigned short* nb_info;      // block-row assembly (HostModel::blocks_ok): per (node, neighbour) first column | mask << 13
-  const unsigned long long* nb_inv;   // per (node, 8 slots, neighbour): local node of the neighbour in each slot
+  const unsigned* gather_tab; // [9][72] the fast kernel's gather in record order: offset | row << 10 | element dof << 12
+  const unsigned* n2e_ksrc32; // the same in 32 bits for the fast kernel: offset in units of 36 doubles << 4 | local node (8: dense rows)
   int transpose;              // the SOE stores A by columns: a slot's "rows" are columns of the element tangent
   // MP constraints (equalDOF): equations shared by several (node, dof) are assembled by row (host_model.hpp, irr_*)
   int max_dup, nirr, irr_max_row;
@@ -1212,139 +1202,99 @@ __global__ void __launch_bounds__(256, XB_ASM_REC_OCC) assemble_A_rec_kernel(Asm
   assemble_A_node<3, MP, 1, true, XB_ASM_REC_CH>(V, nullptr, A, task, first + w, sacc + (size_t)warp * 3 * V.max_row, stab);
 }
 
-// Block-row form of the record assembly (record models without MP constraints; HostModel::blocks_ok).  One warp per
-// node n; lane m owns the 3x3 block A(n, m) of neighbour node m (a node sharing an element with n): for every slot of
-// n in FE_Element order -- the order addA is called in -- whose element holds m as local node K, it adds the element
-// block K_(J,K) (J = n's local node) read straight out of the symmetric record: 9 contiguous doubles, transposed when
-// the record keeps the pair as (K, J).  Nine FP64 accumulators per lane, no shared-memory accumulator, no barriers;
-// every entry of A is written once.  Rows received from other ranks (dense 3 x 24) are read in the same loop.
-//   task (8 words): first slot, slots | neighbours << 16 | own index << 32, node, A offsets of the 3 rows, nb_inv / nb_info offsets
-#ifndef XB_ASM_BLK_OCC
-#define XB_ASM_BLK_OCC 4
+// The record assembly as it runs for a plain brick model (no MP constraints, rows of at most 96 entries, at most 32
+// elements per node): the same gather, additions in the same FE_Element order, written for the unit that bounds it.
+// ncu: the generic kernel above saturates the L1 data pipe (98 % of its wavefronts: 229 per node for the shared-memory
+// accumulator, 180 for the scattered 8-byte gathers).  Here the 72 values a node takes from a record are read in
+// RECORD order -- lane i takes the i-th, (i+32)-th, (i+64)-th of them, so that a load instruction covers contiguous
+// runs (the node's own region, then single blocks of the others) -- and a table says where each lands: row p and element
+// dof c, whose column position comes from the lane holding colpos[c] by shuffle.  Static shared memory (compile-time
+// row stride, 32-bit addressing); 32-bit slot descriptors (offset in units of 36 doubles << 4 | local node, 8 = dense
+// rows received from another rank, which lie behind the records in ONE allocation: a value's address is one 32-bit
+// index off one base pointer); four slots (12 loads per lane) are in flight before the first addition.
+constexpr int FA_L = 96;                                   // longest row taken
+constexpr int FA_S = 101;                                  // accumulator row stride: = 5 mod 16, so that the values of one
+                                                           //   column (rows 0, 1, 2: neighbouring lanes) fall into different banks
+#ifndef XB_ASM_FAST_OCC
+#define XB_ASM_FAST_OCC 5
 #endif
-__global__ void __launch_bounds__(256, XB_ASM_BLK_OCC) assemble_A_blocks_kernel(AsmView V, double* __restrict__ A,
-                                                                               const long long* __restrict__ task,
-                                                                               long long first, long long count) {
-  __shared__ unsigned short btab[64];    // [J][K] -> offset of entry (0,0) of block (J,K) | 0x8000 if stored transposed
-  if (threadIdx.x < 64) {
-    const int J = threadIdx.x >> 3, K = threadIdx.x & 7;
-    const int o = xb::brick_rec_entry(J, 0, K, 0, V.transpose);
-    const int tr = xb::brick_rec_entry(J, 1, K, 0, V.transpose) - o == 1;
-    btab[threadIdx.x] = (unsigned short)(o | (tr ? 0x8000 : 0));
-  }
+__global__ void __launch_bounds__(256, XB_ASM_FAST_OCC) assemble_A_rec_fast_kernel(AsmView V, double* __restrict__ A,
+                                                                                 const long long* __restrict__ task,
+                                                                                 long long first, long long count) {
+  __shared__ double sacc[8][3 * FA_S + 1];
+  // [local node J | 8 = dense rows][item i of 72, record order] -> offset in the record | row p << 10 | element dof c << 12
+  __shared__ unsigned stab[9 * 72];
+  for (int i = threadIdx.x; i < 9 * 72; i += 256) stab[i] = __ldg(V.gather_tab + i);    // (built on the host: xb_device_init)
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * 8 + warp;
   if (w >= count) return;
-  const long long word = lane < 8 ? __ldg(task + (first + w) * 8 + lane) : 0;
+  double* acc = sacc[warp];
+  const long long word = lane < 6 ? __ldg(task + (first + w) * 6 + lane) : 0;
   const long long t0 = __shfl_sync(0xffffffffu, word, 0);
   const long long pk = __shfl_sync(0xffffffffu, word, 1);
-  const long long n = __shfl_sync(0xffffffffu, word, 2);
-  const long long rp0 = __shfl_sync(0xffffffffu, word, 3), rp1 = __shfl_sync(0xffffffffu, word, 4),
-                  rp2 = __shfl_sync(0xffffffffu, word, 5);
-  const long long inv_off = __shfl_sync(0xffffffffu, word, 6), nb_off = __shfl_sync(0xffffffffu, word, 7);
-  const int ns = (int)(pk & 0xFFFF), nnb = (int)((pk >> 16) & 0xFFFF), mself = (int)(pk >> 32);
-  const double c1 = V.c1;
-  const bool dyn = V.c2 != 0.0 || V.c3 != 0.0;
-  if (ns == 0) {   // a node with no element: its rows hold the diagonal only (the DOF_Group's mass terms, or zero)
+  const int ns = (int)(pk & 0xffffffffll), L = (int)(pk >> 32);
+  const unsigned mydesc = lane < ns ? __ldg(V.n2e_ksrc32 + t0 + lane) : 0u;    // the node's slot descriptors (ns <= 32)
+  const unsigned short* cp = V.colpos + t0 * 24 + (lane < 24 ? lane : 0);
+  const double* __restrict__ rec = V.rec;
+  const bool last8 = lane < 8;                             // the third round holds items 64..71
+#pragma unroll
+  for (int c = 0; c < (3 * FA_S + 31) / 32; c++) if (c * 32 + lane < 3 * FA_S) acc[c * 32 + lane] = 0.0;
+  __syncwarp();
+  // the DOF_Group tangents, added before the elements' (TransientIntegrator.cpp:89-107):
+  // Newmark::formNodTangent = c2 * (alphaM * M) + c3 * M on the diagonal
+  if (V.c2 != 0.0 || V.c3 != 0.0) {
+    const long long n = __shfl_sync(0xffffffffu, word, 2);
     if (lane < 3) {
-      const long long rp = lane == 0 ? rp0 : (lane == 1 ? rp1 : rp2);
-      if (rp >= 0) {
-        double t = 0.0;
-        if (dyn) { const double ms = V.mass[n * 3 + lane]; t += (ms * V.alphaM) * V.c2; t += ms * V.c3; }
-        A[rp] = t;
-      }
-    }
-    return;
-  }
-  // where lane m finds the block of slot sI (descriptor d, local node K of the neighbour in that element): entry (p, q)
-  // at src[p * sp + q * sq] -- (3,1) in the record, (1,3) when the record keeps the transposed pair, (24,1) in dense rows
-  auto locate = [&](long long d, unsigned K, const double*& src, int& sp, int& sq) {
-    if (d & 1) {
-      const unsigned bt = btab[(((unsigned)d >> 1) & 7u) * 8 + K];
-      src = V.rec + (d >> 4) + (bt & 0x7FFFu);
-      const bool tr = (bt & 0x8000u) != 0;
-      sp = tr ? 1 : 3; sq = tr ? 3 : 1;
-    } else {
-      src = V.recvK + (d >> 4) + 3 * K;
-      sp = 24; sq = 1;
-    }
-  };
-  for (int m0 = 0; m0 < nnb; m0 += 32) {            // (one round unless the node has more than 32 neighbours)
-    const int m = m0 + lane;
-    const bool live = m < nnb;
-    const unsigned info = live ? __ldg(V.nb_info + nb_off + m) : 0u;
-    double acc[3][3];
-#pragma unroll
-    for (int p = 0; p < 3; p++)
-#pragma unroll
-      for (int q = 0; q < 3; q++) acc[p][q] = 0.0;
-    // the DOF_Group tangents are added before the elements' (TransientIntegrator.cpp:89-107):
-    // Newmark::formNodTangent = c2 * (alphaM * M) + c3 * M on the diagonal
-    if (dyn && m == mself) {
-#pragma unroll
-      for (int p = 0; p < 3; p++) {
-        const double ms = V.mass[n * 3 + p];
+      const unsigned short dp = V.diagpos[n * 3 + lane];
+      if (dp != 0xFFFF) {
+        const double ms = V.mass[n * 3 + lane];
         double t = 0.0;
         t += (ms * V.alphaM) * V.c2;
         t += ms * V.c3;
-        acc[p][p] = t;
+        acc[lane * FA_S + dp] = t;
       }
     }
-    for (int g8 = 0; g8 < ns; g8 += 8) {
-      const unsigned long long inv8 = live ? __ldg(V.nb_inv + inv_off + (long long)(g8 >> 3) * nnb + m) : ~0ull;
-      const long long dmine = (lane < 8 && g8 + lane < ns) ? __ldg(V.n2e_ksrc + t0 + g8 + lane) : 0;   // the 8 slot descriptors
-      // two slots in flight: all 18 loads are issued before the first addition
+    __syncwarp();
+  }
+  const double c1 = V.c1;
+  for (int s0 = 0; s0 < ns; s0 += 4) {
+    double v[4][3];
+    unsigned dst[4][3];           // accumulator index of each value, 0xFFFF: constrained column / no value
 #pragma unroll
-      for (int sI = 0; sI < 8; sI += 2) {
-        if (g8 + sI >= ns) break;                  // (uniform)
-        const long long d0 = __shfl_sync(0xffffffffu, dmine, sI), d1 = __shfl_sync(0xffffffffu, dmine, sI + 1);
-        const unsigned K0 = (unsigned)(inv8 >> (8 * sI)) & 0xFFu, K1 = (unsigned)(inv8 >> (8 * sI + 8)) & 0xFFu;
-        const bool on0 = K0 != 0xFFu, on1 = K1 != 0xFFu && g8 + sI + 1 < ns;
-        const double* s0 = V.rec; const double* s1 = V.rec;
-        int sp0 = 0, sq0 = 0, sp1 = 0, sq1 = 0;
-        if (on0) locate(d0, K0, s0, sp0, sq0);
-        if (on1) locate(d1, K1, s1, sp1, sq1);
-        double b0[3][3], b1[3][3];
+    for (int c = 0; c < 4; c++) {
+      const int sI = s0 + c;
+      const bool ok = sI < ns;    // (uniform)
+      const unsigned d = __shfl_sync(0xffffffffu, mydesc, sI & 31);
+      const unsigned mypos = (ok && lane < 24) ? (unsigned)__ldg(cp + sI * 24) : 0xFFFFu;
+      const unsigned sb = (d >> 4) * 36u;
+      const unsigned* tb = stab + (d & 15u) * 72 + lane;
 #pragma unroll
-        for (int p = 0; p < 3; p++)
-#pragma unroll
-          for (int q = 0; q < 3; q++) {
-            b0[p][q] = on0 ? __ldg(s0 + p * sp0 + q * sq0) : 0.0;
-            b1[p][q] = on1 ? __ldg(s1 + p * sp1 + q * sq1) : 0.0;
-          }
-        if (c1 != 1.0) {
-#pragma unroll
-          for (int p = 0; p < 3; p++)
-#pragma unroll
-            for (int q = 0; q < 3; q++) { b0[p][q] *= c1; b1[p][q] *= c1; }
-        }
-        if (on0) {
-#pragma unroll
-          for (int p = 0; p < 3; p++)
-#pragma unroll
-            for (int q = 0; q < 3; q++) acc[p][q] += b0[p][q];
-        }
-        if (on1) {
-#pragma unroll
-          for (int p = 0; p < 3; p++)
-#pragma unroll
-            for (int q = 0; q < 3; q++) acc[p][q] += b1[p][q];
-        }
+      for (int r = 0; r < 3; r++) {
+        const bool on = ok && (r < 2 || last8);
+        const unsigned e = tb[r < 2 ? 32 * r : (last8 ? 64 : 0)];
+        const unsigned pos = __shfl_sync(0xffffffffu, mypos, e >> 12);
+        v[c][r] = on ? __ldg(rec + (sb + (e & 1023u))) : 0.0;
+        dst[c][r] = (on && pos != 0xFFFFu) ? ((e >> 10) & 3u) * FA_S + pos : 0xFFFFu;
       }
     }
-    if (!live) continue;
-    const unsigned cfirst = info & 0x1FFFu, mask = info >> 13;
 #pragma unroll
-    for (int p = 0; p < 3; p++) {
-      const long long rp = p == 0 ? rp0 : (p == 1 ? rp1 : rp2);
-      if (rp < 0) continue;
-      double* out = A + rp + cfirst;
-      unsigned c = 0;
+    for (int c = 0; c < 4; c++) {   // FE_Element order: the order addA is called in
+      if (s0 + c >= ns) break;      // (uniform)
 #pragma unroll
-      for (int q = 0; q < 3; q++)
-        if (mask & (1u << q)) out[c++] = acc[p][q];
+      for (int r = 0; r < 3; r++)
+        if (dst[c][r] != 0xFFFFu) acc[dst[c][r]] += (c1 == 1.0 ? v[c][r] : v[c][r] * c1);
+      __syncwarp();
     }
+  }
+#pragma unroll
+  for (int p = 0; p < 3; p++) {
+    const long long rp = __shfl_sync(0xffffffffu, word, 3 + p);
+    if (rp < 0) continue;
+    double* out = A + rp;
+#pragma unroll
+    for (int c = 0; c < FA_L / 32; c++)
+      if (c * 32 + lane < L) out[c * 32 + lane] = acc[p * FA_S + c * 32 + lane];
   }
 }
 
@@ -1534,7 +1484,6 @@ struct xb_model {
   unsigned short* dDiag = nullptr;
   double *dDU = nullptr, *dUin = nullptr;   // Node::getIncrDeltaDisp, staging for xb_set_trial_disp
   bool has_beams = false;
-  int tangent_variant = 2;          // brick tangent kernel: (passes, warps per CTA) = 0: (2,6), 1: (2,5), 2: (1,4), 3: (2,4) (xb_set_option)
   int num_sms = 148;
   double alphaM = 0.0;      // Node::setRayleighDampingFactor
   // Element::setRayleighDampingFactors (`rayleigh alphaM betaK betaKinit betaKcomm`) and element masses
@@ -1556,11 +1505,10 @@ struct xb_model {
   std::vector<cudaEvent_t> ev_rows;
   cudaEvent_t ev_start = nullptr, ev_done = nullptr;
   std::vector<cudaEvent_t> ev_chunk;
-  bool ranged = false;              // formTangent of a large batch range by range on two streams also without a host destination (xb_set_option)
+  bool ranged = true;               // formTangent of a large batch range by range on two streams also without a host destination (xb_set_option)
   double* dRec = nullptr;           // stdBrick: symmetric element records (brick_rec.hpp)
   long long* dPkSrc = nullptr;      // record models: descriptors of the outgoing row chunks
-  long long* dTask8 = nullptr;      // block-row assembly: task records
-  bool blocks_on = true;            // use the block-row assembly when the model allows it (xb_set_option "block_assembly")
+  bool fast_asm_on = true;          // record models: the hand-tuned assembly kernel when the model allows it (xb_set_option "fast_assembly")
   int tan_per_sm = 0;               // occupancy of the brick tangent kernel (cached)
   const void* tan_kern = nullptr;
   long long* dTask = nullptr;
@@ -1802,7 +1750,9 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
   for (size_t i = 0; i < h.mats.size(); i++) std::memcpy(&mp[i * 8], h.mats[i].par, sizeof(double) * 8);
   CU(dev_upload(m, &m->dMpar, mp));
   CU(dev_alloc(m, &m->dKe, (size_t)h.kn_total));   // KeN: node-major element-tangent rows (quads, beams)
-  CU(dev_alloc(m, &m->dRec, (size_t)h.rec_total)); // stdBrick: symmetric element records
+  // stdBrick: symmetric element records; the rows received from other ranks lie right behind them (one base pointer
+  // for the assembly's gathers)
+  CU(dev_alloc(m, &m->dRec, (size_t)h.rec_total + (h.rec_mode ? (size_t)h.recv_k_total : 0)));
   CU(dev_alloc(m, &m->dRe, (size_t)h.re_total));
   CU(dev_alloc(m, &m->dA, (size_t)h.nnz()));
   CU(dev_alloc(m, &m->dB, (size_t)h.nrows));
@@ -1974,10 +1924,11 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
   a.c1 = 1.0; a.c2 = 0.0; a.c3 = 0.0; a.alphaM = m->alphaM;
   if (h.nparts > 1) {
     CU(dev_alloc(m, &m->dSendK, (size_t)h.send_k_total));
-    CU(dev_alloc(m, &m->dRecvK, (size_t)h.recv_k_total));
+    if (h.rec_mode) m->dRecvK = m->dRec + h.rec_total;
+    else CU(dev_alloc(m, &m->dRecvK, (size_t)h.recv_k_total));
     CU(dev_alloc(m, &m->dSendR, (size_t)h.send_r_total));
     CU(dev_alloc(m, &m->dRecvR, (size_t)h.recv_r_total));
-    CU(cudaMemset(m->dRecvK, 0, sizeof(double) * std::max<size_t>(h.recv_k_total, 1)));
+    if (h.recv_k_total) CU(cudaMemset(m->dRecvK, 0, sizeof(double) * (size_t)h.recv_k_total));
     CU(cudaMemset(m->dRecvR, 0, sizeof(double) * std::max<size_t>(h.recv_r_total, 1)));
     CU(dev_upload(m, &m->dUkSrc, h.uk_src));
     CU(dev_upload(m, &m->dUkDst, h.uk_dst));
@@ -1988,14 +1939,22 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
   a.recvK = m->dRecvK; a.recvR = m->dRecvR;
   a.rec = m->dRec; a.transpose = h.soe_kind == XB_SOE_SPARSE_GEN_COL ? 1 : 0;
   { long long* ks = nullptr; CU(dev_upload(m, &ks, h.n2e_ksrc)); a.n2e_ksrc = ks; }
-  if (h.blocks_ok) {
-    unsigned short* nbi = nullptr; unsigned long long* inv = nullptr;
-    CU(dev_upload(m, &nbi, h.nb_info));
-    { std::vector<unsigned long long> t(h.nb_inv.begin(), h.nb_inv.end()); CU(dev_upload(m, &inv, t)); }
-    CU(dev_upload(m, &m->dTask8, h.asm_task8));
-    a.nb_info = nbi; a.nb_inv = inv;
+  { unsigned* ks = nullptr; CU(dev_upload(m, &ks, h.n2e_ksrc32)); a.n2e_ksrc32 = ks; }
+  if (h.fast_asm_ok) {
+    // the 72 values local node J takes from a record, in record order (J = 8: dense rows, already in order)
+    std::vector<unsigned> tab(9 * 72);
+    for (int J = 0; J < 9; J++) {
+      std::vector<unsigned> it;
+      for (int p = 0; p < 3; p++)
+        for (int c = 0; c < 24; c++) {
+          const unsigned ro = (unsigned)(J < 8 ? xb::brick_rec_entry(J, p, c / 3, c % 3, a.transpose) : p * 24 + c);
+          it.push_back(ro | ((unsigned)p << 10) | ((unsigned)c << 12));
+        }
+      std::sort(it.begin(), it.end(), [](unsigned x, unsigned y) { return (x & 1023u) < (y & 1023u); });
+      std::copy(it.begin(), it.end(), tab.begin() + J * 72);
+    }
+    unsigned* dt = nullptr; CU(dev_upload(m, &dt, tab)); a.gather_tab = dt;
   }
-  for (auto& d : m->dg) { d.v.sendK = m->dSendK; d.b.sendK = m->dSendK; }
   long long *ptr = nullptr, *n2e_ptr = nullptr, *roff = nullptr, *ncol_ptr = nullptr;
   unsigned short* cp = nullptr;
   CU(dev_upload(m, &ptr, h.ptr));
@@ -2312,20 +2271,8 @@ static int launch_group_tangents(xb_model* m, DevGroup& d, long long ebeg, long 
       if (tc.ac != 0.0) { kern<<<(unsigned)grid, nt, sms, st>>>(d.v, m->dX, ebeg, eend, d.v.tanc, 0, tc.ac, 1); m->launches++; }
       return XB_OK;
     };
-    int rc;
-#define XB_TAN_CASE(NP, NW_)                                                                                                   \
-  rc = tc.on ? (j2 ? go(brick_tangent_rec_kernel<XB_MAT_J2PLASTICITY, 1, NP, NW_>, NW_) : go(brick_tangent_rec_kernel<XB_MAT_ELASTIC_ISOTROPIC, 1, NP, NW_>, NW_)) \
-             : (j2 ? go(brick_tangent_rec_kernel<XB_MAT_J2PLASTICITY, 0, NP, NW_>, NW_) : go(brick_tangent_rec_kernel<XB_MAT_ELASTIC_ISOTROPIC, 0, NP, NW_>, NW_));
-    switch (m->tangent_variant) {
-      case 1:
-        rc = tc.on ? (j2 ? go(brick_tangent_rec5_kernel<XB_MAT_J2PLASTICITY, 1, 2>, 5) : go(brick_tangent_rec5_kernel<XB_MAT_ELASTIC_ISOTROPIC, 1, 2>, 5))
-                   : (j2 ? go(brick_tangent_rec5_kernel<XB_MAT_J2PLASTICITY, 0, 2>, 5) : go(brick_tangent_rec5_kernel<XB_MAT_ELASTIC_ISOTROPIC, 0, 2>, 5));
-        break;
-      case 2: XB_TAN_CASE(1, 4) break;
-      case 3: XB_TAN_CASE(2, 4) break;
-      default: XB_TAN_CASE(2, 6) break;
-    }
-#undef XB_TAN_CASE
+    const int rc = tc.on ? (j2 ? go(brick_tangent_rec_kernel<XB_MAT_J2PLASTICITY, 1, 1, 4>, 4) : go(brick_tangent_rec_kernel<XB_MAT_ELASTIC_ISOTROPIC, 1, 1, 4>, 4))
+                         : (j2 ? go(brick_tangent_rec_kernel<XB_MAT_J2PLASTICITY, 0, 1, 4>, 4) : go(brick_tangent_rec_kernel<XB_MAT_ELASTIC_ISOTROPIC, 0, 1, 4>, 4));
     if (rc < 0) return rc;
     m->launches++;
     if (tc.on && tc.cM != 0.0 && d.has_rho) {
@@ -2483,9 +2430,9 @@ static int launch_assemble(xb_model* m, long long first, long long count, cudaSt
   const int sl = cps <= 8 ? 4 : (cps <= 16 ? 2 : 1);  // slots loaded side by side (assemble_A_kernel, SL)
   static size_t attr[16][64] = {{0}};
   int rc = XB_ERR_UNSUPPORTED;
-  if (m->h.rec_mode && m->h.blocks_ok && m->blocks_on) {
-    // stdBrick without MP constraints: block rows straight out of the symmetric element records
-    assemble_A_blocks_kernel<<<blocks, warps * 32, 0, st>>>(av, m->dA, m->dTask8, first, count);
+  if (m->h.rec_mode && m->h.fast_asm_ok && m->fast_asm_on) {
+    // plain brick model: the hand-tuned form of the gathered assembly
+    assemble_A_rec_fast_kernel<<<blocks, warps * 32, 0, st>>>(av, m->dA, m->dTask, first, count);
     m->launches++;
     rc = XB_OK;
   } else if (m->h.rec_mode) {
@@ -2622,15 +2569,12 @@ int xb_form_tangent(xb_model* m, double* A) {
   return finish_tangent(m, A);
 }
 
-// Run-time options (documented in include/xara_b200.h): "tangent_passes" 1 | 2, "ranged_tangent" 0 | 1
+// Run-time options (documented in include/xara_b200.h): "ranged_tangent" 0 | 1, "fast_assembly" 0 | 1
 int xb_set_option(xb_model* m, const char* name, int value) {
   if (!m || !name) return fail(XB_ERR_ARG, "xb_set_option: null argument");
   const std::string n(name);
-  if (n == "tangent_variant") {
-    if (value < 0 || value > 3) return fail(XB_ERR_ARG, "tangent_variant is 0..3");
-    m->tangent_variant = value;
-  } else if (n == "block_assembly") {
-    m->blocks_on = value != 0;
+  if (n == "fast_assembly") {
+    m->fast_asm_on = value != 0;
   } else if (n == "ranged_tangent") {
     m->ranged = value != 0;
   } else return fail(XB_ERR_ARG, "xb_set_option: unknown option " + n);

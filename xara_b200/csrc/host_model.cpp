@@ -869,6 +869,22 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
     irr_diag.push_back((uint16_t)(std::lower_bound(cl.begin(), cl.end(), row_geq[irr_row[w]]) - cl.begin()));
   }
 
+  // 32-bit descriptors for the hand-tuned record assembly (plain brick models): offset in units of 36 doubles << 4 |
+  // local node, or | 8 for dense rows in the receive buffer, which lies right behind the records
+  n2e_ksrc32.clear();
+  {
+    long long most = 0;
+    for (int i = 0; i < nl; i++) most = std::max(most, n2e_ptr[i + 1] - n2e_ptr[i]);
+    fast_asm_ok = rec_mode && !have_mp && max_row <= 96 && most <= 32 && (rec_total + recv_k_total) / 36 < (1ll << 28);
+  }
+  if (fast_asm_ok) {
+    n2e_ksrc32.resize(n2e_total);
+    for (long long u = 0; u < n2e_total; u++) {
+      const long long d = n2e_ksrc[u];
+      n2e_ksrc32[u] = (d & 1) ? (uint32_t)((((d >> 4) / 36) << 4) | ((d >> 1) & 7)) : (uint32_t)((((rec_total + (d >> 4)) / 36) << 4) | 8);
+    }
+  }
+
   max_dup = 0;
   if (have_mp) {
     for (uint16_t v : colpos) if (v != 0xFFFF) max_dup = std::max(max_dup, (int)(v >> 13));
@@ -945,78 +961,6 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
       for (int j = 0; j < ndf; j++) {
         const int r = row_of_dev[(size_t)i * ndf + j];
         tk[3 + j] = r >= 0 ? ptr[r] : -1;
-      }
-    }
-    // ---- block-row assembly maps of a record model (host_model.hpp, blocks_ok) ----
-    blocks_ok = rec_mode && !have_mp;
-    nb_ptr.clear(); nb_info.clear(); inv_ptr.clear(); nb_inv.clear(); asm_task8.clear();
-    if (blocks_ok) {
-      nb_ptr.assign((size_t)nl + 1, 0); inv_ptr.assign((size_t)nl + 1, 0);
-#pragma omp parallel
-      {
-        std::vector<int> tmp;
-#pragma omp for schedule(dynamic, 4096)
-        for (int i = 0; i < nl; i++) {
-          if (!owned[i] || n2e_ptr[i + 1] == n2e_ptr[i]) continue;
-          G.nbrs(lnode[i], tmp);
-          nb_ptr[i + 1] = (long long)tmp.size();
-          inv_ptr[i + 1] = (long long)tmp.size() * ((n2e_ptr[i + 1] - n2e_ptr[i] + 7) / 8);
-        }
-      }
-      for (int i = 0; i < nl; i++) { nb_ptr[i + 1] += nb_ptr[i]; inv_ptr[i + 1] += inv_ptr[i]; }
-      nb_info.assign((size_t)nb_ptr[nl], 0); nb_inv.assign((size_t)inv_ptr[nl], ~0ull);
-      std::vector<int> self(nl, 0);
-      long long bad_nodes = 0;
-#pragma omp parallel
-      {
-        std::vector<int> tmp;
-#pragma omp for schedule(dynamic, 4096) reduction(+ : bad_nodes)
-        for (int i = 0; i < nl; i++) {
-          if (nb_ptr[i + 1] == nb_ptr[i]) continue;
-          G.nbrs(lnode[i], tmp);
-          const int nnb = (int)tmp.size();
-          const int* cols = &ncol[ncol_ptr[i]];
-          const long long L = ncol_ptr[i + 1] - ncol_ptr[i];
-          if (nnb > 0xFFFF || L >= 0x1FFF) { bad_nodes++; continue; }
-          for (int mI = 0; mI < nnb; mI++) {
-            const int w = tmp[mI];
-            if (w == lnode[i]) self[i] = mI;
-            int mask = 0, first = -1, prev = -1;
-            for (int j = 0; j < ndf; j++) {
-              const int q = gid[(size_t)w * ndf + j];
-              if (q < 0) continue;
-              const int pos = (int)(std::lower_bound(cols, cols + L, q) - cols);
-              if (first < 0) first = pos;
-              else if (pos != prev + 1) bad_nodes++;     // (cannot happen without MP constraints)
-              prev = pos; mask |= 1 << j;
-            }
-            nb_info[nb_ptr[i] + mI] = (uint16_t)((first < 0 ? 0 : first) | (mask << 13));
-          }
-          const long long ns = n2e_ptr[i + 1] - n2e_ptr[i];
-          for (long long sI = 0; sI < ns; sI++) {
-            const EleKind* k; const int* c = G.conn_of(n2e_fe[n2e_ptr[i] + sI], &k);
-            for (int a = 0; a < k->nen; a++) {
-              const int mI = (int)(std::lower_bound(tmp.begin(), tmp.end(), c[a]) - tmp.begin());
-              uint64_t& wd = nb_inv[inv_ptr[i] + (sI / 8) * nnb + mI];
-              const int sh = 8 * (int)(sI % 8);
-              wd = (wd & ~(0xFFull << sh)) | ((uint64_t)a << sh);
-            }
-          }
-        }
-      }
-      if (bad_nodes) { blocks_ok = false; nb_ptr.clear(); nb_info.clear(); inv_ptr.clear(); nb_inv.clear(); }
-      else {
-        asm_task8.assign((size_t)node_perm.size() * 8, 0);
-        for (size_t u = 0; u < node_perm.size(); u++) {
-          const int i = node_perm[u];
-          long long* tk = &asm_task8[u * 8];
-          const long long ns = n2e_ptr[i + 1] - n2e_ptr[i];
-          tk[0] = n2e_ptr[i];
-          tk[1] = ns | ((nb_ptr[i + 1] - nb_ptr[i]) << 16) | ((long long)self[i] << 32);
-          tk[2] = i;
-          for (int j = 0; j < 3; j++) { const int r = row_of_dev[(size_t)i * ndf + j]; tk[3 + j] = r >= 0 ? ptr[r] : -1; }
-          tk[6] = inv_ptr[i]; tk[7] = nb_ptr[i];
-        }
       }
     }
     // rows each range completes: streamable when range c owns exactly the rows [r_c, r_{c+1}) of A

@@ -153,17 +153,10 @@ struct HostModel {
   bool rec_mode = false;            // every batch is stdBrick: element records + gathered assembly
   long long rec_total = 0;          // doubles of element records
   std::vector<long long> pk_src;    // record models: outgoing row chunk c (send buffer offset c * chunk) <- record descriptor
-  // Record models without MP constraints: the block-row form of the assembly (assemble_A_blocks_kernel).  The free dofs
-  // of a node carry consecutive equation numbers, so the columns of node n's rows are runs of <= 3 positions, one run
-  // per neighbour node m (nodes sharing an element with n, ascending node index): lane m of the node's warp owns the
-  // 3x3 block A(n, m) and sums the element blocks K_(J,K) of every slot in FE_Element order.
-  bool blocks_ok = false;
-  std::vector<long long> nb_ptr;    // [nn+1] neighbours of the owned nodes
-  std::vector<uint16_t> nb_info;    // [*] first column position (13 bits) | free-dof mask << 13 of neighbour m
-  std::vector<long long> inv_ptr;   // [nn+1] -> nb_inv, in 8-byte words: ceil(slots / 8) x neighbours per node
-  std::vector<uint64_t> nb_inv;     // [*] byte s of word (g, m): local node of neighbour m in slot 8 g + s, 0xFF if not in it
-  std::vector<long long> asm_task8; // [node_perm.size()][8]: first slot, slots | neighbours << 16 | own neighbour index << 32,
-                                    //   node, A offset of its 3 rows (-1: constrained), offset in nb_inv, offset in nb_info
+  // the same descriptors in 32 bits (offset in units of 36 doubles << 4 | local node, 8 = dense rows) for the hand-tuned
+  // assembly kernel, which takes plain brick models: no MP constraints, rows of at most 96 entries, <= 32 elements per node
+  std::vector<uint32_t> n2e_ksrc32;
+  bool fast_asm_ok = false;
   std::vector<uint8_t> n2e_nd;      // [*] nd = nen*ndf of that element
   std::vector<long long> n2e_fe;    // [*] GLOBAL FE index
   std::vector<uint8_t> n2e_loc;     // [*] local node a
