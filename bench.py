@@ -204,6 +204,69 @@ def workload_name(n, workload="brick"):
 
 
 # ---------------------------------------------------------------------------------------
+# N >= 2 self-test (the driver's GPU test box has one GPU: this is the multi-GPU parity check it can run)
+# ---------------------------------------------------------------------------------------
+def selftest_main(a):
+    """torchrun -N: every rank sets up its partition of a small distorted J2 brick block, the interface rows and
+    residuals cross NCCL, and rank 0 -- which also runs the whole model on its GPU -- checks that every rank's owned
+    rows of A and B equal the single-GPU rows BIT FOR BIT.  Prints one JSON line {"selftest": "ok", ...}."""
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    import torch.distributed as dist
+
+    import xara_b200 as xb
+    from modelspec import J2_STEEL, brick_block
+    torch.cuda.set_device(local)
+    if world < 2:
+        raise SystemExit("--selftest needs torchrun with at least 2 ranks")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    res = []
+    for numberer, soe in ((1, 0), (0, 1)):
+        spec = brick_block(12, 10, 14, mat=J2_STEEL, distort=0.2, seed=3)
+        D = xb.DeviceModel.from_spec(spec, numberer, soe, world, rank).to_device(local)
+        box = [xb.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, 0)
+        D.comm_init(box[0])
+        ug = np.random.default_rng(1).normal(0, 3e-3, (spec.nn, 3))
+        for s_ in range(2):
+            D.set_trial_disp((s_ + 1) * ug[D.node_tags() - 1]); D.update(); D.apply_load(0.7)
+            A, B = D.form_tangent(), D.form_unbalance()
+            if s_ == 0:
+                D.commit()
+        rows = D.row_eqns()
+        gathered = [None] * world
+        dist.gather_object((rows, A, B), gathered if rank == 0 else None, 0)
+        if rank == 0:
+            G = xb.DeviceModel.from_spec(brick_block(12, 10, 14, mat=J2_STEEL, distort=0.2, seed=3), numberer, soe).to_device(local)
+            for s_ in range(2):
+                G.set_trial_disp((s_ + 1) * ug); G.update(); G.apply_load(0.7)
+                Ag, Bg = G.form_tangent(), G.form_unbalance()
+                if s_ == 0:
+                    G.commit()
+            gptr, _ = G.pattern()
+            seen = 0
+            for rws, Ar, Br in gathered:
+                ok = np.array_equal(Br, Bg[rws]) and np.array_equal(Ar, np.concatenate([Ag[gptr[q]:gptr[q + 1]] for q in rws]))
+                if not ok:
+                    raise SystemExit("selftest FAILED: a rank's rows differ from the single-GPU rows")
+                seen += len(rws)
+            if seen != G.neq:
+                raise SystemExit("selftest FAILED: the ranks' rows do not cover the system")
+            res.append({"numberer": numberer, "soe": soe, "equations": int(G.neq), "nnz": int(G.nnz)})
+        dist.barrier()
+    if rank == 0:
+        print(json.dumps({"selftest": "ok", "n_gpus": world, "what": "owned rows of A and B of every rank bitwise equal to the "
+                          "single-GPU rows (stdBrick/J2 12x10x14, two load steps with a commit, NCCL interface exchange)",
+                          "cases": res}), flush=True)
+    dist.destroy_process_group()
+
+
+def load_invariants():
+    p = os.path.join(ROOT, "tests", "golden", "bench_invariants.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
+# ---------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------
 def ours_main(a):
@@ -350,28 +413,80 @@ def ours_main(a):
     # ---- roofline of the dominant kernel (this rank's launches), live numbers ----
     peak, peak_src = peaks()
     which = {"update": 0, "assemble_B": 1, "element_tangent": 3, "assemble_A": 4}
-    if a.workload != "brick":
-        which.pop("update", None) if False else None
     dom = max(which, key=lambda k: ms[k])
     alg = D.algorithmic_bytes(which[dom])
     achieved = alg / (ms[dom] * 1e-3) / 1e9
     path_alg = D.algorithmic_bytes(0) + D.algorithmic_bytes(1) + D.algorithmic_bytes(2)
-    # DRAM traffic of that kernel from the committed `ncu --set full` capture (profiles/ncu_traffic.json, taken on a
-    # smaller block of the same workload), scaled to this rank's element count: per launch, like `achieved`
-    traffic, traffic_src = None, None
+    # per-kernel counters from the committed `ncu --set full` capture (profiles/ncu_traffic.json, taken on a smaller
+    # block of the same workload), scaled to this rank's element count: DRAM bytes and FP64 lane operations per launch
+    tj = {}
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if a.workload == "brick" and os.path.exists(tpath):
         tj = json.load(open(tpath))
-        if dom in tj.get("kernels", {}):
-            traffic = tj["kernels"][dom]["dram_bytes_per_launch"] * (float(D.ne) / tj["elements"])
-            traffic_src = tj["source"]
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+    scale_e = float(D.ne) / tj["elements"] if tj else 0.0
+    kern = {}
+    for nm_, wi in which.items():
+        kb = D.algorithmic_bytes(wi)
+        rec = {"ms": ms[nm_], "algorithmic_GB": kb / 1e9, "hbm_frac": kb / (ms[nm_] * 1e-3) / 1e9 / peak if ms[nm_] > 0 else None}
+        tk = tj.get("kernels", {}).get(nm_, {})
+        if "dram_bytes_per_launch" in tk:
+            rec["dram_traffic_GB"] = tk["dram_bytes_per_launch"] * scale_e / 1e9
+        if "fp64_lane_ops_per_launch" in tk and tj.get("fp64_peak_tdfma"):
+            ops = tk["fp64_lane_ops_per_launch"] * scale_e
+            rec["fp64"] = {"lane_ops": ops, "achieved_tdfma": ops / (ms[nm_] * 1e-3) / 1e12, "peak_tdfma": tj["fp64_peak_tdfma"],
+                           "frac": ops / (ms[nm_] * 1e-3) / 1e12 / tj["fp64_peak_tdfma"]}
+        if "limiter" in tk:
+            rec["limiter"] = tk["limiter"]
+        kern[nm_] = rec
+    traffic = kern[dom].get("dram_traffic_GB")
+    # the floor of the step: the compulsory bytes at the HBM peak against the FP64 work of the kernels that have any
+    # at the measured DFMA peak -- the larger of the two bounds the path from below
+    hbm_floor_ms = path_alg / (peak * 1e9) * 1e3
+    fp64_floor_ms = (sum(k["fp64"]["lane_ops"] for k in kern.values() if "fp64" in k) / (tj["fp64_peak_tdfma"] * 1e12) * 1e3
+                     if tj.get("fp64_peak_tdfma") else None)
+    dom_fp64 = kern[dom].get("fp64", {}).get("frac")
+    bound = "hbm"
+    if dom_fp64 is not None and dom_fp64 > kern[dom]["hbm_frac"]:
+        bound = "fp64"
+    elif kern[dom].get("limiter"):
+        bound = kern[dom]["limiter"]["unit"]
+    roofline = {"bound": bound, "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None if traffic is None else traffic * 1e9,
+                "traffic_source": tj.get("source"), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms[dom],
+                "fp64": kern[dom].get("fp64"), "limiter": kern[dom].get("limiter"),
+                "kernels": kern,
+                "floor_ms": {"hbm": hbm_floor_ms, "fp64": fp64_floor_ms,
+                             "max": max(hbm_floor_ms, fp64_floor_ms or 0.0),
+                             "note": "compulsory bytes of the step at the measured HBM peak; FP64 lane operations of the step "
+                                     "(ncu, profiles/) at the measured DFMA peak (profiles/r2_dmma_ubench.txt)"},
                 "path": {"algorithmic_bytes_per_step": path_alg, "achieved": path_alg / (ms_per_step * 1e-3) / 1e9,
                          "frac": path_alg / (ms_per_step * 1e-3) / 1e9 / peak,
                          "note": "compulsory bytes of update+formUnbalance+formTangent on this rank (state in/out, A and B "
-                                 "out) over the whole step; the element-matrix round trip through HBM is overhead here"}}
+                                 "out) over the whole step; the element records' round trip through HBM is overhead here"}}
+
+    # ---- the linear solve, timed separately and out of path (north_star: left to the reference's SOE solver) ----
+    solve = None
+    if rank == 0 and a.solve_n > 0 and a.workload == "brick" and not a.no_cpu_baseline:
+        try:
+            import scipy.sparse as sp
+            import scipy.sparse.linalg as spl
+            from modelspec import J2_STEEL, brick_block
+            sspec = brick_block(a.solve_n, a.solve_n, a.solve_n, mat=J2_STEEL)
+            S = xb.DeviceModel.from_spec(sspec, xb.NUMBERER_RCM, xb.SOE_SPARSE_GEN_ROW).to_device(local)
+            S.apply_load(1.0)
+            As, Bs = S.form_tangent(), S.form_unbalance()
+            sptr, sidx = S.pattern()
+            M = sp.csr_matrix((As, sidx, sptr), shape=(S.neq, S.neq)).tocsc()
+            t0s = time.perf_counter(); x = spl.spsolve(M, Bs); dts = time.perf_counter() - t0s
+            solve = {"ms": dts * 1e3, "equations": int(S.neq), "nnz": int(S.nnz), "elements": int(sspec.ne),
+                     "residual": float(np.abs(M @ x - Bs).max() / max(np.abs(Bs).max(), 1e-300)),
+                     "solver": "scipy.sparse.linalg.spsolve (SuperLU, host, one core)",
+                     "note": f"out of path and not optimised: the solve of a {a.solve_n}^3 block assembled by the device path (RCM numbering), "
+                             "timed separately as north_star asks; the step numbers above contain no solve"}
+            del S, M
+        except Exception as ex:   # the solve is a side measurement: never let it take the bench line down
+            solve = {"error": repr(ex)}
 
     # ---- end to end through the C-ABI with HOST buffers (pinned), copies inside the timed region ----
     e2e_steps = max(1, min(a.steps, a.e2e_steps)) if a.e2e_steps > 0 else 0
@@ -400,10 +515,31 @@ def ours_main(a):
     if world > 1:
         t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_ms = float(t[0])
         t = torch.tensor([h2d, d2h], device="cuda", dtype=torch.float64); dist.all_reduce(t); h2d, d2h = float(t[0]), float(t[1])
-    checksum = float(An[:1000].sum() + Bn[:1000].sum())
+    # partition-invariant sums of the assembled system (every rank over its OWNED rows, summed over the ranks): the
+    # same numbers whatever N is, up to the order of the final additions
+    scale = None
+    if e2e_steps:
+        geq = D.row_eqns().astype(np.float64)
+        part = np.array([An.sum(), np.abs(An).sum(), Bn.sum(), float(geq @ Bn), np.abs(Bn).sum()])
+        if world > 1:
+            t = torch.tensor(part, device="cuda", dtype=torch.float64); dist.all_reduce(t); part = t.cpu().numpy()
+        inv = {"sum_A": float(part[0]), "sum_abs_A": float(part[1]), "sum_B": float(part[2]), "sum_eq_times_B": float(part[3]),
+               "sum_abs_B": float(part[4])}
+        key = f"{a.workload}:{n}"
+        ref = load_invariants().get(key)
+        if ref is None:
+            scale = {"check": "no N=1 record for this size (tests/golden/bench_invariants.json)", "invariants": inv}
+        else:
+            tolA, tolB = 1e-12 * ref["sum_abs_A"], 1e-12 * ref["sum_abs_B"] * max(1.0, float(D.neq))
+            bad = [k for k, tol in (("sum_A", tolA), ("sum_abs_A", tolA), ("sum_B", tolB), ("sum_abs_B", tolB), ("sum_eq_times_B", tolB))
+                   if abs(inv[k] - ref[k]) > tol]
+            scale = {"check": "ok" if not bad else "MISMATCH " + ",".join(bad), "invariants": inv, "n1_record": ref,
+                     "tolerance": "1e-12 of sum|A| (A), 1e-12 of neq * sum|B| (B)"}
+            if bad:
+                print("bench.py: scale check FAILED: " + json.dumps(scale), file=sys.stderr)
     e2e = None if not e2e_steps else {"value": ngp_global / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "steps": e2e_steps, "result_checksum_rank0": checksum,
+           "steps": e2e_steps,
            "note": "xb_set_trial_disp(host u) + xb_update + xb_form_unbalance(host B) + xb_form_tangent(host A), pinned "
                    "host buffers; every rank moves its own nodes' u in and its owned rows of A, B out (bytes summed over ranks)"}
 
@@ -424,13 +560,15 @@ def ours_main(a):
                            "l2": "inputs larger than L2 (per GPU at N=1: state 7 GB, element matrices 19 GB, A 8 GB vs 126 MB)",
                            "setup_s": {"mesh": t_mesh, "host_setup": t_setup, "upload": t_upload}},
                 "kernel_ms": ms_max, "kernel_ms_rank0": ms,
-                "kernel_ms_note": "separate instrumented pass, formTangent's two kernels run back to back; in the timed "
-                                  "region xb_form_tangent overlaps them on two streams, so ms_per_step < sum(kernel_ms)",
+                "kernel_ms_note": "separate instrumented pass, one kernel after the other on one stream; in the timed region "
+                                  "xb_form_tangent runs range by range on two streams (formTangent_call_ms), which hides the "
+                                  "kernels' tails behind one another",
                 "formTangent_ms": ms_max["element_tangent"] + ms_max["exchange_A"] + ms_max["assemble_A"],
                 "formTangent_call_ms": ft_call_ms,
                 "formUnbalance_ms": ms_max["element_resid"] + ms_max["exchange_B"] + ms_max["assemble_B"],
                 "update_ms": ms_max["update"],
-                "gpu_launches": int(launches_all), "clocks": clk, "e2e": e2e, "roofline": roofline, "cpu_baseline": cb}
+                "gpu_launches": int(launches_all), "clocks": clk, "e2e": e2e, "roofline": roofline, "cpu_baseline": cb,
+                "scale_check": None if scale is None else scale["check"], "scale": scale, "solve_ms": solve}
         json_out.write(json.dumps(line) + "\n"); json_out.flush()
     if world > 1:
         dist.barrier()
@@ -452,10 +590,15 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="name=value for xb_set_option (kernel tuning experiments)")
+    ap.add_argument("--selftest", action="store_true", help="torchrun, N >= 2: bitwise check of the NCCL-exchanged rows against "
+                                                            "the single-GPU rows (prints {\"selftest\": \"ok\"})")
+    ap.add_argument("--solve-n", type=int, default=40, help="size of the block whose linear solve is timed (out of path; 0 = skip)")
     a = ap.parse_args()
     if a.n is None:
         a.n = {"brick": 160, "quad": 1000, "frame": 200, "frame3d": 20}[a.workload]
-    if a.impl == "reference":
+    if a.selftest:
+        selftest_main(a)
+    elif a.impl == "reference":
         reference_main(a)
     else:
         ours_main(a)

@@ -198,7 +198,11 @@ int xb_incr_trial_response(xb_model*, const double* dU, double cu, double cv, do
 /* AnalysisModel::setVel / setAccel and their read-back, [nn][ndf] host arrays */
 int xb_set_trial_vel_accel(xb_model*, const double* v, const double* a);
 int xb_get_trial_vel_accel(xb_model*, double* v, double* a);
-/* Domain::update -> Element::update -> NDMaterial::setTrialStrain for every Gauss point */
+/* Domain::update -> Element::update -> NDMaterial::setTrialStrain for every Gauss point.  The call is asynchronous:
+ * a state determination that fails on the device (J2 return map or force-beam element iteration not converging, where
+ * Domain::update would return < 0) raises a flag that the NEXT call with a host destination (xb_form_tangent /
+ * xb_form_unbalance with a non-null buffer) or xb_synchronize returns as XB_ERR_STATE.  A caller that needs the
+ * reference's immediate failure semantics calls xb_synchronize right after xb_update. */
 int xb_update(xb_model*);
 /* AnalysisModel::applyLoadDomain(lambda) for the Linear-series pattern */
 int xb_apply_load(xb_model*, double lambda);

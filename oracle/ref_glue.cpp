@@ -58,6 +58,8 @@
 #include <MP_ConstraintIter.h>
 #include <LoadPatternIter.h>
 #include <NodalLoadIter.h>
+#include <ElementalLoadIter.h>
+#include <LinearSeries.h>
 
 #include "../include/xara_b200.h"
 
@@ -87,7 +89,11 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
   // 2. SP constraints
   std::vector<int> spn, spd;
   { SP_ConstraintIter& si = dom->getDomainAndLoadPatternSPs(); SP_Constraint* sp;
-    while ((sp = si()) != nullptr) { spn.push_back(sp->getNodeTag()); spd.push_back(sp->getDOF_Number()); } }
+    while ((sp = si()) != nullptr) {
+      // the device path knows homogeneous constraints only (`fix`): an imposed non-zero value (`sp`) stays on the CPU
+      if (sp->getValue() != 0.0) { G.err = "glue: SP_Constraint with a non-zero value: outside the device path"; return -3; }
+      spn.push_back(sp->getNodeTag()); spd.push_back(sp->getDOF_Number());
+    } }
   if (!spn.empty() && xb_add_sp(x, (int)spn.size(), spn.data(), spd.data()) < 0) { G.err = xb_last_error(); return -3; }
   // 2b. MP constraints: `equalDOF` only (identity constraint matrix on the same dofs -- what PlainHandler accepts)
   { MP_ConstraintIter& mi = dom->getMPs(); MP_Constraint* mp;
@@ -143,6 +149,9 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
         const char* ty = q->theMaterial[0]->getType();        // the copy FourNodeQuad asked for: "PlaneStrain" | "PlaneStress"
         const bool pstress = std::strcmp(ty, "PlaneStress") == 0;
         if (!pstress && std::strcmp(ty, "PlaneStrain") != 0) { G.err = "glue: FourNodeQuad material copy is neither PlaneStrain nor PlaneStress"; return -4; }
+        // FourNodeQuad takes the element's own rho instead of the material's when it is non-zero (FourNodeQuad.cpp:395-398);
+        // the device path carries the material density only
+        if (q->rho != 0.0) { G.err = "glue: FourNodeQuad with an element density (rho): outside the device path"; return -5; }
         const double par[6] = {q->thickness, pstress ? 1.0 : 0.0, q->pressure, q->rho, q->b[0], q->b[1]};
         B.par.insert(B.par.end(), par, par + 6);
       } else if (dynamic_cast<ForceBeamColumn2d*>(el) || dynamic_cast<ForceBeamColumn3d*>(el)) {
@@ -221,9 +230,16 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
       G.err = xb_last_error(); return -6;
     }
   }
-  // 4. nodal loads of the load patterns (Linear series)
+  // 4. nodal loads of the load patterns.  The device applies lambda(t) * P with lambda = the domain time, i.e. every
+  // pattern must carry a Linear series with factor 1, must not have been frozen by loadConst, and must hold nodal loads
+  // only -- anything else is refused here rather than silently dropped (element loads, other series: keep the CPU integrator)
   { LoadPatternIter& pi = dom->getLoadPatterns(); LoadPattern* lp;
     while ((lp = pi()) != nullptr) {
+      LinearSeries* ls = dynamic_cast<LinearSeries*>(lp->theSeries);
+      if (!ls || ls->cFactor != 1.0) { G.err = "glue: load pattern whose TimeSeries is not Linear with factor 1: outside the device path"; return -7; }
+      if (lp->isConstant) { G.err = "glue: load pattern frozen by loadConst: outside the device path"; return -7; }
+      { ElementalLoadIter& eli = lp->getElementalLoads();
+        if (eli() != nullptr) { G.err = "glue: ElementalLoad (eleLoad) in a load pattern: outside the device path"; return -7; } }
       NodalLoadIter& li = lp->getNodalLoads(); NodalLoad* nl;
       while ((nl = li()) != nullptr) {
         int type; const Vector& v = nl->getData(type);
@@ -246,13 +262,25 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
     }
     if (!mt.empty() && xb_set_nodal_mass(x, (int)mt.size(), mt.data(), mv.data()) < 0) { G.err = xb_last_error(); return -7; } }
   { ElementIter& ei = dom->getElements(); Element* el = ei();
-    if (el && (el->alphaM != 0.0 || el->betaK != 0.0 || el->betaK0 != 0.0 || el->betaKc != 0.0))
-      if (xb_set_rayleigh(x, el->alphaM, el->betaK, el->betaK0, el->betaKc) < 0) { G.err = xb_last_error(); return -7; }
-    while (el) el = ei(); }   // drain the iterator
+    const double rf[4] = {el ? el->alphaM : 0.0, el ? el->betaK : 0.0, el ? el->betaK0 : 0.0, el ? el->betaKc : 0.0};
+    if (el && (rf[0] != 0.0 || rf[1] != 0.0 || rf[2] != 0.0 || rf[3] != 0.0))
+      if (xb_set_rayleigh(x, rf[0], rf[1], rf[2], rf[3]) < 0) { G.err = xb_last_error(); return -7; }
+    // one set of factors for the whole model (the `rayleigh` command): per-element factors (region -rayleigh) are refused
+    bool same = true;
+    while (el) { if (el->alphaM != rf[0] || el->betaK != rf[1] || el->betaK0 != rf[2] || el->betaKc != rf[3]) same = false; el = ei(); }
+    if (!same) { G.err = "glue: Rayleigh factors differ between elements: outside the device path"; return -7; } }
   // 5. the same numberer / SOE as the analysis; the numbering must be the reference's own
   const int neq = xb_setup(x, numberer, soeKind);
   if (neq < 0) { G.err = xb_last_error(); return -8; }
   if (neq != m->soe->getNumEqn()) { G.err = "glue: equation count differs from the reference's"; return -9; }
+  {   // xb_form_tangent writes xb_nnz doubles straight into the SOE's A: the two patterns must be the same
+    const long long nz = xb_nnz(x);
+    if (nz != (long long)m->ptr()[neq]) { G.err = "glue: non-zero count differs from the reference SOE's"; return -9; }
+    std::vector<long long> xp((size_t)neq + 1); std::vector<int> xi((size_t)nz);
+    xb_get_pattern(x, xp.data(), xi.data());
+    for (int i = 0; i <= neq; i++) if (xp[i] != (long long)m->ptr()[i]) { G.err = "glue: sparse pattern (pointers) differs from the reference SOE's"; return -9; }
+    for (long long i = 0; i < nz; i++) if (xi[i] != m->idx()[i]) { G.err = "glue: sparse pattern (indices) differs from the reference SOE's"; return -9; }
+  }
   std::vector<int> xt(tags.size()), ids(tags.size() * m->ndf);
   xb_get_node_tags(x, xt.data()); xb_get_ids(x, ids.data());
   for (size_t i = 0; i < xt.size(); i++) {
@@ -533,6 +561,13 @@ int glue_setup_loadcontrol(void* h, int numberer, int soeKind, double dlambda, i
   return neq;
 }
 const char* glue_last_error(void* h) { return g_glue[h].err.c_str(); }
+// frees the device model of a glued reference model (call before ref_destroy)
+void glue_destroy(void* h) {
+  auto it = g_glue.find(h);
+  if (it == g_glue.end()) return;
+  if (it->second.x) xb_model_destroy(it->second.x);
+  g_glue.erase(it);
+}
 // how often the reference's algorithm went through each replaced loop: formTangent, formUnbalance, update, commit
 void glue_call_counts(void* h, long* out) {
   B200LoadControl* li = dynamic_cast<B200LoadControl*>(((RefModel*)h)->sinteg);

@@ -786,6 +786,18 @@ class RefBackend(_Backend):
             raise RuntimeError(f"glue set-up failed ({self.neq}): {self.L.glue_last_error(self.h).decode()}")
         self.nnz = self.L.ref_nnz(self.h); self.max_iter = max_iter
 
+    def glue_free(self):
+        """frees the device model behind a glued reference model (oracle/ref_glue.cpp glue_destroy)"""
+        if hasattr(self.L, "glue_destroy"):
+            self.L.glue_destroy.argtypes = [ctypes.c_void_p]; self.L.glue_destroy.restype = None
+            self.L.glue_destroy(self.h)
+
+    def __del__(self):
+        try:
+            self.glue_free()
+        except Exception:
+            pass
+
     def glue_counts(self):
         c = (ctypes.c_long * 4)(); self.L.glue_call_counts.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
         self.L.glue_call_counts(self.h, c)

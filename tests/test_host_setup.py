@@ -120,6 +120,17 @@ def test_error_behaviour():
         m2.update()                                            # no device phase yet: never a CPU fallback
     with pytest.raises(xb.XaraB200Error):
         xb.DeviceModel(2, 2).add_elements(xb.ELE_STDBRICK, [1], [[1] * 8], [1], np.zeros((1, 3)))
+    # FourNodeQuad's own density (par[3]) replaces the material's in the reference (FourNodeQuad.cpp:395-398): refused,
+    # not silently dropped
+    q = xb.DeviceModel(2, 2)
+    q.add_nodes([1, 2, 3, 4], np.array([[0.0, 0], [1, 0], [1, 1], [0, 1]]))
+    q.nd_material(1, xb.MAT_ELASTIC_ISOTROPIC, [100.0, 0.3, 0.0])
+    with pytest.raises(xb.XaraB200Error, match="density"):
+        q.add_elements(xb.ELE_FOURNODEQUAD, [1], [[1, 2, 3, 4]], [1], np.array([[1.0, 0, 0, 2.5, 0, 0]]))   # thick type pressure rho b1 b2
+    q.add_elements(xb.ELE_FOURNODEQUAD, [1], [[1, 2, 3, 4]], [1], np.array([[1.0, 0, 0, 0.0, 0, 0]]))
+    assert q.set_option("ranged_tangent", 0) is q
+    with pytest.raises(xb.XaraB200Error):
+        q.set_option("no_such_option", 1)
 
 
 @pytest.mark.skipif(xb.device_count() > 0, reason="only meaningful on a box without a GPU")

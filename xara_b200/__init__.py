@@ -28,11 +28,11 @@ import os
 import numpy as np
 
 __all__ = ["DeviceModel", "XaraB200Error", "lib", "LIB_PATH", "device_count", "comm_unique_id", "exchange_local",
-           "MAT_ELASTIC_ISOTROPIC", "MAT_J2PLASTICITY", "ELE_STDBRICK", "ELE_FOURNODEQUAD", "ELE_FORCEBEAMCOLUMN2D", "UNI_STEEL02", "UNI_CONCRETE02",
+           "MAT_ELASTIC_ISOTROPIC", "MAT_J2PLASTICITY", "ELE_STDBRICK", "ELE_FOURNODEQUAD", "ELE_FORCEBEAMCOLUMN2D", "ELE_FORCEBEAMCOLUMN3D", "UNI_STEEL02", "UNI_CONCRETE02",
            "NUMBERER_PLAIN", "NUMBERER_RCM", "SOE_SPARSE_GEN_COL", "SOE_SPARSE_GEN_ROW"]
 
 MAT_ELASTIC_ISOTROPIC, MAT_J2PLASTICITY = 0, 1
-ELE_STDBRICK, ELE_FOURNODEQUAD, ELE_FORCEBEAMCOLUMN2D = 0, 1, 2
+ELE_STDBRICK, ELE_FOURNODEQUAD, ELE_FORCEBEAMCOLUMN2D, ELE_FORCEBEAMCOLUMN3D = 0, 1, 2, 3
 UNI_STEEL02, UNI_CONCRETE02 = 0, 1
 NUMBERER_PLAIN, NUMBERER_RCM = 0, 1
 SOE_SPARSE_GEN_COL, SOE_SPARSE_GEN_ROW = 0, 1

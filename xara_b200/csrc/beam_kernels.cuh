@@ -285,112 +285,6 @@ __device__ __forceinline__ void crd2d_basic(double L, double cosT, double sinT, 
   ub[2] = ub[1] + ug[5] - ug[2];
 }
 
-// ForceBeamColumn2d::update (no element loads).  U = trial displacements, DU = Node::getIncrDeltaDisp
-__global__ void __launch_bounds__(64) fbc2d_update_kernel(BeamView B, const double* __restrict__ U,
-                                                          const double* __restrict__ DU, int* fail) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= B.n) return;
-  const long long n = B.n;
-  const int nip = B.nip;
-  const double L = B.geo[e], cosT = B.geo[n + e], sinT = B.geo[2 * n + e];
-  double ug[6], dug[6];
-  for (int a = 0; a < 2; a++) {
-    const int nd = B.conn[e * 2 + a];
-    for (int j = 0; j < 3; j++) { ug[a * 3 + j] = U[(size_t)nd * 3 + j]; dug[a * 3 + j] = DU[(size_t)nd * 3 + j]; }
-  }
-  double v[3], dv[3], vin[3];
-  crd2d_basic(L, cosT, sinT, ug, v);
-  crd2d_basic(L, cosT, sinT, dug, dv);
-  const int initialFlag = B.iflag[e];
-  if (initialFlag != 0 && sqrt(dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]) <= DBL_EPSILON) return;
-  for (int i = 0; i < 3; i++) vin[i] = v[i] - dv[i];
-  double xi[XB_MAXSEC], wt[XB_MAXSEC];
-  lobatto_rule(nip, xi, wt);
-  double Se[3], kv[9];
-  for (int i = 0; i < 3; i++) Se[i] = B.Se[i * n + e];
-  for (int i = 0; i < 9; i++) kv[i] = B.kv[i * n + e];
-  double fs0[4];
-  for (int i = 0; i < 4; i++) fs0[i] = __ldg(B.fs0 + i);
-  double vr[3], f[9], dSe[3], SeTrial[3], kvTrial[9], dvTrial[3], dvToDo[3];
-  double vsSub[XB_MAXSEC][2], fsSub[XB_MAXSEC][4], SsrSub[XB_MAXSEC][2];
-  int numSubdivide = 1;
-  bool converged = false;
-  for (int i = 0; i < 3; i++) { dvToDo[i] = dv[i]; dvTrial[i] = dvToDo[i]; }
-  const double factor = 10;
-  const int maxSubdivisions = 4;
-  while (!converged && numSubdivide <= maxSubdivisions) {
-    for (int l = 0; l < 3; l++) {
-      for (int i = 0; i < 3; i++) SeTrial[i] = Se[i];
-      for (int i = 0; i < 9; i++) kvTrial[i] = kv[i];
-      for (int i = 0; i < nip; i++) {
-        for (int q = 0; q < 2; q++) { vsSub[i][q] = B.vs[(size_t)(i * 2 + q) * n + e]; SsrSub[i][q] = B.Ssr[(size_t)(i * 2 + q) * n + e]; }
-        for (int q = 0; q < 4; q++) fsSub[i][q] = B.fs[(size_t)(i * 4 + q) * n + e];
-      }
-      for (int i = 0; i < 3; i++) dSe[i] = 0.0;
-      for (int j = 0; j < 3; j++) for (int i = 0; i < 3; i++) dSe[i] += kvTrial[i + 3 * j] * dvTrial[j];
-      for (int i = 0; i < 3; i++) SeTrial[i] += dSe[i];
-      int numIters = B.maxIters;
-      if (l == 1) numIters = 10 * B.maxIters;
-      for (int j = 0; j < numIters; j++) {
-        for (int i = 0; i < 9; i++) f[i] = 0.0;
-        vr[0] = vr[1] = vr[2] = 0.0;
-        for (int i = 0; i < nip; i++) {
-          double Ss[2], dSs[2], dvs[2], fb[6], ssec[2], ksec[4];
-          const double xL = xi[i], xL1 = xL - 1.0, wtL = wt[i] * L;
-          Ss[0] = SeTrial[0];
-          Ss[1] = xL1 * SeTrial[1] + xL * SeTrial[2];
-          dSs[0] = Ss[0] - SsrSub[i][0]; dSs[1] = Ss[1] - SsrSub[i][1];
-          const bool initial = (l == 1) || (l == 2 && j == 0);
-          const double* fuse = initial ? fs0 : fsSub[i];
-          dvs[0] = 0.0; dvs[1] = 0.0;
-          for (int c = 0; c < 2; c++) for (int r = 0; r < 2; r++) dvs[r] += fuse[r + 2 * c] * dSs[c];
-          if (initialFlag != 0) { vsSub[i][0] += dvs[0]; vsSub[i][1] += dvs[1]; }
-          section_trial(B, e, i, vsSub[i], ssec, ksec);
-          SsrSub[i][0] = ssec[0]; SsrSub[i][1] = ssec[1];
-          inv2(ksec, fsSub[i]);
-          dSs[0] = Ss[0] - SsrSub[i][0]; dSs[1] = Ss[1] - SsrSub[i][1];
-          dvs[0] = 0.0; dvs[1] = 0.0;
-          for (int c = 0; c < 2; c++) for (int r = 0; r < 2; r++) dvs[r] += fsSub[i][r + 2 * c] * dSs[c];
-          for (int q = 0; q < 6; q++) fb[q] = 0.0;
-          const double* fSec = fsSub[i];
-          for (int jj = 0; jj < 2; jj++) fb[jj + 2 * 0] += fSec[jj + 2 * 0] * wtL;
-          for (int jj = 0; jj < 2; jj++) { const double tmp = fSec[jj + 2 * 1] * wtL; fb[jj + 2 * 1] += xL1 * tmp; fb[jj + 2 * 2] += xL * tmp; }
-          for (int jj = 0; jj < 3; jj++) f[0 + 3 * jj] += fb[0 + 2 * jj];
-          for (int jj = 0; jj < 3; jj++) { const double tmp = fb[1 + 2 * jj]; f[1 + 3 * jj] += xL1 * tmp; f[2 + 3 * jj] += xL * tmp; }
-          dvs[0] += vsSub[i][0]; dvs[1] += vsSub[i][1];
-          { const double dei = dvs[0] * wtL; vr[0] += dei; }
-          { const double dei = dvs[1] * wtL; vr[1] += xL1 * dei; vr[2] += xL * dei; }
-        }
-        inv3(f, kvTrial);
-        for (int i = 0; i < 3; i++) { dv[i] = vin[i]; dv[i] += dvTrial[i]; dv[i] -= vr[i]; }
-        for (int i = 0; i < 3; i++) dSe[i] = 0.0;
-        for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) dSe[r] += kvTrial[r + 3 * c] * dv[c];
-        double dW = 0.0;
-        for (int i = 0; i < 3; i++) dW += dv[i] * dSe[i];
-        for (int i = 0; i < 3; i++) SeTrial[i] += dSe[i];
-        if (fabs(dW) < B.tol) {
-          for (int i = 0; i < 3; i++) { dvToDo[i] -= dvTrial[i]; vin[i] += dvTrial[i]; }
-          if (sqrt(dvToDo[0] * dvToDo[0] + dvToDo[1] * dvToDo[1] + dvToDo[2] * dvToDo[2]) <= DBL_EPSILON) converged = true;
-          else { for (int i = 0; i < 3; i++) dvTrial[i] = dvToDo[i]; numSubdivide = 1; }
-          for (int i = 0; i < 3; i++) Se[i] = SeTrial[i];
-          for (int i = 0; i < 9; i++) kv[i] = kvTrial[i];
-          for (int i = 0; i < 3; i++) B.Se[i * n + e] = Se[i];
-          for (int i = 0; i < 9; i++) B.kv[i * n + e] = kv[i];
-          for (int i = 0; i < nip; i++) {
-            for (int q = 0; q < 2; q++) { B.vs[(size_t)(i * 2 + q) * n + e] = vsSub[i][q]; B.Ssr[(size_t)(i * 2 + q) * n + e] = SsrSub[i][q]; }
-            for (int q = 0; q < 4; q++) B.fs[(size_t)(i * 4 + q) * n + e] = fsSub[i][q];
-          }
-          j = numIters + 1; l = 3;
-        } else {
-          if (j == (numIters - 1) && (l == 2)) { for (int i = 0; i < 3; i++) dvTrial[i] /= factor; numSubdivide++; }
-        }
-      }
-    }
-  }
-  if (!converged) { atomicExch(fail, 2); return; }
-  B.iflag[e] = 1;
-}
-
 // getTangentStiff -> LinearCrdTransf2d::getGlobalStiffMatrix(kv); getResistingForce ->
 // getGlobalResistingForce(Se).  Rows of node a go to that node's slot (node-major storage).
 __global__ void __launch_bounds__(128) fbc2d_form_kernel(BeamView B, int want_k, int want_r, int transpose, BeamDyn dy) {
@@ -561,127 +455,6 @@ __device__ __forceinline__ void crd3d_basic(double L, const double* R, const dou
   ub[5] = ul[9] - ul[3];
 }
 __device__ __forceinline__ double norm6(const double* v) { double s = 0.0; for (int i = 0; i < 6; i++) s += v[i] * v[i]; return sqrt(s); }
-
-// ForceBeamColumn3d::update (no element loads).  U = trial displacements, DU = Node::getIncrDeltaDisp
-__global__ void __launch_bounds__(64) fbc3d_update_kernel(BeamView B, const double* __restrict__ U,
-                                                          const double* __restrict__ DU, int* fail) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= B.n) return;
-  const long long n = B.n;
-  const int nip = B.nip;
-  double R[9];
-  const double L = B.geo[e];
-  for (int q = 0; q < 9; q++) R[q] = B.geo[(size_t)(1 + q) * n + e];
-  double ug[12], dug[12];
-  for (int a = 0; a < 2; a++) {
-    const int nd = B.conn[e * 2 + a];
-    for (int j = 0; j < 6; j++) { ug[a * 6 + j] = U[(size_t)nd * 6 + j]; dug[a * 6 + j] = DU[(size_t)nd * 6 + j]; }
-  }
-  double v[6], dv[6], vin[6];
-  crd3d_basic(L, R, ug, v);
-  crd3d_basic(L, R, dug, dv);
-  const int initialFlag = B.iflag[e];
-  if (initialFlag != 0 && norm6(dv) <= DBL_EPSILON) return;
-  for (int i = 0; i < 6; i++) vin[i] = v[i] - dv[i];
-  double xi[XB_MAXSEC], wt[XB_MAXSEC];
-  lobatto_rule(nip, xi, wt);
-  double Se[6], kv[36];
-  for (int i = 0; i < 6; i++) Se[i] = B.Se[i * n + e];
-  for (int i = 0; i < 36; i++) kv[i] = B.kv[i * n + e];
-  double fs0[16];
-  for (int i = 0; i < 16; i++) fs0[i] = __ldg(B.fs0 + i);
-  double vr[6], f[36], dSe[6], SeTrial[6], kvTrial[36], dvTrial[6], dvToDo[6];
-  double vsSub[XB_MAXSEC][4], fsSub[XB_MAXSEC][16], SsrSub[XB_MAXSEC][4];
-  int numSubdivide = 1;
-  bool converged = false;
-  for (int i = 0; i < 6; i++) { dvToDo[i] = dv[i]; dvTrial[i] = dvToDo[i]; }
-  const double factor = 10.0;
-  const int maxSubdivisions = 10;
-  // Device-only guard: every converged sub-step resets numSubdivide (as in the reference), so a
-  // diverging global iteration can ask for ~10^10 sub-steps; a kernel that long takes the context
-  // down.  Past XB_FBC3D_MAX_PASSES element iterations the update reports the reference's failure.
-  int passes = 0;
-  while (!converged && numSubdivide <= maxSubdivisions) {
-    for (int l = 0; l < 3; l++) {
-      for (int i = 0; i < 6; i++) SeTrial[i] = Se[i];
-      for (int i = 0; i < 36; i++) kvTrial[i] = kv[i];
-      for (int i = 0; i < nip; i++) {
-        for (int q = 0; q < 4; q++) { vsSub[i][q] = B.vs[(size_t)(i * 4 + q) * n + e]; SsrSub[i][q] = B.Ssr[(size_t)(i * 4 + q) * n + e]; }
-        for (int q = 0; q < 16; q++) fsSub[i][q] = B.fs[(size_t)(i * 16 + q) * n + e];
-      }
-      for (int i = 0; i < 6; i++) dSe[i] = 0.0;
-      for (int j = 0; j < 6; j++) for (int i = 0; i < 6; i++) dSe[i] += kvTrial[i + 6 * j] * dvTrial[j];
-      for (int i = 0; i < 6; i++) SeTrial[i] += dSe[i];
-      int numIters = B.maxIters;
-      if (l == 1) numIters = 10 * B.maxIters;
-      for (int j = 0; j < numIters; j++) {
-        if (++passes > XB_FBC3D_MAX_PASSES) { atomicExch(fail, 2); return; }
-        for (int i = 0; i < 36; i++) f[i] = 0.0;
-        for (int i = 0; i < 6; i++) vr[i] = 0.0;
-        for (int i = 0; i < nip; i++) {
-          double Ss[4], dSs[4], dvs[4], fb[24], ssec[4], ksec[16];
-          const double xL = xi[i], xL1 = xL - 1.0, wtL = wt[i] * L;
-          Ss[0] = SeTrial[0];
-          Ss[1] = xL1 * SeTrial[1] + xL * SeTrial[2];
-          Ss[2] = xL1 * SeTrial[3] + xL * SeTrial[4];
-          Ss[3] = SeTrial[5];
-          for (int q = 0; q < 4; q++) dSs[q] = Ss[q] - SsrSub[i][q];
-          const bool initial = (l == 1) || (l == 2 && j == 0);
-          const double* fuse = initial ? fs0 : fsSub[i];
-          for (int q = 0; q < 4; q++) dvs[q] = 0.0;
-          for (int c = 0; c < 4; c++) for (int r = 0; r < 4; r++) dvs[r] += fuse[r + 4 * c] * dSs[c];
-          if (initialFlag != 0) for (int q = 0; q < 4; q++) vsSub[i][q] += dvs[q];
-          section3_trial(B, e, i, vsSub[i], ssec, ksec);
-          for (int q = 0; q < 4; q++) SsrSub[i][q] = ssec[q];
-          section3_flex(ksec, fsSub[i]);
-          for (int q = 0; q < 4; q++) dSs[q] = Ss[q] - SsrSub[i][q];
-          for (int q = 0; q < 4; q++) dvs[q] = 0.0;
-          for (int c = 0; c < 4; c++) for (int r = 0; r < 4; r++) dvs[r] += fsSub[i][r + 4 * c] * dSs[c];
-          for (int q = 0; q < 24; q++) fb[q] = 0.0;
-          const double* fSec = fsSub[i];
-          for (int jj = 0; jj < 4; jj++) fb[jj + 4 * 0] += fSec[jj + 4 * 0] * wtL;
-          for (int jj = 0; jj < 4; jj++) { const double tmp = fSec[jj + 4 * 1] * wtL; fb[jj + 4 * 1] += xL1 * tmp; fb[jj + 4 * 2] += xL * tmp; }
-          for (int jj = 0; jj < 4; jj++) { const double tmp = fSec[jj + 4 * 2] * wtL; fb[jj + 4 * 3] += xL1 * tmp; fb[jj + 4 * 4] += xL * tmp; }
-          for (int jj = 0; jj < 4; jj++) fb[jj + 4 * 5] += fSec[jj + 4 * 3] * wtL;
-          for (int jj = 0; jj < 6; jj++) f[0 + 6 * jj] += fb[0 + 4 * jj];
-          for (int jj = 0; jj < 6; jj++) { const double tmp = fb[1 + 4 * jj]; f[1 + 6 * jj] += xL1 * tmp; f[2 + 6 * jj] += xL * tmp; }
-          for (int jj = 0; jj < 6; jj++) { const double tmp = fb[2 + 4 * jj]; f[3 + 6 * jj] += xL1 * tmp; f[4 + 6 * jj] += xL * tmp; }
-          for (int jj = 0; jj < 6; jj++) f[5 + 6 * jj] += fb[3 + 4 * jj];
-          for (int q = 0; q < 4; q++) dvs[q] += vsSub[i][q];
-          { const double dei = dvs[0] * wtL; vr[0] += dei; }
-          { const double dei = dvs[1] * wtL; vr[1] += xL1 * dei; vr[2] += xL * dei; }
-          { const double dei = dvs[2] * wtL; vr[3] += xL1 * dei; vr[4] += xL * dei; }
-          { const double dei = dvs[3] * wtL; vr[5] += dei; }
-        }
-        if (!inv6_flex(f, kvTrial)) { atomicExch(fail, 2); return; }
-        for (int i = 0; i < 6; i++) { dv[i] = vin[i]; dv[i] += dvTrial[i]; dv[i] -= vr[i]; }
-        for (int i = 0; i < 6; i++) dSe[i] = 0.0;
-        for (int c = 0; c < 6; c++) for (int r = 0; r < 6; r++) dSe[r] += kvTrial[r + 6 * c] * dv[c];
-        double dW = 0.0;
-        for (int i = 0; i < 6; i++) dW += dv[i] * dSe[i];
-        for (int i = 0; i < 6; i++) SeTrial[i] += dSe[i];
-        if (fabs(dW) < B.tol) {
-          for (int i = 0; i < 6; i++) { dvToDo[i] -= dvTrial[i]; vin[i] += dvTrial[i]; }
-          if (norm6(dvToDo) <= DBL_EPSILON) converged = true;
-          else { for (int i = 0; i < 6; i++) dvTrial[i] = dvToDo[i]; numSubdivide = 1; }
-          for (int i = 0; i < 6; i++) Se[i] = SeTrial[i];
-          for (int i = 0; i < 36; i++) kv[i] = kvTrial[i];
-          for (int i = 0; i < 6; i++) B.Se[i * n + e] = Se[i];
-          for (int i = 0; i < 36; i++) B.kv[i * n + e] = kv[i];
-          for (int i = 0; i < nip; i++) {
-            for (int q = 0; q < 4; q++) { B.vs[(size_t)(i * 4 + q) * n + e] = vsSub[i][q]; B.Ssr[(size_t)(i * 4 + q) * n + e] = SsrSub[i][q]; }
-            for (int q = 0; q < 16; q++) B.fs[(size_t)(i * 16 + q) * n + e] = fsSub[i][q];
-          }
-          j = numIters + 1; l = 4;
-        } else {
-          if (j == (numIters - 1) && (l == 2)) { for (int i = 0; i < 6; i++) dvTrial[i] /= factor; numSubdivide++; }
-        }
-      }
-    }
-  }
-  if (!converged) { atomicExch(fail, 2); return; }
-  B.iflag[e] = 1;
-}
 
 // ---- the same update with one LANE PER SECTION (G lanes per element, G = 4 | 8 | 16 >= nIP) ----
 // The thread-per-element form above keeps every section's state in per-thread arrays (4 KB of local

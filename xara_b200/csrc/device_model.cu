@@ -1514,6 +1514,7 @@ struct xb_model {
   long long* dTask = nullptr;
   AsmView av{};
   double lambda = 0.0, lambda_c = 0.0;   // load factor (Domain::currentTime under LoadControl) and its committed value
+  bool trial_written = false;       // an xb_update ran since the last commit (the J2 history commit is a buffer swap)
   long long launches = 0;
   long long alg_bytes[6] = {0, 0, 0, 0, 0, 0};
 };
@@ -1955,6 +1956,7 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
     }
     unsigned* dt = nullptr; CU(dev_upload(m, &dt, tab)); a.gather_tab = dt;
   }
+  for (auto& d : m->dg) { d.v.sendK = m->dSendK; d.b.sendK = m->dSendK; }
   long long *ptr = nullptr, *n2e_ptr = nullptr, *roff = nullptr, *ncol_ptr = nullptr;
   unsigned short* cp = nullptr;
   CU(dev_upload(m, &ptr, h.ptr));
@@ -2163,19 +2165,15 @@ int xb_update(xb_model* m) {
     if (d.v.n == 0) continue;
     if (is_beam(d.kind)) {
       if (d.kind == XB_ELE_FORCEBEAMCOLUMN3D) {
-        // default: one lane per section (G lanes per element); XB_BEAM=element selects the thread-per-element form
-        static const bool per_element = [] { const char* v = getenv("XB_BEAM"); return v && !strcmp(v, "element"); }();
+        // one lane per section (G lanes per element)
         const long long nb = d.b.n;
-        if (per_element) fbc3d_update_kernel<<<(unsigned)((nb + 63) / 64), 64, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
-        else if (d.b.nip <= 4) fbc3d_update_sec_kernel<4><<<(unsigned)((nb * 4 + 127) / 128), 128, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
+        if (d.b.nip <= 4) fbc3d_update_sec_kernel<4><<<(unsigned)((nb * 4 + 127) / 128), 128, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
         else if (d.b.nip <= 8) fbc3d_update_sec_kernel<8><<<(unsigned)((nb * 8 + 127) / 128), 128, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
         else fbc3d_update_sec_kernel<16><<<(unsigned)((nb * 16 + 127) / 128), 128, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
       }
       else {
-        static const bool per_element = [] { const char* v = getenv("XB_BEAM"); return v && !strcmp(v, "element"); }();
         const long long nb = d.b.n;
-        if (per_element) fbc2d_update_kernel<<<(unsigned)((nb + 63) / 64), 64, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
-        else if (d.b.nip <= 4) fbc2d_update_sec_kernel<4><<<(unsigned)((nb * 4 + 127) / 128), 128, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
+        if (d.b.nip <= 4) fbc2d_update_sec_kernel<4><<<(unsigned)((nb * 4 + 127) / 128), 128, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
         else if (d.b.nip <= 8) fbc2d_update_sec_kernel<8><<<(unsigned)((nb * 8 + 127) / 128), 128, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
         else fbc2d_update_sec_kernel<16><<<(unsigned)((nb * 16 + 127) / 128), 128, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
       }
@@ -2200,6 +2198,7 @@ int xb_update(xb_model* m) {
   bytes += (long long)m->h.nn() * (m->h.ndm + m->h.ndf) * 8;  // coordinates + trial displacement, once
   for (auto& g : m->h.groups) bytes += (long long)g.conn.size() * 4;
   m->alg_bytes[0] = bytes;
+  m->trial_written = true;
   CU(cudaGetLastError());
   return XB_OK;
 }
@@ -2678,9 +2677,12 @@ int xb_commit(xb_model* m) {
       // J2PlaneStress::commitState: commitEps22 = strain(2,2)
       if (d.j2ps) CU(cudaMemcpyAsync(d.v.tan + (size_t)7 * d.ngp, d.v.tan + (size_t)6 * d.ngp, sizeof(double) * d.ngp, cudaMemcpyDeviceToDevice, m->stream));
       if (d.v.tanc) CU(cudaMemcpyAsync(d.v.tanc, d.v.tan, sizeof(double) * 8 * d.ngp, cudaMemcpyDeviceToDevice, m->stream));
-      std::swap(d.v.hc, d.v.ht);
+      // the swap is a commit only if an update wrote the trial set since the last one; a second commit in a row
+      // (J2Plasticity::commitState is idempotent) must not bring the older committed set back
+      if (m->trial_written) std::swap(d.v.hc, d.v.ht);
     }
   }
+  m->trial_written = false;
   const size_t nb = sizeof(double) * m->h.nn() * m->h.ndf;
   CU(cudaMemcpyAsync(m->dUc, m->dU, nb, cudaMemcpyDeviceToDevice, m->stream));
   CU(cudaMemcpyAsync(m->dVc, m->dV, nb, cudaMemcpyDeviceToDevice, m->stream));

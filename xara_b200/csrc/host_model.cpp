@@ -187,6 +187,9 @@ int HostModel::add_elements(int kind, int n, const int* tags, const int* conn, c
         if (i == 0) g.j2_plane_stress = (int)p[1] == 1;
         else if (g.j2_plane_stress != ((int)p[1] == 1)) { err = "FourNodeQuad with J2Plasticity: one plane type (PlaneStrain | PlaneStress) per xb_add_elements call"; return XB_ERR_UNSUPPORTED; }
       }
+      // par[3] is the element's own density, which FourNodeQuad uses instead of the material's when non-zero
+      // (FourNodeQuad.cpp:395-398): the device kernels take the material density only
+      if (p[3] != 0.0) { err = "FourNodeQuad: an element density (rho) is not supported; give the density on the nDMaterial"; return XB_ERR_UNSUPPORTED; }
       q[0] = p[0]; q[1] = p[4]; q[2] = p[5]; q[3] = (double)(int)p[1]; q[4] = p[2];
     }
   }
