@@ -592,7 +592,7 @@ def main():
     ap.add_argument("--opt", action="append", default=[], help="name=value for xb_set_option (kernel tuning experiments)")
     ap.add_argument("--selftest", action="store_true", help="torchrun, N >= 2: bitwise check of the NCCL-exchanged rows against "
                                                             "the single-GPU rows (prints {\"selftest\": \"ok\"})")
-    ap.add_argument("--solve-n", type=int, default=40, help="size of the block whose linear solve is timed (out of path; 0 = skip)")
+    ap.add_argument("--solve-n", type=int, default=16, help="size of the block whose linear solve is timed (out of path; 0 = skip)")
     a = ap.parse_args()
     if a.n is None:
         a.n = {"brick": 160, "quad": 1000, "frame": 200, "frame3d": 20}[a.workload]
