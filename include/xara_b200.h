@@ -70,7 +70,16 @@ enum {
 /* LinearSOE storage whose addA semantics the scatter map reproduces */
 enum {
   XB_SOE_SPARSE_GEN_COL = 0, /* SparseGenColLinSOE (colStartA,rowA), SparseGenColLinSOE.cpp:161,264 */
-  XB_SOE_SPARSE_GEN_ROW = 1  /* SparseGenRowLinSOE (rowStartA,colA), SparseGenRowLinSOE.cpp:127,224 */
+  XB_SOE_SPARSE_GEN_ROW = 1, /* SparseGenRowLinSOE (rowStartA,colA), SparseGenRowLinSOE.cpp:127,224 */
+  /* `system BandGeneral`: BandGenLinSOE (bandGEN/BandGenLinSOE.cpp:116 setSize, :208 addA).  A is the LAPACK band
+   * array, ldA = 2 numSubD + numSuperD + 1 doubles per column: entry (row, col) at col ldA + numSubD + numSuperD + row - col */
+  XB_SOE_BAND_GEN = 2,
+  /* `system ProfileSPD`: ProfileSPDLinSOE (profileSPD/ProfileSPDLinSOE.cpp:115 setSize, :214 addA).  Upper profile by
+   * columns, iDiagLoc[col] (1-based) = location of the diagonal: entry (row <= col, col) at iDiagLoc[col] - 1 + row - col */
+  XB_SOE_PROFILE_SPD = 3,
+  /* `system Umfpack`: UmfpackGenLinSOE (umfGEN/UmfpackGenLinSOE.cpp:70 setSize, :142 addA): Ap, Ai, Ax -- the same
+   * sorted compressed columns as SparseGenCol */
+  XB_SOE_UMFPACK_GEN = 4
 };
 
 const char* xb_version(void);
@@ -160,7 +169,15 @@ int xb_num_nodes(const xb_model*);
 long long xb_num_elements(const xb_model*);
 long long xb_num_gauss_points(const xb_model*);
 int xb_num_eqn(const xb_model*);
+/* number of pattern entries of the owned rows: the length of idx in xb_get_pattern (and of A for the compressed SOEs) */
 long long xb_nnz(const xb_model*);
+/* length of the SOE's A array, i.e. of the buffer xb_form_tangent / xb_assemble_tangent fill: xb_nnz for the compressed
+ * SOEs, size * (2 numSubD + numSuperD + 1) for BandGeneral, profileSize for ProfileSPD */
+long long xb_a_size(const xb_model*);
+/* BandGenLinSOE::setSize: numSubD, numSuperD (XB_SOE_BAND_GEN only) */
+int xb_get_band(const xb_model*, int* numSubD, int* numSuperD);
+/* ProfileSPDLinSOE::setSize: iDiagLoc[neq], 1-based as in the reference (XB_SOE_PROFILE_SPD only) */
+int xb_get_profile(const xb_model*, int* iDiagLoc);
 /* node tags in Domain iteration order (ascending, MapOfTaggedObjects); every [nn][..]
  * array below uses this order */
 int xb_get_node_tags(const xb_model*, int* tags);
@@ -168,10 +185,12 @@ int xb_get_node_tags(const xb_model*, int* tags);
 int xb_get_ids(const xb_model*, int* ids);
 /* element tags in FE_Element order (ascending element tag, PlainHandler.cpp:233) */
 int xb_get_element_tags(const xb_model*, int* tags);
-/* colStartA/rowA (CSC) or rowStartA/colA (CSR): ptr [neq+1] (64-bit), idx [nnz] */
+/* colStartA/rowA (CSC) or rowStartA/colA (CSR): ptr [neq+1] (64-bit), idx [nnz].  BandGeneral / ProfileSPD / Umfpack
+ * models return the compressed-column pattern of the DOF graph (Umfpack: its Ap / Ai) */
 int xb_get_pattern(const xb_model*, long long* ptr, int* idx);
 /* the addA location of every entry of FE elements [e0,e1): map[(e-e0)*nd*nd + i*nd + j]
- * = index into A that receives element-matrix entry (i,j), -1 when dropped */
+ * = index into A (of the SOE kind given to xb_setup) that receives element-matrix entry (i,j), -1 when dropped
+ * (constrained dofs; ProfileSPD: the lower triangle) */
 int xb_get_scatter_map(const xb_model*, long long e0, long long e1, long long* map);
 
 /* ---- device phase ---- */

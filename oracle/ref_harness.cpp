@@ -74,6 +74,10 @@
 #undef protected
 #include <SparseGenRowLinSolver.h>
 #include <SparseGenColLinSolver.h>
+#include <BandGenLinSOE.h>
+#include <BandGenLinSolver.h>
+#include <ProfileSPDLinSOE.h>
+#include <ProfileSPDLinSolver.h>
 #include <LoadControl.h>
 #include <Newmark.h>
 #include <TransientIntegrator.h>
@@ -503,6 +507,65 @@ int ref_form_tangent(void* h, double* A) {
   int r = m->integ->formTangent(CURRENT_TANGENT);
   if (A) memcpy(A, m->A(), sizeof(double) * ref_nnz(h));
   return r;
+}
+
+// `system BandGeneral` / `system ProfileSPD` of the SAME analysis: the reference's own BandGenLinSOE (kind 2) or
+// ProfileSPDLinSOE (kind 3) is sized from the AnalysisModel's DOF graph and filled the way
+// IncrementalIntegrator::formTangent does for a static integrator (zeroA; addA(FE_Element::getTangent, getID) in
+// FE_Element order).  layout: kind 2 -> {numSubD, numSuperD}, kind 3 -> iDiagLoc[numEqn].  Returns the length of A.
+namespace {
+class NoBandSolver : public BandGenLinSolver {
+ public:
+  NoBandSolver() : BandGenLinSolver(0) {}
+  int solve() override { return 0; }
+  int setSize() override { return 0; }
+  int sendSelf(int, Channel&) override { return 0; }
+  int recvSelf(int, Channel&, FEM_ObjectBroker&) override { return 0; }
+};
+class NoProfileSolver : public ProfileSPDLinSolver {
+ public:
+  NoProfileSolver() : ProfileSPDLinSolver(0) {}
+  int solve() override { return 0; }
+  int setSize() override { return 0; }
+  int sendSelf(int, Channel&) override { return 0; }
+  int recvSelf(int, Channel&, FEM_ObjectBroker&) override { return 0; }
+};
+struct BandPeek : public BandGenLinSOE {
+  explicit BandPeek(BandGenLinSolver& s) : BandGenLinSOE(s) {}
+  int sub() const { return numSubD; } int super() const { return numSuperD; } int n() const { return size; } const double* a() const { return A; }
+};
+struct ProfilePeek : public ProfileSPDLinSOE {
+  explicit ProfilePeek(ProfileSPDLinSolver& s) : ProfileSPDLinSOE(s) {}
+  int n() const { return size; } int psize() const { return profileSize; } const int* diag() const { return iDiagLoc; } const double* a() const { return A; }
+};
+}  // namespace
+long long ref_store_tangent(void* h, int kind, int* layout, double* A) {
+  RefModel* m = (RefModel*)h;
+  Graph& g = m->amodel->getDOFGraph();
+  long long n = -1;
+  auto fill = [&](LinearSOE& soe) {
+    soe.zeroA();
+    FE_EleIter& eles = m->amodel->getFEs();
+    FE_Element* fe;
+    while ((fe = eles()) != nullptr) soe.addA(fe->getTangent(m->integ), fe->getID());
+  };
+  if (kind == 2) {
+    BandPeek soe(*new NoBandSolver());
+    if (soe.setSize(g) < 0) return -1;
+    fill(soe);
+    layout[0] = soe.sub(); layout[1] = soe.super();
+    n = (long long)soe.n() * (2 * soe.sub() + soe.super() + 1);
+    if (A) memcpy(A, soe.a(), sizeof(double) * n);
+  } else if (kind == 3) {
+    ProfilePeek soe(*new NoProfileSolver());
+    if (soe.setSize(g) < 0) return -1;
+    fill(soe);
+    for (int i = 0; i < soe.n(); i++) layout[i] = soe.diag()[i];
+    n = soe.psize();
+    if (A) memcpy(A, soe.a(), sizeof(double) * n);
+  }
+  m->amodel->clearDOFGraph();
+  return n;
 }
 
 // IncrementalIntegrator::formUnbalance -> B

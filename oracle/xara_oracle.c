@@ -1233,6 +1233,8 @@ typedef struct {
   int* ptr; int* idx; int nnz;        /* colStartA/rowA or rowStartA/colA */
   double* A; double* B;
   double lambda, lambda_c;   /* load factor (Domain::currentTime under LoadControl) and its committed value */
+  /* `system BandGeneral` (2) / `system ProfileSPD` (3) on top of the column graph: orc_set_store */
+  int store_kind, numSubD, numSuperD, profileSize; int* iDiagLoc; double* Astore; long long astore_size;
 } OrcModel;
 
 static int find_node(const OrcModel* m, int tag) {
@@ -1596,11 +1598,67 @@ static int soe_find(const OrcModel* m, int major, int minor) {
   for (int k = m->ptr[major]; k < m->ptr[major + 1]; k++) if (m->idx[k] == minor) return k;
   return -1;
 }
+/* BandGenLinSOE::setSize (bandGEN/BandGenLinSOE.cpp:116-147) / ProfileSPDLinSOE::setSize (profileSPD/ProfileSPDLinSOE.cpp:
+ * 115-168) over the DOF graph (vertex = equation, adjacency = the other equations of its column).  The model must have
+ * been set up with soe_kind 0; returns the length of A.  kind 0 goes back to the compressed columns. */
+long long orc_set_store(void* h, int kind) {
+  OrcModel* m = (OrcModel*)h;
+  free(m->iDiagLoc); free(m->Astore); m->iDiagLoc = NULL; m->Astore = NULL; m->store_kind = 0; m->astore_size = m->nnz;
+  if (kind != 2 && kind != 3) return m->nnz;
+  if (m->soe_kind != 0) return -1;
+  const int size = m->neq;
+  if (kind == 2) {
+    int numSubD = 0, numSuperD = 0;
+    for (int v = 0; v < size; v++)
+      for (int k = m->ptr[v]; k < m->ptr[v + 1]; k++) {
+        int otherNum = m->idx[k];
+        if (otherNum == v) continue;            /* the adjacency list does not hold the vertex itself */
+        int diff = v - otherNum;
+        if (diff > 0) { if (diff > numSuperD) numSuperD = diff; }
+        else if (diff < numSubD) numSubD = diff;
+      }
+    numSubD *= -1;
+    m->numSubD = numSubD; m->numSuperD = numSuperD;
+    m->astore_size = (long long)size * (2 * numSubD + numSuperD + 1);
+  } else {
+    m->iDiagLoc = (int*)calloc(size > 0 ? size : 1, sizeof(int));
+    for (int v = 0; v < size; v++)
+      for (int k = m->ptr[v]; k < m->ptr[v + 1]; k++) {
+        int diff = v - m->idx[k];
+        if (diff > 0 && m->iDiagLoc[v] < diff) m->iDiagLoc[v] = diff;
+      }
+    if (size > 0) m->iDiagLoc[0] = 1;          /* NOTE FORTRAN ARRAY LOCATION */
+    for (int j = 1; j < size; j++) m->iDiagLoc[j] = m->iDiagLoc[j] + 1 + m->iDiagLoc[j - 1];
+    m->profileSize = size > 0 ? m->iDiagLoc[size - 1] : 0;
+    m->astore_size = m->profileSize;
+  }
+  m->store_kind = kind;
+  m->Astore = (double*)calloc(m->astore_size > 0 ? m->astore_size : 1, sizeof(double));
+  return m->astore_size;
+}
+void orc_get_band(void* h, int* out) { OrcModel* m = (OrcModel*)h; out[0] = m->numSubD; out[1] = m->numSuperD; }
+void orc_get_profile(void* h, int* iDiagLoc) { OrcModel* m = (OrcModel*)h; memcpy(iDiagLoc, m->iDiagLoc, sizeof(int) * m->neq); }
+/* where BandGenLinSOE::addA (BandGenLinSOE.cpp:208-249) / ProfileSPDLinSOE::addA (ProfileSPDLinSOE.cpp:214-243) put the
+ * entry of column col, row row; -1 when it is dropped */
+static long long store_loc(const OrcModel* m, int row, int col) {
+  if (m->store_kind == 2) {
+    const int ldA = 2 * m->numSubD + m->numSuperD + 1;
+    long long colii = (long long)col * ldA + m->numSubD + m->numSuperD;
+    int diff = col - row;
+    if (diff > 0) return diff <= m->numSuperD ? colii - diff : -1;
+    diff *= -1;
+    return diff <= m->numSubD ? colii + diff : -1;
+  }
+  int minColRow = col == 0 ? 0 : col - (m->iDiagLoc[col] - m->iDiagLoc[col - 1]) + 1;
+  if (row <= col && row >= minColRow) return (long long)m->iDiagLoc[col] - 1 + (row - col);
+  return -1;
+}
 void orc_scatter_map(void* h, int e, int* map) {
   OrcModel* m = (OrcModel*)h; int ids[32]; int n = ele_ids(m, &m->ele[e], ids);
   for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) {
     int r = ids[i], c = ids[j], k = -1;
-    if (r >= 0 && c >= 0) k = (m->soe_kind == 1) ? soe_find(m, r, c) : soe_find(m, c, r);
+    /* column-oriented addA: column id(j'), row id(i') receives m(i', j') -- entry (i, j) goes to column c = id(j), row r = id(i) */
+    if (r >= 0 && c >= 0) k = m->store_kind ? (int)store_loc(m, r, c) : ((m->soe_kind == 1) ? soe_find(m, r, c) : soe_find(m, c, r));
     map[i * n + j] = k;
   }
 }
@@ -2064,6 +2122,7 @@ int orc_ele_resid(void* h, int e, double* R) {
 int orc_form_tangent(void* h, double* A) {
   OrcModel* m = (OrcModel*)h;
   memset(m->A, 0, sizeof(double) * m->nnz);
+  if (m->store_kind) memset(m->Astore, 0, sizeof(double) * m->astore_size);
   /* TransientIntegrator::formTangent (TransientIntegrator.cpp:89-97): DOF_Group tangents first,
    * Newmark::formNodTangent: zeroTangent; addCtoTang(c2) (C = alphaM*M, Node::getDamp); addMtoTang(c3) */
   if (m->c2 != 0.0 || m->c3 != 0.0)
@@ -2074,6 +2133,7 @@ int orc_form_tangent(void* h, double* A) {
         double t = 0.0;
         t += (m->mass[n * m->ndf + j] * m->alphaM) * m->c2;
         t += m->mass[n * m->ndf + j] * m->c3;
+        if (m->store_kind) { m->Astore[store_loc(m, r, r)] += t; continue; }
         int k = soe_find(m, r, r);
         m->A[k] += t;
       }
@@ -2098,7 +2158,12 @@ int orc_form_tangent(void* h, double* A) {
       double M[576]; ele_M(m, el, M, NULL);
       for (int i = 0; i < nd_e * nd_e; i++) K[i] += M[i] * m->c3;
     }
-    if (m->soe_kind == 1) {
+    if (m->store_kind) {
+      /* BandGenLinSOE::addA / ProfileSPDLinSOE::addA: for (i) col = id(i); for (j) row = id(j); *APtr += m(j,i) */
+      for (int i = 0; i < nd_e; i++) { int col = ids[i]; if (col < 0) continue;
+        for (int j = 0; j < nd_e; j++) { int row = ids[j]; if (row < 0) continue;
+          long long k = store_loc(m, row, col); if (k >= 0) m->Astore[k] += K[j * nd_e + i]; } }
+    } else if (m->soe_kind == 1) {
       for (int i = 0; i < nd_e; i++) { int row = ids[i]; if (row < 0) continue;
         for (int j = 0; j < nd_e; j++) { int col = ids[j]; if (col < 0) continue;
           int k = soe_find(m, row, col); if (k >= 0) m->A[k] += K[i * nd_e + j]; } }
@@ -2108,7 +2173,7 @@ int orc_form_tangent(void* h, double* A) {
           int k = soe_find(m, col, row); if (k >= 0) m->A[k] += K[j * nd_e + i]; } }
     }
   }
-  if (A) memcpy(A, m->A, sizeof(double) * m->nnz);
+  if (A) { if (m->store_kind) memcpy(A, m->Astore, sizeof(double) * m->astore_size); else memcpy(A, m->A, sizeof(double) * m->nnz); }
   return 0;
 }
 
@@ -2231,5 +2296,5 @@ void orc_model_free(void* h) {
   OrcModel* m = (OrcModel*)h; if (!m) return;
   free(m->node_tag); free(m->crd); free(m->trial); free(m->commit_disp); free(m->load); free(m->fixed);
   free(m->mat_tag); free(m->mat_kind); free(m->mat_par); free(m->ele); free(m->id); free(m->ptr); free(m->idx);
-  free(m->A); free(m->B); free(m);
+  free(m->A); free(m->B); free(m->iDiagLoc); free(m->Astore); free(m);
 }

@@ -495,9 +495,22 @@ class OracleBackend(_Backend):
             for row in spec.loads:
                 v = np.ascontiguousarray(row[1:], np.float64)
                 assert L.orc_add_load(self.h, int(row[0]), _p(v)) == 0
-        self.neq = L.orc_setup(self.h, numberer, soe)
+        # soe 2 / 3 / 4: BandGeneral / ProfileSPD / Umfpack -- the column graph, then the SOE's own storage on top of it
+        self.soe = soe
+        self.neq = L.orc_setup(self.h, numberer, soe if soe in (0, 1) else 0)
         self.nnz = L.orc_nnz(self.h)
+        self.a_size = self.nnz
+        if soe in (2, 3):
+            L.orc_set_store.restype = ctypes.c_longlong; L.orc_set_store.argtypes = [ctypes.c_void_p, ctypes.c_int]
+            self.a_size = int(L.orc_set_store(self.h, soe))
+            assert self.a_size >= 0
         self.ne = L.orc_num_ele(self.h)
+
+    def band(self):
+        a = np.zeros(2, np.int32); self.L.orc_get_band(self.h, _p(a)); return int(a[0]), int(a[1])
+
+    def profile(self):
+        a = np.zeros(self.neq, np.int32); self.L.orc_get_profile(self.h, _p(a)); return a
 
     def ids(self):
         a = np.zeros((self.spec.nn, self.spec.ndf), np.int32); self.L.orc_get_ids(self.h, _p(a)); return a
@@ -520,7 +533,7 @@ class OracleBackend(_Backend):
         self.L.orc_apply_load.argtypes = [ctypes.c_void_p, ctypes.c_double]; self.L.orc_apply_load(self.h, lam)
 
     def form_tangent(self):
-        A = np.zeros(self.nnz); self.L.orc_form_tangent(self.h, _p(A)); return A
+        A = np.zeros(self.a_size); self.L.orc_form_tangent(self.h, _p(A)); return A
 
     def form_unbalance(self):
         B = np.zeros(self.neq); self.L.orc_form_unbalance(self.h, _p(B)); return B
@@ -785,6 +798,18 @@ class RefBackend(_Backend):
             self.L.glue_last_error.restype = ctypes.c_char_p; self.L.glue_last_error.argtypes = [ctypes.c_void_p]
             raise RuntimeError(f"glue set-up failed ({self.neq}): {self.L.glue_last_error(self.h).decode()}")
         self.nnz = self.L.ref_nnz(self.h); self.max_iter = max_iter
+
+    def store_tangent(self, kind):
+        """the reference's own BandGenLinSOE (2) / ProfileSPDLinSOE (3) sized and filled from this analysis:
+        -> (layout, A): layout = (numSubD, numSuperD) or iDiagLoc"""
+        self.L.ref_store_tangent.restype = ctypes.c_longlong
+        self.L.ref_store_tangent.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        lay = np.zeros(max(self.neq, 2), np.int32)
+        n = int(self.L.ref_store_tangent(self.h, kind, _p(lay), None))
+        assert n >= 0
+        A = np.zeros(n)
+        assert int(self.L.ref_store_tangent(self.h, kind, _p(lay), _p(A))) == n
+        return ((int(lay[0]), int(lay[1])) if kind == 2 else lay[:self.neq].copy()), A
 
     def glue_free(self):
         """frees the device model behind a glued reference model (oracle/ref_glue.cpp glue_destroy)"""

@@ -576,6 +576,38 @@ def test_shuffled_tags_and_tangent_options_bitwise():
             assert np.array_equal(x, y)
 
 
+@pytest.mark.parametrize("soe", [2, 3, 4], ids=["BandGeneral", "ProfileSPD", "Umfpack"])
+def test_band_profile_umfpack_storage_device_vs_oracle(soe):
+    """`system BandGeneral | ProfileSPD | Umfpack`: the assembly kernels write A into the SOE's own array (LAPACK band,
+    upper profile by columns, Umfpack's Ax) -- against the oracle's restatement of the SOEs' addA, which is pinned to the
+    live BandGenLinSOE / ProfileSPDLinSOE (tests/test_oracle.py); bricks (record assembly), equalDOF (shared rows), quads
+    and force beams, over load steps with commits and the Newmark terms on the diagonal"""
+    rng = np.random.default_rng(8)
+    for spec, sc in ((brick_block(5, 4, 3, distort=0.25, seed=3, body=(0.01, 0.0, -0.02)), 2e-3),
+                     (brick_periodic_equaldof(3, 3, 2, seed=5), 2e-3), (quad_plane(7, 5, mat=J2_STEEL, distort=0.2, seed=4), 2e-3),
+                     (frame2d(2, 3, 2), np.array((0.006, 0.003, 6e-5)))):
+        beam = spec.groups[0].kind in (2, 3)
+        tol = BEAM_RTOL if beam else RTOL
+        mass = rng.uniform(0.01, 0.1, (spec.nn, spec.ndf))
+        O = OracleBackend(spec, 1, soe); O.set_mass(spec.node_tags, mass)
+        D = xb.DeviceModel.from_spec(spec, setup=False); D.set_mass(spec.node_tags, mass); D.setup(1, soe); D.to_device(0)
+        assert D.a_size == O.a_size
+        ids = O.ids()
+        for s_ in range(3):
+            u = rng.normal(0, 1.0, (spec.nn, spec.ndf)) * sc * (s_ + 1); u[ids < 0] = 0
+            tie(spec, u)
+            O.set_trial_disp(u); D.set_trial_disp(u); D.update()
+            O.apply_load(0.3 * s_); D.apply_load(0.3 * s_)
+            if s_ == 2:
+                for m in (O, D):
+                    m.set_transient(1.0, 30.0, 5.0e3)
+            A = D.form_tangent()
+            assert relerr(A, O.form_tangent()) < tol
+            assert np.array_equal(A, D.form_tangent())                     # entries outside the pattern stay exact zeros
+            assert relerr(D.form_unbalance(), O.form_unbalance()) < tol
+            O.commit(); D.commit()
+
+
 def test_launch_and_byte_accounting():
     D = xb.DeviceModel.from_spec(brick_block(3, 3, 3), 0, 0).to_device(0)
     n0 = D.launch_count()

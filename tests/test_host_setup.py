@@ -233,3 +233,24 @@ def test_all_fixed_and_isolated_nodes():
         O = OracleBackend(spec, numberer, 1); D = xb.DeviceModel.from_spec(spec, numberer, 1)
         assert np.array_equal(D.ids(), O.ids())
         assert all(np.array_equal(a, b) for a, b in zip(D.pattern(), O.csr()))
+
+
+@pytest.mark.parametrize("soe", [2, 3, 4])
+@pytest.mark.parametrize("numberer", [0, 1])
+def test_band_profile_umfpack_layout_and_scatter_maps_bit_exact(numberer, soe):
+    """`system BandGeneral | ProfileSPD | Umfpack`: layout (numSubD / numSuperD, iDiagLoc, Ap / Ai) and the addA location of
+    every element-matrix entry against the oracle's restatement of BandGenLinSOE / ProfileSPDLinSOE (pinned to the live
+    classes in tests/test_oracle.py); Umfpack's Ap / Ai are SparseGenCol's colStartA / rowA"""
+    for spec in (brick_block(4, 3, 2, distort=0.2, seed=5), quad_plane(6, 4, distort=0.2, seed=6), frame2d(2, 3, 2),
+                 soil_column_equaldof(6), brick_periodic_equaldof(3, 2, 2)):
+        nd = {0: 24, 1: 8, 2: 6, 3: 12}[spec.groups[0].kind]
+        O = OracleBackend(spec, numberer, soe)
+        D = xb.DeviceModel.from_spec(spec, numberer, soe)
+        assert D.neq == O.neq and D.a_size == O.a_size and np.array_equal(D.ids(), O.ids())
+        assert all(np.array_equal(a, b) for a, b in zip(D.pattern(), O.csr()))
+        if soe == 2:
+            assert D.band() == O.band()
+        if soe == 3:
+            assert np.array_equal(D.profile(), O.profile())
+        for e in range(O.ne):
+            assert np.array_equal(D.scatter_map(e, e + 1, nd).reshape(nd, nd), O.scatter_map(e, nd))

@@ -134,6 +134,41 @@ def test_oracle_vs_live_reference(mat, numberer, soe):
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("numberer", [0, 1])
+def test_band_and_profile_storage_vs_live_reference(numberer):
+    """`system BandGeneral` / `system ProfileSPD`: the oracle's layout (numSubD / numSuperD, iDiagLoc) and its addA into the
+    band / profile array against the reference's own BandGenLinSOE / ProfileSPDLinSOE sized from the same DOF graph and
+    filled in FE_Element order -- layout bit-exact, A to rounding; equalDOF and constrained dofs included"""
+    rng = np.random.default_rng(3)
+    specs = [brick_block(3, 2, 2, distort=0.2, seed=11), quad_plane(5, 4, mat=J2_STEEL, distort=0.2, seed=12), frame2d(2, 2, 2),
+             soil_column_equaldof(5), brick_periodic_equaldof(2, 2, 2)]
+    for spec in specs:
+        beam = spec.groups[0].kind in (2, 3)
+        R = RefBackend(spec, numberer, 0)
+        u = rng.normal(0, 1.0, (spec.nn, spec.ndf)) * np.asarray((0.02, 0.02, 2e-4) if beam else 2e-3); u[R.ids() < 0] = 0
+        tie(spec, u)
+        R.set_trial_disp(u); R.apply_load(0.4); R.form_tangent()
+        for kind in (2, 3):
+            O = OracleBackend(spec, numberer, kind)
+            O.set_trial_disp(u); O.apply_load(0.4)
+            lay, Ar = R.store_tangent(kind)
+            if kind == 2:
+                assert O.band() == lay
+            else:
+                assert np.array_equal(O.profile(), lay)
+            Ao = O.form_tangent()
+            assert len(Ao) == len(Ar) and close(Ao, Ar, 1e-11 if beam else RTOL)
+            # the scatter map says where addA puts every element entry: scattering the element matrices through it
+            # reproduces the array
+            nd = {0: 24, 1: 8, 2: 6, 3: 12}[spec.groups[0].kind]
+            acc = np.zeros(len(Ao))
+            for e in range(O.ne):
+                mp, K = O.scatter_map(e, nd).ravel(), O.ele_tangent(e, nd).ravel()
+                np.add.at(acc, mp[mp >= 0], K[mp >= 0])
+            assert close(acc, Ao, 1e-11 if beam else RTOL)
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
 def test_revert_to_last_commit_vs_live_reference():
     """Domain::revertToLastCommit (Domain.cpp:1925): nodes and elements go back, the load factor of the last commit is
     applied again, then update() -- incl. J2PlaneStress's out-of-plane strain and the force beams' section state"""

@@ -29,13 +29,13 @@ import numpy as np
 
 __all__ = ["DeviceModel", "XaraB200Error", "lib", "LIB_PATH", "device_count", "comm_unique_id", "exchange_local",
            "MAT_ELASTIC_ISOTROPIC", "MAT_J2PLASTICITY", "ELE_STDBRICK", "ELE_FOURNODEQUAD", "ELE_FORCEBEAMCOLUMN2D", "ELE_FORCEBEAMCOLUMN3D", "UNI_STEEL02", "UNI_CONCRETE02",
-           "NUMBERER_PLAIN", "NUMBERER_RCM", "SOE_SPARSE_GEN_COL", "SOE_SPARSE_GEN_ROW"]
+           "NUMBERER_PLAIN", "NUMBERER_RCM", "SOE_SPARSE_GEN_COL", "SOE_SPARSE_GEN_ROW", "SOE_BAND_GEN", "SOE_PROFILE_SPD", "SOE_UMFPACK_GEN"]
 
 MAT_ELASTIC_ISOTROPIC, MAT_J2PLASTICITY = 0, 1
 ELE_STDBRICK, ELE_FOURNODEQUAD, ELE_FORCEBEAMCOLUMN2D, ELE_FORCEBEAMCOLUMN3D = 0, 1, 2, 3
 UNI_STEEL02, UNI_CONCRETE02 = 0, 1
 NUMBERER_PLAIN, NUMBERER_RCM = 0, 1
-SOE_SPARSE_GEN_COL, SOE_SPARSE_GEN_ROW = 0, 1
+SOE_SPARSE_GEN_COL, SOE_SPARSE_GEN_ROW, SOE_BAND_GEN, SOE_PROFILE_SPD, SOE_UMFPACK_GEN = 0, 1, 2, 3, 4
 
 # XARA_B200_LIB: an alternative build of the same library (kernel tuning experiments)
 LIB_PATH = os.environ.get("XARA_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libxara_b200.so")
@@ -91,6 +91,9 @@ def _load():
         "xb_num_gauss_points": (i64, [vp]),
         "xb_num_eqn": (i32, [vp]),
         "xb_nnz": (i64, [vp]),
+        "xb_a_size": (i64, [vp]),
+        "xb_get_band": (i32, [vp, vp, vp]),
+        "xb_get_profile": (i32, [vp, vp]),
         "xb_get_node_tags": (i32, [vp, vp]),
         "xb_get_ids": (i32, [vp, vp]),
         "xb_get_element_tags": (i32, [vp, vp]),
@@ -273,6 +276,7 @@ class DeviceModel:
         self.ne = lib.xb_num_elements(self._h)
         self.ngp = lib.xb_num_gauss_points(self._h)
         self.nnz = lib.xb_nnz(self._h)
+        self.a_size = lib.xb_a_size(self._h)    # length of A: nnz, or the band / profile array
         return self.neq
 
     def node_tags(self):
@@ -378,7 +382,7 @@ class DeviceModel:
 
     def form_tangent(self, out=None, host=True):
         if host and out is None:
-            out = np.empty(self.nnz)
+            out = np.empty(self.a_size)
         self._ck(lib.xb_form_tangent(self._h, _ptr(out) if host else None))
         return out
 
@@ -423,6 +427,18 @@ class DeviceModel:
     def gp_response(self, e, g, order):
         s = np.zeros(order); t = np.zeros((order, order))
         self._ck(lib.xb_get_gp_response(self._h, e, g, _ptr(s), _ptr(t))); return s, t
+
+    def band(self):
+        """BandGenLinSOE's (numSubD, numSuperD)"""
+        a, b = ctypes.c_int(), ctypes.c_int()
+        self._ck(lib.xb_get_band(self._h, ctypes.addressof(a), ctypes.addressof(b)))
+        return a.value, b.value
+
+    def profile(self):
+        """ProfileSPDLinSOE's iDiagLoc (1-based)"""
+        d = np.zeros(self.neq, np.int32)
+        self._ck(lib.xb_get_profile(self._h, _ptr(d)))
+        return d
 
     def launch_count(self):
         return lib.xb_launch_count(self._h)

@@ -1028,6 +1028,7 @@ struct AsmView {
   // record models (stdBrick: brick_rec.hpp): a slot's rows are gathered from the element's symmetric record
   const long long* n2e_ksrc;  // [*] slot descriptor: offset << 4 | local node << 1 | 1 (record), offset << 4 (dense rows in recvK)
   const double* rec;          // element records
+  const long long* a_loc;     // BandGeneral / ProfileSPD: location in A of pattern entry k (-1: not stored); null: k itself
   const unsigned* gather_tab; // [9][72] the fast kernel's gather in record order: offset | row << 10 | element dof << 12
   const unsigned* n2e_ksrc32; // the same in 32 bits for the fast kernel: offset in units of 36 doubles << 4 | local node (8: dense rows)
   int transpose;              // the SOE stores A by columns: a slot's "rows" are columns of the element tangent
@@ -1160,7 +1161,11 @@ __device__ __forceinline__ void assemble_A_node(const AsmView& V, const double* 
     const long long rp = __shfl_sync(0xffffffffu, word, 3 + p);
     if (rp < 0) continue;
     double* out = A + rp;
-    for (int c = lane; c < L; c += 32) out[c] = acc[p * V.max_row + c];
+    if (V.a_loc) {
+      for (int c = lane; c < L; c += 32) { const long long l = V.a_loc[rp + c]; if (l >= 0) A[l] = acc[p * V.max_row + c]; }
+    } else {
+      for (int c = lane; c < L; c += 32) out[c] = acc[p * V.max_row + c];
+    }
   }
 }
 
@@ -1292,9 +1297,15 @@ __global__ void __launch_bounds__(256, XB_ASM_FAST_OCC) assemble_A_rec_fast_kern
     const long long rp = __shfl_sync(0xffffffffu, word, 3 + p);
     if (rp < 0) continue;
     double* out = A + rp;
+    if (V.a_loc) {
 #pragma unroll
-    for (int c = 0; c < FA_L / 32; c++)
-      if (c * 32 + lane < L) out[c * 32 + lane] = acc[p * FA_S + c * 32 + lane];
+      for (int c = 0; c < FA_L / 32; c++)
+        if (c * 32 + lane < L) { const long long l = V.a_loc[rp + c * 32 + lane]; if (l >= 0) A[l] = acc[p * FA_S + c * 32 + lane]; }
+    } else {
+#pragma unroll
+      for (int c = 0; c < FA_L / 32; c++)
+        if (c * 32 + lane < L) out[c * 32 + lane] = acc[p * FA_S + c * 32 + lane];
+    }
   }
 }
 
@@ -1346,7 +1357,11 @@ __global__ void __launch_bounds__(256) assemble_A_irr_kernel(AsmView V, const do
       }
     }
   }
-  for (int c = lane; c < L; c += 32) A[a0 + c] = acc[c];
+  if (V.a_loc) {
+    for (int c = lane; c < L; c += 32) { const long long l = V.a_loc[a0 + c]; if (l >= 0) A[l] = acc[c]; }
+  } else {
+    for (int c = lane; c < L; c += 32) A[a0 + c] = acc[c];
+  }
 }
 
 // formUnbalance for the shared equations: element residual entries in (FE_Element, element dof) order, then the
@@ -1652,6 +1667,7 @@ long long xb_num_elements(const xb_model* m) { return m ? m->h.ne : 0; }
 long long xb_num_gauss_points(const xb_model* m) { return m ? m->h.ngp : 0; }
 int xb_num_eqn(const xb_model* m) { return m ? m->h.neq : 0; }
 long long xb_nnz(const xb_model* m) { return m ? m->h.nnz() : 0; }
+long long xb_a_size(const xb_model* m) { return m ? m->h.a_size() : 0; }
 
 #define NEED_SETUP() if (!m || !m->h.is_setup) return fail(XB_ERR_STATE, "call xb_setup first")
 #define NEED_DEVICE() if (!m || !m->on_device) return fail(XB_ERR_STATE, "call xb_device_init first (no CPU fallback)")
@@ -1694,6 +1710,18 @@ int xb_get_pattern(const xb_model* m, long long* ptr, int* idx) {
   NEED_SETUP();
   std::memcpy(ptr, m->h.ptr.data(), sizeof(long long) * m->h.ptr.size());
   std::memcpy(idx, m->h.idx.data(), sizeof(int) * m->h.idx.size());
+  return XB_OK;
+}
+int xb_get_band(const xb_model* m, int* numSubD, int* numSuperD) {
+  NEED_SETUP();
+  if (m->h.soe_store != XB_SOE_BAND_GEN) return fail(XB_ERR_STATE, "xb_get_band: the model was not set up with XB_SOE_BAND_GEN");
+  *numSubD = m->h.band_sub; *numSuperD = m->h.band_super;
+  return XB_OK;
+}
+int xb_get_profile(const xb_model* m, int* iDiagLoc) {
+  NEED_SETUP();
+  if (m->h.soe_store != XB_SOE_PROFILE_SPD) return fail(XB_ERR_STATE, "xb_get_profile: the model was not set up with XB_SOE_PROFILE_SPD");
+  std::memcpy(iDiagLoc, m->h.profile_diag.data(), sizeof(int) * m->h.profile_diag.size());
   return XB_OK;
 }
 int xb_get_scatter_map(const xb_model* m, long long e0, long long e1, long long* map) {
@@ -1755,7 +1783,8 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
   // for the assembly's gathers)
   CU(dev_alloc(m, &m->dRec, (size_t)h.rec_total + (h.rec_mode ? (size_t)h.recv_k_total : 0)));
   CU(dev_alloc(m, &m->dRe, (size_t)h.re_total));
-  CU(dev_alloc(m, &m->dA, (size_t)h.nnz()));
+  CU(dev_alloc(m, &m->dA, (size_t)h.a_size()));
+  CU(cudaMemset(m->dA, 0, sizeof(double) * std::max<size_t>((size_t)h.a_size(), 1)));   // (band / profile: entries outside the pattern stay zero)
   CU(dev_alloc(m, &m->dB, (size_t)h.nrows));
   CU(dev_alloc(m, &m->dTmp, (size_t)h.neq));
   CU(dev_alloc(m, &m->dFail, 1));
@@ -1941,6 +1970,8 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
   a.rec = m->dRec; a.transpose = h.soe_kind == XB_SOE_SPARSE_GEN_COL ? 1 : 0;
   { long long* ks = nullptr; CU(dev_upload(m, &ks, h.n2e_ksrc)); a.n2e_ksrc = ks; }
   { unsigned* ks = nullptr; CU(dev_upload(m, &ks, h.n2e_ksrc32)); a.n2e_ksrc32 = ks; }
+  a.a_loc = nullptr;
+  if (!h.a_loc.empty()) { long long* al = nullptr; CU(dev_upload(m, &al, h.a_loc)); a.a_loc = al; }
   if (h.fast_asm_ok) {
     // the 72 values local node J takes from a record, in record order (J = 8: dense rows, already in order)
     std::vector<unsigned> tab(9 * 72);
@@ -2482,7 +2513,7 @@ static int finish_tangent(xb_model* m, double* A) {
   m->alg_bytes[2] = bytes;
   CU(cudaGetLastError());
   if (A) {
-    CU(cudaMemcpyAsync(A, m->dA, sizeof(double) * m->h.nnz(), cudaMemcpyDeviceToHost, m->stream));
+    CU(cudaMemcpyAsync(A, m->dA, sizeof(double) * m->h.a_size(), cudaMemcpyDeviceToHost, m->stream));
     return check_fail_flag(m);
   }
   return XB_OK;
@@ -2546,14 +2577,18 @@ int xb_form_tangent(xb_model* m, double* A) {
     }
   }
   account_element_tangent_bytes(m);
-  CU(cudaEventRecord(m->ev_done, m->stream2));
-  CU(cudaStreamWaitEvent(m->stream, m->ev_done, 0));
-  if (m->h.nparts > 1) {     // interface nodes: pack, exchange, assemble on the main stream
+  if (m->h.nparts > 1) {
+    // interface rows: packed and exchanged on the main stream as soon as the last range is formed -- the NCCL
+    // transfer runs while the second stream is still assembling the last ranges' interior nodes
     int rc = pack_for_peers(m, 0);
     if (rc < 0) return rc;
     if ((rc = xb_exchange(m, 0)) < 0) return rc;
     if ((rc = unpack_received_rows(m, m->stream)) < 0) return rc;
-    rc = launch_assemble(m, m->h.chunk_node_ptr[nc], m->h.chunk_node_ptr[nc + 1] - m->h.chunk_node_ptr[nc], m->stream);
+  }
+  CU(cudaEventRecord(m->ev_done, m->stream2));
+  CU(cudaStreamWaitEvent(m->stream, m->ev_done, 0));
+  if (m->h.nparts > 1) {     // the nodes fed by other ranks
+    int rc = launch_assemble(m, m->h.chunk_node_ptr[nc], m->h.chunk_node_ptr[nc + 1] - m->h.chunk_node_ptr[nc], m->stream);
     if (rc < 0) return rc;
   }
   if (stream_out) {

@@ -277,7 +277,12 @@ void rcb(std::vector<long long>& items, long long lo, long long hi, int np, int 
 int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const int* part_in) {
   if (is_setup) { err = "xb_setup called twice"; return XB_ERR_STATE; }
   if (numberer_ != XB_NUMBERER_PLAIN && numberer_ != XB_NUMBERER_RCM) { err = "unknown numberer"; return XB_ERR_ARG; }
-  if (soe_kind_ != XB_SOE_SPARSE_GEN_COL && soe_kind_ != XB_SOE_SPARSE_GEN_ROW) { err = "unknown SOE kind"; return XB_ERR_ARG; }
+  if (soe_kind_ < XB_SOE_SPARSE_GEN_COL || soe_kind_ > XB_SOE_UMFPACK_GEN) { err = "unknown SOE kind"; return XB_ERR_ARG; }
+  soe_store = soe_kind_;
+  if (soe_kind_ != XB_SOE_SPARSE_GEN_ROW) soe_kind_ = XB_SOE_SPARSE_GEN_COL;   // band / profile / Umfpack: column-oriented addA
+  if (nparts_ > 1 && (soe_store == XB_SOE_BAND_GEN || soe_store == XB_SOE_PROFILE_SPD)) {
+    err = "BandGeneral / ProfileSPD storage is for single-GPU models"; return XB_ERR_UNSUPPORTED;
+  }
   if (nparts_ < 1 || rank_ < 0 || rank_ >= nparts_) { err = "bad nparts / rank"; return XB_ERR_ARG; }
   numberer = numberer_; soe_kind = soe_kind_; nparts = nparts_; rank = rank_;
   const int n_nodes = (int)node_tag.size();
@@ -808,6 +813,37 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
   }
   for (size_t w = 0; w < irr_row.size(); w++) std::copy(irr_cols[w].begin(), irr_cols[w].end(), &idx[ptr[irr_row[w]]]);
 
+  // ---- BandGeneral / ProfileSPD: where every pattern entry (column r, row idx[k]) lives in the SOE's own array ----
+  a_loc.clear(); profile_diag.clear(); a_total = nz; band_sub = band_super = 0;
+  if (soe_store == XB_SOE_BAND_GEN) {
+    // BandGenLinSOE::setSize (BandGenLinSOE.cpp:116-147): the largest vertex - other and other - vertex over the DOF graph
+    for (int r = 0; r < nrows; r++)
+      for (long long k = ptr[r]; k < ptr[r + 1]; k++) {
+        const int diff = r - idx[k];
+        if (diff > band_super) band_super = diff;
+        if (-diff > band_sub) band_sub = -diff;
+      }
+    const long long ldA = 2LL * band_sub + band_super + 1;
+    a_total = ldA * nrows;
+    a_loc.resize(nz);
+    // addA (BandGenLinSOE.cpp:208-249): column col, row row -> A[col ldA + numSubD + numSuperD - (col - row)]
+    for (int col = 0; col < nrows; col++)
+      for (long long k = ptr[col]; k < ptr[col + 1]; k++) a_loc[k] = col * ldA + band_sub + band_super - (col - idx[k]);
+  } else if (soe_store == XB_SOE_PROFILE_SPD) {
+    // ProfileSPDLinSOE::setSize (ProfileSPDLinSOE.cpp:115-168): column heights, then running sums (1-based)
+    profile_diag.assign(nrows, 0);
+    for (int r = 0; r < nrows; r++)
+      for (long long k = ptr[r]; k < ptr[r + 1]; k++) profile_diag[r] = std::max(profile_diag[r], r - idx[k]);
+    if (nrows > 0) profile_diag[0] = 1;
+    for (int j = 1; j < nrows; j++) profile_diag[j] = profile_diag[j] + 1 + profile_diag[j - 1];
+    a_total = nrows > 0 ? profile_diag[nrows - 1] : 0;
+    a_loc.assign(nz, -1);
+    // addA (ProfileSPDLinSOE.cpp:214-243): row <= col inside the profile -> A[iDiagLoc[col] - 1 + row - col]
+    for (int col = 0; col < nrows; col++)
+      for (long long k = ptr[col]; k < ptr[col + 1]; k++)
+        if (idx[k] <= col) a_loc[k] = (long long)profile_diag[col] - 1 + (idx[k] - col);
+  }
+
   // position of every owned dof's own equation in its node's list (the diagonal entry of A)
   diagpos.assign((size_t)nl * ndf, 0xFFFF);
   for (int i = 0; i < nl; i++) {
@@ -970,7 +1006,7 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
     const int ng = nchunk;
     auto group_of = [&](int c) { return c; };
     chunk_a_ptr.assign((size_t)ng + 2, 0);
-    rows_streamable = nchunk > 1;
+    rows_streamable = nchunk > 1 && a_loc.empty();
     int next_row = 0;
     for (int gI = 0, c = 0; gI <= ng && rows_streamable; gI++) {
       long long cnt = 0; int lo = nrows, hi = -1;
@@ -1019,7 +1055,10 @@ int HostModel::scatter_map(long long e0, long long e1, long long* map) const {
         const long long r = rit - row_geq.begin();
         const int* b = &idx[ptr[r]]; const int* en = &idx[ptr[r + 1]];
         const int* it = std::lower_bound(b, en, qmin);
-        if (it != en && *it == qmin) out[i * nd + j] = ptr[r] + (it - b);
+        if (it != en && *it == qmin) {
+          const long long k = ptr[r] + (it - b);
+          out[i * nd + j] = a_loc.empty() ? k : a_loc[k];
+        }
       }
   }
   return XB_OK;

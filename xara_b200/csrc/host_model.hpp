@@ -104,7 +104,15 @@ struct HostModel {
 
   // --- analysis (valid after setup) ---
   bool is_setup = false;
-  int numberer = 0, soe_kind = 0;
+  int numberer = 0, soe_kind = 0;   // soe_kind: the pattern's orientation (SparseGenCol | SparseGenRow)
+  // the SOE whose A is filled (XB_SOE_*): the compressed ones, or BandGeneral / ProfileSPD, which keep the compressed-
+  // column pattern for the assembly and map every pattern entry to its location in their own array (a_loc)
+  int soe_store = 0;
+  std::vector<long long> a_loc;     // [nnz] location in A of pattern entry k, -1: not stored (ProfileSPD lower triangle); empty: k itself
+  long long a_total = 0;            // length of A
+  int band_sub = 0, band_super = 0; // BandGenLinSOE::numSubD / numSuperD
+  std::vector<int> profile_diag;    // ProfileSPDLinSOE::iDiagLoc (1-based)
+  long long a_size() const { return a_loc.empty() ? nnz() : a_total; }
   int nparts = 1, rank = 0;
   int neq = 0;                      // GLOBAL number of equations
   int nn_global = 0;
