@@ -221,8 +221,11 @@ def selftest_main(a):
         raise SystemExit("--selftest needs torchrun with at least 2 ranks")
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     res = []
-    for numberer, soe in ((1, 0), (0, 1)):
-        spec = brick_block(12, 10, 14, mat=J2_STEEL, distort=0.2, seed=3)
+    # the third case is large enough (>= 65536 elements per rank at N = 2) for the two-stream formTangent, where the
+    # interface exchange runs beside the assembly of the interior nodes
+    for numberer, soe, dims in ((1, 0, (12, 10, 14)), (0, 1, (12, 10, 14)), (0, 0, (56, 52, 26 * world))):
+        mk = lambda: brick_block(*dims, mat=J2_STEEL, distort=0.2, seed=3)
+        spec = mk()
         D = xb.DeviceModel.from_spec(spec, numberer, soe, world, rank).to_device(local)
         box = [xb.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, 0)
@@ -237,7 +240,7 @@ def selftest_main(a):
         gathered = [None] * world
         dist.gather_object((rows, A, B), gathered if rank == 0 else None, 0)
         if rank == 0:
-            G = xb.DeviceModel.from_spec(brick_block(12, 10, 14, mat=J2_STEEL, distort=0.2, seed=3), numberer, soe).to_device(local)
+            G = xb.DeviceModel.from_spec(mk(), numberer, soe).to_device(local)
             for s_ in range(2):
                 G.set_trial_disp((s_ + 1) * ug); G.update(); G.apply_load(0.7)
                 Ag, Bg = G.form_tangent(), G.form_unbalance()
@@ -252,11 +255,13 @@ def selftest_main(a):
                 seen += len(rws)
             if seen != G.neq:
                 raise SystemExit("selftest FAILED: the ranks' rows do not cover the system")
-            res.append({"numberer": numberer, "soe": soe, "equations": int(G.neq), "nnz": int(G.nnz)})
+            res.append({"numberer": numberer, "soe": soe, "elements": int(G.ne), "equations": int(G.neq), "nnz": int(G.nnz)})
+            del G
         dist.barrier()
     if rank == 0:
         print(json.dumps({"selftest": "ok", "n_gpus": world, "what": "owned rows of A and B of every rank bitwise equal to the "
-                          "single-GPU rows (stdBrick/J2 12x10x14, two load steps with a commit, NCCL interface exchange)",
+                          "single-GPU rows (stdBrick/J2 blocks, two load steps with a commit, NCCL interface exchange; the last case "
+                          "runs the two-stream formTangent)",
                           "cases": res}), flush=True)
     dist.destroy_process_group()
 
@@ -581,7 +586,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=None, help="size parameter of the workload; default: brick 160 (4.096M elements), "
+    ap.add_argument("--n", "--size", dest="n", type=int, default=None, help="size parameter of the workload; default: brick 160 (4.096M elements), "
                                                         "quad 1000, frame 200, frame3d 20")
     ap.add_argument("--workload", default="brick", choices=["brick", "quad", "frame", "frame3d"],
                     help="brick = the headline workload; quad / frame = secondary lines (profiles/), n = cells per side")

@@ -274,6 +274,7 @@ int xb_get_gp_response(xb_model*, long long e, int g, double* stress, double* ta
 /* Run-time tuning of the device path; the results are bit-for-bit the same under every setting.
  *   "ranged_tangent"  0 | 1 (default 1): run xb_form_tangent of a large single-batch brick model range by range on
  *                     two streams also when A stays on the device (with a host destination it always does)
+ *   "tangent_ranges"  1..64 (default 8; before xb_setup): the number of element ranges of the ranged formTangent
  *   "fast_assembly"   0 | 1 (default 1): plain brick models (no MP constraints, rows <= 96 entries, <= 32 elements per
  *                     node) take the hand-tuned record assembly kernel; 0 forces the generic one
  * Returns XB_ERR_ARG for an unknown name or value. */

@@ -2548,7 +2548,10 @@ int xb_form_tangent(xb_model* m, double* A) {
   const int nc = m->h.nchunk;
   const bool stream_out = A != nullptr && m->h.rows_streamable && m->stream3;
   // element damping / mass terms take several passes over the whole batch: no ranges then
-  if (nc <= 1 || m->dg.size() != 1 || m->dg[0].kind != XB_ELE_STDBRICK || !m->stream2 || tan_coef(m).on ||
+  // (one range is still worth the two streams on a partitioned model: the interface exchange runs beside the
+  //  assembly of the interior nodes)
+  const bool big = m->h.ne >= 65536 && m->av.nirr == 0 && m->av.max_dup == 0;
+  if ((nc <= 1 && !(m->h.nparts > 1 && big)) || m->dg.size() != 1 || m->dg[0].kind != XB_ELE_STDBRICK || !m->stream2 || tan_coef(m).on ||
       !(stream_out || m->ranged)) {
     int rc = xb_form_element_tangents(m);
     if (rc < 0) return rc;
@@ -2607,7 +2610,11 @@ int xb_form_tangent(xb_model* m, double* A) {
 int xb_set_option(xb_model* m, const char* name, int value) {
   if (!m || !name) return fail(XB_ERR_ARG, "xb_set_option: null argument");
   const std::string n(name);
-  if (n == "fast_assembly") {
+  if (n == "tangent_ranges") {
+    if (m->h.is_setup) return fail(XB_ERR_STATE, "tangent_ranges must be set before xb_setup");
+    if (value < 1 || value > 64) return fail(XB_ERR_ARG, "tangent_ranges is 1..64");
+    m->h.want_ranges = value;
+  } else if (n == "fast_assembly") {
     m->fast_asm_on = value != 0;
   } else if (n == "ranged_tangent") {
     m->ranged = value != 0;

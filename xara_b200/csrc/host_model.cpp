@@ -936,7 +936,9 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
     const std::vector<Group>& FG = nparts == 1 ? groups : lgroups;
     // With a host destination, xb_form_tangent sends the rows of range c to the host while range c+1 is still
     // being formed (chunk_a_ptr below); the element kernel and the assembly of the previous range also share the SMs.
-    const int want = 8;
+    // one range per ~0.5 M elements, at most `want_ranges` (8): 8 at 4 M elements on one GPU, 1 on each of 8 GPUs --
+    // ranges of less than that are launch-bound (N = 8 measured 2.16 ms per step with 8 ranges of 64 k elements)
+    const int want = (int)std::max<long long>(1, std::min<long long>(want_ranges, ne / 500000));
     nchunk = (FG.size() == 1 && ne >= 65536 && !have_mp) ? want : 1;
     const long long per = nchunk > 1 ? (ne + nchunk - 1) / nchunk : ne;
     std::vector<int> ready(nl, -1);

@@ -180,6 +180,7 @@ struct HostModel {
   // lists the owned nodes by that range (nodes with rows from other ranks last: range nchunk);
   // record models: inside a range in Morton order of the node coordinates, so that the records a
   // node gathers from are still in L2 when its neighbours ask for them.
+  int want_ranges = 8;              // element ranges of the ranged formTangent (xb_set_option "tangent_ranges" before xb_setup)
   int nchunk = 1;
   std::vector<int> node_perm;       // [n_owned_nodes_with_rows]
   std::vector<long long> chunk_node_ptr;   // [nchunk+2]
