@@ -274,6 +274,10 @@ int xb_get_gp_response(xb_model*, long long e, int g, double* stress, double* ta
 /* Run-time tuning of the device path; the results are bit-for-bit the same under every setting.
  *   "ranged_tangent"  0 | 1 (default 1): run xb_form_tangent of a large single-batch brick model range by range on
  *                     two streams also when A stays on the device (with a host destination it always does)
+ *   "brick_storage"   0 | 1 (default 1; before xb_setup): stdBrick tangents leave the tangent kernel as symmetric element
+ *                     records (1: 324 doubles per element, gathered by the assembly) or as node-major rows (0: 576 doubles
+ *                     per element, streamed by the assembly).  Measured on B200 at 4.1 M elements: records 13.2 ms per step
+ *                     and 43.7 GB of DRAM traffic, rows 13.4 - 13.8 ms and 59 GB
  *   "tangent_ranges"  1..64 (default 8; before xb_setup): the number of element ranges of the ranged formTangent
  *   "fast_assembly"   0 | 1 (default 1): plain brick models (no MP constraints, rows <= 96 entries, <= 32 elements per
  *                     node) take the hand-tuned record assembly kernel; 0 forces the generic one

@@ -34,11 +34,11 @@ CASES = {
 NSTEPS = 3
 
 
-def run_case(xb, name):
+def run_case(xb, name, options=None):
     """-> list of sha256 digests: A, B of the untouched model, then of every step of the load history"""
     mk, numberer, soe, sc = CASES[name]
     spec = mk()
-    D = xb.DeviceModel.from_spec(spec, numberer, soe).to_device(0)
+    D = (xb.DeviceModel.from_spec(spec, numberer, soe, options=options) if options else xb.DeviceModel.from_spec(spec, numberer, soe)).to_device(0)
     ids = D.ids()
     rng = np.random.default_rng(1234)
     out = [_digest(D.form_tangent()), _digest(D.form_unbalance())]

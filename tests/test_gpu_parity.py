@@ -530,20 +530,21 @@ def test_full_size_properties_brick():
     assert np.abs(B - P).max() < 1e-12 * max(np.abs(P).max(), 1.0)
 
 
+@pytest.mark.parametrize("storage", [0, 1], ids=["rows", "records"])
 @pytest.mark.parametrize("name", list(R1_CASES))
-def test_tangent_and_unbalance_bits_equal_round1(name):
-    """formTangent through symmetric element records + the gathered assembly reproduces the round-1 device path (node-major
-    element rows) BIT FOR BIT: same block values, same FE_Element order of additions.  The digests were taken on a B200
-    with the round-1 library (tests/golden/make_r1_bits.py)."""
+def test_tangent_and_unbalance_bits_equal_round1(name, storage):
+    """formTangent of round 2 -- the tangent kernel's TMA output as node-major rows (streamed assembly) or as symmetric
+    element records (gathered assembly) -- reproduces the round-1 device path BIT FOR BIT: same block values, same
+    FE_Element order of additions.  The digests were taken on a B200 with the round-1 library (tests/golden/make_r1_bits.py)."""
     import json
     with open(os.path.join(GOLD, "r1_tangent_bits.json")) as f:
         want = json.load(f)[name]
-    assert r1_run_case(xb, name) == want
+    assert r1_run_case(xb, name, {"brick_storage": storage}) == want
 
 
 def test_shuffled_tags_and_tangent_options_bitwise():
     """Element tags arrive shuffled; DOF numbers, pattern and FE order are the reference's all the same and A matches the
-    oracle.  The run-time options (ranged formTangent, hand-tuned or generic gathered assembly) do not change a bit."""
+    oracle.  The options (ranged formTangent, hand-tuned or generic gathered assembly, rows or records) do not change a bit."""
     spec = brick_block(48, 40, 36, mat=J2_STEEL, distort=0.2, seed=3)
     g = spec.groups[0]
     p = np.random.default_rng(0).permutation(len(g.tags))
@@ -555,8 +556,8 @@ def test_shuffled_tags_and_tangent_options_bitwise():
     O.set_trial_disp(u); O.apply_load(0.7)
     Ao, Bo = O.form_tangent(), O.form_unbalance()
     res = {}
-    for opt in ((1, 1), (0, 0), (0, 1), (1, 0)):
-        D = xb.DeviceModel.from_spec(spec, 1, 0).to_device(0)
+    for opt in ((1, 1, 1), (0, 0, 1), (0, 1, 1), (1, 0, 1), (1, 1, 0), (0, 1, 0)):
+        D = xb.DeviceModel.from_spec(spec, 1, 0, options={"brick_storage": opt[2]}).to_device(0)
         D.set_option("ranged_tangent", opt[0]).set_option("fast_assembly", opt[1])
         assert np.array_equal(D.ids(), ids) and np.array_equal(D.element_tags(), O.fe_ids(24)[0])
         D.set_trial_disp(u); D.update(); D.apply_load(0.7)
@@ -571,8 +572,8 @@ def test_shuffled_tags_and_tangent_options_bitwise():
         D.commit()
         D.set_trial_disp(1.5 * u); D.update()
         res[opt] = (A, B, D.form_tangent(host=True), D.form_unbalance())
-    for opt in ((0, 0), (0, 1), (1, 0)):
-        for x, y in zip(res[(1, 1)], res[opt]):
+    for opt in ((0, 0, 1), (0, 1, 1), (1, 0, 1), (1, 1, 0), (0, 1, 0)):
+        for x, y in zip(res[(1, 1, 1)], res[opt]):
             assert np.array_equal(x, y)
 
 

@@ -234,10 +234,12 @@ class DeviceModel:
         self._ck(lib.xb_add_nodal_loads(self._h, len(node_tags), _ptr(node_tags), _ptr(values)))
 
     @classmethod
-    def from_spec(cls, spec, numberer=NUMBERER_PLAIN, soe=SOE_SPARSE_GEN_COL, nparts=1, rank=0, part=None, setup=True):
+    def from_spec(cls, spec, numberer=NUMBERER_PLAIN, soe=SOE_SPARSE_GEN_COL, nparts=1, rank=0, part=None, setup=True, options=None):
         """Build from a tests/modelspec.py ModelSpec (duck-typed); setup=False leaves xb_setup to the caller
-        (e.g. to add nodal masses first)."""
+        (e.g. to add nodal masses first); options: {name: value} for xb_set_option before the set-up."""
         m = cls(spec.ndm, spec.ndf)
+        for k, v in (options or {}).items():
+            m.set_option(k, v)
         m.add_nodes(spec.node_tags, spec.crd)
         if len(spec.fix):
             m.fix(spec.fix[:, 0], spec.fix[:, 1])

@@ -404,9 +404,9 @@ __global__ void __launch_bounds__(128) brick_dyn_resid_kernel(GroupView G, const
 }
 
 // Brick::formInertiaTerms(tangFlag = 1): the consistent mass sum_g rho N_j N_k dvol on the three dofs of every
-// node pair, times cM = c2 alphaM + c3, added to the element tangent already in the element records.  8 lanes per
-// element: lane k evaluates Gauss point k, then owns column node k (the record keeps one orientation of every node
-// pair: m_Jk as lane k sums it stands for m_kJ too).
+// node pair, times cM = c2 alphaM + c3, added to the element tangent already in the node slots / element records.  8
+// lanes per element: lane k evaluates Gauss point k, then owns column node k (a record keeps one orientation of every
+// node pair: m_Jk as lane k sums it stands for m_kJ too).
 __global__ void __launch_bounds__(128) brick_mass_add_kernel(GroupView G, const double* __restrict__ X, int rho_idx, double cM) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long tot = G.n * 8;
@@ -439,6 +439,17 @@ __global__ void __launch_bounds__(128) brick_mass_add_kernel(GroupView G, const 
     for (int j = 0; j < 8; j++) mk[j] += (ng[j] * rdg) * nk;
   }
   if (!live) return;
+  if (G.rec == nullptr) {   // node-major rows: entry (row node j dof p, column node k dof p)
+    const int cps = G.cps;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const long long d = __ldg(G.kdst + e * 8 + j);
+      double* base = d >= 0 ? G.KeN + d : G.sendK + (-d - 1);
+#pragma unroll
+      for (int pdof = 0; pdof < 3; pdof++) base[pdof * cps + 3 * k + pdof] += cM * mk[j];
+    }
+    return;
+  }
   // lane k's blocks of the symmetric record (brick_rec.hpp): K_Jk, J = k .. k+4 (mod 8); the mass block is m_Jk I
   double* reg = G.rec + e * xb::kBrickRec + xb::brick_rec_region(k);
 #pragma unroll
@@ -684,8 +695,10 @@ constexpr int BS_GV = 4 * 8 * 3 + 2;      // per Gauss point: [4 elements][8 nod
 constexpr int BS_CN = 4 * 10;             // per Gauss point: [4 elements][alpha, beta/2, gamma (x dvol), n[6], -]
 constexpr int BS_STAGE = 8 * BS_GV + 8 * BS_CN;                 // 1104 doubles (the coordinates alias the grad N region)
 constexpr int BS_OUT = 4 * xb::kBrickRec;                        // the batch's records: 1296 doubles
-constexpr int BS_WARP = BS_STAGE + BS_OUT;                       // 2400 doubles = 18.75 KB per warp: 12 warps fill an SM's 228 KB
-static_assert(BS_STAGE % 2 == 0 && BS_WARP % 2 == 0, "16-byte alignment of the record image (bulk copy source)");
+constexpr int BS_WARP = BS_STAGE + BS_OUT;                       // 2400 doubles = 18.75 KB per warp
+constexpr int BS_OUT_ROWS = 4 * 576;                             // node-major rows: the batch's four 24 x 24 matrices
+constexpr int BS_WARP_ROWS = BS_STAGE + BS_OUT_ROWS;             // 3408 doubles = 26.6 KB per warp: 8 warps = 213 KB of an SM's 228
+static_assert(BS_STAGE % 2 == 0 && BS_WARP % 2 == 0 && BS_WARP_ROWS % 2 == 0, "16-byte alignment of the output image (bulk copy source)");
 static_assert(4 * BS_XS <= 8 * BS_GV, "the coordinates of a batch fit under the grad N records");
 
 __device__ __forceinline__ void bulk_store_commit(void* gdst, const void* ssrc, unsigned bytes) {
@@ -696,9 +709,11 @@ __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // blocks t = T0 .. T1-1 of lane k (element s of the warp) summed over the 8 Gauss points, into the record image
-template <int MATK, int T0, int T1>
+// (ROWS: into the element's full 24 x 24 matrix, row-major -- both orientations of every block, the diagonal block
+//  transposed for a column-compressed SOE -- whose node slots, 3 rows of 24, then leave as 576-byte bulk copies)
+template <int MATK, int T0, int T1, bool ROWS = false>
 __device__ __forceinline__ void brick_pair_blocks(const double* __restrict__ sN, const double* __restrict__ sC, int s, int k,
-                                                  double* __restrict__ rec_out, const double* __restrict__ rec_old) {
+                                                  double* __restrict__ rec_out, const double* __restrict__ rec_old, int transpose = 0) {
   constexpr int NT = T1 - T0;
   double acc[NT][3][3];
 #pragma unroll
@@ -756,6 +771,24 @@ __device__ __forceinline__ void brick_pair_blocks(const double* __restrict__ sN,
       acc[t - T0][0][0] += sd; acc[t - T0][1][1] += sd; acc[t - T0][2][2] += sd;
     }
   }
+  if (ROWS) {
+#pragma unroll
+    for (int t = T0; t < T1; t++) {
+      if (t == 4 && k >= 4) break;
+      const int J = (k + t) & 7;
+#pragma unroll
+      for (int p = 0; p < 3; p++)
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          if (t == 0) rec_out[(3 * k + (transpose ? q : p)) * 24 + 3 * k + (transpose ? p : q)] = acc[0][p][q];
+          else {
+            rec_out[(3 * J + p) * 24 + 3 * k + q] = acc[t - T0][p][q];
+            rec_out[(3 * k + q) * 24 + 3 * J + p] = acc[t - T0][p][q];
+          }
+        }
+    }
+    return;
+  }
   // lane k's region of the record: blocks t = 0.. one after the other (lanes 4-7 own no block t = 4)
   double* out = rec_out + xb::brick_rec_region(k);
 #pragma unroll
@@ -774,8 +807,8 @@ __device__ __forceinline__ void brick_pair_blocks(const double* __restrict__ sN,
 
 // The work of warp `wid` of `nwarps` on the elements [ebeg, eend): batches wid, wid + nwarps, ... of 4 elements;
 // wbase: the warp's BS_WARP doubles of shared memory.
-template <int MATK, int DYN, int NPASS>
-__device__ __forceinline__ void brick_tangent_rec_range(const GroupView& G, const double* __restrict__ X,
+template <int MATK, int DYN, int NPASS, bool ROWS = false>
+__device__ __forceinline__ void brick_tangent_rec_range(const GroupView& G, const double* __restrict__ X, int transpose,
                                                         long long ebeg, long long eend,
                                                         const double* __restrict__ tsrc_, int tzero_,
                                                         double scale_, int accum_, double* wbase, long long wid, long long nwarps) {
@@ -802,12 +835,14 @@ __device__ __forceinline__ void brick_tangent_rec_range(const GroupView& G, cons
   long long e = ebeg + b * 4 + s; if (e > elast) e = elast;
   int nd = __ldg(G.conn + e * 8 + k), mi = __ldg(G.mat + e);
   double cx[3], ct[8], cm0, cm1;
+  long long cdst = 0;            // ROWS: where the rows of node k of the lane's element go (KeN slot, or the send buffer)
 #pragma unroll
   for (int d = 0; d < 3; d++) cx[d] = __ldg(X + (size_t)nd * 3 + d);
   if (MATK == XB_MAT_J2PLASTICITY) {
 #pragma unroll
     for (int i = 0; i < 8; i++) ct[i] = tzero ? 0.0 : tsrc[(size_t)i * ngp + e * 8 + k];
   }
+  if (ROWS) cdst = __ldg(G.kdst + e * 8 + k);
   cm0 = __ldg(G.mpar + (size_t)mi * 8); cm1 = __ldg(G.mpar + (size_t)mi * 8 + 1);
   long long en = ebeg + (b + stride) * 4 + s; if (en > elast) en = elast;
   nd = __ldg(G.conn + en * 8 + k); mi = __ldg(G.mat + en);
@@ -855,6 +890,7 @@ __device__ __forceinline__ void brick_tangent_rec_range(const GroupView& G, cons
     // ---- request the next batch's inputs; they land while the main loop runs ----
     const long long e0 = ebeg + b * 4;             // this batch's first element
     const bool more = b + stride < nb;
+    double* const mydst = ROWS ? (cdst >= 0 ? G.KeN + cdst : G.sendK + (-cdst - 1)) : nullptr;
     if (more) {
       e = en;
 #pragma unroll
@@ -863,25 +899,36 @@ __device__ __forceinline__ void brick_tangent_rec_range(const GroupView& G, cons
 #pragma unroll
         for (int i = 0; i < 8; i++) ct[i] = tzero ? 0.0 : tsrc[(size_t)i * ngp + e * 8 + k];
       }
+      if (ROWS) cdst = __ldg(G.kdst + e * 8 + k);
       cm0 = __ldg(G.mpar + (size_t)mi * 8); cm1 = __ldg(G.mpar + (size_t)mi * 8 + 1);
       en = ebeg + (b + 2 * stride) * 4 + s; if (en > elast) en = elast;
       nd = __ldg(G.conn + en * 8 + k); mi = __ldg(G.mat + en);
     }
-    // the previous batch's bulk copy has read the record image by now (it was issued a whole main loop ago)
-    if (lane == 0) bulk_store_wait_read();
+    // the previous batch's bulk copies have read the output image by now (they were issued a whole main loop ago)
+    if (ROWS || lane == 0) bulk_store_wait_read();
     __syncwarp();
-    // ---- B: lane k accumulates the blocks K_Jk = sum_g B_J^T (D B_k), J = k .. k+4 (mod 8), into the record image ----
-    {
-      const long long el = e0 + s;                 // (clamped duplicates of the last element are not copied out)
+    // ---- B: lane k accumulates the blocks K_Jk = sum_g B_J^T (D B_k), J = k .. k+4 (mod 8), into the output image ----
+    const long long el = e0 + s;                   // (clamped duplicates of the last element are not copied out)
+    if (ROWS) {
+      double* img = sOut + s * 576;
+      brick_pair_blocks<MATK, 0, 5, true>(sN, sC, s, k, img, nullptr, transpose);
+      if (DYN && accum && el <= elast) {           // add to what the slot holds (a later term of c1 Kt + c2 (bK Kt + bK0 K0 + bKc Kc))
+        __syncwarp();
+        double* slot = img + k * 72;
+        for (int i = 0; i < 72; i++) slot[i] += mydst[i];
+      }
+    } else {
       const double* old = (DYN && accum && el <= elast) ? G.rec + el * xb::kBrickRec : nullptr;
       double* img = sOut + s * xb::kBrickRec;
       if (NPASS == 1) brick_pair_blocks<MATK, 0, 5>(sN, sC, s, k, img, old);
       else { brick_pair_blocks<MATK, 0, 3>(sN, sC, s, k, img, old); brick_pair_blocks<MATK, 3, 5>(sN, sC, s, k, img, old); }
     }
-    // ---- C: the batch's records leave in one bulk copy ----
+    // ---- C: the batch's records leave in one bulk copy; rows: one 576-byte copy per (element, node) slot ----
     fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0) {
+    if (ROWS) {
+      if (el <= elast) bulk_store_commit(mydst, sOut + s * 576 + k * 72, 576u);
+    } else if (lane == 0) {
       const long long rem = eend - e0;
       const unsigned nlive = rem < 4 ? (unsigned)rem : 4u;
       bulk_store_commit(G.rec + e0 * xb::kBrickRec, sOut, nlive * (unsigned)(xb::kBrickRec * sizeof(double)));
@@ -889,7 +936,7 @@ __device__ __forceinline__ void brick_tangent_rec_range(const GroupView& G, cons
     if (!more) break;
     b += stride;
   }
-  if (lane == 0) bulk_store_wait_read();           // shared memory must outlive the copy's reads
+  if (ROWS || lane == 0) bulk_store_wait_read();   // shared memory must outlive the copies' reads
   __syncwarp();
 }
 
@@ -897,16 +944,18 @@ __device__ __forceinline__ void brick_tangent_rec_range(const GroupView& G, cons
 // one pass / 4 warps 2.62 ms; two passes (27 + 18 accumulators) at 4 warps and 192 registers 2.92 ms, at 6 warps and
 // 168 registers (12 warps per SM, 32 bytes of spills) 3.09 ms -- the second pass repeats the per-point set-up (+8 % FP64
 // work) and more warps do not buy it back, so the one-pass form is the only one kept.
-template <int MATK, int DYN, int NPASS, int NW>
-__global__ void __launch_bounds__(NW * 32, 2) brick_tangent_rec_kernel(GroupView G, const double* __restrict__ X,
+template <int MATK, int DYN, int NPASS, int NW, bool ROWS = false>
+__global__ void __launch_bounds__(NW * 32, 2) brick_tangent_rec_kernel(GroupView G, const double* __restrict__ X, int transpose,
                                                                    long long ebeg, long long eend,
                                                                    const double* __restrict__ tsrc_, int tzero_,
                                                                    double scale_, int accum_) {
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5;
-  brick_tangent_rec_range<MATK, DYN, NPASS>(G, X, ebeg, eend, tsrc_, tzero_, scale_, accum_, smem + warp * BS_WARP,
-                                            (long long)blockIdx.x * NW + warp, (long long)gridDim.x * NW);
+  brick_tangent_rec_range<MATK, DYN, NPASS, ROWS>(G, X, transpose, ebeg, eend, tsrc_, tzero_, scale_, accum_,
+                                                  smem + warp * (ROWS ? BS_WARP_ROWS : BS_WARP),
+                                                  (long long)blockIdx.x * NW + warp, (long long)gridDim.x * NW);
 }
+
 // FourNodeQuad::getTangentStiff (FourNodeQuad.cpp:226-281).  4 lanes per element, lane b
 // owns column block beta=b (8 rows x 2 columns); shape functions are recomputed per lane.
 template <int MATK, int DYN>
@@ -1223,6 +1272,7 @@ constexpr int FA_S = 101;                                  // accumulator row st
 #ifndef XB_ASM_FAST_OCC
 #define XB_ASM_FAST_OCC 5
 #endif
+template <bool LOC>   // LOC: BandGeneral / ProfileSPD storage, every entry goes through the location map
 __global__ void __launch_bounds__(256, XB_ASM_FAST_OCC) assemble_A_rec_fast_kernel(AsmView V, double* __restrict__ A,
                                                                                  const long long* __restrict__ task,
                                                                                  long long first, long long count) {
@@ -1297,7 +1347,7 @@ __global__ void __launch_bounds__(256, XB_ASM_FAST_OCC) assemble_A_rec_fast_kern
     const long long rp = __shfl_sync(0xffffffffu, word, 3 + p);
     if (rp < 0) continue;
     double* out = A + rp;
-    if (V.a_loc) {
+    if (LOC) {
 #pragma unroll
       for (int c = 0; c < FA_L / 32; c++)
         if (c * 32 + lane < L) { const long long l = V.a_loc[rp + c * 32 + lane]; if (l >= 0) A[l] = acc[p * FA_S + c * 32 + lane]; }
@@ -2279,10 +2329,11 @@ static int launch_group_tangents(xb_model* m, DevGroup& d, long long ebeg, long 
   if (d.kind == XB_ELE_STDBRICK && tc.on && (ebeg != 0 || eend != d.v.n))
     return fail(XB_ERR_STATE, "Rayleigh damping / element mass: the brick tangent runs over the whole batch");
   if (d.kind == XB_ELE_STDBRICK) {
-    if (!m->h.rec_mode) return fail(XB_ERR_UNSUPPORTED, "stdBrick batches need a 3D model with three dofs per node");
+    const bool rows = !m->h.rec_mode;            // node-major rows (the default) or symmetric element records
+    if (rows && m->h.cp_stride != 24) return fail(XB_ERR_UNSUPPORTED, "stdBrick batches need a 3D model with three dofs per node");
     const long long nbat = (eend - ebeg + 3) / 4;
     auto go = [&](auto kern, int nw) -> int {
-      const size_t sms = sizeof(double) * nw * BS_WARP;
+      const size_t sms = sizeof(double) * nw * (rows ? BS_WARP_ROWS : BS_WARP);
       if ((const void*)kern != m->tan_kern) {   // once per kernel: this call costs more than a launch
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sms));
         int per_sm = 0;
@@ -2294,15 +2345,20 @@ static int launch_group_tangents(xb_model* m, DevGroup& d, long long ebeg, long 
       const unsigned nt = (unsigned)nw * 32;
       // static analysis, or a transient one without element damping / mass: one pass on the current tangent.
       // Otherwise (c1 + c2 betaK) Kt + c2 betaK0 K0 + c2 betaKc Kc, one pass per term (K is linear in D).
-      if (!tc.on) { kern<<<(unsigned)grid, nt, sms, st>>>(d.v, m->dX, ebeg, eend, d.v.tan, 0, 1.0, 0); return XB_OK; }
-      if (!j2) { kern<<<(unsigned)grid, nt, sms, st>>>(d.v, m->dX, ebeg, eend, d.v.tan, 0, tc.at + tc.a0 + tc.ac, 0); return XB_OK; }
-      kern<<<(unsigned)grid, nt, sms, st>>>(d.v, m->dX, ebeg, eend, d.v.tan, 0, tc.at, 0);
-      if (tc.a0 != 0.0) { kern<<<(unsigned)grid, nt, sms, st>>>(d.v, m->dX, ebeg, eend, d.v.tan, 1, tc.a0, 1); m->launches++; }
-      if (tc.ac != 0.0) { kern<<<(unsigned)grid, nt, sms, st>>>(d.v, m->dX, ebeg, eend, d.v.tanc, 0, tc.ac, 1); m->launches++; }
+      if (!tc.on) { kern<<<(unsigned)grid, nt, sms, st>>>(d.v, m->dX, transpose, ebeg, eend, d.v.tan, 0, 1.0, 0); return XB_OK; }
+      if (!j2) { kern<<<(unsigned)grid, nt, sms, st>>>(d.v, m->dX, transpose, ebeg, eend, d.v.tan, 0, tc.at + tc.a0 + tc.ac, 0); return XB_OK; }
+      kern<<<(unsigned)grid, nt, sms, st>>>(d.v, m->dX, transpose, ebeg, eend, d.v.tan, 0, tc.at, 0);
+      if (tc.a0 != 0.0) { kern<<<(unsigned)grid, nt, sms, st>>>(d.v, m->dX, transpose, ebeg, eend, d.v.tan, 1, tc.a0, 1); m->launches++; }
+      if (tc.ac != 0.0) { kern<<<(unsigned)grid, nt, sms, st>>>(d.v, m->dX, transpose, ebeg, eend, d.v.tanc, 0, tc.ac, 1); m->launches++; }
       return XB_OK;
     };
-    const int rc = tc.on ? (j2 ? go(brick_tangent_rec_kernel<XB_MAT_J2PLASTICITY, 1, 1, 4>, 4) : go(brick_tangent_rec_kernel<XB_MAT_ELASTIC_ISOTROPIC, 1, 1, 4>, 4))
-                         : (j2 ? go(brick_tangent_rec_kernel<XB_MAT_J2PLASTICITY, 0, 1, 4>, 4) : go(brick_tangent_rec_kernel<XB_MAT_ELASTIC_ISOTROPIC, 0, 1, 4>, 4));
+    int rc;
+    if (rows)
+      rc = tc.on ? (j2 ? go(brick_tangent_rec_kernel<XB_MAT_J2PLASTICITY, 1, 1, 4, true>, 4) : go(brick_tangent_rec_kernel<XB_MAT_ELASTIC_ISOTROPIC, 1, 1, 4, true>, 4))
+                 : (j2 ? go(brick_tangent_rec_kernel<XB_MAT_J2PLASTICITY, 0, 1, 4, true>, 4) : go(brick_tangent_rec_kernel<XB_MAT_ELASTIC_ISOTROPIC, 0, 1, 4, true>, 4));
+    else
+      rc = tc.on ? (j2 ? go(brick_tangent_rec_kernel<XB_MAT_J2PLASTICITY, 1, 1, 4>, 4) : go(brick_tangent_rec_kernel<XB_MAT_ELASTIC_ISOTROPIC, 1, 1, 4>, 4))
+                 : (j2 ? go(brick_tangent_rec_kernel<XB_MAT_J2PLASTICITY, 0, 1, 4>, 4) : go(brick_tangent_rec_kernel<XB_MAT_ELASTIC_ISOTROPIC, 0, 1, 4>, 4));
     if (rc < 0) return rc;
     m->launches++;
     if (tc.on && tc.cM != 0.0 && d.has_rho) {
@@ -2331,7 +2387,7 @@ static void account_element_tangent_bytes(xb_model* m) {
     if (is_beam(d.kind)) { bytes += d.b.n * (d.b.nb * d.b.nb + 4 * d.b.nb * d.b.nb) * 8; continue; }
     // compact tangent + connectivity in, element matrix out
     // (stdBrick: the symmetric record, 324 doubles)
-    const long long ke_doubles = d.kind == XB_ELE_STDBRICK ? xb::kBrickRec : (long long)d.nd * d.nd;
+    const long long ke_doubles = (d.kind == XB_ELE_STDBRICK && m->h.rec_mode) ? xb::kBrickRec : (long long)d.nd * d.nd;
     bytes += d.ngp * 8 * (d.mat_kind == XB_MAT_J2PLASTICITY ? 8 : 0) + d.v.n * (ke_doubles * 8 + (d.nd / m->h.ndf) * 4);
   }
   bytes += (long long)m->h.nn() * m->h.ndm * 8;
@@ -2462,7 +2518,8 @@ static int launch_assemble(xb_model* m, long long first, long long count, cudaSt
   int rc = XB_ERR_UNSUPPORTED;
   if (m->h.rec_mode && m->h.fast_asm_ok && m->fast_asm_on) {
     // plain brick model: the hand-tuned form of the gathered assembly
-    assemble_A_rec_fast_kernel<<<blocks, warps * 32, 0, st>>>(av, m->dA, m->dTask, first, count);
+    if (av.a_loc) assemble_A_rec_fast_kernel<true><<<blocks, warps * 32, 0, st>>>(av, m->dA, m->dTask, first, count);
+    else assemble_A_rec_fast_kernel<false><<<blocks, warps * 32, 0, st>>>(av, m->dA, m->dTask, first, count);
     m->launches++;
     rc = XB_OK;
   } else if (m->h.rec_mode) {
@@ -2482,7 +2539,7 @@ static int launch_assemble(xb_model* m, long long first, long long count, cudaSt
 #define XB_ASM_CASE(N, S, I)                                                             \
   if (m->h.ndf == N && sl == S)                                                          \
     rc = mp ? go(assemble_A_kernel<N, true, S>, attr[2 * I + 1]) : go(assemble_A_kernel<N, false, S>, attr[2 * I]);
-    XB_ASM_CASE(3, 4, 1) XB_ASM_CASE(2, 4, 2) XB_ASM_CASE(6, 2, 3)
+    XB_ASM_CASE(3, 1, 0) XB_ASM_CASE(3, 4, 1) XB_ASM_CASE(2, 4, 2) XB_ASM_CASE(6, 2, 3)
     XB_ASM_CASE(1, 4, 4) XB_ASM_CASE(2, 1, 5) XB_ASM_CASE(6, 1, 6) XB_ASM_CASE(3, 2, 7)
 #undef XB_ASM_CASE
   }
@@ -2610,7 +2667,11 @@ int xb_form_tangent(xb_model* m, double* A) {
 int xb_set_option(xb_model* m, const char* name, int value) {
   if (!m || !name) return fail(XB_ERR_ARG, "xb_set_option: null argument");
   const std::string n(name);
-  if (n == "tangent_ranges") {
+  if (n == "brick_storage") {
+    if (m->h.is_setup) return fail(XB_ERR_STATE, "brick_storage must be set before xb_setup");
+    if (value != 0 && value != 1) return fail(XB_ERR_ARG, "brick_storage is 0 (node-major rows) or 1 (symmetric element records)");
+    m->h.brick_records = value == 1;
+  } else if (n == "tangent_ranges") {
     if (m->h.is_setup) return fail(XB_ERR_STATE, "tangent_ranges must be set before xb_setup");
     if (value < 1 || value > 64) return fail(XB_ERR_ARG, "tangent_ranges is 1..64");
     m->h.want_ranges = value;
@@ -2810,7 +2871,7 @@ int xb_get_element_tangent(xb_model* m, long long e, double* K) {
   const int nd = k.nen * k.ndf, cps = m->h.cp_stride;
   std::vector<double> tmp((size_t)nd * nd), chunk((size_t)m->h.chunk);
   CU(cudaStreamSynchronize(m->stream));
-  if (g.kind == XB_ELE_STDBRICK) {   // the symmetric element record (brick_rec.hpp)
+  if (g.kind == XB_ELE_STDBRICK && m->h.rec_mode) {   // the symmetric element record (brick_rec.hpp)
     std::vector<double> rec(xb::kBrickRec);
     CU(cudaMemcpy(rec.data(), m->dRec + g.rec_off + m->h.fe_local[e] * xb::kBrickRec, sizeof(double) * xb::kBrickRec, cudaMemcpyDeviceToHost));
     for (int i = 0; i < 24; i++)

@@ -566,7 +566,7 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
   ke_total = re_total = ngp = rec_total = 0;
   // stdBrick tangents are kept as symmetric element records and gathered by the assembly (brick_rec.hpp).  A model
   // with ndf = 3 in 3D holds no other element kind here, so this is the only brick path.
-  rec_mode = !groups.empty() && ndf == 3 && cp_stride == 24;     // (the global batches: the same answer on every rank)
+  rec_mode = brick_records && !groups.empty() && ndf == 3 && cp_stride == 24;     // (the global batches: the same answer on every rank)
   for (const Group& g : groups) if (g.kind != XB_ELE_STDBRICK) rec_mode = false;
   for (size_t gi = 0; gi < LG.size(); gi++) {
     const EleKind& k = ele_kind(LG[gi].kind);

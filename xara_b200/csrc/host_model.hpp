@@ -158,7 +158,10 @@ struct HostModel {
   // gathered from the element record at `offset` (doubles); offset << 4 | 0: ndf dense rows of cp_stride columns at
   // `offset` of the receive buffer (the element lives on another rank).  Empty otherwise (slot u = KeN[u * chunk]).
   std::vector<long long> n2e_ksrc;
-  bool rec_mode = false;            // every batch is stdBrick: element records + gathered assembly
+  bool rec_mode = false;            // every batch is stdBrick and brick_records is on: element records + gathered assembly
+  bool brick_records = true;        // stdBrick tangents as symmetric element records (25 % less HBM traffic and 8 GB less at 4 M
+                                    //   elements, assembly bound by the L1 data pipe) instead of node-major rows (streamed by the
+                                    //   assembly at the HBM rate) -- xb_set_option "brick_storage" before xb_setup
   long long rec_total = 0;          // doubles of element records
   std::vector<long long> pk_src;    // record models: outgoing row chunk c (send buffer offset c * chunk) <- record descriptor
   // the same descriptors in 32 bits (offset in units of 36 doubles << 4 | local node, 8 = dense rows) for the hand-tuned
