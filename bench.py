@@ -550,6 +550,25 @@ def ours_main(a):
     if not a.no_cpu_baseline and world == 1 and a.workload == "brick":
         cb, _ = cpu_arm(a.cpu_steps, 1, 1, a.cpu_sample)
 
+    # ---- the other BASELINE configs on the same box, in the same line (N = 1 only): configs[1] 1000 x 1000 quads and
+    # configs[3] the 195 k-element RC space frame under Newmark, each as a short run of this script ----
+    secondary = None
+    if a.secondary and world == 1 and a.workload == "brick" and not a.no_cpu_baseline:
+        secondary = {}
+        torch.cuda.synchronize()
+        for wl in ("quad", "frame3d"):
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", wl, "--steps", "5", "--warmup", "3",
+                                    "--no-cpu-baseline", "--e2e-steps", "2"], capture_output=True, text=True, timeout=600)
+                d = json.loads(r.stdout.strip().splitlines()[-1])
+                secondary[wl] = {"workload": d["config"]["workload"], "elements": d["config"]["elements"], "gauss_points": d["config"]["gauss_points"],
+                                 "ms_per_step": d["ms_per_step"], "value": d["value"], "unit": d["unit"],
+                                 "kernel_ms": {k: v for k, v in d["kernel_ms"].items() if v > 0.005},
+                                 "e2e_ms_per_step": d["e2e"]["ms_per_step"] if d.get("e2e") else None,
+                                 "dominant": {"kernel": d["roofline"]["kernel"], "hbm_frac": d["roofline"]["frac"]}}
+            except Exception as ex:
+                secondary[wl] = {"error": repr(ex)}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -571,7 +590,7 @@ def ours_main(a):
                 "formUnbalance_ms": ms_max["element_resid"] + ms_max["exchange_B"] + ms_max["assemble_B"],
                 "update_ms": ms_max["update"],
                 "gpu_launches": int(launches_all), "clocks": clk, "e2e": e2e, "roofline": roofline, "cpu_baseline": cb,
-                "scale_check": None if scale is None else scale["check"], "scale": scale, "solve_ms": solve}
+                "scale_check": None if scale is None else scale["check"], "scale": scale, "solve_ms": solve, "secondary": secondary}
         json_out.write(json.dumps(line) + "\n"); json_out.flush()
     if world > 1:
         dist.barrier()
@@ -593,6 +612,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="name=value for xb_set_option (kernel tuning experiments)")
+    ap.add_argument("--no-secondary", dest="secondary", action="store_false",
+                    help="skip the short quad / frame3d runs whose numbers ride along in the brick line at N = 1")
     ap.add_argument("--selftest", action="store_true", help="torchrun, N >= 2: bitwise check of the NCCL-exchanged rows against "
                                                             "the single-GPU rows (prints {\"selftest\": \"ok\"})")
     ap.add_argument("--solve-n", type=int, default=16, help="size of the block whose linear solve is timed (out of path; 0 = skip)")

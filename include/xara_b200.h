@@ -125,6 +125,13 @@ int xb_add_elements(xb_model*, int kind, int n, const int* tags, const int* conn
 /* LoadPattern 1 with a Linear series + NodalLoad (domain/node/NodalLoad.cpp:97):
  * values is [n][ndf]; loads on one node accumulate */
 int xb_add_nodal_loads(xb_model*, int n, const int* node_tags, const double* values);
+/* `eleLoad -ele tags -type -beamUniform wy [wz] wa` on forceBeamColumn elements, in the same Linear pattern as the nodal
+ * loads (Beam2dUniformLoad / Beam3dUniformLoad -> ForceBeamColumn2d/3d::addLoad, ForceBeamColumn2d.cpp:1005): w = [n][3]
+ * = wy, wz, wa (2D: wz ignored).  The element then carries the section forces sp inside its iteration
+ * (computeSectionForces, :1034) and the fixed-end reactions p0 in its resisting force (computeReactions, :407), both
+ * scaled by the load factor of xb_apply_load.  One uniform load per element; point and partial loads: XB_ERR_UNSUPPORTED
+ * at the binding. */
+int xb_add_beam_uniform_loads(xb_model*, int n, const int* ele_tags, const double* w);
 
 /* `mass` command: Node::setMass with a diagonal matrix (domain/node/Node.h:127); mass is [n][ndf].
  * Element masses come from the nDMaterial density (J2Plasticity par[7], ElasticIsotropic par[2]): stdBrick forms

@@ -238,8 +238,17 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
       LinearSeries* ls = dynamic_cast<LinearSeries*>(lp->theSeries);
       if (!ls || ls->cFactor != 1.0) { G.err = "glue: load pattern whose TimeSeries is not Linear with factor 1: outside the device path"; return -7; }
       if (lp->isConstant) { G.err = "glue: load pattern frozen by loadConst: outside the device path"; return -7; }
-      { ElementalLoadIter& eli = lp->getElementalLoads();
-        if (eli() != nullptr) { G.err = "glue: ElementalLoad (eleLoad) in a load pattern: outside the device path"; return -7; } }
+      { ElementalLoadIter& eli = lp->getElementalLoads(); ElementalLoad* el;
+        while ((el = eli()) != nullptr) {   // `eleLoad -beamUniform` on the force beams goes along; every other element load is refused
+          int type; const Vector& data = el->getData(type, 1.0);
+          const int et = el->getElementTag();
+          Element* ele = dom->getElement(et);
+          double w[3] = {0.0, 0.0, 0.0};
+          if (type == LOAD_TAG_Beam2dUniformLoad && dynamic_cast<ForceBeamColumn2d*>(ele)) { w[0] = data(0); w[2] = data(1); }
+          else if (type == LOAD_TAG_Beam3dUniformLoad && dynamic_cast<ForceBeamColumn3d*>(ele)) { w[0] = data(0); w[1] = data(1); w[2] = data(2); }
+          else { G.err = "glue: ElementalLoad other than -beamUniform on a forceBeamColumn: outside the device path"; return -7; }
+          if (xb_add_beam_uniform_loads(x, 1, &et, w) < 0) { G.err = xb_last_error(); return -7; }
+        } }
       NodalLoadIter& li = lp->getNodalLoads(); NodalLoad* nl;
       while ((nl = li()) != nullptr) {
         int type; const Vector& v = nl->getData(type);

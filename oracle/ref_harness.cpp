@@ -74,6 +74,8 @@
 #undef protected
 #include <SparseGenRowLinSolver.h>
 #include <SparseGenColLinSolver.h>
+#include <Beam2dUniformLoad.h>
+#include <Beam3dUniformLoad.h>
 #include <BandGenLinSOE.h>
 #include <BandGenLinSolver.h>
 #include <ProfileSPDLinSOE.h>
@@ -314,6 +316,19 @@ int ref_uni_path(int kind, const double* p, int n, const double* strains, const 
   }
   delete mat;
   return 0;
+}
+
+// `eleLoad -ele tag -type -beamUniform wy [wz] wa` in pattern 1 (Linear series)
+int ref_add_beam_uniform_load(void* h, int eleTag, double wy, double wz, double wa) {
+  RefModel* m = (RefModel*)h;
+  if (m->domain->getLoadPattern(1) == nullptr) {
+    LoadPattern* lp = new LoadPattern(1);
+    lp->setTimeSeries(new LinearSeries());
+    m->domain->addLoadPattern(lp);
+  }
+  ElementalLoad* el = (m->ndm == 2) ? (ElementalLoad*)new Beam2dUniformLoad(10000 + m->nloads++, wy, wa, eleTag)
+                                    : (ElementalLoad*)new Beam3dUniformLoad(10000 + m->nloads++, wy, wz, wa, eleTag);
+  return m->domain->addElementalLoad(el, 1) ? 0 : -1;
 }
 
 int ref_add_load(void* h, int nodeTag, const double* vals) {

@@ -697,6 +697,9 @@ typedef struct {
   int initialFlag;
   double kv[9], Se[3], kvcommit[9], Secommit[3];       /* kv column-major 3x3 */
   double fs[ORC_MAXSEC][4], vs[ORC_MAXSEC][2], Ssr[ORC_MAXSEC][2], vscommit[ORC_MAXSEC][2];
+  /* `eleLoad -beamUniform wy wa` of the Linear pattern: w = {wy, -, wa}; numEleLoads = 1 once Domain::applyLoad ran
+   * (LoadPattern::applyLoad -> ElementalLoad::applyLoad -> ForceBeamColumn2d::addLoad(load, loadFactor)) */
+  int has_load, numEleLoads; double w[3], loadFactor;
 } OrcBeam;
 
 /* quadrature/Frame/LobattoBeamIntegration.cpp: getSectionLocations / getSectionWeights */
@@ -735,7 +738,7 @@ static int beam_update(OrcBeam* b, const double* ug, const double* dug) {
   crd2d_basic(b, ug, v);
   crd2d_basic(b, dug, dv);
   double nrm = sqrt(dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]);
-  if (b->initialFlag != 0 && nrm <= DBL_EPSILON) return 0;
+  if (b->initialFlag != 0 && nrm <= DBL_EPSILON && b->numEleLoads == 0) return 0;
   for (int i = 0; i < 3; i++) vin[i] = v[i] - dv[i];
   const double L = b->L, oneOverL = 1.0 / L;
   double xi[ORC_MAXSEC], wt[ORC_MAXSEC];
@@ -769,6 +772,12 @@ static int beam_update(OrcBeam* b, const double* ug, const double* dug) {
           double xL = xi[i], xL1 = xL - 1.0, wtL = wt[i] * L;
           Ss[0] = SeTrial[0];
           Ss[1] = xL1 * SeTrial[1] + xL * SeTrial[2];
+          if (b->numEleLoads > 0) {   /* computeSectionForces, ForceBeamColumn2d.cpp:1034-1070 (Beam2dUniformLoad) */
+            double x = xi[i] * L;
+            double wa = b->w[2] * b->loadFactor, wy = b->w[0] * b->loadFactor;
+            Ss[0] += wa * (L - x);
+            Ss[1] += wy * 0.5 * x * (x - L);
+          }
           dSs[0] = Ss[0] - SsrSub[i][0]; dSs[1] = Ss[1] - SsrSub[i][1];
           const double* fuse;
           double fs0[4];
@@ -853,7 +862,14 @@ static void beam_form(const OrcBeam* b, double* K, double* R) {
   double q0 = b->Se[0], q1 = b->Se[1], q2 = b->Se[2];
   double V = oneOverL * (q1 + q2);
   double pl[6] = { -q0, V, q1, q0, -V, q2 };
-  pl[0] += 0.0; pl[1] += 0.0; pl[4] += 0.0;
+  double p0[3] = {0.0, 0.0, 0.0};
+  if (b->numEleLoads > 0) {   /* computeReactions, ForceBeamColumn2d.cpp:407-425 */
+    double wa = b->w[2] * b->loadFactor, wy = b->w[0] * b->loadFactor;
+    p0[0] -= wa * b->L;
+    double Vr = 0.5 * wy * b->L;
+    p0[1] -= Vr; p0[2] -= Vr;
+  }
+  pl[0] += p0[0]; pl[1] += p0[1]; pl[4] += p0[2];
   R[0] = cosTheta * pl[0] - sinTheta * pl[1];
   R[1] = sinTheta * pl[0] + cosTheta * pl[1];
   R[3] = cosTheta * pl[3] - sinTheta * pl[4];
@@ -962,6 +978,8 @@ typedef struct {
   int initialFlag;
   double kv[36], Se[6], kvcommit[36], Secommit[6];       /* kv column-major 6x6 */
   double fs[ORC_MAXSEC][16], vs[ORC_MAXSEC][4], Ssr[ORC_MAXSEC][4], vscommit[ORC_MAXSEC][4];
+  /* `eleLoad -beamUniform wy wz wa`: see OrcBeam */
+  int has_load, numEleLoads; double w[3], loadFactor;
 } OrcBeam3;
 
 /* LinearCrdTransf3d::initialize -> computeElemtLengthAndOrient + getLocalAxes, LinearCrdTransf3d.cpp:203-330 */
@@ -1021,7 +1039,7 @@ static int beam3_update(OrcBeam3* b, const double* ug, const double* dug) {
   double v[6], dv[6], vin[6];
   crd3d_basic(b, ug, v);
   crd3d_basic(b, dug, dv);
-  if (b->initialFlag != 0 && norm6(dv) <= DBL_EPSILON) return 0;
+  if (b->initialFlag != 0 && norm6(dv) <= DBL_EPSILON && b->numEleLoads == 0) return 0;
   for (int i = 0; i < 6; i++) vin[i] = v[i] - dv[i];
   const double L = b->L;
   double xi[ORC_MAXSEC], wt[ORC_MAXSEC];
@@ -1055,6 +1073,13 @@ static int beam3_update(OrcBeam3* b, const double* ug, const double* dug) {
           Ss[1] = xL1 * SeTrial[1] + xL * SeTrial[2];
           Ss[2] = xL1 * SeTrial[3] + xL * SeTrial[4];
           Ss[3] = SeTrial[5];
+          if (b->numEleLoads > 0) {   /* computeSectionForces, ForceBeamColumn3d.cpp:1197-1215 (Beam3dUniformLoad) */
+            double x = xi[i] * L;
+            double wy = b->w[0] * b->loadFactor, wz = b->w[1] * b->loadFactor, wa = b->w[2] * b->loadFactor;
+            Ss[0] += wa * (L - x);
+            Ss[1] += wy * 0.5 * x * (x - L);
+            Ss[2] += wz * 0.5 * x * (L - x);
+          }
           for (int q = 0; q < 4; q++) dSs[q] = Ss[q] - SsrSub[i][q];
           const double* fuse;
           double fs0[16];
@@ -1166,7 +1191,16 @@ static void beam3_form(const OrcBeam3* b, double* K, double* Rg) {
   double pl[12];
   pl[0] = -q[0]; pl[1] = oneOverL * (q[1] + q[2]); pl[2] = -oneOverL * (q[3] + q[4]); pl[3] = -q[5];
   pl[4] = q[3]; pl[5] = q[1]; pl[6] = q[0]; pl[7] = -pl[1]; pl[8] = -pl[2]; pl[9] = q[5]; pl[10] = q[4]; pl[11] = q[2];
-  pl[0] += 0.0; pl[1] += 0.0; pl[7] += 0.0; pl[2] += 0.0; pl[8] += 0.0;     /* p0 = 0 */
+  double p0[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  if (b->numEleLoads > 0) {   /* computeReactions, ForceBeamColumn3d.cpp:419-431 */
+    double wy = b->w[0] * b->loadFactor, wz = b->w[1] * b->loadFactor, wa = b->w[2] * b->loadFactor;
+    p0[0] -= wa * b->L;
+    double Vr = 0.5 * wy * b->L;
+    p0[1] -= Vr; p0[2] -= Vr;
+    Vr = 0.5 * wz * b->L;
+    p0[3] -= Vr; p0[4] -= Vr;
+  }
+  pl[0] += p0[0]; pl[1] += p0[1]; pl[7] += p0[2]; pl[2] += p0[3]; pl[8] += p0[4];   /* LinearCrdTransf3d.cpp:727-731 */
   for (int blk = 0; blk < 4; blk++)
     for (int c = 0; c < 3; c++)
       Rg[3 * blk + c] = R[0][c] * pl[3 * blk] + R[1][c] * pl[3 * blk + 1] + R[2][c] * pl[3 * blk + 2];
@@ -1912,7 +1946,29 @@ int orc_incr_response(void* h, const double* dU, double cu, double cv, double ca
   for (int e = 0; e < m->ne; e++) rc |= ele_update(m, &m->ele[e]);
   return rc;
 }
-void orc_apply_load(void* h, double lambda) { ((OrcModel*)h)->lambda = lambda; }
+/* Domain::applyLoad(pseudoTime): zeroLoad on every element, then LoadPattern::applyLoad -> NodalLoad::applyLoad and
+ * ElementalLoad::applyLoad -> Element::addLoad(load, loadFactor) (domain/domain/Domain.cpp applyLoad; Linear series) */
+void orc_apply_load(void* h, double lambda) {
+  OrcModel* m = (OrcModel*)h;
+  m->lambda = lambda;
+  for (int e = 0; e < m->ne; e++) {
+    OrcEle* el = &m->ele[e];
+    if (el->kind == ORC_ELE_FBC2D && el->beam->has_load) { el->beam->numEleLoads = 1; el->beam->loadFactor = lambda; }
+    if (el->kind == ORC_ELE_FBC3D && el->beam3->has_load) { el->beam3->numEleLoads = 1; el->beam3->loadFactor = lambda; }
+  }
+}
+/* `eleLoad -ele tag -type -beamUniform wy [wz] wa` in the model's Linear pattern (Beam2dUniformLoad / Beam3dUniformLoad) */
+int orc_add_beam_uniform_load(void* h, int ele_tag, double wy, double wz, double wa) {
+  OrcModel* m = (OrcModel*)h;
+  for (int e = 0; e < m->ne; e++) {
+    OrcEle* el = &m->ele[e];
+    if (el->tag != ele_tag) continue;
+    if (el->kind == ORC_ELE_FBC2D) { if (el->beam->has_load) return -2; el->beam->has_load = 1; el->beam->w[0] = wy; el->beam->w[1] = 0.0; el->beam->w[2] = wa; return 0; }
+    if (el->kind == ORC_ELE_FBC3D) { if (el->beam3->has_load) return -2; el->beam3->has_load = 1; el->beam3->w[0] = wy; el->beam3->w[1] = wz; el->beam3->w[2] = wa; return 0; }
+    return -3;
+  }
+  return -1;
+}
 
 /* Element::getTangentStiff / getResistingForce of FE element e (row-major) */
 
@@ -2246,12 +2302,18 @@ int orc_revert_to_start(void* h) {
     OrcEle* el = &m->ele[e];
     if (el->kind == ORC_ELE_FBC2D) {
       for (int i = 0; i < el->beam->nip; i++) free(el->beam->sec[i].mat);
+      OrcBeam keep = *el->beam;      /* the element loads are not part of the state: they stay as addLoad left them */
       free(el->beam);
       el->beam = beam2_build(m, el, el->mat, el->par);
+      el->beam->has_load = keep.has_load; el->beam->numEleLoads = keep.numEleLoads; el->beam->loadFactor = keep.loadFactor;
+      memcpy(el->beam->w, keep.w, sizeof keep.w);
     } else if (el->kind == ORC_ELE_FBC3D) {
       for (int i = 0; i < el->beam3->nip; i++) free(el->beam3->sec[i].mat);
+      const int hl = el->beam3->has_load, nl = el->beam3->numEleLoads; const double lf = el->beam3->loadFactor;
+      double wk[3]; memcpy(wk, el->beam3->w, sizeof wk);
       free(el->beam3);
       el->beam3 = beam3_build(m, el, el->mat, el->par);
+      el->beam3->has_load = hl; el->beam3->numEleLoads = nl; el->beam3->loadFactor = lf; memcpy(el->beam3->w, wk, sizeof wk);
     } else {
       for (int g = 0; g < el->nip; g++) {
         OrcGP* gp = &el->gp[g];
@@ -2263,6 +2325,7 @@ int orc_revert_to_start(void* h) {
       }
     }
   }
+  orc_apply_load(h, 0.0);       /* Domain::revertToStart: applyLoad(currentTime = 0), then update() */
   int rc = 0;
   for (int e = 0; e < m->ne; e++) rc |= ele_update(m, &m->ele[e]);
   return rc;
@@ -2271,7 +2334,7 @@ int orc_revert_to_start(void* h) {
 int orc_revert(void* h) {
   OrcModel* m = (OrcModel*)h;
   /* Domain::revertToLastCommit (Domain.cpp:1925): nodes, elements, currentTime = committedTime + applyLoad, then update() */
-  m->lambda = m->lambda_c;
+  orc_apply_load(h, m->lambda_c);
   memcpy(m->trial, m->commit_disp, sizeof(double) * m->nn * m->ndf);
   memset(m->incr, 0, sizeof(double) * m->nn * m->ndf);
   memcpy(m->vel, m->velc, sizeof(double) * m->nn * m->ndf); memcpy(m->acc, m->accc, sizeof(double) * m->nn * m->ndf);

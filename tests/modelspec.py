@@ -54,6 +54,7 @@ class ModelSpec:
     uniaxials: list = field(default_factory=list)   # (tag, kind, params)
     equal_dofs: list = field(default_factory=list)  # `equalDOF`: (retained node tag, constrained node tag, [dofs], 0-based)
     sections: list = field(default_factory=list)    # (tag, y[nf], A[nf], uniaxial tags[nf])
+    beam_loads: list = field(default_factory=list)  # `eleLoad -beamUniform`: (element tag, wy, wz, wa) in the Linear pattern
 
     @property
     def nn(self):
@@ -214,6 +215,24 @@ def rc_section3d(tag=1, h=24.0, b=18.0, cover=1.5, ny=6, nz=4, As=0.6, GJ=2.0e6)
                 continue
             y.append(yy); z.append(zz); A.append(As); m.append(3)
     return (tag, np.array(y), np.array(A), np.array(m, np.int32), np.array(z), GJ)
+
+
+def with_beam_gravity(spec, w=-0.25, axial=0.02, seed=0):
+    """`eleLoad -beamUniform` on the horizontal members (girders): transverse w (+-20 % per element), a little axial load,
+    and -- 3D -- a small lateral component; columns stay unloaded"""
+    rng = np.random.default_rng(seed)
+    ix = {int(t): i for i, t in enumerate(spec.node_tags)}
+    up = spec.ndm - 1
+    loads = []
+    for g in spec.groups:
+        for t, c in zip(g.tags, g.conn):
+            a, b = spec.crd[ix[int(c[0])]], spec.crd[ix[int(c[1])]]
+            if abs(a[up] - b[up]) > 1e-9:
+                continue                                  # a column
+            f = 1.0 + 0.2 * (rng.random() - 0.5)
+            loads.append((int(t), w * f, 0.1 * w * f if spec.ndm == 3 else 0.0, axial * f))
+    spec.beam_loads = loads
+    return spec
 
 
 def frame3d(nx=1, ny=1, nstory=2, ndiv=1, nip=4, bay=240.0, story=144.0, max_iters=10, tol=1e-12,
@@ -495,6 +514,9 @@ class OracleBackend(_Backend):
             for row in spec.loads:
                 v = np.ascontiguousarray(row[1:], np.float64)
                 assert L.orc_add_load(self.h, int(row[0]), _p(v)) == 0
+        L.orc_add_beam_uniform_load.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double]
+        for t, wy, wz, wa in spec.beam_loads:
+            assert L.orc_add_beam_uniform_load(self.h, int(t), float(wy), float(wz), float(wa)) == 0
         # soe 2 / 3 / 4: BandGeneral / ProfileSPD / Umfpack -- the column graph, then the SOE's own storage on top of it
         self.soe = soe
         self.neq = L.orc_setup(self.h, numberer, soe if soe in (0, 1) else 0)
@@ -707,6 +729,10 @@ class RefBackend(_Backend):
             for row in spec.loads:
                 v = np.ascontiguousarray(row[1:], np.float64)
                 assert L.ref_add_load(self.h, int(row[0]), _p(v)) == 0
+        if spec.beam_loads:
+            L.ref_add_beam_uniform_load.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double]
+            for t, wy, wz, wa in spec.beam_loads:
+                assert L.ref_add_beam_uniform_load(self.h, int(t), float(wy), float(wz), float(wa)) == 0
         self.ne = len(self.ele_tags)
         self.max_iter = max_iter
         if defer_setup:       # the caller picks the integrator (setup_transient)

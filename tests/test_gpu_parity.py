@@ -199,7 +199,7 @@ def test_newton_iteration_counts_match_oracle(shape):
 
 
 @pytest.mark.skipif(not (have_ref() and have_glue()), reason="oracle/_ref not built (needs /root/reference)")
-@pytest.mark.parametrize("shape,numberer,soe", [("brick", 1, 0), ("quad", 0, 1), ("mixed", 1, 1), ("soilcolumn_equaldof", 1, 0),
+@pytest.mark.parametrize("shape,numberer,soe", [("brick", 1, 0), ("quad", 0, 1), ("mixed", 1, 1), ("soilcolumn_equaldof", 1, 0), ("frame2d_gravity", 1, 0),
                                                 ("soilcolumn_equaldof", 0, 1)])
 def test_reference_newton_loop_drives_device_path(shape, numberer, soe):
     """The drop-in, end to end: the REFERENCE'S OWN StaticAnalysis objects (AnalysisModel, PlainHandler, numberer,
@@ -214,6 +214,10 @@ def test_reference_newton_loop_drives_device_path(shape, numberer, soe):
     elif shape == "quad":
         def mk():
             sp = quad_plane(16, 4, mat=J2_STEEL, lx=8.0, ly=2.0); sp.loads[:, 1:] = [0.0, -10.0]; return sp
+    elif shape == "frame2d_gravity":
+        def mk():   # `eleLoad -beamUniform` on the girders read out of the load pattern, pushed well into the inelastic range
+            from modelspec import with_beam_gravity
+            sp = with_beam_gravity(frame2d(2, 3, 2, lateral=15.0), w=-0.2, seed=1); return sp
     elif shape == "soilcolumn_equaldof":
         def mk():   # MP_Constraints read out of the Domain (`equalDOF`): sheared soil column with tied sides
             sp = soil_column_equaldof(12, mat=J2_STEEL, distort=0.1)
@@ -607,6 +611,46 @@ def test_band_profile_umfpack_storage_device_vs_oracle(soe):
             assert np.array_equal(A, D.form_tangent())                     # entries outside the pattern stay exact zeros
             assert relerr(D.form_unbalance(), O.form_unbalance()) < tol
             O.commit(); D.commit()
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_beam_uniform_element_loads_device_vs_oracle(dim):
+    """`eleLoad -beamUniform` on force beams: section forces sp inside the element iteration, fixed-end reactions p0 in
+    the resisting force, both scaled by the load factor; against the oracle (pinned to ForceBeamColumn2d/3d with
+    Beam2d/3dUniformLoad, tests/test_oracle.py) over a gravity ramp with commits, a step in which only the load factor
+    moves, a revert to the last commit and a reset"""
+    from modelspec import with_beam_gravity
+    rng = np.random.default_rng(5)
+    spec = with_beam_gravity(frame2d(3, 3, 2) if dim == 2 else frame3d(2, 1, 2), seed=3)
+    nd = 6 if dim == 2 else 12
+    O = OracleBackend(spec, 1, 0)
+    D = xb.DeviceModel.from_spec(spec, 1, 0).to_device(0)
+    ids = O.ids()
+    sc = np.asarray((0.02, 0.02, 2e-4) if dim == 2 else (0.015, 0.015, 0.003, 1e-4, 1e-4, 1e-4))
+    u = np.zeros((spec.nn, spec.ndf))
+
+    def check():
+        assert relerr(D.form_tangent(), O.form_tangent()) < BEAM_RTOL
+        assert relerr(D.form_unbalance(), O.form_unbalance()) < BEAM_RTOL
+        for e in (0, O.ne // 2, O.ne - 1):
+            assert relerr(D.element_resid(e, nd), O.ele_resid(e, nd)) < BEAM_RTOL
+
+    for s_ in range(5):
+        if s_ != 2:                     # step 2: the load factor moves, the displacements do not
+            u = u + rng.normal(0, 1.0, (spec.nn, spec.ndf)) * sc * 0.1; u[ids < 0] = 0
+        lam = 0.25 * (s_ + 1)
+        O.apply_load(lam); O.set_trial_disp(u)
+        D.apply_load(lam); D.set_trial_disp(u); D.update()
+        check()
+        if s_ == 3:                     # a trial state is thrown away: back to the committed load factor and state
+            O.revert(); D.revert_to_last_commit()
+            check()
+        else:
+            O.commit(); D.commit()
+    O.revert_to_start(); D.revert_to_start()
+    check()
+    O.apply_load(0.5); O.set_trial_disp(0.3 * u); D.apply_load(0.5); D.set_trial_disp(0.3 * u); D.update()
+    check()
 
 
 def test_launch_and_byte_accounting():

@@ -134,6 +134,34 @@ def test_oracle_vs_live_reference(mat, numberer, soe):
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("dim", [2, 3])
+def test_beam_uniform_element_loads_vs_live_reference(dim):
+    """`eleLoad -beamUniform` on force beams (ForceBeamColumn2d.cpp:407,1034 / ForceBeamColumn3d.cpp:419,1197): the section
+    forces sp inside the element iteration and the fixed-end reactions p0 in the resisting force -- A, B and the
+    element forces against the reference over a load history in which the load factor grows (gravity ramp), incl. steps
+    with a zero displacement increment (the element must iterate all the same: numEleLoads > 0)"""
+    from modelspec import with_beam_gravity
+    rng = np.random.default_rng(5)
+    spec = with_beam_gravity(frame2d(2, 2, 2) if dim == 2 else frame3d(1, 1, 2), seed=3)
+    assert len(spec.beam_loads) >= 4
+    O, R = OracleBackend(spec, 1, 0), RefBackend(spec, 1, 0)
+    sc = np.asarray((0.02, 0.02, 2e-4) if dim == 2 else (0.015, 0.015, 0.003, 1e-4, 1e-4, 1e-4))
+    u = np.zeros((spec.nn, spec.ndf))
+    for s_ in range(5):
+        if s_ != 2:                     # step 2: the load factor moves, the displacements do not
+            u = u + rng.normal(0, 1.0, (spec.nn, spec.ndf)) * sc * 0.1; u[O.ids() < 0] = 0
+        lam = 0.25 * (s_ + 1)
+        for m in (O, R):
+            m.apply_load(lam); m.set_trial_disp(u)
+        assert close(O.form_tangent(), R.form_tangent(), 1e-11)
+        assert close(O.form_unbalance(), R.form_unbalance(), 1e-11)
+        nd = 6 if dim == 2 else 12
+        for e in range(O.ne):
+            assert close(O.ele_resid(e, nd), R.ele_resid(e, nd), 1e-11)
+        O.commit(); R.commit()
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
 @pytest.mark.parametrize("numberer", [0, 1])
 def test_band_and_profile_storage_vs_live_reference(numberer):
     """`system BandGeneral` / `system ProfileSPD`: the oracle's layout (numSubD / numSuperD, iDiagLoc) and its addA into the

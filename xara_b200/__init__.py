@@ -66,6 +66,7 @@ def _load():
         "xb_add_fiber_section": (i32, [vp, i32, i32, vp, vp, vp]),
         "xb_add_fiber_section3d": (i32, [vp, i32, i32, vp, vp, vp, vp, f64]),
         "xb_add_elements": (i32, [vp, i32, i32, vp, vp, vp, vp, i32]),
+        "xb_add_beam_uniform_loads": (i32, [vp, i32, vp, vp]),
         "xb_add_nodal_loads": (i32, [vp, i32, vp, vp]),
         "xb_set_nodal_mass": (i32, [vp, i32, vp, vp]),
         "xb_set_rayleigh_alpha_m": (i32, [vp, f64]),
@@ -229,6 +230,12 @@ class DeviceModel:
         self._ck(lib.xb_add_elements(self._h, kind, len(tags), _ptr(tags), _ptr(conn), _ptr(mat_tags),
                                      _ptr(par), par.shape[1]))
 
+    def add_beam_uniform_loads(self, ele_tags, w):
+        """`eleLoad -beamUniform`: w [n][3] = wy, wz, wa per element (Linear pattern)"""
+        ele_tags, w = _i32(ele_tags), _f64(w)
+        assert w.ndim == 2 and w.shape[1] == 3 and len(w) == len(ele_tags)
+        self._ck(lib.xb_add_beam_uniform_loads(self._h, len(ele_tags), _ptr(ele_tags), _ptr(w)))
+
     def add_nodal_loads(self, node_tags, values):
         node_tags, values = _i32(node_tags), _f64(values)
         self._ck(lib.xb_add_nodal_loads(self._h, len(node_tags), _ptr(node_tags), _ptr(values)))
@@ -258,6 +265,9 @@ class DeviceModel:
             m.add_elements(g.kind, g.tags, g.conn, g.mat, g.par)
         if spec.loads is not None and len(spec.loads):
             m.add_nodal_loads(spec.loads[:, 0].astype(np.int32), spec.loads[:, 1:])
+        bl = getattr(spec, "beam_loads", [])
+        if bl:
+            m.add_beam_uniform_loads([t for t, *_ in bl], np.array([w for _, *w in bl], np.float64))
         if setup:
             m.setup(numberer, soe, nparts, rank, part)
         return m

@@ -68,6 +68,11 @@ struct BeamView {
   // (getInitialStiff), Kc = kv at the last commit (Element::commitState); both basic, column-major [nb*nb][n]
   double* kv0;
   double* kvK;
+  // `eleLoad -beamUniform` of the Linear pattern: wy, wz, wa per element [3][n] (null: none), the pattern's load factor,
+  // and whether Domain::applyLoad has run (numEleLoads > 0: the element iterates at every update)
+  const double* wl;
+  double lam;
+  int loads_on;
 };
 
 // transient coefficients handed to the form kernels (see TanCoef / DynCoef in device_model.cu)
@@ -348,7 +353,15 @@ __global__ void __launch_bounds__(128) fbc2d_form_kernel(BeamView B, int want_k,
       q0 += qd[0]; q1 += qd[1]; q2 += qd[2];
     }
     const double V = oneOverL * (q1 + q2);
-    const double pl[6] = {-q0, V, q1, q0, -V, q2};
+    double pl[6] = {-q0, V, q1, q0, -V, q2};
+    if (B.wl != nullptr && B.loads_on) {   // computeReactions (ForceBeamColumn2d.cpp:407-425) into LinearCrdTransf2d's pl
+      const double wy = B.wl[e] * B.lam, wa = B.wl[2 * n + e] * B.lam;
+      double p0[3] = {0.0, 0.0, 0.0};
+      p0[0] -= wa * L;
+      const double Vr = 0.5 * wy * L;
+      p0[1] -= Vr; p0[2] -= Vr;
+      pl[0] += p0[0]; pl[1] += p0[1]; pl[4] += p0[2];
+    }
     double* R = B.Re + e * 6;
     R[0] = cosTheta * pl[0] - sinTheta * pl[1];
     R[1] = sinTheta * pl[0] + cosTheta * pl[1];
@@ -561,10 +574,20 @@ __global__ void __launch_bounds__(128, XB_FBC_SEC_OCC) fbc3d_update_sec_kernel(B
     crd3d_basic(L, R, dug, dv);
   }
   const int initialFlag = B.iflag[e];
-  if (initialFlag != 0 && norm6(dv) <= DBL_EPSILON) return;
+  // (all lanes of an element take the same way out: dv and the load flag are the element's)
+  // numEleLoads > 0 for THIS element (ForceBeamColumn3d.cpp: the early return needs numEleLoads == 0)
+  const bool loaded = B.wl != nullptr && B.loads_on && (B.wl[e] != 0.0 || B.wl[n + e] != 0.0 || B.wl[2 * n + e] != 0.0);
+  if (initialFlag != 0 && norm6(dv) <= DBL_EPSILON && !loaded) return;
 #pragma unroll
   for (int q = 0; q < 6; q++) vin[q] = v[q] - dv[q];
   const double xL = lobatto_x(nip, is), xL1 = xL - 1.0, wtL = lobatto_w(nip, is) * L;
+  // `eleLoad -beamUniform`: this section's forces sp (computeSectionForces, ForceBeamColumn3d.cpp:1197-1215)
+  double sp0 = 0.0, sp1 = 0.0, sp2 = 0.0;
+  if (loaded) {
+    const double x = xL * L;
+    const double wy = B.wl[e] * B.lam, wz = B.wl[n + e] * B.lam, wa = B.wl[2 * n + e] * B.lam;
+    sp0 = wa * (L - x); sp1 = wy * 0.5 * x * (x - L); sp2 = wz * 0.5 * x * (L - x);
+  }
   // initial section flexibility: 3x3 block (column-major, stride 3) + torsion
   double f0[9], f0t;
 #pragma unroll
@@ -625,6 +648,7 @@ __global__ void __launch_bounds__(128, XB_FBC_SEC_OCC) fbc3d_update_sec_kernel(B
           Ss[1] = xL1 * SeTrial[1] + xL * SeTrial[2];
           Ss[2] = xL1 * SeTrial[3] + xL * SeTrial[4];
           Ss[3] = SeTrial[5];
+          if (loaded) { Ss[0] += sp0; Ss[1] += sp1; Ss[2] += sp2; }
 #pragma unroll
           for (int q = 0; q < 4; q++) dSs[q] = Ss[q] - SsrS[q];
           const bool initial = (l == 1) || (l == 2 && j == 0);
@@ -778,10 +802,19 @@ __global__ void __launch_bounds__(128, XB_FBC_SEC_OCC) fbc2d_update_sec_kernel(B
     crd2d_basic(L, cosT, sinT, dug, dv);
   }
   const int initialFlag = B.iflag[e];
-  if (initialFlag != 0 && sqrt(dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]) <= DBL_EPSILON) return;
+  // numEleLoads > 0 for THIS element (ForceBeamColumn2d.cpp:575)
+  const bool loaded = B.wl != nullptr && B.loads_on && (B.wl[e] != 0.0 || B.wl[2 * n + e] != 0.0);
+  if (initialFlag != 0 && sqrt(dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]) <= DBL_EPSILON && !loaded) return;
 #pragma unroll
   for (int q = 0; q < 3; q++) vin[q] = v[q] - dv[q];
   const double xL = lobatto_x(nip, is), xL1 = xL - 1.0, wtL = lobatto_w(nip, is) * L;
+  // `eleLoad -beamUniform`: this section's forces sp (computeSectionForces, ForceBeamColumn2d.cpp:1034-1070)
+  double sp0 = 0.0, sp1 = 0.0;
+  if (loaded) {
+    const double x = xL * L;
+    const double wy = B.wl[e] * B.lam, wa = B.wl[2 * n + e] * B.lam;
+    sp0 = wa * (L - x); sp1 = wy * 0.5 * x * (x - L);
+  }
   double f0[4];
 #pragma unroll
   for (int q = 0; q < 4; q++) f0[q] = __ldg(B.fs0 + q);
@@ -824,6 +857,7 @@ __global__ void __launch_bounds__(128, XB_FBC_SEC_OCC) fbc2d_update_sec_kernel(B
           double Ss[2], dSs[2], dvs[2], fb[6], ssec[2], ksec[4];
           Ss[0] = SeTrial[0];
           Ss[1] = xL1 * SeTrial[1] + xL * SeTrial[2];
+          if (loaded) { Ss[0] += sp0; Ss[1] += sp1; }
           dSs[0] = Ss[0] - SsrS[0]; dSs[1] = Ss[1] - SsrS[1];
           const bool initial = (l == 1) || (l == 2 && j == 0);
           dvs[0] = 0.0; dvs[1] = 0.0;
@@ -999,6 +1033,16 @@ __global__ void __launch_bounds__(64) fbc3d_form_kernel(BeamView B, int want_k, 
     double pl[12];
     pl[0] = -q[0]; pl[1] = oneOverL * (q[1] + q[2]); pl[2] = -oneOverL * (q[3] + q[4]); pl[3] = -q[5];
     pl[4] = q[3]; pl[5] = q[1]; pl[6] = q[0]; pl[7] = -pl[1]; pl[8] = -pl[2]; pl[9] = q[5]; pl[10] = q[4]; pl[11] = q[2];
+    if (B.wl != nullptr && B.loads_on) {   // computeReactions (ForceBeamColumn3d.cpp:419-431) into LinearCrdTransf3d.cpp:727-731
+      const double wy = B.wl[e] * B.lam, wz = B.wl[n + e] * B.lam, wa = B.wl[2 * n + e] * B.lam;
+      double p0[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+      p0[0] -= wa * L;
+      double Vr = 0.5 * wy * L;
+      p0[1] -= Vr; p0[2] -= Vr;
+      Vr = 0.5 * wz * L;
+      p0[3] -= Vr; p0[4] -= Vr;
+      pl[0] += p0[0]; pl[1] += p0[1]; pl[7] += p0[2]; pl[2] += p0[3]; pl[8] += p0[4];
+    }
     double* Rg = B.Re + e * 12;
     for (int blk = 0; blk < 4; blk++)
       for (int c = 0; c < 3; c++)

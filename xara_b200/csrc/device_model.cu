@@ -1705,6 +1705,7 @@ int xb_add_elements(xb_model* m, int kind, int n, const int* tags, const int* co
   HOSTCALL(m->h.add_elements(kind, n, tags, conn, mt, par, ps));
 }
 int xb_add_nodal_loads(xb_model* m, int n, const int* t, const double* v) { HOSTCALL(m->h.add_loads(n, t, v)); }
+int xb_add_beam_uniform_loads(xb_model* m, int n, const int* t, const double* w) { HOSTCALL(m->h.add_beam_uniform_loads(n, t, w)); }
 int xb_setup(xb_model* m, int numberer, int soe_kind) { HOSTCALL(m->h.setup(numberer, soe_kind)); }
 int xb_setup_partitioned(xb_model* m, int numberer, int soe_kind, int nparts, int rank, const int* part) {
   HOSTCALL(m->h.setup(numberer, soe_kind, nparts, rank, part));
@@ -1876,7 +1877,7 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
           // LinearCrdTransf3d::computeElemtLengthAndOrient + getLocalAxes (LinearCrdTransf3d.cpp:203-330):
           // x = dx / L, y = vecxz ^ x (normalised), z = x ^ y
           const double* xi = &h.crd[(size_t)a * 3]; const double* xj = &h.crd[(size_t)c * 3];
-          const double* v = &g.par[(size_t)e * 6 + 3];
+          const double* v = &g.par[(size_t)e * k.npar + 3];
           const double dx[3] = {xj[0] - xi[0], xj[1] - xi[1], xj[2] - xi[2]};
           const double L = std::sqrt(dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2]);
           if (L == 0.0) return fail(XB_ERR_ARG, "forceBeamColumn: zero element length");
@@ -1891,6 +1892,14 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
         }
       }
       double* dgeo = nullptr; CU(dev_upload(m, &dgeo, geo)); b.geo = dgeo;
+      {   // `eleLoad -beamUniform`: wy, wz, wa per element, SoA [3][n]; null when the batch carries none
+        std::vector<double> wl((size_t)3 * ne, 0.0);
+        bool any = false;
+        for (long long e = 0; e < ne; e++)
+          for (int q = 0; q < 3; q++) { wl[(size_t)q * ne + e] = g.par[(size_t)e * k.npar + k.npar - 3 + q]; any = any || wl[(size_t)q * ne + e] != 0.0; }
+        b.wl = nullptr; b.lam = 0.0; b.loads_on = 0;
+        if (any) { double* dwl = nullptr; CU(dev_upload(m, &dwl, wl)); b.wl = dwl; }
+      }
       // section template + initial fibre records (Steel02::revertToStart, Concrete02 constructor)
       std::vector<double> fy(nf), fz(nf, 0.0), fA(sd.A), fpar((size_t)nf * 12), ic((size_t)nf * XB_FIB_NV, 0.0), it((size_t)nf * XB_FIB_NV, 0.0);
       std::vector<int> fkind(nf);
@@ -2284,9 +2293,15 @@ int xb_update(xb_model* m) {
   return XB_OK;
 }
 
+// (Domain::applyLoad also hands the element loads their factor: ElementalLoad::applyLoad -> Element::addLoad(load, factor);
+//  from the first call on a loaded force beam iterates at every update, numEleLoads > 0)
+static void beams_take_load_factor(xb_model* m, double lambda) {
+  for (auto& d : m->dg) if (is_beam(d.kind) && d.b.wl) { d.b.lam = lambda; d.b.loads_on = 1; }
+}
 int xb_apply_load(xb_model* m, double lambda) {
   if (!m) return fail(XB_ERR_ARG, "null model");
   m->lambda = lambda;
+  beams_take_load_factor(m, lambda);
   return XB_OK;
 }
 
@@ -2798,6 +2813,7 @@ int xb_revert_to_last_commit(xb_model* m) {
   NEED_DEVICE();
   CU(cudaSetDevice(m->device));
   m->lambda = m->lambda_c;   // Domain::revertToLastCommit (Domain.cpp:1942-1947): currentTime = committedTime, applyLoad
+  beams_take_load_factor(m, m->lambda);
   // Node::revertToLastCommit restores the trial displacement; the material history is
   // untouched (J2Plasticity::revertToLastCommit is empty) and the next update rebuilds
   // the trial state from the committed one.
@@ -2829,6 +2845,7 @@ int xb_revert_to_start(xb_model* m) {
   const size_t nb = sizeof(double) * std::max<size_t>((size_t)m->h.nn() * m->h.ndf, 1);
   for (double* q : {m->dU, m->dUc, m->dV, m->dVc, m->dAcc, m->dAc, m->dDU}) CU(cudaMemsetAsync(q, 0, nb, m->stream));
   m->lambda = m->lambda_c = 0.0;
+  beams_take_load_factor(m, 0.0);      // Domain::revertToStart: applyLoad(0)
   for (auto& d : m->dg) {
     if (is_beam(d.kind)) {
       BeamView& b = d.b;

@@ -13,8 +13,11 @@ namespace xb {
 
 static const EleKind kBrick{8, 3, 8, 6, 3};
 static const EleKind kQuad{4, 2, 4, 3, 5};  // par kept: thickness, b1, b2, type (0 PlaneStrain, 1 PlaneStress), pressure
-static const EleKind kBeam2d{2, 3, 0, 2, 3};  // nip is a property of the batch; par: nIP, maxIters, tol
-static const EleKind kBeam3d{2, 6, 0, 4, 6};  // par: nIP, maxIters, tol, vecxz[3]
+// nip is a property of the batch.  par kept per element: nIP, maxIters, tol, [vecxz[3],] then the uniform element load
+// of the Linear pattern (`eleLoad -beamUniform`): wy, wz, wa (zero: none) -- it travels with the element through the
+// partitioning like every other element parameter
+static const EleKind kBeam2d{2, 3, 0, 2, 6};  // par: nIP, maxIters, tol, wy, wz (unused), wa
+static const EleKind kBeam3d{2, 6, 0, 4, 9};  // par: nIP, maxIters, tol, vecxz[3], wy, wz, wa
 
 const EleKind& ele_kind(int kind) {
   return kind == XB_ELE_STDBRICK ? kBrick : (kind == XB_ELE_FOURNODEQUAD ? kQuad : (kind == XB_ELE_FORCEBEAMCOLUMN3D ? kBeam3d : kBeam2d));
@@ -146,7 +149,8 @@ int HostModel::add_elements(int kind, int n, const int* tags, const int* conn, c
       else if (sidx != g.sec || (int)p[0] != g.nip || (int)p[1] != g.max_iters || p[2] != g.tol) {
         err = "forceBeamColumn: one section / nIP / maxIters / tol per xb_add_elements call"; return XB_ERR_UNSUPPORTED;
       }
-      for (int q = 0; q < k.npar; q++) g.par[(size_t)i * k.npar + q] = p[q];
+      const int nin = b3 ? 6 : 3;            // what the caller gives; the element-load columns start at zero
+      for (int q = 0; q < k.npar; q++) g.par[(size_t)i * k.npar + q] = q < nin ? p[q] : 0.0;
     }
     if (g.nip < 2 || g.nip > 10) { err = "forceBeamColumn: Lobatto integration takes 2..10 points"; return XB_ERR_ARG; }
     if (n > 0) groups.push_back(std::move(g));
@@ -195,6 +199,29 @@ int HostModel::add_elements(int kind, int n, const int* tags, const int* conn, c
   }
   g.mat_kind = mk < 0 ? 0 : mk;
   if (n > 0) groups.push_back(std::move(g));
+  return XB_OK;
+}
+
+// `eleLoad -ele tags -type -beamUniform wy [wz] wa` (Beam2dUniformLoad / Beam3dUniformLoad) in the Linear pattern:
+// ForceBeamColumn2d/3d::addLoad.  w: [n][3] = wy, wz, wa.  One uniform load per element.
+int HostModel::add_beam_uniform_loads(int n, const int* tags, const double* w) {
+  if (is_setup) { err = "xb_add_beam_uniform_loads after xb_setup"; return XB_ERR_STATE; }
+  for (int i = 0; i < n; i++) {
+    bool found = false;
+    for (auto& g : groups) {
+      if (g.kind != XB_ELE_FORCEBEAMCOLUMN2D && g.kind != XB_ELE_FORCEBEAMCOLUMN3D) continue;
+      const int npar = ele_kind(g.kind).npar;
+      for (size_t l = 0; l < g.tag.size() && !found; l++) {
+        if (g.tag[l] != tags[i]) continue;
+        double* q = &g.par[l * npar + npar - 3];
+        if (q[0] != 0.0 || q[1] != 0.0 || q[2] != 0.0) { err = "xb_add_beam_uniform_loads: one uniform load per element"; return XB_ERR_UNSUPPORTED; }
+        q[0] = w[(size_t)i * 3]; q[1] = g.kind == XB_ELE_FORCEBEAMCOLUMN3D ? w[(size_t)i * 3 + 1] : 0.0; q[2] = w[(size_t)i * 3 + 2];
+        found = true;
+      }
+      if (found) break;
+    }
+    if (!found) { err = "xb_add_beam_uniform_loads: no forceBeamColumn element with this tag"; return XB_ERR_ARG; }
+  }
   return XB_OK;
 }
 

@@ -213,6 +213,7 @@ struct HostModel {
   int add_elements(int kind, int n, const int* tags, const int* conn, const int* mat_tags,
                    const double* par, int par_stride);
   int add_loads(int n, const int* tags, const double* vals);
+  int add_beam_uniform_loads(int n, const int* tags, const double* w);
   int add_mass(int n, const int* tags, const double* vals);
   // part: nullptr (built-in recursive coordinate bisection) or [ne] ranks in FE order
   int setup(int numberer, int soe_kind, int nparts = 1, int rank = 0, const int* part = nullptr);
