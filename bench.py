@@ -89,7 +89,9 @@ def workload_spec(n, workload="brick"):
     frame: 2D RC frame of forceBeamColumn elements with Steel02/Concrete02 fibre sections, n bays x n storeys
            (the 2D counterpart of configs[3]);
     frame3d: 3D RC space frame, forceBeamColumn (ForceBeamColumn3d) + FiberSection3d (configs[3])"""
-    from modelspec import ELASTIC, J2_STEEL, brick_block, frame2d, frame3d, quad_plane
+    from modelspec import ELASTIC, J2_STEEL, brick_block, frame2d, frame3d, quad_plane, soil_structure_block
+    if workload == "soil":      # configs[4]: J2 soil block with an elastic footing + pier embedded at the top (two element batches)
+        return soil_structure_block(n, n, n)
     if workload == "quad":
         return quad_plane(n, n, mat=(ELASTIC[0], [1000.0, 0.25, 0.0]), lx=float(n), ly=float(n))
     if workload == "frame":
@@ -100,7 +102,7 @@ def workload_spec(n, workload="brick"):
 
 
 def displacement_field_for(spec, crd, workload):
-    if workload == "brick":
+    if workload in ("brick", "soil"):
         return displacement_field(crd)
     if workload == "quad":
         x, y = crd[:, 0], crd[:, 1]
@@ -197,6 +199,9 @@ def workload_name(n, workload="brick"):
         return f"2D FourNodeQuad plane-strain ElasticIsotropic mesh {n}x{n} = {n * n} elements (BASELINE configs[1])"
     if workload == "frame":
         return f"2D RC frame {n} bays x {n} storeys, forceBeamColumn + fibre sections Steel02/Concrete02, Newmark terms (2D counterpart of BASELINE configs[3])"
+    if workload == "soil":
+        return (f"soil-structure block {n}x{n}x{n} = {n ** 3} stdBrick elements: J2Plasticity soil + ElasticIsotropic footing and pier, two element "
+                "batches (BASELINE configs[4]; its quads cannot share a Domain with bricks here: one ndf per model)")
     if workload == "frame3d":
         return (f"3D RC space frame {n}x{n} bays x {max(1, round(3.8 * n))} storeys, forceBeamColumn (ForceBeamColumn3d) + FiberSection3d "
                 "Steel02/Concrete02, transient Newmark terms (BASELINE configs[3])")
@@ -314,7 +319,19 @@ def ours_main(a):
         D.set_mass(spec.node_tags, mass)
         D.setup(xb.NUMBERER_PLAIN, xb.SOE_SPARSE_GEN_COL, world, rank)
     else:
-        D = xb.DeviceModel.from_spec(spec, xb.NUMBERER_PLAIN, xb.SOE_SPARSE_GEN_COL, world, rank, options=opts)
+        part, part_info = None, None
+        if a.partition == "metis" and world > 1:
+            # DomainPartitioner's way: METIS_PartGraphKway (the reference's own OTHER/METIS, compiled by oracle/ref_build.mk)
+            # on Domain::buildEleGraph's element graph, computed on rank 0 and handed to every rank as part[e]
+            from modelspec import have_metis, metis_partition
+            box = [None]
+            if rank == 0:
+                if not have_metis():
+                    raise SystemExit("--partition metis needs oracle/_ref/libmetis_ref.so (python -c 'import __graft_entry__ as g; g.build()')")
+                tm = time.time(); box[0] = metis_partition(spec, world, fast=True); part_info = {"metis_s": time.time() - tm}
+            dist.broadcast_object_list(box, 0)
+            part = box[0]
+        D = xb.DeviceModel.from_spec(spec, xb.NUMBERER_PLAIN, xb.SOE_SPARSE_GEN_COL, world, rank, part, options=opts)
     t_setup = time.time() - t0
     stream = torch.cuda.Stream()          # a real (non-default) stream: the kernels and the events share it
     torch.cuda.set_stream(stream)
@@ -332,7 +349,7 @@ def ours_main(a):
         clocks.start()
     ids = D.ids()
     u = displacement_field_for(spec, spec.crd[D.node_tags() - 1], a.workload); u[ids < 0] = 0.0
-    nip = {"brick": 8, "quad": 4, "frame": 5, "frame3d": 4}[a.workload]
+    nip = {"brick": 8, "soil": 8, "quad": 4, "frame": 5, "frame3d": 4}[a.workload]
     ngp_global, ne_global = spec.ne * nip, spec.ne
     del spec
     if is_frame:
@@ -546,6 +563,17 @@ def ours_main(a):
            "note": "xb_set_trial_disp(host u) + xb_update + xb_form_unbalance(host B) + xb_form_tangent(host A), pinned "
                    "host buffers; every rank moves its own nodes' u in and its owned rows of A, B out (bytes summed over ranks)"}
 
+    # load balance of the partition: elements, owned rows and interface rows received per rank
+    balance = None
+    if world > 1:
+        mine = torch.tensor([float(D.ne), float(D.nrows), float(sum(int(c[5]) for _, c in D.peers()))], device="cuda", dtype=torch.float64)
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        arr = np.array([v.cpu().numpy() for v in allv])
+        balance = {"elements_per_rank": arr[:, 0].astype(int).tolist(), "rows_per_rank": arr[:, 1].astype(int).tolist(),
+                   "interface_chunks_in_per_rank": arr[:, 2].astype(int).tolist(),
+                   "elements_max_over_mean": float(arr[:, 0].max() / arr[:, 0].mean()),
+                   "interface_chunks_max_over_mean": float(arr[:, 2].max() / max(arr[:, 2].mean(), 1.0))}
     cb = None
     if not a.no_cpu_baseline and world == 1 and a.workload == "brick":
         cb, _ = cpu_arm(a.cpu_steps, 1, 1, a.cpu_sample)
@@ -576,8 +604,11 @@ def ours_main(a):
                 "config": {"workload": workload_name(n, a.workload), "elements": int(ne_global), "gauss_points": int(ngp_global),
                            "equations": int(D.neq), "rank0": {"elements": int(D.ne), "rows": int(D.nrows), "nnz": int(D.nnz),
                                                               "peers": [[int(r), int(c[0]), int(c[1])] for r, c in D.peers()]},
-                           "partition": "none" if world == 1 else f"recursive coordinate bisection, {world} parts, "
-                                        "interface rows exchanged with NCCL send/recv",
+                           "partition": "none" if world == 1 else (
+                               (f"METIS k-way ({world} parts, METIS_PartGraphKway of the reference's OTHER/METIS on the element graph, "
+                                "computed on rank 0)" if a.partition == "metis" else f"recursive coordinate bisection, {world} parts")
+                               + ", interface rows exchanged with NCCL send/recv"),
+                           "balance": balance,
                            "numberer": "Plain", "soe": "SparseGenCol (CSC)",
                            "l2": "inputs larger than L2 (per GPU at N=1: state 7 GB, element matrices 19 GB, A 8 GB vs 126 MB)",
                            "setup_s": {"mesh": t_mesh, "host_setup": t_setup, "upload": t_upload}},
@@ -605,7 +636,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", "--size", dest="n", type=int, default=None, help="size parameter of the workload; default: brick 160 (4.096M elements), "
                                                         "quad 1000, frame 200, frame3d 20")
-    ap.add_argument("--workload", default="brick", choices=["brick", "quad", "frame", "frame3d"],
+    ap.add_argument("--partition", default="rcb", choices=["rcb", "metis"],
+                    help="N > 1: the library's recursive coordinate bisection, or METIS k-way as DomainPartitioner uses it")
+    ap.add_argument("--workload", default="brick", choices=["brick", "quad", "frame", "frame3d", "soil"],
                     help="brick = the headline workload; quad / frame = secondary lines (profiles/), n = cells per side")
     ap.add_argument("--e2e-steps", type=int, default=3, help="0 skips the end-to-end leg (profiling runs only)")
     ap.add_argument("--cpu-sample", type=int, default=22, help="CPU arm sample: elements per side")
@@ -619,7 +652,7 @@ def main():
     ap.add_argument("--solve-n", type=int, default=16, help="size of the block whose linear solve is timed (out of path; 0 = skip)")
     a = ap.parse_args()
     if a.n is None:
-        a.n = {"brick": 160, "quad": 1000, "frame": 200, "frame3d": 20}[a.workload]
+        a.n = {"brick": 160, "quad": 1000, "frame": 200, "frame3d": 20, "soil": 100}[a.workload]
     if a.selftest:
         selftest_main(a)
     elif a.impl == "reference":

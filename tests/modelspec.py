@@ -388,11 +388,26 @@ def element_graph(spec):
     return np.array(xadj, np.int32), np.array(adjncy, np.int32)
 
 
-def metis_partition(spec, nparts):
+def element_graph_fast(spec):
+    """the same graph through a sparse product (node-element incidence N: the pattern of N^T N without its diagonal),
+    for meshes of 10^6 elements where the set-based walk above takes minutes"""
+    import scipy.sparse as sp
+    tags = np.concatenate([g.tags for g in spec.groups])
+    order = np.argsort(tags, kind="stable")
+    conn = np.concatenate([g.conn for g in spec.groups])[order]
+    ne, nen = conn.shape
+    _, nid = np.unique(conn.ravel(), return_inverse=True)
+    N = sp.csr_matrix((np.ones(ne * nen, np.int8), (nid, np.repeat(np.arange(ne), nen))), shape=(nid.max() + 1, ne))
+    A = (N.T @ N).tocsr()
+    A.setdiag(0); A.eliminate_zeros(); A.sort_indices()
+    return A.indptr.astype(np.int32), A.indices.astype(np.int32)
+
+
+def metis_partition(spec, nparts, fast=False):
     """what graph/partitioner/Metis.cpp:320 does for DomainPartitioner: METIS_PartGraphKway (METIS 4 from the
     reference's OTHER/METIS, default options, no weights) on the element graph; part[e] in FE_Element order"""
     L = ctypes.CDLL(METIS_SO)
-    xadj, adjncy = element_graph(spec)
+    xadj, adjncy = element_graph_fast(spec) if fast else element_graph(spec)
     n = ctypes.c_int(len(xadj) - 1); wf = ctypes.c_int(0); nf = ctypes.c_int(0); npart = ctypes.c_int(nparts)
     options = (ctypes.c_int * 5)(0, 0, 0, 0, 0); edgecut = ctypes.c_int(0)
     part = np.zeros(len(xadj) - 1, np.int32)
