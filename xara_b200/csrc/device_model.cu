@@ -53,6 +53,7 @@ struct GroupView {
   double* rec;          // stdBrick: symmetric element records [n][324] (brick_rec.hpp)
   double* sendK;        // rows for nodes other ranks own (interface exchange send buffer)
   int cps;              // columns per row in a slot (cp_stride)
+  int ns;               // dofs per node of the MODEL (stride of U, V, A): a quad's 2-dof nodes may sit in an ndf = 3 model
   double* Re;           // [n][nd]
 };
 
@@ -478,7 +479,7 @@ __global__ void __launch_bounds__(128) quad_update_kernel(GroupView G, const dou
   for (int a = 0; a < 4; a++) {
     const int nd = __ldg(c + a);
     xc[a][0] = __ldg(X + (size_t)nd * 2); xc[a][1] = __ldg(X + (size_t)nd * 2 + 1);
-    u[0][a] = __ldg(U + (size_t)nd * 2); u[1][a] = __ldg(U + (size_t)nd * 2 + 1);
+    u[0][a] = __ldg(U + (size_t)nd * G.ns); u[1][a] = __ldg(U + (size_t)nd * G.ns + 1);
   }
   double xi, eta, shp[3][4];
   quad_point(g, xi, eta);
@@ -577,7 +578,7 @@ __global__ void __launch_bounds__(128, DYN ? 1 : 5) quad_resid_kernel(GroupView 
 #pragma unroll
     for (int a = 0; a < 4; a++) {
       const int nd = __ldg(c + a);
-      vel[a][0] = __ldg(V + (size_t)nd * 2); vel[a][1] = __ldg(V + (size_t)nd * 2 + 1);
+      vel[a][0] = __ldg(V + (size_t)nd * G.ns); vel[a][1] = __ldg(V + (size_t)nd * G.ns + 1);
     }
   }
 #pragma unroll
@@ -651,7 +652,7 @@ __global__ void __launch_bounds__(128, DYN ? 1 : 5) quad_resid_kernel(GroupView 
     for (int a = 0; a < 4; a++) {
       const int nd = __ldg(c + a);
 #pragma unroll
-      for (int q = 0; q < 2; q++) P[2 * a + q] += md[a] * (__ldg(A + (size_t)nd * 2 + q) + dc.aM * vel[a][q]);
+      for (int q = 0; q < 2; q++) P[2 * a + q] += md[a] * (__ldg(A + (size_t)nd * G.ns + q) + dc.aM * vel[a][q]);
     }
   }
   double* out = G.Re + e * 8;
@@ -1696,6 +1697,7 @@ void xb_model_destroy(xb_model* m) {
 
 int xb_add_nodes(xb_model* m, int n, const int* tags, const double* crd) { HOSTCALL(m->h.add_nodes(n, tags, crd)); }
 int xb_add_sp(xb_model* m, int n, const int* t, const int* d) { HOSTCALL(m->h.add_sp(n, t, d)); }
+int xb_set_node_ndf(xb_model* m, int n, const int* t, int ndf) { HOSTCALL(m->h.set_node_ndf(n, t, ndf)); }
 int xb_add_equal_dof(xb_model* m, int r, int c, int n, const int* dofs) { HOSTCALL(m->h.add_equal_dof(r, c, n, dofs)); }
 int xb_add_nd_material(xb_model* m, int tag, int kind, const double* par, int npar) { HOSTCALL(m->h.add_material(tag, kind, par, npar)); }
 int xb_add_uniaxial_material(xb_model* m, int tag, int kind, const double* par, int npar) { HOSTCALL(m->h.add_uniaxial(tag, kind, par, npar)); }
@@ -1997,7 +1999,7 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
     }
     long long* kdst = nullptr;
     CU(dev_upload(m, &kdst, g.kdst));
-    d.v.kdst = kdst; d.v.KeN = m->dKe; d.v.cps = h.cp_stride;
+    d.v.kdst = kdst; d.v.KeN = m->dKe; d.v.cps = h.cp_stride; d.v.ns = h.ndf;
     d.v.rec = h.rec_mode ? m->dRec + g.rec_off : nullptr;
     d.v.Re = m->dRe + g.re_off;
     d.re_off = g.re_off;

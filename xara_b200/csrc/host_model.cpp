@@ -41,6 +41,13 @@ int HostModel::add_sp(int n, const int* tags, const int* dofs) {
   return XB_OK;
 }
 
+int HostModel::set_node_ndf(int n, const int* tags, int nd) {
+  if (is_setup) { err = "xb_set_node_ndf after xb_setup"; return XB_ERR_STATE; }
+  if (nd < 1 || nd > ndf) { err = "xb_set_node_ndf: a node has between 1 and the model's ndf dofs"; return XB_ERR_ARG; }
+  for (int i = 0; i < n; i++) { ndf_node.push_back(tags[i]); ndf_val.push_back(nd); }
+  return XB_OK;
+}
+
 int HostModel::add_material(int tag, int kind, const double* par, int npar) {
   int need = kind == XB_MAT_J2PLASTICITY ? 7 : (kind == XB_MAT_ELASTIC_ISOTROPIC ? 2 : -1);
   if (need < 0) { err = "xb_add_nd_material: unknown kind"; return XB_ERR_ARG; }
@@ -128,7 +135,7 @@ int HostModel::add_elements(int kind, int n, const int* tags, const int* conn, c
   if (is_setup) { err = "xb_add_elements after xb_setup"; return XB_ERR_STATE; }
   if (kind != XB_ELE_STDBRICK && kind != XB_ELE_FOURNODEQUAD && kind != XB_ELE_FORCEBEAMCOLUMN2D && kind != XB_ELE_FORCEBEAMCOLUMN3D) { err = "xb_add_elements: unknown kind"; return XB_ERR_ARG; }
   const EleKind& k = ele_kind(kind);
-  if (k.ndf != ndf) { err = "xb_add_elements: element dofs per node differ from the model's ndf"; return XB_ERR_UNSUPPORTED; }
+  if (k.ndf > ndf) { err = "xb_add_elements: the element has more dofs per node than the model's ndf"; return XB_ERR_UNSUPPORTED; }
   if (kind == XB_ELE_FORCEBEAMCOLUMN2D || kind == XB_ELE_FORCEBEAMCOLUMN3D) {
     const bool b3 = kind == XB_ELE_FORCEBEAMCOLUMN3D;
     if (!b3 && (ndm != 2 || par_stride < 3)) { err = "forceBeamColumn (2D): ndm must be 2 and par = nIP, maxIters, tol"; return XB_ERR_ARG; }
@@ -352,6 +359,27 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
     int ix = nidx(sp_node[i]);
     if (ix < 0) { err = "fix references an unknown node tag"; return XB_ERR_ARG; }
     gid[(size_t)ix * ndf + sp_dof[i]] = -1;
+  }
+  // nodes with fewer dofs than the model's ndf: the missing ones never exist (no equation)
+  std::vector<uint8_t> nndf(n_nodes, (uint8_t)ndf);
+  for (size_t i = 0; i < ndf_node.size(); i++) {
+    const int ix = nidx(ndf_node[i]);
+    if (ix < 0) { err = "xb_set_node_ndf references an unknown node tag"; return XB_ERR_ARG; }
+    nndf[ix] = (uint8_t)ndf_val[i];
+    for (int j = ndf_val[i]; j < ndf; j++) gid[(size_t)ix * ndf + j] = -1;
+  }
+  // an element's nodes carry exactly the element's dofs per node (FourNodeQuad.cpp:133-139, Brick, ForceBeamColumn2d/3d)
+  for (auto& g : groups) {
+    const EleKind& k = ele_kind(g.kind);
+    long long wrong = 0;
+    const long long mconn = (long long)g.conn.size();
+#pragma omp parallel for reduction(+ : wrong) schedule(static)
+    for (long long i = 0; i < mconn; i++) if (nndf[g.conn[i]] != k.ndf) wrong++;
+    if (wrong) { err = "an element is connected to a node whose number of dofs differs from the element's (xb_set_node_ndf)"; return XB_ERR_ARG; }
+  }
+  for (size_t i = 0; i < sp_node.size(); i++) {
+    const int ix = nidx(sp_node[i]);
+    if (ix >= 0 && sp_dof[i] >= nndf[ix]) { err = "fix: dof beyond the node's number of dofs"; return XB_ERR_ARG; }
   }
   // MP_Constraints with an identity matrix (equalDOF): constrained dofs get -4 unless already constrained
   // (PlainHandler.cpp:129-176 warns and keeps the SP)

@@ -90,6 +90,11 @@ struct HostModel {
   std::vector<int> node_tag;        // ascending
   std::vector<double> crd;          // [nn][ndm]
   std::vector<int> sp_node, sp_dof; // fix
+  // nodes created under another `model -ndf` (a FourNodeQuad's 2-dof nodes beside 3-dof frame nodes, FourNodeQuad.cpp:
+  // 133-139): (tag, dofs) pairs; every other node has the model's ndf.  The dofs a node does not have are carried as
+  // constrained (-1): they get no equation, exactly as the node's shorter DOF_Group::myID in the reference
+  std::vector<int> ndf_node, ndf_val;
+  int set_node_ndf(int n, const int* tags, int nd);
   std::vector<Material> mats;
   std::vector<Uniaxial> unis;
   std::vector<FiberSectionDef> secs;
