@@ -98,6 +98,12 @@ void xb_model_destroy(xb_model*);
 int xb_add_nodes(xb_model*, int n, const int* tags, const double* crd);
 /* Domain::addSP_Constraint (Domain.cpp:636) -- homogeneous `fix`; dof is 0-based */
 int xb_add_sp(xb_model*, int n, const int* node_tags, const int* dofs);
+/* Nodes created under another `model -ndf` than the model's: they carry ndf (< the model's) dofs -- a FourNodeQuad's
+ * 2-dof nodes (FourNodeQuad.cpp:133-139 insists on them) beside the 3-dof nodes of a frame, tied with `equalDOF`.  The
+ * dofs such a node does not have get no equation (its DOF_Group::myID is simply shorter in the reference); every
+ * [nn][ndf] array of this interface keeps the model's ndf as its stride.  An element must be connected to nodes that
+ * carry exactly its dofs per node (xb_setup returns XB_ERR_ARG otherwise). */
+int xb_set_node_ndf(xb_model*, int n, const int* node_tags, int ndf);
 /* Domain::addMP_Constraint (Domain.cpp:739) for `equalDOF rNode cNode dofs...`
  * (runtime/commands/domain/constraint.cpp): an MP_Constraint with an identity constraint matrix, the only kind
  * PlainHandler accepts (PlainHandler.cpp:129-176).  The n (0-based) dofs of the constrained node take the

@@ -86,6 +86,13 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
       for (int d = 0; d < m->ndm; d++) crd.push_back(c(d));
     } }
   if (xb_add_nodes(x, (int)tags.size(), tags.data(), crd.data()) < 0) { G.err = xb_last_error(); return -2; }
+  // nodes created under another `model -ndf` (a quad's 2-dof nodes in a 3-dof frame model)
+  { NodeIter& ni = dom->getNodes(); Node* nd;
+    while ((nd = ni()) != nullptr) {
+      const int k = nd->getNumberDOF(), t = nd->getTag();
+      if (k > m->ndf) { G.err = "glue: a node with more dofs than the model's ndf"; return -2; }
+      if (k < m->ndf && xb_set_node_ndf(x, 1, &t, k) < 0) { G.err = xb_last_error(); return -2; }
+    } }
   // 2. SP constraints
   std::vector<int> spn, spd;
   { SP_ConstraintIter& si = dom->getDomainAndLoadPatternSPs(); SP_Constraint* sp;
@@ -295,7 +302,7 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
   for (size_t i = 0; i < xt.size(); i++) {
     const ID& rid = dom->getNode(xt[i])->getDOF_GroupPtr()->getID();
     for (int d = 0; d < m->ndf; d++)
-      if (rid(d) != ids[i * m->ndf + d]) { G.err = "glue: DOF numbering differs from the reference's"; return -10; }
+      if ((d < rid.Size() ? rid(d) : -1) != ids[i * m->ndf + d]) { G.err = "glue: DOF numbering differs from the reference's"; return -10; }
   }
   if (xb_device_init(x, device, nullptr) < 0) { G.err = xb_last_error(); return -11; }
   return neq;

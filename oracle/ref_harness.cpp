@@ -203,6 +203,13 @@ int ref_add_node(void* h, int tag, const double* x) {
   return m->domain->addNode(n) ? 0 : -1;
 }
 
+// a node created under another `model -ndf` (e.g. a FourNodeQuad's 2-dof node in a model whose frame nodes have 3)
+int ref_add_node_ndf(void* h, int tag, const double* x, int ndf) {
+  RefModel* m = (RefModel*)h;
+  Node* n = (m->ndm == 2) ? new Node(tag, ndf, x[0], x[1]) : new Node(tag, ndf, x[0], x[1], x[2]);
+  return m->domain->addNode(n) ? 0 : -1;
+}
+
 int ref_fix(void* h, int nodeTag, int dof) {
   RefModel* m = (RefModel*)h;
   SP_Constraint* sp = new SP_Constraint(nodeTag, dof, 0.0, true);
@@ -338,8 +345,10 @@ int ref_add_load(void* h, int nodeTag, const double* vals) {
     lp->setTimeSeries(new LinearSeries());
     m->domain->addLoadPattern(lp);
   }
-  Vector v(m->ndf);
-  for (int i = 0; i < m->ndf; i++) v(i) = vals[i];
+  Node* node = m->domain->getNode(nodeTag);
+  const int nd = node ? node->getNumberDOF() : m->ndf;       // (a node may carry fewer dofs than the model's ndf)
+  Vector v(nd);
+  for (int i = 0; i < nd; i++) v(i) = vals[i];
   NodalLoad* nl = new NodalLoad(m->nloads++, nodeTag, v);
   return m->domain->addNodalLoad(nl, 1) ? 0 : -1;
 }
@@ -496,10 +505,10 @@ void ref_get_csr(void* h, int* rowStart, int* colA) {
 // then Domain::update -> Element::update (state determination)
 int ref_set_trial_disp(void* h, int n, const int* tags, const double* u) {
   RefModel* m = (RefModel*)h;
-  Vector v(m->ndf);
   for (int i = 0; i < n; i++) {
     Node* nd = m->domain->getNode(tags[i]);
-    for (int j = 0; j < m->ndf; j++) v(j) = u[(size_t)i * m->ndf + j];
+    Vector v(nd->getNumberDOF());
+    for (int j = 0; j < v.Size(); j++) v(j) = u[(size_t)i * m->ndf + j];
     nd->setTrialDisp(v);
   }
   return m->domain->update();
@@ -509,7 +518,7 @@ int ref_get_trial_disp(void* h, int n, const int* tags, double* u) {
   RefModel* m = (RefModel*)h;
   for (int i = 0; i < n; i++) {
     const Vector& d = m->domain->getNode(tags[i])->getTrialDisp();
-    for (int j = 0; j < m->ndf; j++) u[(size_t)i * m->ndf + j] = d(j);
+    for (int j = 0; j < m->ndf; j++) u[(size_t)i * m->ndf + j] = j < d.Size() ? d(j) : 0.0;
   }
   return 0;
 }

@@ -1258,6 +1258,7 @@ typedef struct {
   int nsec; OrcSecDef* sec;           /* fibre section definitions */
   double* load;                       /* [nn][ndf] reference nodal loads (pattern 1, Linear series) */
   int* fixed;                         /* [nn][ndf] 1 when an SP_Constraint holds the dof */
+  int* node_ndf;                      /* [nn] dofs the node really has (<= ndf): a FourNodeQuad's 2-dof nodes next to 3-dof frame nodes */
   int nmp; int* mp;                   /* equalDOF: (retained node, constrained node, dof) index triples */
   int nmat; int* mat_tag; int* mat_kind; double* mat_par; /* [nmat][8] */
   int ne, ecap; OrcEle* ele;          /* ascending element tag after setup */
@@ -1293,8 +1294,17 @@ void* orc_model_new(int ndm, int ndf, int nn, const int* tags, const double* crd
   m->c1 = 1.0; m->c2 = 0.0; m->c3 = 0.0;
   m->load = (double*)calloc((size_t)nn * ndf, sizeof(double));
   m->fixed = (int*)calloc((size_t)nn * ndf, sizeof(int));
+  m->node_ndf = (int*)malloc(sizeof(int) * (nn > 0 ? nn : 1));
+  for (int i = 0; i < nn; i++) m->node_ndf[i] = ndf;
   m->mat_tag = NULL; m->nmat = 0;
   return m;
+}
+/* a node created under another `model -ndf`: it has nd <= ndf dofs; its DOF_Group::myID has nd entries (DOF_Group.cpp),
+ * the missing ones never get an equation.  The nodal arrays keep the model's stride. */
+int orc_set_node_ndf(void* h, int nodeTag, int nd) {
+  OrcModel* m = (OrcModel*)h; int n = find_node(m, nodeTag);
+  if (n < 0 || nd < 1 || nd > m->ndf) return -1;
+  m->node_ndf[n] = nd; return 0;
 }
 int orc_fix(void* h, int nodeTag, int dof) {
   OrcModel* m = (OrcModel*)h; int n = find_node(m, nodeTag);
@@ -1513,7 +1523,10 @@ int orc_setup(void* h, int numberer, int soe_kind) {
   int nn = m->nn, ndf = m->ndf;
   qsort(m->ele, m->ne, sizeof(OrcEle), cmp_ele); /* Domain element map iterates by tag */
   m->id = (int*)malloc(sizeof(int) * nn * ndf);
-  for (int i = 0; i < nn * ndf; i++) m->id[i] = m->fixed[i] ? -1 : -2;
+  for (int i = 0; i < nn * ndf; i++) m->id[i] = (m->fixed[i] || i % ndf >= m->node_ndf[i / ndf]) ? -1 : -2;
+  /* FourNodeQuad.cpp:133-139 (and Brick / ForceBeamColumn alike): the element's nodes must carry its dofs per node */
+  for (int e = 0; e < m->ne; e++)
+    for (int i = 0; i < m->ele[e].nen; i++) if (m->node_ndf[m->ele[e].node[i]] != m->ele[e].ndf_e) return -7;
   for (int i = 0; i < m->nmp; i++) {       /* PlainHandler: -4 unless the dof is already constrained (then a warning) */
     int* idc = &m->id[m->mp[3 * i + 1] * ndf + m->mp[3 * i + 2]];
     if (*idc == -2) *idc = -4;
@@ -1615,7 +1628,7 @@ int orc_num_ele(void* h) { return ((OrcModel*)h)->ne; }
 /* FE_Element::setID (FE_Element.cpp:209-231): element dof -> equation */
 static int ele_ids(const OrcModel* m, const OrcEle* el, int* ids) {
   int n = 0;
-  for (int i = 0; i < el->nen; i++) for (int j = 0; j < m->ndf; j++) ids[n++] = m->id[el->node[i] * m->ndf + j];
+  for (int i = 0; i < el->nen; i++) for (int j = 0; j < el->ndf_e; j++) ids[n++] = m->id[el->node[i] * m->ndf + j];
   return n;
 }
 /* FE ids in FE_Element order, [ne][stride] */
@@ -2359,5 +2372,5 @@ void orc_model_free(void* h) {
   OrcModel* m = (OrcModel*)h; if (!m) return;
   free(m->node_tag); free(m->crd); free(m->trial); free(m->commit_disp); free(m->load); free(m->fixed);
   free(m->mat_tag); free(m->mat_kind); free(m->mat_par); free(m->ele); free(m->id); free(m->ptr); free(m->idx);
-  free(m->A); free(m->B); free(m->iDiagLoc); free(m->Astore); free(m);
+  free(m->A); free(m->B); free(m->iDiagLoc); free(m->Astore); free(m->node_ndf); free(m);
 }

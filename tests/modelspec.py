@@ -55,6 +55,7 @@ class ModelSpec:
     equal_dofs: list = field(default_factory=list)  # `equalDOF`: (retained node tag, constrained node tag, [dofs], 0-based)
     sections: list = field(default_factory=list)    # (tag, y[nf], A[nf], uniaxial tags[nf])
     beam_loads: list = field(default_factory=list)  # `eleLoad -beamUniform`: (element tag, wy, wz, wa) in the Linear pattern
+    node_ndf: dict = field(default_factory=dict)    # node tag -> dofs, for nodes created under another `model -ndf` (< the model's ndf)
 
     @property
     def nn(self):
@@ -215,6 +216,43 @@ def rc_section3d(tag=1, h=24.0, b=18.0, cover=1.5, ny=6, nz=4, As=0.6, GJ=2.0e6)
                 continue
             y.append(yy); z.append(zz); A.append(As); m.append(3)
     return (tag, np.array(y), np.array(A), np.array(m, np.int32), np.array(z), GJ)
+
+
+def soil_frame_2d(nbay=2, nstory=2, ndiv=1, per_bay=3, ny=4, depth=240.0, mat=J2_STEEL, distort=0.1, seed=7, lateral=8.0, gravity=-30.0):
+    """BASELINE configs[4] in 2D, as a real mixed-ndf Domain: a FourNodeQuad soil layer whose nodes were created under
+    `model -ndf 2` carrying an RC frame of forceBeamColumn elements on 3-dof nodes (`model -ndf 3`); every column base
+    sits on a soil surface node and follows it in both translations (`equalDOF soil base 1 2`), its rotation fixed.
+    Soil base fixed, soil sides free; loads on the frame's floor nodes."""
+    fr = frame2d(nbay, nstory, ndiv, lateral=lateral, gravity=gravity)
+    bay = 360.0
+    nx = nbay * per_bay + 2 * per_bay                      # one bay of free field on either side
+    lx = (nbay + 2) * bay
+    so = quad_plane(nx, ny, mat=mat, lx=lx, ly=depth, distort=0.0, body=(0.0, -0.002))
+    rng = np.random.default_rng(seed)
+    scrd = so.crd.copy()
+    inner = (scrd[:, 1] > 1e-9) & (scrd[:, 1] < depth - 1e-9)
+    scrd[inner] += distort * min(lx / nx, depth / ny) * (rng.random((inner.sum(), 2)) - 0.5)
+    ns = so.nn
+    off_n, off_e = ns, so.ne                               # frame node / element tags follow the soil's
+    fcrd = fr.crd + np.array([bay, depth])                 # the frame stands on the soil surface, one bay in
+    tags = np.concatenate([so.node_tags, fr.node_tags + off_n]).astype(np.int32)
+    crd = np.vstack([scrd, fcrd])
+    fix = [(int(t), d) for t in so.node_tags[scrd[:, 1] < 1e-9] for d in range(2)]
+    eq = []
+    for t, (x, y) in zip(fr.node_tags, fr.crd):
+        if y == 0.0:                                       # a column base: tie to the soil node under it, fix the rotation
+            k = int(np.argmin(np.abs(scrd[:, 0] - (x + bay)) + np.abs(scrd[:, 1] - depth)))
+            assert abs(scrd[k, 0] - (x + bay)) < 1e-6 and abs(scrd[k, 1] - depth) < 1e-6
+            eq.append((int(so.node_tags[k]), int(t) + off_n, [0, 1]))
+            fix.append((int(t) + off_n, 2))
+    g0, g1 = so.groups[0], fr.groups[0]
+    groups = [ElementGroup(ELE_QUAD, g0.tags, g0.conn, g0.mat, g0.par),
+              ElementGroup(ELE_FBC2D, g1.tags + off_e, g1.conn + off_n, g1.mat, g1.par)]
+    loads = fr.loads.copy(); loads[:, 0] += off_n
+    spec = ModelSpec(2, 3, tags, crd, np.array(fix, np.int32).reshape(-1, 2), so.materials, groups, loads,
+                     uniaxials=fr.uniaxials, equal_dofs=eq, sections=fr.sections)
+    spec.node_ndf = {int(t): 2 for t in so.node_tags}
+    return spec
 
 
 def with_beam_gravity(spec, w=-0.25, axial=0.02, seed=0):
@@ -499,6 +537,8 @@ class OracleBackend(_Backend):
         crd = np.ascontiguousarray(spec.crd, np.float64)
         self.h = ctypes.c_void_p(L.orc_model_new(spec.ndm, spec.ndf, spec.nn, _p(tags), _p(crd)))
         assert self.h, "node tags must ascend"
+        for t, nd in spec.node_ndf.items():
+            assert L.orc_set_node_ndf(self.h, int(t), int(nd)) == 0
         for t, d in spec.fix:
             assert L.orc_fix(self.h, int(t), int(d)) == 0
         for r, c, dofs in spec.equal_dofs:
@@ -692,7 +732,10 @@ class RefBackend(_Backend):
         self.tags = np.ascontiguousarray(spec.node_tags, np.int32)
         for t, x in zip(spec.node_tags, spec.crd):
             xx = np.zeros(3); xx[:spec.ndm] = x
-            assert L.ref_add_node(self.h, int(t), _p(xx)) == 0
+            if int(t) in spec.node_ndf:
+                assert L.ref_add_node_ndf(self.h, int(t), _p(xx), int(spec.node_ndf[int(t)])) == 0
+            else:
+                assert L.ref_add_node(self.h, int(t), _p(xx)) == 0
         for t, d in spec.fix:
             assert L.ref_fix(self.h, int(t), int(d)) == 0
         for r, c, dofs in spec.equal_dofs:
@@ -764,6 +807,7 @@ class RefBackend(_Backend):
         a = np.zeros((self.spec.nn, self.spec.ndf), np.int32)
         row = np.zeros(self.spec.ndf, np.int32)
         for i, t in enumerate(self.spec.node_tags):
+            row[:] = -1                                        # (a node with fewer dofs fills its first entries only)
             self.L.ref_node_ids(self.h, int(t), _p(row)); a[i] = row
         return a
 

@@ -199,7 +199,7 @@ def test_newton_iteration_counts_match_oracle(shape):
 
 
 @pytest.mark.skipif(not (have_ref() and have_glue()), reason="oracle/_ref not built (needs /root/reference)")
-@pytest.mark.parametrize("shape,numberer,soe", [("brick", 1, 0), ("quad", 0, 1), ("mixed", 1, 1), ("soilcolumn_equaldof", 1, 0), ("frame2d_gravity", 1, 0),
+@pytest.mark.parametrize("shape,numberer,soe", [("brick", 1, 0), ("quad", 0, 1), ("mixed", 1, 1), ("soilcolumn_equaldof", 1, 0), ("frame2d_gravity", 1, 0), ("soil_frame_mixed_ndf", 1, 0),
                                                 ("soilcolumn_equaldof", 0, 1)])
 def test_reference_newton_loop_drives_device_path(shape, numberer, soe):
     """The drop-in, end to end: the REFERENCE'S OWN StaticAnalysis objects (AnalysisModel, PlainHandler, numberer,
@@ -214,6 +214,10 @@ def test_reference_newton_loop_drives_device_path(shape, numberer, soe):
     elif shape == "quad":
         def mk():
             sp = quad_plane(16, 4, mat=J2_STEEL, lx=8.0, ly=2.0); sp.loads[:, 1:] = [0.0, -10.0]; return sp
+    elif shape == "soil_frame_mixed_ndf":
+        def mk():   # quads on 2-dof nodes + force beams on 3-dof nodes, read out of the reference's Domain node by node
+            from modelspec import soil_frame_2d
+            sp = soil_frame_2d(lateral=35.0, gravity=-80.0); return sp
     elif shape == "frame2d_gravity":
         def mk():   # `eleLoad -beamUniform` on the girders read out of the load pattern, pushed well into the inelastic range
             from modelspec import with_beam_gravity
@@ -651,6 +655,43 @@ def test_beam_uniform_element_loads_device_vs_oracle(dim):
     check()
     O.apply_load(0.5); O.set_trial_disp(0.3 * u); D.apply_load(0.5); D.set_trial_disp(0.3 * u); D.update()
     check()
+
+
+@pytest.mark.parametrize("numberer,soe", [(0, 0), (1, 1), (1, 2)])
+def test_mixed_ndf_soil_frame_device_vs_oracle(numberer, soe):
+    """BASELINE configs[4] as a real mixed-ndf Domain on the device: FourNodeQuad / J2 soil on 2-dof nodes, a forceBeamColumn
+    RC frame on 3-dof nodes, `equalDOF` at the column bases (shared rows), two element batches of different dofs per node in
+    one assembly -- A, B, element forces against the oracle (pinned to the live reference) over a load history with commits
+    and a revert; also into BandGeneral storage"""
+    from modelspec import soil_frame_2d
+    rng = np.random.default_rng(11)
+    spec = soil_frame_2d(nbay=2, nstory=3, ndiv=2, per_bay=4, ny=5)
+    O = OracleBackend(spec, numberer, soe)
+    D = xb.DeviceModel.from_spec(spec, numberer, soe).to_device(0)
+    ids = O.ids()
+    assert np.array_equal(D.ids(), ids)
+    nq = len(spec.groups[0].tags)
+    sc = np.array((0.02, 0.02, 2e-4))
+
+    def check():
+        assert relerr(D.form_tangent(), O.form_tangent()) < BEAM_RTOL
+        assert relerr(D.form_unbalance(), O.form_unbalance()) < BEAM_RTOL
+        for e, nd in ((0, 8), (nq - 1, 8), (nq, 6), (O.ne - 1, 6)):
+            assert relerr(D.element_tangent(e, nd), O.ele_tangent(e, nd)) < BEAM_RTOL
+            assert relerr(D.element_resid(e, nd), O.ele_resid(e, nd)) < BEAM_RTOL
+
+    check()
+    for s_ in range(4):
+        u = rng.normal(0, 1.0, (spec.nn, 3)) * sc * 0.3 * (s_ + 1); u[ids < 0] = 0
+        tie(spec, u)
+        O.set_trial_disp(u); D.set_trial_disp(u); D.update()
+        O.apply_load(0.25 * (s_ + 1)); D.apply_load(0.25 * (s_ + 1))
+        check()
+        if s_ == 2:
+            O.revert(); D.revert_to_last_commit()
+            check()
+        else:
+            O.commit(); D.commit()
 
 
 def test_launch_and_byte_accounting():

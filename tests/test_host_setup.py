@@ -254,3 +254,23 @@ def test_band_profile_umfpack_layout_and_scatter_maps_bit_exact(numberer, soe):
             assert np.array_equal(D.profile(), O.profile())
         for e in range(O.ne):
             assert np.array_equal(D.scatter_map(e, e + 1, nd).reshape(nd, nd), O.scatter_map(e, nd))
+
+
+@pytest.mark.parametrize("numberer,soe", [(0, 0), (1, 1), (1, 2)])
+def test_mixed_ndf_soil_frame_bit_exact(numberer, soe):
+    """a FourNodeQuad soil layer on 2-dof nodes carrying a forceBeamColumn frame on 3-dof nodes (`equalDOF` at the column
+    bases): DOF ids, pattern and every element's addA locations against the oracle (pinned to the live reference in
+    tests/test_oracle.py::test_mixed_ndf_soil_frame_vs_live_reference); elements on nodes of the wrong size are refused"""
+    from modelspec import soil_frame_2d
+    spec = soil_frame_2d()
+    O = OracleBackend(spec, numberer, soe)
+    D = xb.DeviceModel.from_spec(spec, numberer, soe)
+    assert D.neq == O.neq and np.array_equal(D.ids(), O.ids())
+    assert all(np.array_equal(a, b) for a, b in zip(D.pattern(), O.csr()))
+    nq = len(spec.groups[0].tags)
+    for e in range(O.ne):
+        nd = 8 if e < nq else 6
+        assert np.array_equal(D.scatter_map(e, e + 1, nd).reshape(nd, nd), O.scatter_map(e, nd))
+    bad = soil_frame_2d(); bad.node_ndf = {}                      # quads on 3-dof nodes: FourNodeQuad.cpp:133-139 says no
+    with pytest.raises(xb.XaraB200Error, match="number of dofs"):
+        xb.DeviceModel.from_spec(bad, numberer, soe)

@@ -326,3 +326,31 @@ def test_displacement_control_vs_golden(name):
     assert close(O._u, g["u"], 1e-9)
     for s, h in enumerate(hist):
         assert np.allclose(h[:-1], g["norms"][s, :len(h) - 1], rtol=1e-5, atol=1e-12)
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("numberer,soe", [(0, 0), (1, 1)])
+def test_mixed_ndf_soil_frame_vs_live_reference(numberer, soe):
+    """BASELINE configs[4] as a real mixed-ndf Domain: FourNodeQuad soil on 2-dof nodes (FourNodeQuad.cpp:133-139 accepts
+    nothing else) carrying a forceBeamColumn frame on 3-dof nodes, the column bases tied to the soil surface with
+    `equalDOF`.  DOF ids, FE_Element ids, pattern bit-exact; A, B to rounding over a load history."""
+    from modelspec import soil_frame_2d
+    rng = np.random.default_rng(11)
+    spec = soil_frame_2d()
+    O, R = OracleBackend(spec, numberer, soe), RefBackend(spec, numberer, soe)
+    assert O.neq == R.neq and O.nnz == R.nnz
+    ids = O.ids()
+    assert np.array_equal(ids, R.ids())
+    assert (ids[[i for i, t in enumerate(spec.node_tags) if int(t) in spec.node_ndf], 2] == -1).all()   # no third dof on soil nodes
+    assert all(np.array_equal(a, b) for a, b in zip(O.csr(), R.csr()))
+    to, io = O.fe_ids(8); tr, ir = R.fe_ids(8)
+    assert len(to) == len(tr) and np.array_equal(io, ir)          # (FE_Element tags count from 0, element tags from 1)
+    sc = np.array((0.02, 0.02, 2e-4))
+    for s in range(3):
+        u = rng.normal(0, 1.0, (spec.nn, 3)) * sc * 0.3 * (s + 1); u[ids < 0] = 0
+        tie(spec, u)
+        O.set_trial_disp(u); R.set_trial_disp(u)
+        O.apply_load(0.3 * (s + 1)); R.apply_load(0.3 * (s + 1))
+        assert close(O.form_tangent(), R.form_tangent(), 1e-11)
+        assert close(O.form_unbalance(), R.form_unbalance(), 1e-11)
+        O.commit(); R.commit()

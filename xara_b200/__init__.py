@@ -59,6 +59,7 @@ def _load():
         "xb_model_create": (vp, [i32, i32]),
         "xb_model_destroy": (None, [vp]),
         "xb_add_nodes": (i32, [vp, i32, vp, vp]),
+        "xb_set_node_ndf": (i32, [vp, i32, vp, i32]),
         "xb_add_sp": (i32, [vp, i32, vp, vp]),
         "xb_add_equal_dof": (i32, [vp, i32, i32, i32, vp]),
         "xb_add_nd_material": (i32, [vp, i32, i32, vp, i32]),
@@ -236,6 +237,11 @@ class DeviceModel:
         assert w.ndim == 2 and w.shape[1] == 3 and len(w) == len(ele_tags)
         self._ck(lib.xb_add_beam_uniform_loads(self._h, len(ele_tags), _ptr(ele_tags), _ptr(w)))
 
+    def set_node_ndf(self, node_tags, ndf):
+        """nodes created under another `model -ndf`: they carry `ndf` (< the model's) dofs"""
+        node_tags = _i32(node_tags)
+        self._ck(lib.xb_set_node_ndf(self._h, len(node_tags), _ptr(node_tags), int(ndf)))
+
     def add_nodal_loads(self, node_tags, values):
         node_tags, values = _i32(node_tags), _f64(values)
         self._ck(lib.xb_add_nodal_loads(self._h, len(node_tags), _ptr(node_tags), _ptr(values)))
@@ -248,6 +254,9 @@ class DeviceModel:
         for k, v in (options or {}).items():
             m.set_option(k, v)
         m.add_nodes(spec.node_tags, spec.crd)
+        nn_ = getattr(spec, "node_ndf", {})
+        for nd in sorted(set(nn_.values())):
+            m.set_node_ndf([t for t, v in nn_.items() if v == nd], nd)
         if len(spec.fix):
             m.fix(spec.fix[:, 0], spec.fix[:, 1])
         for r, c, dofs in getattr(spec, "equal_dofs", []):
