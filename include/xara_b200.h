@@ -41,7 +41,9 @@ enum {
 /* uniaxialMaterial kinds (fibres of a fibre section) */
 enum {
   XB_UNI_STEEL02 = 0,   /* material/uniaxial/steel/Steel02.h:47: Fy,E0,b,R0,cR1,cR2,a1,a2,a3,a4[,sigInit] */
-  XB_UNI_CONCRETE02 = 1 /* material/uniaxial/concrete/Concrete02.cpp:93: fc,epsc0,fcu,epscu,rat,ft,Ets     */
+  XB_UNI_CONCRETE02 = 1,/* material/uniaxial/concrete/Concrete02.cpp:93: fc,epsc0,fcu,epscu,rat,ft,Ets     */
+  XB_UNI_STEEL01 = 2,   /* material/uniaxial/steel/Steel01.cpp:40: fy,E0,b,a1,a2,a3,a4 (the command's defaults 0,55,0,55) */
+  XB_UNI_ELASTIC = 3    /* material/uniaxial/ElasticMaterial.cpp:96: E[,eta,Eneg]; eta must be 0 (no strain rate on this path) */
 };
 
 /* element kinds */
@@ -113,11 +115,16 @@ int xb_set_node_ndf(xb_model*, int n, const int* node_tags, int ndf);
 int xb_add_equal_dof(xb_model*, int retained_node_tag, int constrained_node_tag, int n, const int* dofs);
 /* OPS nDMaterial command; par has npar doubles in the order listed at the kind */
 int xb_add_nd_material(xb_model*, int tag, int kind, const double* par, int npar);
-/* uniaxialMaterial Steel02 | Concrete02 (runtime/commands/modeling/uniaxial.cpp) */
+/* uniaxialMaterial Steel02 | Concrete02 | Steel01 | Elastic (runtime/commands/modeling/uniaxial.cpp) */
 int xb_add_uniaxial_material(xb_model*, int tag, int kind, const double* par, int npar);
 /* section Fiber -> FiberSection2d (material/section/FiberSection2d.cpp:99 addFiber): nf fibres
  * (y, A, uniaxial material tag) in the order given; the centroid is computed as the command does */
 int xb_add_fiber_section(xb_model*, int tag, int nf, const double* y, const double* A, const int* mat_tags);
+/* section Aggregator tag mat1 P mat2 Mz -> SectionAggregator without a base section (material/section/
+ * SectionAggregator.cpp:119, :316 setTrialSectionDeformation, :419 getSectionFlexibility): n uniaxial materials, one
+ * per section response; codes as in SectionForceDeformation.h (2 = P, 1 = Mz).  A 2D forceBeamColumn takes the pair
+ * (P, Mz) in that order -- BASELINE configs[0]'s section; anything else returns XB_ERR_UNSUPPORTED */
+int xb_add_section_aggregator(xb_model*, int tag, int n, const int* mat_tags, const int* codes);
 /* section Fiber tag -GJ gj in a 3D model -> FiberSection3d (material/section/FiberSection3d.cpp:294 addFiber,
  * runtime/commands/modeling/section.cpp:497): fibres (y, z, A, uniaxial tag), response P, Mz, My and an
  * elastic torsion GJ */
@@ -238,6 +245,14 @@ int xb_get_trial_vel_accel(xb_model*, double* v, double* a);
 int xb_update(xb_model*);
 /* AnalysisModel::applyLoadDomain(lambda) for the Linear-series pattern */
 int xb_apply_load(xb_model*, double lambda);
+/* `loadConst` (Domain::setLoadConstant, domain/domain/Domain.cpp; LoadPattern::setLoadConstant, domain/pattern/
+ * LoadPattern.cpp): the nodal loads applied so far stay at the current load factor; the reference load vector is
+ * emptied for the next pattern.  The caller sets the new domain time with xb_apply_load (`loadConst -time 0.0`).
+ * Element loads in a constant pattern return XB_ERR_UNSUPPORTED. */
+int xb_load_const(xb_model*);
+/* `pattern Plain tag Linear { load node values... }` defined after the set-up (the pushover pattern that follows
+ * loadConst): values [n][ndf] are added to the reference loads of the nodes */
+int xb_set_nodal_loads(xb_model*, int n, const int* node_tags, const double* values);
 /* IncrementalIntegrator::formTangent(CURRENT_TANGENT), analysis/integrator/
  * IncrementalIntegrator.cpp:74.  A (nnz doubles, host) may be NULL to keep A resident. */
 int xb_form_tangent(xb_model*, double* A);

@@ -41,6 +41,8 @@
 #include <FiberSection2d.h>
 #include <FiberSection3d.h>
 #include <Steel02.h>
+#include <Steel01.h>
+#include <SectionAggregator.h>
 #include <Concrete02.h>
 #include <ElasticMaterial.h>
 #include <LinearCrdTransf2d.h>
@@ -68,12 +70,50 @@ namespace {
 struct Glue {
   xb_model* x = nullptr;
   std::string err;
+  int numberer = -1, soeKind = -1;
+  std::map<int, int> pattern_state;    // load pattern tag -> 0 live at the last set-up, 1 frozen
 };
 std::map<void*, Glue> g_glue;
+
+// A second `analysis` on a Domain that already lives on the device (configs[0]: gravity under LoadControl, `loadConst
+// -time 0`, then the pushover under DisplacementControl): the element state stays where it is; the load patterns that
+// were frozen since the last set-up become the device's constant loads, the new patterns its reference loads.
+int reattach_xb(RefModel* m, int numberer, int soeKind, Glue& G) {
+  if (numberer != G.numberer || soeKind != G.soeKind) { G.err = "glue: a later analysis must keep the numberer and the system of the first"; return -12; }
+  Domain* dom = m->domain;
+  bool froze = false;
+  std::vector<int> nt; std::vector<double> nv;
+  { LoadPatternIter& pi = dom->getLoadPatterns(); LoadPattern* lp;
+    while ((lp = pi()) != nullptr) {
+      const int tag = lp->getTag();
+      const auto it = G.pattern_state.find(tag);
+      if (it != G.pattern_state.end()) {
+        if (it->second == 0 && lp->isConstant) { froze = true; it->second = 1; }
+        else if (it->second == 0) { G.err = "glue: a live load pattern carried into a later analysis: freeze it with loadConst"; return -12; }
+        continue;
+      }
+      LinearSeries* ls = dynamic_cast<LinearSeries*>(lp->theSeries);
+      if (!ls || ls->cFactor != 1.0 || lp->isConstant) { G.err = "glue: new load pattern that is not a live Linear series: outside the device path"; return -12; }
+      { ElementalLoadIter& eli = lp->getElementalLoads(); if (eli() != nullptr) { G.err = "glue: element loads in a pattern added after the set-up"; return -12; } }
+      NodalLoadIter& li = lp->getNodalLoads(); NodalLoad* nl;
+      while ((nl = li()) != nullptr) {
+        int type; const Vector& v = nl->getData(type);
+        nt.push_back(nl->getNodeTag());
+        for (int d = 0; d < m->ndf; d++) nv.push_back(d < v.Size() ? v(d) : 0.0);
+      }
+      G.pattern_state[tag] = 0;
+    } }
+  if (froze && xb_load_const(G.x) < 0) { G.err = xb_last_error(); return -12; }
+  if (xb_apply_load(G.x, dom->getCurrentTime()) < 0) { G.err = xb_last_error(); return -12; }       // loadConst -time t
+  if (!nt.empty() && xb_set_nodal_loads(G.x, (int)nt.size(), nt.data(), nv.data()) < 0) { G.err = xb_last_error(); return -12; }
+  return 0;
+}
 
 // INTEGRATION.md "B200Assembler::domainChanged": the Domain -> xb_model
 int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
   Domain* dom = m->domain;
+  if (G.x) return reattach_xb(m, numberer, soeKind, G);
+  G.numberer = numberer; G.soeKind = soeKind;
   xb_model* x = xb_model_create(m->ndm, m->ndf);
   if (!x) { G.err = xb_last_error(); return -1; }
   G.x = x;
@@ -186,6 +226,14 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
               kind = XB_UNI_CONCRETE02; np = 7;
               const double q[7] = {c2->fc, c2->epsc0, c2->fcu, c2->epscu, c2->rat, c2->ft, c2->Ets};
               std::memcpy(p, q, sizeof q);
+            } else if (auto* s1 = dynamic_cast<Steel01*>(um)) {
+              kind = XB_UNI_STEEL01; np = 7;
+              const double q[7] = {s1->fy, s1->E0, s1->b, s1->a1, s1->a2, s1->a3, s1->a4};
+              std::memcpy(p, q, sizeof q);
+            } else if (auto* em = dynamic_cast<ElasticMaterial*>(um)) {
+              kind = XB_UNI_ELASTIC; np = 3;
+              const double q[3] = {em->Epos, em->eta, em->Eneg};
+              std::memcpy(p, q, sizeof q);
             } else return -1;
             if (xb_add_uniaxial_material(x, t, kind, p, np) < 0) return -1;
             unis_done[t] = 1;
@@ -208,7 +256,16 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
             auto* tor = dynamic_cast<ElasticMaterial*>(f3->theTorsion);
             if (!tor) { G.err = "glue: torsion other than an ElasticMaterial"; return -5; }
             if (xb_add_fiber_section3d(x, stag, (int)y.size(), y.data(), z.data(), A.data(), mt.data(), tor->getInitialTangent()) < 0) { G.err = xb_last_error(); return -6; }
-          } else { G.err = "glue: section other than a fibre section"; return -5; }
+          } else if (auto* ag = dynamic_cast<SectionAggregator*>(secs[0])) {
+            // section Aggregator of uniaxial materials only (configs[0]: Elastic on P, Steel01 on Mz)
+            if (ag->theSection) { G.err = "glue: section Aggregator on top of another section"; return -5; }
+            std::vector<int> codes;
+            for (int f = 0; f < ag->numMats; f++) {
+              const int t = uniaxial(ag->theAdditions[f]); if (t < 0) { G.err = "glue: unsupported material in a section Aggregator"; return -5; }
+              mt.push_back(t); codes.push_back((*ag->matCodes)(f));
+            }
+            if (xb_add_section_aggregator(x, stag, (int)mt.size(), mt.data(), codes.data()) < 0) { G.err = xb_last_error(); return -6; }
+          } else { G.err = "glue: section other than a fibre section or an Aggregator of uniaxial materials"; return -5; }
           secs_done[stag] = 1;
         }
         // one batch per (section, nIP, maxIters, tol): key them through the map's second index
@@ -244,7 +301,8 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
     while ((lp = pi()) != nullptr) {
       LinearSeries* ls = dynamic_cast<LinearSeries*>(lp->theSeries);
       if (!ls || ls->cFactor != 1.0) { G.err = "glue: load pattern whose TimeSeries is not Linear with factor 1: outside the device path"; return -7; }
-      if (lp->isConstant) { G.err = "glue: load pattern frozen by loadConst: outside the device path"; return -7; }
+      if (lp->isConstant) { G.err = "glue: load pattern frozen by loadConst before the first analysis: outside the device path"; return -7; }
+      G.pattern_state[lp->getTag()] = 0;
       { ElementalLoadIter& eli = lp->getElementalLoads(); ElementalLoad* el;
         while ((el = eli()) != nullptr) {   // `eleLoad -beamUniform` on the force beams goes along; every other element load is refused
           int type; const Vector& data = el->getData(type, 1.0);
@@ -289,7 +347,11 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
   const int neq = xb_setup(x, numberer, soeKind);
   if (neq < 0) { G.err = xb_last_error(); return -8; }
   if (neq != m->soe->getNumEqn()) { G.err = "glue: equation count differs from the reference's"; return -9; }
-  {   // xb_form_tangent writes xb_nnz doubles straight into the SOE's A: the two patterns must be the same
+  if (m->bsoe) {   // system BandGeneral: the band widths and the array length must be the reference's
+    int kl = -1, ku = -1;
+    xb_get_band(x, &kl, &ku);
+    if (kl != m->bsoe->sub() || ku != m->bsoe->super() || xb_a_size(x) != m->bsoe->asize()) { G.err = "glue: band widths differ from the reference BandGenLinSOE's"; return -9; }
+  } else {   // xb_form_tangent writes xb_nnz doubles straight into the SOE's A: the two patterns must be the same
     const long long nz = xb_nnz(x);
     if (nz != (long long)m->ptr()[neq]) { G.err = "glue: non-zero count differs from the reference SOE's"; return -9; }
     std::vector<long long> xp((size_t)neq + 1); std::vector<int> xi((size_t)nz);
@@ -315,8 +377,8 @@ class B200LoadControl : public LoadControl {
   xb_model* x = nullptr;
   RefModel* rm = nullptr;
   long calls[4] = {0, 0, 0, 0};
-  double* soeA() { return rm->rsoe ? rm->rsoe->A : rm->csoe->A; }
-  Vector& soeB() { return rm->rsoe ? rm->rsoe->B : rm->csoe->B; }
+  double* soeA() { return rm->bsoe ? rm->bsoe->a() : (rm->rsoe ? rm->rsoe->A : rm->csoe->A); }
+  Vector& soeB() { return rm->bsoe ? rm->bsoe->bvec() : (rm->rsoe ? rm->rsoe->B : rm->csoe->B); }
 
   int formTangent(int statFlag) override {
     if (statFlag != CURRENT_TANGENT) return LoadControl::formTangent(statFlag);
@@ -371,8 +433,8 @@ class B200DisplacementControl : public DisplacementControl {
   xb_model* x = nullptr;
   RefModel* rm = nullptr;
   long calls[4] = {0, 0, 0, 0};
-  double* soeA() { return rm->rsoe ? rm->rsoe->A : rm->csoe->A; }
-  Vector& soeB() { return rm->rsoe ? rm->rsoe->B : rm->csoe->B; }
+  double* soeA() { return rm->bsoe ? rm->bsoe->a() : (rm->rsoe ? rm->rsoe->A : rm->csoe->A); }
+  Vector& soeB() { return rm->bsoe ? rm->bsoe->bvec() : (rm->rsoe ? rm->rsoe->B : rm->csoe->B); }
   int push(const Vector& dU, double lambda) {          // incrDisp + applyLoadDomain + updateDomain
     AnalysisModel* am = this->getAnalysisModel();
     am->incrDisp(dU);
@@ -471,8 +533,8 @@ class B200Newmark : public Newmark {
   xb_model* x = nullptr;
   RefModel* rm = nullptr;
   long calls[4] = {0, 0, 0, 0};
-  double* soeA() { return rm->rsoe ? rm->rsoe->A : rm->csoe->A; }
-  Vector& soeB() { return rm->rsoe ? rm->rsoe->B : rm->csoe->B; }
+  double* soeA() { return rm->bsoe ? rm->bsoe->a() : (rm->rsoe ? rm->rsoe->A : rm->csoe->A); }
+  Vector& soeB() { return rm->bsoe ? rm->bsoe->bvec() : (rm->rsoe ? rm->rsoe->B : rm->csoe->B); }
 
   int newStep(double deltaT) override {                 // Newmark::newStep (Newmark.cpp:105), unknown = Displacement
     if (deltaT <= 0.0 || beta == 0 || U == nullptr || unknown != 1) return -1;

@@ -45,6 +45,9 @@
 #include <Steel02.h>
 #include <Concrete02.h>
 #include <FiberSection2d.h>
+#include <SectionAggregator.h>
+#include <Steel01.h>
+#include <ElasticMaterial.h>
 #include <FiberSection3d.h>
 #include <ElasticMaterial.h>
 #include <ForceBeamColumn3d.h>
@@ -153,6 +156,34 @@ public:
   int recvSelf(int, Channel&, FEM_ObjectBroker&) override { return 0; }
 };
 
+// `system BandGeneral`: the reference's own BandGenLinSOE (its addA and storage are on the path); its LAPACK solver
+// (dgbsv) has no library here, so the solve -- outside the path -- expands the band and takes the dense route above.
+class BandSOE : public BandGenLinSOE {
+ public:
+  explicit BandSOE(BandGenLinSolver& s) : BandGenLinSOE(s) {}
+  int sub() const { return numSubD; } int super() const { return numSuperD; } int n() const { return size; }
+  double* a() { return A; } double* b() { return B; } double* x() { return X; } Vector& bvec() { return *vectB; }
+  long long asize() const { return (long long)size * (2 * numSubD + numSuperD + 1); }
+};
+class HarnessBandSolver : public BandGenLinSolver {
+ public:
+  HarnessBandSolver() : BandGenLinSolver(0) {}
+  int setSize() override { return 0; }
+  int solve() override {
+    BandSOE* S = static_cast<BandSOE*>(theSOE);
+    const int n = S->n(), kl = S->sub(), ku = S->super(), ldA = 2 * kl + ku + 1;
+    std::vector<int> ptr(n + 1), idx; std::vector<double> val;
+    for (int col = 0; col < n; col++) {            // BandGenLinSOE.cpp:208: (row, col) at A[col ldA + kl + ku - (col - row)]
+      ptr[col] = (int)idx.size();
+      for (int row = std::max(0, col - ku); row <= std::min(n - 1, col + kl); row++) { idx.push_back(row); val.push_back(S->a()[(size_t)col * ldA + kl + ku - (col - row)]); }
+    }
+    ptr[n] = (int)idx.size();
+    return dense_solve(n, ptr.data(), idx.data(), val.data(), true, S->b(), S->x());
+  }
+  int sendSelf(int, Channel&) override { return 0; }
+  int recvSelf(int, Channel&, FEM_ObjectBroker&) override { return 0; }
+};
+
 // SparseGenRowLinSOE leaves LinearSOE::setX pure (its definitions sit under
 // "#if 0" in SparseGenRowLinSOE.h:66); give it the obvious one so it can be built.
 class RowSOE : public SparseGenRowLinSOE {
@@ -167,7 +198,7 @@ struct RefModel {
   Domain* domain = nullptr;
   std::map<int, NDMaterial*> ndmats;
   std::map<int, UniaxialMaterial*> unimats;
-  std::map<int, FiberSection2d*> sections2d;
+  std::map<int, SectionForceDeformation*> sections2d;   // FiberSection2d or SectionAggregator
   std::map<int, FiberSection3d*> sections3d;
   AnalysisModel* amodel = nullptr;
   PlainHandler* handler = nullptr;
@@ -175,10 +206,12 @@ struct RefModel {
   LinearSOE* soe = nullptr;
   SparseGenRowLinSOE* rsoe = nullptr;   // soeKind 1
   SparseGenColLinSOE* csoe = nullptr;   // soeKind 0
-  int n() const { return rsoe ? rsoe->size : csoe->size; }
+  BandSOE* bsoe = nullptr;              // soeKind 2 (`system BandGeneral`): no sparse pattern, ptr() / idx() do not apply
+  int cur_pattern = 1;                  // the load pattern ref_add_load fills
+  int n() const { return bsoe ? bsoe->n() : (rsoe ? rsoe->size : csoe->size); }
   const int* ptr() const { return rsoe ? rsoe->rowStartA : csoe->colStartA; }
   const int* idx() const { return rsoe ? rsoe->colA : csoe->rowA; }
-  const double* A() const { return rsoe ? rsoe->A : csoe->A; }
+  const double* A() const { return bsoe ? bsoe->a() : (rsoe ? rsoe->A : csoe->A); }
   IncrementalIntegrator* integ = nullptr;
   StaticIntegrator* sinteg = nullptr;
   TransientIntegrator* tinteg = nullptr;
@@ -257,8 +290,11 @@ int ref_add_quad(void* h, int tag, const int* nd, int matTag, double thick, int 
   return m->domain->addElement(e) ? 0 : -1;
 }
 
-// kind 0: Steel02 (Fy,E0,b,R0,cR1,cR2,a1,a2,a3,a4,sigInit); kind 1: Concrete02 (fc,epsc0,fcu,epscu,rat,ft,Ets)
+// kind 0: Steel02 (Fy,E0,b,R0,cR1,cR2,a1,a2,a3,a4,sigInit); kind 1: Concrete02 (fc,epsc0,fcu,epscu,rat,ft,Ets);
+// kind 2: Steel01 (fy,E0,b,a1,a2,a3,a4); kind 3: Elastic (E,eta,Eneg)
 static UniaxialMaterial* make_uniaxial(int tag, int kind, const double* p) {
+  if (kind == 2) return new Steel01(tag, p[0], p[1], p[2], p[3], p[4], p[5], p[6]);
+  if (kind == 3) return new ElasticMaterial(tag, p[0], p[1], p[2]);
   if (kind == 0) return new Steel02(tag, p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8], p[9], p[10]);
   if (kind == 1) return new Concrete02(tag, p[0], p[1], p[2], p[3], p[4], p[5], p[6]);
   return nullptr;
@@ -277,6 +313,15 @@ int ref_add_fiber_section(void* h, int tag, int nf, const double* y, const doubl
   for (int i = 0; i < nf; i++)
     if (s->addFiber(*m->unimats.at(matTags[i]), A[i], y[i]) < 0) return -1;
   m->sections2d[tag] = s;
+  return 0;
+}
+// section Aggregator tag mat1 code1 mat2 code2 ... (no base section): SectionAggregator.cpp:119
+int ref_add_section_aggregator(void* h, int tag, int n, const int* matTags, const int* codes) {
+  RefModel* m = (RefModel*)h;
+  std::vector<UniaxialMaterial*> adds(n);
+  ID code(n);
+  for (int i = 0; i < n; i++) { adds[i] = m->unimats.at(matTags[i]); code(i) = codes[i]; }
+  m->sections2d[tag] = new SectionAggregator(tag, n, adds.data(), code);
   return 0;
 }
 // element forceBeamColumn (2D): Lobatto integration, Linear transformation, nIP copies of one section
@@ -328,8 +373,8 @@ int ref_uni_path(int kind, const double* p, int n, const double* strains, const 
 // `eleLoad -ele tag -type -beamUniform wy [wz] wa` in pattern 1 (Linear series)
 int ref_add_beam_uniform_load(void* h, int eleTag, double wy, double wz, double wa) {
   RefModel* m = (RefModel*)h;
-  if (m->domain->getLoadPattern(1) == nullptr) {
-    LoadPattern* lp = new LoadPattern(1);
+  if (m->domain->getLoadPattern(m->cur_pattern) == nullptr) {
+    LoadPattern* lp = new LoadPattern(m->cur_pattern);
     lp->setTimeSeries(new LinearSeries());
     m->domain->addLoadPattern(lp);
   }
@@ -340,8 +385,8 @@ int ref_add_beam_uniform_load(void* h, int eleTag, double wy, double wz, double 
 
 int ref_add_load(void* h, int nodeTag, const double* vals) {
   RefModel* m = (RefModel*)h;
-  if (m->domain->getLoadPattern(1) == nullptr) {
-    LoadPattern* lp = new LoadPattern(1);
+  if (m->domain->getLoadPattern(m->cur_pattern) == nullptr) {
+    LoadPattern* lp = new LoadPattern(m->cur_pattern);
     lp->setTimeSeries(new LinearSeries());
     m->domain->addLoadPattern(lp);
   }
@@ -350,7 +395,17 @@ int ref_add_load(void* h, int nodeTag, const double* vals) {
   Vector v(nd);
   for (int i = 0; i < nd; i++) v(i) = vals[i];
   NodalLoad* nl = new NodalLoad(m->nloads++, nodeTag, v);
-  return m->domain->addNodalLoad(nl, 1) ? 0 : -1;
+  return m->domain->addNodalLoad(nl, m->cur_pattern) ? 0 : -1;
+}
+// `loadConst -time t` (runtime/commands/domain/...: Domain::setLoadConstant, setCurrentTime, setCommittedTime); the next
+// ref_add_load opens a new `pattern Plain n Linear`
+int ref_load_const(void* h, double time) {
+  RefModel* m = (RefModel*)h;
+  m->domain->setLoadConstant();
+  m->domain->setCurrentTime(time);
+  m->domain->setCommittedTime(time);
+  m->cur_pattern++;
+  return 0;
 }
 
 // restates BasicAnalysisBuilder::domainChanged (BasicAnalysisBuilder.cpp:225-300)
@@ -441,7 +496,9 @@ static int ref_setup_common(RefModel* m, int numberer, int soeKind, int testKind
   m->handler = new PlainHandler();
   if (numberer == 0) m->numberer = new PlainNumberer();
   else { RCM* rcm = new RCM(false); m->numberer = new DOF_Numberer(*rcm); }
-  if (soeKind == 1) { m->rsoe = new RowSOE(*new HarnessRowSolver()); m->soe = m->rsoe; }
+  m->rsoe = nullptr; m->csoe = nullptr; m->bsoe = nullptr;     // (a second `analysis` on the same Domain starts over)
+  if (soeKind == 2) { m->bsoe = new BandSOE(*new HarnessBandSolver()); m->soe = m->bsoe; }
+  else if (soeKind == 1) { m->rsoe = new RowSOE(*new HarnessRowSolver()); m->soe = m->rsoe; }
   else { m->csoe = new SparseGenColLinSOE(*new HarnessColSolver()); m->soe = m->csoe; }
   if (testKind == 0) m->test = new CTestNormDispIncr(tol, maxIter, 0);
   else if (testKind == 1) m->test = new CTestNormUnbalance(tol, maxIter, 0);
@@ -468,7 +525,7 @@ static int ref_setup_common(RefModel* m, int numberer, int soeKind, int testKind
 }
 
 int ref_num_eqn(void* h) { return ((RefModel*)h)->soe->getNumEqn(); }
-int ref_nnz(void* h) { RefModel* m = (RefModel*)h; return m->ptr()[m->n()]; }
+int ref_nnz(void* h) { RefModel* m = (RefModel*)h; return m->bsoe ? (int)m->bsoe->asize() : m->ptr()[m->n()]; }
 
 // equation ids of a node's DOF_Group (DOF_Group::getID)
 int ref_node_ids(void* h, int nodeTag, int* ids) {

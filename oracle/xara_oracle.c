@@ -21,7 +21,7 @@
 /* material kinds / element kinds shared with tests (mirrors include/xara_b200.h) */
 enum { ORC_MAT_ELASTIC_ISOTROPIC = 0, ORC_MAT_J2 = 1 };
 enum { ORC_ELE_BRICK = 0, ORC_ELE_QUAD = 1, ORC_ELE_FBC2D = 2, ORC_ELE_FBC3D = 3 };
-enum { ORC_UNI_STEEL02 = 0, ORC_UNI_CONCRETE02 = 1 };
+enum { ORC_UNI_STEEL02 = 0, ORC_UNI_CONCRETE02 = 1, ORC_UNI_STEEL01 = 2, ORC_UNI_ELASTIC = 3 };
 enum { ORC_ND_3D = 0, ORC_ND_PLANE_STRAIN = 1, ORC_ND_PLANE_STRESS = 2 };
 
 /* ======================================================================== */
@@ -449,6 +449,9 @@ typedef struct {
   double epsmin, epsmax, epspl, epss0, sigs0, epsr, sigr; int kon;
   /* Concrete02 history */
   double ecminP, deptP, ecmin, dept;
+  /* Steel01 (Steel01.h: fy, E0, b, a1..a4 above; history C* / T*) and ElasticMaterial (Epos, Eneg) */
+  double minStrainP, maxStrainP, shiftPP, shiftNP, minStrain, maxStrain, shiftP, shiftN; int loadingP, loading;
+  double Epos, Eneg;
   /* common */
   double eP, sigP, epsP, e, sig, eps;
 } OrcUni;
@@ -464,6 +467,16 @@ static void uni_init(OrcUni* m, int kind, const double* p) {
     m->konP = 0; m->epsmaxP = m->Fy / m->E0; m->epsminP = -m->epsmaxP;
     m->epsplP = 0.0; m->epss0P = 0.0; m->sigs0P = 0.0; m->epssrP = 0.0; m->sigsrP = 0.0;
     if (m->sigini != 0.0) { m->epsP = m->sigini / m->E0; m->sigP = m->sigini; }
+  } else if (kind == ORC_UNI_STEEL01) {
+    /* Steel01::Steel01 + revertToStart, Steel01.cpp:40-54, 284-311: p = fy, E0, b, a1, a2, a3, a4 */
+    m->Fy = p[0]; m->E0 = p[1]; m->b = p[2]; m->a1 = p[3]; m->a2 = p[4]; m->a3 = p[5]; m->a4 = p[6];
+    m->minStrainP = m->maxStrainP = 0.0; m->shiftPP = m->shiftNP = 1.0; m->loadingP = 0;
+    m->minStrain = m->maxStrain = 0.0; m->shiftP = m->shiftN = 1.0; m->loading = 0;
+    m->epsP = 0.0; m->sigP = 0.0; m->eP = m->E0; m->eps = 0.0; m->sig = 0.0; m->e = m->E0;
+  } else if (kind == ORC_UNI_ELASTIC) {
+    /* ElasticMaterial(tag, E, eta, Eneg), ElasticMaterial.cpp:96-110: p = E, eta (0 here: no strain rate in this path), Eneg */
+    m->Epos = p[0]; m->Eneg = p[2];
+    m->e = m->eP = m->Epos > m->Eneg ? m->Epos : m->Eneg;
   } else {
     m->fc = p[0]; m->epsc0 = p[1]; m->fcu = p[2]; m->epscu = p[3]; m->rat = p[4]; m->ft = p[5]; m->Ets = p[6];
     m->ecminP = 0.0; m->deptP = 0.0;
@@ -476,6 +489,8 @@ static void uni_init(OrcUni* m, int kind, const double* p) {
   }
 }
 static double uni_initial_tangent(const OrcUni* m) {
+  if (m->kind == ORC_UNI_STEEL01) return m->E0;                                   /* Steel01.h getInitialTangent */
+  if (m->kind == ORC_UNI_ELASTIC) return m->Epos > m->Eneg ? m->Epos : m->Eneg;   /* ElasticMaterial.cpp:186 */
   return m->kind == ORC_UNI_STEEL02 ? m->E0 : 2.0 * m->fc / m->epsc0;   /* Steel02.cpp:107, Concrete02.cpp:161 */
 }
 
@@ -586,7 +601,49 @@ static int concrete02_set_trial(OrcUni* m, double trialStrain) {
   }
   return 0;
 }
+/* Steel01::setTrialStrain + determineTrialState, Steel01.cpp:68-89, 122-196 */
+static int steel01_set_trial(OrcUni* m, double strain) {
+  m->minStrain = m->minStrainP; m->maxStrain = m->maxStrainP; m->shiftP = m->shiftPP; m->shiftN = m->shiftNP;
+  m->loading = m->loadingP; m->eps = m->epsP; m->sig = m->sigP; m->e = m->eP;
+  const double dStrain = strain - m->epsP;
+  if (!(fabs(dStrain) > DBL_EPSILON)) return 0;
+  m->eps = strain;
+  const double fy = m->Fy, E0 = m->E0, b = m->b;
+  double fyOneMinusB = fy * (1.0 - b);
+  double Esh = b * E0;
+  double epsy = fy / E0;
+  double c1 = Esh * m->eps;
+  double c2 = m->shiftN * fyOneMinusB;
+  double c3 = m->shiftP * fyOneMinusB;
+  double c = m->sigP + E0 * dStrain;
+  double c1c3 = c1 + c3;
+  if (c1c3 < c) m->sig = c1c3; else m->sig = c;
+  double c1c2 = c1 - c2;
+  if (c1c2 > m->sig) m->sig = c1c2;
+  if (fabs(m->sig - c) < DBL_EPSILON) m->e = E0; else m->e = Esh;
+  if (m->loading == 0 && dStrain != 0.0) m->loading = dStrain > 0.0 ? 1 : -1;
+  if (m->loading == 1 && dStrain < 0.0) {
+    m->loading = -1;
+    if (m->epsP > m->maxStrain) m->maxStrain = m->epsP;
+    m->shiftN = 1 + m->a1 * pow((m->maxStrain - m->minStrain) / (2.0 * m->a2 * epsy), 0.8);
+  }
+  if (m->loading == -1 && dStrain > 0.0) {
+    m->loading = 1;
+    if (m->epsP < m->minStrain) m->minStrain = m->epsP;
+    m->shiftP = 1 + m->a3 * pow((m->maxStrain - m->minStrain) / (2.0 * m->a4 * epsy), 0.8);
+  }
+  return 0;
+}
+/* ElasticMaterial::setTrialStrain / getStress / getTangent, ElasticMaterial.cpp:137-182 (eta = 0) */
+static int elastic_set_trial(OrcUni* m, double strain) {
+  m->eps = strain;
+  m->sig = strain >= 0.0 ? m->Epos * strain : m->Eneg * strain;
+  m->e = strain > 0.0 ? m->Epos : (strain < 0.0 ? m->Eneg : (m->Epos > m->Eneg ? m->Epos : m->Eneg));
+  return 0;
+}
 static int uni_set_trial(OrcUni* m, double strain) {
+  if (m->kind == ORC_UNI_STEEL01) return steel01_set_trial(m, strain);
+  if (m->kind == ORC_UNI_ELASTIC) return elastic_set_trial(m, strain);
   return m->kind == ORC_UNI_STEEL02 ? steel02_set_trial(m, strain) : concrete02_set_trial(m, strain);
 }
 /* commitState / revertToLastCommit: Steel02.cpp:248-285, Concrete02.cpp:292-320 */
@@ -594,13 +651,19 @@ static void uni_commit(OrcUni* m) {
   if (m->kind == ORC_UNI_STEEL02) {
     m->epsminP = m->epsmin; m->epsmaxP = m->epsmax; m->epsplP = m->epspl; m->epss0P = m->epss0;
     m->sigs0P = m->sigs0; m->epssrP = m->epsr; m->sigsrP = m->sigr; m->konP = m->kon;
-  } else { m->ecminP = m->ecmin; m->deptP = m->dept; }
+  } else if (m->kind == ORC_UNI_STEEL01) {   /* Steel01.cpp:244-262 */
+    m->minStrainP = m->minStrain; m->maxStrainP = m->maxStrain; m->shiftPP = m->shiftP; m->shiftNP = m->shiftN; m->loadingP = m->loading;
+  } else if (m->kind == ORC_UNI_CONCRETE02) { m->ecminP = m->ecmin; m->deptP = m->dept; }
   m->eP = m->e; m->sigP = m->sig; m->epsP = m->eps;
 }
 static void uni_revert(OrcUni* m) {
   if (m->kind == ORC_UNI_STEEL02) {
     m->epsmin = m->epsminP; m->epsmax = m->epsmaxP; m->epspl = m->epsplP; m->epss0 = m->epss0P;
     m->sigs0 = m->sigs0P; m->epsr = m->epssrP; m->sigr = m->sigsrP; m->kon = m->konP;
+  } else if (m->kind == ORC_UNI_STEEL01) {   /* Steel01.cpp:264-281 */
+    m->minStrain = m->minStrainP; m->maxStrain = m->maxStrainP; m->shiftP = m->shiftPP; m->shiftN = m->shiftNP; m->loading = m->loadingP;
+  } else if (m->kind == ORC_UNI_ELASTIC) {   /* ElasticMaterial::revertToLastCommit: the committed strain; stress and tangent follow it */
+    elastic_set_trial(m, m->epsP); return;
   } else { m->ecmin = m->ecminP; m->dept = m->deptP; }
   m->e = m->eP; m->sig = m->sigP; m->eps = m->epsP;
 }
@@ -623,6 +686,8 @@ int orc_uni_path(int kind, const double* p, int n, const double* strains, const 
 typedef struct {
   int nf; double* y; double* A; OrcUni* mat; double yBar;
   double e[2], s[2], k[4];     /* kData column-major 2x2: k[0]=k00 k[1]=k10 k[2]=k01 k[3]=k11 */
+  int agg;                     /* section Aggregator of two uniaxial materials, codes P and Mz (SectionAggregator.cpp:119):
+                                  mat[0] takes the axial strain, mat[1] the curvature; no fibres */
 } OrcSec;
 
 /* FiberSection2d::setTrialSectionDeformation, FiberSection2d.cpp:225-262 */
@@ -631,6 +696,13 @@ static int sec_set_trial(OrcSec* S, const double* d) {
   S->k[0] = S->k[1] = S->k[2] = S->k[3] = 0.0; S->s[0] = S->s[1] = 0.0;
   const double d0 = d[0], d1 = d[1];
   int res = 0;
+  if (S->agg) {   /* SectionAggregator::setTrialSectionDeformation / getSectionTangent / getStressResultant, :316, :365, :483 */
+    res += uni_set_trial(&S->mat[0], d0);
+    res += uni_set_trial(&S->mat[1], d1);
+    S->k[0] = S->mat[0].e; S->k[3] = S->mat[1].e;
+    S->s[0] = S->mat[0].sig; S->s[1] = S->mat[1].sig;
+    return res;
+  }
   for (int i = 0; i < S->nf; i++) {
     const double y = S->y[i] - S->yBar, A = S->A[i];
     double strain = d0 - y * d1;
@@ -648,6 +720,11 @@ static int sec_set_trial(OrcSec* S, const double* d) {
 /* FiberSection2d::revertToLastCommit, FiberSection2d.cpp:376-408 (note sData is ASSIGNED, not summed) */
 static void sec_revert(OrcSec* S) {
   S->k[0] = S->k[1] = S->k[2] = S->k[3] = 0.0; S->s[0] = S->s[1] = 0.0;
+  if (S->agg) {   /* SectionAggregator::revertToLastCommit, :569: the materials only */
+    uni_revert(&S->mat[0]); uni_revert(&S->mat[1]);
+    S->k[0] = S->mat[0].e; S->k[3] = S->mat[1].e; S->s[0] = S->mat[0].sig; S->s[1] = S->mat[1].sig;
+    return;
+  }
   for (int i = 0; i < S->nf; i++) {
     const double y = S->y[i] - S->yBar, A = S->A[i];
     uni_revert(&S->mat[i]);
@@ -674,8 +751,23 @@ static void inv3(const double* a, double* ainv) {
   c[2] =  A[7]*A[11] - A[10]*A[8];  c[5] = -(A[4]*A[11] - A[10]*A[5]); c[8] =  A[4]*A[8] - A[7]*A[5];
   for (int i = 1; i <= 3; ++i) for (int j = 1; j <= 3; ++j) I[j + i * 3] = c[i + j * 3 - 4] / det;
 }
+/* the section's getSectionFlexibility: the inverse of the tangent (fibre section), or SectionAggregator's own
+ * (SectionAggregator.cpp:419-450): 1/k on the diagonal, 1e14 for a zero tangent */
+static void sec_flex(const OrcSec* S, double* f) {
+  if (S->agg) {
+    f[1] = f[2] = 0.0;
+    f[0] = S->k[0] == 0.0 ? 1.e14 : 1 / S->k[0];
+    f[3] = S->k[3] == 0.0 ? 1.e14 : 1 / S->k[3];
+    return;
+  }
+  inv2(S->k, f);
+}
 static void sec_initial_flex(const OrcSec* S, double* f) {   /* FiberSection2d::getInitialTangent + Invert */
   double k[4] = {0, 0, 0, 0};
+  if (S->agg) {   /* SectionAggregator::getInitialFlexibility, :454-479 */
+    f[1] = f[2] = 0.0; f[0] = 1.0 / uni_initial_tangent(&S->mat[0]); f[3] = 1.0 / uni_initial_tangent(&S->mat[1]);
+    return;
+  }
   for (int i = 0; i < S->nf; i++) {
     const double y = S->y[i] - S->yBar, A = S->A[i];
     double ks0 = uni_initial_tangent(&S->mat[i]) * A, ks1 = ks0 * -y;
@@ -790,7 +882,7 @@ static int beam_update(OrcBeam* b, const double* ug, const double* dug) {
           if (b->initialFlag != 0) { vsSub[i][0] += dvs[0]; vsSub[i][1] += dvs[1]; }
           if (sec_set_trial(S, vsSub[i]) < 0) return -1;
           SsrSub[i][0] = S->s[0]; SsrSub[i][1] = S->s[1];
-          inv2(S->k, fsSub[i]);
+          sec_flex(S, fsSub[i]);
           dSs[0] = Ss[0] - SsrSub[i][0]; dSs[1] = Ss[1] - SsrSub[i][1];
           dvs[0] = 0.0; dvs[1] = 0.0;
           for (int c = 0; c < 2; c++) for (int r = 0; r < 2; r++) dvs[r] += fsSub[i][r + 2 * c] * dSs[c];
@@ -890,7 +982,7 @@ static void beam_revert(OrcBeam* b) {
     sec_revert(&b->sec[i]);
     sec_set_trial(&b->sec[i], b->vs[i]);
     b->Ssr[i][0] = b->sec[i].s[0]; b->Ssr[i][1] = b->sec[i].s[1];
-    inv2(b->sec[i].k, b->fs[i]);
+    sec_flex(&b->sec[i], b->fs[i]);
   }
   memcpy(b->Se, b->Secommit, sizeof b->Se); memcpy(b->kv, b->kvcommit, sizeof b->kv);
   b->initialFlag = 0;
@@ -1242,7 +1334,7 @@ typedef struct {
   double* Kc;        /* Element::Kc (committed tangent), row-major nd x nd; allocated while betaKc != 0 */
 } OrcEle;
 
-typedef struct { int tag, nf; double* y; double* z; double* A; int* mat; double GJ; } OrcSecDef;
+typedef struct { int tag, nf; double* y; double* z; double* A; int* mat; double GJ; int agg; } OrcSecDef;
 
 typedef struct {
   int ndm, ndf;
@@ -1256,7 +1348,8 @@ typedef struct {
   double c1, c2, c3;                  /* TransientIntegrator coefficients (Newmark.cpp:117-140); 1,0,0 = static */
   int nuni; int* uni_tag; int* uni_kind; double* uni_par;   /* uniaxial materials [nuni][12] */
   int nsec; OrcSecDef* sec;           /* fibre section definitions */
-  double* load;                       /* [nn][ndf] reference nodal loads (pattern 1, Linear series) */
+  double* load;                       /* [nn][ndf] reference nodal loads (the current pattern, Linear series) */
+  double* cload;                      /* [nn][ndf] loads of the patterns frozen by loadConst (NULL: none) */
   int* fixed;                         /* [nn][ndf] 1 when an SP_Constraint holds the dof */
   int* node_ndf;                      /* [nn] dofs the node really has (<= ndf): a FourNodeQuad's 2-dof nodes next to 3-dof frame nodes */
   int nmp; int* mp;                   /* equalDOF: (retained node, constrained node, dof) index triples */
@@ -1370,14 +1463,14 @@ int orc_add_uniaxial(void* h, int tag, int kind, const double* p) {
   m->uni_par = (double*)realloc(m->uni_par, sizeof(double) * 12 * (m->nuni + 1));
   m->uni_tag[m->nuni] = tag; m->uni_kind[m->nuni] = kind;
   memset(m->uni_par + 12 * m->nuni, 0, 12 * sizeof(double));
-  memcpy(m->uni_par + 12 * m->nuni, p, sizeof(double) * (kind == ORC_UNI_STEEL02 ? 11 : 7));
+  memcpy(m->uni_par + 12 * m->nuni, p, sizeof(double) * (kind == ORC_UNI_STEEL02 ? 11 : (kind == ORC_UNI_ELASTIC ? 3 : 7)));
   m->nuni++; return 0;
 }
 int orc_add_fiber_section(void* h, int tag, int nf, const double* y, const double* A, const int* matTags) {
   OrcModel* m = (OrcModel*)h;
   m->sec = (OrcSecDef*)realloc(m->sec, sizeof(OrcSecDef) * (m->nsec + 1));
   OrcSecDef* d = &m->sec[m->nsec];
-  d->tag = tag; d->nf = nf; d->z = NULL; d->GJ = 0.0;
+  d->tag = tag; d->nf = nf; d->z = NULL; d->GJ = 0.0; d->agg = 0;
   d->y = (double*)malloc(sizeof(double) * nf); d->A = (double*)malloc(sizeof(double) * nf); d->mat = (int*)malloc(sizeof(int) * nf);
   memcpy(d->y, y, sizeof(double) * nf); memcpy(d->A, A, sizeof(double) * nf);
   for (int i = 0; i < nf; i++) {
@@ -1386,6 +1479,18 @@ int orc_add_fiber_section(void* h, int tag, int nf, const double* y, const doubl
     if (d->mat[i] < 0) return -1;
   }
   m->nsec++; return 0;
+}
+/* section Aggregator tag mat1 P mat2 Mz (runtime/commands/modeling/section.cpp -> SectionAggregator.cpp:119): two
+ * uniaxial materials, the first on the axial strain, the second on the curvature -- the order ForceBeamColumn2d's
+ * sections carry (codes: 2 = P, 1 = Mz, SectionForceDeformation.h) */
+int orc_add_section_aggregator(void* h, int tag, int n, const int* matTags, const int* codes) {
+  if (n != 2 || codes[0] != 2 || codes[1] != 1) return -2;
+  const double zero[2] = {0.0, 0.0}, one[2] = {1.0, 1.0};
+  int rc = orc_add_fiber_section(h, tag, 2, zero, one, matTags);
+  if (rc < 0) return rc;
+  OrcModel* m = (OrcModel*)h;
+  m->sec[m->nsec - 1].agg = 1;
+  return 0;
 }
 /* section Fiber tag -GJ gj { fiber y z A mat ... } in a 3D model: FiberSection3d */
 int orc_add_fiber_section3d(void* h, int tag, int nf, const double* y, const double* z, const double* A, const int* matTags, double GJ) {
@@ -1428,13 +1533,14 @@ static OrcBeam* beam2_build(OrcModel* m, OrcEle* e, int sd, const double* par) {
   const OrcSecDef* d = &m->sec[sd];
   for (int i = 0; i < b->nip; i++) {
     OrcSec* S = &b->sec[i];
-    S->nf = d->nf; S->y = d->y; S->A = d->A;
+    S->nf = d->nf; S->y = d->y; S->A = d->A; S->agg = d->agg;
     S->mat = (OrcUni*)malloc(sizeof(OrcUni) * d->nf);
     double ABar = 0.0, QzBar = 0.0;
     for (int f = 0; f < d->nf; f++) {
       uni_init(&S->mat[f], m->uni_kind[d->mat[f]], m->uni_par + 12 * d->mat[f]);
       ABar += d->A[f]; QzBar += d->y[f] * d->A[f]; S->yBar = QzBar / ABar;   /* FiberSection2d::addFiber */
     }
+    if (S->agg) { S->yBar = 0.0; S->k[0] = S->mat[0].e; S->k[3] = S->mat[1].e; }
   }
   /* LinearCrdTransf2d::computeElemtLengthAndOrient */
   double dx0 = m->crd[e->node[1] * 2] - m->crd[e->node[0] * 2], dx1 = m->crd[e->node[1] * 2 + 1] - m->crd[e->node[0] * 2 + 1];
@@ -1495,6 +1601,16 @@ int orc_add_element(void* h, int kind, int tag, const int* nodeTags, int matTag,
 int orc_add_load(void* h, int nodeTag, const double* v) {
   OrcModel* m = (OrcModel*)h; int n = find_node(m, nodeTag); if (n < 0) return -1;
   for (int i = 0; i < m->ndf; i++) m->load[n * m->ndf + i] += v[i];
+  return 0;
+}
+
+/* loadConst (Domain::setLoadConstant): the loads applied so far keep their current factor; the next pattern starts empty.
+ * orc_add_load then fills that pattern. */
+int orc_load_const(void* h) {
+  OrcModel* m = (OrcModel*)h;
+  const size_t n = (size_t)m->nn * m->ndf;
+  if (!m->cload) m->cload = (double*)calloc(n ? n : 1, sizeof(double));
+  for (size_t i = 0; i < n; i++) { m->cload[i] = m->cload[i] + m->load[i] * m->lambda; m->load[i] = 0.0; }
   return 0;
 }
 
@@ -2277,7 +2393,10 @@ int orc_form_unbalance(void* h, double* B) {
       int pos = m->id[n * m->ndf + j];
       if (pos < 0) continue;
       /* Node::getUnbalancedLoadIncInertia (Node.cpp): P - M a - alphaM M v (static: c2 = c3 = 0 and v = a = 0) */
-      double ub = 0.0 + m->load[n * m->ndf + j] * m->lambda;
+      /* Domain::applyLoad: pattern after pattern, NodalLoad::applyLoad -> Node::addUnbalancedLoad(load, factor);
+       * a constant pattern keeps the factor it had at loadConst (LoadPattern.cpp applyLoad) */
+      double ub = m->cload ? (0.0 + m->cload[n * m->ndf + j]) + m->load[n * m->ndf + j] * m->lambda
+                           : 0.0 + m->load[n * m->ndf + j] * m->lambda;
       double ms = m->mass[n * m->ndf + j];
       if (ms != 0.0) { ub -= ms * m->acc[n * m->ndf + j]; if (m->alphaM != 0.0) ub += ms * m->vel[n * m->ndf + j] * -m->alphaM; }
       m->B[pos] += ub;

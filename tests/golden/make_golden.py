@@ -122,6 +122,11 @@ if __name__ == "__main__":
         if only in name:
             spec = mk()
             transient_case(name, spec, mass_fn(spec), gamma, beta, dt)
+    if only in "ex2b_as_written":
+        from modelspec import ex2b_as_written
+        g = ex2b_as_written(glue=False)
+        np.savez_compressed(os.path.join(HERE, "ex2b_as_written.npz"), **g)
+        print("ex2b_as_written gravity iters", g["grav_iters"].tolist(), "push iters", g["push_iters"].tolist(), "lambda_end", g["push_lam"][-1])
     if only in "material_paths":
         material_paths()
     for name, (mk, numberer, soe, scale) in CASES.items():

@@ -26,7 +26,8 @@ GLUE_SO = os.path.join(ROOT, "oracle", "_ref", "libref_glue.so")
 
 MAT_ELASTIC, MAT_J2 = 0, 1
 ELE_BRICK, ELE_QUAD, ELE_FBC2D, ELE_FBC3D = 0, 1, 2, 3
-UNI_STEEL02, UNI_CONCRETE02 = 0, 1
+UNI_STEEL02, UNI_CONCRETE02, UNI_STEEL01, UNI_ELASTIC = 0, 1, 2, 3
+SEC_P, SEC_MZ = 2, 1     # SectionForceDeformation.h response codes
 ND_3D, ND_PLANE_STRAIN, ND_PLANE_STRESS = 0, 1, 2
 NUMBERER_PLAIN, NUMBERER_RCM = 0, 1
 SOE_CSC, SOE_CSR = 0, 1
@@ -471,6 +472,80 @@ def cantilever2d(ndiv=1, nip=5, L=432.0, H=1.0, V=-100.0, max_iters=10, tol=1e-1
                      sections=[rc_section(1)])
 
 
+# tests/Ex2b.Canti2D.InelasticSection.Push.py as written: Steel01 (My, EIcrack, b) on the curvature and an Elastic
+# material (EA) on the axial strain, combined by `section Aggregator`
+EX2B_MY, EX2B_PHIY, EX2B_B = 130000.0, 0.65e-4, 0.01
+EX2B_EA = 57.0 * np.sqrt(4000.0) * (60.0 * 60.0 * 1000.0)
+STEEL01_EX2B = (UNI_STEEL01, (EX2B_MY, EX2B_MY / EX2B_PHIY, EX2B_B, 0.0, 55.0, 0.0, 55.0))
+ELASTIC_EX2B = (UNI_ELASTIC, (EX2B_EA, 0.0, EX2B_EA))
+
+
+def cantilever2d_aggregator(ndiv=1, nip=5, L=432.0, H=2000.0, V=0.0, max_iters=10, tol=1e-12):
+    """BASELINE configs[0] with the section the script defines: `section Aggregator` of an Elastic axial material and a
+    Steel01 moment-curvature material, one forceBeamColumn with 5 Lobatto points, node 1 fixed"""
+    spec = cantilever2d(ndiv, nip, L, H, V, max_iters, tol)
+    spec.uniaxials = [(3, *ELASTIC_EX2B), (2, *STEEL01_EX2B)]
+    spec.sections = [(1, "aggregator", (3, 2))]
+    return spec
+
+
+def ex2b_as_written(glue=False):
+    """tests/Ex2b.Canti2D.InelasticSection.Push.py, statement by statement, on the reference's own classes (glue=False)
+    or with the integrators' model-facing calls routed to the device (glue=True, oracle/ref_glue.cpp):
+    section Aggregator (Elastic P, Steel01 Mz), forceBeamColumn with 5 points, geomTransf Linear; gravity in 10
+    LoadControl steps (numberer Plain, system BandGeneral, test NormDispIncr 1e-8 6, algorithm Newton); loadConst -time 0;
+    pattern Plain 200 Linear {load 2 Hload 0 0}; DisplacementControl node 2 dof 1 0.001 LCol, test EnergyIncr 1e-8 6;
+    50 steps to 5 % drift.  (The script's gravity line is garbled -- "load 2 0 PCol=0" -- and is read as the example
+    it was converted from: load 2 0 -PCol 0.)  -> dict of iteration counts, norms, load factors, displacements"""
+    LCol, weight = 432.0, 2000.0
+    spec = cantilever2d_aggregator(ndiv=1, nip=5, L=LCol, H=0.0, V=-weight)
+    R = RefBackend(spec, defer_setup=True, so=GLUE_SO if glue else None)
+    out = {}
+    if glue: R.setup_glue_loadcontrol(NUMBERER_PLAIN, 2, 0.1, test=0, tol=1e-8, max_iter=6)
+    else: R.setup_loadcontrol(NUMBERER_PLAIN, 2, 0.1, test=0, tol=1e-8, max_iter=6)
+    rc, it, nm = R.analyze_static(10)
+    assert rc == 0, rc
+    out["grav_iters"], out["grav_norms"] = it, nm
+    out["grav_u"] = R.glue_trial_disp() if glue else R.get_trial_disp()
+    R.load_const(0.0)
+    R.add_load(2, (weight, 0.0, 0.0))
+    if glue: R.setup_glue_dispcontrol(NUMBERER_PLAIN, 2, 2, 0, 0.001 * LCol, test=2, tol=1e-8, max_iter=6)
+    else: R.setup_dispcontrol(NUMBERER_PLAIN, 2, 2, 0, 0.001 * LCol, test=2, tol=1e-8, max_iter=6)
+    rc, it, nm, lam = R.analyze_static_lam(50)
+    assert rc == 0, rc
+    out["push_iters"], out["push_norms"], out["push_lam"] = it, nm, lam
+    out["push_u"] = R.glue_trial_disp() if glue else R.get_trial_disp()
+    if glue:
+        out["calls"], out["launches"] = R.glue_counts()
+    return out
+
+
+def ex2b_drive(model, solve, ids, is_dev, tol=1e-10, max_iter=10):
+    """the sequence of ex2b_as_written() on any backend's update / form_* surface (oracle on the CPU, device through the
+    C-ABI): gravity in 10 LoadControl steps (Newton, NormDispIncr), loadConst -time 0, the lateral pattern, 50
+    DisplacementControl steps -> (gravity displacements, push load factors, final displacements)"""
+    LCol, weight = 432.0, 2000.0
+    if not is_dev: model._u = np.zeros(ids.shape)
+
+    def incr(dU):
+        if is_dev:
+            model.incr_trial_disp(dU); model.update()
+        else:
+            model._u[ids >= 0] += dU[ids[ids >= 0]]; model.set_trial_disp(model._u)
+    for s in range(10):                               # LoadControl 0.1, Newton, test NormDispIncr
+        model.apply_load(0.1 * (s + 1))
+        for it in range(max_iter):
+            B = model.form_unbalance(); A = model.form_tangent()
+            dU = solve(A, B); incr(dU)
+            if np.linalg.norm(dU) <= tol: break
+        model.commit()
+    grav_u = (model.trial_disp() if is_dev else model._u).copy()
+    model.load_const(); model.apply_load(0.0)
+    model.add_load(2, (weight, 0.0, 0.0))
+    hist, lam = disp_control(model, solve, ids[1, 0], 0.001 * LCol, 50, tol, max_iter, is_dev)
+    return grav_u, lam, (model.trial_disp() if is_dev else model._u).copy()
+
+
 def disp_control(model, solve, ctrl_eq, incr, nsteps, tol, max_iter, is_dev):
     """StaticAnalysis with `integrator DisplacementControl node dof incr`, `algorithm Newton`,
     `test NormDispIncr tol max_iter`, driven through any backend's update / form_* surface; the linear
@@ -553,6 +628,10 @@ class OracleBackend(_Backend):
         L.orc_add_fiber_section3d.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double]
         for sec in spec.sections:
+            if isinstance(sec[1], str):     # (tag, "aggregator", uniaxial tags for P, Mz)
+                mt = np.ascontiguousarray(sec[2], np.int32); codes = np.array([SEC_P, SEC_MZ], np.int32)
+                assert L.orc_add_section_aggregator(self.h, sec[0], len(mt), _p(mt), _p(codes)) == 0
+                continue
             tag, y, A, mt = sec[:4]
             y, A, mt = np.ascontiguousarray(y, np.float64), np.ascontiguousarray(A, np.float64), np.ascontiguousarray(mt, np.int32)
             if len(sec) == 6:     # 3D: (tag, y, A, mat, z, GJ)
@@ -602,6 +681,12 @@ class OracleBackend(_Backend):
 
     def scatter_map(self, e, nd):
         m = np.zeros(nd * nd, np.int32); self.L.orc_scatter_map(self.h, e, _p(m)); return m.reshape(nd, nd)
+
+    def load_const(self):
+        assert self.L.orc_load_const(self.h) == 0
+
+    def add_load(self, node, vals):
+        assert self.L.orc_add_load(self.h, int(node), _p(np.ascontiguousarray(vals, np.float64))) == 0
 
     def set_trial_disp(self, u):
         u = np.ascontiguousarray(u, np.float64); return self.L.orc_set_trial_disp(self.h, _p(u))
@@ -756,6 +841,10 @@ class RefBackend(_Backend):
         L.ref_add_force_beam3d.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_double, ctypes.c_void_p]
         for sec in spec.sections:
+            if isinstance(sec[1], str):     # (tag, "aggregator", uniaxial tags for P, Mz)
+                mt = np.ascontiguousarray(sec[2], np.int32); codes = np.array([SEC_P, SEC_MZ], np.int32)
+                assert L.ref_add_section_aggregator(self.h, sec[0], len(mt), _p(mt), _p(codes)) == 0
+                continue
             tag, y, A, mt = sec[:4]
             y, A, mt = np.ascontiguousarray(y, np.float64), np.ascontiguousarray(A, np.float64), np.ascontiguousarray(mt, np.int32)
             if len(sec) == 6:
@@ -952,6 +1041,21 @@ class RefBackend(_Backend):
         iters = np.zeros(nsteps, np.int32); norms = np.zeros((nsteps, self.max_iter))
         rc = self.L.ref_analyze_static(self.h, nsteps, _p(iters), _p(norms), self.max_iter)
         return rc, iters, norms
+
+    # ---- `analysis Static` set up after the model (integrator LoadControl), loadConst, a further load pattern ----
+    def setup_loadcontrol(self, numberer, soe, dlambda, test=0, tol=1e-8, max_iter=20):
+        self.L.ref_setup.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_double, ctypes.c_int]
+        self.neq = self.L.ref_setup(self.h, numberer, soe, dlambda, test, tol, max_iter)
+        assert self.neq >= 0, self.neq
+        self.nnz = self.L.ref_nnz(self.h); self.max_iter = max_iter
+
+    def load_const(self, time=0.0):
+        """loadConst -time t; the next add_load opens a new `pattern Plain`"""
+        self.L.ref_load_const.argtypes = [ctypes.c_void_p, ctypes.c_double]
+        assert self.L.ref_load_const(self.h, float(time)) == 0
+
+    def add_load(self, node, vals):
+        assert self.L.ref_add_load(self.h, int(node), _p(np.ascontiguousarray(vals, np.float64))) == 0
 
     # ---- the reference's own DisplacementControl ----
     def setup_dispcontrol(self, numberer, soe, node, dof, incr, test=0, tol=1e-8, max_iter=20):

@@ -919,6 +919,80 @@ def test_frame_fibre_beams_vs_oracle_history():
     assert relerr(D.form_tangent(), D0.form_tangent()) > 0.05
 
 
+@pytest.mark.parametrize("ndiv", [1, 4])
+def test_aggregator_cantilever_device_vs_oracle(ndiv):
+    """forceBeamColumn over `section Aggregator` (Elastic on P, Steel01 on Mz -- the section BASELINE configs[0]'s script
+    defines; SectionAggregator.cpp:316-500, Steel01.cpp:68-196): pushed past yield, released, reversed, with commits, a
+    revertToLastCommit and a reset, device against the oracle (which is pinned to the reference's classes)"""
+    from modelspec import cantilever2d_aggregator
+    spec = cantilever2d_aggregator(ndiv=ndiv)
+    O = OracleBackend(spec, 0, 0)
+    D = xb.DeviceModel.from_spec(spec, 0, 0).to_device(0)
+    ids = O.ids()
+    A0 = O.form_tangent()
+    assert relerr(D.form_tangent(), A0) < BEAM_RTOL
+    rng = np.random.default_rng(9)
+    amp = np.array([10.0, 0.005, 0.04])
+    yielded = False
+    for s, f in enumerate([0.1, 0.5, 1.0, 0.7, 0.2, -0.5, -1.0, 0.3]):
+        h = np.linspace(0.0, 1.0, spec.nn)[:, None]
+        u = f * amp * h ** 2 + rng.normal(0, 1.0, (spec.nn, 3)) * amp * 0.01; u[ids < 0] = 0
+        assert O.set_trial_disp(u) == 0
+        D.set_trial_disp(u); D.update(); D.apply_load(0.1 * s); O.apply_load(0.1 * s)
+        Ao = O.form_tangent()
+        assert relerr(D.form_tangent(), Ao) < BEAM_RTOL and relerr(D.form_unbalance(), O.form_unbalance()) < BEAM_RTOL
+        for e in range(O.ne):
+            assert relerr(D.element_tangent(e, 6), O.ele_tangent(e, 6)) < BEAM_RTOL and relerr(D.element_resid(e, 6), O.ele_resid(e, 6)) < BEAM_RTOL
+        yielded = yielded or relerr(Ao, A0) > 1e-3
+        if s == 4:
+            O.revert(); D.revert_to_last_commit()
+            assert relerr(D.form_tangent(), O.form_tangent()) < BEAM_RTOL and relerr(D.form_unbalance(), O.form_unbalance()) < BEAM_RTOL
+        else:
+            O.commit(); D.commit()
+    assert yielded
+    O.revert_to_start(); D.revert_to_start()
+    z = np.zeros((spec.nn, 3))
+    O.set_trial_disp(z); D.set_trial_disp(z); D.update()
+    assert relerr(D.form_tangent(), A0) < BEAM_RTOL
+
+
+def test_ex2b_as_written_device_vs_golden():
+    """BASELINE configs[0] as the script is written (gravity under LoadControl, loadConst -time 0 = xb_load_const +
+    xb_apply_load, the lateral pattern = xb_set_nodal_loads, pushover under DisplacementControl), driven through the
+    C-ABI, against the history the UNMODIFIED reference produced with `system BandGeneral` (tests/golden/ex2b_as_written.npz)"""
+    from modelspec import cantilever2d_aggregator, ex2b_drive
+    g = np.load(os.path.join(GOLD, "ex2b_as_written.npz"))
+    spec = cantilever2d_aggregator(ndiv=1, H=0.0, V=-2000.0)
+    D = xb.DeviceModel.from_spec(spec, 0, 0).to_device(0)
+    ids = D.ids(); ptr, idx = D.pattern(); neq = D.neq
+
+    def solve(A, b):
+        M = np.zeros((neq, neq))
+        for c in range(neq): M[idx[ptr[c]:ptr[c + 1]], c] = A[ptr[c]:ptr[c + 1]]
+        return np.linalg.solve(M, b)
+
+    grav_u, lam, u = ex2b_drive(D, solve, ids, True)
+    assert relerr(grav_u, g["grav_u"]) < 1e-10
+    assert relerr(lam, g["push_lam"]) < 1e-9 and relerr(u, g["push_u"]) < 1e-9
+
+
+@pytest.mark.skipif(not have_glue(), reason="oracle/_ref not built (needs /root/reference)")
+def test_reference_runs_ex2b_as_written_on_device_path():
+    """tests/Ex2b.Canti2D.InelasticSection.Push.py statement by statement on the reference's OWN objects (Domain,
+    SectionAggregator, Steel01, ElasticMaterial, ForceBeamColumn2d, PlainHandler, PlainNumberer, BandGenLinSOE,
+    NewtonRaphson, CTestNormDispIncr / CTestEnergyIncr, LoadControl, DisplacementControl) with the integrators'
+    model-facing calls routed to the device (oracle/ref_glue.cpp): the device model outlives the first analysis,
+    `loadConst` and the pushover pattern reach it through xb_load_const / xb_set_nodal_loads, A lands in the
+    BandGenLinSOE's own array.  Iteration counts, load factors and displacements are those of the unmodified run."""
+    from modelspec import ex2b_as_written
+    g = np.load(os.path.join(GOLD, "ex2b_as_written.npz"))
+    d = ex2b_as_written(glue=True)
+    assert d["grav_iters"].tolist() == g["grav_iters"].tolist() and d["push_iters"].tolist() == g["push_iters"].tolist()
+    assert relerr(d["grav_u"], g["grav_u"]) < 1e-10
+    assert relerr(d["push_lam"], g["push_lam"]) < 1e-9 and relerr(d["push_u"], g["push_u"]) < 1e-9
+    assert d["calls"][3] == 50 and d["launches"] > 0
+
+
 def test_frame3d_fibre_beams_vs_oracle_history():
     """forceBeamColumn in 3D (ForceBeamColumn3d) + FiberSection3d (Steel02 / Concrete02, elastic torsion):
     cyclic biaxial sway + twist history with commits and a revertToLastCommit, device against the oracle"""

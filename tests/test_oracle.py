@@ -264,6 +264,62 @@ def test_material_paths_vs_live_reference():
             assert len(np.unique(np.round(tr[:, 0, 0], 1))) > 50           # the path really goes plastic
 
 
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+def test_steel01_elastic_paths_vs_live_reference():
+    """Steel01 (Steel01.cpp:68-196, incl. the isotropic-hardening shifts a1..a4) and ElasticMaterial (bilinear Epos / Eneg)
+    against the reference's own classes over cyclic strain paths with commits"""
+    from modelspec import STEEL01_EX2B, UNI_STEEL01, UNI_ELASTIC, ref_uni_path
+    rng = np.random.default_rng(4)
+    for kind, p in (STEEL01_EX2B, (UNI_STEEL01, (60.0, 29000.0, 0.02, 0.05, 20.0, 0.04, 25.0)),
+                    (UNI_ELASTIC, (3.0e4, 0.0, 3.0e4)), (UNI_ELASTIC, (3.0e4, 0.0, 1.0e4))):
+        epsy = p[0] / p[1] if kind == UNI_STEEL01 else 1e-3
+        t = np.linspace(0, 14 * np.pi, 600)
+        strains = 4.0 * epsy * (0.2 + t / t[-1]) * np.sin(t) + rng.normal(0, 0.05 * epsy, 600)
+        strains[100:103] = strains[99]                      # zero increments (|dStrain| <= DBL_EPSILON: nothing moves)
+        commit = (rng.random(600) < 0.7).astype(np.int32)
+        so, to = oracle_uni_path(kind, p, strains, commit)
+        sr, tr = ref_uni_path(kind, p, strains, commit)
+        assert close(so, sr, 1e-14) and np.array_equal(to, tr)             # (the reference is built with FMA contraction)
+        if kind == UNI_STEEL01:
+            assert (tr == p[2] * p[1]).sum() > 50 and (tr == p[1]).sum() > 50      # the path yields and unloads
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("ndiv", [1, 3])
+def test_aggregator_cantilever_vs_live_reference(ndiv):
+    """BASELINE configs[0] as the script defines it: forceBeamColumn over `section Aggregator` (Elastic on P, Steel01 on
+    Mz; SectionAggregator.cpp:316-500: diagonal tangent, flexibility 1/k) -- A, B, element forces against the reference
+    over a pushed-and-released history with commits, a revert to the last commit and a reset"""
+    from modelspec import cantilever2d_aggregator
+    rng = np.random.default_rng(9)
+    spec = cantilever2d_aggregator(ndiv=ndiv)
+    O, R = OracleBackend(spec, 0, 0), RefBackend(spec, 0, 0)
+    assert np.array_equal(O.ids(), R.ids())
+    amp = np.array([10.0, 0.005, 0.04])          # the tip goes to 2.5 x its yield displacement
+    yielded = False
+    for s_, f in enumerate([0.1, 0.5, 1.0, 0.7, 0.2, -0.5, -1.0, 0.3]):
+        h = np.linspace(0.0, 1.0, spec.nn)[:, None]
+        u = f * amp * h ** 2 + rng.normal(0, 1.0, (spec.nn, 3)) * amp * 0.01; u[O.ids() < 0] = 0
+        for m in (O, R):
+            m.set_trial_disp(u); m.apply_load(0.1 * s_)
+        Ao, Ar = O.form_tangent(), R.form_tangent()
+        assert close(Ao, Ar, 1e-12) and close(O.form_unbalance(), R.form_unbalance(), 1e-12)
+        for e in range(O.ne):
+            assert close(O.ele_resid(e, 6), R.ele_resid(e, 6), 1e-12) and close(O.ele_tangent(e, 6), R.ele_tangent(e, 6), 1e-12)
+        if s_ == 0: A0 = Ar.copy()
+        yielded = yielded or abs(Ar[0] - A0[0]) > 0.5 * abs(A0[0])          # the lateral stiffness drops
+        if s_ == 4:                       # a trial state thrown away
+            O.revert(); R.revert()
+            assert close(O.form_tangent(), R.form_tangent(), 1e-12) and close(O.form_unbalance(), R.form_unbalance(), 1e-12)
+        else:
+            O.commit(); R.commit()
+    assert yielded
+    O.revert_to_start(); R.revert_to_start()
+    for m in (O, R):
+        m.set_trial_disp(np.zeros((spec.nn, 3))); m.apply_load(0.0)
+    assert close(O.form_tangent(), R.form_tangent(), 1e-12)
+
+
 def drive_transient_vs_golden(model, g, name, check, is_dev=False):
     """replays the golden Newmark history (the reference's dU per iteration) through `model`"""
     (c1, c2, c3), (a1, a2, a3, a4) = newmark_coeffs(float(g["gamma"]), float(g["beta"]), float(g["dt"]))
@@ -298,6 +354,27 @@ def test_newmark_vs_golden(name):
         assert np.abs(B - Bg).max() <= 1e-11 * bscale          # B -> 0 as Newton converges: scale by the step's first residual
 
     drive_transient_vs_golden(O, g, name, check)
+
+
+def test_ex2b_as_written_vs_golden():
+    """BASELINE configs[0], tests/Ex2b.Canti2D.InelasticSection.Push.py as written (section Aggregator of Elastic + Steel01,
+    gravity under LoadControl, loadConst -time 0, pushover under DisplacementControl; golden: the reference's own classes
+    with `system BandGeneral`, tests/golden/make_golden.py ex2b_as_written) against the same sequence on the oracle"""
+    from modelspec import cantilever2d_aggregator, ex2b_drive
+    g = np.load(os.path.join(GOLD, "ex2b_as_written.npz"))
+    spec = cantilever2d_aggregator(ndiv=1, H=0.0, V=-2000.0)
+    O = OracleBackend(spec, 0, 0)
+    ids = O.ids(); ptr, idx = O.csr(); neq = O.neq
+
+    def solve(A, b):
+        M = np.zeros((neq, neq))
+        for c in range(neq): M[idx[ptr[c]:ptr[c + 1]], c] = A[ptr[c]:ptr[c + 1]]
+        return np.linalg.solve(M, b)
+
+    grav_u, lam, u = ex2b_drive(O, solve, ids, False)
+    assert close(grav_u, g["grav_u"], 1e-10)
+    assert close(lam, g["push_lam"], 1e-9) and close(u, g["push_u"], 1e-9)
+    assert lam[-1] < 0.5 * lam[8] * 50 / 9           # the section yielded: the push curve flattens
 
 
 @pytest.mark.parametrize("name", list(DISPCONTROL_CASES))

@@ -28,12 +28,12 @@ import os
 import numpy as np
 
 __all__ = ["DeviceModel", "XaraB200Error", "lib", "LIB_PATH", "device_count", "comm_unique_id", "exchange_local",
-           "MAT_ELASTIC_ISOTROPIC", "MAT_J2PLASTICITY", "ELE_STDBRICK", "ELE_FOURNODEQUAD", "ELE_FORCEBEAMCOLUMN2D", "ELE_FORCEBEAMCOLUMN3D", "UNI_STEEL02", "UNI_CONCRETE02",
+           "MAT_ELASTIC_ISOTROPIC", "MAT_J2PLASTICITY", "ELE_STDBRICK", "ELE_FOURNODEQUAD", "ELE_FORCEBEAMCOLUMN2D", "ELE_FORCEBEAMCOLUMN3D", "UNI_STEEL02", "UNI_CONCRETE02", "UNI_STEEL01", "UNI_ELASTIC",
            "NUMBERER_PLAIN", "NUMBERER_RCM", "SOE_SPARSE_GEN_COL", "SOE_SPARSE_GEN_ROW", "SOE_BAND_GEN", "SOE_PROFILE_SPD", "SOE_UMFPACK_GEN"]
 
 MAT_ELASTIC_ISOTROPIC, MAT_J2PLASTICITY = 0, 1
 ELE_STDBRICK, ELE_FOURNODEQUAD, ELE_FORCEBEAMCOLUMN2D, ELE_FORCEBEAMCOLUMN3D = 0, 1, 2, 3
-UNI_STEEL02, UNI_CONCRETE02 = 0, 1
+UNI_STEEL02, UNI_CONCRETE02, UNI_STEEL01, UNI_ELASTIC = 0, 1, 2, 3
 NUMBERER_PLAIN, NUMBERER_RCM = 0, 1
 SOE_SPARSE_GEN_COL, SOE_SPARSE_GEN_ROW, SOE_BAND_GEN, SOE_PROFILE_SPD, SOE_UMFPACK_GEN = 0, 1, 2, 3, 4
 
@@ -66,6 +66,9 @@ def _load():
         "xb_add_uniaxial_material": (i32, [vp, i32, i32, vp, i32]),
         "xb_add_fiber_section": (i32, [vp, i32, i32, vp, vp, vp]),
         "xb_add_fiber_section3d": (i32, [vp, i32, i32, vp, vp, vp, vp, f64]),
+        "xb_add_section_aggregator": (i32, [vp, i32, i32, vp, vp]),
+        "xb_load_const": (i32, [vp]),
+        "xb_set_nodal_loads": (i32, [vp, i32, vp, vp]),
         "xb_add_elements": (i32, [vp, i32, i32, vp, vp, vp, vp, i32]),
         "xb_add_beam_uniform_loads": (i32, [vp, i32, vp, vp]),
         "xb_add_nodal_loads": (i32, [vp, i32, vp, vp]),
@@ -221,6 +224,11 @@ class DeviceModel:
         y, A, mat_tags = _f64(y), _f64(A), _i32(mat_tags)
         self._ck(lib.xb_add_fiber_section(self._h, tag, len(y), _ptr(y), _ptr(A), _ptr(mat_tags)))
 
+    def section_aggregator(self, tag, mat_tags, codes=(2, 1)):
+        """section Aggregator tag mat P mat Mz (codes of SectionForceDeformation.h: 2 = P, 1 = Mz)"""
+        mat_tags, codes = _i32(mat_tags), _i32(codes)
+        self._ck(lib.xb_add_section_aggregator(self._h, tag, len(mat_tags), _ptr(mat_tags), _ptr(codes)))
+
     def fiber_section3d(self, tag, y, z, A, mat_tags, GJ):
         y, z, A, mat_tags = _f64(y), _f64(z), _f64(A), _i32(mat_tags)
         self._ck(lib.xb_add_fiber_section3d(self._h, tag, len(y), _ptr(y), _ptr(z), _ptr(A), _ptr(mat_tags), float(GJ)))
@@ -266,7 +274,9 @@ class DeviceModel:
         for tag, kind, p in getattr(spec, "uniaxials", []):
             m.uniaxial_material(tag, kind, p)
         for sec in getattr(spec, "sections", []):
-            if len(sec) == 6:      # 3D: (tag, y, A, mat, z, GJ)
+            if isinstance(sec[1], str):      # (tag, "aggregator", uniaxial tags for P, Mz)
+                m.section_aggregator(sec[0], sec[2])
+            elif len(sec) == 6:      # 3D: (tag, y, A, mat, z, GJ)
                 m.fiber_section3d(sec[0], sec[1], sec[4], sec[2], sec[3], sec[5])
             else:
                 m.fiber_section(*sec)
@@ -400,6 +410,18 @@ class DeviceModel:
 
     def apply_load(self, lam):
         self._ck(lib.xb_apply_load(self._h, float(lam)))
+
+    def load_const(self):
+        """loadConst: the loads applied so far stay at the current factor (follow with apply_load(new time))"""
+        self._ck(lib.xb_load_const(self._h))
+
+    def add_load(self, node, vals):
+        self.set_nodal_loads([node], [vals])
+
+    def set_nodal_loads(self, tags, values):
+        """the next `pattern Plain`: reference loads [n][ndf] of the listed nodes"""
+        tags, values = _i32(tags), _f64(values)
+        self._ck(lib.xb_set_nodal_loads(self._h, len(tags), _ptr(tags), _ptr(values)))
 
     def form_tangent(self, out=None, host=True):
         if host and out is None:

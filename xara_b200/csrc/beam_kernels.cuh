@@ -22,6 +22,7 @@
 namespace xbk {
 
 constexpr int XB_FIB_NV = 11;   // doubles per fibre record
+constexpr int XB_FIB_CURV = 16; // fkind flag: the material of a section Aggregator's Mz response (strain = the curvature)
 constexpr int XB_MAXSEC = 10;
 constexpr int XB_FBC3D_MAX_PASSES = 20000;
 #ifndef XB_FBC_SEC_OCC
@@ -29,6 +30,8 @@ constexpr int XB_FBC3D_MAX_PASSES = 20000;
 #endif   // see fbc3d_update_kernel
 // Steel02 record:   0 epsmin 1 epsmax 2 epspl 3 epss0 4 sigs0 5 epsr 6 sigr 7 kon 8 e 9 sig 10 eps
 // Concrete02 record: 0 ecmin 1 dept 8 e 9 sig 10 eps
+// Steel01 record:    0 minStrain 1 maxStrain 2 shiftP 3 shiftN 4 loading 8 tangent 9 stress 10 strain
+// Elastic record:    8 tangent 9 stress 10 strain
 
 struct BeamView {
   long long n;                 // elements
@@ -42,7 +45,8 @@ struct BeamView {
   const double* fz;            // [nf] z - zBar (3D)
   double GJ;                   // elastic torsion (3D)
   const double* fA;            // [nf]
-  const int* fkind;            // [nf] 0 Steel02, 1 Concrete02
+  const int* fkind;            // [nf] 0 Steel02, 1 Concrete02, 2 Steel01, 3 Elastic (| XB_FIB_CURV)
+  int agg;                     // section Aggregator (P, Mz): flexibility 1/k on the diagonal (SectionAggregator.cpp:419)
   const double* fpar;          // [nf][12] material parameters
   const double* fs0;           // [ord*ord] initial section flexibility (column-major)
   // element state, SoA [k][n]
@@ -250,17 +254,80 @@ __device__ __forceinline__ void concrete02_trial_r(const double* __restrict__ p,
   sig_o = sig; e_o = e;
 }
 
+// Steel01::setTrialStrain + determineTrialState (Steel01.cpp:68-89, 122-196).  p = fy, E0, b, a1, a2, a3, a4
+__device__ __forceinline__ void steel01_trial(const double* __restrict__ p, const double* C, double* T, long long n,
+                                              double strain, double& sig_o, double& e_o) {
+  const double fy = p[0], E0 = p[1], b = p[2], a1 = p[3], a2 = p[4], a3 = p[5], a4 = p[6];
+  double minStrain = C[0], maxStrain = C[1 * n], shiftP = C[2 * n], shiftN = C[3 * n];
+  int loading = (int)C[4 * n];
+  const double Cstrain = C[10 * n], Cstress = C[9 * n];
+  double Tstrain = Cstrain, Tstress = Cstress, Ttangent = C[8 * n];
+  const double dStrain = strain - Cstrain;
+  if (fabs(dStrain) > DBL_EPSILON) {
+    Tstrain = strain;
+    const double fyOneMinusB = fy * (1.0 - b);
+    const double Esh = b * E0;
+    const double epsy = fy / E0;
+    const double c1 = Esh * Tstrain;
+    const double c2 = shiftN * fyOneMinusB;
+    const double c3 = shiftP * fyOneMinusB;
+    const double c = Cstress + E0 * dStrain;
+    const double c1c3 = c1 + c3;
+    if (c1c3 < c) Tstress = c1c3; else Tstress = c;
+    const double c1c2 = c1 - c2;
+    if (c1c2 > Tstress) Tstress = c1c2;
+    if (fabs(Tstress - c) < DBL_EPSILON) Ttangent = E0; else Ttangent = Esh;
+    if (loading == 0 && dStrain != 0.0) loading = dStrain > 0.0 ? 1 : -1;
+    if (loading == 1 && dStrain < 0.0) {
+      loading = -1;
+      if (Cstrain > maxStrain) maxStrain = Cstrain;
+      shiftN = 1 + a1 * pow((maxStrain - minStrain) / (2.0 * a2 * epsy), 0.8);
+    }
+    if (loading == -1 && dStrain > 0.0) {
+      loading = 1;
+      if (Cstrain < minStrain) minStrain = Cstrain;
+      shiftP = 1 + a3 * pow((maxStrain - minStrain) / (2.0 * a4 * epsy), 0.8);
+    }
+  }
+  T[0] = minStrain; T[1 * n] = maxStrain; T[2 * n] = shiftP; T[3 * n] = shiftN; T[4 * n] = (double)loading;
+  T[8 * n] = Ttangent; T[9 * n] = Tstress; T[10 * n] = Tstrain;
+  sig_o = Tstress; e_o = Ttangent;
+}
+// ElasticMaterial::setTrialStrain / getStress / getTangent (ElasticMaterial.cpp:137-182, eta = 0).  p = Epos, eta, Eneg
+__device__ __forceinline__ void elastic_trial(const double* __restrict__ p, double* T, long long n, double strain,
+                                              double& sig_o, double& e_o) {
+  const double Epos = p[0], Eneg = p[2];
+  const double sig = strain >= 0.0 ? Epos * strain : Eneg * strain;
+  const double e = strain > 0.0 ? Epos : (strain < 0.0 ? Eneg : (Epos > Eneg ? Epos : Eneg));
+  T[8 * n] = e; T[9 * n] = sig; T[10 * n] = strain;
+  sig_o = sig; e_o = e;
+}
+__device__ __forceinline__ void uniaxial_trial(int kind, const double* __restrict__ p, const double* C, double* T, long long n,
+                                               double strain, double& stress, double& tangent) {
+  if (kind == 0) steel02_trial(p, C, T, n, strain, stress, tangent);
+  else if (kind == 1) concrete02_trial(p, C, T, n, strain, stress, tangent);
+  else if (kind == 2) steel01_trial(p, C, T, n, strain, stress, tangent);
+  else elastic_trial(p, T, n, strain, stress, tangent);
+}
+
 // FiberSection2d::setTrialSectionDeformation for section i of element e -> s[2], k[4] (column-major)
 __device__ __forceinline__ void section_trial(const BeamView& B, long long e, int i, const double* d, double* s, double* k) {
   k[0] = k[1] = k[2] = k[3] = 0.0; s[0] = s[1] = 0.0;
   const double d0 = d[0], d1 = d[1];
   for (int f = 0; f < B.nf; f++) {
     const double y = __ldg(B.fy + f), A = __ldg(B.fA + f);
-    const double strain = d0 - y * d1;
+    const int kind = __ldg(B.fkind + f);
     const size_t rec = ((size_t)(i * B.nf + f) * XB_FIB_NV) * B.n + e;
     double stress, tangent;
-    if (__ldg(B.fkind + f) == 0) steel02_trial(B.fpar + f * 12, B.fc + rec, B.ft + rec, B.n, strain, stress, tangent);
-    else concrete02_trial(B.fpar + f * 12, B.fc + rec, B.ft + rec, B.n, strain, stress, tangent);
+    if (B.agg) {
+      // section Aggregator (SectionAggregator.cpp:316, :365, :483): material 0 on the axial strain, material 1 on the
+      // curvature; tangent and stress resultant are the materials' own, no coupling
+      uniaxial_trial(kind & 15, B.fpar + f * 12, B.fc + rec, B.ft + rec, B.n, (kind & XB_FIB_CURV) ? d1 : d0, stress, tangent);
+      if (kind & XB_FIB_CURV) { k[3] = tangent; s[1] = stress; } else { k[0] = tangent; s[0] = stress; }
+      continue;
+    }
+    const double strain = d0 - y * d1;
+    uniaxial_trial(kind, B.fpar + f * 12, B.fc + rec, B.ft + rec, B.n, strain, stress, tangent);
     const double ks0 = tangent * A;
     const double ks1 = ks0 * -y;
     k[0] += ks0; k[1] += ks1; k[3] += ks1 * -y;
@@ -268,6 +335,17 @@ __device__ __forceinline__ void section_trial(const BeamView& B, long long e, in
     s[0] += fs0; s[1] += fs0 * -y;
   }
   k[2] = k[1];
+}
+// the section's getSectionFlexibility: inverse of the tangent, or SectionAggregator's own (SectionAggregator.cpp:419-450)
+__device__ __forceinline__ void inv2(const double* a, double* ainv);
+__device__ __forceinline__ void section_flex(const BeamView& B, const double* k, double* f) {
+  if (B.agg) {
+    f[1] = f[2] = 0.0;
+    f[0] = k[0] == 0.0 ? 1.e14 : 1 / k[0];
+    f[3] = k[3] == 0.0 ? 1.e14 : 1 / k[3];
+    return;
+  }
+  inv2(k, f);
 }
 __device__ __forceinline__ void inv2(const double* a, double* ainv) {   // matrix/routines/invGL2.c
   const double det = a[0] * a[3] - a[2] * a[1];
@@ -383,7 +461,7 @@ __global__ void __launch_bounds__(64) fbc2d_revert_kernel(BeamView B) {
     double vs[2], s[2], k[4], fl[4];
     for (int q = 0; q < 2; q++) { vs[q] = B.vsc[(size_t)(i * 2 + q) * n + e]; B.vs[(size_t)(i * 2 + q) * n + e] = vs[q]; }
     section_trial(B, e, i, vs, s, k);
-    inv2(k, fl);
+    section_flex(B, k, fl);
     for (int q = 0; q < 2; q++) B.Ssr[(size_t)(i * 2 + q) * n + e] = s[q];
     for (int q = 0; q < 4; q++) B.fs[(size_t)(i * 4 + q) * n + e] = fl[q];
   }
@@ -416,8 +494,7 @@ __device__ __forceinline__ void section3_trial(const BeamView& B, long long e, i
     const double strain = e0 - y * e1 + z * e2;
     const size_t rec = ((size_t)(i * B.nf + f) * XB_FIB_NV) * B.n + e;
     double stress, tangent;
-    if (__ldg(B.fkind + f) == 0) steel02_trial(B.fpar + f * 12, B.fc + rec, B.ft + rec, B.n, strain, stress, tangent);
-    else concrete02_trial(B.fpar + f * 12, B.fc + rec, B.ft + rec, B.n, strain, stress, tangent);
+    uniaxial_trial(__ldg(B.fkind + f), B.fpar + f * 12, B.fc + rec, B.ft + rec, B.n, strain, stress, tangent);
     const double EA = tangent * A;
     k[0] += EA; k[1] += -y * EA; k[2] += z * EA;
     k[5] += y * y * EA; k[10] += z * z * EA; k[6] += -y * z * EA;
@@ -868,7 +945,7 @@ __global__ void __launch_bounds__(128, XB_FBC_SEC_OCC) fbc2d_update_sec_kernel(B
           if (initialFlag != 0) { vsS[0] += dvs[0]; vsS[1] += dvs[1]; }
           section_trial(B, e, i, vsS, ssec, ksec);
           SsrS[0] = ssec[0]; SsrS[1] = ssec[1];
-          inv2(ksec, fsS);
+          section_flex(B, ksec, fsS);
           dSs[0] = Ss[0] - SsrS[0]; dSs[1] = Ss[1] - SsrS[1];
           dvs[0] = 0.0; dvs[1] = 0.0;
 #pragma unroll

@@ -1066,6 +1066,7 @@ struct AsmView {
   const unsigned short* colpos;  // [*][cp_stride]
   const long long* ncol_ptr;  // [nn+1]
   const double* load;         // [nn][ndf]
+  const double* cload;        // [nn][ndf] loads frozen by `loadConst` (xb_load_const), null: none
   // transient terms (TransientIntegrator::formTangent / formNodUnbalance): nodal mass diagonal,
   // trial velocity / acceleration, Newmark's c1 c2 c3, Rayleigh alphaM.  Static: c1=1, c2=c3=0.
   const double* mass;         // [nn][ndf]
@@ -1429,6 +1430,7 @@ __global__ void __launch_bounds__(128) assemble_B_irr_kernel(AsmView V, const do
   for (long long o = V.irr_own_ptr[w]; o < V.irr_own_ptr[w + 1]; o++) {
     const int i = V.irr_own[o];
     double ub = V.load[i] * lambda;
+    if (V.cload) ub = V.cload[i] + ub;      // the constant patterns were applied first (Domain::applyLoad, pattern order)
     const double ms = V.mass[i];
     if (ms != 0.0) { ub -= ms * V.acc[i]; if (V.alphaM != 0.0) ub += ms * V.vel[i] * -V.alphaM; }
     acc += ub;
@@ -1481,6 +1483,7 @@ __global__ void __launch_bounds__(256) assemble_B_kernel(AsmView V, const double
   }
   // DOF_Group::getUnbalance: Node::getUnbalancedLoadIncInertia = P - M a - alphaM M v
   double ub = V.load[i] * lambda;
+  if (V.cload) ub = V.cload[i] + ub;        // the constant patterns were applied first (Domain::applyLoad, pattern order)
   const double ms = V.mass[i];
   if (ms != 0.0) { ub -= ms * V.acc[i]; if (V.alphaM != 0.0) ub += ms * V.vel[i] * -V.alphaM; }
   acc += ub;
@@ -1558,7 +1561,7 @@ struct xb_model {
   double* dRt = nullptr;    // element resisting forces including inertia and damping (getResistingForceIncInertia)
   double* dRsrc = nullptr;  // what formUnbalance assembles: dRe, or dRt once damping / element mass is in play
   double *dX = nullptr, *dU = nullptr, *dUc = nullptr, *dKe = nullptr, *dRe = nullptr, *dA = nullptr,
-         *dB = nullptr, *dLoad = nullptr, *dMpar = nullptr, *dTmp = nullptr;
+         *dB = nullptr, *dLoad = nullptr, *dLoadC = nullptr, *dMpar = nullptr, *dTmp = nullptr;
   int* dId = nullptr;
   int* dRowOf = nullptr;
   int* dFail = nullptr;
@@ -1702,6 +1705,7 @@ int xb_add_equal_dof(xb_model* m, int r, int c, int n, const int* dofs) { HOSTCA
 int xb_add_nd_material(xb_model* m, int tag, int kind, const double* par, int npar) { HOSTCALL(m->h.add_material(tag, kind, par, npar)); }
 int xb_add_uniaxial_material(xb_model* m, int tag, int kind, const double* par, int npar) { HOSTCALL(m->h.add_uniaxial(tag, kind, par, npar)); }
 int xb_add_fiber_section(xb_model* m, int tag, int nf, const double* y, const double* A, const int* mt) { HOSTCALL(m->h.add_fiber_section(tag, nf, y, A, mt)); }
+int xb_add_section_aggregator(xb_model* m, int tag, int n, const int* mt, const int* codes) { HOSTCALL(m->h.add_section_aggregator(tag, n, mt, codes)); }
 int xb_add_fiber_section3d(xb_model* m, int tag, int nf, const double* y, const double* z, const double* A, const int* mt, double GJ) { HOSTCALL(m->h.add_fiber_section3d(tag, nf, y, z, A, mt, GJ)); }
 int xb_add_elements(xb_model* m, int kind, int n, const int* tags, const int* conn, const int* mt, const double* par, int ps) {
   HOSTCALL(m->h.add_elements(kind, n, tags, conn, mt, par, ps));
@@ -1909,7 +1913,7 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
       double k3[16] = {0};   // FiberSection3d::getInitialTangent, column-major 4x4
       for (int f = 0; f < nf; f++) {
         const xb::Uniaxial& u = h.unis[sd.mat[f]];
-        fy[f] = sd.y[f] - sd.yBar; fkind[f] = u.kind;
+        fy[f] = sd.y[f] - sd.yBar; fkind[f] = u.kind | ((sd.agg && f == 1) ? XB_FIB_CURV : 0);
         if (b3) fz[f] = sd.z[f] - sd.zBar;
         std::memcpy(&fpar[(size_t)f * 12], u.par, sizeof(double) * 12);
         double* C = &ic[(size_t)f * XB_FIB_NV]; double* T = &it[(size_t)f * XB_FIB_NV];
@@ -1920,6 +1924,12 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
           C[0] = -(Fy / E0); C[1] = Fy / E0; C[7] = 0.0; C[8] = E0; C[9] = 0.0; C[10] = 0.0;
           if (sigini != 0.0) { C[10] = sigini / E0; C[9] = sigini; }
           T[8] = E0;
+        } else if (u.kind == XB_UNI_STEEL01) {   // Steel01::revertToStart, Steel01.cpp:284-311
+          E0 = u.par[1];
+          C[2] = 1.0; C[3] = 1.0; C[8] = E0; T[2] = 1.0; T[3] = 1.0; T[8] = E0;
+        } else if (u.kind == XB_UNI_ELASTIC) {   // ElasticMaterial::getInitialTangent, ElasticMaterial.cpp:186
+          E0 = u.par[0] > u.par[2] ? u.par[0] : u.par[2];
+          C[8] = E0; T[8] = E0;
         } else {
           E0 = 2.0 * u.par[0] / u.par[1];
           C[8] = E0; T[8] = E0;
@@ -1935,6 +1945,11 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
       k0[2] = k0[1];
       const double det = k0[0] * k0[3] - k0[2] * k0[1];
       std::vector<double> fs0 = {k0[3] / det, -k0[1] / det, -k0[2] / det, k0[0] / det};
+      b.agg = sd.agg ? 1 : 0;
+      if (sd.agg) {   // SectionAggregator::getInitialFlexibility, SectionAggregator.cpp:454-479: 1 / initial tangent on the diagonal
+        auto e0 = [&](int f) { const xb::Uniaxial& u = h.unis[sd.mat[f]]; return u.kind == XB_UNI_ELASTIC ? (u.par[0] > u.par[2] ? u.par[0] : u.par[2]) : u.par[1]; };
+        fs0 = {1.0 / e0(0), 0.0, 0.0, 1.0 / e0(1)};
+      }
       if (b3) {
         // SectionForceDeformation::getSectionFlexibility of the initial tangent: the P-Mz-My block through the
         // 3x3 cofactor formula (invGL3.c), torsion by division -- as beam_kernels.cuh::section3_flex does
@@ -2010,7 +2025,7 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
 
   AsmView& a = m->av;
   a.nn = (int)nn; a.ndf = h.ndf; a.cp_stride = h.cp_stride; a.max_row = std::max(h.max_row, 1);
-  a.row_of = m->dRowOf; a.load = m->dLoad;
+  a.row_of = m->dRowOf; a.load = m->dLoad; a.cload = nullptr;
   a.mass = m->dMass; a.vel = m->dV; a.acc = m->dAcc; a.diagpos = m->dDiag;
   a.c1 = 1.0; a.c2 = 0.0; a.c3 = 0.0; a.alphaM = m->alphaM;
   if (h.nparts > 1) {
@@ -2304,6 +2319,51 @@ int xb_apply_load(xb_model* m, double lambda) {
   if (!m) return fail(XB_ERR_ARG, "null model");
   m->lambda = lambda;
   beams_take_load_factor(m, lambda);
+  return XB_OK;
+}
+
+// `loadConst -time t` (Domain::setLoadConstant, Domain.cpp; LoadPattern::setLoadConstant): every load applied so far
+// stays at its current factor.  The device keeps one reference load vector P (applied as lambda P) and one constant one:
+// Pc += lambda P, P = 0.  The caller then sets the domain time (xb_apply_load) and the next pattern's loads
+// (xb_set_nodal_loads).
+__global__ void load_const_kernel(long long n, double lambda, double* __restrict__ P, double* __restrict__ Pc) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Pc[i] = Pc[i] + P[i] * lambda;      // NodalLoad::applyLoad -> Node::addUnbalancedLoad(load, factor), pattern after pattern
+  P[i] = 0.0;
+}
+int xb_load_const(xb_model* m) {
+  NEED_DEVICE();
+  CU(cudaSetDevice(m->device));
+  for (auto& d : m->dg) if (is_beam(d.kind) && d.b.wl) return fail(XB_ERR_UNSUPPORTED, "xb_load_const: element loads in a constant pattern are outside the device path");
+  const long long n = (long long)m->h.nn() * m->h.ndf;
+  if (!m->dLoadC) {
+    CU(dev_alloc(m, &m->dLoadC, (size_t)std::max<long long>(n, 1)));
+    CU(cudaMemsetAsync(m->dLoadC, 0, sizeof(double) * std::max<long long>(n, 1), m->stream));
+    m->av.cload = m->dLoadC;
+  }
+  if (n) load_const_kernel<<<(unsigned)((n + 255) / 256), 256, 0, m->stream>>>(n, m->lambda, m->dLoad, m->dLoadC);
+  CU(cudaGetLastError());
+  std::fill(m->h.load.begin(), m->h.load.end(), 0.0);
+  return XB_OK;
+}
+// `pattern Plain n Linear { load node values }` after the set-up: the reference loads of the listed nodes (values
+// [n][ndf], added to what the current pattern already holds for them, as repeated `load` commands do)
+int xb_set_nodal_loads(xb_model* m, int n, const int* tags, const double* vals) {
+  NEED_DEVICE();
+  CU(cudaSetDevice(m->device));
+  const int ndf = m->h.ndf;
+  for (int i = 0; i < n; i++) {
+    const auto it = std::lower_bound(m->h.node_tag.begin(), m->h.node_tag.end(), tags[i]);
+    if (it == m->h.node_tag.end() || *it != tags[i]) {
+      if (m->h.nparts > 1) continue;          // a node another rank holds
+      return fail(XB_ERR_ARG, "xb_set_nodal_loads: unknown node tag");
+    }
+    const size_t k = (size_t)(it - m->h.node_tag.begin()) * ndf;
+    for (int j = 0; j < ndf; j++) m->h.load[k + j] += vals[(size_t)i * ndf + j];
+  }
+  CU(cudaMemcpyAsync(m->dLoad, m->h.load.data(), sizeof(double) * m->h.load.size(), cudaMemcpyHostToDevice, m->stream));
+  CU(cudaStreamSynchronize(m->stream));
   return XB_OK;
 }
 

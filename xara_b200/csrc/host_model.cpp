@@ -62,13 +62,15 @@ int HostModel::add_material(int tag, int kind, const double* par, int npar) {
 
 int HostModel::add_uniaxial(int tag, int kind, const double* par, int npar) {
   if (is_setup) { err = "xb_add_uniaxial_material after xb_setup"; return XB_ERR_STATE; }
-  const int need = kind == XB_UNI_STEEL02 ? 10 : (kind == XB_UNI_CONCRETE02 ? 7 : -1);
+  const int need = kind == XB_UNI_STEEL02 ? 10 : (kind == XB_UNI_CONCRETE02 ? 7 : (kind == XB_UNI_STEEL01 ? 7 : (kind == XB_UNI_ELASTIC ? 1 : -1)));
   if (need < 0) { err = "xb_add_uniaxial_material: unknown kind"; return XB_ERR_ARG; }
   if (npar < need || npar > 12) { err = "xb_add_uniaxial_material: wrong parameter count"; return XB_ERR_ARG; }
+  if (kind == XB_UNI_ELASTIC && npar > 1 && par[1] != 0.0) { err = "uniaxialMaterial Elastic with eta != 0: strain rates are outside the device path"; return XB_ERR_UNSUPPORTED; }
   for (auto& u : unis) if (u.tag == tag) { err = "xb_add_uniaxial_material: duplicate tag"; return XB_ERR_ARG; }
   Uniaxial u{};
   u.tag = tag; u.kind = kind;
   std::memcpy(u.par, par, sizeof(double) * npar);
+  if (kind == XB_UNI_ELASTIC && npar < 3) u.par[2] = u.par[0];   // ElasticMaterial(tag, E, eta): Eneg = E
   if (kind == XB_UNI_CONCRETE02) {   // Concrete02.cpp:101-104: compression quantities are made negative
     for (int i = 0; i < 4; i++) if (u.par[i] > 0) u.par[i] = -u.par[i];
   }
@@ -91,6 +93,18 @@ int HostModel::add_fiber_section(int tag, int nf, const double* y, const double*
     ABar += A[i]; QzBar += y[i] * A[i]; d.yBar = QzBar / ABar;     // FiberSection2d::addFiber, FiberSection2d.cpp:150-154
   }
   secs.push_back(std::move(d));
+  return XB_OK;
+}
+
+int HostModel::add_section_aggregator(int tag, int n, const int* mat_tags, const int* codes) {
+  if (n != 2 || codes[0] != 2 || codes[1] != 1) {
+    err = "section Aggregator: the device path takes two materials with codes P, Mz in that order (a 2D forceBeamColumn section)";
+    return XB_ERR_UNSUPPORTED;
+  }
+  const double zero[2] = {0.0, 0.0}, one[2] = {1.0, 1.0};
+  int rc = add_fiber_section(tag, 2, zero, one, mat_tags);
+  if (rc < 0) return rc;
+  secs.back().agg = true; secs.back().yBar = 0.0;
   return XB_OK;
 }
 

@@ -46,6 +46,8 @@ struct FiberSectionDef {
   std::vector<double> y, A;
   std::vector<int> mat;      // index into HostModel::unis
   double yBar = 0.0;         // FiberSection2d::addFiber keeps QzBar/ABar up to date
+  // section Aggregator of two uniaxial materials (P, Mz): "fibre" 0 takes the axial strain, "fibre" 1 the curvature
+  bool agg = false;
   // section Fiber -GJ in a 3D model (FiberSection3d): fibre z, centroid zBar, elastic torsion GJ
   bool is3d = false;
   std::vector<double> z;
@@ -214,6 +216,7 @@ struct HostModel {
   int add_material(int tag, int kind, const double* par, int npar);
   int add_uniaxial(int tag, int kind, const double* par, int npar);
   int add_fiber_section(int tag, int nf, const double* y, const double* A, const int* mat_tags);
+  int add_section_aggregator(int tag, int n, const int* mat_tags, const int* codes);
   int add_fiber_section3d(int tag, int nf, const double* y, const double* z, const double* A, const int* mat_tags, double GJ);
   int add_elements(int kind, int n, const int* tags, const int* conn, const int* mat_tags,
                    const double* par, int par_stride);
