@@ -47,6 +47,8 @@
 #include <ElasticMaterial.h>
 #include <LinearCrdTransf2d.h>
 #include <LinearCrdTransf3d.h>
+#include <PDeltaCrdTransf2d.h>
+#include <PDeltaCrdTransf3d.h>
 #include <LobattoBeamIntegration.h>
 #include <Brick.h>
 #include <FourNodeQuad.h>
@@ -160,7 +162,7 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
   struct Batch { std::vector<int> tag, conn, mat; std::vector<double> par; };
   std::map<std::pair<int, int>, Batch> batches;     // (xb element kind, xb material kind)
   std::map<int, int> mats_done, secs_done, unis_done;
-  struct BeamKey { int sec, nip, mi; double tol; bool is3; };
+  struct BeamKey { int sec, nip, mi; double tol; bool is3; int transf; };
   std::vector<BeamKey> beam_keys;
   auto material = [&](NDMaterial* nm, int& kind) -> int {
     double p[8] = {0, 0, 0, 0, 0, 0, 0, 0}; int np = 0;
@@ -210,6 +212,13 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
         BeamIntegration* bi = b2 ? b2->beamIntegr : b3->beamIntegr;
         CrdTransf* ct = b2 ? b2->crdTransf : b3->crdTransf;
         if (!dynamic_cast<LobattoBeamIntegration*>(bi)) { G.err = "glue: beam integration other than Lobatto"; return -5; }
+        // geomTransf Linear or PDelta, without joint offsets
+        int transf = -1;
+        if (auto* t = dynamic_cast<LinearCrdTransf2d*>(ct)) { if (!t->nodeIOffset && !t->nodeJOffset) transf = 0; }
+        else if (auto* t = dynamic_cast<LinearCrdTransf3d*>(ct)) { if (!t->nodeIOffset && !t->nodeJOffset) transf = 0; }
+        else if (auto* t = dynamic_cast<PDeltaCrdTransf2d*>(ct)) { if (!t->nodeIOffset && !t->nodeJOffset) transf = 1; }
+        else if (auto* t = dynamic_cast<PDeltaCrdTransf3d*>(ct)) { if (!t->nodeIOffset && !t->nodeJOffset) transf = 1; }
+        if (transf < 0) { G.err = "glue: geomTransf other than Linear / PDelta without joint offsets: outside the device path"; return -5; }
         if ((b2 ? b2->rho : b3->rho) != 0.0) { G.err = "glue: forceBeamColumn with element mass"; return -5; }
         for (int i = 1; i < nsec; i++) if (secs[i]->getTag() != secs[0]->getTag()) { G.err = "glue: sections of one element differ"; return -5; }
         const int stag = secs[0]->getTag();
@@ -272,8 +281,8 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
         const int maxIters = b2 ? b2->maxIters : b3->maxIters; const double tol = b2 ? b2->tol : b3->tol;
         int key = -1;
         for (size_t q = 0; q < beam_keys.size(); q++)
-          if (beam_keys[q].sec == stag && beam_keys[q].nip == nsec && beam_keys[q].mi == maxIters && beam_keys[q].tol == tol && beam_keys[q].is3 == (b3 != nullptr)) key = (int)q;
-        if (key < 0) { beam_keys.push_back({stag, nsec, maxIters, tol, b3 != nullptr}); key = (int)beam_keys.size() - 1; }
+          if (beam_keys[q].sec == stag && beam_keys[q].nip == nsec && beam_keys[q].mi == maxIters && beam_keys[q].tol == tol && beam_keys[q].is3 == (b3 != nullptr) && beam_keys[q].transf == transf) key = (int)q;
+        if (key < 0) { beam_keys.push_back({stag, nsec, maxIters, tol, b3 != nullptr, transf}); key = (int)beam_keys.size() - 1; }
         Batch& B = batches[{b3 ? XB_ELE_FORCEBEAMCOLUMN3D : XB_ELE_FORCEBEAMCOLUMN2D, 1000 + key}];
         B.tag.push_back(el->getTag()); B.mat.push_back(stag);
         const ID& en = el->getExternalNodes();
@@ -284,12 +293,13 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
           ct->getLocalAxes(xa, ya, za);
           for (int d = 0; d < 3; d++) B.par.push_back(za(d));
         }
+        B.par.push_back(transf);
       } else { G.err = "glue: element class outside the device path (keep the CPU integrator)"; return -5; }
     } }
   for (auto& kv : batches) {
     Batch& B = kv.second;
     const int ek = kv.first.first;
-    const int stride = ek == XB_ELE_STDBRICK ? 3 : (ek == XB_ELE_FORCEBEAMCOLUMN2D ? 3 : 6);
+    const int stride = ek == XB_ELE_STDBRICK ? 3 : (ek == XB_ELE_FORCEBEAMCOLUMN2D ? 4 : (ek == XB_ELE_FORCEBEAMCOLUMN3D ? 7 : 6));
     if (xb_add_elements(x, kv.first.first, (int)B.tag.size(), B.tag.data(), B.conn.data(), B.mat.data(), B.par.data(), stride) < 0) {
       G.err = xb_last_error(); return -6;
     }

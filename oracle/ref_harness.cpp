@@ -46,6 +46,8 @@
 #include <Concrete02.h>
 #include <FiberSection2d.h>
 #include <SectionAggregator.h>
+#include <PDeltaCrdTransf2d.h>
+#include <PDeltaCrdTransf3d.h>
 #include <Steel01.h>
 #include <ElasticMaterial.h>
 #include <FiberSection3d.h>
@@ -325,13 +327,18 @@ int ref_add_section_aggregator(void* h, int tag, int n, const int* matTags, cons
   return 0;
 }
 // element forceBeamColumn (2D): Lobatto integration, Linear transformation, nIP copies of one section
-int ref_add_force_beam2d(void* h, int tag, const int* nd, int secTag, int nip, int maxIters, double tol) {
+int ref_add_force_beam2d_t(void* h, int tag, const int* nd, int secTag, int nip, int maxIters, double tol, int transfKind) {
   RefModel* m = (RefModel*)h;
   std::vector<SectionForceDeformation*> secs(nip, m->sections2d.at(secTag));
   LobattoBeamIntegration bi;
-  LinearCrdTransf2d transf(tag);
+  LinearCrdTransf2d lin(tag);
+  PDeltaCrdTransf2d pd(tag);                 // geomTransf PDelta
+  CrdTransf& transf = transfKind == 1 ? (CrdTransf&)pd : (CrdTransf&)lin;
   Element* e = new ForceBeamColumn2d(tag, nd[0], nd[1], nip, secs.data(), bi, transf, 0.0, maxIters, tol);
   return m->domain->addElement(e) ? 0 : -1;
+}
+int ref_add_force_beam2d(void* h, int tag, const int* nd, int secTag, int nip, int maxIters, double tol) {
+  return ref_add_force_beam2d_t(h, tag, nd, secTag, nip, maxIters, tol, 0);
 }
 
 // section Fiber tag -GJ gj { fiber y z A mat ... } in a 3D model (runtime/commands/modeling/section.cpp:497):
@@ -347,14 +354,19 @@ int ref_add_fiber_section3d(void* h, int tag, int nf, const double* y, const dou
 }
 // element forceBeamColumn (3D, frames.cpp:333 -> ForceBeamColumn3d): Lobatto integration,
 // geomTransf Linear with vecxz, nIP copies of one section
-int ref_add_force_beam3d(void* h, int tag, const int* nd, int secTag, int nip, int maxIters, double tol, const double* vecxz) {
+int ref_add_force_beam3d_t(void* h, int tag, const int* nd, int secTag, int nip, int maxIters, double tol, const double* vecxz, int transfKind) {
   RefModel* m = (RefModel*)h;
   std::vector<SectionForceDeformation*> secs(nip, m->sections3d.at(secTag));
   LobattoBeamIntegration bi;
   Vector v(3); v(0) = vecxz[0]; v(1) = vecxz[1]; v(2) = vecxz[2];
-  LinearCrdTransf3d transf(tag, v);
+  LinearCrdTransf3d lin(tag, v);
+  PDeltaCrdTransf3d pd(tag, v);              // geomTransf PDelta
+  CrdTransf& transf = transfKind == 1 ? (CrdTransf&)pd : (CrdTransf&)lin;
   Element* e = new ForceBeamColumn3d(tag, nd[0], nd[1], nip, secs.data(), bi, transf, 0.0, maxIters, tol);
   return m->domain->addElement(e) ? 0 : -1;
+}
+int ref_add_force_beam3d(void* h, int tag, const int* nd, int secTag, int nip, int maxIters, double tol, const double* vecxz) {
+  return ref_add_force_beam3d_t(h, tag, nd, secTag, nip, maxIters, tol, vecxz, 0);
 }
 
 int ref_uni_path(int kind, const double* p, int n, const double* strains, const int* commit,

@@ -792,6 +792,9 @@ typedef struct {
   /* `eleLoad -beamUniform wy wa` of the Linear pattern: w = {wy, -, wa}; numEleLoads = 1 once Domain::applyLoad ran
    * (LoadPattern::applyLoad -> ElementalLoad::applyLoad -> ForceBeamColumn2d::addLoad(load, loadFactor)) */
   int has_load, numEleLoads; double w[3], loadFactor;
+  /* geomTransf PDelta (PDeltaCrdTransf2d.cpp): ul14 is recomputed from the nodes' trial displacements whenever the
+   * element asks for its tangent or resisting force (ForceBeamColumn2d.cpp:402,526 call crdTransf->update()) */
+  int pdelta; const double* utrial; int n0, n1;
 } OrcBeam;
 
 /* quadrature/Frame/LobattoBeamIntegration.cpp: getSectionLocations / getSectionWeights */
@@ -928,8 +931,65 @@ static int beam_update(OrcBeam* b, const double* ug, const double* dug) {
   return 0;
 }
 
+/* PDeltaCrdTransf2d::update / getGlobalStiffMatrix / getGlobalResistingForce (no offsets), PDeltaCrdTransf2d.cpp:349-384,
+ * 566-745, 507-564; K row-major 6x6 */
+static void beam_form_pdelta(const OrcBeam* b, double* K, double* R) {
+  const double cosTheta = b->cosTheta, sinTheta = b->sinTheta, oneOverL = 1.0 / b->L;
+  const double* uI = b->utrial + 3 * b->n0; const double* uJ = b->utrial + 3 * b->n1;
+  const double ul1 = -sinTheta * uI[0] + cosTheta * uI[1];
+  const double ul4 = -sinTheta * uJ[0] + cosTheta * uJ[1];
+  const double ul14 = ul1 - ul4;
+  if (K) {
+    const double* kb = b->kv;
+    double kb00 = kb[0], kb10 = kb[1], kb20 = kb[2], kb01 = kb[3], kb11 = kb[4], kb21 = kb[5], kb02 = kb[6], kb12 = kb[7], kb22 = kb[8];
+    double kl[6][6], tmp[6][6];
+    kl[0][0] = kb00; kl[1][0] = -oneOverL * (kb10 + kb20); kl[2][0] = -kb10; kl[3][0] = -kb00; kl[4][0] = -kl[1][0]; kl[5][0] = -kb20;
+    kl[0][1] = -oneOverL * (kb01 + kb02); kl[1][1] = oneOverL * oneOverL * (kb11 + kb12 + kb21 + kb22); kl[2][1] = oneOverL * (kb11 + kb12);
+    kl[3][1] = -kl[0][1]; kl[4][1] = -kl[1][1]; kl[5][1] = oneOverL * (kb21 + kb22);
+    kl[0][2] = -kb01; kl[1][2] = oneOverL * (kb11 + kb21); kl[2][2] = kb11; kl[3][2] = kb01; kl[4][2] = -kl[1][2]; kl[5][2] = kb21;
+    for (int i = 0; i < 6; i++) { kl[i][3] = -kl[i][0]; kl[i][4] = -kl[i][1]; }
+    kl[0][5] = -kb02; kl[1][5] = oneOverL * (kb12 + kb22); kl[2][5] = kb12; kl[3][5] = kb02; kl[4][5] = -kl[1][5]; kl[5][5] = kb22;
+    const double NoverL = b->Se[0] * oneOverL;          /* geometric stiffness, :628-633 */
+    kl[1][1] += NoverL; kl[4][4] += NoverL; kl[1][4] -= NoverL; kl[4][1] -= NoverL;
+    for (int i = 0; i < 6; i++) {                       /* kl * T, :650-700 */
+      tmp[i][0] = kl[i][0] * cosTheta - kl[i][1] * sinTheta;
+      tmp[i][1] = kl[i][0] * sinTheta + kl[i][1] * cosTheta;
+      tmp[i][2] = kl[i][2];
+      tmp[i][3] = kl[i][3] * cosTheta - kl[i][4] * sinTheta;
+      tmp[i][4] = kl[i][3] * sinTheta + kl[i][4] * cosTheta;
+      tmp[i][5] = kl[i][5];
+    }
+    for (int j = 0; j < 6; j++) {                       /* T^T * (kl * T), :702-745 */
+      K[0 * 6 + j] = cosTheta * tmp[0][j] - sinTheta * tmp[1][j];
+      K[1 * 6 + j] = sinTheta * tmp[0][j] + cosTheta * tmp[1][j];
+      K[2 * 6 + j] = tmp[2][j];
+      K[3 * 6 + j] = cosTheta * tmp[3][j] - sinTheta * tmp[4][j];
+      K[4 * 6 + j] = sinTheta * tmp[3][j] + cosTheta * tmp[4][j];
+      K[5 * 6 + j] = tmp[5][j];
+    }
+  }
+  double q0 = b->Se[0], q1 = b->Se[1], q2 = b->Se[2];
+  double V = oneOverL * (q1 + q2);
+  double pl[6] = { -q0, V, q1, q0, -V, q2 };
+  double p0[3] = {0.0, 0.0, 0.0};
+  if (b->numEleLoads > 0) {
+    double wa = b->w[2] * b->loadFactor, wy = b->w[0] * b->loadFactor;
+    p0[0] -= wa * b->L;
+    double Vr = 0.5 * wy * b->L;
+    p0[1] -= Vr; p0[2] -= Vr;
+  }
+  pl[0] += p0[0]; pl[1] += p0[1]; pl[4] += p0[2];
+  double NoverL = ul14 * q0 * oneOverL;                 /* leaning-column effect, :532-535 */
+  pl[1] += NoverL; pl[4] -= NoverL;
+  R[0] = cosTheta * pl[0] - sinTheta * pl[1];
+  R[1] = sinTheta * pl[0] + cosTheta * pl[1];
+  R[3] = cosTheta * pl[3] - sinTheta * pl[4];
+  R[4] = sinTheta * pl[3] + cosTheta * pl[4];
+  R[2] = pl[2]; R[5] = pl[5];
+}
 /* LinearCrdTransf2d::getGlobalStiffMatrix (no offsets) and getGlobalResistingForce; K row-major 6x6 */
 static void beam_form(const OrcBeam* b, double* K, double* R) {
+  if (b->pdelta) { beam_form_pdelta(b, K, R); return; }
   const double cosTheta = b->cosTheta, sinTheta = b->sinTheta, oneOverL = 1.0 / b->L;
   if (K) {
     const double* kb = b->kv;
@@ -1072,6 +1132,9 @@ typedef struct {
   double fs[ORC_MAXSEC][16], vs[ORC_MAXSEC][4], Ssr[ORC_MAXSEC][4], vscommit[ORC_MAXSEC][4];
   /* `eleLoad -beamUniform wy wz wa`: see OrcBeam */
   int has_load, numEleLoads; double w[3], loadFactor;
+  /* geomTransf PDelta (PDeltaCrdTransf3d.cpp:200-249): ul17, ul28 as of the element's last update() -- ForceBeamColumn3d's
+   * getTangentStiff / getResistingForce do NOT refresh them (ForceBeamColumn3d.cpp:404,555) */
+  int pdelta; double ul17, ul28;
 } OrcBeam3;
 
 /* LinearCrdTransf3d::initialize -> computeElemtLengthAndOrient + getLocalAxes, LinearCrdTransf3d.cpp:203-330 */
@@ -1128,6 +1191,13 @@ static double norm6(const double* v) { double s = 0.0; for (int i = 0; i < 6; i+
 
 /* ForceBeamColumn3d::update, ForceBeamColumn3d.cpp:587-1056 (no element loads; isTorsion = true) */
 static int beam3_update(OrcBeam3* b, const double* ug, const double* dug) {
+  if (b->pdelta) {   /* crdTransf->update(), PDeltaCrdTransf3d.cpp:200-249 (no offsets) */
+    const double ul1 = b->R[1][0] * ug[0] + b->R[1][1] * ug[1] + b->R[1][2] * ug[2];
+    const double ul2 = b->R[2][0] * ug[0] + b->R[2][1] * ug[1] + b->R[2][2] * ug[2];
+    const double ul7 = b->R[1][0] * ug[6] + b->R[1][1] * ug[7] + b->R[1][2] * ug[8];
+    const double ul8 = b->R[2][0] * ug[6] + b->R[2][1] * ug[7] + b->R[2][2] * ug[8];
+    b->ul17 = ul1 - ul7; b->ul28 = ul2 - ul8;
+  }
   double v[6], dv[6], vin[6];
   crd3d_basic(b, ug, v);
   crd3d_basic(b, dug, dv);
@@ -1270,6 +1340,11 @@ static void beam3_form(const OrcBeam3* b, double* K, double* Rg) {
       kl[10][i] = tmp[4][i];
       kl[11][i] = tmp[2][i];
     }
+    if (b->pdelta) {   /* PDeltaCrdTransf3d::getGlobalStiffMatrix, PDeltaCrdTransf3d.cpp:873-881 */
+      const double NoverL = b->Se[0] * oneOverL;
+      kl[1][1] += NoverL; kl[2][2] += NoverL; kl[7][7] += NoverL; kl[8][8] += NoverL;
+      kl[1][7] -= NoverL; kl[7][1] -= NoverL; kl[2][8] -= NoverL; kl[8][2] -= NoverL;
+    }
     for (int m = 0; m < 12; m++)
       for (int blk = 0; blk < 4; blk++)
         for (int c = 0; c < 3; c++)
@@ -1293,6 +1368,12 @@ static void beam3_form(const OrcBeam3* b, double* K, double* Rg) {
     p0[3] -= Vr; p0[4] -= Vr;
   }
   pl[0] += p0[0]; pl[1] += p0[1]; pl[7] += p0[2]; pl[2] += p0[3]; pl[8] += p0[4];   /* LinearCrdTransf3d.cpp:727-731 */
+  if (b->pdelta) {   /* PDeltaCrdTransf3d::getGlobalResistingForce, PDeltaCrdTransf3d.cpp:784-790 */
+    double NoverL = b->ul17 * q[0] * oneOverL;
+    pl[1] += NoverL; pl[7] -= NoverL;
+    NoverL = b->ul28 * q[0] * oneOverL;
+    pl[2] += NoverL; pl[8] -= NoverL;
+  }
   for (int blk = 0; blk < 4; blk++)
     for (int c = 0; c < 3; c++)
       Rg[3 * blk + c] = R[0][c] * pl[3 * blk] + R[1][c] * pl[3 * blk + 1] + R[2][c] * pl[3 * blk + 2];
@@ -1523,6 +1604,7 @@ static OrcBeam3* beam3_build(OrcModel* m, OrcEle* e, int sd, const double* par) 
     }
   }
   if (crd3d_init(b, m->crd + e->node[0] * 3, m->crd + e->node[1] * 3, par + 3) < 0) return NULL;
+  b->pdelta = (int)par[6];     /* par[6]: 0 geomTransf Linear, 1 PDelta */
   return b;
 }
 /* a fresh OrcBeam for element e: sections with their fibres in the initial state, transformation, zero element state */
@@ -1546,6 +1628,7 @@ static OrcBeam* beam2_build(OrcModel* m, OrcEle* e, int sd, const double* par) {
   double dx0 = m->crd[e->node[1] * 2] - m->crd[e->node[0] * 2], dx1 = m->crd[e->node[1] * 2 + 1] - m->crd[e->node[0] * 2 + 1];
   b->L = sqrt(dx0 * dx0 + dx1 * dx1);
   b->cosTheta = dx0 / b->L; b->sinTheta = dx1 / b->L;
+  b->pdelta = (int)par[3]; b->utrial = m->trial; b->n0 = e->node[0]; b->n1 = e->node[1];   /* par[3]: 0 geomTransf Linear, 1 PDelta */
   return b;
 }
 static int quad_update(OrcModel* m, OrcEle* el);

@@ -256,6 +256,14 @@ def soil_frame_2d(nbay=2, nstory=2, ndiv=1, per_bay=3, ny=4, depth=240.0, mat=J2
     return spec
 
 
+def with_pdelta(spec):
+    """`geomTransf PDelta` instead of Linear on every forceBeamColumn of the spec (element parameter 3 in 2D, 6 in 3D)"""
+    for g in spec.groups:
+        if g.kind == ELE_FBC2D: g.par[:, 3] = 1.0
+        elif g.kind == ELE_FBC3D: g.par[:, 6] = 1.0
+    return spec
+
+
 def with_beam_gravity(spec, w=-0.25, axial=0.02, seed=0):
     """`eleLoad -beamUniform` on the horizontal members (girders): transverse w (+-20 % per element), a little axial load,
     and -- 3D -- a small lateral component; columns stay unloaded"""
@@ -831,15 +839,15 @@ class RefBackend(_Backend):
             assert L.ref_add_nd_material(self.h, tag, kind, _p(pp)) == 0
         L.ref_add_quad.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_double,
                                    ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_void_p]
-        L.ref_add_force_beam2d.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
-                                           ctypes.c_int, ctypes.c_double]
+        L.ref_add_force_beam2d_t.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_int, ctypes.c_double, ctypes.c_int]
         for tag, kind, p in spec.uniaxials:
             pp = np.zeros(12); pp[:len(p)] = p
             assert L.ref_add_uniaxial(self.h, tag, kind, _p(pp)) == 0
         L.ref_add_fiber_section3d.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double]
-        L.ref_add_force_beam3d.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
-                                           ctypes.c_int, ctypes.c_double, ctypes.c_void_p]
+        L.ref_add_force_beam3d_t.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_int]
         for sec in spec.sections:
             if isinstance(sec[1], str):     # (tag, "aggregator", uniaxial tags for P, Mz)
                 mt = np.ascontiguousarray(sec[2], np.int32); codes = np.array([SEC_P, SEC_MZ], np.int32)
@@ -861,11 +869,11 @@ class RefBackend(_Backend):
                     assert L.ref_add_brick(self.h, int(g.tags[i]), _p(c), int(g.mat[i]), _p(b)) == 0
                 elif g.kind == ELE_FBC3D:
                     vx = np.ascontiguousarray(g.par[i, 3:6], np.float64)
-                    assert L.ref_add_force_beam3d(self.h, int(g.tags[i]), _p(c), int(g.mat[i]), int(g.par[i, 0]),
-                                                  int(g.par[i, 1]), float(g.par[i, 2]), _p(vx)) == 0
+                    assert L.ref_add_force_beam3d_t(self.h, int(g.tags[i]), _p(c), int(g.mat[i]), int(g.par[i, 0]),
+                                                    int(g.par[i, 1]), float(g.par[i, 2]), _p(vx), int(g.par[i, 6])) == 0
                 elif g.kind == ELE_FBC2D:
-                    assert L.ref_add_force_beam2d(self.h, int(g.tags[i]), _p(c), int(g.mat[i]), int(g.par[i, 0]),
-                                                  int(g.par[i, 1]), float(g.par[i, 2])) == 0
+                    assert L.ref_add_force_beam2d_t(self.h, int(g.tags[i]), _p(c), int(g.mat[i]), int(g.par[i, 0]),
+                                                    int(g.par[i, 1]), float(g.par[i, 2]), int(g.par[i, 3])) == 0
                 else:
                     b = np.ascontiguousarray(g.par[i, 4:6], np.float64)
                     assert L.ref_add_quad(self.h, int(g.tags[i]), _p(c), int(g.mat[i]), float(g.par[i, 0]),

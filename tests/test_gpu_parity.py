@@ -200,7 +200,7 @@ def test_newton_iteration_counts_match_oracle(shape):
 
 @pytest.mark.skipif(not (have_ref() and have_glue()), reason="oracle/_ref not built (needs /root/reference)")
 @pytest.mark.parametrize("shape,numberer,soe", [("brick", 1, 0), ("quad", 0, 1), ("mixed", 1, 1), ("soilcolumn_equaldof", 1, 0), ("frame2d_gravity", 1, 0), ("soil_frame_mixed_ndf", 1, 0),
-                                                ("soilcolumn_equaldof", 0, 1)])
+                                                ("soilcolumn_equaldof", 0, 1), ("frame2d_pdelta", 1, 0), ("frame3d_pdelta", 1, 0)])
 def test_reference_newton_loop_drives_device_path(shape, numberer, soe):
     """The drop-in, end to end: the REFERENCE'S OWN StaticAnalysis objects (AnalysisModel, PlainHandler, numberer,
     SparseGenCol/Row SOE and solver, NewtonRaphson, CTestNormDispIncr, LoadControl::newStep) run a load-controlled
@@ -222,6 +222,11 @@ def test_reference_newton_loop_drives_device_path(shape, numberer, soe):
         def mk():   # `eleLoad -beamUniform` on the girders read out of the load pattern, pushed well into the inelastic range
             from modelspec import with_beam_gravity
             sp = with_beam_gravity(frame2d(2, 3, 2, lateral=15.0), w=-0.2, seed=1); return sp
+    elif shape in ("frame2d_pdelta", "frame3d_pdelta"):
+        def mk():   # `geomTransf PDelta` read out of the elements' CrdTransf: heavy gravity, then the lateral push
+            from modelspec import with_pdelta
+            return with_pdelta(frame2d(2, 3, 2, lateral=15.0, gravity=-150.0) if shape == "frame2d_pdelta"
+                               else frame3d(1, 1, 2, ndiv=2, lateral=(18.0, 10.0), gravity=-90.0))
     elif shape == "soilcolumn_equaldof":
         def mk():   # MP_Constraints read out of the Domain (`equalDOF`): sheared soil column with tied sides
             sp = soil_column_equaldof(12, mat=J2_STEEL, distort=0.1)
@@ -917,6 +922,49 @@ def test_frame_fibre_beams_vs_oracle_history():
     # the history went well past yield: the tangent is far from the initial one
     D0 = xb.DeviceModel.from_spec(spec, 1, 0).to_device(0)
     assert relerr(D.form_tangent(), D0.form_tangent()) > 0.05
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_pdelta_transformation_device_vs_oracle(dim):
+    """forceBeamColumn under `geomTransf PDelta` (PDeltaCrdTransf2d.cpp / PDeltaCrdTransf3d.cpp: geometric stiffness N/L,
+    leaning-column shear): sway history under gravity with commits and a revert to the last commit, device against the
+    oracle (pinned to the reference's classes, incl. the 3D element's stale relative displacements after a revert)"""
+    from modelspec import with_beam_gravity, with_pdelta
+    rng = np.random.default_rng(6)
+    mk = (lambda: frame2d(2, 3, 2, gravity=-120.0)) if dim == 2 else (lambda: frame3d(1, 1, 2, gravity=-40.0))
+    spec = with_pdelta(with_beam_gravity(mk(), seed=4))
+    O = OracleBackend(spec, 1, 0); Ol = OracleBackend(with_beam_gravity(mk(), seed=4), 1, 0)
+    D = xb.DeviceModel.from_spec(spec, 1, 0).to_device(0)
+    ids = O.ids()
+    hcol = spec.crd[:, 1] if dim == 2 else spec.crd[:, 2]
+    H = hcol.max(); h = hcol / H
+    nd = 6 if dim == 2 else 12
+    differs = False
+    for s, a in enumerate([0.3, 0.7, 1.1, 1.5, 1.9, 2.3]):
+        u = np.zeros((spec.nn, spec.ndf))
+        if dim == 2:
+            u[:, 0] = a * h ** 1.5; u[:, 1] = -0.01 * h; u[:, 2] = -1.5 * a * h ** 0.5 / H
+            u += rng.normal(0, 1.0, u.shape) * (2e-3, 1e-3, 2e-5)
+        else:
+            u[:, 0] = a * h ** 1.5; u[:, 1] = 0.6 * a * h ** 1.5; u[:, 2] = -0.01 * h
+            u[:, 3] = 0.9 * a * h ** 0.5 / H; u[:, 4] = -1.5 * a * h ** 0.5 / H
+            u += rng.normal(0, 1.0, u.shape) * (2e-3, 2e-3, 1e-3, 2e-5, 2e-5, 2e-5)
+        u[ids < 0] = 0
+        lam = 0.2 * (s + 1)
+        for m in (O, Ol):
+            m.apply_load(lam); assert m.set_trial_disp(u) == 0
+        D.apply_load(lam); D.set_trial_disp(u); D.update()
+        Ao, Bo = O.form_tangent(), O.form_unbalance()
+        assert relerr(D.form_tangent(), Ao) < BEAM_RTOL and relerr(D.form_unbalance(), Bo) < BEAM_RTOL
+        for e in range(O.ne):
+            assert relerr(D.element_tangent(e, nd), O.ele_tangent(e, nd)) < BEAM_RTOL and relerr(D.element_resid(e, nd), O.ele_resid(e, nd)) < BEAM_RTOL
+        differs = differs or (relerr(Ao, Ol.form_tangent()) > 1e-8 and relerr(Bo, Ol.form_unbalance()) > 1e-8)
+        if s == 5:
+            O.revert(); D.revert_to_last_commit()
+            assert relerr(D.form_tangent(), O.form_tangent()) < BEAM_RTOL and relerr(D.form_unbalance(), O.form_unbalance()) < BEAM_RTOL
+        else:
+            O.commit(); Ol.commit(); D.commit()
+    assert differs
 
 
 @pytest.mark.parametrize("ndiv", [1, 4])

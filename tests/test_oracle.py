@@ -320,6 +320,51 @@ def test_aggregator_cantilever_vs_live_reference(ndiv):
     assert close(O.form_tangent(), R.form_tangent(), 1e-12)
 
 
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("dim", [2, 3])
+def test_pdelta_transformation_vs_live_reference(dim):
+    """`geomTransf PDelta` under forceBeamColumn (PDeltaCrdTransf2d.cpp:349-745, PDeltaCrdTransf3d.cpp:200-249, 784-790,
+    873-881): the geometric stiffness N/L and the leaning-column shear ul14 N/L against the reference's classes over a
+    sway history under gravity (axial forces present), with commits and a revert to the last commit -- after which the 3D
+    element keeps the relative displacements of its last update (ForceBeamColumn3d never refreshes the transformation
+    in getResistingForce), the 2D one does not (ForceBeamColumn2d.cpp:402,526)"""
+    from modelspec import with_pdelta, with_beam_gravity
+    rng = np.random.default_rng(6)
+    mk = (lambda: frame2d(2, 3, 2, gravity=-120.0)) if dim == 2 else (lambda: frame3d(1, 1, 2, gravity=-40.0))
+    spec = with_pdelta(with_beam_gravity(mk(), seed=4))
+    lin = with_beam_gravity(mk(), seed=4)
+    O, R, Rl = OracleBackend(spec, 1, 0), RefBackend(spec, 1, 0), RefBackend(lin, 1, 0)
+    hcol = spec.crd[:, 1] if dim == 2 else spec.crd[:, 2]
+    H = hcol.max(); h = hcol / H
+    nd = 6 if dim == 2 else 12
+    differs = False
+    for s_, a in enumerate([0.3, 0.7, 1.1, 1.5, 1.9, 2.3]):          # inches of roof drift (the last step is thrown away)
+        u = np.zeros((spec.nn, spec.ndf))
+        if dim == 2:
+            u[:, 0] = a * h ** 1.5; u[:, 1] = -0.01 * h; u[:, 2] = -1.5 * a * h ** 0.5 / H
+            u += rng.normal(0, 1.0, u.shape) * (2e-3, 1e-3, 2e-5)
+        else:
+            u[:, 0] = a * h ** 1.5; u[:, 1] = 0.6 * a * h ** 1.5; u[:, 2] = -0.01 * h
+            u[:, 3] = 0.9 * a * h ** 0.5 / H; u[:, 4] = -1.5 * a * h ** 0.5 / H
+            u += rng.normal(0, 1.0, u.shape) * (2e-3, 2e-3, 1e-3, 2e-5, 2e-5, 2e-5)
+        u[O.ids() < 0] = 0
+        lam = 0.2 * (s_ + 1)
+        for m in (O, R, Rl):
+            m.apply_load(lam); m.set_trial_disp(u)
+        Ao, Ar = O.form_tangent(), R.form_tangent()
+        Bo, Br = O.form_unbalance(), R.form_unbalance()
+        assert close(Ao, Ar, 1e-11) and close(Bo, Br, 1e-11)
+        for e in range(O.ne):
+            assert close(O.ele_resid(e, nd), R.ele_resid(e, nd), 1e-11) and close(O.ele_tangent(e, nd), R.ele_tangent(e, nd), 1e-11)
+        differs = differs or (not close(Ar, Rl.form_tangent(), 1e-8) and not close(Br, Rl.form_unbalance(), 1e-8))   # (1000 x the parity tolerance)
+        if s_ == 5:
+            O.revert(); R.revert(); Rl.revert()
+            assert close(O.form_tangent(), R.form_tangent(), 1e-11) and close(O.form_unbalance(), R.form_unbalance(), 1e-11)
+        else:
+            O.commit(); R.commit(); Rl.commit()
+    assert differs          # the P-Delta terms are really there: the Linear transformation gives another system
+
+
 def drive_transient_vs_golden(model, g, name, check, is_dev=False):
     """replays the golden Newmark history (the reference's dU per iteration) through `model`"""
     (c1, c2, c3), (a1, a2, a3, a4) = newmark_coeffs(float(g["gamma"]), float(g["beta"]), float(g["dt"]))

@@ -77,6 +77,13 @@ struct BeamView {
   const double* wl;
   double lam;
   int loads_on;
+  // geomTransf PDelta (PDeltaCrdTransf2d.cpp / PDeltaCrdTransf3d.cpp): geometric stiffness N/L and leaning-column shear.
+  // 2D: the relative transverse displacement is taken from the trial displacements U whenever the element forms its
+  // forces (ForceBeamColumn2d.cpp:402,526 refresh the transformation); 3D: ul17, ul28 as of the element's last update
+  // (ForceBeamColumn3d never refreshes it), kept in ul [2][n]
+  int pdelta;
+  const double* U;
+  double* ul;
 };
 
 // transient coefficients handed to the form kernels (see TanCoef / DynCoef in device_model.cu)
@@ -403,6 +410,19 @@ __global__ void __launch_bounds__(128) fbc2d_form_kernel(BeamView B, int want_k,
       kg[3][c] = -kg[0][c]; kg[4][c] = -kg[1][c];
       kg[5][c] = tmp[2][c];
     }
+    if (B.pdelta) {
+      // PDeltaCrdTransf2d::getGlobalStiffMatrix (PDeltaCrdTransf2d.cpp:628-633): N/L on the local transverse dofs,
+      // kl[1][1], kl[4][4] += N/L, kl[1][4], kl[4][1] -= N/L; in global axes N/L t t' with t = (-sin, cos)
+      const double NoverL = B.Se[e] * oneOverL;
+      const double t[2] = {-sinTheta, cosTheta};
+#pragma unroll
+      for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          const double g = NoverL * t[i] * t[j];
+          kg[i][j] += g; kg[3 + i][3 + j] += g; kg[i][3 + j] -= g; kg[3 + i][j] -= g;
+        }
+    }
     for (int a = 0; a < 2; a++) {
       const long long d = B.kdst[e * 2 + a];
       double* base = d >= 0 ? B.KeN + d : B.sendK + (-d - 1);
@@ -439,6 +459,13 @@ __global__ void __launch_bounds__(128) fbc2d_form_kernel(BeamView B, int want_k,
       const double Vr = 0.5 * wy * L;
       p0[1] -= Vr; p0[2] -= Vr;
       pl[0] += p0[0]; pl[1] += p0[1]; pl[4] += p0[2];
+    }
+    if (B.pdelta) {   // PDeltaCrdTransf2d::update + getGlobalResistingForce (PDeltaCrdTransf2d.cpp:349-384, 532-535)
+      const double* uI = B.U + (size_t)B.conn[e * 2] * 3; const double* uJ = B.U + (size_t)B.conn[e * 2 + 1] * 3;
+      const double ul1 = -sinTheta * uI[0] + cosTheta * uI[1];
+      const double ul4 = -sinTheta * uJ[0] + cosTheta * uJ[1];
+      const double NoverL = (ul1 - ul4) * q0 * oneOverL;
+      pl[1] += NoverL; pl[4] -= NoverL;
     }
     double* R = B.Re + e * 6;
     R[0] = cosTheta * pl[0] - sinTheta * pl[1];
@@ -649,6 +676,11 @@ __global__ void __launch_bounds__(128, XB_FBC_SEC_OCC) fbc3d_update_sec_kernel(B
     }
     crd3d_basic(L, R, ug, v);
     crd3d_basic(L, R, dug, dv);
+    if (B.pdelta && act && i == 0) {   // crdTransf->update(): PDeltaCrdTransf3d.cpp:200-249 (before any early return)
+      const double ul1 = R[3] * ug[0] + R[4] * ug[1] + R[5] * ug[2], ul2 = R[6] * ug[0] + R[7] * ug[1] + R[8] * ug[2];
+      const double ul7 = R[3] * ug[6] + R[4] * ug[7] + R[5] * ug[8], ul8 = R[6] * ug[6] + R[7] * ug[7] + R[8] * ug[8];
+      B.ul[e] = ul1 - ul7; B.ul[n + e] = ul2 - ul8;
+    }
   }
   const int initialFlag = B.iflag[e];
   // (all lanes of an element take the same way out: dv and the load flag are the element's)
@@ -1070,6 +1102,11 @@ __global__ void __launch_bounds__(64) fbc3d_form_kernel(BeamView B, int want_k, 
       kl[10][i] = tmp[4][i];
       kl[11][i] = tmp[2][i];
     }
+    if (B.pdelta) {   // PDeltaCrdTransf3d::getGlobalStiffMatrix, PDeltaCrdTransf3d.cpp:873-881
+      const double NoverL = B.Se[e] * oneOverL;
+      kl[1][1] += NoverL; kl[2][2] += NoverL; kl[7][7] += NoverL; kl[8][8] += NoverL;
+      kl[1][7] -= NoverL; kl[7][1] -= NoverL; kl[2][8] -= NoverL; kl[8][2] -= NoverL;
+    }
     for (int m = 0; m < 12; m++)
       for (int blk = 0; blk < 4; blk++)
         for (int c = 0; c < 3; c++)
@@ -1119,6 +1156,12 @@ __global__ void __launch_bounds__(64) fbc3d_form_kernel(BeamView B, int want_k, 
       Vr = 0.5 * wz * L;
       p0[3] -= Vr; p0[4] -= Vr;
       pl[0] += p0[0]; pl[1] += p0[1]; pl[7] += p0[2]; pl[2] += p0[3]; pl[8] += p0[4];
+    }
+    if (B.pdelta) {   // PDeltaCrdTransf3d::getGlobalResistingForce, PDeltaCrdTransf3d.cpp:784-790
+      double NoverL = B.ul[e] * q[0] * oneOverL;
+      pl[1] += NoverL; pl[7] -= NoverL;
+      NoverL = B.ul[n + e] * q[0] * oneOverL;
+      pl[2] += NoverL; pl[8] -= NoverL;
     }
     double* Rg = B.Re + e * 12;
     for (int blk = 0; blk < 4; blk++)

@@ -1946,6 +1946,8 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
       const double det = k0[0] * k0[3] - k0[2] * k0[1];
       std::vector<double> fs0 = {k0[3] / det, -k0[1] / det, -k0[2] / det, k0[0] / det};
       b.agg = sd.agg ? 1 : 0;
+      b.pdelta = g.transf == 1 ? 1 : 0; b.U = m->dU; b.ul = nullptr;
+      if (b.pdelta && b3) { CU(dev_alloc(m, &b.ul, (size_t)2 * std::max<long long>(ne, 1))); CU(cudaMemset(b.ul, 0, sizeof(double) * 2 * std::max<long long>(ne, 1))); }
       if (sd.agg) {   // SectionAggregator::getInitialFlexibility, SectionAggregator.cpp:454-479: 1 / initial tangent on the diagonal
         auto e0 = [&](int f) { const xb::Uniaxial& u = h.unis[sd.mat[f]]; return u.kind == XB_UNI_ELASTIC ? (u.par[0] > u.par[2] ? u.par[0] : u.par[2]) : u.par[1]; };
         fs0 = {1.0 / e0(0), 0.0, 0.0, 1.0 / e0(1)};
@@ -2175,6 +2177,9 @@ int xb_set_rayleigh_alpha_m(xb_model* m, double alphaM) {
 // device side of `rayleigh`: buffers the damping terms need, sized on first use
 static int apply_rayleigh(xb_model* m) {
   if (!m->on_device) return XB_OK;
+  if (m->rayK != 0.0 || m->rayK0 != 0.0 || m->rayKc != 0.0)
+    for (auto& d : m->dg) if (is_beam(d.kind) && d.b.pdelta)
+      return fail(XB_ERR_UNSUPPORTED, "stiffness-proportional Rayleigh damping on forceBeamColumn elements with geomTransf PDelta is outside the device path");
   CU(cudaSetDevice(m->device));
   const bool dyn = any_rayleigh(m) || m->any_rho;
   if (dyn && !m->dRt) {

@@ -166,9 +166,13 @@ int HostModel::add_elements(int kind, int n, const int* tags, const int* conn, c
       for (size_t j = 0; j < secs.size(); j++) if (secs[j].tag == mat_tags[i]) sidx = (int)j;
       if (sidx < 0) { err = "forceBeamColumn: unknown section tag"; return XB_ERR_ARG; }
       if (secs[sidx].is3d != b3) { err = "forceBeamColumn: a 3D element needs xb_add_fiber_section3d, a 2D one xb_add_fiber_section"; return XB_ERR_ARG; }
-      if (i == 0) { g.sec = sidx; g.nip = (int)p[0]; g.max_iters = (int)p[1]; g.tol = p[2]; }
-      else if (sidx != g.sec || (int)p[0] != g.nip || (int)p[1] != g.max_iters || p[2] != g.tol) {
-        err = "forceBeamColumn: one section / nIP / maxIters / tol per xb_add_elements call"; return XB_ERR_UNSUPPORTED;
+      // geomTransf: the parameter behind the ones above (2D: par[3], 3D: par[6]) when the caller's rows are that long
+      const int tpos = b3 ? 6 : 3;
+      const int transf = par_stride > tpos ? (int)p[tpos] : 0;
+      if (transf != 0 && transf != 1) { err = "forceBeamColumn: geomTransf is 0 (Linear) or 1 (PDelta); Corotational is outside the device path"; return XB_ERR_UNSUPPORTED; }
+      if (i == 0) { g.sec = sidx; g.nip = (int)p[0]; g.max_iters = (int)p[1]; g.tol = p[2]; g.transf = transf; }
+      else if (sidx != g.sec || (int)p[0] != g.nip || (int)p[1] != g.max_iters || p[2] != g.tol || transf != g.transf) {
+        err = "forceBeamColumn: one section / nIP / maxIters / tol / geomTransf per xb_add_elements call"; return XB_ERR_UNSUPPORTED;
       }
       const int nin = b3 ? 6 : 3;            // what the caller gives; the element-load columns start at zero
       for (int q = 0; q < k.npar; q++) g.par[(size_t)i * k.npar + q] = q < nin ? p[q] : 0.0;

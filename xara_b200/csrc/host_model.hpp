@@ -64,6 +64,7 @@ struct Group {
   std::vector<double> par;   // [n][npar]
   // forceBeamColumn batches: one fibre section, nIP Lobatto points, element iteration controls
   int sec = -1, nip = 0, max_iters = 10;
+  int transf = 0;            // geomTransf of the batch: 0 Linear, 1 PDelta
   double tol = 1e-12;
   bool j2_plane_stress = false;   // FourNodeQuad batch whose J2Plasticity copies are J2PlaneStress
   std::vector<long long> kdst;  // [n][nen] where the rows of node a of element l go: >= 0 offset of the
