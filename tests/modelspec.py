@@ -256,6 +256,17 @@ def soil_frame_2d(nbay=2, nstory=2, ndiv=1, per_bay=3, ny=4, depth=240.0, mat=J2
     return spec
 
 
+def steel01_elastic_frame(dim):
+    """an RC frame whose bars are Steel01 (with isotropic hardening) and whose cover is a bilinear Elastic material: the
+    uniaxial kinds of BASELINE configs[0] as fibres of FiberSection2d / FiberSection3d"""
+    spec = frame2d(2, 2, 2, lateral=20.0) if dim == 2 else frame3d(1, 1, 2, ndiv=2, lateral=(18.0, 10.0))
+    uni = dict((t, (k, p)) for t, k, p in spec.uniaxials)
+    uni[2] = (UNI_ELASTIC, (2500.0, 0.0, 3600.0))                       # cover: softer in tension
+    uni[3] = (UNI_STEEL01, (60.0, 29000.0, 0.015, 0.02, 30.0, 0.02, 30.0))
+    spec.uniaxials = [(t, *uni[t]) for t in sorted(uni)]
+    return spec
+
+
 def with_pdelta(spec):
     """`geomTransf PDelta` instead of Linear on every forceBeamColumn of the spec (element parameter 3 in 2D, 6 in 3D)"""
     for g in spec.groups:

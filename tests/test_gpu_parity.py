@@ -925,6 +925,36 @@ def test_frame_fibre_beams_vs_oracle_history():
 
 
 @pytest.mark.parametrize("dim", [2, 3])
+def test_steel01_elastic_fibres_device_vs_oracle(dim):
+    """Steel01 and Elastic fibres inside FiberSection2d / FiberSection3d (the new uniaxial kinds as ordinary fibres):
+    sway history with commits and a revert, device against the oracle"""
+    from modelspec import steel01_elastic_frame
+    rng = np.random.default_rng(8)
+    spec = steel01_elastic_frame(dim)
+    O = OracleBackend(spec, 1, 0)
+    D = xb.DeviceModel.from_spec(spec, 1, 0).to_device(0)
+    ids = O.ids()
+    hcol = spec.crd[:, 1] if dim == 2 else spec.crd[:, 2]
+    H = hcol.max(); h = hcol / H
+    A0 = O.form_tangent().copy()
+    for s, a in enumerate([0.3, 0.8, 1.4, 2.0, 2.4]):
+        u = np.zeros((spec.nn, spec.ndf))
+        u[:, 0] = a * h ** 1.5
+        u[:, 2 if dim == 2 else 4] = -1.5 * a * h ** 0.5 / H
+        u += rng.normal(0, 1.0, u.shape) * ((2e-3, 1e-3, 2e-5) if dim == 2 else (2e-3, 2e-3, 1e-3, 2e-5, 2e-5, 2e-5))
+        u[ids < 0] = 0
+        O.apply_load(0.2 * (s + 1)); assert O.set_trial_disp(u) == 0
+        D.apply_load(0.2 * (s + 1)); D.set_trial_disp(u); D.update()
+        assert relerr(D.form_tangent(), O.form_tangent()) < BEAM_RTOL and relerr(D.form_unbalance(), O.form_unbalance()) < BEAM_RTOL
+        if s == 4:
+            O.revert(); D.revert_to_last_commit()
+            assert relerr(D.form_tangent(), O.form_tangent()) < BEAM_RTOL and relerr(D.form_unbalance(), O.form_unbalance()) < BEAM_RTOL
+        else:
+            O.commit(); D.commit()
+    assert relerr(O.form_tangent(), A0) > 0.05
+
+
+@pytest.mark.parametrize("dim", [2, 3])
 def test_pdelta_transformation_device_vs_oracle(dim):
     """forceBeamColumn under `geomTransf PDelta` (PDeltaCrdTransf2d.cpp / PDeltaCrdTransf3d.cpp: geometric stiffness N/L,
     leaning-column shear): sway history under gravity with commits and a revert to the last commit, device against the

@@ -322,6 +322,31 @@ def test_aggregator_cantilever_vs_live_reference(ndiv):
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
 @pytest.mark.parametrize("dim", [2, 3])
+def test_steel01_elastic_fibres_vs_live_reference(dim):
+    """Steel01 bars and an Elastic (bilinear Epos / Eneg) cover inside FiberSection2d / FiberSection3d: the new uniaxial
+    kinds as ordinary fibres, against the reference's classes over a sway history with commits"""
+    from modelspec import steel01_elastic_frame
+    rng = np.random.default_rng(8)
+    spec = steel01_elastic_frame(dim)
+    O, R = OracleBackend(spec, 1, 0), RefBackend(spec, 1, 0)
+    hcol = spec.crd[:, 1] if dim == 2 else spec.crd[:, 2]
+    H = hcol.max(); h = hcol / H
+    A0 = R.form_tangent().copy()
+    for s_, a in enumerate([0.3, 0.8, 1.4, 2.0]):
+        u = np.zeros((spec.nn, spec.ndf))
+        u[:, 0] = a * h ** 1.5
+        u[:, 2 if dim == 2 else 4] = -1.5 * a * h ** 0.5 / H
+        u += rng.normal(0, 1.0, u.shape) * ((2e-3, 1e-3, 2e-5) if dim == 2 else (2e-3, 2e-3, 1e-3, 2e-5, 2e-5, 2e-5))
+        u[O.ids() < 0] = 0
+        for m in (O, R):
+            m.apply_load(0.25 * (s_ + 1)); m.set_trial_disp(u)
+        assert close(O.form_tangent(), R.form_tangent(), 1e-11) and close(O.form_unbalance(), R.form_unbalance(), 1e-11)
+        O.commit(); R.commit()
+    assert not close(R.form_tangent(), A0, 0.05)           # well past yield
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("dim", [2, 3])
 def test_pdelta_transformation_vs_live_reference(dim):
     """`geomTransf PDelta` under forceBeamColumn (PDeltaCrdTransf2d.cpp:349-745, PDeltaCrdTransf3d.cpp:200-249, 784-790,
     873-881): the geometric stiffness N/L and the leaning-column shear ul14 N/L against the reference's classes over a
