@@ -145,6 +145,11 @@ int xb_add_nodal_loads(xb_model*, int n, const int* node_tags, const double* val
  * scaled by the load factor of xb_apply_load.  One uniform load per element; point and partial loads: XB_ERR_UNSUPPORTED
  * at the binding. */
 int xb_add_beam_uniform_loads(xb_model*, int n, const int* ele_tags, const double* w);
+/* `eleLoad -ele tags -type -beamPoint Py [Pz] xL [N]` of the Linear pattern (Beam2dPointLoad / Beam3dPointLoad ->
+ * ForceBeamColumn2d.cpp:442-455, 1138-1181; ForceBeamColumn3d.cpp:457-475, 1314-1373): p is [n][4] = Py, Pz (3D), N, xL = a/L.
+ * One point load per element (beside at most one uniform load); a load with xL outside [0, 1] is ignored, as the
+ * element does. */
+int xb_add_beam_point_loads(xb_model*, int n, const int* ele_tags, const double* p);
 
 /* `mass` command: Node::setMass with a diagonal matrix (domain/node/Node.h:127); mass is [n][ndf].
  * Element masses come from the nDMaterial density (J2Plasticity par[7], ElasticIsotropic par[2]): stdBrick forms
@@ -245,7 +250,7 @@ int xb_get_trial_vel_accel(xb_model*, double* v, double* a);
 int xb_update(xb_model*);
 /* AnalysisModel::applyLoadDomain(lambda) for the Linear-series pattern */
 int xb_apply_load(xb_model*, double lambda);
-/* `loadConst` (Domain::setLoadConstant, domain/domain/Domain.cpp; LoadPattern::setLoadConstant, domain/pattern/
+/* `loadConst` (Domain::setLoadConstant, domain/domain/Domain.cpp:1814; LoadPattern::setLoadConstant, domain/pattern/
  * LoadPattern.cpp): the nodal loads applied so far stay at the current load factor; the reference load vector is
  * emptied for the next pattern.  The caller sets the new domain time with xb_apply_load (`loadConst -time 0.0`).
  * Element loads in a constant pattern return XB_ERR_UNSUPPORTED. */

@@ -321,7 +321,16 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
           double w[3] = {0.0, 0.0, 0.0};
           if (type == LOAD_TAG_Beam2dUniformLoad && dynamic_cast<ForceBeamColumn2d*>(ele)) { w[0] = data(0); w[2] = data(1); }
           else if (type == LOAD_TAG_Beam3dUniformLoad && dynamic_cast<ForceBeamColumn3d*>(ele)) { w[0] = data(0); w[1] = data(1); w[2] = data(2); }
-          else { G.err = "glue: ElementalLoad other than -beamUniform on a forceBeamColumn: outside the device path"; return -7; }
+          else if (type == LOAD_TAG_Beam2dPointLoad && dynamic_cast<ForceBeamColumn2d*>(ele)) {   // Ptrans, Paxial, x/L
+            const double p4[4] = {data(0), 0.0, data(1), data(2)};
+            if (xb_add_beam_point_loads(x, 1, &et, p4) < 0) { G.err = xb_last_error(); return -7; }
+            continue;
+          } else if (type == LOAD_TAG_Beam3dPointLoad && dynamic_cast<ForceBeamColumn3d*>(ele)) {   // Py, Pz, Px, x/L
+            const double p4[4] = {data(0), data(1), data(2), data(3)};
+            if (xb_add_beam_point_loads(x, 1, &et, p4) < 0) { G.err = xb_last_error(); return -7; }
+            continue;
+          }
+          else { G.err = "glue: ElementalLoad other than -beamUniform / -beamPoint on a forceBeamColumn: outside the device path"; return -7; }
           if (xb_add_beam_uniform_loads(x, 1, &et, w) < 0) { G.err = xb_last_error(); return -7; }
         } }
       NodalLoadIter& li = lp->getNodalLoads(); NodalLoad* nl;

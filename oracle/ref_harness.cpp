@@ -81,6 +81,8 @@
 #include <SparseGenColLinSolver.h>
 #include <Beam2dUniformLoad.h>
 #include <Beam3dUniformLoad.h>
+#include <Beam2dPointLoad.h>
+#include <Beam3dPointLoad.h>
 #include <BandGenLinSOE.h>
 #include <BandGenLinSolver.h>
 #include <ProfileSPDLinSOE.h>
@@ -392,6 +394,19 @@ int ref_add_beam_uniform_load(void* h, int eleTag, double wy, double wz, double 
   }
   ElementalLoad* el = (m->ndm == 2) ? (ElementalLoad*)new Beam2dUniformLoad(10000 + m->nloads++, wy, wa, eleTag)
                                     : (ElementalLoad*)new Beam3dUniformLoad(10000 + m->nloads++, wy, wz, wa, eleTag);
+  return m->domain->addElementalLoad(el, 1) ? 0 : -1;
+}
+
+// `eleLoad -ele tag -type -beamPoint Py [Pz] xL [N]` in pattern 1
+int ref_add_beam_point_load(void* h, int eleTag, double Py, double Pz, double N, double aOverL) {
+  RefModel* m = (RefModel*)h;
+  if (m->domain->getLoadPattern(m->cur_pattern) == nullptr) {
+    LoadPattern* lp = new LoadPattern(m->cur_pattern);
+    lp->setTimeSeries(new LinearSeries());
+    m->domain->addLoadPattern(lp);
+  }
+  ElementalLoad* el = (m->ndm == 2) ? (ElementalLoad*)new Beam2dPointLoad(20000 + m->nloads++, Py, aOverL, eleTag, N)
+                                    : (ElementalLoad*)new Beam3dPointLoad(20000 + m->nloads++, Py, Pz, aOverL, eleTag, N);
   return m->domain->addElementalLoad(el, 1) ? 0 : -1;
 }
 

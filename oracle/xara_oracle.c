@@ -792,6 +792,8 @@ typedef struct {
   /* `eleLoad -beamUniform wy wa` of the Linear pattern: w = {wy, -, wa}; numEleLoads = 1 once Domain::applyLoad ran
    * (LoadPattern::applyLoad -> ElementalLoad::applyLoad -> ForceBeamColumn2d::addLoad(load, loadFactor)) */
   int has_load, numEleLoads; double w[3], loadFactor;
+  /* `eleLoad -beamPoint Py xL [N]` (Beam2dPointLoad): pt = {Py, -, N, aOverL} */
+  int has_point; double pt[4];
   /* geomTransf PDelta (PDeltaCrdTransf2d.cpp): ul14 is recomputed from the nodes' trial displacements whenever the
    * element asks for its tangent or resisting force (ForceBeamColumn2d.cpp:402,526 call crdTransf->update()) */
   int pdelta; const double* utrial; int n0, n1;
@@ -872,6 +874,13 @@ static int beam_update(OrcBeam* b, const double* ug, const double* dug) {
             double wa = b->w[2] * b->loadFactor, wy = b->w[0] * b->loadFactor;
             Ss[0] += wa * (L - x);
             Ss[1] += wy * 0.5 * x * (x - L);
+            if (b->has_point) {       /* Beam2dPointLoad, ForceBeamColumn2d.cpp:1138-1181 */
+              double P = b->pt[0] * b->loadFactor, N = b->pt[2] * b->loadFactor, aOverL = b->pt[3];
+              double a = aOverL * L;
+              double V1 = P * (1.0 - aOverL), V2 = P * aOverL;
+              if (x <= a) { Ss[0] += N; Ss[1] -= x * V1; }
+              else Ss[1] -= (L - x) * V2;
+            }
           }
           dSs[0] = Ss[0] - SsrSub[i][0]; dSs[1] = Ss[1] - SsrSub[i][1];
           const double* fuse;
@@ -977,6 +986,11 @@ static void beam_form_pdelta(const OrcBeam* b, double* K, double* R) {
     p0[0] -= wa * b->L;
     double Vr = 0.5 * wy * b->L;
     p0[1] -= Vr; p0[2] -= Vr;
+    if (b->has_point) {               /* Beam2dPointLoad, ForceBeamColumn2d.cpp:442-455 */
+      double P = b->pt[0] * b->loadFactor, N = b->pt[2] * b->loadFactor, aOverL = b->pt[3];
+      double V1 = P * (1.0 - aOverL), V2 = P * aOverL;
+      p0[0] -= N; p0[1] -= V1; p0[2] -= V2;
+    }
   }
   pl[0] += p0[0]; pl[1] += p0[1]; pl[4] += p0[2];
   double NoverL = ul14 * q0 * oneOverL;                 /* leaning-column effect, :532-535 */
@@ -1020,6 +1034,11 @@ static void beam_form(const OrcBeam* b, double* K, double* R) {
     p0[0] -= wa * b->L;
     double Vr = 0.5 * wy * b->L;
     p0[1] -= Vr; p0[2] -= Vr;
+    if (b->has_point) {               /* Beam2dPointLoad, ForceBeamColumn2d.cpp:442-455 */
+      double P = b->pt[0] * b->loadFactor, N = b->pt[2] * b->loadFactor, aOverL = b->pt[3];
+      double V1 = P * (1.0 - aOverL), V2 = P * aOverL;
+      p0[0] -= N; p0[1] -= V1; p0[2] -= V2;
+    }
   }
   pl[0] += p0[0]; pl[1] += p0[1]; pl[4] += p0[2];
   R[0] = cosTheta * pl[0] - sinTheta * pl[1];
@@ -1132,6 +1151,8 @@ typedef struct {
   double fs[ORC_MAXSEC][16], vs[ORC_MAXSEC][4], Ssr[ORC_MAXSEC][4], vscommit[ORC_MAXSEC][4];
   /* `eleLoad -beamUniform wy wz wa`: see OrcBeam */
   int has_load, numEleLoads; double w[3], loadFactor;
+  /* `eleLoad -beamPoint Py Pz xL [N]` (Beam3dPointLoad): pt = {Py, Pz, N, aOverL} */
+  int has_point; double pt[4];
   /* geomTransf PDelta (PDeltaCrdTransf3d.cpp:200-249): ul17, ul28 as of the element's last update() -- ForceBeamColumn3d's
    * getTangentStiff / getResistingForce do NOT refresh them (ForceBeamColumn3d.cpp:404,555) */
   int pdelta; double ul17, ul28;
@@ -1241,6 +1262,13 @@ static int beam3_update(OrcBeam3* b, const double* ug, const double* dug) {
             Ss[0] += wa * (L - x);
             Ss[1] += wy * 0.5 * x * (x - L);
             Ss[2] += wz * 0.5 * x * (L - x);
+            if (b->has_point) {       /* Beam3dPointLoad, ForceBeamColumn3d.cpp:1314-1373 */
+              double Py = b->pt[0] * b->loadFactor, Pz = b->pt[1] * b->loadFactor, N = b->pt[2] * b->loadFactor, aOverL = b->pt[3];
+              double a = aOverL * L;
+              double Vy1 = Py * (1.0 - aOverL), Vy2 = Py * aOverL, Vz1 = Pz * (1.0 - aOverL), Vz2 = Pz * aOverL;
+              if (x <= a) { Ss[0] += N; Ss[1] -= x * Vy1; Ss[2] += x * Vz1; }
+              else { Ss[1] -= (L - x) * Vy2; Ss[2] += (L - x) * Vz2; }
+            }
           }
           for (int q = 0; q < 4; q++) dSs[q] = Ss[q] - SsrSub[i][q];
           const double* fuse;
@@ -1366,6 +1394,13 @@ static void beam3_form(const OrcBeam3* b, double* K, double* Rg) {
     p0[1] -= Vr; p0[2] -= Vr;
     Vr = 0.5 * wz * b->L;
     p0[3] -= Vr; p0[4] -= Vr;
+    if (b->has_point) {               /* Beam3dPointLoad, ForceBeamColumn3d.cpp:457-475 */
+      double Py = b->pt[0] * b->loadFactor, Pz = b->pt[1] * b->loadFactor, N = b->pt[2] * b->loadFactor, aOverL = b->pt[3];
+      double V1 = Py * (1.0 - aOverL), V2 = Py * aOverL;
+      p0[0] -= N; p0[1] -= V1; p0[2] -= V2;
+      V1 = Pz * (1.0 - aOverL); V2 = Pz * aOverL;
+      p0[3] -= V1; p0[4] -= V2;
+    }
   }
   pl[0] += p0[0]; pl[1] += p0[1]; pl[7] += p0[2]; pl[2] += p0[3]; pl[8] += p0[4];   /* LinearCrdTransf3d.cpp:727-731 */
   if (b->pdelta) {   /* PDeltaCrdTransf3d::getGlobalResistingForce, PDeltaCrdTransf3d.cpp:784-790 */
@@ -2165,8 +2200,8 @@ void orc_apply_load(void* h, double lambda) {
   m->lambda = lambda;
   for (int e = 0; e < m->ne; e++) {
     OrcEle* el = &m->ele[e];
-    if (el->kind == ORC_ELE_FBC2D && el->beam->has_load) { el->beam->numEleLoads = 1; el->beam->loadFactor = lambda; }
-    if (el->kind == ORC_ELE_FBC3D && el->beam3->has_load) { el->beam3->numEleLoads = 1; el->beam3->loadFactor = lambda; }
+    if (el->kind == ORC_ELE_FBC2D && (el->beam->has_load || el->beam->has_point)) { el->beam->numEleLoads = el->beam->has_load + el->beam->has_point; el->beam->loadFactor = lambda; }
+    if (el->kind == ORC_ELE_FBC3D && (el->beam3->has_load || el->beam3->has_point)) { el->beam3->numEleLoads = el->beam3->has_load + el->beam3->has_point; el->beam3->loadFactor = lambda; }
   }
 }
 /* `eleLoad -ele tag -type -beamUniform wy [wz] wa` in the model's Linear pattern (Beam2dUniformLoad / Beam3dUniformLoad) */
@@ -2177,6 +2212,21 @@ int orc_add_beam_uniform_load(void* h, int ele_tag, double wy, double wz, double
     if (el->tag != ele_tag) continue;
     if (el->kind == ORC_ELE_FBC2D) { if (el->beam->has_load) return -2; el->beam->has_load = 1; el->beam->w[0] = wy; el->beam->w[1] = 0.0; el->beam->w[2] = wa; return 0; }
     if (el->kind == ORC_ELE_FBC3D) { if (el->beam3->has_load) return -2; el->beam3->has_load = 1; el->beam3->w[0] = wy; el->beam3->w[1] = wz; el->beam3->w[2] = wa; return 0; }
+    return -3;
+  }
+  return -1;
+}
+
+/* `eleLoad -ele tag -type -beamPoint Py [Pz] xL [N]` in the model's Linear pattern (Beam2dPointLoad / Beam3dPointLoad); a
+ * load with xL outside [0, 1] is ignored by the element (ForceBeamColumn2d.cpp:447) and is not kept */
+int orc_add_beam_point_load(void* h, int ele_tag, double Py, double Pz, double N, double aOverL) {
+  OrcModel* m = (OrcModel*)h;
+  for (int e = 0; e < m->ne; e++) {
+    OrcEle* el = &m->ele[e];
+    if (el->tag != ele_tag) continue;
+    if (aOverL < 0.0 || aOverL > 1.0) return 0;
+    if (el->kind == ORC_ELE_FBC2D) { if (el->beam->has_point) return -2; el->beam->has_point = 1; el->beam->pt[0] = Py; el->beam->pt[1] = 0.0; el->beam->pt[2] = N; el->beam->pt[3] = aOverL; return 0; }
+    if (el->kind == ORC_ELE_FBC3D) { if (el->beam3->has_point) return -2; el->beam3->has_point = 1; el->beam3->pt[0] = Py; el->beam3->pt[1] = Pz; el->beam3->pt[2] = N; el->beam3->pt[3] = aOverL; return 0; }
     return -3;
   }
   return -1;
@@ -2522,13 +2572,16 @@ int orc_revert_to_start(void* h) {
       el->beam = beam2_build(m, el, el->mat, el->par);
       el->beam->has_load = keep.has_load; el->beam->numEleLoads = keep.numEleLoads; el->beam->loadFactor = keep.loadFactor;
       memcpy(el->beam->w, keep.w, sizeof keep.w);
+      el->beam->has_point = keep.has_point; memcpy(el->beam->pt, keep.pt, sizeof keep.pt);
     } else if (el->kind == ORC_ELE_FBC3D) {
       for (int i = 0; i < el->beam3->nip; i++) free(el->beam3->sec[i].mat);
       const int hl = el->beam3->has_load, nl = el->beam3->numEleLoads; const double lf = el->beam3->loadFactor;
       double wk[3]; memcpy(wk, el->beam3->w, sizeof wk);
+      const int hp = el->beam3->has_point; double pk[4]; memcpy(pk, el->beam3->pt, sizeof pk);
       free(el->beam3);
       el->beam3 = beam3_build(m, el, el->mat, el->par);
       el->beam3->has_load = hl; el->beam3->numEleLoads = nl; el->beam3->loadFactor = lf; memcpy(el->beam3->w, wk, sizeof wk);
+      el->beam3->has_point = hp; memcpy(el->beam3->pt, pk, sizeof pk);
     } else {
       for (int g = 0; g < el->nip; g++) {
         OrcGP* gp = &el->gp[g];

@@ -56,6 +56,7 @@ class ModelSpec:
     equal_dofs: list = field(default_factory=list)  # `equalDOF`: (retained node tag, constrained node tag, [dofs], 0-based)
     sections: list = field(default_factory=list)    # (tag, y[nf], A[nf], uniaxial tags[nf])
     beam_loads: list = field(default_factory=list)  # `eleLoad -beamUniform`: (element tag, wy, wz, wa) in the Linear pattern
+    beam_point_loads: list = field(default_factory=list)  # `eleLoad -beamPoint`: (element tag, Py, Pz, N, xL)
     node_ndf: dict = field(default_factory=dict)    # node tag -> dofs, for nodes created under another `model -ndf` (< the model's ndf)
 
     @property
@@ -264,6 +265,20 @@ def steel01_elastic_frame(dim):
     uni[2] = (UNI_ELASTIC, (2500.0, 0.0, 3600.0))                       # cover: softer in tension
     uni[3] = (UNI_STEEL01, (60.0, 29000.0, 0.015, 0.02, 30.0, 0.02, 30.0))
     spec.uniaxials = [(t, *uni[t]) for t in sorted(uni)]
+    return spec
+
+
+def with_beam_point_loads(spec, P=-6.0, seed=0):
+    """`eleLoad -beamPoint Py [Pz] xL N` on every other forceBeamColumn (xL drawn in [0.15, 0.85], so that some points
+    fall between, some beyond, the Lobatto sections), a small axial component along"""
+    rng = np.random.default_rng(seed)
+    out = []
+    for g in spec.groups:
+        if g.kind not in (ELE_FBC2D, ELE_FBC3D): continue
+        for t in g.tags[::2]:
+            out.append((int(t), P * rng.uniform(0.5, 1.5), (0.4 * P * rng.uniform(0.5, 1.5)) if g.kind == ELE_FBC3D else 0.0,
+                        0.1 * P * rng.uniform(-1, 1), float(rng.uniform(0.15, 0.85))))
+    spec.beam_point_loads = out
     return spec
 
 
@@ -670,6 +685,9 @@ class OracleBackend(_Backend):
         L.orc_add_beam_uniform_load.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double]
         for t, wy, wz, wa in spec.beam_loads:
             assert L.orc_add_beam_uniform_load(self.h, int(t), float(wy), float(wz), float(wa)) == 0
+        L.orc_add_beam_point_load.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_double] * 4
+        for t, py, pz, pn, xl in spec.beam_point_loads:
+            assert L.orc_add_beam_point_load(self.h, int(t), float(py), float(pz), float(pn), float(xl)) == 0
         # soe 2 / 3 / 4: BandGeneral / ProfileSPD / Umfpack -- the column graph, then the SOE's own storage on top of it
         self.soe = soe
         self.neq = L.orc_setup(self.h, numberer, soe if soe in (0, 1) else 0)
@@ -895,6 +913,10 @@ class RefBackend(_Backend):
             for row in spec.loads:
                 v = np.ascontiguousarray(row[1:], np.float64)
                 assert L.ref_add_load(self.h, int(row[0]), _p(v)) == 0
+        if spec.beam_point_loads:
+            L.ref_add_beam_point_load.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_double] * 4
+            for t, py, pz, pn, xl in spec.beam_point_loads:
+                assert L.ref_add_beam_point_load(self.h, int(t), float(py), float(pz), float(pn), float(xl)) == 0
         if spec.beam_loads:
             L.ref_add_beam_uniform_load.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double]
             for t, wy, wz, wa in spec.beam_loads:

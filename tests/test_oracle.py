@@ -134,16 +134,20 @@ def test_oracle_vs_live_reference(mat, numberer, soe):
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("loads", ["uniform", "point", "both"])
 @pytest.mark.parametrize("dim", [2, 3])
-def test_beam_uniform_element_loads_vs_live_reference(dim):
-    """`eleLoad -beamUniform` on force beams (ForceBeamColumn2d.cpp:407,1034 / ForceBeamColumn3d.cpp:419,1197): the section
+def test_beam_uniform_element_loads_vs_live_reference(dim, loads):
+    """`eleLoad -beamPoint` (Beam2d/3dPointLoad: ForceBeamColumn2d.cpp:442-455, 1138-1181; ForceBeamColumn3d.cpp:457-475,
+    1314-1373; points between and beyond the Lobatto sections) and `eleLoad -beamUniform` on force beams (ForceBeamColumn2d.cpp:407,1034 / ForceBeamColumn3d.cpp:419,1197): the section
     forces sp inside the element iteration and the fixed-end reactions p0 in the resisting force -- A, B and the
     element forces against the reference over a load history in which the load factor grows (gravity ramp), incl. steps
     with a zero displacement increment (the element must iterate all the same: numEleLoads > 0)"""
-    from modelspec import with_beam_gravity
+    from modelspec import with_beam_gravity, with_beam_point_loads
     rng = np.random.default_rng(5)
-    spec = with_beam_gravity(frame2d(2, 2, 2) if dim == 2 else frame3d(1, 1, 2), seed=3)
-    assert len(spec.beam_loads) >= 4
+    spec = frame2d(2, 2, 2) if dim == 2 else frame3d(1, 1, 2)
+    if loads != "point": spec = with_beam_gravity(spec, seed=3)
+    if loads != "uniform": spec = with_beam_point_loads(spec, seed=2)
+    assert len(spec.beam_loads) + len(spec.beam_point_loads) >= 4
     O, R = OracleBackend(spec, 1, 0), RefBackend(spec, 1, 0)
     sc = np.asarray((0.02, 0.02, 2e-4) if dim == 2 else (0.015, 0.015, 0.003, 1e-4, 1e-4, 1e-4))
     u = np.zeros((spec.nn, spec.ndf))

@@ -71,6 +71,7 @@ def _load():
         "xb_set_nodal_loads": (i32, [vp, i32, vp, vp]),
         "xb_add_elements": (i32, [vp, i32, i32, vp, vp, vp, vp, i32]),
         "xb_add_beam_uniform_loads": (i32, [vp, i32, vp, vp]),
+        "xb_add_beam_point_loads": (i32, [vp, i32, vp, vp]),
         "xb_add_nodal_loads": (i32, [vp, i32, vp, vp]),
         "xb_set_nodal_mass": (i32, [vp, i32, vp, vp]),
         "xb_set_rayleigh_alpha_m": (i32, [vp, f64]),
@@ -239,6 +240,11 @@ class DeviceModel:
         self._ck(lib.xb_add_elements(self._h, kind, len(tags), _ptr(tags), _ptr(conn), _ptr(mat_tags),
                                      _ptr(par), par.shape[1]))
 
+    def add_beam_point_loads(self, ele_tags, p):
+        """eleLoad -beamPoint: p [n][4] = Py, Pz, N, xL per element"""
+        ele_tags, p = _i32(ele_tags), _f64(p)
+        self._ck(lib.xb_add_beam_point_loads(self._h, len(ele_tags), _ptr(ele_tags), _ptr(p)))
+
     def add_beam_uniform_loads(self, ele_tags, w):
         """`eleLoad -beamUniform`: w [n][3] = wy, wz, wa per element (Linear pattern)"""
         ele_tags, w = _i32(ele_tags), _f64(w)
@@ -284,6 +290,9 @@ class DeviceModel:
             m.add_elements(g.kind, g.tags, g.conn, g.mat, g.par)
         if spec.loads is not None and len(spec.loads):
             m.add_nodal_loads(spec.loads[:, 0].astype(np.int32), spec.loads[:, 1:])
+        bp = getattr(spec, "beam_point_loads", [])
+        if bp:
+            m.add_beam_point_loads([t for t, *_ in bp], np.array([q for _, *q in bp], np.float64))
         bl = getattr(spec, "beam_loads", [])
         if bl:
             m.add_beam_uniform_loads([t for t, *_ in bl], np.array([w for _, *w in bl], np.float64))

@@ -74,9 +74,10 @@ struct BeamView {
   double* kvK;
   // `eleLoad -beamUniform` of the Linear pattern: wy, wz, wa per element [3][n] (null: none), the pattern's load factor,
   // and whether Domain::applyLoad has run (numEleLoads > 0: the element iterates at every update)
-  const double* wl;
+  const double* wl;            // [7][n]: wy, wz, wa, then `eleLoad -beamPoint` Py, Pz, N, aOverL (has_point)
   double lam;
   int loads_on;
+  int has_point;
   // geomTransf PDelta (PDeltaCrdTransf2d.cpp / PDeltaCrdTransf3d.cpp): geometric stiffness N/L and leaning-column shear.
   // 2D: the relative transverse displacement is taken from the trial displacements U whenever the element forms its
   // forces (ForceBeamColumn2d.cpp:402,526 refresh the transformation); 3D: ul17, ul28 as of the element's last update
@@ -458,6 +459,11 @@ __global__ void __launch_bounds__(128) fbc2d_form_kernel(BeamView B, int want_k,
       p0[0] -= wa * L;
       const double Vr = 0.5 * wy * L;
       p0[1] -= Vr; p0[2] -= Vr;
+      if (B.has_point) {   // Beam2dPointLoad (ForceBeamColumn2d.cpp:442-455); no point load on this element: zeros
+        const double P = B.wl[3 * n + e] * B.lam, N = B.wl[5 * n + e] * B.lam, aOverL = B.wl[6 * n + e];
+        const double V1 = P * (1.0 - aOverL), V2 = P * aOverL;
+        p0[0] -= N; p0[1] -= V1; p0[2] -= V2;
+      }
       pl[0] += p0[0]; pl[1] += p0[1]; pl[4] += p0[2];
     }
     if (B.pdelta) {   // PDeltaCrdTransf2d::update + getGlobalResistingForce (PDeltaCrdTransf2d.cpp:349-384, 532-535)
@@ -685,7 +691,8 @@ __global__ void __launch_bounds__(128, XB_FBC_SEC_OCC) fbc3d_update_sec_kernel(B
   const int initialFlag = B.iflag[e];
   // (all lanes of an element take the same way out: dv and the load flag are the element's)
   // numEleLoads > 0 for THIS element (ForceBeamColumn3d.cpp: the early return needs numEleLoads == 0)
-  const bool loaded = B.wl != nullptr && B.loads_on && (B.wl[e] != 0.0 || B.wl[n + e] != 0.0 || B.wl[2 * n + e] != 0.0);
+  const bool pointed = B.wl != nullptr && B.loads_on && B.has_point && (B.wl[3 * n + e] != 0.0 || B.wl[4 * n + e] != 0.0 || B.wl[5 * n + e] != 0.0);
+  const bool loaded = pointed || (B.wl != nullptr && B.loads_on && (B.wl[e] != 0.0 || B.wl[n + e] != 0.0 || B.wl[2 * n + e] != 0.0));
   if (initialFlag != 0 && norm6(dv) <= DBL_EPSILON && !loaded) return;
 #pragma unroll
   for (int q = 0; q < 6; q++) vin[q] = v[q] - dv[q];
@@ -696,6 +703,13 @@ __global__ void __launch_bounds__(128, XB_FBC_SEC_OCC) fbc3d_update_sec_kernel(B
     const double x = xL * L;
     const double wy = B.wl[e] * B.lam, wz = B.wl[n + e] * B.lam, wa = B.wl[2 * n + e] * B.lam;
     sp0 = wa * (L - x); sp1 = wy * 0.5 * x * (x - L); sp2 = wz * 0.5 * x * (L - x);
+    if (pointed) {   // Beam3dPointLoad (ForceBeamColumn3d.cpp:1314-1373)
+      const double Py = B.wl[3 * n + e] * B.lam, Pz = B.wl[4 * n + e] * B.lam, N = B.wl[5 * n + e] * B.lam, aOverL = B.wl[6 * n + e];
+      const double a = aOverL * L;
+      const double Vy1 = Py * (1.0 - aOverL), Vy2 = Py * aOverL, Vz1 = Pz * (1.0 - aOverL), Vz2 = Pz * aOverL;
+      if (x <= a) { sp0 += N; sp1 -= x * Vy1; sp2 += x * Vz1; }
+      else { sp1 -= (L - x) * Vy2; sp2 += (L - x) * Vz2; }
+    }
   }
   // initial section flexibility: 3x3 block (column-major, stride 3) + torsion
   double f0[9], f0t;
@@ -912,7 +926,8 @@ __global__ void __launch_bounds__(128, XB_FBC_SEC_OCC) fbc2d_update_sec_kernel(B
   }
   const int initialFlag = B.iflag[e];
   // numEleLoads > 0 for THIS element (ForceBeamColumn2d.cpp:575)
-  const bool loaded = B.wl != nullptr && B.loads_on && (B.wl[e] != 0.0 || B.wl[2 * n + e] != 0.0);
+  const bool pointed = B.wl != nullptr && B.loads_on && B.has_point && (B.wl[3 * n + e] != 0.0 || B.wl[5 * n + e] != 0.0);
+  const bool loaded = pointed || (B.wl != nullptr && B.loads_on && (B.wl[e] != 0.0 || B.wl[2 * n + e] != 0.0));
   if (initialFlag != 0 && sqrt(dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]) <= DBL_EPSILON && !loaded) return;
 #pragma unroll
   for (int q = 0; q < 3; q++) vin[q] = v[q] - dv[q];
@@ -923,6 +938,13 @@ __global__ void __launch_bounds__(128, XB_FBC_SEC_OCC) fbc2d_update_sec_kernel(B
     const double x = xL * L;
     const double wy = B.wl[e] * B.lam, wa = B.wl[2 * n + e] * B.lam;
     sp0 = wa * (L - x); sp1 = wy * 0.5 * x * (x - L);
+    if (pointed) {   // Beam2dPointLoad (ForceBeamColumn2d.cpp:1138-1181)
+      const double P = B.wl[3 * n + e] * B.lam, N = B.wl[5 * n + e] * B.lam, aOverL = B.wl[6 * n + e];
+      const double a = aOverL * L;
+      const double V1 = P * (1.0 - aOverL), V2 = P * aOverL;
+      if (x <= a) { sp0 += N; sp1 -= x * V1; }
+      else sp1 -= (L - x) * V2;
+    }
   }
   double f0[4];
 #pragma unroll
@@ -1155,6 +1177,13 @@ __global__ void __launch_bounds__(64) fbc3d_form_kernel(BeamView B, int want_k, 
       p0[1] -= Vr; p0[2] -= Vr;
       Vr = 0.5 * wz * L;
       p0[3] -= Vr; p0[4] -= Vr;
+      if (B.has_point) {   // Beam3dPointLoad (ForceBeamColumn3d.cpp:457-475)
+        const double Py = B.wl[3 * n + e] * B.lam, Pz = B.wl[4 * n + e] * B.lam, N = B.wl[5 * n + e] * B.lam, aOverL = B.wl[6 * n + e];
+        double V1 = Py * (1.0 - aOverL), V2 = Py * aOverL;
+        p0[0] -= N; p0[1] -= V1; p0[2] -= V2;
+        V1 = Pz * (1.0 - aOverL); V2 = Pz * aOverL;
+        p0[3] -= V1; p0[4] -= V2;
+      }
       pl[0] += p0[0]; pl[1] += p0[1]; pl[7] += p0[2]; pl[2] += p0[3]; pl[8] += p0[4];
     }
     if (B.pdelta) {   // PDeltaCrdTransf3d::getGlobalResistingForce, PDeltaCrdTransf3d.cpp:784-790

@@ -1711,6 +1711,7 @@ int xb_add_elements(xb_model* m, int kind, int n, const int* tags, const int* co
   HOSTCALL(m->h.add_elements(kind, n, tags, conn, mt, par, ps));
 }
 int xb_add_nodal_loads(xb_model* m, int n, const int* t, const double* v) { HOSTCALL(m->h.add_loads(n, t, v)); }
+int xb_add_beam_point_loads(xb_model* m, int n, const int* t, const double* p) { HOSTCALL(m->h.add_beam_point_loads(n, t, p)); }
 int xb_add_beam_uniform_loads(xb_model* m, int n, const int* t, const double* w) { HOSTCALL(m->h.add_beam_uniform_loads(n, t, w)); }
 int xb_setup(xb_model* m, int numberer, int soe_kind) { HOSTCALL(m->h.setup(numberer, soe_kind)); }
 int xb_setup_partitioned(xb_model* m, int numberer, int soe_kind, int nparts, int rank, const int* part) {
@@ -1904,7 +1905,18 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
         for (long long e = 0; e < ne; e++)
           for (int q = 0; q < 3; q++) { wl[(size_t)q * ne + e] = g.par[(size_t)e * k.npar + k.npar - 3 + q]; any = any || wl[(size_t)q * ne + e] != 0.0; }
         b.wl = nullptr; b.lam = 0.0; b.loads_on = 0;
-        if (any) { double* dwl = nullptr; CU(dev_upload(m, &dwl, wl)); b.wl = dwl; }
+        // `eleLoad -beamPoint`: Py, Pz, N, aOverL per element, SoA [4][n] behind the three rows of the uniform load (an
+        // element without a point load carries zeros: its terms vanish); one array for both kinds of load
+        std::vector<double> pl((size_t)4 * ne, 0.0);
+        bool anyp = false;
+        for (long long e = 0; e < ne; e++) {
+          const double* q = &g.par[(size_t)e * k.npar + k.npar - 8];
+          if (q[4] == 0.0) continue;
+          anyp = true;
+          for (int c = 0; c < 4; c++) pl[(size_t)c * ne + e] = q[c];
+        }
+        b.has_point = anyp ? 1 : 0;
+        if (any || anyp) { wl.insert(wl.end(), pl.begin(), pl.end()); double* dwl = nullptr; CU(dev_upload(m, &dwl, wl)); b.wl = dwl; }
       }
       // section template + initial fibre records (Steel02::revertToStart, Concrete02 constructor)
       std::vector<double> fy(nf), fz(nf, 0.0), fA(sd.A), fpar((size_t)nf * 12), ic((size_t)nf * XB_FIB_NV, 0.0), it((size_t)nf * XB_FIB_NV, 0.0);

@@ -13,11 +13,11 @@ namespace xb {
 
 static const EleKind kBrick{8, 3, 8, 6, 3};
 static const EleKind kQuad{4, 2, 4, 3, 5};  // par kept: thickness, b1, b2, type (0 PlaneStrain, 1 PlaneStress), pressure
-// nip is a property of the batch.  par kept per element: nIP, maxIters, tol, [vecxz[3],] then the uniform element load
-// of the Linear pattern (`eleLoad -beamUniform`): wy, wz, wa (zero: none) -- it travels with the element through the
-// partitioning like every other element parameter
-static const EleKind kBeam2d{2, 3, 0, 2, 6};  // par: nIP, maxIters, tol, wy, wz (unused), wa
-static const EleKind kBeam3d{2, 6, 0, 4, 9};  // par: nIP, maxIters, tol, vecxz[3], wy, wz, wa
+// nip is a property of the batch.  par kept per element: nIP, maxIters, tol, [vecxz[3],] then the element loads of the
+// Linear pattern: `eleLoad -beamPoint` Py, Pz, N, aOverL (has-load flag in a 5th value) and `eleLoad -beamUniform` wy, wz, wa
+// (zero: none) -- they travel with the element through the partitioning like every other element parameter
+static const EleKind kBeam2d{2, 3, 0, 2, 11};  // par: nIP, maxIters, tol, point load[5], wy, wz (unused), wa
+static const EleKind kBeam3d{2, 6, 0, 4, 14};  // par: nIP, maxIters, tol, vecxz[3], point load[5], wy, wz, wa
 
 const EleKind& ele_kind(int kind) {
   return kind == XB_ELE_STDBRICK ? kBrick : (kind == XB_ELE_FOURNODEQUAD ? kQuad : (kind == XB_ELE_FORCEBEAMCOLUMN3D ? kBeam3d : kBeam2d));
@@ -254,6 +254,29 @@ int HostModel::add_loads(int n, const int* tags, const double* vals) {
   if (is_setup) { err = "xb_add_nodal_loads after xb_setup"; return XB_ERR_STATE; }
   load_node.insert(load_node.end(), tags, tags + n);
   load_val.insert(load_val.end(), vals, vals + (size_t)n * ndf);
+  return XB_OK;
+}
+
+int HostModel::add_beam_point_loads(int n, const int* tags, const double* pv) {
+  if (is_setup) { err = "xb_add_beam_point_loads after xb_setup"; return XB_ERR_STATE; }
+  for (int i = 0; i < n; i++) {
+    const double* q4 = pv + (size_t)i * 4;
+    bool found = false;
+    for (auto& g : groups) {
+      if (g.kind != XB_ELE_FORCEBEAMCOLUMN2D && g.kind != XB_ELE_FORCEBEAMCOLUMN3D) continue;
+      const int npar = ele_kind(g.kind).npar;
+      for (size_t l = 0; l < g.tag.size() && !found; l++) {
+        if (g.tag[l] != tags[i]) continue;
+        found = true;
+        if (q4[3] < 0.0 || q4[3] > 1.0) break;      // the element ignores such a load (ForceBeamColumn2d.cpp:447)
+        double* q = &g.par[l * npar + npar - 8];
+        if (q[4] != 0.0) { err = "xb_add_beam_point_loads: one point load per element"; return XB_ERR_UNSUPPORTED; }
+        q[0] = q4[0]; q[1] = g.kind == XB_ELE_FORCEBEAMCOLUMN3D ? q4[1] : 0.0; q[2] = q4[2]; q[3] = q4[3]; q[4] = 1.0;
+      }
+      if (found) break;
+    }
+    if (!found) { err = "xb_add_beam_point_loads: no forceBeamColumn element with this tag"; return XB_ERR_ARG; }
+  }
   return XB_OK;
 }
 

@@ -223,6 +223,7 @@ struct HostModel {
                    const double* par, int par_stride);
   int add_loads(int n, const int* tags, const double* vals);
   int add_beam_uniform_loads(int n, const int* tags, const double* w);
+  int add_beam_point_loads(int n, const int* tags, const double* p);
   int add_mass(int n, const int* tags, const double* vals);
   // part: nullptr (built-in recursive coordinate bisection) or [ne] ranks in FE order
   int setup(int numberer, int soe_kind, int nparts = 1, int rank = 0, const int* part = nullptr);
