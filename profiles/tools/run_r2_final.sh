@@ -6,4 +6,4 @@ tail -4 gpurun_out/r2_bench_default.err
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:'fbc3d_update_sec' --launch-skip 4 --launch-count 1 -f \
   -o gpurun_out/r2_full_frame3d python bench.py --workload frame3d --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 0 > gpurun_out/r2_full_frame3d.log 2>&1
 tail -2 gpurun_out/r2_full_frame3d.log | cut -c1-200
-python scratch/ncu_summary.py gpurun_out/r2_full_frame3d.ncu-rep > gpurun_out/r2_ncu_frame3d.txt 2>&1; cat gpurun_out/r2_ncu_frame3d.txt
+python profiles/tools/ncu_summary.py gpurun_out/r2_full_frame3d.ncu-rep > gpurun_out/r2_ncu_frame3d.txt 2>&1; cat gpurun_out/r2_ncu_frame3d.txt

@@ -1,5 +1,5 @@
 #!/bin/bash
-# kernel_ms of the brick step for alternative builds of the library: scratch/try_libs.sh N lib1 lib2 ...
+# kernel_ms of the brick step for alternative builds of the library: profiles/tools/try_libs.sh N lib1 lib2 ...
 cd /root/repo
 N=$1; shift
 for lib in "$@"; do

@@ -1,5 +1,5 @@
 #!/bin/bash
-# kernel_ms of the brick step for option sets: scratch/try_opts.sh N lib "opt1=v,opt2=v" ...
+# kernel_ms of the brick step for option sets: profiles/tools/try_opts.sh N lib "opt1=v,opt2=v" ...
 cd /root/repo
 N=$1; LIB=$2; shift; shift
 for o in "$@"; do
