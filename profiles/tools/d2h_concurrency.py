@@ -3,7 +3,7 @@
 kernels): what bounds the end-to-end leg of bench.py at N > 1, where every rank pulls its rows of A (8 GB in all)
 through the host's PCIe / memory system at once.
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 scratch/d2h_concurrency.py [--numa]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 profiles/tools/d2h_concurrency.py [--numa]
 
 --numa binds every rank (and therefore the pages of its pinned buffer, first touch) to the CPUs `nvidia-smi topo -m`
 lists as local to its GPU.  Prints one JSON line: per-rank and aggregate GB/s, alone and all together."""
