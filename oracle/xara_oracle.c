@@ -2287,10 +2287,10 @@ static void ele_K(OrcModel* m, OrcEle* el, int which, double* K) {
   else if (el->kind == ORC_ELE_QUAD) quad_form(m, el, which, K, R);
   else if (el->kind == ORC_ELE_FBC2D) {
     if (which == 1) beam_form(el->beam, K, R);
-    else { OrcBeam t = *el->beam; beam_initial_kv(el->beam, t.kv); beam_form(&t, K, R); }
+    else { OrcBeam t = *el->beam; beam_initial_kv(el->beam, t.kv); t.pdelta = 0; beam_form(&t, K, R); }   /* getInitialGlobalStiffMatrix: no geometric part */
   } else {
     if (which == 1) beam3_form(el->beam3, K, R);
-    else { OrcBeam3 t = *el->beam3; beam3_initial_kv(el->beam3, t.kv); beam3_form(&t, K, R); }
+    else { OrcBeam3 t = *el->beam3; beam3_initial_kv(el->beam3, t.kv); t.pdelta = 0; beam3_form(&t, K, R); }
   }
 }
 

@@ -1,6 +1,6 @@
 """The models behind tests/golden/*.npz (generated from the reference by tests/golden/make_golden.py)."""
 from modelspec import (ELASTIC, J2_STEEL, brick_block, brick_periodic_equaldof, cantilever2d, frame2d, frame2d_diaphragm_equaldof,
-                       frame3d, quad_plane, quad_plane_stress_pressure, soil_column_equaldof)
+                       frame3d, quad_plane, quad_plane_stress_pressure, soil_column_equaldof, with_pdelta)
 
 # name -> (spec factory, numberer, soe, displacement scale)
 CASES = {
@@ -70,6 +70,9 @@ RAYLEIGH_CASES = {
     # with `equalDOF`: the nodal masses / nodal unbalance of every dof on a shared equation, in DOF_Group order
     "rayleigh_soilcolumn_equaldof": (lambda: soil_column_equaldof(6, mat=J2_STEEL_RHO), _uniform_mass(0.05), 0.5, 0.25, 0.02, RAYLEIGH),
     "rayleigh_frame2d_equaldof": (lambda: frame2d_diaphragm_equaldof(2, 2, 1, lateral=30.0), _uniform_mass(0.05, 0.0), 0.5, 0.25, 0.02, RAYLEIGH),
+    # `geomTransf PDelta`: the geometric stiffness inside Kt and Kc of Element::getDamp, none inside the initial stiffness
+    "rayleigh_frame2d_pdelta": (lambda: with_pdelta(frame2d(2, 2, 2, lateral=30.0, gravity=-150.0)), _uniform_mass(0.05, 0.0), 0.5, 0.25, 0.02, RAYLEIGH),
+    "rayleigh_frame3d_pdelta": (lambda: with_pdelta(frame3d(1, 1, 2, ndiv=2, lateral=(25.0, 15.0), gravity=-90.0)), _uniform_mass(0.05, 0.0), 0.5, 0.25, 0.02, RAYLEIGH),
 }
 
 

@@ -72,6 +72,7 @@ struct BeamView {
   // (getInitialStiff), Kc = kv at the last commit (Element::commitState); both basic, column-major [nb*nb][n]
   double* kv0;
   double* kvK;
+  double* nK;                  // [n] the axial force kvK was taken at (the geometric part of Kc under geomTransf PDelta)
   // `eleLoad -beamUniform` of the Linear pattern: wy, wz, wa per element [3][n] (null: none), the pattern's load factor,
   // and whether Domain::applyLoad has run (numEleLoads > 0: the element iterates at every update)
   const double* wl;            // [7][n]: wy, wz, wa, then `eleLoad -beamPoint` Py, Pz, N, aOverL (has_point)
@@ -414,7 +415,9 @@ __global__ void __launch_bounds__(128) fbc2d_form_kernel(BeamView B, int want_k,
     if (B.pdelta) {
       // PDeltaCrdTransf2d::getGlobalStiffMatrix (PDeltaCrdTransf2d.cpp:628-633): N/L on the local transverse dofs,
       // kl[1][1], kl[4][4] += N/L, kl[1][4], kl[4][1] -= N/L; in global axes N/L t t' with t = (-sin, cos)
-      const double NoverL = B.Se[e] * oneOverL;
+      // (transient with element damping: (c1 + c2 betaK) Kt + c2 betaKc Kc carry their own axial forces; the initial
+      //  stiffness has no geometric part, PDeltaCrdTransf2d::getInitialGlobalStiffMatrix)
+      const double NoverL = (dy.k_on ? dy.at * B.Se[e] + (dy.ac != 0.0 ? dy.ac * B.nK[e] : 0.0) : B.Se[e]) * oneOverL;
       const double t[2] = {-sinTheta, cosTheta};
 #pragma unroll
       for (int i = 0; i < 2; i++)
@@ -433,6 +436,8 @@ __global__ void __launch_bounds__(128) fbc2d_form_kernel(BeamView B, int want_k,
   }
   if (want_r) {
     double q0 = B.Se[e], q1 = B.Se[n + e], q2 = B.Se[2 * n + e];
+    const double q0s = q0;               // the element's own axial force (the P-Delta shear is not a damping term)
+    double gdv = 0.0;                    // PDelta: geometric part of (bK Kt + bKc Kc) v, on the local transverse dofs
     if (dy.r_on) {
       // Element::getRayleighDampingForces with stiffness-proportional terms: T^T [kd (T v)], kd basic
       double vg[6], vb[3];
@@ -441,6 +446,10 @@ __global__ void __launch_bounds__(128) fbc2d_form_kernel(BeamView B, int want_k,
         for (int j = 0; j < 3; j++) vg[a * 3 + j] = dy.V[(size_t)nd * 3 + j];
       }
       crd2d_basic(L, cosTheta, sinTheta, vg, vb);
+      if (B.pdelta) {
+        const double gd = (dy.bK * B.Se[e] + (dy.bKc != 0.0 ? dy.bKc * B.nK[e] : 0.0)) * oneOverL;
+        gdv = gd * ((-sinTheta * vg[0] + cosTheta * vg[1]) - (-sinTheta * vg[3] + cosTheta * vg[4]));
+      }
       double qd[3] = {0, 0, 0};
       for (int c = 0; c < 3; c++)
         for (int r = 0; r < 3; r++) {
@@ -470,8 +479,9 @@ __global__ void __launch_bounds__(128) fbc2d_form_kernel(BeamView B, int want_k,
       const double* uI = B.U + (size_t)B.conn[e * 2] * 3; const double* uJ = B.U + (size_t)B.conn[e * 2 + 1] * 3;
       const double ul1 = -sinTheta * uI[0] + cosTheta * uI[1];
       const double ul4 = -sinTheta * uJ[0] + cosTheta * uJ[1];
-      const double NoverL = (ul1 - ul4) * q0 * oneOverL;
+      const double NoverL = (ul1 - ul4) * q0s * oneOverL;
       pl[1] += NoverL; pl[4] -= NoverL;
+      pl[1] += gdv; pl[4] -= gdv;
     }
     double* R = B.Re + e * 6;
     R[0] = cosTheta * pl[0] - sinTheta * pl[1];
@@ -1125,7 +1135,7 @@ __global__ void __launch_bounds__(64) fbc3d_form_kernel(BeamView B, int want_k, 
       kl[11][i] = tmp[2][i];
     }
     if (B.pdelta) {   // PDeltaCrdTransf3d::getGlobalStiffMatrix, PDeltaCrdTransf3d.cpp:873-881
-      const double NoverL = B.Se[e] * oneOverL;
+      const double NoverL = (dy.k_on ? dy.at * B.Se[e] + (dy.ac != 0.0 ? dy.ac * B.nK[e] : 0.0) : B.Se[e]) * oneOverL;
       kl[1][1] += NoverL; kl[2][2] += NoverL; kl[7][7] += NoverL; kl[8][8] += NoverL;
       kl[1][7] -= NoverL; kl[7][1] -= NoverL; kl[2][8] -= NoverL; kl[8][2] -= NoverL;
     }
@@ -1148,6 +1158,8 @@ __global__ void __launch_bounds__(64) fbc3d_form_kernel(BeamView B, int want_k, 
   if (want_r) {
     double q[6];
     for (int i = 0; i < 6; i++) q[i] = B.Se[i * n + e];
+    const double q0s = q[0];
+    double gdv1 = 0.0, gdv2 = 0.0;       // PDelta: geometric part of (bK Kt + bKc Kc) v on the local y and z dofs
     if (dy.r_on) {
       double vg[12], vb[6], Rf[9];
       for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) Rf[3 * r + c] = R[r][c];
@@ -1156,6 +1168,11 @@ __global__ void __launch_bounds__(64) fbc3d_form_kernel(BeamView B, int want_k, 
         for (int j = 0; j < 6; j++) vg[a * 6 + j] = dy.V[(size_t)nd * 6 + j];
       }
       crd3d_basic(L, Rf, vg, vb);
+      if (B.pdelta) {
+        const double gd = (dy.bK * B.Se[e] + (dy.bKc != 0.0 ? dy.bKc * B.nK[e] : 0.0)) * oneOverL;
+        gdv1 = gd * ((R[1][0] * vg[0] + R[1][1] * vg[1] + R[1][2] * vg[2]) - (R[1][0] * vg[6] + R[1][1] * vg[7] + R[1][2] * vg[8]));
+        gdv2 = gd * ((R[2][0] * vg[0] + R[2][1] * vg[1] + R[2][2] * vg[2]) - (R[2][0] * vg[6] + R[2][1] * vg[7] + R[2][2] * vg[8]));
+      }
       double qd[6] = {0, 0, 0, 0, 0, 0};
       for (int c = 0; c < 6; c++)
         for (int r = 0; r < 6; r++) {
@@ -1187,10 +1204,11 @@ __global__ void __launch_bounds__(64) fbc3d_form_kernel(BeamView B, int want_k, 
       pl[0] += p0[0]; pl[1] += p0[1]; pl[7] += p0[2]; pl[2] += p0[3]; pl[8] += p0[4];
     }
     if (B.pdelta) {   // PDeltaCrdTransf3d::getGlobalResistingForce, PDeltaCrdTransf3d.cpp:784-790
-      double NoverL = B.ul[e] * q[0] * oneOverL;
+      double NoverL = B.ul[e] * q0s * oneOverL;
       pl[1] += NoverL; pl[7] -= NoverL;
-      NoverL = B.ul[n + e] * q[0] * oneOverL;
+      NoverL = B.ul[n + e] * q0s * oneOverL;
       pl[2] += NoverL; pl[8] -= NoverL;
+      pl[1] += gdv1; pl[7] -= gdv1; pl[2] += gdv2; pl[8] -= gdv2;
     }
     double* Rg = B.Re + e * 12;
     for (int blk = 0; blk < 4; blk++)

@@ -2189,9 +2189,7 @@ int xb_set_rayleigh_alpha_m(xb_model* m, double alphaM) {
 // device side of `rayleigh`: buffers the damping terms need, sized on first use
 static int apply_rayleigh(xb_model* m) {
   if (!m->on_device) return XB_OK;
-  if (m->rayK != 0.0 || m->rayK0 != 0.0 || m->rayKc != 0.0)
-    for (auto& d : m->dg) if (is_beam(d.kind) && d.b.pdelta)
-      return fail(XB_ERR_UNSUPPORTED, "stiffness-proportional Rayleigh damping on forceBeamColumn elements with geomTransf PDelta is outside the device path");
+
   CU(cudaSetDevice(m->device));
   const bool dyn = any_rayleigh(m) || m->any_rho;
   if (dyn && !m->dRt) {
@@ -2213,6 +2211,8 @@ static int apply_rayleigh(xb_model* m) {
       if (m->rayKc != 0.0 && !b.kvK) {   // Element::setRayleighDampingFactors: Kc = new Matrix(getTangentStiff())
         CU(dev_alloc(m, &b.kvK, nk));
         CU(cudaMemcpyAsync(b.kvK, b.kv, sizeof(double) * nk, cudaMemcpyDeviceToDevice, m->stream));
+        CU(dev_alloc(m, &b.nK, (size_t)std::max<long long>(b.n, 1)));     // the axial force that tangent carries (PDelta)
+        CU(cudaMemcpyAsync(b.nK, b.Se, sizeof(double) * b.n, cudaMemcpyDeviceToDevice, m->stream));
       }
       continue;
     }
@@ -2869,7 +2869,10 @@ int xb_commit(xb_model* m) {
       CU(cudaMemcpyAsync(b.Sec, b.Se, sizeof(double) * b.nb * b.n, cudaMemcpyDeviceToDevice, m->stream));
       CU(cudaMemcpyAsync(b.kvc, b.kv, sizeof(double) * b.nb * b.nb * b.n, cudaMemcpyDeviceToDevice, m->stream));
       // Element::commitState: *Kc = getTangentStiff()
-      if (b.kvK) CU(cudaMemcpyAsync(b.kvK, b.kv, sizeof(double) * b.nb * b.nb * b.n, cudaMemcpyDeviceToDevice, m->stream));
+      if (b.kvK) {
+        CU(cudaMemcpyAsync(b.kvK, b.kv, sizeof(double) * b.nb * b.nb * b.n, cudaMemcpyDeviceToDevice, m->stream));
+        CU(cudaMemcpyAsync(b.nK, b.Se, sizeof(double) * b.n, cudaMemcpyDeviceToDevice, m->stream));
+      }
     } else if (d.mat_kind == XB_MAT_J2PLASTICITY) {
       // J2PlaneStress::commitState: commitEps22 = strain(2,2)
       if (d.j2ps) CU(cudaMemcpyAsync(d.v.tan + (size_t)7 * d.ngp, d.v.tan + (size_t)6 * d.ngp, sizeof(double) * d.ngp, cudaMemcpyDeviceToDevice, m->stream));
