@@ -26,7 +26,7 @@ constexpr int XB_FIB_CURV = 16; // fkind flag: the material of a section Aggrega
 constexpr int XB_MAXSEC = 10;
 constexpr int XB_FBC3D_MAX_PASSES = 20000;
 #ifndef XB_FBC_SEC_OCC
-#define XB_FBC_SEC_OCC 6
+#define XB_FBC_SEC_OCC 5
 #endif   // see fbc3d_update_kernel
 // Steel02 record:   0 epsmin 1 epsmax 2 epspl 3 epss0 4 sigs0 5 epsr 6 sigr 7 kon 8 e 9 sig 10 eps
 // Concrete02 record: 0 ecmin 1 dept 8 e 9 sig 10 eps
