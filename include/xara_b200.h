@@ -145,6 +145,12 @@ int xb_add_nodal_loads(xb_model*, int n, const int* node_tags, const double* val
  * scaled by the load factor of xb_apply_load.  One uniform load per element; point and partial loads: XB_ERR_UNSUPPORTED
  * at the binding. */
 int xb_add_beam_uniform_loads(xb_model*, int n, const int* ele_tags, const double* w);
+/* `element forceBeamColumn ... -integration Legendre | Radau | NewtonCotes | Trapezoidal | UserDefined ...` (the
+ * BeamIntegration classes under quadrature/Frame/): the nip section locations and weights, as fractions of the element
+ * length, exactly as the element's BeamIntegration object returns them (getSectionLocations / getSectionWeights,
+ * ForceBeamColumn2d.cpp:598-602) -- xi, wt are [n][nip].  Without this call an element integrates with the Lobatto
+ * tables (quadrature/Frame/LobattoBeamIntegration.cpp).  All elements of one xb_add_elements call or none. */
+int xb_set_beam_integration(xb_model*, int n, const int* ele_tags, int nip, const double* xi, const double* wt);
 /* `eleLoad -ele tags -type -beamPoint Py [Pz] xL [N]` of the Linear pattern (Beam2dPointLoad / Beam3dPointLoad ->
  * ForceBeamColumn2d.cpp:442-455, 1138-1181; ForceBeamColumn3d.cpp:457-475, 1314-1373): p is [n][4] = Py, Pz (3D), N, xL = a/L.
  * One point load per element (beside at most one uniform load); a load with xL outside [0, 1] is ignored, as the

@@ -162,7 +162,9 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
   struct Batch { std::vector<int> tag, conn, mat; std::vector<double> par; };
   std::map<std::pair<int, int>, Batch> batches;     // (xb element kind, xb material kind)
   std::map<int, int> mats_done, secs_done, unis_done;
-  struct BeamKey { int sec, nip, mi; double tol; bool is3; int transf; };
+  struct BeamKey { int sec, nip, mi; double tol; bool is3; int transf; int lobatto; };
+  struct BeamRule { int tag, nip; std::vector<double> xi, wt; };
+  std::vector<BeamRule> beam_rules;
   std::vector<BeamKey> beam_keys;
   auto material = [&](NDMaterial* nm, int& kind) -> int {
     double p[8] = {0, 0, 0, 0, 0, 0, 0, 0}; int np = 0;
@@ -211,7 +213,14 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
         SectionForceDeformation** secs = b2 ? b2->sections : b3->sections;
         BeamIntegration* bi = b2 ? b2->beamIntegr : b3->beamIntegr;
         CrdTransf* ct = b2 ? b2->crdTransf : b3->crdTransf;
-        if (!dynamic_cast<LobattoBeamIntegration*>(bi)) { G.err = "glue: beam integration other than Lobatto"; return -5; }
+        // any BeamIntegration whose sections are all the same: the locations and weights are the reference object's own
+        if (!dynamic_cast<LobattoBeamIntegration*>(bi)) {
+          BeamRule br; br.tag = el->getTag(); br.nip = nsec; br.xi.resize(nsec); br.wt.resize(nsec);
+          const double Lr = ct->getInitialLength();
+          bi->getSectionLocations(nsec, Lr, br.xi.data());
+          bi->getSectionWeights(nsec, Lr, br.wt.data());
+          beam_rules.push_back(br);
+        }
         // geomTransf Linear or PDelta, without joint offsets
         int transf = -1;
         if (auto* t = dynamic_cast<LinearCrdTransf2d*>(ct)) { if (!t->nodeIOffset && !t->nodeJOffset) transf = 0; }
@@ -280,9 +289,10 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
         // one batch per (section, nIP, maxIters, tol): key them through the map's second index
         const int maxIters = b2 ? b2->maxIters : b3->maxIters; const double tol = b2 ? b2->tol : b3->tol;
         int key = -1;
+        const int lob = dynamic_cast<LobattoBeamIntegration*>(bi) ? 1 : 0;      // (a batch integrates by Lobatto or by per-element rules)
         for (size_t q = 0; q < beam_keys.size(); q++)
-          if (beam_keys[q].sec == stag && beam_keys[q].nip == nsec && beam_keys[q].mi == maxIters && beam_keys[q].tol == tol && beam_keys[q].is3 == (b3 != nullptr) && beam_keys[q].transf == transf) key = (int)q;
-        if (key < 0) { beam_keys.push_back({stag, nsec, maxIters, tol, b3 != nullptr, transf}); key = (int)beam_keys.size() - 1; }
+          if (beam_keys[q].sec == stag && beam_keys[q].nip == nsec && beam_keys[q].mi == maxIters && beam_keys[q].tol == tol && beam_keys[q].is3 == (b3 != nullptr) && beam_keys[q].transf == transf && beam_keys[q].lobatto == lob) key = (int)q;
+        if (key < 0) { beam_keys.push_back({stag, nsec, maxIters, tol, b3 != nullptr, transf, lob}); key = (int)beam_keys.size() - 1; }
         Batch& B = batches[{b3 ? XB_ELE_FORCEBEAMCOLUMN3D : XB_ELE_FORCEBEAMCOLUMN2D, 1000 + key}];
         B.tag.push_back(el->getTag()); B.mat.push_back(stag);
         const ID& en = el->getExternalNodes();
@@ -304,6 +314,8 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
       G.err = xb_last_error(); return -6;
     }
   }
+  for (const BeamRule& br : beam_rules)
+    if (xb_set_beam_integration(x, 1, &br.tag, br.nip, br.xi.data(), br.wt.data()) < 0) { G.err = xb_last_error(); return -6; }
   // 4. nodal loads of the load patterns.  The device applies lambda(t) * P with lambda = the domain time, i.e. every
   // pattern must carry a Linear series with factor 1, must not have been frozen by loadConst, and must hold nodal loads
   // only -- anything else is refused here rather than silently dropped (element loads, other series: keep the CPU integrator)

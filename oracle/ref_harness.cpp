@@ -47,6 +47,10 @@
 #include <FiberSection2d.h>
 #include <SectionAggregator.h>
 #include <PDeltaCrdTransf2d.h>
+#include <LegendreBeamIntegration.h>
+#include <RadauBeamIntegration.h>
+#include <NewtonCotesBeamIntegration.h>
+#include <TrapezoidalBeamIntegration.h>
 #include <PDeltaCrdTransf3d.h>
 #include <Steel01.h>
 #include <ElasticMaterial.h>
@@ -329,10 +333,29 @@ int ref_add_section_aggregator(void* h, int tag, int n, const int* matTags, cons
   return 0;
 }
 // element forceBeamColumn (2D): Lobatto integration, Linear transformation, nIP copies of one section
+// -integration: 0 Lobatto, 1 Legendre, 2 Radau, 3 NewtonCotes, 4 Trapezoidal
+static BeamIntegration* make_beam_integration(int kind) {
+  switch (kind) {
+    case 1: return new LegendreBeamIntegration();
+    case 2: return new RadauBeamIntegration();
+    case 3: return new NewtonCotesBeamIntegration();
+    case 4: return new TrapezoidalBeamIntegration();
+    default: return new LobattoBeamIntegration();
+  }
+}
+// what the rule gives for nip sections on an element of length L: locations and weights as fractions of L
+int ref_beam_rule(int kind, int nip, double L, double* xi, double* wt) {
+  BeamIntegration* bi = make_beam_integration(kind);
+  bi->getSectionLocations(nip, L, xi);
+  bi->getSectionWeights(nip, L, wt);
+  delete bi;
+  return 0;
+}
 int ref_add_force_beam2d_t(void* h, int tag, const int* nd, int secTag, int nip, int maxIters, double tol, int transfKind) {
   RefModel* m = (RefModel*)h;
   std::vector<SectionForceDeformation*> secs(nip, m->sections2d.at(secTag));
-  LobattoBeamIntegration bi;
+  BeamIntegration* bip = make_beam_integration(transfKind / 16); transfKind %= 16;      // (integration kind in the upper bits)
+  BeamIntegration& bi = *bip;
   LinearCrdTransf2d lin(tag);
   PDeltaCrdTransf2d pd(tag);                 // geomTransf PDelta
   CrdTransf& transf = transfKind == 1 ? (CrdTransf&)pd : (CrdTransf&)lin;
@@ -359,7 +382,8 @@ int ref_add_fiber_section3d(void* h, int tag, int nf, const double* y, const dou
 int ref_add_force_beam3d_t(void* h, int tag, const int* nd, int secTag, int nip, int maxIters, double tol, const double* vecxz, int transfKind) {
   RefModel* m = (RefModel*)h;
   std::vector<SectionForceDeformation*> secs(nip, m->sections3d.at(secTag));
-  LobattoBeamIntegration bi;
+  BeamIntegration* bip = make_beam_integration(transfKind / 16); transfKind %= 16;
+  BeamIntegration& bi = *bip;
   Vector v(3); v(0) = vecxz[0]; v(1) = vecxz[1]; v(2) = vecxz[2];
   LinearCrdTransf3d lin(tag, v);
   PDeltaCrdTransf3d pd(tag, v);              // geomTransf PDelta

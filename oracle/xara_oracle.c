@@ -794,6 +794,9 @@ typedef struct {
   int has_load, numEleLoads; double w[3], loadFactor;
   /* `eleLoad -beamPoint Py xL [N]` (Beam2dPointLoad): pt = {Py, -, N, aOverL} */
   int has_point; double pt[4];
+  /* beam integration other than Lobatto: the section locations and weights the element's BeamIntegration object returns
+   * (getSectionLocations / getSectionWeights), handed over by the caller (orc_set_beam_integration) */
+  int user_rule; double rxi[ORC_MAXSEC], rwt[ORC_MAXSEC];
   /* geomTransf PDelta (PDeltaCrdTransf2d.cpp): ul14 is recomputed from the nodes' trial displacements whenever the
    * element asks for its tangent or resisting force (ForceBeamColumn2d.cpp:402,526 call crdTransf->update()) */
   int pdelta; const double* utrial; int n0, n1;
@@ -839,7 +842,7 @@ static int beam_update(OrcBeam* b, const double* ug, const double* dug) {
   for (int i = 0; i < 3; i++) vin[i] = v[i] - dv[i];
   const double L = b->L, oneOverL = 1.0 / L;
   double xi[ORC_MAXSEC], wt[ORC_MAXSEC];
-  lobatto(b->nip, xi, wt);
+  if (b->user_rule) { memcpy(xi, b->rxi, sizeof(double) * b->nip); memcpy(wt, b->rwt, sizeof(double) * b->nip); } else lobatto(b->nip, xi, wt);
   double vr[3], f[9], dSe[3], SeTrial[3], kvTrial[9], dvTrial[3], dvToDo[3];
   double vsSub[ORC_MAXSEC][2], fsSub[ORC_MAXSEC][4], SsrSub[ORC_MAXSEC][2];
   int numSubdivide = 1, converged = 0;
@@ -1153,6 +1156,7 @@ typedef struct {
   int has_load, numEleLoads; double w[3], loadFactor;
   /* `eleLoad -beamPoint Py Pz xL [N]` (Beam3dPointLoad): pt = {Py, Pz, N, aOverL} */
   int has_point; double pt[4];
+  int user_rule; double rxi[ORC_MAXSEC], rwt[ORC_MAXSEC];     /* see OrcBeam */
   /* geomTransf PDelta (PDeltaCrdTransf3d.cpp:200-249): ul17, ul28 as of the element's last update() -- ForceBeamColumn3d's
    * getTangentStiff / getResistingForce do NOT refresh them (ForceBeamColumn3d.cpp:404,555) */
   int pdelta; double ul17, ul28;
@@ -1226,7 +1230,7 @@ static int beam3_update(OrcBeam3* b, const double* ug, const double* dug) {
   for (int i = 0; i < 6; i++) vin[i] = v[i] - dv[i];
   const double L = b->L;
   double xi[ORC_MAXSEC], wt[ORC_MAXSEC];
-  lobatto(b->nip, xi, wt);
+  if (b->user_rule) { memcpy(xi, b->rxi, sizeof(double) * b->nip); memcpy(wt, b->rwt, sizeof(double) * b->nip); } else lobatto(b->nip, xi, wt);
   double vr[6], f[36], dSe[6], SeTrial[6], kvTrial[36], dvTrial[6], dvToDo[6];
   double vsSub[ORC_MAXSEC][4], fsSub[ORC_MAXSEC][16], SsrSub[ORC_MAXSEC][4];
   int numSubdivide = 1, converged = 0;
@@ -2217,6 +2221,40 @@ int orc_add_beam_uniform_load(void* h, int ele_tag, double wy, double wz, double
   return -1;
 }
 
+/* `element forceBeamColumn ... -integration Legendre | Radau | NewtonCotes | Trapezoidal | ...`: the nip section locations
+ * and weights (fractions of L) that the element's BeamIntegration returns, in place of the Lobatto tables */
+int orc_set_beam_integration(void* h, int ele_tag, int nip, const double* xi, const double* wt) {
+  OrcModel* m = (OrcModel*)h;
+  for (int e = 0; e < m->ne; e++) {
+    OrcEle* el = &m->ele[e];
+    if (el->tag != ele_tag) continue;
+    /* the element was built (and updated once, Domain::addElement) with the Lobatto tables: build it again with its rule
+     * (part of the element's definition: call this before any element load is added) */
+    if (el->kind == ORC_ELE_FBC2D) {
+      if (nip != el->beam->nip) return -2;
+      for (int i = 0; i < el->beam->nip; i++) free(el->beam->sec[i].mat);
+      free(el->beam);
+      el->beam = beam2_build(m, el, el->mat, el->par);
+      el->beam->user_rule = 1; memcpy(el->beam->rxi, xi, sizeof(double) * nip); memcpy(el->beam->rwt, wt, sizeof(double) * nip);
+      double ug[6], dug[6];
+      for (int a = 0; a < 2; a++) for (int j = 0; j < 3; j++) { ug[a * 3 + j] = m->trial[el->node[a] * 3 + j]; dug[a * 3 + j] = m->incr[el->node[a] * 3 + j]; }
+      return beam_update(el->beam, ug, dug) < 0 ? -4 : 0;
+    }
+    if (el->kind == ORC_ELE_FBC3D) {
+      if (nip != el->beam3->nip) return -2;
+      for (int i = 0; i < el->beam3->nip; i++) free(el->beam3->sec[i].mat);
+      free(el->beam3);
+      el->beam3 = beam3_build(m, el, el->mat, el->par);
+      el->beam3->user_rule = 1; memcpy(el->beam3->rxi, xi, sizeof(double) * nip); memcpy(el->beam3->rwt, wt, sizeof(double) * nip);
+      double ug[12], dug[12];
+      for (int a = 0; a < 2; a++) for (int j = 0; j < 6; j++) { ug[a * 6 + j] = m->trial[el->node[a] * 6 + j]; dug[a * 6 + j] = m->incr[el->node[a] * 6 + j]; }
+      return beam3_update(el->beam3, ug, dug) < 0 ? -4 : 0;
+    }
+    return -3;
+  }
+  return -1;
+}
+
 /* `eleLoad -ele tag -type -beamPoint Py [Pz] xL [N]` in the model's Linear pattern (Beam2dPointLoad / Beam3dPointLoad); a
  * load with xL outside [0, 1] is ignored by the element (ForceBeamColumn2d.cpp:447) and is not kept */
 int orc_add_beam_point_load(void* h, int ele_tag, double Py, double Pz, double N, double aOverL) {
@@ -2244,7 +2282,7 @@ static int ele_nd(const OrcEle* el) { return el->nen * el->ndf_e; }
 /* ForceBeamColumn2d::getInitialFlexibility + Matrix::Invert (ForceBeamColumn2d.cpp getInitialStiff) */
 static void beam_initial_kv(const OrcBeam* b, double* kv0) {
   double xi[ORC_MAXSEC], wt[ORC_MAXSEC], f[9];
-  lobatto(b->nip, xi, wt);
+  if (b->user_rule) { memcpy(xi, b->rxi, sizeof(double) * b->nip); memcpy(wt, b->rwt, sizeof(double) * b->nip); } else lobatto(b->nip, xi, wt);
   for (int i = 0; i < 9; i++) f[i] = 0.0;
   for (int i = 0; i < b->nip; i++) {
     double fSec[4], fb[6];
@@ -2261,7 +2299,7 @@ static void beam_initial_kv(const OrcBeam* b, double* kv0) {
 /* ForceBeamColumn3d::getInitialFlexibility (ForceBeamColumn3d.cpp:2003) + Matrix::Invert */
 static void beam3_initial_kv(const OrcBeam3* b, double* kv0) {
   double xi[ORC_MAXSEC], wt[ORC_MAXSEC], f[36];
-  lobatto(b->nip, xi, wt);
+  if (b->user_rule) { memcpy(xi, b->rxi, sizeof(double) * b->nip); memcpy(wt, b->rwt, sizeof(double) * b->nip); } else lobatto(b->nip, xi, wt);
   for (int i = 0; i < 36; i++) f[i] = 0.0;
   for (int i = 0; i < b->nip; i++) {
     double fSec[16], fb[24];
@@ -2573,15 +2611,18 @@ int orc_revert_to_start(void* h) {
       el->beam->has_load = keep.has_load; el->beam->numEleLoads = keep.numEleLoads; el->beam->loadFactor = keep.loadFactor;
       memcpy(el->beam->w, keep.w, sizeof keep.w);
       el->beam->has_point = keep.has_point; memcpy(el->beam->pt, keep.pt, sizeof keep.pt);
+      el->beam->user_rule = keep.user_rule; memcpy(el->beam->rxi, keep.rxi, sizeof keep.rxi); memcpy(el->beam->rwt, keep.rwt, sizeof keep.rwt);
     } else if (el->kind == ORC_ELE_FBC3D) {
       for (int i = 0; i < el->beam3->nip; i++) free(el->beam3->sec[i].mat);
       const int hl = el->beam3->has_load, nl = el->beam3->numEleLoads; const double lf = el->beam3->loadFactor;
       double wk[3]; memcpy(wk, el->beam3->w, sizeof wk);
       const int hp = el->beam3->has_point; double pk[4]; memcpy(pk, el->beam3->pt, sizeof pk);
+      const int ur = el->beam3->user_rule; double rx[ORC_MAXSEC], rw[ORC_MAXSEC]; memcpy(rx, el->beam3->rxi, sizeof rx); memcpy(rw, el->beam3->rwt, sizeof rw);
       free(el->beam3);
       el->beam3 = beam3_build(m, el, el->mat, el->par);
       el->beam3->has_load = hl; el->beam3->numEleLoads = nl; el->beam3->loadFactor = lf; memcpy(el->beam3->w, wk, sizeof wk);
       el->beam3->has_point = hp; memcpy(el->beam3->pt, pk, sizeof pk);
+      el->beam3->user_rule = ur; memcpy(el->beam3->rxi, rx, sizeof rx); memcpy(el->beam3->rwt, rw, sizeof rw);
     } else {
       for (int g = 0; g < el->nip; g++) {
         OrcGP* gp = &el->gp[g];

@@ -57,6 +57,8 @@ class ModelSpec:
     sections: list = field(default_factory=list)    # (tag, y[nf], A[nf], uniaxial tags[nf])
     beam_loads: list = field(default_factory=list)  # `eleLoad -beamUniform`: (element tag, wy, wz, wa) in the Linear pattern
     beam_point_loads: list = field(default_factory=list)  # `eleLoad -beamPoint`: (element tag, Py, Pz, N, xL)
+    beam_integration: int = 0          # forceBeamColumn -integration: 0 Lobatto, 1 Legendre, 2 Radau, 3 NewtonCotes, 4 Trapezoidal
+    beam_rules: tuple = None           # (element tags, xi [n][nip], wt [n][nip]) as the reference's BeamIntegration returns them
     node_ndf: dict = field(default_factory=dict)    # node tag -> dofs, for nodes created under another `model -ndf` (< the model's ndf)
 
     @property
@@ -265,6 +267,27 @@ def steel01_elastic_frame(dim):
     uni[2] = (UNI_ELASTIC, (2500.0, 0.0, 3600.0))                       # cover: softer in tension
     uni[3] = (UNI_STEEL01, (60.0, 29000.0, 0.015, 0.02, 30.0, 0.02, 30.0))
     spec.uniaxials = [(t, *uni[t]) for t in sorted(uni)]
+    return spec
+
+
+def with_beam_integration(spec, kind):
+    """`-integration Legendre | Radau | NewtonCotes | Trapezoidal` (kind 1..4) on every forceBeamColumn: the reference
+    backend builds the elements with that BeamIntegration class; oracle and device get the section locations and weights
+    the class returns (ref_beam_rule), which is what the binding reads out of the element"""
+    L = ctypes.CDLL(REF_SO)
+    L.ref_beam_rule.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p]
+    tags, xis, wts = [], [], []
+    for g in spec.groups:
+        if g.kind not in (ELE_FBC2D, ELE_FBC3D): continue
+        nip = int(g.par[0, 0])
+        for t, c in zip(g.tags, g.conn):
+            idx = [list(spec.node_tags).index(int(q)) for q in c]
+            Lel = float(np.linalg.norm(spec.crd[idx[1]] - spec.crd[idx[0]]))
+            xi = np.zeros(nip); wt = np.zeros(nip)
+            assert L.ref_beam_rule(kind, nip, Lel, _p(xi), _p(wt)) == 0
+            tags.append(int(t)); xis.append(xi); wts.append(wt)
+    spec.beam_integration = kind
+    spec.beam_rules = (np.array(tags, np.int32), np.array(xis), np.array(wts))
     return spec
 
 
@@ -682,6 +705,10 @@ class OracleBackend(_Backend):
             for row in spec.loads:
                 v = np.ascontiguousarray(row[1:], np.float64)
                 assert L.orc_add_load(self.h, int(row[0]), _p(v)) == 0
+        if spec.beam_rules:      # (part of the element definition: before the element loads)
+            L.orc_set_beam_integration.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+            for t, xi, wt in zip(*spec.beam_rules):
+                assert L.orc_set_beam_integration(self.h, int(t), len(xi), _p(np.ascontiguousarray(xi)), _p(np.ascontiguousarray(wt))) == 0
         L.orc_add_beam_uniform_load.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double]
         for t, wy, wz, wa in spec.beam_loads:
             assert L.orc_add_beam_uniform_load(self.h, int(t), float(wy), float(wz), float(wa)) == 0
@@ -899,10 +926,10 @@ class RefBackend(_Backend):
                 elif g.kind == ELE_FBC3D:
                     vx = np.ascontiguousarray(g.par[i, 3:6], np.float64)
                     assert L.ref_add_force_beam3d_t(self.h, int(g.tags[i]), _p(c), int(g.mat[i]), int(g.par[i, 0]),
-                                                    int(g.par[i, 1]), float(g.par[i, 2]), _p(vx), int(g.par[i, 6])) == 0
+                                                    int(g.par[i, 1]), float(g.par[i, 2]), _p(vx), int(g.par[i, 6]) + 16 * spec.beam_integration) == 0
                 elif g.kind == ELE_FBC2D:
                     assert L.ref_add_force_beam2d_t(self.h, int(g.tags[i]), _p(c), int(g.mat[i]), int(g.par[i, 0]),
-                                                    int(g.par[i, 1]), float(g.par[i, 2]), int(g.par[i, 3])) == 0
+                                                    int(g.par[i, 1]), float(g.par[i, 2]), int(g.par[i, 3]) + 16 * spec.beam_integration) == 0
                 else:
                     b = np.ascontiguousarray(g.par[i, 4:6], np.float64)
                     assert L.ref_add_quad(self.h, int(g.tags[i]), _p(c), int(g.mat[i]), float(g.par[i, 0]),

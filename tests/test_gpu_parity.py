@@ -200,7 +200,7 @@ def test_newton_iteration_counts_match_oracle(shape):
 
 @pytest.mark.skipif(not (have_ref() and have_glue()), reason="oracle/_ref not built (needs /root/reference)")
 @pytest.mark.parametrize("shape,numberer,soe", [("brick", 1, 0), ("quad", 0, 1), ("mixed", 1, 1), ("soilcolumn_equaldof", 1, 0), ("frame2d_gravity", 1, 0), ("soil_frame_mixed_ndf", 1, 0),
-                                                ("soilcolumn_equaldof", 0, 1), ("frame2d_pdelta", 1, 0), ("frame3d_pdelta", 1, 0), ("frame3d_eleloads", 1, 0)])
+                                                ("soilcolumn_equaldof", 0, 1), ("frame2d_pdelta", 1, 0), ("frame3d_pdelta", 1, 0), ("frame3d_eleloads", 1, 0), ("frame2d_legendre", 1, 0), ("frame3d_radau", 1, 0)])
 def test_reference_newton_loop_drives_device_path(shape, numberer, soe):
     """The drop-in, end to end: the REFERENCE'S OWN StaticAnalysis objects (AnalysisModel, PlainHandler, numberer,
     SparseGenCol/Row SOE and solver, NewtonRaphson, CTestNormDispIncr, LoadControl::newStep) run a load-controlled
@@ -226,6 +226,11 @@ def test_reference_newton_loop_drives_device_path(shape, numberer, soe):
         def mk():   # `eleLoad -beamUniform` and `-beamPoint` (Beam3dUniformLoad, Beam3dPointLoad) read out of the load pattern
             from modelspec import with_beam_gravity, with_beam_point_loads
             return with_beam_point_loads(with_beam_gravity(frame3d(1, 1, 2, ndiv=2, lateral=(14.0, 8.0)), w=-0.06, seed=1), P=-2.5, seed=2)
+    elif shape in ("frame2d_legendre", "frame3d_radau"):
+        def mk():   # -integration Legendre / Radau: the binding reads the section locations and weights out of the element's BeamIntegration
+            from modelspec import with_beam_integration
+            return (with_beam_integration(frame2d(2, 3, 2, nip=4, lateral=28.0, gravity=-60.0), 1) if shape == "frame2d_legendre"
+                    else with_beam_integration(frame3d(1, 1, 2, ndiv=2, nip=5, lateral=(25.0, 15.0), gravity=-40.0), 2))
     elif shape in ("frame2d_pdelta", "frame3d_pdelta"):
         def mk():   # `geomTransf PDelta` read out of the elements' CrdTransf: heavy gravity, then the lateral push
             from modelspec import with_pdelta
@@ -933,6 +938,46 @@ def test_frame_fibre_beams_vs_oracle_history():
     # the history went well past yield: the tangent is far from the initial one
     D0 = xb.DeviceModel.from_spec(spec, 1, 0).to_device(0)
     assert relerr(D.form_tangent(), D0.form_tangent()) > 0.05
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (the rules come from the reference's BeamIntegration classes)")
+@pytest.mark.parametrize("kind", [1, 2, 3, 4])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_beam_integration_rules_device_vs_oracle(dim, kind):
+    """forceBeamColumn -integration Legendre | Radau | NewtonCotes | Trapezoidal (xb_set_beam_integration: the section
+    locations and weights the reference's BeamIntegration object returns, per element), with uniform and point element
+    loads, commits, a revert and a reset: device against the oracle (pinned to the reference's classes for every rule)"""
+    from modelspec import with_beam_integration, with_beam_gravity, with_beam_point_loads
+    rng = np.random.default_rng(11)
+    spec = frame2d(2, 2, 2, nip=4) if dim == 2 else frame3d(1, 1, 2, nip=5)
+    spec = with_beam_integration(with_beam_point_loads(with_beam_gravity(spec, seed=3), seed=2), kind)
+    O = OracleBackend(spec, 1, 0)
+    D = xb.DeviceModel.from_spec(spec, 1, 0).to_device(0)
+    ids = O.ids()
+    hcol = spec.crd[:, 1] if dim == 2 else spec.crd[:, 2]
+    H = hcol.max(); h = hcol / H
+    nd = 6 if dim == 2 else 12
+    assert relerr(D.form_tangent(), O.form_tangent()) < BEAM_RTOL
+    for s, a in enumerate([0.2, 0.5, 0.8, 1.1]):        # (the history of the CPU test against the reference)
+        u = np.zeros((spec.nn, spec.ndf))
+        u[:, 0] = a * h ** 1.5
+        u[:, 2 if dim == 2 else 4] = -1.5 * a * h ** 0.5 / H
+        u += rng.normal(0, 1.0, u.shape) * ((2e-3, 1e-3, 2e-5) if dim == 2 else (2e-3, 2e-3, 1e-3, 2e-5, 2e-5, 2e-5))
+        u[ids < 0] = 0
+        O.apply_load(0.25 * (s + 1)); assert O.set_trial_disp(u) == 0
+        D.apply_load(0.25 * (s + 1)); D.set_trial_disp(u); D.update()
+        assert relerr(D.form_tangent(), O.form_tangent()) < BEAM_RTOL and relerr(D.form_unbalance(), O.form_unbalance()) < BEAM_RTOL
+        for e in (0, O.ne // 2, O.ne - 1):
+            assert relerr(D.element_resid(e, nd), O.ele_resid(e, nd)) < BEAM_RTOL
+        if s == 3:
+            O.revert(); D.revert_to_last_commit()
+            assert relerr(D.form_tangent(), O.form_tangent()) < BEAM_RTOL and relerr(D.form_unbalance(), O.form_unbalance()) < BEAM_RTOL
+        else:
+            O.commit(); D.commit()
+    O.revert_to_start(); D.revert_to_start()
+    O.apply_load(0.0); D.apply_load(0.0)
+    z = np.zeros((spec.nn, spec.ndf)); O.set_trial_disp(z); D.set_trial_disp(z); D.update()
+    assert relerr(D.form_tangent(), O.form_tangent()) < BEAM_RTOL
 
 
 @pytest.mark.parametrize("dim", [2, 3])

@@ -350,6 +350,41 @@ def test_steel01_elastic_fibres_vs_live_reference(dim):
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("kind", [1, 2, 3, 4])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_beam_integration_rules_vs_live_reference(dim, kind):
+    """forceBeamColumn -integration Legendre (1) | Radau (2) | NewtonCotes (3) | Trapezoidal (4): the reference builds its
+    elements with that BeamIntegration class (quadrature/Frame/*BeamIntegration.cpp); the oracle takes the section locations
+    and weights the class returns -- what the binding reads out of the element -- instead of its Lobatto tables.  Point and
+    uniform element loads along (their section forces depend on the locations)."""
+    from modelspec import with_beam_integration, with_beam_gravity, with_beam_point_loads
+    rng = np.random.default_rng(11)
+    spec = frame2d(2, 2, 2, nip=4) if dim == 2 else frame3d(1, 1, 2, nip=5)
+    spec = with_beam_integration(with_beam_point_loads(with_beam_gravity(spec, seed=3), seed=2), kind)
+    lob = with_beam_point_loads(with_beam_gravity(frame2d(2, 2, 2, nip=4) if dim == 2 else frame3d(1, 1, 2, nip=5), seed=3), seed=2)
+    O, R, Rl = OracleBackend(spec, 1, 0), RefBackend(spec, 1, 0), RefBackend(lob, 1, 0)
+    hcol = spec.crd[:, 1] if dim == 2 else spec.crd[:, 2]
+    H = hcol.max(); h = hcol / H
+    nd = 6 if dim == 2 else 12
+    differs = False
+    for s_, a in enumerate([0.2, 0.5, 0.8, 1.1]):
+        u = np.zeros((spec.nn, spec.ndf))
+        u[:, 0] = a * h ** 1.5
+        u[:, 2 if dim == 2 else 4] = -1.5 * a * h ** 0.5 / H
+        u += rng.normal(0, 1.0, u.shape) * ((2e-3, 1e-3, 2e-5) if dim == 2 else (2e-3, 2e-3, 1e-3, 2e-5, 2e-5, 2e-5))
+        u[O.ids() < 0] = 0
+        for m in (O, R, Rl):
+            m.apply_load(0.25 * (s_ + 1)); m.set_trial_disp(u)
+        Ar, Br = R.form_tangent(), R.form_unbalance()
+        assert close(O.form_tangent(), Ar, 1e-11) and close(O.form_unbalance(), Br, 1e-11)
+        for e in range(O.ne):
+            assert close(O.ele_resid(e, nd), R.ele_resid(e, nd), 1e-11)
+        differs = differs or not close(Ar, Rl.form_tangent(), 1e-4)
+        O.commit(); R.commit(); Rl.commit()
+    assert differs                     # another rule, another tangent
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
 @pytest.mark.parametrize("dim", [2, 3])
 def test_pdelta_transformation_vs_live_reference(dim):
     """`geomTransf PDelta` under forceBeamColumn (PDeltaCrdTransf2d.cpp:349-745, PDeltaCrdTransf3d.cpp:200-249, 784-790,

@@ -72,6 +72,7 @@ def _load():
         "xb_add_elements": (i32, [vp, i32, i32, vp, vp, vp, vp, i32]),
         "xb_add_beam_uniform_loads": (i32, [vp, i32, vp, vp]),
         "xb_add_beam_point_loads": (i32, [vp, i32, vp, vp]),
+        "xb_set_beam_integration": (i32, [vp, i32, vp, i32, vp, vp]),
         "xb_add_nodal_loads": (i32, [vp, i32, vp, vp]),
         "xb_set_nodal_mass": (i32, [vp, i32, vp, vp]),
         "xb_set_rayleigh_alpha_m": (i32, [vp, f64]),
@@ -240,6 +241,11 @@ class DeviceModel:
         self._ck(lib.xb_add_elements(self._h, kind, len(tags), _ptr(tags), _ptr(conn), _ptr(mat_tags),
                                      _ptr(par), par.shape[1]))
 
+    def set_beam_integration(self, ele_tags, xi, wt):
+        """section locations / weights [n][nip] (fractions of L) of a beam integration other than Lobatto"""
+        ele_tags, xi, wt = _i32(ele_tags), _f64(xi), _f64(wt)
+        self._ck(lib.xb_set_beam_integration(self._h, len(ele_tags), _ptr(ele_tags), xi.shape[1], _ptr(xi), _ptr(wt)))
+
     def add_beam_point_loads(self, ele_tags, p):
         """eleLoad -beamPoint: p [n][4] = Py, Pz, N, xL per element"""
         ele_tags, p = _i32(ele_tags), _f64(p)
@@ -290,6 +296,9 @@ class DeviceModel:
             m.add_elements(g.kind, g.tags, g.conn, g.mat, g.par)
         if spec.loads is not None and len(spec.loads):
             m.add_nodal_loads(spec.loads[:, 0].astype(np.int32), spec.loads[:, 1:])
+        br = getattr(spec, "beam_rules", None)
+        if br:
+            m.set_beam_integration(*br)
         bp = getattr(spec, "beam_point_loads", [])
         if bp:
             m.add_beam_point_loads([t for t, *_ in bp], np.array([q for _, *q in bp], np.float64))

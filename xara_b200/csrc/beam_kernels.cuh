@@ -86,6 +86,8 @@ struct BeamView {
   int pdelta;
   const double* U;
   double* ul;
+  // beam integration other than Lobatto (xb_set_beam_integration): [2 nip][n] locations then weights, fractions of L; null: Lobatto
+  const double* rule;
 };
 
 // transient coefficients handed to the form kernels (see TanCoef / DynCoef in device_model.cu)
@@ -613,6 +615,9 @@ __constant__ double LOBATTO_W[11][10] = {{0},{0},{1.0,1.0},{0.333333333333333,1.
     {0.02222222222,0.1333059908,0.2248893421,0.2920426836,0.3275397611,0.3275397611,0.2920426836,0.2248893421,0.1333059908,0.02222222222}};
 __device__ __forceinline__ double lobatto_x(int n, int i) { return 0.5 * (LOBATTO_X[n][i] + 1.0); }
 __device__ __forceinline__ double lobatto_w(int n, int i) { return LOBATTO_W[n][i] * 0.5; }
+// section i of element e: location and weight as fractions of L (BeamIntegration::getSectionLocations / getSectionWeights)
+__device__ __forceinline__ double rule_x(const BeamView& B, long long e, int i) { return B.rule ? B.rule[(size_t)i * B.n + e] : lobatto_x(B.nip, i); }
+__device__ __forceinline__ double rule_w(const BeamView& B, long long e, int i) { return B.rule ? B.rule[(size_t)(B.nip + i) * B.n + e] : lobatto_w(B.nip, i); }
 // sum over the sections of an element in section order: lanes gbase .. gbase + nip - 1 of the warp
 __device__ __forceinline__ double group_sum_ordered(double x, unsigned gmask, int gbase, int nip) {
   double s = __shfl_sync(gmask, x, gbase);
@@ -706,7 +711,7 @@ __global__ void __launch_bounds__(128, XB_FBC_SEC_OCC) fbc3d_update_sec_kernel(B
   if (initialFlag != 0 && norm6(dv) <= DBL_EPSILON && !loaded) return;
 #pragma unroll
   for (int q = 0; q < 6; q++) vin[q] = v[q] - dv[q];
-  const double xL = lobatto_x(nip, is), xL1 = xL - 1.0, wtL = lobatto_w(nip, is) * L;
+  const double xL = rule_x(B, e, is), xL1 = xL - 1.0, wtL = rule_w(B, e, is) * L;
   // `eleLoad -beamUniform`: this section's forces sp (computeSectionForces, ForceBeamColumn3d.cpp:1197-1215)
   double sp0 = 0.0, sp1 = 0.0, sp2 = 0.0;
   if (loaded) {
@@ -941,7 +946,7 @@ __global__ void __launch_bounds__(128, XB_FBC_SEC_OCC) fbc2d_update_sec_kernel(B
   if (initialFlag != 0 && sqrt(dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]) <= DBL_EPSILON && !loaded) return;
 #pragma unroll
   for (int q = 0; q < 3; q++) vin[q] = v[q] - dv[q];
-  const double xL = lobatto_x(nip, is), xL1 = xL - 1.0, wtL = lobatto_w(nip, is) * L;
+  const double xL = rule_x(B, e, is), xL1 = xL - 1.0, wtL = rule_w(B, e, is) * L;
   // `eleLoad -beamUniform`: this section's forces sp (computeSectionForces, ForceBeamColumn2d.cpp:1034-1070)
   double sp0 = 0.0, sp1 = 0.0;
   if (loaded) {
@@ -1247,7 +1252,7 @@ __global__ void fbc_kv0_kernel(BeamView B) {
     for (int q = 0; q < 9; q++) f[q] = 0.0;
     for (int q = 0; q < 4; q++) fS[q] = __ldg(B.fs0 + q);
     for (int i = 0; i < B.nip; i++) {
-      const double xL = lobatto_x(B.nip, i), xL1 = xL - 1.0, wtL = lobatto_w(B.nip, i) * L;
+      const double xL = rule_x(B, e, i), xL1 = xL - 1.0, wtL = rule_w(B, e, i) * L;
       double fb[6];
       for (int q = 0; q < 6; q++) fb[q] = 0.0;
       for (int jj = 0; jj < 2; jj++) fb[jj + 2 * 0] += fS[jj + 2 * 0] * wtL;
@@ -1264,7 +1269,7 @@ __global__ void fbc_kv0_kernel(BeamView B) {
     for (int c = 0; c < 3; c++) for (int r = 0; r < 3; r++) fS[r + 3 * c] = __ldg(B.fs0 + r + 4 * c);
     const double fT = __ldg(B.fs0 + 15);
     for (int i = 0; i < B.nip; i++) {
-      const double xL = lobatto_x(B.nip, i), xL1 = xL - 1.0, wtL = lobatto_w(B.nip, i) * L;
+      const double xL = rule_x(B, e, i), xL1 = xL - 1.0, wtL = rule_w(B, e, i) * L;
       double fb[3][5];
       for (int r = 0; r < 3; r++) {
         fb[r][0] = fS[r + 3 * 0] * wtL;

@@ -1711,6 +1711,7 @@ int xb_add_elements(xb_model* m, int kind, int n, const int* tags, const int* co
   HOSTCALL(m->h.add_elements(kind, n, tags, conn, mt, par, ps));
 }
 int xb_add_nodal_loads(xb_model* m, int n, const int* t, const double* v) { HOSTCALL(m->h.add_loads(n, t, v)); }
+int xb_set_beam_integration(xb_model* m, int n, const int* t, int nip, const double* xi, const double* wt) { HOSTCALL(m->h.set_beam_integration(n, t, nip, xi, wt)); }
 int xb_add_beam_point_loads(xb_model* m, int n, const int* t, const double* p) { HOSTCALL(m->h.add_beam_point_loads(n, t, p)); }
 int xb_add_beam_uniform_loads(xb_model* m, int n, const int* t, const double* w) { HOSTCALL(m->h.add_beam_uniform_loads(n, t, w)); }
 int xb_setup(xb_model* m, int numberer, int soe_kind) { HOSTCALL(m->h.setup(numberer, soe_kind)); }
@@ -1959,6 +1960,13 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
       std::vector<double> fs0 = {k0[3] / det, -k0[1] / det, -k0[2] / det, k0[0] / det};
       b.agg = sd.agg ? 1 : 0;
       b.pdelta = g.transf == 1 ? 1 : 0; b.U = m->dU; b.ul = nullptr;
+      b.rule = nullptr;
+      if (!g.rule.empty()) {   // per-element section locations / weights, SoA [2 nip][n]
+        std::vector<double> rs((size_t)2 * g.nip * ne);
+        for (long long e = 0; e < ne; e++)
+          for (int q = 0; q < 2 * g.nip; q++) rs[(size_t)q * ne + e] = g.rule[(size_t)e * 2 * g.nip + q];
+        double* dr = nullptr; CU(dev_upload(m, &dr, rs)); b.rule = dr;
+      }
       if (b.pdelta && b3) { CU(dev_alloc(m, &b.ul, (size_t)2 * std::max<long long>(ne, 1))); CU(cudaMemset(b.ul, 0, sizeof(double) * 2 * std::max<long long>(ne, 1))); }
       if (sd.agg) {   // SectionAggregator::getInitialFlexibility, SectionAggregator.cpp:454-479: 1 / initial tangent on the diagonal
         auto e0 = [&](int f) { const xb::Uniaxial& u = h.unis[sd.mat[f]]; return u.kind == XB_UNI_ELASTIC ? (u.par[0] > u.par[2] ? u.par[0] : u.par[2]) : u.par[1]; };

@@ -257,6 +257,28 @@ int HostModel::add_loads(int n, const int* tags, const double* vals) {
   return XB_OK;
 }
 
+int HostModel::set_beam_integration(int n, const int* tags, int nip, const double* xi, const double* wt) {
+  if (is_setup) { err = "xb_set_beam_integration after xb_setup"; return XB_ERR_STATE; }
+  for (int i = 0; i < n; i++) {
+    bool found = false;
+    for (auto& g : groups) {
+      if (g.kind != XB_ELE_FORCEBEAMCOLUMN2D && g.kind != XB_ELE_FORCEBEAMCOLUMN3D) continue;
+      for (size_t l = 0; l < g.tag.size() && !found; l++) {
+        if (g.tag[l] != tags[i]) continue;
+        found = true;
+        if (nip != g.nip) { err = "xb_set_beam_integration: nip differs from the element's"; return XB_ERR_ARG; }
+        if (g.rule.empty()) { g.rule.assign(g.tag.size() * 2 * (size_t)nip, 0.0); g.rule_set.assign(g.tag.size(), 0); }
+        std::memcpy(&g.rule[l * 2 * nip], xi + (size_t)i * nip, sizeof(double) * nip);
+        std::memcpy(&g.rule[l * 2 * nip + nip], wt + (size_t)i * nip, sizeof(double) * nip);
+        g.rule_set[l] = 1;
+      }
+      if (found) break;
+    }
+    if (!found) { err = "xb_set_beam_integration: no forceBeamColumn element with this tag"; return XB_ERR_ARG; }
+  }
+  return XB_OK;
+}
+
 int HostModel::add_beam_point_loads(int n, const int* tags, const double* pv) {
   if (is_setup) { err = "xb_add_beam_point_loads after xb_setup"; return XB_ERR_STATE; }
   for (int i = 0; i < n; i++) {
@@ -350,6 +372,8 @@ void rcb(std::vector<long long>& items, long long lo, long long hi, int np, int 
 }  // namespace
 
 int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const int* part_in) {
+  for (const Group& g : groups)
+    for (uint8_t f : g.rule_set) if (!f) { err = "xb_set_beam_integration: every element of an xb_add_elements call, or none"; return XB_ERR_ARG; }
   if (is_setup) { err = "xb_setup called twice"; return XB_ERR_STATE; }
   if (numberer_ != XB_NUMBERER_PLAIN && numberer_ != XB_NUMBERER_RCM) { err = "unknown numberer"; return XB_ERR_ARG; }
   if (soe_kind_ < XB_SOE_SPARSE_GEN_COL || soe_kind_ > XB_SOE_UMFPACK_GEN) { err = "unknown SOE kind"; return XB_ERR_ARG; }
@@ -633,6 +657,7 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
     for (size_t gi = 0; gi < groups.size(); gi++) {
       lgroups[gi].kind = groups[gi].kind; lgroups[gi].mat_kind = groups[gi].mat_kind; lgroups[gi].j2_plane_stress = groups[gi].j2_plane_stress;
       lgroups[gi].sec = groups[gi].sec; lgroups[gi].nip = groups[gi].nip; lgroups[gi].max_iters = groups[gi].max_iters; lgroups[gi].tol = groups[gi].tol;
+      lgroups[gi].transf = groups[gi].transf;
     }
     std::vector<std::vector<int>> newidx(groups.size());
     for (size_t gi = 0; gi < groups.size(); gi++) newidx[gi].assign(groups[gi].n(), -1);
@@ -648,6 +673,7 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
         lg.tag.push_back(g.tag[l]); lg.mat.push_back(g.mat[l]);
         for (int a = 0; a < k.nen; a++) lg.conn.push_back(g2l[g.conn[(size_t)l * k.nen + a]]);
         for (int q = 0; q < k.npar; q++) lg.par.push_back(g.par[(size_t)l * k.npar + q]);
+        if (!g.rule.empty()) { lg.rule.insert(lg.rule.end(), &g.rule[(size_t)l * 2 * g.nip], &g.rule[(size_t)(l + 1) * 2 * g.nip]); lg.rule_set.push_back(g.rule_set[l]); }
       }
     }
     ne = 0;

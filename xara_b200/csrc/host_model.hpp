@@ -65,6 +65,8 @@ struct Group {
   // forceBeamColumn batches: one fibre section, nIP Lobatto points, element iteration controls
   int sec = -1, nip = 0, max_iters = 10;
   int transf = 0;            // geomTransf of the batch: 0 Linear, 1 PDelta
+  std::vector<double> rule;  // forceBeamColumn: per element nip locations then nip weights (xb_set_beam_integration); empty: Lobatto
+  std::vector<uint8_t> rule_set;
   double tol = 1e-12;
   bool j2_plane_stress = false;   // FourNodeQuad batch whose J2Plasticity copies are J2PlaneStress
   std::vector<long long> kdst;  // [n][nen] where the rows of node a of element l go: >= 0 offset of the
@@ -224,6 +226,7 @@ struct HostModel {
   int add_loads(int n, const int* tags, const double* vals);
   int add_beam_uniform_loads(int n, const int* tags, const double* w);
   int add_beam_point_loads(int n, const int* tags, const double* p);
+  int set_beam_integration(int n, const int* tags, int nip, const double* xi, const double* wt);
   int add_mass(int n, const int* tags, const double* vals);
   // part: nullptr (built-in recursive coordinate bisection) or [ne] ranks in FE order
   int setup(int numberer, int soe_kind, int nparts = 1, int rank = 0, const int* part = nullptr);
