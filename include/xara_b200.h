@@ -43,7 +43,8 @@ enum {
   XB_UNI_STEEL02 = 0,   /* material/uniaxial/steel/Steel02.h:47: Fy,E0,b,R0,cR1,cR2,a1,a2,a3,a4[,sigInit] */
   XB_UNI_CONCRETE02 = 1,/* material/uniaxial/concrete/Concrete02.cpp:93: fc,epsc0,fcu,epscu,rat,ft,Ets     */
   XB_UNI_STEEL01 = 2,   /* material/uniaxial/steel/Steel01.cpp:40: fy,E0,b,a1,a2,a3,a4 (the command's defaults 0,55,0,55) */
-  XB_UNI_ELASTIC = 3    /* material/uniaxial/ElasticMaterial.cpp:96: E[,eta,Eneg]; eta must be 0 (no strain rate on this path) */
+  XB_UNI_ELASTIC = 3,   /* material/uniaxial/ElasticMaterial.cpp:96: E[,eta,Eneg]; eta must be 0 (no strain rate on this path) */
+  XB_UNI_CONCRETE01 = 4 /* material/uniaxial/concrete/Concrete01.cpp:89: fpc,epsc0,fpcu,epscu (Kent-Scott-Park, no tension) */
 };
 
 /* element kinds */
@@ -115,7 +116,7 @@ int xb_set_node_ndf(xb_model*, int n, const int* node_tags, int ndf);
 int xb_add_equal_dof(xb_model*, int retained_node_tag, int constrained_node_tag, int n, const int* dofs);
 /* OPS nDMaterial command; par has npar doubles in the order listed at the kind */
 int xb_add_nd_material(xb_model*, int tag, int kind, const double* par, int npar);
-/* uniaxialMaterial Steel02 | Concrete02 | Steel01 | Elastic (runtime/commands/modeling/uniaxial.cpp) */
+/* uniaxialMaterial Steel02 | Concrete02 | Steel01 | Elastic | Concrete01 (runtime/commands/modeling/uniaxial.cpp) */
 int xb_add_uniaxial_material(xb_model*, int tag, int kind, const double* par, int npar);
 /* section Fiber -> FiberSection2d (material/section/FiberSection2d.cpp:99 addFiber): nf fibres
  * (y, A, uniaxial material tag) in the order given; the centroid is computed as the command does */

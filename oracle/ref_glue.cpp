@@ -42,6 +42,7 @@
 #include <FiberSection3d.h>
 #include <Steel02.h>
 #include <Steel01.h>
+#include <Concrete01.h>
 #include <SectionAggregator.h>
 #include <Concrete02.h>
 #include <ElasticMaterial.h>
@@ -247,6 +248,10 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
             } else if (auto* s1 = dynamic_cast<Steel01*>(um)) {
               kind = XB_UNI_STEEL01; np = 7;
               const double q[7] = {s1->fy, s1->E0, s1->b, s1->a1, s1->a2, s1->a3, s1->a4};
+              std::memcpy(p, q, sizeof q);
+            } else if (auto* c1 = dynamic_cast<Concrete01*>(um)) {
+              kind = XB_UNI_CONCRETE01; np = 4;
+              const double q[4] = {c1->fpc, c1->epsc0, c1->fpcu, c1->epscu};
               std::memcpy(p, q, sizeof q);
             } else if (auto* em = dynamic_cast<ElasticMaterial*>(um)) {
               kind = XB_UNI_ELASTIC; np = 3;

@@ -53,6 +53,7 @@
 #include <TrapezoidalBeamIntegration.h>
 #include <PDeltaCrdTransf3d.h>
 #include <Steel01.h>
+#include <Concrete01.h>
 #include <ElasticMaterial.h>
 #include <FiberSection3d.h>
 #include <ElasticMaterial.h>
@@ -303,6 +304,7 @@ int ref_add_quad(void* h, int tag, const int* nd, int matTag, double thick, int 
 static UniaxialMaterial* make_uniaxial(int tag, int kind, const double* p) {
   if (kind == 2) return new Steel01(tag, p[0], p[1], p[2], p[3], p[4], p[5], p[6]);
   if (kind == 3) return new ElasticMaterial(tag, p[0], p[1], p[2]);
+  if (kind == 4) return new Concrete01(tag, p[0], p[1], p[2], p[3]);          // fpc, epsc0, fpcu, epscu
   if (kind == 0) return new Steel02(tag, p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8], p[9], p[10]);
   if (kind == 1) return new Concrete02(tag, p[0], p[1], p[2], p[3], p[4], p[5], p[6]);
   return nullptr;

@@ -21,7 +21,7 @@
 /* material kinds / element kinds shared with tests (mirrors include/xara_b200.h) */
 enum { ORC_MAT_ELASTIC_ISOTROPIC = 0, ORC_MAT_J2 = 1 };
 enum { ORC_ELE_BRICK = 0, ORC_ELE_QUAD = 1, ORC_ELE_FBC2D = 2, ORC_ELE_FBC3D = 3 };
-enum { ORC_UNI_STEEL02 = 0, ORC_UNI_CONCRETE02 = 1, ORC_UNI_STEEL01 = 2, ORC_UNI_ELASTIC = 3 };
+enum { ORC_UNI_STEEL02 = 0, ORC_UNI_CONCRETE02 = 1, ORC_UNI_STEEL01 = 2, ORC_UNI_ELASTIC = 3, ORC_UNI_CONCRETE01 = 4 };
 enum { ORC_ND_3D = 0, ORC_ND_PLANE_STRAIN = 1, ORC_ND_PLANE_STRESS = 2 };
 
 /* ======================================================================== */
@@ -452,6 +452,8 @@ typedef struct {
   /* Steel01 (Steel01.h: fy, E0, b, a1..a4 above; history C* / T*) and ElasticMaterial (Epos, Eneg) */
   double minStrainP, maxStrainP, shiftPP, shiftNP, minStrain, maxStrain, shiftP, shiftN; int loadingP, loading;
   double Epos, Eneg;
+  /* Concrete01 (Concrete01.h: fpc, epsc0, fpcu, epscu in fc, epsc0, fcu, epscu above; history C* / T*) */
+  double endStrainP, unloadSlopeP, endStrain, unloadSlope;     /* (min strain: minStrainP / minStrain) */
   /* common */
   double eP, sigP, epsP, e, sig, eps;
 } OrcUni;
@@ -473,6 +475,15 @@ static void uni_init(OrcUni* m, int kind, const double* p) {
     m->minStrainP = m->maxStrainP = 0.0; m->shiftPP = m->shiftNP = 1.0; m->loadingP = 0;
     m->minStrain = m->maxStrain = 0.0; m->shiftP = m->shiftN = 1.0; m->loading = 0;
     m->epsP = 0.0; m->sigP = 0.0; m->eP = m->E0; m->eps = 0.0; m->sig = 0.0; m->e = m->E0;
+  } else if (kind == ORC_UNI_CONCRETE01) {
+    /* Concrete01::Concrete01, Concrete01.cpp:89-123: p = fpc, epsc0, fpcu, epscu, made negative */
+    m->fc = p[0]; m->epsc0 = p[1]; m->fcu = p[2]; m->epscu = p[3];
+    if (m->fc > 0.0) m->fc = -m->fc;
+    if (m->epsc0 > 0.0) m->epsc0 = -m->epsc0;
+    if (m->fcu > 0.0) m->fcu = -m->fcu;
+    if (m->epscu > 0.0) m->epscu = -m->epscu;
+    const double Ec0 = 2 * m->fc / m->epsc0;
+    m->eP = Ec0; m->unloadSlopeP = Ec0; m->e = Ec0; m->unloadSlope = Ec0;
   } else if (kind == ORC_UNI_ELASTIC) {
     /* ElasticMaterial(tag, E, eta, Eneg), ElasticMaterial.cpp:96-110: p = E, eta (0 here: no strain rate in this path), Eneg */
     m->Epos = p[0]; m->Eneg = p[2];
@@ -490,6 +501,7 @@ static void uni_init(OrcUni* m, int kind, const double* p) {
 }
 static double uni_initial_tangent(const OrcUni* m) {
   if (m->kind == ORC_UNI_STEEL01) return m->E0;                                   /* Steel01.h getInitialTangent */
+  if (m->kind == ORC_UNI_CONCRETE01) return 2.0 * m->fc / m->epsc0;               /* Concrete01.h getInitialTangent */
   if (m->kind == ORC_UNI_ELASTIC) return m->Epos > m->Eneg ? m->Epos : m->Eneg;   /* ElasticMaterial.cpp:186 */
   return m->kind == ORC_UNI_STEEL02 ? m->E0 : 2.0 * m->fc / m->epsc0;   /* Steel02.cpp:107, Concrete02.cpp:161 */
 }
@@ -641,7 +653,56 @@ static int elastic_set_trial(OrcUni* m, double strain) {
   m->e = strain > 0.0 ? m->Epos : (strain < 0.0 ? m->Eneg : (m->Epos > m->Eneg ? m->Epos : m->Eneg));
   return 0;
 }
+/* Concrete01::setTrialStrain with reload / envelope / unload, Concrete01.cpp:146-206, 313-385 */
+static void concrete01_envelope(OrcUni* m) {
+  if (m->eps > m->epsc0) {
+    double eta = m->eps / m->epsc0;
+    m->sig = m->fc * (2 * eta - eta * eta);
+    double Ec0 = 2.0 * m->fc / m->epsc0;
+    m->e = Ec0 * (1.0 - eta);
+  } else if (m->eps > m->epscu) {
+    m->e = (m->fc - m->fcu) / (m->epsc0 - m->epscu);
+    m->sig = m->fc + m->e * (m->eps - m->epsc0);
+  } else { m->sig = m->fcu; m->e = 0.0; }
+}
+static void concrete01_unload(OrcUni* m) {
+  double tempStrain = m->minStrain;
+  if (tempStrain < m->epscu) tempStrain = m->epscu;
+  double eta = tempStrain / m->epsc0;
+  double ratio = 0.707 * (eta - 2.0) + 0.834;
+  if (eta < 2.0) ratio = 0.145 * eta * eta + 0.13 * eta;
+  m->endStrain = ratio * m->epsc0;
+  double temp1 = m->minStrain - m->endStrain;
+  double Ec0 = 2.0 * m->fc / m->epsc0;
+  double temp2 = m->sig / Ec0;
+  if (temp1 > -DBL_EPSILON) m->unloadSlope = Ec0;
+  else if (temp1 <= temp2) { m->endStrain = m->minStrain - temp1; m->unloadSlope = m->sig / temp1; }
+  else { m->endStrain = m->minStrain - temp2; m->unloadSlope = Ec0; }
+}
+static void concrete01_reload(OrcUni* m) {
+  if (m->eps <= m->minStrain) { m->minStrain = m->eps; concrete01_envelope(m); concrete01_unload(m); }
+  else if (m->eps <= m->endStrain) { m->e = m->unloadSlope; m->sig = m->e * (m->eps - m->endStrain); }
+  else { m->sig = 0.0; m->e = 0.0; }
+}
+static int concrete01_set_trial(OrcUni* m, double strain) {
+  m->minStrain = m->minStrainP; m->endStrain = m->endStrainP; m->unloadSlope = m->unloadSlopeP;
+  m->sig = m->sigP; m->e = m->eP; m->eps = m->epsP;
+  double dStrain = strain - m->epsP;
+  if (fabs(dStrain) < DBL_EPSILON) return 0;
+  m->eps = strain;
+  if (m->eps > 0.0) { m->sig = 0; m->e = 0; return 0; }
+  m->unloadSlope = m->unloadSlopeP;
+  double tempStress = m->sigP + m->unloadSlope * m->eps - m->unloadSlope * m->epsP;
+  if (strain < m->epsP) {
+    m->minStrain = m->minStrainP; m->endStrain = m->endStrainP;
+    concrete01_reload(m);
+    if (tempStress > m->sig) { m->sig = tempStress; m->e = m->unloadSlope; }
+  } else if (tempStress <= 0.0) { m->sig = tempStress; m->e = m->unloadSlope; }
+  else { m->sig = 0.0; m->e = 0.0; }
+  return 0;
+}
 static int uni_set_trial(OrcUni* m, double strain) {
+  if (m->kind == ORC_UNI_CONCRETE01) return concrete01_set_trial(m, strain);
   if (m->kind == ORC_UNI_STEEL01) return steel01_set_trial(m, strain);
   if (m->kind == ORC_UNI_ELASTIC) return elastic_set_trial(m, strain);
   return m->kind == ORC_UNI_STEEL02 ? steel02_set_trial(m, strain) : concrete02_set_trial(m, strain);
@@ -653,6 +714,8 @@ static void uni_commit(OrcUni* m) {
     m->sigs0P = m->sigs0; m->epssrP = m->epsr; m->sigsrP = m->sigr; m->konP = m->kon;
   } else if (m->kind == ORC_UNI_STEEL01) {   /* Steel01.cpp:244-262 */
     m->minStrainP = m->minStrain; m->maxStrainP = m->maxStrain; m->shiftPP = m->shiftP; m->shiftNP = m->shiftN; m->loadingP = m->loading;
+  } else if (m->kind == ORC_UNI_CONCRETE01) {   /* Concrete01.cpp:402-418 */
+    m->minStrainP = m->minStrain; m->unloadSlopeP = m->unloadSlope; m->endStrainP = m->endStrain;
   } else if (m->kind == ORC_UNI_CONCRETE02) { m->ecminP = m->ecmin; m->deptP = m->dept; }
   m->eP = m->e; m->sigP = m->sig; m->epsP = m->eps;
 }
@@ -662,6 +725,8 @@ static void uni_revert(OrcUni* m) {
     m->sigs0 = m->sigs0P; m->epsr = m->epssrP; m->sigr = m->sigsrP; m->kon = m->konP;
   } else if (m->kind == ORC_UNI_STEEL01) {   /* Steel01.cpp:264-281 */
     m->minStrain = m->minStrainP; m->maxStrain = m->maxStrainP; m->shiftP = m->shiftPP; m->shiftN = m->shiftNP; m->loading = m->loadingP;
+  } else if (m->kind == ORC_UNI_CONCRETE01) {   /* Concrete01.cpp:420-433 */
+    m->minStrain = m->minStrainP; m->endStrain = m->endStrainP; m->unloadSlope = m->unloadSlopeP;
   } else if (m->kind == ORC_UNI_ELASTIC) {   /* ElasticMaterial::revertToLastCommit: the committed strain; stress and tangent follow it */
     elastic_set_trial(m, m->epsP); return;
   } else { m->ecmin = m->ecminP; m->dept = m->deptP; }
@@ -1583,7 +1648,7 @@ int orc_add_uniaxial(void* h, int tag, int kind, const double* p) {
   m->uni_par = (double*)realloc(m->uni_par, sizeof(double) * 12 * (m->nuni + 1));
   m->uni_tag[m->nuni] = tag; m->uni_kind[m->nuni] = kind;
   memset(m->uni_par + 12 * m->nuni, 0, 12 * sizeof(double));
-  memcpy(m->uni_par + 12 * m->nuni, p, sizeof(double) * (kind == ORC_UNI_STEEL02 ? 11 : (kind == ORC_UNI_ELASTIC ? 3 : 7)));
+  memcpy(m->uni_par + 12 * m->nuni, p, sizeof(double) * (kind == ORC_UNI_STEEL02 ? 11 : (kind == ORC_UNI_ELASTIC ? 3 : (kind == ORC_UNI_CONCRETE01 ? 4 : 7))));
   m->nuni++; return 0;
 }
 int orc_add_fiber_section(void* h, int tag, int nf, const double* y, const double* A, const int* matTags) {

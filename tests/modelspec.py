@@ -26,7 +26,7 @@ GLUE_SO = os.path.join(ROOT, "oracle", "_ref", "libref_glue.so")
 
 MAT_ELASTIC, MAT_J2 = 0, 1
 ELE_BRICK, ELE_QUAD, ELE_FBC2D, ELE_FBC3D = 0, 1, 2, 3
-UNI_STEEL02, UNI_CONCRETE02, UNI_STEEL01, UNI_ELASTIC = 0, 1, 2, 3
+UNI_STEEL02, UNI_CONCRETE02, UNI_STEEL01, UNI_ELASTIC, UNI_CONCRETE01 = 0, 1, 2, 3, 4
 SEC_P, SEC_MZ = 2, 1     # SectionForceDeformation.h response codes
 ND_3D, ND_PLANE_STRAIN, ND_PLANE_STRESS = 0, 1, 2
 NUMBERER_PLAIN, NUMBERER_RCM = 0, 1
@@ -260,10 +260,12 @@ def soil_frame_2d(nbay=2, nstory=2, ndiv=1, per_bay=3, ny=4, depth=240.0, mat=J2
 
 
 def steel01_elastic_frame(dim):
-    """an RC frame whose bars are Steel01 (with isotropic hardening) and whose cover is a bilinear Elastic material: the
-    uniaxial kinds of BASELINE configs[0] as fibres of FiberSection2d / FiberSection3d"""
+    """an RC frame whose bars are Steel01 (with isotropic hardening), whose core is Concrete01 and whose cover is a bilinear
+    Elastic material: the uniaxial kinds of BASELINE configs[0], and the concrete most RC examples use, as fibres of
+    FiberSection2d / FiberSection3d"""
     spec = frame2d(2, 2, 2, lateral=20.0) if dim == 2 else frame3d(1, 1, 2, ndiv=2, lateral=(18.0, 10.0))
     uni = dict((t, (k, p)) for t, k, p in spec.uniaxials)
+    uni[1] = (UNI_CONCRETE01, (-6.0, -0.004, -5.0, -0.014))             # core: Kent-Scott-Park, no tension
     uni[2] = (UNI_ELASTIC, (2500.0, 0.0, 3600.0))                       # cover: softer in tension
     uni[3] = (UNI_STEEL01, (60.0, 29000.0, 0.015, 0.02, 30.0, 0.02, 30.0))
     spec.uniaxials = [(t, *uni[t]) for t in sorted(uni)]

@@ -200,7 +200,7 @@ def test_newton_iteration_counts_match_oracle(shape):
 
 @pytest.mark.skipif(not (have_ref() and have_glue()), reason="oracle/_ref not built (needs /root/reference)")
 @pytest.mark.parametrize("shape,numberer,soe", [("brick", 1, 0), ("quad", 0, 1), ("mixed", 1, 1), ("soilcolumn_equaldof", 1, 0), ("frame2d_gravity", 1, 0), ("soil_frame_mixed_ndf", 1, 0),
-                                                ("soilcolumn_equaldof", 0, 1), ("frame2d_pdelta", 1, 0), ("frame3d_pdelta", 1, 0), ("frame3d_eleloads", 1, 0), ("frame2d_legendre", 1, 0), ("frame3d_radau", 1, 0)])
+                                                ("soilcolumn_equaldof", 0, 1), ("frame2d_pdelta", 1, 0), ("frame3d_pdelta", 1, 0), ("frame3d_eleloads", 1, 0), ("frame2d_legendre", 1, 0), ("frame3d_radau", 1, 0), ("frame2d_concrete01", 1, 0)])
 def test_reference_newton_loop_drives_device_path(shape, numberer, soe):
     """The drop-in, end to end: the REFERENCE'S OWN StaticAnalysis objects (AnalysisModel, PlainHandler, numberer,
     SparseGenCol/Row SOE and solver, NewtonRaphson, CTestNormDispIncr, LoadControl::newStep) run a load-controlled
@@ -226,6 +226,10 @@ def test_reference_newton_loop_drives_device_path(shape, numberer, soe):
         def mk():   # `eleLoad -beamUniform` and `-beamPoint` (Beam3dUniformLoad, Beam3dPointLoad) read out of the load pattern
             from modelspec import with_beam_gravity, with_beam_point_loads
             return with_beam_point_loads(with_beam_gravity(frame3d(1, 1, 2, ndiv=2, lateral=(14.0, 8.0)), w=-0.06, seed=1), P=-2.5, seed=2)
+    elif shape == "frame2d_concrete01":
+        def mk():   # Concrete01 core, Steel01 bars, bilinear Elastic cover read out of the reference's FiberSection2d
+            from modelspec import steel01_elastic_frame
+            return steel01_elastic_frame(2)
     elif shape in ("frame2d_legendre", "frame3d_radau"):
         def mk():   # -integration Legendre / Radau: the binding reads the section locations and weights out of the element's BeamIntegration
             from modelspec import with_beam_integration

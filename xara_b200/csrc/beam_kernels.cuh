@@ -32,6 +32,7 @@ constexpr int XB_FBC3D_MAX_PASSES = 20000;
 // Concrete02 record: 0 ecmin 1 dept 8 e 9 sig 10 eps
 // Steel01 record:    0 minStrain 1 maxStrain 2 shiftP 3 shiftN 4 loading 8 tangent 9 stress 10 strain
 // Elastic record:    8 tangent 9 stress 10 strain
+// Concrete01 record: 0 minStrain 1 endStrain 2 unloadSlope 8 tangent 9 stress 10 strain
 
 struct BeamView {
   long long n;                 // elements
@@ -45,7 +46,7 @@ struct BeamView {
   const double* fz;            // [nf] z - zBar (3D)
   double GJ;                   // elastic torsion (3D)
   const double* fA;            // [nf]
-  const int* fkind;            // [nf] 0 Steel02, 1 Concrete02, 2 Steel01, 3 Elastic (| XB_FIB_CURV)
+  const int* fkind;            // [nf] 0 Steel02, 1 Concrete02, 2 Steel01, 3 Elastic, 4 Concrete01 (| XB_FIB_CURV)
   int agg;                     // section Aggregator (P, Mz): flexibility 1/k on the diagonal (SectionAggregator.cpp:419)
   const double* fpar;          // [nf][12] material parameters
   const double* fs0;           // [ord*ord] initial section flexibility (column-major)
@@ -313,11 +314,67 @@ __device__ __forceinline__ void elastic_trial(const double* __restrict__ p, doub
   T[8 * n] = e; T[9 * n] = sig; T[10 * n] = strain;
   sig_o = sig; e_o = e;
 }
+// Concrete01::setTrialStrain with reload / envelope / unload (Concrete01.cpp:146-206, 313-385).  p = fpc, epsc0, fpcu, epscu
+// (made negative on the host)
+__device__ __forceinline__ void concrete01_trial(const double* __restrict__ p, const double* C, double* T, long long n,
+                                                 double strain, double& sig_o, double& e_o) {
+  const double fpc = p[0], epsc0 = p[1], fpcu = p[2], epscu = p[3];
+  const double CminStrain = C[0], CendStrain = C[1 * n], CunloadSlope = C[2 * n];
+  const double Cstrain = C[10 * n], Cstress = C[9 * n];
+  double TminStrain = CminStrain, TendStrain = CendStrain, TunloadSlope = CunloadSlope;
+  double Tstress = Cstress, Ttangent = C[8 * n], Tstrain = Cstrain;
+  const double dStrain = strain - Cstrain;
+  if (!(fabs(dStrain) < DBL_EPSILON)) {
+    Tstrain = strain;
+    if (Tstrain > 0.0) { Tstress = 0; Ttangent = 0; }
+    else {
+      const double tempStress = Cstress + TunloadSlope * Tstrain - TunloadSlope * Cstrain;
+      if (strain < Cstrain) {
+        // reload()
+        if (Tstrain <= TminStrain) {
+          TminStrain = Tstrain;
+          // envelope()
+          if (Tstrain > epsc0) {
+            const double eta = Tstrain / epsc0;
+            Tstress = fpc * (2 * eta - eta * eta);
+            const double Ec0 = 2.0 * fpc / epsc0;
+            Ttangent = Ec0 * (1.0 - eta);
+          } else if (Tstrain > epscu) {
+            Ttangent = (fpc - fpcu) / (epsc0 - epscu);
+            Tstress = fpc + Ttangent * (Tstrain - epsc0);
+          } else { Tstress = fpcu; Ttangent = 0.0; }
+          // unload()
+          double tempStrain = TminStrain;
+          if (tempStrain < epscu) tempStrain = epscu;
+          const double eta = tempStrain / epsc0;
+          double ratio = 0.707 * (eta - 2.0) + 0.834;
+          if (eta < 2.0) ratio = 0.145 * eta * eta + 0.13 * eta;
+          TendStrain = ratio * epsc0;
+          const double temp1 = TminStrain - TendStrain;
+          const double Ec0 = 2.0 * fpc / epsc0;
+          const double temp2 = Tstress / Ec0;
+          if (temp1 > -DBL_EPSILON) TunloadSlope = Ec0;
+          else if (temp1 <= temp2) { TendStrain = TminStrain - temp1; TunloadSlope = Tstress / temp1; }
+          else { TendStrain = TminStrain - temp2; TunloadSlope = Ec0; }
+        } else if (Tstrain <= TendStrain) {
+          Ttangent = TunloadSlope;
+          Tstress = Ttangent * (Tstrain - TendStrain);
+        } else { Tstress = 0.0; Ttangent = 0.0; }
+        if (tempStress > Tstress) { Tstress = tempStress; Ttangent = TunloadSlope; }
+      } else if (tempStress <= 0.0) { Tstress = tempStress; Ttangent = TunloadSlope; }
+      else { Tstress = 0.0; Ttangent = 0.0; }
+    }
+  }
+  T[0] = TminStrain; T[1 * n] = TendStrain; T[2 * n] = TunloadSlope;
+  T[8 * n] = Ttangent; T[9 * n] = Tstress; T[10 * n] = Tstrain;
+  sig_o = Tstress; e_o = Ttangent;
+}
 __device__ __forceinline__ void uniaxial_trial(int kind, const double* __restrict__ p, const double* C, double* T, long long n,
                                                double strain, double& stress, double& tangent) {
   if (kind == 0) steel02_trial(p, C, T, n, strain, stress, tangent);
   else if (kind == 1) concrete02_trial(p, C, T, n, strain, stress, tangent);
   else if (kind == 2) steel01_trial(p, C, T, n, strain, stress, tangent);
+  else if (kind == 4) concrete01_trial(p, C, T, n, strain, stress, tangent);
   else elastic_trial(p, T, n, strain, stress, tangent);
 }
 

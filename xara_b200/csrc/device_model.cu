@@ -1940,6 +1940,9 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
         } else if (u.kind == XB_UNI_STEEL01) {   // Steel01::revertToStart, Steel01.cpp:284-311
           E0 = u.par[1];
           C[2] = 1.0; C[3] = 1.0; C[8] = E0; T[2] = 1.0; T[3] = 1.0; T[8] = E0;
+        } else if (u.kind == XB_UNI_CONCRETE01) {   // Concrete01::Concrete01, Concrete01.cpp:109-113: Ctangent = CunloadSlope = Ec0
+          E0 = 2.0 * u.par[0] / u.par[1];
+          C[2] = E0; C[8] = E0; T[2] = E0; T[8] = E0;
         } else if (u.kind == XB_UNI_ELASTIC) {   // ElasticMaterial::getInitialTangent, ElasticMaterial.cpp:186
           E0 = u.par[0] > u.par[2] ? u.par[0] : u.par[2];
           C[8] = E0; T[8] = E0;
@@ -1969,7 +1972,12 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
       }
       if (b.pdelta && b3) { CU(dev_alloc(m, &b.ul, (size_t)2 * std::max<long long>(ne, 1))); CU(cudaMemset(b.ul, 0, sizeof(double) * 2 * std::max<long long>(ne, 1))); }
       if (sd.agg) {   // SectionAggregator::getInitialFlexibility, SectionAggregator.cpp:454-479: 1 / initial tangent on the diagonal
-        auto e0 = [&](int f) { const xb::Uniaxial& u = h.unis[sd.mat[f]]; return u.kind == XB_UNI_ELASTIC ? (u.par[0] > u.par[2] ? u.par[0] : u.par[2]) : u.par[1]; };
+        auto e0 = [&](int f) {
+          const xb::Uniaxial& u = h.unis[sd.mat[f]];
+          if (u.kind == XB_UNI_ELASTIC) return u.par[0] > u.par[2] ? u.par[0] : u.par[2];
+          if (u.kind == XB_UNI_CONCRETE02 || u.kind == XB_UNI_CONCRETE01) return 2.0 * u.par[0] / u.par[1];
+          return u.par[1];
+        };
         fs0 = {1.0 / e0(0), 0.0, 0.0, 1.0 / e0(1)};
       }
       if (b3) {
