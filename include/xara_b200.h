@@ -154,7 +154,7 @@ int xb_add_beam_uniform_loads(xb_model*, int n, const int* ele_tags, const doubl
 int xb_set_beam_integration(xb_model*, int n, const int* ele_tags, int nip, const double* xi, const double* wt);
 /* `eleLoad -ele tags -type -beamPoint Py [Pz] xL [N]` of the Linear pattern (Beam2dPointLoad / Beam3dPointLoad ->
  * ForceBeamColumn2d.cpp:442-455, 1138-1181; ForceBeamColumn3d.cpp:457-475, 1314-1373): p is [n][4] = Py, Pz (3D), N, xL = a/L.
- * One point load per element (beside at most one uniform load); a load with xL outside [0, 1] is ignored, as the
+ * One point load per element (beside its uniform loads, whose intensities add up); a load with xL outside [0, 1] is ignored, as the
  * element does. */
 int xb_add_beam_point_loads(xb_model*, int n, const int* ele_tags, const double* p);
 

@@ -2279,8 +2279,10 @@ int orc_add_beam_uniform_load(void* h, int ele_tag, double wy, double wz, double
   for (int e = 0; e < m->ne; e++) {
     OrcEle* el = &m->ele[e];
     if (el->tag != ele_tag) continue;
-    if (el->kind == ORC_ELE_FBC2D) { if (el->beam->has_load) return -2; el->beam->has_load = 1; el->beam->w[0] = wy; el->beam->w[1] = 0.0; el->beam->w[2] = wa; return 0; }
-    if (el->kind == ORC_ELE_FBC3D) { if (el->beam3->has_load) return -2; el->beam3->has_load = 1; el->beam3->w[0] = wy; el->beam3->w[1] = wz; el->beam3->w[2] = wa; return 0; }
+    /* (a further uniform load on the same element: the element loops over its loads and adds their terms, all at the
+     *  pattern's factor -- kept here as one load with the summed intensities) */
+    if (el->kind == ORC_ELE_FBC2D) { el->beam->has_load = 1; el->beam->w[0] += wy; el->beam->w[2] += wa; return 0; }
+    if (el->kind == ORC_ELE_FBC3D) { el->beam3->has_load = 1; el->beam3->w[0] += wy; el->beam3->w[1] += wz; el->beam3->w[2] += wa; return 0; }
     return -3;
   }
   return -1;

@@ -651,6 +651,8 @@ def test_beam_uniform_element_loads_device_vs_oracle(dim, loads):
     spec = frame2d(3, 3, 2) if dim == 2 else frame3d(2, 1, 2)
     if loads != "point": spec = with_beam_gravity(spec, seed=3)
     if loads != "uniform": spec = with_beam_point_loads(spec, seed=2)
+    if loads == "both":       # a second uniform load on the loaded elements: the intensities add up
+        spec.beam_loads = spec.beam_loads + [(t, 0.4 * wy, 0.3 * wz, -0.5 * wa) for t, wy, wz, wa in spec.beam_loads[::2]]
     nd = 6 if dim == 2 else 12
     O = OracleBackend(spec, 1, 0)
     D = xb.DeviceModel.from_spec(spec, 1, 0).to_device(0)

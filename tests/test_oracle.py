@@ -147,6 +147,8 @@ def test_beam_uniform_element_loads_vs_live_reference(dim, loads):
     spec = frame2d(2, 2, 2) if dim == 2 else frame3d(1, 1, 2)
     if loads != "point": spec = with_beam_gravity(spec, seed=3)
     if loads != "uniform": spec = with_beam_point_loads(spec, seed=2)
+    if loads == "both":       # a second uniform load (live on top of dead) on the loaded elements
+        spec.beam_loads = spec.beam_loads + [(t, 0.4 * wy, 0.3 * wz, -0.5 * wa) for t, wy, wz, wa in spec.beam_loads[::2]]
     assert len(spec.beam_loads) + len(spec.beam_point_loads) >= 4
     O, R = OracleBackend(spec, 1, 0), RefBackend(spec, 1, 0)
     sc = np.asarray((0.02, 0.02, 2e-4) if dim == 2 else (0.015, 0.015, 0.003, 1e-4, 1e-4, 1e-4))

@@ -239,8 +239,9 @@ int HostModel::add_beam_uniform_loads(int n, const int* tags, const double* w) {
       for (size_t l = 0; l < g.tag.size() && !found; l++) {
         if (g.tag[l] != tags[i]) continue;
         double* q = &g.par[l * npar + npar - 3];
-        if (q[0] != 0.0 || q[1] != 0.0 || q[2] != 0.0) { err = "xb_add_beam_uniform_loads: one uniform load per element"; return XB_ERR_UNSUPPORTED; }
-        q[0] = w[(size_t)i * 3]; q[1] = g.kind == XB_ELE_FORCEBEAMCOLUMN3D ? w[(size_t)i * 3 + 1] : 0.0; q[2] = w[(size_t)i * 3 + 2];
+        // several uniform loads on one element (dead + live): the element adds their section forces and reactions, all
+        // at the pattern's load factor (ForceBeamColumn2d.cpp:1034-1070) -- one load with the summed intensities
+        q[0] += w[(size_t)i * 3]; q[1] += g.kind == XB_ELE_FORCEBEAMCOLUMN3D ? w[(size_t)i * 3 + 1] : 0.0; q[2] += w[(size_t)i * 3 + 2];
         found = true;
       }
       if (found) break;
