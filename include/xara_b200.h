@@ -259,8 +259,9 @@ int xb_update(xb_model*);
 int xb_apply_load(xb_model*, double lambda);
 /* `loadConst` (Domain::setLoadConstant, domain/domain/Domain.cpp:1814; LoadPattern::setLoadConstant, domain/pattern/
  * LoadPattern.cpp): the nodal loads applied so far stay at the current load factor; the reference load vector is
- * emptied for the next pattern.  The caller sets the new domain time with xb_apply_load (`loadConst -time 0.0`).
- * Element loads in a constant pattern return XB_ERR_UNSUPPORTED. */
+ * emptied for the next pattern; the beam element loads (xb_add_beam_uniform_loads / xb_add_beam_point_loads, which all
+ * belong to the patterns defined before the set-up) keep that factor too -- the gravity-then-pushover sequence of an RC
+ * frame.  The caller sets the new domain time with xb_apply_load (`loadConst -time 0.0`). */
 int xb_load_const(xb_model*);
 /* `pattern Plain tag Linear { load node values... }` defined after the set-up (the pushover pattern that follows
  * loadConst): values [n][ndf] are added to the reference loads of the nodes */

@@ -452,6 +452,8 @@ typedef struct {
   /* Steel01 (Steel01.h: fy, E0, b, a1..a4 above; history C* / T*) and ElasticMaterial (Epos, Eneg) */
   double minStrainP, maxStrainP, shiftPP, shiftNP, minStrain, maxStrain, shiftP, shiftN; int loadingP, loading;
   double Epos, Eneg;
+  int in_fibre;   /* ElasticMaterial inside a fibre section: the section calls setTrial(), whose tangent at a strain of exactly
+                     zero is Epos (ElasticMaterial.cpp:146-160), not getTangent()'s max(Epos, Eneg) (:174-182) */
   /* Concrete01 (Concrete01.h: fpc, epsc0, fpcu, epscu in fc, epsc0, fcu, epscu above; history C* / T*) */
   double endStrainP, unloadSlopeP, endStrain, unloadSlope;     /* (min strain: minStrainP / minStrain) */
   /* common */
@@ -650,7 +652,7 @@ static int steel01_set_trial(OrcUni* m, double strain) {
 static int elastic_set_trial(OrcUni* m, double strain) {
   m->eps = strain;
   m->sig = strain >= 0.0 ? m->Epos * strain : m->Eneg * strain;
-  m->e = strain > 0.0 ? m->Epos : (strain < 0.0 ? m->Eneg : (m->Epos > m->Eneg ? m->Epos : m->Eneg));
+  m->e = strain > 0.0 ? m->Epos : (strain < 0.0 ? m->Eneg : (m->in_fibre ? m->Epos : (m->Epos > m->Eneg ? m->Epos : m->Eneg)));
   return 0;
 }
 /* Concrete01::setTrialStrain with reload / envelope / unload, Concrete01.cpp:146-206, 313-385 */
@@ -1546,6 +1548,7 @@ typedef struct {
   int* ptr; int* idx; int nnz;        /* colStartA/rowA or rowStartA/colA */
   double* A; double* B;
   double lambda, lambda_c;   /* load factor (Domain::currentTime under LoadControl) and its committed value */
+  int ele_loads_const; double ele_lambda;   /* loadConst: the element loads keep the factor they had (LoadPattern::applyLoad, isConstant) */
   /* `system BandGeneral` (2) / `system ProfileSPD` (3) on top of the column graph: orc_set_store */
   int store_kind, numSubD, numSuperD, profileSize; int* iDiagLoc; double* Astore; long long astore_size;
 } OrcModel;
@@ -1703,6 +1706,7 @@ static OrcBeam3* beam3_build(OrcModel* m, OrcEle* e, int sd, const double* par) 
     double ABar = 0.0, QzBar = 0.0, QyBar = 0.0;
     for (int f = 0; f < d->nf; f++) {
       uni_init(&S->mat[f], m->uni_kind[d->mat[f]], m->uni_par + 12 * d->mat[f]);
+      S->mat[f].in_fibre = 1;
       ABar += d->A[f]; QzBar += d->y[f] * d->A[f]; QyBar += d->z[f] * d->A[f];   /* FiberSection3d::addFiber */
       S->yBar = QzBar / ABar; S->zBar = QyBar / ABar;
     }
@@ -1724,6 +1728,7 @@ static OrcBeam* beam2_build(OrcModel* m, OrcEle* e, int sd, const double* par) {
     double ABar = 0.0, QzBar = 0.0;
     for (int f = 0; f < d->nf; f++) {
       uni_init(&S->mat[f], m->uni_kind[d->mat[f]], m->uni_par + 12 * d->mat[f]);
+      S->mat[f].in_fibre = d->agg ? 0 : 1;
       ABar += d->A[f]; QzBar += d->y[f] * d->A[f]; S->yBar = QzBar / ABar;   /* FiberSection2d::addFiber */
     }
     if (S->agg) { S->yBar = 0.0; S->k[0] = S->mat[0].e; S->k[3] = S->mat[1].e; }
@@ -1798,6 +1803,7 @@ int orc_load_const(void* h) {
   const size_t n = (size_t)m->nn * m->ndf;
   if (!m->cload) m->cload = (double*)calloc(n ? n : 1, sizeof(double));
   for (size_t i = 0; i < n; i++) { m->cload[i] = m->cload[i] + m->load[i] * m->lambda; m->load[i] = 0.0; }
+  if (!m->ele_loads_const) { m->ele_loads_const = 1; m->ele_lambda = m->lambda; }
   return 0;
 }
 
@@ -2267,10 +2273,11 @@ int orc_incr_response(void* h, const double* dU, double cu, double cv, double ca
 void orc_apply_load(void* h, double lambda) {
   OrcModel* m = (OrcModel*)h;
   m->lambda = lambda;
+  const double lf = m->ele_loads_const ? m->ele_lambda : lambda;
   for (int e = 0; e < m->ne; e++) {
     OrcEle* el = &m->ele[e];
-    if (el->kind == ORC_ELE_FBC2D && (el->beam->has_load || el->beam->has_point)) { el->beam->numEleLoads = el->beam->has_load + el->beam->has_point; el->beam->loadFactor = lambda; }
-    if (el->kind == ORC_ELE_FBC3D && (el->beam3->has_load || el->beam3->has_point)) { el->beam3->numEleLoads = el->beam3->has_load + el->beam3->has_point; el->beam3->loadFactor = lambda; }
+    if (el->kind == ORC_ELE_FBC2D && (el->beam->has_load || el->beam->has_point)) { el->beam->numEleLoads = el->beam->has_load + el->beam->has_point; el->beam->loadFactor = lf; }
+    if (el->kind == ORC_ELE_FBC3D && (el->beam3->has_load || el->beam3->has_point)) { el->beam3->numEleLoads = el->beam3->has_load + el->beam3->has_point; el->beam3->loadFactor = lf; }
   }
 }
 /* `eleLoad -ele tag -type -beamUniform wy [wz] wa` in the model's Linear pattern (Beam2dUniformLoad / Beam3dUniformLoad) */

@@ -946,6 +946,49 @@ def test_frame_fibre_beams_vs_oracle_history():
     assert relerr(D.form_tangent(), D0.form_tangent()) > 0.05
 
 
+@pytest.mark.parametrize("dim", [2, 3])
+def test_gravity_then_pushover_load_const_device_vs_oracle(dim):
+    """Gravity (nodal loads, `eleLoad -beamUniform` / `-beamPoint`) ramped to its full value, xb_load_const +
+    xb_apply_load(0) (`loadConst -time 0`), a lateral pattern through xb_set_nodal_loads, then the push: the frozen loads --
+    nodal and element -- keep their factor, the new pattern follows the domain time; a revert to the last commit on the way.
+    Device against the oracle (pinned to the reference for this sequence, tests/test_oracle.py)."""
+    from modelspec import with_beam_gravity, with_beam_point_loads
+    rng = np.random.default_rng(13)
+    mk = (lambda: frame2d(2, 2, 2, lateral=0.0, gravity=-60.0)) if dim == 2 else (lambda: frame3d(1, 1, 2, lateral=(0.0, 0.0), gravity=-30.0))
+    spec = with_beam_point_loads(with_beam_gravity(mk(), w=-0.08, seed=1), P=-2.0, seed=2)
+    O = OracleBackend(spec, 1, 0)
+    D = xb.DeviceModel.from_spec(spec, 1, 0).to_device(0)
+    ids = O.ids()
+    hcol = spec.crd[:, 1] if dim == 2 else spec.crd[:, 2]
+    H = hcol.max(); h = hcol / H
+    nd = 6 if dim == 2 else 12
+    pattern = rng.normal(0, 1.0, (spec.nn, spec.ndf)) * ((2e-3, 1e-3, 2e-5) if dim == 2 else (2e-3, 2e-3, 1e-3, 2e-5, 2e-5, 2e-5))
+
+    def step(a, lam, commit=True):
+        u = np.zeros((spec.nn, spec.ndf))
+        u[:, 0] = a * h ** 1.5; u[:, 1 if dim == 2 else 2] = -0.01 * h
+        u += pattern * (a / 0.06); u[ids < 0] = 0
+        O.apply_load(lam); assert O.set_trial_disp(u) == 0
+        D.apply_load(lam); D.set_trial_disp(u); D.update()
+        assert relerr(D.form_tangent(), O.form_tangent()) < BEAM_RTOL and relerr(D.form_unbalance(), O.form_unbalance()) < BEAM_RTOL
+        for e in (0, O.ne // 2, O.ne - 1):
+            assert relerr(D.element_resid(e, nd), O.ele_resid(e, nd)) < BEAM_RTOL
+        if commit: O.commit(); D.commit()
+    for s in range(3):
+        step(0.02 * (s + 1), (s + 1) / 3.0)
+    O.load_const(); O.apply_load(0.0); D.load_const(); D.apply_load(0.0)
+    top = [int(t) for t, c in zip(spec.node_tags, spec.crd) if c[1 if dim == 2 else 2] == H]
+    for t in top:
+        v = np.zeros(spec.ndf); v[0] = 12.0
+        O.add_load(t, v); D.add_load(t, v)
+    step(0.07, 0.0)
+    step(0.3, 0.3)
+    step(0.6, 0.6, commit=False)
+    O.revert(); D.revert_to_last_commit()             # back to time 0.3: the frozen loads stay in full
+    assert relerr(D.form_unbalance(), O.form_unbalance()) < BEAM_RTOL and relerr(D.form_tangent(), O.form_tangent()) < BEAM_RTOL
+    step(0.6, 0.6)
+
+
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (the rules come from the reference's BeamIntegration classes)")
 @pytest.mark.parametrize("kind", [1, 2, 3, 4])
 @pytest.mark.parametrize("dim", [2, 3])

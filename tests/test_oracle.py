@@ -342,6 +342,9 @@ def test_steel01_elastic_fibres_vs_live_reference(dim):
     hcol = spec.crd[:, 1] if dim == 2 else spec.crd[:, 2]
     H = hcol.max(); h = hcol / H
     A0 = R.form_tangent().copy()
+    # virgin state, every fibre at a strain of exactly zero: a fibre section asks ElasticMaterial::setTrial, whose tangent
+    # there is Epos -- not getTangent()'s max(Epos, Eneg), which a section Aggregator gets (ElasticMaterial.cpp:146-182)
+    assert close(O.form_tangent(), A0, 1e-12)
     for s_, a in enumerate([0.3, 0.8, 1.4, 2.0]):
         u = np.zeros((spec.nn, spec.ndf))
         u[:, 0] = a * h ** 1.5
@@ -353,6 +356,50 @@ def test_steel01_elastic_fibres_vs_live_reference(dim):
         assert close(O.form_tangent(), R.form_tangent(), 1e-11) and close(O.form_unbalance(), R.form_unbalance(), 1e-11)
         O.commit(); R.commit()
     assert not close(R.form_tangent(), A0, 0.05)           # well past yield
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("dim", [2, 3])
+def test_gravity_then_pushover_load_const_vs_live_reference(dim):
+    """The usual RC-frame sequence: gravity (nodal loads and `eleLoad -beamUniform` / `-beamPoint`) ramped to its full
+    value, `loadConst -time 0`, then a lateral pattern.  The frozen pattern keeps its factor for nodal and element loads
+    alike (Domain::setLoadConstant, LoadPattern::applyLoad) while the new one follows the domain time."""
+    from modelspec import with_beam_gravity, with_beam_point_loads
+    rng = np.random.default_rng(13)
+    mk = (lambda: frame2d(2, 2, 2, lateral=0.0, gravity=-60.0)) if dim == 2 else (lambda: frame3d(1, 1, 2, lateral=(0.0, 0.0), gravity=-30.0))
+    spec = with_beam_point_loads(with_beam_gravity(mk(), w=-0.08, seed=1), P=-2.0, seed=2)
+    O, R = OracleBackend(spec, 1, 0), RefBackend(spec, 1, 0)
+    ids = O.ids()
+    hcol = spec.crd[:, 1] if dim == 2 else spec.crd[:, 2]
+    H = hcol.max(); h = hcol / H
+    nd = 6 if dim == 2 else 12
+    noise = (2e-3, 1e-3, 2e-5) if dim == 2 else (2e-3, 2e-3, 1e-3, 2e-5, 2e-5, 2e-5)
+
+    pattern = rng.normal(0, 1.0, (spec.nn, spec.ndf)) * noise          # one irregular pattern, growing with the drift
+
+    def step(a, lam):
+        u = np.zeros((spec.nn, spec.ndf))
+        u[:, 0] = a * h ** 1.5; u[:, 1 if dim == 2 else 2] = -0.01 * h
+        u += pattern * (a / 0.06); u[ids < 0] = 0
+        for m in (O, R):
+            m.apply_load(lam); m.set_trial_disp(u)
+        assert close(O.form_tangent(), R.form_tangent(), 1e-11) and close(O.form_unbalance(), R.form_unbalance(), 1e-11)
+        for e in range(O.ne):
+            assert close(O.ele_resid(e, nd), R.ele_resid(e, nd), 1e-11)
+        B = R.form_unbalance().copy()
+        O.commit(); R.commit()
+        return B
+    for s_ in range(3):
+        Bg = step(0.02 * (s_ + 1), (s_ + 1) / 3.0)                 # gravity ramp
+    O.load_const(); O.apply_load(0.0); R.load_const(0.0)
+    top = [int(t) for t, c in zip(spec.node_tags, spec.crd) if c[1 if dim == 2 else 2] == H]
+    for t in top:
+        v = np.zeros(spec.ndf); v[0] = 12.0
+        O.add_load(t, v); R.add_load(t, v)
+    B0 = step(0.07, 0.0)                                           # time 0: the gravity loads are still there in full
+    assert np.abs(B0).max() > 0.2 * np.abs(Bg).max()
+    for s_ in range(3):
+        step(0.3 * (s_ + 1), 0.3 * (s_ + 1))                       # the push
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")

@@ -305,12 +305,14 @@ __device__ __forceinline__ void steel01_trial(const double* __restrict__ p, cons
   T[8 * n] = Ttangent; T[9 * n] = Tstress; T[10 * n] = Tstrain;
   sig_o = Tstress; e_o = Ttangent;
 }
-// ElasticMaterial::setTrialStrain / getStress / getTangent (ElasticMaterial.cpp:137-182, eta = 0).  p = Epos, eta, Eneg
+// ElasticMaterial (ElasticMaterial.cpp:137-182, eta = 0).  p = Epos, eta, Eneg.  A fibre section calls setTrial(), whose
+// tangent at a strain of exactly zero is Epos (:146-160); a section Aggregator calls setTrialStrain() + getTangent(),
+// which gives max(Epos, Eneg) there (:174-182)
 __device__ __forceinline__ void elastic_trial(const double* __restrict__ p, double* T, long long n, double strain,
-                                              double& sig_o, double& e_o) {
+                                              double& sig_o, double& e_o, bool in_fibre) {
   const double Epos = p[0], Eneg = p[2];
   const double sig = strain >= 0.0 ? Epos * strain : Eneg * strain;
-  const double e = strain > 0.0 ? Epos : (strain < 0.0 ? Eneg : (Epos > Eneg ? Epos : Eneg));
+  const double e = strain > 0.0 ? Epos : (strain < 0.0 ? Eneg : (in_fibre ? Epos : (Epos > Eneg ? Epos : Eneg)));
   T[8 * n] = e; T[9 * n] = sig; T[10 * n] = strain;
   sig_o = sig; e_o = e;
 }
@@ -370,12 +372,12 @@ __device__ __forceinline__ void concrete01_trial(const double* __restrict__ p, c
   sig_o = Tstress; e_o = Ttangent;
 }
 __device__ __forceinline__ void uniaxial_trial(int kind, const double* __restrict__ p, const double* C, double* T, long long n,
-                                               double strain, double& stress, double& tangent) {
+                                               double strain, double& stress, double& tangent, bool in_fibre = true) {
   if (kind == 0) steel02_trial(p, C, T, n, strain, stress, tangent);
   else if (kind == 1) concrete02_trial(p, C, T, n, strain, stress, tangent);
   else if (kind == 2) steel01_trial(p, C, T, n, strain, stress, tangent);
   else if (kind == 4) concrete01_trial(p, C, T, n, strain, stress, tangent);
-  else elastic_trial(p, T, n, strain, stress, tangent);
+  else elastic_trial(p, T, n, strain, stress, tangent, in_fibre);
 }
 
 // FiberSection2d::setTrialSectionDeformation for section i of element e -> s[2], k[4] (column-major)
@@ -390,7 +392,7 @@ __device__ __forceinline__ void section_trial(const BeamView& B, long long e, in
     if (B.agg) {
       // section Aggregator (SectionAggregator.cpp:316, :365, :483): material 0 on the axial strain, material 1 on the
       // curvature; tangent and stress resultant are the materials' own, no coupling
-      uniaxial_trial(kind & 15, B.fpar + f * 12, B.fc + rec, B.ft + rec, B.n, (kind & XB_FIB_CURV) ? d1 : d0, stress, tangent);
+      uniaxial_trial(kind & 15, B.fpar + f * 12, B.fc + rec, B.ft + rec, B.n, (kind & XB_FIB_CURV) ? d1 : d0, stress, tangent, false);
       if (kind & XB_FIB_CURV) { k[3] = tangent; s[1] = stress; } else { k[0] = tangent; s[0] = stress; }
       continue;
     }

@@ -1583,6 +1583,8 @@ struct xb_model {
   long long* dTask = nullptr;
   AsmView av{};
   double lambda = 0.0, lambda_c = 0.0;   // load factor (Domain::currentTime under LoadControl) and its committed value
+  bool ele_loads_const = false;          // xb_load_const: the element loads stay at ele_lambda
+  double ele_lambda = 0.0;
   bool trial_written = false;       // an xb_update ran since the last commit (the J2 history commit is a buffer swap)
   long long launches = 0;
   long long alg_bytes[6] = {0, 0, 0, 0, 0, 0};
@@ -2346,7 +2348,8 @@ int xb_update(xb_model* m) {
 // (Domain::applyLoad also hands the element loads their factor: ElementalLoad::applyLoad -> Element::addLoad(load, factor);
 //  from the first call on a loaded force beam iterates at every update, numEleLoads > 0)
 static void beams_take_load_factor(xb_model* m, double lambda) {
-  for (auto& d : m->dg) if (is_beam(d.kind) && d.b.wl) { d.b.lam = lambda; d.b.loads_on = 1; }
+  // (element loads of a pattern that loadConst froze keep the factor they had then: LoadPattern::applyLoad with isConstant)
+  for (auto& d : m->dg) if (is_beam(d.kind) && d.b.wl) { d.b.lam = m->ele_loads_const ? m->ele_lambda : lambda; d.b.loads_on = 1; }
 }
 int xb_apply_load(xb_model* m, double lambda) {
   if (!m) return fail(XB_ERR_ARG, "null model");
@@ -2368,7 +2371,8 @@ __global__ void load_const_kernel(long long n, double lambda, double* __restrict
 int xb_load_const(xb_model* m) {
   NEED_DEVICE();
   CU(cudaSetDevice(m->device));
-  for (auto& d : m->dg) if (is_beam(d.kind) && d.b.wl) return fail(XB_ERR_UNSUPPORTED, "xb_load_const: element loads in a constant pattern are outside the device path");
+  // the element loads (all of them belong to the patterns defined so far) keep the current factor from now on
+  if (!m->ele_loads_const) { m->ele_loads_const = true; m->ele_lambda = m->lambda; }
   const long long n = (long long)m->h.nn() * m->h.ndf;
   if (!m->dLoadC) {
     CU(dev_alloc(m, &m->dLoadC, (size_t)std::max<long long>(n, 1)));
