@@ -1159,6 +1159,47 @@ def test_ex2b_as_written_device_vs_golden():
     assert relerr(lam, g["push_lam"]) < 1e-9 and relerr(u, g["push_u"]) < 1e-9
 
 
+@pytest.mark.skipif(not (have_ref() and have_glue()), reason="oracle/_ref not built (needs /root/reference)")
+def test_reference_gravity_then_pushover_on_device_path():
+    """An RC frame the way it is usually analysed: gravity with `eleLoad -beamUniform` / `-beamPoint` and nodal loads in five
+    LoadControl steps, `loadConst -time 0`, a lateral `pattern Plain`, a second `analysis Static` that pushes in eight steps --
+    on the reference's own objects, unmodified (CPU) and with both analyses' integrators routed to the device (the second
+    one re-attaches to the device model of the first: xb_load_const freezes nodal and element loads, xb_set_nodal_loads
+    brings the push pattern).  Same iteration counts in both phases, same displacements."""
+    from modelspec import GLUE_SO, RefBackend, with_beam_gravity, with_beam_point_loads
+
+    def run(tol, glue):
+        spec = with_beam_point_loads(with_beam_gravity(frame2d(2, 3, 2, lateral=0.0, gravity=-60.0), w=-0.08, seed=1), P=-2.0, seed=2)
+        R = RefBackend(spec, defer_setup=True, so=GLUE_SO if glue else None)
+        (R.setup_glue_loadcontrol if glue else R.setup_loadcontrol)(1, 0, 0.2, test=0, tol=tol, max_iter=25)
+        rc, it1, nm1 = R.analyze_static(5)
+        assert rc == 0
+        R.load_const(0.0)
+        H = spec.crd[:, 1].max()
+        for t, c in zip(spec.node_tags, spec.crd):
+            if c[1] > 0 and c[0] == 0.0: R.add_load(int(t), (22.0 * c[1] / H, 0.0, 0.0))
+        (R.setup_glue_loadcontrol if glue else R.setup_loadcontrol)(1, 0, 0.125, test=0, tol=tol, max_iter=25)
+        rc, it2, nm2 = R.analyze_static(8)
+        assert rc == 0
+        u = R.glue_trial_disp() if glue else R.get_trial_disp()
+        return np.concatenate([it1, it2]), np.vstack([nm1, nm2]), u, (R.glue_counts() if glue else None)
+
+    best = None
+    for tol in (1e-6, 1e-7, 1e-8, 1e-9):
+        it, nm, u, _ = run(tol, False)
+        margin = min(min(nm[s, it[s] - 2] / tol if it[s] > 1 else 1e9, tol / max(nm[s, it[s] - 1], 1e-300)) for s in range(len(it)))
+        if best is None or margin > best[0]:
+            best = (margin, tol, it, nm, u)
+    margin, tol, it_cpu, nm_cpu, u_cpu = best
+    assert margin >= 2.0 and it_cpu[5:].max() >= 4, (margin, it_cpu)
+    it_dev, nm_dev, u_dev, (calls, launches) = run(tol, True)
+    assert it_dev.tolist() == it_cpu.tolist()
+    for s in range(len(it_cpu)):
+        assert np.allclose(nm_dev[s, :it_dev[s] - 1], nm_cpu[s, :it_cpu[s] - 1], rtol=1e-5, atol=1e-11)
+    assert relerr(u_dev, u_cpu) < 1e-8
+    assert calls[3] == 8 and launches > 0
+
+
 @pytest.mark.skipif(not have_glue(), reason="oracle/_ref not built (needs /root/reference)")
 def test_reference_runs_ex2b_as_written_on_device_path():
     """tests/Ex2b.Canti2D.InelasticSection.Push.py statement by statement on the reference's OWN objects (Domain,
