@@ -54,14 +54,18 @@ enum {
                              par = thickness, type (0 PlaneStrain, 1 PlaneStress; with J2Plasticity the copy is
                              J2PlaneStrain / J2PlaneStress: one type per xb_add_elements call), surface pressure
                              (setPressureLoadAtNodes, FourNodeQuad.cpp:1206), rho (unused: the material's), b1, b2 */
-  XB_ELE_FORCEBEAMCOLUMN2D = 2,/* element/Frame/Other/Force/ForceBeamColumn2d.cpp, 2 nodes x 3 dof, Lobatto
-                             integration, Linear transformation; mat_tags name the fibre section;
-                             par = nIP, maxIters, tol (one section/nIP/maxIters/tol per call)          */
+  XB_ELE_FORCEBEAMCOLUMN2D = 2,/* element/Frame/Other/Force/ForceBeamColumn2d.cpp, 2 nodes x 3 dof; mat_tags name the
+                             section (xb_add_fiber_section or xb_add_section_aggregator);
+                             par = nIP, maxIters, tol [, geomTransf: 0 Linear | 1 PDelta (coordTransformation/
+                             PDeltaCrdTransf2d.cpp) [, rho: `-mass`, mass per unit length, lumped]] -- rows of 3, 4 or 5
+                             values, no joint offsets; one section/nIP/maxIters/tol/geomTransf per call.  Lobatto
+                             integration unless xb_set_beam_integration hands over another rule's points          */
   XB_ELE_FORCEBEAMCOLUMN3D = 3 /* `element forceBeamColumn` in a 3D model (runtime/commands/modeling/element/
                              frames.cpp:333) = element/Frame/Other/Force/ForceBeamColumn3d.cpp, 2 nodes x 6 dof,
                              Lobatto integration, `geomTransf Linear` (LinearCrdTransf3d, no offsets); mat_tags
                              name a section added with xb_add_fiber_section3d;
-                             par = nIP, maxIters, tol, vecxz[3] (one section/nIP/maxIters/tol per call)  */
+                             par = nIP, maxIters, tol, vecxz[3] [, geomTransf: 0 Linear | 1 PDelta [, rho]] -- rows of
+                             6, 7 or 8 values (one section/nIP/maxIters/tol/geomTransf per call)  */
 };
 
 /* DOF numberers (analysis/numberer) */

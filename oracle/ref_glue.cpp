@@ -229,7 +229,6 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
         else if (auto* t = dynamic_cast<PDeltaCrdTransf2d*>(ct)) { if (!t->nodeIOffset && !t->nodeJOffset) transf = 1; }
         else if (auto* t = dynamic_cast<PDeltaCrdTransf3d*>(ct)) { if (!t->nodeIOffset && !t->nodeJOffset) transf = 1; }
         if (transf < 0) { G.err = "glue: geomTransf other than Linear / PDelta without joint offsets: outside the device path"; return -5; }
-        if ((b2 ? b2->rho : b3->rho) != 0.0) { G.err = "glue: forceBeamColumn with element mass"; return -5; }
         for (int i = 1; i < nsec; i++) if (secs[i]->getTag() != secs[0]->getTag()) { G.err = "glue: sections of one element differ"; return -5; }
         const int stag = secs[0]->getTag();
         if (!secs_done.count(stag)) {
@@ -309,12 +308,13 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
           for (int d = 0; d < 3; d++) B.par.push_back(za(d));
         }
         B.par.push_back(transf);
+        B.par.push_back(b2 ? b2->rho : b3->rho);      // -mass: lumped, travels as nodal mass on the device
       } else { G.err = "glue: element class outside the device path (keep the CPU integrator)"; return -5; }
     } }
   for (auto& kv : batches) {
     Batch& B = kv.second;
     const int ek = kv.first.first;
-    const int stride = ek == XB_ELE_STDBRICK ? 3 : (ek == XB_ELE_FORCEBEAMCOLUMN2D ? 4 : (ek == XB_ELE_FORCEBEAMCOLUMN3D ? 7 : 6));
+    const int stride = ek == XB_ELE_STDBRICK ? 3 : (ek == XB_ELE_FORCEBEAMCOLUMN2D ? 5 : (ek == XB_ELE_FORCEBEAMCOLUMN3D ? 8 : 6));
     if (xb_add_elements(x, kv.first.first, (int)B.tag.size(), B.tag.data(), B.conn.data(), B.mat.data(), B.par.data(), stride) < 0) {
       G.err = xb_last_error(); return -6;
     }

@@ -217,6 +217,7 @@ struct RefModel {
   SparseGenColLinSOE* csoe = nullptr;   // soeKind 0
   BandSOE* bsoe = nullptr;              // soeKind 2 (`system BandGeneral`): no sparse pattern, ptr() / idx() do not apply
   int cur_pattern = 1;                  // the load pattern ref_add_load fills
+  double beam_rho = 0.0;                // `-mass` of the forceBeamColumn elements being added
   int n() const { return bsoe ? bsoe->n() : (rsoe ? rsoe->size : csoe->size); }
   const int* ptr() const { return rsoe ? rsoe->rowStartA : csoe->colStartA; }
   const int* idx() const { return rsoe ? rsoe->colA : csoe->rowA; }
@@ -361,9 +362,11 @@ int ref_add_force_beam2d_t(void* h, int tag, const int* nd, int secTag, int nip,
   LinearCrdTransf2d lin(tag);
   PDeltaCrdTransf2d pd(tag);                 // geomTransf PDelta
   CrdTransf& transf = transfKind == 1 ? (CrdTransf&)pd : (CrdTransf&)lin;
-  Element* e = new ForceBeamColumn2d(tag, nd[0], nd[1], nip, secs.data(), bi, transf, 0.0, maxIters, tol);
+  Element* e = new ForceBeamColumn2d(tag, nd[0], nd[1], nip, secs.data(), bi, transf, m->beam_rho, maxIters, tol);
   return m->domain->addElement(e) ? 0 : -1;
 }
+// `-mass rho` of the forceBeamColumn elements added from now on
+int ref_set_beam_rho(void* h, double rho) { ((RefModel*)h)->beam_rho = rho; return 0; }
 int ref_add_force_beam2d(void* h, int tag, const int* nd, int secTag, int nip, int maxIters, double tol) {
   return ref_add_force_beam2d_t(h, tag, nd, secTag, nip, maxIters, tol, 0);
 }
@@ -390,7 +393,7 @@ int ref_add_force_beam3d_t(void* h, int tag, const int* nd, int secTag, int nip,
   LinearCrdTransf3d lin(tag, v);
   PDeltaCrdTransf3d pd(tag, v);              // geomTransf PDelta
   CrdTransf& transf = transfKind == 1 ? (CrdTransf&)pd : (CrdTransf&)lin;
-  Element* e = new ForceBeamColumn3d(tag, nd[0], nd[1], nip, secs.data(), bi, transf, 0.0, maxIters, tol);
+  Element* e = new ForceBeamColumn3d(tag, nd[0], nd[1], nip, secs.data(), bi, transf, m->beam_rho, maxIters, tol);
   return m->domain->addElement(e) ? 0 : -1;
 }
 int ref_add_force_beam3d(void* h, int tag, const int* nd, int secTag, int nip, int maxIters, double tol, const double* vecxz) {

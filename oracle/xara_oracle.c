@@ -2449,6 +2449,14 @@ static void ele_M(OrcModel* m, OrcEle* el, double* M, double* inertia) {
         jj += 3;
       }
     }
+  } else if (el->kind == ORC_ELE_FBC2D || el->kind == ORC_ELE_FBC3D) {
+    /* ForceBeamColumn2d::getMass (ForceBeamColumn2d.cpp) / ForceBeamColumn3d::getMass: lumped, 0.5 rho L on the translations */
+    const int b3 = el->kind == ORC_ELE_FBC3D;
+    const double rho = el->par[b3 ? 7 : 4];
+    if (rho == 0.0) return;
+    const double L = b3 ? el->beam3->L : el->beam->L;
+    const int ndfe = b3 ? 6 : 3, ntr = b3 ? 3 : 2;
+    for (int a = 0; a < 2; a++) for (int p = 0; p < ntr; p++) { const int i = a * ndfe + p; M[i * nd + i] = 0.5 * L * rho; }
   } else if (el->kind == ORC_ELE_QUAD) {
     double rhoi[4], sum = 0.0;
     for (int i = 0; i < 4; i++) { rhoi[i] = el->gp[i].rho; sum += rhoi[i]; }
@@ -2505,7 +2513,18 @@ static void ele_add_inertia_and_damping(OrcModel* m, OrcEle* el, double* R) {
       }
       add_damp = any_rayleigh(m);
     }
-  } else add_damp = (m->betaK != 0.0 || m->betaK0 != 0.0 || m->betaKc != 0.0);
+  } else {
+    /* ForceBeamColumn2d / 3d::getResistingForceIncInertia: m a on the translations when rho != 0, then the damping forces */
+    const int b3 = el->kind == ORC_ELE_FBC3D;
+    const double rho = el->par[b3 ? 7 : 4];
+    if (rho != 0.0) {
+      const double L = b3 ? el->beam3->L : el->beam->L;
+      const double mm = 0.5 * rho * L;
+      const int ndfe = b3 ? 6 : 3, ntr = b3 ? 3 : 2;
+      for (int a = 0; a < 2; a++) for (int p = 0; p < ntr; p++) R[a * ndfe + p] += mm * m->acc[(size_t)el->node[a] * m->ndf + p];
+      add_damp = any_rayleigh(m);
+    } else add_damp = (m->betaK != 0.0 || m->betaK0 != 0.0 || m->betaKc != 0.0);
+  }
   if (!add_damp) return;
   /* Element::getRayleighDampingForces: F = D v, column by column (Vector::addMatrixVector(0.0, D, v, 1.0)) */
   ele_damp(m, el, D);
@@ -2584,7 +2603,7 @@ int orc_form_tangent(void* h, double* A) {
       double D[576]; ele_damp(m, el, D);
       for (int i = 0; i < nd_e * nd_e; i++) K[i] += D[i] * m->c2;
     }
-    if (m->c3 != 0.0 && (el->kind == ORC_ELE_BRICK || el->kind == ORC_ELE_QUAD)) {
+    if (m->c3 != 0.0) {      /* (a force beam without -mass: a zero matrix) */
       double M[576]; ele_M(m, el, M, NULL);
       for (int i = 0; i < nd_e * nd_e; i++) K[i] += M[i] * m->c3;
     }

@@ -1,6 +1,6 @@
 """The models behind tests/golden/*.npz (generated from the reference by tests/golden/make_golden.py)."""
 from modelspec import (ELASTIC, J2_STEEL, brick_block, brick_periodic_equaldof, cantilever2d, frame2d, frame2d_diaphragm_equaldof,
-                       frame3d, quad_plane, quad_plane_stress_pressure, soil_column_equaldof, with_pdelta)
+                       frame3d, quad_plane, quad_plane_stress_pressure, soil_column_equaldof, with_beam_rho, with_pdelta)
 
 # name -> (spec factory, numberer, soe, displacement scale)
 CASES = {
@@ -72,6 +72,9 @@ RAYLEIGH_CASES = {
     "rayleigh_frame2d_equaldof": (lambda: frame2d_diaphragm_equaldof(2, 2, 1, lateral=30.0), _uniform_mass(0.05, 0.0), 0.5, 0.25, 0.02, RAYLEIGH),
     # `geomTransf PDelta`: the geometric stiffness inside Kt and Kc of Element::getDamp, none inside the initial stiffness
     "rayleigh_frame2d_pdelta": (lambda: with_pdelta(frame2d(2, 2, 2, lateral=30.0, gravity=-150.0)), _uniform_mass(0.05, 0.0), 0.5, 0.25, 0.02, RAYLEIGH),
+    # `forceBeamColumn -mass rho`: the elements' lumped mass in the tangent, the inertia and the alphaM damping forces
+    "rayleigh_frame2d_rho": (lambda: with_beam_rho(frame2d(2, 2, 2, lateral=30.0), 2.0e-3), _uniform_mass(0.03, 0.0), 0.5, 0.25, 0.02, RAYLEIGH),
+    "rayleigh_frame3d_rho": (lambda: with_beam_rho(with_pdelta(frame3d(1, 1, 2, ndiv=2, lateral=(25.0, 15.0), gravity=-60.0)), 1.5e-3), _uniform_mass(0.03, 0.0), 0.5, 0.25, 0.02, RAYLEIGH),
     "rayleigh_frame3d_pdelta": (lambda: with_pdelta(frame3d(1, 1, 2, ndiv=2, lateral=(25.0, 15.0), gravity=-90.0)), _uniform_mass(0.05, 0.0), 0.5, 0.25, 0.02, RAYLEIGH),
 }
 

@@ -307,6 +307,14 @@ def with_beam_point_loads(spec, P=-6.0, seed=0):
     return spec
 
 
+def with_beam_rho(spec, rho=2.0e-3):
+    """`element forceBeamColumn ... -mass rho` (mass per unit length; element parameter 4 in 2D, 7 in 3D)"""
+    for g in spec.groups:
+        if g.kind == ELE_FBC2D: g.par[:, 4] = rho
+        elif g.kind == ELE_FBC3D: g.par[:, 7] = rho
+    return spec
+
+
 def with_pdelta(spec):
     """`geomTransf PDelta` instead of Linear on every forceBeamColumn of the spec (element parameter 3 in 2D, 6 in 3D)"""
     for g in spec.groups:
@@ -926,10 +934,14 @@ class RefBackend(_Backend):
                     b = np.ascontiguousarray(g.par[i, :3], np.float64)
                     assert L.ref_add_brick(self.h, int(g.tags[i]), _p(c), int(g.mat[i]), _p(b)) == 0
                 elif g.kind == ELE_FBC3D:
+                    L.ref_set_beam_rho.argtypes = [ctypes.c_void_p, ctypes.c_double]
+                    L.ref_set_beam_rho(self.h, float(g.par[i, 7]))
                     vx = np.ascontiguousarray(g.par[i, 3:6], np.float64)
                     assert L.ref_add_force_beam3d_t(self.h, int(g.tags[i]), _p(c), int(g.mat[i]), int(g.par[i, 0]),
                                                     int(g.par[i, 1]), float(g.par[i, 2]), _p(vx), int(g.par[i, 6]) + 16 * spec.beam_integration) == 0
                 elif g.kind == ELE_FBC2D:
+                    L.ref_set_beam_rho.argtypes = [ctypes.c_void_p, ctypes.c_double]
+                    L.ref_set_beam_rho(self.h, float(g.par[i, 4]))
                     assert L.ref_add_force_beam2d_t(self.h, int(g.tags[i]), _p(c), int(g.mat[i]), int(g.par[i, 0]),
                                                     int(g.par[i, 1]), float(g.par[i, 2]), int(g.par[i, 3]) + 16 * spec.beam_integration) == 0
                 else:

@@ -380,7 +380,7 @@ def test_reference_displacement_control_drives_device_path(name):
 
 
 @pytest.mark.skipif(not (have_ref() and have_glue()), reason="oracle/_ref not built (needs /root/reference)")
-@pytest.mark.parametrize("shape", ["frame2d", "frame3d", "frame2d_pdelta", "frame3d_pdelta"])
+@pytest.mark.parametrize("shape", ["frame2d", "frame3d", "frame2d_pdelta", "frame3d_pdelta", "frame2d_rho"])
 def test_reference_newmark_loop_drives_device_frames(shape):
     """BASELINE configs[3] in small: RC frames of forceBeamColumn elements (Steel02 / Concrete02 fibre sections),
     transient Newmark with nodal masses and Rayleigh damping, run by the reference's own objects on the CPU and
@@ -390,6 +390,9 @@ def test_reference_newmark_loop_drives_device_frames(shape):
     from modelspec import with_pdelta
     if shape == "frame2d": mk = lambda: frame2d(2, 2, 2, lateral=30.0)
     elif shape == "frame3d": mk = lambda: frame3d(1, 1, 2, ndiv=2, lateral=(25.0, 15.0))
+    elif shape == "frame2d_rho":               # forceBeamColumn -mass: the glue reads rho out of the elements
+        from modelspec import with_beam_rho
+        mk = lambda: with_beam_rho(frame2d(2, 2, 2, lateral=30.0), 2.0e-3)
     elif shape == "frame2d_pdelta": mk = lambda: with_pdelta(frame2d(2, 2, 2, lateral=30.0, gravity=-150.0))      # geomTransf PDelta + rayleigh
     else: mk = lambda: with_pdelta(frame3d(1, 1, 2, ndiv=2, lateral=(25.0, 15.0), gravity=-90.0))
     nsteps, dt, gamma, beta, max_iter = 6, 0.02, 0.5, 0.25, 25
@@ -1301,7 +1304,8 @@ def test_partitioned_frame_matches_single_gpu():
 @pytest.mark.parametrize("name", ["newmark_brick_j2", "newmark_frame2d", "newmark_frame3d", "rayleigh_brick_j2",
                                   "rayleigh_quad_j2", "rayleigh_frame2d", "rayleigh_frame3d",
                                   "rayleigh_soilcolumn_equaldof", "rayleigh_frame2d_equaldof", "rayleigh_quad_planestress",
-                                  "rayleigh_quad_planestress_j2", "rayleigh_frame2d_pdelta", "rayleigh_frame3d_pdelta"])
+                                  "rayleigh_quad_planestress_j2", "rayleigh_frame2d_pdelta", "rayleigh_frame3d_pdelta",
+                                  "rayleigh_frame2d_rho", "rayleigh_frame3d_rho"])
 def test_newmark_device_vs_golden_reference_history(name):
     """Newmark (displacement form, nodal masses): the device replays the history recorded from the
     reference's own Newmark integrator -- c1 K + c3 M tangent, P - M a - R unbalance, predictor,

@@ -3,6 +3,7 @@
 #include "host_model.hpp"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
@@ -16,8 +17,8 @@ static const EleKind kQuad{4, 2, 4, 3, 5};  // par kept: thickness, b1, b2, type
 // nip is a property of the batch.  par kept per element: nIP, maxIters, tol, [vecxz[3],] then the element loads of the
 // Linear pattern: `eleLoad -beamPoint` Py, Pz, N, aOverL (has-load flag in a 5th value) and `eleLoad -beamUniform` wy, wz, wa
 // (zero: none) -- they travel with the element through the partitioning like every other element parameter
-static const EleKind kBeam2d{2, 3, 0, 2, 11};  // par: nIP, maxIters, tol, point load[5], wy, wz (unused), wa
-static const EleKind kBeam3d{2, 6, 0, 4, 14};  // par: nIP, maxIters, tol, vecxz[3], point load[5], wy, wz, wa
+static const EleKind kBeam2d{2, 3, 0, 2, 12};  // par: nIP, maxIters, tol, rho, point load[5], wy, wz (unused), wa
+static const EleKind kBeam3d{2, 6, 0, 4, 15};  // par: nIP, maxIters, tol, vecxz[3], rho, point load[5], wy, wz, wa
 
 const EleKind& ele_kind(int kind) {
   return kind == XB_ELE_STDBRICK ? kBrick : (kind == XB_ELE_FOURNODEQUAD ? kQuad : (kind == XB_ELE_FORCEBEAMCOLUMN3D ? kBeam3d : kBeam2d));
@@ -176,6 +177,9 @@ int HostModel::add_elements(int kind, int n, const int* tags, const int* conn, c
       }
       const int nin = b3 ? 6 : 3;            // what the caller gives; the element-load columns start at zero
       for (int q = 0; q < k.npar; q++) g.par[(size_t)i * k.npar + q] = q < nin ? p[q] : 0.0;
+      // `-mass rho` (mass per unit length, lumped: ForceBeamColumn2d::getMass): the parameter behind geomTransf
+      const int rpos = b3 ? 7 : 4;
+      if (par_stride > rpos) g.par[(size_t)i * k.npar + k.npar - 9] = p[rpos];
     }
     if (g.nip < 2 || g.nip > 10) { err = "forceBeamColumn: Lobatto integration takes 2..10 points"; return XB_ERR_ARG; }
     if (n > 0) groups.push_back(std::move(g));
@@ -473,6 +477,21 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
     int ix = nidx(mass_node[i]);
     if (ix < 0) { err = "mass references an unknown node tag"; return XB_ERR_ARG; }
     for (int j = 0; j < ndf; j++) gmass[(size_t)ix * ndf + j] = mass_val[i * ndf + j];   // Node::setMass replaces
+  }
+  // forceBeamColumn -mass rho: the element's mass matrix is lumped (ForceBeamColumn2d::getMass, 3d: 0.5 rho L on the
+  // translational dofs of both nodes; the rayleigh command gives elements and nodes one alphaM), i.e. nodal masses
+  for (auto& g : groups) {
+    if (g.kind != XB_ELE_FORCEBEAMCOLUMN2D && g.kind != XB_ELE_FORCEBEAMCOLUMN3D) continue;
+    const int npar = ele_kind(g.kind).npar;
+    for (long long l = 0; l < g.n(); l++) {
+      const double rho = g.par[(size_t)l * npar + npar - 9];
+      if (rho == 0.0) continue;
+      const int a = g.conn[(size_t)l * 2], b = g.conn[(size_t)l * 2 + 1];
+      double L2 = 0.0;
+      for (int d = 0; d < ndm; d++) { const double dx = crd[(size_t)b * ndm + d] - crd[(size_t)a * ndm + d]; L2 += dx * dx; }
+      const double mL = 0.5 * rho * std::sqrt(L2);
+      for (int d = 0; d < ndm; d++) { gmass[(size_t)a * ndf + d] += mL; gmass[(size_t)b * ndf + d] += mL; }
+    }
   }
 
   // ---- FE_Element order: Domain element map by ascending tag (PlainHandler.cpp:228-250) ----
