@@ -224,11 +224,20 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
         }
         // geomTransf Linear or PDelta, without joint offsets
         int transf = -1;
-        if (auto* t = dynamic_cast<LinearCrdTransf2d*>(ct)) { if (!t->nodeIOffset && !t->nodeJOffset) transf = 0; }
+        double off2[4] = {0.0, 0.0, 0.0, 0.0};      // 2D: -jntOffset goes along
+        if (auto* t = dynamic_cast<LinearCrdTransf2d*>(ct)) {
+          transf = 0;
+          if (t->nodeIOffset) { off2[0] = t->nodeIOffset[0]; off2[1] = t->nodeIOffset[1]; }
+          if (t->nodeJOffset) { off2[2] = t->nodeJOffset[0]; off2[3] = t->nodeJOffset[1]; }
+        }
         else if (auto* t = dynamic_cast<LinearCrdTransf3d*>(ct)) { if (!t->nodeIOffset && !t->nodeJOffset) transf = 0; }
-        else if (auto* t = dynamic_cast<PDeltaCrdTransf2d*>(ct)) { if (!t->nodeIOffset && !t->nodeJOffset) transf = 1; }
+        else if (auto* t = dynamic_cast<PDeltaCrdTransf2d*>(ct)) {
+          transf = 1;
+          if (t->nodeIOffset) { off2[0] = t->nodeIOffset[0]; off2[1] = t->nodeIOffset[1]; }
+          if (t->nodeJOffset) { off2[2] = t->nodeJOffset[0]; off2[3] = t->nodeJOffset[1]; }
+        }
         else if (auto* t = dynamic_cast<PDeltaCrdTransf3d*>(ct)) { if (!t->nodeIOffset && !t->nodeJOffset) transf = 1; }
-        if (transf < 0) { G.err = "glue: geomTransf other than Linear / PDelta without joint offsets: outside the device path"; return -5; }
+        if (transf < 0) { G.err = "glue: geomTransf other than Linear / PDelta (3D: without joint offsets): outside the device path"; return -5; }
         for (int i = 1; i < nsec; i++) if (secs[i]->getTag() != secs[0]->getTag()) { G.err = "glue: sections of one element differ"; return -5; }
         const int stag = secs[0]->getTag();
         if (!secs_done.count(stag)) {
@@ -309,12 +318,13 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
         }
         B.par.push_back(transf);
         B.par.push_back(b2 ? b2->rho : b3->rho);      // -mass: lumped, travels as nodal mass on the device
+        if (b2) for (int q = 0; q < 4; q++) B.par.push_back(off2[q]);
       } else { G.err = "glue: element class outside the device path (keep the CPU integrator)"; return -5; }
     } }
   for (auto& kv : batches) {
     Batch& B = kv.second;
     const int ek = kv.first.first;
-    const int stride = ek == XB_ELE_STDBRICK ? 3 : (ek == XB_ELE_FORCEBEAMCOLUMN2D ? 5 : (ek == XB_ELE_FORCEBEAMCOLUMN3D ? 8 : 6));
+    const int stride = ek == XB_ELE_STDBRICK ? 3 : (ek == XB_ELE_FORCEBEAMCOLUMN2D ? 9 : (ek == XB_ELE_FORCEBEAMCOLUMN3D ? 8 : 6));
     if (xb_add_elements(x, kv.first.first, (int)B.tag.size(), B.tag.data(), B.conn.data(), B.mat.data(), B.par.data(), stride) < 0) {
       G.err = xb_last_error(); return -6;
     }

@@ -218,6 +218,7 @@ struct RefModel {
   BandSOE* bsoe = nullptr;              // soeKind 2 (`system BandGeneral`): no sparse pattern, ptr() / idx() do not apply
   int cur_pattern = 1;                  // the load pattern ref_add_load fills
   double beam_rho = 0.0;                // `-mass` of the forceBeamColumn elements being added
+  double beam_off[6] = {0, 0, 0, 0, 0, 0};   // joint offsets of the elements being added (I: 0..2, J: 3..5)
   int n() const { return bsoe ? bsoe->n() : (rsoe ? rsoe->size : csoe->size); }
   const int* ptr() const { return rsoe ? rsoe->rowStartA : csoe->colStartA; }
   const int* idx() const { return rsoe ? rsoe->colA : csoe->rowA; }
@@ -359,12 +360,19 @@ int ref_add_force_beam2d_t(void* h, int tag, const int* nd, int secTag, int nip,
   std::vector<SectionForceDeformation*> secs(nip, m->sections2d.at(secTag));
   BeamIntegration* bip = make_beam_integration(transfKind / 16); transfKind %= 16;      // (integration kind in the upper bits)
   BeamIntegration& bi = *bip;
-  LinearCrdTransf2d lin(tag);
-  PDeltaCrdTransf2d pd(tag);                 // geomTransf PDelta
+  Vector oI(2), oJ(2);                        // -jntOffset dXi dYi dXj dYj
+  oI(0) = m->beam_off[0]; oI(1) = m->beam_off[1]; oJ(0) = m->beam_off[3]; oJ(1) = m->beam_off[4];
+  const bool off = oI(0) != 0.0 || oI(1) != 0.0 || oJ(0) != 0.0 || oJ(1) != 0.0;
+  LinearCrdTransf2d lin0(tag), lin1(tag, oI, oJ);
+  PDeltaCrdTransf2d pd0(tag), pd1(tag, oI, oJ);      // geomTransf PDelta
+  LinearCrdTransf2d& lin = off ? lin1 : lin0;
+  PDeltaCrdTransf2d& pd = off ? pd1 : pd0;
   CrdTransf& transf = transfKind == 1 ? (CrdTransf&)pd : (CrdTransf&)lin;
   Element* e = new ForceBeamColumn2d(tag, nd[0], nd[1], nip, secs.data(), bi, transf, m->beam_rho, maxIters, tol);
   return m->domain->addElement(e) ? 0 : -1;
 }
+// `geomTransf ... -jntOffset`: offsets (global components, I then J, three values each) of the elements added from now on
+int ref_set_beam_offsets(void* h, const double* off6) { for (int i = 0; i < 6; i++) ((RefModel*)h)->beam_off[i] = off6[i]; return 0; }
 // `-mass rho` of the forceBeamColumn elements added from now on
 int ref_set_beam_rho(void* h, double rho) { ((RefModel*)h)->beam_rho = rho; return 0; }
 int ref_add_force_beam2d(void* h, int tag, const int* nd, int secTag, int nip, int maxIters, double tol) {

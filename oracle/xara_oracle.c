@@ -867,6 +867,9 @@ typedef struct {
   /* geomTransf PDelta (PDeltaCrdTransf2d.cpp): ul14 is recomputed from the nodes' trial displacements whenever the
    * element asks for its tangent or resisting force (ForceBeamColumn2d.cpp:402,526 call crdTransf->update()) */
   int pdelta; const double* utrial; int n0, n1;
+  /* rigid joint offsets (geomTransf ... -jntOffset dXi dYi dXj dYj; LinearCrdTransf2d.cpp / PDeltaCrdTransf2d.cpp nodeIOffset,
+   * nodeJOffset): the element ends sit at node + offset and follow the node rigidly, u_end = u + theta x offset */
+  int has_off; double off[4];
 } OrcBeam;
 
 /* quadrature/Frame/LobattoBeamIntegration.cpp: getSectionLocations / getSectionWeights */
@@ -900,8 +903,12 @@ static void crd2d_basic(const OrcBeam* b, const double* ug, double* ub) {
 }
 
 /* ForceBeamColumn2d::update, ForceBeamColumn2d.cpp:559-933 (no element loads) */
-static int beam_update(OrcBeam* b, const double* ug, const double* dug) {
+static void beam_end_disp(const OrcBeam* b, double* ug);
+static int beam_update(OrcBeam* b, const double* ug_, const double* dug_) {
   double v[3], dv[3], vin[3];
+  double ug[6], dug[6];
+  memcpy(ug, ug_, sizeof ug); memcpy(dug, dug_, sizeof dug);
+  beam_end_disp(b, ug); beam_end_disp(b, dug);
   crd2d_basic(b, ug, v);
   crd2d_basic(b, dug, dv);
   double nrm = sqrt(dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]);
@@ -1012,9 +1019,18 @@ static int beam_update(OrcBeam* b, const double* ug, const double* dug) {
 
 /* PDeltaCrdTransf2d::update / getGlobalStiffMatrix / getGlobalResistingForce (no offsets), PDeltaCrdTransf2d.cpp:349-384,
  * 566-745, 507-564; K row-major 6x6 */
+/* displacements of the element ends from those of the nodes (joint offsets): u_end = u + theta x offset */
+static void beam_end_disp(const OrcBeam* b, double* ug) {
+  if (!b->has_off) return;
+  ug[0] += -ug[2] * b->off[1]; ug[1] += ug[2] * b->off[0];
+  ug[3] += -ug[5] * b->off[3]; ug[4] += ug[5] * b->off[2];
+}
 static void beam_form_pdelta(const OrcBeam* b, double* K, double* R) {
   const double cosTheta = b->cosTheta, sinTheta = b->sinTheta, oneOverL = 1.0 / b->L;
-  const double* uI = b->utrial + 3 * b->n0; const double* uJ = b->utrial + 3 * b->n1;
+  double ue[6];
+  for (int j = 0; j < 3; j++) { ue[j] = b->utrial[3 * b->n0 + j]; ue[3 + j] = b->utrial[3 * b->n1 + j]; }
+  beam_end_disp(b, ue);
+  const double* uI = ue; const double* uJ = ue + 3;
   const double ul1 = -sinTheta * uI[0] + cosTheta * uI[1];
   const double ul4 = -sinTheta * uJ[0] + cosTheta * uJ[1];
   const double ul14 = ul1 - ul4;
@@ -1071,8 +1087,22 @@ static void beam_form_pdelta(const OrcBeam* b, double* K, double* R) {
   R[4] = sinTheta * pl[3] + cosTheta * pl[4];
   R[2] = pl[2]; R[5] = pl[5];
 }
-/* LinearCrdTransf2d::getGlobalStiffMatrix (no offsets) and getGlobalResistingForce; K row-major 6x6 */
+static void beam_form_end(const OrcBeam* b, double* K, double* R);
+/* tangent and resisting force at the NODES: those of the element ends, pulled back through the rigid offsets
+ * (K_node = To' K_end To, R_node = To' R_end with u_end = To u_node; the t02, t12, t35, t45 terms of
+ * LinearCrdTransf2d::getGlobalStiffMatrix / getGlobalResistingForce, LinearCrdTransf2d.cpp) */
 static void beam_form(const OrcBeam* b, double* K, double* R) {
+  beam_form_end(b, K, R);
+  if (!b->has_off) return;
+  const double c[2][2] = {{-b->off[1], b->off[0]}, {-b->off[3], b->off[2]}};     /* To[3a + p][3a + 2] */
+  if (K) {
+    for (int i = 0; i < 6; i++) for (int a = 0; a < 2; a++) K[i * 6 + 3 * a + 2] += K[i * 6 + 3 * a] * c[a][0] + K[i * 6 + 3 * a + 1] * c[a][1];
+    for (int j = 0; j < 6; j++) for (int a = 0; a < 2; a++) K[(3 * a + 2) * 6 + j] += c[a][0] * K[(3 * a) * 6 + j] + c[a][1] * K[(3 * a + 1) * 6 + j];
+  }
+  for (int a = 0; a < 2; a++) R[3 * a + 2] += c[a][0] * R[3 * a] + c[a][1] * R[3 * a + 1];
+}
+/* LinearCrdTransf2d::getGlobalStiffMatrix and getGlobalResistingForce at the element ends; K row-major 6x6 */
+static void beam_form_end(const OrcBeam* b, double* K, double* R) {
   if (b->pdelta) { beam_form_pdelta(b, K, R); return; }
   const double cosTheta = b->cosTheta, sinTheta = b->sinTheta, oneOverL = 1.0 / b->L;
   if (K) {
@@ -1227,6 +1257,7 @@ typedef struct {
   /* geomTransf PDelta (PDeltaCrdTransf3d.cpp:200-249): ul17, ul28 as of the element's last update() -- ForceBeamColumn3d's
    * getTangentStiff / getResistingForce do NOT refresh them (ForceBeamColumn3d.cpp:404,555) */
   int pdelta; double ul17, ul28;
+  int has_off; double off[6];      /* -jntOffset dXi dYi dZi dXj dYj dZj (LinearCrdTransf3d.cpp / PDeltaCrdTransf3d.cpp) */
 } OrcBeam3;
 
 /* LinearCrdTransf3d::initialize -> computeElemtLengthAndOrient + getLocalAxes, LinearCrdTransf3d.cpp:203-330 */
@@ -1513,7 +1544,7 @@ typedef struct {
   int nen, ndf_e;    /* nodes, dofs per node used by the element */
   int node[8];       /* node indices (into model arrays, tag-sorted) */
   int mat;           /* material index */
-  double par[8];     /* brick: b1,b2,b3 ; quad: thickness,type,pressure,rho,b1,b2 */
+  double par[16];    /* brick: b1,b2,b3 ; quad: thickness,type,pressure,rho,b1,b2 ; beams: see orc_add_element */
   OrcGP gp[8];
   int nip;
   OrcBeam* beam;     /* ORC_ELE_FBC2D */
@@ -1735,6 +1766,9 @@ static OrcBeam* beam2_build(OrcModel* m, OrcEle* e, int sd, const double* par) {
   }
   /* LinearCrdTransf2d::computeElemtLengthAndOrient */
   double dx0 = m->crd[e->node[1] * 2] - m->crd[e->node[0] * 2], dx1 = m->crd[e->node[1] * 2 + 1] - m->crd[e->node[0] * 2 + 1];
+  /* par[5..8]: -jntOffset dXi dYi dXj dYj (computeElemtLengthAndOrient adds nodeJOffset, subtracts nodeIOffset) */
+  for (int q = 0; q < 4; q++) { b->off[q] = par[5 + q]; if (b->off[q] != 0.0) b->has_off = 1; }
+  if (b->has_off) { dx0 += b->off[2]; dx1 += b->off[3]; dx0 -= b->off[0]; dx1 -= b->off[1]; }
   b->L = sqrt(dx0 * dx0 + dx1 * dx1);
   b->cosTheta = dx0 / b->L; b->sinTheta = dx1 / b->L;
   b->pdelta = (int)par[3]; b->utrial = m->trial; b->n0 = e->node[0]; b->n1 = e->node[1];   /* par[3]: 0 geomTransf Linear, 1 PDelta */
@@ -1760,7 +1794,7 @@ int orc_add_element(void* h, int kind, int tag, const int* nodeTags, int matTag,
     OrcBeam3* b = beam3_build(m, e, sd, par);
     if (!b) return -3;
     e->beam3 = b; e->nip = b->nip; e->mat = sd;
-    memcpy(e->par, par, 8 * sizeof(double));
+    memcpy(e->par, par, 16 * sizeof(double));
     double ug[12], dug[12];   /* Domain::addElement calls element->update() (Domain.cpp:391) */
     for (int a = 0; a < 2; a++) for (int j = 0; j < 6; j++) { ug[a * 6 + j] = m->trial[e->node[a] * 6 + j]; dug[a * 6 + j] = m->incr[e->node[a] * 6 + j]; }
     if (beam3_update(b, ug, dug) < 0) return -4;
@@ -1775,7 +1809,7 @@ int orc_add_element(void* h, int kind, int tag, const int* nodeTags, int matTag,
     OrcBeam* b = beam2_build(m, e, sd, par);
     if (!b) return -3;
     e->beam = b; e->nip = b->nip; e->mat = sd;
-    memcpy(e->par, par, 8 * sizeof(double));
+    memcpy(e->par, par, 16 * sizeof(double));
     /* Domain::addElement calls element->update() (Domain.cpp:391) */
     double ug[6], dug[6];
     for (int a = 0; a < 2; a++) for (int j = 0; j < 3; j++) { ug[a * 3 + j] = m->trial[e->node[a] * 3 + j]; dug[a * 3 + j] = m->incr[e->node[a] * 3 + j]; }
@@ -1783,7 +1817,7 @@ int orc_add_element(void* h, int kind, int tag, const int* nodeTags, int matTag,
     m->ne++; return 0;
   }
   e->mat = find_mat(m, matTag); if (e->mat < 0) return -2;
-  memcpy(e->par, par, 8 * sizeof(double));
+  memset(e->par, 0, sizeof e->par); memcpy(e->par, par, 8 * sizeof(double));
   int type = (kind == ORC_ELE_BRICK) ? ORC_ND_3D : ((int)par[1] == 1 ? ORC_ND_PLANE_STRESS : ORC_ND_PLANE_STRAIN);
   for (int i = 0; i < e->nip; i++) gp_init(&e->gp[i], m->mat_kind[e->mat], type, m->mat_par + 8 * e->mat);
   /* Domain::addElement calls element->update() (Domain.cpp:391): J2PlaneStress condenses its tangent there */

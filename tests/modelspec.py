@@ -315,6 +315,24 @@ def with_beam_rho(spec, rho=2.0e-3):
     return spec
 
 
+def with_joint_offsets(spec, frac=0.06, seed=0):
+    """`geomTransf ... -jntOffset`: rigid end zones on every forceBeamColumn -- each end is moved along the member by a
+    random fraction (up to `frac`) of its length, plus a small lateral eccentricity (element parameters 5..8 in 2D:
+    dXi dYi dXj dYj)"""
+    rng = np.random.default_rng(seed)
+    for g in spec.groups:
+        if g.kind != ELE_FBC2D: continue
+        par = np.zeros((len(g.tags), 14)); par[:, :g.par.shape[1]] = g.par
+        for i, c in enumerate(g.conn):
+            idx = [list(spec.node_tags).index(int(q)) for q in c]
+            d = spec.crd[idx[1]] - spec.crd[idx[0]]
+            nrm = np.array([-d[1], d[0]])
+            par[i, 5:7] = rng.uniform(0.3, 1.0) * frac * d + rng.uniform(-0.2, 0.2) * frac * nrm
+            par[i, 7:9] = -rng.uniform(0.3, 1.0) * frac * d + rng.uniform(-0.2, 0.2) * frac * nrm
+        g.par = par
+    return spec
+
+
 def with_pdelta(spec):
     """`geomTransf PDelta` instead of Linear on every forceBeamColumn of the spec (element parameter 3 in 2D, 6 in 3D)"""
     for g in spec.groups:
@@ -708,7 +726,7 @@ class OracleBackend(_Backend):
                 assert L.orc_add_fiber_section(self.h, tag, len(y), _p(y), _p(A), _p(mt)) == 0
         for g in spec.groups:
             for i in range(len(g.tags)):
-                c = np.ascontiguousarray(g.conn[i], np.int32); pr = np.ascontiguousarray(g.par[i], np.float64)
+                c = np.ascontiguousarray(g.conn[i], np.int32); pr = np.zeros(16); pr[:len(g.par[i])] = g.par[i]
                 rc = L.orc_add_element(self.h, g.kind, int(g.tags[i]), _p(c), int(g.mat[i]), _p(pr))
                 assert rc == 0, rc
         if spec.loads is not None:
@@ -942,6 +960,9 @@ class RefBackend(_Backend):
                 elif g.kind == ELE_FBC2D:
                     L.ref_set_beam_rho.argtypes = [ctypes.c_void_p, ctypes.c_double]
                     L.ref_set_beam_rho(self.h, float(g.par[i, 4]))
+                    o6 = np.zeros(6)
+                    if g.par.shape[1] >= 9: o6[0:2] = g.par[i, 5:7]; o6[3:5] = g.par[i, 7:9]
+                    L.ref_set_beam_offsets(self.h, _p(o6))
                     assert L.ref_add_force_beam2d_t(self.h, int(g.tags[i]), _p(c), int(g.mat[i]), int(g.par[i, 0]),
                                                     int(g.par[i, 1]), float(g.par[i, 2]), int(g.par[i, 3]) + 16 * spec.beam_integration) == 0
                 else:

@@ -359,6 +359,41 @@ def test_steel01_elastic_fibres_vs_live_reference(dim):
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("pdelta", [0, 1])
+def test_joint_offsets_vs_live_reference(pdelta):
+    """`geomTransf Linear | PDelta ... -jntOffset` (rigid end zones; the nodeIOffset / nodeJOffset terms of
+    LinearCrdTransf2d.cpp and PDeltaCrdTransf2d.cpp): element length and orientation between the offset ends, basic
+    deformations, tangent and resisting force pulled back to the nodes -- against the reference's classes over a sway
+    history under gravity element loads, with commits and a revert"""
+    from modelspec import with_joint_offsets, with_beam_gravity, with_pdelta
+    rng = np.random.default_rng(21)
+    mk = lambda: with_beam_gravity(frame2d(2, 2, 2, gravity=-80.0), w=-0.08, seed=1)
+    spec = with_joint_offsets(mk(), seed=3)
+    if pdelta: spec = with_pdelta(spec)
+    O, R, Rn = OracleBackend(spec, 1, 0), RefBackend(spec, 1, 0), RefBackend(with_pdelta(mk()) if pdelta else mk(), 1, 0)
+    assert close(O.form_tangent(), R.form_tangent(), 1e-11)
+    H = spec.crd[:, 1].max(); h = spec.crd[:, 1] / H
+    pattern = rng.normal(0, 1.0, (spec.nn, 3)) * (2e-3, 1e-3, 2e-5)
+    differs = False
+    for s_, a in enumerate([0.2, 0.5, 0.8, 1.1, 1.4]):
+        u = np.zeros((spec.nn, 3)); u[:, 0] = a * h ** 1.5; u[:, 2] = -1.5 * a * h ** 0.5 / H
+        u += pattern * (a / 0.5); u[O.ids() < 0] = 0
+        for m in (O, R, Rn):
+            m.apply_load(0.2 * (s_ + 1)); m.set_trial_disp(u)
+        Ar, Br = R.form_tangent(), R.form_unbalance()
+        assert close(O.form_tangent(), Ar, 1e-11) and close(O.form_unbalance(), Br, 1e-11)
+        for e in range(O.ne):
+            assert close(O.ele_resid(e, 6), R.ele_resid(e, 6), 1e-11) and close(O.ele_tangent(e, 6), R.ele_tangent(e, 6), 1e-11)
+        differs = differs or not close(Ar, Rn.form_tangent(), 1e-3)
+        if s_ == 4:
+            O.revert(); R.revert()
+            assert close(O.form_tangent(), R.form_tangent(), 1e-11) and close(O.form_unbalance(), R.form_unbalance(), 1e-11)
+        else:
+            O.commit(); R.commit(); Rn.commit()
+    assert differs
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
 @pytest.mark.parametrize("dim", [2, 3])
 def test_gravity_then_pushover_load_const_vs_live_reference(dim):
     """The usual RC-frame sequence: gravity (nodal loads and `eleLoad -beamUniform` / `-beamPoint`) ramped to its full

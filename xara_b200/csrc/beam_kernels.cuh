@@ -89,6 +89,10 @@ struct BeamView {
   double* ul;
   // beam integration other than Lobatto (xb_set_beam_integration): [2 nip][n] locations then weights, fractions of L; null: Lobatto
   const double* rule;
+  // rigid joint offsets of a 2D batch (geomTransf -jntOffset; nodeIOffset / nodeJOffset of LinearCrdTransf2d.cpp,
+  // PDeltaCrdTransf2d.cpp): [4][n] dXi dYi dXj dYj, null: none.  The element ends follow their nodes rigidly,
+  // u_end = u + theta x offset; tangent and forces are pulled back to the nodes with the transpose of that map
+  const double* off;
 };
 
 // transient coefficients handed to the form kernels (see TanCoef / DynCoef in device_model.cu)
@@ -380,6 +384,14 @@ __device__ __forceinline__ void uniaxial_trial(int kind, const double* __restric
   else elastic_trial(p, T, n, strain, stress, tangent, in_fibre);
 }
 
+// displacements (or velocities) of the element ends from those of the nodes: u_end = u + theta x offset (2D)
+__device__ __forceinline__ void fbc2d_end_disp(const BeamView& B, long long e, double* ug) {
+  if (!B.off) return;
+  const double oix = B.off[e], oiy = B.off[B.n + e], ojx = B.off[2 * B.n + e], ojy = B.off[3 * B.n + e];
+  ug[0] += -ug[2] * oiy; ug[1] += ug[2] * oix;
+  ug[3] += -ug[5] * ojy; ug[4] += ug[5] * ojx;
+}
+
 // FiberSection2d::setTrialSectionDeformation for section i of element e -> s[2], k[4] (column-major)
 __device__ __forceinline__ void section_trial(const BeamView& B, long long e, int i, const double* d, double* s, double* k) {
   k[0] = k[1] = k[2] = k[3] = 0.0; s[0] = s[1] = 0.0;
@@ -488,6 +500,11 @@ __global__ void __launch_bounds__(128) fbc2d_form_kernel(BeamView B, int want_k,
           kg[i][j] += g; kg[3 + i][3 + j] += g; kg[i][3 + j] -= g; kg[3 + i][j] -= g;
         }
     }
+    if (B.off) {   // K_node = To' K_end To (the t02, t12, t35, t45 terms of LinearCrdTransf2d::getGlobalStiffMatrix)
+      const double cf[2][2] = {{-B.off[n + e], B.off[e]}, {-B.off[3 * n + e], B.off[2 * n + e]}};
+      for (int i = 0; i < 6; i++) for (int a = 0; a < 2; a++) kg[i][3 * a + 2] += kg[i][3 * a] * cf[a][0] + kg[i][3 * a + 1] * cf[a][1];
+      for (int j = 0; j < 6; j++) for (int a = 0; a < 2; a++) kg[3 * a + 2][j] += cf[a][0] * kg[3 * a][j] + cf[a][1] * kg[3 * a + 1][j];
+    }
     for (int a = 0; a < 2; a++) {
       const long long d = B.kdst[e * 2 + a];
       double* base = d >= 0 ? B.KeN + d : B.sendK + (-d - 1);
@@ -506,6 +523,7 @@ __global__ void __launch_bounds__(128) fbc2d_form_kernel(BeamView B, int want_k,
         const int nd = B.conn[e * 2 + a];
         for (int j = 0; j < 3; j++) vg[a * 3 + j] = dy.V[(size_t)nd * 3 + j];
       }
+      fbc2d_end_disp(B, e, vg);
       crd2d_basic(L, cosTheta, sinTheta, vg, vb);
       if (B.pdelta) {
         const double gd = (dy.bK * B.Se[e] + (dy.bKc != 0.0 ? dy.bKc * B.nK[e] : 0.0)) * oneOverL;
@@ -537,7 +555,10 @@ __global__ void __launch_bounds__(128) fbc2d_form_kernel(BeamView B, int want_k,
       pl[0] += p0[0]; pl[1] += p0[1]; pl[4] += p0[2];
     }
     if (B.pdelta) {   // PDeltaCrdTransf2d::update + getGlobalResistingForce (PDeltaCrdTransf2d.cpp:349-384, 532-535)
-      const double* uI = B.U + (size_t)B.conn[e * 2] * 3; const double* uJ = B.U + (size_t)B.conn[e * 2 + 1] * 3;
+      double ue[6];
+      for (int j = 0; j < 3; j++) { ue[j] = B.U[(size_t)B.conn[e * 2] * 3 + j]; ue[3 + j] = B.U[(size_t)B.conn[e * 2 + 1] * 3 + j]; }
+      fbc2d_end_disp(B, e, ue);
+      const double* uI = ue; const double* uJ = ue + 3;
       const double ul1 = -sinTheta * uI[0] + cosTheta * uI[1];
       const double ul4 = -sinTheta * uJ[0] + cosTheta * uJ[1];
       const double NoverL = (ul1 - ul4) * q0s * oneOverL;
@@ -551,6 +572,10 @@ __global__ void __launch_bounds__(128) fbc2d_form_kernel(BeamView B, int want_k,
     R[3] = cosTheta * pl[3] - sinTheta * pl[4];
     R[4] = sinTheta * pl[3] + cosTheta * pl[4];
     R[5] = pl[5];
+    if (B.off) {   // R_node = To' R_end: the end forces' moments about the nodes
+      R[2] += -B.off[n + e] * R[0] + B.off[e] * R[1];
+      R[5] += -B.off[3 * n + e] * R[3] + B.off[2 * n + e] * R[4];
+    }
   }
 }
 
@@ -995,6 +1020,7 @@ __global__ void __launch_bounds__(128, XB_FBC_SEC_OCC) fbc2d_update_sec_kernel(B
 #pragma unroll
       for (int j = 0; j < 3; j++) { ug[a * 3 + j] = U[(size_t)nd * 3 + j]; dug[a * 3 + j] = DU[(size_t)nd * 3 + j]; }
     }
+    fbc2d_end_disp(B, e, ug); fbc2d_end_disp(B, e, dug);
     crd2d_basic(L, cosT, sinT, ug, v);
     crd2d_basic(L, cosT, sinT, dug, dv);
   }

@@ -1879,7 +1879,11 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
         const int a = g.conn[e * 2], c = g.conn[e * 2 + 1];
         if (!b3) {
           // LinearCrdTransf2d::computeElemtLengthAndOrient (LinearCrdTransf2d.cpp)
-          const double dx0 = h.crd[(size_t)c * 2] - h.crd[(size_t)a * 2], dx1 = h.crd[(size_t)c * 2 + 1] - h.crd[(size_t)a * 2 + 1];
+          double dx0 = h.crd[(size_t)c * 2] - h.crd[(size_t)a * 2], dx1 = h.crd[(size_t)c * 2 + 1] - h.crd[(size_t)a * 2 + 1];
+          {   // -jntOffset: the element runs between node I + offset I and node J + offset J
+            const double* o = &g.par[(size_t)e * k.npar + k.npar - 13];
+            dx0 += o[2]; dx1 += o[3]; dx0 -= o[0]; dx1 -= o[1];
+          }
           const double L = std::sqrt(dx0 * dx0 + dx1 * dx1);
           if (L == 0.0) return fail(XB_ERR_ARG, "forceBeamColumn: zero element length");
           geo[e] = L; geo[ne + e] = dx0 / L; geo[2 * ne + e] = dx1 / L;
@@ -1965,6 +1969,13 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
       std::vector<double> fs0 = {k0[3] / det, -k0[1] / det, -k0[2] / det, k0[0] / det};
       b.agg = sd.agg ? 1 : 0;
       b.pdelta = g.transf == 1 ? 1 : 0; b.U = m->dU; b.ul = nullptr;
+      b.off = nullptr;
+      if (!b3) {   // rigid joint offsets, SoA [4][n]; null when the batch has none
+        std::vector<double> os((size_t)4 * ne); bool anyo = false;
+        for (long long e = 0; e < ne; e++)
+          for (int q = 0; q < 4; q++) { os[(size_t)q * ne + e] = g.par[(size_t)e * k.npar + k.npar - 13 + q]; anyo = anyo || os[(size_t)q * ne + e] != 0.0; }
+        if (anyo) { double* dof = nullptr; CU(dev_upload(m, &dof, os)); b.off = dof; }
+      }
       b.rule = nullptr;
       if (!g.rule.empty()) {   // per-element section locations / weights, SoA [2 nip][n]
         std::vector<double> rs((size_t)2 * g.nip * ne);
