@@ -63,10 +63,11 @@ enum {
                              integration unless xb_set_beam_integration hands over another rule's points          */
   XB_ELE_FORCEBEAMCOLUMN3D = 3 /* `element forceBeamColumn` in a 3D model (runtime/commands/modeling/element/
                              frames.cpp:333) = element/Frame/Other/Force/ForceBeamColumn3d.cpp, 2 nodes x 6 dof,
-                             Lobatto integration, `geomTransf Linear` (LinearCrdTransf3d, no offsets); mat_tags
+                             Lobatto integration unless xb_set_beam_integration hands over another rule; mat_tags
                              name a section added with xb_add_fiber_section3d;
-                             par = nIP, maxIters, tol, vecxz[3] [, geomTransf: 0 Linear | 1 PDelta [, rho]] -- rows of
-                             6, 7 or 8 values (one section/nIP/maxIters/tol/geomTransf per call)  */
+                             par = nIP, maxIters, tol, vecxz[3] [, geomTransf: 0 Linear | 1 PDelta (LinearCrdTransf3d /
+                             PDeltaCrdTransf3d) [, rho [, dXi, dYi, dZi, dXj, dYj, dZj: `-jntOffset`]]] -- rows of
+                             6, 7, 8 or 14 values (one section/nIP/maxIters/tol/geomTransf per call)  */
 };
 
 /* DOF numberers (analysis/numberer) */

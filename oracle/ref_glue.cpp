@@ -230,14 +230,23 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
           if (t->nodeIOffset) { off2[0] = t->nodeIOffset[0]; off2[1] = t->nodeIOffset[1]; }
           if (t->nodeJOffset) { off2[2] = t->nodeJOffset[0]; off2[3] = t->nodeJOffset[1]; }
         }
-        else if (auto* t = dynamic_cast<LinearCrdTransf3d*>(ct)) { if (!t->nodeIOffset && !t->nodeJOffset) transf = 0; }
+        double off3[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        if (auto* t = dynamic_cast<LinearCrdTransf3d*>(ct)) {
+          transf = 0;
+          if (t->nodeIOffset) for (int q = 0; q < 3; q++) off3[q] = t->nodeIOffset[q];
+          if (t->nodeJOffset) for (int q = 0; q < 3; q++) off3[3 + q] = t->nodeJOffset[q];
+        }
         else if (auto* t = dynamic_cast<PDeltaCrdTransf2d*>(ct)) {
           transf = 1;
           if (t->nodeIOffset) { off2[0] = t->nodeIOffset[0]; off2[1] = t->nodeIOffset[1]; }
           if (t->nodeJOffset) { off2[2] = t->nodeJOffset[0]; off2[3] = t->nodeJOffset[1]; }
         }
-        else if (auto* t = dynamic_cast<PDeltaCrdTransf3d*>(ct)) { if (!t->nodeIOffset && !t->nodeJOffset) transf = 1; }
-        if (transf < 0) { G.err = "glue: geomTransf other than Linear / PDelta (3D: without joint offsets): outside the device path"; return -5; }
+        else if (auto* t = dynamic_cast<PDeltaCrdTransf3d*>(ct)) {
+          transf = 1;
+          if (t->nodeIOffset) for (int q = 0; q < 3; q++) off3[q] = t->nodeIOffset[q];
+          if (t->nodeJOffset) for (int q = 0; q < 3; q++) off3[3 + q] = t->nodeJOffset[q];
+        }
+        if (transf < 0) { G.err = "glue: geomTransf other than Linear / PDelta: outside the device path"; return -5; }
         for (int i = 1; i < nsec; i++) if (secs[i]->getTag() != secs[0]->getTag()) { G.err = "glue: sections of one element differ"; return -5; }
         const int stag = secs[0]->getTag();
         if (!secs_done.count(stag)) {
@@ -319,12 +328,13 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
         B.par.push_back(transf);
         B.par.push_back(b2 ? b2->rho : b3->rho);      // -mass: lumped, travels as nodal mass on the device
         if (b2) for (int q = 0; q < 4; q++) B.par.push_back(off2[q]);
+        else for (int q = 0; q < 6; q++) B.par.push_back(off3[q]);
       } else { G.err = "glue: element class outside the device path (keep the CPU integrator)"; return -5; }
     } }
   for (auto& kv : batches) {
     Batch& B = kv.second;
     const int ek = kv.first.first;
-    const int stride = ek == XB_ELE_STDBRICK ? 3 : (ek == XB_ELE_FORCEBEAMCOLUMN2D ? 9 : (ek == XB_ELE_FORCEBEAMCOLUMN3D ? 8 : 6));
+    const int stride = ek == XB_ELE_STDBRICK ? 3 : (ek == XB_ELE_FORCEBEAMCOLUMN2D ? 9 : (ek == XB_ELE_FORCEBEAMCOLUMN3D ? 14 : 6));
     if (xb_add_elements(x, kv.first.first, (int)B.tag.size(), B.tag.data(), B.conn.data(), B.mat.data(), B.par.data(), stride) < 0) {
       G.err = xb_last_error(); return -6;
     }

@@ -398,8 +398,13 @@ int ref_add_force_beam3d_t(void* h, int tag, const int* nd, int secTag, int nip,
   BeamIntegration* bip = make_beam_integration(transfKind / 16); transfKind %= 16;
   BeamIntegration& bi = *bip;
   Vector v(3); v(0) = vecxz[0]; v(1) = vecxz[1]; v(2) = vecxz[2];
-  LinearCrdTransf3d lin(tag, v);
-  PDeltaCrdTransf3d pd(tag, v);              // geomTransf PDelta
+  Vector oI(3), oJ(3);                        // -jntOffset dXi dYi dZi dXj dYj dZj
+  for (int q = 0; q < 3; q++) { oI(q) = m->beam_off[q]; oJ(q) = m->beam_off[3 + q]; }
+  const bool off = oI.Norm() != 0.0 || oJ.Norm() != 0.0;
+  LinearCrdTransf3d lin0(tag, v), lin1(tag, v, oI, oJ);
+  PDeltaCrdTransf3d pd0(tag, v), pd1(tag, v, oI, oJ);      // geomTransf PDelta
+  LinearCrdTransf3d& lin = off ? lin1 : lin0;
+  PDeltaCrdTransf3d& pd = off ? pd1 : pd0;
   CrdTransf& transf = transfKind == 1 ? (CrdTransf&)pd : (CrdTransf&)lin;
   Element* e = new ForceBeamColumn3d(tag, nd[0], nd[1], nip, secs.data(), bi, transf, m->beam_rho, maxIters, tol);
   return m->domain->addElement(e) ? 0 : -1;

@@ -1313,7 +1313,19 @@ static int inv6_flex(const double* f, double* kv) {
 static double norm6(const double* v) { double s = 0.0; for (int i = 0; i < 6; i++) s += v[i] * v[i]; return sqrt(s); }
 
 /* ForceBeamColumn3d::update, ForceBeamColumn3d.cpp:587-1056 (no element loads; isTorsion = true) */
-static int beam3_update(OrcBeam3* b, const double* ug, const double* dug) {
+/* displacements of the element ends from those of the nodes (joint offsets): u_end = u + theta x offset */
+static void beam3_end_disp(const OrcBeam3* b, double* ug) {
+  if (!b->has_off) return;
+  for (int a = 0; a < 2; a++) {
+    const double* d = b->off + 3 * a; double* u = ug + 6 * a;
+    const double tx = u[3], ty = u[4], tz = u[5];
+    u[0] += ty * d[2] - tz * d[1]; u[1] += tz * d[0] - tx * d[2]; u[2] += tx * d[1] - ty * d[0];
+  }
+}
+static int beam3_update(OrcBeam3* b, const double* ug_, const double* dug_) {
+  double ug[12], dug[12];
+  memcpy(ug, ug_, sizeof ug); memcpy(dug, dug_, sizeof dug);
+  beam3_end_disp(b, ug); beam3_end_disp(b, dug);
   if (b->pdelta) {   /* crdTransf->update(), PDeltaCrdTransf3d.cpp:200-249 (no offsets) */
     const double ul1 = b->R[1][0] * ug[0] + b->R[1][1] * ug[1] + b->R[1][2] * ug[2];
     const double ul2 = b->R[2][0] * ug[0] + b->R[2][1] * ug[1] + b->R[2][2] * ug[2];
@@ -1436,7 +1448,25 @@ static int beam3_update(OrcBeam3* b, const double* ug, const double* dug) {
 
 /* LinearCrdTransf3d::getGlobalStiffMatrix (no offsets, :767-926) and getGlobalResistingForce (:699-765);
  * K row-major 12x12 */
+static void beam3_form_end(const OrcBeam3* b, double* K, double* Rg);
+/* tangent and resisting force at the NODES: K_node = To' K_end To, R_node = To' R_end with u_end = To u_node (the joint-offset
+ * terms of LinearCrdTransf3d::getGlobalStiffMatrix / getGlobalResistingForce) */
 static void beam3_form(const OrcBeam3* b, double* K, double* Rg) {
+  beam3_form_end(b, K, Rg);
+  if (!b->has_off) return;
+  for (int a = 0; a < 2; a++) {
+    const double* d = b->off + 3 * a;
+    const double C[3][3] = {{0.0, d[2], -d[1]}, {-d[2], 0.0, d[0]}, {d[1], -d[0], 0.0}};      /* u_end = u + C theta */
+    if (K) {
+      for (int i = 0; i < 12; i++) for (int j = 0; j < 3; j++)
+        K[i * 12 + 6 * a + 3 + j] += K[i * 12 + 6 * a] * C[0][j] + K[i * 12 + 6 * a + 1] * C[1][j] + K[i * 12 + 6 * a + 2] * C[2][j];
+      for (int i = 0; i < 12; i++) for (int j = 0; j < 3; j++)
+        K[(6 * a + 3 + j) * 12 + i] += C[0][j] * K[(6 * a) * 12 + i] + C[1][j] * K[(6 * a + 1) * 12 + i] + C[2][j] * K[(6 * a + 2) * 12 + i];
+    }
+    for (int j = 0; j < 3; j++) Rg[6 * a + 3 + j] += C[0][j] * Rg[6 * a] + C[1][j] * Rg[6 * a + 1] + C[2][j] * Rg[6 * a + 2];
+  }
+}
+static void beam3_form_end(const OrcBeam3* b, double* K, double* Rg) {
   const double oneOverL = 1.0 / b->L;
   const double (*R)[3] = b->R;
   if (K) {
@@ -1742,7 +1772,11 @@ static OrcBeam3* beam3_build(OrcModel* m, OrcEle* e, int sd, const double* par) 
       S->yBar = QzBar / ABar; S->zBar = QyBar / ABar;
     }
   }
-  if (crd3d_init(b, m->crd + e->node[0] * 3, m->crd + e->node[1] * 3, par + 3) < 0) return NULL;
+  /* par[8..13]: -jntOffset dXi dYi dZi dXj dYj dZj: the element runs between the offset ends (computeElemtLengthAndOrient) */
+  double xi3[3], xj3[3];
+  for (int q = 0; q < 6; q++) { b->off[q] = par[8 + q]; if (b->off[q] != 0.0) b->has_off = 1; }
+  for (int q = 0; q < 3; q++) { xi3[q] = m->crd[e->node[0] * 3 + q] + b->off[q]; xj3[q] = m->crd[e->node[1] * 3 + q] + b->off[3 + q]; }
+  if (crd3d_init(b, xi3, xj3, par + 3) < 0) return NULL;
   b->pdelta = (int)par[6];     /* par[6]: 0 geomTransf Linear, 1 PDelta */
   return b;
 }

@@ -321,14 +321,19 @@ def with_joint_offsets(spec, frac=0.06, seed=0):
     dXi dYi dXj dYj)"""
     rng = np.random.default_rng(seed)
     for g in spec.groups:
-        if g.kind != ELE_FBC2D: continue
+        if g.kind not in (ELE_FBC2D, ELE_FBC3D): continue
         par = np.zeros((len(g.tags), 14)); par[:, :g.par.shape[1]] = g.par
         for i, c in enumerate(g.conn):
             idx = [list(spec.node_tags).index(int(q)) for q in c]
             d = spec.crd[idx[1]] - spec.crd[idx[0]]
-            nrm = np.array([-d[1], d[0]])
-            par[i, 5:7] = rng.uniform(0.3, 1.0) * frac * d + rng.uniform(-0.2, 0.2) * frac * nrm
-            par[i, 7:9] = -rng.uniform(0.3, 1.0) * frac * d + rng.uniform(-0.2, 0.2) * frac * nrm
+            if g.kind == ELE_FBC2D:
+                nrm = np.array([-d[1], d[0]])
+                par[i, 5:7] = rng.uniform(0.3, 1.0) * frac * d + rng.uniform(-0.2, 0.2) * frac * nrm
+                par[i, 7:9] = -rng.uniform(0.3, 1.0) * frac * d + rng.uniform(-0.2, 0.2) * frac * nrm
+            else:        # 3D (parameters 8..13: dXi dYi dZi dXj dYj dZj): along the member plus a small eccentricity
+                L = np.linalg.norm(d)
+                par[i, 8:11] = rng.uniform(0.3, 1.0) * frac * d + rng.uniform(-0.2, 0.2, 3) * frac * L
+                par[i, 11:14] = -rng.uniform(0.3, 1.0) * frac * d + rng.uniform(-0.2, 0.2, 3) * frac * L
         g.par = par
     return spec
 
@@ -954,6 +959,9 @@ class RefBackend(_Backend):
                 elif g.kind == ELE_FBC3D:
                     L.ref_set_beam_rho.argtypes = [ctypes.c_void_p, ctypes.c_double]
                     L.ref_set_beam_rho(self.h, float(g.par[i, 7]))
+                    o6 = np.zeros(6)
+                    if g.par.shape[1] >= 14: o6[:] = g.par[i, 8:14]
+                    L.ref_set_beam_offsets(self.h, _p(o6))
                     vx = np.ascontiguousarray(g.par[i, 3:6], np.float64)
                     assert L.ref_add_force_beam3d_t(self.h, int(g.tags[i]), _p(c), int(g.mat[i]), int(g.par[i, 0]),
                                                     int(g.par[i, 1]), float(g.par[i, 2]), _p(vx), int(g.par[i, 6]) + 16 * spec.beam_integration) == 0

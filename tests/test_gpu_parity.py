@@ -200,7 +200,7 @@ def test_newton_iteration_counts_match_oracle(shape):
 
 @pytest.mark.skipif(not (have_ref() and have_glue()), reason="oracle/_ref not built (needs /root/reference)")
 @pytest.mark.parametrize("shape,numberer,soe", [("brick", 1, 0), ("quad", 0, 1), ("mixed", 1, 1), ("soilcolumn_equaldof", 1, 0), ("frame2d_gravity", 1, 0), ("soil_frame_mixed_ndf", 1, 0),
-                                                ("soilcolumn_equaldof", 0, 1), ("frame2d_pdelta", 1, 0), ("frame3d_pdelta", 1, 0), ("frame3d_eleloads", 1, 0), ("frame2d_legendre", 1, 0), ("frame3d_radau", 1, 0), ("frame2d_concrete01", 1, 0), ("frame2d_jntoffset", 1, 0)])
+                                                ("soilcolumn_equaldof", 0, 1), ("frame2d_pdelta", 1, 0), ("frame3d_pdelta", 1, 0), ("frame3d_eleloads", 1, 0), ("frame2d_legendre", 1, 0), ("frame3d_radau", 1, 0), ("frame2d_concrete01", 1, 0), ("frame2d_jntoffset", 1, 0), ("frame3d_jntoffset", 1, 0)])
 def test_reference_newton_loop_drives_device_path(shape, numberer, soe):
     """The drop-in, end to end: the REFERENCE'S OWN StaticAnalysis objects (AnalysisModel, PlainHandler, numberer,
     SparseGenCol/Row SOE and solver, NewtonRaphson, CTestNormDispIncr, LoadControl::newStep) run a load-controlled
@@ -226,10 +226,11 @@ def test_reference_newton_loop_drives_device_path(shape, numberer, soe):
         def mk():   # `eleLoad -beamUniform` and `-beamPoint` (Beam3dUniformLoad, Beam3dPointLoad) read out of the load pattern
             from modelspec import with_beam_gravity, with_beam_point_loads
             return with_beam_point_loads(with_beam_gravity(frame3d(1, 1, 2, ndiv=2, lateral=(14.0, 8.0)), w=-0.06, seed=1), P=-2.5, seed=2)
-    elif shape == "frame2d_jntoffset":
+    elif shape in ("frame2d_jntoffset", "frame3d_jntoffset"):
         def mk():   # rigid end zones under geomTransf PDelta: nodeIOffset / nodeJOffset read out of the elements' CrdTransf
             from modelspec import with_joint_offsets, with_pdelta
-            return with_pdelta(with_joint_offsets(frame2d(2, 3, 2, lateral=15.0, gravity=-150.0), seed=3))
+            return with_pdelta(with_joint_offsets(frame2d(2, 3, 2, lateral=15.0, gravity=-150.0) if shape == "frame2d_jntoffset"
+                                                  else frame3d(1, 1, 2, ndiv=2, lateral=(18.0, 10.0), gravity=-90.0), seed=3))
     elif shape == "frame2d_concrete01":
         def mk():   # Concrete01 core, Steel01 bars, bilinear Elastic cover read out of the reference's FiberSection2d
             from modelspec import steel01_elastic_frame
@@ -953,29 +954,34 @@ def test_frame_fibre_beams_vs_oracle_history():
     assert relerr(D.form_tangent(), D0.form_tangent()) > 0.05
 
 
+@pytest.mark.parametrize("dim", [2, 3])
 @pytest.mark.parametrize("pdelta", [0, 1])
-def test_joint_offsets_device_vs_oracle(pdelta):
-    """`geomTransf Linear | PDelta ... -jntOffset` on 2D force beams (rigid end zones): sway history under gravity element
-    loads with commits, a revert and a reset, with Rayleigh damping terms in a transient step at the end; device against
-    the oracle (pinned to LinearCrdTransf2d / PDeltaCrdTransf2d with offsets)"""
+def test_joint_offsets_device_vs_oracle(pdelta, dim):
+    """`geomTransf Linear | PDelta ... -jntOffset` on 2D / 3D force beams (rigid end zones): sway history under gravity
+    element loads with commits, a revert and a reset, with Rayleigh damping terms in a transient step at the end; device
+    against the oracle (pinned to Linear / PDeltaCrdTransf2d / 3d with offsets)"""
     from modelspec import with_joint_offsets, with_beam_gravity, with_pdelta
     rng = np.random.default_rng(21)
-    spec = with_joint_offsets(with_beam_gravity(frame2d(3, 2, 2, gravity=-80.0), w=-0.08, seed=1), seed=3)
+    base = frame2d(3, 2, 2, gravity=-80.0) if dim == 2 else frame3d(1, 2, 2, gravity=-40.0)
+    spec = with_joint_offsets(with_beam_gravity(base, w=-0.08 if dim == 2 else -0.06, seed=1), seed=3)
     if pdelta: spec = with_pdelta(spec)
-    mass = np.zeros((spec.nn, 3)); mass[:, :2] = 0.05
+    ndf, nd = spec.ndf, 2 * spec.ndf
+    mass = np.zeros((spec.nn, ndf)); mass[:, :dim] = 0.05
     O = OracleBackend(spec, 1, 0); O.set_mass(spec.node_tags, mass)
     D = xb.DeviceModel.from_spec(spec, setup=False); D.set_mass(spec.node_tags, mass); D.setup(1, 0); D.to_device(0)
     ids = O.ids()
     assert relerr(D.form_tangent(), O.form_tangent()) < BEAM_RTOL
-    H = spec.crd[:, 1].max(); h = spec.crd[:, 1] / H
-    pattern = rng.normal(0, 1.0, (spec.nn, 3)) * (2e-3, 1e-3, 2e-5)
+    hc = spec.crd[:, 1] if dim == 2 else spec.crd[:, 2]
+    H = hc.max(); h = hc / H
+    pattern = rng.normal(0, 1.0, (spec.nn, ndf)) * ((2e-3, 1e-3, 2e-5) if dim == 2 else (2e-3, 2e-3, 1e-3, 2e-5, 2e-5, 2e-5))
 
     def check():
         assert relerr(D.form_tangent(), O.form_tangent()) < BEAM_RTOL and relerr(D.form_unbalance(), O.form_unbalance()) < BEAM_RTOL
         for e in (0, O.ne // 2, O.ne - 1):
-            assert relerr(D.element_resid(e, 6), O.ele_resid(e, 6)) < BEAM_RTOL and relerr(D.element_tangent(e, 6), O.ele_tangent(e, 6)) < BEAM_RTOL
-    for s, a in enumerate([0.2, 0.5, 0.8, 1.1, 1.4]):
-        u = np.zeros((spec.nn, 3)); u[:, 0] = a * h ** 1.5; u[:, 2] = -1.5 * a * h ** 0.5 / H
+            assert relerr(D.element_resid(e, nd), O.ele_resid(e, nd)) < BEAM_RTOL and relerr(D.element_tangent(e, nd), O.ele_tangent(e, nd)) < BEAM_RTOL
+    for s, a in enumerate([0.2, 0.5, 0.8, 1.1, 1.4] if dim == 2 else [0.2, 0.4, 0.6, 0.8, 1.0]):
+        u = np.zeros((spec.nn, ndf)); u[:, 0] = a * h ** 1.5; u[:, 2 if dim == 2 else 4] = -1.5 * a * h ** 0.5 / H
+        if dim == 3: u[:, 1] = 0.5 * a * h ** 1.5; u[:, 3] = 0.7 * a * h ** 0.5 / H
         u += pattern * (a / 0.5); u[ids < 0] = 0
         O.apply_load(0.2 * (s + 1)); assert O.set_trial_disp(u) == 0
         D.apply_load(0.2 * (s + 1)); D.set_trial_disp(u); D.update()
@@ -987,7 +993,7 @@ def test_joint_offsets_device_vs_oracle(pdelta):
     # a transient step with all four Rayleigh factors: the damping forces go through the offsets as well
     for m in (O, D):
         m.set_rayleigh(0.3, 0.002, 0.001, 0.0015); m.set_transient(1.0, 50.0, 5000.0)
-    v = rng.normal(0, 0.5, (spec.nn, 3)); acc = rng.normal(0, 5.0, (spec.nn, 3)); v[ids < 0] = 0; acc[ids < 0] = 0
+    v = rng.normal(0, 0.5, (spec.nn, ndf)); acc = rng.normal(0, 5.0, (spec.nn, ndf)); v[ids < 0] = 0; acc[ids < 0] = 0
     O.set_vel_accel(v, acc); D.set_vel_accel(v, acc)
     assert relerr(D.form_tangent(), O.form_tangent()) < BEAM_RTOL and relerr(D.form_unbalance(), O.form_unbalance()) < BEAM_RTOL
 

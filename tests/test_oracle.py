@@ -359,35 +359,41 @@ def test_steel01_elastic_fibres_vs_live_reference(dim):
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("dim", [2, 3])
 @pytest.mark.parametrize("pdelta", [0, 1])
-def test_joint_offsets_vs_live_reference(pdelta):
+def test_joint_offsets_vs_live_reference(pdelta, dim):
     """`geomTransf Linear | PDelta ... -jntOffset` (rigid end zones; the nodeIOffset / nodeJOffset terms of
     LinearCrdTransf2d.cpp and PDeltaCrdTransf2d.cpp): element length and orientation between the offset ends, basic
     deformations, tangent and resisting force pulled back to the nodes -- against the reference's classes over a sway
     history under gravity element loads, with commits and a revert"""
     from modelspec import with_joint_offsets, with_beam_gravity, with_pdelta
     rng = np.random.default_rng(21)
-    mk = lambda: with_beam_gravity(frame2d(2, 2, 2, gravity=-80.0), w=-0.08, seed=1)
+    mk = (lambda: with_beam_gravity(frame2d(2, 2, 2, gravity=-80.0), w=-0.08, seed=1)) if dim == 2 else \
+         (lambda: with_beam_gravity(frame3d(1, 1, 2, gravity=-40.0), w=-0.06, seed=1))
     spec = with_joint_offsets(mk(), seed=3)
     if pdelta: spec = with_pdelta(spec)
     O, R, Rn = OracleBackend(spec, 1, 0), RefBackend(spec, 1, 0), RefBackend(with_pdelta(mk()) if pdelta else mk(), 1, 0)
     assert close(O.form_tangent(), R.form_tangent(), 1e-11)
-    H = spec.crd[:, 1].max(); h = spec.crd[:, 1] / H
-    pattern = rng.normal(0, 1.0, (spec.nn, 3)) * (2e-3, 1e-3, 2e-5)
+    hc = spec.crd[:, 1] if dim == 2 else spec.crd[:, 2]
+    H = hc.max(); h = hc / H
+    nd = 6 if dim == 2 else 12
+    pattern = rng.normal(0, 1.0, (spec.nn, spec.ndf)) * ((2e-3, 1e-3, 2e-5) if dim == 2 else (2e-3, 2e-3, 1e-3, 2e-5, 2e-5, 2e-5))
     differs = False
-    for s_, a in enumerate([0.2, 0.5, 0.8, 1.1, 1.4]):
-        u = np.zeros((spec.nn, 3)); u[:, 0] = a * h ** 1.5; u[:, 2] = -1.5 * a * h ** 0.5 / H
+    BT = 1e-11 if dim == 2 else 1e-10          # (the element state is the fixed point of an iteration converged to |dW| < 1e-12)
+    for s_, a in enumerate([0.2, 0.5, 0.8, 1.1, 1.4] if dim == 2 else [0.2, 0.4, 0.6, 0.8, 1.0]):
+        u = np.zeros((spec.nn, spec.ndf)); u[:, 0] = a * h ** 1.5; u[:, 2 if dim == 2 else 4] = -1.5 * a * h ** 0.5 / H
+        if dim == 3: u[:, 1] = 0.5 * a * h ** 1.5; u[:, 3] = 0.7 * a * h ** 0.5 / H
         u += pattern * (a / 0.5); u[O.ids() < 0] = 0
         for m in (O, R, Rn):
             m.apply_load(0.2 * (s_ + 1)); m.set_trial_disp(u)
         Ar, Br = R.form_tangent(), R.form_unbalance()
-        assert close(O.form_tangent(), Ar, 1e-11) and close(O.form_unbalance(), Br, 1e-11)
+        assert close(O.form_tangent(), Ar, BT) and close(O.form_unbalance(), Br, BT)
         for e in range(O.ne):
-            assert close(O.ele_resid(e, 6), R.ele_resid(e, 6), 1e-11) and close(O.ele_tangent(e, 6), R.ele_tangent(e, 6), 1e-11)
+            assert close(O.ele_resid(e, nd), R.ele_resid(e, nd), BT) and close(O.ele_tangent(e, nd), R.ele_tangent(e, nd), BT)
         differs = differs or not close(Ar, Rn.form_tangent(), 1e-3)
         if s_ == 4:
             O.revert(); R.revert()
-            assert close(O.form_tangent(), R.form_tangent(), 1e-11) and close(O.form_unbalance(), R.form_unbalance(), 1e-11)
+            assert close(O.form_tangent(), R.form_tangent(), BT) and close(O.form_unbalance(), R.form_unbalance(), BT)
         else:
             O.commit(); R.commit(); Rn.commit()
     assert differs

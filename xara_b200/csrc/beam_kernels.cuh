@@ -89,8 +89,8 @@ struct BeamView {
   double* ul;
   // beam integration other than Lobatto (xb_set_beam_integration): [2 nip][n] locations then weights, fractions of L; null: Lobatto
   const double* rule;
-  // rigid joint offsets of a 2D batch (geomTransf -jntOffset; nodeIOffset / nodeJOffset of LinearCrdTransf2d.cpp,
-  // PDeltaCrdTransf2d.cpp): [4][n] dXi dYi dXj dYj, null: none.  The element ends follow their nodes rigidly,
+  // rigid joint offsets (geomTransf -jntOffset; nodeIOffset / nodeJOffset of Linear / PDeltaCrdTransf2d.cpp, 3d.cpp):
+  // 2D [4][n] dXi dYi dXj dYj, 3D [6][n] dXi dYi dZi dXj dYj dZj, null: none.  The element ends follow their nodes rigidly,
   // u_end = u + theta x offset; tangent and forces are pulled back to the nodes with the transpose of that map
   const double* off;
 };
@@ -390,6 +390,18 @@ __device__ __forceinline__ void fbc2d_end_disp(const BeamView& B, long long e, d
   const double oix = B.off[e], oiy = B.off[B.n + e], ojx = B.off[2 * B.n + e], ojy = B.off[3 * B.n + e];
   ug[0] += -ug[2] * oiy; ug[1] += ug[2] * oix;
   ug[3] += -ug[5] * ojy; ug[4] += ug[5] * ojx;
+}
+
+// the same in 3D: u_end = u + theta x offset, per node
+__device__ __forceinline__ void fbc3d_end_disp(const BeamView& B, long long e, double* ug) {
+  if (!B.off) return;
+#pragma unroll
+  for (int a = 0; a < 2; a++) {
+    const double dx = B.off[(size_t)(3 * a) * B.n + e], dy = B.off[(size_t)(3 * a + 1) * B.n + e], dz = B.off[(size_t)(3 * a + 2) * B.n + e];
+    double* u = ug + 6 * a;
+    const double tx = u[3], ty = u[4], tz = u[5];
+    u[0] += ty * dz - tz * dy; u[1] += tz * dx - tx * dz; u[2] += tx * dy - ty * dx;
+  }
 }
 
 // FiberSection2d::setTrialSectionDeformation for section i of element e -> s[2], k[4] (column-major)
@@ -779,6 +791,7 @@ __global__ void __launch_bounds__(128, XB_FBC_SEC_OCC) fbc3d_update_sec_kernel(B
 #pragma unroll
       for (int j = 0; j < 6; j++) { ug[a * 6 + j] = U[(size_t)nd * 6 + j]; dug[a * 6 + j] = DU[(size_t)nd * 6 + j]; }
     }
+    fbc3d_end_disp(B, e, ug); fbc3d_end_disp(B, e, dug);
     crd3d_basic(L, R, ug, v);
     crd3d_basic(L, R, dug, dv);
     if (B.pdelta && act && i == 0) {   // crdTransf->update(): PDeltaCrdTransf3d.cpp:200-249 (before any early return)
@@ -1238,6 +1251,16 @@ __global__ void __launch_bounds__(64) fbc3d_form_kernel(BeamView B, int want_k, 
       for (int blk = 0; blk < 4; blk++)
         for (int c = 0; c < 3; c++)
           kl[3 * blk + c][m] = R[0][c] * tmp[3 * blk][m] + R[1][c] * tmp[3 * blk + 1][m] + R[2][c] * tmp[3 * blk + 2][m];
+    if (B.off) {   // K_node = To' K_end To (the joint-offset terms of LinearCrdTransf3d::getGlobalStiffMatrix)
+      for (int a = 0; a < 2; a++) {
+        const double dx = B.off[(size_t)(3 * a) * n + e], dy = B.off[(size_t)(3 * a + 1) * n + e], dz = B.off[(size_t)(3 * a + 2) * n + e];
+        const double C[3][3] = {{0.0, dz, -dy}, {-dz, 0.0, dx}, {dy, -dx, 0.0}};      // u_end = u + C theta
+        for (int i = 0; i < 12; i++) for (int j = 0; j < 3; j++)
+          kl[i][6 * a + 3 + j] += kl[i][6 * a] * C[0][j] + kl[i][6 * a + 1] * C[1][j] + kl[i][6 * a + 2] * C[2][j];
+        for (int i = 0; i < 12; i++) for (int j = 0; j < 3; j++)
+          kl[6 * a + 3 + j][i] += C[0][j] * kl[6 * a][i] + C[1][j] * kl[6 * a + 1][i] + C[2][j] * kl[6 * a + 2][i];
+      }
+    }
     for (int a = 0; a < 2; a++) {
       const long long d = B.kdst[e * 2 + a];
       double* base = d >= 0 ? B.KeN + d : B.sendK + (-d - 1);
@@ -1257,6 +1280,7 @@ __global__ void __launch_bounds__(64) fbc3d_form_kernel(BeamView B, int want_k, 
         const int nd = B.conn[e * 2 + a];
         for (int j = 0; j < 6; j++) vg[a * 6 + j] = dy.V[(size_t)nd * 6 + j];
       }
+      fbc3d_end_disp(B, e, vg);
       crd3d_basic(L, Rf, vg, vb);
       if (B.pdelta) {
         const double gd = (dy.bK * B.Se[e] + (dy.bKc != 0.0 ? dy.bKc * B.nK[e] : 0.0)) * oneOverL;
@@ -1304,6 +1328,13 @@ __global__ void __launch_bounds__(64) fbc3d_form_kernel(BeamView B, int want_k, 
     for (int blk = 0; blk < 4; blk++)
       for (int c = 0; c < 3; c++)
         Rg[3 * blk + c] = R[0][c] * pl[3 * blk] + R[1][c] * pl[3 * blk + 1] + R[2][c] * pl[3 * blk + 2];
+    if (B.off) {   // R_node = To' R_end: the end forces' moments about the nodes, d x F
+      for (int a = 0; a < 2; a++) {
+        const double dx = B.off[(size_t)(3 * a) * n + e], dy = B.off[(size_t)(3 * a + 1) * n + e], dz = B.off[(size_t)(3 * a + 2) * n + e];
+        const double Fx = Rg[6 * a], Fy = Rg[6 * a + 1], Fz = Rg[6 * a + 2];
+        Rg[6 * a + 3] += dy * Fz - dz * Fy; Rg[6 * a + 4] += dz * Fx - dx * Fz; Rg[6 * a + 5] += dx * Fy - dy * Fx;
+      }
+    }
   }
 }
 

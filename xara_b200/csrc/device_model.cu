@@ -1892,7 +1892,8 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
           // x = dx / L, y = vecxz ^ x (normalised), z = x ^ y
           const double* xi = &h.crd[(size_t)a * 3]; const double* xj = &h.crd[(size_t)c * 3];
           const double* v = &g.par[(size_t)e * k.npar + 3];
-          const double dx[3] = {xj[0] - xi[0], xj[1] - xi[1], xj[2] - xi[2]};
+          const double* o = &g.par[(size_t)e * k.npar + k.npar - 15];      // -jntOffset: between the offset ends
+          const double dx[3] = {xj[0] + o[3] - (xi[0] + o[0]), xj[1] + o[4] - (xi[1] + o[1]), xj[2] + o[5] - (xi[2] + o[2])};
           const double L = std::sqrt(dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2]);
           if (L == 0.0) return fail(XB_ERR_ARG, "forceBeamColumn: zero element length");
           const double x[3] = {dx[0] / L, dx[1] / L, dx[2] / L};
@@ -1970,10 +1971,11 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
       b.agg = sd.agg ? 1 : 0;
       b.pdelta = g.transf == 1 ? 1 : 0; b.U = m->dU; b.ul = nullptr;
       b.off = nullptr;
-      if (!b3) {   // rigid joint offsets, SoA [4][n]; null when the batch has none
-        std::vector<double> os((size_t)4 * ne); bool anyo = false;
+      {   // rigid joint offsets, SoA [4][n] (2D) / [6][n] (3D); null when the batch has none
+        const int no = b3 ? 6 : 4, at = b3 ? 15 : 13;
+        std::vector<double> os((size_t)no * ne); bool anyo = false;
         for (long long e = 0; e < ne; e++)
-          for (int q = 0; q < 4; q++) { os[(size_t)q * ne + e] = g.par[(size_t)e * k.npar + k.npar - 13 + q]; anyo = anyo || os[(size_t)q * ne + e] != 0.0; }
+          for (int q = 0; q < no; q++) { os[(size_t)q * ne + e] = g.par[(size_t)e * k.npar + k.npar - at + q]; anyo = anyo || os[(size_t)q * ne + e] != 0.0; }
         if (anyo) { double* dof = nullptr; CU(dev_upload(m, &dof, os)); b.off = dof; }
       }
       b.rule = nullptr;

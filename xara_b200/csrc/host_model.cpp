@@ -18,7 +18,7 @@ static const EleKind kQuad{4, 2, 4, 3, 5};  // par kept: thickness, b1, b2, type
 // Linear pattern: `eleLoad -beamPoint` Py, Pz, N, aOverL (has-load flag in a 5th value) and `eleLoad -beamUniform` wy, wz, wa
 // (zero: none) -- they travel with the element through the partitioning like every other element parameter
 static const EleKind kBeam2d{2, 3, 0, 2, 16};  // par: nIP, maxIters, tol, joint offsets[4], rho, point load[5], wy, wz (unused), wa
-static const EleKind kBeam3d{2, 6, 0, 4, 15};  // par: nIP, maxIters, tol, vecxz[3], rho, point load[5], wy, wz, wa
+static const EleKind kBeam3d{2, 6, 0, 4, 21};  // par: nIP, maxIters, tol, vecxz[3], joint offsets[6], rho, point load[5], wy, wz, wa
 
 const EleKind& ele_kind(int kind) {
   return kind == XB_ELE_STDBRICK ? kBrick : (kind == XB_ELE_FOURNODEQUAD ? kQuad : (kind == XB_ELE_FORCEBEAMCOLUMN3D ? kBeam3d : kBeam2d));
@@ -182,7 +182,8 @@ int HostModel::add_elements(int kind, int n, const int* tags, const int* conn, c
       if (par_stride > rpos) g.par[(size_t)i * k.npar + k.npar - 9] = p[rpos];
       // `geomTransf ... -jntOffset dXi dYi dXj dYj` (2D): the four parameters behind rho
       if (!b3 && par_stride >= 9) for (int q = 0; q < 4; q++) g.par[(size_t)i * k.npar + k.npar - 13 + q] = p[5 + q];
-      if (b3 && par_stride >= 14) for (int q = 0; q < 6; q++) if (p[8 + q] != 0.0) { err = "forceBeamColumn (3D): joint offsets are outside the device path"; return XB_ERR_UNSUPPORTED; }
+      // 3D: -jntOffset dXi dYi dZi dXj dYj dZj, parameters 8..13
+      if (b3 && par_stride >= 14) for (int q = 0; q < 6; q++) g.par[(size_t)i * k.npar + k.npar - 15 + q] = p[8 + q];
     }
     if (g.nip < 2 || g.nip > 10) { err = "forceBeamColumn: Lobatto integration takes 2..10 points"; return XB_ERR_ARG; }
     if (n > 0) groups.push_back(std::move(g));
@@ -493,7 +494,9 @@ int HostModel::setup(int numberer_, int soe_kind_, int nparts_, int rank_, const
       double L2 = 0.0;
       for (int d = 0; d < ndm; d++) {
         double dx = crd[(size_t)b * ndm + d] - crd[(size_t)a * ndm + d];
-        if (g.kind == XB_ELE_FORCEBEAMCOLUMN2D) dx += g.par[(size_t)l * npar + npar - 11 + d] - g.par[(size_t)l * npar + npar - 13 + d];   // (between the offset ends)
+        // (between the offset ends)
+        if (g.kind == XB_ELE_FORCEBEAMCOLUMN2D) dx += g.par[(size_t)l * npar + npar - 11 + d] - g.par[(size_t)l * npar + npar - 13 + d];
+        else dx += g.par[(size_t)l * npar + npar - 12 + d] - g.par[(size_t)l * npar + npar - 15 + d];
         L2 += dx * dx;
       }
       const double mL = 0.5 * rho * std::sqrt(L2);
