@@ -57,7 +57,8 @@ enum {
   XB_ELE_FORCEBEAMCOLUMN2D = 2,/* element/Frame/Other/Force/ForceBeamColumn2d.cpp, 2 nodes x 3 dof; mat_tags name the
                              section (xb_add_fiber_section or xb_add_section_aggregator);
                              par = nIP, maxIters, tol [, geomTransf: 0 Linear | 1 PDelta (coordTransformation/
-                             PDeltaCrdTransf2d.cpp) [, rho: `-mass`, mass per unit length, lumped [, dXi, dYi, dXj,
+                             PDeltaCrdTransf2d.cpp) | 2 Corotational (CorotCrdTransf2d.cpp; no joint offsets, no
+                             stiffness-proportional Rayleigh terms: XB_ERR_UNSUPPORTED) [, rho: `-mass`, mass per unit length, lumped [, dXi, dYi, dXj,
                              dYj: `-jntOffset`, rigid end zones]]] -- rows of 3, 4, 5 or 9 values; one
                              section/nIP/maxIters/tol/geomTransf per call.  Lobatto
                              integration unless xb_set_beam_integration hands over another rule's points          */

@@ -49,6 +49,7 @@
 #include <LinearCrdTransf2d.h>
 #include <LinearCrdTransf3d.h>
 #include <PDeltaCrdTransf2d.h>
+#include <CorotCrdTransf2d.h>
 #include <PDeltaCrdTransf3d.h>
 #include <LobattoBeamIntegration.h>
 #include <Brick.h>
@@ -241,12 +242,16 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
           if (t->nodeIOffset) { off2[0] = t->nodeIOffset[0]; off2[1] = t->nodeIOffset[1]; }
           if (t->nodeJOffset) { off2[2] = t->nodeJOffset[0]; off2[3] = t->nodeJOffset[1]; }
         }
+        else if (auto* t = dynamic_cast<CorotCrdTransf2d*>(ct)) {
+          if (t->nodeOffsets) { G.err = "glue: geomTransf Corotational with joint offsets: outside the device path"; return -5; }
+          transf = 2;
+        }
         else if (auto* t = dynamic_cast<PDeltaCrdTransf3d*>(ct)) {
           transf = 1;
           if (t->nodeIOffset) for (int q = 0; q < 3; q++) off3[q] = t->nodeIOffset[q];
           if (t->nodeJOffset) for (int q = 0; q < 3; q++) off3[3 + q] = t->nodeJOffset[q];
         }
-        if (transf < 0) { G.err = "glue: geomTransf other than Linear / PDelta: outside the device path"; return -5; }
+        if (transf < 0) { G.err = "glue: geomTransf other than Linear / PDelta / Corotational (2D): outside the device path"; return -5; }
         for (int i = 1; i < nsec; i++) if (secs[i]->getTag() != secs[0]->getTag()) { G.err = "glue: sections of one element differ"; return -5; }
         const int stag = secs[0]->getTag();
         if (!secs_done.count(stag)) {

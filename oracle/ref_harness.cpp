@@ -47,6 +47,7 @@
 #include <FiberSection2d.h>
 #include <SectionAggregator.h>
 #include <PDeltaCrdTransf2d.h>
+#include <CorotCrdTransf2d.h>
 #include <LegendreBeamIntegration.h>
 #include <RadauBeamIntegration.h>
 #include <NewtonCotesBeamIntegration.h>
@@ -367,7 +368,8 @@ int ref_add_force_beam2d_t(void* h, int tag, const int* nd, int secTag, int nip,
   PDeltaCrdTransf2d pd0(tag), pd1(tag, oI, oJ);      // geomTransf PDelta
   LinearCrdTransf2d& lin = off ? lin1 : lin0;
   PDeltaCrdTransf2d& pd = off ? pd1 : pd0;
-  CrdTransf& transf = transfKind == 1 ? (CrdTransf&)pd : (CrdTransf&)lin;
+  CorotCrdTransf2d cor(tag, oI, oJ);                 // geomTransf Corotational
+  CrdTransf& transf = transfKind == 2 ? (CrdTransf&)cor : (transfKind == 1 ? (CrdTransf&)pd : (CrdTransf&)lin);
   Element* e = new ForceBeamColumn2d(tag, nd[0], nd[1], nip, secs.data(), bi, transf, m->beam_rho, maxIters, tol);
   return m->domain->addElement(e) ? 0 : -1;
 }

@@ -870,6 +870,9 @@ typedef struct {
   /* rigid joint offsets (geomTransf ... -jntOffset dXi dYi dXj dYj; LinearCrdTransf2d.cpp / PDeltaCrdTransf2d.cpp nodeIOffset,
    * nodeJOffset): the element ends sit at node + offset and follow the node rigidly, u_end = u + theta x offset */
   int has_off; double off[4];
+  /* geomTransf Corotational (CorotCrdTransf2d.cpp, no joint offsets): the basic deformations of the last
+   * crdTransf->update() (ub; the next update's ubpr) and of the last commit (ubcommit) */
+  int corot; double cub[3], cubc[3];
 } OrcBeam;
 
 /* quadrature/Frame/LobattoBeamIntegration.cpp: getSectionLocations / getSectionWeights */
@@ -902,6 +905,31 @@ static void crd2d_basic(const OrcBeam* b, const double* ug, double* ub) {
   ub[2] = ub[1] + ug[5] - ug[2];
 }
 
+/* CorotCrdTransf2d::update (CorotCrdTransf2d.cpp:179-231, no offsets): local end displacements, the deformed chord
+ * (compElemtLengthAndOrientWRTLocalSystem, :272-299) and the basic deformations with the rigid-body rotation alpha
+ * taken out (transfLocalDisplsToBasic, :344-355).  cg = Lx, Ly, Ln, cosAlpha, sinAlpha */
+static int corot2d_geom(const OrcBeam* b, const double* ug, double* cg, double* ub) {
+  const double cosTheta = b->cosTheta, sinTheta = b->sinTheta;
+  double ul[6];
+  ul[0] = cosTheta * ug[0] + sinTheta * ug[1];
+  ul[1] = cosTheta * ug[1] - sinTheta * ug[0];
+  ul[2] = ug[2];
+  ul[3] = cosTheta * ug[3] + sinTheta * ug[4];
+  ul[4] = cosTheta * ug[4] - sinTheta * ug[3];
+  ul[5] = ug[5];
+  const double dulx = ul[3] - ul[0], duly = ul[4] - ul[1];
+  const double Lx = b->L + dulx, Ly = duly;
+  const double Ln = sqrt(Lx * Lx + Ly * Ly);
+  if (Ln == 0.0) return -2;
+  const double cosAlpha = Lx / Ln, sinAlpha = Ly / Ln;
+  cg[0] = Lx; cg[1] = Ly; cg[2] = Ln; cg[3] = cosAlpha; cg[4] = sinAlpha;
+  if (ub) {
+    const double alpha = atan2(sinAlpha, cosAlpha);
+    ub[0] = Ln - b->L; ub[1] = ul[2] - alpha; ub[2] = ul[5] - alpha;
+  }
+  return 0;
+}
+
 /* ForceBeamColumn2d::update, ForceBeamColumn2d.cpp:559-933 (no element loads) */
 static void beam_end_disp(const OrcBeam* b, double* ug);
 static int beam_update(OrcBeam* b, const double* ug_, const double* dug_) {
@@ -909,8 +937,14 @@ static int beam_update(OrcBeam* b, const double* ug_, const double* dug_) {
   double ug[6], dug[6];
   memcpy(ug, ug_, sizeof ug); memcpy(dug, dug_, sizeof dug);
   beam_end_disp(b, ug); beam_end_disp(b, dug);
+  if (b->corot) {   /* CorotCrdTransf2d::update (:179-231), getBasicIncrDeltaDisp = ub - ubpr (:364-371) */
+    double cg[5];
+    if (corot2d_geom(b, ug, cg, v) < 0) return -1;
+    for (int i = 0; i < 3; i++) { dv[i] = v[i] - b->cub[i]; b->cub[i] = v[i]; }
+  } else {
   crd2d_basic(b, ug, v);
   crd2d_basic(b, dug, dv);
+  }
   double nrm = sqrt(dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]);
   if (b->initialFlag != 0 && nrm <= DBL_EPSILON && b->numEleLoads == 0) return 0;
   for (int i = 0; i < 3; i++) vin[i] = v[i] - dv[i];
@@ -1087,6 +1121,84 @@ static void beam_form_pdelta(const OrcBeam* b, double* K, double* R) {
   R[4] = sinTheta * pl[3] + cosTheta * pl[4];
   R[2] = pl[2]; R[5] = pl[5];
 }
+/* CorotCrdTransf2d::getGlobalStiffMatrix (:525-701) / getGlobalResistingForce (:483-522), no offsets; the 2D element
+ * refreshes the transformation from the nodes' trial displacements before either (ForceBeamColumn2d.cpp:402,526).
+ * K row-major 6x6 */
+static void beam_form_corot(const OrcBeam* b, double* K, double* R) {
+  const double cosTheta = b->cosTheta, sinTheta = b->sinTheta;
+  double ue[6], cg[5];
+  for (int j = 0; j < 3; j++) { ue[j] = b->utrial[3 * b->n0 + j]; ue[3 + j] = b->utrial[3 * b->n1 + j]; }
+  corot2d_geom(b, ue, cg, NULL);
+  const double Ln = cg[2], cosAlpha = cg[3], sinAlpha = cg[4];
+  double Tbl[3][6];        /* compTransfMatrixBasicLocal, :315-341 */
+  Tbl[0][0] = -cosAlpha; Tbl[1][0] = -sinAlpha / Ln; Tbl[2][0] = -sinAlpha / Ln;
+  Tbl[0][1] = -sinAlpha; Tbl[1][1] = cosAlpha / Ln; Tbl[2][1] = cosAlpha / Ln;
+  Tbl[0][2] = 0; Tbl[1][2] = 1; Tbl[2][2] = 0;
+  Tbl[0][3] = cosAlpha; Tbl[1][3] = sinAlpha / Ln; Tbl[2][3] = sinAlpha / Ln;
+  Tbl[0][4] = sinAlpha; Tbl[1][4] = -cosAlpha / Ln; Tbl[2][4] = -cosAlpha / Ln;
+  Tbl[0][5] = 0; Tbl[1][5] = 0; Tbl[2][5] = 1;
+  const double* pb = b->Se;
+  if (K) {
+    double kl[6][6], tk[3][6];
+    /* kl = Tbl^T kb Tbl (Matrix::addMatrixTripleProduct); kv column-major 3x3 */
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 6; j++) {
+      double t = 0.0;
+      for (int k = 0; k < 3; k++) t += b->kv[i + 3 * k] * Tbl[k][j];
+      tk[i][j] = t;
+    }
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) {
+      double t = 0.0;
+      for (int k = 0; k < 3; k++) t += Tbl[k][i] * tk[k][j];
+      kl[i][j] = t;
+    }
+    /* getGeomStiffMatrix, :908-953 */
+    const double s2 = sinAlpha * sinAlpha, c2 = cosAlpha * cosAlpha, cs = sinAlpha * cosAlpha;
+    double kg0[6][6], kg12[6][6];
+    memset(kg0, 0, sizeof kg0); memset(kg12, 0, sizeof kg12);
+    kg0[0][0] = kg0[3][3] = s2; kg0[0][1] = kg0[3][4] = -cs; kg0[1][0] = kg0[4][3] = -cs; kg0[1][1] = kg0[4][4] = c2;
+    kg0[0][3] = kg0[3][0] = -s2; kg0[0][4] = kg0[3][1] = cs; kg0[1][3] = kg0[4][0] = cs; kg0[1][4] = kg0[4][1] = -c2;
+    kg12[0][0] = kg12[3][3] = -2 * cs; kg12[0][1] = kg12[3][4] = c2 - s2; kg12[1][0] = kg12[4][3] = c2 - s2; kg12[1][1] = kg12[4][4] = 2 * cs;
+    kg12[0][3] = kg12[3][0] = 2 * cs; kg12[0][4] = kg12[3][1] = -c2 + s2; kg12[1][3] = kg12[4][0] = -c2 + s2; kg12[1][4] = kg12[4][1] = -2 * cs;
+    const double f0 = pb[0] / Ln, f12 = (pb[1] + pb[2]) / (Ln * Ln);
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) kl[i][j] += kg0[i][j] * f0 + kg12[i][j] * f12;
+    /* kg = Tlg^T kl Tlg, block by block, :543-644 */
+    const double S2 = sinTheta * sinTheta, C2 = cosTheta * cosTheta, CS = sinTheta * cosTheta;
+    for (int bi = 0; bi < 2; bi++) for (int bj = 0; bj < 2; bj++) {
+      const int r = 3 * bi, c = 3 * bj;
+      const double k11 = kl[r][c], k12 = kl[r][c + 1], k13 = kl[r][c + 2], k21 = kl[r + 1][c], k22 = kl[r + 1][c + 1], k23 = kl[r + 1][c + 2],
+                   k31 = kl[r + 2][c], k32 = kl[r + 2][c + 1], k33 = kl[r + 2][c + 2];
+      K[(r + 0) * 6 + c + 0] = C2 * k11 + S2 * k22 - CS * (k21 + k12);
+      K[(r + 1) * 6 + c + 0] = C2 * k21 - S2 * k12 + CS * (k11 - k22);
+      K[(r + 2) * 6 + c + 0] = cosTheta * k31 - sinTheta * k32;
+      K[(r + 0) * 6 + c + 1] = C2 * k12 - S2 * k21 + CS * (k11 - k22);
+      K[(r + 1) * 6 + c + 1] = C2 * k22 + S2 * k11 + CS * (k21 + k12);
+      K[(r + 2) * 6 + c + 1] = sinTheta * k31 + cosTheta * k32;
+      K[(r + 0) * 6 + c + 2] = cosTheta * k13 - sinTheta * k23;
+      K[(r + 1) * 6 + c + 2] = sinTheta * k13 + cosTheta * k23;
+      K[(r + 2) * 6 + c + 2] = k33;
+    }
+  }
+  double pl[6];
+  for (int j = 0; j < 6; j++) pl[j] = Tbl[0][j] * pb[0] + Tbl[1][j] * pb[1] + Tbl[2][j] * pb[2];   /* pl = Tbl^T pb */
+  double p0[3] = {0.0, 0.0, 0.0};
+  if (b->numEleLoads > 0) {          /* computeReactions, ForceBeamColumn2d.cpp:407-462 */
+    double wa = b->w[2] * b->loadFactor, wy = b->w[0] * b->loadFactor;
+    p0[0] -= wa * b->L;
+    double Vr = 0.5 * wy * b->L;
+    p0[1] -= Vr; p0[2] -= Vr;
+    if (b->has_point) {
+      double P = b->pt[0] * b->loadFactor, N = b->pt[2] * b->loadFactor, aOverL = b->pt[3];
+      double V1 = P * (1.0 - aOverL), V2 = P * aOverL;
+      p0[0] -= N; p0[1] -= V1; p0[2] -= V2;
+    }
+  }
+  pl[0] += p0[0]; pl[1] += p0[1]; pl[4] += p0[2];      /* member loads in the local system, :493-497 */
+  R[0] = cosTheta * pl[0] - sinTheta * pl[1];
+  R[1] = sinTheta * pl[0] + cosTheta * pl[1];
+  R[3] = cosTheta * pl[3] - sinTheta * pl[4];
+  R[4] = sinTheta * pl[3] + cosTheta * pl[4];
+  R[2] = pl[2]; R[5] = pl[5];
+}
 static void beam_form_end(const OrcBeam* b, double* K, double* R);
 /* tangent and resisting force at the NODES: those of the element ends, pulled back through the rigid offsets
  * (K_node = To' K_end To, R_node = To' R_end with u_end = To u_node; the t02, t12, t35, t45 terms of
@@ -1104,6 +1216,7 @@ static void beam_form(const OrcBeam* b, double* K, double* R) {
 /* LinearCrdTransf2d::getGlobalStiffMatrix and getGlobalResistingForce at the element ends; K row-major 6x6 */
 static void beam_form_end(const OrcBeam* b, double* K, double* R) {
   if (b->pdelta) { beam_form_pdelta(b, K, R); return; }
+  if (b->corot) { beam_form_corot(b, K, R); return; }
   const double cosTheta = b->cosTheta, sinTheta = b->sinTheta, oneOverL = 1.0 / b->L;
   if (K) {
     const double* kb = b->kv;
@@ -1154,8 +1267,11 @@ static void beam_commit(OrcBeam* b) {
     for (int f = 0; f < b->sec[i].nf; f++) uni_commit(&b->sec[i].mat[f]);
   }
   memcpy(b->kvcommit, b->kv, sizeof b->kv); memcpy(b->Secommit, b->Se, sizeof b->Se);
+  memcpy(b->cubc, b->cub, sizeof b->cub);       /* CorotCrdTransf2d::commitState */
 }
 static void beam_revert(OrcBeam* b) {
+  /* CorotCrdTransf2d::revertToLastCommit: ub = ubcommit, update() at the (already reverted) nodes' displacements */
+  memcpy(b->cub, b->cubc, sizeof b->cub);
   for (int i = 0; i < b->nip; i++) {
     memcpy(b->vs[i], b->vscommit[i], sizeof b->vs[i]);
     sec_revert(&b->sec[i]);
@@ -1805,7 +1921,8 @@ static OrcBeam* beam2_build(OrcModel* m, OrcEle* e, int sd, const double* par) {
   if (b->has_off) { dx0 += b->off[2]; dx1 += b->off[3]; dx0 -= b->off[0]; dx1 -= b->off[1]; }
   b->L = sqrt(dx0 * dx0 + dx1 * dx1);
   b->cosTheta = dx0 / b->L; b->sinTheta = dx1 / b->L;
-  b->pdelta = (int)par[3]; b->utrial = m->trial; b->n0 = e->node[0]; b->n1 = e->node[1];   /* par[3]: 0 geomTransf Linear, 1 PDelta */
+  b->pdelta = (int)par[3] == 1; b->corot = (int)par[3] == 2; b->utrial = m->trial; b->n0 = e->node[0]; b->n1 = e->node[1];   /* par[3]: 0 geomTransf Linear, 1 PDelta, 2 Corotational */
+  if (b->corot && b->has_off) return NULL;
   return b;
 }
 static int quad_update(OrcModel* m, OrcEle* el);

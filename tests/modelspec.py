@@ -346,6 +346,13 @@ def with_pdelta(spec):
     return spec
 
 
+def with_corot(spec):
+    """`geomTransf Corotational` on every 2D forceBeamColumn of the spec (element parameter 3 = 2)"""
+    for g in spec.groups:
+        if g.kind == ELE_FBC2D: g.par[:, 3] = 2.0
+    return spec
+
+
 def with_beam_gravity(spec, w=-0.25, axial=0.02, seed=0):
     """`eleLoad -beamUniform` on the horizontal members (girders): transverse w (+-20 % per element), a little axial load,
     and -- 3D -- a small lateral component; columns stay unloaded"""

@@ -200,7 +200,7 @@ def test_newton_iteration_counts_match_oracle(shape):
 
 @pytest.mark.skipif(not (have_ref() and have_glue()), reason="oracle/_ref not built (needs /root/reference)")
 @pytest.mark.parametrize("shape,numberer,soe", [("brick", 1, 0), ("quad", 0, 1), ("mixed", 1, 1), ("soilcolumn_equaldof", 1, 0), ("frame2d_gravity", 1, 0), ("soil_frame_mixed_ndf", 1, 0),
-                                                ("soilcolumn_equaldof", 0, 1), ("frame2d_pdelta", 1, 0), ("frame3d_pdelta", 1, 0), ("frame3d_eleloads", 1, 0), ("frame2d_legendre", 1, 0), ("frame3d_radau", 1, 0), ("frame2d_concrete01", 1, 0), ("frame2d_jntoffset", 1, 0), ("frame3d_jntoffset", 1, 0)])
+                                                ("soilcolumn_equaldof", 0, 1), ("frame2d_pdelta", 1, 0), ("frame3d_pdelta", 1, 0), ("frame3d_eleloads", 1, 0), ("frame2d_legendre", 1, 0), ("frame3d_radau", 1, 0), ("frame2d_concrete01", 1, 0), ("frame2d_jntoffset", 1, 0), ("frame3d_jntoffset", 1, 0), ("frame2d_corot", 1, 0)])
 def test_reference_newton_loop_drives_device_path(shape, numberer, soe):
     """The drop-in, end to end: the REFERENCE'S OWN StaticAnalysis objects (AnalysisModel, PlainHandler, numberer,
     SparseGenCol/Row SOE and solver, NewtonRaphson, CTestNormDispIncr, LoadControl::newStep) run a load-controlled
@@ -231,6 +231,10 @@ def test_reference_newton_loop_drives_device_path(shape, numberer, soe):
             from modelspec import with_joint_offsets, with_pdelta
             return with_pdelta(with_joint_offsets(frame2d(2, 3, 2, lateral=15.0, gravity=-150.0) if shape == "frame2d_jntoffset"
                                                   else frame3d(1, 1, 2, ndiv=2, lateral=(18.0, 10.0), gravity=-90.0), seed=3))
+    elif shape == "frame2d_corot":
+        def mk():   # `geomTransf Corotational` (CorotCrdTransf2d) told from the others by dynamic_cast: heavy gravity, then the push
+            from modelspec import with_corot
+            return with_corot(frame2d(2, 3, 2, lateral=15.0, gravity=-150.0))
     elif shape == "frame2d_concrete01":
         def mk():   # Concrete01 core, Steel01 bars, bilinear Elastic cover read out of the reference's FiberSection2d
             from modelspec import steel01_elastic_frame
@@ -994,6 +998,58 @@ def test_joint_offsets_device_vs_oracle(pdelta, dim):
     for m in (O, D):
         m.set_rayleigh(0.3, 0.002, 0.001, 0.0015); m.set_transient(1.0, 50.0, 5000.0)
     v = rng.normal(0, 0.5, (spec.nn, ndf)); acc = rng.normal(0, 5.0, (spec.nn, ndf)); v[ids < 0] = 0; acc[ids < 0] = 0
+    O.set_vel_accel(v, acc); D.set_vel_accel(v, acc)
+    assert relerr(D.form_tangent(), O.form_tangent()) < BEAM_RTOL and relerr(D.form_unbalance(), O.form_unbalance()) < BEAM_RTOL
+
+
+@pytest.mark.parametrize("loads", [0, 1])
+def test_corotational_device_vs_oracle(loads):
+    """`geomTransf Corotational` on 2D force beams (CorotCrdTransf2d): large-displacement sway history (drifts of several
+    per cent), with and without element loads, commits, a revert to the last commit and a reset; a Newmark step with
+    mass-proportional damping at the end (stiffness-proportional Rayleigh terms on corotational beams are refused).
+    Device against the oracle (pinned to the reference's classes, tests/test_oracle.py)."""
+    from modelspec import with_corot, with_beam_gravity, with_beam_point_loads
+    rng = np.random.default_rng(33)
+    spec = frame2d(3, 2, 2, gravity=-80.0)
+    if loads: spec = with_beam_point_loads(with_beam_gravity(spec, w=-0.08, seed=1), P=-2.0, seed=2)
+    spec = with_corot(spec)
+    mass = np.zeros((spec.nn, 3)); mass[:, :2] = 0.05
+    O = OracleBackend(spec, 1, 0); O.set_mass(spec.node_tags, mass)
+    D = xb.DeviceModel.from_spec(spec, setup=False); D.set_mass(spec.node_tags, mass); D.setup(1, 0); D.to_device(0)
+    ids = O.ids()
+    H = spec.crd[:, 1].max(); h = spec.crd[:, 1] / H
+    pattern = rng.normal(0, 1.0, (spec.nn, 3)) * (2e-3, 1e-3, 2e-5)
+
+    def check():
+        assert relerr(D.form_tangent(), O.form_tangent()) < BEAM_RTOL and relerr(D.form_unbalance(), O.form_unbalance()) < BEAM_RTOL
+        for e in (0, O.ne // 2, O.ne - 1):
+            assert relerr(D.element_resid(e, 6), O.ele_resid(e, 6)) < BEAM_RTOL and relerr(D.element_tangent(e, 6), O.ele_tangent(e, 6)) < BEAM_RTOL
+    check()
+    for rep in range(2):
+        # (with element loads the force-based iteration gives up earlier on the way back: a milder history)
+        for s, a in enumerate([0.5, 1.0, 1.5, 2.5, 3.5, 3.0] if loads else [0.5, 1.5, 3.0, 5.0, 7.0, 5.5]):
+            u = np.zeros((spec.nn, 3)); u[:, 0] = a * h ** 1.5; u[:, 2] = -1.5 * a * h ** 0.5 / H
+            u += pattern * (a / 0.5); u[ids < 0] = 0
+            O.apply_load(0.2 * (s + 1)); assert O.set_trial_disp(u) == 0
+            D.apply_load(0.2 * (s + 1)); D.set_trial_disp(u); D.update()
+            check()
+            if s == 4:
+                O.revert(); D.revert_to_last_commit(); check()
+            else:
+                O.commit(); D.commit()
+        if rep == 0:      # `reset`, then the same history again: same numbers as the first time
+            A1 = D.form_tangent().copy()
+            O.revert_to_start(); D.revert_to_start(); check()
+        else:
+            assert np.array_equal(A1, D.form_tangent())
+    # far from the linear transformation's tangent
+    Dl = xb.DeviceModel.from_spec(frame2d(3, 2, 2, gravity=-80.0), 1, 0).to_device(0)
+    assert relerr(D.form_tangent(), Dl.form_tangent()) > 0.05
+    with pytest.raises(Exception):
+        D.set_rayleigh(0.3, 0.002, 0.0, 0.0)
+    for m in (O, D):
+        m.set_rayleigh(0.3, 0.0, 0.0, 0.0); m.set_transient(1.0, 50.0, 5000.0)
+    v = rng.normal(0, 0.5, (spec.nn, 3)); acc = rng.normal(0, 5.0, (spec.nn, 3)); v[ids < 0] = 0; acc[ids < 0] = 0
     O.set_vel_accel(v, acc); D.set_vel_accel(v, acc)
     assert relerr(D.form_tangent(), O.form_tangent()) < BEAM_RTOL and relerr(D.form_unbalance(), O.form_unbalance()) < BEAM_RTOL
 

@@ -634,3 +634,40 @@ def test_mixed_ndf_soil_frame_vs_live_reference(numberer, soe):
         assert close(O.form_tangent(), R.form_tangent(), 1e-11)
         assert close(O.form_unbalance(), R.form_unbalance(), 1e-11)
         O.commit(); R.commit()
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("loads", [0, 1])
+def test_corotational_transformation_vs_live_reference(loads):
+    """`geomTransf Corotational` on 2D force beams (CorotCrdTransf2d.cpp: basic deformations with the rigid-body rotation of
+    the chord taken out, exact basic-to-local force transformation, geometric stiffness): a sway history with LARGE
+    displacements (storey drifts of several per cent plus rotations), commits and a revert, against the reference's
+    classes -- assembled A and B, every element's tangent and resisting force"""
+    from modelspec import with_corot, with_beam_gravity, with_beam_point_loads
+    rng = np.random.default_rng(33)
+    def mk():
+        sp = frame2d(2, 2, 2, gravity=-80.0)
+        if loads: sp = with_beam_point_loads(with_beam_gravity(sp, w=-0.08, seed=1), P=-2.0, seed=2)
+        return sp
+    spec = with_corot(mk())
+    O, R, Rn = OracleBackend(spec, 1, 0), RefBackend(spec, 1, 0), RefBackend(mk(), 1, 0)
+    assert close(O.form_tangent(), R.form_tangent(), 1e-11)
+    H = spec.crd[:, 1].max(); h = spec.crd[:, 1] / H
+    pattern = rng.normal(0, 1.0, (spec.nn, 3)) * (2e-3, 1e-3, 2e-5)
+    differs = False
+    for s_, a in enumerate([0.5, 1.5, 3.0, 5.0, 7.0, 5.5]):
+        u = np.zeros((spec.nn, 3)); u[:, 0] = a * h ** 1.5; u[:, 2] = -1.5 * a * h ** 0.5 / H
+        u += pattern * (a / 0.5); u[O.ids() < 0] = 0
+        for m in (O, R, Rn):
+            m.apply_load(0.2 * (s_ + 1)); m.set_trial_disp(u)
+        Ar, Br = R.form_tangent(), R.form_unbalance()
+        assert close(O.form_tangent(), Ar, 1e-11) and close(O.form_unbalance(), Br, 1e-11)
+        for e in range(O.ne):
+            assert close(O.ele_resid(e, 6), R.ele_resid(e, 6), 1e-11) and close(O.ele_tangent(e, 6), R.ele_tangent(e, 6), 1e-11)
+        differs = differs or not close(Ar, Rn.form_tangent(), 1e-3)
+        if s_ == 4:
+            O.revert(); R.revert()
+            assert close(O.form_tangent(), R.form_tangent(), 1e-11) and close(O.form_unbalance(), R.form_unbalance(), 1e-11)
+        else:
+            O.commit(); R.commit(); Rn.commit()
+    assert differs

@@ -85,6 +85,9 @@ struct BeamView {
   // forces (ForceBeamColumn2d.cpp:402,526 refresh the transformation); 3D: ul17, ul28 as of the element's last update
   // (ForceBeamColumn3d never refreshes it), kept in ul [2][n]
   int pdelta;
+  // geomTransf Corotational (2D, CorotCrdTransf2d.cpp, no joint offsets): ul = [6][n], the basic deformations ub of the last
+  // crdTransf->update() (rows 0..2: the next update's ubpr) and of the last commit (rows 3..5: ubcommit)
+  int corot;
   const double* U;
   double* ul;
   // beam integration other than Lobatto (xb_set_beam_integration): [2 nip][n] locations then weights, fractions of L; null: Lobatto
@@ -462,6 +465,24 @@ __device__ __forceinline__ void crd2d_basic(double L, double cosT, double sinT, 
   ub[2] = ub[1] + ug[5] - ug[2];
 }
 
+// CorotCrdTransf2d::update (CorotCrdTransf2d.cpp:179-231, no offsets): local end displacements, the deformed chord
+// (compElemtLengthAndOrientWRTLocalSystem, :272-299), basic deformations with the chord's rigid rotation taken out
+// (transfLocalDisplsToBasic, :344-355).  cg = Ln, cosAlpha, sinAlpha; false: zero deformed length
+__device__ __forceinline__ bool corot2d_geom(double L, double cosT, double sinT, const double* ug, double* cg, double* ub) {
+  const double ul0 = cosT * ug[0] + sinT * ug[1], ul1 = cosT * ug[1] - sinT * ug[0];
+  const double ul3 = cosT * ug[3] + sinT * ug[4], ul4 = cosT * ug[4] - sinT * ug[3];
+  const double Lx = L + (ul3 - ul0), Ly = ul4 - ul1;
+  const double Ln = sqrt(Lx * Lx + Ly * Ly);
+  if (Ln == 0.0) return false;
+  const double cosA = Lx / Ln, sinA = Ly / Ln;
+  cg[0] = Ln; cg[1] = cosA; cg[2] = sinA;
+  if (ub) {
+    const double alpha = atan2(sinA, cosA);
+    ub[0] = Ln - L; ub[1] = ug[2] - alpha; ub[2] = ug[5] - alpha;
+  }
+  return true;
+}
+
 // getTangentStiff -> LinearCrdTransf2d::getGlobalStiffMatrix(kv); getResistingForce ->
 // getGlobalResistingForce(Se).  Rows of node a go to that node's slot (node-major storage).
 __global__ void __launch_bounds__(128) fbc2d_form_kernel(BeamView B, int want_k, int want_r, int transpose, BeamDyn dy) {
@@ -469,7 +490,69 @@ __global__ void __launch_bounds__(128) fbc2d_form_kernel(BeamView B, int want_k,
   if (e >= B.n) return;
   const long long n = B.n;
   const double L = B.geo[e], cosTheta = B.geo[n + e], sinTheta = B.geo[2 * n + e], oneOverL = 1.0 / L;
-  if (want_k) {
+  // geomTransf Corotational: the 2D element refreshes the transformation from the nodes' trial displacements before it
+  // forms its tangent or its forces (ForceBeamColumn2d.cpp:402,526)
+  double Ln = L, cosA = 1.0, sinA = 0.0;
+  if (B.corot) {
+    double ue[6], cg[3];
+    for (int j = 0; j < 3; j++) { ue[j] = B.U[(size_t)B.conn[e * 2] * 3 + j]; ue[3 + j] = B.U[(size_t)B.conn[e * 2 + 1] * 3 + j]; }
+    if (corot2d_geom(L, cosTheta, sinTheta, ue, cg, nullptr)) { Ln = cg[0]; cosA = cg[1]; sinA = cg[2]; }
+  }
+  if (want_k && B.corot) {
+    // CorotCrdTransf2d::getGlobalStiffMatrix (:525-644): kl = Tbl' kb Tbl + geometric stiffness (getGeomStiffMatrix, :908-953),
+    // then local -> global.  Transient without element damping: the whole tangent times c1 (host: no stiffness-proportional
+    // Rayleigh terms on corotational beams)
+    const double at = dy.k_on ? dy.at : 1.0;
+    double kb[9];
+    for (int i = 0; i < 9; i++) kb[i] = at * B.kv[i * n + e];
+    const double Tbl[3][6] = {{-cosA, -sinA, 0.0, cosA, sinA, 0.0},
+                              {-sinA / Ln, cosA / Ln, 1.0, sinA / Ln, -cosA / Ln, 0.0},
+                              {-sinA / Ln, cosA / Ln, 0.0, sinA / Ln, -cosA / Ln, 1.0}};
+    double tk[3][6], kl[6][6];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 6; j++) tk[i][j] = kb[i] * Tbl[0][j] + kb[i + 3] * Tbl[1][j] + kb[i + 6] * Tbl[2][j];
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+      for (int j = 0; j < 6; j++) kl[i][j] = Tbl[0][i] * tk[0][j] + Tbl[1][i] * tk[1][j] + Tbl[2][i] * tk[2][j];
+    {
+      const double s2 = sinA * sinA, c2 = cosA * cosA, cs = sinA * cosA;
+      const double f0 = at * B.Se[e] / Ln, f12 = at * (B.Se[n + e] + B.Se[2 * n + e]) / (Ln * Ln);
+      // the 2x2 block g on the translational dofs of a node: +g on (I,I), (J,J), -g on (I,J), (J,I)
+      const double g[2][2] = {{s2 * f0 - 2 * cs * f12, -cs * f0 + (c2 - s2) * f12}, {-cs * f0 + (c2 - s2) * f12, c2 * f0 + 2 * cs * f12}};
+#pragma unroll
+      for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) { kl[i][j] += g[i][j]; kl[3 + i][3 + j] += g[i][j]; kl[i][3 + j] -= g[i][j]; kl[3 + i][j] -= g[i][j]; }
+    }
+    double kg[6][6];
+    const double S2 = sinTheta * sinTheta, C2 = cosTheta * cosTheta, CS = sinTheta * cosTheta;
+#pragma unroll
+    for (int bi = 0; bi < 2; bi++)
+#pragma unroll
+      for (int bj = 0; bj < 2; bj++) {
+        const int r = 3 * bi, c = 3 * bj;
+        const double k11 = kl[r][c], k12 = kl[r][c + 1], k13 = kl[r][c + 2], k21 = kl[r + 1][c], k22 = kl[r + 1][c + 1], k23 = kl[r + 1][c + 2],
+                     k31 = kl[r + 2][c], k32 = kl[r + 2][c + 1], k33 = kl[r + 2][c + 2];
+        kg[r][c] = C2 * k11 + S2 * k22 - CS * (k21 + k12);
+        kg[r + 1][c] = C2 * k21 - S2 * k12 + CS * (k11 - k22);
+        kg[r + 2][c] = cosTheta * k31 - sinTheta * k32;
+        kg[r][c + 1] = C2 * k12 - S2 * k21 + CS * (k11 - k22);
+        kg[r + 1][c + 1] = C2 * k22 + S2 * k11 + CS * (k21 + k12);
+        kg[r + 2][c + 1] = sinTheta * k31 + cosTheta * k32;
+        kg[r][c + 2] = cosTheta * k13 - sinTheta * k23;
+        kg[r + 1][c + 2] = sinTheta * k13 + cosTheta * k23;
+        kg[r + 2][c + 2] = k33;
+      }
+    for (int a = 0; a < 2; a++) {
+      const long long d = B.kdst[e * 2 + a];
+      double* base = d >= 0 ? B.KeN + d : B.sendK + (-d - 1);
+      for (int p = 0; p < 3; p++)
+        for (int c = 0; c < 6; c++) base[p * B.cps + c] = transpose ? kg[c][a * 3 + p] : kg[a * 3 + p][c];
+    }
+  } else if (want_k) {
     double kb[9];
     for (int i = 0; i < 9; i++) kb[i] = B.kv[i * n + e];
     if (dy.k_on) {
@@ -553,6 +636,11 @@ __global__ void __launch_bounds__(128) fbc2d_form_kernel(BeamView B, int want_k,
     }
     const double V = oneOverL * (q1 + q2);
     double pl[6] = {-q0, V, q1, q0, -V, q2};
+    if (B.corot) {   // CorotCrdTransf2d::getGlobalResistingForce (:483-522): pl = Tbl' pb on the deformed chord
+      const double Vc = (q1 + q2) / Ln;
+      pl[0] = -cosA * q0 - sinA * Vc; pl[1] = -sinA * q0 + cosA * Vc; pl[2] = q1;
+      pl[3] = cosA * q0 + sinA * Vc; pl[4] = sinA * q0 - cosA * Vc; pl[5] = q2;
+    }
     if (B.wl != nullptr && B.loads_on) {   // computeReactions (ForceBeamColumn2d.cpp:407-425) into LinearCrdTransf2d's pl
       const double wy = B.wl[e] * B.lam, wa = B.wl[2 * n + e] * B.lam;
       double p0[3] = {0.0, 0.0, 0.0};
@@ -1034,8 +1122,20 @@ __global__ void __launch_bounds__(128, XB_FBC_SEC_OCC) fbc2d_update_sec_kernel(B
       for (int j = 0; j < 3; j++) { ug[a * 3 + j] = U[(size_t)nd * 3 + j]; dug[a * 3 + j] = DU[(size_t)nd * 3 + j]; }
     }
     fbc2d_end_disp(B, e, ug); fbc2d_end_disp(B, e, dug);
-    crd2d_basic(L, cosT, sinT, ug, v);
-    crd2d_basic(L, cosT, sinT, dug, dv);
+    if (B.corot) {   // crdTransf->update(); getBasicIncrDeltaDisp = ub - ubpr (CorotCrdTransf2d.cpp:364-371), before any early return
+      double cg[3];
+      if (!corot2d_geom(L, cosT, sinT, ug, cg, v)) { if (i == 0) atomicExch(fail, 2); return; }
+#pragma unroll
+      for (int q = 0; q < 3; q++) dv[q] = v[q] - B.ul[(size_t)q * n + e];
+      __syncwarp(gmask);      // every lane of the element has read ubpr
+      if (i == 0) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) B.ul[(size_t)q * n + e] = v[q];
+      }
+    } else {
+      crd2d_basic(L, cosT, sinT, ug, v);
+      crd2d_basic(L, cosT, sinT, dug, dv);
+    }
   }
   const int initialFlag = B.iflag[e];
   // numEleLoads > 0 for THIS element (ForceBeamColumn2d.cpp:575)

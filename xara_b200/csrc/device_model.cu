@@ -1969,7 +1969,7 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
       const double det = k0[0] * k0[3] - k0[2] * k0[1];
       std::vector<double> fs0 = {k0[3] / det, -k0[1] / det, -k0[2] / det, k0[0] / det};
       b.agg = sd.agg ? 1 : 0;
-      b.pdelta = g.transf == 1 ? 1 : 0; b.U = m->dU; b.ul = nullptr;
+      b.pdelta = g.transf == 1 ? 1 : 0; b.corot = g.transf == 2 ? 1 : 0; b.U = m->dU; b.ul = nullptr;
       b.off = nullptr;
       {   // rigid joint offsets, SoA [4][n] (2D) / [6][n] (3D); null when the batch has none
         const int no = b3 ? 6 : 4, at = b3 ? 15 : 13;
@@ -1984,6 +1984,10 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
         for (long long e = 0; e < ne; e++)
           for (int q = 0; q < 2 * g.nip; q++) rs[(size_t)q * ne + e] = g.rule[(size_t)e * 2 * g.nip + q];
         double* dr = nullptr; CU(dev_upload(m, &dr, rs)); b.rule = dr;
+      }
+      if (b.corot) {   // ub of the last update and of the last commit
+        if (b.off) return fail(XB_ERR_UNSUPPORTED, "forceBeamColumn: geomTransf Corotational with joint offsets is outside the device path");
+        CU(dev_alloc(m, &b.ul, (size_t)6 * std::max<long long>(ne, 1))); CU(cudaMemset(b.ul, 0, sizeof(double) * 6 * std::max<long long>(ne, 1)));
       }
       if (b.pdelta && b3) { CU(dev_alloc(m, &b.ul, (size_t)2 * std::max<long long>(ne, 1))); CU(cudaMemset(b.ul, 0, sizeof(double) * 2 * std::max<long long>(ne, 1))); }
       if (sd.agg) {   // SectionAggregator::getInitialFlexibility, SectionAggregator.cpp:454-479: 1 / initial tangent on the diagonal
@@ -2259,6 +2263,9 @@ static int apply_rayleigh(xb_model* m) {
 
 int xb_set_rayleigh(xb_model* m, double alphaM, double betaK, double betaK0, double betaKc) {
   if (!m) return fail(XB_ERR_ARG, "null model");
+  if (betaK != 0.0 || betaK0 != 0.0 || betaKc != 0.0)
+    for (const auto& g : m->h.groups)
+      if (g.transf == 2) return fail(XB_ERR_UNSUPPORTED, "rayleigh: stiffness-proportional damping on corotational beams is outside the device path");
   m->rayM = alphaM; m->rayK = betaK; m->rayK0 = betaK0; m->rayKc = betaKc;
   m->alphaM = alphaM; m->av.alphaM = alphaM;      // Domain::setRayleighDampingFactors also sets every node's factor
   return apply_rayleigh(m);
@@ -2901,6 +2908,7 @@ int xb_commit(xb_model* m) {
       CU(cudaMemcpyAsync(b.vsc, b.vs, sizeof(double) * b.nip * b.ord * b.n, cudaMemcpyDeviceToDevice, m->stream));
       CU(cudaMemcpyAsync(b.Sec, b.Se, sizeof(double) * b.nb * b.n, cudaMemcpyDeviceToDevice, m->stream));
       CU(cudaMemcpyAsync(b.kvc, b.kv, sizeof(double) * b.nb * b.nb * b.n, cudaMemcpyDeviceToDevice, m->stream));
+      if (b.corot) CU(cudaMemcpyAsync(b.ul + (size_t)3 * b.n, b.ul, sizeof(double) * 3 * b.n, cudaMemcpyDeviceToDevice, m->stream));   // CorotCrdTransf2d::commitState
       // Element::commitState: *Kc = getTangentStiff()
       if (b.kvK) {
         CU(cudaMemcpyAsync(b.kvK, b.kv, sizeof(double) * b.nb * b.nb * b.n, cudaMemcpyDeviceToDevice, m->stream));
@@ -2944,6 +2952,8 @@ int xb_revert_to_last_commit(xb_model* m) {
       CU(cudaMemcpyAsync(d.b.ft, d.b.fc, sizeof(double) * d.fib_doubles, cudaMemcpyDeviceToDevice, m->stream));
       if (d.kind == XB_ELE_FORCEBEAMCOLUMN3D) fbc3d_revert_kernel<<<(unsigned)((d.b.n + 63) / 64), 64, 0, m->stream>>>(d.b);
       else fbc2d_revert_kernel<<<(unsigned)((d.b.n + 63) / 64), 64, 0, m->stream>>>(d.b);
+      // CorotCrdTransf2d::revertToLastCommit: ub = ubcommit (its update() at the reverted nodes gives the same)
+      if (d.b.corot) CU(cudaMemcpyAsync(d.b.ul, d.b.ul + (size_t)3 * d.b.n, sizeof(double) * 3 * d.b.n, cudaMemcpyDeviceToDevice, m->stream));
       m->launches++;
     }
   CU(cudaGetLastError());
@@ -2971,6 +2981,7 @@ int xb_revert_to_start(xb_model* m) {
       for (double* q : {b.vs, b.vsc, b.Ssr}) CU(cudaMemsetAsync(q, 0, sizeof(double) * b.nip * ord * ne, m->stream));
       CU(cudaMemsetAsync(b.fs, 0, sizeof(double) * b.nip * ord * ord * ne, m->stream));
       CU(cudaMemsetAsync(b.iflag, 0, sizeof(int) * ne, m->stream));
+      if (b.corot) CU(cudaMemsetAsync(b.ul, 0, sizeof(double) * 6 * ne, m->stream));      // CorotCrdTransf2d::revertToStart
       const long long tot = (long long)d.fib_nrec * b.n;
       fiber_init_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, m->stream>>>(b.n, d.fib_nrec, d.fib_ic, d.fib_it, d.fib_per_sec, b.fc, b.ft);
       m->launches++;

@@ -170,7 +170,7 @@ int HostModel::add_elements(int kind, int n, const int* tags, const int* conn, c
       // geomTransf: the parameter behind the ones above (2D: par[3], 3D: par[6]) when the caller's rows are that long
       const int tpos = b3 ? 6 : 3;
       const int transf = par_stride > tpos ? (int)p[tpos] : 0;
-      if (transf != 0 && transf != 1) { err = "forceBeamColumn: geomTransf is 0 (Linear) or 1 (PDelta); Corotational is outside the device path"; return XB_ERR_UNSUPPORTED; }
+      if (transf != 0 && transf != 1 && !(transf == 2 && !b3)) { err = "forceBeamColumn: geomTransf is 0 (Linear), 1 (PDelta) or -- 2D -- 2 (Corotational); a 3D corotational transformation is outside the device path"; return XB_ERR_UNSUPPORTED; }
       if (i == 0) { g.sec = sidx; g.nip = (int)p[0]; g.max_iters = (int)p[1]; g.tol = p[2]; g.transf = transf; }
       else if (sidx != g.sec || (int)p[0] != g.nip || (int)p[1] != g.max_iters || p[2] != g.tol || transf != g.transf) {
         err = "forceBeamColumn: one section / nIP / maxIters / tol / geomTransf per xb_add_elements call"; return XB_ERR_UNSUPPORTED;

@@ -64,7 +64,7 @@ struct Group {
   std::vector<double> par;   // [n][npar]
   // forceBeamColumn batches: one fibre section, nIP Lobatto points, element iteration controls
   int sec = -1, nip = 0, max_iters = 10;
-  int transf = 0;            // geomTransf of the batch: 0 Linear, 1 PDelta
+  int transf = 0;            // geomTransf of the batch: 0 Linear, 1 PDelta, 2 Corotational (2D)
   std::vector<double> rule;  // forceBeamColumn: per element nip locations then nip weights (xb_set_beam_integration); empty: Lobatto
   std::vector<uint8_t> rule_set;
   double tol = 1e-12;
