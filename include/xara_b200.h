@@ -164,6 +164,11 @@ int xb_set_beam_integration(xb_model*, int n, const int* ele_tags, int nip, cons
  * One point load per element (beside its uniform loads, whose intensities add up); a load with xL outside [0, 1] is ignored, as the
  * element does. */
 int xb_add_beam_point_loads(xb_model*, int n, const int* ele_tags, const double* p);
+/* `eleLoad -ele tags -type -beamUniform wya wyb? ... aOverL bOverL` on part of a 2D element (Beam2dPartialUniformLoad ->
+ * ForceBeamColumn2d.cpp:426-443 reactions, :1073-1137 section forces): a trapezoidal load between a = aOverL L and
+ * b = bOverL L; p is [n][6] = wTrans_a, wTrans_b, wAxial_a, wAxial_b, aOverL, bOverL (the load's getData order).  One such
+ * load per element, beside its uniform and point loads; 0 <= aOverL < bOverL <= 1; 2D elements only (XB_ERR_UNSUPPORTED). */
+int xb_add_beam_partial_loads(xb_model*, int n, const int* ele_tags, const double* p);
 
 /* `mass` command: Node::setMass with a diagonal matrix (domain/node/Node.h:127); mass is [n][ndf].
  * Element masses come from the nDMaterial density (J2Plasticity par[7], ElasticIsotropic par[2]): stdBrick forms
@@ -266,7 +271,7 @@ int xb_update(xb_model*);
 int xb_apply_load(xb_model*, double lambda);
 /* `loadConst` (Domain::setLoadConstant, domain/domain/Domain.cpp:1814; LoadPattern::setLoadConstant, domain/pattern/
  * LoadPattern.cpp): the nodal loads applied so far stay at the current load factor; the reference load vector is
- * emptied for the next pattern; the beam element loads (xb_add_beam_uniform_loads / xb_add_beam_point_loads, which all
+ * emptied for the next pattern; the beam element loads (xb_add_beam_uniform_loads / xb_add_beam_point_loads / xb_add_beam_partial_loads, which all
  * belong to the patterns defined before the set-up) keep that factor too -- the gravity-then-pushover sequence of an RC
  * frame.  The caller sets the new domain time with xb_apply_load (`loadConst -time 0.0`). */
 int xb_load_const(xb_model*);

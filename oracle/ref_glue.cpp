@@ -372,6 +372,11 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
             if (xb_add_beam_point_loads(x, 1, &et, p4) < 0) { G.err = xb_last_error(); return -7; }
             continue;
           }
+          else if (type == LOAD_TAG_Beam2dPartialUniformLoad && dynamic_cast<ForceBeamColumn2d*>(ele)) {   // wTa, wTb, wAa, wAb, a/L, b/L
+            const double p6[6] = {data(0), data(1), data(2), data(3), data(4), data(5)};
+            if (xb_add_beam_partial_loads(x, 1, &et, p6) < 0) { G.err = xb_last_error(); return -7; }
+            continue;
+          }
           else { G.err = "glue: ElementalLoad other than -beamUniform / -beamPoint on a forceBeamColumn: outside the device path"; return -7; }
           if (xb_add_beam_uniform_loads(x, 1, &et, w) < 0) { G.err = xb_last_error(); return -7; }
         } }

@@ -88,6 +88,7 @@
 #include <Beam2dUniformLoad.h>
 #include <Beam3dUniformLoad.h>
 #include <Beam2dPointLoad.h>
+#include <Beam2dPartialUniformLoad.h>
 #include <Beam3dPointLoad.h>
 #include <BandGenLinSOE.h>
 #include <BandGenLinSolver.h>
@@ -451,6 +452,19 @@ int ref_add_beam_point_load(void* h, int eleTag, double Py, double Pz, double N,
   }
   ElementalLoad* el = (m->ndm == 2) ? (ElementalLoad*)new Beam2dPointLoad(20000 + m->nloads++, Py, aOverL, eleTag, N)
                                     : (ElementalLoad*)new Beam3dPointLoad(20000 + m->nloads++, Py, Pz, aOverL, eleTag, N);
+  return m->domain->addElementalLoad(el, 1) ? 0 : -1;
+}
+
+// `eleLoad -ele tag -type -beamUniform wya wyb ... aOverL bOverL` (2D, trapezoidal over part of the element) in pattern 1
+int ref_add_beam_partial_load(void* h, int eleTag, const double* q) {
+  RefModel* m = (RefModel*)h;
+  if (m->ndm != 2) return -2;
+  if (m->domain->getLoadPattern(m->cur_pattern) == nullptr) {
+    LoadPattern* lp = new LoadPattern(m->cur_pattern);
+    lp->setTimeSeries(new LinearSeries());
+    m->domain->addLoadPattern(lp);
+  }
+  ElementalLoad* el = new Beam2dPartialUniformLoad(30000 + m->nloads++, q[0], q[1], q[2], q[3], q[4], q[5], eleTag);
   return m->domain->addElementalLoad(el, 1) ? 0 : -1;
 }
 

@@ -861,6 +861,9 @@ typedef struct {
   int has_load, numEleLoads; double w[3], loadFactor;
   /* `eleLoad -beamPoint Py xL [N]` (Beam2dPointLoad): pt = {Py, -, N, aOverL} */
   int has_point; double pt[4];
+  /* `eleLoad -beamUniform` over part of the element (Beam2dPartialUniformLoad): pq = wTrans_a, wTrans_b, wAxial_a,
+   * wAxial_b, aOverL, bOverL (getData's order) */
+  int has_partial; double pq[6];
   /* beam integration other than Lobatto: the section locations and weights the element's BeamIntegration object returns
    * (getSectionLocations / getSectionWeights), handed over by the caller (orc_set_beam_integration) */
   int user_rule; double rxi[ORC_MAXSEC], rwt[ORC_MAXSEC];
@@ -903,6 +906,44 @@ static void crd2d_basic(const OrcBeam* b, const double* ug, double* ub) {
   ub[0] = -b->cosTheta * ug[0] - b->sinTheta * ug[1] + b->cosTheta * ug[3] + b->sinTheta * ug[4];
   ub[1] = -sl * ug[0] + cl * ug[1] + ug[2] + sl * ug[3] - cl * ug[4];
   ub[2] = ub[1] + ug[5] - ug[2];
+}
+
+/* Beam2dPartialUniformLoad: reactions (computeReactions, ForceBeamColumn2d.cpp:426-443) and section forces at x
+ * (computeSectionForces, :1073-1137) */
+static void beam2_partial_p0(const OrcBeam* bm, double* p0) {
+  if (!bm->has_partial) return;
+  const double lf = bm->loadFactor, L = bm->L;
+  double waa = bm->pq[2] * lf, wab = bm->pq[3] * lf, wya = bm->pq[0] * lf, wyb = bm->pq[1] * lf;
+  double a = bm->pq[4] * L, b = bm->pq[5] * L;
+  p0[0] -= waa * (b - a) + 0.5 * (wab - waa) * (b - a);
+  double Fy = wya * (b - a);
+  double c = a + 0.5 * (b - a);
+  p0[1] -= Fy * (1 - c / L);
+  p0[2] -= Fy * c / L;
+  Fy = 0.5 * (wyb - wya) * (b - a);
+  c = a + 2.0 / 3.0 * (b - a);
+  p0[1] -= Fy * (1 - c / L);
+  p0[2] -= Fy * c / L;
+}
+static void beam2_partial_sp(const OrcBeam* bm, double x, double* Ss) {
+  if (!bm->has_partial) return;
+  const double lf = bm->loadFactor, L = bm->L;
+  double waa = bm->pq[2] * lf, wab = bm->pq[3] * lf, wya = bm->pq[0] * lf, wyb = bm->pq[1] * lf;
+  double a = bm->pq[4] * L, b = bm->pq[5] * L;
+  double Fa = waa * (b - a) + 0.5 * (wab - waa) * (b - a);
+  double Fy = wya * (b - a);
+  double c = a + 0.5 * (b - a);
+  double VI = Fy * (1 - c / L), VJ = Fy * c / L;
+  Fy = 0.5 * (wyb - wya) * (b - a);
+  c = a + 2.0 / 3.0 * (b - a);
+  VI += Fy * (1 - c / L); VJ += Fy * c / L;
+  if (x <= a) { Ss[0] += Fa; Ss[1] -= VI * x; }
+  else if (x >= b) Ss[1] += VJ * (x - L);
+  else {
+    double wx = wya + (wyb - wya) / (b - a) * (x - a);
+    Ss[0] += Fa - waa * (x - a) - 0.5 * (wab - waa) / (b - a) * (x - a) * (x - a);
+    Ss[1] += -VI * x + wya * (x - a) * 0.5 * (x - a) + 0.5 * (wx - wya) * (x - a) * (x - a) / 3.0;
+  }
 }
 
 /* CorotCrdTransf2d::update (CorotCrdTransf2d.cpp:179-231, no offsets): local end displacements, the deformed chord
@@ -992,6 +1033,7 @@ static int beam_update(OrcBeam* b, const double* ug_, const double* dug_) {
               if (x <= a) { Ss[0] += N; Ss[1] -= x * V1; }
               else Ss[1] -= (L - x) * V2;
             }
+            beam2_partial_sp(b, x, Ss);
           }
           dSs[0] = Ss[0] - SsrSub[i][0]; dSs[1] = Ss[1] - SsrSub[i][1];
           const double* fuse;
@@ -1111,6 +1153,7 @@ static void beam_form_pdelta(const OrcBeam* b, double* K, double* R) {
       double V1 = P * (1.0 - aOverL), V2 = P * aOverL;
       p0[0] -= N; p0[1] -= V1; p0[2] -= V2;
     }
+    beam2_partial_p0(b, p0);
   }
   pl[0] += p0[0]; pl[1] += p0[1]; pl[4] += p0[2];
   double NoverL = ul14 * q0 * oneOverL;                 /* leaning-column effect, :532-535 */
@@ -1191,6 +1234,7 @@ static void beam_form_corot(const OrcBeam* b, double* K, double* R) {
       double V1 = P * (1.0 - aOverL), V2 = P * aOverL;
       p0[0] -= N; p0[1] -= V1; p0[2] -= V2;
     }
+    beam2_partial_p0(b, p0);
   }
   pl[0] += p0[0]; pl[1] += p0[1]; pl[4] += p0[2];      /* member loads in the local system, :493-497 */
   R[0] = cosTheta * pl[0] - sinTheta * pl[1];
@@ -1252,6 +1296,7 @@ static void beam_form_end(const OrcBeam* b, double* K, double* R) {
       double V1 = P * (1.0 - aOverL), V2 = P * aOverL;
       p0[0] -= N; p0[1] -= V1; p0[2] -= V2;
     }
+    beam2_partial_p0(b, p0);
   }
   pl[0] += p0[0]; pl[1] += p0[1]; pl[4] += p0[2];
   R[0] = cosTheta * pl[0] - sinTheta * pl[1];
@@ -2461,7 +2506,7 @@ void orc_apply_load(void* h, double lambda) {
   const double lf = m->ele_loads_const ? m->ele_lambda : lambda;
   for (int e = 0; e < m->ne; e++) {
     OrcEle* el = &m->ele[e];
-    if (el->kind == ORC_ELE_FBC2D && (el->beam->has_load || el->beam->has_point)) { el->beam->numEleLoads = el->beam->has_load + el->beam->has_point; el->beam->loadFactor = lf; }
+    if (el->kind == ORC_ELE_FBC2D && (el->beam->has_load || el->beam->has_point || el->beam->has_partial)) { el->beam->numEleLoads = el->beam->has_load + el->beam->has_point + el->beam->has_partial; el->beam->loadFactor = lf; }
     if (el->kind == ORC_ELE_FBC3D && (el->beam3->has_load || el->beam3->has_point)) { el->beam3->numEleLoads = el->beam3->has_load + el->beam3->has_point; el->beam3->loadFactor = lf; }
   }
 }
@@ -2525,6 +2570,20 @@ int orc_add_beam_point_load(void* h, int ele_tag, double Py, double Pz, double N
     if (el->kind == ORC_ELE_FBC2D) { if (el->beam->has_point) return -2; el->beam->has_point = 1; el->beam->pt[0] = Py; el->beam->pt[1] = 0.0; el->beam->pt[2] = N; el->beam->pt[3] = aOverL; return 0; }
     if (el->kind == ORC_ELE_FBC3D) { if (el->beam3->has_point) return -2; el->beam3->has_point = 1; el->beam3->pt[0] = Py; el->beam3->pt[1] = Pz; el->beam3->pt[2] = N; el->beam3->pt[3] = aOverL; return 0; }
     return -3;
+  }
+  return -1;
+}
+
+/* `eleLoad -beamUniform` over part of a 2D element (Beam2dPartialUniformLoad): q = wTrans_a, wTrans_b, wAxial_a, wAxial_b, aOverL, bOverL */
+int orc_add_beam_partial_load(void* h, int ele_tag, const double* q) {
+  OrcModel* m = (OrcModel*)h;
+  for (int e = 0; e < m->ne; e++) {
+    OrcEle* el = &m->ele[e];
+    if (el->tag != ele_tag) continue;
+    if (el->kind != ORC_ELE_FBC2D) return -3;
+    if (el->beam->has_partial) return -2;
+    el->beam->has_partial = 1; memcpy(el->beam->pq, q, sizeof el->beam->pq);
+    return 0;
   }
   return -1;
 }
@@ -2889,6 +2948,7 @@ int orc_revert_to_start(void* h) {
       el->beam->has_load = keep.has_load; el->beam->numEleLoads = keep.numEleLoads; el->beam->loadFactor = keep.loadFactor;
       memcpy(el->beam->w, keep.w, sizeof keep.w);
       el->beam->has_point = keep.has_point; memcpy(el->beam->pt, keep.pt, sizeof keep.pt);
+      el->beam->has_partial = keep.has_partial; memcpy(el->beam->pq, keep.pq, sizeof keep.pq);
       el->beam->user_rule = keep.user_rule; memcpy(el->beam->rxi, keep.rxi, sizeof keep.rxi); memcpy(el->beam->rwt, keep.rwt, sizeof keep.rwt);
     } else if (el->kind == ORC_ELE_FBC3D) {
       for (int i = 0; i < el->beam3->nip; i++) free(el->beam3->sec[i].mat);

@@ -57,6 +57,7 @@ class ModelSpec:
     sections: list = field(default_factory=list)    # (tag, y[nf], A[nf], uniaxial tags[nf])
     beam_loads: list = field(default_factory=list)  # `eleLoad -beamUniform`: (element tag, wy, wz, wa) in the Linear pattern
     beam_point_loads: list = field(default_factory=list)  # `eleLoad -beamPoint`: (element tag, Py, Pz, N, xL)
+    beam_partial_loads: list = field(default_factory=list)  # 2D partial `-beamUniform`: (element tag, wya, wyb, waa, wab, aOverL, bOverL)
     beam_integration: int = 0          # forceBeamColumn -integration: 0 Lobatto, 1 Legendre, 2 Radau, 3 NewtonCotes, 4 Trapezoidal
     beam_rules: tuple = None           # (element tags, xi [n][nip], wt [n][nip]) as the reference's BeamIntegration returns them
     node_ndf: dict = field(default_factory=dict)    # node tag -> dofs, for nodes created under another `model -ndf` (< the model's ndf)
@@ -312,6 +313,23 @@ def with_beam_rho(spec, rho=2.0e-3):
     for g in spec.groups:
         if g.kind == ELE_FBC2D: g.par[:, 4] = rho
         elif g.kind == ELE_FBC3D: g.par[:, 7] = rho
+    return spec
+
+
+def with_beam_partial_loads(spec, w=-0.12, seed=0):
+    """a trapezoidal `eleLoad -beamUniform wya wyb waa wab aOverL bOverL` (Beam2dPartialUniformLoad) over a random part of
+    every girder of a 2D frame -- section points fall before, inside and behind the loaded stretch"""
+    rng = np.random.default_rng(seed)
+    ix = {int(t): i for i, t in enumerate(spec.node_tags)}
+    out = []
+    for g in spec.groups:
+        for t, c in zip(g.tags, g.conn):
+            a, b = spec.crd[ix[int(c[0])]], spec.crd[ix[int(c[1])]]
+            if abs(a[1] - b[1]) > 1e-9: continue          # a column
+            aL = rng.uniform(0.05, 0.45); bL = rng.uniform(0.55, 0.95)
+            wa = w * rng.uniform(0.6, 1.4); wb = w * rng.uniform(0.6, 1.4)
+            out.append((int(t), wa, wb, 0.05 * wa, -0.03 * wb, aL, bL))
+    spec.beam_partial_loads = out
     return spec
 
 
@@ -755,6 +773,9 @@ class OracleBackend(_Backend):
         L.orc_add_beam_point_load.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_double] * 4
         for t, py, pz, pn, xl in spec.beam_point_loads:
             assert L.orc_add_beam_point_load(self.h, int(t), float(py), float(pz), float(pn), float(xl)) == 0
+        L.orc_add_beam_partial_load.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        for t, *q in spec.beam_partial_loads:
+            assert L.orc_add_beam_partial_load(self.h, int(t), _p(np.array(q, np.float64))) == 0
         # soe 2 / 3 / 4: BandGeneral / ProfileSPD / Umfpack -- the column graph, then the SOE's own storage on top of it
         self.soe = soe
         self.neq = L.orc_setup(self.h, numberer, soe if soe in (0, 1) else 0)
@@ -990,6 +1011,10 @@ class RefBackend(_Backend):
             for row in spec.loads:
                 v = np.ascontiguousarray(row[1:], np.float64)
                 assert L.ref_add_load(self.h, int(row[0]), _p(v)) == 0
+        if spec.beam_partial_loads:
+            L.ref_add_beam_partial_load.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+            for t, *q in spec.beam_partial_loads:
+                assert L.ref_add_beam_partial_load(self.h, int(t), _p(np.array(q, np.float64))) == 0
         if spec.beam_point_loads:
             L.ref_add_beam_point_load.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_double] * 4
             for t, py, pz, pn, xl in spec.beam_point_loads:

@@ -134,8 +134,7 @@ def test_oracle_vs_live_reference(mat, numberer, soe):
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
-@pytest.mark.parametrize("loads", ["uniform", "point", "both"])
-@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("dim,loads", [(2, "uniform"), (2, "point"), (2, "both"), (3, "uniform"), (3, "point"), (3, "both"), (2, "partial"), (2, "all")])
 def test_beam_uniform_element_loads_vs_live_reference(dim, loads):
     """`eleLoad -beamPoint` (Beam2d/3dPointLoad: ForceBeamColumn2d.cpp:442-455, 1138-1181; ForceBeamColumn3d.cpp:457-475,
     1314-1373; points between and beyond the Lobatto sections) and `eleLoad -beamUniform` on force beams (ForceBeamColumn2d.cpp:407,1034 / ForceBeamColumn3d.cpp:419,1197): the section
@@ -145,11 +144,16 @@ def test_beam_uniform_element_loads_vs_live_reference(dim, loads):
     from modelspec import with_beam_gravity, with_beam_point_loads
     rng = np.random.default_rng(5)
     spec = frame2d(2, 2, 2) if dim == 2 else frame3d(1, 1, 2)
-    if loads != "point": spec = with_beam_gravity(spec, seed=3)
-    if loads != "uniform": spec = with_beam_point_loads(spec, seed=2)
+    # "partial" / "all" (2D): a trapezoidal load over part of every girder (Beam2dPartialUniformLoad, ForceBeamColumn2d.cpp:426-443,
+    # 1073-1137), alone and on top of the other two kinds
+    if loads not in ("point", "partial"): spec = with_beam_gravity(spec, seed=3)
+    if loads not in ("uniform", "partial"): spec = with_beam_point_loads(spec, seed=2)
+    if loads in ("partial", "all"):
+        from modelspec import with_beam_partial_loads
+        spec = with_beam_partial_loads(spec, seed=4)
     if loads == "both":       # a second uniform load (live on top of dead) on the loaded elements
         spec.beam_loads = spec.beam_loads + [(t, 0.4 * wy, 0.3 * wz, -0.5 * wa) for t, wy, wz, wa in spec.beam_loads[::2]]
-    assert len(spec.beam_loads) + len(spec.beam_point_loads) >= 4
+    assert len(spec.beam_loads) + len(spec.beam_point_loads) + len(spec.beam_partial_loads) >= 4
     O, R = OracleBackend(spec, 1, 0), RefBackend(spec, 1, 0)
     sc = np.asarray((0.02, 0.02, 2e-4) if dim == 2 else (0.015, 0.015, 0.003, 1e-4, 1e-4, 1e-4))
     u = np.zeros((spec.nn, spec.ndf))

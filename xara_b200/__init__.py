@@ -72,6 +72,7 @@ def _load():
         "xb_add_elements": (i32, [vp, i32, i32, vp, vp, vp, vp, i32]),
         "xb_add_beam_uniform_loads": (i32, [vp, i32, vp, vp]),
         "xb_add_beam_point_loads": (i32, [vp, i32, vp, vp]),
+        "xb_add_beam_partial_loads": (i32, [vp, i32, vp, vp]),
         "xb_set_beam_integration": (i32, [vp, i32, vp, i32, vp, vp]),
         "xb_add_nodal_loads": (i32, [vp, i32, vp, vp]),
         "xb_set_nodal_mass": (i32, [vp, i32, vp, vp]),
@@ -251,6 +252,11 @@ class DeviceModel:
         ele_tags, p = _i32(ele_tags), _f64(p)
         self._ck(lib.xb_add_beam_point_loads(self._h, len(ele_tags), _ptr(ele_tags), _ptr(p)))
 
+    def add_beam_partial_loads(self, ele_tags, p):
+        """`eleLoad -beamUniform` over part of a 2D element: p [n][6] = wya, wyb, waa, wab, aOverL, bOverL"""
+        ele_tags, p = _i32(ele_tags), _f64(p)
+        self._ck(lib.xb_add_beam_partial_loads(self._h, len(ele_tags), _ptr(ele_tags), _ptr(p)))
+
     def add_beam_uniform_loads(self, ele_tags, w):
         """`eleLoad -beamUniform`: w [n][3] = wy, wz, wa per element (Linear pattern)"""
         ele_tags, w = _i32(ele_tags), _f64(w)
@@ -302,6 +308,9 @@ class DeviceModel:
         bp = getattr(spec, "beam_point_loads", [])
         if bp:
             m.add_beam_point_loads([t for t, *_ in bp], np.array([q for _, *q in bp], np.float64))
+        bq = getattr(spec, "beam_partial_loads", [])
+        if bq:
+            m.add_beam_partial_loads([t for t, *_ in bq], np.array([q for _, *q in bq], np.float64))
         bl = getattr(spec, "beam_loads", [])
         if bl:
             m.add_beam_uniform_loads([t for t, *_ in bl], np.array([w for _, *w in bl], np.float64))

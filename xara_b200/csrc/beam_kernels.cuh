@@ -80,6 +80,7 @@ struct BeamView {
   double lam;
   int loads_on;
   int has_point;
+  int has_partial;             // 2D: rows 7..12 of wl hold Beam2dPartialUniformLoad's wya, wyb, waa, wab, aOverL, bOverL
   // geomTransf PDelta (PDeltaCrdTransf2d.cpp / PDeltaCrdTransf3d.cpp): geometric stiffness N/L and leaning-column shear.
   // 2D: the relative transverse displacement is taken from the trial displacements U whenever the element forms its
   // forces (ForceBeamColumn2d.cpp:402,526 refresh the transformation); 3D: ul17, ul28 as of the element's last update
@@ -652,6 +653,17 @@ __global__ void __launch_bounds__(128) fbc2d_form_kernel(BeamView B, int want_k,
         const double V1 = P * (1.0 - aOverL), V2 = P * aOverL;
         p0[0] -= N; p0[1] -= V1; p0[2] -= V2;
       }
+      if (B.has_partial && B.wl[12 * n + e] > B.wl[11 * n + e]) {   // Beam2dPartialUniformLoad (ForceBeamColumn2d.cpp:426-443)
+        const double wya = B.wl[7 * n + e] * B.lam, wyb = B.wl[8 * n + e] * B.lam, waa = B.wl[9 * n + e] * B.lam, wab = B.wl[10 * n + e] * B.lam;
+        const double a = B.wl[11 * n + e] * L, b = B.wl[12 * n + e] * L;
+        p0[0] -= waa * (b - a) + 0.5 * (wab - waa) * (b - a);
+        double Fy = wya * (b - a);
+        double c = a + 0.5 * (b - a);
+        p0[1] -= Fy * (1 - c / L); p0[2] -= Fy * c / L;
+        Fy = 0.5 * (wyb - wya) * (b - a);
+        c = a + 2.0 / 3.0 * (b - a);
+        p0[1] -= Fy * (1 - c / L); p0[2] -= Fy * c / L;
+      }
       pl[0] += p0[0]; pl[1] += p0[1]; pl[4] += p0[2];
     }
     if (B.pdelta) {   // PDeltaCrdTransf2d::update + getGlobalResistingForce (PDeltaCrdTransf2d.cpp:349-384, 532-535)
@@ -1140,7 +1152,8 @@ __global__ void __launch_bounds__(128, XB_FBC_SEC_OCC) fbc2d_update_sec_kernel(B
   const int initialFlag = B.iflag[e];
   // numEleLoads > 0 for THIS element (ForceBeamColumn2d.cpp:575)
   const bool pointed = B.wl != nullptr && B.loads_on && B.has_point && (B.wl[3 * n + e] != 0.0 || B.wl[5 * n + e] != 0.0);
-  const bool loaded = pointed || (B.wl != nullptr && B.loads_on && (B.wl[e] != 0.0 || B.wl[2 * n + e] != 0.0));
+  const bool partial = B.wl != nullptr && B.loads_on && B.has_partial && B.wl[12 * n + e] > B.wl[11 * n + e];
+  const bool loaded = pointed || partial || (B.wl != nullptr && B.loads_on && (B.wl[e] != 0.0 || B.wl[2 * n + e] != 0.0));
   if (initialFlag != 0 && sqrt(dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]) <= DBL_EPSILON && !loaded) return;
 #pragma unroll
   for (int q = 0; q < 3; q++) vin[q] = v[q] - dv[q];
@@ -1157,6 +1170,24 @@ __global__ void __launch_bounds__(128, XB_FBC_SEC_OCC) fbc2d_update_sec_kernel(B
       const double V1 = P * (1.0 - aOverL), V2 = P * aOverL;
       if (x <= a) { sp0 += N; sp1 -= x * V1; }
       else sp1 -= (L - x) * V2;
+    }
+    if (partial) {   // Beam2dPartialUniformLoad (ForceBeamColumn2d.cpp:1073-1137)
+      const double wya = B.wl[7 * n + e] * B.lam, wyb = B.wl[8 * n + e] * B.lam, waa = B.wl[9 * n + e] * B.lam, wab = B.wl[10 * n + e] * B.lam;
+      const double a = B.wl[11 * n + e] * L, b = B.wl[12 * n + e] * L;
+      const double Fa = waa * (b - a) + 0.5 * (wab - waa) * (b - a);
+      double Fy = wya * (b - a);
+      double c = a + 0.5 * (b - a);
+      double VI = Fy * (1 - c / L), VJ = Fy * c / L;
+      Fy = 0.5 * (wyb - wya) * (b - a);
+      c = a + 2.0 / 3.0 * (b - a);
+      VI += Fy * (1 - c / L); VJ += Fy * c / L;
+      if (x <= a) { sp0 += Fa; sp1 -= VI * x; }
+      else if (x >= b) sp1 += VJ * (x - L);
+      else {
+        const double wx = wya + (wyb - wya) / (b - a) * (x - a);
+        sp0 += Fa - waa * (x - a) - 0.5 * (wab - waa) / (b - a) * (x - a) * (x - a);
+        sp1 += -VI * x + wya * (x - a) * 0.5 * (x - a) + 0.5 * (wx - wya) * (x - a) * (x - a) / 3.0;
+      }
     }
   }
   double f0[4];

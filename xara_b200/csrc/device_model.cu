@@ -1715,6 +1715,7 @@ int xb_add_elements(xb_model* m, int kind, int n, const int* tags, const int* co
 int xb_add_nodal_loads(xb_model* m, int n, const int* t, const double* v) { HOSTCALL(m->h.add_loads(n, t, v)); }
 int xb_set_beam_integration(xb_model* m, int n, const int* t, int nip, const double* xi, const double* wt) { HOSTCALL(m->h.set_beam_integration(n, t, nip, xi, wt)); }
 int xb_add_beam_point_loads(xb_model* m, int n, const int* t, const double* p) { HOSTCALL(m->h.add_beam_point_loads(n, t, p)); }
+int xb_add_beam_partial_loads(xb_model* m, int n, const int* t, const double* p) { HOSTCALL(m->h.add_beam_partial_loads(n, t, p)); }
 int xb_add_beam_uniform_loads(xb_model* m, int n, const int* t, const double* w) { HOSTCALL(m->h.add_beam_uniform_loads(n, t, w)); }
 int xb_setup(xb_model* m, int numberer, int soe_kind) { HOSTCALL(m->h.setup(numberer, soe_kind)); }
 int xb_setup_partitioned(xb_model* m, int numberer, int soe_kind, int nparts, int rank, const int* part) {
@@ -1924,7 +1925,25 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
           for (int c = 0; c < 4; c++) pl[(size_t)c * ne + e] = q[c];
         }
         b.has_point = anyp ? 1 : 0;
-        if (any || anyp) { wl.insert(wl.end(), pl.begin(), pl.end()); double* dwl = nullptr; CU(dev_upload(m, &dwl, wl)); b.wl = dwl; }
+        // 2D `eleLoad -beamUniform` over part of the element: wya, wyb, waa, wab, aOverL, bOverL, SoA [6][n] behind the point
+        // loads' rows (an element without one carries zeros: aOverL = bOverL = 0 marks it)
+        std::vector<double> pp;
+        bool anyq = false;
+        if (!b3) {
+          pp.assign((size_t)6 * ne, 0.0);
+          for (long long e = 0; e < ne; e++) {
+            const double* q = &g.par[(size_t)e * k.npar + 3];
+            if (q[6] == 0.0) continue;
+            anyq = true;
+            for (int c = 0; c < 6; c++) pp[(size_t)c * ne + e] = q[c];
+          }
+        }
+        b.has_partial = anyq ? 1 : 0;
+        if (any || anyp || anyq) {
+          wl.insert(wl.end(), pl.begin(), pl.end());
+          if (anyq) wl.insert(wl.end(), pp.begin(), pp.end());
+          double* dwl = nullptr; CU(dev_upload(m, &dwl, wl)); b.wl = dwl;
+        }
       }
       // section template + initial fibre records (Steel02::revertToStart, Concrete02 constructor)
       std::vector<double> fy(nf), fz(nf, 0.0), fA(sd.A), fpar((size_t)nf * 12), ic((size_t)nf * XB_FIB_NV, 0.0), it((size_t)nf * XB_FIB_NV, 0.0);

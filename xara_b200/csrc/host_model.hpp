@@ -226,6 +226,7 @@ struct HostModel {
   int add_loads(int n, const int* tags, const double* vals);
   int add_beam_uniform_loads(int n, const int* tags, const double* w);
   int add_beam_point_loads(int n, const int* tags, const double* p);
+  int add_beam_partial_loads(int n, const int* tags, const double* p);
   int set_beam_integration(int n, const int* tags, int nip, const double* xi, const double* wt);
   int add_mass(int n, const int* tags, const double* vals);
   // part: nullptr (built-in recursive coordinate bisection) or [ne] ranks in FE order
