@@ -164,10 +164,11 @@ int xb_set_beam_integration(xb_model*, int n, const int* ele_tags, int nip, cons
  * One point load per element (beside its uniform loads, whose intensities add up); a load with xL outside [0, 1] is ignored, as the
  * element does. */
 int xb_add_beam_point_loads(xb_model*, int n, const int* ele_tags, const double* p);
-/* `eleLoad -ele tags -type -beamUniform wya wyb? ... aOverL bOverL` on part of a 2D element (Beam2dPartialUniformLoad ->
- * ForceBeamColumn2d.cpp:426-443 reactions, :1073-1137 section forces): a trapezoidal load between a = aOverL L and
- * b = bOverL L; p is [n][6] = wTrans_a, wTrans_b, wAxial_a, wAxial_b, aOverL, bOverL (the load's getData order).  One such
- * load per element, beside its uniform and point loads; 0 <= aOverL < bOverL <= 1; 2D elements only (XB_ERR_UNSUPPORTED). */
+/* `eleLoad -beamUniform` over part of an element, trapezoidal between a = aOverL L and b = bOverL L
+ * (Beam2dPartialUniformLoad -> ForceBeamColumn2d.cpp:426-443 reactions, :1073-1137 section forces;
+ * Beam3dPartialUniformLoad -> ForceBeamColumn3d.cpp:432-456, 1224-1313): p is [n][8] = wy_a, wy_b, wAxial_a, wAxial_b,
+ * aOverL, bOverL, wz_a, wz_b (the last two: 3D elements only).  One such load per element, beside its uniform and point
+ * loads; 0 <= aOverL < bOverL <= 1. */
 int xb_add_beam_partial_loads(xb_model*, int n, const int* ele_tags, const double* p);
 
 /* `mass` command: Node::setMass with a diagonal matrix (domain/node/Node.h:127); mass is [n][ndf].

@@ -373,8 +373,13 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
             continue;
           }
           else if (type == LOAD_TAG_Beam2dPartialUniformLoad && dynamic_cast<ForceBeamColumn2d*>(ele)) {   // wTa, wTb, wAa, wAb, a/L, b/L
-            const double p6[6] = {data(0), data(1), data(2), data(3), data(4), data(5)};
-            if (xb_add_beam_partial_loads(x, 1, &et, p6) < 0) { G.err = xb_last_error(); return -7; }
+            const double p8[8] = {data(0), data(1), data(2), data(3), data(4), data(5), 0.0, 0.0};
+            if (xb_add_beam_partial_loads(x, 1, &et, p8) < 0) { G.err = xb_last_error(); return -7; }
+            continue;
+          }
+          else if (type == LOAD_TAG_Beam3dPartialUniformLoad && dynamic_cast<ForceBeamColumn3d*>(ele)) {   // wya, wza, waa, a/L, b/L, wyb, wzb, wab
+            const double p8[8] = {data(0), data(5), data(2), data(7), data(3), data(4), data(1), data(6)};
+            if (xb_add_beam_partial_loads(x, 1, &et, p8) < 0) { G.err = xb_last_error(); return -7; }
             continue;
           }
           else { G.err = "glue: ElementalLoad other than -beamUniform / -beamPoint on a forceBeamColumn: outside the device path"; return -7; }

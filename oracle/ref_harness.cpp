@@ -89,6 +89,7 @@
 #include <Beam3dUniformLoad.h>
 #include <Beam2dPointLoad.h>
 #include <Beam2dPartialUniformLoad.h>
+#include <Beam3dPartialUniformLoad.h>
 #include <Beam3dPointLoad.h>
 #include <BandGenLinSOE.h>
 #include <BandGenLinSolver.h>
@@ -458,13 +459,14 @@ int ref_add_beam_point_load(void* h, int eleTag, double Py, double Pz, double N,
 // `eleLoad -ele tag -type -beamUniform wya wyb ... aOverL bOverL` (2D, trapezoidal over part of the element) in pattern 1
 int ref_add_beam_partial_load(void* h, int eleTag, const double* q) {
   RefModel* m = (RefModel*)h;
-  if (m->ndm != 2) return -2;
   if (m->domain->getLoadPattern(m->cur_pattern) == nullptr) {
     LoadPattern* lp = new LoadPattern(m->cur_pattern);
     lp->setTimeSeries(new LinearSeries());
     m->domain->addLoadPattern(lp);
   }
-  ElementalLoad* el = new Beam2dPartialUniformLoad(30000 + m->nloads++, q[0], q[1], q[2], q[3], q[4], q[5], eleTag);
+  // q = wy_a, wy_b, wAxial_a, wAxial_b, aOverL, bOverL, wz_a, wz_b
+  ElementalLoad* el = (m->ndm == 2) ? (ElementalLoad*)new Beam2dPartialUniformLoad(30000 + m->nloads++, q[0], q[1], q[2], q[3], q[4], q[5], eleTag)
+                                    : (ElementalLoad*)new Beam3dPartialUniformLoad(30000 + m->nloads++, q[0], q[6], q[2], q[4], q[5], q[1], q[7], q[3], eleTag);
   return m->domain->addElementalLoad(el, 1) ? 0 : -1;
 }
 

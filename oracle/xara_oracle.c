@@ -1414,6 +1414,8 @@ typedef struct {
   int has_load, numEleLoads; double w[3], loadFactor;
   /* `eleLoad -beamPoint Py Pz xL [N]` (Beam3dPointLoad): pt = {Py, Pz, N, aOverL} */
   int has_point; double pt[4];
+  /* Beam3dPartialUniformLoad: pq = wy_a, wy_b, wAxial_a, wAxial_b, aOverL, bOverL, wz_a, wz_b */
+  int has_partial; double pq[8];
   int user_rule; double rxi[ORC_MAXSEC], rwt[ORC_MAXSEC];     /* see OrcBeam */
   /* geomTransf PDelta (PDeltaCrdTransf3d.cpp:200-249): ul17, ul28 as of the element's last update() -- ForceBeamColumn3d's
    * getTangentStiff / getResistingForce do NOT refresh them (ForceBeamColumn3d.cpp:404,555) */
@@ -1543,6 +1545,26 @@ static int beam3_update(OrcBeam3* b, const double* ug_, const double* dug_) {
               double Vy1 = Py * (1.0 - aOverL), Vy2 = Py * aOverL, Vz1 = Pz * (1.0 - aOverL), Vz2 = Pz * aOverL;
               if (x <= a) { Ss[0] += N; Ss[1] -= x * Vy1; Ss[2] += x * Vz1; }
               else { Ss[1] -= (L - x) * Vy2; Ss[2] += (L - x) * Vz2; }
+            }
+            if (b->has_partial) {     /* Beam3dPartialUniformLoad, ForceBeamColumn3d.cpp:1224-1313 */
+              const double lf = b->loadFactor;
+              double wy = b->pq[0] * lf, wz = b->pq[6] * lf, wa = b->pq[2] * lf, a = b->pq[4] * L, bb = b->pq[5] * L;
+              double wyb = b->pq[1] * lf, wzb = b->pq[7] * lf, wab = b->pq[3] * lf;
+              double Fa = wa * (bb - a) + 0.5 * (wab - wa) * (bb - a);
+              double Fy = wy * (bb - a), Fz = wz * (bb - a);
+              double c = a + 0.5 * (bb - a);
+              double VyI = Fy * (1 - c / L), VyJ = Fy * c / L, VzI = Fz * (1 - c / L), VzJ = Fz * c / L;
+              Fy = 0.5 * (wyb - wy) * (bb - a); Fz = 0.5 * (wzb - wz) * (bb - a);
+              c = a + 2.0 / 3.0 * (bb - a);
+              VyI += Fy * (1 - c / L); VyJ += Fy * c / L; VzI += Fz * (1 - c / L); VzJ += Fz * c / L;
+              if (x <= a) { Ss[0] += Fa; Ss[1] -= VyI * x; Ss[2] += VzI * x; }
+              else if (x >= bb) { Ss[1] += VyJ * (x - L); Ss[2] -= VzJ * (x - L); }
+              else {
+                double wyy = wy + (wyb - wy) / (bb - a) * (x - a), wzz = wz + (wzb - wz) / (bb - a) * (x - a);
+                Ss[0] += Fa - wa * (x - a) - 0.5 * (wab - wa) / (bb - a) * (x - a) * (x - a);
+                Ss[1] += -VyI * x + 0.5 * wy * (x - a) * (x - a) + 0.5 * (wyy - wy) * (x - a) * (x - a) / 3.0;
+                Ss[2] += VzI * x - 0.5 * wz * (x - a) * (x - a) - 0.5 * (wzz - wz) * (x - a) * (x - a) / 3.0;
+              }
             }
           }
           for (int q = 0; q < 4; q++) dSs[q] = Ss[q] - SsrSub[i][q];
@@ -1693,6 +1715,22 @@ static void beam3_form_end(const OrcBeam3* b, double* K, double* Rg) {
       p0[0] -= N; p0[1] -= V1; p0[2] -= V2;
       V1 = Pz * (1.0 - aOverL); V2 = Pz * aOverL;
       p0[3] -= V1; p0[4] -= V2;
+    }
+    if (b->has_partial) {             /* Beam3dPartialUniformLoad, ForceBeamColumn3d.cpp:432-456 */
+      const double lf = b->loadFactor, L = b->L;
+      double wy = b->pq[0] * lf, wz = b->pq[6] * lf, wa = b->pq[2] * lf, a = b->pq[4] * L, bb = b->pq[5] * L;
+      double wyb = b->pq[1] * lf, wzb = b->pq[7] * lf, wab = b->pq[3] * lf;
+      p0[0] -= wa * (bb - a) + 0.5 * (wab - wa) * (bb - a);
+      double c = a + 0.5 * (bb - a);
+      double Fy = wy * (bb - a);
+      p0[1] -= Fy * (1 - c / L); p0[2] -= Fy * c / L;
+      double Fz = wz * (bb - a);
+      p0[3] -= Fz * (1 - c / L); p0[4] -= Fz * c / L;
+      c = a + 2.0 / 3.0 * (bb - a);
+      Fy = 0.5 * (wyb - wy) * (bb - a);
+      p0[1] -= Fy * (1 - c / L); p0[2] -= Fy * c / L;
+      Fz = 0.5 * (wzb - wz) * (bb - a);
+      p0[3] -= Fz * (1 - c / L); p0[4] -= Fz * c / L;
     }
   }
   pl[0] += p0[0]; pl[1] += p0[1]; pl[7] += p0[2]; pl[2] += p0[3]; pl[8] += p0[4];   /* LinearCrdTransf3d.cpp:727-731 */
@@ -2507,7 +2545,7 @@ void orc_apply_load(void* h, double lambda) {
   for (int e = 0; e < m->ne; e++) {
     OrcEle* el = &m->ele[e];
     if (el->kind == ORC_ELE_FBC2D && (el->beam->has_load || el->beam->has_point || el->beam->has_partial)) { el->beam->numEleLoads = el->beam->has_load + el->beam->has_point + el->beam->has_partial; el->beam->loadFactor = lf; }
-    if (el->kind == ORC_ELE_FBC3D && (el->beam3->has_load || el->beam3->has_point)) { el->beam3->numEleLoads = el->beam3->has_load + el->beam3->has_point; el->beam3->loadFactor = lf; }
+    if (el->kind == ORC_ELE_FBC3D && (el->beam3->has_load || el->beam3->has_point || el->beam3->has_partial)) { el->beam3->numEleLoads = el->beam3->has_load + el->beam3->has_point + el->beam3->has_partial; el->beam3->loadFactor = lf; }
   }
 }
 /* `eleLoad -ele tag -type -beamUniform wy [wz] wa` in the model's Linear pattern (Beam2dUniformLoad / Beam3dUniformLoad) */
@@ -2574,12 +2612,17 @@ int orc_add_beam_point_load(void* h, int ele_tag, double Py, double Pz, double N
   return -1;
 }
 
-/* `eleLoad -beamUniform` over part of a 2D element (Beam2dPartialUniformLoad): q = wTrans_a, wTrans_b, wAxial_a, wAxial_b, aOverL, bOverL */
+/* `eleLoad -beamUniform` over part of an element (Beam2d/3dPartialUniformLoad): q[8] = wy_a, wy_b, wAxial_a, wAxial_b, aOverL, bOverL, wz_a, wz_b (3D) */
 int orc_add_beam_partial_load(void* h, int ele_tag, const double* q) {
   OrcModel* m = (OrcModel*)h;
   for (int e = 0; e < m->ne; e++) {
     OrcEle* el = &m->ele[e];
     if (el->tag != ele_tag) continue;
+    if (el->kind == ORC_ELE_FBC3D) {      /* q[0..7] = wy_a, wy_b, wAxial_a, wAxial_b, aOverL, bOverL, wz_a, wz_b */
+      if (el->beam3->has_partial) return -2;
+      el->beam3->has_partial = 1; memcpy(el->beam3->pq, q, sizeof el->beam3->pq);
+      return 0;
+    }
     if (el->kind != ORC_ELE_FBC2D) return -3;
     if (el->beam->has_partial) return -2;
     el->beam->has_partial = 1; memcpy(el->beam->pq, q, sizeof el->beam->pq);
@@ -2955,11 +2998,13 @@ int orc_revert_to_start(void* h) {
       const int hl = el->beam3->has_load, nl = el->beam3->numEleLoads; const double lf = el->beam3->loadFactor;
       double wk[3]; memcpy(wk, el->beam3->w, sizeof wk);
       const int hp = el->beam3->has_point; double pk[4]; memcpy(pk, el->beam3->pt, sizeof pk);
+      const int hq = el->beam3->has_partial; double qk[8]; memcpy(qk, el->beam3->pq, sizeof qk);
       const int ur = el->beam3->user_rule; double rx[ORC_MAXSEC], rw[ORC_MAXSEC]; memcpy(rx, el->beam3->rxi, sizeof rx); memcpy(rw, el->beam3->rwt, sizeof rw);
       free(el->beam3);
       el->beam3 = beam3_build(m, el, el->mat, el->par);
       el->beam3->has_load = hl; el->beam3->numEleLoads = nl; el->beam3->loadFactor = lf; memcpy(el->beam3->w, wk, sizeof wk);
       el->beam3->has_point = hp; memcpy(el->beam3->pt, pk, sizeof pk);
+      el->beam3->has_partial = hq; memcpy(el->beam3->pq, qk, sizeof qk);
       el->beam3->user_rule = ur; memcpy(el->beam3->rxi, rx, sizeof rx); memcpy(el->beam3->rwt, rw, sizeof rw);
     } else {
       for (int g = 0; g < el->nip; g++) {

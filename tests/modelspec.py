@@ -57,7 +57,7 @@ class ModelSpec:
     sections: list = field(default_factory=list)    # (tag, y[nf], A[nf], uniaxial tags[nf])
     beam_loads: list = field(default_factory=list)  # `eleLoad -beamUniform`: (element tag, wy, wz, wa) in the Linear pattern
     beam_point_loads: list = field(default_factory=list)  # `eleLoad -beamPoint`: (element tag, Py, Pz, N, xL)
-    beam_partial_loads: list = field(default_factory=list)  # 2D partial `-beamUniform`: (element tag, wya, wyb, waa, wab, aOverL, bOverL)
+    beam_partial_loads: list = field(default_factory=list)  # partial `-beamUniform`: (element tag, wya, wyb, waa, wab, aOverL, bOverL, wza, wzb)
     beam_integration: int = 0          # forceBeamColumn -integration: 0 Lobatto, 1 Legendre, 2 Radau, 3 NewtonCotes, 4 Trapezoidal
     beam_rules: tuple = None           # (element tags, xi [n][nip], wt [n][nip]) as the reference's BeamIntegration returns them
     node_ndf: dict = field(default_factory=dict)    # node tag -> dofs, for nodes created under another `model -ndf` (< the model's ndf)
@@ -317,18 +317,21 @@ def with_beam_rho(spec, rho=2.0e-3):
 
 
 def with_beam_partial_loads(spec, w=-0.12, seed=0):
-    """a trapezoidal `eleLoad -beamUniform wya wyb waa wab aOverL bOverL` (Beam2dPartialUniformLoad) over a random part of
-    every girder of a 2D frame -- section points fall before, inside and behind the loaded stretch"""
+    """a trapezoidal `eleLoad -beamUniform ... aOverL bOverL` (Beam2d / Beam3dPartialUniformLoad) over a random part of every
+    girder -- section points fall before, inside and behind the loaded stretch.  Entries: (element tag, wy_a, wy_b, wAxial_a,
+    wAxial_b, aOverL, bOverL, wz_a, wz_b)"""
     rng = np.random.default_rng(seed)
     ix = {int(t): i for i, t in enumerate(spec.node_tags)}
+    up = spec.ndm - 1
     out = []
     for g in spec.groups:
         for t, c in zip(g.tags, g.conn):
             a, b = spec.crd[ix[int(c[0])]], spec.crd[ix[int(c[1])]]
-            if abs(a[1] - b[1]) > 1e-9: continue          # a column
+            if abs(a[up] - b[up]) > 1e-9: continue          # a column
             aL = rng.uniform(0.05, 0.45); bL = rng.uniform(0.55, 0.95)
             wa = w * rng.uniform(0.6, 1.4); wb = w * rng.uniform(0.6, 1.4)
-            out.append((int(t), wa, wb, 0.05 * wa, -0.03 * wb, aL, bL))
+            wz = (0.15 * wa, -0.1 * wb) if spec.ndm == 3 else (0.0, 0.0)
+            out.append((int(t), wa, wb, 0.05 * wa, -0.03 * wb, aL, bL) + wz)
     spec.beam_partial_loads = out
     return spec
 

@@ -200,7 +200,7 @@ def test_newton_iteration_counts_match_oracle(shape):
 
 @pytest.mark.skipif(not (have_ref() and have_glue()), reason="oracle/_ref not built (needs /root/reference)")
 @pytest.mark.parametrize("shape,numberer,soe", [("brick", 1, 0), ("quad", 0, 1), ("mixed", 1, 1), ("soilcolumn_equaldof", 1, 0), ("frame2d_gravity", 1, 0), ("soil_frame_mixed_ndf", 1, 0),
-                                                ("soilcolumn_equaldof", 0, 1), ("frame2d_pdelta", 1, 0), ("frame3d_pdelta", 1, 0), ("frame3d_eleloads", 1, 0), ("frame2d_legendre", 1, 0), ("frame3d_radau", 1, 0), ("frame2d_concrete01", 1, 0), ("frame2d_jntoffset", 1, 0), ("frame3d_jntoffset", 1, 0), ("frame2d_corot", 1, 0), ("frame2d_partial_load", 1, 0)])
+                                                ("soilcolumn_equaldof", 0, 1), ("frame2d_pdelta", 1, 0), ("frame3d_pdelta", 1, 0), ("frame3d_eleloads", 1, 0), ("frame2d_legendre", 1, 0), ("frame3d_radau", 1, 0), ("frame2d_concrete01", 1, 0), ("frame2d_jntoffset", 1, 0), ("frame3d_jntoffset", 1, 0), ("frame2d_corot", 1, 0), ("frame2d_partial_load", 1, 0), ("frame3d_partial_load", 1, 0)])
 def test_reference_newton_loop_drives_device_path(shape, numberer, soe):
     """The drop-in, end to end: the REFERENCE'S OWN StaticAnalysis objects (AnalysisModel, PlainHandler, numberer,
     SparseGenCol/Row SOE and solver, NewtonRaphson, CTestNormDispIncr, LoadControl::newStep) run a load-controlled
@@ -222,10 +222,11 @@ def test_reference_newton_loop_drives_device_path(shape, numberer, soe):
         def mk():   # `eleLoad -beamUniform` on the girders read out of the load pattern, pushed well into the inelastic range
             from modelspec import with_beam_gravity
             sp = with_beam_gravity(frame2d(2, 3, 2, lateral=15.0), w=-0.2, seed=1); return sp
-    elif shape == "frame2d_partial_load":
-        def mk():   # trapezoidal `eleLoad -beamUniform ... aOverL bOverL` (Beam2dPartialUniformLoad) read out of the load pattern
+    elif shape in ("frame2d_partial_load", "frame3d_partial_load"):
+        def mk():   # trapezoidal `eleLoad -beamUniform ... aOverL bOverL` (Beam2d / Beam3dPartialUniformLoad) read out of the load pattern
             from modelspec import with_beam_partial_loads
-            return with_beam_partial_loads(frame2d(2, 3, 2, lateral=15.0), w=-0.3, seed=4)
+            return (with_beam_partial_loads(frame2d(2, 3, 2, lateral=15.0), w=-0.3, seed=4) if shape == "frame2d_partial_load"
+                    else with_beam_partial_loads(frame3d(1, 1, 2, ndiv=2, lateral=(14.0, 8.0)), w=-0.1, seed=4))
     elif shape == "frame3d_eleloads":
         def mk():   # `eleLoad -beamUniform` and `-beamPoint` (Beam3dUniformLoad, Beam3dPointLoad) read out of the load pattern
             from modelspec import with_beam_gravity, with_beam_point_loads
@@ -655,7 +656,7 @@ def test_band_profile_umfpack_storage_device_vs_oracle(soe):
             O.commit(); D.commit()
 
 
-@pytest.mark.parametrize("dim,loads", [(2, "uniform"), (2, "point"), (2, "both"), (3, "uniform"), (3, "point"), (3, "both"), (2, "partial"), (2, "all")])
+@pytest.mark.parametrize("dim,loads", [(2, "uniform"), (2, "point"), (2, "both"), (3, "uniform"), (3, "point"), (3, "both"), (2, "partial"), (2, "all"), (3, "partial"), (3, "all")])
 def test_beam_uniform_element_loads_device_vs_oracle(dim, loads):
     """`eleLoad -beamUniform` and `-beamPoint` (Beam2d/3dPointLoad, ForceBeamColumn2d.cpp:442,1138 / 3d.cpp:457,1314) on force beams: section forces sp inside the element iteration, fixed-end reactions p0 in
     the resisting force, both scaled by the load factor; against the oracle (pinned to ForceBeamColumn2d/3d with
@@ -664,8 +665,8 @@ def test_beam_uniform_element_loads_device_vs_oracle(dim, loads):
     from modelspec import with_beam_gravity, with_beam_point_loads
     rng = np.random.default_rng(5)
     spec = frame2d(3, 3, 2) if dim == 2 else frame3d(2, 1, 2)
-    # "partial" / "all" (2D): a trapezoidal load over part of every girder (Beam2dPartialUniformLoad, ForceBeamColumn2d.cpp:426-443,
-    # 1073-1137), alone and on top of the other two kinds
+    # "partial" / "all": a trapezoidal load over part of every girder (Beam2d/3dPartialUniformLoad, ForceBeamColumn2d.cpp:426-443,
+    # 1073-1137; ForceBeamColumn3d.cpp:432-456, 1224-1313), alone and on top of the other two kinds
     if loads not in ("point", "partial"): spec = with_beam_gravity(spec, seed=3)
     if loads not in ("uniform", "partial"): spec = with_beam_point_loads(spec, seed=2)
     if loads in ("partial", "all"):

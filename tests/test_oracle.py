@@ -134,7 +134,7 @@ def test_oracle_vs_live_reference(mat, numberer, soe):
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
-@pytest.mark.parametrize("dim,loads", [(2, "uniform"), (2, "point"), (2, "both"), (3, "uniform"), (3, "point"), (3, "both"), (2, "partial"), (2, "all")])
+@pytest.mark.parametrize("dim,loads", [(2, "uniform"), (2, "point"), (2, "both"), (3, "uniform"), (3, "point"), (3, "both"), (2, "partial"), (2, "all"), (3, "partial"), (3, "all")])
 def test_beam_uniform_element_loads_vs_live_reference(dim, loads):
     """`eleLoad -beamPoint` (Beam2d/3dPointLoad: ForceBeamColumn2d.cpp:442-455, 1138-1181; ForceBeamColumn3d.cpp:457-475,
     1314-1373; points between and beyond the Lobatto sections) and `eleLoad -beamUniform` on force beams (ForceBeamColumn2d.cpp:407,1034 / ForceBeamColumn3d.cpp:419,1197): the section
@@ -144,8 +144,8 @@ def test_beam_uniform_element_loads_vs_live_reference(dim, loads):
     from modelspec import with_beam_gravity, with_beam_point_loads
     rng = np.random.default_rng(5)
     spec = frame2d(2, 2, 2) if dim == 2 else frame3d(1, 1, 2)
-    # "partial" / "all" (2D): a trapezoidal load over part of every girder (Beam2dPartialUniformLoad, ForceBeamColumn2d.cpp:426-443,
-    # 1073-1137), alone and on top of the other two kinds
+    # "partial" / "all": a trapezoidal load over part of every girder (Beam2d/3dPartialUniformLoad, ForceBeamColumn2d.cpp:426-443,
+    # 1073-1137; ForceBeamColumn3d.cpp:432-456, 1224-1313), alone and on top of the other two kinds
     if loads not in ("point", "partial"): spec = with_beam_gravity(spec, seed=3)
     if loads not in ("uniform", "partial"): spec = with_beam_point_loads(spec, seed=2)
     if loads in ("partial", "all"):

@@ -253,8 +253,9 @@ class DeviceModel:
         self._ck(lib.xb_add_beam_point_loads(self._h, len(ele_tags), _ptr(ele_tags), _ptr(p)))
 
     def add_beam_partial_loads(self, ele_tags, p):
-        """`eleLoad -beamUniform` over part of a 2D element: p [n][6] = wya, wyb, waa, wab, aOverL, bOverL"""
+        """`eleLoad -beamUniform` over part of an element: p [n][8] = wya, wyb, waa, wab, aOverL, bOverL, wza, wzb (3D)"""
         ele_tags, p = _i32(ele_tags), _f64(p)
+        assert p.ndim == 2 and p.shape[1] == 8
         self._ck(lib.xb_add_beam_partial_loads(self._h, len(ele_tags), _ptr(ele_tags), _ptr(p)))
 
     def add_beam_uniform_loads(self, ele_tags, w):
@@ -310,7 +311,7 @@ class DeviceModel:
             m.add_beam_point_loads([t for t, *_ in bp], np.array([q for _, *q in bp], np.float64))
         bq = getattr(spec, "beam_partial_loads", [])
         if bq:
-            m.add_beam_partial_loads([t for t, *_ in bq], np.array([q for _, *q in bq], np.float64))
+            m.add_beam_partial_loads([t for t, *_ in bq], np.array([(list(q) + [0.0, 0.0])[:8] for _, *q in bq], np.float64))
         bl = getattr(spec, "beam_loads", [])
         if bl:
             m.add_beam_uniform_loads([t for t, *_ in bl], np.array([w for _, *w in bl], np.float64))

@@ -80,7 +80,7 @@ struct BeamView {
   double lam;
   int loads_on;
   int has_point;
-  int has_partial;             // 2D: rows 7..12 of wl hold Beam2dPartialUniformLoad's wya, wyb, waa, wab, aOverL, bOverL
+  int has_partial;             // rows 7..14 of wl hold Beam2d/3dPartialUniformLoad's wya, wyb, waa, wab, aOverL, bOverL, wza, wzb
   // geomTransf PDelta (PDeltaCrdTransf2d.cpp / PDeltaCrdTransf3d.cpp): geometric stiffness N/L and leaning-column shear.
   // 2D: the relative transverse displacement is taken from the trial displacements U whenever the element forms its
   // forces (ForceBeamColumn2d.cpp:402,526 refresh the transformation); 3D: ul17, ul28 as of the element's last update
@@ -904,7 +904,8 @@ __global__ void __launch_bounds__(128, XB_FBC_SEC_OCC) fbc3d_update_sec_kernel(B
   // (all lanes of an element take the same way out: dv and the load flag are the element's)
   // numEleLoads > 0 for THIS element (ForceBeamColumn3d.cpp: the early return needs numEleLoads == 0)
   const bool pointed = B.wl != nullptr && B.loads_on && B.has_point && (B.wl[3 * n + e] != 0.0 || B.wl[4 * n + e] != 0.0 || B.wl[5 * n + e] != 0.0);
-  const bool loaded = pointed || (B.wl != nullptr && B.loads_on && (B.wl[e] != 0.0 || B.wl[n + e] != 0.0 || B.wl[2 * n + e] != 0.0));
+  const bool partial = B.wl != nullptr && B.loads_on && B.has_partial && B.wl[12 * n + e] > B.wl[11 * n + e];
+  const bool loaded = pointed || partial || (B.wl != nullptr && B.loads_on && (B.wl[e] != 0.0 || B.wl[n + e] != 0.0 || B.wl[2 * n + e] != 0.0));
   if (initialFlag != 0 && norm6(dv) <= DBL_EPSILON && !loaded) return;
 #pragma unroll
   for (int q = 0; q < 6; q++) vin[q] = v[q] - dv[q];
@@ -921,6 +922,26 @@ __global__ void __launch_bounds__(128, XB_FBC_SEC_OCC) fbc3d_update_sec_kernel(B
       const double Vy1 = Py * (1.0 - aOverL), Vy2 = Py * aOverL, Vz1 = Pz * (1.0 - aOverL), Vz2 = Pz * aOverL;
       if (x <= a) { sp0 += N; sp1 -= x * Vy1; sp2 += x * Vz1; }
       else { sp1 -= (L - x) * Vy2; sp2 += (L - x) * Vz2; }
+    }
+    if (partial) {   // Beam3dPartialUniformLoad (ForceBeamColumn3d.cpp:1224-1313)
+      const double wya = B.wl[7 * n + e] * B.lam, wyb = B.wl[8 * n + e] * B.lam, waa = B.wl[9 * n + e] * B.lam, wab = B.wl[10 * n + e] * B.lam;
+      const double wza = B.wl[13 * n + e] * B.lam, wzb = B.wl[14 * n + e] * B.lam;
+      const double a = B.wl[11 * n + e] * L, b = B.wl[12 * n + e] * L;
+      const double Fa = waa * (b - a) + 0.5 * (wab - waa) * (b - a);
+      double Fy = wya * (b - a), Fz = wza * (b - a);
+      double c = a + 0.5 * (b - a);
+      double VyI = Fy * (1 - c / L), VyJ = Fy * c / L, VzI = Fz * (1 - c / L), VzJ = Fz * c / L;
+      Fy = 0.5 * (wyb - wya) * (b - a); Fz = 0.5 * (wzb - wza) * (b - a);
+      c = a + 2.0 / 3.0 * (b - a);
+      VyI += Fy * (1 - c / L); VyJ += Fy * c / L; VzI += Fz * (1 - c / L); VzJ += Fz * c / L;
+      if (x <= a) { sp0 += Fa; sp1 -= VyI * x; sp2 += VzI * x; }
+      else if (x >= b) { sp1 += VyJ * (x - L); sp2 -= VzJ * (x - L); }
+      else {
+        const double wyy = wya + (wyb - wya) / (b - a) * (x - a), wzz = wza + (wzb - wza) / (b - a) * (x - a);
+        sp0 += Fa - waa * (x - a) - 0.5 * (wab - waa) / (b - a) * (x - a) * (x - a);
+        sp1 += -VyI * x + 0.5 * wya * (x - a) * (x - a) + 0.5 * (wyy - wya) * (x - a) * (x - a) / 3.0;
+        sp2 += VzI * x - 0.5 * wza * (x - a) * (x - a) - 0.5 * (wzz - wza) * (x - a) * (x - a) / 3.0;
+      }
     }
   }
   // initial section flexibility: 3x3 block (column-major, stride 3) + torsion
@@ -1445,6 +1466,22 @@ __global__ void __launch_bounds__(64) fbc3d_form_kernel(BeamView B, int want_k, 
         p0[0] -= N; p0[1] -= V1; p0[2] -= V2;
         V1 = Pz * (1.0 - aOverL); V2 = Pz * aOverL;
         p0[3] -= V1; p0[4] -= V2;
+      }
+      if (B.has_partial && B.wl[12 * n + e] > B.wl[11 * n + e]) {   // Beam3dPartialUniformLoad (ForceBeamColumn3d.cpp:432-456)
+        const double wya = B.wl[7 * n + e] * B.lam, wyb = B.wl[8 * n + e] * B.lam, waa = B.wl[9 * n + e] * B.lam, wab = B.wl[10 * n + e] * B.lam;
+        const double wza = B.wl[13 * n + e] * B.lam, wzb = B.wl[14 * n + e] * B.lam;
+        const double a = B.wl[11 * n + e] * L, b = B.wl[12 * n + e] * L;
+        p0[0] -= waa * (b - a) + 0.5 * (wab - waa) * (b - a);
+        double c = a + 0.5 * (b - a);
+        double Fy = wya * (b - a);
+        p0[1] -= Fy * (1 - c / L); p0[2] -= Fy * c / L;
+        double Fz = wza * (b - a);
+        p0[3] -= Fz * (1 - c / L); p0[4] -= Fz * c / L;
+        c = a + 2.0 / 3.0 * (b - a);
+        Fy = 0.5 * (wyb - wya) * (b - a);
+        p0[1] -= Fy * (1 - c / L); p0[2] -= Fy * c / L;
+        Fz = 0.5 * (wzb - wza) * (b - a);
+        p0[3] -= Fz * (1 - c / L); p0[4] -= Fz * c / L;
       }
       pl[0] += p0[0]; pl[1] += p0[1]; pl[7] += p0[2]; pl[2] += p0[3]; pl[8] += p0[4];
     }

@@ -1925,18 +1925,15 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
           for (int c = 0; c < 4; c++) pl[(size_t)c * ne + e] = q[c];
         }
         b.has_point = anyp ? 1 : 0;
-        // 2D `eleLoad -beamUniform` over part of the element: wya, wyb, waa, wab, aOverL, bOverL, SoA [6][n] behind the point
+        // `eleLoad -beamUniform` over part of the element: wya, wyb, waa, wab, aOverL, bOverL, wza, wzb, SoA [8][n] behind the point
         // loads' rows (an element without one carries zeros: aOverL = bOverL = 0 marks it)
-        std::vector<double> pp;
+        std::vector<double> pp((size_t)8 * ne, 0.0);
         bool anyq = false;
-        if (!b3) {
-          pp.assign((size_t)6 * ne, 0.0);
-          for (long long e = 0; e < ne; e++) {
-            const double* q = &g.par[(size_t)e * k.npar + 3];
-            if (q[6] == 0.0) continue;
-            anyq = true;
-            for (int c = 0; c < 6; c++) pp[(size_t)c * ne + e] = q[c];
-          }
+        for (long long e = 0; e < ne; e++) {
+          const double* q = &g.par[(size_t)e * k.npar + (b3 ? 6 : 3)];
+          if (q[8] == 0.0) continue;
+          anyq = true;
+          for (int c = 0; c < 8; c++) pp[(size_t)c * ne + e] = q[c];
         }
         b.has_partial = anyq ? 1 : 0;
         if (any || anyp || anyq) {

@@ -17,9 +17,9 @@ static const EleKind kQuad{4, 2, 4, 3, 5};  // par kept: thickness, b1, b2, type
 // nip is a property of the batch.  par kept per element: nIP, maxIters, tol, [vecxz[3],] then the element loads of the
 // Linear pattern: `eleLoad -beamPoint` Py, Pz, N, aOverL (has-load flag in a 5th value) and `eleLoad -beamUniform` wy, wz, wa
 // (zero: none) -- they travel with the element through the partitioning like every other element parameter
-// (2D: `eleLoad -beamUniform` over part of the element, Beam2dPartialUniformLoad: wya, wyb, waa, wab, aOverL, bOverL + has-load flag)
-static const EleKind kBeam2d{2, 3, 0, 2, 23};  // par: nIP, maxIters, tol, partial load[7], joint offsets[4], rho, point load[5], wy, wz (unused), wa
-static const EleKind kBeam3d{2, 6, 0, 4, 21};  // par: nIP, maxIters, tol, vecxz[3], joint offsets[6], rho, point load[5], wy, wz, wa
+// (`eleLoad -beamUniform` over part of the element, Beam2d/3dPartialUniformLoad: wya, wyb, waa, wab, aOverL, bOverL, wza, wzb + has-load flag)
+static const EleKind kBeam2d{2, 3, 0, 2, 25};  // par: nIP, maxIters, tol, partial load[9], joint offsets[4], rho, point load[5], wy, wz (unused), wa
+static const EleKind kBeam3d{2, 6, 0, 4, 30};  // par: nIP, maxIters, tol, vecxz[3], partial load[9], joint offsets[6], rho, point load[5], wy, wz, wa
 
 const EleKind& ele_kind(int kind) {
   return kind == XB_ELE_STDBRICK ? kBrick : (kind == XB_ELE_FOURNODEQUAD ? kQuad : (kind == XB_ELE_FORCEBEAMCOLUMN3D ? kBeam3d : kBeam2d));
@@ -292,22 +292,20 @@ int HostModel::set_beam_integration(int n, const int* tags, int nip, const doubl
 int HostModel::add_beam_partial_loads(int n, const int* tags, const double* pv) {
   if (is_setup) { err = "xb_add_beam_partial_loads after xb_setup"; return XB_ERR_STATE; }
   for (int i = 0; i < n; i++) {
-    const double* q6 = pv + (size_t)i * 6;
-    if (!(q6[4] >= 0.0 && q6[4] < q6[5] && q6[5] <= 1.0)) { err = "xb_add_beam_partial_loads: 0 <= aOverL < bOverL <= 1"; return XB_ERR_ARG; }
+    const double* q8 = pv + (size_t)i * 8;
+    if (!(q8[4] >= 0.0 && q8[4] < q8[5] && q8[5] <= 1.0)) { err = "xb_add_beam_partial_loads: 0 <= aOverL < bOverL <= 1"; return XB_ERR_ARG; }
     bool found = false;
     for (auto& g : groups) {
-      if (g.kind == XB_ELE_FORCEBEAMCOLUMN3D)
-        for (size_t l = 0; l < g.tag.size(); l++)
-          if (g.tag[l] == tags[i]) { err = "xb_add_beam_partial_loads: partial uniform loads on 3D elements are outside the device path"; return XB_ERR_UNSUPPORTED; }
-      if (g.kind != XB_ELE_FORCEBEAMCOLUMN2D) continue;
+      if (g.kind != XB_ELE_FORCEBEAMCOLUMN2D && g.kind != XB_ELE_FORCEBEAMCOLUMN3D) continue;
+      const bool b3 = g.kind == XB_ELE_FORCEBEAMCOLUMN3D;
       const int npar = ele_kind(g.kind).npar;
       for (size_t l = 0; l < g.tag.size() && !found; l++) {
         if (g.tag[l] != tags[i]) continue;
         found = true;
-        double* q = &g.par[l * npar + 3];
-        if (q[6] != 0.0) { err = "xb_add_beam_partial_loads: one partial uniform load per element"; return XB_ERR_UNSUPPORTED; }
-        for (int c = 0; c < 6; c++) q[c] = q6[c];
-        q[6] = 1.0;
+        double* q = &g.par[l * npar + (b3 ? 6 : 3)];
+        if (q[8] != 0.0) { err = "xb_add_beam_partial_loads: one partial uniform load per element"; return XB_ERR_UNSUPPORTED; }
+        for (int c = 0; c < 8; c++) q[c] = (c < 6 || b3) ? q8[c] : 0.0;
+        q[8] = 1.0;
       }
       if (found) break;
     }
