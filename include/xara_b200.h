@@ -44,7 +44,9 @@ enum {
   XB_UNI_CONCRETE02 = 1,/* material/uniaxial/concrete/Concrete02.cpp:93: fc,epsc0,fcu,epscu,rat,ft,Ets     */
   XB_UNI_STEEL01 = 2,   /* material/uniaxial/steel/Steel01.cpp:40: fy,E0,b,a1,a2,a3,a4 (the command's defaults 0,55,0,55) */
   XB_UNI_ELASTIC = 3,   /* material/uniaxial/ElasticMaterial.cpp:96: E[,eta,Eneg]; eta must be 0 (no strain rate on this path) */
-  XB_UNI_CONCRETE01 = 4 /* material/uniaxial/concrete/Concrete01.cpp:89: fpc,epsc0,fpcu,epscu (Kent-Scott-Park, no tension) */
+  XB_UNI_CONCRETE01 = 4,/* material/uniaxial/concrete/Concrete01.cpp:89: fpc,epsc0,fpcu,epscu (Kent-Scott-Park, no tension) */
+  XB_UNI_ELASTICPP = 5  /* material/uniaxial/ElasticPPMaterial.cpp:88: E,epsyP,epsyN,eps0 (elastic - perfectly plastic; the
+                           plastic strain moves at commitState, :190-224) */
 };
 
 /* element kinds */

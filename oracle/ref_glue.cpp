@@ -43,6 +43,7 @@
 #include <Steel02.h>
 #include <Steel01.h>
 #include <Concrete01.h>
+#include <ElasticPPMaterial.h>
 #include <SectionAggregator.h>
 #include <Concrete02.h>
 #include <ElasticMaterial.h>
@@ -274,6 +275,11 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
             } else if (auto* c1 = dynamic_cast<Concrete01*>(um)) {
               kind = XB_UNI_CONCRETE01; np = 4;
               const double q[4] = {c1->fpc, c1->epsc0, c1->fpcu, c1->epscu};
+              std::memcpy(p, q, sizeof q);
+            } else if (auto* pp = dynamic_cast<ElasticPPMaterial*>(um)) {   // (the yield strains back out of the yield stresses, as getCopy does)
+              if (pp->ep != 0.0) return -1;
+              kind = XB_UNI_ELASTICPP; np = 4;
+              const double q[4] = {pp->E, pp->fyp / pp->E, pp->fyn / pp->E, pp->ezero};
               std::memcpy(p, q, sizeof q);
             } else if (auto* em = dynamic_cast<ElasticMaterial*>(um)) {
               kind = XB_UNI_ELASTIC; np = 3;

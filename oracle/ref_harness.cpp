@@ -55,6 +55,7 @@
 #include <PDeltaCrdTransf3d.h>
 #include <Steel01.h>
 #include <Concrete01.h>
+#include <ElasticPPMaterial.h>
 #include <ElasticMaterial.h>
 #include <FiberSection3d.h>
 #include <ElasticMaterial.h>
@@ -310,6 +311,7 @@ static UniaxialMaterial* make_uniaxial(int tag, int kind, const double* p) {
   if (kind == 2) return new Steel01(tag, p[0], p[1], p[2], p[3], p[4], p[5], p[6]);
   if (kind == 3) return new ElasticMaterial(tag, p[0], p[1], p[2]);
   if (kind == 4) return new Concrete01(tag, p[0], p[1], p[2], p[3]);          // fpc, epsc0, fpcu, epscu
+  if (kind == 5) return new ElasticPPMaterial(tag, p[0], p[1], p[2], p[3]);   // E, epsyP, epsyN, eps0
   if (kind == 0) return new Steel02(tag, p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8], p[9], p[10]);
   if (kind == 1) return new Concrete02(tag, p[0], p[1], p[2], p[3], p[4], p[5], p[6]);
   return nullptr;

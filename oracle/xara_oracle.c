@@ -21,7 +21,7 @@
 /* material kinds / element kinds shared with tests (mirrors include/xara_b200.h) */
 enum { ORC_MAT_ELASTIC_ISOTROPIC = 0, ORC_MAT_J2 = 1 };
 enum { ORC_ELE_BRICK = 0, ORC_ELE_QUAD = 1, ORC_ELE_FBC2D = 2, ORC_ELE_FBC3D = 3 };
-enum { ORC_UNI_STEEL02 = 0, ORC_UNI_CONCRETE02 = 1, ORC_UNI_STEEL01 = 2, ORC_UNI_ELASTIC = 3, ORC_UNI_CONCRETE01 = 4 };
+enum { ORC_UNI_STEEL02 = 0, ORC_UNI_CONCRETE02 = 1, ORC_UNI_STEEL01 = 2, ORC_UNI_ELASTIC = 3, ORC_UNI_CONCRETE01 = 4, ORC_UNI_ELASTICPP = 5 };
 enum { ORC_ND_3D = 0, ORC_ND_PLANE_STRAIN = 1, ORC_ND_PLANE_STRESS = 2 };
 
 /* ======================================================================== */
@@ -456,6 +456,8 @@ typedef struct {
                      zero is Epos (ElasticMaterial.cpp:146-160), not getTangent()'s max(Epos, Eneg) (:174-182) */
   /* Concrete01 (Concrete01.h: fpc, epsc0, fpcu, epscu in fc, epsc0, fcu, epscu above; history C* / T*) */
   double endStrainP, unloadSlopeP, endStrain, unloadSlope;     /* (min strain: minStrainP / minStrain) */
+  /* ElasticPPMaterial (ElasticPPMaterial.h: fyp, fyn, ezero, E in Epos, plastic strain ep -- updated at commitState) */
+  double fyp, fyn, ezero, ep;
   /* common */
   double eP, sigP, epsP, e, sig, eps;
 } OrcUni;
@@ -486,6 +488,13 @@ static void uni_init(OrcUni* m, int kind, const double* p) {
     if (m->epscu > 0.0) m->epscu = -m->epscu;
     const double Ec0 = 2 * m->fc / m->epsc0;
     m->eP = Ec0; m->unloadSlopeP = Ec0; m->e = Ec0; m->unloadSlope = Ec0;
+  } else if (kind == ORC_UNI_ELASTICPP) {
+    /* ElasticPPMaterial(tag, E, eyp, eyn, ezero), ElasticPPMaterial.cpp:88-107: p = E, epsyP, epsyN, eps0 */
+    double eyp = p[1], eyn = p[2];
+    if (eyp < 0) eyp *= -1.;
+    if (eyn > 0) eyn *= -1.;
+    m->Epos = p[0]; m->fyp = m->Epos * eyp; m->fyn = m->Epos * eyn; m->ezero = p[3]; m->ep = 0.0;
+    m->e = m->eP = m->Epos;
   } else if (kind == ORC_UNI_ELASTIC) {
     /* ElasticMaterial(tag, E, eta, Eneg), ElasticMaterial.cpp:96-110: p = E, eta (0 here: no strain rate in this path), Eneg */
     m->Epos = p[0]; m->Eneg = p[2];
@@ -505,6 +514,7 @@ static double uni_initial_tangent(const OrcUni* m) {
   if (m->kind == ORC_UNI_STEEL01) return m->E0;                                   /* Steel01.h getInitialTangent */
   if (m->kind == ORC_UNI_CONCRETE01) return 2.0 * m->fc / m->epsc0;               /* Concrete01.h getInitialTangent */
   if (m->kind == ORC_UNI_ELASTIC) return m->Epos > m->Eneg ? m->Epos : m->Eneg;   /* ElasticMaterial.cpp:186 */
+  if (m->kind == ORC_UNI_ELASTICPP) return m->Epos;                               /* ElasticPPMaterial.h getInitialTangent */
   return m->kind == ORC_UNI_STEEL02 ? m->E0 : 2.0 * m->fc / m->epsc0;   /* Steel02.cpp:107, Concrete02.cpp:161 */
 }
 
@@ -703,7 +713,20 @@ static int concrete01_set_trial(OrcUni* m, double strain) {
   else { m->sig = 0.0; m->e = 0.0; }
   return 0;
 }
+/* ElasticPPMaterial::setTrialStrain, ElasticPPMaterial.cpp:123-167 */
+static int elasticpp_set_trial(OrcUni* m, double strain) {
+  const double E = m->Epos;
+  m->eps = strain;
+  double sigtrial = E * (m->eps - m->ezero - m->ep);
+  double f;
+  if (sigtrial >= 0.0) f = sigtrial - m->fyp; else f = -sigtrial + m->fyn;
+  double fYieldSurface = -E * DBL_EPSILON;
+  if (f <= fYieldSurface) { m->sig = sigtrial; m->e = E; }
+  else { m->sig = sigtrial > 0.0 ? m->fyp : m->fyn; m->e = 0.0; }
+  return 0;
+}
 static int uni_set_trial(OrcUni* m, double strain) {
+  if (m->kind == ORC_UNI_ELASTICPP) return elasticpp_set_trial(m, strain);
   if (m->kind == ORC_UNI_CONCRETE01) return concrete01_set_trial(m, strain);
   if (m->kind == ORC_UNI_STEEL01) return steel01_set_trial(m, strain);
   if (m->kind == ORC_UNI_ELASTIC) return elastic_set_trial(m, strain);
@@ -719,6 +742,14 @@ static void uni_commit(OrcUni* m) {
   } else if (m->kind == ORC_UNI_CONCRETE01) {   /* Concrete01.cpp:402-418 */
     m->minStrainP = m->minStrain; m->unloadSlopeP = m->unloadSlope; m->endStrainP = m->endStrain;
   } else if (m->kind == ORC_UNI_CONCRETE02) { m->ecminP = m->ecmin; m->deptP = m->dept; }
+  else if (m->kind == ORC_UNI_ELASTICPP) {   /* ElasticPPMaterial::commitState, ElasticPPMaterial.cpp:190-224: the plastic strain moves here */
+    const double E = m->Epos;
+    double sigtrial = E * (m->eps - m->ezero - m->ep);
+    double f;
+    if (sigtrial >= 0.0) f = sigtrial - m->fyp; else f = -sigtrial + m->fyn;
+    double fYieldSurface = -E * DBL_EPSILON;
+    if (f > fYieldSurface) { if (sigtrial > 0.0) m->ep += f / E; else m->ep -= f / E; }
+  }
   m->eP = m->e; m->sigP = m->sig; m->epsP = m->eps;
 }
 static void uni_revert(OrcUni* m) {
@@ -731,6 +762,7 @@ static void uni_revert(OrcUni* m) {
     m->minStrain = m->minStrainP; m->endStrain = m->endStrainP; m->unloadSlope = m->unloadSlopeP;
   } else if (m->kind == ORC_UNI_ELASTIC) {   /* ElasticMaterial::revertToLastCommit: the committed strain; stress and tangent follow it */
     elastic_set_trial(m, m->epsP); return;
+  } else if (m->kind == ORC_UNI_ELASTICPP) {   /* ElasticPPMaterial::revertToLastCommit: strain, tangent, stress (ep has not moved) */
   } else { m->ecmin = m->ecminP; m->dept = m->deptP; }
   m->e = m->eP; m->sig = m->sigP; m->eps = m->epsP;
 }
@@ -1911,7 +1943,7 @@ int orc_add_uniaxial(void* h, int tag, int kind, const double* p) {
   m->uni_par = (double*)realloc(m->uni_par, sizeof(double) * 12 * (m->nuni + 1));
   m->uni_tag[m->nuni] = tag; m->uni_kind[m->nuni] = kind;
   memset(m->uni_par + 12 * m->nuni, 0, 12 * sizeof(double));
-  memcpy(m->uni_par + 12 * m->nuni, p, sizeof(double) * (kind == ORC_UNI_STEEL02 ? 11 : (kind == ORC_UNI_ELASTIC ? 3 : (kind == ORC_UNI_CONCRETE01 ? 4 : 7))));
+  memcpy(m->uni_par + 12 * m->nuni, p, sizeof(double) * (kind == ORC_UNI_STEEL02 ? 11 : (kind == ORC_UNI_ELASTIC ? 3 : ((kind == ORC_UNI_CONCRETE01 || kind == ORC_UNI_ELASTICPP) ? 4 : 7))));
   m->nuni++; return 0;
 }
 int orc_add_fiber_section(void* h, int tag, int nf, const double* y, const double* A, const int* matTags) {

@@ -26,7 +26,7 @@ GLUE_SO = os.path.join(ROOT, "oracle", "_ref", "libref_glue.so")
 
 MAT_ELASTIC, MAT_J2 = 0, 1
 ELE_BRICK, ELE_QUAD, ELE_FBC2D, ELE_FBC3D = 0, 1, 2, 3
-UNI_STEEL02, UNI_CONCRETE02, UNI_STEEL01, UNI_ELASTIC, UNI_CONCRETE01 = 0, 1, 2, 3, 4
+UNI_STEEL02, UNI_CONCRETE02, UNI_STEEL01, UNI_ELASTIC, UNI_CONCRETE01, UNI_ELASTICPP = 0, 1, 2, 3, 4, 5
 SEC_P, SEC_MZ = 2, 1     # SectionForceDeformation.h response codes
 ND_3D, ND_PLANE_STRAIN, ND_PLANE_STRESS = 0, 1, 2
 NUMBERER_PLAIN, NUMBERER_RCM = 0, 1
@@ -260,7 +260,7 @@ def soil_frame_2d(nbay=2, nstory=2, ndiv=1, per_bay=3, ny=4, depth=240.0, mat=J2
     return spec
 
 
-def steel01_elastic_frame(dim):
+def steel01_elastic_frame(dim, bars="steel01"):
     """an RC frame whose bars are Steel01 (with isotropic hardening), whose core is Concrete01 and whose cover is a bilinear
     Elastic material: the uniaxial kinds of BASELINE configs[0], and the concrete most RC examples use, as fibres of
     FiberSection2d / FiberSection3d"""
@@ -269,6 +269,8 @@ def steel01_elastic_frame(dim):
     uni[1] = (UNI_CONCRETE01, (-6.0, -0.004, -5.0, -0.014))             # core: Kent-Scott-Park, no tension
     uni[2] = (UNI_ELASTIC, (2500.0, 0.0, 3600.0))                       # cover: softer in tension
     uni[3] = (UNI_STEEL01, (60.0, 29000.0, 0.015, 0.02, 30.0, 0.02, 30.0))
+    if bars == "elasticpp":       # `uniaxialMaterial ElasticPP E epsyP epsyN eps0`: bars without hardening, weaker in compression, pre-strained
+        uni[3] = (UNI_ELASTICPP, (29000.0, 60.0 / 29000.0, -50.0 / 29000.0, 1.0e-4))
     spec.uniaxials = [(t, *uni[t]) for t in sorted(uni)]
     return spec
 

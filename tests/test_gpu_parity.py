@@ -200,7 +200,7 @@ def test_newton_iteration_counts_match_oracle(shape):
 
 @pytest.mark.skipif(not (have_ref() and have_glue()), reason="oracle/_ref not built (needs /root/reference)")
 @pytest.mark.parametrize("shape,numberer,soe", [("brick", 1, 0), ("quad", 0, 1), ("mixed", 1, 1), ("soilcolumn_equaldof", 1, 0), ("frame2d_gravity", 1, 0), ("soil_frame_mixed_ndf", 1, 0),
-                                                ("soilcolumn_equaldof", 0, 1), ("frame2d_pdelta", 1, 0), ("frame3d_pdelta", 1, 0), ("frame3d_eleloads", 1, 0), ("frame2d_legendre", 1, 0), ("frame3d_radau", 1, 0), ("frame2d_concrete01", 1, 0), ("frame2d_jntoffset", 1, 0), ("frame3d_jntoffset", 1, 0), ("frame2d_corot", 1, 0), ("frame2d_partial_load", 1, 0), ("frame3d_partial_load", 1, 0)])
+                                                ("soilcolumn_equaldof", 0, 1), ("frame2d_pdelta", 1, 0), ("frame3d_pdelta", 1, 0), ("frame3d_eleloads", 1, 0), ("frame2d_legendre", 1, 0), ("frame3d_radau", 1, 0), ("frame2d_concrete01", 1, 0), ("frame2d_jntoffset", 1, 0), ("frame3d_jntoffset", 1, 0), ("frame2d_corot", 1, 0), ("frame2d_partial_load", 1, 0), ("frame3d_partial_load", 1, 0), ("frame2d_elasticpp", 1, 0)])
 def test_reference_newton_loop_drives_device_path(shape, numberer, soe):
     """The drop-in, end to end: the REFERENCE'S OWN StaticAnalysis objects (AnalysisModel, PlainHandler, numberer,
     SparseGenCol/Row SOE and solver, NewtonRaphson, CTestNormDispIncr, LoadControl::newStep) run a load-controlled
@@ -240,6 +240,10 @@ def test_reference_newton_loop_drives_device_path(shape, numberer, soe):
         def mk():   # `geomTransf Corotational` (CorotCrdTransf2d) told from the others by dynamic_cast: heavy gravity, then the push
             from modelspec import with_corot
             return with_corot(frame2d(2, 3, 2, lateral=15.0, gravity=-150.0))
+    elif shape == "frame2d_elasticpp":
+        def mk():   # ElasticPP bars read out of the reference's FiberSection2d (E, fyp / E, fyn / E, ezero)
+            from modelspec import steel01_elastic_frame
+            return steel01_elastic_frame(2, "elasticpp")
     elif shape == "frame2d_concrete01":
         def mk():   # Concrete01 core, Steel01 bars, bilinear Elastic cover read out of the reference's FiberSection2d
             from modelspec import steel01_elastic_frame
@@ -1146,13 +1150,14 @@ def test_beam_integration_rules_device_vs_oracle(dim, kind):
     assert relerr(D.form_tangent(), O.form_tangent()) < BEAM_RTOL
 
 
+@pytest.mark.parametrize("bars", ["steel01", "elasticpp"])
 @pytest.mark.parametrize("dim", [2, 3])
-def test_steel01_elastic_fibres_device_vs_oracle(dim):
+def test_steel01_elastic_fibres_device_vs_oracle(dim, bars):
     """Steel01 and Elastic fibres inside FiberSection2d / FiberSection3d (the new uniaxial kinds as ordinary fibres):
     sway history with commits and a revert, device against the oracle"""
     from modelspec import steel01_elastic_frame
     rng = np.random.default_rng(8)
-    spec = steel01_elastic_frame(dim)
+    spec = steel01_elastic_frame(dim, bars)          # "elasticpp": ElasticPPMaterial bars
     O = OracleBackend(spec, 1, 0)
     D = xb.DeviceModel.from_spec(spec, 1, 0).to_device(0)
     ids = O.ids()

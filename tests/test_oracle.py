@@ -280,11 +280,12 @@ def test_steel01_elastic_paths_vs_live_reference():
     against the reference's own classes over cyclic strain paths with commits"""
     from modelspec import STEEL01_EX2B, UNI_STEEL01, UNI_ELASTIC, ref_uni_path
     rng = np.random.default_rng(4)
-    from modelspec import UNI_CONCRETE01
-    for kind, p in (STEEL01_EX2B, (UNI_STEEL01, (60.0, 29000.0, 0.02, 0.05, 20.0, 0.04, 25.0)),
+    from modelspec import UNI_CONCRETE01, UNI_ELASTICPP
+    for kind, p in ((UNI_ELASTICPP, (2.9e4, 2.0e-3, -1.5e-3, 1.0e-4)), (UNI_ELASTICPP, (2.9e4, -1.0e-3, 1.0e-3, 0.0)), STEEL01_EX2B, (UNI_STEEL01, (60.0, 29000.0, 0.02, 0.05, 20.0, 0.04, 25.0)),
                     (UNI_ELASTIC, (3.0e4, 0.0, 3.0e4)), (UNI_ELASTIC, (3.0e4, 0.0, 1.0e4)),
                     (UNI_CONCRETE01, (-6.0, -0.004, -5.0, -0.014)), (UNI_CONCRETE01, (5.0, 0.002, 1.0, 0.006))):
         epsy = p[0] / p[1] if kind == UNI_STEEL01 else (1.5e-3 if kind == UNI_CONCRETE01 else 1e-3)
+        if kind == UNI_ELASTICPP: epsy = 0.5e-3
         t = np.linspace(0, 14 * np.pi, 600)
         strains = 4.0 * epsy * (0.2 + t / t[-1]) * np.sin(t) + rng.normal(0, 0.05 * epsy, 600)
         strains[100:103] = strains[99]                      # zero increments (|dStrain| <= DBL_EPSILON: nothing moves)
@@ -294,6 +295,8 @@ def test_steel01_elastic_paths_vs_live_reference():
         assert close(so, sr, 1e-14) and (close(to, tr, 1e-13) if kind == UNI_CONCRETE01 else np.array_equal(to, tr))   # (the reference is built with FMA contraction)
         if kind == UNI_CONCRETE01:
             assert (sr == 0.0).sum() > 50 and sr.min() < 0.9 * -abs(p[0]) and len(np.unique(np.round(tr, 2))) > 30   # cracks open, crushing, unloading slopes
+        if kind == UNI_ELASTICPP:
+            assert (tr == 0.0).sum() > 50 and (tr == p[0]).sum() > 50              # plastic plateaus and elastic unloading
         if kind == UNI_STEEL01:
             assert (tr == p[2] * p[1]).sum() > 50 and (tr == p[1]).sum() > 50      # the path yields and unloads
 
@@ -335,13 +338,14 @@ def test_aggregator_cantilever_vs_live_reference(ndiv):
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("bars", ["steel01", "elasticpp"])
 @pytest.mark.parametrize("dim", [2, 3])
-def test_steel01_elastic_fibres_vs_live_reference(dim):
+def test_steel01_elastic_fibres_vs_live_reference(dim, bars):
     """Steel01 bars and an Elastic (bilinear Epos / Eneg) cover inside FiberSection2d / FiberSection3d: the new uniaxial
     kinds as ordinary fibres, against the reference's classes over a sway history with commits"""
     from modelspec import steel01_elastic_frame
     rng = np.random.default_rng(8)
-    spec = steel01_elastic_frame(dim)
+    spec = steel01_elastic_frame(dim, bars)          # "elasticpp": ElasticPPMaterial bars (the plastic strain moves at commitState)
     O, R = OracleBackend(spec, 1, 0), RefBackend(spec, 1, 0)
     hcol = spec.crd[:, 1] if dim == 2 else spec.crd[:, 2]
     H = hcol.max(); h = hcol / H

@@ -28,12 +28,12 @@ import os
 import numpy as np
 
 __all__ = ["DeviceModel", "XaraB200Error", "lib", "LIB_PATH", "device_count", "comm_unique_id", "exchange_local",
-           "MAT_ELASTIC_ISOTROPIC", "MAT_J2PLASTICITY", "ELE_STDBRICK", "ELE_FOURNODEQUAD", "ELE_FORCEBEAMCOLUMN2D", "ELE_FORCEBEAMCOLUMN3D", "UNI_STEEL02", "UNI_CONCRETE02", "UNI_STEEL01", "UNI_ELASTIC", "UNI_CONCRETE01",
+           "MAT_ELASTIC_ISOTROPIC", "MAT_J2PLASTICITY", "ELE_STDBRICK", "ELE_FOURNODEQUAD", "ELE_FORCEBEAMCOLUMN2D", "ELE_FORCEBEAMCOLUMN3D", "UNI_STEEL02", "UNI_CONCRETE02", "UNI_STEEL01", "UNI_ELASTIC", "UNI_CONCRETE01", "UNI_ELASTICPP",
            "NUMBERER_PLAIN", "NUMBERER_RCM", "SOE_SPARSE_GEN_COL", "SOE_SPARSE_GEN_ROW", "SOE_BAND_GEN", "SOE_PROFILE_SPD", "SOE_UMFPACK_GEN"]
 
 MAT_ELASTIC_ISOTROPIC, MAT_J2PLASTICITY = 0, 1
 ELE_STDBRICK, ELE_FOURNODEQUAD, ELE_FORCEBEAMCOLUMN2D, ELE_FORCEBEAMCOLUMN3D = 0, 1, 2, 3
-UNI_STEEL02, UNI_CONCRETE02, UNI_STEEL01, UNI_ELASTIC, UNI_CONCRETE01 = 0, 1, 2, 3, 4
+UNI_STEEL02, UNI_CONCRETE02, UNI_STEEL01, UNI_ELASTIC, UNI_CONCRETE01, UNI_ELASTICPP = 0, 1, 2, 3, 4, 5
 NUMBERER_PLAIN, NUMBERER_RCM = 0, 1
 SOE_SPARSE_GEN_COL, SOE_SPARSE_GEN_ROW, SOE_BAND_GEN, SOE_PROFILE_SPD, SOE_UMFPACK_GEN = 0, 1, 2, 3, 4
 

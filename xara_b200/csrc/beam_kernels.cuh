@@ -324,6 +324,25 @@ __device__ __forceinline__ void elastic_trial(const double* __restrict__ p, doub
   T[8 * n] = e; T[9 * n] = sig; T[10 * n] = strain;
   sig_o = sig; e_o = e;
 }
+// ElasticPPMaterial::setTrialStrain (ElasticPPMaterial.cpp:123-167).  p = E, fyp, fyn, ezero (host).  The plastic strain ep
+// moves at commitState (:190-224) from the trial strain of that moment: the trial record carries the value the commit will
+// give it (T[0]); the commit is the copy trial -> committed like every other fibre record
+__device__ __forceinline__ void elasticpp_trial(const double* __restrict__ p, const double* C, double* T, long long n,
+                                                double strain, double& sig_o, double& e_o) {
+  const double E = p[0], fyp = p[1], fyn = p[2], ezero = p[3];
+  const double ep = C[0];
+  const double sigtrial = E * (strain - ezero - ep);
+  const double f = sigtrial >= 0.0 ? sigtrial - fyp : -sigtrial + fyn;
+  const double fYieldSurface = -E * DBL_EPSILON;
+  double sig, e, epn = ep;
+  if (f <= fYieldSurface) { sig = sigtrial; e = E; }
+  else {
+    sig = sigtrial > 0.0 ? fyp : fyn; e = 0.0;
+    if (sigtrial > 0.0) epn += f / E; else epn -= f / E;
+  }
+  T[0] = epn; T[8 * n] = e; T[9 * n] = sig; T[10 * n] = strain;
+  sig_o = sig; e_o = e;
+}
 // Concrete01::setTrialStrain with reload / envelope / unload (Concrete01.cpp:146-206, 313-385).  p = fpc, epsc0, fpcu, epscu
 // (made negative on the host)
 __device__ __forceinline__ void concrete01_trial(const double* __restrict__ p, const double* C, double* T, long long n,
@@ -385,6 +404,7 @@ __device__ __forceinline__ void uniaxial_trial(int kind, const double* __restric
   else if (kind == 1) concrete02_trial(p, C, T, n, strain, stress, tangent);
   else if (kind == 2) steel01_trial(p, C, T, n, strain, stress, tangent);
   else if (kind == 4) concrete01_trial(p, C, T, n, strain, stress, tangent);
+  else if (kind == 5) elasticpp_trial(p, C, T, n, strain, stress, tangent);
   else elastic_trial(p, T, n, strain, stress, tangent, in_fibre);
 }
 

@@ -1969,6 +1969,9 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
         } else if (u.kind == XB_UNI_ELASTIC) {   // ElasticMaterial::getInitialTangent, ElasticMaterial.cpp:186
           E0 = u.par[0] > u.par[2] ? u.par[0] : u.par[2];
           C[8] = E0; T[8] = E0;
+        } else if (u.kind == XB_UNI_ELASTICPP) {   // ElasticPPMaterial: trialTangent = commitTangent = E, ep = 0
+          E0 = u.par[0];
+          C[8] = E0; T[8] = E0;
         } else {
           E0 = 2.0 * u.par[0] / u.par[1];
           C[8] = E0; T[8] = E0;
@@ -2010,6 +2013,7 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
         auto e0 = [&](int f) {
           const xb::Uniaxial& u = h.unis[sd.mat[f]];
           if (u.kind == XB_UNI_ELASTIC) return u.par[0] > u.par[2] ? u.par[0] : u.par[2];
+          if (u.kind == XB_UNI_ELASTICPP) return u.par[0];
           if (u.kind == XB_UNI_CONCRETE02 || u.kind == XB_UNI_CONCRETE01) return 2.0 * u.par[0] / u.par[1];
           return u.par[1];
         };

@@ -64,7 +64,7 @@ int HostModel::add_material(int tag, int kind, const double* par, int npar) {
 
 int HostModel::add_uniaxial(int tag, int kind, const double* par, int npar) {
   if (is_setup) { err = "xb_add_uniaxial_material after xb_setup"; return XB_ERR_STATE; }
-  const int need = kind == XB_UNI_STEEL02 ? 10 : (kind == XB_UNI_CONCRETE02 ? 7 : (kind == XB_UNI_STEEL01 ? 7 : (kind == XB_UNI_ELASTIC ? 1 : (kind == XB_UNI_CONCRETE01 ? 4 : -1))));
+  const int need = kind == XB_UNI_STEEL02 ? 10 : (kind == XB_UNI_CONCRETE02 ? 7 : (kind == XB_UNI_STEEL01 ? 7 : (kind == XB_UNI_ELASTIC ? 1 : ((kind == XB_UNI_CONCRETE01 || kind == XB_UNI_ELASTICPP) ? 4 : -1))));
   if (need < 0) { err = "xb_add_uniaxial_material: unknown kind"; return XB_ERR_ARG; }
   if (npar < need || npar > 12) { err = "xb_add_uniaxial_material: wrong parameter count"; return XB_ERR_ARG; }
   if (kind == XB_UNI_ELASTIC && npar > 1 && par[1] != 0.0) { err = "uniaxialMaterial Elastic with eta != 0: strain rates are outside the device path"; return XB_ERR_UNSUPPORTED; }
@@ -73,6 +73,12 @@ int HostModel::add_uniaxial(int tag, int kind, const double* par, int npar) {
   u.tag = tag; u.kind = kind;
   std::memcpy(u.par, par, sizeof(double) * npar);
   if (kind == XB_UNI_ELASTIC && npar < 3) u.par[2] = u.par[0];   // ElasticMaterial(tag, E, eta): Eneg = E
+  if (kind == XB_UNI_ELASTICPP) {   // ElasticPPMaterial(tag, E, eyp, eyn, ezero), ElasticPPMaterial.cpp:88-107: par becomes E, fyp, fyn, ezero
+    double eyp = u.par[1], eyn = u.par[2];
+    if (eyp < 0) eyp *= -1.;
+    if (eyn > 0) eyn *= -1.;
+    u.par[1] = u.par[0] * eyp; u.par[2] = u.par[0] * eyn;
+  }
   if (kind == XB_UNI_CONCRETE02 || kind == XB_UNI_CONCRETE01) {   // Concrete02.cpp:101-104, Concrete01.cpp:96-107: compression quantities are made negative
     for (int i = 0; i < 4; i++) if (u.par[i] > 0) u.par[i] = -u.par[i];
   }
