@@ -133,6 +133,28 @@ def test_error_behaviour():
         q.set_option("no_such_option", 1)
 
 
+def test_beam_edges_refused_on_the_host():
+    """what the device path does not cover is refused when the model is described, not computed wrongly: a corotational
+    transformation in 3D, a partial uniform load with aOverL >= bOverL or a second one on the same element, stiffness-
+    proportional Rayleigh terms on corotational beams"""
+    from modelspec import frame2d, frame3d, with_corot, with_beam_partial_loads
+    sp3 = frame3d(1, 1, 1)
+    for g in sp3.groups: g.par[:, 6] = 2.0
+    with pytest.raises(xb.XaraB200Error, match="[Cc]orotational"):
+        xb.DeviceModel.from_spec(sp3, setup=False)
+    sp = with_beam_partial_loads(with_corot(frame2d(1, 1, 1)), seed=1)
+    m = xb.DeviceModel.from_spec(sp, setup=False)
+    t = [sp.beam_partial_loads[0][0]]
+    with pytest.raises(xb.XaraB200Error, match="one partial"):
+        m.add_beam_partial_loads(t, np.array([[-0.1, -0.1, 0, 0, 0.2, 0.8, 0, 0]]))
+    col = [int(x) for x in sp.groups[0].tags if int(x) not in {q[0] for q in sp.beam_partial_loads}][:1]
+    with pytest.raises(xb.XaraB200Error, match="aOverL"):
+        m.add_beam_partial_loads(col, np.array([[-0.1, -0.1, 0, 0, 0.8, 0.2, 0, 0]]))
+    with pytest.raises(xb.XaraB200Error, match="corotational"):
+        m.set_rayleigh(0.1, 0.002, 0.0, 0.0)
+    m.set_rayleigh(0.1, 0.0, 0.0, 0.0)          # mass-proportional damping alone is fine
+
+
 @pytest.mark.skipif(xb.device_count() > 0, reason="only meaningful on a box without a GPU")
 def test_no_cpu_fallback_without_device():
     D = xb.DeviceModel.from_spec(brick_block(1, 1, 1), 0, 0)
