@@ -51,6 +51,7 @@
 #include <LinearCrdTransf3d.h>
 #include <PDeltaCrdTransf2d.h>
 #include <CorotCrdTransf2d.h>
+#include <TransformationConstraintHandler.h>
 #include <PDeltaCrdTransf3d.h>
 #include <LobattoBeamIntegration.h>
 #include <Brick.h>
@@ -438,6 +439,16 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
   }
   std::vector<int> xt(tags.size()), ids(tags.size() * m->ndf);
   xb_get_node_tags(x, xt.data()); xb_get_ids(x, ids.data());
+  // `constraints Transformation`: with homogeneous SPs and identity MP constraints the TransformationConstraintHandler numbers
+  // the same equations and gives the same pattern as PlainHandler (tests/test_oracle.py), but its enforceSPs() calls
+  // Element::update() once more on every element next to a constrained node at each applyLoad
+  // (TransformationConstraintHandler.cpp:462-483).  After a commit that second update turns the consistent tangent of a
+  // yielded J2 point into the elastic one (zero strain increment) and makes a force-based beam iterate again from where it
+  // stood: the reference's OWN Newton histories differ between its two handlers once the model yields.  The device path
+  // reproduces the PlainHandler system; a Domain analysed under the Transformation handler keeps the CPU integrator.
+  if (dynamic_cast<TransformationConstraintHandler*>(m->handler) != nullptr) {
+    G.err = "glue: `constraints Transformation` re-updates constrained elements at every applyLoad; the device path follows `constraints Plain`"; return -10;
+  }
   for (size_t i = 0; i < xt.size(); i++) {
     const ID& rid = dom->getNode(xt[i])->getDOF_GroupPtr()->getID();
     for (int d = 0; d < m->ndf; d++)

@@ -67,6 +67,7 @@
 
 #include <AnalysisModel.h>
 #include <PlainHandler.h>
+#include <TransformationConstraintHandler.h>
 #include <PlainNumberer.h>
 #include <DOF_Numberer.h>
 #include <RCM.h>
@@ -214,7 +215,8 @@ struct RefModel {
   std::map<int, SectionForceDeformation*> sections2d;   // FiberSection2d or SectionAggregator
   std::map<int, FiberSection3d*> sections3d;
   AnalysisModel* amodel = nullptr;
-  PlainHandler* handler = nullptr;
+  ConstraintHandler* handler = nullptr;
+  int handler_kind = 0;          // `constraints Plain` (0) | `constraints Transformation` (1)
   DOF_Numberer* numberer = nullptr;
   LinearSOE* soe = nullptr;
   SparseGenRowLinSOE* rsoe = nullptr;   // soeKind 1
@@ -582,7 +584,7 @@ int ref_analyze_transient(void* h, int nsteps, double dt, int* iters, double* no
 
 static int ref_setup_common(RefModel* m, int numberer, int soeKind, int testKind, double tol, int maxIter) {
   m->amodel = new AnalysisModel();
-  m->handler = new PlainHandler();
+  m->handler = m->handler_kind == 1 ? (ConstraintHandler*)new TransformationConstraintHandler() : (ConstraintHandler*)new PlainHandler();
   if (numberer == 0) m->numberer = new PlainNumberer();
   else { RCM* rcm = new RCM(false); m->numberer = new DOF_Numberer(*rcm); }
   m->rsoe = nullptr; m->csoe = nullptr; m->bsoe = nullptr;     // (a second `analysis` on the same Domain starts over)
@@ -612,6 +614,9 @@ static int ref_setup_common(RefModel* m, int numberer, int soeKind, int testKind
   if (m->integ->domainChanged() < 0) return -4;
   return m->amodel->getNumEqn();
 }
+
+// `constraints Plain | Transformation` of the analyses set up from now on
+int ref_set_handler(void* h, int kind) { ((RefModel*)h)->handler_kind = kind; return 0; }
 
 int ref_num_eqn(void* h) { return ((RefModel*)h)->soe->getNumEqn(); }
 int ref_nnz(void* h) { RefModel* m = (RefModel*)h; return m->bsoe ? (int)m->bsoe->asize() : m->ptr()[m->n()]; }

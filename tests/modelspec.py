@@ -939,7 +939,7 @@ class RefBackend(_Backend):
     """The reference's own Domain / AnalysisModel / LinearSOE, through oracle/ref_harness.cpp."""
 
     def __init__(self, spec: ModelSpec, numberer=NUMBERER_PLAIN, soe=SOE_CSC, dlambda=1.0,
-                 test=0, tol=1e-8, max_iter=20, defer_setup=False, so=None):
+                 test=0, tol=1e-8, max_iter=20, defer_setup=False, so=None, handler=0):
         L = ctypes.CDLL(so or REF_SO)
         self.L, self.spec = L, spec
         L.ref_model_new.restype = ctypes.c_void_p
@@ -1030,6 +1030,7 @@ class RefBackend(_Backend):
                 assert L.ref_add_beam_uniform_load(self.h, int(t), float(wy), float(wz), float(wa)) == 0
         self.ne = len(self.ele_tags)
         self.max_iter = max_iter
+        L.ref_set_handler(self.h, int(handler))      # `constraints Plain` (0) | `constraints Transformation` (1)
         if defer_setup:       # the caller picks the integrator (setup_transient)
             return
         L.ref_setup.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,

@@ -679,3 +679,53 @@ def test_corotational_transformation_vs_live_reference(loads):
         else:
             O.commit(); R.commit(); Rn.commit()
     assert differs
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("numberer", [0, 1])
+def test_transformation_handler_numbers_and_assembles_as_plain(numberer):
+    """`constraints Transformation` with homogeneous SPs and `equalDOF` constraints (identity constraint matrices): the
+    reference's TransformationConstraintHandler gives the SAME equation numbers and SparseGenCol pattern as its PlainHandler
+    (same DOF_Group / FE_Element tags and DOF-group graph; a constrained node's dofs take the retained node's equations
+    either way) and, state for state, bitwise the same A and B for the continuum elements.  But its enforceSPs() updates
+    every element next to a constrained node once more at each applyLoad (TransformationConstraintHandler.cpp:462-483): after
+    a commit that turns the consistent tangent of a yielded J2 point into the elastic one and makes a force beam iterate
+    again, so the reference's OWN Newton histories differ between its two handlers once the model yields (asserted at the
+    end).  The device path follows PlainHandler; the binding refuses a Domain analysed under the Transformation handler."""
+    rng = np.random.default_rng(17)
+    specs = [soil_column_equaldof(6, mat=J2_STEEL, distort=0.1), brick_periodic_equaldof(3, 2, 2), brick_block(3, 3, 3, mat=J2_STEEL, distort=0.2, seed=2),
+             quad_plane(6, 4, mat=J2_STEEL, distort=0.2, seed=3)]
+    for spec in specs:
+        P, T = RefBackend(spec, numberer, 0, handler=0), RefBackend(spec, numberer, 0, handler=1)
+        assert P.neq == T.neq and P.nnz == T.nnz
+        (pp, pi), (tp, ti) = P.csr(), T.csr()
+        assert np.array_equal(pp, tp) and np.array_equal(pi, ti)
+        _, fp = P.fe_ids(); _, ft = T.fe_ids()
+        for a, b in zip(fp, ft):                    # the same equations per FE_Element (a TransformationFE lists them in its own order)
+            assert sorted(set(a.tolist()) - {-9, -1}) == sorted(set(b.tolist()) - {-9, -1})
+        for s_ in range(3):
+            u = rng.normal(0, 2e-3 * (s_ + 1), (spec.nn, spec.ndf)); u[P.ids() < 0] = 0; tie(spec, u)
+            for m in (P, T):
+                m.set_trial_disp(u); m.apply_load(0.3 * (s_ + 1))
+            assert np.array_equal(P.form_tangent(), T.form_tangent()) and np.array_equal(P.form_unbalance(), T.form_unbalance())
+            P.commit(); T.commit()
+    # force beams: equal numbering and pattern, values to the element tolerance only
+    spec = frame2d(2, 2, 2)
+    P, T = RefBackend(spec, numberer, 0, handler=0), RefBackend(spec, numberer, 0, handler=1)
+    assert np.array_equal(P.ids(), T.ids()) and all(np.array_equal(a, b) for a, b in zip(P.csr(), T.csr()))
+    u = rng.normal(0, 1.0, (spec.nn, 3)) * (0.02, 0.02, 2e-4); u[P.ids() < 0] = 0
+    for m in (P, T):
+        m.set_trial_disp(u); m.apply_load(0.4)
+    assert close(P.form_tangent(), T.form_tangent(), 1e-5)
+    # the same load-controlled Newton analysis under both handlers: identical while elastic, different once the soil yields
+    def mk():
+        sp = soil_column_equaldof(12, mat=J2_STEEL, distort=0.1)
+        sp.loads = np.array([[1 + 2 * 12, 22.0 * 8, -3.0 * 8], [1 + 2 * 6, 10.0 * 8, 0.0]]); return sp
+    hist = []
+    for h in (0, 1):
+        C = RefBackend(mk(), numberer, 0, dlambda=1.0 / 8, test=0, tol=1e-7, max_iter=25, handler=h)
+        rc, iters, norms = C.analyze_static(8)
+        assert rc == 0
+        hist.append(norms)
+    assert np.allclose(hist[0][:4], hist[1][:4], rtol=1e-9, atol=1e-14)
+    assert not np.allclose(hist[0][5:, 0], hist[1][5:, 0], rtol=1e-5)
