@@ -327,7 +327,7 @@ int xb_get_element_tangent(xb_model*, long long e, double* K);
 int xb_get_element_resid(xb_model*, long long e, double* R);
 int xb_get_gp_response(xb_model*, long long e, int g, double* stress, double* tangent);
 
-/* Run-time tuning of the device path; the results are bit-for-bit the same under every setting.
+/* Run-time tuning of the device path; the results are bit-for-bit the same under every tuning setting.
  *   "ranged_tangent"  0 | 1 (default 1): run xb_form_tangent of a large single-batch brick model range by range on
  *                     two streams also when A stays on the device (with a host destination it always does)
  *   "brick_storage"   0 | 1 (default 1; before xb_setup): stdBrick tangents leave the tangent kernel as symmetric element
@@ -337,6 +337,13 @@ int xb_get_gp_response(xb_model*, long long e, int g, double* stress, double* ta
  *   "tangent_ranges"  1..64 (default 8; before xb_setup): the number of element ranges of the ranged formTangent
  *   "fast_assembly"   0 | 1 (default 1): plain brick models (no MP constraints, rows <= 96 entries, <= 32 elements per
  *                     node) take the hand-tuned record assembly kernel; 0 forces the generic one
+ * And one that follows the reference's `constraints` command (it changes results exactly as the command does there):
+ *   "constraints_transformation"  0 | 1 (default 0 = `constraints Plain`; before xb_device_init): `constraints Transformation`
+ *                     with fix / equalDOF constraints numbers and assembles like PlainHandler, but its enforceSPs() updates
+ *                     every element with a constrained node once more at each applyLoad (analysis/handler/
+ *                     TransformationConstraintHandler.cpp:462-483) -- after a commit that leaves a yielded J2 point with its
+ *                     elastic tangent for the next step's first iteration.  With 1, xb_apply_load repeats that update on
+ *                     the same stdBrick / FourNodeQuad elements; models with forceBeamColumn elements: XB_ERR_UNSUPPORTED
  * Returns XB_ERR_ARG for an unknown name or value. */
 int xb_set_option(xb_model*, const char* name, int value);
 

@@ -51,6 +51,7 @@
 #include <LinearCrdTransf3d.h>
 #include <PDeltaCrdTransf2d.h>
 #include <CorotCrdTransf2d.h>
+#include <TransformationDOF_Group.h>
 #include <TransformationConstraintHandler.h>
 #include <PDeltaCrdTransf3d.h>
 #include <LobattoBeamIntegration.h>
@@ -440,17 +441,38 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
   std::vector<int> xt(tags.size()), ids(tags.size() * m->ndf);
   xb_get_node_tags(x, xt.data()); xb_get_ids(x, ids.data());
   // `constraints Transformation`: with homogeneous SPs and identity MP constraints the TransformationConstraintHandler numbers
-  // the same equations and gives the same pattern as PlainHandler (tests/test_oracle.py), but its enforceSPs() calls
-  // Element::update() once more on every element next to a constrained node at each applyLoad
-  // (TransformationConstraintHandler.cpp:462-483).  After a commit that second update turns the consistent tangent of a
-  // yielded J2 point into the elastic one (zero strain increment) and makes a force-based beam iterate again from where it
-  // stood: the reference's OWN Newton histories differ between its two handlers once the model yields.  The device path
-  // reproduces the PlainHandler system; a Domain analysed under the Transformation handler keeps the CPU integrator.
-  if (dynamic_cast<TransformationConstraintHandler*>(m->handler) != nullptr) {
-    G.err = "glue: `constraints Transformation` re-updates constrained elements at every applyLoad; the device path follows `constraints Plain`"; return -10;
+  // the same equations and gives the same pattern as PlainHandler (tests/test_oracle.py); only the layout of a constrained
+  // node's ID differs -- TransformationDOF_Group::getID is [the node's own unconstrained dofs..., the retained node's
+  // retained dofs...] (TransformationDOF_Group.cpp:60-110, doneID :921-945).  Its enforceSPs() also calls Element::update()
+  // once more on every element next to a constrained node at each applyLoad (TransformationConstraintHandler.cpp:462-483):
+  // after a commit that leaves a yielded J2 point with its elastic tangent for the first iteration of the next step, so the
+  // reference's Newton histories differ between its two handlers.  The device does the same second update when told
+  // (`constraints_transformation`); a force-based beam would iterate again from where it stood, so beams stay on Plain.
+  std::map<int, size_t> row_of;
+  for (size_t i = 0; i < xt.size(); i++) row_of[xt[i]] = i;
+  const bool transf_handler = dynamic_cast<TransformationConstraintHandler*>(m->handler) != nullptr;
+  if (transf_handler) {
+    ElementIter& ei = dom->getElements(); Element* el;
+    while ((el = ei()) != nullptr)
+      if (dynamic_cast<ForceBeamColumn2d*>(el) || dynamic_cast<ForceBeamColumn3d*>(el)) { G.err = "glue: forceBeamColumn under `constraints Transformation` (the handler updates constrained elements twice per step): use `constraints Plain`"; return -10; }
+    if (xb_set_option(x, "constraints_transformation", 1) < 0) { G.err = xb_last_error(); return -10; }
   }
   for (size_t i = 0; i < xt.size(); i++) {
-    const ID& rid = dom->getNode(xt[i])->getDOF_GroupPtr()->getID();
+    DOF_Group* grp = dom->getNode(xt[i])->getDOF_GroupPtr();
+    const ID& rid = grp->getID();
+    TransformationDOF_Group* tg = transf_handler ? dynamic_cast<TransformationDOF_Group*>(grp) : nullptr;
+    if (tg && tg->theMP) {
+      const ID& cd = tg->theMP->getConstrainedDOFs(); const ID& rd = tg->theMP->getRetainedDOFs();
+      std::vector<int> want;
+      const int nnd = dom->getNode(xt[i])->getNumberDOF();
+      for (int d = 0; d < nnd; d++) if (cd.getLocation(d) < 0) want.push_back(ids[i * m->ndf + d]);
+      auto it = row_of.find(tg->theMP->getNodeRetained());
+      if (it == row_of.end()) { G.err = "glue: retained node of an MP_Constraint not in the model"; return -10; }
+      for (int j = 0; j < rd.Size(); j++) want.push_back(ids[it->second * m->ndf + rd(j)]);
+      if ((int)want.size() != rid.Size()) { G.err = "glue: DOF numbering differs from the reference's (constrained node)"; return -10; }
+      for (int k = 0; k < rid.Size(); k++) if (rid(k) != want[k]) { G.err = "glue: DOF numbering differs from the reference's (constrained node)"; return -10; }
+      continue;
+    }
     for (int d = 0; d < m->ndf; d++)
       if ((d < rid.Size() ? rid(d) : -1) != ids[i * m->ndf + d]) { G.err = "glue: DOF numbering differs from the reference's"; return -10; }
   }

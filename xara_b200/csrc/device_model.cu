@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/xara_b200.h"
@@ -55,6 +56,8 @@ struct GroupView {
   int cps;              // columns per row in a slot (cp_stride)
   int ns;               // dofs per node of the MODEL (stride of U, V, A): a quad's 2-dof nodes may sit in an ndf = 3 model
   double* Re;           // [n][nd]
+  const unsigned char* umask;   // null, or [n]: update only the marked elements (`constraints Transformation`: the handler's
+                                // enforceSPs() updates the elements next to constrained nodes once more at every applyLoad)
 };
 
 // Transient analysis with element damping / mass.  FE_Element::getTangent under Newmark::formEleTangent
@@ -171,7 +174,8 @@ __global__ void __launch_bounds__(128, UPD_OCC) brick_update_kernel(GroupView G,
                                                            const double* __restrict__ U, int* fail) {
   const long long gp_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long ngp = G.n * 8;
-  const bool live = gp_raw < ngp;                 // dead lanes still take part in the shuffles below
+  // dead lanes (beyond the batch, or of an element a masked update leaves alone) still take part in the shuffles below
+  const bool live = gp_raw < ngp && (G.umask == nullptr || G.umask[gp_raw >> 3] != 0);
   const long long gp = live ? gp_raw : ngp - 1;
   const long long e = gp >> 3;
   const int g = (int)(gp_raw & 7);
@@ -471,6 +475,7 @@ __global__ void __launch_bounds__(128) quad_update_kernel(GroupView G, const dou
   const long long gp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long ngp = G.n * 4;
   if (gp >= ngp) return;
+  if (G.umask != nullptr && G.umask[gp >> 2] == 0) return;      // masked update: not this element
   const long long e = gp >> 2;
   const int g = (int)(gp & 3);
   const int* c = G.conn + e * 4;
@@ -1527,6 +1532,7 @@ struct DevGroup {
   int kind = 0, mat_kind = 0, nip = 0, nst = 0, nd = 0;
   long long ngp = 0, re_off = 0;
   bool has_rho = false;      // some material of the batch has a density (element mass)
+  const unsigned char* dmask = nullptr;   // `constraints Transformation`: elements with a constrained node (fix / equalDOF-constrained)
   size_t fib_doubles = 0;    // size of one fibre-record buffer
 };
 
@@ -1577,6 +1583,7 @@ struct xb_model {
   bool ranged = true;               // formTangent of a large batch range by range on two streams also without a host destination (xb_set_option)
   double* dRec = nullptr;           // stdBrick: symmetric element records (brick_rec.hpp)
   long long* dPkSrc = nullptr;      // record models: descriptors of the outgoing row chunks
+  bool transf_handler = false;      // xb_set_option "constraints_transformation": see xb_apply_load
   bool fast_asm_on = true;          // record models: the hand-tuned assembly kernel when the model allows it (xb_set_option "fast_assembly")
   int tan_per_sm = 0;               // occupancy of the brick tangent kernel (cached)
   const void* tan_kern = nullptr;
@@ -1988,6 +1995,7 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
       const double det = k0[0] * k0[3] - k0[2] * k0[1];
       std::vector<double> fs0 = {k0[3] / det, -k0[1] / det, -k0[2] / det, k0[0] / det};
       b.agg = sd.agg ? 1 : 0;
+      if (m->transf_handler) return fail(XB_ERR_UNSUPPORTED, "constraints_transformation: forceBeamColumn elements are outside it (the handler's second update makes a force beam iterate again)");
       b.pdelta = g.transf == 1 ? 1 : 0; b.corot = g.transf == 2 ? 1 : 0; b.U = m->dU; b.ul = nullptr;
       b.off = nullptr;
       {   // rigid joint offsets, SoA [4][n] (2D) / [6][n] (3D); null when the batch has none
@@ -2089,6 +2097,16 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
     d.re_off = g.re_off;
     for (int mi : g.mat) if (h.mats[mi].par[g.mat_kind == XB_MAT_J2PLASTICITY ? 7 : 2] != 0.0) { d.has_rho = true; break; }
     if (d.has_rho) m->any_rho = true;
+    if (m->transf_handler && g.n() > 0) {
+      // TransformationConstraintHandler::handle (TransformationConstraintHandler.cpp:260-300): an element with a node that carries an
+      // SP_Constraint or is the constrained node of an MP_Constraint becomes a TransformationFE
+      std::unordered_set<int> cn(h.sp_node.begin(), h.sp_node.end());
+      cn.insert(h.mp_c.begin(), h.mp_c.end());
+      std::vector<unsigned char> mk((size_t)g.n(), 0);
+      for (long long e = 0; e < g.n(); e++)
+        for (int a = 0; a < k.nen; a++) if (cn.count(h.node_tag[g.conn[(size_t)e * k.nen + a]])) { mk[e] = 1; break; }
+      unsigned char* dm = nullptr; CU(dev_upload(m, &dm, mk)); d.dmask = dm;
+    }
     m->dg.push_back(d);
   }
 
@@ -2391,10 +2409,36 @@ static void beams_take_load_factor(xb_model* m, double lambda) {
   // (element loads of a pattern that loadConst froze keep the factor they had then: LoadPattern::applyLoad with isConstant)
   for (auto& d : m->dg) if (is_beam(d.kind) && d.b.wl) { d.b.lam = m->ele_loads_const ? m->ele_lambda : lambda; d.b.loads_on = 1; }
 }
+static void launch_continuum_update(xb_model* m, const DevGroup& d, const GroupView& v) {
+  const unsigned blocks = (unsigned)((d.ngp + 127) / 128);
+  const bool j2 = d.mat_kind == XB_MAT_J2PLASTICITY;
+  if (d.kind == XB_ELE_STDBRICK) {
+    if (j2) brick_update_kernel<XB_MAT_J2PLASTICITY><<<blocks, 128, 0, m->stream>>>(v, m->dX, m->dU, m->dFail);
+    else brick_update_kernel<XB_MAT_ELASTIC_ISOTROPIC><<<blocks, 128, 0, m->stream>>>(v, m->dX, m->dU, m->dFail);
+  } else {
+    if (j2) quad_update_kernel<XB_MAT_J2PLASTICITY><<<blocks, 128, 0, m->stream>>>(v, m->dX, m->dU, m->dFail);
+    else quad_update_kernel<XB_MAT_ELASTIC_ISOTROPIC><<<blocks, 128, 0, m->stream>>>(v, m->dX, m->dU, m->dFail);
+  }
+  m->launches++;
+}
 int xb_apply_load(xb_model* m, double lambda) {
   if (!m) return fail(XB_ERR_ARG, "null model");
   m->lambda = lambda;
   beams_take_load_factor(m, lambda);
+  if (m->transf_handler && m->on_device) {
+    // `constraints Transformation`: AnalysisModel::applyLoadDomain ends in TransformationConstraintHandler::applyLoad ->
+    // enforceSPs(), which calls Element::update() on every element next to a constrained node
+    // (TransformationConstraintHandler.cpp:462-483).  At an unchanged trial state that changes nothing -- except right after a
+    // commit, where the zero strain increment leaves a yielded J2 point with its elastic tangent for the first iteration
+    // of the next step.  The same elements are updated here; the committed history is not touched (no trial_written).
+    CU(cudaSetDevice(m->device));
+    for (auto& d : m->dg) {
+      if (is_beam(d.kind) || d.v.n == 0 || d.dmask == nullptr) continue;
+      GroupView v = d.v; v.umask = d.dmask;
+      launch_continuum_update(m, d, v);
+    }
+    CU(cudaGetLastError());
+  }
   return XB_OK;
 }
 
@@ -2829,6 +2873,9 @@ int xb_set_option(xb_model* m, const char* name, int value) {
     if (m->h.is_setup) return fail(XB_ERR_STATE, "tangent_ranges must be set before xb_setup");
     if (value < 1 || value > 64) return fail(XB_ERR_ARG, "tangent_ranges is 1..64");
     m->h.want_ranges = value;
+  } else if (n == "constraints_transformation") {
+    if (m->on_device) return fail(XB_ERR_STATE, "constraints_transformation must be set before xb_device_init");
+    m->transf_handler = value != 0;
   } else if (n == "fast_assembly") {
     m->fast_asm_on = value != 0;
   } else if (n == "ranged_tangent") {
