@@ -330,7 +330,7 @@ def test_reference_loop_reads_plane_stress_and_pressure_out_of_the_domain():
 
 
 @pytest.mark.skipif(not (have_ref() and have_glue()), reason="oracle/_ref not built (needs /root/reference)")
-@pytest.mark.parametrize("shape", ["brick", "quad"])
+@pytest.mark.parametrize("shape", ["brick", "quad", "brick@T", "quad@T"])
 def test_reference_newmark_loop_drives_device_path(shape):
     """The transient drop-in: the reference's own Newmark bookkeeping (U, Udot, Udotdot, predictor), NewtonRaphson and
     convergence test, with newStep / update / formTangent / formUnbalance / commit of the integrator routed to the
@@ -339,6 +339,8 @@ def test_reference_newmark_loop_drives_device_path(shape):
     the unmodified reference run."""
     from golden_cases import J2_STEEL_RHO, RAYLEIGH
     from modelspec import GLUE_SO, RefBackend
+    handler = 1 if shape.endswith("@T") else 0          # "...@T": `constraints Transformation` on both sides
+    shape = shape.split("@")[0]
     if shape == "brick":
         mk = lambda: brick_block(3, 3, 4, mat=J2_STEEL_RHO, lz=3.0, load=(240.0, 0.0, -30.0), distort=0.15, seed=3)
     else:
@@ -348,7 +350,7 @@ def test_reference_newmark_loop_drives_device_path(shape):
 
     def build(so=None):
         spec = mk()
-        R = RefBackend(spec, defer_setup=True, so=so)
+        R = RefBackend(spec, defer_setup=True, so=so, handler=handler)
         mass = np.zeros((spec.nn, spec.ndf)); mass[:] = 0.05
         R.set_mass(spec.node_tags, mass); R.set_rayleigh(*RAYLEIGH)
         return R
