@@ -56,8 +56,8 @@ struct GroupView {
   int cps;              // columns per row in a slot (cp_stride)
   int ns;               // dofs per node of the MODEL (stride of U, V, A): a quad's 2-dof nodes may sit in an ndf = 3 model
   double* Re;           // [n][nd]
-  const unsigned char* umask;   // null, or [n]: update only the marked elements (`constraints Transformation`: the handler's
-                                // enforceSPs() updates the elements next to constrained nodes once more at every applyLoad)
+  const int* ulist;     // null, or [nlist]: update only these elements (`constraints Transformation`: the handler's
+  long long nlist;      // enforceSPs() updates the elements next to constrained nodes once more at every applyLoad)
 };
 
 // Transient analysis with element damping / mass.  FE_Element::getTangent under Newmark::formEleTangent
@@ -169,16 +169,17 @@ constexpr int UPD_XS = 50;   // per element in shared memory: X[8][3], U[8][3] +
 #ifndef UPD_STASH
 #define UPD_STASH 0
 #endif
-template <int MATK>
+template <int MATK, bool LISTED = false>
 __global__ void __launch_bounds__(128, UPD_OCC) brick_update_kernel(GroupView G, const double* __restrict__ X,
                                                            const double* __restrict__ U, int* fail) {
   const long long gp_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long ngp = G.n * 8;
-  // dead lanes (beyond the batch, or of an element a masked update leaves alone) still take part in the shuffles below
-  const bool live = gp_raw < ngp && (G.umask == nullptr || G.umask[gp_raw >> 3] != 0);
-  const long long gp = live ? gp_raw : ngp - 1;
-  const long long e = gp >> 3;
+  const long long nrun = (LISTED ? G.nlist : G.n) * 8;   // a listed update runs over the listed elements only
+  const bool live = gp_raw < nrun;                // dead lanes still take part in the shuffles below
+  const long long gpl = live ? gp_raw : nrun - 1;
+  const long long e = LISTED ? (long long)__ldg(G.ulist + (gpl >> 3)) : (gpl >> 3);
   const int g = (int)(gp_raw & 7);
+  const long long gp = e * 8 + (live ? g : 7);
   // lane g fetches node g of its element (coordinates and trial displacements); the 8 lanes of
   // the element exchange them through shared memory
   __shared__ __align__(16) double sXU[16 * UPD_XS];
@@ -472,12 +473,12 @@ __global__ void __launch_bounds__(128) brick_mass_add_kernel(GroupView G, const 
 template <int MATK>
 __global__ void __launch_bounds__(128) quad_update_kernel(GroupView G, const double* __restrict__ X,
                                                           const double* __restrict__ U, int* fail) {
-  const long long gp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long gpl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long ngp = G.n * 4;
-  if (gp >= ngp) return;
-  if (G.umask != nullptr && G.umask[gp >> 2] == 0) return;      // masked update: not this element
-  const long long e = gp >> 2;
-  const int g = (int)(gp & 3);
+  if (gpl >= (G.ulist != nullptr ? G.nlist : G.n) * 4) return;
+  const long long e = G.ulist != nullptr ? (long long)__ldg(G.ulist + (gpl >> 2)) : (gpl >> 2);   // listed update: see GroupView
+  const int g = (int)(gpl & 3);
+  const long long gp = e * 4 + g;
   const int* c = G.conn + e * 4;
   double xc[4][2], u[2][4];
 #pragma unroll
@@ -1532,7 +1533,8 @@ struct DevGroup {
   int kind = 0, mat_kind = 0, nip = 0, nst = 0, nd = 0;
   long long ngp = 0, re_off = 0;
   bool has_rho = false;      // some material of the batch has a density (element mass)
-  const unsigned char* dmask = nullptr;   // `constraints Transformation`: elements with a constrained node (fix / equalDOF-constrained)
+  const int* dlist = nullptr;   // `constraints Transformation`: the elements with a constrained node (fix / equalDOF-constrained)
+  long long nlist = 0;
   size_t fib_doubles = 0;    // size of one fibre-record buffer
 };
 
@@ -2102,10 +2104,10 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
       // SP_Constraint or is the constrained node of an MP_Constraint becomes a TransformationFE
       std::unordered_set<int> cn(h.sp_node.begin(), h.sp_node.end());
       cn.insert(h.mp_c.begin(), h.mp_c.end());
-      std::vector<unsigned char> mk((size_t)g.n(), 0);
+      std::vector<int> el;
       for (long long e = 0; e < g.n(); e++)
-        for (int a = 0; a < k.nen; a++) if (cn.count(h.node_tag[g.conn[(size_t)e * k.nen + a]])) { mk[e] = 1; break; }
-      unsigned char* dm = nullptr; CU(dev_upload(m, &dm, mk)); d.dmask = dm;
+        for (int a = 0; a < k.nen; a++) if (cn.count(h.node_tag[g.conn[(size_t)e * k.nen + a]])) { el.push_back((int)e); break; }
+      if (!el.empty()) { int* dl = nullptr; CU(dev_upload(m, &dl, el)); d.dlist = dl; d.nlist = (long long)el.size(); }
     }
     m->dg.push_back(d);
   }
@@ -2410,10 +2412,14 @@ static void beams_take_load_factor(xb_model* m, double lambda) {
   for (auto& d : m->dg) if (is_beam(d.kind) && d.b.wl) { d.b.lam = m->ele_loads_const ? m->ele_lambda : lambda; d.b.loads_on = 1; }
 }
 static void launch_continuum_update(xb_model* m, const DevGroup& d, const GroupView& v) {
-  const unsigned blocks = (unsigned)((d.ngp + 127) / 128);
+  const unsigned blocks = (unsigned)(((v.ulist ? v.nlist * d.nip : d.ngp) + 127) / 128);
   const bool j2 = d.mat_kind == XB_MAT_J2PLASTICITY;
   if (d.kind == XB_ELE_STDBRICK) {
-    if (j2) brick_update_kernel<XB_MAT_J2PLASTICITY><<<blocks, 128, 0, m->stream>>>(v, m->dX, m->dU, m->dFail);
+    if (v.ulist) {
+      if (j2) brick_update_kernel<XB_MAT_J2PLASTICITY, true><<<blocks, 128, 0, m->stream>>>(v, m->dX, m->dU, m->dFail);
+      else brick_update_kernel<XB_MAT_ELASTIC_ISOTROPIC, true><<<blocks, 128, 0, m->stream>>>(v, m->dX, m->dU, m->dFail);
+    }
+    else if (j2) brick_update_kernel<XB_MAT_J2PLASTICITY><<<blocks, 128, 0, m->stream>>>(v, m->dX, m->dU, m->dFail);
     else brick_update_kernel<XB_MAT_ELASTIC_ISOTROPIC><<<blocks, 128, 0, m->stream>>>(v, m->dX, m->dU, m->dFail);
   } else {
     if (j2) quad_update_kernel<XB_MAT_J2PLASTICITY><<<blocks, 128, 0, m->stream>>>(v, m->dX, m->dU, m->dFail);
@@ -2433,8 +2439,8 @@ int xb_apply_load(xb_model* m, double lambda) {
     // of the next step.  The same elements are updated here; the committed history is not touched (no trial_written).
     CU(cudaSetDevice(m->device));
     for (auto& d : m->dg) {
-      if (is_beam(d.kind) || d.v.n == 0 || d.dmask == nullptr) continue;
-      GroupView v = d.v; v.umask = d.dmask;
+      if (is_beam(d.kind) || d.v.n == 0 || d.dlist == nullptr) continue;
+      GroupView v = d.v; v.ulist = d.dlist; v.nlist = d.nlist;
       launch_continuum_update(m, d, v);
     }
     CU(cudaGetLastError());
