@@ -270,8 +270,13 @@ int xb_get_trial_vel_accel(xb_model*, double* v, double* a);
  * xb_form_unbalance with a non-null buffer) or xb_synchronize returns as XB_ERR_STATE.  A caller that needs the
  * reference's immediate failure semantics calls xb_synchronize right after xb_update. */
 int xb_update(xb_model*);
-/* AnalysisModel::applyLoadDomain(lambda) for the Linear-series pattern */
+/* AnalysisModel::applyLoadDomain(lambda) for the Linear-series pattern: Domain::applyLoad, then the constraint handler's
+ * applyLoad -- nothing under `constraints Plain`; under "constraints_transformation" (xb_set_option) the second
+ * Element::update of the elements with a constrained node */
 int xb_apply_load(xb_model*, double lambda);
+/* the load factor alone (no handler action): for an integrator that re-reads the domain time where the reference does not
+ * call applyLoadDomain, e.g. before formUnbalance */
+int xb_set_load_factor(xb_model*, double lambda);
 /* `loadConst` (Domain::setLoadConstant, domain/domain/Domain.cpp:1814; LoadPattern::setLoadConstant, domain/pattern/
  * LoadPattern.cpp): the nodal loads applied so far stay at the current load factor; the reference load vector is
  * emptied for the next pattern; the beam element loads (xb_add_beam_uniform_loads / xb_add_beam_point_loads / xb_add_beam_partial_loads, which all
@@ -342,8 +347,8 @@ int xb_get_gp_response(xb_model*, long long e, int g, double* stress, double* ta
  *                     with fix / equalDOF constraints numbers and assembles like PlainHandler, but its enforceSPs() updates
  *                     every element with a constrained node once more at each applyLoad (analysis/handler/
  *                     TransformationConstraintHandler.cpp:462-483) -- after a commit that leaves a yielded J2 point with its
- *                     elastic tangent for the next step's first iteration.  With 1, xb_apply_load repeats that update on
- *                     the same stdBrick / FourNodeQuad elements; models with forceBeamColumn elements: XB_ERR_UNSUPPORTED
+ *                     elastic tangent for the next step's first iteration, and makes a force-based beam iterate
+ *                     once more from where it stood.  With 1, xb_apply_load repeats that update on the same elements
  * Returns XB_ERR_ARG for an unknown name or value. */
 int xb_set_option(xb_model*, const char* name, int value);
 

@@ -447,14 +447,11 @@ int domain_to_xb(RefModel* m, int numberer, int soeKind, int device, Glue& G) {
   // once more on every element next to a constrained node at each applyLoad (TransformationConstraintHandler.cpp:462-483):
   // after a commit that leaves a yielded J2 point with its elastic tangent for the first iteration of the next step, so the
   // reference's Newton histories differ between its two handlers.  The device does the same second update when told
-  // (`constraints_transformation`); a force-based beam would iterate again from where it stood, so beams stay on Plain.
+  // (`constraints_transformation`); a force-based beam iterates again from where it stood, there as here.
   std::map<int, size_t> row_of;
   for (size_t i = 0; i < xt.size(); i++) row_of[xt[i]] = i;
   const bool transf_handler = dynamic_cast<TransformationConstraintHandler*>(m->handler) != nullptr;
   if (transf_handler) {
-    ElementIter& ei = dom->getElements(); Element* el;
-    while ((el = ei()) != nullptr)
-      if (dynamic_cast<ForceBeamColumn2d*>(el) || dynamic_cast<ForceBeamColumn3d*>(el)) { G.err = "glue: forceBeamColumn under `constraints Transformation` (the handler updates constrained elements twice per step): use `constraints Plain`"; return -10; }
     if (xb_set_option(x, "constraints_transformation", 1) < 0) { G.err = xb_last_error(); return -10; }
   }
   for (size_t i = 0; i < xt.size(); i++) {
@@ -501,10 +498,16 @@ class B200LoadControl : public LoadControl {
     if (statFlag != CURRENT_TANGENT) return LoadControl::formTangent(statFlag, iFactor, cFactor);
     return this->formTangent(statFlag);
   }
+  // LoadControl::newStep (final) ends in AnalysisModel::applyLoadDomain -- under `constraints Transformation` that is where
+  // the handler updates the constrained elements once more.  The first formUnbalance of a step follows it directly
+  // (NewtonRaphson::solveCurrentStep), so that call carries xb_apply_load; the later ones only re-read the domain time
+  bool step_begins = true;
   // StaticIntegrator::formUnbalance is final: zeroB(); formElementResidual(); formNodalUnbalance()
   int formElementResidual() override {
     calls[1]++;
-    if (xb_apply_load(x, this->getAnalysisModel()->getCurrentDomainTime()) < 0) return -1;
+    const double t = this->getAnalysisModel()->getCurrentDomainTime();
+    if ((step_begins ? xb_apply_load(x, t) : xb_set_load_factor(x, t)) < 0) return -1;
+    step_begins = false;
     Vector& B = soeB();
     return xb_form_unbalance(x, &B(0));         // elements and nodal loads, the whole right-hand side
   }
@@ -523,12 +526,14 @@ class B200LoadControl : public LoadControl {
   }
   int commit() override {
     calls[3]++;
+    step_begins = true;
     if (xb_commit(x) < 0) return -1;
     return LoadControl::commit();
   }
   // a failed step: BasicAnalysisBuilder::analyzeStatic / analyzeTransient call Domain::revertToLastCommit and then this
   // (BasicAnalysisBuilder.cpp:372-413, 488-519); the device state goes back with it
   int revertToLastStep() override {
+    step_begins = true;
     const int rc = LoadControl::revertToLastStep();
     if (x && xb_revert_to_last_commit(x) < 0) return -1;
     return rc;
@@ -615,7 +620,7 @@ class B200DisplacementControl : public DisplacementControl {
   int formElementResidual() override {
     if (!x) return DisplacementControl::formElementResidual();   // domainChanged before the device model exists
     calls[1]++;
-    if (xb_apply_load(x, this->getAnalysisModel()->getCurrentDomainTime()) < 0) return -1;
+    if (xb_set_load_factor(x, this->getAnalysisModel()->getCurrentDomainTime()) < 0) return -1;
     Vector& B = soeB();
     return xb_form_unbalance(x, &B(0));
   }

@@ -19,13 +19,6 @@ def _setup(spec, **kw):
     return D
 
 
-def test_transformation_handler_with_force_beams_is_refused():
-    """`constraints Transformation` re-updates the elements next to constrained nodes at every applyLoad; the device does the
-    same for the continuum elements, but a force-based beam would iterate again from where it stood"""
-    with pytest.raises(RuntimeError, match="Transformation"):
-        _setup(frame2d(1, 1, 1), handler=1)
-
-
 def test_corotational_with_joint_offsets_is_refused():
     with pytest.raises(RuntimeError, match="joint offsets"):
         _setup(with_joint_offsets(with_corot(frame2d(1, 1, 1)), seed=1))

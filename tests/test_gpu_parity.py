@@ -201,7 +201,7 @@ def test_newton_iteration_counts_match_oracle(shape):
 @pytest.mark.skipif(not (have_ref() and have_glue()), reason="oracle/_ref not built (needs /root/reference)")
 @pytest.mark.parametrize("shape,numberer,soe", [("brick", 1, 0), ("quad", 0, 1), ("mixed", 1, 1), ("soilcolumn_equaldof", 1, 0), ("frame2d_gravity", 1, 0), ("soil_frame_mixed_ndf", 1, 0),
                                                 ("soilcolumn_equaldof", 0, 1), ("frame2d_pdelta", 1, 0), ("frame3d_pdelta", 1, 0), ("frame3d_eleloads", 1, 0), ("frame2d_legendre", 1, 0), ("frame3d_radau", 1, 0), ("frame2d_concrete01", 1, 0), ("frame2d_jntoffset", 1, 0), ("frame3d_jntoffset", 1, 0), ("frame2d_corot", 1, 0), ("frame2d_partial_load", 1, 0), ("frame3d_partial_load", 1, 0), ("frame2d_elasticpp", 1, 0),
-                                                ("soilcolumn_equaldof@T", 1, 0), ("brick@T", 0, 1), ("quad@T", 1, 0), ("mixed@T", 1, 1)])
+                                                ("soilcolumn_equaldof@T", 1, 0), ("brick@T", 0, 1), ("quad@T", 1, 0), ("mixed@T", 1, 1), ("frame2d_gravity@T", 1, 0), ("frame3d_pdelta@T", 1, 0), ("soil_frame_mixed_ndf@T", 1, 0)])
 def test_reference_newton_loop_drives_device_path(shape, numberer, soe):
     """The drop-in, end to end: the REFERENCE'S OWN StaticAnalysis objects (AnalysisModel, PlainHandler, numberer,
     SparseGenCol/Row SOE and solver, NewtonRaphson, CTestNormDispIncr, LoadControl::newStep) run a load-controlled

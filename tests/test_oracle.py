@@ -692,7 +692,7 @@ def test_transformation_handler_numbers_and_assembles_as_plain(numberer):
     a commit that turns the consistent tangent of a yielded J2 point into the elastic one and makes a force beam iterate
     again, so the reference's OWN Newton histories differ between its two handlers once the model yields (asserted at the
     end).  The device path follows PlainHandler by default and repeats the handler's second update on the same elements when the
-    binding finds a Transformation handler (`constraints_transformation`, tests/test_gpu_parity.py `...@T`); beams stay on Plain."""
+    binding finds a Transformation handler (`constraints_transformation`, tests/test_gpu_parity.py `...@T`)."""
     rng = np.random.default_rng(17)
     specs = [soil_column_equaldof(6, mat=J2_STEEL, distort=0.1), brick_periodic_equaldof(3, 2, 2), brick_block(3, 3, 3, mat=J2_STEEL, distort=0.2, seed=2),
              quad_plane(6, 4, mat=J2_STEEL, distort=0.2, seed=3)]

@@ -113,6 +113,7 @@ def _load():
         "xb_get_trial_disp": (i32, [vp, vp]),
         "xb_update": (i32, [vp]),
         "xb_apply_load": (i32, [vp, f64]),
+        "xb_set_load_factor": (i32, [vp, f64]),
         "xb_form_tangent": (i32, [vp, vp]),
         "xb_form_unbalance": (i32, [vp, vp]),
         "xb_form_element_tangents": (i32, [vp]),

@@ -80,6 +80,8 @@ struct BeamView {
   double lam;
   int loads_on;
   int has_point;
+  const int* ulist;            // null, or [nlist]: update only these elements (`constraints Transformation`, see GroupView::ulist)
+  long long nlist;
   int has_partial;             // rows 7..14 of wl hold Beam2d/3dPartialUniformLoad's wya, wyb, waa, wab, aOverL, bOverL, wza, wzb
   // geomTransf PDelta (PDeltaCrdTransf2d.cpp / PDeltaCrdTransf3d.cpp): geometric stiffness N/L and leaning-column shear.
   // 2D: the relative transverse displacement is taken from the trial displacements U whenever the element forms its
@@ -888,9 +890,10 @@ template <int G>
 __global__ void __launch_bounds__(128, XB_FBC_SEC_OCC) fbc3d_update_sec_kernel(BeamView B, const double* __restrict__ U,
                                                                const double* __restrict__ DU, int* fail) {
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long e = tid / G;
-  const int i = (int)(tid - e * G);          // this lane's section
-  if (e >= B.n) return;                      // a whole group leaves together
+  const long long le = tid / G;
+  const int i = (int)(tid - le * G);         // this lane's section
+  if (le >= (B.ulist != nullptr ? B.nlist : B.n)) return;      // a whole group leaves together
+  const long long e = B.ulist != nullptr ? (long long)B.ulist[le] : le;      // listed update: see GroupView::ulist
   const int lane = threadIdx.x & 31;
   const int gbase = lane & ~(G - 1);
   const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << gbase;
@@ -1154,9 +1157,10 @@ template <int G>
 __global__ void __launch_bounds__(128, XB_FBC_SEC_OCC) fbc2d_update_sec_kernel(BeamView B, const double* __restrict__ U,
                                                                                const double* __restrict__ DU, int* fail) {
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long e = tid / G;
-  const int i = (int)(tid - e * G);
-  if (e >= B.n) return;
+  const long long le = tid / G;
+  const int i = (int)(tid - le * G);
+  if (le >= (B.ulist != nullptr ? B.nlist : B.n)) return;
+  const long long e = B.ulist != nullptr ? (long long)B.ulist[le] : le;
   const int lane = threadIdx.x & 31;
   const int gbase = lane & ~(G - 1);
   const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << gbase;

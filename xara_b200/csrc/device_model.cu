@@ -1997,7 +1997,6 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
       const double det = k0[0] * k0[3] - k0[2] * k0[1];
       std::vector<double> fs0 = {k0[3] / det, -k0[1] / det, -k0[2] / det, k0[0] / det};
       b.agg = sd.agg ? 1 : 0;
-      if (m->transf_handler) return fail(XB_ERR_UNSUPPORTED, "constraints_transformation: forceBeamColumn elements are outside it (the handler's second update makes a force beam iterate again)");
       b.pdelta = g.transf == 1 ? 1 : 0; b.corot = g.transf == 2 ? 1 : 0; b.U = m->dU; b.ul = nullptr;
       b.off = nullptr;
       {   // rigid joint offsets, SoA [4][n] (2D) / [6][n] (3D); null when the batch has none
@@ -2070,6 +2069,15 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
       CU(dev_upload(m, &kdst, g.kdst));
       b.kdst = kdst; b.KeN = m->dKe; b.cps = h.cp_stride; b.Re = m->dRe + g.re_off;
       d.re_off = g.re_off;
+      b.ulist = nullptr; b.nlist = 0;
+      if (m->transf_handler && ne > 0) {   // the elements with a constrained node (see the continuum batches below)
+        std::unordered_set<int> cn(h.sp_node.begin(), h.sp_node.end());
+        cn.insert(h.mp_c.begin(), h.mp_c.end());
+        std::vector<int> el;
+        for (long long e = 0; e < ne; e++)
+          if (cn.count(h.node_tag[g.conn[(size_t)e * 2]]) || cn.count(h.node_tag[g.conn[(size_t)e * 2 + 1]])) el.push_back((int)e);
+        if (!el.empty()) { int* dl = nullptr; CU(dev_upload(m, &dl, el)); d.dlist = dl; d.nlist = (long long)el.size(); }
+      }
       m->dg.push_back(d);
       continue;
     }
@@ -2359,6 +2367,21 @@ int xb_get_trial_disp(xb_model* m, double* u) {
   return XB_OK;
 }
 
+// ForceBeamColumn2d/3d::update of a batch, one lane per section (G lanes per element); B.ulist: of the listed elements only
+static void launch_beam_update(xb_model* m, int kind, const BeamView& B) {
+  const long long nb = B.ulist ? B.nlist : B.n;
+  if (kind == XB_ELE_FORCEBEAMCOLUMN3D) {
+    if (B.nip <= 4) fbc3d_update_sec_kernel<4><<<(unsigned)((nb * 4 + 127) / 128), 128, 0, m->stream>>>(B, m->dU, m->dDU, m->dFail);
+    else if (B.nip <= 8) fbc3d_update_sec_kernel<8><<<(unsigned)((nb * 8 + 127) / 128), 128, 0, m->stream>>>(B, m->dU, m->dDU, m->dFail);
+    else fbc3d_update_sec_kernel<16><<<(unsigned)((nb * 16 + 127) / 128), 128, 0, m->stream>>>(B, m->dU, m->dDU, m->dFail);
+  } else {
+    if (B.nip <= 4) fbc2d_update_sec_kernel<4><<<(unsigned)((nb * 4 + 127) / 128), 128, 0, m->stream>>>(B, m->dU, m->dDU, m->dFail);
+    else if (B.nip <= 8) fbc2d_update_sec_kernel<8><<<(unsigned)((nb * 8 + 127) / 128), 128, 0, m->stream>>>(B, m->dU, m->dDU, m->dFail);
+    else fbc2d_update_sec_kernel<16><<<(unsigned)((nb * 16 + 127) / 128), 128, 0, m->stream>>>(B, m->dU, m->dDU, m->dFail);
+  }
+  m->launches++;
+}
+
 int xb_update(xb_model* m) {
   NEED_DEVICE();
   CU(cudaSetDevice(m->device));
@@ -2366,20 +2389,7 @@ int xb_update(xb_model* m) {
   for (auto& d : m->dg) {
     if (d.v.n == 0) continue;
     if (is_beam(d.kind)) {
-      if (d.kind == XB_ELE_FORCEBEAMCOLUMN3D) {
-        // one lane per section (G lanes per element)
-        const long long nb = d.b.n;
-        if (d.b.nip <= 4) fbc3d_update_sec_kernel<4><<<(unsigned)((nb * 4 + 127) / 128), 128, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
-        else if (d.b.nip <= 8) fbc3d_update_sec_kernel<8><<<(unsigned)((nb * 8 + 127) / 128), 128, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
-        else fbc3d_update_sec_kernel<16><<<(unsigned)((nb * 16 + 127) / 128), 128, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
-      }
-      else {
-        const long long nb = d.b.n;
-        if (d.b.nip <= 4) fbc2d_update_sec_kernel<4><<<(unsigned)((nb * 4 + 127) / 128), 128, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
-        else if (d.b.nip <= 8) fbc2d_update_sec_kernel<8><<<(unsigned)((nb * 8 + 127) / 128), 128, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
-        else fbc2d_update_sec_kernel<16><<<(unsigned)((nb * 16 + 127) / 128), 128, 0, m->stream>>>(d.b, m->dU, m->dDU, m->dFail);
-      }
-      m->launches++;
+      launch_beam_update(m, d.kind, d.b);
       bytes += (long long)d.b.n * d.b.nip * d.b.nf * XB_FIB_NV * 8 * 2;   // one section pass: records in, out
       continue;
     }
@@ -2439,12 +2449,23 @@ int xb_apply_load(xb_model* m, double lambda) {
     // of the next step.  The same elements are updated here; the committed history is not touched (no trial_written).
     CU(cudaSetDevice(m->device));
     for (auto& d : m->dg) {
-      if (is_beam(d.kind) || d.v.n == 0 || d.dlist == nullptr) continue;
+      if (d.dlist == nullptr) continue;
+      if (is_beam(d.kind)) {   // a force-based beam iterates once more from where it stands, with the same increment
+        BeamView b = d.b; b.ulist = d.dlist; b.nlist = d.nlist;
+        launch_beam_update(m, d.kind, b);
+        continue;
+      }
       GroupView v = d.v; v.ulist = d.dlist; v.nlist = d.nlist;
       launch_continuum_update(m, d, v);
     }
     CU(cudaGetLastError());
   }
+  return XB_OK;
+}
+int xb_set_load_factor(xb_model* m, double lambda) {
+  if (!m) return fail(XB_ERR_ARG, "null model");
+  m->lambda = lambda;
+  beams_take_load_factor(m, lambda);
   return XB_OK;
 }
 
