@@ -2014,6 +2014,7 @@ int xb_device_init(xb_model* m, int device, void* cuda_stream) {
         double* dr = nullptr; CU(dev_upload(m, &dr, rs)); b.rule = dr;
       }
       if (b.corot) {   // ub of the last update and of the last commit
+        if (m->rayK != 0.0 || m->rayK0 != 0.0 || m->rayKc != 0.0) return fail(XB_ERR_UNSUPPORTED, "rayleigh: stiffness-proportional damping on corotational beams is outside the device path");
         if (b.off) return fail(XB_ERR_UNSUPPORTED, "forceBeamColumn: geomTransf Corotational with joint offsets is outside the device path");
         CU(dev_alloc(m, &b.ul, (size_t)6 * std::max<long long>(ne, 1))); CU(cudaMemset(b.ul, 0, sizeof(double) * 6 * std::max<long long>(ne, 1)));
       }
@@ -2367,6 +2368,23 @@ int xb_get_trial_disp(xb_model* m, double* u) {
   return XB_OK;
 }
 
+// Brick::update / FourNodeQuad::update of a batch, one thread per Gauss point; v.ulist: of the listed elements only
+static void launch_continuum_update(xb_model* m, const DevGroup& d, const GroupView& v) {
+  const unsigned blocks = (unsigned)(((v.ulist ? v.nlist * d.nip : d.ngp) + 127) / 128);
+  const bool j2 = d.mat_kind == XB_MAT_J2PLASTICITY;
+  if (d.kind == XB_ELE_STDBRICK) {
+    if (v.ulist) {
+      if (j2) brick_update_kernel<XB_MAT_J2PLASTICITY, true><<<blocks, 128, 0, m->stream>>>(v, m->dX, m->dU, m->dFail);
+      else brick_update_kernel<XB_MAT_ELASTIC_ISOTROPIC, true><<<blocks, 128, 0, m->stream>>>(v, m->dX, m->dU, m->dFail);
+    }
+    else if (j2) brick_update_kernel<XB_MAT_J2PLASTICITY><<<blocks, 128, 0, m->stream>>>(v, m->dX, m->dU, m->dFail);
+    else brick_update_kernel<XB_MAT_ELASTIC_ISOTROPIC><<<blocks, 128, 0, m->stream>>>(v, m->dX, m->dU, m->dFail);
+  } else {
+    if (j2) quad_update_kernel<XB_MAT_J2PLASTICITY><<<blocks, 128, 0, m->stream>>>(v, m->dX, m->dU, m->dFail);
+    else quad_update_kernel<XB_MAT_ELASTIC_ISOTROPIC><<<blocks, 128, 0, m->stream>>>(v, m->dX, m->dU, m->dFail);
+  }
+  m->launches++;
+}
 // ForceBeamColumn2d/3d::update of a batch, one lane per section (G lanes per element); B.ulist: of the listed elements only
 static void launch_beam_update(xb_model* m, int kind, const BeamView& B) {
   const long long nb = B.ulist ? B.nlist : B.n;
@@ -2393,16 +2411,8 @@ int xb_update(xb_model* m) {
       bytes += (long long)d.b.n * d.b.nip * d.b.nf * XB_FIB_NV * 8 * 2;   // one section pass: records in, out
       continue;
     }
-    const unsigned blocks = (unsigned)((d.ngp + 127) / 128);
     const bool j2 = d.mat_kind == XB_MAT_J2PLASTICITY;
-    if (d.kind == XB_ELE_STDBRICK) {
-      if (j2) brick_update_kernel<XB_MAT_J2PLASTICITY><<<blocks, 128, 0, m->stream>>>(d.v, m->dX, m->dU, m->dFail);
-      else brick_update_kernel<XB_MAT_ELASTIC_ISOTROPIC><<<blocks, 128, 0, m->stream>>>(d.v, m->dX, m->dU, m->dFail);
-    } else {
-      if (j2) quad_update_kernel<XB_MAT_J2PLASTICITY><<<blocks, 128, 0, m->stream>>>(d.v, m->dX, m->dU, m->dFail);
-      else quad_update_kernel<XB_MAT_ELASTIC_ISOTROPIC><<<blocks, 128, 0, m->stream>>>(d.v, m->dX, m->dU, m->dFail);
-    }
-    m->launches++;
+    launch_continuum_update(m, d, d.v);
     // per Gauss point: committed history read (7) + trial history, stress, compact tangent written
     bytes += d.ngp * 8 * (j2 ? (7 + 7 + d.nst + 8) : d.nst);
     if (d.kind == XB_ELE_STDBRICK) bytes += d.v.n * d.nd * 8;   // + the element residual it leaves behind
@@ -2420,22 +2430,6 @@ int xb_update(xb_model* m) {
 static void beams_take_load_factor(xb_model* m, double lambda) {
   // (element loads of a pattern that loadConst froze keep the factor they had then: LoadPattern::applyLoad with isConstant)
   for (auto& d : m->dg) if (is_beam(d.kind) && d.b.wl) { d.b.lam = m->ele_loads_const ? m->ele_lambda : lambda; d.b.loads_on = 1; }
-}
-static void launch_continuum_update(xb_model* m, const DevGroup& d, const GroupView& v) {
-  const unsigned blocks = (unsigned)(((v.ulist ? v.nlist * d.nip : d.ngp) + 127) / 128);
-  const bool j2 = d.mat_kind == XB_MAT_J2PLASTICITY;
-  if (d.kind == XB_ELE_STDBRICK) {
-    if (v.ulist) {
-      if (j2) brick_update_kernel<XB_MAT_J2PLASTICITY, true><<<blocks, 128, 0, m->stream>>>(v, m->dX, m->dU, m->dFail);
-      else brick_update_kernel<XB_MAT_ELASTIC_ISOTROPIC, true><<<blocks, 128, 0, m->stream>>>(v, m->dX, m->dU, m->dFail);
-    }
-    else if (j2) brick_update_kernel<XB_MAT_J2PLASTICITY><<<blocks, 128, 0, m->stream>>>(v, m->dX, m->dU, m->dFail);
-    else brick_update_kernel<XB_MAT_ELASTIC_ISOTROPIC><<<blocks, 128, 0, m->stream>>>(v, m->dX, m->dU, m->dFail);
-  } else {
-    if (j2) quad_update_kernel<XB_MAT_J2PLASTICITY><<<blocks, 128, 0, m->stream>>>(v, m->dX, m->dU, m->dFail);
-    else quad_update_kernel<XB_MAT_ELASTIC_ISOTROPIC><<<blocks, 128, 0, m->stream>>>(v, m->dX, m->dU, m->dFail);
-  }
-  m->launches++;
 }
 int xb_apply_load(xb_model* m, double lambda) {
   if (!m) return fail(XB_ERR_ARG, "null model");
