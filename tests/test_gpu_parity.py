@@ -406,6 +406,32 @@ def test_reference_displacement_control_drives_device_path(name):
 
 
 @pytest.mark.skipif(not (have_ref() and have_glue()), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("name", ["dc_cantilever_fiber", "dc_frame3d", "dc_brick_j2"])
+def test_reference_displacement_control_under_transformation_handler(name):
+    """`constraints Transformation` + `integrator DisplacementControl`: here the reference calls applyLoadDomain -- and with it
+    the handler's second update of the elements with a constrained node -- in EVERY iteration, between incrDisp and
+    updateDomain (DisplacementControl.cpp:121,210): a force beam at the fixed base is updated twice per iteration with the
+    same increment.  The unmodified reference on the CPU against the same loop over the device path
+    (`constraints_transformation`): same iteration counts, load factors, displacements."""
+    from golden_cases import DISPCONTROL_CASES, control_node
+    from modelspec import GLUE_SO, RefBackend
+    mk, numberer, soe, node, dof, incr, nsteps, tol, max_iter = DISPCONTROL_CASES[name]
+    nd = control_node(mk(), node)
+    C = RefBackend(mk(), defer_setup=True, handler=1)
+    C.setup_dispcontrol(numberer, soe, nd, dof, incr, test=0, tol=tol, max_iter=max_iter)
+    rc, it_cpu, nm_cpu, lam_cpu = C.analyze_static_lam(nsteps)
+    assert rc == 0
+    D = RefBackend(mk(), defer_setup=True, so=GLUE_SO, handler=1)
+    D.setup_glue_dispcontrol(numberer, soe, nd, dof, incr, test=0, tol=tol, max_iter=max_iter)
+    rc, it_dev, nm_dev, lam_dev = D.analyze_static_lam(nsteps)
+    assert rc == 0
+    assert it_dev.tolist() == it_cpu.tolist()
+    assert relerr(lam_dev, lam_cpu) < 1e-8 and relerr(D.glue_trial_disp(), C.get_trial_disp()) < 1e-8
+    for s in range(nsteps):
+        assert np.allclose(nm_dev[s, :it_dev[s] - 1], nm_cpu[s, :it_cpu[s] - 1], rtol=1e-5, atol=1e-12)
+
+
+@pytest.mark.skipif(not (have_ref() and have_glue()), reason="oracle/_ref not built (needs /root/reference)")
 @pytest.mark.parametrize("shape", ["frame2d", "frame3d", "frame2d_pdelta", "frame3d_pdelta", "frame2d_rho"])
 def test_reference_newmark_loop_drives_device_frames(shape):
     """BASELINE configs[3] in small: RC frames of forceBeamColumn elements (Steel02 / Concrete02 fibre sections),
