@@ -432,7 +432,7 @@ def test_reference_displacement_control_under_transformation_handler(name):
 
 
 @pytest.mark.skipif(not (have_ref() and have_glue()), reason="oracle/_ref not built (needs /root/reference)")
-@pytest.mark.parametrize("shape", ["frame2d", "frame3d", "frame2d_pdelta", "frame3d_pdelta", "frame2d_rho"])
+@pytest.mark.parametrize("shape", ["frame2d", "frame3d", "frame2d_pdelta", "frame3d_pdelta", "frame2d_rho", "frame2d@T", "frame3d_pdelta@T"])
 def test_reference_newmark_loop_drives_device_frames(shape):
     """BASELINE configs[3] in small: RC frames of forceBeamColumn elements (Steel02 / Concrete02 fibre sections),
     transient Newmark with nodal masses and Rayleigh damping, run by the reference's own objects on the CPU and
@@ -440,6 +440,8 @@ def test_reference_newmark_loop_drives_device_frames(shape):
     from golden_cases import RAYLEIGH
     from modelspec import GLUE_SO, RefBackend
     from modelspec import with_pdelta
+    handler = 1 if shape.endswith("@T") else 0          # "...@T": `constraints Transformation` on both sides
+    shape = shape.split("@")[0]
     if shape == "frame2d": mk = lambda: frame2d(2, 2, 2, lateral=30.0)
     elif shape == "frame3d": mk = lambda: frame3d(1, 1, 2, ndiv=2, lateral=(25.0, 15.0))
     elif shape == "frame2d_rho":               # forceBeamColumn -mass: the glue reads rho out of the elements
@@ -451,7 +453,7 @@ def test_reference_newmark_loop_drives_device_frames(shape):
 
     def build(so=None):
         spec = mk()
-        R = RefBackend(spec, defer_setup=True, so=so)
+        R = RefBackend(spec, defer_setup=True, so=so, handler=handler)
         mass = np.zeros((spec.nn, spec.ndf)); mass[:, :spec.ndm] = 0.05
         R.set_mass(spec.node_tags, mass); R.set_rayleigh(*RAYLEIGH)
         return R
