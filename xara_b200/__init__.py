@@ -438,7 +438,13 @@ class DeviceModel:
         self._ck(lib.xb_update(self._h))
 
     def apply_load(self, lam):
+        """AnalysisModel::applyLoadDomain: the domain time / load factor and the constraint handler's applyLoad (under
+        set_option("constraints_transformation", 1): the second update of the elements with a constrained node)"""
         self._ck(lib.xb_apply_load(self._h, float(lam)))
+
+    def set_load_factor(self, lam):
+        """the load factor alone (no handler action)"""
+        self._ck(lib.xb_set_load_factor(self._h, float(lam)))
 
     def load_const(self):
         """loadConst: the loads applied so far stay at the current factor (follow with apply_load(new time))"""
@@ -516,7 +522,8 @@ class DeviceModel:
         return lib.xb_launch_count(self._h)
 
     def set_option(self, name: str, value: int):
-        """run-time tuning (include/xara_b200.h, xb_set_option); results do not depend on it"""
+        """run-time options (include/xara_b200.h, xb_set_option): tuning switches, which do not change results, and
+        "constraints_transformation", which follows the reference's `constraints Transformation`"""
         self._ck(lib.xb_set_option(self._h, name.encode(), int(value)))
         return self
 
